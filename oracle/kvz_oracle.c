@@ -1,0 +1,1047 @@
+/*
+ * kvz_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE (see kvz_oracle.h).
+ *
+ * CPU restatement of the reference's generic strategies.  Written from the
+ * behaviour of /root/reference/src/strategies/generic/<group>-generic.c (cited per function as
+ * ref:<file>:<lines>), not copied from it: transforms are written as the matrix
+ * products the butterflies compute, Hadamards as generic-N loops, tables are
+ * generated from their defining rules.  tests/test_oracle_*.py pin every function
+ * against the reference's golden constants and against the compiled reference.
+ */
+#include "kvz_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_MIN(a, b) ((a) < (b) ? (a) : (b))
+#define ORC_MAX(a, b) ((a) > (b) ? (a) : (b))
+#define ORC_CLIP(lo, hi, v) ((v) < (lo) ? (lo) : ((v) > (hi) ? (hi) : (v)))
+
+int orc_bitdepth(void) { return ORC_BITDEPTH; }
+
+/* ref:picture-generic.c:40-82 -- the "fast clip" bit tricks equal a plain clamp to
+ * [0, PIXEL_MAX] for every int16/int32 input except that the 16-bit variant negates
+ * in int (so -32768 clamps to 0 as expected). A plain clamp is the restatement. */
+static inline orc_pix clip_pix(int v) { return (orc_pix)ORC_CLIP(0, ORC_PIXEL_MAX, v); }
+
+/* ======================================================================= */
+/* picture group                                                           */
+/* ======================================================================= */
+
+/* ref:picture-generic.c:98-111 -- strided SAD, no bit-depth shift */
+unsigned orc_reg_sad(const orc_pix *a, const orc_pix *b, int w, int h, unsigned s1, unsigned s2)
+{
+  unsigned sad = 0;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x)
+      sad += (unsigned)abs((int)a[y * s1 + x] - (int)b[y * s2 + x]);
+  return sad;
+}
+
+/* ref:picture-generic.c:475-501 -- contiguous NxN SAD, >> (bitdepth-8) */
+unsigned orc_sad_nxn(int n, const orc_pix *a, const orc_pix *b)
+{
+  unsigned sum = 0;
+  for (int i = 0; i < n * n; ++i) sum += (unsigned)abs((int)a[i] - (int)b[i]);
+  return sum >> (ORC_BITDEPTH - 8);
+}
+
+/* ref:picture-generic.c:512-534 -- preds is kvz_pixel[2][32*32]; only [0],[1] used */
+void orc_sad_nxn_dual(int n, const orc_pix *preds, const orc_pix *orig, unsigned *costs)
+{
+  /* NOTE: pred_buffer rows are 32*32 pixels apart regardless of n (strategies-picture.h:48).
+   * For n == 64 the reference indexes past one row into the next; keep that layout. */
+  costs[0] = orc_sad_nxn(n, preds, orig);
+  costs[1] = orc_sad_nxn(n, preds + 32 * 32, orig);
+}
+
+/* In-place 1-D Walsh-Hadamard butterflies over `len` values with stride `st`.
+ * The reference (picture-generic.c:117-208, 252-340) hard-codes one particular
+ * butterfly ordering whose output is a permutation (with identical magnitudes) of
+ * the natural-ordered transform; SATD only sums |coeff|, so ordering is irrelevant. */
+static void wht_1d(int32_t *v, int len, int st)
+{
+  for (int half = 1; half < len; half <<= 1)
+    for (int base = 0; base < len; base += 2 * half)
+      for (int k = 0; k < half; ++k) {
+        int32_t p = v[(base + k) * st], q = v[(base + k + half) * st];
+        v[(base + k) * st] = p + q;
+        v[(base + k + half) * st] = p - q;
+      }
+}
+
+static unsigned hadamard_abs_sum(int32_t *d, int n)
+{
+  for (int r = 0; r < n; ++r) wht_1d(d + r * n, n, 1);
+  for (int c = 0; c < n; ++c) wht_1d(d + c, n, n);
+  unsigned s = 0;
+  for (int i = 0; i < n * n; ++i) s += (unsigned)abs(d[i]);
+  return s;
+}
+
+/* ref:picture-generic.c:117-208,213-236 -- 4x4: (sum+1)>>1 */
+static unsigned satd4_sub(const orc_pix *a, int sa, const orc_pix *b, int sb)
+{
+  int32_t d[16];
+  for (int y = 0; y < 4; ++y)
+    for (int x = 0; x < 4; ++x) d[y * 4 + x] = (int)a[y * sa + x] - (int)b[y * sb + x];
+  return (hadamard_abs_sum(d, 4) + 1) >> 1;
+}
+
+/* ref:picture-generic.c:252-340 -- 8x8: (sum+2)>>2 */
+static unsigned satd8_sub(const orc_pix *a, int sa, const orc_pix *b, int sb)
+{
+  int32_t d[64];
+  for (int y = 0; y < 8; ++y)
+    for (int x = 0; x < 8; ++x) d[y * 8 + x] = (int)a[y * sa + x] - (int)b[y * sb + x];
+  return (hadamard_abs_sum(d, 8) + 2) >> 2;
+}
+
+/* ref:picture-generic.c:213-221 (4x4, no bit-depth shift!) and
+ * strategies-picture.h:53-69 (N>=8: sum of 8x8 sub-block SATDs, >> (bitdepth-8)) */
+unsigned orc_satd_nxn(int n, const orc_pix *a, const orc_pix *b)
+{
+  if (n == 4) return satd4_sub(a, 4, b, 4);
+  unsigned sum = 0;
+  for (int y = 0; y < n; y += 8)
+    for (int x = 0; x < n; x += 8) sum += satd8_sub(a + y * n + x, n, b + y * n + x, n);
+  return sum >> (ORC_BITDEPTH - 8);
+}
+
+/* ref:picture-generic.c:363-402 */
+void orc_satd_nxn_dual(int n, const orc_pix *preds, const orc_pix *orig, unsigned *costs)
+{
+  /* 4x4: satd_4x4_generic(orig, preds[k]); N>=8: satd_8x8_subblock(preds[k], orig).
+   * |H(a-b)| == |H(b-a)| so argument order does not matter. */
+  costs[0] = orc_satd_nxn(n, preds, orig);
+  costs[1] = orc_satd_nxn(n, preds + 32 * 32, orig);
+}
+
+/* ref:strategies-picture.h:75-113 (SATD_ANY_SIZE) */
+unsigned orc_satd_any_size(int w, int h, const orc_pix *b1, int s1, const orc_pix *b2, int s2)
+{
+  unsigned sum = 0;
+  if (w % 8 != 0) {               /* first 4-wide column as 4x4 blocks */
+    for (int y = 0; y < h; y += 4) sum += satd4_sub(b1 + y * s1, s1, b2 + y * s2, s2);
+    b1 += 4; b2 += 4; w -= 4;
+  }
+  if (h % 8 != 0) {               /* first 4-high row as 4x4 blocks */
+    for (int x = 0; x < w; x += 4) sum += satd4_sub(b1 + x, s1, b2 + x, s2);
+    b1 += 4 * s1; b2 += 4 * s2; h -= 4;
+  }
+  for (int y = 0; y < h; y += 8)
+    for (int x = 0; x < w; x += 8) sum += satd8_sub(b1 + y * s1 + x, s1, b2 + y * s2 + x, s2);
+  return sum >> (ORC_BITDEPTH - 8);
+}
+
+/* ref:picture-generic.c:404-471 (SATD_ANY_SIZE_MULTI_GENERIC) -- including the quirk that
+ * when height % 8 == 4 the 8x8 pass restarts from row 0 of the ORIGINAL pointers
+ * (rows 0..3 counted twice, the last 4 rows never), see SURVEY.md H5. */
+void orc_satd_any_size_quad(int w, int h, const orc_pix *const preds[4], int stride,
+                            const orc_pix *orig, int orig_stride, unsigned num_modes,
+                            unsigned *costs, int8_t *valid)
+{
+  (void)num_modes; (void)valid;
+  const int wmod = w % 8;
+  for (int k = 0; k < 4; ++k) costs[k] = 0;
+  if (wmod != 0) {
+    for (int y = 0; y < h; y += 4)
+      for (int k = 0; k < 4; ++k)
+        costs[k] += satd4_sub(orig + y * orig_stride, orig_stride, preds[k] + y * stride, stride);
+    w -= 4;
+  }
+  if (h % 8 != 0) {
+    /* first row of 4x4 blocks: starts at column 0 of preds AND orig, runs over the
+     * (already reduced) width */
+    for (int x = 0; x < w; x += 4)
+      for (int k = 0; k < 4; ++k)
+        costs[k] += satd4_sub(orig + x, orig_stride, preds[k] + x, stride);
+    h -= 4;
+  }
+  for (int y = h % 8; y < h; y += 8)
+    for (int x = wmod; x < w; x += 8)
+      for (int k = 0; k < 4; ++k)
+        costs[k] += satd8_sub(orig + y * orig_stride + x, orig_stride, preds[k] + y * stride + x, stride);
+  for (int k = 0; k < 4; ++k) costs[k] >>= (ORC_BITDEPTH - 8);
+}
+
+/* ref:picture-generic.c:536-551 */
+unsigned orc_pixels_calc_ssd(const orc_pix *ref, const orc_pix *rec, int ref_stride, int rec_stride, int width)
+{
+  int ssd = 0;
+  for (int y = 0; y < width; ++y)
+    for (int x = 0; x < width; ++x) {
+      int d = (int)ref[x + y * ref_stride] - (int)rec[x + y * rec_stride];
+      ssd += d * d;
+    }
+  return (unsigned)(ssd >> (2 * (ORC_BITDEPTH - 8)));
+}
+
+/* ref:picture-generic.c:687-701 */
+uint32_t orc_ver_sad(const orc_pix *pic, const orc_pix *ref, int w, int h, uint32_t pic_stride)
+{
+  uint32_t sad = 0;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) sad += (uint32_t)abs((int)pic[y * pic_stride + x] - (int)ref[x]);
+  return sad;
+}
+
+static uint32_t hor_sad_col(const orc_pix *pic, const orc_pix *ref, int w, int h, uint32_t ps, uint32_t rs)
+{
+  uint32_t sad = 0;
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) sad += (uint32_t)abs((int)pic[y * ps + x] - (int)ref[y * rs]);
+  return sad;
+}
+
+/* ref:picture-generic.c:714-752 */
+uint32_t orc_hor_sad(const orc_pix *pic, const orc_pix *ref, int w, int h, uint32_t ps,
+                     uint32_t rs, uint32_t left, uint32_t right)
+{
+  uint32_t r = 0;
+  if (left) {
+    r += hor_sad_col(pic, ref + left, (int)left, h, ps, rs);
+    r += orc_reg_sad(pic + left, ref + left, w - (int)left, h, ps, rs);
+  } else if (right) {
+    r += orc_reg_sad(pic, ref, w - (int)right, h, ps, rs);
+    r += hor_sad_col(pic + w - right, ref + w - right - 1, (int)right, h, ps, rs);
+  } else {
+    r += orc_reg_sad(pic, ref, w, h, ps, rs);
+  }
+  return r;
+}
+
+/* ref:picture-generic.c:553-668 -- one plane; inputs are contiguous pu_w*pu_h */
+void orc_bipred_average_plane(orc_pix *dst, unsigned dst_stride, const void *l0, const void *l1,
+                              int l0_is_im, int l1_is_im, unsigned w, unsigned h)
+{
+  const int shift = 15 - ORC_BITDEPTH;
+  const int offset = 1 << (shift - 1);
+  for (unsigned i = 0; i < w * h; ++i) {
+    int16_t s0 = l0_is_im ? ((const int16_t *)l0)[i] : (int16_t)(((const orc_pix *)l0)[i] << (14 - ORC_BITDEPTH));
+    int16_t s1 = l1_is_im ? ((const int16_t *)l1)[i] : (int16_t)(((const orc_pix *)l1)[i] << (14 - ORC_BITDEPTH));
+    int32_t r = ((int32_t)s0 + (int32_t)s1 + offset) >> shift;
+    dst[(i / w) * dst_stride + (i % w)] = clip_pix(r);
+  }
+}
+
+/* ref:picture-generic.c:755-778 */
+double orc_pixel_var(const orc_pix *arr, uint32_t len)
+{
+  double sum = 0, var = 0;
+  for (uint32_t i = 0; i < len; ++i) sum += arr[i];
+  double mean = sum / (double)len;
+  for (uint32_t i = 0; i < len; ++i) { double t = (double)arr[i] - mean; var += t * t; }
+  return var / len;
+}
+
+/* ======================================================================= */
+/* dct group                                                               */
+/* ======================================================================= */
+
+/* HEVC core transform matrix entries.  The 32-point matrix is
+ * M32[k][i] = C[(k*(2i+1)) mod 128] where C follows the cosine symmetries
+ * C[64-m] = -C[m], C[128-m] = C[m] and C[0..32] is the spec's coefficient list;
+ * the N-point matrix is rows 0, 32/N, 2*32/N... truncated to N columns.
+ * tests pin this against the reference's kvz_g_dct_{4,8,16,32} tables
+ * (ref:dct-generic.c:38-120). */
+static int dct_coef(int n, int k, int i)
+{
+  static const int c32[33] = { 64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
+                               61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4, 0 };
+  int m = ((k * (32 / n)) * (2 * i + 1)) % 128;
+  if (m > 64) m = 128 - m;          /* C[128-m] = C[m] */
+  return m <= 32 ? c32[m] : -c32[64 - m];
+}
+
+static const int dst4_mat[4][4] = { /* DST-VII, ref:dct-generic.c:38-44 */
+  { 29, 55, 74, 84 }, { 74, 74, 0, -74 }, { 84, -29, -74, 55 }, { 55, -84, 74, -29 } };
+
+static int tr_coef(int n, int is_dst, int k, int i) { return is_dst ? dst4_mat[k][i] : dct_coef(n, k, i); }
+
+/* One forward pass: dst[k*n + j] = (short)((sum_i M[k][i]*src[j*n+i] + add) >> shift)
+ * (what partial_butterfly_N computes, ref:dct-generic.c:255-279 etc.; result is
+ * TRUNCATED to int16, not clipped). */
+static void fwd_pass(int n, int is_dst, const int16_t *src, int16_t *dst, int shift)
+{
+  const int32_t add = 1 << (shift - 1);
+  for (int j = 0; j < n; ++j)
+    for (int k = 0; k < n; ++k) {
+      int32_t acc = 0;
+      for (int i = 0; i < n; ++i) acc += tr_coef(n, is_dst, k, i) * src[j * n + i];
+      dst[k * n + j] = (int16_t)((acc + add) >> shift);
+    }
+}
+
+/* One inverse pass: dst[j*n + k] = clip16((sum_i M[i][k]*src[i*n+j] + add) >> shift)
+ * (ref:dct-generic.c:281-303 etc.; CLIPPED to int16). */
+static void inv_pass(int n, int is_dst, const int16_t *src, int16_t *dst, int shift)
+{
+  const int32_t add = 1 << (shift - 1);
+  for (int j = 0; j < n; ++j)
+    for (int k = 0; k < n; ++k) {
+      int32_t acc = 0;
+      for (int i = 0; i < n; ++i) acc += tr_coef(n, is_dst, i, k) * src[i * n + j];
+      int32_t v = (acc + add) >> shift;
+      dst[j * n + k] = (int16_t)ORC_CLIP(-32768, 32767, v);
+    }
+}
+
+static int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+
+/* ref:dct-generic.c:579-588 */
+void orc_dct_nxn(int n, int bitdepth, const int16_t *in, int16_t *out)
+{
+  int16_t tmp[32 * 32];
+  fwd_pass(n, 0, in, tmp, ilog2(n) - 1 + (bitdepth - 8));
+  fwd_pass(n, 0, tmp, out, ilog2(n) + 6);
+}
+/* ref:dct-generic.c:590-599 */
+void orc_idct_nxn(int n, int bitdepth, const int16_t *in, int16_t *out)
+{
+  int16_t tmp[32 * 32];
+  inv_pass(n, 0, in, tmp, 7);
+  inv_pass(n, 0, tmp, out, 12 - (bitdepth - 8));
+}
+/* ref:dct-generic.c:611-619 */
+void orc_dst_4x4(int bitdepth, const int16_t *in, int16_t *out)
+{
+  int16_t tmp[16];
+  fwd_pass(4, 1, in, tmp, 1 + (bitdepth - 8));
+  fwd_pass(4, 1, tmp, out, 8);
+}
+/* ref:dct-generic.c:621-629 */
+void orc_idst_4x4(int bitdepth, const int16_t *in, int16_t *out)
+{
+  int16_t tmp[16];
+  inv_pass(4, 1, in, tmp, 7);
+  inv_pass(4, 1, tmp, out, 12 - (bitdepth - 8));
+}
+
+/* ======================================================================= */
+/* quant group                                                             */
+/* ======================================================================= */
+
+/* ref:transform.c:56-62 (chroma QP mapping table) built from its defining rule:
+ * identity below 30, then the HEVC table 29,30,31,32,33,33,34,34,35,35,36,36,37,37, then qp-6. */
+static int chroma_scale(int qp)
+{
+  static const int mid[14] = { 29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37, 37 };
+  if (qp < 30) return qp;
+  if (qp < 44) return mid[qp - 30];
+  return qp - 6;
+}
+
+/* ref:transform.c:88-102 */
+int32_t orc_get_scaled_qp(int type, int qp, int qp_offset)
+{
+  if (type == 0) return qp + qp_offset;
+  int q = ORC_CLIP(-qp_offset, 57, qp);
+  return q < 0 ? q + qp_offset : chroma_scale(q) + qp_offset;
+}
+
+/* Coefficient scan tables (ref:tables.c:10-70 kvz_g_sig_last_scan[scan_idx][log2-1]),
+ * generated: 4x4 coefficient groups visited in the scan order, and the same order
+ * inside each group.  scan_idx 0 = up-right diagonal, 1 = horizontal, 2 = vertical. */
+static uint32_t scan_tab[3][6][32 * 32];
+static int scan_ready = 0;
+
+static int order_small(int scan_idx, int dim, int *xs, int *ys)
+{
+  int n = 0;
+  if (scan_idx == 1) { for (int y = 0; y < dim; ++y) for (int x = 0; x < dim; ++x) { xs[n] = x; ys[n++] = y; } }
+  else if (scan_idx == 2) { for (int x = 0; x < dim; ++x) for (int y = 0; y < dim; ++y) { xs[n] = x; ys[n++] = y; } }
+  else {
+    for (int d = 0; d < 2 * dim - 1; ++d)           /* anti-diagonals, bottom-left to top-right */
+      for (int y = ORC_MIN(d, dim - 1); y >= 0 && d - y < dim; --y) { xs[n] = d - y; ys[n++] = y; }
+  }
+  return n;
+}
+
+static void build_scans(void)
+{
+  int xs[64], ys[64], cx[64], cy[64];
+  for (int s = 0; s < 3; ++s)
+    for (int l = 1; l <= 5; ++l) {
+      int w = 1 << l, n = 0;
+      if (l <= 2) {
+        int cnt = order_small(s, w, xs, ys);
+        for (int i = 0; i < cnt; ++i) scan_tab[s][l][n++] = (uint32_t)(ys[i] * w + xs[i]);
+      } else {
+        int ncg = order_small(s, w / 4, cx, cy);
+        int nin = order_small(s, 4, xs, ys);
+        for (int g = 0; g < ncg; ++g)
+          for (int i = 0; i < nin; ++i)
+            scan_tab[s][l][n++] = (uint32_t)((cy[g] * 4 + ys[i]) * w + cx[g] * 4 + xs[i]);
+      }
+    }
+  scan_ready = 1;
+}
+
+const uint32_t *orc_scan_table(int scan_idx, int log2_size)
+{
+  if (!scan_ready) build_scans();
+  return scan_tab[scan_idx][log2_size];
+}
+
+static const int quant_scales[6] = { 26214, 23302, 20560, 18396, 16384, 14564 };  /* ref:scalinglist.c:78 */
+static const int inv_quant_scales[6] = { 40, 45, 51, 57, 64, 72 };                /* ref:scalinglist.c:79 */
+
+/* ref:quant-generic.c:50-180 (kvz_quant_generic), flat scaling list */
+void orc_quant(const orc_quant_params *p, const int16_t *coef, int16_t *q_coef, int w, int h,
+               int type, int scan_idx, int block_type)
+{
+  (void)block_type;
+  const int log2_tr = ilog2(w);
+  const uint32_t *scan = orc_scan_table(scan_idx, log2_tr);
+  const int qp_scaled = orc_get_scaled_qp(type, p->qp, (p->bitdepth - 8) * 6);
+  const int qc = quant_scales[qp_scaled % 6];
+  const int transform_shift = 15 - p->bitdepth - log2_tr;
+  const int q_bits = 14 + qp_scaled / 6 + transform_shift;
+  const int32_t add = (p->slice_is_intra ? 171 : 85) << (q_bits - 9);
+  const int q_bits8 = q_bits - 8;
+  uint32_t ac_sum = 0;
+
+  for (int n = 0; n < w * h; ++n) {
+    int32_t level = coef[n];
+    int64_t abs_level = (int64_t)abs(level);
+    int32_t sign = level < 0 ? -1 : 1;
+    level = (int32_t)((abs_level * qc + add) >> q_bits);
+    ac_sum += (uint32_t)level;
+    level *= sign;
+    q_coef[n] = (int16_t)ORC_CLIP(-32768, 32767, level);
+  }
+  if (!p->signhide_enable || ac_sum < 2) return;
+
+  int32_t delta_u[32 * 32];
+  for (int n = 0; n < w * h; ++n) {
+    int64_t abs_level = (int64_t)abs((int32_t)coef[n]);
+    int32_t level = (int32_t)((abs_level * qc + add) >> q_bits);
+    delta_u[n] = (int32_t)((abs_level * qc - ((int64_t)level << q_bits)) >> q_bits8);
+  }
+
+  int last_cg = -1;
+  for (int subset = (w * h - 1) >> 4; subset >= 0; --subset) {
+    const int subpos = subset << 4;
+    int first_nz = 16, last_nz = -1, abssum = 0;
+    for (int n = 15; n >= 0; --n) if (q_coef[scan[n + subpos]]) { last_nz = n; break; }
+    for (int n = 0; n < 16; ++n) if (q_coef[scan[n + subpos]]) { first_nz = n; break; }
+    for (int n = first_nz; n <= last_nz; ++n) abssum += q_coef[scan[n + subpos]];
+    if (last_nz >= 0 && last_cg == -1) last_cg = 1;
+
+    if (last_nz - first_nz >= 4) {
+      int signbit = q_coef[scan[subpos + first_nz]] > 0 ? 0 : 1;
+      if (signbit != (abssum & 1)) {
+        int32_t min_cost = 0x7fffffff, cur_cost = 0x7fffffff;
+        int min_pos = -1;
+        int16_t final_change = 0, cur_change = 0;
+        for (int n = (last_cg == 1 ? last_nz : 15); n >= 0; --n) {
+          uint32_t blk = scan[n + subpos];
+          if (q_coef[blk] != 0) {
+            if (delta_u[blk] > 0) { cur_cost = -delta_u[blk]; cur_change = 1; }
+            else if (n == first_nz && abs(q_coef[blk]) == 1) { cur_cost = 0x7fffffff; }
+            else { cur_cost = delta_u[blk]; cur_change = -1; }
+          } else if (n < first_nz && ((coef[blk] >= 0) ? 0 : 1) != signbit) {
+            cur_cost = 0x7fffffff;
+          } else { cur_cost = -delta_u[blk]; cur_change = 1; }
+          if (cur_cost < min_cost) { min_cost = cur_cost; final_change = cur_change; min_pos = (int)blk; }
+        }
+        if (q_coef[min_pos] == 32767 || q_coef[min_pos] == -32768) final_change = -1;
+        if (coef[min_pos] >= 0) q_coef[min_pos] = (int16_t)(q_coef[min_pos] + final_change);
+        else q_coef[min_pos] = (int16_t)(q_coef[min_pos] - final_change);
+      }
+    }
+    if (last_cg == 1) last_cg = 0;
+  }
+}
+
+/* ref:quant-generic.c:298-340 (kvz_dequant_generic), scaling_list.enable == 0 branch */
+void orc_dequant(const orc_quant_params *p, const int16_t *q_coef, int16_t *coef, int w, int h,
+                 int type, int block_type)
+{
+  (void)block_type;
+  const int transform_shift = 15 - p->bitdepth - ilog2(w);
+  const int qp_scaled = orc_get_scaled_qp(type, p->qp, (p->bitdepth - 8) * 6);
+  const int shift = 20 - 14 - transform_shift;
+  const int32_t scale = inv_quant_scales[qp_scaled % 6] << (qp_scaled / 6);
+  const int32_t add = 1 << (shift - 1);
+  for (int n = 0; n < w * h; ++n) {
+    int32_t v = (q_coef[n] * scale + add) >> shift;
+    coef[n] = (int16_t)ORC_CLIP(-32768, 32767, v);
+  }
+}
+
+/* ref:quant-generic.c:198-292 (kvz_quantize_residual_generic), RDOQ-off branch;
+ * transform choice ref:strategies-dct.c:78-96 (DST for 4x4 intra luma);
+ * transform skip ref:transform.c:150-185 */
+int orc_quantize_residual(const orc_quant_params *p, int width, int color, int scan_idx,
+                          int use_trskip, int cu_is_intra, int in_stride, int out_stride,
+                          const orc_pix *ref_in, const orc_pix *pred_in, orc_pix *rec_out,
+                          int16_t *coeff_out, int early_skip)
+{
+  int16_t residual[32 * 32], coeff[32 * 32] = { 0 };
+  const int use_dst = (width == 4 && color == 0 && cu_is_intra);
+  const int ts_shift = 15 - p->bitdepth - ilog2(width);
+  int has_coeffs = 0;
+
+  for (int y = 0; y < width; ++y)
+    for (int x = 0; x < width; ++x)
+      residual[x + y * width] = (int16_t)((int)ref_in[x + y * in_stride] - (int)pred_in[x + y * in_stride]);
+
+  if (use_trskip) {
+    for (int i = 0; i < width * width; ++i) coeff[i] = (int16_t)((uint16_t)residual[i] << ts_shift);
+  } else if (use_dst) orc_dst_4x4(p->bitdepth, residual, coeff);
+  else orc_dct_nxn(width, p->bitdepth, residual, coeff);
+
+  orc_quant(p, coeff, coeff_out, width, width, color == 0 ? 0 : 2, scan_idx, cu_is_intra ? 1 : 2);
+
+  for (int i = 0; i < width * width; ++i) if (coeff_out[i] != 0) { has_coeffs = 1; break; }
+
+  if (has_coeffs && !early_skip) {
+    orc_dequant(p, coeff_out, coeff, width, width, color == 0 ? 0 : (color == 1 ? 2 : 3), cu_is_intra ? 1 : 2);
+    if (use_trskip) {
+      const int32_t off = 1 << (ts_shift - 1);
+      for (int i = 0; i < width * width; ++i) residual[i] = (int16_t)((coeff[i] + off) >> ts_shift);
+    } else if (use_dst) orc_idst_4x4(p->bitdepth, coeff, residual);
+    else orc_idct_nxn(width, p->bitdepth, coeff, residual);
+    for (int y = 0; y < width; ++y)
+      for (int x = 0; x < width; ++x) {
+        int16_t val = (int16_t)(residual[x + y * width] + pred_in[x + y * in_stride]);
+        rec_out[x + y * out_stride] = (orc_pix)ORC_CLIP(0, ORC_PIXEL_MAX, val);
+      }
+  } else if (rec_out != pred_in) {
+    for (int y = 0; y < width; ++y)
+      for (int x = 0; x < width; ++x) rec_out[x + y * out_stride] = pred_in[x + y * in_stride];
+  }
+  return has_coeffs;
+}
+
+/* ref:quant-generic.c:342-349 */
+uint32_t orc_coeff_abs_sum(const int16_t *c, size_t length)
+{
+  uint32_t s = 0;
+  for (size_t i = 0; i < length; ++i) s += (uint32_t)abs((int)c[i]);
+  return s;
+}
+
+/* ref:quant-generic.c:351-375 */
+double orc_fast_coeff_cost(const int16_t *coeff, int32_t width, uint64_t weights)
+{
+  uint32_t sum = 0;
+  for (int i = 0; i < width * width; ++i) {
+    uint32_t a = (uint32_t)abs((int)coeff[i]);
+    if (a > 3) a = 3;
+    sum += (uint32_t)((weights >> (16 * a)) & 0xffff);
+  }
+  return (double)sum / 256.0;
+}
+
+/* ======================================================================= */
+/* intra group                                                             */
+/* ======================================================================= */
+
+/* ref:intra-generic.c:49-155 */
+void orc_angular_pred(int log2_width, int mode, const orc_pix *ref_top, const orc_pix *ref_left, orc_pix *dst)
+{
+  static const int disp_tab[9] = { 0, 2, 5, 9, 13, 17, 21, 26, 32 };
+  static const int inv_tab[9] = { 0, 4096, 1638, 910, 630, 482, 390, 315, 256 };
+  const int w = 1 << log2_width;
+  const int vertical = mode >= 18;
+  const int mdisp = vertical ? mode - 26 : 10 - mode;
+  const int adisp = abs(mdisp);
+  const int sdisp = (mdisp < 0 ? -1 : 1) * disp_tab[adisp];
+  const orc_pix *main_in = (vertical ? ref_top : ref_left) + 1;   /* index 0 = block coord 0 */
+  const orc_pix *side_in = (vertical ? ref_left : ref_top) + 1;
+  orc_pix ext[2 * 32 + 1 + 32];
+  const orc_pix *rmain = main_in;
+
+  if (sdisp < 0) {
+    orc_pix *m = ext + w;                                           /* m[-w .. w-1] */
+    for (int x = -1; x < w; ++x) m[x] = main_in[x];
+    int acc = 128;
+    const int last = (w * sdisp) >> 5;
+    for (int x = -2; x >= last; --x) {
+      acc += inv_tab[adisp];
+      m[x] = side_in[(acc >> 8) - 1];
+    }
+    rmain = m;
+  }
+
+  /* compute in the "vertical" orientation, transpose on write for horizontal modes */
+  int pos = 0;
+  for (int y = 0; y < w; ++y) {
+    pos += sdisp;
+    const int di = pos >> 5, df = pos & 31;
+    for (int x = 0; x < w; ++x) {
+      int v;
+      if (sdisp == 0) v = rmain[x];
+      else if (df) v = ((32 - df) * rmain[x + di] + df * rmain[x + di + 1] + 16) >> 5;
+      else v = rmain[x + di];
+      if (vertical) dst[y * w + x] = (orc_pix)v; else dst[x * w + y] = (orc_pix)v;
+    }
+  }
+}
+
+/* ref:intra-generic.c:165-201 */
+void orc_intra_pred_planar(int log2_width, const orc_pix *ref_top, const orc_pix *ref_left, orc_pix *dst)
+{
+  const int w = 1 << log2_width;
+  const int tr = ref_top[w + 1], bl = ref_left[w + 1];
+  for (int y = 0; y < w; ++y)
+    for (int x = 0; x < w; ++x) {
+      int hor = (w - 1 - x) * ref_left[y + 1] + (x + 1) * tr;
+      int ver = (w - 1 - y) * ref_top[x + 1] + (y + 1) * bl;
+      dst[y * w + x] = (orc_pix)((ver + hor + w) >> (log2_width + 1));
+    }
+}
+
+static int dc_value(int log2_width, const orc_pix *ref_top, const orc_pix *ref_left)
+{
+  const int w = 1 << log2_width;
+  int sum = 0;
+  for (int i = 0; i < w; ++i) sum += ref_top[i + 1] + ref_left[i + 1];
+  return (orc_pix)((sum + w) >> (log2_width + 1));
+}
+
+/* ref:intra-generic.c:210-241 */
+void orc_intra_pred_filtered_dc(int log2_width, const orc_pix *ref_top, const orc_pix *ref_left, orc_pix *dst)
+{
+  const int w = 1 << log2_width;
+  const int dc = dc_value(log2_width, ref_top, ref_left);
+  for (int y = 0; y < w; ++y)
+    for (int x = 0; x < w; ++x) dst[y * w + x] = (orc_pix)dc;
+  dst[0] = (orc_pix)((ref_left[1] + 2 * dc + ref_top[1] + 2) / 4);
+  for (int x = 1; x < w; ++x) dst[x] = (orc_pix)((ref_top[x + 1] + 3 * dc + 2) / 4);
+  for (int y = 1; y < w; ++y) dst[y * w] = (orc_pix)((ref_left[y + 1] + 3 * dc + 2) / 4);
+}
+
+/* ref:intra.c:176-204 ([1 2 1] smoothing of both reference arrays) */
+static void filter_refs(int log2_width, const orc_pix *top, const orc_pix *left, orc_pix *ftop, orc_pix *fleft)
+{
+  const int rw = 2 * (1 << log2_width) + 1;
+  fleft[0] = (orc_pix)((left[1] + 2 * left[0] + top[1] + 2) / 4);
+  ftop[0] = fleft[0];
+  for (int i = 1; i < rw - 1; ++i) {
+    fleft[i] = (orc_pix)((left[i - 1] + 2 * left[i] + left[i + 1] + 2) / 4);
+    ftop[i] = (orc_pix)((top[i - 1] + 2 * top[i] + top[i + 1] + 2) / 4);
+  }
+  fleft[rw - 1] = left[rw - 1];
+  ftop[rw - 1] = top[rw - 1];
+}
+
+/* ref:intra.c:252-302 (kvz_intra_predict) incl. intra_pred_dc :229-249 and
+ * intra_post_process_angular :207-219 */
+void orc_intra_predict(int log2_width, int mode, int color, const orc_pix *ref_top, const orc_pix *ref_left,
+                       orc_pix *dst, int filter_boundary)
+{
+  static const int thres[4] = { 0, 7, 1, 0 };    /* by log2_width-2; ref:intra.c:271 */
+  const int w = 1 << log2_width;
+  orc_pix ftop[65], fleft[65];
+  const orc_pix *top = ref_top, *left = ref_left;
+  int use_filtered = 0;
+  if (color != 0 || mode == 1 || w == 4) use_filtered = 0;
+  else if (mode == 0) use_filtered = 1;
+  else {
+    int dist = ORC_MIN(abs(mode - 26), abs(mode - 10));
+    use_filtered = dist > thres[log2_width - 2];
+  }
+  if (use_filtered) { filter_refs(log2_width, ref_top, ref_left, ftop, fleft); top = ftop; left = fleft; }
+
+  if (mode == 0) orc_intra_pred_planar(log2_width, top, left, dst);
+  else if (mode == 1) {
+    if (color == 0 && w < 32) orc_intra_pred_filtered_dc(log2_width, top, left, dst);
+    else { int dc = dc_value(log2_width, top, left); for (int i = 0; i < w * w; ++i) dst[i] = (orc_pix)dc; }
+  } else {
+    orc_angular_pred(log2_width, mode, top, left, dst);
+    if (color == 0 && w < 32 && filter_boundary && (mode == 10 || mode == 26)) {
+      const orc_pix *r = (mode == 10) ? top : left;
+      const int st = (mode == 10) ? 1 : w;
+      for (int i = 0; i < w; ++i) {
+        int v = dst[i * st] + ((r[i + 1] - r[0]) >> 1);
+        dst[i * st] = clip_pix(v);
+      }
+    }
+  }
+}
+
+/* Availability tables ref:intra.c:47-82 (num_ref_pixels_top/left[uy][ux]) regenerated from
+ * their rule: 4x4 units inside a 64x64 CTU are coded in z-order, so a neighbouring unit is
+ * available iff its z-order index is smaller; the CTU above (and above-right) and the CTU to
+ * the left are complete, the CTUs to the right / below-left are not. */
+static int zidx(int ux, int uy)
+{
+  int z = 0;
+  for (int b = 0; b < 4; ++b) z |= (((ux >> b) & 1) << (2 * b)) | (((uy >> b) & 1) << (2 * b + 1));
+  return z;
+}
+static int ref_px_top(int uy, int ux)
+{
+  if (uy == 0) return 64;
+  int n = 0;
+  while (ux + n < 16 && zidx(ux + n, uy - 1) < zidx(ux, uy)) ++n;
+  return 4 * n;
+}
+static int ref_px_left(int uy, int ux)
+{
+  if (ux == 0) return 4 * (16 - uy);
+  int n = 0;
+  while (uy + n < 16 && zidx(ux - 1, uy + n) < zidx(ux, uy)) ++n;
+  return 4 * n;
+}
+
+/* ref:intra.c:305-559 (kvz_intra_build_reference{,_any,_inner}) over a frame plane:
+ * lcu->rec / top_ref / left_ref are all views of the same reconstruction, so
+ * top_border = rec[(y-1)*stride + x], left_border = rec[y*stride + x-1]. */
+void orc_intra_build_reference(int log2_width, int color, int luma_x, int luma_y, int pic_w, int pic_h,
+                               const orc_pix *rec, int stride, orc_pix *out_top, orc_pix *out_left)
+{
+  const int is_c = color != 0;
+  const int w = 1 << log2_width;
+  const int lx = luma_x % 64, ly = luma_y % 64;
+  const int px = luma_x >> is_c, py = luma_y >> is_c;       /* plane coordinates */
+  const orc_pix dc = (orc_pix)(1 << (ORC_BITDEPTH - 1));
+  const int inner = luma_x > 0 && luma_y > 0;
+  #define REC(xx, yy) rec[(yy) * stride + (xx)]
+
+  int avail_l = 0, avail_t = 0;
+  if (luma_x > 0) {
+    avail_l = ref_px_left(ly / 4, lx / 4) >> is_c;
+    avail_l = ORC_MIN(avail_l, 2 * w);
+    avail_l = ORC_MIN(avail_l, (pic_h - luma_y) >> is_c);
+  }
+  if (luma_y > 0) {
+    avail_t = ref_px_top(ly / 4, lx / 4) >> is_c;
+    avail_t = ORC_MIN(avail_t, 2 * w);
+    avail_t = ORC_MIN(avail_t, (pic_w - luma_x) >> is_c);
+  }
+
+  if (inner) {
+    /* _inner copies in groups of 4 (at least one group), then extends the last copied value */
+    out_left[0] = out_top[0] = REC(px - 1, py - 1);
+    int i = 0;
+    do { for (int k = 0; k < 4; ++k) out_left[i + 1 + k] = REC(px - 1, py + i + k); i += 4; } while (i < avail_l);
+    orc_pix near = out_left[i];
+    for (; i < 2 * w; ++i) out_left[i + 1] = near;
+    i = 0;
+    do { for (int k = 0; k < 4; ++k) out_top[i + 1 + k] = REC(px + i + k, py - 1); i += 4; } while (i < avail_t);
+    near = out_top[i];
+    for (; i < 2 * w; ++i) out_top[i + 1] = near;
+  } else {
+    if (luma_x > 0) {
+      for (int i = 0; i < avail_l; ++i) out_left[i + 1] = REC(px - 1, py + i);
+      orc_pix near = out_left[avail_l];
+      for (int i = avail_l; i < 2 * w; ++i) out_left[i + 1] = near;
+    } else {
+      orc_pix near = luma_y > 0 ? REC(px, py - 1) : dc;
+      for (int i = 0; i < 2 * w; ++i) out_left[i + 1] = near;
+    }
+    /* (luma_x > 0 && luma_y > 0) is false here */
+    out_left[0] = out_left[1];
+    out_top[0] = out_left[1];
+    if (luma_y > 0) {
+      for (int i = 0; i < avail_t; ++i) out_top[i + 1] = REC(px + i, py - 1);
+      orc_pix near = REC(px + avail_t - 1, py - 1);
+      for (int i = avail_t; i < 2 * w; ++i) out_top[i + 1] = near;
+    } else {
+      orc_pix near = luma_x > 0 ? REC(px - 1, py) : dc;
+      for (int i = 0; i < 2 * w; ++i) out_top[i + 1] = near;
+    }
+  }
+  #undef REC
+}
+
+/* ======================================================================= */
+/* ipol group                                                              */
+/* ======================================================================= */
+
+static const int8_t luma_fir[4][8] = {          /* ref:filter.c:66-72 */
+  { 0, 0, 0, 64, 0, 0, 0, 0 }, { -1, 4, -10, 58, 17, -5, 1, 0 },
+  { -1, 4, -11, 40, 40, -11, 4, -1 }, { 0, 1, -5, 17, 58, -10, 4, -1 } };
+static const int8_t chroma_fir[8][4] = {        /* ref:filter.c:74-84 */
+  { 0, 64, 0, 0 }, { -2, 58, 10, -2 }, { -4, 54, 16, -2 }, { -6, 46, 28, -4 },
+  { -4, 36, 36, -4 }, { -4, 28, 46, -6 }, { -2, 16, 54, -4 }, { -2, 10, 58, -2 } };
+
+static int32_t fir_px(const int8_t *f, int taps, const orc_pix *d, int st)
+{ int32_t t = 0; for (int i = 0; i < taps; ++i) t += f[i] * d[i * st]; return t; }
+static int32_t fir_im(const int8_t *f, int taps, const int16_t *d, int st)
+{ int32_t t = 0; for (int i = 0; i < taps; ++i) t += f[i] * d[i * st]; return t; }
+
+/* shared body of ref:ipol-generic.c:134-211 (luma) and :681-758 (chroma) */
+static void sample_sep(const orc_pix *src, int ss, int w, int h, orc_pix *dst_px, int16_t *dst_im, int ds,
+                       const int8_t *hf, const int8_t *vf, int taps)
+{
+  const int off = taps / 2 - 1;                 /* 3 luma, 1 chroma */
+  const int shift1 = ORC_BITDEPTH - 8, shift2 = 6;
+  const int wp_shift = 14 - ORC_BITDEPTH, wp_off = 1 << (wp_shift - 1);
+  int16_t tmp[(64 + 7) * 64];
+  for (int y = 0; y < h + taps - 1; ++y)
+    for (int x = 0; x < w; ++x)
+      tmp[y * 64 + x] = (int16_t)(fir_px(hf, taps, &src[ss * (y - off) + (x - off)], 1) >> shift1);
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      int32_t v = fir_im(vf, taps, &tmp[y * 64 + x], 64) >> shift2;
+      if (dst_px) dst_px[y * ds + x] = clip_pix((v + wp_off) >> wp_shift);
+      else dst_im[y * ds + x] = (int16_t)v;
+    }
+}
+
+void orc_sample_quarterpel_luma(const orc_pix *src, int ss, int w, int h, orc_pix *dst, int ds, int mvx, int mvy)
+{ sample_sep(src, ss, w, h, dst, NULL, ds, luma_fir[mvx & 3], luma_fir[mvy & 3], 8); }
+void orc_sample_quarterpel_luma_hi(const orc_pix *src, int ss, int w, int h, int16_t *dst, int ds, int mvx, int mvy)
+{ sample_sep(src, ss, w, h, NULL, dst, ds, luma_fir[mvx & 3], luma_fir[mvy & 3], 8); }
+void orc_sample_octpel_chroma(const orc_pix *src, int ss, int w, int h, orc_pix *dst, int ds, int mvx, int mvy)
+{ sample_sep(src, ss, w, h, dst, NULL, ds, chroma_fir[mvx & 7], chroma_fir[mvy & 7], 4); }
+void orc_sample_octpel_chroma_hi(const orc_pix *src, int ss, int w, int h, int16_t *dst, int ds, int mvx, int mvy)
+{ sample_sep(src, ss, w, h, NULL, dst, ds, chroma_fir[mvx & 7], chroma_fir[mvy & 7], 4); }
+
+/* --- fractional motion estimation filters, ref:ipol-generic.c:213-679 ---
+ * State shared between the four stages:
+ *   im[k][y*64+x]  : horizontal 8-tap (phase k: im[0]=0, im[1]=2/4, im[3]=left qpel, im[4]=right qpel)
+ *                    of source row (y-3), column window starting at x-2  (i.e. x - 3 + 1)
+ *   col[k][y]      : the same filter for the column one to the left (x = -3 window), rows y-3
+ * Every output sample is  clip(( (int16)(vertical_8tap >> 6) + 32) >> 6)  (8-bit). */
+#define IM(k) (im + (k) * ORC_IPOL_IM_SIZE)
+#define COL(k) (cols + (k) * ORC_FIRST_COLS)
+#define FLT(k) (filtered + (k) * 64 * 64)
+
+static orc_pix fme_round(int16_t s)
+{
+  const int wp_shift = 14 - ORC_BITDEPTH, wp_off = 1 << (wp_shift - 1);
+  return clip_pix((s + wp_off) >> wp_shift);
+}
+
+static void fme_hor(const orc_pix *src, int ss, int w, int rows, int first_y, const int8_t *f,
+                    int16_t *im_k, int16_t *col_k)
+{
+  const int shift1 = ORC_BITDEPTH - 8;
+  for (int y = first_y; y < rows; ++y) {
+    for (int x = 0; x < w; ++x)
+      im_k[y * 64 + x] = (int16_t)(fir_px(f, 8, &src[ss * (y - 3) + (x - 3 + 1)], 1) >> shift1);
+    col_k[y] = (int16_t)(fir_px(f, 8, &src[ss * (y - 3) + (0 - 3)], 1) >> shift1);
+  }
+}
+
+/* vertical stage helper used by the qpel functions: one output plane */
+static void fme_ver_plane(orc_pix *out, int w, int h, const int8_t *vf, const int16_t *im_k,
+                          const int16_t *col_k, int use_col_for_x0, int yoff)
+{
+  for (int y = 0; y < h; ++y) {
+    if (use_col_for_x0)
+      out[y * 64 + 0] = fme_round((int16_t)(fir_im(vf, 8, &col_k[y + yoff], 1) >> 6));
+    for (int x = use_col_for_x0; x < w; ++x)
+      out[y * 64 + x] = fme_round((int16_t)(fir_im(vf, 8, &im_k[(y + yoff) * 64 + x - use_col_for_x0], 64) >> 6));
+  }
+}
+
+void orc_filter_fme(int stage, const orc_pix *src, int ss, int w, int h, orc_pix *filtered,
+                    int16_t *im, int fme_level, int16_t *cols, int hpel_off_x, int hpel_off_y)
+{
+  const int shift1 = ORC_BITDEPTH - 8;
+  const int rows = h + 7 + 1;
+  if (stage == 0) {
+    /* ref:ipol-generic.c:213-330 */
+    fme_hor(src, ss, w, rows, 0, luma_fir[0], IM(0), COL(0));
+    fme_hor(src, ss, w, rows, fme_level > 1 ? 0 : 1, luma_fir[2], IM(1), COL(2));
+    for (int y = 0; y < h; ++y)                        /* right: hpel horizontal only */
+      for (int x = 0; x < w; ++x) FLT(1)[y * 64 + x] = fme_round(IM(1)[(3 + 1) * 64 + y * 64 + x]);
+    for (int y = 0; y < h; ++y) {                      /* left: shifted copy + extra column */
+      FLT(0)[y * 64] = fme_round(COL(2)[y + 3 + 1]);
+      for (int x = 1; x < w; ++x) FLT(0)[y * 64 + x] = FLT(1)[y * 64 + x - 1];
+    }
+    for (int y = 0; y <= h; ++y)                       /* top (rows 0..h-1) and bottom (rows 1..h) */
+      for (int x = 0; x < w; ++x) {
+        int16_t s = (int16_t)(fir_px(luma_fir[2], 8, &src[ss * (y - 3) + x + 1], ss) >> shift1);
+        orc_pix v = fme_round(s);
+        if (y < h) FLT(2)[y * 64 + x] = v;
+        if (y > 0) FLT(3)[(y - 1) * 64 + x] = v;
+      }
+  } else if (stage == 1) {
+    /* ref:ipol-generic.c:332-405 : diagonal hpel = vertical fir2 over im[1] / col[2] */
+    for (int y = 0; y <= h; ++y) {
+      /* column x of "right" blocks from im[1]; column 0 of "left" blocks from col[2] */
+      orc_pix c0 = fme_round((int16_t)(fir_im(luma_fir[2], 8, &COL(2)[y], 1) >> 6));
+      if (y < h) FLT(0)[y * 64] = c0;                  /* top-left */
+      if (y > 0) FLT(2)[(y - 1) * 64] = c0;            /* bottom-left */
+      for (int x = 0; x < w; ++x) {
+        orc_pix v = fme_round((int16_t)(fir_im(luma_fir[2], 8, &IM(1)[y * 64 + x], 64) >> 6));
+        if (y < h) { FLT(1)[y * 64 + x] = v; if (x + 1 < w) FLT(0)[y * 64 + x + 1] = v; }
+        if (y > 0) { FLT(3)[(y - 1) * 64 + x] = v; if (x + 1 < w) FLT(2)[(y - 1) * 64 + x + 1] = v; }
+      }
+    }
+  } else if (stage == 2) {
+    /* ref:ipol-generic.c:407-563 */
+    const int8_t *hfl = hpel_off_x != 0 ? luma_fir[1] : luma_fir[3];
+    const int8_t *hfr = hpel_off_x != 0 ? luma_fir[3] : luma_fir[1];
+    fme_hor(src, ss, w, rows, 0, hfl, IM(3), COL(1));
+    fme_hor(src, ss, w, rows, 0, hfr, IM(4), COL(3));
+    const int off_x_l = hpel_off_x < 1 ? 0 : 1, off_x_r = hpel_off_x < 0 ? 0 : 1;
+    const int off_y_t = hpel_off_y < 1 ? 0 : 1, off_y_b = hpel_off_y < 0 ? 0 : 1;
+    const int sample_off_y = hpel_off_y < 0 ? 0 : 1;
+    const int sample_off_x = hpel_off_x > -1 ? 1 : 0;
+    const int8_t *vlr = hpel_off_y != 0 ? luma_fir[2] : luma_fir[0];
+    const int8_t *vt = hpel_off_y != 0 ? luma_fir[1] : luma_fir[3];
+    const int8_t *vb = hpel_off_y != 0 ? luma_fir[3] : luma_fir[1];
+    const int16_t *hp_im = hpel_off_x != 0 ? IM(1) : IM(0);
+    const int16_t *hp_col = hpel_off_x != 0 ? COL(2) : COL(0);
+    fme_ver_plane(FLT(0), w, h, vlr, IM(3), COL(1), !off_x_l, sample_off_y);
+    fme_ver_plane(FLT(1), w, h, vlr, IM(4), COL(3), !off_x_r, sample_off_y);
+    fme_ver_plane(FLT(2), w, h, vt, hp_im, hp_col, !sample_off_x, off_y_t);
+    fme_ver_plane(FLT(3), w, h, vb, hp_im, hp_col, !sample_off_x, off_y_b);
+  } else {
+    /* ref:ipol-generic.c:565-679 */
+    const int off_x_l = hpel_off_x < 1 ? 0 : 1, off_x_r = hpel_off_x < 0 ? 0 : 1;
+    const int off_y_t = hpel_off_y < 1 ? 0 : 1, off_y_b = hpel_off_y < 0 ? 0 : 1;
+    const int8_t *vt = hpel_off_y != 0 ? luma_fir[1] : luma_fir[3];
+    const int8_t *vb = hpel_off_y != 0 ? luma_fir[3] : luma_fir[1];
+    fme_ver_plane(FLT(0), w, h, vt, IM(3), COL(1), !off_x_l, off_y_t);
+    fme_ver_plane(FLT(1), w, h, vt, IM(4), COL(3), !off_x_r, off_y_t);
+    fme_ver_plane(FLT(2), w, h, vb, IM(3), COL(1), !off_x_l, off_y_b);
+    fme_ver_plane(FLT(3), w, h, vb, IM(4), COL(3), !off_x_r, off_y_b);
+  }
+}
+
+/* ref:ipol-generic.c:761-814 */
+int orc_get_extended_block(const orc_pix *src, int src_w, int src_h, int src_s, int blk_x, int blk_y,
+                           int blk_w, int blk_h, int pad_l, int pad_r, int pad_t, int pad_b, int pad_b_simd,
+                           orc_pix *buf, int *ext_off, int *ext_origin_off, int *ext_s)
+{
+  const int min_y = blk_y - pad_t, max_y = blk_y + blk_h + pad_b + pad_b_simd - 1;
+  const int min_x = blk_x - pad_l, max_x = blk_x + blk_w + pad_r - 1;
+  if (min_y >= 0 && max_y < src_h && min_x >= 0 && max_x < src_w) {
+    *ext_off = (blk_y - pad_t) * src_s + (blk_x - pad_l);
+    *ext_origin_off = blk_y * src_s + blk_x;
+    *ext_s = src_s;
+    return 0;
+  }
+  const int es = pad_l + blk_w + pad_r;
+  *ext_off = 0; *ext_s = es; *ext_origin_off = pad_t * es + pad_l;
+  int y;
+  for (y = -pad_t; y < blk_h + pad_b; ++y) {
+    const int cy = ORC_CLIP(0, src_h - 1, blk_y + y);
+    for (int x = 0; x < es; ++x) {
+      const int cx = ORC_CLIP(0, src_w - 1, min_x + x);
+      buf[(y + pad_t) * es + x] = src[cy * src_s + cx];
+    }
+  }
+  for (int ys = 0; ys < pad_b_simd; ++ys) memset(buf + (y + pad_t + ys) * es, 0, (size_t)es * sizeof(orc_pix));
+  buf[(blk_h + pad_b + pad_t + pad_b_simd - 1) * es + pad_l + blk_w + pad_r] = 0;
+  return 1;
+}
+
+/* ======================================================================= */
+/* sao group                                                               */
+/* ======================================================================= */
+
+static const int eo_dx[4][2] = { { -1, 1 }, { 0, 0 }, { -1, 1 }, { 1, -1 } };   /* ref:sao.h:71-76 */
+static const int eo_dy[4][2] = { { 0, 0 }, { -1, 1 }, { -1, 1 }, { -1, 1 } };
+
+static int sgn(int v) { return (v > 0) - (v < 0); }
+/* ref:sao_shared_generics.h:41-50 */
+static int eo_cat(int a, int b, int c)
+{
+  static const int map[5] = { 1, 2, 0, 3, 4 };
+  return map[2 + sgn(c - a) + sgn(c - b)];
+}
+
+/* ref:sao-generic.c:50-81 */
+void orc_calc_sao_edge_dir(int bitdepth, const orc_pix *orig, const orc_pix *rec, int eo_class,
+                           int bw, int bh, int cat_sum_cnt[2][5])
+{
+  const int offset = bitdepth != 8 ? 1 << (bitdepth - 9) : 0;
+  for (int y = 1; y < bh - 1; ++y)
+    for (int x = 1; x < bw - 1; ++x) {
+      int c = rec[y * bw + x];
+      int a = rec[(y + eo_dy[eo_class][0]) * bw + x + eo_dx[eo_class][0]];
+      int b = rec[(y + eo_dy[eo_class][1]) * bw + x + eo_dx[eo_class][1]];
+      int cat = eo_cat(a, b, c);
+      cat_sum_cnt[0][cat] += (orig[y * bw + x] - c + offset) >> (bitdepth - 8);
+      cat_sum_cnt[1][cat] += 1;
+    }
+}
+
+/* ref:sao_shared_generics.h:52-91 */
+int orc_sao_edge_ddistortion(int bitdepth, const orc_pix *orig, const orc_pix *rec, int bw, int bh,
+                             int eo_class, const int offsets[5])
+{
+  const int bit_offset = bitdepth != 8 ? 1 << (bitdepth - 9) : 0;
+  int sum = 0;
+  for (int y = 1; y < bh - 1; ++y)
+    for (int x = 1; x < bw - 1; ++x) {
+      int c = rec[y * bw + x];
+      int a = rec[(y + eo_dy[eo_class][0]) * bw + x + eo_dx[eo_class][0]];
+      int b = rec[(y + eo_dy[eo_class][1]) * bw + x + eo_dx[eo_class][1]];
+      int off = offsets[eo_cat(a, b, c)];
+      if (off != 0) {
+        int diff = (orig[y * bw + x] - c + bit_offset) >> (bitdepth - 8);
+        int delta = diff - off;
+        sum += delta * delta - diff * diff;
+      }
+    }
+  return sum;
+}
+
+/* ref:sao_shared_generics.h:93-130 */
+int orc_sao_band_ddistortion(int bitdepth, const orc_pix *orig, const orc_pix *rec, int bw, int bh,
+                             int band_pos, const int sao_bands[4])
+{
+  const int shift = bitdepth - 5;
+  int sum = 0;
+  for (int i = 0; i < bw * bh; ++i) {
+    int band = (rec[i] >> shift) - band_pos;
+    int off = (band >= 0 && band <= 3) ? sao_bands[band] : 0;
+    if (off != 0) {
+      int diff = orig[i] - rec[i];
+      int delta = diff - off;
+      sum += delta * delta - diff * diff;
+    }
+  }
+  return sum;
+}
+
+/* ref:sao-generic.c:84-124 + kvz_calc_sao_offset_array ref:sao.c:180-202 */
+void orc_sao_reconstruct_color(int bitdepth, const orc_pix *rec, orc_pix *new_rec, int sao_type, int eo_class,
+                               const int band_position[2], const int offsets[10], int stride, int new_stride,
+                               int bw, int bh, int color)
+{
+  const int offset_v = color == 2 ? 5 : 0;
+  if (sao_type == 1) {
+    const int values = 1 << bitdepth, shift = bitdepth - 5;
+    const int bp = band_position[color == 2 ? 1 : 0];
+    for (int y = 0; y < bh; ++y)
+      for (int x = 0; x < bw; ++x) {
+        int val = rec[y * stride + x];
+        int d = (val >> shift) - bp;
+        if (d >= 0 && d <= 3) val = ORC_CLIP(0, values - 1, val + offsets[d + 1 + offset_v]);
+        new_rec[y * new_stride + x] = (orc_pix)val;
+      }
+  } else {
+    for (int y = 0; y < bh; ++y)
+      for (int x = 0; x < bw; ++x) {
+        const orc_pix *c = &rec[y * stride + x];
+        int a = c[eo_dy[eo_class][0] * stride + eo_dx[eo_class][0]];
+        int b = c[eo_dy[eo_class][1] * stride + eo_dx[eo_class][1]];
+        int v = c[0] + offsets[eo_cat(a, b, c[0]) + offset_v];
+        new_rec[y * new_stride + x] = (orc_pix)ORC_CLIP(0, (1 << ORC_BITDEPTH) - 1, v);
+      }
+  }
+}
+
+/* ======================================================================= */
+/* nal group                                                               */
+/* ======================================================================= */
+
+/* ref:nal-generic.c:57-82 (the generic4/generic8 variants :84-184 compute the same sum) */
+void orc_array_checksum(const orc_pix *data, int height, int width, int stride, unsigned char out[4])
+{
+  uint32_t sum = 0;
+  for (int y = 0; y < height; ++y)
+    for (int x = 0; x < width; ++x) {
+      const uint8_t mask = (uint8_t)((x & 0xff) ^ (y & 0xff) ^ (x >> 8) ^ (y >> 8));
+      sum += (uint32_t)((data[y * stride + x] & 0xff) ^ mask);
+#if ORC_BITDEPTH > 8
+      sum += (uint32_t)(((data[y * stride + x] >> 8) & 0xff) ^ mask);
+#endif
+    }
+  out[0] = (unsigned char)(sum >> 24); out[1] = (unsigned char)(sum >> 16);
+  out[2] = (unsigned char)(sum >> 8); out[3] = (unsigned char)sum;
+}

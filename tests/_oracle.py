@@ -1,0 +1,518 @@
+"""ctypes access to the parity checkers (TEST INFRASTRUCTURE ONLY).
+
+* ``Oracle``  -- oracle/libkvz_oracle.so, our plain-C restatement of the reference's
+  generic strategies (oracle/kvz_oracle.c).
+* ``Ref``     -- oracle/_ref/libkvzref_shim.so, the UNMODIFIED reference compiled from
+  /root/reference (oracle/Makefile `ref` target) behind oracle/ref_shim.c.
+
+Nothing in kvazaar_b200/ imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+
+
+def aligned(n, dtype, align=64, pad=64, fill=0):
+    """`align`-byte aligned array with `pad` readable slack bytes behind it: the reference's SIMD
+    strategies use aligned loads / over-reads (MALLOC_SIMD_PADDED, SIMD_ALIGNMENT,
+    src/global.h:244-268)."""
+    item = np.dtype(dtype).itemsize
+    raw = np.zeros(n * item + align + pad, np.uint8)
+    off = (-raw.ctypes.data) % align
+    out = raw[off:off + n * item].view(dtype)
+    if fill:
+        out[:] = fill
+    return out
+
+
+def al(a, dtype=None):
+    a = np.asarray(a)
+    out = aligned(a.size, dtype or a.dtype)
+    out[:] = a.ravel()
+    return out
+
+
+def P(a):
+    """numpy array -> void* (keeps no reference; caller holds the array)."""
+    if a is None:
+        return C.c_void_p(0)
+    assert a.flags["C_CONTIGUOUS"] or a.ndim <= 1 or a.strides[-1] == a.itemsize
+    return C.c_void_p(a.ctypes.data)
+
+
+def build_oracle():
+    so = os.path.join(ORACLE_DIR, "libkvz_oracle.so")
+    src = os.path.join(ORACLE_DIR, "kvz_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
+    return so
+
+
+def build_ref():
+    """Build oracle/_ref from /root/reference when it is present (this container);
+    on the GPU box the prebuilt files travel with the snapshot."""
+    so = os.path.join(REF_DIR, "libkvzref_shim.so")
+    if os.path.isdir("/root/reference/src"):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref", "-j8"])
+    return so if os.path.exists(so) else None
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = C.CDLL(build_oracle())
+        L = self.lib
+        for name in ("orc_reg_sad", "orc_sad_nxn", "orc_satd_nxn", "orc_satd_any_size", "orc_pixels_calc_ssd",
+                     "orc_ver_sad", "orc_hor_sad", "orc_coeff_abs_sum"):
+            getattr(L, name).restype = C.c_uint32
+        L.orc_pixel_var.restype = C.c_double
+        L.orc_fast_coeff_cost.restype = C.c_double
+        L.orc_fast_coeff_cost.argtypes = [C.c_void_p, C.c_int32, C.c_uint64]
+        L.orc_coeff_abs_sum.argtypes = [C.c_void_p, C.c_size_t]
+        L.orc_scan_table.restype = C.POINTER(C.c_uint32)
+        self.bitdepth = L.orc_bitdepth()
+        self.pix = np.uint8 if self.bitdepth == 8 else np.uint16
+
+    # picture
+    def reg_sad(self, a, b, w, h, s1, s2):
+        return self.lib.orc_reg_sad(P(a), P(b), w, h, s1, s2)
+
+    def sad_nxn(self, n, a, b):
+        return self.lib.orc_sad_nxn(n, P(a), P(b))
+
+    def satd_nxn(self, n, a, b):
+        return self.lib.orc_satd_nxn(n, P(a), P(b))
+
+    def _dual(self, fn, n, preds, orig):
+        costs = np.zeros(2, np.uint32)
+        fn(n, P(preds), P(orig), P(costs))
+        return costs
+
+    def sad_nxn_dual(self, n, preds, orig):
+        return self._dual(self.lib.orc_sad_nxn_dual, n, preds, orig)
+
+    def satd_nxn_dual(self, n, preds, orig):
+        return self._dual(self.lib.orc_satd_nxn_dual, n, preds, orig)
+
+    def satd_any_size(self, w, h, b1, s1, b2, s2):
+        return self.lib.orc_satd_any_size(w, h, P(b1), s1, P(b2), s2)
+
+    def satd_any_size_quad(self, w, h, preds4, stride, orig, orig_stride):
+        ptrs = (C.c_void_p * 4)(*[p.ctypes.data for p in preds4])
+        costs = np.zeros(4, np.uint32)
+        valid = np.ones(4, np.int8)
+        self.lib.orc_satd_any_size_quad(w, h, ptrs, stride, P(orig), orig_stride, 4, P(costs), P(valid))
+        return costs
+
+    def pixels_calc_ssd(self, ref, rec, rs, cs, width):
+        return self.lib.orc_pixels_calc_ssd(P(ref), P(rec), rs, cs, width)
+
+    def ver_sad(self, pic, ref, w, h, ps):
+        return self.lib.orc_ver_sad(P(pic), P(ref), w, h, ps)
+
+    def hor_sad(self, pic, ref, w, h, ps, rs, left, right):
+        return self.lib.orc_hor_sad(P(pic), P(ref), w, h, ps, rs, left, right)
+
+    def bipred_average_plane(self, l0, l1, l0_im, l1_im, w, h, dst_stride):
+        dst = np.zeros(h * dst_stride, self.pix)
+        self.lib.orc_bipred_average_plane(P(dst), dst_stride, P(l0), P(l1), int(l0_im), int(l1_im), w, h)
+        return dst
+
+    def pixel_var(self, buf):
+        return self.lib.orc_pixel_var(P(buf), buf.size)
+
+    # dct
+    def _tr(self, fn, n, bitdepth, inp):
+        out = np.zeros(n * n, np.int16)
+        inp = np.ascontiguousarray(inp, np.int16)
+        if n is None:
+            fn(bitdepth, P(inp), P(out))
+        else:
+            fn(n, bitdepth, P(inp), P(out))
+        return out
+
+    def dct(self, n, bitdepth, inp):
+        return self._tr(self.lib.orc_dct_nxn, n, bitdepth, inp)
+
+    def idct(self, n, bitdepth, inp):
+        return self._tr(self.lib.orc_idct_nxn, n, bitdepth, inp)
+
+    def dst4(self, bitdepth, inp):
+        out = np.zeros(16, np.int16)
+        self.lib.orc_dst_4x4(bitdepth, P(np.ascontiguousarray(inp, np.int16)), P(out))
+        return out
+
+    def idst4(self, bitdepth, inp):
+        out = np.zeros(16, np.int16)
+        self.lib.orc_idst_4x4(bitdepth, P(np.ascontiguousarray(inp, np.int16)), P(out))
+        return out
+
+    # quant
+    @staticmethod
+    def qparams(qp, bitdepth=8, intra=1, signhide=0):
+        return np.array([qp, bitdepth, intra, signhide], np.int32)
+
+    def scan_table(self, scan_idx, log2):
+        p = self.lib.orc_scan_table(scan_idx, log2)
+        return np.ctypeslib.as_array(p, shape=(1 << (2 * log2),)).copy()
+
+    def quant(self, qp, coef, w, h, type_, scan_idx, block_type, intra=1, signhide=0, bitdepth=8):
+        q = np.zeros(w * h, np.int16)
+        prm = self.qparams(qp, bitdepth, intra, signhide)
+        self.lib.orc_quant(P(prm), P(coef), P(q), w, h, type_, scan_idx, block_type)
+        return q
+
+    def dequant(self, qp, q, w, h, type_, block_type, bitdepth=8):
+        c = np.zeros(w * h, np.int16)
+        prm = self.qparams(qp, bitdepth)
+        self.lib.orc_dequant(P(prm), P(q), P(c), w, h, type_, block_type)
+        return c
+
+    def quantize_residual(self, qp, width, color, scan_idx, trskip, cu_intra, stride, ref, pred, intra_slice=1,
+                          signhide=0, bitdepth=8, early_skip=0):
+        rec = np.zeros(width * stride, self.pix)
+        coeff = np.zeros(width * width, np.int16)
+        prm = self.qparams(qp, bitdepth, intra_slice, signhide)
+        has = self.lib.orc_quantize_residual(P(prm), width, color, scan_idx, trskip, cu_intra, stride, stride,
+                                             P(ref), P(pred), P(rec), P(coeff), early_skip)
+        return has, rec, coeff
+
+    def coeff_abs_sum(self, c):
+        return self.lib.orc_coeff_abs_sum(P(c), c.size)
+
+    def fast_coeff_cost(self, c, width, weights):
+        return self.lib.orc_fast_coeff_cost(P(c), width, weights)
+
+    # intra
+    def angular(self, log2w, mode, top, left):
+        dst = np.zeros(1 << (2 * log2w), self.pix)
+        self.lib.orc_angular_pred(log2w, mode, P(top), P(left), P(dst))
+        return dst
+
+    def planar(self, log2w, top, left):
+        dst = np.zeros(1 << (2 * log2w), self.pix)
+        self.lib.orc_intra_pred_planar(log2w, P(top), P(left), P(dst))
+        return dst
+
+    def filtered_dc(self, log2w, top, left):
+        dst = np.zeros(1 << (2 * log2w), self.pix)
+        self.lib.orc_intra_pred_filtered_dc(log2w, P(top), P(left), P(dst))
+        return dst
+
+    def intra_predict(self, log2w, mode, color, top, left, filter_boundary):
+        dst = np.zeros(1 << (2 * log2w), self.pix)
+        self.lib.orc_intra_predict(log2w, mode, color, P(top), P(left), P(dst), filter_boundary)
+        return dst
+
+    def intra_build_reference(self, log2w, color, lx, ly, pic_w, pic_h, plane, stride):
+        n = 2 * (1 << log2w) + 1
+        top = np.zeros(n, self.pix)
+        left = np.zeros(n, self.pix)
+        self.lib.orc_intra_build_reference(log2w, color, lx, ly, pic_w, pic_h, P(plane), stride, P(top), P(left))
+        return top, left
+
+    # ipol
+    def sample(self, kind, src_arr, origin_off, stride, w, h, mvx, mvy, dst_stride=None):
+        """kind in {'luma','luma_hi','chroma','chroma_hi'}; src_arr flat, origin_off = index of block origin."""
+        ds = dst_stride or w
+        hi = kind.endswith("_hi")
+        dst = np.zeros(h * ds, np.int16 if hi else self.pix)
+        fn = {"luma": self.lib.orc_sample_quarterpel_luma, "luma_hi": self.lib.orc_sample_quarterpel_luma_hi,
+              "chroma": self.lib.orc_sample_octpel_chroma, "chroma_hi": self.lib.orc_sample_octpel_chroma_hi}[kind]
+        fn(C.c_void_p(src_arr.ctypes.data + origin_off * src_arr.itemsize), stride, w, h, P(dst), ds, mvx, mvy)
+        return dst
+
+    IM_SIZE = (71 + 1) * 64 + 1
+    FIRST_COLS = 71 + 1
+
+    def fme_state(self):
+        return (np.zeros(4 * 64 * 64, self.pix), np.zeros(5 * self.IM_SIZE, np.int16),
+                np.zeros(5 * self.FIRST_COLS, np.int16))
+
+    def filter_fme(self, stage, src_arr, origin_off, stride, w, h, state, fme_level, off_x, off_y):
+        filt, im, cols = state
+        self.lib.orc_filter_fme(stage, C.c_void_p(src_arr.ctypes.data + origin_off * src_arr.itemsize), stride, w, h,
+                                P(filt), P(im), fme_level, P(cols), off_x, off_y)
+
+    def get_extended_block(self, src, src_w, src_h, src_s, bx, by, bw, bh, pl, pr, pt, pb, pbs):
+        buf = np.full((pt + bh + pb + pbs) * (pl + bw + pr) + 1, 0xAB, self.pix)
+        out = (C.c_int * 3)()
+        r = self.lib.orc_get_extended_block(P(src), src_w, src_h, src_s, bx, by, bw, bh, pl, pr, pt, pb, pbs, P(buf),
+                                            C.byref(out, 0), C.byref(out, 4), C.byref(out, 8))
+        return r, buf, tuple(out)
+
+    # sao
+    def calc_sao_edge_dir(self, bitdepth, orig, rec, eo, bw, bh):
+        out = np.zeros(10, np.int32)
+        self.lib.orc_calc_sao_edge_dir(bitdepth, P(orig), P(rec), eo, bw, bh, P(out))
+        return out
+
+    def sao_edge_ddistortion(self, bitdepth, orig, rec, bw, bh, eo, offsets):
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        return self.lib.orc_sao_edge_ddistortion(bitdepth, P(orig), P(rec), bw, bh, eo, P(offsets))
+
+    def sao_band_ddistortion(self, bitdepth, orig, rec, bw, bh, band_pos, bands):
+        bands = np.ascontiguousarray(bands, np.int32)
+        return self.lib.orc_sao_band_ddistortion(bitdepth, P(orig), P(rec), bw, bh, band_pos, P(bands))
+
+    def sao_reconstruct_color(self, bitdepth, rec_arr, origin_off, sao_type, eo, band_position, offsets, stride,
+                              new_stride, bw, bh, color):
+        out = np.zeros(bh * new_stride, self.pix)
+        bp = np.ascontiguousarray(band_position, np.int32)
+        of = np.ascontiguousarray(offsets, np.int32)
+        self.lib.orc_sao_reconstruct_color(bitdepth, C.c_void_p(rec_arr.ctypes.data + origin_off * rec_arr.itemsize),
+                                           P(out), sao_type, eo, P(bp), P(of), stride, new_stride, bw, bh, color)
+        return out
+
+    # nal
+    def array_checksum(self, data, height, width, stride):
+        out = np.zeros(4, np.uint8)
+        self.lib.orc_array_checksum(P(data), height, width, stride, P(out))
+        return out
+
+
+class Ref:
+    """The compiled, unmodified reference (8-bit build)."""
+
+    def __init__(self):
+        so = build_ref()
+        if so is None:
+            raise FileNotFoundError("oracle/_ref not built and /root/reference absent")
+        self.lib = C.CDLL(so)
+        L = self.lib
+        L.kvzref_find.restype = C.c_void_p
+        L.kvzref_find.argtypes = [C.c_char_p, C.c_char_p]
+        L.kvzref_selected.restype = C.c_void_p
+        L.kvzref_selected.argtypes = [C.c_char_p]
+        L.kvzref_selected_name.restype = C.c_char_p
+        L.kvzref_selected_name.argtypes = [C.c_char_p]
+        L.kvzref_scan_table.restype = C.POINTER(C.c_uint32)
+        L.kvzref_ctx_open.restype = C.c_void_p
+        L.kvzref_entry.restype = C.c_char_p
+        assert L.kvzref_init() == 1
+        self.pix = np.uint8 if L.kvzref_bitdepth() == 8 else np.uint16
+        self._ctx = {}
+
+    def ctx(self, qp=22, signhide=0, rdoq=0, w=64, h=64):
+        key = (qp, signhide, rdoq, w, h)
+        if key not in self._ctx:
+            c = self.lib.kvzref_ctx_open(w, h, qp, signhide, rdoq)
+            assert c
+            self._ctx[key] = C.c_void_p(c)
+        return self._ctx[key]
+
+    def entries(self):
+        out = []
+        for i in range(self.lib.kvzref_count()):
+            name = C.c_char_p()
+            prio = C.c_int()
+            t = self.lib.kvzref_entry(i, C.byref(name), C.byref(prio))
+            out.append((t.decode(), name.value.decode(), prio.value))
+        return out
+
+    def fn(self, type_, impl, restype, *argtypes):
+        p = self.lib.kvzref_find(type_.encode(), impl.encode() if impl else None)
+        assert p, (type_, impl)
+        return C.CFUNCTYPE(restype, *argtypes)(p)
+
+    def selected_name(self, type_):
+        return self.lib.kvzref_selected_name(type_.encode()).decode()
+
+    # -- picture (plain typedefs; called straight through the registry pointer)
+    def reg_sad(self, a, b, w, h, s1, s2, impl="generic"):
+        f = self.fn("reg_sad", impl, C.c_uint, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_uint)
+        return f(P(a), P(b), w, h, s1, s2)
+
+    def nxn(self, kind, n, a, b, impl="generic"):
+        f = self.fn(f"{kind}_{n}x{n}", impl, C.c_uint, C.c_void_p, C.c_void_p)
+        return f(P(a), P(b))
+
+    def nxn_dual(self, kind, n, preds, orig, impl="generic"):
+        f = self.fn(f"{kind}_{n}x{n}_dual", impl, None, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p)
+        costs = aligned(2, np.uint32)
+        f(P(preds), P(orig), 2, P(costs))
+        return costs
+
+    def satd_any_size(self, w, h, b1, s1, b2, s2, impl="generic"):
+        f = self.fn("satd_any_size", impl, C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int)
+        return f(w, h, P(b1), s1, P(b2), s2)
+
+    def satd_any_size_quad(self, w, h, preds4, stride, orig, orig_stride, impl="generic"):
+        f = self.fn("satd_any_size_quad", impl, None, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                    C.c_uint, C.c_void_p, C.c_void_p)
+        ptrs = (C.c_void_p * 4)(*[p.ctypes.data for p in preds4])
+        costs = aligned(4, np.uint32)
+        valid = aligned(4, np.int8, fill=1)
+        f(w, h, C.cast(ptrs, C.c_void_p), stride, P(orig), orig_stride, 4, P(costs), P(valid))
+        return costs
+
+    def pixels_calc_ssd(self, ref, rec, rs, cs, width, impl="generic"):
+        f = self.fn("pixels_calc_ssd", impl, C.c_uint, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int)
+        return f(P(ref), P(rec), rs, cs, width)
+
+    def ver_sad(self, pic, ref, w, h, ps, impl="generic"):
+        f = self.fn("ver_sad", impl, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint32)
+        return f(P(pic), P(ref), w, h, ps)
+
+    def hor_sad(self, pic, ref, w, h, ps, rs, left, right, impl="generic"):
+        f = self.fn("hor_sad", impl, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint32, C.c_uint32,
+                    C.c_uint32, C.c_uint32)
+        return f(P(pic), P(ref), w, h, ps, rs, left, right)
+
+    def pixel_var(self, buf, impl="generic"):
+        f = self.fn("pixel_var", impl, C.c_double, C.c_void_p, C.c_uint32)
+        return f(P(buf), buf.size)
+
+    def bipred_average(self, px0, px1, im0, im1, pu_x, pu_y, pu_w, pu_h, flags0, flags1, impl="generic"):
+        """px*/im* = dict(y=,u=,v=) of contiguous arrays; returns (rec_y[64*64], rec_u[32*32], rec_v)."""
+        oy = aligned(64 * 64, self.pix)
+        ou = aligned(32 * 32, self.pix)
+        ov = aligned(32 * 32, self.pix)
+        a = []
+        for pl in "yuv":
+            a += [P(px0[pl]), P(px1[pl]), P(im0[pl]), P(im1[pl])]
+        self.lib.kvzref_bipred_average(impl.encode(), *a, pu_x, pu_y, pu_w, pu_h, flags0, flags1, P(oy), P(ou), P(ov))
+        return oy, ou, ov
+
+    # -- dct
+    def transform(self, name, bitdepth, inp, n, impl="generic"):
+        f = self.fn(name, impl, None, C.c_int8, C.c_void_p, C.c_void_p)
+        out = aligned(n * n, np.int16)
+        inp = al(inp, np.int16)
+        f(bitdepth, P(inp), P(out))
+        return out
+
+    def dct_coef(self, n, k, i):
+        return self.lib.kvzref_dct_coef(n, k, i)
+
+    def scan_table(self, scan_idx, log2):
+        p = self.lib.kvzref_scan_table(scan_idx, log2)
+        return np.ctypeslib.as_array(p, shape=(1 << (2 * log2),)).copy()
+
+    # -- quant
+    def quant(self, qp, coef, w, h, type_, scan_idx, block_type, intra=1, signhide=0, impl="generic"):
+        q = aligned(w * h, np.int16)
+        coef = al(coef, np.int16)
+        self.lib.kvzref_quant(self.ctx(qp, signhide), impl.encode(), qp, intra, P(coef), P(q), w, h, type_, scan_idx,
+                              block_type)
+        return q
+
+    def dequant(self, qp, q, w, h, type_, block_type, impl="generic"):
+        c = aligned(w * h, np.int16)
+        q = al(q, np.int16)
+        self.lib.kvzref_dequant(self.ctx(qp), impl.encode(), qp, P(q), P(c), w, h, type_, block_type)
+        return c
+
+    def quantize_residual(self, qp, width, color, scan_idx, trskip, cu_intra, stride, ref, pred, intra_slice=1,
+                          signhide=0, early_skip=0, impl="generic"):
+        rec = aligned(width * stride, self.pix)
+        coeff = aligned(width * width, np.int16)
+        has = self.lib.kvzref_quantize_residual(self.ctx(qp, signhide, 0), impl.encode(), qp, intra_slice, width, color,
+                                                scan_idx, trskip, cu_intra, stride, stride, P(ref), P(pred), P(rec),
+                                                P(coeff), early_skip)
+        return has, rec, coeff
+
+    def coeff_abs_sum(self, c, impl="generic"):
+        f = self.fn("coeff_abs_sum", impl, C.c_uint32, C.c_void_p, C.c_size_t)
+        return f(P(c), c.size)
+
+    def fast_coeff_cost(self, c, width, weights, impl="generic"):
+        f = self.fn("fast_coeff_cost", impl, C.c_double, C.c_void_p, C.c_int32, C.c_uint64)
+        return f(P(c), width, weights)
+
+    # -- intra
+    def angular(self, log2w, mode, top, left, impl="generic"):
+        f = self.fn("angular_pred", impl, None, C.c_int8, C.c_int8, C.c_void_p, C.c_void_p, C.c_void_p)
+        dst = aligned(1 << (2 * log2w), self.pix)
+        f(log2w, mode, P(top), P(left), P(dst))
+        return dst
+
+    def planar(self, log2w, top, left, impl="generic"):
+        f = self.fn("intra_pred_planar", impl, None, C.c_int8, C.c_void_p, C.c_void_p, C.c_void_p)
+        dst = aligned(1 << (2 * log2w), self.pix)
+        f(log2w, P(top), P(left), P(dst))
+        return dst
+
+    def filtered_dc(self, log2w, top, left, impl="generic"):
+        f = self.fn("intra_pred_filtered_dc", impl, None, C.c_int8, C.c_void_p, C.c_void_p, C.c_void_p)
+        dst = aligned(1 << (2 * log2w), self.pix)
+        f(log2w, P(top), P(left), P(dst))
+        return dst
+
+    def intra_predict(self, log2w, mode, color, top, left, filter_boundary):
+        dst = aligned(1 << (2 * log2w), self.pix)
+        self.lib.kvzref_intra_predict(log2w, mode, color, P(top), P(left), P(dst), filter_boundary)
+        return dst
+
+    def intra_build_reference(self, log2w, color, lx, ly, pic_w, pic_h, plane, stride):
+        n = 2 * (1 << log2w) + 1
+        top = aligned(n, self.pix)
+        left = aligned(n, self.pix)
+        self.lib.kvzref_intra_build_reference(log2w, color, lx, ly, pic_w, pic_h, P(plane), stride, P(top), P(left))
+        return top, left
+
+    # -- ipol
+    def sample(self, kind, src_arr, origin_off, stride, w, h, mvx, mvy, dst_stride=None, impl="generic"):
+        ds = dst_stride or w
+        hi = kind.endswith("_hi")
+        dst = aligned(h * ds, np.int16 if hi else self.pix)
+        t = {"luma": "sample_quarterpel_luma", "luma_hi": "sample_quarterpel_luma_hi",
+             "chroma": "sample_octpel_chroma", "chroma_hi": "sample_octpel_chroma_hi"}[kind]
+        self.lib.kvzref_sample(self.ctx(), t.encode(), impl.encode(),
+                               C.c_void_p(src_arr.ctypes.data + origin_off * src_arr.itemsize), stride, w, h, P(dst),
+                               ds, mvx, mvy)
+        return dst
+
+    def fme_state(self):
+        ims = self.lib.kvzref_ipol_im_size()
+        fc = self.lib.kvzref_ipol_first_cols()
+        return (aligned(4 * 64 * 64, self.pix), aligned(5 * ims, np.int16), aligned(5 * fc, np.int16))
+
+    def filter_fme(self, stage, src_arr, origin_off, stride, w, h, state, fme_level, off_x, off_y, impl="generic"):
+        filt, im, cols = state
+        self.lib.kvzref_filter_fme(self.ctx(), impl.encode(), stage,
+                                   C.c_void_p(src_arr.ctypes.data + origin_off * src_arr.itemsize), stride, w, h,
+                                   P(filt), P(im), fme_level, P(cols), off_x, off_y)
+
+    def get_extended_block(self, src, src_w, src_h, src_s, bx, by, bw, bh, pl, pr, pt, pb, pbs, impl="generic"):
+        buf = aligned((pt + bh + pb + pbs) * (pl + bw + pr) + 1, self.pix, fill=0xAB)
+        out = (C.c_int * 3)()
+        r = self.lib.kvzref_get_extended_block(impl.encode(), P(src), src_w, src_h, src_s, bx, by, bw, bh, pl, pr, pt,
+                                               pb, pbs, P(buf), C.byref(out, 0), C.byref(out, 4), C.byref(out, 8))
+        return r, buf, tuple(out)
+
+    # -- sao
+    def calc_sao_edge_dir(self, orig, rec, eo, bw, bh, impl="generic"):
+        out = aligned(10, np.int32)
+        self.lib.kvzref_calc_sao_edge_dir(self.ctx(), impl.encode(), P(orig), P(rec), eo, bw, bh, P(out))
+        return out
+
+    def sao_edge_ddistortion(self, orig, rec, bw, bh, eo, offsets, impl="generic"):
+        offsets = al(offsets, np.int32)
+        return self.lib.kvzref_sao_edge_ddistortion(self.ctx(), impl.encode(), P(orig), P(rec), bw, bh, eo, P(offsets))
+
+    def sao_band_ddistortion(self, orig, rec, bw, bh, band_pos, bands, impl="generic"):
+        bands = al(bands, np.int32)
+        return self.lib.kvzref_sao_band_ddistortion(self.ctx(), impl.encode(), P(orig), P(rec), bw, bh, band_pos,
+                                                    P(bands))
+
+    def sao_reconstruct_color(self, rec_arr, origin_off, sao_type, eo, band_position, offsets, stride, new_stride, bw,
+                              bh, color, impl="generic"):
+        out = aligned(bh * new_stride, self.pix)
+        bp = al(band_position, np.int32)
+        of = al(offsets, np.int32)
+        self.lib.kvzref_sao_reconstruct_color(self.ctx(), impl.encode(),
+                                              C.c_void_p(rec_arr.ctypes.data + origin_off * rec_arr.itemsize), P(out),
+                                              sao_type, eo, P(bp), P(of), stride, new_stride, bw, bh, color)
+        return out
+
+    # -- nal
+    def array_checksum(self, data, height, width, stride, impl="generic"):
+        out = aligned(4, np.uint8)
+        self.lib.kvzref_array_checksum(impl.encode(), P(data), height, width, stride, P(out))
+        return out
