@@ -1,0 +1,29 @@
+# Builds the product library kvazaar_b200/libkvzcuda.so (sm_100a only) and, via oracle/Makefile, the test oracles.
+NVCC      ?= nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+# -fmad=false: cost arithmetic must not be contracted into FMAs; everything else is integer.
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-Wall -Iinclude
+SRCDIR    := kvazaar_b200/csrc
+OBJDIR    := build/obj
+SRCS      := $(wildcard $(SRCDIR)/*.cu)
+OBJS      := $(patsubst $(SRCDIR)/%.cu,$(OBJDIR)/%.o,$(SRCS))
+LIB       := kvazaar_b200/libkvzcuda.so
+
+.PHONY: all lib oracle ref clean
+all: lib oracle ref
+lib: $(LIB)
+
+$(OBJDIR)/%.o: $(SRCDIR)/%.cu $(wildcard $(SRCDIR)/*.cuh) include/kvz_cuda.h
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -lcudart -ldl -lpthread
+
+oracle:
+	$(MAKE) -s -C oracle oracle
+ref:
+	$(MAKE) -s -C oracle ref
+
+clean:
+	rm -rf build $(LIB)

@@ -1,0 +1,222 @@
+/*
+ * kvz_cuda.h -- C ABI of libkvzcuda.so: a B200 (sm_100a) "cuda" strategy for Kvazaar's
+ * per-CTU strategy kernels (reference: /root/reference/src/strategies).
+ *
+ * Plain C, no reference headers, no torch types: pointers, sizes and small POD structs only.
+ * Three layers, bottom-up:
+ *
+ *   1. BATCHED DEVICE API  (kvz_cuda_*_batch / *_frame, device pointers + cudaStream_t as void*)
+ *      -- the throughput path: one launch evaluates many blocks / a whole frame of CTUs.
+ *   2. PER-CALL STRATEGY FUNCTIONS (kvz_cuda_strat_* with the reference's exact typedefs,
+ *      host pointers, synchronous) -- what the dispatch table binds; each stages its operands
+ *      through a per-thread pinned buffer and runs layer 1 with count == 1.
+ *   3. REGISTRARS  int kvz_strategy_register_<group>_cuda(void *opaque, uint8_t bitdepth)
+ *      -- same shape as kvz_strategy_register_picture_avx2 (ref: avx2/picture-avx2.c:1718),
+ *      called from kvz_strategy_register_<group>() (ref: strategies-picture.c:84-103).
+ *      They call back into the host's kvz_strategyselector_register
+ *      (ref: strategyselector.h:99) -- resolved at run time, see kvz_cuda_set_register_fn.
+ *      Registrars for the groups whose typedefs take encoder structs (quant, sao, ipol,
+ *      bipred_average) live in integration/strategies-cuda-glue.c, which is compiled
+ *      against the host's headers and forwards plain parameters to this ABI.
+ *
+ * All functions return 0 on success and a negative KVZ_CUDA_E_* code on failure unless noted;
+ * kvz_cuda_last_error() gives the message.  Every pixel argument is `const void *`:
+ * uint8_t when bitdepth == 8, uint16_t when bitdepth > 8 (the reference's compile-time
+ * kvz_pixel, ref: kvazaar.h:90-98).  coeff_t == int16_t (ref: global.h:115).
+ */
+#ifndef KVZ_CUDA_H_
+#define KVZ_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KVZ_CUDA_PRIORITY 50           /* > avx2's 40 (ref: picture-avx2.c:1722) */
+#define KVZ_CUDA_E_NODEVICE  (-1)
+#define KVZ_CUDA_E_ARG       (-2)
+#define KVZ_CUDA_E_RUNTIME   (-3)
+
+/* ------------------------------------------------------------------ lifecycle */
+int  kvz_cuda_init(int device);              /* idempotent; picks the device for this process */
+void kvz_cuda_shutdown(void);
+int  kvz_cuda_available(void);               /* 1 if a device was initialised */
+const char *kvz_cuda_last_error(void);
+int  kvz_cuda_sm_count(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+uint64_t kvz_cuda_launch_count(void);
+/* event timing of the library's own launches on a stream: bracket a region */
+int  kvz_cuda_sync(void *stream);
+
+/* ------------------------------------------------------------------ 3. registrars */
+typedef int (*kvz_cuda_register_fn)(void *opaque, const char *type, const char *strategy_name,
+                                    int priority, void *fptr);   /* ref: strategyselector.h:99 */
+/* Optional: give the callback explicitly; otherwise dlsym(RTLD_DEFAULT, "kvz_strategyselector_register"). */
+void kvz_cuda_set_register_fn(kvz_cuda_register_fn fn);
+int kvz_strategy_register_picture_cuda(void *opaque, uint8_t bitdepth);   /* ref: strategies-picture.h:115-227 */
+int kvz_strategy_register_dct_cuda(void *opaque, uint8_t bitdepth);       /* ref: strategies-dct.h:44-82 */
+int kvz_strategy_register_intra_cuda(void *opaque, uint8_t bitdepth);     /* ref: strategies-intra.h:45-75 */
+int kvz_strategy_register_nal_cuda(void *opaque, uint8_t bitdepth);       /* ref: strategies-nal.h:54-68 */
+int kvz_strategy_register_quant_plain_cuda(void *opaque, uint8_t bitdepth); /* coeff_abs_sum, fast_coeff_cost */
+/* lookup of a per-call function by its strategy type string (what the registrars register) */
+void *kvz_cuda_strategy_fptr(const char *type, uint8_t bitdepth);
+
+/* ------------------------------------------------------------------ 1. batched device API */
+
+/* ---- picture group ---- */
+/* count pairs of contiguous NxN blocks (N in 4,8,16,32,64): a[i*N*N ..], b[i*N*N ..]
+ * out[i] = sad_NxN / satd_NxN of pair i (ref: picture-generic.c:475-501, 213-221, strategies-picture.h:53-69) */
+int kvz_cuda_sad_nxn_batch(int n, int bitdepth, const void *a, const void *b, int count, uint32_t *out, void *stream);
+int kvz_cuda_satd_nxn_batch(int n, int bitdepth, const void *a, const void *b, int count, uint32_t *out, void *stream);
+/* num_modes predictions per block against one orig (dual = 2 modes, pitch 32*32, ref: picture-generic.c:363-402,
+ * 512-534): pred k of block i at preds + (i*block_pitch + k*mode_pitch) pixels; costs[i*num_modes + k] */
+int kvz_cuda_cost_nxn_multi_batch(int use_satd, int n, int bitdepth, const void *preds, int64_t block_pitch,
+                                  int mode_pitch, int num_modes, const void *orig, int count, uint32_t *costs,
+                                  void *stream);
+
+typedef struct {           /* one strided block pair inside two planes */
+  int32_t off_a, off_b;    /* pixel offsets of the top-left samples */
+  int16_t w, h;
+  int16_t left, right;     /* hor_sad only */
+} kvz_cuda_blk;
+#define KVZ_CUDA_OP_REG_SAD   0   /* ref: picture-generic.c:98-111  (no bit-depth shift) */
+#define KVZ_CUDA_OP_SATD_ANY  1   /* ref: strategies-picture.h:75-113 */
+#define KVZ_CUDA_OP_SSD       2   /* ref: picture-generic.c:536-551 (w x w) */
+#define KVZ_CUDA_OP_VER_SAD   3   /* ref: picture-generic.c:687-701 (b = one row) */
+#define KVZ_CUDA_OP_HOR_SAD   4   /* ref: picture-generic.c:714-752 */
+int kvz_cuda_block_cost_batch(int op, int bitdepth, const void *plane_a, int stride_a, const void *plane_b,
+                              int stride_b, const kvz_cuda_blk *descs, int count, uint32_t *out, void *stream);
+
+typedef struct { int32_t off_pred[4]; int32_t off_orig; int16_t w, h; } kvz_cuda_quad;
+/* ref: picture-generic.c:404-471, quirk for height % 8 == 4 reproduced; costs[i*4 + k] */
+int kvz_cuda_satd_any_size_quad_batch(int bitdepth, const void *pred_base, int pred_stride, const void *orig_base,
+                                      int orig_stride, const kvz_cuda_quad *descs, int count, uint32_t *costs,
+                                      void *stream);
+/* one plane of bipred_average (ref: picture-generic.c:553-668): l0/l1 contiguous w*h, pixel or int16 intermediate */
+int kvz_cuda_bipred_average_plane(int bitdepth, void *dst, int dst_stride, const void *l0, const void *l1,
+                                  int l0_is_im, int l1_is_im, int w, int h, void *stream);
+/* pixel_var (ref: picture-generic.c:755-778) of `count` contiguous arrays of `len` pixels; sequential double sums */
+int kvz_cuda_pixel_var_batch(int bitdepth, const void *buf, uint32_t len, int count, double *out, void *stream);
+
+/* ---- dct group (ref: dct-generic.c:579-629) ---- */
+#define KVZ_CUDA_TR_DCT  0
+#define KVZ_CUDA_TR_IDCT 1
+#define KVZ_CUDA_TR_DST  2   /* 4x4 only */
+#define KVZ_CUDA_TR_IDST 3
+int kvz_cuda_transform_batch(int kind, int n, int bitdepth, const int16_t *in, int16_t *out, int count, void *stream);
+
+/* ---- quant group (ref: quant-generic.c) ---- */
+typedef struct {
+  int32_t qp;               /* state->qp */
+  int32_t bitdepth;         /* encoder->bitdepth */
+  int32_t slice_is_intra;   /* state->frame->slicetype == KVZ_SLICE_I */
+  int32_t signhide_enable;  /* encoder->cfg.signhide_enable */
+  int32_t scaling_list_enable; /* must be 0: flat lists only (all BASELINE configs) */
+} kvz_cuda_quant_params;
+/* count blocks of n x n coefficients; type 0 luma / 2 chroma(quant) / 2,3 chroma(dequant); scan_idx per block or NULL=0 */
+int kvz_cuda_quant_batch(const kvz_cuda_quant_params *p, const int16_t *coef, int16_t *q_coef, int n, int type,
+                         const int8_t *scan_idx, int count, void *stream);
+int kvz_cuda_dequant_batch(const kvz_cuda_quant_params *p, const int16_t *q_coef, int16_t *coef, int n, int type,
+                           int count, void *stream);
+typedef struct {
+  int32_t off_ref, off_pred, off_rec;  /* pixel offsets into the three planes */
+  int32_t off_coeff;                   /* coeff_t offset into coeff_out */
+  uint8_t width;                       /* 4,8,16,32 */
+  uint8_t color;                       /* 0 Y, 1 U, 2 V */
+  uint8_t scan_idx, use_trskip, cu_is_intra, early_skip;
+  uint8_t phase;                       /* 0 whole function; 1 residual+forward transform only (coefficients to
+                                          coeff_out, no quantisation); 2 dequant+inverse+reconstruct only (coeff_out
+                                          holds the quantised levels).  Phases 1/2 bracket the host's kvz_rdoq. */
+  uint8_t pad;
+} kvz_cuda_tu;
+/* kvz_quantize_residual, RDOQ-off branch (ref: quant-generic.c:198-292): residual -> DCT/DST/trskip -> quant ->
+ * has_coeffs -> dequant -> inverse -> rec = clip(pred + res).  has_coeffs[i] in {0,1}. */
+int kvz_cuda_quantize_residual_batch(const kvz_cuda_quant_params *p, const void *ref_plane, const void *pred_plane,
+                                     int in_stride, void *rec_plane, int out_stride, int16_t *coeff_out,
+                                     const kvz_cuda_tu *tus, int count, int32_t *has_coeffs, void *stream);
+int kvz_cuda_coeff_abs_sum_batch(const int16_t *coeffs, size_t length, int count, uint32_t *out, void *stream);
+/* returns the integer sum (the reference returns sum / 256.0) */
+int kvz_cuda_fast_coeff_cost_batch(const int16_t *coeffs, int width, uint64_t weights, int count, uint32_t *out,
+                                   void *stream);
+
+/* ---- intra group (ref: intra-generic.c, intra.c:176-302) ---- */
+/* level 0: the three dispatched kernels (mode 0 planar, 1 filtered DC, 2..34 angular) on the refs as given.
+ * level 1: kvz_intra_predict semantics (reference smoothing, DC/edge post filters, color). */
+int kvz_cuda_intra_predict_batch(int level, int log2_width, int color, int filter_boundary, int bitdepth,
+                                 const void *ref_top, const void *ref_left /* [count][2w+1] */,
+                                 const int8_t *modes, int count, void *dst /* [count][w*w] */, void *stream);
+/* kvz_intra_build_reference over a frame-level reconstruction plane (ref: intra.c:305-559) */
+int kvz_cuda_intra_build_reference_batch(int log2_width, int color, int bitdepth, const void *rec_plane, int stride,
+                                         int pic_w, int pic_h, const int32_t *luma_xy /* [count][2] */, int count,
+                                         void *out_top, void *out_left, void *stream);
+/* Fused frame-level rough intra search (the search_intra_rough inner loop, ref: search_intra.c:391-530, batched
+ * for every block of the frame): for each width-w block of the luma plane, build refs from rec_plane, predict
+ * all 35 modes (kvz_intra_predict semantics, filter_boundary=1) and cost them with satd_NxN against src_plane.
+ * costs: [num_blocks][35] in raster order of blocks. */
+int kvz_cuda_intra_rough_search_frame(int log2_width, int bitdepth, const void *src_plane, const void *rec_plane,
+                                      int stride, int pic_w, int pic_h, uint32_t *costs, void *stream);
+
+/* ---- ipol group (ref: ipol-generic.c) ---- */
+typedef struct { int32_t off_src, off_dst; int16_t w, h; int16_t mvx, mvy; } kvz_cuda_ipol;
+#define KVZ_CUDA_IPOL_LUMA 0
+#define KVZ_CUDA_IPOL_LUMA_HI 1
+#define KVZ_CUDA_IPOL_CHROMA 2
+#define KVZ_CUDA_IPOL_CHROMA_HI 3
+int kvz_cuda_sample_batch(int kind, int bitdepth, const void *src_plane, int src_stride, void *dst_base,
+                          int dst_stride, const kvz_cuda_ipol *descs, int count, void *stream);
+#define KVZ_CUDA_IPOL_IM_SIZE ((71 + 1) * 64 + 1)  /* KVZ_IPOL_MAX_IM_SIZE_LUMA_SIMD, ref: strategies-ipol.h:53 */
+#define KVZ_CUDA_IPOL_FIRST_COLS (71 + 1)
+/* FME stage 0..3 = hpel hor/ver, hpel diag, qpel hor/ver, qpel diag (ref: ipol-generic.c:213-679) for `count`
+ * blocks; per-block state arrays filtered[4][64*64], hor_intermediate[5][IM_SIZE], hor_first_cols[5][FIRST_COLS] */
+int kvz_cuda_filter_fme_batch(int stage, int bitdepth, const void *src_plane, int src_stride, const int32_t *src_off,
+                              int w, int h, void *filtered, int16_t *hor_intermediate, int fme_level,
+                              int16_t *hor_first_cols, const int8_t *hpel_off /* [count][2] */, int count,
+                              void *stream);
+/* border-replicated copy of (blk + padding) into buf (ref: ipol-generic.c:761-814), always built */
+int kvz_cuda_extend_block(int bitdepth, const void *src, int src_w, int src_h, int src_s, int blk_x, int blk_y,
+                          int blk_w, int blk_h, int pad_l, int pad_r, int pad_t, int pad_b, int pad_b_simd, void *buf,
+                          void *stream);
+
+/* ---- sao group (ref: sao-generic.c, sao_shared_generics.h) ---- */
+typedef struct { int32_t off_orig, off_rec; int16_t bw, bh; } kvz_cuda_sao_blk;   /* contiguous bw*bh blocks */
+/* all four EO classes at once: out[i][eo][2][5] */
+int kvz_cuda_sao_edge_stats_batch(int bitdepth, const void *orig, const void *rec, const kvz_cuda_sao_blk *blks,
+                                  int count, int32_t *cat_sum_cnt, void *stream);
+/* offsets[i][5]; eo_class[i] */
+int kvz_cuda_sao_edge_ddistortion_batch(int bitdepth, const void *orig, const void *rec, const kvz_cuda_sao_blk *blks,
+                                        const int8_t *eo_class, const int32_t *offsets, int count, int32_t *out,
+                                        void *stream);
+int kvz_cuda_sao_band_ddistortion_batch(int bitdepth, const void *orig, const void *rec, const kvz_cuda_sao_blk *blks,
+                                        const int32_t *band_pos, const int32_t *bands /* [i][4] */, int count,
+                                        int32_t *out, void *stream);
+typedef struct {
+  int32_t off_rec, off_new;       /* pixel offsets (rec may be read 1 px around the block for edge types) */
+  int16_t bw, bh;
+  int8_t  type;                   /* 0 none(copy), 1 band, 2 edge  (ref: sao.h sao_type) */
+  int8_t  eo_class, color, pad;
+  int32_t band_position[2];
+  int32_t offsets[10];
+} kvz_cuda_sao_rec;
+int kvz_cuda_sao_reconstruct_batch(int bitdepth, const void *rec, int stride, void *new_rec, int new_stride,
+                                   const kvz_cuda_sao_rec *descs, int count, void *stream);
+
+/* ---- nal group (ref: nal-generic.c:57-82) ---- */
+/* out4: 4 bytes, big-endian checksum, device memory */
+int kvz_cuda_array_checksum(int bitdepth, const void *data, int height, int width, int stride, uint8_t *out4,
+                            void *stream);
+
+/* ------------------------------------------------------------------ host-buffer conveniences */
+/* device memory helpers so that C hosts need no CUDA headers */
+void *kvz_cuda_malloc(size_t bytes);
+void  kvz_cuda_free(void *p);
+void *kvz_cuda_host_alloc(size_t bytes);     /* pinned */
+void  kvz_cuda_host_free(void *p);
+int   kvz_cuda_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int   kvz_cuda_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KVZ_CUDA_H_ */

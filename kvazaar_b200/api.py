@@ -1,0 +1,292 @@
+"""Python face of the batched device API (include/kvz_cuda.h, layer 1).
+
+Every function takes torch CUDA tensors (uint8 for 8-bit pixels, int16-viewed-uint16 for >8-bit, int16
+coefficients), launches on torch's current stream and returns torch tensors.  Names and argument meaning follow
+the reference's strategy functions (src/strategies/strategies-*.h); descriptors are numpy structured arrays with
+the layout of the C structs.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import lib, KvzCudaError
+
+# numpy dtypes matching the C structs of include/kvz_cuda.h
+BLK = np.dtype([("off_a", "<i4"), ("off_b", "<i4"), ("w", "<i2"), ("h", "<i2"), ("left", "<i2"), ("right", "<i2")])
+QUAD = np.dtype([("off_pred", "<i4", 4), ("off_orig", "<i4"), ("w", "<i2"), ("h", "<i2")])
+TU = np.dtype([("off_ref", "<i4"), ("off_pred", "<i4"), ("off_rec", "<i4"), ("off_coeff", "<i4"), ("width", "u1"),
+               ("color", "u1"), ("scan_idx", "u1"), ("use_trskip", "u1"), ("cu_is_intra", "u1"), ("early_skip", "u1"),
+               ("phase", "u1"), ("pad", "u1")])
+IPOL = np.dtype([("off_src", "<i4"), ("off_dst", "<i4"), ("w", "<i2"), ("h", "<i2"), ("mvx", "<i2"), ("mvy", "<i2")])
+SAO_BLK = np.dtype([("off_orig", "<i4"), ("off_rec", "<i4"), ("bw", "<i2"), ("bh", "<i2")])
+SAO_REC = np.dtype([("off_rec", "<i4"), ("off_new", "<i4"), ("bw", "<i2"), ("bh", "<i2"), ("type", "i1"),
+                    ("eo_class", "i1"), ("color", "i1"), ("pad", "i1"), ("band_position", "<i4", 2),
+                    ("offsets", "<i4", 10)])
+assert BLK.itemsize == 16 and QUAD.itemsize == 24 and TU.itemsize == 24 and IPOL.itemsize == 16
+assert SAO_BLK.itemsize == 12 and SAO_REC.itemsize == 64
+
+OP_REG_SAD, OP_SATD_ANY, OP_SSD, OP_VER_SAD, OP_HOR_SAD = range(5)
+TR_DCT, TR_IDCT, TR_DST, TR_IDST = range(4)
+IPOL_LUMA, IPOL_LUMA_HI, IPOL_CHROMA, IPOL_CHROMA_HI = range(4)
+IPOL_IM_SIZE = (71 + 1) * 64 + 1
+IPOL_FIRST_COLS = 71 + 1
+
+
+class QuantParams(C.Structure):
+    _fields_ = [("qp", C.c_int32), ("bitdepth", C.c_int32), ("slice_is_intra", C.c_int32),
+                ("signhide_enable", C.c_int32), ("scaling_list_enable", C.c_int32)]
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise KvzCudaError("no CUDA device: the cuda strategy has no CPU fallback")
+    return torch
+
+
+def _ck(rc):
+    if rc != 0:
+        raise KvzCudaError(f"libkvzcuda error {rc}: {lib().kvz_cuda_last_error().decode()}")
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(_torch().cuda.current_stream().cuda_stream)
+
+
+def _bits(t):
+    torch = _torch()
+    return 8 if t.dtype == torch.uint8 else 10
+
+
+def to_dev(a):
+    """numpy array (incl. structured descriptor arrays) -> CUDA tensor (uint16 is carried as int16)."""
+    torch = _torch()
+    a = np.ascontiguousarray(a)
+    if a.dtype.fields is not None:
+        return torch.from_numpy(a.view(np.uint8).copy()).cuda()
+    if a.dtype == np.uint16:
+        a = a.view(np.int16)
+    if a.dtype == np.uint32:
+        a = a.view(np.int32)
+    return torch.from_numpy(a.copy()).cuda()
+
+
+def init(device=-1):
+    _ck(lib().kvz_cuda_init(device))
+
+
+def launch_count():
+    return int(lib().kvz_cuda_launch_count())
+
+
+# ------------------------------------------------------------------ picture group
+def _nxn(fn, n, a, b, count):
+    torch = _torch()
+    out = torch.empty(count, dtype=torch.int32, device=a.device)
+    _ck(fn(n, _bits(a), _p(a), _p(b), count, _p(out), _stream()))
+    return out
+
+
+def sad_nxn_batch(n, a, b, count):
+    return _nxn(lib().kvz_cuda_sad_nxn_batch, n, a, b, count)
+
+
+def satd_nxn_batch(n, a, b, count):
+    return _nxn(lib().kvz_cuda_satd_nxn_batch, n, a, b, count)
+
+
+def cost_nxn_multi_batch(use_satd, n, preds, block_pitch, mode_pitch, num_modes, orig, count):
+    torch = _torch()
+    out = torch.empty(count * num_modes, dtype=torch.int32, device=preds.device)
+    _ck(lib().kvz_cuda_cost_nxn_multi_batch(int(use_satd), n, _bits(preds), _p(preds), C.c_int64(block_pitch),
+                                            mode_pitch, num_modes, _p(orig), count, _p(out), _stream()))
+    return out.view(count, num_modes)
+
+
+def block_cost_batch(op, plane_a, stride_a, plane_b, stride_b, descs):
+    torch = _torch()
+    d = to_dev(descs)
+    out = torch.empty(len(descs), dtype=torch.int32, device=plane_a.device)
+    _ck(lib().kvz_cuda_block_cost_batch(op, _bits(plane_a), _p(plane_a), stride_a, _p(plane_b), stride_b, _p(d),
+                                        len(descs), _p(out), _stream()))
+    return out
+
+
+def satd_any_size_quad_batch(pred_base, pred_stride, orig_base, orig_stride, descs):
+    torch = _torch()
+    d = to_dev(descs)
+    out = torch.empty(len(descs) * 4, dtype=torch.int32, device=pred_base.device)
+    _ck(lib().kvz_cuda_satd_any_size_quad_batch(_bits(pred_base), _p(pred_base), pred_stride, _p(orig_base),
+                                                orig_stride, _p(d), len(descs), _p(out), _stream()))
+    return out.view(-1, 4)
+
+
+def bipred_average_plane(dst, dst_stride, l0, l1, l0_is_im, l1_is_im, w, h, bitdepth=8):
+    _ck(lib().kvz_cuda_bipred_average_plane(bitdepth, _p(dst), dst_stride, _p(l0), _p(l1), int(l0_is_im),
+                                            int(l1_is_im), w, h, _stream()))
+    return dst
+
+
+def pixel_var_batch(buf, length, count):
+    torch = _torch()
+    out = torch.empty(count, dtype=torch.float64, device=buf.device)
+    _ck(lib().kvz_cuda_pixel_var_batch(_bits(buf), _p(buf), C.c_uint32(length), count, _p(out), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------ dct / quant groups
+def transform_batch(kind, n, bitdepth, inp, count):
+    torch = _torch()
+    out = torch.empty_like(inp)
+    _ck(lib().kvz_cuda_transform_batch(kind, n, bitdepth, _p(inp), _p(out), count, _stream()))
+    return out
+
+
+def quant_params(qp, bitdepth=8, slice_is_intra=1, signhide=0):
+    return QuantParams(qp, bitdepth, slice_is_intra, signhide, 0)
+
+
+def quant_batch(params, coef, n, type_, scan_idx, count):
+    torch = _torch()
+    out = torch.empty_like(coef)
+    _ck(lib().kvz_cuda_quant_batch(C.byref(params), _p(coef), _p(out), n, type_, _p(scan_idx), count, _stream()))
+    return out
+
+
+def dequant_batch(params, q_coef, n, type_, count):
+    torch = _torch()
+    out = torch.empty_like(q_coef)
+    _ck(lib().kvz_cuda_dequant_batch(C.byref(params), _p(q_coef), _p(out), n, type_, count, _stream()))
+    return out
+
+
+def quantize_residual_batch(params, ref_plane, pred_plane, in_stride, rec_plane, out_stride, coeff_out, tus):
+    torch = _torch()
+    d = to_dev(tus)
+    has = torch.empty(len(tus), dtype=torch.int32, device=ref_plane.device)
+    _ck(lib().kvz_cuda_quantize_residual_batch(C.byref(params), _p(ref_plane), _p(pred_plane), in_stride,
+                                               _p(rec_plane), out_stride, _p(coeff_out), _p(d), len(tus), _p(has),
+                                               _stream()))
+    return has
+
+
+def coeff_abs_sum_batch(coeffs, length, count):
+    torch = _torch()
+    out = torch.empty(count, dtype=torch.int32, device=coeffs.device)
+    _ck(lib().kvz_cuda_coeff_abs_sum_batch(_p(coeffs), C.c_size_t(length), count, _p(out), _stream()))
+    return out
+
+
+def fast_coeff_cost_batch(coeffs, width, weights, count):
+    torch = _torch()
+    out = torch.empty(count, dtype=torch.int32, device=coeffs.device)
+    _ck(lib().kvz_cuda_fast_coeff_cost_batch(_p(coeffs), width, C.c_uint64(weights), count, _p(out), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------ intra group
+def intra_predict_batch(level, log2w, color, filter_boundary, ref_top, ref_left, modes, count):
+    torch = _torch()
+    out = torch.empty(count << (2 * log2w), dtype=ref_top.dtype, device=ref_top.device)
+    _ck(lib().kvz_cuda_intra_predict_batch(level, log2w, color, int(filter_boundary), _bits(ref_top), _p(ref_top),
+                                           _p(ref_left), _p(modes), count, _p(out), _stream()))
+    return out
+
+
+def intra_build_reference_batch(log2w, color, rec_plane, stride, pic_w, pic_h, luma_xy):
+    torch = _torch()
+    xy = to_dev(np.ascontiguousarray(luma_xy, np.int32))
+    count = len(luma_xy)
+    n = 2 * (1 << log2w) + 1
+    top = torch.empty(count * n, dtype=rec_plane.dtype, device=rec_plane.device)
+    left = torch.empty_like(top)
+    _ck(lib().kvz_cuda_intra_build_reference_batch(log2w, color, _bits(rec_plane), _p(rec_plane), stride, pic_w, pic_h,
+                                                   _p(xy), count, _p(top), _p(left), _stream()))
+    return top.view(count, n), left.view(count, n)
+
+
+def intra_rough_search_frame(log2w, src_plane, rec_plane, stride, pic_w, pic_h, out=None):
+    torch = _torch()
+    w = 1 << log2w
+    nblk = (pic_w // w) * (pic_h // w)
+    if out is None:
+        out = torch.empty(nblk * 35, dtype=torch.int32, device=src_plane.device)
+    _ck(lib().kvz_cuda_intra_rough_search_frame(log2w, _bits(src_plane), _p(src_plane), _p(rec_plane), stride, pic_w,
+                                                pic_h, _p(out), _stream()))
+    return out.view(nblk, 35)
+
+
+# ------------------------------------------------------------------ ipol group
+def sample_batch(kind, src_plane, src_stride, dst, dst_stride, descs):
+    d = to_dev(descs)
+    _ck(lib().kvz_cuda_sample_batch(kind, _bits(src_plane), _p(src_plane), src_stride, _p(dst), dst_stride, _p(d),
+                                    len(descs), _stream()))
+    return dst
+
+
+def filter_fme_batch(stage, src_plane, src_stride, src_off, w, h, filtered, hor_intermediate, fme_level,
+                     hor_first_cols, hpel_off):
+    so = to_dev(np.ascontiguousarray(src_off, np.int32))
+    ho = to_dev(np.ascontiguousarray(hpel_off, np.int8)) if hpel_off is not None else None
+    _ck(lib().kvz_cuda_filter_fme_batch(stage, _bits(src_plane), _p(src_plane), src_stride, _p(so), w, h, _p(filtered),
+                                        _p(hor_intermediate), fme_level, _p(hor_first_cols), _p(ho), len(src_off),
+                                        _stream()))
+
+
+def extend_block(src, src_w, src_h, src_s, bx, by, bw, bh, pl, pr, pt, pb, pbs):
+    torch = _torch()
+    buf = torch.empty((pl + bw + pr) * (pt + bh + pb + pbs) + 1, dtype=src.dtype, device=src.device)
+    _ck(lib().kvz_cuda_extend_block(_bits(src), _p(src), src_w, src_h, src_s, bx, by, bw, bh, pl, pr, pt, pb, pbs,
+                                    _p(buf), _stream()))
+    return buf
+
+
+# ------------------------------------------------------------------ sao group
+def sao_edge_stats_batch(bitdepth, orig, rec, blks):
+    torch = _torch()
+    d = to_dev(blks)
+    out = torch.empty(len(blks) * 40, dtype=torch.int32, device=orig.device)
+    _ck(lib().kvz_cuda_sao_edge_stats_batch(bitdepth, _p(orig), _p(rec), _p(d), len(blks), _p(out), _stream()))
+    return out.view(len(blks), 4, 2, 5)
+
+
+def sao_edge_ddistortion_batch(bitdepth, orig, rec, blks, eo_class, offsets):
+    torch = _torch()
+    d = to_dev(blks)
+    eo = to_dev(np.ascontiguousarray(eo_class, np.int8))
+    of = to_dev(np.ascontiguousarray(offsets, np.int32))
+    out = torch.empty(len(blks), dtype=torch.int32, device=orig.device)
+    _ck(lib().kvz_cuda_sao_edge_ddistortion_batch(bitdepth, _p(orig), _p(rec), _p(d), _p(eo), _p(of), len(blks),
+                                                  _p(out), _stream()))
+    return out
+
+
+def sao_band_ddistortion_batch(bitdepth, orig, rec, blks, band_pos, bands):
+    torch = _torch()
+    d = to_dev(blks)
+    bp = to_dev(np.ascontiguousarray(band_pos, np.int32))
+    bd = to_dev(np.ascontiguousarray(bands, np.int32))
+    out = torch.empty(len(blks), dtype=torch.int32, device=orig.device)
+    _ck(lib().kvz_cuda_sao_band_ddistortion_batch(bitdepth, _p(orig), _p(rec), _p(d), _p(bp), _p(bd), len(blks),
+                                                  _p(out), _stream()))
+    return out
+
+
+def sao_reconstruct_batch(bitdepth, rec, stride, new_rec, new_stride, descs):
+    d = to_dev(descs)
+    _ck(lib().kvz_cuda_sao_reconstruct_batch(bitdepth, _p(rec), stride, _p(new_rec), new_stride, _p(d), len(descs),
+                                             _stream()))
+    return new_rec
+
+
+# ------------------------------------------------------------------ nal group
+def array_checksum(data, height, width, stride, out=None):
+    torch = _torch()
+    if out is None:
+        out = torch.empty(4, dtype=torch.uint8, device=data.device)
+    _ck(lib().kvz_cuda_array_checksum(_bits(data), _p(data), height, width, stride, _p(out), _stream()))
+    return out

@@ -1,0 +1,265 @@
+// dct_quant.cu -- dct group (DCT/IDCT 4..32, DST 4) and quant group (quant, dequant, quantize_residual,
+// coeff_abs_sum, fast_coeff_cost).  Reference: src/strategies/generic/dct-generic.c, quant-generic.c.
+#include "common.cuh"
+#include "transform.cuh"
+
+namespace kvzc {
+
+// One CTA handles G = max(1, 256 / N^2) transform blocks; both passes run out of shared memory.
+__global__ void __launch_bounds__(256) transform_kernel(int kind, int n, int bitdepth, const int16_t *__restrict__ in,
+                                                        int16_t *__restrict__ out, int count, int g_per_cta)
+{
+  __shared__ int16_t s_a[32 * 32];
+  __shared__ int16_t s_b[32 * 32];
+  __shared__ int8_t s_m[32 * 32];
+  const bool inverse = kind == KVZ_CUDA_TR_IDCT || kind == KVZ_CUDA_TR_IDST;
+  const bool dst = kind == KVZ_CUDA_TR_DST || kind == KVZ_CUDA_TR_IDST;
+  const int nn = n * n;
+  const int first = blockIdx.x * g_per_cta;
+  const int g = min(g_per_cta, count - first);
+  load_matrix(s_m, n, dst, !inverse);
+  const uint32_t *src32 = reinterpret_cast<const uint32_t *>(in + (size_t)first * nn);
+  uint32_t *sa32 = reinterpret_cast<uint32_t *>(s_a);
+  for (int e = threadIdx.x; e < g * nn / 2; e += blockDim.x) sa32[e] = __ldg(src32 + e);
+  __syncthreads();
+  const int l2 = ilog2(n);
+  if (!inverse) {
+    fwd_pass(s_a, s_b, s_m, n, g, l2 - 1 + (bitdepth - 8));   // ref: dct-generic.c:582-583
+    __syncthreads();
+    fwd_pass(s_b, s_a, s_m, n, g, l2 + 6);
+  } else {
+    inv_pass(s_a, s_b, s_m, n, g, 7);                          // ref: dct-generic.c:593-594
+    __syncthreads();
+    inv_pass(s_b, s_a, s_m, n, g, 12 - (bitdepth - 8));
+  }
+  __syncthreads();
+  uint32_t *dst32 = reinterpret_cast<uint32_t *>(out + (size_t)first * nn);
+  for (int e = threadIdx.x; e < g * nn / 2; e += blockDim.x) dst32[e] = sa32[e];
+}
+
+// quant / dequant of `count` n x n blocks, one CTA per block
+__global__ void __launch_bounds__(256) quant_kernel(kvz_cuda_quant_params p, const int16_t *__restrict__ coef,
+                                                    int16_t *__restrict__ q_coef, int n, int type,
+                                                    const int8_t *__restrict__ scan_idx)
+{
+  __shared__ int16_t s_c[32 * 32];
+  __shared__ int16_t s_q[32 * 32];
+  __shared__ int32_t s_d[32 * 32];
+  const int nn = n * n;
+  const size_t base = (size_t)blockIdx.x * nn;
+  for (int e = threadIdx.x; e < nn; e += blockDim.x) s_c[e] = coef[base + e];
+  __syncthreads();
+  quant_block(p, s_c, s_q, s_d, n, type, scan_idx ? scan_idx[blockIdx.x] : 0);
+  __syncthreads();
+  for (int e = threadIdx.x; e < nn; e += blockDim.x) q_coef[base + e] = s_q[e];
+}
+
+__global__ void __launch_bounds__(256) dequant_kernel(kvz_cuda_quant_params p, const int16_t *__restrict__ q_coef,
+                                                      int16_t *__restrict__ coef, int n, int type, long total)
+{
+  const int transform_shift = 15 - p.bitdepth - ilog2(n);
+  const int qp_scaled = scaled_qp(type, p.qp, (p.bitdepth - 8) * 6);
+  const int shift = 20 - 14 - transform_shift;
+  const int scale = c_inv_quant_scales[qp_scaled % 6] << (qp_scaled / 6);
+  const int add = 1 << (shift - 1);
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x)
+    coef[e] = (int16_t)clip3(-32768, 32767, ((int)q_coef[e] * scale + add) >> shift);
+}
+
+// kvz_quantize_residual, RDOQ-off branch (ref: quant-generic.c:198-292): one CTA per TU.
+template <class T>
+__global__ void __launch_bounds__(256) quantize_residual_kernel(kvz_cuda_quant_params p, const T *__restrict__ ref_plane,
+                                                                const T *__restrict__ pred_plane, int in_stride,
+                                                                T *__restrict__ rec_plane, int out_stride,
+                                                                int16_t *__restrict__ coeff_out,
+                                                                const kvz_cuda_tu *__restrict__ tus,
+                                                                int32_t *__restrict__ has_coeffs)
+{
+  __shared__ int16_t s_a[32 * 32];
+  __shared__ int16_t s_b[32 * 32];
+  __shared__ int16_t s_q[32 * 32];
+  __shared__ int32_t s_d[32 * 32];
+  __shared__ int8_t s_m[32 * 32];
+  __shared__ int s_has;
+  constexpr int PIXMAX = (1 << PixTraits<T>::kBits) - 1;
+  const kvz_cuda_tu tu = tus[blockIdx.x];
+  const int n = tu.width, nn = n * n, l2 = ilog2(n);
+  const bool use_dst = (n == 4 && tu.color == 0 && tu.cu_is_intra);   // ref: strategies-dct.c:78-96
+  const int ts_shift = 15 - p.bitdepth - l2;                           // ref: transform.c:150-185
+  const T *ref = ref_plane + tu.off_ref;
+  const T *pred = pred_plane + tu.off_pred;
+  T *rec = rec_plane + tu.off_rec;
+  if (threadIdx.x == 0) s_has = 0;
+  if (tu.phase != 2) {
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+      const int y = e / n, x = e - y * n;
+      s_a[e] = (int16_t)((int)ref[y * in_stride + x] - (int)pred[y * in_stride + x]);
+    }
+    if (!tu.use_trskip) load_matrix(s_m, n, use_dst, true);
+    __syncthreads();
+    // forward: s_a (residual) -> s_b (coeff)
+    if (tu.use_trskip) {
+      for (int e = threadIdx.x; e < nn; e += blockDim.x) s_b[e] = (int16_t)((uint16_t)s_a[e] << ts_shift);
+    } else {
+      fwd_pass(s_a, s_q, s_m, n, 1, l2 - 1 + (p.bitdepth - 8));
+      __syncthreads();
+      fwd_pass(s_q, s_b, s_m, n, 1, l2 + 6);
+    }
+    __syncthreads();
+    if (tu.phase == 1) {   // the host runs kvz_rdoq on these coefficients
+      for (int e = threadIdx.x; e < nn; e += blockDim.x) coeff_out[tu.off_coeff + e] = s_b[e];
+      if (threadIdx.x == 0) has_coeffs[blockIdx.x] = 0;
+      return;
+    }
+    quant_block(p, s_b, s_q, s_d, n, tu.color == 0 ? 0 : 2, tu.scan_idx);
+    __syncthreads();
+  } else {
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) s_q[e] = coeff_out[tu.off_coeff + e];
+    __syncthreads();
+  }
+  int any = 0;
+  for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+    const int16_t v = s_q[e];
+    if (tu.phase == 0) coeff_out[tu.off_coeff + e] = v;
+    any |= v != 0;
+  }
+  if (any) atomicOr(&s_has, 1);
+  __syncthreads();
+  const int has = s_has;
+  if (threadIdx.x == 0) has_coeffs[blockIdx.x] = has;
+  if (has && !tu.early_skip) {
+    dequant_block(p, s_q, s_b, n, tu.color == 0 ? 0 : (tu.color == 1 ? 2 : 3));
+    __syncthreads();
+    if (tu.use_trskip) {
+      const int off = 1 << (ts_shift - 1);
+      for (int e = threadIdx.x; e < nn; e += blockDim.x) s_a[e] = (int16_t)(((int)s_b[e] + off) >> ts_shift);
+    } else {
+      load_matrix(s_m, n, use_dst, false);
+      __syncthreads();
+      inv_pass(s_b, s_q, s_m, n, 1, 7);
+      __syncthreads();
+      inv_pass(s_q, s_a, s_m, n, 1, 12 - (p.bitdepth - 8));
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+      const int y = e / n, x = e - y * n;
+      const int16_t val = (int16_t)(s_a[e] + (int)pred[y * in_stride + x]);
+      rec[y * out_stride + x] = (T)clip3(0, PIXMAX, (int)val);
+    }
+  } else if (rec != pred) {
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+      const int y = e / n, x = e - y * n;
+      rec[y * out_stride + x] = pred[y * in_stride + x];
+    }
+  }
+}
+
+// coeff_abs_sum (ref: quant-generic.c:342-349) / fast_coeff_cost (:351-375): one warp per array
+__global__ void __launch_bounds__(128) coeff_sum_kernel(const int16_t *__restrict__ c, size_t length, int count,
+                                                        int use_weights, unsigned long long weights,
+                                                        uint32_t *__restrict__ out)
+{
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= count) return;
+  const int16_t *p = c + (size_t)warp * length;
+  uint32_t s = 0;
+  for (size_t i = lane; i < length; i += 32) {
+    uint32_t a = (uint32_t)abs((int)p[i]);
+    if (use_weights) { if (a > 3) a = 3; a = (uint32_t)((weights >> (16 * a)) & 0xffff); }
+    s += a;
+  }
+  s = (uint32_t)warp_sum((int)s);
+  if (lane == 0) out[warp] = s;
+}
+
+}  // namespace kvzc
+
+using namespace kvzc;
+
+extern "C" {
+
+int kvz_cuda_transform_batch(int kind, int n, int bitdepth, const int16_t *in, int16_t *out, int count, void *stream)
+{
+  KVZC_REQUIRE_DEVICE();
+  KVZC_ARG(in && out && count >= 0 && kind >= 0 && kind <= 3);
+  KVZC_ARG(n == 4 || ((kind == KVZ_CUDA_TR_DCT || kind == KVZ_CUDA_TR_IDCT) && (n == 8 || n == 16 || n == 32)));
+  if (count == 0) return 0;
+  const int g = n * n >= 256 ? (n == 16 ? 4 : 1) : 1024 / (n * n);   // blocks per CTA (<= 1024 coefficients staged)
+  transform_kernel<<<(count + g - 1) / g, 256, 0, as_stream(stream)>>>(kind, n, bitdepth, in, out, count, g);
+  KVZC_LAUNCHED();
+  return 0;
+}
+
+static int check_qp(const kvz_cuda_quant_params *p)
+{
+  KVZC_ARG(p != nullptr);
+  if (p->scaling_list_enable) { set_error("scaling lists are not supported by the cuda strategy (flat lists only)"); return KVZ_CUDA_E_ARG; }
+  KVZC_ARG(p->bitdepth >= 8 && p->bitdepth <= 10 && p->qp >= -12 && p->qp <= 63);
+  return 0;
+}
+
+int kvz_cuda_quant_batch(const kvz_cuda_quant_params *p, const int16_t *coef, int16_t *q_coef, int n, int type,
+                         const int8_t *scan_idx, int count, void *stream)
+{
+  KVZC_REQUIRE_DEVICE();
+  if (int r = check_qp(p)) return r;
+  KVZC_ARG(coef && q_coef && (n == 4 || n == 8 || n == 16 || n == 32));
+  if (count == 0) return 0;
+  quant_kernel<<<count, n * n < 256 ? (n * n < 32 ? 32 : n * n) : 256, 0, as_stream(stream)>>>(*p, coef, q_coef, n, type, scan_idx);
+  KVZC_LAUNCHED();
+  return 0;
+}
+
+int kvz_cuda_dequant_batch(const kvz_cuda_quant_params *p, const int16_t *q_coef, int16_t *coef, int n, int type,
+                           int count, void *stream)
+{
+  KVZC_REQUIRE_DEVICE();
+  if (int r = check_qp(p)) return r;
+  KVZC_ARG(coef && q_coef && (n == 4 || n == 8 || n == 16 || n == 32));
+  if (count == 0) return 0;
+  const long total = (long)count * n * n;
+  long gl = (total + 255) / 256; if (gl > 148L * 16) gl = 148L * 16;
+  const int grid = (int)gl;
+  dequant_kernel<<<grid, 256, 0, as_stream(stream)>>>(*p, q_coef, coef, n, type, total);
+  KVZC_LAUNCHED();
+  return 0;
+}
+
+int kvz_cuda_quantize_residual_batch(const kvz_cuda_quant_params *p, const void *ref_plane, const void *pred_plane,
+                                     int in_stride, void *rec_plane, int out_stride, int16_t *coeff_out,
+                                     const kvz_cuda_tu *tus, int count, int32_t *has_coeffs, void *stream)
+{
+  KVZC_REQUIRE_DEVICE();
+  if (int r = check_qp(p)) return r;
+  KVZC_ARG(ref_plane && pred_plane && rec_plane && coeff_out && tus && has_coeffs);
+  if (count == 0) return 0;
+  if (p->bitdepth == 8)
+    quantize_residual_kernel<uint8_t><<<count, 256, 0, as_stream(stream)>>>(*p, (const uint8_t *)ref_plane, (const uint8_t *)pred_plane, in_stride, (uint8_t *)rec_plane, out_stride, coeff_out, tus, has_coeffs);
+  else
+    quantize_residual_kernel<uint16_t><<<count, 256, 0, as_stream(stream)>>>(*p, (const uint16_t *)ref_plane, (const uint16_t *)pred_plane, in_stride, (uint16_t *)rec_plane, out_stride, coeff_out, tus, has_coeffs);
+  KVZC_LAUNCHED();
+  return 0;
+}
+
+int kvz_cuda_coeff_abs_sum_batch(const int16_t *coeffs, size_t length, int count, uint32_t *out, void *stream)
+{
+  KVZC_REQUIRE_DEVICE();
+  KVZC_ARG(coeffs && out);
+  if (count == 0) return 0;
+  coeff_sum_kernel<<<(count * 32 + 127) / 128, 128, 0, as_stream(stream)>>>(coeffs, length, count, 0, 0ull, out);
+  KVZC_LAUNCHED();
+  return 0;
+}
+
+int kvz_cuda_fast_coeff_cost_batch(const int16_t *coeffs, int width, uint64_t weights, int count, uint32_t *out,
+                                   void *stream)
+{
+  KVZC_REQUIRE_DEVICE();
+  KVZC_ARG(coeffs && out && width > 0);
+  if (count == 0) return 0;
+  coeff_sum_kernel<<<(count * 32 + 127) / 128, 128, 0, as_stream(stream)>>>(coeffs, (size_t)width * width, count, 1, (unsigned long long)weights, out);
+  KVZC_LAUNCHED();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,203 @@
+// transform.cuh -- block-cooperative HEVC integer transforms and (de)quantisation on shared memory.
+//
+// The reference's partial butterflies (ref: dct-generic.c:255-577) evaluate, per pass, the exact integer matrix
+// product  dst[k*N + j] = (sum_i M[k][i] * src[j*N + i] + add) >> shift   (forward, result TRUNCATED to int16) and
+//          dst[j*N + k] = clip16((sum_i M[i][k] * src[i*N + j] + add) >> shift)   (inverse).
+// Integer addition is associative, so a plain dot product reproduces them bit for bit.
+#pragma once
+#include "common.cuh"
+
+namespace kvzc {
+
+// C[m], m = 0..32: the HEVC core-transform coefficient list; M32[k][i] = sgn * C[fold((k*(2i+1)) mod 128)]
+// (cosine symmetries C[64-m] = -C[m], C[128-m] = C[m]); the N-point matrix takes rows 0, 32/N, 2*32/N, ...
+static __constant__ int8_t c_tr32[33] = { 64, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
+                                   61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9, 4, 0 };
+static __constant__ int8_t c_dst4[16] = { 29, 55, 74, 84, 74, 74, 0, -74, 84, -29, -74, 55, 55, -84, 74, -29 };
+
+__device__ __forceinline__ int tr_coef(int n, bool dst, int k, int i)
+{
+  if (dst) return c_dst4[k * 4 + i];
+  int m = ((k * (32 / n)) * (2 * i + 1)) & 127;
+  if (m > 64) m = 128 - m;
+  return m <= 32 ? (int)c_tr32[m] : -(int)c_tr32[64 - m];
+}
+
+// Fill `mat` (N*N int8, shared) so that mat[i*N + k] = M[k][i] when `transposed` (forward use) or M[i][k] (inverse).
+__device__ __forceinline__ void load_matrix(int8_t *mat, int n, bool dst, bool transposed)
+{
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, k = e % n;
+    mat[e] = (int8_t)(transposed ? tr_coef(n, dst, k, i) : tr_coef(n, dst, i, k));
+  }
+}
+
+// forward pass over `g` blocks stored back to back: dst[k*N+j] = (short)((sum_i M[k][i]*src[j*N+i] + add) >> shift)
+// matT[i*N + k] = M[k][i]
+__device__ __forceinline__ void fwd_pass(const int16_t *src, int16_t *dst, const int8_t *matT, int n, int g, int shift)
+{
+  const int add = 1 << (shift - 1);
+  const int nn = n * n;
+  for (int e = threadIdx.x; e < g * nn; e += blockDim.x) {
+    const int blk = e / nn, r = e - blk * nn, j = r / n, k = r - j * n;
+    const int16_t *s = src + blk * nn + j * n;
+    int acc = 0;
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) acc += (int)matT[i * n + k] * (int)s[i];
+    dst[blk * nn + k * n + j] = (int16_t)((acc + add) >> shift);
+  }
+}
+
+// inverse pass: dst[j*N+k] = clip16((sum_i M[i][k]*src[i*N+j] + add) >> shift);  mat[i*N + k] = M[i][k]
+__device__ __forceinline__ void inv_pass(const int16_t *src, int16_t *dst, const int8_t *mat, int n, int g, int shift)
+{
+  const int add = 1 << (shift - 1);
+  const int nn = n * n;
+  for (int e = threadIdx.x; e < g * nn; e += blockDim.x) {
+    const int blk = e / nn, r = e - blk * nn, j = r / n, k = r - j * n;
+    const int16_t *s = src + blk * nn + j;
+    int acc = 0;
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) acc += (int)mat[i * n + k] * (int)s[i * n];
+    dst[blk * nn + j * n + k] = (int16_t)clip3(-32768, 32767, (acc + add) >> shift);
+  }
+}
+
+__device__ __forceinline__ int ilog2(int n) { return 31 - __clz(n); }
+
+// ---- quantisation ---------------------------------------------------------------------------
+static __constant__ int c_quant_scales[6] = { 26214, 23302, 20560, 18396, 16384, 14564 };   // ref: scalinglist.c:78
+static __constant__ int c_inv_quant_scales[6] = { 40, 45, 51, 57, 64, 72 };                 // ref: scalinglist.c:79
+
+// ref: transform.c:56-62,88-102 (kvz_get_scaled_qp with the chroma QP mapping table folded into its rule)
+__device__ __host__ __forceinline__ int scaled_qp(int type, int qp, int qp_offset)
+{
+  if (type == 0) return qp + qp_offset;
+  int q = qp < -qp_offset ? -qp_offset : (qp > 57 ? 57 : qp);
+  if (q < 0) return q + qp_offset;
+  int c;
+  if (q < 30) c = q;
+  else if (q >= 44) c = q - 6;
+  else { const int mid[14] = { 29, 30, 31, 32, 33, 33, 34, 34, 35, 35, 36, 36, 37, 37 }; c = mid[q - 30]; }
+  return c + qp_offset;
+}
+
+// position of scan index `idx` for an n x n block (ref: tables.c kvz_g_sig_last_scan): 4x4 coefficient groups
+// visited in scan order, same order inside a group; 0 = up-right diagonal, 1 = horizontal, 2 = vertical.
+__device__ __forceinline__ int scan_pos_small(int scan_idx, int dim_log2, int idx)   // dim 1,2,4,8 (log2 0..3)
+{
+  const int dim = 1 << dim_log2;
+  if (scan_idx == 1) return idx;                                              // (y = idx / dim, x = idx % dim)
+  if (scan_idx == 2) return (idx & (dim - 1)) * dim + (idx >> dim_log2);      // x = idx / dim, y = idx % dim
+  // diagonal: walk anti-diagonals d = x + y from bottom-left (max y) to top-right
+  int d = 0, start = 0;
+  for (;; ++d) {
+    const int ylo = max(0, d - (dim - 1)), yhi = min(d, dim - 1), len = yhi - ylo + 1;
+    if (idx < start + len) { const int y = yhi - (idx - start); return y * dim + (d - y); }
+    start += len;
+  }
+}
+__device__ __forceinline__ int scan_pos(int scan_idx, int log2_n, int idx)
+{
+  if (log2_n <= 2) return scan_pos_small(scan_idx, log2_n, idx);
+  const int n = 1 << log2_n;
+  const int cg = scan_pos_small(scan_idx, log2_n - 2, idx >> 4);              // group (y*(n/4) + x)
+  const int in = scan_pos_small(scan_idx, 2, idx & 15);
+  const int gw = n >> 2;
+  return ((cg / gw) * 4 + (in >> 2)) * n + (cg % gw) * 4 + (in & 3);
+}
+
+struct QuantConsts {
+  int qc, q_bits, add, q_bits8;
+};
+__device__ __forceinline__ QuantConsts quant_consts(const kvz_cuda_quant_params &p, int log2_n, int type)
+{
+  QuantConsts c;
+  const int qp_scaled = scaled_qp(type, p.qp, (p.bitdepth - 8) * 6);
+  c.qc = c_quant_scales[qp_scaled % 6];
+  const int transform_shift = 15 - p.bitdepth - log2_n;
+  c.q_bits = 14 + qp_scaled / 6 + transform_shift;
+  c.add = (p.slice_is_intra ? 171 : 85) << (c.q_bits - 9);
+  c.q_bits8 = c.q_bits - 8;
+  return c;
+}
+
+// kvz_quant (ref: quant-generic.c:50-180) for ONE n x n block held in shared memory.
+// coef -> q (both shared, n*n); delta_u: n*n int32 shared scratch; all threads of the CTA participate.
+__device__ __forceinline__ void quant_block(const kvz_cuda_quant_params &p, const int16_t *coef, int16_t *q,
+                                            int32_t *delta_u, int n, int type, int scan_idx)
+{
+  const int log2_n = ilog2(n);
+  const QuantConsts c = quant_consts(p, log2_n, type);
+  int ac = 0;
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int level_in = coef[e];
+    const long long abs_level = abs(level_in);
+    int level = (int)((abs_level * c.qc + c.add) >> c.q_bits);
+    ac += level;
+    delta_u[e] = (int)((abs_level * c.qc - ((long long)level << c.q_bits)) >> c.q_bits8);
+    level = level_in < 0 ? -level : level;
+    q[e] = (int16_t)clip3(-32768, 32767, level);
+  }
+  ac = block_sum(ac);
+  __shared__ int s_ac;
+  __shared__ int s_cg_nz[64];
+  if (threadIdx.x == 0) s_ac = ac;
+  const int num_cg = (n * n) >> 4;
+  // per coefficient-group "has a non-zero" flags (before any sign hiding), in scan order
+  for (int g = threadIdx.x; g < num_cg; g += blockDim.x) {
+    int nz = 0;
+    for (int k = 0; k < 16; ++k) nz |= q[scan_pos(scan_idx, log2_n, g * 16 + k)] != 0;
+    s_cg_nz[g] = nz;
+  }
+  __syncthreads();
+  if (!p.signhide_enable || s_ac < 2) return;
+  // one thread per coefficient group: the groups only interact through "is this the last non-zero group"
+  for (int g = threadIdx.x; g < num_cg; g += blockDim.x) {
+    if (!s_cg_nz[g]) continue;
+    bool last_cg = true;
+    for (int h = g + 1; h < num_cg; ++h) if (s_cg_nz[h]) { last_cg = false; break; }
+    int pos[16];
+    int first_nz = 16, last_nz = -1, abssum = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) pos[k] = scan_pos(scan_idx, log2_n, g * 16 + k);
+    for (int k = 15; k >= 0; --k) if (q[pos[k]]) { last_nz = k; break; }
+    for (int k = 0; k < 16; ++k) if (q[pos[k]]) { first_nz = k; break; }
+    for (int k = first_nz; k <= last_nz; ++k) abssum += q[pos[k]];
+    if (last_nz - first_nz < 4) continue;
+    const int signbit = q[pos[first_nz]] > 0 ? 0 : 1;
+    if (signbit == (abssum & 1)) continue;
+    int min_cost = 0x7fffffff, cur_cost = 0x7fffffff, min_pos = -1;
+    int final_change = 0, cur_change = 0;
+    for (int k = (last_cg ? last_nz : 15); k >= 0; --k) {
+      const int b = pos[k];
+      if (q[b] != 0) {
+        if (delta_u[b] > 0) { cur_cost = -delta_u[b]; cur_change = 1; }
+        else if (k == first_nz && abs((int)q[b]) == 1) { cur_cost = 0x7fffffff; }
+        else { cur_cost = delta_u[b]; cur_change = -1; }
+      } else if (k < first_nz && ((coef[b] >= 0) ? 0 : 1) != signbit) {
+        cur_cost = 0x7fffffff;
+      } else { cur_cost = -delta_u[b]; cur_change = 1; }
+      if (cur_cost < min_cost) { min_cost = cur_cost; final_change = cur_change; min_pos = b; }
+    }
+    if (q[min_pos] == 32767 || q[min_pos] == -32768) final_change = -1;
+    if (coef[min_pos] >= 0) q[min_pos] = (int16_t)(q[min_pos] + final_change);
+    else q[min_pos] = (int16_t)(q[min_pos] - final_change);
+  }
+  __syncthreads();
+}
+
+// kvz_dequant (ref: quant-generic.c:298-340), flat scaling lists, one n x n block in shared memory
+__device__ __forceinline__ void dequant_block(const kvz_cuda_quant_params &p, const int16_t *q, int16_t *coef, int n,
+                                              int type)
+{
+  const int transform_shift = 15 - p.bitdepth - ilog2(n);
+  const int qp_scaled = scaled_qp(type, p.qp, (p.bitdepth - 8) * 6);
+  const int shift = 20 - 14 - transform_shift;
+  const int scale = c_inv_quant_scales[qp_scaled % 6] << (qp_scaled / 6);
+  const int add = 1 << (shift - 1);
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x)
+    coef[e] = (int16_t)clip3(-32768, 32767, ((int)q[e] * scale + add) >> shift);
+}
+
+}  // namespace kvzc
