@@ -180,7 +180,11 @@ int kvz_cuda_extend_block(int bitdepth, const void *src, int src_w, int src_h, i
                           void *stream);
 
 /* ---- sao group (ref: sao-generic.c, sao_shared_generics.h) ---- */
-typedef struct { int32_t off_orig, off_rec; int16_t bw, bh; } kvz_cuda_sao_blk;   /* contiguous bw*bh blocks */
+typedef struct {
+  int32_t off_orig, off_rec;
+  int16_t bw, bh;
+  int32_t stride_orig, stride_rec;   /* 0 = contiguous copy (stride == bw), what sao.c:605-669 hands to the strategies */
+} kvz_cuda_sao_blk;
 /* all four EO classes at once: out[i][eo][2][5] */
 int kvz_cuda_sao_edge_stats_batch(int bitdepth, const void *orig, const void *rec, const kvz_cuda_sao_blk *blks,
                                   int count, int32_t *cat_sum_cnt, void *stream);
@@ -206,6 +210,48 @@ int kvz_cuda_sao_reconstruct_batch(int bitdepth, const void *rec, int stride, vo
 /* out4: 4 bytes, big-endian checksum, device memory */
 int kvz_cuda_array_checksum(int bitdepth, const void *data, int height, int width, int stride, uint8_t *out4,
                             void *stream);
+
+/* ------------------------------------------------------------------ frame-level pass (framepass.cu) */
+/* Every strategy kernel of an all-intra frame, batched over all CTUs and all four quadtree depths
+ * (luma block width 32,16,8,4 = depth index 0..3; chroma width/2 for depth 0..2): rough search of 35 modes ->
+ * best mode -> prediction + quantize_residual reconstruction + SSD, then SAO statistics/decision/reconstruction
+ * on the 8x8-level reconstruction and the picture checksum.  I420 frames, 8-bit. */
+typedef struct { int32_t width, height, bitdepth, qp, signhide; } kvz_cuda_fp_params;
+typedef struct {
+  int32_t nblk[4];                 /* blocks per depth: (W / w) * (H / w) */
+  int32_t nctu;                    /* 64x64 CTUs (partial ones included) */
+  uint64_t host_bytes;             /* size of the result blob the host receives */
+  /* byte offsets inside the result blob */
+  uint64_t mode_y[4];              /* int8   [nblk]  best intra mode */
+  uint64_t cost_y[4];              /* uint32 [nblk]  its SATD cost */
+  uint64_t has_y[4];               /* uint8  [nblk]  has_coeffs */
+  uint64_t ssd_y[4];               /* uint32 [nblk]  SSD(src, rec) */
+  uint64_t coeff_y[4];             /* int16  [nblk][w*w] quantised coefficients, block-contiguous */
+  uint64_t has_u[3], has_v[3], ssd_u[3], ssd_v[3], coeff_u[3], coeff_v[3];
+  uint64_t sao_stats;              /* int32 [3*nctu][4][2][5]  (plane-major: Y CTUs, U CTUs, V CTUs) */
+  uint64_t sao_dd;                 /* int32 [4][3*nctu] edge delta-distortion per class */
+  uint64_t sao_band_dd;            /* int32 [3*nctu] */
+  uint64_t sao_best;               /* int8  [3*nctu] chosen class or -1 */
+  uint64_t sao_rec;                /* pixels: SAO-filtered I420 frame */
+  uint64_t checksum;               /* 3 x 4 bytes, big-endian, Y U V */
+} kvz_cuda_fp_layout;
+typedef struct kvz_cuda_frame_pass kvz_cuda_frame_pass;
+kvz_cuda_frame_pass *kvz_cuda_fp_create(const kvz_cuda_fp_params *p);   /* NULL on failure */
+void   kvz_cuda_fp_destroy(kvz_cuda_frame_pass *fp);
+int    kvz_cuda_fp_layout_get(const kvz_cuda_frame_pass *fp, kvz_cuda_fp_layout *out);
+int    kvz_cuda_fp_layout_for(const kvz_cuda_fp_params *p, kvz_cuda_fp_layout *out);   /* no device needed */
+void  *kvz_cuda_fp_result_dev(kvz_cuda_frame_pass *fp);                 /* device address of the result blob */
+size_t kvz_cuda_fp_frame_bytes(const kvz_cuda_frame_pass *fp);          /* W*H*3/2 */
+/* frames already in HBM; rec_in_dev = reconstruction the references are taken from (NULL = the source) */
+int    kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void *rec_in_dev, void *stream);
+/* Per-stage device timing with CUDA events on the launching stream.  Stage index: depth d = 0..3 -> 4*d + {0 rough
+ * search, 1 mode selection, 2 luma recon, 3 chroma recon}; 16 SAO statistics, 17 SAO offsets + delta-distortions,
+ * 18 SAO decision + reconstruction, 19 checksums.  get_timing returns accumulated ms per stage over `runs` runs. */
+#define KVZ_CUDA_FP_STAGES 20
+int    kvz_cuda_fp_set_timing(kvz_cuda_frame_pass *fp, int enable);
+int    kvz_cuda_fp_get_timing(kvz_cuda_frame_pass *fp, double *ms_total /* [KVZ_CUDA_FP_STAGES] */, int *runs);
+/* host frame in (pinned for async), result blob out (host_bytes): H2D + pass + D2H enqueued on `stream` */
+int    kvz_cuda_fp_run_host(kvz_cuda_frame_pass *fp, const void *src_host, void *result_host, void *stream);
 
 /* ------------------------------------------------------------------ host-buffer conveniences */
 /* device memory helpers so that C hosts need no CUDA headers */

@@ -18,12 +18,13 @@ TU = np.dtype([("off_ref", "<i4"), ("off_pred", "<i4"), ("off_rec", "<i4"), ("of
                ("color", "u1"), ("scan_idx", "u1"), ("use_trskip", "u1"), ("cu_is_intra", "u1"), ("early_skip", "u1"),
                ("phase", "u1"), ("pad", "u1")])
 IPOL = np.dtype([("off_src", "<i4"), ("off_dst", "<i4"), ("w", "<i2"), ("h", "<i2"), ("mvx", "<i2"), ("mvy", "<i2")])
-SAO_BLK = np.dtype([("off_orig", "<i4"), ("off_rec", "<i4"), ("bw", "<i2"), ("bh", "<i2")])
+SAO_BLK = np.dtype([("off_orig", "<i4"), ("off_rec", "<i4"), ("bw", "<i2"), ("bh", "<i2"), ("stride_orig", "<i4"),
+                    ("stride_rec", "<i4")])
 SAO_REC = np.dtype([("off_rec", "<i4"), ("off_new", "<i4"), ("bw", "<i2"), ("bh", "<i2"), ("type", "i1"),
                     ("eo_class", "i1"), ("color", "i1"), ("pad", "i1"), ("band_position", "<i4", 2),
                     ("offsets", "<i4", 10)])
 assert BLK.itemsize == 16 and QUAD.itemsize == 24 and TU.itemsize == 24 and IPOL.itemsize == 16
-assert SAO_BLK.itemsize == 12 and SAO_REC.itemsize == 64
+assert SAO_BLK.itemsize == 20 and SAO_REC.itemsize == 64
 
 OP_REG_SAD, OP_SATD_ANY, OP_SSD, OP_VER_SAD, OP_HOR_SAD = range(5)
 TR_DCT, TR_IDCT, TR_DST, TR_IDST = range(4)
@@ -290,3 +291,111 @@ def array_checksum(data, height, width, stride, out=None):
         out = torch.empty(4, dtype=torch.uint8, device=data.device)
     _ck(lib().kvz_cuda_array_checksum(_bits(data), _p(data), height, width, stride, _p(out), _stream()))
     return out
+
+
+# ------------------------------------------------------------------ frame-level pass (framepass.cu)
+class FpParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bitdepth", C.c_int32), ("qp", C.c_int32),
+                ("signhide", C.c_int32)]
+
+
+class FpLayout(C.Structure):
+    _fields_ = [("nblk", C.c_int32 * 4), ("nctu", C.c_int32), ("host_bytes", C.c_uint64),
+                ("mode_y", C.c_uint64 * 4), ("cost_y", C.c_uint64 * 4), ("has_y", C.c_uint64 * 4),
+                ("ssd_y", C.c_uint64 * 4), ("coeff_y", C.c_uint64 * 4),
+                ("has_u", C.c_uint64 * 3), ("has_v", C.c_uint64 * 3), ("ssd_u", C.c_uint64 * 3),
+                ("ssd_v", C.c_uint64 * 3), ("coeff_u", C.c_uint64 * 3), ("coeff_v", C.c_uint64 * 3),
+                ("sao_stats", C.c_uint64), ("sao_dd", C.c_uint64), ("sao_band_dd", C.c_uint64),
+                ("sao_best", C.c_uint64), ("sao_rec", C.c_uint64), ("checksum", C.c_uint64)]
+
+
+def fp_layout_for(width, height, qp=27, signhide=0):
+    """Result-blob layout; needs no GPU."""
+    lay = FpLayout()
+    prm = FpParams(width, height, 8, qp, signhide)
+    _ck(lib().kvz_cuda_fp_layout_for(C.byref(prm), C.byref(lay)))
+    return lay
+
+
+class FramePass:
+    """One in-flight frame of the frame-level pass (device buffers owned by the library)."""
+
+    def __init__(self, width, height, qp=27, signhide=0):
+        _torch()
+        L = lib()
+        L.kvz_cuda_fp_create.restype = C.c_void_p
+        L.kvz_cuda_fp_result_dev.restype = C.c_void_p
+        L.kvz_cuda_fp_result_dev.argtypes = [C.c_void_p]
+        L.kvz_cuda_fp_frame_bytes.restype = C.c_size_t
+        L.kvz_cuda_fp_frame_bytes.argtypes = [C.c_void_p]
+        self.params = FpParams(width, height, 8, qp, signhide)
+        h = L.kvz_cuda_fp_create(C.byref(self.params))
+        if not h:
+            raise KvzCudaError(f"kvz_cuda_fp_create failed: {L.kvz_cuda_last_error().decode()}")
+        self.h = C.c_void_p(h)
+        self.layout = FpLayout()
+        _ck(L.kvz_cuda_fp_layout_get(self.h, C.byref(self.layout)))
+        self.host_bytes = int(self.layout.host_bytes)
+        self.frame_bytes = int(L.kvz_cuda_fp_frame_bytes(self.h))
+        self.width, self.height = width, height
+
+    def close(self):
+        if self.h:
+            lib().kvz_cuda_fp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_dev(self, src, rec_in=None):
+        _ck(lib().kvz_cuda_fp_run_dev(self.h, _p(src), _p(rec_in), _stream()))
+
+    def run_host(self, src_host, result_host):
+        """src_host / result_host: pinned CPU uint8 tensors (frame_bytes / host_bytes)."""
+        _ck(lib().kvz_cuda_fp_run_host(self.h, C.c_void_p(src_host.data_ptr()), C.c_void_p(result_host.data_ptr()),
+                                       _stream()))
+
+    def result_host(self):
+        """Synchronous copy of the result blob to a numpy array."""
+        torch = _torch()
+        out = np.empty(self.host_bytes, np.uint8)
+        torch.cuda.current_stream().synchronize()
+        _ck(lib().kvz_cuda_memcpy_d2h(C.c_void_p(out.ctypes.data), C.c_void_p(lib().kvz_cuda_fp_result_dev(self.h)),
+                                      C.c_size_t(self.host_bytes), _stream()))
+        torch.cuda.current_stream().synchronize()
+        return out
+
+
+def fp_sections(layout, width, height):
+    """name -> (offset, dtype, count) for every section of the result blob."""
+    out = {}
+    for d in range(4):
+        w = 32 >> d
+        nb = layout.nblk[d]
+        out[f"mode_y{d}"] = (layout.mode_y[d], np.int8, nb)
+        out[f"cost_y{d}"] = (layout.cost_y[d], np.uint32, nb)
+        out[f"has_y{d}"] = (layout.has_y[d], np.uint8, nb)
+        out[f"ssd_y{d}"] = (layout.ssd_y[d], np.uint32, nb)
+        out[f"coeff_y{d}"] = (layout.coeff_y[d], np.int16, nb * w * w)
+        if d < 3:
+            wc = w // 2
+            for c in "uv":
+                out[f"has_{c}{d}"] = (getattr(layout, f"has_{c}")[d], np.uint8, nb)
+                out[f"ssd_{c}{d}"] = (getattr(layout, f"ssd_{c}")[d], np.uint32, nb)
+                out[f"coeff_{c}{d}"] = (getattr(layout, f"coeff_{c}")[d], np.int16, nb * wc * wc)
+    n3 = 3 * layout.nctu
+    out["sao_stats"] = (layout.sao_stats, np.int32, n3 * 40)
+    out["sao_dd"] = (layout.sao_dd, np.int32, n3 * 4)
+    out["sao_band_dd"] = (layout.sao_band_dd, np.int32, n3)
+    out["sao_best"] = (layout.sao_best, np.int8, n3)
+    out["sao_rec"] = (layout.sao_rec, np.uint8, width * height * 3 // 2)
+    out["checksum"] = (layout.checksum, np.uint8, 12)
+    return out
+
+
+def fp_section(blob, sections, name):
+    off, dt, n = sections[name]
+    return blob[off: off + n * np.dtype(dt).itemsize].view(dt)

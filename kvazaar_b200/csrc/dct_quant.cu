@@ -75,83 +75,13 @@ __global__ void __launch_bounds__(256) quantize_residual_kernel(kvz_cuda_quant_p
                                                                 const kvz_cuda_tu *__restrict__ tus,
                                                                 int32_t *__restrict__ has_coeffs)
 {
-  __shared__ int16_t s_a[32 * 32];
-  __shared__ int16_t s_b[32 * 32];
-  __shared__ int16_t s_q[32 * 32];
-  __shared__ int32_t s_d[32 * 32];
-  __shared__ int8_t s_m[32 * 32];
-  __shared__ int s_has;
-  constexpr int PIXMAX = (1 << PixTraits<T>::kBits) - 1;
+  __shared__ TuScratch s;
   const kvz_cuda_tu tu = tus[blockIdx.x];
-  const int n = tu.width, nn = n * n, l2 = ilog2(n);
-  const bool use_dst = (n == 4 && tu.color == 0 && tu.cu_is_intra);   // ref: strategies-dct.c:78-96
-  const int ts_shift = 15 - p.bitdepth - l2;                           // ref: transform.c:150-185
-  const T *ref = ref_plane + tu.off_ref;
-  const T *pred = pred_plane + tu.off_pred;
-  T *rec = rec_plane + tu.off_rec;
-  if (threadIdx.x == 0) s_has = 0;
-  if (tu.phase != 2) {
-    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
-      const int y = e / n, x = e - y * n;
-      s_a[e] = (int16_t)((int)ref[y * in_stride + x] - (int)pred[y * in_stride + x]);
-    }
-    if (!tu.use_trskip) load_matrix(s_m, n, use_dst, true);
-    __syncthreads();
-    // forward: s_a (residual) -> s_b (coeff)
-    if (tu.use_trskip) {
-      for (int e = threadIdx.x; e < nn; e += blockDim.x) s_b[e] = (int16_t)((uint16_t)s_a[e] << ts_shift);
-    } else {
-      fwd_pass(s_a, s_q, s_m, n, 1, l2 - 1 + (p.bitdepth - 8));
-      __syncthreads();
-      fwd_pass(s_q, s_b, s_m, n, 1, l2 + 6);
-    }
-    __syncthreads();
-    if (tu.phase == 1) {   // the host runs kvz_rdoq on these coefficients
-      for (int e = threadIdx.x; e < nn; e += blockDim.x) coeff_out[tu.off_coeff + e] = s_b[e];
-      if (threadIdx.x == 0) has_coeffs[blockIdx.x] = 0;
-      return;
-    }
-    quant_block(p, s_b, s_q, s_d, n, tu.color == 0 ? 0 : 2, tu.scan_idx);
-    __syncthreads();
-  } else {
-    for (int e = threadIdx.x; e < nn; e += blockDim.x) s_q[e] = coeff_out[tu.off_coeff + e];
-    __syncthreads();
-  }
-  int any = 0;
-  for (int e = threadIdx.x; e < nn; e += blockDim.x) {
-    const int16_t v = s_q[e];
-    if (tu.phase == 0) coeff_out[tu.off_coeff + e] = v;
-    any |= v != 0;
-  }
-  if (any) atomicOr(&s_has, 1);
-  __syncthreads();
-  const int has = s_has;
+  const int has = quantize_residual_tu<T>(s, p, tu.width, tu.color, tu.scan_idx, tu.use_trskip, tu.cu_is_intra,
+                                          tu.early_skip, tu.phase, ref_plane + tu.off_ref, in_stride,
+                                          pred_plane + tu.off_pred, in_stride, rec_plane + tu.off_rec, out_stride,
+                                          coeff_out + tu.off_coeff);
   if (threadIdx.x == 0) has_coeffs[blockIdx.x] = has;
-  if (has && !tu.early_skip) {
-    dequant_block(p, s_q, s_b, n, tu.color == 0 ? 0 : (tu.color == 1 ? 2 : 3));
-    __syncthreads();
-    if (tu.use_trskip) {
-      const int off = 1 << (ts_shift - 1);
-      for (int e = threadIdx.x; e < nn; e += blockDim.x) s_a[e] = (int16_t)(((int)s_b[e] + off) >> ts_shift);
-    } else {
-      load_matrix(s_m, n, use_dst, false);
-      __syncthreads();
-      inv_pass(s_b, s_q, s_m, n, 1, 7);
-      __syncthreads();
-      inv_pass(s_q, s_a, s_m, n, 1, 12 - (p.bitdepth - 8));
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
-      const int y = e / n, x = e - y * n;
-      const int16_t val = (int16_t)(s_a[e] + (int)pred[y * in_stride + x]);
-      rec[y * out_stride + x] = (T)clip3(0, PIXMAX, (int)val);
-    }
-  } else if (rec != pred) {
-    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
-      const int y = e / n, x = e - y * n;
-      rec[y * out_stride + x] = pred[y * in_stride + x];
-    }
-  }
 }
 
 // coeff_abs_sum (ref: quant-generic.c:342-349) / fast_coeff_cost (:351-375): one warp per array

@@ -28,6 +28,7 @@ __global__ void __launch_bounds__(256) sao_edge_stats_kernel(int bitdepth, const
   const kvz_cuda_sao_blk d = blks[blockIdx.x];
   const T *orig = orig_base + d.off_orig, *rec = rec_base + d.off_rec;
   const int bw = d.bw, bh = d.bh;
+  const int so = d.stride_orig ? d.stride_orig : bw, sr = d.stride_rec ? d.stride_rec : bw;
   const int offset = bitdepth != 8 ? 1 << (bitdepth - 9) : 0, shift = bitdepth - 8;
   for (int i = threadIdx.x; i < 40; i += blockDim.x) (&s_acc[0][0][0])[i] = 0;
   __syncthreads();
@@ -39,13 +40,13 @@ __global__ void __launch_bounds__(256) sao_edge_stats_kernel(int bitdepth, const
   const int iw = bw - 2, ih = bh - 2;
   for (int i = threadIdx.x; i < iw * ih; i += blockDim.x) {
     const int y = 1 + i / iw, x = 1 + i % iw;
-    const int c = rec[y * bw + x];
-    const int diff = ((int)orig[y * bw + x] - c + offset) >> shift;
+    const int c = rec[y * sr + x];
+    const int diff = ((int)orig[y * so + x] - c + offset) >> shift;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       int ax, ay, bx, by;
       eo_offsets(e, ax, ay, bx, by);
-      const int cat = eo_cat(rec[(y + ay) * bw + x + ax], rec[(y + by) * bw + x + bx], c);
+      const int cat = eo_cat(rec[(y + ay) * sr + x + ax], rec[(y + by) * sr + x + bx], c);
 #pragma unroll
       for (int k = 0; k < 5; ++k) { const int hit = cat == k; sum[e][k] += hit ? diff : 0; cnt[e][k] += hit; }
     }
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(256) sao_edge_dd_kernel(int bitdepth, const T 
   const kvz_cuda_sao_blk d = blks[blockIdx.x];
   const T *orig = orig_base + d.off_orig, *rec = rec_base + d.off_rec;
   const int bw = d.bw, bh = d.bh, eo = eo_class[blockIdx.x];
+  const int so = d.stride_orig ? d.stride_orig : bw, sr = d.stride_rec ? d.stride_rec : bw;
   const int bit_offset = bitdepth != 8 ? 1 << (bitdepth - 9) : 0, shift = bitdepth - 8;
   int off[5];
 #pragma unroll
@@ -81,13 +83,13 @@ __global__ void __launch_bounds__(256) sao_edge_dd_kernel(int bitdepth, const T 
   const int iw = bw - 2, ih = bh - 2;
   for (int i = threadIdx.x; i < iw * ih; i += blockDim.x) {
     const int y = 1 + i / iw, x = 1 + i % iw;
-    const int c = rec[y * bw + x];
-    const int cat = eo_cat(rec[(y + ay) * bw + x + ax], rec[(y + by) * bw + x + bx], c);
+    const int c = rec[y * sr + x];
+    const int cat = eo_cat(rec[(y + ay) * sr + x + ax], rec[(y + by) * sr + x + bx], c);
     int o = off[0];
 #pragma unroll
     for (int k = 1; k < 5; ++k) o = cat == k ? off[k] : o;
     if (o != 0) {
-      const int diff = ((int)orig[y * bw + x] - c + bit_offset) >> shift;
+      const int diff = ((int)orig[y * so + x] - c + bit_offset) >> shift;
       const int delta = diff - o;
       sum += delta * delta - diff * diff;
     }
@@ -106,18 +108,20 @@ __global__ void __launch_bounds__(256) sao_band_dd_kernel(int bitdepth, const T 
   const kvz_cuda_sao_blk d = blks[blockIdx.x];
   const T *orig = orig_base + d.off_orig, *rec = rec_base + d.off_rec;
   const int shift = bitdepth - 5, bp = band_pos[blockIdx.x];
+  const int so = d.stride_orig ? d.stride_orig : d.bw, sr = d.stride_rec ? d.stride_rec : d.bw;
   int bnd[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) bnd[k] = bands[(size_t)blockIdx.x * 4 + k];
   int sum = 0;
   for (int i = threadIdx.x; i < d.bw * d.bh; i += blockDim.x) {
-    const int r = rec[i];
+    const int y = i / d.bw, x = i - y * d.bw;
+    const int r = rec[y * sr + x];
     const int band = (r >> shift) - bp;
     int o = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) o = band == k ? bnd[k] : o;
     if (o != 0) {
-      const int diff = (int)orig[i] - r;
+      const int diff = (int)orig[y * so + x] - r;
       const int delta = diff - o;
       sum += delta * delta - diff * diff;
     }

@@ -200,4 +200,88 @@ __device__ __forceinline__ void dequant_block(const kvz_cuda_quant_params &p, co
     coef[e] = (int16_t)clip3(-32768, 32767, ((int)q[e] * scale + add) >> shift);
 }
 
+// ---- kvz_quantize_residual for one TU, all threads of the CTA (ref: quant-generic.c:198-292, RDOQ-off branch) ----
+struct TuScratch {
+  int16_t a[32 * 32], b[32 * 32], q[32 * 32];
+  int32_t d[32 * 32];
+  int8_t m[32 * 32];
+  int has;
+};
+
+// ref/pred/rec point at the TU's top-left sample; pred may live in shared memory (pred_stride = width).
+// phase: 0 whole function, 1 residual + forward transform only, 2 dequant + inverse + reconstruction only.
+// Returns has_coeffs (0 for phase 1).
+template <class T>
+__device__ __forceinline__ int quantize_residual_tu(TuScratch &s, const kvz_cuda_quant_params &p, int n, int color,
+                                                    int scan_idx, bool use_trskip, bool cu_is_intra, bool early_skip,
+                                                    int phase, const T *ref, int ref_stride, const T *pred,
+                                                    int pred_stride, T *rec, int rec_stride, int16_t *coeff_out)
+{
+  constexpr int PIXMAX = (1 << PixTraits<T>::kBits) - 1;
+  const int nn = n * n, l2 = ilog2(n);
+  const bool use_dst = (n == 4 && color == 0 && cu_is_intra);      // ref: strategies-dct.c:78-96
+  const int ts_shift = 15 - p.bitdepth - l2;                        // ref: transform.c:150-185
+  if (threadIdx.x == 0) s.has = 0;
+  if (phase != 2) {
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+      const int y = e / n, x = e - y * n;
+      s.a[e] = (int16_t)((int)ref[y * ref_stride + x] - (int)pred[y * pred_stride + x]);
+    }
+    if (!use_trskip) load_matrix(s.m, n, use_dst, true);
+    __syncthreads();
+    if (use_trskip) {
+      for (int e = threadIdx.x; e < nn; e += blockDim.x) s.b[e] = (int16_t)((uint16_t)s.a[e] << ts_shift);
+    } else {
+      fwd_pass(s.a, s.q, s.m, n, 1, l2 - 1 + (p.bitdepth - 8));
+      __syncthreads();
+      fwd_pass(s.q, s.b, s.m, n, 1, l2 + 6);
+    }
+    __syncthreads();
+    if (phase == 1) {   // the host runs kvz_rdoq on these coefficients
+      for (int e = threadIdx.x; e < nn; e += blockDim.x) coeff_out[e] = s.b[e];
+      return 0;
+    }
+    quant_block(p, s.b, s.q, s.d, n, color == 0 ? 0 : 2, scan_idx);
+    __syncthreads();
+  } else {
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) s.q[e] = coeff_out[e];
+    __syncthreads();
+  }
+  int any = 0;
+  for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+    const int16_t v = s.q[e];
+    if (phase == 0) coeff_out[e] = v;
+    any |= v != 0;
+  }
+  if (any) atomicOr(&s.has, 1);
+  __syncthreads();
+  const int has = s.has;
+  if (has && !early_skip) {
+    dequant_block(p, s.q, s.b, n, color == 0 ? 0 : (color == 1 ? 2 : 3));
+    __syncthreads();
+    if (use_trskip) {
+      const int off = 1 << (ts_shift - 1);
+      for (int e = threadIdx.x; e < nn; e += blockDim.x) s.a[e] = (int16_t)(((int)s.b[e] + off) >> ts_shift);
+    } else {
+      load_matrix(s.m, n, use_dst, false);
+      __syncthreads();
+      inv_pass(s.b, s.q, s.m, n, 1, 7);
+      __syncthreads();
+      inv_pass(s.q, s.a, s.m, n, 1, 12 - (p.bitdepth - 8));
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+      const int y = e / n, x = e - y * n;
+      const int16_t val = (int16_t)(s.a[e] + (int)pred[y * pred_stride + x]);
+      rec[y * rec_stride + x] = (T)clip3(0, PIXMAX, (int)val);
+    }
+  } else if ((const void *)rec != (const void *)pred) {
+    for (int e = threadIdx.x; e < nn; e += blockDim.x) {
+      const int y = e / n, x = e - y * n;
+      rec[y * rec_stride + x] = pred[y * pred_stride + x];
+    }
+  }
+  return has;
+}
+
 }  // namespace kvzc

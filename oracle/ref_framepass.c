@@ -1,0 +1,208 @@
+/*
+ * ref_framepass.c -- TEST / BASELINE INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * The frame-level hot-path pass (see kvazaar_b200/csrc/framepass.cu for the definition) executed on the CPU through
+ * the UNMODIFIED reference's own strategy function pointers -- i.e. whatever kvz_strategyselector_init selected on
+ * this host (AVX2 where available), exactly like the reference encoder would call them -- with a pthread pool
+ * over blocks.  It is (1) the parity checker for the CUDA frame pass (byte-identical result blob) and (2) the
+ * `--impl reference` / cpu_baseline arm of bench.py.  The only non-reference arithmetic is the frame-plane
+ * restatement of kvz_intra_build_reference from oracle/kvz_oracle.c (the reference's version needs an lcu_t)
+ * and the three integer decision rules of the pass (argmin, SAO offset = clip(sum / count), SAO class argmin).
+ */
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "global.h"
+#include "kvazaar.h"
+#include "kvazaar_internal.h"
+#include "encoder.h"
+#include "encoderstate.h"
+#include "strategyselector.h"
+#include "cu.h"
+#include "intra.h"
+#include "sao.h"
+#include "nal.h"
+
+#include "../include/kvz_cuda.h"   /* kvz_cuda_fp_layout only: the blob layout both arms fill */
+#include "kvz_oracle.h"
+
+typedef struct { const kvz_api *api; kvz_config *cfg; kvz_encoder *enc; } kvzref_ctx;   /* as in ref_shim.c */
+
+typedef struct {
+  kvzref_ctx *ctx;
+  const uint8_t *src;
+  int W, H, qp;
+  const kvz_cuda_fp_layout *L;
+  uint8_t *blob;
+  uint8_t *rec[3][4];       /* per colour, per depth reconstruction planes (scratch, not part of the blob) */
+  int stage;
+  volatile int next;
+  int total;
+  int wl[4];
+} job_t;
+
+static void *xaligned(size_t bytes) { void *p = NULL; if (posix_memalign(&p, 64, bytes + 64)) abort(); memset(p, 0, bytes + 64); return p; }
+
+static int scan_for(int is_c, int w, int mode)
+{
+  if ((!is_c && w <= 8) || (is_c && w == 4)) return (mode >= 6 && mode <= 14) ? 2 : ((mode >= 22 && mode <= 30) ? 1 : 0);
+  return 0;
+}
+
+/* one block of one depth: rough search + selection + luma recon (+ chroma recon) */
+static void do_block(job_t *j, int d, int b, kvz_pixel *buf /* scratch: 6 * 1024 px, aligned */)
+{
+  const int W = j->W, H = j->H, w = j->wl[d], log2w = 5 - d;
+  const int bx = b % (W / w), by = b / (W / w);
+  const kvz_cuda_fp_layout *L = j->L;
+  encoder_state_t *state = &j->ctx->enc->states[0];
+  kvz_pixel *orig = buf, *pred = buf + 1024, *recb = buf + 2048, *pred2 = buf + 3072;
+  kvz_intra_references refs;
+  cu_info_t cu; memset(&cu, 0, sizeof(cu));
+  cu.type = CU_INTRA; cu.part_size = SIZE_2Nx2N;
+
+  /* --- luma rough search: 35 modes, SATD against the source block */
+  memset(&refs, 0, sizeof(refs));
+  orc_intra_build_reference(log2w, 0, bx * w, by * w, W, H, j->src, W, refs.ref.top, refs.ref.left);
+  for (int y = 0; y < w; ++y) memcpy(orig + y * w, j->src + (size_t)(by * w + y) * W + bx * w, w);
+  cost_pixel_nxn_func *satd = kvz_pixels_get_satd_func(w);
+  unsigned best = 0; int best_mode = 0;
+  for (int mode = 0; mode < 35; ++mode) {
+    kvz_intra_predict(&refs, log2w, mode, COLOR_Y, pred, true);
+    const unsigned c = satd(pred, orig);
+    if (mode == 0 || c < best) { best = c; best_mode = mode; }
+  }
+  ((int8_t *)(j->blob + L->mode_y[d]))[b] = (int8_t)best_mode;
+  ((uint32_t *)(j->blob + L->cost_y[d]))[b] = best;
+
+  /* --- luma reconstruction of the chosen mode */
+  kvz_intra_predict(&refs, log2w, best_mode, COLOR_Y, pred, true);
+  coeff_t *coeff = (coeff_t *)(j->blob + L->coeff_y[d]) + (size_t)b * w * w;
+  int has = kvz_quantize_residual(state, &cu, w, COLOR_Y, scan_for(0, w, best_mode), 0, w, w, orig, pred, recb, coeff, false);
+  (j->blob + L->has_y[d])[b] = (uint8_t)has;
+  ((uint32_t *)(j->blob + L->ssd_y[d]))[b] = kvz_pixels_calc_ssd(orig, recb, w, w, w);
+  for (int y = 0; y < w; ++y) memcpy(j->rec[0][d] + (size_t)(by * w + y) * W + bx * w, recb + y * w, w);
+
+  /* --- chroma, co-located luma mode */
+  if (d < 3) {
+    const int wc = w / 2, Wc = W / 2;
+    for (int color = 1; color <= 2; ++color) {
+      const uint8_t *plane = j->src + (color == 1 ? (size_t)W * H : (size_t)W * H * 5 / 4);
+      memset(&refs, 0, sizeof(refs));
+      orc_intra_build_reference(log2w - 1, color, bx * w, by * w, W, H, plane, Wc, refs.ref.top, refs.ref.left);
+      for (int y = 0; y < wc; ++y) memcpy(orig + y * wc, plane + (size_t)(by * wc + y) * Wc + bx * wc, wc);
+      kvz_intra_predict(&refs, log2w - 1, best_mode, (color_t)color, pred2, true);
+      coeff_t *cc = (coeff_t *)(j->blob + (color == 1 ? L->coeff_u[d] : L->coeff_v[d])) + (size_t)b * wc * wc;
+      has = kvz_quantize_residual(state, &cu, wc, (color_t)color, scan_for(1, wc, best_mode), 0, wc, wc, orig, pred2, recb, cc, false);
+      (j->blob + (color == 1 ? L->has_u[d] : L->has_v[d]))[b] = (uint8_t)has;
+      ((uint32_t *)(j->blob + (color == 1 ? L->ssd_u[d] : L->ssd_v[d])))[b] = kvz_pixels_calc_ssd(orig, recb, wc, wc, wc);
+      for (int y = 0; y < wc; ++y) memcpy(j->rec[color][d] + (size_t)(by * wc + y) * Wc + bx * wc, recb + y * wc, wc);
+    }
+  }
+}
+
+/* SAO for one (plane, CTU): statistics, offsets, delta-distortions, decision, reconstruction */
+static void do_sao(job_t *j, int i, kvz_pixel *buf /* 2 * 4096 px */)
+{
+  const int W = j->W, H = j->H;
+  const kvz_cuda_fp_layout *L = j->L;
+  const int nctu = L->nctu, nctu3 = 3 * nctu;
+  const int color = i / nctu, ctu = i % nctu, cx = (W + 63) / 64;
+  const int Wp = color ? W / 2 : W, Hp = color ? H / 2 : H, lw = color ? 32 : 64;
+  const int x0 = (ctu % cx) * lw, y0 = (ctu / cx) * lw;
+  const int bw = MIN(lw, Wp - x0), bh = MIN(lw, Hp - y0);
+  const uint8_t *splane = j->src + (color == 0 ? 0 : (color == 1 ? (size_t)W * H : (size_t)W * H * 5 / 4));
+  const uint8_t *rplane = j->rec[color][2];
+  uint8_t *sao_plane = j->blob + L->sao_rec + (color == 0 ? 0 : (color == 1 ? (size_t)W * H : (size_t)W * H * 5 / 4));
+  const encoder_control_t *enc = j->ctx->enc->control;
+  encoder_state_t *state = &j->ctx->enc->states[0];
+  kvz_pixel *orig = buf, *rec = buf + 4096;
+  /* contiguous copies, as sao_search_luma/chroma hand them to the strategies (ref: sao.c:605-669) */
+  for (int y = 0; y < bh; ++y) { memcpy(orig + y * bw, splane + (size_t)(y0 + y) * Wp + x0, bw); memcpy(rec + y * bw, rplane + (size_t)(y0 + y) * Wp + x0, bw); }
+  int32_t *stats = (int32_t *)(j->blob + L->sao_stats) + (size_t)i * 40;
+  int32_t *dd = (int32_t *)(j->blob + L->sao_dd);
+  int offsets[4][NUM_SAO_EDGE_CATEGORIES];
+  int best_eo = 0, best_dd = 0;
+  for (int eo = 0; eo < 4; ++eo) {
+    int csc[2][NUM_SAO_EDGE_CATEGORIES]; memset(csc, 0, sizeof(csc));
+    kvz_calc_sao_edge_dir(enc, orig, rec, eo, bw, bh, csc);
+    memcpy(stats + eo * 10, csc, sizeof(csc));
+    offsets[eo][0] = 0;
+    for (int k = 1; k < 5; ++k) offsets[eo][k] = csc[1][k] ? CLIP(-7, 7, csc[0][k] / csc[1][k]) : 0;
+    const int v = kvz_sao_edge_ddistortion(enc, orig, rec, bw, bh, eo, offsets[eo]);
+    dd[(size_t)eo * nctu3 + i] = v;
+    if (eo == 0 || v < best_dd) { best_dd = v; best_eo = eo; }
+  }
+  const int bands[4] = { 1, -1, 2, -2 };
+  ((int32_t *)(j->blob + L->sao_band_dd))[i] = kvz_sao_band_ddistortion(state, orig, rec, bw, bh, (i * 7) % 29, bands);
+  ((int8_t *)(j->blob + L->sao_best))[i] = (int8_t)(best_dd < 0 ? best_eo : -1);
+  /* reconstruction rectangle: CTU area minus the picture's one-pixel border */
+  const int rx0 = MAX(x0, 1), ry0 = MAX(y0, 1), rx1 = MIN(x0 + bw, Wp - 1), ry1 = MIN(y0 + bh, Hp - 1);
+  if (best_dd < 0 && rx1 > rx0 && ry1 > ry0) {
+    sao_info_t sao; memset(&sao, 0, sizeof(sao));
+    sao.type = SAO_TYPE_EDGE; sao.eo_class = (sao_eo_class)best_eo;
+    for (int k = 0; k < 5; ++k) sao.offsets[k + (color == 2 ? 5 : 0)] = offsets[best_eo][k];
+    kvz_sao_reconstruct_color(enc, rplane + (size_t)ry0 * Wp + rx0, sao_plane + (size_t)ry0 * Wp + rx0, &sao, Wp, Wp,
+                              rx1 - rx0, ry1 - ry0, (color_t)color);
+  }
+}
+
+static void *worker(void *arg)
+{
+  job_t *j = (job_t *)arg;
+  kvz_pixel *buf = (kvz_pixel *)xaligned(8192 * sizeof(kvz_pixel));
+  for (;;) {
+    const int i = __sync_fetch_and_add(&j->next, 1);
+    if (i >= j->total) break;
+    if (j->stage == 0) {
+      int d = 0, b = i;
+      while (b >= j->L->nblk[d]) { b -= j->L->nblk[d]; ++d; }
+      do_block(j, d, b, buf);
+    } else {
+      do_sao(j, i, buf);
+    }
+  }
+  free(buf);
+  return NULL;
+}
+
+static void run_stage(job_t *j, int stage, int total, int nthreads)
+{
+  pthread_t th[256];
+  j->stage = stage; j->next = 0; j->total = total;
+  if (nthreads > 256) nthreads = 256;
+  for (int t = 1; t < nthreads; ++t) pthread_create(&th[t], NULL, worker, j);
+  worker(j);
+  for (int t = 1; t < nthreads; ++t) pthread_join(th[t], NULL);
+}
+
+/* ctx must have been opened with rdoq = 0, signhide as wanted, qp = the pass QP (kvzref_ctx_open in ref_shim.c) */
+int kvzref_frame_pass(kvzref_ctx *ctx, const uint8_t *src, int W, int H, int qp, const kvz_cuda_fp_layout *L,
+                      uint8_t *blob, int nthreads)
+{
+  if (KVZ_BIT_DEPTH != 8) return -1;
+  job_t j; memset(&j, 0, sizeof(j));
+  j.ctx = ctx; j.src = src; j.W = W; j.H = H; j.qp = qp; j.L = L; j.blob = blob;
+  encoder_state_t *st = &ctx->enc->states[0];
+  st->qp = (int8_t)qp; st->frame->slicetype = KVZ_SLICE_I;
+  for (int d = 0; d < 4; ++d) {
+    j.wl[d] = 32 >> d;
+    j.rec[0][d] = (uint8_t *)xaligned((size_t)W * H);
+    if (d < 3) { j.rec[1][d] = (uint8_t *)xaligned((size_t)W * H / 4); j.rec[2][d] = (uint8_t *)xaligned((size_t)W * H / 4); }
+  }
+  run_stage(&j, 0, L->nblk[0] + L->nblk[1] + L->nblk[2] + L->nblk[3], nthreads);
+  /* SAO works on the 8x8-level reconstruction; unfiltered pixels are copied first */
+  memcpy(blob + L->sao_rec, j.rec[0][2], (size_t)W * H);
+  memcpy(blob + L->sao_rec + (size_t)W * H, j.rec[1][2], (size_t)W * H / 4);
+  memcpy(blob + L->sao_rec + (size_t)W * H * 5 / 4, j.rec[2][2], (size_t)W * H / 4);
+  run_stage(&j, 1, 3 * L->nctu, nthreads);
+  for (int color = 0; color < 3; ++color) {
+    const int Wp = color ? W / 2 : W, Hp = color ? H / 2 : H;
+    unsigned char ck[SEI_HASH_MAX_LENGTH] = { 0 };
+    kvz_array_checksum(blob + L->sao_rec + (color == 0 ? 0 : (color == 1 ? (size_t)W * H : (size_t)W * H * 5 / 4)), Hp, Wp, Wp, ck, 8);
+    memcpy(blob + L->checksum + 4 * color, ck, 4);
+  }
+  for (int d = 0; d < 4; ++d) for (int c = 0; c < 3; ++c) free(j.rec[c][d]);
+  return 0;
+}

@@ -123,6 +123,7 @@ kvzref_ctx *kvzref_ctx_open(int width, int height, int qp, int signhide, int rdo
   c->cfg->threads = 0; c->cfg->owf = 0; c->cfg->wpp = 0;
   c->cfg->signhide_enable = signhide; c->cfg->rdoq_enable = rdoq;
   c->cfg->hash = KVZ_HASH_NONE;
+  c->cfg->enable_logging_output = 0;
   c->enc = c->api->encoder_open(c->cfg);
   if (!c->enc) { free(c); return NULL; }
   return c;

@@ -516,3 +516,14 @@ class Ref:
         out = aligned(4, np.uint8)
         self.lib.kvzref_array_checksum(impl.encode(), P(data), height, width, stride, P(out))
         return out
+
+
+def ref_frame_pass(ref, src, width, height, qp, layout, nthreads=8, signhide=0):
+    """The frame-level pass through the compiled reference's own (AVX2) strategy pointers -> result blob."""
+    L = ref.lib
+    blob = aligned(int(layout.host_bytes), np.uint8)
+    src = al(src)
+    ctx = ref.ctx(qp, signhide, 0, width, height)
+    rc = L.kvzref_frame_pass(ctx, P(src), width, height, qp, C.byref(layout), P(blob), nthreads)
+    assert rc == 0
+    return blob

@@ -401,7 +401,8 @@ def test_extend_block(cuda_lib, orc):
         for (bw, bh) in [(8, 8), (16, 4), (32, 16)]:
             for pads in [(3, 4, 3, 4, 0), (3, 4, 3, 4, 1), (1, 2, 1, 2, 3)]:
                 o = orc.get_extended_block(src, sw, sh, ss, bx, by, bw, bh, *pads)
-                assert o[0] == 1
+                if not o[0]:
+                    continue      # block + padding inside the frame: the reference returns a pointer, no copy
                 got = host(kb.extend_block(dev(kb, src), sw, sh, ss, bx, by, bw, bh, *pads))
                 assert np.array_equal(got, o[1][: got.size]), (bx, by, bw, bh, pads)
 
@@ -418,7 +419,7 @@ def test_sao_batches(cuda_lib, orc):
         o = cs.rand_pix(r, bw * bh, kind=cs.KINDS[i % 3])
         rc = np.clip(o.astype(int) + r.integers(-3, 4, bw * bh), 0, 255).astype(np.uint8)
         origs.append(o); recs.append(rc)
-        blks[i] = (off, off, bw, bh)
+        blks[i] = (off, off, bw, bh, 0, 0)
         off += bw * bh
     do, dr = dev(kb, np.concatenate(origs)), dev(kb, np.concatenate(recs))
     stats = host(kb.sao_edge_stats_batch(8, do, dr, blks))

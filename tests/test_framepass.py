@@ -1,0 +1,85 @@
+"""The frame-level pass: CPU checks of the reference arm (ref_framepass.c) and the GPU-vs-reference blob parity."""
+import numpy as np
+import pytest
+
+import _cases as cs
+
+
+def synth_frame(width, height, seed=1234, frame_idx=0):
+    """Deterministic I420 frame: diagonal ramp + drifting low-frequency sinusoid + +-4 noise."""
+    r = np.random.default_rng(seed + frame_idx)
+    y, x = np.mgrid[0:height, 0:width]
+    luma = (x + y) * 0.11 + 60 * np.sin((x + 3 * frame_idx) / 37.0) * np.cos(y / 29.0) + 128 + r.integers(-4, 5, (height, width))
+    cy, cx = np.mgrid[0:height // 2, 0:width // 2]
+    u = 128 + 40 * np.sin(cx / 23.0 + frame_idx * 0.1) + r.integers(-2, 3, cx.shape)
+    v = 128 + 40 * np.cos(cy / 19.0) + r.integers(-2, 3, cx.shape)
+    return np.concatenate([np.clip(p, 0, 255).astype(np.uint8).ravel() for p in (luma, u, v)])
+
+
+def test_layout_needs_no_gpu():
+    import kvazaar_b200 as kb
+    lay = kb.fp_layout_for(1920, 1080)
+    assert list(lay.nblk) == [60 * 33, 120 * 67, 240 * 135, 480 * 270]
+    assert lay.nctu == 30 * 17
+    assert lay.host_bytes > 1920 * 1080 * 3 // 2
+
+
+def test_reference_frame_pass_is_self_consistent(ref, orc):
+    """The CPU arm against independent oracle computations on a small frame."""
+    import kvazaar_b200 as kb
+    W, H, qp = 136, 72, 27
+    src = synth_frame(W, H)
+    lay = kb.fp_layout_for(W, H, qp)
+    blob = __import__("_oracle").ref_frame_pass(ref, src, W, H, qp, lay, nthreads=4)
+    sec = kb.fp_sections(lay, W, H)
+    g = lambda n: kb.fp_section(blob, sec, n)  # noqa: E731
+    luma = cs.al(src[: W * H])
+    # depth 2 (8x8): recompute block (3, 2) with the oracle only
+    d, w, bx, by = 2, 8, 3, 2
+    b = by * (W // w) + bx
+    top, left = orc.intra_build_reference(3, 0, bx * w, by * w, W, H, luma, W)
+    blk = cs.al(np.ascontiguousarray(luma.reshape(H, W)[by * w:(by + 1) * w, bx * w:(bx + 1) * w]).ravel())
+    costs = [orc.satd_nxn(w, cs.al(orc.intra_predict(3, m, 0, top, left, 1)), blk) for m in range(35)]
+    assert g("mode_y2")[b] == int(np.argmin(costs)) and g("cost_y2")[b] == min(costs)
+    mode = int(g("mode_y2")[b])
+    pred = cs.al(orc.intra_predict(3, mode, 0, top, left, 1))
+    scan = 2 if 6 <= mode <= 14 else (1 if 22 <= mode <= 30 else 0)
+    has, rec, coeff = orc.quantize_residual(qp, w, 0, scan, 0, 1, w, blk, pred)
+    assert g("has_y2")[b] == has
+    assert np.array_equal(g("coeff_y2")[b * 64:(b + 1) * 64], coeff)
+    assert g("ssd_y2")[b] == orc.pixels_calc_ssd(blk, rec, w, w, w)
+    # checksum section == oracle checksum of the SAO-filtered planes
+    sao_rec = g("sao_rec")
+    for c, (off, pw, ph) in enumerate([(0, W, H), (W * H, W // 2, H // 2), (W * H * 5 // 4, W // 2, H // 2)]):
+        assert np.array_equal(g("checksum")[4 * c: 4 * c + 4], orc.array_checksum(cs.al(sao_rec[off: off + pw * ph]), ph, pw, pw))
+    # threads do not change the result
+    blob1 = __import__("_oracle").ref_frame_pass(ref, src, W, H, qp, lay, nthreads=1)
+    assert np.array_equal(blob, blob1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", [(136, 72), (200, 136), (320, 192)])
+def test_cuda_frame_pass_matches_reference(cuda_lib, ref, dims):
+    """Byte-identical result blob: CUDA frame pass vs the reference's own strategy functions."""
+    import torch
+    from _oracle import ref_frame_pass
+    kb = cuda_lib
+    W, H = dims
+    qp = 27
+    src = synth_frame(W, H, frame_idx=W)
+    fp = kb.FramePass(W, H, qp)
+    fp.run_dev(kb.to_dev(src))
+    got = fp.result_host()
+    want = ref_frame_pass(ref, src, W, H, qp, fp.layout, nthreads=4)
+    sec = kb.fp_sections(fp.layout, W, H)
+    for name in sec:
+        a, b = kb.fp_section(got, sec, name), kb.fp_section(want, sec, name)
+        assert np.array_equal(a, b), (name, int(np.argmax(a != b)), a[a != b][:4], b[a != b][:4])
+    # host-buffer entry point gives the same blob
+    src_pin = torch.from_numpy(src.copy()).pin_memory()
+    res_pin = torch.empty(fp.host_bytes, dtype=torch.uint8).pin_memory()
+    fp.run_host(src_pin, res_pin)
+    torch.cuda.synchronize()
+    for name in sec:
+        assert np.array_equal(kb.fp_section(res_pin.numpy(), sec, name), kb.fp_section(want, sec, name)), name
+    fp.close()
