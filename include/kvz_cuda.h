@@ -63,6 +63,28 @@ int kvz_strategy_register_quant_plain_cuda(void *opaque, uint8_t bitdepth); /* c
 /* lookup of a per-call function by its strategy type string (what the registrars register) */
 void *kvz_cuda_strategy_fptr(const char *type, uint8_t bitdepth);
 
+/* ------------------------------------------------------------------ 2b. plain-parameter per-call entries */
+/* Host pointers, synchronous; what integration/strategies-cuda-glue.c calls after unpacking encoder_state_t /
+ * encoder_control_t / sao_info_t / kvz_epol_args / lcu_t (ref: strategies-quant.h:49-65, strategies-sao.h:49-68,
+ * strategies-ipol.h:64-102, strategies-picture.h:136-148). */
+struct kvz_cuda_quant_params_s;
+void kvz_cuda_call_quant(const struct kvz_cuda_quant_params_s *p, const int16_t *coef, int16_t *q_coef, int n, int type, int scan_idx);
+void kvz_cuda_call_dequant(const struct kvz_cuda_quant_params_s *p, const int16_t *q_coef, int16_t *coef, int n, int type);
+int  kvz_cuda_call_quantize_residual(const struct kvz_cuda_quant_params_s *p, int width, int color, int scan_idx, int use_trskip,
+                                     int cu_is_intra, int early_skip, int phase, int in_stride, int out_stride,
+                                     const void *ref_in, const void *pred_in, void *rec_out, int16_t *coeff_out);
+void kvz_cuda_call_sao_edge_stats(int bitdepth, const void *orig, const void *rec, int eo_class, int bw, int bh, int *cat_sum_cnt);
+int  kvz_cuda_call_sao_edge_ddistortion(int bitdepth, const void *orig, const void *rec, int bw, int bh, int eo_class, const int *offsets);
+int  kvz_cuda_call_sao_band_ddistortion(int bitdepth, const void *orig, const void *rec, int bw, int bh, int band_pos, const int *bands);
+void kvz_cuda_call_sao_reconstruct(int bitdepth, const void *rec_data, void *new_rec_data, int sao_type, int eo_class,
+                                   const int *band_position, const int *offsets, int stride, int new_stride, int bw, int bh, int color);
+void kvz_cuda_call_sample(int kind, int bitdepth, const void *src, int src_stride, int w, int h, void *dst, int dst_stride, int mvx, int mvy);
+void kvz_cuda_call_filter_fme(int stage, int bitdepth, const void *src, int src_stride, int w, int h, void *filtered,
+                              int16_t *hor_intermediate, int fme_level, int16_t *hor_first_cols, int hpel_off_x, int hpel_off_y);
+void kvz_cuda_call_extend_block(int bitdepth, const void *src, int src_w, int src_h, int src_s, int blk_x, int blk_y, int blk_w,
+                                int blk_h, int pad_l, int pad_r, int pad_t, int pad_b, int pad_b_simd, void *buf);
+void kvz_cuda_call_bipred_plane(int bitdepth, void *dst, int dst_stride, const void *l0, const void *l1, int l0_is_im, int l1_is_im, int w, int h);
+
 /* ------------------------------------------------------------------ 1. batched device API */
 
 /* ---- picture group ---- */
@@ -108,7 +130,7 @@ int kvz_cuda_pixel_var_batch(int bitdepth, const void *buf, uint32_t len, int co
 int kvz_cuda_transform_batch(int kind, int n, int bitdepth, const int16_t *in, int16_t *out, int count, void *stream);
 
 /* ---- quant group (ref: quant-generic.c) ---- */
-typedef struct {
+typedef struct kvz_cuda_quant_params_s {
   int32_t qp;               /* state->qp */
   int32_t bitdepth;         /* encoder->bitdepth */
   int32_t slice_is_intra;   /* state->frame->slicetype == KVZ_SLICE_I */

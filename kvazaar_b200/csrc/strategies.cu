@@ -243,6 +243,233 @@ int register_group(void *opaque, uint8_t bitdepth, const char *group)
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------
+// Plain-parameter per-call entries for the strategy types whose reference typedefs take encoder structs
+// (quant, sao, ipol, bipred_average).  integration/strategies-cuda-glue.c unpacks the structs and calls these.
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+void kvz_cuda_call_quant(const kvz_cuda_quant_params *p, const int16_t *coef, int16_t *q_coef, int n, int type, int scan_idx)
+{
+  Call c(2 * (size_t)n * n * sizeof(int16_t) + 512);
+  if (!c.ok) die("staging");
+  const int16_t *dc = c.in(coef, (size_t)n * n);
+  const int8_t sc = (int8_t)scan_idx;
+  const int8_t *ds = c.in(&sc, 1);
+  int16_t *dq = c.out<int16_t>((size_t)n * n);
+  MUST(c.upload());
+  MUST(kvz_cuda_quant_batch(p, dc, dq, n, type, ds, 1, c.s.stream));
+  MUST(c.download());
+  memcpy(q_coef, c.host_ptr(dq), (size_t)n * n * sizeof(int16_t));
+}
+
+void kvz_cuda_call_dequant(const kvz_cuda_quant_params *p, const int16_t *q_coef, int16_t *coef, int n, int type)
+{
+  Call c(2 * (size_t)n * n * sizeof(int16_t) + 512);
+  if (!c.ok) die("staging");
+  const int16_t *dq = c.in(q_coef, (size_t)n * n);
+  int16_t *dc = c.out<int16_t>((size_t)n * n);
+  MUST(c.upload());
+  MUST(kvz_cuda_dequant_batch(p, dq, dc, n, type, 1, c.s.stream));
+  MUST(c.download());
+  memcpy(coef, c.host_ptr(dc), (size_t)n * n * sizeof(int16_t));
+}
+
+// kvz_quantize_residual with plain parameters.  phase as in kvz_cuda_tu.  Returns has_coeffs.
+int kvz_cuda_call_quantize_residual(const kvz_cuda_quant_params *p, int width, int color, int scan_idx, int use_trskip,
+                                    int cu_is_intra, int early_skip, int phase, int in_stride, int out_stride,
+                                    const void *ref_in, const void *pred_in, void *rec_out, int16_t *coeff_out)
+{
+  const size_t px = p->bitdepth == 8 ? 1 : 2;
+  const int n = width;
+  Call c(3 * (size_t)n * n * px + (size_t)n * n * 2 + 1024);
+  if (!c.ok) die("staging");
+  // inputs compacted to stride n; the coefficient buffer is an input for phase 2 and an output otherwise
+  const uint8_t *dref = c.in2d((const uint8_t *)ref_in, (int)(n * px), n, (long)in_stride * px);
+  const uint8_t *dpred = c.in2d((const uint8_t *)pred_in, (int)(n * px), n, (long)in_stride * px);
+  int16_t *dcoef_in = phase == 2 ? c.in(coeff_out, (size_t)n * n) : nullptr;
+  kvz_cuda_tu tu; memset(&tu, 0, sizeof(tu));
+  tu.width = (uint8_t)n; tu.color = (uint8_t)color; tu.scan_idx = (uint8_t)scan_idx; tu.use_trskip = (uint8_t)use_trskip;
+  tu.cu_is_intra = (uint8_t)cu_is_intra; tu.early_skip = (uint8_t)early_skip; tu.phase = (uint8_t)phase;
+  const kvz_cuda_tu *dtu = c.in(&tu, 1);
+  uint8_t *drec = c.out<uint8_t>((size_t)n * n * px);
+  int16_t *dcoef = phase == 2 ? dcoef_in : c.out<int16_t>((size_t)n * n);
+  int32_t *dhas = c.out<int32_t>(1);
+  MUST(c.upload());
+  MUST(kvz_cuda_quantize_residual_batch(p, dref, dpred, n, drec, n, dcoef, dtu, 1, dhas, c.s.stream));
+  MUST(c.download());
+  const int has = *c.host_ptr(dhas);
+  if (phase != 2) memcpy(coeff_out, c.host_ptr(dcoef), (size_t)n * n * sizeof(int16_t));
+  if (phase != 1) {
+    const uint8_t *hrec = c.host_ptr(drec);
+    for (int y = 0; y < n; ++y) memcpy((uint8_t *)rec_out + (size_t)y * out_stride * px, hrec + (size_t)y * n * px, n * px);
+  }
+  return has;
+}
+
+void kvz_cuda_call_sao_edge_stats(int bitdepth, const void *orig, const void *rec, int eo_class, int bw, int bh, int *cat_sum_cnt)
+{
+  const size_t px = bitdepth == 8 ? 1 : 2;
+  Call c(2 * (size_t)bw * bh * px + 1024);
+  if (!c.ok) die("staging");
+  const uint8_t *dorig = c.in((const uint8_t *)orig, (size_t)bw * bh * px), *drec = c.in((const uint8_t *)rec, (size_t)bw * bh * px);
+  kvz_cuda_sao_blk b = { 0, 0, (int16_t)bw, (int16_t)bh, 0, 0 };
+  const kvz_cuda_sao_blk *db = c.in(&b, 1);
+  int32_t *out = c.out<int32_t>(40);
+  MUST(c.upload());
+  MUST(kvz_cuda_sao_edge_stats_batch(bitdepth, dorig, drec, db, 1, out, c.s.stream));
+  MUST(c.download());
+  const int32_t *h = c.host_ptr(out) + eo_class * 10;
+  for (int k = 0; k < 10; ++k) cat_sum_cnt[k] += h[k];          // the reference accumulates (sao-generic.c:76-77)
+}
+
+int kvz_cuda_call_sao_edge_ddistortion(int bitdepth, const void *orig, const void *rec, int bw, int bh, int eo_class, const int *offsets)
+{
+  const size_t px = bitdepth == 8 ? 1 : 2;
+  Call c(2 * (size_t)bw * bh * px + 1024);
+  if (!c.ok) die("staging");
+  const uint8_t *dorig = c.in((const uint8_t *)orig, (size_t)bw * bh * px), *drec = c.in((const uint8_t *)rec, (size_t)bw * bh * px);
+  kvz_cuda_sao_blk b = { 0, 0, (int16_t)bw, (int16_t)bh, 0, 0 };
+  const kvz_cuda_sao_blk *db = c.in(&b, 1);
+  const int8_t eo = (int8_t)eo_class;
+  const int8_t *deo = c.in(&eo, 1);
+  const int32_t *doff = c.in((const int32_t *)offsets, 5);
+  int32_t *out = c.out<int32_t>(1);
+  MUST(c.upload());
+  MUST(kvz_cuda_sao_edge_ddistortion_batch(bitdepth, dorig, drec, db, deo, doff, 1, out, c.s.stream));
+  MUST(c.download());
+  return *c.host_ptr(out);
+}
+
+int kvz_cuda_call_sao_band_ddistortion(int bitdepth, const void *orig, const void *rec, int bw, int bh, int band_pos, const int *bands)
+{
+  const size_t px = bitdepth == 8 ? 1 : 2;
+  Call c(2 * (size_t)bw * bh * px + 1024);
+  if (!c.ok) die("staging");
+  const uint8_t *dorig = c.in((const uint8_t *)orig, (size_t)bw * bh * px), *drec = c.in((const uint8_t *)rec, (size_t)bw * bh * px);
+  kvz_cuda_sao_blk b = { 0, 0, (int16_t)bw, (int16_t)bh, 0, 0 };
+  const kvz_cuda_sao_blk *db = c.in(&b, 1);
+  const int32_t bp = band_pos;
+  const int32_t *dbp = c.in(&bp, 1), *dbands = c.in((const int32_t *)bands, 4);
+  int32_t *out = c.out<int32_t>(1);
+  MUST(c.upload());
+  MUST(kvz_cuda_sao_band_ddistortion_batch(bitdepth, dorig, drec, db, dbp, dbands, 1, out, c.s.stream));
+  MUST(c.download());
+  return *c.host_ptr(out);
+}
+
+// sao_reconstruct_color: rec_data points at the block; edge types read one sample around it (the caller
+// guarantees that halo exists, exactly as for the reference function).
+void kvz_cuda_call_sao_reconstruct(int bitdepth, const void *rec_data, void *new_rec_data, int sao_type, int eo_class,
+                                   const int *band_position, const int *offsets, int stride, int new_stride, int bw, int bh, int color)
+{
+  const size_t px = bitdepth == 8 ? 1 : 2;
+  const int halo = sao_type == 2 ? 1 : 0;
+  const int ww = bw + 2 * halo, hh = bh + 2 * halo;
+  Call c((size_t)ww * hh * px + (size_t)bw * bh * px + 1024);
+  if (!c.ok) die("staging");
+  const uint8_t *drec = c.in2d((const uint8_t *)rec_data - ((size_t)halo * stride + halo) * px, (int)(ww * px), hh, (long)stride * px);
+  kvz_cuda_sao_rec d; memset(&d, 0, sizeof(d));
+  d.off_rec = halo * ww + halo; d.off_new = 0; d.bw = (int16_t)bw; d.bh = (int16_t)bh;
+  d.type = (int8_t)sao_type; d.eo_class = (int8_t)eo_class; d.color = (int8_t)color;
+  d.band_position[0] = band_position[0]; d.band_position[1] = band_position[1];
+  for (int k = 0; k < 10; ++k) d.offsets[k] = offsets[k];
+  const kvz_cuda_sao_rec *dd = c.in(&d, 1);
+  uint8_t *dnew = c.out<uint8_t>((size_t)bw * bh * px);
+  MUST(c.upload());
+  MUST(kvz_cuda_sao_reconstruct_batch(bitdepth, drec, ww, dnew, bw, dd, 1, c.s.stream));
+  MUST(c.download());
+  const uint8_t *h = c.host_ptr(dnew);
+  for (int y = 0; y < bh; ++y) memcpy((uint8_t *)new_rec_data + (size_t)y * new_stride * px, h + (size_t)y * bw * px, bw * px);
+}
+
+// sample_quarterpel_luma(_hi) / sample_octpel_chroma(_hi); kind = KVZ_CUDA_IPOL_*
+void kvz_cuda_call_sample(int kind, int bitdepth, const void *src, int src_stride, int w, int h, void *dst, int dst_stride, int mvx, int mvy)
+{
+  const size_t px = bitdepth == 8 ? 1 : 2;
+  const int taps = kind >= KVZ_CUDA_IPOL_CHROMA ? 4 : 8, off = taps / 2 - 1;
+  const int ww = w + taps - 1, hh = h + taps - 1;
+  const size_t opx = (kind & 1) ? 2 : px;
+  Call c((size_t)ww * hh * px + (size_t)w * h * opx + 1024);
+  if (!c.ok) die("staging");
+  const uint8_t *dsrc = c.in2d((const uint8_t *)src - ((size_t)off * src_stride + off) * px, (int)(ww * px), hh, (long)src_stride * px);
+  kvz_cuda_ipol d = { off * ww + off, 0, (int16_t)w, (int16_t)h, (int16_t)mvx, (int16_t)mvy };
+  const kvz_cuda_ipol *dd = c.in(&d, 1);
+  uint8_t *ddst = c.out<uint8_t>((size_t)w * h * opx);
+  MUST(c.upload());
+  MUST(kvz_cuda_sample_batch(kind, bitdepth, dsrc, ww, ddst, w, dd, 1, c.s.stream));
+  MUST(c.download());
+  const uint8_t *hres = c.host_ptr(ddst);
+  for (int y = 0; y < h; ++y) memcpy((uint8_t *)dst + (size_t)y * dst_stride * opx, hres + (size_t)y * w * opx, w * opx);
+}
+
+// The four FME stages; filtered [4][64*64] pixels, hor_intermediate [5][KVZ_CUDA_IPOL_IM_SIZE], hor_first_cols [5][KVZ_CUDA_IPOL_FIRST_COLS].
+void kvz_cuda_call_filter_fme(int stage, int bitdepth, const void *src, int src_stride, int w, int h, void *filtered,
+                              int16_t *hor_intermediate, int fme_level, int16_t *hor_first_cols, int hpel_off_x, int hpel_off_y)
+{
+  const size_t px = bitdepth == 8 ? 1 : 2;
+  // source window: rows -3 .. h+4 (h + 8 rows), columns -3 .. w+4+1
+  const int ww = w + 1 + 7 + 1, hh = h + 1 + 7;
+  const size_t n_im = (size_t)5 * KVZ_CUDA_IPOL_IM_SIZE, n_col = (size_t)5 * KVZ_CUDA_IPOL_FIRST_COLS, n_f = (size_t)4 * 4096;
+  Call c((size_t)ww * hh * px + n_im * 2 + n_col * 2 + n_f * px + 2048);
+  if (!c.ok) die("staging");
+  // state arrays are both input and output: place them in the input region, read them back from the same place
+  int16_t *dim = c.in(hor_intermediate, n_im);
+  int16_t *dcol = c.in(hor_first_cols, n_col);
+  uint8_t *dflt = c.in((const uint8_t *)filtered, n_f * px);
+  const uint8_t *dsrc = c.in2d((const uint8_t *)src - ((size_t)3 * src_stride + 3) * px, (int)(ww * px), hh, (long)src_stride * px);
+  const int32_t soff = 3 * ww + 3;
+  const int32_t *dsoff = c.in(&soff, 1);
+  const int8_t ho[2] = { (int8_t)hpel_off_x, (int8_t)hpel_off_y };
+  const int8_t *dho = c.in(ho, 2);
+  MUST(c.upload());
+  MUST(kvz_cuda_filter_fme_batch(stage, bitdepth, dsrc, ww, dsoff, w, h, dflt, dim, fme_level, dcol, dho, 1, c.s.stream));
+  // download the three state arrays (they sit at the start of the staging buffer)
+  const size_t span = (size_t)((uint8_t *)dflt + n_f * px - c.s.d);
+  if (cudaMemcpyAsync(c.s.h, c.s.d, span, cudaMemcpyDeviceToHost, c.s.stream) != cudaSuccess || cudaStreamSynchronize(c.s.stream) != cudaSuccess) die("fme download");
+  memcpy(hor_intermediate, c.host_ptr(dim), n_im * 2);
+  memcpy(hor_first_cols, c.host_ptr(dcol), n_col * 2);
+  memcpy(filtered, c.host_ptr(dflt), n_f * px);
+}
+
+void kvz_cuda_call_extend_block(int bitdepth, const void *src, int src_w, int src_h, int src_s, int blk_x, int blk_y, int blk_w,
+                                int blk_h, int pad_l, int pad_r, int pad_t, int pad_b, int pad_b_simd, void *buf)
+{
+  const size_t px = bitdepth == 8 ? 1 : 2;
+  // only the rows/columns the block can touch are staged: the clipped source window
+  const int x0 = blk_x - pad_l < 0 ? 0 : (blk_x - pad_l > src_w - 1 ? src_w - 1 : blk_x - pad_l);
+  const int x1 = blk_x + blk_w + pad_r - 1 < 0 ? 0 : (blk_x + blk_w + pad_r - 1 > src_w - 1 ? src_w - 1 : blk_x + blk_w + pad_r - 1);
+  const int y0 = blk_y - pad_t < 0 ? 0 : (blk_y - pad_t > src_h - 1 ? src_h - 1 : blk_y - pad_t);
+  const int y1 = blk_y + blk_h + pad_b - 1 < 0 ? 0 : (blk_y + blk_h + pad_b - 1 > src_h - 1 ? src_h - 1 : blk_y + blk_h + pad_b - 1);
+  const int ww = x1 - x0 + 1, hh = y1 - y0 + 1;
+  const size_t total = (size_t)(pad_l + blk_w + pad_r) * (pad_t + blk_h + pad_b + pad_b_simd) + 1;
+  Call c((size_t)ww * hh * px + total * px + 1024);
+  if (!c.ok) die("staging");
+  const uint8_t *dsrc = c.in2d((const uint8_t *)src + ((size_t)y0 * src_s + x0) * px, (int)(ww * px), hh, (long)src_s * px);
+  uint8_t *dbuf = c.out<uint8_t>(total * px);
+  MUST(c.upload());
+  MUST(kvz_cuda_extend_block(bitdepth, dsrc, ww, hh, ww, blk_x - x0, blk_y - y0, blk_w, blk_h, pad_l, pad_r, pad_t, pad_b, pad_b_simd, dbuf, c.s.stream));
+  MUST(c.download());
+  memcpy(buf, c.host_ptr(dbuf), total * px);
+}
+
+void kvz_cuda_call_bipred_plane(int bitdepth, void *dst, int dst_stride, const void *l0, const void *l1, int l0_is_im, int l1_is_im, int w, int h)
+{
+  const size_t px = bitdepth == 8 ? 1 : 2;
+  Call c((size_t)w * h * (2 + 2 + px) + 1024);
+  if (!c.ok) die("staging");
+  const uint8_t *d0 = c.in((const uint8_t *)l0, (size_t)w * h * (l0_is_im ? 2 : px));
+  const uint8_t *d1 = c.in((const uint8_t *)l1, (size_t)w * h * (l1_is_im ? 2 : px));
+  uint8_t *dd = c.out<uint8_t>((size_t)w * h * px);
+  MUST(c.upload());
+  MUST(kvz_cuda_bipred_average_plane(bitdepth, dd, w, d0, d1, l0_is_im, l1_is_im, w, h, c.s.stream));
+  MUST(c.download());
+  const uint8_t *hres = c.host_ptr(dd);
+  for (int y = 0; y < h; ++y) memcpy((uint8_t *)dst + (size_t)y * dst_stride * px, hres + (size_t)y * w * px, w * px);
+}
+
+}  // extern "C"
+
 extern "C" {
 
 void kvz_cuda_set_register_fn(kvz_cuda_register_fn fn) { g_register = fn; }
