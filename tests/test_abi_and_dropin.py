@@ -83,7 +83,7 @@ def test_reference_greatest_suites_over_cuda_entries():
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     out = r.stdout + r.stderr
     m = re.search(r"(\d+) cuda entries appended", out)
-    assert m and int(m.group(1)) >= 45, out[-2000:]
+    assert m and int(m.group(1)) >= 40, out[-2000:]
     assert r.returncode == 0, out[-3000:]
     assert re.search(r"Pass: \d+, fail: 0", out) or "fail: 0" in out, out[-2000:]
 
