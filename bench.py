@@ -98,14 +98,16 @@ def run_reference(args):
     ref = Ref()
     cores = os.cpu_count() or 1
     lay = kb.fp_layout_for(W, H, QP)
-    frames = synth_frames(4)
+    from _oracle import aligned, al
+    frames = [al(f) for f in synth_frames(4)]
+    blob = aligned(int(lay.host_bytes), np.uint8)
     nper = args.ref_frames
     for _ in range(max(1, args.warmup)):
-        ref_frame_pass(ref, frames[0], W, H, QP, lay, nthreads=cores)
+        ref_frame_pass(ref, frames[0], W, H, QP, lay, nthreads=cores, blob=blob, src_is_aligned=True)
     t0 = time.perf_counter()
     for s in range(args.steps):
         for f in range(nper):
-            ref_frame_pass(ref, frames[(s * nper + f) % len(frames)], W, H, QP, lay, nthreads=cores)
+            ref_frame_pass(ref, frames[(s * nper + f) % len(frames)], W, H, QP, lay, nthreads=cores, blob=blob, src_is_aligned=True)
     dt = time.perf_counter() - t0
     fps = args.steps * nper / dt
     sample = f"{args.steps * nper} frames {W}x{H} through the reference's selected strategy functions ({ref.selected_name('satd_8x8')})"
@@ -128,11 +130,13 @@ def cpu_baseline(budget_s=15.0):
         return {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
     cores = os.cpu_count() or 1
     lay = kb.fp_layout_for(W, H, QP)
-    frames = synth_frames(2)
-    ref_frame_pass(ref, frames[0], W, H, QP, lay, nthreads=cores)
+    from _oracle import aligned, al
+    frames = [al(f) for f in synth_frames(2)]
+    blob = aligned(int(lay.host_bytes), np.uint8)
+    ref_frame_pass(ref, frames[0], W, H, QP, lay, nthreads=cores, blob=blob, src_is_aligned=True)
     n, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < budget_s and n < 400:
-        ref_frame_pass(ref, frames[n % 2], W, H, QP, lay, nthreads=cores)
+    while time.perf_counter() - t0 < budget_s and n < 2000:
+        ref_frame_pass(ref, frames[n % 2], W, H, QP, lay, nthreads=cores, blob=blob, src_is_aligned=True)
         n += 1
     dt = time.perf_counter() - t0
     out = {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "reference",

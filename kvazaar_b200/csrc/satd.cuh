@@ -25,18 +25,10 @@ __device__ __forceinline__ int packed_absmax(int x)
 
 #define KVZC_BFLY(p, q) { const int t__ = (p) - (q); (p) = (p) + (q); (q) = t__; }
 
-// Raw sum of |H d H^T| for one 8x8 block of 8-bit pixels; a[r], b[r] = the 8 bytes of row r.
-// Returns sum (caller applies (s + 2) >> 2).
-__device__ __forceinline__ uint32_t hadamard8x8_u8(const uint2 (&a)[8], const uint2 (&b)[8])
+// Raw sum of |H d H^T| from packed difference lanes d[row][k]: k=0 cols (0,2), k=1 cols (1,3), k=2 cols (4,6),
+// k=3 cols (5,7), each register = lo + hi*65536.  Returns sum (caller applies (s + 2) >> 2).
+__device__ __forceinline__ uint32_t hadamard8x8_lanes(int (&d)[8][4])
 {
-  int d[8][4];   // [row][k]: k=0 cols (0,2), k=1 cols (1,3), k=2 cols (4,6), k=3 cols (5,7)
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    d[r][0] = (int)prmt(a[r].x, 0u, 0x4240) - (int)prmt(b[r].x, 0u, 0x4240);
-    d[r][1] = (int)prmt(a[r].x, 0u, 0x4341) - (int)prmt(b[r].x, 0u, 0x4341);
-    d[r][2] = (int)prmt(a[r].y, 0u, 0x4240) - (int)prmt(b[r].y, 0u, 0x4240);
-    d[r][3] = (int)prmt(a[r].y, 0u, 0x4341) - (int)prmt(b[r].y, 0u, 0x4341);
-  }
 #pragma unroll
   for (int r = 0; r < 8; ++r) {           // horizontal, distances 1 and 4 (distance 2 is in-register, done last)
     KVZC_BFLY(d[r][0], d[r][1]); KVZC_BFLY(d[r][2], d[r][3]);
@@ -56,6 +48,36 @@ __device__ __forceinline__ uint32_t hadamard8x8_u8(const uint2 (&a)[8], const ui
   for (int r = 0; r < 8; ++r)
 #pragma unroll
     for (int k = 0; k < 4; ++k) s += packed_absmax(d[r][k]);
+  return (uint32_t)(2 * s);
+}
+
+// Raw sum of |H d H^T| for one 8x8 block of 8-bit pixels; a[r], b[r] = the 8 bytes of row r.
+__device__ __forceinline__ uint32_t hadamard8x8_u8(const uint2 (&a)[8], const uint2 (&b)[8])
+{
+  int d[8][4];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    d[r][0] = (int)prmt(a[r].x, 0u, 0x4240) - (int)prmt(b[r].x, 0u, 0x4240);
+    d[r][1] = (int)prmt(a[r].x, 0u, 0x4341) - (int)prmt(b[r].x, 0u, 0x4341);
+    d[r][2] = (int)prmt(a[r].y, 0u, 0x4240) - (int)prmt(b[r].y, 0u, 0x4240);
+    d[r][3] = (int)prmt(a[r].y, 0u, 0x4341) - (int)prmt(b[r].y, 0u, 0x4341);
+  }
+  return hadamard8x8_lanes(d);
+}
+
+// 4x4 from packed difference lanes d[row][k]: k=0 cols (0,2), k=1 cols (1,3). Returns raw sum (caller: (s+1)>>1).
+__device__ __forceinline__ uint32_t hadamard4x4_lanes(int (&d)[4][2])
+{
+#pragma unroll
+  for (int r = 0; r < 4; ++r) KVZC_BFLY(d[r][0], d[r][1]);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    KVZC_BFLY(d[0][k], d[1][k]); KVZC_BFLY(d[2][k], d[3][k]);
+    KVZC_BFLY(d[0][k], d[2][k]); KVZC_BFLY(d[1][k], d[3][k]);
+  }
+  int s = 0;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { s += packed_absmax(d[r][0]); s += packed_absmax(d[r][1]); }
   return (uint32_t)(2 * s);
 }
 

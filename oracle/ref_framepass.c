@@ -152,15 +152,21 @@ static void *worker(void *arg)
 {
   job_t *j = (job_t *)arg;
   kvz_pixel *buf = (kvz_pixel *)xaligned(8192 * sizeof(kvz_pixel));
+  /* work is claimed in chunks so that 100+ threads do not serialise on the shared counter (and neighbouring
+   * blocks, whose outputs share cache lines, stay on one thread) */
+  const int chunk = j->stage == 0 ? 256 : 4;
   for (;;) {
-    const int i = __sync_fetch_and_add(&j->next, 1);
-    if (i >= j->total) break;
-    if (j->stage == 0) {
-      int d = 0, b = i;
-      while (b >= j->L->nblk[d]) { b -= j->L->nblk[d]; ++d; }
-      do_block(j, d, b, buf);
-    } else {
-      do_sao(j, i, buf);
+    const int i0 = __sync_fetch_and_add(&j->next, chunk);
+    if (i0 >= j->total) break;
+    const int i1 = i0 + chunk < j->total ? i0 + chunk : j->total;
+    for (int i = i0; i < i1; ++i) {
+      if (j->stage == 0) {
+        int d = 0, b = i;
+        while (b >= j->L->nblk[d]) { b -= j->L->nblk[d]; ++d; }
+        do_block(j, d, b, buf);
+      } else {
+        do_sao(j, i, buf);
+      }
     }
   }
   free(buf);

@@ -518,11 +518,14 @@ class Ref:
         return out
 
 
-def ref_frame_pass(ref, src, width, height, qp, layout, nthreads=8, signhide=0):
-    """The frame-level pass through the compiled reference's own (AVX2) strategy pointers -> result blob."""
+def ref_frame_pass(ref, src, width, height, qp, layout, nthreads=8, signhide=0, blob=None, src_is_aligned=False):
+    """The frame-level pass through the compiled reference's own (AVX2) strategy pointers -> result blob.
+    `blob` may be a reusable aligned buffer (bench.py keeps allocation out of the timed region)."""
     L = ref.lib
-    blob = aligned(int(layout.host_bytes), np.uint8)
-    src = al(src)
+    if blob is None:
+        blob = aligned(int(layout.host_bytes), np.uint8)
+    if not src_is_aligned:
+        src = al(src)
     ctx = ref.ctx(qp, signhide, 0, width, height)
     rc = L.kvzref_frame_pass(ctx, P(src), width, height, qp, C.byref(layout), P(blob), nthreads)
     assert rc == 0
