@@ -35,59 +35,162 @@ __global__ void __launch_bounds__(256) select_best_kernel(const uint32_t *__rest
   best[b] = bc;
 }
 
-// One CTA per block: kvz_intra_recon_cu for one TU of one colour plane.
-template <class T>
+// kvz_intra_recon_cu for G TUs of one colour plane per CTA (G = 256 / N^2, at least 1): references -> prediction of
+// the chosen mode -> residual -> DCT/DST -> quant (+ sign hiding) -> dequant -> inverse -> reconstruction, SSD.
+// All G TUs walk the same barrier sequence; data-dependent decisions (has_coeffs, ac_sum < 2) are predicates.
+template <class T, int LOG2W>
 __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params p, const T *__restrict__ src,
                                                           const T *__restrict__ rec_in, int stride, int pic_w, int pic_h,
-                                                          int color, int log2w, int blocks_x,
+                                                          int color, int blocks_x, int nblk,
                                                           const int8_t *__restrict__ modes, T *__restrict__ rec_out,
                                                           int16_t *__restrict__ coeff, uint8_t *__restrict__ has_out,
                                                           uint32_t *__restrict__ ssd_out)
 {
-  __shared__ TuScratch s;
-  __shared__ T s_top[68], s_left[68], s_ftop[68], s_fleft[68];
-  __shared__ T s_pred[32 * 32];
-  __shared__ int s_dc;
-  const int w = 1 << log2w, n = 2 * w + 1, ww = w * w;
+  constexpr int W = 1 << LOG2W, WW = W * W, NREF = 2 * W + 1;
+  constexpr int G = WW >= 256 ? 1 : 256 / WW;
+  constexpr int E = G * WW;                         // elements per CTA (256 or 1024)
+  constexpr int PIXMAX = (1 << PixTraits<T>::kBits) - 1;
+  constexpr int NCG = WW / 16;                      // coefficient groups per TU
+  __shared__ int16_t s_a[E], s_b[E], s_q[E];
+  __shared__ int32_t s_d[E];
+  __shared__ int8_t s_m[WW];
+  __shared__ T s_ref[G][4][NREF + 3];
+  __shared__ T s_pred[E];
+  __shared__ int s_dc[G], s_mode[G], s_has[G], s_ac[G], s_ssd[G];
+  __shared__ uint8_t s_cgnz[G][NCG];
   const int is_c = color != 0;
-  const int bx = blockIdx.x % blocks_x, by = blockIdx.x / blocks_x;
-  const int px = bx * w, py = by * w;
-  const int mode = modes[blockIdx.x];
-  const BuildRefCtx c = build_ref_ctx(log2w, color, px << is_c, py << is_c, pic_w, pic_h);
-  for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) {
-    const bool is_top = i < n;
-    const int k = is_top ? i : i - n;
-    (is_top ? s_top : s_left)[k] = (T)build_ref_entry(c, rec_in, stride, is_top, k);
+  const int first = blockIdx.x * G;
+  const int l2 = LOG2W;
+  const bool use_dst = (W == 4 && color == 0);                          // intra luma 4x4, ref: strategies-dct.c:78-96
+
+  // ---- references, smoothed references, DC, mode
+  for (int e = threadIdx.x; e < G * 2 * NREF; e += blockDim.x) {
+    const int gb = e / (2 * NREF), r = e - gb * 2 * NREF;
+    const bool is_top = r < NREF;
+    const int k = is_top ? r : r - NREF, b = first + gb;
+    int v = 0;
+    if (b < nblk) {
+      const BuildRefCtx c = build_ref_ctx(LOG2W, color, ((b % blocks_x) * W) << is_c, ((b / blocks_x) * W) << is_c, pic_w, pic_h);
+      v = build_ref_entry(c, rec_in, stride, is_top, k);
+    }
+    s_ref[gb][is_top ? 0 : 1][k] = (T)v;
+  }
+  if (threadIdx.x < G) {
+    const int b = first + threadIdx.x;
+    s_mode[threadIdx.x] = b < nblk ? modes[b] : 0;
+    s_has[threadIdx.x] = 0; s_ac[threadIdx.x] = 0; s_ssd[threadIdx.x] = 0;
+  }
+  load_matrix(s_m, W, use_dst, true);
+  __syncthreads();
+  for (int e = threadIdx.x; e < G * 2 * NREF; e += blockDim.x) {
+    const int gb = e / (2 * NREF), r = e - gb * 2 * NREF;
+    const bool is_top = r < NREF;
+    const int k = is_top ? r : r - NREF;
+    s_ref[gb][is_top ? 2 : 3][k] = (T)filter_ref_entry(s_ref[gb][0], s_ref[gb][1], is_top, k, NREF);
+  }
+  if (threadIdx.x < G) s_dc[threadIdx.x] = dc_value(LOG2W, s_ref[threadIdx.x][0], s_ref[threadIdx.x][1]);
+  __syncthreads();
+
+  // ---- prediction and residual
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const int gb = e / WW, r = e - gb * WW, y = r >> LOG2W, x = r & (W - 1), b = first + gb;
+    int pv = 0, sv = 0;
+    if (b < nblk) {
+      pv = intra_predict_px(LOG2W, s_mode[gb], color, true, s_ref[gb][0], s_ref[gb][1], s_ref[gb][2], s_ref[gb][3], s_dc[gb], x, y);
+      sv = src[(long)((b / blocks_x) * W + y) * stride + (b % blocks_x) * W + x];
+    }
+    s_pred[e] = (T)pv;
+    s_a[e] = (int16_t)(sv - pv);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) {
-    const bool is_top = i < n;
-    const int k = is_top ? i : i - n;
-    (is_top ? s_ftop : s_fleft)[k] = (T)filter_ref_entry(s_top, s_left, is_top, k, n);
+
+  // ---- forward transform (ref: dct-generic.c:579-588, 611-619)
+  fwd_pass(s_a, s_q, s_m, W, G, l2 - 1 + (p.bitdepth - 8));
+  __syncthreads();
+  fwd_pass(s_q, s_b, s_m, W, G, l2 + 6);
+  __syncthreads();
+
+  // ---- quantisation (ref: quant-generic.c:50-180)
+  const QuantConsts qc = quant_consts(p, l2, is_c ? 2 : 0);
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const int gb = e / WW;
+    const int level_in = s_b[e];
+    const long long abs_level = abs(level_in);
+    int level = (int)((abs_level * qc.qc + qc.add) >> qc.q_bits);
+    s_d[e] = (int)((abs_level * qc.qc - ((long long)level << qc.q_bits)) >> qc.q_bits8);
+    if (p.signhide_enable && level) atomicAdd(&s_ac[gb], level);
+    level = level_in < 0 ? -level : level;
+    s_q[e] = (int16_t)clip3(-32768, 32767, level);
   }
-  if (threadIdx.x == 0) s_dc = dc_value(log2w, s_top, s_left);
   __syncthreads();
-  for (int e = threadIdx.x; e < ww; e += blockDim.x)
-    s_pred[e] = (T)intra_predict_px(log2w, mode, color, true, s_top, s_left, s_ftop, s_fleft, s_dc, e & (w - 1), e >> log2w);
-  __syncthreads();
-  // scan order (ref: encoderstate.c:1761-1775): mode dependent for 4x4/8x8 luma and 4x4 chroma
-  int scan = 0;
-  if ((!is_c && w <= 8) || (is_c && w == 4)) scan = (mode >= 6 && mode <= 14) ? 2 : ((mode >= 22 && mode <= 30) ? 1 : 0);
-  const T *ref = src + (long)py * stride + px;
-  T *rec = rec_out + (long)py * stride + px;
-  const int has = quantize_residual_tu<T>(s, p, w, color, scan, false, true, false, 0, ref, stride, s_pred, w, rec, stride,
-                                          coeff + (size_t)blockIdx.x * ww);
-  __syncthreads();
-  int ssd = 0;
-  for (int e = threadIdx.x; e < ww; e += blockDim.x) {
-    const int y = e >> log2w, x = e & (w - 1);
-    const int d = (int)ref[y * stride + x] - (int)rec[y * stride + x];
-    ssd += d * d;
+  if (p.signhide_enable) {
+    for (int i = threadIdx.x; i < G * NCG; i += blockDim.x) {
+      const int gb = i / NCG, cg = i - gb * NCG;
+      const int mode = s_mode[gb];
+      const int scan = ((!is_c && W <= 8) || (is_c && W == 4)) ? ((mode >= 6 && mode <= 14) ? 2 : ((mode >= 22 && mode <= 30) ? 1 : 0)) : 0;
+      int nz = 0;
+      for (int k = 0; k < 16; ++k) nz |= s_q[gb * WW + scan_pos(scan, l2, cg * 16 + k)] != 0;
+      s_cgnz[gb][cg] = (uint8_t)nz;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < G * NCG; i += blockDim.x) {
+      const int gb = i / NCG, cg = i - gb * NCG;
+      if (s_ac[gb] < 2 || !s_cgnz[gb][cg]) continue;
+      const int mode = s_mode[gb];
+      const int scan = ((!is_c && W <= 8) || (is_c && W == 4)) ? ((mode >= 6 && mode <= 14) ? 2 : ((mode >= 22 && mode <= 30) ? 1 : 0)) : 0;
+      sign_hide_group(s_b + gb * WW, s_q + gb * WW, s_d + gb * WW, s_cgnz[gb], NCG, cg, scan, l2);
+    }
+    __syncthreads();
   }
-  ssd = block_sum(ssd);
-  if (threadIdx.x == 0) {
-    has_out[blockIdx.x] = (uint8_t)has;
-    ssd_out[blockIdx.x] = (uint32_t)(ssd >> (2 * (PixTraits<T>::kBits - 8)));
+
+  // ---- coefficients out, has_coeffs
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const int gb = e / WW, b = first + gb;
+    const int16_t v = s_q[e];
+    if (b < nblk) {
+      coeff[(size_t)b * WW + (e - gb * WW)] = v;
+      if (v != 0) s_has[gb] = 1;
+    }
+  }
+  // ---- dequant (ref: quant-generic.c:298-340) -> s_b
+  {
+    const int transform_shift = 15 - p.bitdepth - l2;
+    const int qp_scaled = scaled_qp(is_c ? (color == 1 ? 2 : 3) : 0, p.qp, (p.bitdepth - 8) * 6);
+    const int shift = 20 - 14 - transform_shift;
+    const int scale = c_inv_quant_scales[qp_scaled % 6] << (qp_scaled / 6);
+    const int add = 1 << (shift - 1);
+    for (int e = threadIdx.x; e < E; e += blockDim.x) s_b[e] = (int16_t)clip3(-32768, 32767, ((int)s_q[e] * scale + add) >> shift);
+  }
+  load_matrix(s_m, W, use_dst, false);
+  __syncthreads();
+  inv_pass(s_b, s_q, s_m, W, G, 7);
+  __syncthreads();
+  inv_pass(s_q, s_a, s_m, W, G, 12 - (p.bitdepth - 8));
+  __syncthreads();
+
+  // ---- reconstruction + SSD (ref: quant-generic.c:263-292, picture-generic.c:536-551)
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const int gb = e / WW, r = e - gb * WW, y = r >> LOG2W, x = r & (W - 1), b = first + gb;
+    int sq = 0;
+    if (b < nblk) {                                   // (no early exit: every lane takes part in the shuffles below)
+      const int pv = s_pred[e];
+      int rv = pv;
+      if (s_has[gb]) rv = clip3(0, PIXMAX, (int)(int16_t)(s_a[e] + pv));
+      const long off = (long)((b / blocks_x) * W + y) * stride + (b % blocks_x) * W + x;
+      rec_out[off] = (T)rv;
+      const int dv = (int)src[off] - rv;
+      sq = dv * dv;
+    }
+    // reduce within the lanes of this warp that belong to the same TU, then one atomic per TU per warp
+    constexpr int SEG = WW < 32 ? WW : 32;
+#pragma unroll
+    for (int o = SEG / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if ((threadIdx.x & (SEG - 1)) == 0) atomicAdd(&s_ssd[gb], sq);
+  }
+  __syncthreads();
+  if (threadIdx.x < G && first + threadIdx.x < nblk) {
+    has_out[first + threadIdx.x] = (uint8_t)s_has[threadIdx.x];
+    ssd_out[first + threadIdx.x] = (uint32_t)(s_ssd[threadIdx.x] >> (2 * (PixTraits<T>::kBits - 8)));
   }
 }
 
@@ -123,6 +226,21 @@ __global__ void sao_decide_kernel(const int32_t *__restrict__ dd, const int32_t 
 }  // namespace kvzc
 
 using namespace kvzc;
+
+static int launch_recon(const kvz_cuda_quant_params &qp, const uint8_t *src, const uint8_t *rin, int stride, int pic_w, int pic_h,
+                        int color, int log2w, int blocks_x, int nblk, const int8_t *modes, uint8_t *rec, int16_t *coeff,
+                        uint8_t *has, uint32_t *ssd, cudaStream_t st)
+{
+  const int ww = 1 << (2 * log2w), g = ww >= 256 ? 1 : 256 / ww, grid = (nblk + g - 1) / g;
+  switch (log2w) {
+    case 2: intra_recon_kernel<uint8_t, 2><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
+    case 3: intra_recon_kernel<uint8_t, 3><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
+    case 4: intra_recon_kernel<uint8_t, 4><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
+    default: intra_recon_kernel<uint8_t, 5><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
+  }
+  KVZC_LAUNCHED();
+  return 0;
+}
 
 struct Section { size_t off, bytes; };
 
@@ -289,20 +407,17 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
     select_best_kernel<<<(nb + 255) / 256, 256, 0, st>>>(costs, nb, modes, (uint32_t *)(B + L.cost_y[d]));
     KVZC_LAUNCHED();
     fp_mark(fp, d * 4 + 2, st);
-    const int threads = w * w < 256 ? (w * w < 32 ? 32 : w * w) : 256;
-    intra_recon_kernel<uint8_t><<<nb, threads, 0, st>>>(qp, src, rin, W, W, H, 0, log2w, W / w, modes, B + fp->off_rec_y[d],
-                                                        (int16_t *)(B + L.coeff_y[d]), B + L.has_y[d], (uint32_t *)(B + L.ssd_y[d]));
-    KVZC_LAUNCHED();
+    if (int r = launch_recon(qp, src, rin, W, W, H, 0, log2w, W / w, nb, modes, B + fp->off_rec_y[d],
+                             (int16_t *)(B + L.coeff_y[d]), B + L.has_y[d], (uint32_t *)(B + L.ssd_y[d]), st)) return r;
     fp_mark(fp, d * 4 + 3, st);
     if (d < 3) {
-      const int wc = w / 2, tc = wc * wc < 256 ? (wc * wc < 32 ? 32 : wc * wc) : 256;
+      const int wc = w / 2;
       for (int color = 1; color <= 2; ++color) {
-        intra_recon_kernel<uint8_t><<<nb, tc, 0, st>>>(qp, src + poff[color], rin + poff[color], W / 2, W, H, color, log2w - 1,
-                                                       (W / 2) / wc, modes, B + (color == 1 ? fp->off_rec_u[d] : fp->off_rec_v[d]),
-                                                       (int16_t *)(B + (color == 1 ? L.coeff_u[d] : L.coeff_v[d])),
-                                                       B + (color == 1 ? L.has_u[d] : L.has_v[d]),
-                                                       (uint32_t *)(B + (color == 1 ? L.ssd_u[d] : L.ssd_v[d])));
-        KVZC_LAUNCHED();
+        if (int r = launch_recon(qp, src + poff[color], rin + poff[color], W / 2, W, H, color, log2w - 1, (W / 2) / wc, nb, modes,
+                                 B + (color == 1 ? fp->off_rec_u[d] : fp->off_rec_v[d]),
+                                 (int16_t *)(B + (color == 1 ? L.coeff_u[d] : L.coeff_v[d])),
+                                 B + (color == 1 ? L.has_u[d] : L.has_v[d]),
+                                 (uint32_t *)(B + (color == 1 ? L.ssd_u[d] : L.ssd_v[d])), st)) return r;
       }
     }
   }
