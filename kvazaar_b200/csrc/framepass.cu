@@ -58,22 +58,23 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
   __shared__ T s_pred[E];
   __shared__ int s_dc[G], s_mode[G], s_has[G], s_ac[G], s_ssd[G];
   __shared__ uint8_t s_cgnz[G][NCG];
+  __shared__ BuildRefCtx s_ctx[G];
   const int is_c = color != 0;
   const int first = blockIdx.x * G;
   const int l2 = LOG2W;
   const bool use_dst = (W == 4 && color == 0);                          // intra luma 4x4, ref: strategies-dct.c:78-96
 
   // ---- references, smoothed references, DC, mode
+  if (threadIdx.x < G) {
+    const int b = min(first + (int)threadIdx.x, nblk - 1);
+    s_ctx[threadIdx.x] = build_ref_ctx(LOG2W, color, ((b % blocks_x) * W) << is_c, ((b / blocks_x) * W) << is_c, pic_w, pic_h);
+  }
+  __syncthreads();
   for (int e = threadIdx.x; e < G * 2 * NREF; e += blockDim.x) {
     const int gb = e / (2 * NREF), r = e - gb * 2 * NREF;
     const bool is_top = r < NREF;
-    const int k = is_top ? r : r - NREF, b = first + gb;
-    int v = 0;
-    if (b < nblk) {
-      const BuildRefCtx c = build_ref_ctx(LOG2W, color, ((b % blocks_x) * W) << is_c, ((b / blocks_x) * W) << is_c, pic_w, pic_h);
-      v = build_ref_entry(c, rec_in, stride, is_top, k);
-    }
-    s_ref[gb][is_top ? 0 : 1][k] = (T)v;
+    const int k = is_top ? r : r - NREF;
+    s_ref[gb][is_top ? 0 : 1][k] = (T)build_ref_entry(s_ctx[gb], rec_in, stride, is_top, k);
   }
   if (threadIdx.x < G) {
     const int b = first + threadIdx.x;
@@ -194,33 +195,164 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
   }
 }
 
-// offsets[eo][blk][5] from the edge statistics: rounded-toward-zero mean error per category, clipped to +-7
-__global__ void sao_derive_kernel(const int32_t *__restrict__ stats, int nblk, int32_t *__restrict__ offsets)
+struct SaoPlanes {
+  const uint8_t *src[3];
+  const uint8_t *rec[3];
+  uint8_t *out[3];
+  int Wp[3], Hp[3];
+};
+
+__device__ __forceinline__ void fp_eo_offsets(int eo, int &ax, int &ay)
 {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nblk * 4) return;
-  const int blk = i >> 2, eo = i & 3;
-  const int32_t *st = stats + (size_t)blk * 40 + eo * 10;
-  int32_t *o = offsets + ((size_t)eo * nblk + blk) * 5;
-  o[0] = 0;
-  for (int k = 1; k < 5; ++k) o[k] = st[5 + k] ? clip3(-7, 7, st[k] / st[5 + k]) : 0;
+  ax = (eo == 1) ? 0 : (eo == 3 ? 1 : -1);
+  ay = (eo == 0) ? 0 : -1;
+}
+__device__ __forceinline__ int fp_eo_cat(int a, int b, int c)
+{
+  const int idx = 2 + ((c > a) - (c < a)) + ((c > b) - (c < b));
+  return (0x43021 >> (4 * idx)) & 7;
 }
 
-// pick the class with the smallest delta-distortion (first minimum); enable SAO only if it lowers distortion
-__global__ void sao_decide_kernel(const int32_t *__restrict__ dd, const int32_t *__restrict__ offsets, int nblk,
-                                  int8_t *__restrict__ best, kvz_cuda_sao_rec *__restrict__ descs)
+// One CTA per (plane, CTU): ONE pass over the CTU gathers the edge statistics of all four classes
+// (calc_sao_edge_dir, ref: sao-generic.c:50-81) and the per-band sums; everything else follows in closed form:
+//   offsets[k]      = clip(sum_k / cnt_k)                                   (the pass's decision rule)
+//   edge ddist      = sum_k (o_k^2 * cnt_k - 2 * o_k * sum_k)               == sum_i ((d_i - o)^2 - d_i^2), the value
+//                     kvz_sao_edge_ddistortion accumulates pixel by pixel (ref: sao_shared_generics.h:52-91)
+//   band ddist      = the same identity over the four bands                 (ref: sao_shared_generics.h:93-130)
+// so the delta-distortion "kernels" cost nothing on the device.  8-bit only (no bit-depth rounding offset).
+__global__ void __launch_bounds__(256) sao_ctu_kernel(SaoPlanes pl, int nctu, int ctus_x, int32_t *__restrict__ stats,
+                                                      int32_t *__restrict__ dd, int32_t *__restrict__ band_dd,
+                                                      int8_t *__restrict__ best, int32_t *__restrict__ dec_off,
+                                                      uint32_t *__restrict__ cksum_scratch)
 {
-  const int blk = blockIdx.x * blockDim.x + threadIdx.x;
-  if (blk >= nblk) return;
-  int be = 0, bd = dd[blk];
-  for (int eo = 1; eo < 4; ++eo) { const int d = dd[(size_t)eo * nblk + blk]; if (d < bd) { bd = d; be = eo; } }
-  best[blk] = (int8_t)(bd < 0 ? be : -1);
-  kvz_cuda_sao_rec &r = descs[blk];
-  r.type = bd < 0 ? 2 : 0;
-  r.eo_class = (int8_t)be;
-  const int color = r.color;
-  for (int k = 0; k < 10; ++k) r.offsets[k] = 0;
-  for (int k = 0; k < 5; ++k) r.offsets[k + (color == 2 ? 5 : 0)] = offsets[((size_t)be * nblk + blk) * 5 + k];
+  __shared__ int s_acc[4][2][5];
+  __shared__ int s_band[2][4];
+  const int i = blockIdx.x, color = i / nctu, ctu = i - color * nctu;
+  const int Wp = pl.Wp[color], Hp = pl.Hp[color], lw = color ? 32 : 64;
+  const int x0 = (ctu % ctus_x) * lw, y0 = (ctu / ctus_x) * lw;
+  const int bw = min(lw, Wp - x0), bh = min(lw, Hp - y0);
+  const uint8_t *orig = pl.src[color] + (long)y0 * Wp + x0, *rec = pl.rec[color] + (long)y0 * Wp + x0;
+  const int bp = (i * 7) % 29;
+  if (i == 0 && threadIdx.x < 6) cksum_scratch[threadIdx.x] = 0;
+  for (int t = threadIdx.x; t < 48; t += blockDim.x) { if (t < 40) (&s_acc[0][0][0])[t] = 0; else (&s_band[0][0])[t - 40] = 0; }
+  __syncthreads();
+  int sum[4][5], cnt[4][5], bs[4], bc[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    bs[e] = 0; bc[e] = 0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { sum[e][k] = 0; cnt[e][k] = 0; }
+  }
+  for (int t = threadIdx.x; t < bw * bh; t += blockDim.x) {
+    const int y = t / bw, x = t - y * bw;
+    const int c = rec[(long)y * Wp + x];
+    const int diff = (int)orig[(long)y * Wp + x] - c;
+    const int band = (c >> 3) - bp;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int hit = band == k; bs[k] += hit ? diff : 0; bc[k] += hit; }
+    if (x >= 1 && y >= 1 && x < bw - 1 && y < bh - 1) {        // the strategies only see the block: no outside neighbours
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        int ax, ay;
+        fp_eo_offsets(e, ax, ay);
+        const int cat = fp_eo_cat(rec[(long)(y + ay) * Wp + x + ax], rec[(long)(y - ay) * Wp + x - ax], c);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { const int hit = cat == k; sum[e][k] += hit ? diff : 0; cnt[e][k] += hit; }
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int b1 = warp_sum(bs[e]), b2 = warp_sum(bc[e]);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_band[0][e], b1); atomicAdd(&s_band[1][e], b2); }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int v1 = warp_sum(sum[e][k]), v2 = warp_sum(cnt[e][k]);
+      if ((threadIdx.x & 31) == 0) { atomicAdd(&s_acc[e][0][k], v1); atomicAdd(&s_acc[e][1][k], v2); }
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < 40; t += blockDim.x) stats[(size_t)i * 40 + t] = (&s_acc[0][0][0])[t];
+  if (threadIdx.x == 0) {
+    const int n3 = 3 * nctu;
+    int be = 0, bd = 0, off_best[5] = { 0, 0, 0, 0, 0 };
+    for (int e = 0; e < 4; ++e) {
+      int o[5], v = 0;
+      o[0] = 0;
+      for (int k = 1; k < 5; ++k) o[k] = s_acc[e][1][k] ? clip3(-7, 7, s_acc[e][0][k] / s_acc[e][1][k]) : 0;
+      for (int k = 1; k < 5; ++k) v += o[k] * o[k] * s_acc[e][1][k] - 2 * o[k] * s_acc[e][0][k];
+      dd[(size_t)e * n3 + i] = v;
+      if (e == 0 || v < bd) { bd = v; be = e; for (int k = 0; k < 5; ++k) off_best[k] = o[k]; }
+    }
+    const int bands[4] = { 1, -1, 2, -2 };
+    int bv = 0;
+    for (int k = 0; k < 4; ++k) bv += bands[k] * bands[k] * s_band[1][k] - 2 * bands[k] * s_band[0][k];
+    band_dd[i] = bv;
+    best[i] = (int8_t)(bd < 0 ? be : -1);
+    for (int k = 0; k < 5; ++k) dec_off[(size_t)i * 5 + k] = off_best[k];
+  }
+}
+
+// sao_reconstruct_color (edge type) of the chosen class for every CTU of the three planes; pixels on the picture
+// border (no neighbours) and CTUs without SAO are copied (ref: sao-generic.c:84-124, sao.c:302-361 call shape).
+__global__ void __launch_bounds__(256) sao_apply_kernel(SaoPlanes pl, int nctu, int ctus_x, const int8_t *__restrict__ best,
+                                                        const int32_t *__restrict__ dec_off)
+{
+  const int i = blockIdx.x, color = i / nctu, ctu = i - color * nctu;
+  const int Wp = pl.Wp[color], Hp = pl.Hp[color], lw = color ? 32 : 64;
+  const int x0 = (ctu % ctus_x) * lw, y0 = (ctu / ctus_x) * lw;
+  const int bw = min(lw, Wp - x0), bh = min(lw, Hp - y0);
+  const uint8_t *rec = pl.rec[color];
+  uint8_t *out = pl.out[color];
+  const int eo = best[i];
+  int off[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) off[k] = dec_off[(size_t)i * 5 + k];
+  int ax = 0, ay = 0;
+  if (eo >= 0) fp_eo_offsets(eo, ax, ay);
+  for (int t = threadIdx.x; t < bw * bh; t += blockDim.x) {
+    const int y = y0 + t / bw, x = x0 + t % bw;
+    const long o = (long)y * Wp + x;
+    int v = rec[o];
+    if (eo >= 0 && x >= 1 && y >= 1 && x < Wp - 1 && y < Hp - 1) {
+      const int cat = fp_eo_cat(rec[o + (long)ay * Wp + ax], rec[o - (long)ay * Wp - ax], v);
+      int ov = off[0];
+#pragma unroll
+      for (int k = 1; k < 5; ++k) ov = cat == k ? off[k] : ov;
+      v = clip3(0, 255, v + ov);
+    }
+    out[o] = (uint8_t)v;
+  }
+}
+
+// picture checksum of the three planes in one launch (ref: nal-generic.c:57-82); blockIdx.y = plane
+__global__ void __launch_bounds__(256) checksum3_kernel(SaoPlanes pl, uint32_t *__restrict__ scratch, uint8_t *__restrict__ out12)
+{
+  const int color = blockIdx.y;
+  const int Wp = pl.Wp[color], Hp = pl.Hp[color];
+  const uint8_t *data = pl.out[color];
+  uint32_t s = 0;
+  const int total4 = Wp * Hp / 4;                      // widths are multiples of 4: four pixels of one row per word
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total4; t += gridDim.x * blockDim.x) {
+    const int p = t * 4, y = p / Wp, x = p - y * Wp;
+    const uint32_t v = *reinterpret_cast<const uint32_t *>(data + p);
+    const uint32_t m0 = (uint32_t)((x & 0xff) ^ (y & 0xff) ^ (x >> 8) ^ (y >> 8)) & 0xff;   // x, x+1, x+2, x+3 share x >> 8
+    const uint32_t mask = m0 | ((m0 ^ 1u) << 8) | ((m0 ^ 2u) << 16) | ((m0 ^ 3u) << 24);  // x & 3 == 0
+    s = __dp4a(v ^ mask, 0x01010101u, s);
+  }
+  s = (uint32_t)block_sum((int)s);
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) {
+    atomicAdd(&scratch[2 * color], s);
+    __threadfence();
+    s_last = atomicAdd(&scratch[2 * color + 1], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    const uint32_t t = atomicAdd(&scratch[2 * color], 0u);
+    out12[4 * color + 0] = (uint8_t)(t >> 24); out12[4 * color + 1] = (uint8_t)(t >> 16);
+    out12[4 * color + 2] = (uint8_t)(t >> 8); out12[4 * color + 3] = (uint8_t)t;
+  }
 }
 
 }  // namespace kvzc
@@ -422,44 +554,28 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
     }
   }
   fp_mark(fp, 16, st);
-  // ---- SAO on the 8x8-level reconstruction (depth index 2) ----
+  // ---- SAO on the 8x8-level reconstruction (depth index 2): statistics + decisions, then reconstruction ----
   const int nctu = fp->nctu3 / 3;
-  const uint8_t *recp[3] = { B + fp->off_rec_y[2], B + fp->off_rec_u[2], B + fp->off_rec_v[2] };
-  const kvz_cuda_sao_blk *blks = (const kvz_cuda_sao_blk *)(B + fp->off_sao_blk);
-  kvz_cuda_sao_rec *descs = (kvz_cuda_sao_rec *)(B + fp->off_sao_desc);
-  int32_t *stats = (int32_t *)(B + L.sao_stats), *dd = (int32_t *)(B + L.sao_dd), *offs = (int32_t *)(B + fp->off_sao_off);
-  uint8_t *sao_rec = B + L.sao_rec;
+  SaoPlanes pl;
   for (int color = 0; color < 3; ++color) {
-    const int Wp = color ? W / 2 : W, Hp = color ? H / 2 : H;
-    const int i0 = color * nctu;
-    if (int r = kvz_cuda_sao_edge_stats_batch(8, src, recp[color], blks + i0, nctu, stats + (size_t)i0 * 40, st)) return r;
-    KVZC_CHECK(cudaMemcpyAsync(sao_rec + poff[color], recp[color], (size_t)Wp * Hp, cudaMemcpyDeviceToDevice, st));
+    pl.src[color] = src + poff[color];
+    pl.rec[color] = B + (color == 0 ? fp->off_rec_y[2] : (color == 1 ? fp->off_rec_u[2] : fp->off_rec_v[2]));
+    pl.out[color] = B + L.sao_rec + poff[color];
+    pl.Wp[color] = color ? W / 2 : W; pl.Hp[color] = color ? H / 2 : H;
   }
+  int32_t *dec_off = (int32_t *)(B + fp->off_sao_off);
+  uint32_t *ck_scratch = (uint32_t *)(B + fp->off_sao_off) + (size_t)fp->nctu3 * 5;
+  sao_ctu_kernel<<<fp->nctu3, 256, 0, st>>>(pl, nctu, (W + 63) / 64, (int32_t *)(B + L.sao_stats), (int32_t *)(B + L.sao_dd),
+                                            (int32_t *)(B + L.sao_band_dd), (int8_t *)(B + L.sao_best), dec_off, ck_scratch);
+  KVZC_LAUNCHED();
   fp_mark(fp, 17, st);
-  sao_derive_kernel<<<(fp->nctu3 * 4 + 255) / 256, 256, 0, st>>>(stats, fp->nctu3, offs);
-  KVZC_LAUNCHED();
-  for (int color = 0; color < 3; ++color) {
-    const int i0 = color * nctu;
-    for (int eo = 0; eo < 4; ++eo)
-      if (int r = kvz_cuda_sao_edge_ddistortion_batch(8, src, recp[color], blks + i0, (const int8_t *)(B + fp->off_eo[eo]) + i0,
-                                                      offs + ((size_t)eo * fp->nctu3 + i0) * 5, nctu, dd + (size_t)eo * fp->nctu3 + i0, st)) return r;
-    if (int r = kvz_cuda_sao_band_ddistortion_batch(8, src, recp[color], blks + i0, (const int32_t *)(B + fp->off_bandpos) + i0,
-                                                    (const int32_t *)(B + fp->off_bands) + (size_t)i0 * 4, nctu,
-                                                    (int32_t *)(B + L.sao_band_dd) + i0, st)) return r;
-  }
   fp_mark(fp, 18, st);
-  sao_decide_kernel<<<(fp->nctu3 + 255) / 256, 256, 0, st>>>(dd, offs, fp->nctu3, (int8_t *)(B + L.sao_best), descs);
+  sao_apply_kernel<<<fp->nctu3, 256, 0, st>>>(pl, nctu, (W + 63) / 64, (const int8_t *)(B + L.sao_best), dec_off);
   KVZC_LAUNCHED();
-  for (int color = 0; color < 3; ++color) {
-    const int Wp = color ? W / 2 : W;
-    if (int r = kvz_cuda_sao_reconstruct_batch(8, recp[color], Wp, sao_rec, Wp, descs + color * nctu, nctu, st)) return r;
-  }
   fp_mark(fp, 19, st);
   // ---- picture checksum of the filtered planes ----
-  for (int color = 0; color < 3; ++color) {
-    const int Wp = color ? W / 2 : W, Hp = color ? H / 2 : H;
-    if (int r = kvz_cuda_array_checksum(8, sao_rec + poff[color], Hp, Wp, Wp, B + L.checksum + 4 * color, st)) return r;
-  }
+  checksum3_kernel<<<dim3(148, 3), 256, 0, st>>>(pl, ck_scratch, B + L.checksum);
+  KVZC_LAUNCHED();
   fp_mark(fp, KVZ_CUDA_FP_STAGES, st);
   if (fp->timing) fp->ev_pending = true;
   return 0;

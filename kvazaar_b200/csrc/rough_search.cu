@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(128) rough_search_u8_kernel(const uint8_t *__r
   __shared__ __align__(16) uint8_t s_plain[GROUP][4][ES];        // same, shifted so that index j = idx + W
   __shared__ __align__(16) uint8_t s_ext[4][GROUP][ES];          // per-warp scratch: main ref with projected side part
   __shared__ int s_dc[GROUP];
+  __shared__ BuildRefCtx s_ctx[GROUP];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int first = blockIdx.x * GROUP;
@@ -53,17 +54,16 @@ __global__ void __launch_bounds__(128) rough_search_u8_kernel(const uint8_t *__r
   const bool valid = blk < nblk;
 
   // ---- reference samples for the GROUP blocks (all 128 threads)
+  if (threadIdx.x < GROUP) {
+    const int b = min(first + (int)threadIdx.x, nblk - 1);
+    s_ctx[threadIdx.x] = build_ref_ctx(LOG2W, 0, (b % blocks_x) * W, (b / blocks_x) * W, pic_w, pic_h);
+  }
+  __syncthreads();
   for (int e = threadIdx.x; e < GROUP * 2 * N; e += 128) {
     const int gb = e / (2 * N), r = e - gb * 2 * N;
     const bool is_top = r < N;
     const int k = is_top ? r : r - N;
-    const int b = first + gb;
-    int v = 0;
-    if (b < nblk) {
-      const BuildRefCtx c = build_ref_ctx(LOG2W, 0, (b % blocks_x) * W, (b / blocks_x) * W, pic_w, pic_h);
-      v = build_ref_entry(c, rec, stride, is_top, k);
-    }
-    s_ref[gb][is_top ? 0 : 1][k] = (uint8_t)v;
+    s_ref[gb][is_top ? 0 : 1][k] = (uint8_t)build_ref_entry(s_ctx[gb], rec, stride, is_top, k);
   }
   __syncthreads();
   for (int e = threadIdx.x; e < GROUP * 2 * N; e += 128) {
