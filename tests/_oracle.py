@@ -46,26 +46,26 @@ def P(a):
     return C.c_void_p(a.ctypes.data)
 
 
-def build_oracle():
-    so = os.path.join(ORACLE_DIR, "libkvz_oracle.so")
+def build_oracle(bitdepth=8):
+    so = os.path.join(ORACLE_DIR, "libkvz_oracle.so" if bitdepth == 8 else "libkvz_oracle_10b.so")
     src = os.path.join(ORACLE_DIR, "kvz_oracle.c")
     if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
         subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
     return so
 
 
-def build_ref():
+def build_ref(bitdepth=8):
     """Build oracle/_ref from /root/reference when it is present (this container);
     on the GPU box the prebuilt files travel with the snapshot."""
-    so = os.path.join(REF_DIR, "libkvzref_shim.so")
+    so = os.path.join(REF_DIR, "libkvzref_shim.so" if bitdepth == 8 else "libkvzref_shim_10b.so")
     if os.path.isdir("/root/reference/src"):
-        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref", "-j8"])
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref", "-j8", f"BITDEPTH={bitdepth}"])
     return so if os.path.exists(so) else None
 
 
 class Oracle:
-    def __init__(self):
-        self.lib = C.CDLL(build_oracle())
+    def __init__(self, bitdepth=8):
+        self.lib = C.CDLL(build_oracle(bitdepth))
         L = self.lib
         for name in ("orc_reg_sad", "orc_sad_nxn", "orc_satd_nxn", "orc_satd_any_size", "orc_pixels_calc_ssd",
                      "orc_ver_sad", "orc_hor_sad", "orc_coeff_abs_sum"):
@@ -161,23 +161,23 @@ class Oracle:
         p = self.lib.orc_scan_table(scan_idx, log2)
         return np.ctypeslib.as_array(p, shape=(1 << (2 * log2),)).copy()
 
-    def quant(self, qp, coef, w, h, type_, scan_idx, block_type, intra=1, signhide=0, bitdepth=8):
+    def quant(self, qp, coef, w, h, type_, scan_idx, block_type, intra=1, signhide=0, bitdepth=None):
         q = np.zeros(w * h, np.int16)
-        prm = self.qparams(qp, bitdepth, intra, signhide)
+        prm = self.qparams(qp, bitdepth or self.bitdepth, intra, signhide)
         self.lib.orc_quant(P(prm), P(coef), P(q), w, h, type_, scan_idx, block_type)
         return q
 
-    def dequant(self, qp, q, w, h, type_, block_type, bitdepth=8):
+    def dequant(self, qp, q, w, h, type_, block_type, bitdepth=None):
         c = np.zeros(w * h, np.int16)
-        prm = self.qparams(qp, bitdepth)
+        prm = self.qparams(qp, bitdepth or self.bitdepth)
         self.lib.orc_dequant(P(prm), P(q), P(c), w, h, type_, block_type)
         return c
 
     def quantize_residual(self, qp, width, color, scan_idx, trskip, cu_intra, stride, ref, pred, intra_slice=1,
-                          signhide=0, bitdepth=8, early_skip=0):
+                          signhide=0, bitdepth=None, early_skip=0):
         rec = np.zeros(width * stride, self.pix)
         coeff = np.zeros(width * width, np.int16)
-        prm = self.qparams(qp, bitdepth, intra_slice, signhide)
+        prm = self.qparams(qp, bitdepth or self.bitdepth, intra_slice, signhide)
         has = self.lib.orc_quantize_residual(P(prm), width, color, scan_idx, trskip, cu_intra, stride, stride,
                                              P(ref), P(pred), P(rec), P(coeff), early_skip)
         return has, rec, coeff
@@ -277,10 +277,10 @@ class Oracle:
 
 
 class Ref:
-    """The compiled, unmodified reference (8-bit build)."""
+    """The compiled, unmodified reference (8-bit build, or the -DKVZ_BIT_DEPTH=10 build)."""
 
-    def __init__(self):
-        so = build_ref()
+    def __init__(self, bitdepth=8):
+        so = build_ref(bitdepth)
         if so is None:
             raise FileNotFoundError("oracle/_ref not built and /root/reference absent")
         self.lib = C.CDLL(so)

@@ -28,6 +28,21 @@ def ref():
 
 
 @pytest.fixture(scope="session")
+def orc10():
+    from _oracle import Oracle
+    return Oracle(10)
+
+
+@pytest.fixture(scope="session")
+def ref10():
+    from _oracle import Ref
+    try:
+        return Ref(10)
+    except (FileNotFoundError, OSError) as e:  # pragma: no cover
+        pytest.skip(f"compiled 10-bit reference unavailable: {e}")
+
+
+@pytest.fixture(scope="session")
 def cuda_lib():
     """The product library through its public Python host layer; fails loudly if missing."""
     import torch
