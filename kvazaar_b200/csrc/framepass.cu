@@ -35,9 +35,10 @@ __global__ void __launch_bounds__(256) select_best_kernel(const uint32_t *__rest
   best[b] = bc;
 }
 
-// kvz_intra_recon_cu for G TUs of one colour plane per CTA (G = 256 / N^2, at least 1): references -> prediction of
-// the chosen mode -> residual -> DCT/DST -> quant (+ sign hiding) -> dequant -> inverse -> reconstruction, SSD.
-// All G TUs walk the same barrier sequence; data-dependent decisions (has_coeffs, ac_sum < 2) are predicates.
+// kvz_intra_recon_cu for a tile of 1024 samples (G = 1024 / W^2 TUs of one colour plane) per 256-thread CTA:
+// references -> prediction of the chosen mode -> residual -> DCT/DST -> quant (+ sign hiding) -> dequant -> inverse
+// -> reconstruction, SSD.  All TUs walk the same barrier sequence; data-dependent decisions (has_coeffs,
+// ac_sum < 2) are predicates.  Transforms use the DP2A matrix passes of transform.cuh.
 template <class T, int LOG2W>
 __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params p, const T *__restrict__ src,
                                                           const T *__restrict__ rec_in, int stride, int pic_w, int pic_h,
@@ -47,16 +48,16 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
                                                           uint32_t *__restrict__ ssd_out)
 {
   constexpr int W = 1 << LOG2W, WW = W * W, NREF = 2 * W + 1;
-  constexpr int G = WW >= 256 ? 1 : 256 / WW;
-  constexpr int E = G * WW;                         // elements per CTA (256 or 1024)
+  constexpr int E = 1024, G = E / WW;               // 1, 4, 16, 64 TUs per CTA
   constexpr int PIXMAX = (1 << PixTraits<T>::kBits) - 1;
   constexpr int NCG = WW / 16;                      // coefficient groups per TU
-  __shared__ int16_t s_a[E], s_b[E], s_q[E];
+  __shared__ __align__(16) int16_t s_a[E], s_b[E], s_q[E];
   __shared__ int32_t s_d[E];
-  __shared__ int8_t s_m[WW];
+  __shared__ __align__(16) uint32_t s_pf[WW / 4], s_pi[WW / 4];
   __shared__ T s_ref[G][4][NREF + 3];
   __shared__ T s_pred[E];
-  __shared__ int s_dc[G], s_mode[G], s_has[G], s_ac[G], s_ssd[G];
+  __shared__ int s_dc[G], s_has[G], s_ac[G], s_ssd[G];
+  __shared__ int8_t s_mode[G];
   __shared__ uint8_t s_cgnz[G][NCG];
   __shared__ BuildRefCtx s_ctx[G];
   const int is_c = color != 0;
@@ -65,10 +66,14 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
   const bool use_dst = (W == 4 && color == 0);                          // intra luma 4x4, ref: strategies-dct.c:78-96
 
   // ---- references, smoothed references, DC, mode
-  if (threadIdx.x < G) {
-    const int b = min(first + (int)threadIdx.x, nblk - 1);
-    s_ctx[threadIdx.x] = build_ref_ctx(LOG2W, color, ((b % blocks_x) * W) << is_c, ((b / blocks_x) * W) << is_c, pic_w, pic_h);
+  for (int gb = threadIdx.x; gb < G; gb += blockDim.x) {
+    const int b = min(first + gb, nblk - 1);
+    s_ctx[gb] = build_ref_ctx(LOG2W, color, ((b % blocks_x) * W) << is_c, ((b / blocks_x) * W) << is_c, pic_w, pic_h);
+    s_mode[gb] = first + gb < nblk ? modes[first + gb] : 0;
+    s_has[gb] = 0; s_ac[gb] = 0; s_ssd[gb] = 0;
   }
+  load_matrix_packed<W>(s_pf, use_dst, false);
+  load_matrix_packed<W>(s_pi, use_dst, true);
   __syncthreads();
   for (int e = threadIdx.x; e < G * 2 * NREF; e += blockDim.x) {
     const int gb = e / (2 * NREF), r = e - gb * 2 * NREF;
@@ -76,12 +81,6 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
     const int k = is_top ? r : r - NREF;
     s_ref[gb][is_top ? 0 : 1][k] = (T)build_ref_entry(s_ctx[gb], rec_in, stride, is_top, k);
   }
-  if (threadIdx.x < G) {
-    const int b = first + threadIdx.x;
-    s_mode[threadIdx.x] = b < nblk ? modes[b] : 0;
-    s_has[threadIdx.x] = 0; s_ac[threadIdx.x] = 0; s_ssd[threadIdx.x] = 0;
-  }
-  load_matrix(s_m, W, use_dst, true);
   __syncthreads();
   for (int e = threadIdx.x; e < G * 2 * NREF; e += blockDim.x) {
     const int gb = e / (2 * NREF), r = e - gb * 2 * NREF;
@@ -89,7 +88,7 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
     const int k = is_top ? r : r - NREF;
     s_ref[gb][is_top ? 2 : 3][k] = (T)filter_ref_entry(s_ref[gb][0], s_ref[gb][1], is_top, k, NREF);
   }
-  if (threadIdx.x < G) s_dc[threadIdx.x] = dc_value(LOG2W, s_ref[threadIdx.x][0], s_ref[threadIdx.x][1]);
+  for (int gb = threadIdx.x; gb < G; gb += blockDim.x) s_dc[gb] = dc_value(LOG2W, s_ref[gb][0], s_ref[gb][1]);
   __syncthreads();
 
   // ---- prediction and residual
@@ -105,10 +104,10 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
   }
   __syncthreads();
 
-  // ---- forward transform (ref: dct-generic.c:579-588, 611-619)
-  fwd_pass(s_a, s_q, s_m, W, G, l2 - 1 + (p.bitdepth - 8));
+  // ---- forward transform (ref: dct-generic.c:579-588, 611-619): tmp[k][j], then coef[k][j]
+  mat_pass_dp2a<W, true, false>(s_a, s_q, s_pf, l2 - 1 + (p.bitdepth - 8));
   __syncthreads();
-  fwd_pass(s_q, s_b, s_m, W, G, l2 + 6);
+  mat_pass_dp2a<W, true, false>(s_q, s_b, s_pf, l2 + 6);
   __syncthreads();
 
   // ---- quantisation (ref: quant-generic.c:50-180)
@@ -144,29 +143,29 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
     __syncthreads();
   }
 
-  // ---- coefficients out, has_coeffs
-  for (int e = threadIdx.x; e < E; e += blockDim.x) {
-    const int gb = e / WW, b = first + gb;
-    const int16_t v = s_q[e];
-    if (b < nblk) {
-      coeff[(size_t)b * WW + (e - gb * WW)] = v;
-      if (v != 0) s_has[gb] = 1;
-    }
-  }
-  // ---- dequant (ref: quant-generic.c:298-340) -> s_b
+  // ---- coefficients out, has_coeffs, dequant (ref: quant-generic.c:298-340) into the TRANSPOSED layout the
+  //      inverse passes consume
   {
     const int transform_shift = 15 - p.bitdepth - l2;
     const int qp_scaled = scaled_qp(is_c ? (color == 1 ? 2 : 3) : 0, p.qp, (p.bitdepth - 8) * 6);
     const int shift = 20 - 14 - transform_shift;
     const int scale = c_inv_quant_scales[qp_scaled % 6] << (qp_scaled / 6);
     const int add = 1 << (shift - 1);
-    for (int e = threadIdx.x; e < E; e += blockDim.x) s_b[e] = (int16_t)clip3(-32768, 32767, ((int)s_q[e] * scale + add) >> shift);
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      const int gb = e / WW, r = e - gb * WW, y = r >> LOG2W, x = r & (W - 1), b = first + gb;
+      const int16_t v = s_q[e];
+      if (b < nblk) {
+        coeff[(size_t)b * WW + r] = v;
+        if (v != 0) s_has[gb] = 1;
+      }
+      s_b[gb * WW + x * W + y] = (int16_t)clip3(-32768, 32767, ((int)v * scale + add) >> shift);
+    }
   }
-  load_matrix(s_m, W, use_dst, false);
   __syncthreads();
-  inv_pass(s_b, s_q, s_m, W, G, 7);
+  // ---- inverse transform (ref: dct-generic.c:590-599, 621-629)
+  mat_pass_dp2a<W, true, true>(s_b, s_a, s_pi, 7);
   __syncthreads();
-  inv_pass(s_q, s_a, s_m, W, G, 12 - (p.bitdepth - 8));
+  mat_pass_dp2a<W, false, true>(s_a, s_b, s_pi, 12 - (p.bitdepth - 8));
   __syncthreads();
 
   // ---- reconstruction + SSD (ref: quant-generic.c:263-292, picture-generic.c:536-551)
@@ -176,7 +175,7 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
     if (b < nblk) {                                   // (no early exit: every lane takes part in the shuffles below)
       const int pv = s_pred[e];
       int rv = pv;
-      if (s_has[gb]) rv = clip3(0, PIXMAX, (int)(int16_t)(s_a[e] + pv));
+      if (s_has[gb]) rv = clip3(0, PIXMAX, (int)(int16_t)(s_b[e] + pv));
       const long off = (long)((b / blocks_x) * W + y) * stride + (b % blocks_x) * W + x;
       rec_out[off] = (T)rv;
       const int dv = (int)src[off] - rv;
@@ -189,10 +188,11 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
     if ((threadIdx.x & (SEG - 1)) == 0) atomicAdd(&s_ssd[gb], sq);
   }
   __syncthreads();
-  if (threadIdx.x < G && first + threadIdx.x < nblk) {
-    has_out[first + threadIdx.x] = (uint8_t)s_has[threadIdx.x];
-    ssd_out[first + threadIdx.x] = (uint32_t)(s_ssd[threadIdx.x] >> (2 * (PixTraits<T>::kBits - 8)));
-  }
+  for (int gb = threadIdx.x; gb < G; gb += blockDim.x)
+    if (first + gb < nblk) {
+      has_out[first + gb] = (uint8_t)s_has[gb];
+      ssd_out[first + gb] = (uint32_t)(s_ssd[gb] >> (2 * (PixTraits<T>::kBits - 8)));
+    }
 }
 
 struct SaoPlanes {
@@ -363,7 +363,7 @@ static int launch_recon(const kvz_cuda_quant_params &qp, const uint8_t *src, con
                         int color, int log2w, int blocks_x, int nblk, const int8_t *modes, uint8_t *rec, int16_t *coeff,
                         uint8_t *has, uint32_t *ssd, cudaStream_t st)
 {
-  const int ww = 1 << (2 * log2w), g = ww >= 256 ? 1 : 256 / ww, grid = (nblk + g - 1) / g;
+  const int ww = 1 << (2 * log2w), g = 1024 / ww, grid = (nblk + g - 1) / g;
   switch (log2w) {
     case 2: intra_recon_kernel<uint8_t, 2><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
     case 3: intra_recon_kernel<uint8_t, 3><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;

@@ -63,6 +63,62 @@ __device__ __forceinline__ void inv_pass(const int16_t *src, int16_t *dst, const
   }
 }
 
+// ---- DP2A formulation used by the fused frame-pass kernels -------------------------------------------------------
+// v[k][j] = sum_i A[k][i] * src[j*W + i] over a tile of 1024 coefficients (1024 / W^2 blocks back to back), with
+// A = M (forward) or A = M^T (inverse, fed with the transposed input).  The |coefficients| <= 90 fit int8 and the
+// data is int16, so one IDP2A does two exact multiply-adds; A is stored as 4-packed rows
+// P[(i / 4) * W + k] = { A[k][i], A[k][i+1], A[k][i+2], A[k][i+3] } so lanes with consecutive k read consecutive
+// words.  Each of the 256 threads owns a 2 (k) x 2 (j) output tile: 4 LDS + 8 IDP2A per 16 multiply-adds.
+template <int W>
+__device__ __forceinline__ void load_matrix_packed(uint32_t *P, bool dst, bool transposed)
+{
+  for (int e = threadIdx.x; e < W * W / 4; e += blockDim.x) {
+    const int i4 = e / W, k = e % W;
+    uint32_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = 4 * i4 + b;
+      const int c = transposed ? tr_coef(W, dst, i, k) : tr_coef(W, dst, k, i);
+      v |= (uint32_t)(c & 0xff) << (8 * b);
+    }
+    P[e] = v;
+  }
+}
+
+// STORE_KJ: result stored at out[k*W + j] (what the next pass reads as "row k"), else at out[j*W + k].
+// CLIP: clip to int16 (inverse passes) instead of truncating (forward passes).  blockDim.x == 256, tile = 1024.
+template <int W, bool STORE_KJ, bool CLIP>
+__device__ __forceinline__ void mat_pass_dp2a(const int16_t *src, int16_t *out, const uint32_t *P, int shift)
+{
+  constexpr int WW = W * W, ITEMS = WW / 4;              // 2x2 output tiles per block
+  const int t = threadIdx.x;
+  const int gb = t / ITEMS, r = t - gb * ITEMS;
+  const int kp = r % (W / 2), jp = r / (W / 2);
+  const int k0 = 2 * kp, j0 = 2 * jp;
+  const int16_t *s0 = src + gb * WW + j0 * W, *s1 = s0 + W;
+  int a00 = 0, a01 = 0, a10 = 0, a11 = 0;                // a[k][j]
+#pragma unroll
+  for (int i4 = 0; i4 < W / 4; ++i4) {
+    const uint2 m = *reinterpret_cast<const uint2 *>(P + i4 * W + k0);      // rows k0, k0+1, columns 4*i4 .. +3
+    const uint2 x0 = *reinterpret_cast<const uint2 *>(s0 + 4 * i4);          // src[j0][4*i4 .. +3]
+    const uint2 x1 = *reinterpret_cast<const uint2 *>(s1 + 4 * i4);
+    a00 = __dp2a_lo((int)x0.x, (int)m.x, a00); a00 = __dp2a_hi((int)x0.y, (int)m.x, a00);
+    a01 = __dp2a_lo((int)x1.x, (int)m.x, a01); a01 = __dp2a_hi((int)x1.y, (int)m.x, a01);
+    a10 = __dp2a_lo((int)x0.x, (int)m.y, a10); a10 = __dp2a_hi((int)x0.y, (int)m.y, a10);
+    a11 = __dp2a_lo((int)x1.x, (int)m.y, a11); a11 = __dp2a_hi((int)x1.y, (int)m.y, a11);
+  }
+  const int add = 1 << (shift - 1);
+  auto fin = [&](int v) -> int { v = (v + add) >> shift; return CLIP ? clip3(-32768, 32767, v) : (int)(int16_t)v; };
+  int16_t *o = out + gb * WW;
+  if (STORE_KJ) {
+    *reinterpret_cast<uint32_t *>(o + k0 * W + j0) = (uint32_t)(uint16_t)fin(a00) | ((uint32_t)(uint16_t)fin(a01) << 16);
+    *reinterpret_cast<uint32_t *>(o + (k0 + 1) * W + j0) = (uint32_t)(uint16_t)fin(a10) | ((uint32_t)(uint16_t)fin(a11) << 16);
+  } else {
+    *reinterpret_cast<uint32_t *>(o + j0 * W + k0) = (uint32_t)(uint16_t)fin(a00) | ((uint32_t)(uint16_t)fin(a10) << 16);
+    *reinterpret_cast<uint32_t *>(o + (j0 + 1) * W + k0) = (uint32_t)(uint16_t)fin(a01) | ((uint32_t)(uint16_t)fin(a11) << 16);
+  }
+}
+
 __device__ __forceinline__ int ilog2(int n) { return 31 - __clz(n); }
 
 // ---- quantisation ---------------------------------------------------------------------------
