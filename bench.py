@@ -29,8 +29,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-W, H, QP = 1920, 1080, 27
+W, H, QP, SIGNHIDE = 1920, 1080, 27, 0
 WORKLOAD = "1920x1080 8-bit synthetic I420, all-intra, QP27 (preset medium: SAO on, signhide off), frame-level hot-path pass"
+
+
+def set_workload(name):
+    """configs[1] (default, the one the metric is quoted on) or the configs[2] shape (2160p, QP22, sign hiding)."""
+    global W, H, QP, SIGNHIDE, WORKLOAD
+    if name == "2160p":
+        W, H, QP, SIGNHIDE = 3840, 2160, 22, 1
+        WORKLOAD = "3840x2160 8-bit synthetic I420, all-intra, QP22 (preset veryslow shape: SAO on, signhide on), frame-level hot-path pass"
 
 
 def peaks():
@@ -99,17 +107,17 @@ def run_reference(args):
         return
     ref = Ref()
     cores = os.cpu_count() or 1
-    lay = kb.fp_layout_for(W, H, QP)
+    lay = kb.fp_layout_for(W, H, QP, SIGNHIDE)
     from _oracle import aligned, al
     frames = [al(f) for f in synth_frames(4)]
     blob = aligned(int(lay.host_bytes), np.uint8)
     nper = args.ref_frames
     for _ in range(max(1, args.warmup)):
-        ref_frame_pass(ref, frames[0], W, H, QP, lay, nthreads=cores, blob=blob, src_is_aligned=True)
+        ref_frame_pass(ref, frames[0], W, H, QP, lay, nthreads=cores, signhide=SIGNHIDE, blob=blob, src_is_aligned=True)
     t0 = time.perf_counter()
     for s in range(args.steps):
         for f in range(nper):
-            ref_frame_pass(ref, frames[(s * nper + f) % len(frames)], W, H, QP, lay, nthreads=cores, blob=blob, src_is_aligned=True)
+            ref_frame_pass(ref, frames[(s * nper + f) % len(frames)], W, H, QP, lay, nthreads=cores, signhide=SIGNHIDE, blob=blob, src_is_aligned=True)
     dt = time.perf_counter() - t0
     fps = args.steps * nper / dt
     sample = f"{args.steps * nper} frames {W}x{H} through the reference's selected strategy functions ({ref.selected_name('satd_8x8')})"
@@ -131,14 +139,14 @@ def cpu_baseline(budget_s=15.0):
     except Exception as e:  # pragma: no cover
         return {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
     cores = os.cpu_count() or 1
-    lay = kb.fp_layout_for(W, H, QP)
+    lay = kb.fp_layout_for(W, H, QP, SIGNHIDE)
     from _oracle import aligned, al
     frames = [al(f) for f in synth_frames(2)]
     blob = aligned(int(lay.host_bytes), np.uint8)
-    ref_frame_pass(ref, frames[0], W, H, QP, lay, nthreads=cores, blob=blob, src_is_aligned=True)
+    ref_frame_pass(ref, frames[0], W, H, QP, lay, nthreads=cores, signhide=SIGNHIDE, blob=blob, src_is_aligned=True)
     n, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < budget_s and n < 2000:
-        ref_frame_pass(ref, frames[n % 2], W, H, QP, lay, nthreads=cores, blob=blob, src_is_aligned=True)
+        ref_frame_pass(ref, frames[n % 2], W, H, QP, lay, nthreads=cores, signhide=SIGNHIDE, blob=blob, src_is_aligned=True)
         n += 1
     dt = time.perf_counter() - t0
     out = {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "reference",
@@ -175,7 +183,7 @@ def run_cuda(args):
     fps_step = args.frames_per_step
     inflight = 4
     streams = [torch.cuda.Stream() for _ in range(inflight)]
-    passes = [kb.FramePass(W, H, QP) for _ in range(inflight)]
+    passes = [kb.FramePass(W, H, QP, SIGNHIDE) for _ in range(inflight)]
     frames_np = synth_frames(fps_step)
     # every rank gets its own frames (sharding = frame i of the job -> rank i mod world)
     frames_np = [np.roll(f, rank * 977) for f in frames_np]
@@ -337,7 +345,9 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=8)
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the reference arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="1080p", choices=["1080p", "2160p"], help="1080p = BASELINE configs[1] (default)")
     args = ap.parse_args()
+    set_workload(args.workload)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -23,6 +23,9 @@
 
 namespace kvzc {
 
+int rough_search_u8(int log2w, const uint8_t *src, const uint8_t *rec, int stride, int pic_w, int pic_h, uint32_t *costs,
+                    int8_t *best_mode, uint32_t *best_cost, cudaStream_t st);
+
 __global__ void __launch_bounds__(256) select_best_kernel(const uint32_t *__restrict__ costs, int nblk,
                                                           int8_t *__restrict__ mode, uint32_t *__restrict__ best)
 {
@@ -390,6 +393,7 @@ struct kvz_cuda_frame_pass {
   std::vector<uint8_t> host_init;       // initial content of the descriptor sections
   size_t init_off = 0, init_bytes = 0;
   // optional per-stage CUDA-event timing (bench.py's live roofline measurement)
+  bool keep_costs = false;               // also write the [nblk][35] cost tables (device-only section)
   bool timing = false;
   cudaEvent_t ev[KVZ_CUDA_FP_STAGES + 1] = {};
   double ms_acc[KVZ_CUDA_FP_STAGES] = {};
@@ -534,10 +538,9 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
     if (nb == 0) { fp_mark(fp, d * 4 + 1, st); fp_mark(fp, d * 4 + 2, st); fp_mark(fp, d * 4 + 3, st); continue; }
     uint32_t *costs = (uint32_t *)(B + fp->off_costs35[d]);
     int8_t *modes = (int8_t *)(B + L.mode_y[d]);
-    if (int r = kvz_cuda_intra_rough_search_frame(log2w, 8, src, rin, W, W, H, costs, st)) return r;
+    // rough search with the mode selection fused in; the 35-entry cost tables stay on chip unless asked for
+    if (int r = rough_search_u8(log2w, src, rin, W, W, H, fp->keep_costs ? costs : nullptr, modes, (uint32_t *)(B + L.cost_y[d]), st)) return r;
     fp_mark(fp, d * 4 + 1, st);
-    select_best_kernel<<<(nb + 255) / 256, 256, 0, st>>>(costs, nb, modes, (uint32_t *)(B + L.cost_y[d]));
-    KVZC_LAUNCHED();
     fp_mark(fp, d * 4 + 2, st);
     if (int r = launch_recon(qp, src, rin, W, W, H, 0, log2w, W / w, nb, modes, B + fp->off_rec_y[d],
                              (int16_t *)(B + L.coeff_y[d]), B + L.has_y[d], (uint32_t *)(B + L.ssd_y[d]), st)) return r;

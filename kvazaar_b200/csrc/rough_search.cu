@@ -30,7 +30,8 @@ __device__ __forceinline__ uint32_t interp2(uint32_t a, uint32_t b, uint32_t f0,
 template <int LOG2W>
 __global__ void __launch_bounds__(128) rough_search_u8_kernel(const uint8_t *__restrict__ src, const uint8_t *__restrict__ rec,
                                                               int stride, int pic_w, int pic_h, int blocks_x, int nblk,
-                                                              uint32_t *__restrict__ costs)
+                                                              uint32_t *__restrict__ costs, int8_t *__restrict__ best_mode,
+                                                              uint32_t *__restrict__ best_cost)
 {
   constexpr int W = 1 << LOG2W;
   constexpr int S = W >= 8 ? W / 8 : 1, SUBS = S * S, GROUP = 32 / SUBS;
@@ -45,6 +46,7 @@ __global__ void __launch_bounds__(128) rough_search_u8_kernel(const uint8_t *__r
   __shared__ __align__(16) uint8_t s_ext[4][GROUP][ES];          // per-warp scratch: main ref with projected side part
   __shared__ int s_dc[GROUP];
   __shared__ BuildRefCtx s_ctx[GROUP];
+  __shared__ uint32_t s_cost[GROUP][36];                         // per-block cost table for the fused mode selection
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int first = blockIdx.x * GROUP;
@@ -118,7 +120,6 @@ __global__ void __launch_bounds__(128) rough_search_u8_kernel(const uint8_t *__r
     }
   }
 
-  uint32_t *cost_out = costs + (size_t)blk * 35;
   for (int m = warp; m < 35; m += 4) {
     int d[R][K];
     if (m < 2) {
@@ -201,28 +202,45 @@ __global__ void __launch_bounds__(128) rough_search_u8_kernel(const uint8_t *__r
     else cost = (hadamard4x4_lanes(d) + 1) >> 1;
 #pragma unroll
     for (int o = SUBS / 2; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
-    if (valid && sub == 0) cost_out[m] = cost;
+    if (sub == 0) s_cost[g][m] = cost;
+  }
+  __syncthreads();
+  // ---- the 35 costs of every block (optional) and the fused selection: first minimum (search order of the pass)
+  if (costs)
+    for (int e = threadIdx.x; e < GROUP * 35; e += 128) {
+      const int gb = e / 35, m = e - gb * 35;
+      if (first + gb < nblk) costs[(size_t)(first + gb) * 35 + m] = s_cost[gb][m];
+    }
+  if (best_mode && threadIdx.x < GROUP && first + (int)threadIdx.x < nblk) {
+    uint32_t bc = s_cost[threadIdx.x][0];
+    int bm = 0;
+    for (int m = 1; m < 35; ++m) { const uint32_t c = s_cost[threadIdx.x][m]; if (c < bc) { bc = c; bm = m; } }
+    best_mode[first + threadIdx.x] = (int8_t)bm;
+    best_cost[first + threadIdx.x] = bc;
   }
 }
 
 template <int LOG2W>
-static int launch(const uint8_t *src, const uint8_t *rec, int stride, int pic_w, int pic_h, uint32_t *costs, cudaStream_t st)
+static int launch(const uint8_t *src, const uint8_t *rec, int stride, int pic_w, int pic_h, uint32_t *costs, int8_t *best_mode,
+                  uint32_t *best_cost, cudaStream_t st)
 {
   constexpr int W = 1 << LOG2W, SUBS = W >= 8 ? (W / 8) * (W / 8) : 1, GROUP = 32 / SUBS;
   const int bx = pic_w / W, nblk = bx * (pic_h / W);
   if (nblk == 0) return 0;
-  rough_search_u8_kernel<LOG2W><<<(nblk + GROUP - 1) / GROUP, 128, 0, st>>>(src, rec, stride, pic_w, pic_h, bx, nblk, costs);
+  rough_search_u8_kernel<LOG2W><<<(nblk + GROUP - 1) / GROUP, 128, 0, st>>>(src, rec, stride, pic_w, pic_h, bx, nblk, costs, best_mode, best_cost);
   KVZC_LAUNCHED();
   return 0;
 }
 
-int rough_search_u8(int log2w, const uint8_t *src, const uint8_t *rec, int stride, int pic_w, int pic_h, uint32_t *costs, cudaStream_t st)
+// costs (35 per block) and best_mode/best_cost (one per block) are both optional outputs
+int rough_search_u8(int log2w, const uint8_t *src, const uint8_t *rec, int stride, int pic_w, int pic_h, uint32_t *costs,
+                    int8_t *best_mode, uint32_t *best_cost, cudaStream_t st)
 {
   switch (log2w) {
-    case 2: return launch<2>(src, rec, stride, pic_w, pic_h, costs, st);
-    case 3: return launch<3>(src, rec, stride, pic_w, pic_h, costs, st);
-    case 4: return launch<4>(src, rec, stride, pic_w, pic_h, costs, st);
-    default: return launch<5>(src, rec, stride, pic_w, pic_h, costs, st);
+    case 2: return launch<2>(src, rec, stride, pic_w, pic_h, costs, best_mode, best_cost, st);
+    case 3: return launch<3>(src, rec, stride, pic_w, pic_h, costs, best_mode, best_cost, st);
+    case 4: return launch<4>(src, rec, stride, pic_w, pic_h, costs, best_mode, best_cost, st);
+    default: return launch<5>(src, rec, stride, pic_w, pic_h, costs, best_mode, best_cost, st);
   }
 }
 
