@@ -275,6 +275,30 @@ int    kvz_cuda_fp_get_timing(kvz_cuda_frame_pass *fp, double *ms_total /* [KVZ_
 /* host frame in (pinned for async), result blob out (host_bytes): H2D + pass + D2H enqueued on `stream` */
 int    kvz_cuda_fp_run_host(kvz_cuda_frame_pass *fp, const void *src_host, void *result_host, void *stream);
 
+/* ------------------------------------------------------------------ frame-level INTER pass (interpass.cu) */
+/* Every 16x16 luma PU at least one PU away from the picture border: integer full search (+-search_range, SAD),
+ * search_frac-style fractional search (hpel/qpel filter stages + SATD), motion compensation (luma 1/4, chroma 1/8
+ * pel) and inter residual coding + SSD, against one reference frame.  I420, 8-bit. */
+typedef struct { int32_t width, height, bitdepth, qp, search_range; } kvz_cuda_ip_params;
+typedef struct {
+  int32_t npu, pus_x, pus_y;        /* active PUs: pus_x * pus_y, PU (i % pus_x + 1, i / pus_x + 1) of the 16x16 grid */
+  uint64_t host_bytes;
+  uint64_t mv_int;                  /* int16 [npu][2]  integer MV (x, y), full-pel */
+  uint64_t sad_int;                 /* uint32[npu]     its SAD */
+  uint64_t mv_final;                /* int16 [npu][2]  final MV, quarter-pel */
+  uint64_t satd_best;               /* uint32[npu]     its SATD */
+  uint64_t has_y, ssd_y, coeff_y;   /* int32[npu], uint32[npu], int16[npu][256] */
+  uint64_t has_u, has_v, ssd_u, ssd_v, coeff_u, coeff_v;   /* chroma: int16[npu][64] */
+  uint64_t rec;                     /* reconstructed I420 frame (PUs outside the active area stay 0) */
+} kvz_cuda_ip_layout;
+typedef struct kvz_cuda_inter_pass kvz_cuda_inter_pass;
+kvz_cuda_inter_pass *kvz_cuda_ip_create(const kvz_cuda_ip_params *p);
+void  kvz_cuda_ip_destroy(kvz_cuda_inter_pass *ip);
+int   kvz_cuda_ip_layout_for(const kvz_cuda_ip_params *p, kvz_cuda_ip_layout *out);   /* no device needed */
+void *kvz_cuda_ip_result_dev(kvz_cuda_inter_pass *ip);
+int   kvz_cuda_ip_run_dev(kvz_cuda_inter_pass *ip, const void *cur_dev, const void *ref_dev, void *stream);
+int   kvz_cuda_ip_run_host(kvz_cuda_inter_pass *ip, const void *cur_host, const void *ref_host, void *result_host, void *stream);
+
 /* ------------------------------------------------------------------ host-buffer conveniences */
 /* device memory helpers so that C hosts need no CUDA headers */
 void *kvz_cuda_malloc(size_t bytes);

@@ -399,3 +399,81 @@ def fp_sections(layout, width, height):
 def fp_section(blob, sections, name):
     off, dt, n = sections[name]
     return blob[off: off + n * np.dtype(dt).itemsize].view(dt)
+
+
+# ------------------------------------------------------------------ frame-level INTER pass (interpass.cu)
+class IpParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bitdepth", C.c_int32), ("qp", C.c_int32),
+                ("search_range", C.c_int32)]
+
+
+class IpLayout(C.Structure):
+    _fields_ = [("npu", C.c_int32), ("pus_x", C.c_int32), ("pus_y", C.c_int32), ("host_bytes", C.c_uint64)] + \
+               [(n, C.c_uint64) for n in ("mv_int", "sad_int", "mv_final", "satd_best", "has_y", "ssd_y", "coeff_y",
+                                          "has_u", "has_v", "ssd_u", "ssd_v", "coeff_u", "coeff_v", "rec")]
+
+
+def ip_layout_for(width, height, qp=27, search_range=8):
+    lay = IpLayout()
+    prm = IpParams(width, height, 8, qp, search_range)
+    _ck(lib().kvz_cuda_ip_layout_for(C.byref(prm), C.byref(lay)))
+    return lay
+
+
+def ip_sections(layout, width, height):
+    n = layout.npu
+    out = {"mv_int": (layout.mv_int, np.int16, 2 * n), "sad_int": (layout.sad_int, np.uint32, n),
+           "mv_final": (layout.mv_final, np.int16, 2 * n), "satd_best": (layout.satd_best, np.uint32, n),
+           "has_y": (layout.has_y, np.int32, n), "ssd_y": (layout.ssd_y, np.uint32, n), "coeff_y": (layout.coeff_y, np.int16, n * 256),
+           "rec": (layout.rec, np.uint8, width * height * 3 // 2)}
+    for c in "uv":
+        out[f"has_{c}"] = (getattr(layout, f"has_{c}"), np.int32, n)
+        out[f"ssd_{c}"] = (getattr(layout, f"ssd_{c}"), np.uint32, n)
+        out[f"coeff_{c}"] = (getattr(layout, f"coeff_{c}"), np.int16, n * 64)
+    return out
+
+
+class InterPass:
+    """One in-flight frame of the frame-level inter pass."""
+
+    def __init__(self, width, height, qp=27, search_range=8):
+        _torch()
+        L = lib()
+        L.kvz_cuda_ip_create.restype = C.c_void_p
+        L.kvz_cuda_ip_result_dev.restype = C.c_void_p
+        L.kvz_cuda_ip_result_dev.argtypes = [C.c_void_p]
+        self.params = IpParams(width, height, 8, qp, search_range)
+        h = L.kvz_cuda_ip_create(C.byref(self.params))
+        if not h:
+            raise KvzCudaError(f"kvz_cuda_ip_create failed: {L.kvz_cuda_last_error().decode()}")
+        self.h = C.c_void_p(h)
+        self.layout = ip_layout_for(width, height, qp, search_range)
+        self.host_bytes = int(self.layout.host_bytes)
+        self.frame_bytes = width * height * 3 // 2
+
+    def close(self):
+        if self.h:
+            lib().kvz_cuda_ip_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_dev(self, cur, ref):
+        _ck(lib().kvz_cuda_ip_run_dev(self.h, _p(cur), _p(ref), _stream()))
+
+    def run_host(self, cur_host, ref_host, result_host):
+        _ck(lib().kvz_cuda_ip_run_host(self.h, C.c_void_p(cur_host.data_ptr()), C.c_void_p(ref_host.data_ptr()),
+                                       C.c_void_p(result_host.data_ptr()), _stream()))
+
+    def result_host(self):
+        torch = _torch()
+        out = np.empty(self.host_bytes, np.uint8)
+        torch.cuda.current_stream().synchronize()
+        _ck(lib().kvz_cuda_memcpy_d2h(C.c_void_p(out.ctypes.data), C.c_void_p(lib().kvz_cuda_ip_result_dev(self.h)),
+                                      C.c_size_t(self.host_bytes), _stream()))
+        torch.cuda.current_stream().synchronize()
+        return out

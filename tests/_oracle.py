@@ -530,3 +530,13 @@ def ref_frame_pass(ref, src, width, height, qp, layout, nthreads=8, signhide=0, 
     rc = L.kvzref_frame_pass(ctx, P(src), width, height, qp, C.byref(layout), P(blob), nthreads)
     assert rc == 0
     return blob
+
+
+def ref_inter_pass(ref, cur, refframe, width, height, qp, search_range, layout, nthreads=8):
+    """The frame-level inter pass through the compiled reference's own (AVX2) strategy pointers -> result blob."""
+    blob = aligned(int(layout.host_bytes), np.uint8)
+    cur, refframe = al(cur), al(refframe)
+    ctx = ref.ctx(qp, 0, 0, width, height)
+    rc = ref.lib.kvzref_inter_pass(ctx, P(cur), P(refframe), width, height, qp, search_range, C.byref(layout), P(blob), nthreads)
+    assert rc == 0
+    return blob
