@@ -42,7 +42,9 @@ __global__ void __launch_bounds__(256) select_best_kernel(const uint32_t *__rest
 // references -> prediction of the chosen mode -> residual -> DCT/DST -> quant (+ sign hiding) -> dequant -> inverse
 // -> reconstruction, SSD.  All TUs walk the same barrier sequence; data-dependent decisions (has_coeffs,
 // ac_sum < 2) are predicates.  Transforms use the DP2A matrix passes of transform.cuh.
-template <class T, int LOG2W>
+// INTER = true: the same walk for an inter CU's TU grid -- rec_in is then the motion-compensated PREDICTION plane,
+// modes is unused, the scan is diagonal, no DST, and has_out is an int32 array (inter pass blob layout).
+template <class T, int LOG2W, bool INTER = false>
 __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params p, const T *__restrict__ src,
                                                           const T *__restrict__ rec_in, int stride, int pic_w, int pic_h,
                                                           int color, int blocks_x, int nblk,
@@ -66,18 +68,19 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
   const int is_c = color != 0;
   const int first = blockIdx.x * G;
   const int l2 = LOG2W;
-  const bool use_dst = (W == 4 && color == 0);                          // intra luma 4x4, ref: strategies-dct.c:78-96
+  const bool use_dst = (!INTER && W == 4 && color == 0);                // intra luma 4x4, ref: strategies-dct.c:78-96
 
   // ---- references, smoothed references, DC, mode
   for (int gb = threadIdx.x; gb < G; gb += blockDim.x) {
     const int b = min(first + gb, nblk - 1);
-    s_ctx[gb] = build_ref_ctx(LOG2W, color, ((b % blocks_x) * W) << is_c, ((b / blocks_x) * W) << is_c, pic_w, pic_h);
-    s_mode[gb] = first + gb < nblk ? modes[first + gb] : 0;
+    if (!INTER) s_ctx[gb] = build_ref_ctx(LOG2W, color, ((b % blocks_x) * W) << is_c, ((b / blocks_x) * W) << is_c, pic_w, pic_h);
+    s_mode[gb] = (!INTER && first + gb < nblk) ? modes[first + gb] : 0;
     s_has[gb] = 0; s_ac[gb] = 0; s_ssd[gb] = 0;
   }
   load_matrix_packed<W>(s_pf, use_dst, false);
   load_matrix_packed<W>(s_pi, use_dst, true);
   __syncthreads();
+  if (!INTER) {
   for (int e = threadIdx.x; e < G * 2 * NREF; e += blockDim.x) {
     const int gb = e / (2 * NREF), r = e - gb * 2 * NREF;
     const bool is_top = r < NREF;
@@ -93,14 +96,17 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
   }
   for (int gb = threadIdx.x; gb < G; gb += blockDim.x) s_dc[gb] = dc_value(LOG2W, s_ref[gb][0], s_ref[gb][1]);
   __syncthreads();
+  }
 
   // ---- prediction and residual
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
     const int gb = e / WW, r = e - gb * WW, y = r >> LOG2W, x = r & (W - 1), b = first + gb;
     int pv = 0, sv = 0;
     if (b < nblk) {
-      pv = intra_predict_px(LOG2W, s_mode[gb], color, true, s_ref[gb][0], s_ref[gb][1], s_ref[gb][2], s_ref[gb][3], s_dc[gb], x, y);
-      sv = src[(long)((b / blocks_x) * W + y) * stride + (b % blocks_x) * W + x];
+      const long off = (long)((b / blocks_x) * W + y) * stride + (b % blocks_x) * W + x;
+      if (INTER) pv = rec_in[off];
+      else pv = intra_predict_px(LOG2W, s_mode[gb], color, true, s_ref[gb][0], s_ref[gb][1], s_ref[gb][2], s_ref[gb][3], s_dc[gb], x, y);
+      sv = src[off];
     }
     s_pred[e] = (T)pv;
     s_a[e] = (int16_t)(sv - pv);
@@ -193,7 +199,8 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
   __syncthreads();
   for (int gb = threadIdx.x; gb < G; gb += blockDim.x)
     if (first + gb < nblk) {
-      has_out[first + gb] = (uint8_t)s_has[gb];
+      if (INTER) reinterpret_cast<int32_t *>(has_out)[first + gb] = s_has[gb];
+      else has_out[first + gb] = (uint8_t)s_has[gb];
       ssd_out[first + gb] = (uint32_t)(s_ssd[gb] >> (2 * (PixTraits<T>::kBits - 8)));
     }
 }
@@ -361,6 +368,24 @@ __global__ void __launch_bounds__(256) checksum3_kernel(SaoPlanes pl, uint32_t *
 }  // namespace kvzc
 
 using namespace kvzc;
+
+// inter CU residual coding over a TU grid (used by interpass.cu): src/pred/rec point at the grid's first sample
+namespace kvzc {
+int launch_recon_inter(const kvz_cuda_quant_params &qp, const uint8_t *src, const uint8_t *pred, int stride, int color, int log2w,
+                       int blocks_x, int nblk, uint8_t *rec, int16_t *coeff, int32_t *has, uint32_t *ssd, cudaStream_t st)
+{
+  const int ww = 1 << (2 * log2w), g = 1024 / ww, grid = (nblk + g - 1) / g;
+  uint8_t *h8 = reinterpret_cast<uint8_t *>(has);
+  switch (log2w) {
+    case 2: intra_recon_kernel<uint8_t, 2, true><<<grid, 256, 0, st>>>(qp, src, pred, stride, 0, 0, color, blocks_x, nblk, nullptr, rec, coeff, h8, ssd); break;
+    case 3: intra_recon_kernel<uint8_t, 3, true><<<grid, 256, 0, st>>>(qp, src, pred, stride, 0, 0, color, blocks_x, nblk, nullptr, rec, coeff, h8, ssd); break;
+    case 4: intra_recon_kernel<uint8_t, 4, true><<<grid, 256, 0, st>>>(qp, src, pred, stride, 0, 0, color, blocks_x, nblk, nullptr, rec, coeff, h8, ssd); break;
+    default: intra_recon_kernel<uint8_t, 5, true><<<grid, 256, 0, st>>>(qp, src, pred, stride, 0, 0, color, blocks_x, nblk, nullptr, rec, coeff, h8, ssd); break;
+  }
+  KVZC_LAUNCHED();
+  return 0;
+}
+}  // namespace kvzc
 
 static int launch_recon(const kvz_cuda_quant_params &qp, const uint8_t *src, const uint8_t *rin, int stride, int pic_w, int pic_h,
                         int color, int log2w, int blocks_x, int nblk, const int8_t *modes, uint8_t *rec, int16_t *coeff,

@@ -21,34 +21,47 @@ namespace kvzc {
 
 constexpr int PU = 16;
 
-struct IpGeom { int W, H, ax, ay, n, R; };       // ax x ay active PUs starting at PU (1,1)
+struct IpGeom { int W, H, ax, ay, n, R; };
+
+int launch_recon_inter(const kvz_cuda_quant_params &qp, const uint8_t *src, const uint8_t *pred, int stride, int color, int log2w,
+                       int blocks_x, int nblk, uint8_t *rec, int16_t *coeff, int32_t *has, uint32_t *ssd, cudaStream_t st);   // framepass.cu       // ax x ay active PUs starting at PU (1,1)
 
 __device__ __forceinline__ void pu_xy(const IpGeom &g, int i, int &x, int &y) { x = (1 + i % g.ax) * PU; y = (1 + i / g.ax) * PU; }
 
-// 1. integer full search: one CTA per PU, one thread per candidate (ceil((2R+1)^2 / 32) warps)
+// 1. integer full search: one CTA per PU, one thread per candidate (ceil((2R+1)^2 / 32) warps).  The PU and the
+//    search window live in shared memory as 32-bit words; a candidate row is 16 bytes at an arbitrary byte offset:
+//    five aligned words funnel-shifted into four, then __vabsdiffu4 + __dp4a (4 absolute differences per pair).
 __global__ void __launch_bounds__(320) me_full_search_kernel(IpGeom g, const uint8_t *__restrict__ cur, const uint8_t *__restrict__ ref,
                                                              int16_t *__restrict__ mv_int, uint32_t *__restrict__ sad_int)
 {
-  __shared__ uint8_t s_cur[PU * PU];
-  __shared__ uint8_t s_ref[(PU + 16) * (PU + 16 + 4)];
+  constexpr int WSP = 40;                                         // padded window row: (16 + 2*8) bytes + slack, 10 words
+  __shared__ __align__(16) uint32_t s_cur[PU * PU / 4];
+  __shared__ __align__(16) uint32_t s_ref[(PU + 16) * WSP / 4];
   __shared__ unsigned long long s_best;
-  const int R = g.R, D = 2 * R + 1, WS = PU + 2 * R, WSP = WS + 4;
+  const int R = g.R, D = 2 * R + 1, WS = PU + 2 * R;
   int x0, y0;
   pu_xy(g, blockIdx.x, x0, y0);
-  for (int i = threadIdx.x; i < PU * PU; i += blockDim.x) s_cur[i] = cur[(long)(y0 + i / PU) * g.W + x0 + i % PU];
-  for (int i = threadIdx.x; i < WS * WS; i += blockDim.x) {
-    const int yy = i / WS, xx = i - yy * WS;
-    s_ref[yy * WSP + xx] = ref[(long)(y0 - R + yy) * g.W + x0 - R + xx];
+  uint8_t *cb = reinterpret_cast<uint8_t *>(s_cur), *rb = reinterpret_cast<uint8_t *>(s_ref);
+  for (int i = threadIdx.x; i < PU * PU; i += blockDim.x) cb[i] = cur[(long)(y0 + i / PU) * g.W + x0 + i % PU];
+  for (int i = threadIdx.x; i < WS * WSP; i += blockDim.x) {
+    const int yy = i / WSP, xx = i - yy * WSP;
+    rb[i] = xx < WS ? ref[(long)(y0 - R + yy) * g.W + x0 - R + xx] : 0;
   }
   if (threadIdx.x == 0) s_best = ~0ull;
   __syncthreads();
   for (int c = threadIdx.x; c < D * D; c += blockDim.x) {
     const int dy = c / D, dx = c - dy * D;
+    const uint32_t sh = (uint32_t)(dx & 3) * 8;
     uint32_t sad = 0;
+#pragma unroll 4
     for (int y = 0; y < PU; ++y) {
-      const uint8_t *r = s_ref + (dy + y) * WSP + dx;
-#pragma unroll
-      for (int x = 0; x < PU; ++x) sad += (uint32_t)abs((int)s_cur[y * PU + x] - (int)r[x]);
+      const uint32_t *r = s_ref + (dy + y) * (WSP / 4) + (dx >> 2);
+      const uint32_t w0 = r[0], w1 = r[1], w2 = r[2], w3 = r[3], w4 = r[4];
+      const uint4 cw = *reinterpret_cast<const uint4 *>(s_cur + y * 4);
+      sad = __dp4a(__vabsdiffu4(cw.x, __funnelshift_r(w0, w1, sh)), 0x01010101u, sad);
+      sad = __dp4a(__vabsdiffu4(cw.y, __funnelshift_r(w1, w2, sh)), 0x01010101u, sad);
+      sad = __dp4a(__vabsdiffu4(cw.z, __funnelshift_r(w2, w3, sh)), 0x01010101u, sad);
+      sad = __dp4a(__vabsdiffu4(cw.w, __funnelshift_r(w3, w4, sh)), 0x01010101u, sad);
     }
     atomicMin(&s_best, ((unsigned long long)sad << 32) | (unsigned)c);     // first minimum in raster order
   }
@@ -264,19 +277,15 @@ int kvz_cuda_ip_run_dev(kvz_cuda_inter_pass *ip, const void *cur_dev, const void
   if (int r = kvz_cuda_sample_batch(KVZ_CUDA_IPOL_LUMA, 8, ref, W, pred, W, desc_y, n, st)) return r;
   if (int r = kvz_cuda_sample_batch(KVZ_CUDA_IPOL_CHROMA, 8, ref + poff[1], Wc, pred + poff[1], Wc, desc_c, n, st)) return r;
   if (int r = kvz_cuda_sample_batch(KVZ_CUDA_IPOL_CHROMA, 8, ref + poff[2], Wc, pred + poff[2], Wc, desc_c, n, st)) return r;
+  // residual coding of the active PU grid (origin PU (1,1)): one grouped transform/quant/recon/SSD launch per plane
   kvz_cuda_quant_params qp = { ip->prm.qp, 8, 0 /* P slice */, 0, 0 };
-  if (int r = kvz_cuda_quantize_residual_batch(&qp, cur, pred, W, rec, W, (int16_t *)(B + L.coeff_y), (const kvz_cuda_tu *)(B + ip->o_tu_y), n,
-                                               (int32_t *)(B + L.has_y), st)) return r;
-  if (int r = kvz_cuda_block_cost_batch(KVZ_CUDA_OP_SSD, 8, cur, W, rec, W, (const kvz_cuda_blk *)(B + ip->o_ssd_y), n, (uint32_t *)(B + L.ssd_y), st)) return r;
-  for (int c = 1; c <= 2; ++c) {
-    // the chroma TU descriptors carry color = 1; V differs from U only in the dequant type (3 vs 2), which is the
-    // same for flat scaling lists (kvz_get_scaled_qp depends on type != 0 only) -- so one descriptor set serves both
-    if (int r = kvz_cuda_quantize_residual_batch(&qp, cur + poff[c], pred + poff[c], Wc, rec + poff[c], Wc,
-                                                 (int16_t *)(B + (c == 1 ? L.coeff_u : L.coeff_v)), (const kvz_cuda_tu *)(B + ip->o_tu_c), n,
-                                                 (int32_t *)(B + (c == 1 ? L.has_u : L.has_v)), st)) return r;
-    if (int r = kvz_cuda_block_cost_batch(KVZ_CUDA_OP_SSD, 8, cur + poff[c], Wc, rec + poff[c], Wc, (const kvz_cuda_blk *)(B + ip->o_ssd_c), n,
-                                          (uint32_t *)(B + (c == 1 ? L.ssd_u : L.ssd_v)), st)) return r;
-  }
+  const size_t oy = (size_t)PU * W + PU, oc = (size_t)(PU / 2) * Wc + PU / 2;
+  if (int r = launch_recon_inter(qp, cur + oy, pred + oy, W, 0, 4, g.ax, n, rec + oy, (int16_t *)(B + L.coeff_y), (int32_t *)(B + L.has_y),
+                                 (uint32_t *)(B + L.ssd_y), st)) return r;
+  for (int c = 1; c <= 2; ++c)
+    if (int r = launch_recon_inter(qp, cur + poff[c] + oc, pred + poff[c] + oc, Wc, c, 3, g.ax, n, rec + poff[c] + oc,
+                                   (int16_t *)(B + (c == 1 ? L.coeff_u : L.coeff_v)), (int32_t *)(B + (c == 1 ? L.has_u : L.has_v)),
+                                   (uint32_t *)(B + (c == 1 ? L.ssd_u : L.ssd_v)), st)) return r;
   return 0;
 }
 

@@ -87,12 +87,13 @@ __device__ __forceinline__ void load_matrix_packed(uint32_t *P, bool dst, bool t
 
 // STORE_KJ: result stored at out[k*W + j] (what the next pass reads as "row k"), else at out[j*W + k].
 // CLIP: clip to int16 (inverse passes) instead of truncating (forward passes).  blockDim.x == 256, tile = 1024.
-template <int W, bool STORE_KJ, bool CLIP>
+template <int W, bool STORE_KJ, bool CLIP, int G = 1024 / (W * W)>
 __device__ __forceinline__ void mat_pass_dp2a(const int16_t *src, int16_t *out, const uint32_t *P, int shift)
 {
   constexpr int WW = W * W, ITEMS = WW / 4;              // 2x2 output tiles per block
   const int t = threadIdx.x;
   const int gb = t / ITEMS, r = t - gb * ITEMS;
+  if (gb >= G) return;                                   // tiles smaller than 1024 samples leave threads idle
   const int kp = r % (W / 2), jp = r / (W / 2);
   const int k0 = 2 * kp, j0 = 2 * jp;
   const int16_t *s0 = src + gb * WW + j0 * W, *s1 = s0 + W;
@@ -266,11 +267,30 @@ __device__ __forceinline__ void dequant_block(const kvz_cuda_quant_params &p, co
     coef[e] = (int16_t)clip3(-32768, 32767, ((int)q[e] * scale + add) >> shift);
 }
 
+// runtime-width dispatch onto the templated DP2A passes (one TU, 256-thread CTA)
+__device__ __forceinline__ void load_packed_any(uint32_t *P, int n, bool dst, bool transposed)
+{
+  if (n == 4) load_matrix_packed<4>(P, dst, transposed);
+  else if (n == 8) load_matrix_packed<8>(P, dst, transposed);
+  else if (n == 16) load_matrix_packed<16>(P, dst, transposed);
+  else load_matrix_packed<32>(P, dst, transposed);
+}
+template <bool STORE_KJ, bool CLIP>
+__device__ __forceinline__ void pass_any(const int16_t *src, int16_t *out, const uint32_t *P, int n, int shift)
+{
+  if (n == 4) mat_pass_dp2a<4, STORE_KJ, CLIP, 1>(src, out, P, shift);
+  else if (n == 8) mat_pass_dp2a<8, STORE_KJ, CLIP, 1>(src, out, P, shift);
+  else if (n == 16) mat_pass_dp2a<16, STORE_KJ, CLIP, 1>(src, out, P, shift);
+  else mat_pass_dp2a<32, STORE_KJ, CLIP, 1>(src, out, P, shift);
+}
+
 // ---- kvz_quantize_residual for one TU, all threads of the CTA (ref: quant-generic.c:198-292, RDOQ-off branch) ----
 struct TuScratch {
-  int16_t a[32 * 32], b[32 * 32], q[32 * 32];
+  __align__(16) int16_t a[32 * 32];
+  __align__(16) int16_t b[32 * 32];
+  __align__(16) int16_t q[32 * 32];
   int32_t d[32 * 32];
-  int8_t m[32 * 32];
+  __align__(16) int8_t m[32 * 32];      // 4-packed transform matrix (32 * 32 / 4 words)
   int has;
 };
 
@@ -293,14 +313,14 @@ __device__ __forceinline__ int quantize_residual_tu(TuScratch &s, const kvz_cuda
       const int y = e / n, x = e - y * n;
       s.a[e] = (int16_t)((int)ref[y * ref_stride + x] - (int)pred[y * pred_stride + x]);
     }
-    if (!use_trskip) load_matrix(s.m, n, use_dst, true);
+    if (!use_trskip) load_packed_any(reinterpret_cast<uint32_t *>(s.m), n, use_dst, false);
     __syncthreads();
     if (use_trskip) {
       for (int e = threadIdx.x; e < nn; e += blockDim.x) s.b[e] = (int16_t)((uint16_t)s.a[e] << ts_shift);
     } else {
-      fwd_pass(s.a, s.q, s.m, n, 1, l2 - 1 + (p.bitdepth - 8));
+      pass_any<true, false>(s.a, s.q, reinterpret_cast<const uint32_t *>(s.m), n, l2 - 1 + (p.bitdepth - 8));
       __syncthreads();
-      fwd_pass(s.q, s.b, s.m, n, 1, l2 + 6);
+      pass_any<true, false>(s.q, s.b, reinterpret_cast<const uint32_t *>(s.m), n, l2 + 6);
     }
     __syncthreads();
     if (phase == 1) {   // the host runs kvz_rdoq on these coefficients
@@ -329,11 +349,13 @@ __device__ __forceinline__ int quantize_residual_tu(TuScratch &s, const kvz_cuda
       const int off = 1 << (ts_shift - 1);
       for (int e = threadIdx.x; e < nn; e += blockDim.x) s.a[e] = (int16_t)(((int)s.b[e] + off) >> ts_shift);
     } else {
-      load_matrix(s.m, n, use_dst, false);
+      // inverse = the same DP2A passes with A = M^T on the transposed coefficients (see mat_pass_dp2a)
+      for (int e = threadIdx.x; e < nn; e += blockDim.x) { const int y = e / n, x = e - y * n; s.q[x * n + y] = s.b[e]; }
+      load_packed_any(reinterpret_cast<uint32_t *>(s.m), n, use_dst, true);
       __syncthreads();
-      inv_pass(s.b, s.q, s.m, n, 1, 7);
+      pass_any<true, true>(s.q, s.b, reinterpret_cast<const uint32_t *>(s.m), n, 7);
       __syncthreads();
-      inv_pass(s.q, s.a, s.m, n, 1, 12 - (p.bitdepth - 8));
+      pass_any<false, true>(s.b, s.a, reinterpret_cast<const uint32_t *>(s.m), n, 12 - (p.bitdepth - 8));
     }
     __syncthreads();
     for (int e = threadIdx.x; e < nn; e += blockDim.x) {
