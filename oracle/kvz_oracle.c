@@ -1045,3 +1045,174 @@ void orc_array_checksum(const orc_pix *data, int height, int width, int stride, 
   out[0] = (unsigned char)(sum >> 24); out[1] = (unsigned char)(sum >> 16);
   out[2] = (unsigned char)(sum >> 8); out[3] = (unsigned char)sum;
 }
+
+/* ======================================================================================================
+ * Deblocking filter, frame level (ref: src/filter.c:95-792).
+ *
+ * The reference filters LCU by LCU (kvz_filter_deblock_lcu, filter.c:783-792) and delays the rightmost four
+ * columns of every horizontal edge to the next LCU so that horizontal-edge filtering only ever sees columns whose
+ * vertical edges are done.  Per frame this equals the two-pass form restated here: every vertical edge of the
+ * 8x8 grid first, then every horizontal edge on the result.  An edge unit is the left (top) edge of one 8x8
+ * luma block; whether it is filtered is decided from the SCU at the unit's origin (TU or PU boundary,
+ * filter.c:194-246, 711-727); the strength is decided per 4-sample part from the two SCUs across the edge
+ * (filter.c:385-470).
+ *
+ * CU records: 20 bytes per 4x4 SCU, byte-compatible with the reference's cu_info_t on x86-64 SysV
+ * (src/cu.h:126-165); pinned by tests/test_deblock.py::test_cu_record_layout.
+ * ====================================================================================================== */
+static int dbk_tc_table(int i)
+{
+  /* run-length form of the HEVC tc table (filter.c:41-49) */
+  static const unsigned char runs[][2] = { {18,0},{9,1},{4,2},{4,3},{3,4},{2,5},{2,6},{1,7},{1,8},{1,9},{1,10},{1,11},
+                                           {1,13},{1,14},{1,16},{1,18},{1,20},{1,22},{1,24} };
+  for (unsigned r = 0; r < sizeof(runs) / sizeof(runs[0]); ++r) {
+    if (i < runs[r][0]) return runs[r][1];
+    i -= runs[r][0];
+  }
+  return 24;
+}
+static int dbk_beta_table(int i) { return i < 16 ? 0 : (i < 29 ? i - 10 : 2 * i - 38); }   /* filter.c:51-59 */
+
+typedef struct { int type, depth, part_size, tr_depth, cbf, qp, mv_dir; int mv[2][2]; int mv_ref[2]; } dbk_cu;
+static dbk_cu dbk_cu_at(const orc_dbk_params *p, const uint8_t *cus, int x, int y)
+{
+  const uint8_t *r = cus + 20 * ((size_t)(x >> 2) + (size_t)(y >> 2) * p->cu_stride_scu);
+  dbk_cu c;
+  c.type = r[0] & 3; c.depth = (r[0] >> 2) & 7; c.part_size = (r[0] >> 5) & 7;
+  c.tr_depth = r[1] & 7;
+  c.cbf = r[4] | (r[5] << 8);
+  c.qp = r[6];
+  for (int l = 0; l < 2; ++l) for (int k = 0; k < 2; ++k) c.mv[l][k] = (int16_t)(r[8 + 4 * l + 2 * k] | (r[9 + 4 * l + 2 * k] << 8));
+  c.mv_ref[0] = r[16]; c.mv_ref[1] = r[17];
+  c.mv_dir = (r[18] >> 6) & 3;
+  return c;
+}
+static int dbk_edge_wanted(const orc_dbk_params *p, const uint8_t *cus, int x, int y, int hor, int *tu_boundary)
+{
+  const dbk_cu s = dbk_cu_at(p, cus, x, y);
+  const int tu_w = 64 >> s.tr_depth, cu_w = 64 >> s.depth;
+  const int pos = hor ? y : x;
+  *tu_boundary = (pos & (tu_w - 1)) == 0;
+  if (*tu_boundary) return 1;
+  /* PU boundary of the containing CU (filter.c:216-246): the CU origin or the split position */
+  const dbk_cu cu = dbk_cu_at(p, cus, x & ~(cu_w - 1), y & ~(cu_w - 1));
+  const int cu_pos = pos & ~(cu_w - 1);
+  static const int split_x[8] = { 0, 0, 2, 2, 0, 0, 1, 3 }, split_y[8] = { 0, 2, 0, 2, 1, 3, 0, 0 };
+  const int q = hor ? split_y[cu.part_size] : split_x[cu.part_size];
+  return pos == cu_pos || (q && pos == cu_pos + q * cu_w / 4);
+}
+static int dbk_qp(const orc_dbk_params *p, const uint8_t *cus, int x, int y, int hor)
+{
+  if (!p->per_cu_qp) return p->qp;                                     /* filter.c:262-266 */
+  const int qp_p = hor ? dbk_cu_at(p, cus, x, y - 1).qp : dbk_cu_at(p, cus, x - 1, y).qp;
+  return (qp_p + dbk_cu_at(p, cus, x, y).qp + 1) >> 1;
+}
+static int dbk_cbf_y(const dbk_cu *c) { static const int m[5] = { 0x1f, 0x0f, 0x07, 0x03, 0x01 }; return (c->cbf & m[c->tr_depth > 4 ? 4 : c->tr_depth]) != 0; }
+static int dbk_far(const int *a, const int *b) { return abs(a[0] - b[0]) >= 4 || abs(a[1] - b[1]) >= 4; }
+static int dbk_strength(const orc_dbk_params *p, const dbk_cu *P, const dbk_cu *Q, int tu_boundary)
+{
+  if (Q->type == 1 || P->type == 1) return 2;
+  if (tu_boundary && (dbk_cbf_y(Q) || dbk_cbf_y(P))) return 1;
+  if (P->mv_dir != 3 && Q->mv_dir != 3) {
+    /* mv_dir 0 never occurs for a coded inter CU; keep the reference's (dir - 1) & 1 wrap harmless */
+    const int lp = (P->mv_dir - 1) & 1, lq = (Q->mv_dir - 1) & 1;
+    if (dbk_far(Q->mv[lq], P->mv[lp])) return 1;
+    if (Q->mv_ref[lq] != P->mv_ref[lp]) return 1;
+  }
+  if (!p->slice_is_b) return 0;
+  int mvp[2][2], mvq[2][2];
+  for (int l = 0; l < 2; ++l) for (int k = 0; k < 2; ++k) {
+    mvp[l][k] = (P->mv_dir & (1 << l)) ? P->mv[l][k] : 0;
+    mvq[l][k] = (Q->mv_dir & (1 << l)) ? Q->mv[l][k] : 0;
+  }
+  const int rp0 = (P->mv_dir & 1) ? p->ref_LX[0][P->mv_ref[0] & 15] : -1, rp1 = (P->mv_dir & 2) ? p->ref_LX[1][P->mv_ref[1] & 15] : -1;
+  const int rq0 = (Q->mv_dir & 1) ? p->ref_LX[0][Q->mv_ref[0] & 15] : -1, rq1 = (Q->mv_dir & 2) ? p->ref_LX[1][Q->mv_ref[1] & 15] : -1;
+  if (!((rp0 == rq0 && rp1 == rq1) || (rp0 == rq1 && rp1 == rq0))) return 1;
+  const int straight = dbk_far(mvq[0], mvp[0]) || dbk_far(mvq[1], mvp[1]);
+  const int crossed = dbk_far(mvq[1], mvp[0]) || dbk_far(mvq[0], mvp[1]);
+  if (rp0 != rp1) return rp0 == rq0 ? straight : crossed;
+  return straight && crossed;
+}
+
+/* one 4-sample luma part; px points at q0 of line 0, xs = step across the edge, ys = step along it */
+static void dbk_luma_part(orc_pix *px, long xs, long ys, int beta, int tc)
+{
+  int b[4][8];
+  for (int l = 0; l < 4; ++l) for (int i = -4; i < 4; ++i) b[l][i + 4] = px[l * ys + i * xs];
+  const int dp0 = abs(b[0][1] - 2 * b[0][2] + b[0][3]), dq0 = abs(b[0][4] - 2 * b[0][5] + b[0][6]);
+  const int dp3 = abs(b[3][1] - 2 * b[3][2] + b[3][3]), dq3 = abs(b[3][4] - 2 * b[3][5] + b[3][6]);
+  const int dp = dp0 + dp3, dq = dq0 + dq3;
+  if (dp + dq >= beta) return;
+  const int strong = 2 * (dp0 + dq0) < (beta >> 2) && 2 * (dp3 + dq3) < (beta >> 2) &&
+                     abs(b[0][3] - b[0][4]) < ((5 * tc + 1) >> 1) && abs(b[3][3] - b[3][4]) < ((5 * tc + 1) >> 1) &&
+                     abs(b[0][0] - b[0][3]) + abs(b[0][4] - b[0][7]) < (beta >> 3) &&
+                     abs(b[3][0] - b[3][3]) + abs(b[3][4] - b[3][7]) < (beta >> 3);
+  const int side = (beta + (beta >> 1)) >> 3;
+  for (int l = 0; l < 4; ++l) {
+    const int *m = b[l];
+    int o[8];
+    for (int i = 0; i < 8; ++i) o[i] = m[i];
+    if (strong) {                                                       /* filter.c:95-118 */
+      o[1] = ORC_CLIP(m[1] - 2 * tc, m[1] + 2 * tc, (2 * m[0] + 3 * m[1] + m[2] + m[3] + m[4] + 4) >> 3);
+      o[2] = ORC_CLIP(m[2] - 2 * tc, m[2] + 2 * tc, (m[1] + m[2] + m[3] + m[4] + 2) >> 2);
+      o[3] = ORC_CLIP(m[3] - 2 * tc, m[3] + 2 * tc, (m[1] + 2 * m[2] + 2 * m[3] + 2 * m[4] + m[5] + 4) >> 3);
+      o[4] = ORC_CLIP(m[4] - 2 * tc, m[4] + 2 * tc, (m[2] + 2 * m[3] + 2 * m[4] + 2 * m[5] + m[6] + 4) >> 3);
+      o[5] = ORC_CLIP(m[5] - 2 * tc, m[5] + 2 * tc, (m[3] + m[4] + m[5] + m[6] + 2) >> 2);
+      o[6] = ORC_CLIP(m[6] - 2 * tc, m[6] + 2 * tc, (m[3] + m[4] + m[5] + 3 * m[6] + 2 * m[7] + 4) >> 3);
+    } else {                                                            /* filter.c:128-170 */
+      int delta = (9 * (m[4] - m[3]) - 3 * (m[5] - m[2]) + 8) >> 4;
+      if (abs(delta) >= tc * 10) continue;
+      delta = ORC_CLIP(-tc, tc, delta);
+      o[3] = ORC_CLIP(0, ORC_PIXEL_MAX, m[3] + delta);
+      o[4] = ORC_CLIP(0, ORC_PIXEL_MAX, m[4] - delta);
+      if (dp < side) o[2] = ORC_CLIP(0, ORC_PIXEL_MAX, m[2] + ORC_CLIP(-(tc >> 1), tc >> 1, (((m[1] + m[3] + 1) >> 1) - m[2] + delta) >> 1));
+      if (dq < side) o[5] = ORC_CLIP(0, ORC_PIXEL_MAX, m[5] + ORC_CLIP(-(tc >> 1), tc >> 1, (((m[6] + m[4] + 1) >> 1) - m[5] - delta) >> 1));
+    }
+    for (int i = 1; i < 7; ++i) px[l * ys + (i - 4) * xs] = (orc_pix)o[i];
+  }
+}
+static void dbk_chroma_part(orc_pix *px, long xs, long ys, int tc)    /* filter.c:175-192 */
+{
+  for (int l = 0; l < 4; ++l) {
+    orc_pix *s = px + l * ys;
+    const int m2 = s[-2 * xs], m3 = s[-xs], m4 = s[0], m5 = s[xs];
+    const int delta = ORC_CLIP(-tc, tc, (((m4 - m3) * 4) + m2 - m5 + 4) >> 3);
+    s[-xs] = (orc_pix)ORC_CLIP(0, ORC_PIXEL_MAX, m3 + delta);
+    s[0] = (orc_pix)ORC_CLIP(0, ORC_PIXEL_MAX, m4 - delta);
+  }
+}
+
+void orc_deblock_frame(const orc_dbk_params *p, orc_pix *y, orc_pix *u, orc_pix *v, const uint8_t *cus)
+{
+  const int W = p->width, H = p->height, Wc = W / 2;
+  const int scale = 1 << (ORC_BITDEPTH - 8);
+  for (int hor = 0; hor < 2; ++hor) {
+    for (int ey = 0; ey < H; ey += 8) for (int ex = 0; ex < W; ex += 8) {
+      if (hor ? ey == 0 : ex == 0) continue;                            /* filter.c:654-656 */
+      int tu_boundary;
+      if (!dbk_edge_wanted(p, cus, ex, ey, hor, &tu_boundary)) continue;
+      const int qp = dbk_qp(p, cus, ex, ey, hor);
+      const int beta = dbk_beta_table(ORC_CLIP(0, 51, qp + 2 * p->beta_offset_div2)) * scale;
+      for (int part = 0; part < 2; ++part) {
+        const int px = hor ? ex + 4 * part : ex, py = hor ? ey : ey + 4 * part;
+        if (px >= W || py >= H) continue;
+        const dbk_cu Q = dbk_cu_at(p, cus, px, py), P = dbk_cu_at(p, cus, hor ? px : px - 1, hor ? py - 1 : py);
+        const int bs = dbk_strength(p, &P, &Q, tu_boundary);
+        if (!bs) continue;
+        const int tc = dbk_tc_table(ORC_CLIP(0, 53, qp + 2 * (bs - 1) + 2 * p->tc_offset_div2)) * scale;
+        dbk_luma_part(y + (size_t)py * W + px, hor ? W : 1, hor ? 1 : W, beta, tc);
+      }
+      /* chroma: edges on the 8x8 chroma grid, only next to intra CUs (filter.c:560-626, 681-686) */
+      if (u && v && ((hor ? ey : ex) & 15) == 0) {
+        const int cx = ex / 2, cy = ey / 2;
+        if (cx >= Wc || cy >= H / 2) continue;
+        const dbk_cu Q = dbk_cu_at(p, cus, ex, ey), P = dbk_cu_at(p, cus, hor ? ex : ex - 2, hor ? ey - 2 : ey);
+        if (Q.type != 1 && P.type != 1) continue;
+        const int qpc = chroma_scale(dbk_qp(p, cus, ex, ey, hor));
+        const int tc = dbk_tc_table(ORC_CLIP(0, 53, qpc + 2 + 2 * p->tc_offset_div2)) * scale;
+        dbk_chroma_part(u + (size_t)cy * Wc + cx, hor ? Wc : 1, hor ? 1 : Wc, tc);
+        dbk_chroma_part(v + (size_t)cy * Wc + cx, hor ? Wc : 1, hor ? 1 : Wc, tc);
+      }
+    }
+  }
+}

@@ -141,6 +141,19 @@ void orc_sao_reconstruct_color(int bitdepth, const orc_pix *rec, orc_pix *new_re
 /* ---- nal group (nal-generic.c) ---- */
 void orc_array_checksum(const orc_pix *data, int height, int width, int stride, unsigned char out[4]);
 
+/* ---- deblocking, frame level (filter.c:95-792) ---- */
+typedef struct {
+  int32_t width, height;          /* luma size, multiples of 8 */
+  int32_t qp;                     /* state->qp, used when per_cu_qp == 0 (max_qp_delta_depth < 0) */
+  int32_t beta_offset_div2, tc_offset_div2;
+  int32_t slice_is_b;             /* frame->slicetype == KVZ_SLICE_B */
+  int32_t per_cu_qp;
+  int32_t cu_stride_scu;          /* cu_array stride in 4x4 SCUs */
+  uint8_t ref_LX[2][16];          /* frame->ref_LX (encoderstate.h:125) */
+} orc_dbk_params;
+/* cus: 20-byte records per SCU in the reference's cu_info_t memory layout; planes are filtered in place */
+void orc_deblock_frame(const orc_dbk_params *p, orc_pix *y, orc_pix *u, orc_pix *v, const uint8_t *cus);
+
 #ifdef __cplusplus
 }
 #endif

@@ -317,3 +317,53 @@ void kvzref_array_checksum(const char *impl, const kvz_pixel *data, int height, 
   ((cksum_fn *)kvzref_find("array_checksum", impl))(data, height, width, stride, tmp, KVZ_BIT_DEPTH);
   memcpy(out, tmp, 4);
 }
+
+/* ---- deblocking (not a strategy: kvz_filter_deblock_lcu, filter.c:783) ---- */
+#include "filter.h"
+int kvzref_sizeof_cu_info(void) { return (int)sizeof(cu_info_t); }
+/* build one cu_info_t through the reference's own bitfields, for pinning the 20-byte record layout */
+void kvzref_make_cu_info(int type, int depth, int part_size, int tr_depth, int cbf, int qp, int mv_dir,
+                         const int16_t mv[4], const uint8_t mv_ref[2], uint8_t *out)
+{
+  cu_info_t cu; memset(&cu, 0, sizeof(cu));
+  cu.type = type; cu.depth = depth; cu.part_size = part_size; cu.tr_depth = tr_depth; cu.cbf = (uint16_t)cbf; cu.qp = (uint8_t)qp;
+  if (type != CU_INTRA) {
+    cu.inter.mv[0][0] = mv[0]; cu.inter.mv[0][1] = mv[1]; cu.inter.mv[1][0] = mv[2]; cu.inter.mv[1][1] = mv[3];
+    cu.inter.mv_ref[0] = mv_ref[0]; cu.inter.mv_ref[1] = mv_ref[1]; cu.inter.mv_dir = mv_dir;
+  }
+  memcpy(out, &cu, sizeof(cu));
+}
+int kvzref_deblock_frame(kvzref_ctx *c, kvz_pixel *y, kvz_pixel *u, kvz_pixel *v, const uint8_t *cus, int cu_stride_scu,
+                         int qp, int beta_offset_div2, int tc_offset_div2, int slice_type, int per_cu_qp, const uint8_t *ref_LX)
+{
+  encoder_state_t *st = &c->enc->states[0];
+  videoframe_t *frame = st->tile->frame;
+  encoder_control_t *ctrl = (encoder_control_t *)st->encoder_control;
+  const int W = frame->width, H = frame->height;
+  if (!frame->rec) frame->rec = kvz_image_alloc(KVZ_CSP_420, W, H);
+  if (!frame->cu_array) frame->cu_array = kvz_cu_array_alloc(W, H);
+  if (!frame->rec || !frame->cu_array) return -1;
+  cu_array_t *cua = frame->cu_array;
+  const int scu_w = cua->stride / 4, scu_h = cua->height / 4;
+  for (int r = 0; r < scu_h && r * 4 < ((H + 3) & ~3); ++r)
+    memcpy(&cua->data[(size_t)r * scu_w], cus + (size_t)r * cu_stride_scu * sizeof(cu_info_t), (size_t)((W + 3) / 4) * sizeof(cu_info_t));
+  kvz_picture *rec = frame->rec;
+  for (int r = 0; r < H; ++r) memcpy(rec->y + (size_t)r * rec->stride, y + (size_t)r * W, (size_t)W * sizeof(kvz_pixel));
+  for (int r = 0; r < H / 2; ++r) {
+    memcpy(rec->u + (size_t)r * (rec->stride / 2), u + (size_t)r * (W / 2), (size_t)(W / 2) * sizeof(kvz_pixel));
+    memcpy(rec->v + (size_t)r * (rec->stride / 2), v + (size_t)r * (W / 2), (size_t)(W / 2) * sizeof(kvz_pixel));
+  }
+  st->qp = (int8_t)qp;
+  st->frame->slicetype = (enum kvz_slice_type)slice_type;
+  st->frame->max_qp_delta_depth = per_cu_qp ? 0 : -1;
+  if (ref_LX) memcpy(st->frame->ref_LX, ref_LX, 32);
+  ctrl->cfg.deblock_beta = (int8_t)beta_offset_div2; ctrl->cfg.deblock_tc = (int8_t)tc_offset_div2;
+  for (int ly = 0; ly < H; ly += LCU_WIDTH) for (int lx = 0; lx < W; lx += LCU_WIDTH) kvz_filter_deblock_lcu(st, lx, ly);
+  for (int r = 0; r < H; ++r) memcpy(y + (size_t)r * W, rec->y + (size_t)r * rec->stride, (size_t)W * sizeof(kvz_pixel));
+  for (int r = 0; r < H / 2; ++r) {
+    memcpy(u + (size_t)r * (W / 2), rec->u + (size_t)r * (rec->stride / 2), (size_t)(W / 2) * sizeof(kvz_pixel));
+    memcpy(v + (size_t)r * (W / 2), rec->v + (size_t)r * (rec->stride / 2), (size_t)(W / 2) * sizeof(kvz_pixel));
+  }
+  st->frame->max_qp_delta_depth = -1;
+  return 0;
+}

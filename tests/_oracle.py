@@ -63,6 +63,95 @@ def build_ref(bitdepth=8):
     return so if os.path.exists(so) else None
 
 
+class DbkParams(C.Structure):
+    """orc_dbk_params / kvz_cuda_dbk_params (same field order)."""
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("qp", C.c_int32), ("beta_offset_div2", C.c_int32),
+                ("tc_offset_div2", C.c_int32), ("slice_is_b", C.c_int32), ("per_cu_qp", C.c_int32),
+                ("cu_stride_scu", C.c_int32), ("ref_LX", C.c_uint8 * 32)]
+
+
+def make_cu_records(type_, depth, part_size, tr_depth, cbf, qp, mv_dir, mv, mv_ref):
+    """Pack per-SCU field arrays into 20-byte records (the reference's cu_info_t layout on x86-64,
+    src/cu.h:126-165; pinned against the compiled reference by tests/test_deblock.py)."""
+    shape = np.shape(type_)
+    r = np.zeros(shape + (20,), np.uint8)
+    r[..., 0] = (np.asarray(type_) & 3) | ((np.asarray(depth) & 7) << 2) | ((np.asarray(part_size) & 7) << 5)
+    r[..., 1] = np.asarray(tr_depth) & 7
+    cbf = np.asarray(cbf).astype(np.uint16)
+    r[..., 4] = cbf & 0xff
+    r[..., 5] = cbf >> 8
+    r[..., 6] = qp
+    inter = np.asarray(type_) != 1
+    mvb = np.ascontiguousarray(np.asarray(mv, np.int16)).view(np.uint8).reshape(shape + (8,))
+    r[..., 8:16] = np.where(inter[..., None], mvb, 0)
+    r[..., 16] = np.where(inter, np.asarray(mv_ref)[..., 0], 0)
+    r[..., 17] = np.where(inter, np.asarray(mv_ref)[..., 1], 0)
+    r[..., 18] = np.where(inter, (np.asarray(mv_dir) & 3) << 6, 0)
+    return r
+
+
+def random_cu_grid(rng, width, height, intra_only=False, p_split=(0.7, 0.6, 0.5), max_mv=24):
+    """Random CU/TU quadtree per 64x64 LCU -> [rows_scu, stride_scu, 20] records (stride padded to whole LCUs,
+    like kvz_cu_array_alloc, cu.c:113-131)."""
+    ws, hs = (width + 63) // 64 * 16, (height + 63) // 64 * 16
+    f = {k: np.zeros((hs, ws), np.int32) for k in ("type", "depth", "part", "trd", "cbf", "qp", "dir")}
+    mv = np.zeros((hs, ws, 4), np.int16)
+    mref = np.zeros((hs, ws, 2), np.uint8)
+
+    def leaf(x, y, d):
+        w = 16 >> d                                      # in SCUs
+        intra = intra_only or rng.random() < 0.4
+        if intra:
+            part = 3 if (d == 3 and rng.random() < 0.5) else 0
+        else:
+            part = int(rng.integers(0, 8)) if d < 3 else int(rng.integers(0, 3))
+            if d == 0 and part > 3:
+                part = int(rng.integers(0, 3))
+        trd = max(d, 1)
+        if part == 3:
+            trd = 4
+        elif rng.random() < 0.5 and trd < 3:
+            trd += 1
+        sl = (slice(y, y + w), slice(x, x + w))
+        f["type"][sl] = 1 if intra else 2
+        f["depth"][sl] = d
+        f["part"][sl] = part
+        f["trd"][sl] = trd
+        f["qp"][sl] = int(rng.integers(20, 40))
+        # per-TU cbf bits for luma (bit 0x10 >> tr_depth) so cbf_is_set(cbf, tr_depth, Y) varies between TUs
+        tw = max(16 >> trd, 1)
+        for ty in range(y, y + w, tw):
+            for tx in range(x, x + w, tw):
+                f["cbf"][ty:ty + tw, tx:tx + tw] = (0x10 >> trd) if rng.random() < 0.5 else 0
+        if not intra:
+            # one motion per PU: approximate with per-half randomness so PU edges separate different motion
+            for hy in range(2):
+                for hx in range(2):
+                    sub = (slice(y + hy * w // 2, y + (hy + 1) * w // 2 if w > 1 else y + 1),
+                           slice(x + hx * w // 2, x + (hx + 1) * w // 2 if w > 1 else x + 1))
+                    if w == 1 and (hx or hy):
+                        continue
+                    same = rng.random() < 0.5
+                    base = rng.integers(-max_mv, max_mv + 1, 4)
+                    f["dir"][sub] = int(rng.integers(1, 4))
+                    mv[sub] = base if not same else np.array([4, -4, 8, 0])
+                    mref[sub] = rng.integers(0, 2, 2)
+
+    def rec(x, y, d):
+        if d < 3 and rng.random() < p_split[d]:
+            h = 8 >> d
+            for dy in (0, h):
+                for dx in (0, h):
+                    rec(x + dx, y + dy, d + 1)
+        else:
+            leaf(x, y, d)
+
+    for ly in range(0, hs, 16):
+        for lx in range(0, ws, 16):
+            rec(lx, ly, 0)
+    return make_cu_records(f["type"], f["depth"], f["part"], f["trd"], f["cbf"], f["qp"], f["dir"], mv.reshape(hs, ws, 2, 2), mref)
+
+
 class Oracle:
     def __init__(self, bitdepth=8):
         self.lib = C.CDLL(build_oracle(bitdepth))
@@ -274,6 +363,17 @@ class Oracle:
         out = np.zeros(4, np.uint8)
         self.lib.orc_array_checksum(P(data), height, width, stride, P(out))
         return out
+
+    # -- deblocking (frame level)
+    def deblock_frame(self, y, u, v, cus, width, height, qp, beta=0, tc=0, slice_is_b=0, per_cu_qp=0, ref_lx=None):
+        """y/u/v: flat planes (copied); cus: uint8 [rows_scu, stride_scu, 20].  Returns filtered (y, u, v)."""
+        prm = DbkParams(width, height, qp, beta, tc, slice_is_b, per_cu_qp, cus.shape[1])
+        if ref_lx is not None:
+            C.memmove(prm.ref_LX, np.ascontiguousarray(ref_lx, np.uint8).ctypes.data, 32)
+        y, u, v = y.copy(), u.copy(), v.copy()
+        cus = np.ascontiguousarray(cus)
+        self.lib.orc_deblock_frame(C.byref(prm), P(y), P(u), P(v), P(cus))
+        return y, u, v
 
 
 class Ref:
@@ -510,6 +610,21 @@ class Ref:
                                               C.c_void_p(rec_arr.ctypes.data + origin_off * rec_arr.itemsize), P(out),
                                               sao_type, eo, P(bp), P(of), stride, new_stride, bw, bh, color)
         return out
+
+    # -- deblocking (kvz_filter_deblock_lcu over every LCU of a frame)
+    def deblock_frame(self, y, u, v, cus, width, height, qp, beta=0, tc=0, slice_type=2, per_cu_qp=0, ref_lx=None):
+        y, u, v = al(y), al(u), al(v)
+        cus = al(np.ascontiguousarray(cus).ravel())
+        lx = al(np.asarray(ref_lx, np.uint8).ravel()) if ref_lx is not None else None
+        rc = self.lib.kvzref_deblock_frame(self.ctx(qp, 0, 0, width, height), P(y), P(u), P(v), P(cus), cus.size // 20 // ((height + 63) // 64 * 16),
+                                           qp, beta, tc, slice_type, per_cu_qp, P(lx))
+        assert rc == 0
+        return y, u, v
+
+    def make_cu_info(self, type_, depth, part_size, tr_depth, cbf, qp, mv_dir, mv, mv_ref):
+        out = aligned(32, np.uint8)
+        self.lib.kvzref_make_cu_info(type_, depth, part_size, tr_depth, cbf, qp, mv_dir, P(al(mv, np.int16)), P(al(mv_ref, np.uint8)), P(out))
+        return out[:self.lib.kvzref_sizeof_cu_info()].copy()
 
     # -- nal
     def array_checksum(self, data, height, width, stride, impl="generic"):
