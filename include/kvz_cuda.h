@@ -300,6 +300,30 @@ int   kvz_cuda_ip_run_dev(kvz_cuda_inter_pass *ip, const void *cur_dev, const vo
 int   kvz_cuda_ip_run_host(kvz_cuda_inter_pass *ip, const void *cur_host, const void *ref_host, void *result_host, void *stream);
 
 /* ------------------------------------------------------------------ host-buffer conveniences */
+/* ---------------------------------------------------------------------------------------------------------
+ * Deblocking filter, frame level.  Replaces the per-LCU kvz_filter_deblock_lcu
+ * (src/filter.c:783-792, called from encoder_state_worker_encode_lcu_search, src/encoderstate.c:669-675) by two
+ * passes over the frame (all vertical edges, then all horizontal edges) -- the same result, see csrc/deblock.cu.
+ * `cus`: one 20-byte record per 4x4 SCU = the memory image of the reference's cu_info_t (src/cu.h:126-165,
+ * x86-64 SysV), row stride cu_stride_scu records: a binding passes frame->cu_array->data and stride / 4.
+ * Planes are filtered in place.  U/V may both be NULL (4:0:0).
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct kvz_cuda_dbk_params {
+  int32_t width, height;           /* luma size, multiples of 8 */
+  int32_t qp;                      /* state->qp, used when per_cu_qp == 0 (frame->max_qp_delta_depth < 0, filter.c:262) */
+  int32_t beta_offset_div2;        /* cfg.deblock_beta */
+  int32_t tc_offset_div2;          /* cfg.deblock_tc */
+  int32_t slice_is_b;              /* frame->slicetype == KVZ_SLICE_B (filter.c:404) */
+  int32_t per_cu_qp;               /* average the cu_info_t.qp of both sides (filter.c:268-282) */
+  int32_t cu_stride_scu;           /* cu_array->stride / 4 */
+  uint8_t ref_LX[2][16];           /* frame->ref_LX (src/encoderstate.h:125), B slices only */
+} kvz_cuda_dbk_params;
+int kvz_cuda_deblock_frame(const kvz_cuda_dbk_params *p, int bitdepth, void *y_dev, void *u_dev, void *v_dev,
+                           const void *cus_dev, void *stream);
+/* host buffers (kvz_picture planes with luma stride `stride`, chroma stride / 2); synchronous */
+int kvz_cuda_call_deblock_frame(const kvz_cuda_dbk_params *p, int bitdepth, void *y, void *u, void *v, int stride,
+                                const void *cus);
+
 /* device memory helpers so that C hosts need no CUDA headers */
 void *kvz_cuda_malloc(size_t bytes);
 void  kvz_cuda_free(void *p);

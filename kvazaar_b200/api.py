@@ -293,6 +293,35 @@ def array_checksum(data, height, width, stride, out=None):
     return out
 
 
+# ------------------------------------------------------------------ deblocking (deblock.cu)
+class DbkParams(C.Structure):
+    """kvz_cuda_dbk_params."""
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("qp", C.c_int32), ("beta_offset_div2", C.c_int32),
+                ("tc_offset_div2", C.c_int32), ("slice_is_b", C.c_int32), ("per_cu_qp", C.c_int32),
+                ("cu_stride_scu", C.c_int32), ("ref_LX", C.c_uint8 * 32)]
+
+
+def deblock_frame(y, u, v, cus, width, height, qp, beta_offset_div2=0, tc_offset_div2=0, slice_is_b=0, per_cu_qp=0,
+                  ref_lx=None):
+    """kvz_filter_deblock_lcu over a whole frame (src/filter.c:783), in place on the CUDA plane tensors.
+    `cus`: uint8 CUDA tensor [rows_scu, stride_scu, 20] -- the reference's cu_info_t records."""
+    prm = DbkParams(width, height, qp, beta_offset_div2, tc_offset_div2, slice_is_b, per_cu_qp, int(cus.shape[1]))
+    if ref_lx is not None:
+        C.memmove(prm.ref_LX, np.ascontiguousarray(ref_lx, np.uint8).ctypes.data, 32)
+    _ck(lib().kvz_cuda_deblock_frame(C.byref(prm), _bits(y), _p(y), _p(u), _p(v), _p(cus), _stream()))
+    return y, u, v
+
+
+def call_deblock_frame(y, u, v, stride, cus, width, height, qp, beta_offset_div2=0, tc_offset_div2=0, slice_is_b=0,
+                       per_cu_qp=0, ref_lx=None, bitdepth=8):
+    """Host-buffer form (numpy arrays, in place) -- what the binding in INTEGRATION.md calls."""
+    prm = DbkParams(width, height, qp, beta_offset_div2, tc_offset_div2, slice_is_b, per_cu_qp, int(cus.shape[1]))
+    if ref_lx is not None:
+        C.memmove(prm.ref_LX, np.ascontiguousarray(ref_lx, np.uint8).ctypes.data, 32)
+    _ck(lib().kvz_cuda_call_deblock_frame(C.byref(prm), bitdepth, C.c_void_p(y.ctypes.data), C.c_void_p(u.ctypes.data),
+                                          C.c_void_p(v.ctypes.data), stride, C.c_void_p(cus.ctypes.data)))
+
+
 # ------------------------------------------------------------------ frame-level pass (framepass.cu)
 class FpParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bitdepth", C.c_int32), ("qp", C.c_int32),

@@ -85,3 +85,46 @@ def test_oracle_deblock_10bit(orc10, ref10):
     got = orc10.deblock_frame(y, u, v, cus, w, h, 30, 0, 0, 0, 0, None)
     for a, b in zip(got, want):
         assert np.array_equal(a, np.asarray(b))
+
+
+# ---------------------------------------------------------------------------------------------- GPU parity
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", CASES + [(1920, 1080, 27, 0, 0, 2, 0, True), (832, 480, 32, 1, -1, 0, 1, False)])
+def test_cuda_deblock_vs_oracle_and_reference(cuda_lib, orc, ref, case):
+    from kvazaar_b200 import api
+    w, h, qp, beta, tc, slice_type, per_cu_qp, intra_only = case
+    rng = np.random.default_rng(hash(case) & 0xffff)
+    y, u, v = rough_frame(rng, w, h)
+    cus = random_cu_grid(rng, w, h, intra_only=intra_only)
+    ref_lx = rng.integers(0, 3, (2, 16)).astype(np.uint8)
+    want = orc.deblock_frame(y, u, v, cus, w, h, qp, beta, tc, int(slice_type == 0), per_cu_qp, ref_lx)
+    dy, du, dv = api.to_dev(y), api.to_dev(u), api.to_dev(v)
+    api.deblock_frame(dy, du, dv, api.to_dev(cus), w, h, qp, beta, tc, int(slice_type == 0), per_cu_qp, ref_lx)
+    for name, a, b in zip("yuv", (dy, du, dv), want):
+        assert np.array_equal(a.cpu().numpy(), b), f"plane {name} differs from the oracle"
+    if w * h <= 832 * 480:
+        rw = ref.deblock_frame(y, u, v, cus, w, h, qp, beta, tc, slice_type, per_cu_qp, ref_lx)
+        for a, b in zip((dy, du, dv), rw):
+            assert np.array_equal(a.cpu().numpy(), np.asarray(b))
+    # host-buffer form with a padded stride
+    stride = w + 16
+    hy = np.zeros((h, stride), np.uint8); hy[:, :w] = y.reshape(h, w)
+    hu = np.zeros((h // 2, stride // 2), np.uint8); hu[:, :w // 2] = u.reshape(h // 2, w // 2)
+    hv = np.zeros((h // 2, stride // 2), np.uint8); hv[:, :w // 2] = v.reshape(h // 2, w // 2)
+    api.call_deblock_frame(hy, hu, hv, stride, np.ascontiguousarray(cus), w, h, qp, beta, tc, int(slice_type == 0), per_cu_qp, ref_lx)
+    assert np.array_equal(hy[:, :w].ravel(), want[0]) and np.array_equal(hu[:, :w // 2].ravel(), want[1])
+    assert np.array_equal(hv[:, :w // 2].ravel(), want[2])
+
+
+@pytest.mark.gpu
+def test_cuda_deblock_10bit(cuda_lib, orc10):
+    from kvazaar_b200 import api
+    rng = np.random.default_rng(78)
+    w, h = 320, 136
+    y, u, v = rough_frame(rng, w, h, 10)
+    cus = random_cu_grid(rng, w, h)
+    want = orc10.deblock_frame(y, u, v, cus, w, h, 33, 0, 0, 0, 0, None)
+    dy, du, dv = api.to_dev(y), api.to_dev(u), api.to_dev(v)
+    api.deblock_frame(dy, du, dv, api.to_dev(cus), w, h, 33)
+    for a, b in zip((dy, du, dv), want):
+        assert np.array_equal(a.cpu().numpy().view(np.uint16), b)
