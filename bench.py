@@ -256,10 +256,10 @@ def run_cuda(args):
     L.kvz_cuda_fp_set_timing(fp.h, 0)
     stage_ms = [ms_stage[i] / max(1, runs.value) for i in range(20)]
     names = [f"{k}_w{32 >> d}" for d in range(4) for k in ("rough_search", "select", "recon_luma", "recon_chroma")] + \
-            ["sao_stats", "sao_ddist", "sao_reconstruct", "checksum"]
+            ["deblock", "sao_stats_decide", "sao_reconstruct", "checksum"]
     stages = {names[i]: round(stage_ms[i], 4) for i in range(20)}
     # per-LAUNCH time of each kernel (the chroma stage holds two launches: U and V)
-    per_launch = [stage_ms[i] / (2 if names[i].startswith("recon_chroma") else 1) for i in range(20)]
+    per_launch = [stage_ms[i] / (2 if names[i].startswith("recon_chroma") or names[i] == "deblock" else 1) for i in range(20)]
     dom = int(np.argmax(per_launch))
     ncu = {}
     try:
@@ -278,7 +278,9 @@ def run_cuda(args):
         if kind == "recon_chroma":       # one of the two chroma planes, blocks of w/2
             wc = w // 2
             return (W // w) * (H // w) * (wc * wc + 4 * wc + 1 + wc * wc + 2 * wc * wc + 5)
-        if kind == "sao_stats":          # source + reconstruction of all three planes in, 40+4+1 ints per CTU-plane out
+        if kind == "deblock":            # per pass (launch): the three reconstruction planes in and out + 20-byte CU records in
+            return 2 * W * H * 3 // 2 + (W // 4) * (H // 4) * 20
+        if kind == "sao_stats_decide":   # source + reconstruction of all three planes in, 40+4+1 ints per CTU-plane out
             return 2 * W * H * 3 // 2 + 3 * ((W + 63) // 64) * ((H + 63) // 64) * 46 * 4
         return None
 
@@ -287,7 +289,7 @@ def run_cuda(args):
     if alg:
         ach = alg / (per_launch[dom] / 1000.0) / 1e9
         kname = {"rough_search": "rough_search_u8_kernel", "recon_luma": "intra_recon_kernel", "recon_chroma": "intra_recon_kernel",
-                 "sao_stats": "sao_ctu_kernel"}.get(names[dom].rsplit("_w", 1)[0], names[dom])
+                 "sao_stats_decide": "sao_ctu_kernel", "deblock": "deblock_pass_kernel"}.get(names[dom].rsplit("_w", 1)[0], names[dom])
         roof = {"kernel": f"{kname} [{names[dom]}]", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": ncu.get(names[dom], {}).get("dram_bytes_per_launch"), "ms_per_launch": per_launch[dom],
                 "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,

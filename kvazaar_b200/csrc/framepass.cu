@@ -9,6 +9,8 @@
 //                          kvz_quantize_residual's RDOQ-off branch, quant-generic.c:198-292; kvz_pixels_calc_ssd)
 //   4. chroma recon      : same for U and V with w/2 blocks and the co-located luma mode (d = 0..2)
 // then on the 8x8-level reconstruction:
+//   4b. deblocking       : every 8x8 edge of that uniform intra quadtree, luma + chroma, in place
+//                          (kvz_filter_deblock_lcu, filter.c:783-792; csrc/deblock.cu)
 //   5. SAO               : edge statistics (4 classes), offsets, edge / band delta-distortion, reconstruction per CTU
 //                          (sao_search_*, sao.c:605-669 and kvz_sao_reconstruct, sao.c:302-361 call shapes)
 //   6. picture checksum  : array_checksum of the three SAO-filtered planes          (nal.c:77-86)
@@ -414,7 +416,7 @@ struct kvz_cuda_frame_pass {
   uint8_t *blob = nullptr;              // device: host-visible sections first, device-only sections after
   // device-only
   size_t off_costs35[4], off_rec_y[4], off_rec_u[3], off_rec_v[3];
-  size_t off_sao_blk, off_sao_desc, off_sao_off, off_eo[4], off_bandpos, off_bands, off_src_copy;
+  size_t off_sao_off, off_dbk_cus, off_src_copy;
   std::vector<uint8_t> host_init;       // initial content of the descriptor sections
   size_t init_off = 0, init_bytes = 0;
   // optional per-stage CUDA-event timing (bench.py's live roofline measurement)
@@ -479,39 +481,20 @@ static kvz_cuda_frame_pass *fp_build(const kvz_cuda_fp_params *p, bool alloc)
   for (int d = 0; d < 3; ++d) { fp->off_rec_u[d] = take((size_t)W * H / 4); fp->off_rec_v[d] = take((size_t)W * H / 4); }
   fp->off_sao_off = take(4 * (size_t)4 * fp->nctu3 * 5);
   fp->off_src_copy = take((size_t)W * H * 3 / 2);
-  // descriptor sections, initialised from the host once
+  // deblocking input: the CU records of the uniform 8x8 intra quadtree whose reconstruction SAO works on
+  // (cu_info_t image: type = CU_INTRA, depth = 3, part_size = 2Nx2N, tr_depth = 3), initialised from the host once
   fp->init_off = off;
-  fp->off_sao_blk = take(sizeof(kvz_cuda_sao_blk) * fp->nctu3);
-  fp->off_sao_desc = take(sizeof(kvz_cuda_sao_rec) * fp->nctu3);
-  for (int e = 0; e < 4; ++e) fp->off_eo[e] = take(fp->nctu3);
-  fp->off_bandpos = take(4 * (size_t)fp->nctu3);
-  fp->off_bands = take(4 * (size_t)fp->nctu3 * 4);
+  fp->off_dbk_cus = take((size_t)(W / 4) * (H / 4) * 20);
   fp->init_bytes = off - fp->init_off;
   fp->total_bytes = off;
-  fp->host_init.assign(fp->init_bytes, 0);
-  uint8_t *base = fp->host_init.data() - fp->init_off;
-  kvz_cuda_sao_blk *blk = (kvz_cuda_sao_blk *)(base + fp->off_sao_blk);
-  kvz_cuda_sao_rec *desc = (kvz_cuda_sao_rec *)(base + fp->off_sao_desc);
-  int32_t *bandpos = (int32_t *)(base + fp->off_bandpos), *bands = (int32_t *)(base + fp->off_bands);
-  // planes of the I420 frame: offsets and strides
-  const size_t poff[3] = { 0, (size_t)W * H, (size_t)W * H * 5 / 4 };
-  for (int i = 0; i < fp->nctu3; ++i) {
-    const int color = i / nctu, ctu = i % nctu, x0 = (ctu % cx) * 64 >> (color ? 1 : 0), y0 = (ctu / cx) * 64 >> (color ? 1 : 0);
-    const int Wp = color ? W / 2 : W, Hp = color ? H / 2 : H, lw = color ? 32 : 64;
-    const int bw = Wp - x0 < lw ? Wp - x0 : lw, bh = Hp - y0 < lw ? Hp - y0 : lw;
-    blk[i].off_orig = (int32_t)(poff[color] + (size_t)y0 * Wp + x0);
-    blk[i].off_rec = (int32_t)((size_t)y0 * Wp + x0);      // relative to the plane passed per colour (see run)
-    blk[i].bw = (int16_t)bw; blk[i].bh = (int16_t)bh; blk[i].stride_orig = Wp; blk[i].stride_rec = Wp;
-    // reconstruction rectangle: the CTU area minus the 1-pixel picture border (neighbours must exist)
-    const int rx0 = x0 < 1 ? 1 : x0, ry0 = y0 < 1 ? 1 : y0;
-    const int rx1 = x0 + bw > Wp - 1 ? Wp - 1 : x0 + bw, ry1 = y0 + bh > Hp - 1 ? Hp - 1 : y0 + bh;
-    desc[i].off_rec = (int32_t)((size_t)ry0 * Wp + rx0);
-    desc[i].off_new = (int32_t)(poff[color] + (size_t)ry0 * Wp + rx0);
-    desc[i].bw = (int16_t)(rx1 - rx0); desc[i].bh = (int16_t)(ry1 - ry0);
-    desc[i].color = (int8_t)color;
-    for (int e = 0; e < 4; ++e) (base + fp->off_eo[e])[i] = (uint8_t)e;
-    bandpos[i] = (i * 7) % 29;
-    bands[4 * i + 0] = 1; bands[4 * i + 1] = -1; bands[4 * i + 2] = 2; bands[4 * i + 3] = -2;
+  if (alloc) {
+    fp->host_init.assign(fp->init_bytes, 0);
+    uint8_t *rec = fp->host_init.data() + (fp->off_dbk_cus - fp->init_off);
+    for (size_t i = 0; i < (size_t)(W / 4) * (H / 4); ++i) {
+      rec[20 * i + 0] = (uint8_t)(1 | (3 << 2));
+      rec[20 * i + 1] = 3;
+      rec[20 * i + 6] = (uint8_t)p->qp;
+    }
   }
   if (!alloc) return fp;
   if (cudaMalloc((void **)&fp->blob, fp->total_bytes) != cudaSuccess) { set_error("frame pass: cudaMalloc(%zu) failed", fp->total_bytes); delete fp; return nullptr; }
@@ -582,7 +565,15 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
     }
   }
   fp_mark(fp, 16, st);
-  // ---- SAO on the 8x8-level reconstruction (depth index 2): statistics + decisions, then reconstruction ----
+  // ---- deblocking of the 8x8-level reconstruction (depth index 2) in place: every 8x8 edge is an intra TU edge ----
+  {
+    kvz_cuda_dbk_params dp;
+    memset(&dp, 0, sizeof(dp));
+    dp.width = W; dp.height = H; dp.qp = fp->prm.qp; dp.cu_stride_scu = W / 4;
+    if (int r = kvz_cuda_deblock_frame(&dp, 8, B + fp->off_rec_y[2], B + fp->off_rec_u[2], B + fp->off_rec_v[2], B + fp->off_dbk_cus, st)) return r;
+  }
+  fp_mark(fp, 17, st);
+  // ---- SAO on the deblocked reconstruction: statistics + decisions, then reconstruction ----
   const int nctu = fp->nctu3 / 3;
   SaoPlanes pl;
   for (int color = 0; color < 3; ++color) {
@@ -596,7 +587,6 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
   sao_ctu_kernel<<<fp->nctu3, 256, 0, st>>>(pl, nctu, (W + 63) / 64, (int32_t *)(B + L.sao_stats), (int32_t *)(B + L.sao_dd),
                                             (int32_t *)(B + L.sao_band_dd), (int8_t *)(B + L.sao_best), dec_off, ck_scratch);
   KVZC_LAUNCHED();
-  fp_mark(fp, 17, st);
   fp_mark(fp, 18, st);
   sao_apply_kernel<<<fp->nctu3, 256, 0, st>>>(pl, nctu, (W + 63) / 64, (const int8_t *)(B + L.sao_best), dec_off);
   KVZC_LAUNCHED();

@@ -22,6 +22,9 @@
 #include "cu.h"
 #include "intra.h"
 #include "sao.h"
+#include "filter.h"
+#include "cu.h"
+#include "videoframe.h"
 #include "nal.h"
 
 #include "../include/kvz_cuda.h"   /* kvz_cuda_fp_layout only: the blob layout both arms fill */
@@ -40,6 +43,7 @@ typedef struct {
   volatile int next;
   int total;
   int wl[4];
+  int *dbk_done;            /* per LCU row: number of LCUs deblocked (wavefront progress) */
 } job_t;
 
 static void *xaligned(size_t bytes) { void *p = NULL; if (posix_memalign(&p, 64, bytes + 64)) abort(); memset(p, 0, bytes + 64); return p; }
@@ -148,13 +152,29 @@ static void do_sao(job_t *j, int i, kvz_pixel *buf /* 2 * 4096 px */)
   }
 }
 
+/* deblocking of one LCU row with the reference's own wavefront rule: LCU (x, y) runs after (x + 1, y - 1)
+ * (encoderstate.c:1156-1190 dependencies); rows are claimed in order, progress is published per row */
+static void do_deblock_row(job_t *j, int row)
+{
+  encoder_state_t *st = &j->ctx->enc->states[0];
+  const int lcus_x = (j->W + 63) / 64;
+  for (int x = 0; x < lcus_x; ++x) {
+    if (row > 0) {
+      const int need = x + 2 < lcus_x ? x + 2 : lcus_x;
+      while (__atomic_load_n(&j->dbk_done[row - 1], __ATOMIC_ACQUIRE) < need) { }
+    }
+    kvz_filter_deblock_lcu(st, x * 64, row * 64);
+    __atomic_store_n(&j->dbk_done[row], x + 1, __ATOMIC_RELEASE);
+  }
+}
+
 static void *worker(void *arg)
 {
   job_t *j = (job_t *)arg;
   kvz_pixel *buf = (kvz_pixel *)xaligned(8192 * sizeof(kvz_pixel));
   /* work is claimed in chunks so that 100+ threads do not serialise on the shared counter (and neighbouring
    * blocks, whose outputs share cache lines, stay on one thread) */
-  const int chunk = j->stage == 0 ? 256 : 4;
+  const int chunk = j->stage == 0 ? 256 : (j->stage == 2 ? 1 : 4);
   for (;;) {
     const int i0 = __sync_fetch_and_add(&j->next, chunk);
     if (i0 >= j->total) break;
@@ -164,6 +184,8 @@ static void *worker(void *arg)
         int d = 0, b = i;
         while (b >= j->L->nblk[d]) { b -= j->L->nblk[d]; ++d; }
         do_block(j, d, b, buf);
+      } else if (j->stage == 2) {
+        do_deblock_row(j, i);
       } else {
         do_sao(j, i, buf);
       }
@@ -198,7 +220,27 @@ int kvzref_frame_pass(kvzref_ctx *ctx, const uint8_t *src, int W, int H, int qp,
     if (d < 3) { j.rec[1][d] = (uint8_t *)xaligned((size_t)W * H / 4); j.rec[2][d] = (uint8_t *)xaligned((size_t)W * H / 4); }
   }
   run_stage(&j, 0, L->nblk[0] + L->nblk[1] + L->nblk[2] + L->nblk[3], nthreads);
-  /* SAO works on the 8x8-level reconstruction; unfiltered pixels are copied first */
+  /* deblocking of the 8x8-level reconstruction (every CU: intra 8x8, 2Nx2N, one TU) through kvz_filter_deblock_lcu */
+  {
+    videoframe_t *frame = st->tile->frame;
+    if (!frame->cu_array) frame->cu_array = kvz_cu_array_alloc(W, H);
+    cu_info_t cu; memset(&cu, 0, sizeof(cu));
+    cu.type = CU_INTRA; cu.depth = 3; cu.part_size = SIZE_2Nx2N; cu.tr_depth = 3; cu.qp = (uint8_t)qp;
+    const int n_scu = (frame->cu_array->stride / 4) * (frame->cu_array->height / 4);
+    for (int i = 0; i < n_scu; ++i) frame->cu_array->data[i] = cu;
+    kvz_picture *saved = frame->rec, pic;
+    memset(&pic, 0, sizeof(pic));
+    pic.y = pic.data[0] = j.rec[0][2]; pic.u = pic.data[1] = j.rec[1][2]; pic.v = pic.data[2] = j.rec[2][2];
+    pic.width = W; pic.height = H; pic.stride = W; pic.chroma_format = KVZ_CSP_420;
+    frame->rec = &pic;
+    st->frame->max_qp_delta_depth = -1;
+    const int rows = (H + 63) / 64;
+    j.dbk_done = (int *)calloc((size_t)rows, sizeof(int));
+    run_stage(&j, 2, rows, nthreads < rows ? nthreads : rows);
+    free(j.dbk_done);
+    frame->rec = saved;
+  }
+  /* SAO works on the deblocked 8x8-level reconstruction; unfiltered pixels are copied first */
   memcpy(blob + L->sao_rec, j.rec[0][2], (size_t)W * H);
   memcpy(blob + L->sao_rec + (size_t)W * H, j.rec[1][2], (size_t)W * H / 4);
   memcpy(blob + L->sao_rec + (size_t)W * H * 5 / 4, j.rec[2][2], (size_t)W * H / 4);
