@@ -301,6 +301,41 @@ int   kvz_cuda_ip_run_host(kvz_cuda_inter_pass *ip, const void *cur_host, const 
 
 /* ------------------------------------------------------------------ host-buffer conveniences */
 /* ---------------------------------------------------------------------------------------------------------
+ * RDOQ: kvz_rdoq (src/rdo.c:661-977) incl. kvz_rdoq_sign_hiding (rdo.c:518-653) and the
+ * find_last_scanpos strategy (quant-generic.c:376-399), flat scaling lists.
+ * The CABAC context models enter as the memory image of the reference's `cabac_data_t.ctx` member
+ * (src/cabac.h:66-102: one uc_state byte per context model): a binding copies &state->cabac.ctx.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct kvz_cuda_cabac_ctx {            /* field order = src/cabac.h:67-101 */
+  uint8_t sao_merge_flag_model, sao_type_idx_model, split_flag_model[3], intra_mode_model, chroma_pred_model[2],
+          inter_dir[5], trans_subdiv_model[3], qt_cbf_model_luma[4], qt_cbf_model_chroma[4], cu_qp_delta_abs[4],
+          part_size_model[4], cu_sig_coeff_group_model[4], cu_sig_model_luma[27], cu_sig_model_chroma[15],
+          cu_ctx_last_y_luma[15], cu_ctx_last_y_chroma[15], cu_ctx_last_x_luma[15], cu_ctx_last_x_chroma[15],
+          cu_one_model_luma[16], cu_one_model_chroma[8], cu_abs_model_luma[4], cu_abs_model_chroma[2],
+          cu_pred_mode_model, cu_skip_flag_model[3], cu_merge_idx_ext_model, cu_merge_flag_ext_model,
+          cu_transquant_bypass, cu_mvd_model[2], cu_ref_pic_model[2], mvp_idx_model[2], cu_qt_root_cbf_model,
+          transform_skip_model_luma, transform_skip_model_chroma;
+} kvz_cuda_cabac_ctx;
+typedef struct kvz_cuda_rdoq_params {
+  double  lambda;            /* state->lambda */
+  int32_t qp;                /* state->qp */
+  int32_t bitdepth;
+  int32_t signhide_enable;   /* cfg.signhide_enable */
+  int32_t pad;
+} kvz_cuda_rdoq_params;
+typedef struct kvz_cuda_rdoq_tu {
+  int32_t off_coef;          /* coeff_t offset of the n x n transform coefficients in `coef` */
+  int32_t off_dest;          /* coeff_t offset of the quantised levels in `dest` */
+  uint8_t type;              /* 0 luma, 2 chroma (the reference passes 2 for U and V, quant-generic.c:239) */
+  uint8_t scan_idx;          /* 0 diagonal, 1 horizontal, 2 vertical */
+  uint8_t block_type;        /* cu type: 1 intra, 2 inter */
+  uint8_t tr_depth;          /* cur_cu->tr_depth - cur_cu->depth (+1 for NxN), quant-generic.c:237-238 */
+} kvz_cuda_rdoq_tu;
+/* `count` TUs of width n (4, 8, 16 or 32); ctx_dev: one kvz_cuda_cabac_ctx shared by the batch */
+int kvz_cuda_rdoq_batch(const kvz_cuda_rdoq_params *p, const kvz_cuda_cabac_ctx *ctx_dev, const int16_t *coef, int16_t *dest,
+                        int n, const kvz_cuda_rdoq_tu *tus, int count, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Deblocking filter, frame level.  Replaces the per-LCU kvz_filter_deblock_lcu
  * (src/filter.c:783-792, called from encoder_state_worker_encode_lcu_search, src/encoderstate.c:669-675) by two
  * passes over the frame (all vertical edges, then all horizontal edges) -- the same result, see csrc/deblock.cu.

@@ -293,6 +293,32 @@ def array_checksum(data, height, width, stride, out=None):
     return out
 
 
+# ------------------------------------------------------------------ RDOQ (rdoq.cu)
+RDOQ_TU = np.dtype([("off_coef", "<i4"), ("off_dest", "<i4"), ("type", "u1"), ("scan_idx", "u1"), ("block_type", "u1"),
+                    ("tr_depth", "u1")])
+CABAC_CTX_BYTES = 184          # sizeof(cabac_data_t.ctx), src/cabac.h:66-102 (pinned by tests/test_rdoq.py)
+
+
+class RdoqParams(C.Structure):
+    _fields_ = [("lambda_", C.c_double), ("qp", C.c_int32), ("bitdepth", C.c_int32), ("signhide_enable", C.c_int32),
+                ("pad", C.c_int32)]
+
+
+def rdoq_batch(coef, n, tus, cabac_ctx, qp, lambda_, bitdepth=8, signhide=0, dest=None):
+    """kvz_rdoq (src/rdo.c:661) for `len(tus)` TUs of width n.  coef: int16 CUDA tensor; tus: RDOQ_TU array;
+    cabac_ctx: uint8[CABAC_CTX_BYTES] image of state->cabac.ctx.  Returns the quantised levels (int16 tensor)."""
+    torch = _torch()
+    if dest is None:
+        dest = torch.zeros_like(coef)
+    prm = RdoqParams(lambda_, qp, bitdepth, signhide, 0)
+    ctx = cabac_ctx if hasattr(cabac_ctx, "data_ptr") else to_dev(np.asarray(cabac_ctx, np.uint8))
+    assert ctx.numel() == CABAC_CTX_BYTES
+    tus_d = tus if hasattr(tus, "data_ptr") else to_dev(tus)
+    count = tus_d.numel() // RDOQ_TU.itemsize
+    _ck(lib().kvz_cuda_rdoq_batch(C.byref(prm), _p(ctx), _p(coef), _p(dest), n, _p(tus_d), count, _stream()))
+    return dest
+
+
 # ------------------------------------------------------------------ deblocking (deblock.cu)
 class DbkParams(C.Structure):
     """kvz_cuda_dbk_params."""

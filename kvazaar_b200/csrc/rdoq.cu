@@ -1,0 +1,52 @@
+// rdoq.cu -- batched kvz_rdoq: one warp per TU (see rdoq.cuh).
+#include "rdoq.cuh"
+
+namespace kvzc {
+
+template <int LOG2N, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) rdoq_kernel(kvz_cuda_rdoq_params p, const kvz_cuda_cabac_ctx *__restrict__ cabac,
+                                                          const int16_t *__restrict__ coef, int16_t *__restrict__ dest,
+                                                          const kvz_cuda_rdoq_tu *__restrict__ tus, int count)
+{
+  constexpr int NN = 1 << (2 * LOG2N);
+  __shared__ RdoqScratch<NN> scratch[WARPS];
+  __shared__ kvz_cuda_cabac_ctx s_ctx;
+  __shared__ __align__(4) int16_t s_coef[WARPS][NN], s_q[WARPS][NN];
+  for (int i = threadIdx.x; i < (int)sizeof(kvz_cuda_cabac_ctx); i += blockDim.x) ((uint8_t *)&s_ctx)[i] = ((const uint8_t *)cabac)[i];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * WARPS + warp;
+  const bool active = t < count;
+  kvz_cuda_rdoq_tu tu = {};
+  if (active) {
+    tu = tus[t];
+    for (int e = lane; e < NN; e += 32) s_coef[warp][e] = coef[tu.off_coef + e];
+  }
+  __syncthreads();
+  if (!active) return;
+  rdoq_tu<NN>(p, &s_ctx, s_coef[warp], s_q[warp], LOG2N, tu.type, tu.scan_idx, tu.block_type, tu.tr_depth, scratch[warp], lane);
+  for (int e = lane; e < NN; e += 32) dest[tu.off_dest + e] = s_q[warp][e];
+}
+
+}  // namespace kvzc
+
+using namespace kvzc;
+
+extern "C" int kvz_cuda_rdoq_batch(const kvz_cuda_rdoq_params *p, const kvz_cuda_cabac_ctx *ctx_dev, const int16_t *coef, int16_t *dest,
+                                   int n, const kvz_cuda_rdoq_tu *tus, int count, void *stream)
+{
+  KVZC_REQUIRE_DEVICE();
+  KVZC_ARG(p && ctx_dev && coef && dest && tus && count >= 0);
+  KVZC_ARG(n == 4 || n == 8 || n == 16 || n == 32);
+  KVZC_ARG(p->bitdepth == 8 || p->bitdepth == 10);
+  KVZC_ARG(p->lambda > 0);
+  if (count == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  switch (n) {
+    case 4: rdoq_kernel<2, 8><<<(count + 7) / 8, 256, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); break;
+    case 8: rdoq_kernel<3, 8><<<(count + 7) / 8, 256, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); break;
+    case 16: rdoq_kernel<4, 4><<<(count + 3) / 4, 128, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); break;
+    default: rdoq_kernel<5, 1><<<count, 32, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); break;
+  }
+  KVZC_LAUNCHED();
+  return 0;
+}

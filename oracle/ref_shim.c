@@ -367,3 +367,46 @@ int kvzref_deblock_frame(kvzref_ctx *c, kvz_pixel *y, kvz_pixel *u, kvz_pixel *v
   st->frame->max_qp_delta_depth = -1;
   return 0;
 }
+
+/* ---- RDOQ (not a strategy: kvz_rdoq, rdo.c:661) ---- */
+#include "rdo.h"
+#include "context.h"
+int kvzref_cabac_ctx_size(void) { return (int)sizeof(((cabac_data_t *)0)->ctx); }
+/* the context models after kvz_init_contexts for (qp, slice_type) -> out[kvzref_cabac_ctx_size()] */
+void kvzref_init_contexts(kvzref_ctx *c, int qp, int slice_type, uint8_t *out)
+{
+  encoder_state_t *st = &c->enc->states[0];
+  kvz_init_contexts(st, (int8_t)qp, (int8_t)slice_type);
+  memcpy(out, &st->cabac.ctx, sizeof(st->cabac.ctx));
+}
+/* byte offsets of the members RDOQ reads, for pinning kvz_cuda_cabac_ctx */
+void kvzref_cabac_ctx_offsets(int32_t *out)
+{
+  typedef cabac_data_t T;
+  const size_t base = offsetof(T, ctx);
+  int i = 0;
+  out[i++] = (int32_t)(offsetof(T, ctx.qt_cbf_model_luma) - base);
+  out[i++] = (int32_t)(offsetof(T, ctx.qt_cbf_model_chroma) - base);
+  out[i++] = (int32_t)(offsetof(T, ctx.cu_sig_coeff_group_model) - base);
+  out[i++] = (int32_t)(offsetof(T, ctx.cu_sig_model_luma) - base);
+  out[i++] = (int32_t)(offsetof(T, ctx.cu_sig_model_chroma) - base);
+  out[i++] = (int32_t)(offsetof(T, ctx.cu_ctx_last_y_luma) - base);
+  out[i++] = (int32_t)(offsetof(T, ctx.cu_ctx_last_y_chroma) - base);
+  out[i++] = (int32_t)(offsetof(T, ctx.cu_ctx_last_x_luma) - base);
+  out[i++] = (int32_t)(offsetof(T, ctx.cu_ctx_last_x_chroma) - base);
+  out[i++] = (int32_t)(offsetof(T, ctx.cu_one_model_luma) - base);
+  out[i++] = (int32_t)(offsetof(T, ctx.cu_one_model_chroma) - base);
+  out[i++] = (int32_t)(offsetof(T, ctx.cu_abs_model_luma) - base);
+  out[i++] = (int32_t)(offsetof(T, ctx.cu_abs_model_chroma) - base);
+  out[i++] = (int32_t)(offsetof(T, ctx.cu_qt_root_cbf_model) - base);
+}
+/* kvz_rdoq on one TU with the given context models, lambda and qp.  ctx must be opened with the wanted signhide. */
+void kvzref_rdoq(kvzref_ctx *c, int qp, double lambda, const uint8_t *cabac_ctx, coeff_t *coef, coeff_t *dest, int width,
+                 int type, int scan_mode, int block_type, int tr_depth)
+{
+  encoder_state_t *st = &c->enc->states[0];
+  st->qp = (int8_t)qp;
+  st->lambda = lambda;
+  memcpy(&st->cabac.ctx, cabac_ctx, sizeof(st->cabac.ctx));
+  kvz_rdoq(st, coef, dest, width, width, (int8_t)type, (int8_t)scan_mode, (int8_t)block_type, (int8_t)tr_depth);
+}

@@ -626,6 +626,29 @@ class Ref:
         self.lib.kvzref_make_cu_info(type_, depth, part_size, tr_depth, cbf, qp, mv_dir, P(al(mv, np.int16)), P(al(mv_ref, np.uint8)), P(out))
         return out[:self.lib.kvzref_sizeof_cu_info()].copy()
 
+    # -- RDOQ (kvz_rdoq, not a strategy)
+    def cabac_ctx_size(self):
+        return self.lib.kvzref_cabac_ctx_size()
+
+    def cabac_ctx_offsets(self):
+        out = aligned(16, np.int32)
+        self.lib.kvzref_cabac_ctx_offsets(P(out))
+        return out[:14].copy()
+
+    def init_contexts(self, qp, slice_type):
+        out = aligned(256, np.uint8)
+        self.lib.kvzref_init_contexts(self.ctx(qp), qp, slice_type, P(out))
+        return out[:self.cabac_ctx_size()].copy()
+
+    def rdoq(self, coef, width, qp, lambda_, cabac_ctx, type_=0, scan_mode=0, block_type=1, tr_depth=0, signhide=0):
+        coef = al(coef, np.int16)
+        dest = aligned(width * width, np.int16)
+        dest[:] = 0x55
+        cc = al(cabac_ctx, np.uint8)
+        self.lib.kvzref_rdoq(self.ctx(qp, signhide, 1), qp, C.c_double(lambda_), P(cc), P(coef), P(dest), width, type_, scan_mode,
+                             block_type, tr_depth)
+        return dest.copy()
+
     # -- nal
     def array_checksum(self, data, height, width, stride, impl="generic"):
         out = aligned(4, np.uint8)

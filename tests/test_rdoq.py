@@ -1,0 +1,82 @@
+"""RDOQ on device (ref: kvz_rdoq, src/rdo.c:661-977) against the compiled reference, bit-exact.
+
+The reference function is called through oracle/ref_shim.c with the same context models, lambda and QP.  (No plain-C
+restatement of RDOQ exists in oracle/kvz_oracle.c: the compiled reference itself is the checker for this row.)
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+
+def synth_coeffs(rng, n, count, energy):
+    """Transform-coefficient-like blocks: Laplacian magnitudes decaying with frequency, a few outliers."""
+    fy, fx = np.mgrid[0:n, 0:n]
+    decay = np.exp(-(fx + fy) / (n * rng.uniform(0.08, 0.6, (count, 1, 1))))
+    c = rng.laplace(0, 1, (count, n, n)) * decay * energy * rng.uniform(0.05, 2.0, (count, 1, 1))
+    c[rng.random(count) < 0.1] = 0                                    # empty blocks
+    hot = rng.random((count, n, n)) < 0.002
+    c = np.where(hot, rng.integers(-32768, 32768, (count, n, n)), c)
+    return np.clip(np.rint(c), -32768, 32767).astype(np.int16)
+
+
+def test_cabac_ctx_layout(ref):
+    """kvz_cuda_cabac_ctx (include/kvz_cuda.h) has the reference's member offsets (src/cabac.h:66-102)."""
+    from kvazaar_b200 import api
+    assert ref.cabac_ctx_size() == api.CABAC_CTX_BYTES
+    sizes = [("sao_merge_flag_model", 1), ("sao_type_idx_model", 1), ("split_flag_model", 3), ("intra_mode_model", 1),
+             ("chroma_pred_model", 2), ("inter_dir", 5), ("trans_subdiv_model", 3), ("qt_cbf_model_luma", 4),
+             ("qt_cbf_model_chroma", 4), ("cu_qp_delta_abs", 4), ("part_size_model", 4), ("cu_sig_coeff_group_model", 4),
+             ("cu_sig_model_luma", 27), ("cu_sig_model_chroma", 15), ("cu_ctx_last_y_luma", 15), ("cu_ctx_last_y_chroma", 15),
+             ("cu_ctx_last_x_luma", 15), ("cu_ctx_last_x_chroma", 15), ("cu_one_model_luma", 16), ("cu_one_model_chroma", 8),
+             ("cu_abs_model_luma", 4), ("cu_abs_model_chroma", 2), ("cu_pred_mode_model", 1), ("cu_skip_flag_model", 3),
+             ("cu_merge_idx_ext_model", 1), ("cu_merge_flag_ext_model", 1), ("cu_transquant_bypass", 1), ("cu_mvd_model", 2),
+             ("cu_ref_pic_model", 2), ("mvp_idx_model", 2), ("cu_qt_root_cbf_model", 1), ("transform_skip_model_luma", 1),
+             ("transform_skip_model_chroma", 1)]
+    off, o = {}, 0
+    for name, sz in sizes:
+        off[name] = o
+        o += sz
+    assert o == api.CABAC_CTX_BYTES
+    names = ["qt_cbf_model_luma", "qt_cbf_model_chroma", "cu_sig_coeff_group_model", "cu_sig_model_luma", "cu_sig_model_chroma",
+             "cu_ctx_last_y_luma", "cu_ctx_last_y_chroma", "cu_ctx_last_x_luma", "cu_ctx_last_x_chroma", "cu_one_model_luma",
+             "cu_one_model_chroma", "cu_abs_model_luma", "cu_abs_model_chroma", "cu_qt_root_cbf_model"]
+    assert [off[k] for k in names] == list(ref.cabac_ctx_offsets())
+
+
+def lambda_for(qp):
+    return 0.57 * 2.0 ** ((qp - 12) / 3.0)
+
+
+CASES = [(n, qp, type_, signhide) for n in (4, 8, 16, 32) for qp in (22, 27, 37) for type_ in (0, 2) for signhide in (0, 1)
+         if not (n == 32 and type_ == 2)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,qp,type_,signhide", CASES)
+def test_cuda_rdoq_vs_reference(cuda_lib, ref, n, qp, type_, signhide):
+    from kvazaar_b200 import api
+    rng = np.random.default_rng(1000 * n + 10 * qp + type_ + signhide)
+    count = {4: 400, 8: 300, 16: 120, 32: 40}[n]
+    coef = synth_coeffs(rng, n, count, energy=6.0 * 2.0 ** ((qp - 4) / 6.0))
+    tus = np.zeros(count, api.RDOQ_TU)
+    tus["off_coef"] = tus["off_dest"] = np.arange(count) * n * n
+    tus["type"] = type_
+    tus["scan_idx"] = rng.integers(0, 3, count) if n <= 8 else 0
+    tus["block_type"] = rng.integers(1, 3, count)
+    tus["tr_depth"] = rng.integers(0, 3, count)
+    # half of the cases use the slice-initial context models, half random states
+    ctxs = [ref.init_contexts(qp, 2), ref.init_contexts(qp, 1), rng.integers(0, 126, api.CABAC_CTX_BYTES).astype(np.uint8)]
+    for ci, cabac in enumerate(ctxs):
+        lam = lambda_for(qp) * (1.0 if ci == 0 else float(rng.uniform(0.3, 3.0)))
+        got = api.rdoq_batch(api.to_dev(coef.ravel()), n, tus, cabac, qp, lam, 8, signhide).cpu().numpy().reshape(count, n * n)
+        bad = []
+        nonzero = 0
+        for i in range(count):
+            want = ref.rdoq(coef[i].ravel(), n, qp, lam, cabac, type_, int(tus["scan_idx"][i]), int(tus["block_type"][i]),
+                            int(tus["tr_depth"][i]), signhide)
+            nonzero += int(np.count_nonzero(want))
+            if not np.array_equal(want, got[i]):
+                bad.append(i)
+        assert not bad, f"ctx {ci}: {len(bad)} of {count} TUs differ, first {bad[:5]}"
+        assert nonzero > 0
