@@ -73,6 +73,13 @@ void kvz_cuda_call_dequant(const struct kvz_cuda_quant_params_s *p, const int16_
 int  kvz_cuda_call_quantize_residual(const struct kvz_cuda_quant_params_s *p, int width, int color, int scan_idx, int use_trskip,
                                      int cu_is_intra, int early_skip, int phase, int in_stride, int out_stride,
                                      const void *ref_in, const void *pred_in, void *rec_out, int16_t *coeff_out);
+/* the same with cfg.rdoq_enable: kvz_rdoq runs on the device between the two halves; cabac = &state->cabac.ctx,
+ * rp->lambda = state->lambda, tr_depth as in quant-generic.c:237-238 */
+struct kvz_cuda_rdoq_params; struct kvz_cuda_cabac_ctx;
+int  kvz_cuda_call_quantize_residual_rdoq(const struct kvz_cuda_quant_params_s *p, const struct kvz_cuda_rdoq_params *rp,
+                                          const struct kvz_cuda_cabac_ctx *cabac, int width, int color, int scan_idx, int use_trskip,
+                                          int cu_is_intra, int early_skip, int tr_depth, int in_stride, int out_stride,
+                                          const void *ref_in, const void *pred_in, void *rec_out, int16_t *coeff_out);
 void kvz_cuda_call_sao_edge_stats(int bitdepth, const void *orig, const void *rec, int eo_class, int bw, int bh, int *cat_sum_cnt);
 int  kvz_cuda_call_sao_edge_ddistortion(int bitdepth, const void *orig, const void *rec, int bw, int bh, int eo_class, const int *offsets);
 int  kvz_cuda_call_sao_band_ddistortion(int bitdepth, const void *orig, const void *rec, int bw, int bh, int band_pos, const int *bands);
@@ -151,7 +158,7 @@ typedef struct {
   uint8_t phase;                       /* 0 whole function; 1 residual+forward transform only (coefficients to
                                           coeff_out, no quantisation); 2 dequant+inverse+reconstruct only (coeff_out
                                           holds the quantised levels).  Phases 1/2 bracket the host's kvz_rdoq. */
-  uint8_t pad;
+  uint8_t tr_depth;                    /* RDOQ only: cur_cu->tr_depth - cur_cu->depth (+1 for NxN), quant-generic.c:237 */
 } kvz_cuda_tu;
 /* kvz_quantize_residual, RDOQ-off branch (ref: quant-generic.c:198-292): residual -> DCT/DST/trskip -> quant ->
  * has_coeffs -> dequant -> inverse -> rec = clip(pred + res).  has_coeffs[i] in {0,1}. */
@@ -331,6 +338,13 @@ typedef struct kvz_cuda_rdoq_tu {
   uint8_t block_type;        /* cu type: 1 intra, 2 inter */
   uint8_t tr_depth;          /* cur_cu->tr_depth - cur_cu->depth (+1 for NxN), quant-generic.c:237-238 */
 } kvz_cuda_rdoq_tu;
+/* kvz_quantize_residual with the RDOQ branch taken (quant-generic.c:234-240) entirely on the device: residual +
+ * forward transform, kvz_rdoq, dequant + inverse transform + reconstruction.  widths_mask: OR of the TU widths in
+ * the batch (4 | 8 | 16 | 32).  Descriptors as for kvz_cuda_quantize_residual_batch (phase must be 0). */
+int kvz_cuda_quantize_residual_rdoq_batch(const kvz_cuda_quant_params *p, const kvz_cuda_rdoq_params *rp,
+                                          const kvz_cuda_cabac_ctx *ctx_dev, const void *ref_plane, const void *pred_plane,
+                                          int in_stride, void *rec_plane, int out_stride, int16_t *coeff_out,
+                                          const kvz_cuda_tu *tus, int count, int widths_mask, int32_t *has_coeffs, void *stream);
 /* `count` TUs of width n (4, 8, 16 or 32); ctx_dev: one kvz_cuda_cabac_ctx shared by the batch */
 int kvz_cuda_rdoq_batch(const kvz_cuda_rdoq_params *p, const kvz_cuda_cabac_ctx *ctx_dev, const int16_t *coef, int16_t *dest,
                         int n, const kvz_cuda_rdoq_tu *tus, int count, void *stream);

@@ -97,6 +97,10 @@ struct Call {
   }
 };
 
+// rdoq.cu: kvz_rdoq in place on the coefficients of the TUs of width n (used by the quantize_residual RDOQ branch)
+int rdoq_launch_tus(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ctx_dev, int16_t *coeff, const kvz_cuda_tu *tus, int count, int n,
+                    cudaStream_t st);
+
 // ---------------------------------------------------------------- device side
 template <class T> struct PixTraits;
 template <> struct PixTraits<uint8_t> { static constexpr int kBits = 8; };

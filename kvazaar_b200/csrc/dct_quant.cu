@@ -73,12 +73,12 @@ __global__ void __launch_bounds__(256) quantize_residual_kernel(kvz_cuda_quant_p
                                                                 T *__restrict__ rec_plane, int out_stride,
                                                                 int16_t *__restrict__ coeff_out,
                                                                 const kvz_cuda_tu *__restrict__ tus,
-                                                                int32_t *__restrict__ has_coeffs)
+                                                                int32_t *__restrict__ has_coeffs, int phase_override)
 {
   __shared__ TuScratch s;
   const kvz_cuda_tu tu = tus[blockIdx.x];
   const int has = quantize_residual_tu<T>(s, p, tu.width, tu.color, tu.scan_idx, tu.use_trskip, tu.cu_is_intra,
-                                          tu.early_skip, tu.phase, ref_plane + tu.off_ref, in_stride,
+                                          tu.early_skip, phase_override >= 0 ? phase_override : tu.phase, ref_plane + tu.off_ref, in_stride,
                                           pred_plane + tu.off_pred, in_stride, rec_plane + tu.off_rec, out_stride,
                                           coeff_out + tu.off_coeff);
   if (threadIdx.x == 0) has_coeffs[blockIdx.x] = has;
@@ -164,12 +164,37 @@ int kvz_cuda_quantize_residual_batch(const kvz_cuda_quant_params *p, const void 
   KVZC_ARG(ref_plane && pred_plane && rec_plane && coeff_out && tus && has_coeffs);
   if (count == 0) return 0;
   if (p->bitdepth == 8)
-    quantize_residual_kernel<uint8_t><<<count, 256, 0, as_stream(stream)>>>(*p, (const uint8_t *)ref_plane, (const uint8_t *)pred_plane, in_stride, (uint8_t *)rec_plane, out_stride, coeff_out, tus, has_coeffs);
+    quantize_residual_kernel<uint8_t><<<count, 256, 0, as_stream(stream)>>>(*p, (const uint8_t *)ref_plane, (const uint8_t *)pred_plane, in_stride, (uint8_t *)rec_plane, out_stride, coeff_out, tus, has_coeffs, -1);
   else
-    quantize_residual_kernel<uint16_t><<<count, 256, 0, as_stream(stream)>>>(*p, (const uint16_t *)ref_plane, (const uint16_t *)pred_plane, in_stride, (uint16_t *)rec_plane, out_stride, coeff_out, tus, has_coeffs);
+    quantize_residual_kernel<uint16_t><<<count, 256, 0, as_stream(stream)>>>(*p, (const uint16_t *)ref_plane, (const uint16_t *)pred_plane, in_stride, (uint16_t *)rec_plane, out_stride, coeff_out, tus, has_coeffs, -1);
   KVZC_LAUNCHED();
   return 0;
 }
+
+int kvz_cuda_quantize_residual_rdoq_batch(const kvz_cuda_quant_params *p, const kvz_cuda_rdoq_params *rp,
+                                          const kvz_cuda_cabac_ctx *ctx_dev, const void *ref_plane, const void *pred_plane,
+                                          int in_stride, void *rec_plane, int out_stride, int16_t *coeff_out,
+                                          const kvz_cuda_tu *tus, int count, int widths_mask, int32_t *has_coeffs, void *stream)
+{
+  KVZC_REQUIRE_DEVICE();
+  KVZC_ARG(p && rp && ctx_dev && ref_plane && pred_plane && rec_plane && coeff_out && tus && has_coeffs);
+  KVZC_ARG(p->scaling_list_enable == 0 && (p->bitdepth == 8 || p->bitdepth == 10) && rp->bitdepth == p->bitdepth && rp->qp == p->qp);
+  KVZC_ARG((widths_mask & ~(4 | 8 | 16 | 32)) == 0 && widths_mask != 0);
+  if (count == 0) return 0;
+  cudaStream_t st = as_stream(stream);
+  for (int phase = 1; phase <= 2; ++phase) {
+    if (p->bitdepth == 8)
+      quantize_residual_kernel<uint8_t><<<count, 256, 0, st>>>(*p, (const uint8_t *)ref_plane, (const uint8_t *)pred_plane, in_stride, (uint8_t *)rec_plane, out_stride, coeff_out, tus, has_coeffs, phase);
+    else
+      quantize_residual_kernel<uint16_t><<<count, 256, 0, st>>>(*p, (const uint16_t *)ref_plane, (const uint16_t *)pred_plane, in_stride, (uint16_t *)rec_plane, out_stride, coeff_out, tus, has_coeffs, phase);
+    KVZC_LAUNCHED();
+    if (phase == 1)
+      for (int n = 4; n <= 32; n <<= 1)
+        if (widths_mask & n) if (int r = rdoq_launch_tus(*rp, ctx_dev, coeff_out, tus, count, n, st)) return r;
+  }
+  return 0;
+}
+
 
 int kvz_cuda_coeff_abs_sum_batch(const int16_t *coeffs, size_t length, int count, uint32_t *out, void *stream)
 {

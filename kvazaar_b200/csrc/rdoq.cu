@@ -27,6 +27,41 @@ __global__ void __launch_bounds__(WARPS * 32) rdoq_kernel(kvz_cuda_rdoq_params p
   for (int e = lane; e < NN; e += 32) dest[tu.off_dest + e] = s_q[warp][e];
 }
 
+// The same for kvz_cuda_tu descriptors (quantize_residual's RDOQ branch): in place on coeff; TUs of other widths
+// are skipped (one launch per width present in the batch).
+template <int LOG2N, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) rdoq_tu_kernel(kvz_cuda_rdoq_params p, const kvz_cuda_cabac_ctx *__restrict__ cabac,
+                                                             int16_t *__restrict__ coeff, const kvz_cuda_tu *__restrict__ tus, int count)
+{
+  constexpr int NN = 1 << (2 * LOG2N);
+  __shared__ RdoqScratch<NN> scratch[WARPS];
+  __shared__ kvz_cuda_cabac_ctx s_ctx;
+  __shared__ __align__(4) int16_t s_coef[WARPS][NN], s_q[WARPS][NN];
+  for (int i = threadIdx.x; i < (int)sizeof(kvz_cuda_cabac_ctx); i += blockDim.x) ((uint8_t *)&s_ctx)[i] = ((const uint8_t *)cabac)[i];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * WARPS + warp;
+  kvz_cuda_tu tu = {};
+  bool active = t < count;
+  if (active) { tu = tus[t]; active = tu.width == (1 << LOG2N); }
+  if (active) for (int e = lane; e < NN; e += 32) s_coef[warp][e] = coeff[tu.off_coeff + e];
+  __syncthreads();
+  if (!active) return;
+  rdoq_tu<NN>(p, &s_ctx, s_coef[warp], s_q[warp], LOG2N, tu.color == 0 ? 0 : 2, tu.scan_idx, tu.cu_is_intra ? 1 : 2, tu.tr_depth, scratch[warp], lane);
+  for (int e = lane; e < NN; e += 32) coeff[tu.off_coeff + e] = s_q[warp][e];
+}
+
+int rdoq_launch_tus(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ctx_dev, int16_t *coeff, const kvz_cuda_tu *tus, int count, int n, cudaStream_t st)
+{
+  switch (n) {
+    case 4: rdoq_tu_kernel<2, 8><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, tus, count); break;
+    case 8: rdoq_tu_kernel<3, 8><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, tus, count); break;
+    case 16: rdoq_tu_kernel<4, 4><<<(count + 3) / 4, 128, 0, st>>>(p, ctx_dev, coeff, tus, count); break;
+    default: rdoq_tu_kernel<5, 1><<<count, 32, 0, st>>>(p, ctx_dev, coeff, tus, count); break;
+  }
+  KVZC_LAUNCHED();
+  return 0;
+}
+
 }  // namespace kvzc
 
 using namespace kvzc;

@@ -307,6 +307,34 @@ int kvz_cuda_call_quantize_residual(const kvz_cuda_quant_params *p, int width, i
   return has;
 }
 
+// kvz_quantize_residual with RDOQ, whole function on the device (one upload, three launches, one download)
+int kvz_cuda_call_quantize_residual_rdoq(const kvz_cuda_quant_params *p, const kvz_cuda_rdoq_params *rp, const kvz_cuda_cabac_ctx *cabac,
+                                         int width, int color, int scan_idx, int use_trskip, int cu_is_intra, int early_skip, int tr_depth,
+                                         int in_stride, int out_stride, const void *ref_in, const void *pred_in, void *rec_out, int16_t *coeff_out)
+{
+  const size_t px = p->bitdepth == 8 ? 1 : 2;
+  const int n = width;
+  Call c(3 * (size_t)n * n * px + (size_t)n * n * 2 + 2048);
+  if (!c.ok) die("staging");
+  const uint8_t *dref = c.in2d((const uint8_t *)ref_in, (int)(n * px), n, (long)in_stride * px);
+  const uint8_t *dpred = c.in2d((const uint8_t *)pred_in, (int)(n * px), n, (long)in_stride * px);
+  kvz_cuda_tu tu; memset(&tu, 0, sizeof(tu));
+  tu.width = (uint8_t)n; tu.color = (uint8_t)color; tu.scan_idx = (uint8_t)scan_idx; tu.use_trskip = (uint8_t)use_trskip;
+  tu.cu_is_intra = (uint8_t)cu_is_intra; tu.early_skip = (uint8_t)early_skip; tu.tr_depth = (uint8_t)tr_depth;
+  const kvz_cuda_tu *dtu = c.in(&tu, 1);
+  const kvz_cuda_cabac_ctx *dctx = c.in(cabac, 1);
+  uint8_t *drec = c.out<uint8_t>((size_t)n * n * px);
+  int16_t *dcoef = c.out<int16_t>((size_t)n * n);
+  int32_t *dhas = c.out<int32_t>(1);
+  MUST(c.upload());
+  MUST(kvz_cuda_quantize_residual_rdoq_batch(p, rp, dctx, dref, dpred, n, drec, n, dcoef, dtu, 1, n, dhas, c.s.stream));
+  MUST(c.download());
+  memcpy(coeff_out, c.host_ptr(dcoef), (size_t)n * n * sizeof(int16_t));
+  const uint8_t *hrec = c.host_ptr(drec);
+  for (int y = 0; y < n; ++y) memcpy((uint8_t *)rec_out + (size_t)y * out_stride * px, hrec + (size_t)y * n * px, n * px);
+  return *c.host_ptr(dhas);
+}
+
 void kvz_cuda_call_sao_edge_stats(int bitdepth, const void *orig, const void *rec, int eo_class, int bw, int bh, int *cat_sum_cnt)
 {
   const size_t px = bitdepth == 8 ? 1 : 2;
