@@ -245,7 +245,11 @@ int kvz_cuda_array_checksum(int bitdepth, const void *data, int height, int widt
  * (luma block width 32,16,8,4 = depth index 0..3; chroma width/2 for depth 0..2): rough search of 35 modes ->
  * best mode -> prediction + quantize_residual reconstruction + SSD, then SAO statistics/decision/reconstruction
  * on the 8x8-level reconstruction and the picture checksum.  I420 frames, 8-bit. */
-typedef struct { int32_t width, height, bitdepth, qp, signhide; } kvz_cuda_fp_params;
+typedef struct {
+  int32_t width, height, bitdepth, qp, signhide;
+  int32_t rdoq;      /* cfg.rdoq_enable: quantise with kvz_rdoq (slice-initial context models) instead of kvz_quant */
+  double  lambda;    /* state->lambda for RDOQ; 0 = the reference's constant-QP value 0.57 * 2^((qp - 12) / 3) (rate_control.c:678-691) */
+} kvz_cuda_fp_params;
 typedef struct {
   int32_t nblk[4];                 /* blocks per depth: (W / w) * (H / w) */
   int32_t nctu;                    /* 64x64 CTUs (partial ones included) */
@@ -323,6 +327,8 @@ typedef struct kvz_cuda_cabac_ctx {            /* field order = src/cabac.h:67-1
           cu_transquant_bypass, cu_mvd_model[2], cu_ref_pic_model[2], mvp_idx_model[2], cu_qt_root_cbf_model,
           transform_skip_model_luma, transform_skip_model_chroma;
 } kvz_cuda_cabac_ctx;
+/* kvz_init_contexts (src/context.c:221-304): the context models at the start of a slice.  slice_type: 0 B, 1 P, 2 I.  Host only. */
+int kvz_cuda_cabac_ctx_init(int qp, int slice_type, kvz_cuda_cabac_ctx *out);
 typedef struct kvz_cuda_rdoq_params {
   double  lambda;            /* state->lambda */
   int32_t qp;                /* state->qp */

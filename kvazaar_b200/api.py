@@ -351,7 +351,7 @@ def call_deblock_frame(y, u, v, stride, cus, width, height, qp, beta_offset_div2
 # ------------------------------------------------------------------ frame-level pass (framepass.cu)
 class FpParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bitdepth", C.c_int32), ("qp", C.c_int32),
-                ("signhide", C.c_int32)]
+                ("signhide", C.c_int32), ("rdoq", C.c_int32), ("lambda_", C.c_double)]
 
 
 class FpLayout(C.Structure):
@@ -367,7 +367,7 @@ class FpLayout(C.Structure):
 def fp_layout_for(width, height, qp=27, signhide=0):
     """Result-blob layout; needs no GPU."""
     lay = FpLayout()
-    prm = FpParams(width, height, 8, qp, signhide)
+    prm = FpParams(width, height, 8, qp, signhide, 0, 0.0)
     _ck(lib().kvz_cuda_fp_layout_for(C.byref(prm), C.byref(lay)))
     return lay
 
@@ -375,7 +375,7 @@ def fp_layout_for(width, height, qp=27, signhide=0):
 class FramePass:
     """One in-flight frame of the frame-level pass (device buffers owned by the library)."""
 
-    def __init__(self, width, height, qp=27, signhide=0):
+    def __init__(self, width, height, qp=27, signhide=0, rdoq=0, lambda_=0.0):
         _torch()
         L = lib()
         L.kvz_cuda_fp_create.restype = C.c_void_p
@@ -383,7 +383,7 @@ class FramePass:
         L.kvz_cuda_fp_result_dev.argtypes = [C.c_void_p]
         L.kvz_cuda_fp_frame_bytes.restype = C.c_size_t
         L.kvz_cuda_fp_frame_bytes.argtypes = [C.c_void_p]
-        self.params = FpParams(width, height, 8, qp, signhide)
+        self.params = FpParams(width, height, 8, qp, signhide, rdoq, lambda_)
         h = L.kvz_cuda_fp_create(C.byref(self.params))
         if not h:
             raise KvzCudaError(f"kvz_cuda_fp_create failed: {L.kvz_cuda_last_error().decode()}")

@@ -101,6 +101,9 @@ struct Call {
 int rdoq_launch_tus(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ctx_dev, int16_t *coeff, const kvz_cuda_tu *tus, int count, int n,
                     cudaStream_t st);
 
+int rdoq_launch_grid(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ctx_dev, int16_t *coeff, int count, int log2n, const int8_t *modes,
+                     int is_chroma, int tr_depth, cudaStream_t st);
+
 // ---------------------------------------------------------------- device side
 template <class T> struct PixTraits;
 template <> struct PixTraits<uint8_t> { static constexpr int kBits = 8; };

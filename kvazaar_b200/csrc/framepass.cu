@@ -46,7 +46,9 @@ __global__ void __launch_bounds__(256) select_best_kernel(const uint32_t *__rest
 // ac_sum < 2) are predicates.  Transforms use the DP2A matrix passes of transform.cuh.
 // INTER = true: the same walk for an inter CU's TU grid -- rec_in is then the motion-compensated PREDICTION plane,
 // modes is unused, the scan is diagonal, no DST, and has_out is an int32 array (inter pass blob layout).
-template <class T, int LOG2W, bool INTER = false>
+// PHASE splits the walk around kvz_rdoq (quant-generic.c:234-240): 0 = whole function with kvz_quant; 1 = up to the
+// forward transform (coefficients -> coeff); 2 = from the quantised levels in coeff (written by rdoq_grid) onwards.
+template <class T, int LOG2W, bool INTER = false, int PHASE = 0>
 __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params p, const T *__restrict__ src,
                                                           const T *__restrict__ rec_in, int stride, int pic_w, int pic_h,
                                                           int color, int blocks_x, int nblk,
@@ -112,14 +114,23 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
     }
     s_pred[e] = (T)pv;
     s_a[e] = (int16_t)(sv - pv);
+    if (PHASE == 2) s_q[e] = b < nblk ? coeff[(size_t)b * WW + r] : (int16_t)0;
   }
   __syncthreads();
 
+  if (PHASE != 2) {
   // ---- forward transform (ref: dct-generic.c:579-588, 611-619): tmp[k][j], then coef[k][j]
   mat_pass_dp2a<W, true, false>(s_a, s_q, s_pf, l2 - 1 + (p.bitdepth - 8));
   __syncthreads();
   mat_pass_dp2a<W, true, false>(s_q, s_b, s_pf, l2 + 6);
   __syncthreads();
+  if (PHASE == 1) {
+    for (int e = threadIdx.x; e < E; e += blockDim.x) {
+      const int gb = e / WW, r = e - gb * WW, b = first + gb;
+      if (b < nblk) coeff[(size_t)b * WW + r] = s_b[e];
+    }
+    return;
+  }
 
   // ---- quantisation (ref: quant-generic.c:50-180)
   const QuantConsts qc = quant_consts(p, l2, is_c ? 2 : 0);
@@ -153,6 +164,7 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
     }
     __syncthreads();
   }
+  }  // PHASE != 2
 
   // ---- coefficients out, has_coeffs, dequant (ref: quant-generic.c:298-340) into the TRANSPOSED layout the
   //      inverse passes consume
@@ -166,7 +178,7 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
       const int gb = e / WW, r = e - gb * WW, y = r >> LOG2W, x = r & (W - 1), b = first + gb;
       const int16_t v = s_q[e];
       if (b < nblk) {
-        coeff[(size_t)b * WW + r] = v;
+        if (PHASE != 2) coeff[(size_t)b * WW + r] = v;
         if (v != 0) s_has[gb] = 1;
       }
       s_b[gb * WW + x * W + y] = (int16_t)clip3(-32768, 32767, ((int)v * scale + add) >> shift);
@@ -389,6 +401,22 @@ int launch_recon_inter(const kvz_cuda_quant_params &qp, const uint8_t *src, cons
 }
 }  // namespace kvzc
 
+template <int PHASE>
+static int launch_recon_phase(const kvz_cuda_quant_params &qp, const uint8_t *src, const uint8_t *rin, int stride, int pic_w, int pic_h,
+                              int color, int log2w, int blocks_x, int nblk, const int8_t *modes, uint8_t *rec, int16_t *coeff,
+                              uint8_t *has, uint32_t *ssd, cudaStream_t st)
+{
+  const int ww = 1 << (2 * log2w), g = 1024 / ww, grid = (nblk + g - 1) / g;
+  switch (log2w) {
+    case 2: intra_recon_kernel<uint8_t, 2, false, PHASE><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
+    case 3: intra_recon_kernel<uint8_t, 3, false, PHASE><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
+    case 4: intra_recon_kernel<uint8_t, 4, false, PHASE><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
+    default: intra_recon_kernel<uint8_t, 5, false, PHASE><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
+  }
+  KVZC_LAUNCHED();
+  return 0;
+}
+
 static int launch_recon(const kvz_cuda_quant_params &qp, const uint8_t *src, const uint8_t *rin, int stride, int pic_w, int pic_h,
                         int color, int log2w, int blocks_x, int nblk, const int8_t *modes, uint8_t *rec, int16_t *coeff,
                         uint8_t *has, uint32_t *ssd, cudaStream_t st)
@@ -416,7 +444,8 @@ struct kvz_cuda_frame_pass {
   uint8_t *blob = nullptr;              // device: host-visible sections first, device-only sections after
   // device-only
   size_t off_costs35[4], off_rec_y[4], off_rec_u[3], off_rec_v[3];
-  size_t off_sao_off, off_dbk_cus, off_src_copy;
+  size_t off_sao_off, off_dbk_cus, off_cabac, off_src_copy;
+  kvz_cuda_rdoq_params rdoq;
   std::vector<uint8_t> host_init;       // initial content of the descriptor sections
   size_t init_off = 0, init_bytes = 0;
   // optional per-stage CUDA-event timing (bench.py's live roofline measurement)
@@ -427,6 +456,23 @@ struct kvz_cuda_frame_pass {
   int runs_timed = 0;
   bool ev_pending = false;
 };
+
+// transform-depth below the CU that the pass assumes per quadtree depth index (32x32 TU inside a 64x64 CU, 4x4 = NxN
+// split of an 8x8 CU); it only selects the cbf context of RDOQ (rdo.c:895-899).  The CPU arm uses the same table.
+static const int k_fp_tr_depth[4] = { 1, 0, 0, 1 };
+
+// prediction -> transform -> quantisation -> reconstruction of one plane at one depth; with RDOQ the fused kernel is
+// split around the RDOQ launch (quant-generic.c:234-240)
+static int fp_recon(kvz_cuda_frame_pass *fp, const kvz_cuda_quant_params &qp, const uint8_t *src, const uint8_t *rin, int stride, int pic_w,
+                    int pic_h, int color, int log2w, int blocks_x, int nblk, const int8_t *modes, uint8_t *rec, int16_t *coeff, uint8_t *has,
+                    uint32_t *ssd, int d, cudaStream_t st)
+{
+  if (!fp->prm.rdoq) return launch_recon(qp, src, rin, stride, pic_w, pic_h, color, log2w, blocks_x, nblk, modes, rec, coeff, has, ssd, st);
+  if (int r = launch_recon_phase<1>(qp, src, rin, stride, pic_w, pic_h, color, log2w, blocks_x, nblk, modes, rec, coeff, has, ssd, st)) return r;
+  if (int r = rdoq_launch_grid(fp->rdoq, (const kvz_cuda_cabac_ctx *)(fp->blob + fp->off_cabac), coeff, nblk, log2w, modes, color != 0,
+                               k_fp_tr_depth[d], st)) return r;
+  return launch_recon_phase<2>(qp, src, rin, stride, pic_w, pic_h, color, log2w, blocks_x, nblk, modes, rec, coeff, has, ssd, st);
+}
 
 static void fp_mark(kvz_cuda_frame_pass *fp, int idx, cudaStream_t st) { if (fp->timing) cudaEventRecord(fp->ev[idx], st); }
 static void fp_collect(kvz_cuda_frame_pass *fp)
@@ -485,6 +531,7 @@ static kvz_cuda_frame_pass *fp_build(const kvz_cuda_fp_params *p, bool alloc)
   // (cu_info_t image: type = CU_INTRA, depth = 3, part_size = 2Nx2N, tr_depth = 3), initialised from the host once
   fp->init_off = off;
   fp->off_dbk_cus = take((size_t)(W / 4) * (H / 4) * 20);
+  fp->off_cabac = take(sizeof(kvz_cuda_cabac_ctx));      // slice-initial context models for RDOQ (I slice)
   fp->init_bytes = off - fp->init_off;
   fp->total_bytes = off;
   if (alloc) {
@@ -495,7 +542,10 @@ static kvz_cuda_frame_pass *fp_build(const kvz_cuda_fp_params *p, bool alloc)
       rec[20 * i + 1] = 3;
       rec[20 * i + 6] = (uint8_t)p->qp;
     }
+    if (kvz_cuda_cabac_ctx_init(p->qp, 2, (kvz_cuda_cabac_ctx *)(fp->host_init.data() + (fp->off_cabac - fp->init_off))) != 0) { delete fp; return nullptr; }
   }
+  fp->rdoq.lambda = p->lambda > 0 ? p->lambda : 0.57 * pow(2.0, (p->qp - 12) / 3.0);
+  fp->rdoq.qp = p->qp; fp->rdoq.bitdepth = 8; fp->rdoq.signhide_enable = p->signhide; fp->rdoq.pad = 0;
   if (!alloc) return fp;
   if (cudaMalloc((void **)&fp->blob, fp->total_bytes) != cudaSuccess) { set_error("frame pass: cudaMalloc(%zu) failed", fp->total_bytes); delete fp; return nullptr; }
   cudaMemset(fp->blob, 0, fp->total_bytes);
@@ -550,17 +600,17 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
     if (int r = rough_search_u8(log2w, src, rin, W, W, H, fp->keep_costs ? costs : nullptr, modes, (uint32_t *)(B + L.cost_y[d]), st)) return r;
     fp_mark(fp, d * 4 + 1, st);
     fp_mark(fp, d * 4 + 2, st);
-    if (int r = launch_recon(qp, src, rin, W, W, H, 0, log2w, W / w, nb, modes, B + fp->off_rec_y[d],
-                             (int16_t *)(B + L.coeff_y[d]), B + L.has_y[d], (uint32_t *)(B + L.ssd_y[d]), st)) return r;
+    if (int r = fp_recon(fp, qp, src, rin, W, W, H, 0, log2w, W / w, nb, modes, B + fp->off_rec_y[d],
+                         (int16_t *)(B + L.coeff_y[d]), B + L.has_y[d], (uint32_t *)(B + L.ssd_y[d]), d, st)) return r;
     fp_mark(fp, d * 4 + 3, st);
     if (d < 3) {
       const int wc = w / 2;
       for (int color = 1; color <= 2; ++color) {
-        if (int r = launch_recon(qp, src + poff[color], rin + poff[color], W / 2, W, H, color, log2w - 1, (W / 2) / wc, nb, modes,
-                                 B + (color == 1 ? fp->off_rec_u[d] : fp->off_rec_v[d]),
-                                 (int16_t *)(B + (color == 1 ? L.coeff_u[d] : L.coeff_v[d])),
-                                 B + (color == 1 ? L.has_u[d] : L.has_v[d]),
-                                 (uint32_t *)(B + (color == 1 ? L.ssd_u[d] : L.ssd_v[d])), st)) return r;
+        if (int r = fp_recon(fp, qp, src + poff[color], rin + poff[color], W / 2, W, H, color, log2w - 1, (W / 2) / wc, nb, modes,
+                             B + (color == 1 ? fp->off_rec_u[d] : fp->off_rec_v[d]),
+                             (int16_t *)(B + (color == 1 ? L.coeff_u[d] : L.coeff_v[d])),
+                             B + (color == 1 ? L.has_u[d] : L.has_v[d]),
+                             (uint32_t *)(B + (color == 1 ? L.ssd_u[d] : L.ssd_v[d])), d, st)) return r;
       }
     }
   }

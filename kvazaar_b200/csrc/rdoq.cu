@@ -50,6 +50,43 @@ __global__ void __launch_bounds__(WARPS * 32) rdoq_tu_kernel(kvz_cuda_rdoq_param
   for (int e = lane; e < NN; e += 32) coeff[tu.off_coeff + e] = s_q[warp][e];
 }
 
+// Uniform TU grid of the frame-level pass: TU t occupies coeff[t * NN ..), every TU intra; the scan follows the
+// intra mode exactly as in the reconstruction kernel (kvz_get_scan_order, search_intra.c / intra.c call sites).
+template <int LOG2N, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) rdoq_grid_kernel(kvz_cuda_rdoq_params p, const kvz_cuda_cabac_ctx *__restrict__ cabac,
+                                                               int16_t *__restrict__ coeff, int count, const int8_t *__restrict__ modes,
+                                                               int is_chroma, int tr_depth)
+{
+  constexpr int NN = 1 << (2 * LOG2N), W = 1 << LOG2N;
+  __shared__ RdoqScratch<NN> scratch[WARPS];
+  __shared__ kvz_cuda_cabac_ctx s_ctx;
+  __shared__ __align__(4) int16_t s_coef[WARPS][NN], s_q[WARPS][NN];
+  for (int i = threadIdx.x; i < (int)sizeof(kvz_cuda_cabac_ctx); i += blockDim.x) ((uint8_t *)&s_ctx)[i] = ((const uint8_t *)cabac)[i];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * WARPS + warp;
+  const bool active = t < count;
+  if (active) for (int e = lane; e < NN; e += 32) s_coef[warp][e] = coeff[(size_t)t * NN + e];
+  __syncthreads();
+  if (!active) return;
+  int scan = 0;
+  if ((!is_chroma && W <= 8) || (is_chroma && W == 4)) { const int m = modes[t]; scan = (m >= 6 && m <= 14) ? 2 : ((m >= 22 && m <= 30) ? 1 : 0); }
+  rdoq_tu<NN>(p, &s_ctx, s_coef[warp], s_q[warp], LOG2N, is_chroma ? 2 : 0, scan, 1, tr_depth, scratch[warp], lane);
+  for (int e = lane; e < NN; e += 32) coeff[(size_t)t * NN + e] = s_q[warp][e];
+}
+
+int rdoq_launch_grid(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ctx_dev, int16_t *coeff, int count, int log2n, const int8_t *modes,
+                     int is_chroma, int tr_depth, cudaStream_t st)
+{
+  switch (log2n) {
+    case 2: rdoq_grid_kernel<2, 8><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); break;
+    case 3: rdoq_grid_kernel<3, 8><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); break;
+    case 4: rdoq_grid_kernel<4, 4><<<(count + 3) / 4, 128, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); break;
+    default: rdoq_grid_kernel<5, 1><<<count, 32, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); break;
+  }
+  KVZC_LAUNCHED();
+  return 0;
+}
+
 int rdoq_launch_tus(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ctx_dev, int16_t *coeff, const kvz_cuda_tu *tus, int count, int n, cudaStream_t st)
 {
   switch (n) {

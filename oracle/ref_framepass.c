@@ -21,6 +21,8 @@
 #include "strategyselector.h"
 #include "cu.h"
 #include "intra.h"
+#include <math.h>
+#include "context.h"
 #include "sao.h"
 #include "filter.h"
 #include "cu.h"
@@ -65,6 +67,9 @@ static void do_block(job_t *j, int d, int b, kvz_pixel *buf /* scratch: 6 * 1024
   kvz_intra_references refs;
   cu_info_t cu; memset(&cu, 0, sizeof(cu));
   cu.type = CU_INTRA; cu.part_size = SIZE_2Nx2N;
+  /* transform depth below the CU as the pass defines it per depth index (csrc/framepass.cu k_fp_tr_depth); only
+   * kvz_rdoq's cbf context reads it (quant-generic.c:237, rdo.c:895-899) */
+  { static const int trd[4] = { 1, 0, 0, 1 }; cu.depth = 0; cu.tr_depth = trd[d]; }
 
   /* --- luma rough search: 35 modes, SATD against the source block */
   memset(&refs, 0, sizeof(refs));
@@ -214,6 +219,10 @@ int kvzref_frame_pass(kvzref_ctx *ctx, const uint8_t *src, int W, int H, int qp,
   j.ctx = ctx; j.src = src; j.W = W; j.H = H; j.qp = qp; j.L = L; j.blob = blob;
   encoder_state_t *st = &ctx->enc->states[0];
   st->qp = (int8_t)qp; st->frame->slicetype = KVZ_SLICE_I;
+  /* RDOQ inputs (used when the ctx was opened with rdoq = 1): slice-initial context models, constant-QP lambda
+   * (qp_to_lambda, rate_control.c:678-691) */
+  kvz_init_contexts(st, (int8_t)qp, KVZ_SLICE_I);
+  st->lambda = 0.57 * pow(2.0, (qp - 12) / 3.0);
   for (int d = 0; d < 4; ++d) {
     j.wl[d] = 32 >> d;
     j.rec[0][d] = (uint8_t *)xaligned((size_t)W * H);

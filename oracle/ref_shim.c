@@ -121,7 +121,7 @@ kvzref_ctx *kvzref_ctx_open(int width, int height, int qp, int signhide, int rdo
   c->api->config_init(c->cfg);
   c->cfg->width = width; c->cfg->height = height; c->cfg->qp = qp;
   c->cfg->threads = 0; c->cfg->owf = 0; c->cfg->wpp = 0;
-  c->cfg->signhide_enable = signhide; c->cfg->rdoq_enable = rdoq;
+  c->cfg->signhide_enable = signhide; c->cfg->rdoq_enable = rdoq; c->cfg->rdoq_skip = 0;
   c->cfg->hash = KVZ_HASH_NONE;
   c->cfg->enable_logging_output = 0;
   c->enc = c->api->encoder_open(c->cfg);

@@ -58,20 +58,22 @@ def test_reference_frame_pass_is_self_consistent(ref, orc):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("dims,qp,signhide", [((136, 72), 27, 0), ((200, 136), 27, 0), ((320, 192), 27, 0),
-                                               ((200, 136), 22, 1), ((136, 72), 37, 1), ((320, 192), 17, 1)])
-def test_cuda_frame_pass_matches_reference(cuda_lib, ref, dims, qp, signhide):
+@pytest.mark.parametrize("dims,qp,signhide,rdoq", [((136, 72), 27, 0, 0), ((200, 136), 27, 0, 0), ((320, 192), 27, 0, 0),
+                                                    ((200, 136), 22, 1, 0), ((136, 72), 37, 1, 0), ((320, 192), 17, 1, 0),
+                                                    ((200, 136), 27, 0, 1), ((320, 192), 22, 1, 1), ((136, 72), 32, 0, 1)])
+def test_cuda_frame_pass_matches_reference(cuda_lib, ref, dims, qp, signhide, rdoq):
     """Byte-identical result blob: CUDA frame pass vs the reference's own strategy functions (medium-like:
-    signhide off; veryslow-like: QP 22 with sign-bit hiding)."""
+    signhide off; veryslow-like: QP 22 with sign-bit hiding; rdoq = 1: kvz_rdoq instead of kvz_quant, as medium and
+    veryslow configure it)."""
     import torch
     from _oracle import ref_frame_pass
     kb = cuda_lib
     W, H = dims
     src = synth_frame(W, H, frame_idx=W + qp)
-    fp = kb.FramePass(W, H, qp, signhide)
+    fp = kb.FramePass(W, H, qp, signhide, rdoq)
     fp.run_dev(kb.to_dev(src))
     got = fp.result_host()
-    want = ref_frame_pass(ref, src, W, H, qp, fp.layout, nthreads=4, signhide=signhide)
+    want = ref_frame_pass(ref, src, W, H, qp, fp.layout, nthreads=4, signhide=signhide, rdoq=rdoq)
     sec = kb.fp_sections(fp.layout, W, H)
     for name in sec:
         a, b = kb.fp_section(got, sec, name), kb.fp_section(want, sec, name)

@@ -44,6 +44,20 @@ def test_cabac_ctx_layout(ref):
     assert [off[k] for k in names] == list(ref.cabac_ctx_offsets())
 
 
+def test_cabac_ctx_init_matches_reference(ref):
+    """kvz_cuda_cabac_ctx_init (csrc/cabac_init.cu, host code: needs no GPU) == kvz_init_contexts for every QP / slice type."""
+    from kvazaar_b200 import api, lib
+    skip = [26, 27]                                  # cu_qp_delta_abs[2..3]: never initialised by the reference
+    for slice_type in (0, 1, 2):
+        for qp in range(0, 52):
+            out = np.zeros(api.CABAC_CTX_BYTES, np.uint8)
+            assert lib().kvz_cuda_cabac_ctx_init(qp, slice_type, C.c_void_p(out.ctypes.data)) == 0
+            want = ref.init_contexts(qp, slice_type)
+            keep = np.ones(api.CABAC_CTX_BYTES, bool)
+            keep[skip] = False
+            assert np.array_equal(out[keep], want[keep]), (slice_type, qp)
+
+
 def lambda_for(qp):
     return 0.57 * 2.0 ** ((qp - 12) / 3.0)
 
