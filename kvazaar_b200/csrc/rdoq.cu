@@ -3,13 +3,13 @@
 
 namespace kvzc {
 
-template <int LOG2N, int WARPS>
+template <int LOG2N, int WARPS, bool SH>
 __global__ void __launch_bounds__(WARPS * 32) rdoq_kernel(kvz_cuda_rdoq_params p, const kvz_cuda_cabac_ctx *__restrict__ cabac,
                                                           const int16_t *__restrict__ coef, int16_t *__restrict__ dest,
                                                           const kvz_cuda_rdoq_tu *__restrict__ tus, int count)
 {
   constexpr int NN = 1 << (2 * LOG2N);
-  __shared__ RdoqScratch<NN> scratch[WARPS];
+  __shared__ RdoqScratch<NN, SH> scratch[WARPS];
   __shared__ kvz_cuda_cabac_ctx s_ctx;
   __shared__ __align__(4) int16_t s_coef[WARPS][NN], s_q[WARPS][NN];
   for (int i = threadIdx.x; i < (int)sizeof(kvz_cuda_cabac_ctx); i += blockDim.x) ((uint8_t *)&s_ctx)[i] = ((const uint8_t *)cabac)[i];
@@ -23,18 +23,18 @@ __global__ void __launch_bounds__(WARPS * 32) rdoq_kernel(kvz_cuda_rdoq_params p
   }
   __syncthreads();
   if (!active) return;
-  rdoq_tu<NN>(p, &s_ctx, s_coef[warp], s_q[warp], LOG2N, tu.type, tu.scan_idx, tu.block_type, tu.tr_depth, scratch[warp], lane);
+  rdoq_tu<NN, SH>(p, &s_ctx, s_coef[warp], s_q[warp], LOG2N, tu.type, tu.scan_idx, tu.block_type, tu.tr_depth, scratch[warp], lane);
   for (int e = lane; e < NN; e += 32) dest[tu.off_dest + e] = s_q[warp][e];
 }
 
 // The same for kvz_cuda_tu descriptors (quantize_residual's RDOQ branch): in place on coeff; TUs of other widths
 // are skipped (one launch per width present in the batch).
-template <int LOG2N, int WARPS>
+template <int LOG2N, int WARPS, bool SH>
 __global__ void __launch_bounds__(WARPS * 32) rdoq_tu_kernel(kvz_cuda_rdoq_params p, const kvz_cuda_cabac_ctx *__restrict__ cabac,
                                                              int16_t *__restrict__ coeff, const kvz_cuda_tu *__restrict__ tus, int count)
 {
   constexpr int NN = 1 << (2 * LOG2N);
-  __shared__ RdoqScratch<NN> scratch[WARPS];
+  __shared__ RdoqScratch<NN, SH> scratch[WARPS];
   __shared__ kvz_cuda_cabac_ctx s_ctx;
   __shared__ __align__(4) int16_t s_coef[WARPS][NN], s_q[WARPS][NN];
   for (int i = threadIdx.x; i < (int)sizeof(kvz_cuda_cabac_ctx); i += blockDim.x) ((uint8_t *)&s_ctx)[i] = ((const uint8_t *)cabac)[i];
@@ -46,19 +46,19 @@ __global__ void __launch_bounds__(WARPS * 32) rdoq_tu_kernel(kvz_cuda_rdoq_param
   if (active) for (int e = lane; e < NN; e += 32) s_coef[warp][e] = coeff[tu.off_coeff + e];
   __syncthreads();
   if (!active) return;
-  rdoq_tu<NN>(p, &s_ctx, s_coef[warp], s_q[warp], LOG2N, tu.color == 0 ? 0 : 2, tu.scan_idx, tu.cu_is_intra ? 1 : 2, tu.tr_depth, scratch[warp], lane);
+  rdoq_tu<NN, SH>(p, &s_ctx, s_coef[warp], s_q[warp], LOG2N, tu.color == 0 ? 0 : 2, tu.scan_idx, tu.cu_is_intra ? 1 : 2, tu.tr_depth, scratch[warp], lane);
   for (int e = lane; e < NN; e += 32) coeff[tu.off_coeff + e] = s_q[warp][e];
 }
 
 // Uniform TU grid of the frame-level pass: TU t occupies coeff[t * NN ..), every TU intra; the scan follows the
 // intra mode exactly as in the reconstruction kernel (kvz_get_scan_order, search_intra.c / intra.c call sites).
-template <int LOG2N, int WARPS>
+template <int LOG2N, int WARPS, bool SH>
 __global__ void __launch_bounds__(WARPS * 32) rdoq_grid_kernel(kvz_cuda_rdoq_params p, const kvz_cuda_cabac_ctx *__restrict__ cabac,
                                                                int16_t *__restrict__ coeff, int count, const int8_t *__restrict__ modes,
                                                                int is_chroma, int tr_depth)
 {
   constexpr int NN = 1 << (2 * LOG2N), W = 1 << LOG2N;
-  __shared__ RdoqScratch<NN> scratch[WARPS];
+  __shared__ RdoqScratch<NN, SH> scratch[WARPS];
   __shared__ kvz_cuda_cabac_ctx s_ctx;
   __shared__ __align__(4) int16_t s_coef[WARPS][NN], s_q[WARPS][NN];
   for (int i = threadIdx.x; i < (int)sizeof(kvz_cuda_cabac_ctx); i += blockDim.x) ((uint8_t *)&s_ctx)[i] = ((const uint8_t *)cabac)[i];
@@ -70,18 +70,19 @@ __global__ void __launch_bounds__(WARPS * 32) rdoq_grid_kernel(kvz_cuda_rdoq_par
   if (!active) return;
   int scan = 0;
   if ((!is_chroma && W <= 8) || (is_chroma && W == 4)) { const int m = modes[t]; scan = (m >= 6 && m <= 14) ? 2 : ((m >= 22 && m <= 30) ? 1 : 0); }
-  rdoq_tu<NN>(p, &s_ctx, s_coef[warp], s_q[warp], LOG2N, is_chroma ? 2 : 0, scan, 1, tr_depth, scratch[warp], lane);
+  rdoq_tu<NN, SH>(p, &s_ctx, s_coef[warp], s_q[warp], LOG2N, is_chroma ? 2 : 0, scan, 1, tr_depth, scratch[warp], lane);
   for (int e = lane; e < NN; e += 32) coeff[(size_t)t * NN + e] = s_q[warp][e];
 }
 
 int rdoq_launch_grid(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ctx_dev, int16_t *coeff, int count, int log2n, const int8_t *modes,
                      int is_chroma, int tr_depth, cudaStream_t st)
 {
+  const bool SHV = p.signhide_enable != 0;
   switch (log2n) {
-    case 2: rdoq_grid_kernel<2, 8><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); break;
-    case 3: rdoq_grid_kernel<3, 8><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); break;
-    case 4: rdoq_grid_kernel<4, 4><<<(count + 3) / 4, 128, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); break;
-    default: rdoq_grid_kernel<5, 1><<<count, 32, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); break;
+    case 2: if (SHV) rdoq_grid_kernel<2, 8, true><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); else rdoq_grid_kernel<2, 8, false><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); break;
+    case 3: if (SHV) rdoq_grid_kernel<3, 8, true><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); else rdoq_grid_kernel<3, 8, false><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); break;
+    case 4: if (SHV) rdoq_grid_kernel<4, 2, true><<<(count + 1) / 2, 64, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); else rdoq_grid_kernel<4, 2, false><<<(count + 1) / 2, 64, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); break;
+    default: if (SHV) rdoq_grid_kernel<5, 1, true><<<count, 32, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); else rdoq_grid_kernel<5, 1, false><<<count, 32, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); break;
   }
   KVZC_LAUNCHED();
   return 0;
@@ -89,11 +90,12 @@ int rdoq_launch_grid(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ct
 
 int rdoq_launch_tus(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ctx_dev, int16_t *coeff, const kvz_cuda_tu *tus, int count, int n, cudaStream_t st)
 {
+  const bool SHV = p.signhide_enable != 0;
   switch (n) {
-    case 4: rdoq_tu_kernel<2, 8><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, tus, count); break;
-    case 8: rdoq_tu_kernel<3, 8><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, tus, count); break;
-    case 16: rdoq_tu_kernel<4, 4><<<(count + 3) / 4, 128, 0, st>>>(p, ctx_dev, coeff, tus, count); break;
-    default: rdoq_tu_kernel<5, 1><<<count, 32, 0, st>>>(p, ctx_dev, coeff, tus, count); break;
+    case 4: if (SHV) rdoq_tu_kernel<2, 8, true><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, tus, count); else rdoq_tu_kernel<2, 8, false><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, tus, count); break;
+    case 8: if (SHV) rdoq_tu_kernel<3, 8, true><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, tus, count); else rdoq_tu_kernel<3, 8, false><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, tus, count); break;
+    case 16: if (SHV) rdoq_tu_kernel<4, 2, true><<<(count + 1) / 2, 64, 0, st>>>(p, ctx_dev, coeff, tus, count); else rdoq_tu_kernel<4, 2, false><<<(count + 1) / 2, 64, 0, st>>>(p, ctx_dev, coeff, tus, count); break;
+    default: if (SHV) rdoq_tu_kernel<5, 1, true><<<count, 32, 0, st>>>(p, ctx_dev, coeff, tus, count); else rdoq_tu_kernel<5, 1, false><<<count, 32, 0, st>>>(p, ctx_dev, coeff, tus, count); break;
   }
   KVZC_LAUNCHED();
   return 0;
@@ -113,11 +115,12 @@ extern "C" int kvz_cuda_rdoq_batch(const kvz_cuda_rdoq_params *p, const kvz_cuda
   KVZC_ARG(p->lambda > 0);
   if (count == 0) return 0;
   cudaStream_t st = as_stream(stream);
+  const bool SHV = p->signhide_enable != 0;
   switch (n) {
-    case 4: rdoq_kernel<2, 8><<<(count + 7) / 8, 256, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); break;
-    case 8: rdoq_kernel<3, 8><<<(count + 7) / 8, 256, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); break;
-    case 16: rdoq_kernel<4, 4><<<(count + 3) / 4, 128, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); break;
-    default: rdoq_kernel<5, 1><<<count, 32, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); break;
+    case 4: if (SHV) rdoq_kernel<2, 8, true><<<(count + 7) / 8, 256, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); else rdoq_kernel<2, 8, false><<<(count + 7) / 8, 256, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); break;
+    case 8: if (SHV) rdoq_kernel<3, 8, true><<<(count + 7) / 8, 256, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); else rdoq_kernel<3, 8, false><<<(count + 7) / 8, 256, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); break;
+    case 16: if (SHV) rdoq_kernel<4, 2, true><<<(count + 1) / 2, 64, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); else rdoq_kernel<4, 2, false><<<(count + 1) / 2, 64, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); break;
+    default: if (SHV) rdoq_kernel<5, 1, true><<<count, 32, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); else rdoq_kernel<5, 1, false><<<count, 32, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); break;
   }
   KVZC_LAUNCHED();
   return 0;

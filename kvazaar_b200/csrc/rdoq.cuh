@@ -36,14 +36,19 @@ constexpr int RDOQ_ONE_BIT = 1 << 15;
 // position group of a last-significant coordinate (g_group_idx, rdo.c: 0,1,2,3,4,4,5,5,6,6,6,6,7,7,7,7,8..,9..)
 __device__ __forceinline__ int last_group(int x) { if (x < 4) return x; const int l = 31 - __clz(x); return 2 * l + ((x >> (l - 1)) & 1); }
 
-template <int NN>
+// SH = sign hiding enabled: only then the per-position rate tables of kvz_sh_rates_t exist
+template <int NN, bool SH>
 struct RdoqScratch {
   double cost_coeff[NN], cost_sig[NN], cost_coeff0[NN];
-  int32_t inc[NN], dec[NN], sig_inc[NN], qdelta[NN];       // kvz_sh_rates_t (rdo.h:49-58)
+  int32_t inc[SH ? NN : 1], dec[SH ? NN : 1], sig_inc[SH ? NN : 1], qdelta[SH ? NN : 1];       // kvz_sh_rates_t (rdo.h:49-58)
+  uint16_t blk[NN];                                        // scan position -> raster position
   double cg_sig_cost[NN / 16];
   int32_t cg_flag[NN / 16];
   int32_t last_x_bits[12], last_y_bits[12];
-  int32_t last_scanpos;
+  // per coefficient group, filled by lanes 0..15 before lane 0 walks the group
+  double prep_c0[16], prep_sig0[16], prep_sig1[16];
+  int32_t prep_ld[16], prep_ctx_sig[16];
+  int32_t best_last_p1;
 };
 
 struct RdoqModels {      // views into the kvz_cuda_cabac_ctx image for one texture type
@@ -135,7 +140,7 @@ __device__ __forceinline__ int rdoq_sig_ctx(int pattern, int scan_idx, int px, i
 
 // Sign-bit hiding on RDOQ output (rdo.c:518-653).  Serial; one thread.
 template <int NN>
-__device__ void rdoq_sign_hiding(const RdoqScratch<NN> &s, double lambda, int bitdepth, int qp_scaled, int scan_idx, int log2n, int last_pos,
+__device__ void rdoq_sign_hiding(const RdoqScratch<NN, true> &s, double lambda, int bitdepth, int qp_scaled, int scan_idx, int log2n, int last_pos,
                                  const int16_t *coef, int16_t *q)
 {
   const int inv_quant = c_inv_quant_scales[qp_scaled % 6];
@@ -143,9 +148,7 @@ __device__ void rdoq_sign_hiding(const RdoqScratch<NN> &s, double lambda, int bi
   const int last_cg = (last_pos - 1) >> 4;
   for (int cg = last_cg; cg >= 0; --cg) {
     const int base = cg << 4;
-    int pos[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) pos[k] = scan_pos(scan_idx, log2n, base + k);
+    const uint16_t *pos = s.blk + base;
     int last_nz = -1, first_nz = 16;
     for (int k = 15; k >= 0; --k) if (q[pos[k]]) { last_nz = k; break; }
     for (int k = 0; k <= last_nz; ++k) if (q[pos[k]]) { first_nz = k; break; }
@@ -188,12 +191,17 @@ __device__ void rdoq_sign_hiding(const RdoqScratch<NN> &s, double lambda, int bi
   }
 }
 
-// kvz_rdoq for one TU by one warp (all 32 lanes must call; `lane` = lane id).  coef / q: n x n row-major, any memory
-// space the warp can read / write coherently (shared or global).  type: 0 luma, 2 chroma (the reference passes 2 for
-// U and V, quant-generic.c:239).  block_type: 1 intra, 2 inter.  tr_depth: depth below the CU (+1 for NxN).
-template <int NN>
+// kvz_rdoq for one TU by one warp (all 32 lanes must call; `lane` = lane id).  coef / q: n x n row-major in shared
+// memory.  type: 0 luma, 2 chroma (the reference passes 2 for U and V, quant-generic.c:239).  block_type: 1 intra,
+// 2 inter.  tr_depth: depth below the CU (+1 for NxN).
+//
+// Work split: everything that does not depend on the serial context state is done by the lanes in parallel -- the scan
+// table, the last significant position, and per coefficient group (once its neighbour pattern is known) the
+// distortion of level 0 and the significance costs of its 16 positions.  Lane 0 then walks the group: level choice,
+// context-set / Rice state, and the cost sums in the reference's order (double additions are not associative).
+template <int NN, bool SH>
 __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *cabac, const int16_t *coef, int16_t *q, int log2n, int type,
-                        int scan_idx, int block_type, int tr_depth, RdoqScratch<NN> &s, int lane)
+                        int scan_idx, int block_type, int tr_depth, RdoqScratch<NN, SH> &s, int lane)
 {
   const int n = 1 << log2n, nn = n * n;
   const int transform_shift = 15 - p.bitdepth - log2n;
@@ -201,84 +209,138 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
   const int q_bits = 14 + qp_scaled / 6 + transform_shift;
   const int qc = c_quant_scales[qp_scaled % 6];                          // flat scaling list
   const int half = 1 << (q_bits - 1);
+  const double lambda = p.lambda;
+  // error scale (scalinglist.c:351-368): 2^15 * 2^(-2 * transform_shift) / q / q / 2^(2 * (bitdepth - 8))
+  const double err_scale = ldexp(32768.0, -2 * transform_shift) / qc / qc / (1 << (2 * (p.bitdepth - 8)));
+  const RdoqModels m = rdoq_models(cabac, type);
 
-  // ---- last significant scan position (find_last_scanpos): position-parallel, then a warp maximum
+  // ---- scan table and last significant scan position (find_last_scanpos)
   int my_last = -1;
   for (int sp = lane; sp < nn; sp += 32) {
-    const int ld = min(abs((int)coef[scan_pos(scan_idx, log2n, sp)]) * qc, 0x7FFFFFFF - half);
+    const int blk = scan_pos(scan_idx, log2n, sp);
+    s.blk[sp] = (uint16_t)blk;
+    const int ld = min(abs((int)coef[blk]) * qc, 0x7FFFFFFF - half);
     if (((ld + half) >> q_bits) > 0) my_last = sp;                       // increasing sp: the last assignment is the largest
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) my_last = max(my_last, __shfl_xor_sync(0xffffffffu, my_last, o));
   const int last_scanpos = my_last;
-  for (int sp = lane; sp < nn; sp += 32) if (sp > last_scanpos) q[scan_pos(scan_idx, log2n, sp)] = 0;
+  __syncwarp();
+  for (int sp = lane; sp < nn; sp += 32) if (sp > last_scanpos) q[s.blk[sp]] = 0;
   if (last_scanpos < 0) { __syncwarp(); return; }
   for (int g = lane; g < nn / 16; g += 32) { s.cg_flag[g] = 0; s.cg_sig_cost[g] = 0; }
+  if (lane == 0) {
+    if (SH) s.sig_inc[s.blk[last_scanpos]] = 0;
+    // last-position bin costs (calc_last_bits, rdo.c:479-508)
+    const int cb = log2n - 2;
+    const int off = type ? 0 : (cb * 3 + ((cb + 1) >> 2));
+    const int sh = type ? cb : ((cb + 3) >> 2);
+    int bx = 0, by = 0, ctx;
+    const int groups = last_group(n - 1);
+    for (ctx = 0; ctx < groups; ++ctx) {
+      const int o = off + (ctx >> sh);
+      s.last_x_bits[ctx] = bx + ebits(m.last_x[o], 0); bx += ebits(m.last_x[o], 1);
+      s.last_y_bits[ctx] = by + ebits(m.last_y[o], 0); by += ebits(m.last_y[o], 1);
+    }
+    s.last_x_bits[ctx] = bx; s.last_y_bits[ctx] = by;
+  }
   __syncwarp();
 
-  if (lane == 0) {
-    const RdoqModels m = rdoq_models(cabac, type);
-    const double lambda = p.lambda;
-    // error scale (scalinglist.c:351-368): 2^15 * 2^(-2 * transform_shift) / q / q / 2^(2 * (bitdepth - 8))
-    const double err_scale = ldexp(32768.0, -2 * transform_shift) / qc / qc / (1 << (2 * (p.bitdepth - 8)));
-    const int cg_last = last_scanpos >> 4;
-    const int cgs_side = n >> 2;
-    int ctx_set = (last_scanpos > 0 && type == 0) ? 2 : 0;
-    int c1 = 1, c2 = 0, rice = 0;
-    uint32_t c1_idx = 0, c2_idx = 0;
-    double base_cost = 0, block_uncoded_cost = 0;
-    s.sig_inc[scan_pos(scan_idx, log2n, last_scanpos)] = 0;
+  const int cg_last = last_scanpos >> 4;
+  const int cgs_side = n >> 2;
+  // serial state (meaningful in lane 0 only)
+  int ctx_set = (last_scanpos > 0 && type == 0) ? 2 : 0;
+  int c1 = 1, c2 = 0, rice = 0;
+  uint32_t c1_idx = 0, c2_idx = 0;
+  double base_cost = 0, block_uncoded_cost = 0;
 
-    // last-position bin costs (calc_last_bits, rdo.c:479-508)
-    {
-      const int cb = log2n - 2;
-      const int off = type ? 0 : (cb * 3 + ((cb + 1) >> 2));
-      const int sh = type ? cb : ((cb + 3) >> 2);
-      int bx = 0, by = 0, ctx;
-      const int groups = last_group(n - 1);
-      for (ctx = 0; ctx < groups; ++ctx) {
-        const int o = off + (ctx >> sh);
-        s.last_x_bits[ctx] = bx + ebits(m.last_x[o], 0); bx += ebits(m.last_x[o], 1);
-        s.last_y_bits[ctx] = by + ebits(m.last_y[o], 0); by += ebits(m.last_y[o], 1);
-      }
-      s.last_x_bits[ctx] = bx; s.last_y_bits[ctx] = by;
-    }
-
-    for (int cg = cg_last; cg >= 0; --cg) {
-      const int cg_first = scan_pos(scan_idx, log2n, cg << 4);            // raster position of the group's first coefficient
-      const int cgx = (cg_first & (n - 1)) >> 2, cgy = (cg_first >> log2n) >> 2;
-      const int cg_blk = cgy * cgs_side + cgx;
-      // neighbouring coded groups: right and below (context.c:315-351)
-      const int right = (cgx < cgs_side - 1) ? (s.cg_flag[cgy * cgs_side + cgx + 1] != 0) : 0;
-      const int lower = (cgy < cgs_side - 1) ? (s.cg_flag[(cgy + 1) * cgs_side + cgx] != 0) : 0;
-      const int pattern = (n == 4) ? -1 : right + (lower << 1);
-      double st_coded = 0, st_uncoded = 0, st_sig = 0, st_sig0 = 0;
-      int nnz_before_pos0 = 0;
-      for (int k = 15; k >= 0; --k) {
-        const int sp = (cg << 4) + k;
-        if (sp > last_scanpos) continue;
-        const int blk = scan_pos(scan_idx, log2n, sp);
+  for (int cg = cg_last; cg >= 0; --cg) {
+    const int cg_first = s.blk[cg << 4];                                  // raster position of the group's first coefficient
+    const int cgx = (cg_first & (n - 1)) >> 2, cgy = (cg_first >> log2n) >> 2;
+    const int cg_blk = cgy * cgs_side + cgx;
+    // neighbouring coded groups: right and below (context.c:315-351); both were decided earlier in this walk
+    const int right = (cgx < cgs_side - 1) ? (s.cg_flag[cgy * cgs_side + cgx + 1] != 0) : 0;
+    const int lower = (cgy < cgs_side - 1) ? (s.cg_flag[(cgy + 1) * cgs_side + cgx] != 0) : 0;
+    const int pattern = (n == 4) ? -1 : right + (lower << 1);
+    // position-parallel part of the group: distortion of level 0, significance costs; positions that can only be
+    // zero (max_abs_level == 0, rdo.c:428-432) are finished here except for their place in the ordered cost sums
+    bool valid = false, cand = false;
+    if (lane < 16) {
+      const int sp = (cg << 4) + lane;
+      if (sp <= last_scanpos) {
+        valid = true;
+        const int blk = s.blk[sp];
         const int ld = min(abs((int)coef[blk]) * qc, 0x7FFFFFFF - half);
-        const uint32_t max_abs = (uint32_t)((ld + half) >> q_bits);
         const double err = (double)ld;
         const double c0 = err * err * err_scale;
-        s.cost_coeff0[sp] = c0;
+        s.prep_ld[lane] = ld;
+        s.prep_c0[lane] = c0;
+        cand = sp == last_scanpos || ((ld + half) >> q_bits) != 0;
+        if (sp != last_scanpos) {
+          const int ctx_sig = rdoq_sig_ctx(pattern, scan_idx, blk & (n - 1), blk >> log2n, log2n, type);
+          const double sig0 = lambda * ebits(m.sig[ctx_sig], 0);
+          s.prep_sig0[lane] = sig0;
+          s.prep_sig1[lane] = lambda * ebits(m.sig[ctx_sig], 1);
+          if (SH) s.sig_inc[blk] = ebits(m.sig[ctx_sig], 1) - ebits(m.sig[ctx_sig], 0);
+          if (!cand) {
+            s.cost_coeff0[sp] = c0; s.cost_sig[sp] = sig0; s.cost_coeff[sp] = c0 + sig0;
+            q[blk] = 0;
+            if (SH) s.qdelta[blk] = ld >> (q_bits - 8);
+          }
+        }
+      }
+    }
+    const unsigned valid_mask = __ballot_sync(0xffffffffu, valid), cand_mask = __ballot_sync(0xffffffffu, cand);
+    __syncwarp();
+
+    if (lane == 0) {
+      double st_coded = 0, st_uncoded = 0, st_sig = 0, st_sig0 = 0;
+      int nnz_before_pos0 = 0;
+#pragma unroll 4
+      for (int k = 15; k >= 0; --k) {
+        if (!((valid_mask >> k) & 1)) continue;
+        const int sp = (cg << 4) + k;
+        const double c0 = s.prep_c0[k];
         block_uncoded_cost += c0;
+        if (!((cand_mask >> k) & 1)) {
+          // level 0 is the only candidate: coded cost = c0 + cost of a zero significance flag
+          const double cs = s.prep_sig0[k];
+          base_cost += c0 + cs;
+          st_sig += cs;
+          if (k == 0) st_sig0 = cs;
+          if (SH) s.inc[s.blk[sp]] = ebits(m.one[4 * ctx_set + c1], 0);
+          if (k == 0 && sp > 0) {
+            c2 = 0; rice = 0; c1_idx = 0; c2_idx = 0;
+            ctx_set = (sp == 16 || type != 0) ? 0 : 2;
+            if (c1 == 0) ++ctx_set;
+            c1 = 1;
+          }
+          continue;
+        }
+        const int blk = s.blk[sp];
+        const int ld = s.prep_ld[k];
+        const uint32_t max_abs = (uint32_t)((ld + half) >> q_bits);
+        s.cost_coeff0[sp] = c0;
         const int one_ctx = 4 * ctx_set + c1, abs_ctx = ctx_set + c2;
-        uint32_t level;
+        const bool last = sp == last_scanpos;
+        // kvz_get_coded_level (rdo.c:413-452)
+        uint32_t level = 0;
         double cc, cs = 0;
-        if (sp == last_scanpos) {
-          cs = s.cost_sig[sp];                                            // (left untouched by the reference when last)
-          level = rdoq_pick_level(m, lambda, cc, c0, cs, ld, max_abs, 0, one_ctx, abs_ctx, rice, c1_idx, c2_idx, q_bits, err_scale, true);
-        } else {
-          const int py = blk >> log2n, px = blk & (n - 1);
-          const int ctx_sig = rdoq_sig_ctx(pattern, scan_idx, px, py, log2n, type);
-          level = rdoq_pick_level(m, lambda, cc, c0, cs, ld, max_abs, ctx_sig, one_ctx, abs_ctx, rice, c1_idx, c2_idx, q_bits, err_scale, false);
-          if (p.signhide_enable) s.sig_inc[blk] = ebits(m.sig[ctx_sig], 1) - ebits(m.sig[ctx_sig], 0);
+        if (!last && max_abs < 3) { cs = s.prep_sig0[k]; cc = c0 + cs; }
+        else cc = 1.7e+308;
+        if (max_abs != 0) {
+          const double sig_now = last ? 0.0 : s.prep_sig1[k];
+          const int lo = max_abs > 1 ? (int)max_abs - 1 : 1;
+          for (int lvl = (int)max_abs; lvl >= lo; --lvl) {
+            const double err = (double)(ld - lvl * (1 << q_bits));
+            double c = err * err * err_scale + lambda * rdoq_level_rate(m, (uint32_t)lvl, one_ctx, abs_ctx, rice, c1_idx, c2_idx);
+            c += sig_now;
+            if (c < cc) { level = (uint32_t)lvl; cc = c; cs = sig_now; }
+          }
         }
         s.cost_coeff[sp] = cc;
         s.cost_sig[sp] = cs;
-        if (p.signhide_enable) {
+        if (SH) {
           s.qdelta[blk] = (ld - (int)level * (1 << q_bits)) >> (q_bits - 8);
           if (level > 0) {
             const int now = rdoq_level_rate(m, level, one_ctx, abs_ctx, rice, c1_idx, c2_idx);
@@ -296,7 +358,7 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
         if (level >= 1) ++c1_idx;
         if (level > 1) { c1 = 0; c2 += (c2 < 2); ++c2_idx; }
         else if (c1 < 3 && c1 > 0 && level) ++c1;
-        if ((sp & 15) == 0 && sp > 0) {                                    // context set for the next group down the scan
+        if (k == 0 && sp > 0) {                                            // context set for the next group down the scan
           c2 = 0; rice = 0; c1_idx = 0; c2_idx = 0;
           ctx_set = (sp == 16 || type != 0) ? 0 : 2;
           if (c1 == 0) ++ctx_set;
@@ -313,9 +375,7 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
       }
 
       if (cg) {
-        const int r2 = (cgx < cgs_side - 1) ? (s.cg_flag[cgy * cgs_side + cgx + 1] != 0) : 0;
-        const int l2 = (cgy < cgs_side - 1) ? (s.cg_flag[(cgy + 1) * cgs_side + cgx] != 0) : 0;
-        const int ctx_cg = r2 || l2;
+        const int ctx_cg = right || lower;
         if (s.cg_flag[cg_blk] == 0) {
           s.cg_sig_cost[cg] = lambda * ebits(m.cg[ctx_cg], 0);
           base_cost += s.cg_sig_cost[cg] - st_sig;
@@ -333,7 +393,7 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
             base_cost = cost_zero_cg;
             s.cg_sig_cost[cg] = lambda * ebits(m.cg[ctx_cg], 0);
             for (int k = 15; k >= 0; --k) {
-              const int sp = (cg << 4) + k, blk = scan_pos(scan_idx, log2n, sp);
+              const int sp = (cg << 4) + k, blk = s.blk[sp];
               if (q[blk]) { q[blk] = 0; s.cost_coeff[sp] = s.cost_coeff0[sp]; s.cost_sig[sp] = 0; }
             }
           }
@@ -342,7 +402,10 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
         s.cg_flag[cg_blk] = 1;
       }
     }
+    __syncwarp();
+  }
 
+  if (lane == 0) {
     // ---- best last position (rdo.c:884-945)
     double best_cost;
     if (block_type != 1 && type == 0) {
@@ -356,14 +419,14 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
     int best_last_p1 = 0;
     bool found_last = false;
     for (int cg = cg_last; cg >= 0 && !found_last; --cg) {
-      const int cg_first = scan_pos(scan_idx, log2n, cg << 4);
+      const int cg_first = s.blk[cg << 4];
       const int cg_blk = ((cg_first >> log2n) >> 2) * cgs_side + ((cg_first & (n - 1)) >> 2);
       base_cost -= s.cg_sig_cost[cg];
       if (!s.cg_flag[cg_blk]) continue;
       for (int k = 15; k >= 0; --k) {
         const int sp = (cg << 4) + k;
         if (sp > last_scanpos) continue;
-        const int blk = scan_pos(scan_idx, log2n, sp);
+        const int blk = s.blk[sp];
         if (q[blk]) {
           const int py = blk >> log2n, px = blk & (n - 1);
           const int gx = last_group(scan_idx == 2 ? py : px), gy = last_group(scan_idx == 2 ? px : py);
@@ -380,17 +443,27 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
         }
       }
     }
+    s.best_last_p1 = best_last_p1;
+  }
+  __syncwarp();
 
-    // ---- signs, clean-up, sign hiding
-    unsigned abs_sum = 0;
-    for (int sp = 0; sp < best_last_p1; ++sp) {
-      const int blk = scan_pos(scan_idx, log2n, sp);
+  // ---- signs and clean-up in parallel, then sign hiding
+  const int best_last_p1 = s.best_last_p1;
+  int abs_sum = 0;
+  for (int sp = lane; sp <= last_scanpos; sp += 32) {
+    const int blk = s.blk[sp];
+    if (sp < best_last_p1) {
       const int level = q[blk];
-      abs_sum += (unsigned)level;
+      abs_sum += level;
       q[blk] = (int16_t)(coef[blk] < 0 ? -level : level);
+    } else {
+      q[blk] = 0;
     }
-    for (int sp = best_last_p1; sp <= last_scanpos; ++sp) q[scan_pos(scan_idx, log2n, sp)] = 0;
-    if (p.signhide_enable && abs_sum >= 2) rdoq_sign_hiding(s, lambda, p.bitdepth, qp_scaled, scan_idx, log2n, best_last_p1, coef, q);
+  }
+  if constexpr (SH) {
+    abs_sum = warp_sum(abs_sum);
+    __syncwarp();
+    if (lane == 0 && abs_sum >= 2) rdoq_sign_hiding<NN>(s, lambda, p.bitdepth, qp_scaled, scan_idx, log2n, best_last_p1, coef, q);
   }
   __syncwarp();
 }
