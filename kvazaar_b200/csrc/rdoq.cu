@@ -11,6 +11,8 @@ __global__ void __launch_bounds__(WARPS * 32) rdoq_kernel(kvz_cuda_rdoq_params p
   constexpr int NN = 1 << (2 * LOG2N);
   __shared__ RdoqScratch<NN, SH> scratch[WARPS];
   __shared__ kvz_cuda_cabac_ctx s_ctx;
+  __shared__ int32_t s_ebits[128];
+  rdoq_load_ebits(s_ebits);
   __shared__ __align__(4) int16_t s_coef[WARPS][NN], s_q[WARPS][NN];
   for (int i = threadIdx.x; i < (int)sizeof(kvz_cuda_cabac_ctx); i += blockDim.x) ((uint8_t *)&s_ctx)[i] = ((const uint8_t *)cabac)[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -23,7 +25,7 @@ __global__ void __launch_bounds__(WARPS * 32) rdoq_kernel(kvz_cuda_rdoq_params p
   }
   __syncthreads();
   if (!active) return;
-  rdoq_tu<NN, SH>(p, &s_ctx, s_coef[warp], s_q[warp], LOG2N, tu.type, tu.scan_idx, tu.block_type, tu.tr_depth, scratch[warp], lane);
+  rdoq_tu<NN, SH>(p, &s_ctx, s_ebits, s_coef[warp], s_q[warp], LOG2N, tu.type, tu.scan_idx, tu.block_type, tu.tr_depth, scratch[warp], lane);
   for (int e = lane; e < NN; e += 32) dest[tu.off_dest + e] = s_q[warp][e];
 }
 
@@ -36,6 +38,8 @@ __global__ void __launch_bounds__(WARPS * 32) rdoq_tu_kernel(kvz_cuda_rdoq_param
   constexpr int NN = 1 << (2 * LOG2N);
   __shared__ RdoqScratch<NN, SH> scratch[WARPS];
   __shared__ kvz_cuda_cabac_ctx s_ctx;
+  __shared__ int32_t s_ebits[128];
+  rdoq_load_ebits(s_ebits);
   __shared__ __align__(4) int16_t s_coef[WARPS][NN], s_q[WARPS][NN];
   for (int i = threadIdx.x; i < (int)sizeof(kvz_cuda_cabac_ctx); i += blockDim.x) ((uint8_t *)&s_ctx)[i] = ((const uint8_t *)cabac)[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -46,7 +50,7 @@ __global__ void __launch_bounds__(WARPS * 32) rdoq_tu_kernel(kvz_cuda_rdoq_param
   if (active) for (int e = lane; e < NN; e += 32) s_coef[warp][e] = coeff[tu.off_coeff + e];
   __syncthreads();
   if (!active) return;
-  rdoq_tu<NN, SH>(p, &s_ctx, s_coef[warp], s_q[warp], LOG2N, tu.color == 0 ? 0 : 2, tu.scan_idx, tu.cu_is_intra ? 1 : 2, tu.tr_depth, scratch[warp], lane);
+  rdoq_tu<NN, SH>(p, &s_ctx, s_ebits, s_coef[warp], s_q[warp], LOG2N, tu.color == 0 ? 0 : 2, tu.scan_idx, tu.cu_is_intra ? 1 : 2, tu.tr_depth, scratch[warp], lane);
   for (int e = lane; e < NN; e += 32) coeff[tu.off_coeff + e] = s_q[warp][e];
 }
 
@@ -60,6 +64,8 @@ __global__ void __launch_bounds__(WARPS * 32) rdoq_grid_kernel(kvz_cuda_rdoq_par
   constexpr int NN = 1 << (2 * LOG2N), W = 1 << LOG2N;
   __shared__ RdoqScratch<NN, SH> scratch[WARPS];
   __shared__ kvz_cuda_cabac_ctx s_ctx;
+  __shared__ int32_t s_ebits[128];
+  rdoq_load_ebits(s_ebits);
   __shared__ __align__(4) int16_t s_coef[WARPS][NN], s_q[WARPS][NN];
   for (int i = threadIdx.x; i < (int)sizeof(kvz_cuda_cabac_ctx); i += blockDim.x) ((uint8_t *)&s_ctx)[i] = ((const uint8_t *)cabac)[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -70,7 +76,7 @@ __global__ void __launch_bounds__(WARPS * 32) rdoq_grid_kernel(kvz_cuda_rdoq_par
   if (!active) return;
   int scan = 0;
   if ((!is_chroma && W <= 8) || (is_chroma && W == 4)) { const int m = modes[t]; scan = (m >= 6 && m <= 14) ? 2 : ((m >= 22 && m <= 30) ? 1 : 0); }
-  rdoq_tu<NN, SH>(p, &s_ctx, s_coef[warp], s_q[warp], LOG2N, is_chroma ? 2 : 0, scan, 1, tr_depth, scratch[warp], lane);
+  rdoq_tu<NN, SH>(p, &s_ctx, s_ebits, s_coef[warp], s_q[warp], LOG2N, is_chroma ? 2 : 0, scan, 1, tr_depth, scratch[warp], lane);
   for (int e = lane; e < NN; e += 32) coeff[(size_t)t * NN + e] = s_q[warp][e];
 }
 

@@ -17,19 +17,23 @@ namespace kvzc {
 
 // HM's fractional-bit estimates per CABAC state (15 fractional bits), split by symbol = MPS / LPS
 // (kvz_entropy_bits, rdo.c:69-79: entry [2s] is the MPS cost of state s, [2s + 1] the LPS cost)
-static __constant__ int32_t c_ebits_mps[64] = {
+static __device__ const int32_t c_ebits_mps[64] = {
   32768, 30426, 28306, 26378, 24617, 23005, 21523, 20159, 18899, 17734, 16653, 15650, 14717, 13849, 13038, 12282,
   11575, 10914, 10294, 9714, 9169, 8658, 8178, 7727, 7303, 6903, 6527, 6173, 5840, 5525, 5228, 4948,
   4684, 4435, 4199, 3977, 3767, 3568, 3380, 3202, 3034, 2876, 2725, 2583, 2448, 2321, 2200, 2086,
   1978, 1875, 1778, 1686, 1599, 1517, 1439, 1364, 1294, 1228, 1165, 1105, 1048, 994, 943, 895 };
-static __constant__ int32_t c_ebits_lps[64] = {
+static __device__ const int32_t c_ebits_lps[64] = {
   32768, 35232, 37696, 40159, 42623, 45087, 47551, 50015, 52479, 54942, 57406, 59870, 62334, 64798, 67262, 69725,
   72189, 74653, 77117, 79581, 82044, 84508, 86972, 89436, 91900, 94363, 96827, 99291, 101755, 104219, 106683, 109146,
   111610, 114074, 116538, 119002, 121465, 123929, 126393, 128857, 131321, 133785, 136248, 138712, 141176, 143640, 146104, 148568,
   151031, 153495, 155959, 158423, 160887, 163351, 165814, 168278, 170742, 173207, 175669, 178134, 180598, 183061, 185525, 187989 };
 
-// cost in 1/32768 bits of coding `bin` with the context whose state byte is `st` (bit 0 = MPS value)
-__device__ __forceinline__ int ebits(uint8_t st, int bin) { return ((st ^ bin) & 1) ? c_ebits_lps[st >> 1] : c_ebits_mps[st >> 1]; }
+// The 128-entry table in the reference's indexing (state byte ^ bin), staged in shared memory by the kernels: lanes
+// look up different states at the same time, which constant memory would serialise.
+__device__ __forceinline__ void rdoq_load_ebits(int32_t *table /* [128] */)
+{
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) table[i] = (i & 1) ? c_ebits_lps[i >> 1] : c_ebits_mps[i >> 1];
+}
 
 constexpr int RDOQ_ONE_BIT = 1 << 15;
 
@@ -39,11 +43,12 @@ __device__ __forceinline__ int last_group(int x) { if (x < 4) return x; const in
 // SH = sign hiding enabled: only then the per-position rate tables of kvz_sh_rates_t exist
 template <int NN, bool SH>
 struct RdoqScratch {
-  double cost_coeff[NN], cost_sig[NN], cost_coeff0[NN];
+  double cost_coeff[NN], cost_sig[NN];                     // (the level-0 distortion cost_coeff0 is recomputed where needed)
   int32_t inc[SH ? NN : 1], dec[SH ? NN : 1], sig_inc[SH ? NN : 1], qdelta[SH ? NN : 1];       // kvz_sh_rates_t (rdo.h:49-58)
   uint16_t blk[NN];                                        // scan position -> raster position
   double cg_sig_cost[NN / 16];
   int32_t cg_flag[NN / 16];
+  uint16_t cg_nz[NN / 16];                                 // per group: positions (bit k) whose level is non-zero
   int32_t last_x_bits[12], last_y_bits[12];
   // per coefficient group, filled by lanes 0..15 before lane 0 walks the group
   double prep_c0[16], prep_sig0[16], prep_sig1[16];
@@ -53,12 +58,16 @@ struct RdoqScratch {
 
 struct RdoqModels {      // views into the kvz_cuda_cabac_ctx image for one texture type
   const uint8_t *sig, *one, *abs, *cg, *last_x, *last_y, *cbf;
+  const int32_t *eb;     // entropy-bit table, see rdoq_load_ebits
   uint8_t root_cbf;
 };
+// cost in 1/32768 bits of coding `bin` with the context whose state byte is `st` (bit 0 = MPS value)
+#define ebits(st, bin) (m.eb[(st) ^ (bin)])
 
-__device__ __forceinline__ RdoqModels rdoq_models(const kvz_cuda_cabac_ctx *c, int type)
+__device__ __forceinline__ RdoqModels rdoq_models(const kvz_cuda_cabac_ctx *c, const int32_t *eb, int type)
 {
   RdoqModels m;
+  m.eb = eb;
   m.sig = type ? c->cu_sig_model_chroma : c->cu_sig_model_luma;
   m.one = type ? c->cu_one_model_chroma : c->cu_one_model_luma;
   m.abs = type ? c->cu_abs_model_chroma : c->cu_abs_model_luma;
@@ -200,7 +209,7 @@ __device__ void rdoq_sign_hiding(const RdoqScratch<NN, true> &s, double lambda, 
 // distortion of level 0 and the significance costs of its 16 positions.  Lane 0 then walks the group: level choice,
 // context-set / Rice state, and the cost sums in the reference's order (double additions are not associative).
 template <int NN, bool SH>
-__device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *cabac, const int16_t *coef, int16_t *q, int log2n, int type,
+__device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *cabac, const int32_t *ebits_table, const int16_t *coef, int16_t *q, int log2n, int type,
                         int scan_idx, int block_type, int tr_depth, RdoqScratch<NN, SH> &s, int lane)
 {
   const int n = 1 << log2n, nn = n * n;
@@ -212,7 +221,9 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
   const double lambda = p.lambda;
   // error scale (scalinglist.c:351-368): 2^15 * 2^(-2 * transform_shift) / q / q / 2^(2 * (bitdepth - 8))
   const double err_scale = ldexp(32768.0, -2 * transform_shift) / qc / qc / (1 << (2 * (p.bitdepth - 8)));
-  const RdoqModels m = rdoq_models(cabac, type);
+  const RdoqModels m = rdoq_models(cabac, ebits_table, type);
+  // distortion of quantising the coefficient at raster position blk to 0 (cost_coeff0, rdo.c:770-771)
+  auto level0_cost = [&](int blk) { const double e = (double)min(abs((int)coef[blk]) * qc, 0x7FFFFFFF - half); return e * e * err_scale; };
 
   // ---- scan table and last significant scan position (find_last_scanpos)
   int my_last = -1;
@@ -283,7 +294,7 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
           s.prep_sig1[lane] = lambda * ebits(m.sig[ctx_sig], 1);
           if (SH) s.sig_inc[blk] = ebits(m.sig[ctx_sig], 1) - ebits(m.sig[ctx_sig], 0);
           if (!cand) {
-            s.cost_coeff0[sp] = c0; s.cost_sig[sp] = sig0; s.cost_coeff[sp] = c0 + sig0;
+            s.cost_sig[sp] = sig0; s.cost_coeff[sp] = c0 + sig0;
             q[blk] = 0;
             if (SH) s.qdelta[blk] = ld >> (q_bits - 8);
           }
@@ -296,15 +307,26 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
     if (lane == 0) {
       double st_coded = 0, st_uncoded = 0, st_sig = 0, st_sig0 = 0;
       int nnz_before_pos0 = 0;
-#pragma unroll 4
+      unsigned nz_mask = 0;
+      // the group's 32 inputs of the ordered sums come into registers first (independent loads), so that the walk
+      // below is bound by the three addition chains only
+      // (large TUs only: small ones rarely reach past their first groups, and the unrolled walk costs registers)
+      constexpr bool BIG = NN >= 1024;
+      double c0r[BIG ? 16 : 1], s0r[BIG ? 16 : 1];
+      if constexpr (BIG) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { c0r[k] = s.prep_c0[k]; s0r[k] = s.prep_sig0[k]; }
+      }
+#pragma unroll (BIG ? 16 : 1)
       for (int k = 15; k >= 0; --k) {
         if (!((valid_mask >> k) & 1)) continue;
         const int sp = (cg << 4) + k;
-        const double c0 = s.prep_c0[k];
+        double c0, sig0k;
+        if constexpr (BIG) { c0 = c0r[k]; sig0k = s0r[k]; } else { c0 = s.prep_c0[k]; sig0k = s.prep_sig0[k]; }
         block_uncoded_cost += c0;
         if (!((cand_mask >> k) & 1)) {
           // level 0 is the only candidate: coded cost = c0 + cost of a zero significance flag
-          const double cs = s.prep_sig0[k];
+          const double cs = sig0k;
           base_cost += c0 + cs;
           st_sig += cs;
           if (k == 0) st_sig0 = cs;
@@ -320,13 +342,12 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
         const int blk = s.blk[sp];
         const int ld = s.prep_ld[k];
         const uint32_t max_abs = (uint32_t)((ld + half) >> q_bits);
-        s.cost_coeff0[sp] = c0;
         const int one_ctx = 4 * ctx_set + c1, abs_ctx = ctx_set + c2;
         const bool last = sp == last_scanpos;
         // kvz_get_coded_level (rdo.c:413-452)
         uint32_t level = 0;
         double cc, cs = 0;
-        if (!last && max_abs < 3) { cs = s.prep_sig0[k]; cc = c0 + cs; }
+        if (!last && max_abs < 3) { cs = sig0k; cc = c0 + cs; }
         else cc = 1.7e+308;
         if (max_abs != 0) {
           const double sig_now = last ? 0.0 : s.prep_sig1[k];
@@ -367,6 +388,7 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
         st_sig += cs;
         if (k == 0) st_sig0 = cs;
         if (level) {
+          nz_mask |= 1u << k;
           s.cg_flag[cg_blk] = 1;
           st_coded += cc - cs;
           st_uncoded += c0;
@@ -389,18 +411,20 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
           cost_zero_cg -= st_coded;
           cost_zero_cg -= st_sig;
           if (cost_zero_cg < base_cost) {
+            nz_mask = 0;
             s.cg_flag[cg_blk] = 0;
             base_cost = cost_zero_cg;
             s.cg_sig_cost[cg] = lambda * ebits(m.cg[ctx_cg], 0);
             for (int k = 15; k >= 0; --k) {
               const int sp = (cg << 4) + k, blk = s.blk[sp];
-              if (q[blk]) { q[blk] = 0; s.cost_coeff[sp] = s.cost_coeff0[sp]; s.cost_sig[sp] = 0; }
+              if (q[blk]) { q[blk] = 0; s.cost_coeff[sp] = level0_cost(blk); s.cost_sig[sp] = 0; }
             }
           }
         }
       } else {
         s.cg_flag[cg_blk] = 1;
       }
+      s.cg_nz[cg] = (uint16_t)nz_mask;
     }
     __syncwarp();
   }
@@ -423,24 +447,32 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
       const int cg_blk = ((cg_first >> log2n) >> 2) * cgs_side + ((cg_first & (n - 1)) >> 2);
       base_cost -= s.cg_sig_cost[cg];
       if (!s.cg_flag[cg_blk]) continue;
+      const unsigned nz = s.cg_nz[cg];
+      const int top = cg == cg_last ? (last_scanpos & 15) : 15;
+      constexpr bool BIG = NN >= 1024;
+      double csr[BIG ? 16 : 1];
+      if constexpr (BIG) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) csr[k] = s.cost_sig[(cg << 4) + k];
+      }
+#pragma unroll (BIG ? 16 : 1)
       for (int k = 15; k >= 0; --k) {
+        if (k > top) continue;
         const int sp = (cg << 4) + k;
-        if (sp > last_scanpos) continue;
+        double csk;
+        if constexpr (BIG) csk = csr[k]; else csk = s.cost_sig[sp];
+        if (!((nz >> k) & 1)) { base_cost -= csk; continue; }
         const int blk = s.blk[sp];
-        if (q[blk]) {
-          const int py = blk >> log2n, px = blk & (n - 1);
-          const int gx = last_group(scan_idx == 2 ? py : px), gy = last_group(scan_idx == 2 ? px : py);
-          double bits = s.last_x_bits[gx] + s.last_y_bits[gy];
-          if (gx > 3) bits += RDOQ_ONE_BIT * ((gx - 2) >> 1);
-          if (gy > 3) bits += RDOQ_ONE_BIT * ((gy - 2) >> 1);
-          const double total = base_cost + lambda * bits - s.cost_sig[sp];
-          if (total < best_cost) { best_last_p1 = sp + 1; best_cost = total; }
-          if (q[blk] > 1) { found_last = true; break; }
-          base_cost -= s.cost_coeff[sp];
-          base_cost += s.cost_coeff0[sp];
-        } else {
-          base_cost -= s.cost_sig[sp];
-        }
+        const int py = blk >> log2n, px = blk & (n - 1);
+        const int gx = last_group(scan_idx == 2 ? py : px), gy = last_group(scan_idx == 2 ? px : py);
+        double bits = s.last_x_bits[gx] + s.last_y_bits[gy];
+        if (gx > 3) bits += RDOQ_ONE_BIT * ((gx - 2) >> 1);
+        if (gy > 3) bits += RDOQ_ONE_BIT * ((gy - 2) >> 1);
+        const double total = base_cost + lambda * bits - csk;
+        if (total < best_cost) { best_last_p1 = sp + 1; best_cost = total; }
+        if (q[blk] > 1) { found_last = true; break; }
+        base_cost -= s.cost_coeff[sp];
+        base_cost += level0_cost(blk);
       }
     }
     s.best_last_p1 = best_last_p1;
