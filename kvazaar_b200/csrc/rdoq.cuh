@@ -148,8 +148,8 @@ __device__ __forceinline__ int rdoq_sig_ctx(int pattern, int scan_idx, int px, i
 }
 
 // Sign-bit hiding on RDOQ output (rdo.c:518-653).  Serial; one thread.
-template <int NN>
-__device__ void rdoq_sign_hiding(const RdoqScratch<NN, true> &s, double lambda, int bitdepth, int qp_scaled, int scan_idx, int log2n, int last_pos,
+template <class Scratch>
+__device__ void rdoq_sign_hiding(const Scratch &s, double lambda, int bitdepth, int qp_scaled, int scan_idx, int log2n, int last_pos,
                                  const int16_t *coef, int16_t *q)
 {
   const int inv_quant = c_inv_quant_scales[qp_scaled % 6];
@@ -157,7 +157,7 @@ __device__ void rdoq_sign_hiding(const RdoqScratch<NN, true> &s, double lambda, 
   const int last_cg = (last_pos - 1) >> 4;
   for (int cg = last_cg; cg >= 0; --cg) {
     const int base = cg << 4;
-    const uint16_t *pos = s.blk + base;
+    const auto *pos = s.blk + base;
     int last_nz = -1, first_nz = 16;
     for (int k = 15; k >= 0; --k) if (q[pos[k]]) { last_nz = k; break; }
     for (int k = 0; k <= last_nz; ++k) if (q[pos[k]]) { first_nz = k; break; }
@@ -495,9 +495,222 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
   if constexpr (SH) {
     abs_sum = warp_sum(abs_sum);
     __syncwarp();
-    if (lane == 0 && abs_sum >= 2) rdoq_sign_hiding<NN>(s, lambda, p.bitdepth, qp_scaled, scan_idx, log2n, best_last_p1, coef, q);
+    if (lane == 0 && abs_sum >= 2) rdoq_sign_hiding(s, lambda, p.bitdepth, qp_scaled, scan_idx, log2n, best_last_p1, coef, q);
   }
   __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// One THREAD per TU, for 4x4 and 8x8 blocks: there are 10^4..10^5 of them per frame and most are empty, so running
+// HM's chain once per lane beats one chain per warp.  Same arithmetic, same order; the cost tables live in the
+// thread's local memory, the scan table and the entropy table in shared memory.
+template <int NN, bool SH>
+struct RdoqLocal {
+  double cost_coeff[NN], cost_sig[NN];
+  int32_t inc[SH ? NN : 1], dec[SH ? NN : 1], sig_inc[SH ? NN : 1], qdelta[SH ? NN : 1];
+  double cg_sig_cost[NN / 16];
+  int32_t cg_flag[NN / 16];
+  int32_t last_x_bits[8], last_y_bits[8];
+  const uint8_t *blk;                                      // scan position -> raster position (shared memory)
+};
+
+template <int NN, bool SH>
+__device__ void rdoq_tu_thread(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *cabac, const int32_t *ebits_table, const int16_t *coef,
+                               int16_t *q, int log2n, int type, int scan_idx, int block_type, int tr_depth, RdoqLocal<NN, SH> &s)
+{
+  const int n = 1 << log2n;
+  const int transform_shift = 15 - p.bitdepth - log2n;
+  const int qp_scaled = scaled_qp(type, p.qp, (p.bitdepth - 8) * 6);
+  const int q_bits = 14 + qp_scaled / 6 + transform_shift;
+  const int qc = c_quant_scales[qp_scaled % 6];
+  const int half = 1 << (q_bits - 1);
+  const double lambda = p.lambda;
+  const double err_scale = ldexp(32768.0, -2 * transform_shift) / qc / qc / (1 << (2 * (p.bitdepth - 8)));
+  const RdoqModels m = rdoq_models(cabac, ebits_table, type);
+  auto level_double = [&](int blk) { return min(abs((int)coef[blk]) * qc, 0x7FFFFFFF - half); };
+
+  // find_last_scanpos (quant-generic.c:376-399)
+  int last_scanpos = -1;
+  for (int sp = NN - 1; sp >= 0; --sp) {
+    const int blk = s.blk[sp];
+    if (((level_double(blk) + half) >> q_bits) > 0) { last_scanpos = sp; break; }
+    q[blk] = 0;
+  }
+  if (last_scanpos < 0) return;
+  for (int g = 0; g < NN / 16; ++g) { s.cg_flag[g] = 0; s.cg_sig_cost[g] = 0; }
+  if (SH) s.sig_inc[s.blk[last_scanpos]] = 0;
+  {
+    const int cb = log2n - 2;
+    const int off = type ? 0 : (cb * 3 + ((cb + 1) >> 2));
+    const int sh = type ? cb : ((cb + 3) >> 2);
+    int bx = 0, by = 0, ctx;
+    const int groups = last_group(n - 1);
+    for (ctx = 0; ctx < groups; ++ctx) {
+      const int o = off + (ctx >> sh);
+      s.last_x_bits[ctx] = bx + ebits(m.last_x[o], 0); bx += ebits(m.last_x[o], 1);
+      s.last_y_bits[ctx] = by + ebits(m.last_y[o], 0); by += ebits(m.last_y[o], 1);
+    }
+    s.last_x_bits[ctx] = bx; s.last_y_bits[ctx] = by;
+  }
+
+  const int cg_last = last_scanpos >> 4;
+  const int cgs_side = n >> 2;
+  int ctx_set = (last_scanpos > 0 && type == 0) ? 2 : 0;
+  int c1 = 1, c2 = 0, rice = 0;
+  uint32_t c1_idx = 0, c2_idx = 0;
+  double base_cost = 0, block_uncoded_cost = 0;
+
+  for (int cg = cg_last; cg >= 0; --cg) {
+    const int cg_first = s.blk[cg << 4];
+    const int cgx = (cg_first & (n - 1)) >> 2, cgy = (cg_first >> log2n) >> 2;
+    const int cg_blk = cgy * cgs_side + cgx;
+    const int right = (cgx < cgs_side - 1) ? (s.cg_flag[cgy * cgs_side + cgx + 1] != 0) : 0;
+    const int lower = (cgy < cgs_side - 1) ? (s.cg_flag[(cgy + 1) * cgs_side + cgx] != 0) : 0;
+    const int pattern = (n == 4) ? -1 : right + (lower << 1);
+    double st_coded = 0, st_uncoded = 0, st_sig = 0, st_sig0 = 0;
+    int nnz_before_pos0 = 0;
+    for (int k = 15; k >= 0; --k) {
+      const int sp = (cg << 4) + k;
+      if (sp > last_scanpos) continue;
+      const int blk = s.blk[sp];
+      const int ld = level_double(blk);
+      const uint32_t max_abs = (uint32_t)((ld + half) >> q_bits);
+      const double err0 = (double)ld;
+      const double c0 = err0 * err0 * err_scale;
+      block_uncoded_cost += c0;
+      const int one_ctx = 4 * ctx_set + c1, abs_ctx = ctx_set + c2;
+      const bool last = sp == last_scanpos;
+      int ctx_sig = 0;
+      if (!last) {
+        ctx_sig = rdoq_sig_ctx(pattern, scan_idx, blk & (n - 1), blk >> log2n, log2n, type);
+        if (SH) s.sig_inc[blk] = ebits(m.sig[ctx_sig], 1) - ebits(m.sig[ctx_sig], 0);
+      }
+      uint32_t level = 0;
+      double cc, cs = 0;
+      if (!last && max_abs < 3) { cs = lambda * ebits(m.sig[ctx_sig], 0); cc = c0 + cs; }
+      else cc = 1.7e+308;
+      if (max_abs != 0) {
+        const double sig_now = last ? 0.0 : lambda * ebits(m.sig[ctx_sig], 1);
+        const int lo = max_abs > 1 ? (int)max_abs - 1 : 1;
+        for (int lvl = (int)max_abs; lvl >= lo; --lvl) {
+          const double err = (double)(ld - lvl * (1 << q_bits));
+          double c = err * err * err_scale + lambda * rdoq_level_rate(m, (uint32_t)lvl, one_ctx, abs_ctx, rice, c1_idx, c2_idx);
+          c += sig_now;
+          if (c < cc) { level = (uint32_t)lvl; cc = c; cs = sig_now; }
+        }
+      }
+      s.cost_coeff[sp] = cc;
+      s.cost_sig[sp] = cs;
+      if (SH) {
+        s.qdelta[blk] = (ld - (int)level * (1 << q_bits)) >> (q_bits - 8);
+        if (level > 0) {
+          const int now = rdoq_level_rate(m, level, one_ctx, abs_ctx, rice, c1_idx, c2_idx);
+          s.inc[blk] = rdoq_level_rate(m, level + 1, one_ctx, abs_ctx, rice, c1_idx, c2_idx) - now;
+          s.dec[blk] = rdoq_level_rate(m, level - 1, one_ctx, abs_ctx, rice, c1_idx, c2_idx) - now;
+        } else {
+          s.inc[blk] = ebits(m.one[one_ctx], 0);
+        }
+      }
+      q[blk] = (int16_t)level;
+      base_cost += cc;
+      const uint32_t base_level = (c1_idx < 8) ? (2 + (c2_idx < 1)) : 1;
+      if (level >= base_level && level > (uint32_t)(3 * (1 << rice))) rice = min(rice + 1, 4);
+      if (level >= 1) ++c1_idx;
+      if (level > 1) { c1 = 0; c2 += (c2 < 2); ++c2_idx; }
+      else if (c1 < 3 && c1 > 0 && level) ++c1;
+      if (k == 0 && sp > 0) {
+        c2 = 0; rice = 0; c1_idx = 0; c2_idx = 0;
+        ctx_set = (sp == 16 || type != 0) ? 0 : 2;
+        if (c1 == 0) ++ctx_set;
+        c1 = 1;
+      }
+      st_sig += cs;
+      if (k == 0) st_sig0 = cs;
+      if (level) {
+        s.cg_flag[cg_blk] = 1;
+        st_coded += cc - cs;
+        st_uncoded += c0;
+        if (k != 0) ++nnz_before_pos0;
+      }
+    }
+    if (cg) {
+      const int ctx_cg = right || lower;
+      if (s.cg_flag[cg_blk] == 0) {
+        s.cg_sig_cost[cg] = lambda * ebits(m.cg[ctx_cg], 0);
+        base_cost += s.cg_sig_cost[cg] - st_sig;
+      } else if (cg < cg_last) {
+        if (nnz_before_pos0 == 0) { base_cost -= st_sig0; st_sig -= st_sig0; }
+        double cost_zero_cg = base_cost;
+        s.cg_sig_cost[cg] = lambda * ebits(m.cg[ctx_cg], 1);
+        base_cost += s.cg_sig_cost[cg];
+        cost_zero_cg += lambda * ebits(m.cg[ctx_cg], 0);
+        cost_zero_cg += st_uncoded;
+        cost_zero_cg -= st_coded;
+        cost_zero_cg -= st_sig;
+        if (cost_zero_cg < base_cost) {
+          s.cg_flag[cg_blk] = 0;
+          base_cost = cost_zero_cg;
+          s.cg_sig_cost[cg] = lambda * ebits(m.cg[ctx_cg], 0);
+          for (int k = 15; k >= 0; --k) {
+            const int sp = (cg << 4) + k, blk = s.blk[sp];
+            if (q[blk]) { q[blk] = 0; const double e = (double)level_double(blk); s.cost_coeff[sp] = e * e * err_scale; s.cost_sig[sp] = 0; }
+          }
+        }
+      }
+    } else {
+      s.cg_flag[cg_blk] = 1;
+    }
+  }
+
+  // best last position (rdo.c:884-945)
+  double best_cost;
+  if (block_type != 1 && type == 0) {
+    best_cost = block_uncoded_cost + lambda * ebits(m.root_cbf, 0);
+    base_cost += lambda * ebits(m.root_cbf, 1);
+  } else {
+    const int ctx_cbf = type ? tr_depth : !tr_depth;
+    best_cost = block_uncoded_cost + lambda * ebits(m.cbf[ctx_cbf], 0);
+    base_cost += lambda * ebits(m.cbf[ctx_cbf], 1);
+  }
+  int best_last_p1 = 0;
+  bool found_last = false;
+  for (int cg = cg_last; cg >= 0 && !found_last; --cg) {
+    const int cg_first = s.blk[cg << 4];
+    const int cg_blk = ((cg_first >> log2n) >> 2) * cgs_side + ((cg_first & (n - 1)) >> 2);
+    base_cost -= s.cg_sig_cost[cg];
+    if (!s.cg_flag[cg_blk]) continue;
+    for (int k = 15; k >= 0; --k) {
+      const int sp = (cg << 4) + k;
+      if (sp > last_scanpos) continue;
+      const int blk = s.blk[sp];
+      if (q[blk]) {
+        const int py = blk >> log2n, px = blk & (n - 1);
+        const int gx = last_group(scan_idx == 2 ? py : px), gy = last_group(scan_idx == 2 ? px : py);
+        double bits = s.last_x_bits[gx] + s.last_y_bits[gy];
+        if (gx > 3) bits += RDOQ_ONE_BIT * ((gx - 2) >> 1);
+        if (gy > 3) bits += RDOQ_ONE_BIT * ((gy - 2) >> 1);
+        const double total = base_cost + lambda * bits - s.cost_sig[sp];
+        if (total < best_cost) { best_last_p1 = sp + 1; best_cost = total; }
+        if (q[blk] > 1) { found_last = true; break; }
+        base_cost -= s.cost_coeff[sp];
+        const double e = (double)level_double(blk);
+        base_cost += e * e * err_scale;
+      } else {
+        base_cost -= s.cost_sig[sp];
+      }
+    }
+  }
+  unsigned abs_sum = 0;
+  for (int sp = 0; sp < best_last_p1; ++sp) {
+    const int blk = s.blk[sp];
+    const int level = q[blk];
+    abs_sum += (unsigned)level;
+    q[blk] = (int16_t)(coef[blk] < 0 ? -level : level);
+  }
+  for (int sp = best_last_p1; sp <= last_scanpos; ++sp) q[s.blk[sp]] = 0;
+  if constexpr (SH) {
+    if (abs_sum >= 2) rdoq_sign_hiding(s, lambda, p.bitdepth, qp_scaled, scan_idx, log2n, best_last_p1, coef, q);
+  }
 }
 
 }  // namespace kvzc
