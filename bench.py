@@ -253,16 +253,18 @@ def run_cuda(args):
         for i in range(max(8, fps_step)):
             fp.run_dev(frames_dev[i % fps_step])
     torch.cuda.synchronize()
-    ms_stage = (C.c_double * 20)()
+    NST = 32
+    ms_stage = (C.c_double * NST)()
     runs = C.c_int()
     L.kvz_cuda_fp_get_timing(fp.h, ms_stage, C.byref(runs))
     L.kvz_cuda_fp_set_timing(fp.h, 0)
-    stage_ms = [ms_stage[i] / max(1, runs.value) for i in range(20)]
-    names = [f"{k}_w{32 >> d}" for d in range(4) for k in ("rough_search", "select", "recon_luma", "recon_chroma")] + \
+    stage_ms = [ms_stage[i] / max(1, runs.value) for i in range(NST)]
+    names = [f"{k}_w{32 >> d}" for d in range(4) for k in ("rough_search", "recon_luma", "rdoq_luma", "recon_luma_inv", "recon_chroma",
+                                                           "rdoq_chroma", "recon_chroma_inv")] + \
             ["deblock", "sao_stats_decide", "sao_reconstruct", "checksum"]
-    stages = {names[i]: round(stage_ms[i], 4) for i in range(20)}
-    # per-LAUNCH time of each kernel (the chroma stage holds two launches: U and V)
-    per_launch = [stage_ms[i] / (2 if names[i].startswith("recon_chroma") or names[i] == "deblock" else 1) for i in range(20)]
+    stages = {names[i]: round(stage_ms[i], 4) for i in range(NST) if stage_ms[i] > 0.0005}
+    # per-LAUNCH time of each kernel (chroma stages hold two launches: U and V; deblocking two passes)
+    per_launch = [stage_ms[i] / (2 if "chroma" in names[i] or names[i] == "deblock" else 1) for i in range(NST)]
     dom = int(np.argmax(per_launch))
     ncu = {}
     try:
@@ -276,11 +278,15 @@ def run_cuda(args):
         w = int(wtxt)
         if kind == "rough_search":       # source block + 4w+1 reference samples in, 35 costs out
             return (W // w) * (H // w) * (w * w + 4 * w + 1 + 35 * 4)
-        if kind == "recon_luma":         # source + refs in; reconstruction + int16 coefficients + has + ssd out
+        if kind in ("recon_luma", "recon_luma_inv"):   # source + refs in; reconstruction + int16 coefficients + has + ssd out
             return (W // w) * (H // w) * (w * w + 4 * w + 1 + w * w + 2 * w * w + 5)
-        if kind == "recon_chroma":       # one of the two chroma planes, blocks of w/2
+        if kind in ("recon_chroma", "recon_chroma_inv"):   # one of the two chroma planes, blocks of w/2
             wc = w // 2
             return (W // w) * (H // w) * (wc * wc + 4 * wc + 1 + wc * wc + 2 * wc * wc + 5)
+        if kind == "rdoq_luma":          # int16 coefficients in, int16 levels out
+            return W * H * 4
+        if kind == "rdoq_chroma":
+            return (W // 2) * (H // 2) * 4
         if kind == "deblock":            # per pass (launch): the three reconstruction planes in and out + 20-byte CU records in
             return 2 * W * H * 3 // 2 + (W // 4) * (H // 4) * 20
         if kind == "sao_stats_decide":   # source + reconstruction of all three planes in, 40+4+1 ints per CTU-plane out
@@ -292,6 +298,8 @@ def run_cuda(args):
     if alg:
         ach = alg / (per_launch[dom] / 1000.0) / 1e9
         kname = {"rough_search": "rough_search_u8_kernel", "recon_luma": "intra_recon_kernel", "recon_chroma": "intra_recon_kernel",
+                 "recon_luma_inv": "intra_recon_kernel", "recon_chroma_inv": "intra_recon_kernel", "rdoq_luma": "rdoq_grid_kernel",
+                 "rdoq_chroma": "rdoq_grid_kernel",
                  "sao_stats_decide": "sao_ctu_kernel", "deblock": "deblock_pass_kernel"}.get(names[dom].rsplit("_w", 1)[0], names[dom])
         roof = {"kernel": f"{kname} [{names[dom]}]", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": ncu.get(names[dom], {}).get("dram_bytes_per_launch"), "ms_per_launch": per_launch[dom],
@@ -351,7 +359,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the reference arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="1080p", choices=["1080p", "2160p"], help="1080p = BASELINE configs[1] (default)")
-    ap.add_argument("--rdoq", type=int, default=0, choices=[0, 1], help="quantise with kvz_rdoq (medium/veryslow presets) instead of kvz_quant")
+    ap.add_argument("--rdoq", type=int, default=1, choices=[0, 1], help="1 (default): quantise with kvz_rdoq as the medium / veryslow presets do; 0: kvz_quant")
     args = ap.parse_args()
     set_workload(args.workload, args.rdoq)
     if args.impl == "reference":

@@ -277,10 +277,11 @@ void  *kvz_cuda_fp_result_dev(kvz_cuda_frame_pass *fp);                 /* devic
 size_t kvz_cuda_fp_frame_bytes(const kvz_cuda_frame_pass *fp);          /* W*H*3/2 */
 /* frames already in HBM; rec_in_dev = reconstruction the references are taken from (NULL = the source) */
 int    kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void *rec_in_dev, void *stream);
-/* Per-stage device timing with CUDA events on the launching stream.  Stage index: depth d = 0..3 -> 4*d + {0 rough
- * search, 1 mode selection, 2 luma recon, 3 chroma recon}; 16 SAO statistics, 17 SAO offsets + delta-distortions,
- * 18 SAO decision + reconstruction, 19 checksums.  get_timing returns accumulated ms per stage over `runs` runs. */
-#define KVZ_CUDA_FP_STAGES 20
+/* Per-stage device timing with CUDA events on the launching stream.  Stage index: depth d = 0..3 -> 7*d + {0 rough
+ * search (+ mode selection), 1 luma recon (fused, or its forward half with RDOQ), 2 luma RDOQ, 3 luma inverse half,
+ * 4 chroma forward (U+V), 5 chroma RDOQ (U+V), 6 chroma inverse (U+V)}; 28 deblocking (2 passes), 29 SAO statistics +
+ * decisions, 30 SAO reconstruction, 31 checksums.  get_timing returns accumulated ms per stage over `runs` runs. */
+#define KVZ_CUDA_FP_STAGES 32
 int    kvz_cuda_fp_set_timing(kvz_cuda_frame_pass *fp, int enable);
 int    kvz_cuda_fp_get_timing(kvz_cuda_frame_pass *fp, double *ms_total /* [KVZ_CUDA_FP_STAGES] */, int *runs);
 /* host frame in (pinned for async), result blob out (host_bytes): H2D + pass + D2H enqueued on `stream` */

@@ -461,19 +461,6 @@ struct kvz_cuda_frame_pass {
 // split of an 8x8 CU); it only selects the cbf context of RDOQ (rdo.c:895-899).  The CPU arm uses the same table.
 static const int k_fp_tr_depth[4] = { 1, 0, 0, 1 };
 
-// prediction -> transform -> quantisation -> reconstruction of one plane at one depth; with RDOQ the fused kernel is
-// split around the RDOQ launch (quant-generic.c:234-240)
-static int fp_recon(kvz_cuda_frame_pass *fp, const kvz_cuda_quant_params &qp, const uint8_t *src, const uint8_t *rin, int stride, int pic_w,
-                    int pic_h, int color, int log2w, int blocks_x, int nblk, const int8_t *modes, uint8_t *rec, int16_t *coeff, uint8_t *has,
-                    uint32_t *ssd, int d, cudaStream_t st)
-{
-  if (!fp->prm.rdoq) return launch_recon(qp, src, rin, stride, pic_w, pic_h, color, log2w, blocks_x, nblk, modes, rec, coeff, has, ssd, st);
-  if (int r = launch_recon_phase<1>(qp, src, rin, stride, pic_w, pic_h, color, log2w, blocks_x, nblk, modes, rec, coeff, has, ssd, st)) return r;
-  if (int r = rdoq_launch_grid(fp->rdoq, (const kvz_cuda_cabac_ctx *)(fp->blob + fp->off_cabac), coeff, nblk, log2w, modes, color != 0,
-                               k_fp_tr_depth[d], st)) return r;
-  return launch_recon_phase<2>(qp, src, rin, stride, pic_w, pic_h, color, log2w, blocks_x, nblk, modes, rec, coeff, has, ssd, st);
-}
-
 static void fp_mark(kvz_cuda_frame_pass *fp, int idx, cudaStream_t st) { if (fp->timing) cudaEventRecord(fp->ev[idx], st); }
 static void fp_collect(kvz_cuda_frame_pass *fp)
 {
@@ -590,31 +577,55 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
   kvz_cuda_quant_params qp = { fp->prm.qp, 8, 1, fp->prm.signhide, 0 };
   const size_t poff[3] = { 0, (size_t)W * H, (size_t)W * H * 5 / 4 };
   if (fp->timing) fp_collect(fp);
+  const bool rdoq = fp->prm.rdoq != 0;
+  const kvz_cuda_cabac_ctx *cabac = (const kvz_cuda_cabac_ctx *)(B + fp->off_cabac);
   for (int d = 0; d < 4; ++d) {
     const int w = fp->wl[d], log2w = 5 - d, nb = fp->nblk[d];
-    fp_mark(fp, d * 4 + 0, st);
-    if (nb == 0) { fp_mark(fp, d * 4 + 1, st); fp_mark(fp, d * 4 + 2, st); fp_mark(fp, d * 4 + 3, st); continue; }
+    const int s0 = d * 7;                 // stage slots: rough, luma fwd (or fused), luma rdoq, luma inv, chroma fwd, chroma rdoq, chroma inv
+    fp_mark(fp, s0 + 0, st);
+    if (nb == 0) { for (int k = 1; k < 7; ++k) fp_mark(fp, s0 + k, st); continue; }
     uint32_t *costs = (uint32_t *)(B + fp->off_costs35[d]);
     int8_t *modes = (int8_t *)(B + L.mode_y[d]);
     // rough search with the mode selection fused in; the 35-entry cost tables stay on chip unless asked for
     if (int r = rough_search_u8(log2w, src, rin, W, W, H, fp->keep_costs ? costs : nullptr, modes, (uint32_t *)(B + L.cost_y[d]), st)) return r;
-    fp_mark(fp, d * 4 + 1, st);
-    fp_mark(fp, d * 4 + 2, st);
-    if (int r = fp_recon(fp, qp, src, rin, W, W, H, 0, log2w, W / w, nb, modes, B + fp->off_rec_y[d],
-                         (int16_t *)(B + L.coeff_y[d]), B + L.has_y[d], (uint32_t *)(B + L.ssd_y[d]), d, st)) return r;
-    fp_mark(fp, d * 4 + 3, st);
-    if (d < 3) {
-      const int wc = w / 2;
-      for (int color = 1; color <= 2; ++color) {
-        if (int r = fp_recon(fp, qp, src + poff[color], rin + poff[color], W / 2, W, H, color, log2w - 1, (W / 2) / wc, nb, modes,
-                             B + (color == 1 ? fp->off_rec_u[d] : fp->off_rec_v[d]),
-                             (int16_t *)(B + (color == 1 ? L.coeff_u[d] : L.coeff_v[d])),
-                             B + (color == 1 ? L.has_u[d] : L.has_v[d]),
-                             (uint32_t *)(B + (color == 1 ? L.ssd_u[d] : L.ssd_v[d])), d, st)) return r;
+    fp_mark(fp, s0 + 1, st);
+    // luma: prediction -> transform -> quantisation -> reconstruction; with RDOQ the fused kernel is split around the
+    // RDOQ launch (quant-generic.c:234-240)
+    {
+      uint8_t *rec = B + fp->off_rec_y[d], *has = B + L.has_y[d];
+      int16_t *coeff = (int16_t *)(B + L.coeff_y[d]);
+      uint32_t *ssd = (uint32_t *)(B + L.ssd_y[d]);
+      if (!rdoq) {
+        if (int r = launch_recon(qp, src, rin, W, W, H, 0, log2w, W / w, nb, modes, rec, coeff, has, ssd, st)) return r;
+        fp_mark(fp, s0 + 2, st); fp_mark(fp, s0 + 3, st);
+      } else {
+        if (int r = launch_recon_phase<1>(qp, src, rin, W, W, H, 0, log2w, W / w, nb, modes, rec, coeff, has, ssd, st)) return r;
+        fp_mark(fp, s0 + 2, st);
+        if (int r = rdoq_launch_grid(fp->rdoq, cabac, coeff, nb, log2w, modes, 0, k_fp_tr_depth[d], st)) return r;
+        fp_mark(fp, s0 + 3, st);
+        if (int r = launch_recon_phase<2>(qp, src, rin, W, W, H, 0, log2w, W / w, nb, modes, rec, coeff, has, ssd, st)) return r;
       }
     }
+    fp_mark(fp, s0 + 4, st);
+    if (d == 3) { fp_mark(fp, s0 + 5, st); fp_mark(fp, s0 + 6, st); continue; }
+    const int wc = w / 2;
+    for (int step = 0; step < 3; ++step) {
+      for (int color = 1; color <= 2 && (rdoq || step == 0); ++color) {
+        const uint8_t *csrc = src + poff[color], *crin = rin + poff[color];
+        uint8_t *rec = B + (color == 1 ? fp->off_rec_u[d] : fp->off_rec_v[d]), *has = B + (color == 1 ? L.has_u[d] : L.has_v[d]);
+        int16_t *coeff = (int16_t *)(B + (color == 1 ? L.coeff_u[d] : L.coeff_v[d]));
+        uint32_t *ssd = (uint32_t *)(B + (color == 1 ? L.ssd_u[d] : L.ssd_v[d]));
+        int r = 0;
+        if (!rdoq) r = launch_recon(qp, csrc, crin, W / 2, W, H, color, log2w - 1, (W / 2) / wc, nb, modes, rec, coeff, has, ssd, st);
+        else if (step == 0) r = launch_recon_phase<1>(qp, csrc, crin, W / 2, W, H, color, log2w - 1, (W / 2) / wc, nb, modes, rec, coeff, has, ssd, st);
+        else if (step == 1) r = rdoq_launch_grid(fp->rdoq, cabac, coeff, nb, log2w - 1, modes, 1, k_fp_tr_depth[d], st);
+        else r = launch_recon_phase<2>(qp, csrc, crin, W / 2, W, H, color, log2w - 1, (W / 2) / wc, nb, modes, rec, coeff, has, ssd, st);
+        if (r) return r;
+      }
+      if (step < 2) fp_mark(fp, s0 + 5 + step, st);
+    }
   }
-  fp_mark(fp, 16, st);
+  fp_mark(fp, 28, st);
   // ---- deblocking of the 8x8-level reconstruction (depth index 2) in place: every 8x8 edge is an intra TU edge ----
   {
     kvz_cuda_dbk_params dp;
@@ -622,7 +633,7 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
     dp.width = W; dp.height = H; dp.qp = fp->prm.qp; dp.cu_stride_scu = W / 4;
     if (int r = kvz_cuda_deblock_frame(&dp, 8, B + fp->off_rec_y[2], B + fp->off_rec_u[2], B + fp->off_rec_v[2], B + fp->off_dbk_cus, st)) return r;
   }
-  fp_mark(fp, 17, st);
+  fp_mark(fp, 29, st);
   // ---- SAO on the deblocked reconstruction: statistics + decisions, then reconstruction ----
   const int nctu = fp->nctu3 / 3;
   SaoPlanes pl;
@@ -637,10 +648,10 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
   sao_ctu_kernel<<<fp->nctu3, 256, 0, st>>>(pl, nctu, (W + 63) / 64, (int32_t *)(B + L.sao_stats), (int32_t *)(B + L.sao_dd),
                                             (int32_t *)(B + L.sao_band_dd), (int8_t *)(B + L.sao_best), dec_off, ck_scratch);
   KVZC_LAUNCHED();
-  fp_mark(fp, 18, st);
+  fp_mark(fp, 30, st);
   sao_apply_kernel<<<fp->nctu3, 256, 0, st>>>(pl, nctu, (W + 63) / 64, (const int8_t *)(B + L.sao_best), dec_off);
   KVZC_LAUNCHED();
-  fp_mark(fp, 19, st);
+  fp_mark(fp, 31, st);
   // ---- picture checksum of the filtered planes ----
   checksum3_kernel<<<dim3(148, 3), 256, 0, st>>>(pl, ck_scratch, B + L.checksum);
   KVZC_LAUNCHED();

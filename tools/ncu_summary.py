@@ -23,19 +23,30 @@ def stage_of(name, grid):
     m = re.search(r"rough_search_u8_kernel<(\d)>", name)
     if m:
         return f"rough_search_w{1 << int(m.group(1))}"
-    m = re.search(r"intra_recon_kernel<unsigned char, (\d)>", name)
+    m = re.search(r"intra_recon_kernel<unsigned char, (\d)(?:, (?:false|\(bool\)0), (\d))?>", name)
     if m:
         w = 1 << int(m.group(1))
-        g = max(1, 256 // (w * w))
+        g = max(1, 1024 // (w * w))
         luma = -(-((W // w) * (H // w)) // g)
+        suffix = "_inv" if m.group(2) == "2" else ""
         if grid == luma:
-            return f"recon_luma_w{w}"
-        return f"recon_chroma_w{2 * w}"
+            return f"recon_luma{suffix}_w{w}"
+        return f"recon_chroma{suffix}_w{2 * w}"
+    m = re.search(r"rdoq_grid(?:_thread)?_kernel<(\d)", name)
+    if m:
+        w = 1 << int(m.group(1))
+        thread = "thread" in name
+        per = 128 if thread else {4: 8, 8: 8, 16: 2, 32: 1}[w]
+        luma = -(-((W // w) * (H // w)) // per)
+        return f"rdoq_luma_w{w}" if grid == luma else f"rdoq_chroma_w{2 * w}"
+    m = re.search(r"deblock_pass_kernel<unsigned char, (?:\(bool\))?(\w+)>", name)
+    if m:
+        return "deblock_hor" if m.group(1) in ("true", "1") else "deblock_ver"
     m = re.search(r"satd_nxn_kernel<unsigned char, (\d+)>", name)
     if m:
         return f"satd_nxn_kernel_{m.group(1)}"
     if "sao_ctu_kernel" in name:
-        return "sao_stats"
+        return "sao_stats_decide"
     return re.sub(r"\(.*", "", name).split("::")[-1]
 
 

@@ -10,7 +10,7 @@ from test_framepass import synth_frame  # noqa: E402
 
 W, H = 1920, 1080
 kb.init(0)
-fp = kb.FramePass(W, H, 27)
+fp = kb.FramePass(W, H, 27, 0, int(os.environ.get("RDOQ", "1")))
 frames = [kb.to_dev(synth_frame(W, H, frame_idx=i)) for i in range(2)]
 for i in range(int(os.environ.get("PASSES", "3"))):
     fp.run_dev(frames[i % 2])
