@@ -267,10 +267,11 @@ def run_cuda(args):
     per_launch = [stage_ms[i] / (2 if "chroma" in names[i] or names[i] == "deblock" else 1) for i in range(NST)]
     dom = int(np.argmax(per_launch))
     ncu = {}
-    try:
-        ncu = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
-    except Exception:
-        pass
+    for fn in ("r01_ncu_summary.json", "r01b_ncu_summary.json"):      # later captures override earlier ones
+        try:
+            ncu.update(json.load(open(os.path.join(ROOT, "profiles", fn))))
+        except Exception:
+            pass
 
     def alg_bytes(name):
         """Bytes one launch must move through HBM."""
@@ -304,9 +305,13 @@ def run_cuda(args):
         roof = {"kernel": f"{kname} [{names[dom]}]", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": ncu.get(names[dom], {}).get("dram_bytes_per_launch"), "ms_per_launch": per_launch[dom],
                 "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
-                "note": "fused per-block kernels keep predictions / transforms on chip: they are instruction-issue bound "
-                        f"(ncu: {ncu.get(names[dom], {}).get('issue_active_pct', 'n/a')}% issue-active), not HBM bound; "
-                        "roofline_satd_batch is the HBM-streaming kernel of the north star"}
+                "note": ("RDOQ is HM's serial per-TU chain (one lane of a warp walks the scan in double precision): latency bound, "
+                         f"ncu {ncu.get(names[dom], {}).get('issue_active_pct', 'n/a')}% issue-active at "
+                         f"{ncu.get(names[dom], {}).get('warps_active_pct', 'n/a')}% warps-active; "
+                         if names[dom].startswith("rdoq") else
+                         "fused per-block kernels keep predictions / transforms on chip: they are instruction-issue bound "
+                         f"(ncu: {ncu.get(names[dom], {}).get('issue_active_pct', 'n/a')}% issue-active), not HBM bound; ")
+                        + "roofline_satd_batch is the HBM-streaming kernel of the north star"}
 
     # ---- the batched SATD kernel of the north_star (block pairs streamed from HBM), inputs > L2
     n_pairs = 4 * 1024 * 1024            # 4M 8x8 pairs = 512 MiB of pixels > 126 MB L2
