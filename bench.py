@@ -184,7 +184,7 @@ def run_cuda(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = kb.lib()
     fps_step = args.frames_per_step
-    inflight = 4
+    inflight = args.inflight
     streams = [torch.cuda.Stream() for _ in range(inflight)]
     passes = [kb.FramePass(W, H, QP, SIGNHIDE, RDOQ) for _ in range(inflight)]
     frames_np = synth_frames(fps_step)
@@ -361,6 +361,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=8)
+    ap.add_argument("--inflight", type=int, default=4, help="frames in flight (one stream + one result blob each)")
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the reference arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="1080p", choices=["1080p", "2160p"], help="1080p = BASELINE configs[1] (default)")

@@ -36,3 +36,56 @@ def gather_result_sizes(nbytes):
     out = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
     dist.all_gather(out, t)
     return [int(x[0]) for x in out]
+
+
+# ---------------------------------------------------------------------------------------------- tiles
+def tile_grid(width, height, cols, rows, ctu=64):
+    """Uniform tile boundaries in luma samples, split on CTU columns/rows exactly like the reference
+    (encoder.c:383-391: boundary i = (i * size_in_ctus) / count).  Returns (x_edges, y_edges)."""
+    wc, hc = (width + ctu - 1) // ctu, (height + ctu - 1) // ctu
+    xs = [min(width, (i * wc // cols) * ctu) for i in range(cols)] + [width]
+    ys = [min(height, (j * hc // rows) * ctu) for j in range(rows)] + [height]
+    return xs, ys
+
+
+def tile_of_rank(rank, cols, rows):
+    """Tile t -> GPU t (raster order), 8 tiles of a 4x2 grid on 8 GPUs."""
+    t = rank % (cols * rows)
+    return t % cols, t // cols
+
+
+def allgather_tile_reconstructions(frame, width, height, cols, rows):
+    """Every rank has reconstructed its own tile inside `frame` (planar I420 tensor of the whole picture, uint8 or
+    int16); after the call every rank holds the complete reconstruction -- the reference waits for ALL tiles of the
+    previous frame before it starts a dependant (encoderstate.c:1007-1010).  One all_gather of the padded tile
+    payloads; ranks beyond cols*rows contribute nothing."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return frame
+    world, rank = dist.get_world_size(), dist.get_rank()
+    xs, ys = tile_grid(width, height, cols, rows)
+    planes = [(0, width, height, 1), (width * height, width // 2, height // 2, 2), (width * height * 5 // 4, width // 2, height // 2, 2)]
+
+    def tile_views(t, buf):
+        tx, ty = t % cols, t // cols
+        out = []
+        for off, pw, ph, sub in planes:
+            x0, x1, y0, y1 = xs[tx] // sub, xs[tx + 1] // sub, ys[ty] // sub, ys[ty + 1] // sub
+            out.append(buf[off:off + pw * ph].view(ph, pw)[y0:y1, x0:x1])
+        return out
+
+    ntiles = cols * rows
+    sizes = [sum(v.numel() for v in tile_views(t, frame)) for t in range(ntiles)]
+    cap = max(sizes)
+    mine = torch.zeros(cap, dtype=frame.dtype, device=frame.device)
+    if rank < ntiles:
+        mine[:sizes[rank]] = torch.cat([v.reshape(-1) for v in tile_views(rank, frame)])
+    gathered = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(gathered, mine)
+    for t in range(min(ntiles, world)):
+        if t == rank:
+            continue
+        pos = 0
+        for v in tile_views(t, frame):
+            v.copy_(gathered[t][pos:pos + v.numel()].view(v.shape))
+            pos += v.numel()
+    return frame
