@@ -253,14 +253,14 @@ def run_cuda(args):
         for i in range(max(8, fps_step)):
             fp.run_dev(frames_dev[i % fps_step])
     torch.cuda.synchronize()
-    NST = 32
+    NST = 40
     ms_stage = (C.c_double * NST)()
     runs = C.c_int()
     L.kvz_cuda_fp_get_timing(fp.h, ms_stage, C.byref(runs))
     L.kvz_cuda_fp_set_timing(fp.h, 0)
     stage_ms = [ms_stage[i] / max(1, runs.value) for i in range(NST)]
-    names = [f"{k}_w{32 >> d}" for d in range(4) for k in ("rough_search", "recon_luma", "rdoq_luma", "recon_luma_inv", "recon_chroma",
-                                                           "rdoq_chroma", "recon_chroma_inv")] + \
+    names = [f"{k}_w{32 >> d}" for d in range(4) for k in ("rough_search", "recon_luma", "rdoq_luma", "recon_luma_inv", "bits_luma",
+                                                           "recon_chroma", "rdoq_chroma", "recon_chroma_inv", "bits_chroma")] + \
             ["deblock", "sao_stats_decide", "sao_reconstruct", "checksum"]
     stages = {names[i]: round(stage_ms[i], 4) for i in range(NST) if stage_ms[i] > 0.0005}
     # per-LAUNCH time of each kernel (chroma stages hold two launches: U and V; deblocking two passes)
@@ -284,6 +284,10 @@ def run_cuda(args):
         if kind in ("recon_chroma", "recon_chroma_inv"):   # one of the two chroma planes, blocks of w/2
             wc = w // 2
             return (W // w) * (H // w) * (wc * wc + 4 * wc + 1 + wc * wc + 2 * wc * wc + 5)
+        if kind == "bits_luma":          # int16 levels in, one double per block out
+            return W * H * 2 + (W // w) * (H // w) * 8
+        if kind == "bits_chroma":
+            return (W // 2) * (H // 2) * 2 + (W // w) * (H // w) * 8
         if kind == "rdoq_luma":          # int16 coefficients in, int16 levels out
             return W * H * 4
         if kind == "rdoq_chroma":
@@ -300,7 +304,7 @@ def run_cuda(args):
         ach = alg / (per_launch[dom] / 1000.0) / 1e9
         kname = {"rough_search": "rough_search_u8_kernel", "recon_luma": "intra_recon_kernel", "recon_chroma": "intra_recon_kernel",
                  "recon_luma_inv": "intra_recon_kernel", "recon_chroma_inv": "intra_recon_kernel", "rdoq_luma": "rdoq_grid_kernel",
-                 "rdoq_chroma": "rdoq_grid_kernel",
+                 "rdoq_chroma": "rdoq_grid_kernel", "bits_luma": "coeff_cost_grid_kernel", "bits_chroma": "coeff_cost_grid_kernel",
                  "sao_stats_decide": "sao_ctu_kernel", "deblock": "deblock_pass_kernel"}.get(names[dom].rsplit("_w", 1)[0], names[dom])
         roof = {"kernel": f"{kname} [{names[dom]}]", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": ncu.get(names[dom], {}).get("dram_bytes_per_launch"), "ms_per_launch": per_launch[dom],

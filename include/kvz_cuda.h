@@ -267,6 +267,8 @@ typedef struct {
   uint64_t sao_best;               /* int8  [3*nctu] chosen class or -1 */
   uint64_t sao_rec;                /* pixels: SAO-filtered I420 frame */
   uint64_t checksum;               /* 3 x 4 bytes, big-endian, Y U V */
+  uint64_t bits_y[4];              /* double [nblk]  CABAC bit cost of the block's quantised coefficients (kvz_get_coeff_cost) */
+  uint64_t bits_u[3], bits_v[3];
 } kvz_cuda_fp_layout;
 typedef struct kvz_cuda_frame_pass kvz_cuda_frame_pass;
 kvz_cuda_frame_pass *kvz_cuda_fp_create(const kvz_cuda_fp_params *p);   /* NULL on failure */
@@ -277,11 +279,12 @@ void  *kvz_cuda_fp_result_dev(kvz_cuda_frame_pass *fp);                 /* devic
 size_t kvz_cuda_fp_frame_bytes(const kvz_cuda_frame_pass *fp);          /* W*H*3/2 */
 /* frames already in HBM; rec_in_dev = reconstruction the references are taken from (NULL = the source) */
 int    kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void *rec_in_dev, void *stream);
-/* Per-stage device timing with CUDA events on the launching stream.  Stage index: depth d = 0..3 -> 7*d + {0 rough
+/* Per-stage device timing with CUDA events on the launching stream.  Stage index: depth d = 0..3 -> 9*d + {0 rough
  * search (+ mode selection), 1 luma recon (fused, or its forward half with RDOQ), 2 luma RDOQ, 3 luma inverse half,
- * 4 chroma forward (U+V), 5 chroma RDOQ (U+V), 6 chroma inverse (U+V)}; 28 deblocking (2 passes), 29 SAO statistics +
- * decisions, 30 SAO reconstruction, 31 checksums.  get_timing returns accumulated ms per stage over `runs` runs. */
-#define KVZ_CUDA_FP_STAGES 32
+ * 4 luma coefficient bit cost, 5 chroma forward (U+V), 6 chroma RDOQ (U+V), 7 chroma inverse (U+V), 8 chroma bit cost
+ * (U+V)}; 36 deblocking (2 passes), 37 SAO statistics + decisions, 38 SAO reconstruction, 39 checksums.  get_timing
+ * returns accumulated ms per stage over `runs` runs. */
+#define KVZ_CUDA_FP_STAGES 40
 int    kvz_cuda_fp_set_timing(kvz_cuda_frame_pass *fp, int enable);
 int    kvz_cuda_fp_get_timing(kvz_cuda_frame_pass *fp, double *ms_total /* [KVZ_CUDA_FP_STAGES] */, int *runs);
 /* host frame in (pinned for async), result blob out (host_bytes): H2D + pass + D2H enqueued on `stream` */
@@ -355,6 +358,20 @@ int kvz_cuda_quantize_residual_rdoq_batch(const kvz_cuda_quant_params *p, const 
 /* `count` TUs of width n (4, 8, 16 or 32); ctx_dev: one kvz_cuda_cabac_ctx shared by the batch */
 int kvz_cuda_rdoq_batch(const kvz_cuda_rdoq_params *p, const kvz_cuda_cabac_ctx *ctx_dev, const int16_t *coef, int16_t *dest,
                         int n, const kvz_cuda_rdoq_tu *tus, int count, void *stream);
+
+/* CABAC bit cost of quantised coefficients: the CABAC branch of kvz_get_coeff_cost (src/rdo.c:291-330), i.e.
+ * kvz_encode_coeff_nxn in only_count mode (encode_coding_tree-generic.c:40-290).  Descriptors: kvz_cuda_rdoq_tu with
+ * off_coef = offset of the n x n levels, type 0 luma / 2 chroma, scan_idx, and `block_type` carrying the TU's
+ * transform_skip flag (only read for 4x4 with trskip_enable); off_dest / tr_depth unused.  bits_out[count] doubles.
+ * update = cabac->update: the context models adapt inside each TU; ctx_out (optional, [count]) receives them. */
+typedef struct kvz_cuda_coeff_cost_params {
+  int32_t signhide_enable;   /* cfg.signhide_enable */
+  int32_t trskip_enable;     /* cfg.trskip_enable */
+  int32_t update;            /* cabac->update */
+  int32_t pad;
+} kvz_cuda_coeff_cost_params;
+int kvz_cuda_coeff_cost_batch(const kvz_cuda_coeff_cost_params *p, const kvz_cuda_cabac_ctx *ctx_dev, const int16_t *coeff, int n,
+                              const kvz_cuda_rdoq_tu *tus, int count, double *bits_out, kvz_cuda_cabac_ctx *ctx_out, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Deblocking filter, frame level.  Replaces the per-LCU kvz_filter_deblock_lcu

@@ -319,6 +319,24 @@ def rdoq_batch(coef, n, tus, cabac_ctx, qp, lambda_, bitdepth=8, signhide=0, des
     return dest
 
 
+class CoeffCostParams(C.Structure):
+    _fields_ = [("signhide_enable", C.c_int32), ("trskip_enable", C.c_int32), ("update", C.c_int32), ("pad", C.c_int32)]
+
+
+def coeff_cost_batch(coeff, n, tus, cabac_ctx, signhide=0, trskip_enable=0, update=0, want_ctx=False):
+    """CABAC bit cost per TU (kvz_get_coeff_cost's CABAC branch, src/rdo.c:291-330).  tus: RDOQ_TU array (off_coef, type,
+    scan_idx, block_type = transform_skip flag).  Returns float64 tensor [count] (and the adapted context models)."""
+    torch = _torch()
+    ctx = cabac_ctx if hasattr(cabac_ctx, "data_ptr") else to_dev(np.asarray(cabac_ctx, np.uint8))
+    tus_d = tus if hasattr(tus, "data_ptr") else to_dev(tus)
+    count = tus_d.numel() // RDOQ_TU.itemsize
+    bits = torch.zeros(count, dtype=torch.float64, device=coeff.device)
+    ctx_out = torch.zeros(count * CABAC_CTX_BYTES, dtype=torch.uint8, device=coeff.device) if want_ctx else None
+    prm = CoeffCostParams(signhide, trskip_enable, update, 0)
+    _ck(lib().kvz_cuda_coeff_cost_batch(C.byref(prm), _p(ctx), _p(coeff), n, _p(tus_d), count, _p(bits), _p(ctx_out), _stream()))
+    return (bits, ctx_out) if want_ctx else bits
+
+
 # ------------------------------------------------------------------ deblocking (deblock.cu)
 class DbkParams(C.Structure):
     """kvz_cuda_dbk_params."""
@@ -361,7 +379,8 @@ class FpLayout(C.Structure):
                 ("has_u", C.c_uint64 * 3), ("has_v", C.c_uint64 * 3), ("ssd_u", C.c_uint64 * 3),
                 ("ssd_v", C.c_uint64 * 3), ("coeff_u", C.c_uint64 * 3), ("coeff_v", C.c_uint64 * 3),
                 ("sao_stats", C.c_uint64), ("sao_dd", C.c_uint64), ("sao_band_dd", C.c_uint64),
-                ("sao_best", C.c_uint64), ("sao_rec", C.c_uint64), ("checksum", C.c_uint64)]
+                ("sao_best", C.c_uint64), ("sao_rec", C.c_uint64), ("checksum", C.c_uint64),
+                ("bits_y", C.c_uint64 * 4), ("bits_u", C.c_uint64 * 3), ("bits_v", C.c_uint64 * 3)]
 
 
 def fp_layout_for(width, height, qp=27, signhide=0):
@@ -435,12 +454,14 @@ def fp_sections(layout, width, height):
         out[f"has_y{d}"] = (layout.has_y[d], np.uint8, nb)
         out[f"ssd_y{d}"] = (layout.ssd_y[d], np.uint32, nb)
         out[f"coeff_y{d}"] = (layout.coeff_y[d], np.int16, nb * w * w)
+        out[f"bits_y{d}"] = (layout.bits_y[d], np.float64, nb)
         if d < 3:
             wc = w // 2
             for c in "uv":
                 out[f"has_{c}{d}"] = (getattr(layout, f"has_{c}")[d], np.uint8, nb)
                 out[f"ssd_{c}{d}"] = (getattr(layout, f"ssd_{c}")[d], np.uint32, nb)
                 out[f"coeff_{c}{d}"] = (getattr(layout, f"coeff_{c}")[d], np.int16, nb * wc * wc)
+                out[f"bits_{c}{d}"] = (getattr(layout, f"bits_{c}")[d], np.float64, nb)
     n3 = 3 * layout.nctu
     out["sao_stats"] = (layout.sao_stats, np.int32, n3 * 40)
     out["sao_dd"] = (layout.sao_dd, np.int32, n3 * 4)

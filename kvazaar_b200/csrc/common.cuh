@@ -104,6 +104,10 @@ int rdoq_launch_tus(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ctx
 int rdoq_launch_grid(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ctx_dev, int16_t *coeff, int count, int log2n, const int8_t *modes,
                      int is_chroma, int tr_depth, cudaStream_t st);
 
+// coeff_cost.cu: CABAC bit cost of every TU of a uniform grid (frame-level pass)
+int coeff_cost_launch_grid(int signhide, const kvz_cuda_cabac_ctx *ctx_dev, const int16_t *coeff, int count, int log2n, const int8_t *modes,
+                           int is_chroma, double *bits_out, cudaStream_t st);
+
 // ---------------------------------------------------------------- device side
 template <class T> struct PixTraits;
 template <> struct PixTraits<uint8_t> { static constexpr int kBits = 8; };

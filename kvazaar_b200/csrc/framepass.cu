@@ -495,10 +495,12 @@ static kvz_cuda_frame_pass *fp_build(const kvz_cuda_fp_params *p, bool alloc)
     L.nblk[d] = nb;
     L.mode_y[d] = take(nb); L.cost_y[d] = take(4 * (size_t)nb); L.has_y[d] = take(nb); L.ssd_y[d] = take(4 * (size_t)nb);
     L.coeff_y[d] = take(2 * (size_t)nb * w * w);
+    L.bits_y[d] = take(8 * (size_t)nb);
     if (d < 3) {
       const int wc = w / 2;
       L.has_u[d] = take(nb); L.has_v[d] = take(nb); L.ssd_u[d] = take(4 * (size_t)nb); L.ssd_v[d] = take(4 * (size_t)nb);
       L.coeff_u[d] = take(2 * (size_t)nb * wc * wc); L.coeff_v[d] = take(2 * (size_t)nb * wc * wc);
+      L.bits_u[d] = take(8 * (size_t)nb); L.bits_v[d] = take(8 * (size_t)nb);
     }
   }
   const int cx = (W + 63) / 64, cy = (H + 63) / 64, nctu = cx * cy;
@@ -581,9 +583,9 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
   const kvz_cuda_cabac_ctx *cabac = (const kvz_cuda_cabac_ctx *)(B + fp->off_cabac);
   for (int d = 0; d < 4; ++d) {
     const int w = fp->wl[d], log2w = 5 - d, nb = fp->nblk[d];
-    const int s0 = d * 7;                 // stage slots: rough, luma fwd (or fused), luma rdoq, luma inv, chroma fwd, chroma rdoq, chroma inv
+    const int s0 = d * 9;                 // stage slots: rough, luma fwd (or fused), luma rdoq, luma inv, luma bits, chroma fwd, rdoq, inv, bits
     fp_mark(fp, s0 + 0, st);
-    if (nb == 0) { for (int k = 1; k < 7; ++k) fp_mark(fp, s0 + k, st); continue; }
+    if (nb == 0) { for (int k = 1; k < 9; ++k) fp_mark(fp, s0 + k, st); continue; }
     uint32_t *costs = (uint32_t *)(B + fp->off_costs35[d]);
     int8_t *modes = (int8_t *)(B + L.mode_y[d]);
     // rough search with the mode selection fused in; the 35-entry cost tables stay on chip unless asked for
@@ -607,25 +609,29 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
       }
     }
     fp_mark(fp, s0 + 4, st);
-    if (d == 3) { fp_mark(fp, s0 + 5, st); fp_mark(fp, s0 + 6, st); continue; }
+    // CABAC bit cost of the luma levels (kvz_get_coeff_cost, rdo.c:291-330) with the slice-initial context models
+    if (int r = coeff_cost_launch_grid(fp->prm.signhide, cabac, (const int16_t *)(B + L.coeff_y[d]), nb, log2w, modes, 0, (double *)(B + L.bits_y[d]), st)) return r;
+    fp_mark(fp, s0 + 5, st);
+    if (d == 3) { fp_mark(fp, s0 + 6, st); fp_mark(fp, s0 + 7, st); fp_mark(fp, s0 + 8, st); continue; }
     const int wc = w / 2;
-    for (int step = 0; step < 3; ++step) {
-      for (int color = 1; color <= 2 && (rdoq || step == 0); ++color) {
+    for (int step = 0; step < 4; ++step) {
+      for (int color = 1; color <= 2 && (rdoq || step == 0 || step == 3); ++color) {
         const uint8_t *csrc = src + poff[color], *crin = rin + poff[color];
         uint8_t *rec = B + (color == 1 ? fp->off_rec_u[d] : fp->off_rec_v[d]), *has = B + (color == 1 ? L.has_u[d] : L.has_v[d]);
         int16_t *coeff = (int16_t *)(B + (color == 1 ? L.coeff_u[d] : L.coeff_v[d]));
         uint32_t *ssd = (uint32_t *)(B + (color == 1 ? L.ssd_u[d] : L.ssd_v[d]));
         int r = 0;
-        if (!rdoq) r = launch_recon(qp, csrc, crin, W / 2, W, H, color, log2w - 1, (W / 2) / wc, nb, modes, rec, coeff, has, ssd, st);
+        if (step == 3) r = coeff_cost_launch_grid(fp->prm.signhide, cabac, coeff, nb, log2w - 1, modes, 1, (double *)(B + (color == 1 ? L.bits_u[d] : L.bits_v[d])), st);
+        else if (!rdoq) r = launch_recon(qp, csrc, crin, W / 2, W, H, color, log2w - 1, (W / 2) / wc, nb, modes, rec, coeff, has, ssd, st);
         else if (step == 0) r = launch_recon_phase<1>(qp, csrc, crin, W / 2, W, H, color, log2w - 1, (W / 2) / wc, nb, modes, rec, coeff, has, ssd, st);
         else if (step == 1) r = rdoq_launch_grid(fp->rdoq, cabac, coeff, nb, log2w - 1, modes, 1, k_fp_tr_depth[d], st);
         else r = launch_recon_phase<2>(qp, csrc, crin, W / 2, W, H, color, log2w - 1, (W / 2) / wc, nb, modes, rec, coeff, has, ssd, st);
         if (r) return r;
       }
-      if (step < 2) fp_mark(fp, s0 + 5 + step, st);
+      if (step < 3) fp_mark(fp, s0 + 6 + step, st);
     }
   }
-  fp_mark(fp, 28, st);
+  fp_mark(fp, 36, st);
   // ---- deblocking of the 8x8-level reconstruction (depth index 2) in place: every 8x8 edge is an intra TU edge ----
   {
     kvz_cuda_dbk_params dp;
@@ -633,7 +639,7 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
     dp.width = W; dp.height = H; dp.qp = fp->prm.qp; dp.cu_stride_scu = W / 4;
     if (int r = kvz_cuda_deblock_frame(&dp, 8, B + fp->off_rec_y[2], B + fp->off_rec_u[2], B + fp->off_rec_v[2], B + fp->off_dbk_cus, st)) return r;
   }
-  fp_mark(fp, 29, st);
+  fp_mark(fp, 37, st);
   // ---- SAO on the deblocked reconstruction: statistics + decisions, then reconstruction ----
   const int nctu = fp->nctu3 / 3;
   SaoPlanes pl;
@@ -648,10 +654,10 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
   sao_ctu_kernel<<<fp->nctu3, 256, 0, st>>>(pl, nctu, (W + 63) / 64, (int32_t *)(B + L.sao_stats), (int32_t *)(B + L.sao_dd),
                                             (int32_t *)(B + L.sao_band_dd), (int8_t *)(B + L.sao_best), dec_off, ck_scratch);
   KVZC_LAUNCHED();
-  fp_mark(fp, 30, st);
+  fp_mark(fp, 38, st);
   sao_apply_kernel<<<fp->nctu3, 256, 0, st>>>(pl, nctu, (W + 63) / 64, (const int8_t *)(B + L.sao_best), dec_off);
   KVZC_LAUNCHED();
-  fp_mark(fp, 31, st);
+  fp_mark(fp, 39, st);
   // ---- picture checksum of the filtered planes ----
   checksum3_kernel<<<dim3(148, 3), 256, 0, st>>>(pl, ck_scratch, B + L.checksum);
   KVZC_LAUNCHED();

@@ -23,6 +23,7 @@
 #include "intra.h"
 #include <math.h>
 #include "context.h"
+#include "rdo.h"
 #include "sao.h"
 #include "filter.h"
 #include "cu.h"
@@ -91,6 +92,7 @@ static void do_block(job_t *j, int d, int b, kvz_pixel *buf /* scratch: 6 * 1024
   int has = kvz_quantize_residual(state, &cu, w, COLOR_Y, scan_for(0, w, best_mode), 0, w, w, orig, pred, recb, coeff, false);
   (j->blob + L->has_y[d])[b] = (uint8_t)has;
   ((uint32_t *)(j->blob + L->ssd_y[d]))[b] = kvz_pixels_calc_ssd(orig, recb, w, w, w);
+  ((double *)(j->blob + L->bits_y[d]))[b] = kvz_get_coeff_cost(state, coeff, w, 0, (int8_t)scan_for(0, w, best_mode));
   for (int y = 0; y < w; ++y) memcpy(j->rec[0][d] + (size_t)(by * w + y) * W + bx * w, recb + y * w, w);
 
   /* --- chroma, co-located luma mode */
@@ -105,6 +107,7 @@ static void do_block(job_t *j, int d, int b, kvz_pixel *buf /* scratch: 6 * 1024
       coeff_t *cc = (coeff_t *)(j->blob + (color == 1 ? L->coeff_u[d] : L->coeff_v[d])) + (size_t)b * wc * wc;
       has = kvz_quantize_residual(state, &cu, wc, (color_t)color, scan_for(1, wc, best_mode), 0, wc, wc, orig, pred2, recb, cc, false);
       (j->blob + (color == 1 ? L->has_u[d] : L->has_v[d]))[b] = (uint8_t)has;
+      ((double *)(j->blob + (color == 1 ? L->bits_u[d] : L->bits_v[d])))[b] = kvz_get_coeff_cost(state, cc, wc, 2, (int8_t)scan_for(1, wc, best_mode));
       ((uint32_t *)(j->blob + (color == 1 ? L->ssd_u[d] : L->ssd_v[d])))[b] = kvz_pixels_calc_ssd(orig, recb, wc, wc, wc);
       for (int y = 0; y < wc; ++y) memcpy(j->rec[color][d] + (size_t)(by * wc + y) * Wc + bx * wc, recb + y * wc, wc);
     }
@@ -223,6 +226,9 @@ int kvzref_frame_pass(kvzref_ctx *ctx, const uint8_t *src, int W, int H, int qp,
    * (qp_to_lambda, rate_control.c:678-691) */
   kvz_init_contexts(st, (int8_t)qp, KVZ_SLICE_I);
   st->lambda = 0.57 * pow(2.0, (qp - 12) / 3.0);
+  /* coefficient bit cost (kvz_get_coeff_cost, rdo.c:291-330): CABAC counting on the same models, no adaptation */
+  memcpy(&st->search_cabac.ctx, &st->cabac.ctx, sizeof(st->cabac.ctx));
+  st->search_cabac.update = 0;
   for (int d = 0; d < 4; ++d) {
     j.wl[d] = 32 >> d;
     j.rec[0][d] = (uint8_t *)xaligned((size_t)W * H);

@@ -410,3 +410,26 @@ void kvzref_rdoq(kvzref_ctx *c, int qp, double lambda, const uint8_t *cabac_ctx,
   memcpy(&st->cabac.ctx, cabac_ctx, sizeof(st->cabac.ctx));
   kvz_rdoq(st, coef, dest, width, width, (int8_t)type, (int8_t)scan_mode, (int8_t)block_type, (int8_t)tr_depth);
 }
+
+/* ---- coefficient bit cost: kvz_encode_coeff_nxn in only_count mode (what get_coeff_cabac_cost runs, rdo.c:223-264) ---- */
+typedef void (encode_coeff_fn)(encoder_state_t *, cabac_data_t *, const coeff_t *, uint8_t, uint8_t, int8_t, int8_t, double *);
+double kvzref_coeff_cost(kvzref_ctx *c, const char *impl, const uint8_t *cabac_ctx, int update, int trskip_enable, const coeff_t *coeff,
+                         int width, int type, int scan_mode, int tr_skip, uint8_t *ctx_after)
+{
+  encoder_state_t *st = &c->enc->states[0];
+  encoder_control_t *ctrl = (encoder_control_t *)st->encoder_control;
+  ctrl->cfg.trskip_enable = trskip_enable;
+  int found = 0;
+  for (int i = 0; i < width * width; ++i) if (coeff[i]) { found = 1; break; }
+  if (!found) return 0;                                     /* rdo.c:231-238 */
+  cabac_data_t cabac_copy;
+  memcpy(&cabac_copy, &st->search_cabac, sizeof(cabac_copy));
+  memcpy(&cabac_copy.ctx, cabac_ctx, sizeof(cabac_copy.ctx));
+  cabac_copy.only_count = 1;
+  cabac_copy.update = update ? 1 : 0;
+  double bits = 0;
+  ((encode_coeff_fn *)kvzref_find("encode_coeff_nxn", impl))(st, &cabac_copy, coeff, (uint8_t)width, (uint8_t)type, (int8_t)scan_mode,
+                                                            (int8_t)tr_skip, &bits);
+  if (ctx_after) memcpy(ctx_after, &cabac_copy.ctx, sizeof(cabac_copy.ctx));
+  return bits;
+}

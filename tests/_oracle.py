@@ -623,7 +623,8 @@ class Ref:
 
     def make_cu_info(self, type_, depth, part_size, tr_depth, cbf, qp, mv_dir, mv, mv_ref):
         out = aligned(32, np.uint8)
-        self.lib.kvzref_make_cu_info(type_, depth, part_size, tr_depth, cbf, qp, mv_dir, P(al(mv, np.int16)), P(al(mv_ref, np.uint8)), P(out))
+        mv_a, ref_a = al(mv, np.int16), al(mv_ref, np.uint8)          # keep the buffers alive across the call
+        self.lib.kvzref_make_cu_info(type_, depth, part_size, tr_depth, cbf, qp, mv_dir, P(mv_a), P(ref_a), P(out))
         return out[:self.lib.kvzref_sizeof_cu_info()].copy()
 
     # -- RDOQ (kvz_rdoq, not a strategy)
@@ -648,6 +649,16 @@ class Ref:
         self.lib.kvzref_rdoq(self.ctx(qp, signhide, 1), qp, C.c_double(lambda_), P(cc), P(coef), P(dest), width, type_, scan_mode,
                              block_type, tr_depth)
         return dest.copy()
+
+    def coeff_cost(self, coeff, width, cabac_ctx, type_=0, scan_mode=0, tr_skip=0, signhide=0, trskip_enable=0, update=0, impl="generic"):
+        """kvz_encode_coeff_nxn in only_count mode -> (bits, context models afterwards)."""
+        self.lib.kvzref_coeff_cost.restype = C.c_double
+        after = aligned(256, np.uint8)
+        cc = al(cabac_ctx, np.uint8)
+        co = al(coeff, np.int16)                                       # keep the buffer alive across the call
+        bits = self.lib.kvzref_coeff_cost(self.ctx(27, signhide, 0), impl.encode(), P(cc), update, trskip_enable, P(co), width,
+                                          type_, scan_mode, tr_skip, P(after))
+        return float(bits), after[:self.cabac_ctx_size()].copy()
 
     # -- nal
     def array_checksum(self, data, height, width, stride, impl="generic"):

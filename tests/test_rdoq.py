@@ -94,3 +94,50 @@ def test_cuda_rdoq_vs_reference(cuda_lib, ref, n, qp, type_, signhide):
                 bad.append(i)
         assert not bad, f"ctx {ci}: {len(bad)} of {count} TUs differ, first {bad[:5]}"
         assert nonzero > 0
+
+
+# ------------------------------------------------------------------------------------------ coefficient bit cost
+def synth_levels(rng, n, count):
+    """Quantised-level-like blocks: sparse, small magnitudes, a few large ones, low frequencies denser."""
+    fy, fx = np.mgrid[0:n, 0:n]
+    dens = np.exp(-(fx + fy) / (n * rng.uniform(0.05, 0.8, (count, 1, 1))))
+    nz = rng.random((count, n, n)) < dens * rng.uniform(0.05, 1.0, (count, 1, 1))
+    mag = np.rint(np.abs(rng.laplace(0, 1.2, (count, n, n)))).astype(np.int64) + 1
+    mag = np.where(rng.random((count, n, n)) < 0.01, rng.integers(1, 3000, (count, n, n)), mag)
+    lv = np.where(nz, mag * rng.choice([-1, 1], (count, n, n)), 0)
+    lv[rng.random(count) < 0.08] = 0
+    return np.clip(lv, -32768, 32767).astype(np.int16)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,type_,signhide,update", [(n, t, s, u) for n in (4, 8, 16, 32) for t in (0, 2) for s in (0, 1) for u in (0, 1)
+                                                     if not (n == 32 and t == 2)])
+def test_cuda_coeff_cost_vs_reference(cuda_lib, ref, n, type_, signhide, update):
+    """kvz_cuda_coeff_cost_batch == kvz_encode_coeff_nxn in only_count mode (generic and the selected AVX2 version):
+    the double bit count and, with update = 1, the adapted context models, bit for bit."""
+    from kvazaar_b200 import api
+    rng = np.random.default_rng(77 * n + type_ + 3 * signhide + 5 * update)
+    count = {4: 300, 8: 200, 16: 80, 32: 30}[n]
+    lv = synth_levels(rng, n, count)
+    tus = np.zeros(count, api.RDOQ_TU)
+    tus["off_coef"] = np.arange(count) * n * n
+    tus["type"] = type_
+    tus["scan_idx"] = rng.integers(0, 3, count) if n <= 8 else 0
+    tus["block_type"] = rng.integers(0, 2, count)                         # transform_skip flag
+    trskip = 1
+    for cabac in (ref.init_contexts(32, 2), rng.integers(0, 126, api.CABAC_CTX_BYTES).astype(np.uint8)):
+        bits, ctx_out = api.coeff_cost_batch(api.to_dev(lv.ravel()), n, tus, cabac, signhide, trskip, update, want_ctx=True)
+        bits = bits.cpu().numpy()
+        ctx_out = ctx_out.cpu().numpy().reshape(count, -1)
+        some = 0
+        for i in range(count):
+            want, after = ref.coeff_cost(lv[i].ravel(), n, cabac, type_, int(tus["scan_idx"][i]), int(tus["block_type"][i]), signhide, trskip, update)
+            assert want == bits[i], (i, want, bits[i])
+            if update and want > 0:
+                assert np.array_equal(after, ctx_out[i]), i
+            some += want > 0
+            if i % 7 == 0:                                                # the AVX2 strategy counts the same bits
+                w2, _ = ref.coeff_cost(lv[i].ravel(), n, cabac, type_, int(tus["scan_idx"][i]), int(tus["block_type"][i]), signhide, trskip, update,
+                                       impl=ref.selected_name("encode_coeff_nxn"))
+                assert w2 == want
+        assert some > count // 2
