@@ -264,7 +264,7 @@ def run_cuda(args):
             ["deblock", "sao_stats_decide", "sao_reconstruct", "checksum"]
     stages = {names[i]: round(stage_ms[i], 4) for i in range(NST) if stage_ms[i] > 0.0005}
     # per-LAUNCH time of each kernel (chroma stages hold two launches: U and V; deblocking two passes)
-    per_launch = [stage_ms[i] / (2 if "chroma" in names[i] or names[i] == "deblock" else 1) for i in range(NST)]
+    per_launch = [stage_ms[i] / (2 if names[i].startswith("recon_chroma") or names[i] == "deblock" else 1) for i in range(NST)]
     dom = int(np.argmax(per_launch))
     ncu = {}
     for fn in ("r01_ncu_summary.json", "r01b_ncu_summary.json"):      # later captures override earlier ones
@@ -286,12 +286,12 @@ def run_cuda(args):
             return (W // w) * (H // w) * (wc * wc + 4 * wc + 1 + wc * wc + 2 * wc * wc + 5)
         if kind == "bits_luma":          # int16 levels in, one double per block out
             return W * H * 2 + (W // w) * (H // w) * 8
-        if kind == "bits_chroma":
-            return (W // 2) * (H // 2) * 2 + (W // w) * (H // w) * 8
+        if kind == "bits_chroma":        # U and V in one launch
+            return 2 * ((W // 2) * (H // 2) * 2 + (W // w) * (H // w) * 8)
         if kind == "rdoq_luma":          # int16 coefficients in, int16 levels out
             return W * H * 4
-        if kind == "rdoq_chroma":
-            return (W // 2) * (H // 2) * 4
+        if kind == "rdoq_chroma":        # U and V in one launch
+            return 2 * (W // 2) * (H // 2) * 4
         if kind == "deblock":            # per pass (launch): the three reconstruction planes in and out + 20-byte CU records in
             return 2 * W * H * 3 // 2 + (W // 4) * (H // 4) * 20
         if kind == "sao_stats_decide":   # source + reconstruction of all three planes in, 40+4+1 ints per CTU-plane out

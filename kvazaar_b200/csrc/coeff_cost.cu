@@ -185,16 +185,18 @@ __global__ void __launch_bounds__(128) coeff_cost_kernel(kvz_cuda_coeff_cost_par
 // Uniform TU grid of the frame-level pass (TU t at coeff[t * n * n], intra; scan from the intra mode as in the
 // reconstruction kernel).  No context adaptation; transform skip disabled.
 __global__ void __launch_bounds__(128) coeff_cost_grid_kernel(int signhide, const kvz_cuda_cabac_ctx *__restrict__ cabac,
-                                                              const int16_t *__restrict__ coeff, int count, int log2n,
-                                                              const int8_t *__restrict__ modes, int is_chroma, double *__restrict__ bits_out)
+                                                              const int16_t *__restrict__ coeff, const int16_t *__restrict__ coeff2, int count,
+                                                              int log2n, const int8_t *__restrict__ modes, int is_chroma,
+                                                              double *__restrict__ bits_out, double *__restrict__ bits_out2)
 {
   __shared__ kvz_cuda_cabac_ctx s_ctx;
   __shared__ int32_t s_ebits[128];
   rdoq_load_ebits(s_ebits);
   for (int i = threadIdx.x; i < (int)sizeof(kvz_cuda_cabac_ctx); i += blockDim.x) ((uint8_t *)&s_ctx)[i] = ((const uint8_t *)cabac)[i];
   __syncthreads();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (coeff2 ? 2 * count : count)) return;
+  if (t >= count) { t -= count; coeff = coeff2; bits_out = bits_out2; }      // second plane (V) of a U+V launch
   const int w = 1 << log2n;
   int scan = 0;
   if ((!is_chroma && w <= 8) || (is_chroma && w == 4)) { const int m = modes[t]; scan = (m >= 6 && m <= 14) ? 2 : ((m >= 22 && m <= 30) ? 1 : 0); }
@@ -203,10 +205,11 @@ __global__ void __launch_bounds__(128) coeff_cost_grid_kernel(int signhide, cons
   bits_out[t] = coeff_cost_tu(c, coeff + (size_t)t * w * w, log2n, is_chroma ? 2 : 0, scan, 0, 0, signhide);
 }
 
-int coeff_cost_launch_grid(int signhide, const kvz_cuda_cabac_ctx *ctx_dev, const int16_t *coeff, int count, int log2n, const int8_t *modes,
-                           int is_chroma, double *bits_out, cudaStream_t st)
+int coeff_cost_launch_grid(int signhide, const kvz_cuda_cabac_ctx *ctx_dev, const int16_t *coeff, const int16_t *coeff2, int count, int log2n,
+                           const int8_t *modes, int is_chroma, double *bits_out, double *bits_out2, cudaStream_t st)
 {
-  coeff_cost_grid_kernel<<<(count + 127) / 128, 128, 0, st>>>(signhide, ctx_dev, coeff, count, log2n, modes, is_chroma, bits_out);
+  const int total = coeff2 ? 2 * count : count;
+  coeff_cost_grid_kernel<<<(total + 127) / 128, 128, 0, st>>>(signhide, ctx_dev, coeff, coeff2, count, log2n, modes, is_chroma, bits_out, bits_out2);
   KVZC_LAUNCHED();
   return 0;
 }

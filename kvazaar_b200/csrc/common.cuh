@@ -101,12 +101,12 @@ struct Call {
 int rdoq_launch_tus(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ctx_dev, int16_t *coeff, const kvz_cuda_tu *tus, int count, int n,
                     cudaStream_t st);
 
-int rdoq_launch_grid(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ctx_dev, int16_t *coeff, int count, int log2n, const int8_t *modes,
-                     int is_chroma, int tr_depth, cudaStream_t st);
+int rdoq_launch_grid(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ctx_dev, int16_t *coeff, int16_t *coeff2, int count, int log2n,
+                     const int8_t *modes, int is_chroma, int tr_depth, cudaStream_t st);   // coeff2: second plane (V) or NULL
 
 // coeff_cost.cu: CABAC bit cost of every TU of a uniform grid (frame-level pass)
-int coeff_cost_launch_grid(int signhide, const kvz_cuda_cabac_ctx *ctx_dev, const int16_t *coeff, int count, int log2n, const int8_t *modes,
-                           int is_chroma, double *bits_out, cudaStream_t st);
+int coeff_cost_launch_grid(int signhide, const kvz_cuda_cabac_ctx *ctx_dev, const int16_t *coeff, const int16_t *coeff2, int count, int log2n,
+                           const int8_t *modes, int is_chroma, double *bits_out, double *bits_out2, cudaStream_t st);
 
 // ---------------------------------------------------------------- device side
 template <class T> struct PixTraits;

@@ -603,28 +603,33 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
       } else {
         if (int r = launch_recon_phase<1>(qp, src, rin, W, W, H, 0, log2w, W / w, nb, modes, rec, coeff, has, ssd, st)) return r;
         fp_mark(fp, s0 + 2, st);
-        if (int r = rdoq_launch_grid(fp->rdoq, cabac, coeff, nb, log2w, modes, 0, k_fp_tr_depth[d], st)) return r;
+        if (int r = rdoq_launch_grid(fp->rdoq, cabac, coeff, nullptr, nb, log2w, modes, 0, k_fp_tr_depth[d], st)) return r;
         fp_mark(fp, s0 + 3, st);
         if (int r = launch_recon_phase<2>(qp, src, rin, W, W, H, 0, log2w, W / w, nb, modes, rec, coeff, has, ssd, st)) return r;
       }
     }
     fp_mark(fp, s0 + 4, st);
     // CABAC bit cost of the luma levels (kvz_get_coeff_cost, rdo.c:291-330) with the slice-initial context models
-    if (int r = coeff_cost_launch_grid(fp->prm.signhide, cabac, (const int16_t *)(B + L.coeff_y[d]), nb, log2w, modes, 0, (double *)(B + L.bits_y[d]), st)) return r;
+    if (int r = coeff_cost_launch_grid(fp->prm.signhide, cabac, (const int16_t *)(B + L.coeff_y[d]), nullptr, nb, log2w, modes, 0, (double *)(B + L.bits_y[d]), nullptr, st)) return r;
     fp_mark(fp, s0 + 5, st);
     if (d == 3) { fp_mark(fp, s0 + 6, st); fp_mark(fp, s0 + 7, st); fp_mark(fp, s0 + 8, st); continue; }
     const int wc = w / 2;
     for (int step = 0; step < 4; ++step) {
-      for (int color = 1; color <= 2 && (rdoq || step == 0 || step == 3); ++color) {
+      // RDOQ and the bit cost take U and V in ONE launch (twice the TUs in flight for these latency-bound kernels)
+      if (step == 1 && rdoq) {
+        if (int r = rdoq_launch_grid(fp->rdoq, cabac, (int16_t *)(B + L.coeff_u[d]), (int16_t *)(B + L.coeff_v[d]), nb, log2w - 1, modes, 1, k_fp_tr_depth[d], st)) return r;
+      } else if (step == 3) {
+        if (int r = coeff_cost_launch_grid(fp->prm.signhide, cabac, (const int16_t *)(B + L.coeff_u[d]), (const int16_t *)(B + L.coeff_v[d]), nb, log2w - 1,
+                                           modes, 1, (double *)(B + L.bits_u[d]), (double *)(B + L.bits_v[d]), st)) return r;
+      } else
+      for (int color = 1; color <= 2 && (rdoq || step == 0); ++color) {
         const uint8_t *csrc = src + poff[color], *crin = rin + poff[color];
         uint8_t *rec = B + (color == 1 ? fp->off_rec_u[d] : fp->off_rec_v[d]), *has = B + (color == 1 ? L.has_u[d] : L.has_v[d]);
         int16_t *coeff = (int16_t *)(B + (color == 1 ? L.coeff_u[d] : L.coeff_v[d]));
         uint32_t *ssd = (uint32_t *)(B + (color == 1 ? L.ssd_u[d] : L.ssd_v[d]));
         int r = 0;
-        if (step == 3) r = coeff_cost_launch_grid(fp->prm.signhide, cabac, coeff, nb, log2w - 1, modes, 1, (double *)(B + (color == 1 ? L.bits_u[d] : L.bits_v[d])), st);
-        else if (!rdoq) r = launch_recon(qp, csrc, crin, W / 2, W, H, color, log2w - 1, (W / 2) / wc, nb, modes, rec, coeff, has, ssd, st);
+        if (!rdoq) r = launch_recon(qp, csrc, crin, W / 2, W, H, color, log2w - 1, (W / 2) / wc, nb, modes, rec, coeff, has, ssd, st);
         else if (step == 0) r = launch_recon_phase<1>(qp, csrc, crin, W / 2, W, H, color, log2w - 1, (W / 2) / wc, nb, modes, rec, coeff, has, ssd, st);
-        else if (step == 1) r = rdoq_launch_grid(fp->rdoq, cabac, coeff, nb, log2w - 1, modes, 1, k_fp_tr_depth[d], st);
         else r = launch_recon_phase<2>(qp, csrc, crin, W / 2, W, H, color, log2w - 1, (W / 2) / wc, nb, modes, rec, coeff, has, ssd, st);
         if (r) return r;
       }

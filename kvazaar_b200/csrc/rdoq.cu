@@ -58,8 +58,8 @@ __global__ void __launch_bounds__(WARPS * 32) rdoq_tu_kernel(kvz_cuda_rdoq_param
 // intra mode exactly as in the reconstruction kernel (kvz_get_scan_order, search_intra.c / intra.c call sites).
 template <int LOG2N, int WARPS, bool SH>
 __global__ void __launch_bounds__(WARPS * 32) rdoq_grid_kernel(kvz_cuda_rdoq_params p, const kvz_cuda_cabac_ctx *__restrict__ cabac,
-                                                               int16_t *__restrict__ coeff, int count, const int8_t *__restrict__ modes,
-                                                               int is_chroma, int tr_depth)
+                                                               int16_t *__restrict__ coeff, int16_t *__restrict__ coeff2, int count,
+                                                               const int8_t *__restrict__ modes, int is_chroma, int tr_depth)
 {
   constexpr int NN = 1 << (2 * LOG2N), W = 1 << LOG2N;
   __shared__ RdoqScratch<NN, SH> scratch[WARPS];
@@ -69,22 +69,25 @@ __global__ void __launch_bounds__(WARPS * 32) rdoq_grid_kernel(kvz_cuda_rdoq_par
   __shared__ __align__(4) int16_t s_coef[WARPS][NN], s_q[WARPS][NN];
   for (int i = threadIdx.x; i < (int)sizeof(kvz_cuda_cabac_ctx); i += blockDim.x) ((uint8_t *)&s_ctx)[i] = ((const uint8_t *)cabac)[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = blockIdx.x * WARPS + warp;
-  const bool active = t < count;
-  if (active) for (int e = lane; e < NN; e += 32) s_coef[warp][e] = coeff[(size_t)t * NN + e];
+  // two planes (U and V) can share one launch: TU indices [count, 2 * count) address coeff2
+  int t = blockIdx.x * WARPS + warp;
+  const bool active = t < (coeff2 ? 2 * count : count);
+  int16_t *base = coeff;
+  if (t >= count) { t -= count; base = coeff2; }
+  if (active) for (int e = lane; e < NN; e += 32) s_coef[warp][e] = base[(size_t)t * NN + e];
   __syncthreads();
   if (!active) return;
   int scan = 0;
   if ((!is_chroma && W <= 8) || (is_chroma && W == 4)) { const int m = modes[t]; scan = (m >= 6 && m <= 14) ? 2 : ((m >= 22 && m <= 30) ? 1 : 0); }
   rdoq_tu<NN, SH>(p, &s_ctx, s_ebits, s_coef[warp], s_q[warp], LOG2N, is_chroma ? 2 : 0, scan, 1, tr_depth, scratch[warp], lane);
-  for (int e = lane; e < NN; e += 32) coeff[(size_t)t * NN + e] = s_q[warp][e];
+  for (int e = lane; e < NN; e += 32) base[(size_t)t * NN + e] = s_q[warp][e];
 }
 
 // Thread-per-TU form of the uniform grid for 4x4 and 8x8 TUs (rdoq_tu_thread).
 template <int LOG2N, bool SH>
 __global__ void __launch_bounds__(128) rdoq_grid_thread_kernel(kvz_cuda_rdoq_params p, const kvz_cuda_cabac_ctx *__restrict__ cabac,
-                                                               int16_t *__restrict__ coeff, int count, const int8_t *__restrict__ modes,
-                                                               int is_chroma, int tr_depth)
+                                                               int16_t *__restrict__ coeff, int16_t *__restrict__ coeff2, int count,
+                                                               const int8_t *__restrict__ modes, int is_chroma, int tr_depth)
 {
   constexpr int NN = 1 << (2 * LOG2N), W = 1 << LOG2N;
   __shared__ kvz_cuda_cabac_ctx s_ctx;
@@ -94,8 +97,9 @@ __global__ void __launch_bounds__(128) rdoq_grid_thread_kernel(kvz_cuda_rdoq_par
   for (int i = threadIdx.x; i < (int)sizeof(kvz_cuda_cabac_ctx); i += blockDim.x) ((uint8_t *)&s_ctx)[i] = ((const uint8_t *)cabac)[i];
   for (int i = threadIdx.x; i < 3 * NN; i += blockDim.x) s_scan[i / NN][i % NN] = (uint8_t)scan_pos(i / NN, LOG2N, i % NN);
   __syncthreads();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (coeff2 ? 2 * count : count)) return;
+  if (t >= count) { t -= count; coeff = coeff2; }
   int16_t coef[NN], q[NN];
   const uint4 *src = reinterpret_cast<const uint4 *>(coeff + (size_t)t * NN);
   bool any = false;
@@ -112,15 +116,16 @@ __global__ void __launch_bounds__(128) rdoq_grid_thread_kernel(kvz_cuda_rdoq_par
   for (int i = 0; i < NN / 8; ++i) dst[i] = reinterpret_cast<const uint4 *>(q)[i];
 }
 
-int rdoq_launch_grid(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ctx_dev, int16_t *coeff, int count, int log2n, const int8_t *modes,
-                     int is_chroma, int tr_depth, cudaStream_t st)
+int rdoq_launch_grid(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ctx_dev, int16_t *coeff, int16_t *coeff2, int count, int log2n,
+                     const int8_t *modes, int is_chroma, int tr_depth, cudaStream_t st)
 {
+  const int total = coeff2 ? 2 * count : count;
   const bool SHV = p.signhide_enable != 0;
   switch (log2n) {
-    case 2: if (SHV) rdoq_grid_thread_kernel<2, true><<<(count + 127) / 128, 128, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); else rdoq_grid_thread_kernel<2, false><<<(count + 127) / 128, 128, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); break;
-    case 3: if (SHV) rdoq_grid_kernel<3, 8, true><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); else rdoq_grid_kernel<3, 8, false><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); break;
-    case 4: if (SHV) rdoq_grid_kernel<4, 2, true><<<(count + 1) / 2, 64, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); else rdoq_grid_kernel<4, 2, false><<<(count + 1) / 2, 64, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); break;
-    default: if (SHV) rdoq_grid_kernel<5, 1, true><<<count, 32, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); else rdoq_grid_kernel<5, 1, false><<<count, 32, 0, st>>>(p, ctx_dev, coeff, count, modes, is_chroma, tr_depth); break;
+    case 2: if (SHV) rdoq_grid_thread_kernel<2, true><<<(total + 127) / 128, 128, 0, st>>>(p, ctx_dev, coeff, coeff2, count, modes, is_chroma, tr_depth); else rdoq_grid_thread_kernel<2, false><<<(total + 127) / 128, 128, 0, st>>>(p, ctx_dev, coeff, coeff2, count, modes, is_chroma, tr_depth); break;
+    case 3: if (SHV) rdoq_grid_kernel<3, 8, true><<<(total + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, coeff2, count, modes, is_chroma, tr_depth); else rdoq_grid_kernel<3, 8, false><<<(total + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, coeff2, count, modes, is_chroma, tr_depth); break;
+    case 4: if (SHV) rdoq_grid_kernel<4, 2, true><<<(total + 1) / 2, 64, 0, st>>>(p, ctx_dev, coeff, coeff2, count, modes, is_chroma, tr_depth); else rdoq_grid_kernel<4, 2, false><<<(total + 1) / 2, 64, 0, st>>>(p, ctx_dev, coeff, coeff2, count, modes, is_chroma, tr_depth); break;
+    default: if (SHV) rdoq_grid_kernel<5, 1, true><<<total, 32, 0, st>>>(p, ctx_dev, coeff, coeff2, count, modes, is_chroma, tr_depth); else rdoq_grid_kernel<5, 1, false><<<total, 32, 0, st>>>(p, ctx_dev, coeff, coeff2, count, modes, is_chroma, tr_depth); break;
   }
   KVZC_LAUNCHED();
   return 0;
