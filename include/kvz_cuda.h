@@ -269,6 +269,11 @@ typedef struct {
   uint64_t checksum;               /* 3 x 4 bytes, big-endian, Y U V */
   uint64_t bits_y[4];              /* double [nblk]  CABAC bit cost of the block's quantised coefficients (kvz_get_coeff_cost) */
   uint64_t bits_u[3], bits_v[3];
+  /* the coefficient sections sit together at the end of the blob: [coeff_begin, host_bytes) */
+  uint64_t coeff_begin;
+  /* compact form of that region (kvz_cuda_fp_run_host_compact): 32-byte chunks, one bitmap bit per chunk */
+  uint64_t n_chunks;               /* (host_bytes - coeff_begin) / 32 */
+  uint64_t compact_header_bytes;   /* 256 + bitmap, = offset of the packed chunks inside the compact buffer */
 } kvz_cuda_fp_layout;
 typedef struct kvz_cuda_frame_pass kvz_cuda_frame_pass;
 kvz_cuda_frame_pass *kvz_cuda_fp_create(const kvz_cuda_fp_params *p);   /* NULL on failure */
@@ -287,6 +292,16 @@ int    kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const v
 #define KVZ_CUDA_FP_STAGES 40
 int    kvz_cuda_fp_set_timing(kvz_cuda_frame_pass *fp, int enable);
 int    kvz_cuda_fp_get_timing(kvz_cuda_frame_pass *fp, double *ms_total /* [KVZ_CUDA_FP_STAGES] */, int *runs);
+/* Compact result: quantised coefficients are ~99 % zeros, so the coefficient region travels as a bitmap (bit c set =
+ * 32-byte chunk c of [coeff_begin, host_bytes) holds a non-zero value) plus the non-zero chunks back to back, in chunk
+ * order.  small_host receives blob[0, coeff_begin); compact_host receives
+ *   uint32 nonzero_chunks, uint32 n_chunks, uint32 chunks_copied, pad to 256 | bitmap (n_chunks / 8, padded) | chunks
+ * and must hold compact_header_bytes + budget_chunks * 32 bytes.  If nonzero_chunks > budget_chunks the tail stays on
+ * the device (kvz_cuda_fp_result_dev() + host_bytes' compact region; fetch with kvz_cuda_fp_compact_fetch).  Lossless:
+ * tests/test_framepass.py rebuilds the full region from it. */
+int    kvz_cuda_fp_run_host_compact(kvz_cuda_frame_pass *fp, const void *src_host, void *small_host, void *compact_host,
+                                    uint32_t budget_chunks, void *stream);
+int    kvz_cuda_fp_compact_fetch(kvz_cuda_frame_pass *fp, uint32_t first_chunk, uint32_t count, void *dst_host, void *stream);
 /* host frame in (pinned for async), result blob out (host_bytes): H2D + pass + D2H enqueued on `stream` */
 int    kvz_cuda_fp_run_host(kvz_cuda_frame_pass *fp, const void *src_host, void *result_host, void *stream);
 

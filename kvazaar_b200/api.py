@@ -380,7 +380,8 @@ class FpLayout(C.Structure):
                 ("ssd_v", C.c_uint64 * 3), ("coeff_u", C.c_uint64 * 3), ("coeff_v", C.c_uint64 * 3),
                 ("sao_stats", C.c_uint64), ("sao_dd", C.c_uint64), ("sao_band_dd", C.c_uint64),
                 ("sao_best", C.c_uint64), ("sao_rec", C.c_uint64), ("checksum", C.c_uint64),
-                ("bits_y", C.c_uint64 * 4), ("bits_u", C.c_uint64 * 3), ("bits_v", C.c_uint64 * 3)]
+                ("bits_y", C.c_uint64 * 4), ("bits_u", C.c_uint64 * 3), ("bits_v", C.c_uint64 * 3),
+                ("coeff_begin", C.c_uint64), ("n_chunks", C.c_uint64), ("compact_header_bytes", C.c_uint64)]
 
 
 def fp_layout_for(width, height, qp=27, signhide=0):
@@ -432,6 +433,13 @@ class FramePass:
         _ck(lib().kvz_cuda_fp_run_host(self.h, C.c_void_p(src_host.data_ptr()), C.c_void_p(result_host.data_ptr()),
                                        _stream()))
 
+    def run_host_compact(self, src_host, small_host, compact_host, budget_chunks):
+        """Like run_host, but the coefficient region comes back as bitmap + non-zero 32-byte chunks (see
+        kvz_cuda_fp_run_host_compact).  small_host: layout.coeff_begin bytes; compact_host: layout.compact_header_bytes +
+        32 * budget_chunks bytes (pinned uint8 tensors)."""
+        _ck(lib().kvz_cuda_fp_run_host_compact(self.h, C.c_void_p(src_host.data_ptr()), C.c_void_p(small_host.data_ptr()),
+                                               C.c_void_p(compact_host.data_ptr()), C.c_uint32(budget_chunks), _stream()))
+
     def result_host(self):
         """Synchronous copy of the result blob to a numpy array."""
         torch = _torch()
@@ -470,6 +478,20 @@ def fp_sections(layout, width, height):
     out["sao_rec"] = (layout.sao_rec, np.uint8, width * height * 3 // 2)
     out["checksum"] = (layout.checksum, np.uint8, 12)
     return out
+
+
+def fp_expand_compact(layout, small, compact):
+    """Rebuild the full result blob from the compact form (numpy uint8 arrays).  Host-side inverse of the device
+    compaction: bit c of the bitmap set <=> the next 32 bytes of the packed stream belong at chunk c."""
+    n_chunks, hdr = int(layout.n_chunks), int(layout.compact_header_bytes)
+    head = compact[:12].view(np.uint32)
+    nonzero, copied = int(head[0]), (len(compact) - hdr) // 32
+    assert int(head[1]) == n_chunks and nonzero <= copied, "compact buffer truncated: fetch the tail with kvz_cuda_fp_compact_fetch"
+    bits = np.unpackbits(compact[256:256 + (n_chunks + 7) // 8], bitorder="little")[:n_chunks].astype(bool)
+    assert int(bits.sum()) == nonzero
+    region = np.zeros((n_chunks, 32), np.uint8)
+    region[bits] = compact[hdr:hdr + nonzero * 32].reshape(nonzero, 32)
+    return np.concatenate([small[:int(layout.coeff_begin)], region.ravel()])
 
 
 def fp_section(blob, sections, name):

@@ -379,6 +379,77 @@ __global__ void __launch_bounds__(256) checksum3_kernel(SaoPlanes pl, uint32_t *
   }
 }
 
+// ---- compact form of the coefficient region: bitmap of non-zero 32-byte chunks + the chunks themselves, in order.
+// Three small launches: per-tile (1024 chunks) counts, exclusive scan of the tile counts, ordered write.
+constexpr int CMP_TILE = 1024;
+__device__ __forceinline__ bool chunk_nonzero(const uint4 *p) { const uint4 a = p[0], b = p[1]; return (a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w) != 0; }
+
+__global__ void __launch_bounds__(256) compact_count_kernel(const uint4 *__restrict__ region, uint32_t n_chunks, uint32_t *__restrict__ tile_counts)
+{
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int k = 0; k < CMP_TILE / 256; ++k) {
+    const uint32_t c = blockIdx.x * CMP_TILE + k * 256 + threadIdx.x;
+    if (c < n_chunks && chunk_nonzero(region + 2 * (size_t)c)) ++mine;
+  }
+  mine = warp_sum(mine);
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s_cnt, mine);
+  __syncthreads();
+  if (threadIdx.x == 0) tile_counts[blockIdx.x] = (uint32_t)s_cnt;
+}
+
+// one CTA: exclusive scan of the tile counts in place, total -> header
+__global__ void __launch_bounds__(1024) compact_scan_kernel(uint32_t *__restrict__ tile_counts, int n_tiles, uint32_t n_chunks, uint32_t *__restrict__ header)
+{
+  __shared__ uint32_t s_part[1024];
+  const int per = (n_tiles + 1023) / 1024;
+  uint32_t local = 0;
+  for (int k = 0; k < per; ++k) { const int i = threadIdx.x * per + k; if (i < n_tiles) local += tile_counts[i]; }
+  s_part[threadIdx.x] = local;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {                       // Hillis-Steele inclusive scan
+    const uint32_t v = threadIdx.x >= o ? s_part[threadIdx.x - o] : 0;
+    __syncthreads();
+    s_part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = s_part[threadIdx.x] - local;
+  for (int k = 0; k < per; ++k) { const int i = threadIdx.x * per + k; if (i < n_tiles) { const uint32_t c = tile_counts[i]; tile_counts[i] = run; run += c; } }
+  if (threadIdx.x == 1023) { header[0] = s_part[1023]; header[1] = n_chunks; }
+}
+
+__global__ void __launch_bounds__(256) compact_write_kernel(const uint4 *__restrict__ region, uint32_t n_chunks, const uint32_t *__restrict__ tile_offsets,
+                                                            uint32_t *__restrict__ bitmap, uint4 *__restrict__ packed)
+{
+  __shared__ uint32_t s_warp_cnt[CMP_TILE / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t masks[CMP_TILE / 256];
+#pragma unroll
+  for (int k = 0; k < CMP_TILE / 256; ++k) {
+    const uint32_t c = blockIdx.x * CMP_TILE + k * 256 + threadIdx.x;
+    const bool nz = c < n_chunks && chunk_nonzero(region + 2 * (size_t)c);
+    masks[k] = __ballot_sync(0xffffffffu, nz);
+    if (lane == 0) {
+      s_warp_cnt[k * 8 + warp] = __popc(masks[k]);
+      if (blockIdx.x * CMP_TILE + k * 256 + warp * 32 < n_chunks) bitmap[(blockIdx.x * CMP_TILE + k * 256) / 32 + warp] = masks[k];
+    }
+  }
+  __syncthreads();
+  const uint32_t base = tile_offsets[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < CMP_TILE / 256; ++k) {
+    if (!((masks[k] >> lane) & 1)) continue;
+    uint32_t before = 0;
+    for (int j = 0; j < k * 8 + warp; ++j) before += s_warp_cnt[j];           // chunk order = (k, warp, lane)
+    const uint32_t dst = base + before + __popc(masks[k] & ((1u << lane) - 1));
+    const uint32_t c = blockIdx.x * CMP_TILE + k * 256 + threadIdx.x;
+    packed[2 * (size_t)dst] = region[2 * (size_t)c];
+    packed[2 * (size_t)dst + 1] = region[2 * (size_t)c + 1];
+  }
+}
+
 }  // namespace kvzc
 
 using namespace kvzc;
@@ -444,7 +515,7 @@ struct kvz_cuda_frame_pass {
   uint8_t *blob = nullptr;              // device: host-visible sections first, device-only sections after
   // device-only
   size_t off_costs35[4], off_rec_y[4], off_rec_u[3], off_rec_v[3];
-  size_t off_sao_off, off_dbk_cus, off_cabac, off_src_copy;
+  size_t off_sao_off, off_dbk_cus, off_cabac, off_src_copy, off_compact, off_tile_counts;
   kvz_cuda_rdoq_params rdoq;
   std::vector<uint8_t> host_init;       // initial content of the descriptor sections
   size_t init_off = 0, init_bytes = 0;
@@ -494,12 +565,9 @@ static kvz_cuda_frame_pass *fp_build(const kvz_cuda_fp_params *p, bool alloc)
     const int nb = fp->nblk[d] = (W / w) * (H / w);
     L.nblk[d] = nb;
     L.mode_y[d] = take(nb); L.cost_y[d] = take(4 * (size_t)nb); L.has_y[d] = take(nb); L.ssd_y[d] = take(4 * (size_t)nb);
-    L.coeff_y[d] = take(2 * (size_t)nb * w * w);
     L.bits_y[d] = take(8 * (size_t)nb);
     if (d < 3) {
-      const int wc = w / 2;
       L.has_u[d] = take(nb); L.has_v[d] = take(nb); L.ssd_u[d] = take(4 * (size_t)nb); L.ssd_v[d] = take(4 * (size_t)nb);
-      L.coeff_u[d] = take(2 * (size_t)nb * wc * wc); L.coeff_v[d] = take(2 * (size_t)nb * wc * wc);
       L.bits_u[d] = take(8 * (size_t)nb); L.bits_v[d] = take(8 * (size_t)nb);
     }
   }
@@ -510,7 +578,18 @@ static kvz_cuda_frame_pass *fp_build(const kvz_cuda_fp_params *p, bool alloc)
   L.sao_band_dd = take(4 * (size_t)fp->nctu3); L.sao_best = take(fp->nctu3);
   L.sao_rec = take((size_t)W * H * 3 / 2);
   L.checksum = take(16);
+  // the (large, sparse) coefficient sections come last so that the compact result is two copies: the head + the packed chunks
+  L.coeff_begin = off;
+  for (int d = 0; d < 4; ++d) {
+    const int w = fp->wl[d], nb = fp->nblk[d];
+    L.coeff_y[d] = take(2 * (size_t)nb * w * w);
+    if (d < 3) { const int wc = w / 2; L.coeff_u[d] = take(2 * (size_t)nb * wc * wc); L.coeff_v[d] = take(2 * (size_t)nb * wc * wc); }
+  }
   L.host_bytes = fp->host_bytes = off;
+  L.n_chunks = (L.host_bytes - L.coeff_begin) / 32;
+  L.compact_header_bytes = 256 + align_up((size_t)(L.n_chunks + 7) / 8);
+  fp->off_compact = take(L.compact_header_bytes + (size_t)L.n_chunks * 32);
+  fp->off_tile_counts = take(4 * ((size_t)L.n_chunks / 1024 + 2));
   for (int d = 0; d < 4; ++d) fp->off_costs35[d] = take(4 * (size_t)fp->nblk[d] * 35);
   for (int d = 0; d < 4; ++d) fp->off_rec_y[d] = take((size_t)W * H);
   for (int d = 0; d < 3; ++d) { fp->off_rec_u[d] = take((size_t)W * H / 4); fp->off_rec_v[d] = take((size_t)W * H / 4); }
@@ -688,6 +767,42 @@ int kvz_cuda_fp_get_timing(kvz_cuda_frame_pass *fp, double *ms_total, int *runs)
   fp_collect(fp);
   for (int i = 0; i < KVZ_CUDA_FP_STAGES; ++i) ms_total[i] = fp->ms_acc[i];
   *runs = fp->runs_timed;
+  return 0;
+}
+
+int kvz_cuda_fp_run_host_compact(kvz_cuda_frame_pass *fp, const void *src_host, void *small_host, void *compact_host, uint32_t budget_chunks,
+                                 void *stream)
+{
+  KVZC_REQUIRE_DEVICE();
+  KVZC_ARG(fp && src_host && small_host && compact_host);
+  cudaStream_t st = as_stream(stream);
+  const kvz_cuda_fp_layout &L = fp->lay;
+  uint8_t *B = fp->blob;
+  uint8_t *src_dev = B + fp->off_src_copy;
+  KVZC_CHECK(cudaMemcpyAsync(src_dev, src_host, kvz_cuda_fp_frame_bytes(fp), cudaMemcpyHostToDevice, st));
+  if (int r = kvz_cuda_fp_run_dev(fp, src_dev, nullptr, st)) return r;
+  const uint32_t n_chunks = (uint32_t)L.n_chunks, n_tiles = (n_chunks + CMP_TILE - 1) / CMP_TILE;
+  uint8_t *cmp = B + fp->off_compact;
+  uint32_t *tiles = (uint32_t *)(B + fp->off_tile_counts);
+  const uint4 *region = (const uint4 *)(B + L.coeff_begin);
+  compact_count_kernel<<<n_tiles, 256, 0, st>>>(region, n_chunks, tiles);
+  KVZC_LAUNCHED();
+  compact_scan_kernel<<<1, 1024, 0, st>>>(tiles, (int)n_tiles, n_chunks, (uint32_t *)cmp);
+  KVZC_LAUNCHED();
+  compact_write_kernel<<<n_tiles, 256, 0, st>>>(region, n_chunks, tiles, (uint32_t *)(cmp + 256), (uint4 *)(cmp + L.compact_header_bytes));
+  KVZC_LAUNCHED();
+  if (budget_chunks > n_chunks) budget_chunks = n_chunks;
+  KVZC_CHECK(cudaMemcpyAsync(small_host, B, L.coeff_begin, cudaMemcpyDeviceToHost, st));
+  KVZC_CHECK(cudaMemcpyAsync(compact_host, cmp, L.compact_header_bytes + (size_t)budget_chunks * 32, cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+int kvz_cuda_fp_compact_fetch(kvz_cuda_frame_pass *fp, uint32_t first_chunk, uint32_t count, void *dst_host, void *stream)
+{
+  KVZC_REQUIRE_DEVICE();
+  KVZC_ARG(fp && dst_host && (uint64_t)first_chunk + count <= fp->lay.n_chunks);
+  KVZC_CHECK(cudaMemcpyAsync(dst_host, fp->blob + fp->off_compact + fp->lay.compact_header_bytes + (size_t)first_chunk * 32, (size_t)count * 32,
+                             cudaMemcpyDeviceToHost, as_stream(stream)));
   return 0;
 }
 

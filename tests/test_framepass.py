@@ -85,4 +85,15 @@ def test_cuda_frame_pass_matches_reference(cuda_lib, ref, dims, qp, signhide, rd
     torch.cuda.synchronize()
     for name in sec:
         assert np.array_equal(kb.fp_section(res_pin.numpy(), sec, name), kb.fp_section(want, sec, name)), name
+    # compact result (bitmap + non-zero coefficient chunks) expands to the same blob
+    L = fp.layout
+    assert int(L.coeff_begin) + 32 * int(L.n_chunks) == fp.host_bytes
+    small = torch.zeros(int(L.coeff_begin), dtype=torch.uint8).pin_memory()
+    compact = torch.zeros(int(L.compact_header_bytes) + 32 * int(L.n_chunks), dtype=torch.uint8).pin_memory()
+    fp.run_host_compact(src_pin, small, compact, int(L.n_chunks))
+    torch.cuda.synchronize()
+    full = kb.fp_expand_compact(L, small.numpy(), compact.numpy())
+    assert np.array_equal(full, res_pin.numpy()), "compact result does not expand to the full blob"
+    nonzero = int(compact.numpy()[:4].view(np.uint32)[0])
+    assert 0 < nonzero < int(L.n_chunks)                      # dense at low QP on tiny frames, ~5 % at 1080p QP27
     fp.close()
