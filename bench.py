@@ -368,7 +368,8 @@ def run_cuda(args):
                 "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "frames_per_step": fps_step, "frames_in_flight": inflight, "parallelism": f"frames/{world}",
-                           "l2": "working set per step (8 distinct 3.1 MB frames + 4 x ~95 MB result/scratch blobs) exceeds the 126 MB L2"},
+                           "l2": f"working set per step ({fps_step} distinct {passes[0].frame_bytes / 1e6:.1f} MB frames + {inflight} result/scratch blobs of "
+                                 f"{passes[0].host_bytes / 1e6:.0f}+ MB each) exceeds the 126 MB L2"},
                 "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": fps_step * passes[0].frame_bytes,
                         "d2h_bytes_per_step": fps_step * d2h_compact, "ms_per_step": ms_e2e / args.steps,
                         "result": "compact: blob head + bitmap + non-zero 32-byte coefficient chunks (lossless)",

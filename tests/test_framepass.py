@@ -97,3 +97,32 @@ def test_cuda_frame_pass_matches_reference(cuda_lib, ref, dims, qp, signhide, rd
     nonzero = int(compact.numpy()[:4].view(np.uint32)[0])
     assert 0 < nonzero < int(L.n_chunks)                      # dense at low QP on tiny frames, ~5 % at 1080p QP27
     fp.close()
+
+
+@pytest.mark.gpu
+def test_cuda_frame_pass_full_size_1080p_medium(cuda_lib, ref):
+    """BASELINE configs[1] at its full size (1920x1080, QP27, RDOQ + deblocking + SAO): every section of the result blob
+    equals the pass through the reference's strategy functions; the compact result expands to the same bytes."""
+    import os
+    import torch
+    from _oracle import ref_frame_pass
+    kb = cuda_lib
+    W, H, qp = 1920, 1080, 27
+    src = synth_frame(W, H, frame_idx=5)
+    fp = kb.FramePass(W, H, qp, 0, 1)
+    src_pin = torch.from_numpy(src.copy()).pin_memory()
+    res_pin = torch.empty(fp.host_bytes, dtype=torch.uint8).pin_memory()
+    fp.run_host(src_pin, res_pin)
+    torch.cuda.synchronize()
+    want = ref_frame_pass(ref, src, W, H, qp, fp.layout, nthreads=min(64, os.cpu_count() or 8), signhide=0, rdoq=1)
+    sec = kb.fp_sections(fp.layout, W, H)
+    for name in sec:
+        a, b = kb.fp_section(res_pin.numpy(), sec, name), kb.fp_section(want, sec, name)
+        assert np.array_equal(a, b), (name, int(np.argmax(a != b)))
+    L = fp.layout
+    small = torch.zeros(int(L.coeff_begin), dtype=torch.uint8).pin_memory()
+    compact = torch.zeros(int(L.compact_header_bytes) + 32 * (int(L.n_chunks) // 8), dtype=torch.uint8).pin_memory()
+    fp.run_host_compact(src_pin, small, compact, int(L.n_chunks) // 8)
+    torch.cuda.synchronize()
+    assert np.array_equal(kb.fp_expand_compact(L, small.numpy(), compact.numpy()), res_pin.numpy())
+    fp.close()
