@@ -77,14 +77,14 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
   // ---- references, smoothed references, DC, mode
   for (int gb = threadIdx.x; gb < G; gb += blockDim.x) {
     const int b = min(first + gb, nblk - 1);
-    if (!INTER) s_ctx[gb] = build_ref_ctx(LOG2W, color, ((b % blocks_x) * W) << is_c, ((b / blocks_x) * W) << is_c, pic_w, pic_h);
+    if (!INTER && PHASE != 2) s_ctx[gb] = build_ref_ctx(LOG2W, color, ((b % blocks_x) * W) << is_c, ((b / blocks_x) * W) << is_c, pic_w, pic_h);
     s_mode[gb] = (!INTER && first + gb < nblk) ? modes[first + gb] : 0;
     s_has[gb] = 0; s_ac[gb] = 0; s_ssd[gb] = 0;
   }
   load_matrix_packed<W>(s_pf, use_dst, false);
   load_matrix_packed<W>(s_pi, use_dst, true);
   __syncthreads();
-  if (!INTER) {
+  if (!INTER && PHASE != 2) {
   for (int e = threadIdx.x; e < G * 2 * NREF; e += blockDim.x) {
     const int gb = e / (2 * NREF), r = e - gb * 2 * NREF;
     const bool is_top = r < NREF;
@@ -109,8 +109,10 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
     if (b < nblk) {
       const long off = (long)((b / blocks_x) * W + y) * stride + (b % blocks_x) * W + x;
       if (INTER) pv = rec_in[off];
+      else if (PHASE == 2) pv = rec_out[off];          // the forward half parked the prediction in the reconstruction plane
       else pv = intra_predict_px(LOG2W, s_mode[gb], color, true, s_ref[gb][0], s_ref[gb][1], s_ref[gb][2], s_ref[gb][3], s_dc[gb], x, y);
       sv = src[off];
+      if (PHASE == 1) rec_out[off] = (T)pv;
     }
     s_pred[e] = (T)pv;
     s_a[e] = (int16_t)(sv - pv);
