@@ -28,18 +28,6 @@ namespace kvzc {
 int rough_search_u8(int log2w, const uint8_t *src, const uint8_t *rec, int stride, int pic_w, int pic_h, uint32_t *costs,
                     int8_t *best_mode, uint32_t *best_cost, cudaStream_t st);
 
-__global__ void __launch_bounds__(256) select_best_kernel(const uint32_t *__restrict__ costs, int nblk,
-                                                          int8_t *__restrict__ mode, uint32_t *__restrict__ best)
-{
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= nblk) return;
-  uint32_t bc = costs[(size_t)b * 35];
-  int bm = 0;
-  for (int m = 1; m < 35; ++m) { const uint32_t c = costs[(size_t)b * 35 + m]; if (c < bc) { bc = c; bm = m; } }
-  mode[b] = (int8_t)bm;
-  best[b] = bc;
-}
-
 // kvz_intra_recon_cu for a tile of 1024 samples (G = 1024 / W^2 TUs of one colour plane) per 256-thread CTA:
 // references -> prediction of the chosen mode -> residual -> DCT/DST -> quant (+ sign hiding) -> dequant -> inverse
 // -> reconstruction, SSD.  All TUs walk the same barrier sequence; data-dependent decisions (has_coeffs,
@@ -516,13 +504,12 @@ struct kvz_cuda_frame_pass {
   size_t host_bytes, total_bytes;
   uint8_t *blob = nullptr;              // device: host-visible sections first, device-only sections after
   // device-only
-  size_t off_costs35[4], off_rec_y[4], off_rec_u[3], off_rec_v[3];
+  size_t off_rec_y[4], off_rec_u[3], off_rec_v[3];
   size_t off_sao_off, off_dbk_cus, off_cabac, off_src_copy, off_compact, off_tile_counts;
   kvz_cuda_rdoq_params rdoq;
   std::vector<uint8_t> host_init;       // initial content of the descriptor sections
   size_t init_off = 0, init_bytes = 0;
   // optional per-stage CUDA-event timing (bench.py's live roofline measurement)
-  bool keep_costs = false;               // also write the [nblk][35] cost tables (device-only section)
   bool timing = false;
   cudaEvent_t ev[KVZ_CUDA_FP_STAGES + 1] = {};
   double ms_acc[KVZ_CUDA_FP_STAGES] = {};
@@ -592,7 +579,6 @@ static kvz_cuda_frame_pass *fp_build(const kvz_cuda_fp_params *p, bool alloc)
   L.compact_header_bytes = 256 + align_up((size_t)(L.n_chunks + 7) / 8);
   fp->off_compact = take(L.compact_header_bytes + (size_t)L.n_chunks * 32);
   fp->off_tile_counts = take(4 * ((size_t)L.n_chunks / 1024 + 2));
-  for (int d = 0; d < 4; ++d) fp->off_costs35[d] = take(4 * (size_t)fp->nblk[d] * 35);
   for (int d = 0; d < 4; ++d) fp->off_rec_y[d] = take((size_t)W * H);
   for (int d = 0; d < 3; ++d) { fp->off_rec_u[d] = take((size_t)W * H / 4); fp->off_rec_v[d] = take((size_t)W * H / 4); }
   fp->off_sao_off = take(4 * (size_t)4 * fp->nctu3 * 5);
@@ -667,10 +653,9 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
     const int s0 = d * 9;                 // stage slots: rough, luma fwd (or fused), luma rdoq, luma inv, luma bits, chroma fwd, rdoq, inv, bits
     fp_mark(fp, s0 + 0, st);
     if (nb == 0) { for (int k = 1; k < 9; ++k) fp_mark(fp, s0 + k, st); continue; }
-    uint32_t *costs = (uint32_t *)(B + fp->off_costs35[d]);
     int8_t *modes = (int8_t *)(B + L.mode_y[d]);
-    // rough search with the mode selection fused in; the 35-entry cost tables stay on chip unless asked for
-    if (int r = rough_search_u8(log2w, src, rin, W, W, H, fp->keep_costs ? costs : nullptr, modes, (uint32_t *)(B + L.cost_y[d]), st)) return r;
+    // rough search with the mode selection fused in; the 35-entry cost tables stay on chip
+    if (int r = rough_search_u8(log2w, src, rin, W, W, H, nullptr, modes, (uint32_t *)(B + L.cost_y[d]), st)) return r;
     fp_mark(fp, s0 + 1, st);
     // luma: prediction -> transform -> quantisation -> reconstruction; with RDOQ the fused kernel is split around the
     // RDOQ launch (quant-generic.c:234-240)
