@@ -158,9 +158,9 @@ def cpu_baseline(budget_s=15.0):
     cli = os.path.join(ROOT, "oracle", "_ref", "kvazaar")
     if os.path.exists(cli):
         try:
-            yuv = "/tmp/kvz_bench_1080p.yuv"
+            yuv = f"/tmp/kvz_bench_{H}p.yuv"
             np.concatenate(synth_frames(4)).tofile(yuv)
-            r = subprocess.run([cli, "-i", yuv, "--input-res", f"{W}x{H}", "-o", "/tmp/kvz_bench.hevc", "--preset", "medium", "-q", str(QP),
+            r = subprocess.run([cli, "-i", yuv, "--input-res", f"{W}x{H}", "-o", "/tmp/kvz_bench.hevc", "--preset", "veryslow" if W > 1920 else "medium", "-q", str(QP),
                                 "-p", "1"], capture_output=True, text=True, timeout=120)
             for ln in (r.stderr + r.stdout).splitlines():
                 if ln.strip().startswith("FPS:"):
