@@ -29,19 +29,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-W, H, QP, SIGNHIDE, RDOQ = 1920, 1080, 27, 0, 0
+W, H, QP, SIGNHIDE, RDOQ, TRSKIP = 1920, 1080, 27, 0, 0, 0
 WORKLOAD = "1920x1080 8-bit synthetic I420, all-intra, QP27 (preset medium: SAO on, signhide off), frame-level hot-path pass"
 
 
 def set_workload(name, rdoq):
     """configs[1] (default, the one the metric is quoted on) or the configs[2] shape (2160p, QP22, sign hiding)."""
-    global W, H, QP, SIGNHIDE, RDOQ, WORKLOAD
+    global W, H, QP, SIGNHIDE, RDOQ, TRSKIP, WORKLOAD
     RDOQ = int(rdoq)
     q = "RDOQ on" if RDOQ else "RDOQ off (kvz_quant)"
     WORKLOAD = f"1920x1080 8-bit synthetic I420, all-intra, QP27 (preset medium: deblock + SAO on, signhide off, {q}), frame-level hot-path pass"
     if name == "2160p":
-        W, H, QP, SIGNHIDE = 3840, 2160, 22, 1
-        WORKLOAD = f"3840x2160 8-bit synthetic I420, all-intra, QP22 (preset veryslow shape: deblock + SAO on, signhide on, {q}), frame-level hot-path pass"
+        W, H, QP, SIGNHIDE, TRSKIP = 3840, 2160, 22, 1, 1
+        WORKLOAD = f"3840x2160 8-bit synthetic I420, all-intra, QP22 (preset veryslow shape: deblock + SAO on, signhide on, transform skip on, {q}), frame-level hot-path pass"
 
 
 def peaks():
@@ -116,11 +116,11 @@ def run_reference(args):
     blob = aligned(int(lay.host_bytes), np.uint8)
     nper = args.ref_frames
     for _ in range(max(1, args.warmup)):
-        ref_frame_pass(ref, frames[0], W, H, QP, lay, nthreads=cores, signhide=SIGNHIDE, blob=blob, src_is_aligned=True, rdoq=RDOQ)
+        ref_frame_pass(ref, frames[0], W, H, QP, lay, nthreads=cores, signhide=SIGNHIDE, blob=blob, src_is_aligned=True, rdoq=RDOQ, trskip=TRSKIP)
     t0 = time.perf_counter()
     for s in range(args.steps):
         for f in range(nper):
-            ref_frame_pass(ref, frames[(s * nper + f) % len(frames)], W, H, QP, lay, nthreads=cores, signhide=SIGNHIDE, blob=blob, src_is_aligned=True, rdoq=RDOQ)
+            ref_frame_pass(ref, frames[(s * nper + f) % len(frames)], W, H, QP, lay, nthreads=cores, signhide=SIGNHIDE, blob=blob, src_is_aligned=True, rdoq=RDOQ, trskip=TRSKIP)
     dt = time.perf_counter() - t0
     fps = args.steps * nper / dt
     sample = f"{args.steps * nper} frames {W}x{H} through the reference's selected strategy functions ({ref.selected_name('satd_8x8')})"
@@ -146,10 +146,10 @@ def cpu_baseline(budget_s=15.0):
     from _oracle import aligned, al
     frames = [al(f) for f in synth_frames(2)]
     blob = aligned(int(lay.host_bytes), np.uint8)
-    ref_frame_pass(ref, frames[0], W, H, QP, lay, nthreads=cores, signhide=SIGNHIDE, blob=blob, src_is_aligned=True, rdoq=RDOQ)
+    ref_frame_pass(ref, frames[0], W, H, QP, lay, nthreads=cores, signhide=SIGNHIDE, blob=blob, src_is_aligned=True, rdoq=RDOQ, trskip=TRSKIP)
     n, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < budget_s and n < 2000:
-        ref_frame_pass(ref, frames[n % 2], W, H, QP, lay, nthreads=cores, signhide=SIGNHIDE, blob=blob, src_is_aligned=True, rdoq=RDOQ)
+        ref_frame_pass(ref, frames[n % 2], W, H, QP, lay, nthreads=cores, signhide=SIGNHIDE, blob=blob, src_is_aligned=True, rdoq=RDOQ, trskip=TRSKIP)
         n += 1
     dt = time.perf_counter() - t0
     out = {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "reference",
@@ -186,7 +186,7 @@ def run_cuda(args):
     fps_step = args.frames_per_step
     inflight = args.inflight
     streams = [torch.cuda.Stream() for _ in range(inflight)]
-    passes = [kb.FramePass(W, H, QP, SIGNHIDE, RDOQ) for _ in range(inflight)]
+    passes = [kb.FramePass(W, H, QP, SIGNHIDE, RDOQ, 0.0, TRSKIP) for _ in range(inflight)]
     frames_np = synth_frames(fps_step)
     # every rank gets its own frames (sharding = frame i of the job -> rank i mod world)
     frames_np = [np.roll(f, rank * 977) for f in frames_np]

@@ -248,6 +248,8 @@ int kvz_cuda_array_checksum(int bitdepth, const void *data, int height, int widt
 typedef struct {
   int32_t width, height, bitdepth, qp, signhide;
   int32_t rdoq;      /* cfg.rdoq_enable: quantise with kvz_rdoq (slice-initial context models) instead of kvz_quant */
+  int32_t trskip;    /* cfg.trskip_enable: 4x4 luma TUs also try transform skip (kvz_quantize_residual_trskip, transform.c:241-288) */
+  int32_t pad;
   double  lambda;    /* state->lambda for RDOQ; 0 = the reference's constant-QP value 0.57 * 2^((qp - 12) / 3) (rate_control.c:678-691) */
 } kvz_cuda_fp_params;
 typedef struct {
@@ -269,6 +271,7 @@ typedef struct {
   uint64_t checksum;               /* 3 x 4 bytes, big-endian, Y U V */
   uint64_t bits_y[4];              /* double [nblk]  CABAC bit cost of the block's quantised coefficients (kvz_get_coeff_cost) */
   uint64_t bits_u[3], bits_v[3];
+  uint64_t trskip_y;               /* uint8 [nblk[3]]  1 = the 4x4 luma TU uses transform skip (0 everywhere without params.trskip) */
   /* the coefficient sections sit together at the end of the blob: [coeff_begin, host_bytes) */
   uint64_t coeff_begin;
   /* compact form of that region (kvz_cuda_fp_run_host_compact): 32-byte chunks, one bitmap bit per chunk */

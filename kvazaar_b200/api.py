@@ -369,7 +369,7 @@ def call_deblock_frame(y, u, v, stride, cus, width, height, qp, beta_offset_div2
 # ------------------------------------------------------------------ frame-level pass (framepass.cu)
 class FpParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("bitdepth", C.c_int32), ("qp", C.c_int32),
-                ("signhide", C.c_int32), ("rdoq", C.c_int32), ("lambda_", C.c_double)]
+                ("signhide", C.c_int32), ("rdoq", C.c_int32), ("trskip", C.c_int32), ("pad", C.c_int32), ("lambda_", C.c_double)]
 
 
 class FpLayout(C.Structure):
@@ -380,14 +380,14 @@ class FpLayout(C.Structure):
                 ("ssd_v", C.c_uint64 * 3), ("coeff_u", C.c_uint64 * 3), ("coeff_v", C.c_uint64 * 3),
                 ("sao_stats", C.c_uint64), ("sao_dd", C.c_uint64), ("sao_band_dd", C.c_uint64),
                 ("sao_best", C.c_uint64), ("sao_rec", C.c_uint64), ("checksum", C.c_uint64),
-                ("bits_y", C.c_uint64 * 4), ("bits_u", C.c_uint64 * 3), ("bits_v", C.c_uint64 * 3),
+                ("bits_y", C.c_uint64 * 4), ("bits_u", C.c_uint64 * 3), ("bits_v", C.c_uint64 * 3), ("trskip_y", C.c_uint64),
                 ("coeff_begin", C.c_uint64), ("n_chunks", C.c_uint64), ("compact_header_bytes", C.c_uint64)]
 
 
 def fp_layout_for(width, height, qp=27, signhide=0):
     """Result-blob layout; needs no GPU."""
     lay = FpLayout()
-    prm = FpParams(width, height, 8, qp, signhide, 0, 0.0)
+    prm = FpParams(width, height, 8, qp, signhide, 0, 0, 0, 0.0)
     _ck(lib().kvz_cuda_fp_layout_for(C.byref(prm), C.byref(lay)))
     return lay
 
@@ -395,7 +395,7 @@ def fp_layout_for(width, height, qp=27, signhide=0):
 class FramePass:
     """One in-flight frame of the frame-level pass (device buffers owned by the library)."""
 
-    def __init__(self, width, height, qp=27, signhide=0, rdoq=0, lambda_=0.0):
+    def __init__(self, width, height, qp=27, signhide=0, rdoq=0, lambda_=0.0, trskip=0):
         _torch()
         L = lib()
         L.kvz_cuda_fp_create.restype = C.c_void_p
@@ -403,7 +403,7 @@ class FramePass:
         L.kvz_cuda_fp_result_dev.argtypes = [C.c_void_p]
         L.kvz_cuda_fp_frame_bytes.restype = C.c_size_t
         L.kvz_cuda_fp_frame_bytes.argtypes = [C.c_void_p]
-        self.params = FpParams(width, height, 8, qp, signhide, rdoq, lambda_)
+        self.params = FpParams(width, height, 8, qp, signhide, rdoq, trskip, 0, lambda_)
         h = L.kvz_cuda_fp_create(C.byref(self.params))
         if not h:
             raise KvzCudaError(f"kvz_cuda_fp_create failed: {L.kvz_cuda_last_error().decode()}")
@@ -463,6 +463,8 @@ def fp_sections(layout, width, height):
         out[f"ssd_y{d}"] = (layout.ssd_y[d], np.uint32, nb)
         out[f"coeff_y{d}"] = (layout.coeff_y[d], np.int16, nb * w * w)
         out[f"bits_y{d}"] = (layout.bits_y[d], np.float64, nb)
+        if d == 3:
+            out["trskip_y"] = (layout.trskip_y, np.uint8, nb)
         if d < 3:
             wc = w // 2
             for c in "uv":

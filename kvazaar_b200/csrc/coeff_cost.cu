@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(128) coeff_cost_kernel(kvz_cuda_coeff_cost_par
 
 // Uniform TU grid of the frame-level pass (TU t at coeff[t * n * n], intra; scan from the intra mode as in the
 // reconstruction kernel).  No context adaptation; transform skip disabled.
-__global__ void __launch_bounds__(128) coeff_cost_grid_kernel(int signhide, const kvz_cuda_cabac_ctx *__restrict__ cabac,
+__global__ void __launch_bounds__(128) coeff_cost_grid_kernel(int signhide, int trskip_enable, const kvz_cuda_cabac_ctx *__restrict__ cabac,
                                                               const int16_t *__restrict__ coeff, const int16_t *__restrict__ coeff2, int count,
                                                               int log2n, const int8_t *__restrict__ modes, int is_chroma,
                                                               double *__restrict__ bits_out, double *__restrict__ bits_out2)
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(128) coeff_cost_grid_kernel(int signhide, cons
   if ((!is_chroma && w <= 8) || (is_chroma && w == 4)) { const int m = modes[t]; scan = (m >= 6 && m <= 14) ? 2 : ((m >= 22 && m <= 30) ? 1 : 0); }
   CostCtx c;
   c.eb = s_ebits; c.update = false; c.models = (uint8_t *)&s_ctx;
-  bits_out[t] = coeff_cost_tu(c, coeff + (size_t)t * w * w, log2n, is_chroma ? 2 : 0, scan, 0, 0, signhide);
+  bits_out[t] = coeff_cost_tu(c, coeff + (size_t)t * w * w, log2n, is_chroma ? 2 : 0, scan, trskip_enable, 0, signhide);   // the flag is counted as 0 (rdo.c:251-258)
 }
 
 
@@ -360,13 +360,13 @@ __global__ void __launch_bounds__(128) coeff_cost_grid_warp_kernel(int signhide,
 }
 
 int coeff_cost_launch_grid(int signhide, const kvz_cuda_cabac_ctx *ctx_dev, const int16_t *coeff, const int16_t *coeff2, int count, int log2n,
-                           const int8_t *modes, int is_chroma, double *bits_out, double *bits_out2, cudaStream_t st)
+                           const int8_t *modes, int trskip_enable, double *bits_out, double *bits_out2, cudaStream_t st, int is_chroma)
 {
   const int total = coeff2 ? 2 * count : count;
   if (log2n >= 4)      // 16x16 / 32x32: diagonal scan only, a warp per TU
     coeff_cost_grid_warp_kernel<<<(total + 3) / 4, 128, 0, st>>>(signhide, ctx_dev, coeff, coeff2, count, log2n, is_chroma, bits_out, bits_out2);
   else
-    coeff_cost_grid_kernel<<<(total + 127) / 128, 128, 0, st>>>(signhide, ctx_dev, coeff, coeff2, count, log2n, modes, is_chroma, bits_out, bits_out2);
+    coeff_cost_grid_kernel<<<(total + 127) / 128, 128, 0, st>>>(signhide, trskip_enable, ctx_dev, coeff, coeff2, count, log2n, modes, is_chroma, bits_out, bits_out2);
   KVZC_LAUNCHED();
   return 0;
 }

@@ -106,7 +106,7 @@ int rdoq_launch_grid(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ct
 
 // coeff_cost.cu: CABAC bit cost of every TU of a uniform grid (frame-level pass)
 int coeff_cost_launch_grid(int signhide, const kvz_cuda_cabac_ctx *ctx_dev, const int16_t *coeff, const int16_t *coeff2, int count, int log2n,
-                           const int8_t *modes, int is_chroma, double *bits_out, double *bits_out2, cudaStream_t st);
+                           const int8_t *modes, int trskip_enable, double *bits_out, double *bits_out2, cudaStream_t st, int is_chroma = 0);
 
 // ---------------------------------------------------------------- device side
 template <class T> struct PixTraits;

@@ -36,7 +36,8 @@ int rough_search_u8(int log2w, const uint8_t *src, const uint8_t *rec, int strid
 // modes is unused, the scan is diagonal, no DST, and has_out is an int32 array (inter pass blob layout).
 // PHASE splits the walk around kvz_rdoq (quant-generic.c:234-240): 0 = whole function with kvz_quant; 1 = up to the
 // forward transform (coefficients -> coeff); 2 = from the quantised levels in coeff (written by rdoq_grid) onwards.
-template <class T, int LOG2W, bool INTER = false, int PHASE = 0>
+// TRSKIP (4x4 luma only): transform skip instead of the DST (kvz_transformskip / kvz_itransformskip, transform.c:150-185).
+template <class T, int LOG2W, bool INTER = false, int PHASE = 0, bool TRSKIP = false>
 __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params p, const T *__restrict__ src,
                                                           const T *__restrict__ rec_in, int stride, int pic_w, int pic_h,
                                                           int color, int blocks_x, int nblk,
@@ -110,9 +111,14 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
 
   if (PHASE != 2) {
   // ---- forward transform (ref: dct-generic.c:579-588, 611-619): tmp[k][j], then coef[k][j]
-  mat_pass_dp2a<W, true, false>(s_a, s_q, s_pf, l2 - 1 + (p.bitdepth - 8));
-  __syncthreads();
-  mat_pass_dp2a<W, true, false>(s_q, s_b, s_pf, l2 + 6);
+  if constexpr (TRSKIP) {
+    const int ts_shift = 15 - p.bitdepth - l2;
+    for (int e = threadIdx.x; e < E; e += blockDim.x) s_b[e] = (int16_t)((uint16_t)s_a[e] << ts_shift);
+  } else {
+    mat_pass_dp2a<W, true, false>(s_a, s_q, s_pf, l2 - 1 + (p.bitdepth - 8));
+    __syncthreads();
+    mat_pass_dp2a<W, true, false>(s_q, s_b, s_pf, l2 + 6);
+  }
   __syncthreads();
   if (PHASE == 1) {
     for (int e = threadIdx.x; e < E; e += blockDim.x) {
@@ -171,15 +177,19 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
         if (PHASE != 2) coeff[(size_t)b * WW + r] = v;
         if (v != 0) s_has[gb] = 1;
       }
-      s_b[gb * WW + x * W + y] = (int16_t)clip3(-32768, 32767, ((int)v * scale + add) >> shift);
+      const int dq = clip3(-32768, 32767, ((int)v * scale + add) >> shift);
+      if constexpr (TRSKIP) { const int ts_shift = 15 - p.bitdepth - l2; s_b[e] = (int16_t)((dq + (1 << (ts_shift - 1))) >> ts_shift); }
+      else s_b[gb * WW + x * W + y] = (int16_t)dq;
     }
   }
   __syncthreads();
   // ---- inverse transform (ref: dct-generic.c:590-599, 621-629)
-  mat_pass_dp2a<W, true, true>(s_b, s_a, s_pi, 7);
-  __syncthreads();
-  mat_pass_dp2a<W, false, true>(s_a, s_b, s_pi, 12 - (p.bitdepth - 8));
-  __syncthreads();
+  if constexpr (!TRSKIP) {
+    mat_pass_dp2a<W, true, true>(s_b, s_a, s_pi, 7);
+    __syncthreads();
+    mat_pass_dp2a<W, false, true>(s_a, s_b, s_pi, 12 - (p.bitdepth - 8));
+    __syncthreads();
+  }
 
   // ---- reconstruction + SSD (ref: quant-generic.c:263-292, picture-generic.c:536-551)
   for (int e = threadIdx.x; e < E; e += blockDim.x) {
@@ -478,6 +488,39 @@ static int launch_recon_phase(const kvz_cuda_quant_params &qp, const uint8_t *sr
   return 0;
 }
 
+// 4x4 luma with transform skip (PHASE 0 fused / 1 forward / 2 inverse)
+template <int PHASE>
+static int launch_recon_trskip(const kvz_cuda_quant_params &qp, const uint8_t *src, const uint8_t *rin, int stride, int pic_w, int pic_h,
+                               int blocks_x, int nblk, const int8_t *modes, uint8_t *rec, int16_t *coeff, uint8_t *has, uint32_t *ssd, cudaStream_t st)
+{
+  intra_recon_kernel<uint8_t, 2, false, PHASE, true><<<(nblk + 63) / 64, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, 0, blocks_x, nblk, modes, rec, coeff, has, ssd);
+  KVZC_LAUNCHED();
+  return 0;
+}
+
+// kvz_quantize_residual_trskip's decision per 4x4 luma TU (transform.c:241-288): keep the DST result unless the
+// transform-skip result has the strictly smaller  SSD + bits * lambda; the winner's data replaces the main sections.
+__global__ void __launch_bounds__(256) trskip_select_kernel(int nblk, int blocks_x, int stride, double lambda, const uint32_t *__restrict__ ssd_ts,
+                                                            const double *__restrict__ bits_ts, const uint8_t *__restrict__ has_ts,
+                                                            const int16_t *__restrict__ coeff_ts, const uint8_t *__restrict__ rec_ts,
+                                                            uint32_t *__restrict__ ssd, double *__restrict__ bits, uint8_t *__restrict__ has,
+                                                            int16_t *__restrict__ coeff, uint8_t *__restrict__ rec, uint8_t *__restrict__ flag)
+{
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblk) return;
+  const double cost_ns = (double)ssd[b] + bits[b] * lambda;
+  const double cost_ts = (double)ssd_ts[b] + bits_ts[b] * lambda;
+  const bool use_ts = !(cost_ns <= cost_ts);
+  flag[b] = use_ts;
+  if (!use_ts) return;
+  ssd[b] = ssd_ts[b]; bits[b] = bits_ts[b]; has[b] = has_ts[b];
+  const uint4 *cs = reinterpret_cast<const uint4 *>(coeff_ts + (size_t)b * 16);
+  uint4 *cd = reinterpret_cast<uint4 *>(coeff + (size_t)b * 16);
+  cd[0] = cs[0]; cd[1] = cs[1];
+  const long o = (long)((b / blocks_x) * 4) * stride + (b % blocks_x) * 4;
+  for (int y = 0; y < 4; ++y) *reinterpret_cast<uint32_t *>(rec + o + (long)y * stride) = *reinterpret_cast<const uint32_t *>(rec_ts + o + (long)y * stride);
+}
+
 static int launch_recon(const kvz_cuda_quant_params &qp, const uint8_t *src, const uint8_t *rin, int stride, int pic_w, int pic_h,
                         int color, int log2w, int blocks_x, int nblk, const int8_t *modes, uint8_t *rec, int16_t *coeff,
                         uint8_t *has, uint32_t *ssd, cudaStream_t st)
@@ -506,6 +549,7 @@ struct kvz_cuda_frame_pass {
   // device-only
   size_t off_rec_y[4], off_rec_u[3], off_rec_v[3];
   size_t off_sao_off, off_dbk_cus, off_cabac, off_src_copy, off_compact, off_tile_counts;
+  size_t off_ts_rec = 0, off_ts_coeff = 0, off_ts_has = 0, off_ts_ssd = 0, off_ts_bits = 0;
   kvz_cuda_rdoq_params rdoq;
   std::vector<uint8_t> host_init;       // initial content of the descriptor sections
   size_t init_off = 0, init_bytes = 0;
@@ -555,6 +599,7 @@ static kvz_cuda_frame_pass *fp_build(const kvz_cuda_fp_params *p, bool alloc)
     L.nblk[d] = nb;
     L.mode_y[d] = take(nb); L.cost_y[d] = take(4 * (size_t)nb); L.has_y[d] = take(nb); L.ssd_y[d] = take(4 * (size_t)nb);
     L.bits_y[d] = take(8 * (size_t)nb);
+    if (d == 3) L.trskip_y = take(nb);
     if (d < 3) {
       L.has_u[d] = take(nb); L.has_v[d] = take(nb); L.ssd_u[d] = take(4 * (size_t)nb); L.ssd_v[d] = take(4 * (size_t)nb);
       L.bits_u[d] = take(8 * (size_t)nb); L.bits_v[d] = take(8 * (size_t)nb);
@@ -577,6 +622,11 @@ static kvz_cuda_frame_pass *fp_build(const kvz_cuda_fp_params *p, bool alloc)
   L.host_bytes = fp->host_bytes = off;
   L.n_chunks = (L.host_bytes - L.coeff_begin) / 32;
   L.compact_header_bytes = 256 + align_up((size_t)(L.n_chunks + 7) / 8);
+  if (p->trskip) {            // scratch of the transform-skip candidate of every 4x4 luma TU
+    const size_t nb3 = fp->nblk[3];
+    fp->off_ts_rec = take((size_t)W * H); fp->off_ts_coeff = take(2 * nb3 * 16); fp->off_ts_has = take(nb3);
+    fp->off_ts_ssd = take(4 * nb3); fp->off_ts_bits = take(8 * nb3);
+  }
   fp->off_compact = take(L.compact_header_bytes + (size_t)L.n_chunks * 32);
   fp->off_tile_counts = take(4 * ((size_t)L.n_chunks / 1024 + 2));
   for (int d = 0; d < 4; ++d) fp->off_rec_y[d] = take((size_t)W * H);
@@ -676,7 +726,27 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
     }
     fp_mark(fp, s0 + 4, st);
     // CABAC bit cost of the luma levels (kvz_get_coeff_cost, rdo.c:291-330) with the slice-initial context models
-    if (int r = coeff_cost_launch_grid(fp->prm.signhide, cabac, (const int16_t *)(B + L.coeff_y[d]), nullptr, nb, log2w, modes, 0, (double *)(B + L.bits_y[d]), nullptr, st)) return r;
+    const int ts_flag = (d == 3 && fp->prm.trskip) ? 1 : 0;              // 4x4 TUs: the transform_skip_flag bin is part of the count
+    if (int r = coeff_cost_launch_grid(fp->prm.signhide, cabac, (const int16_t *)(B + L.coeff_y[d]), nullptr, nb, log2w, modes, ts_flag, (double *)(B + L.bits_y[d]), nullptr, st)) return r;
+    if (ts_flag) {
+      // the transform-skip candidate of every 4x4 luma TU, then kvz_quantize_residual_trskip's choice (stage slot: luma bits)
+      uint8_t *rec_ts = B + fp->off_ts_rec, *has_ts = B + fp->off_ts_has;
+      int16_t *coeff_ts = (int16_t *)(B + fp->off_ts_coeff);
+      uint32_t *ssd_ts = (uint32_t *)(B + fp->off_ts_ssd);
+      double *bits_ts = (double *)(B + fp->off_ts_bits);
+      if (!rdoq) {
+        if (int r = launch_recon_trskip<0>(qp, src, rin, W, W, H, W / w, nb, modes, rec_ts, coeff_ts, has_ts, ssd_ts, st)) return r;
+      } else {
+        if (int r = launch_recon_trskip<1>(qp, src, rin, W, W, H, W / w, nb, modes, rec_ts, coeff_ts, has_ts, ssd_ts, st)) return r;
+        if (int r = rdoq_launch_grid(fp->rdoq, cabac, coeff_ts, nullptr, nb, log2w, modes, 0, k_fp_tr_depth[d], st)) return r;
+        if (int r = launch_recon_trskip<2>(qp, src, rin, W, W, H, W / w, nb, modes, rec_ts, coeff_ts, has_ts, ssd_ts, st)) return r;
+      }
+      if (int r = coeff_cost_launch_grid(fp->prm.signhide, cabac, coeff_ts, nullptr, nb, log2w, modes, 1, bits_ts, nullptr, st)) return r;
+      trskip_select_kernel<<<(nb + 255) / 256, 256, 0, st>>>(nb, W / w, W, fp->rdoq.lambda, ssd_ts, bits_ts, has_ts, coeff_ts, rec_ts,
+                                                             (uint32_t *)(B + L.ssd_y[d]), (double *)(B + L.bits_y[d]), B + L.has_y[d],
+                                                             (int16_t *)(B + L.coeff_y[d]), B + fp->off_rec_y[d], B + L.trskip_y);
+      KVZC_LAUNCHED();
+    }
     fp_mark(fp, s0 + 5, st);
     if (d == 3) { fp_mark(fp, s0 + 6, st); fp_mark(fp, s0 + 7, st); fp_mark(fp, s0 + 8, st); continue; }
     const int wc = w / 2;
@@ -686,7 +756,7 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
         if (int r = rdoq_launch_grid(fp->rdoq, cabac, (int16_t *)(B + L.coeff_u[d]), (int16_t *)(B + L.coeff_v[d]), nb, log2w - 1, modes, 1, k_fp_tr_depth[d], st)) return r;
       } else if (step == 3) {
         if (int r = coeff_cost_launch_grid(fp->prm.signhide, cabac, (const int16_t *)(B + L.coeff_u[d]), (const int16_t *)(B + L.coeff_v[d]), nb, log2w - 1,
-                                           modes, 1, (double *)(B + L.bits_u[d]), (double *)(B + L.bits_v[d]), st)) return r;
+                                           modes, fp->prm.trskip /* counted for 4x4 chroma TUs too */, (double *)(B + L.bits_u[d]), (double *)(B + L.bits_v[d]), st, 1)) return r;
       } else
       for (int color = 1; color <= 2 && (rdoq || step == 0); ++color) {
         const uint8_t *csrc = src + poff[color], *crin = rin + poff[color];

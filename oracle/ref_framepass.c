@@ -24,6 +24,7 @@
 #include <math.h>
 #include "context.h"
 #include "rdo.h"
+#include "transform.h"
 #include "sao.h"
 #include "filter.h"
 #include "cu.h"
@@ -89,7 +90,16 @@ static void do_block(job_t *j, int d, int b, kvz_pixel *buf /* scratch: 6 * 1024
   /* --- luma reconstruction of the chosen mode */
   kvz_intra_predict(&refs, log2w, best_mode, COLOR_Y, pred, true);
   coeff_t *coeff = (coeff_t *)(j->blob + L->coeff_y[d]) + (size_t)b * w * w;
-  int has = kvz_quantize_residual(state, &cu, w, COLOR_Y, scan_for(0, w, best_mode), 0, w, w, orig, pred, recb, coeff, false);
+  int has;
+  if (w == 4 && state->encoder_control->cfg.trskip_enable) {
+    /* 4x4 luma: DST or transform skip, whichever has the smaller SSD + bits * lambda (transform.c:241-288, as quantize_tr_residual calls it) */
+    int8_t tr_skip = 0;
+    has = kvz_quantize_residual_trskip(state, &cu, w, COLOR_Y, scan_for(0, w, best_mode), &tr_skip, w, w, orig, pred, recb, coeff);
+    (j->blob + L->trskip_y)[b] = (uint8_t)tr_skip;
+  } else {
+    has = kvz_quantize_residual(state, &cu, w, COLOR_Y, scan_for(0, w, best_mode), 0, w, w, orig, pred, recb, coeff, false);
+    if (w == 4) (j->blob + L->trskip_y)[b] = 0;
+  }
   (j->blob + L->has_y[d])[b] = (uint8_t)has;
   ((uint32_t *)(j->blob + L->ssd_y[d]))[b] = kvz_pixels_calc_ssd(orig, recb, w, w, w);
   ((double *)(j->blob + L->bits_y[d]))[b] = kvz_get_coeff_cost(state, coeff, w, 0, (int8_t)scan_for(0, w, best_mode));

@@ -433,3 +433,9 @@ double kvzref_coeff_cost(kvzref_ctx *c, const char *impl, const uint8_t *cabac_c
   if (ctx_after) memcpy(ctx_after, &cabac_copy.ctx, sizeof(cabac_copy.ctx));
   return bits;
 }
+
+/* cfg.trskip_enable of an opened context (the frame pass tries transform skip on 4x4 luma TUs when set) */
+void kvzref_set_trskip(kvzref_ctx *c, int enable)
+{
+  ((encoder_control_t *)c->enc->states[0].encoder_control)->cfg.trskip_enable = enable;
+}

@@ -667,7 +667,7 @@ class Ref:
         return out
 
 
-def ref_frame_pass(ref, src, width, height, qp, layout, nthreads=8, signhide=0, blob=None, src_is_aligned=False, rdoq=0):
+def ref_frame_pass(ref, src, width, height, qp, layout, nthreads=8, signhide=0, blob=None, src_is_aligned=False, rdoq=0, trskip=0):
     """The frame-level pass through the compiled reference's own (AVX2) strategy pointers -> result blob.
     `blob` may be a reusable aligned buffer (bench.py keeps allocation out of the timed region)."""
     L = ref.lib
@@ -676,6 +676,7 @@ def ref_frame_pass(ref, src, width, height, qp, layout, nthreads=8, signhide=0, 
     if not src_is_aligned:
         src = al(src)
     ctx = ref.ctx(qp, signhide, rdoq, width, height)
+    L.kvzref_set_trskip(ctx, trskip)
     rc = L.kvzref_frame_pass(ctx, P(src), width, height, qp, C.byref(layout), P(blob), nthreads)
     assert rc == 0
     return blob

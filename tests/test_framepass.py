@@ -60,7 +60,8 @@ def test_reference_frame_pass_is_self_consistent(ref, orc):
 @pytest.mark.gpu
 @pytest.mark.parametrize("dims,qp,signhide,rdoq", [((136, 72), 27, 0, 0), ((200, 136), 27, 0, 0), ((320, 192), 27, 0, 0),
                                                     ((200, 136), 22, 1, 0), ((136, 72), 37, 1, 0), ((320, 192), 17, 1, 0),
-                                                    ((200, 136), 27, 0, 1), ((320, 192), 22, 1, 1), ((136, 72), 32, 0, 1)])
+                                                    ((200, 136), 27, 0, 1), ((320, 192), 22, 1, 1), ((136, 72), 32, 0, 1),
+                                                    ((320, 192), 22, 1, 3), ((200, 136), 27, 0, 2), ((136, 72), 17, 1, 3)])
 def test_cuda_frame_pass_matches_reference(cuda_lib, ref, dims, qp, signhide, rdoq):
     """Byte-identical result blob: CUDA frame pass vs the reference's own strategy functions (medium-like:
     signhide off; veryslow-like: QP 22 with sign-bit hiding; rdoq = 1: kvz_rdoq instead of kvz_quant, as medium and
@@ -69,11 +70,18 @@ def test_cuda_frame_pass_matches_reference(cuda_lib, ref, dims, qp, signhide, rd
     from _oracle import ref_frame_pass
     kb = cuda_lib
     W, H = dims
+    trskip, rdoq = rdoq >> 1, rdoq & 1                     # bit 1 of the parameter: also try transform skip on 4x4 luma (veryslow)
     src = synth_frame(W, H, frame_idx=W + qp)
-    fp = kb.FramePass(W, H, qp, signhide, rdoq)
+    if trskip:                                              # text-like content in a corner so that transform skip wins somewhere
+        y = src[:W * H].reshape(H, W)
+        y[:64, :64] = np.where((np.add.outer(np.arange(64), np.arange(64)) // 3) % 2, 40, 220).astype(np.uint8)
+    fp = kb.FramePass(W, H, qp, signhide, rdoq, 0.0, trskip)
     fp.run_dev(kb.to_dev(src))
     got = fp.result_host()
-    want = ref_frame_pass(ref, src, W, H, qp, fp.layout, nthreads=4, signhide=signhide, rdoq=rdoq)
+    want = ref_frame_pass(ref, src, W, H, qp, fp.layout, nthreads=4, signhide=signhide, rdoq=rdoq, trskip=trskip)
+    if trskip:
+        flags = kb.fp_section(want, kb.fp_sections(fp.layout, W, H), "trskip_y")
+        assert 0 < int(flags.sum()) < flags.size, "transform skip never (or always) chosen: the case does not exercise the choice"
     sec = kb.fp_sections(fp.layout, W, H)
     for name in sec:
         a, b = kb.fp_section(got, sec, name), kb.fp_section(want, sec, name)
