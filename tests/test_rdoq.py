@@ -109,6 +109,28 @@ def synth_levels(rng, n, count):
     return np.clip(lv, -32768, 32767).astype(np.int16)
 
 
+def test_python_coeff_cost_port_vs_reference(ref, orc):
+    """oracle/coeff_cost_port.py (plain restatement of the bit count) == the compiled reference, on the CPU."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("coeff_cost_port", os.path.join(os.path.dirname(__file__), "..", "oracle", "coeff_cost_port.py"))
+    port = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(port)
+    rng = np.random.default_rng(11)
+    for n, count in ((4, 60), (8, 40), (16, 12), (32, 5)):
+        lv = synth_levels(rng, n, count)
+        for type_ in (0, 2):
+            if n == 32 and type_ == 2:
+                continue
+            for cabac in (ref.init_contexts(27, 2), rng.integers(0, 126, ref.cabac_ctx_size()).astype(np.uint8)):
+                for i in range(count):
+                    scan_idx = int(rng.integers(0, 3)) if n <= 8 else 0
+                    signhide, tr_skip = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+                    want, _ = ref.coeff_cost(lv[i].ravel(), n, cabac, type_, scan_idx, tr_skip, signhide, 1, 0)
+                    scan = orc.scan_table(scan_idx, n.bit_length() - 1)
+                    assert port.cost(lv[i], n, type_, scan_idx, cabac, scan, signhide, 1, tr_skip) == want, (n, type_, i)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("n,type_,signhide,update", [(n, t, s, u) for n in (4, 8, 16, 32) for t in (0, 2) for s in (0, 1) for u in (0, 1)
                                                      if not (n == 32 and t == 2)])
