@@ -12,6 +12,7 @@
 
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 
 #define ORC_MIN(a, b) ((a) < (b) ? (a) : (b))
 #define ORC_MAX(a, b) ((a) > (b) ? (a) : (b))
@@ -1216,3 +1217,351 @@ void orc_deblock_frame(const orc_dbk_params *p, orc_pix *y, orc_pix *u, orc_pix 
     }
   }
 }
+
+/* ======================================================================================================
+ * RDOQ (ref: kvz_rdoq src/rdo.c:661-977, kvz_get_coded_level :395-452, kvz_get_ic_rate :346-393,
+ * calc_last_bits / get_rate_last :465-508, kvz_rdoq_sign_hiding :518-653, find_last_scanpos_generic
+ * quant-generic.c:376-399, context derivation src/context.c:315-397).  Flat scaling lists.
+ * `cabac`: memory image of cabac_data_t.ctx (src/cabac.h:66-102), one state byte per context model.
+ * Pinned against the compiled reference by tests/test_rdoq.py::test_oracle_rdoq_vs_reference (CPU).
+ * ====================================================================================================== */
+#define ORC_MIN(a, b) ((a) < (b) ? (a) : (b))
+#define ORC_MAX(a, b) ((a) > (b) ? (a) : (b))
+#define SCANPOS(sp) ((int)s->blk[sp])
+/* kvz_entropy_bits (rdo.c:69-79) by MPS / LPS symbol of each of the 64 probability states */
+static const int32_t ebits_mps[64] = {
+  32768, 30426, 28306, 26378, 24617, 23005, 21523, 20159, 18899, 17734, 16653, 15650, 14717, 13849, 13038, 12282,
+  11575, 10914, 10294, 9714, 9169, 8658, 8178, 7727, 7303, 6903, 6527, 6173, 5840, 5525, 5228, 4948,
+  4684, 4435, 4199, 3977, 3767, 3568, 3380, 3202, 3034, 2876, 2725, 2583, 2448, 2321, 2200, 2086,
+  1978, 1875, 1778, 1686, 1599, 1517, 1439, 1364, 1294, 1228, 1165, 1105, 1048, 994, 943, 895 };
+static const int32_t ebits_lps[64] = {
+  32768, 35232, 37696, 40159, 42623, 45087, 47551, 50015, 52479, 54942, 57406, 59870, 62334, 64798, 67262, 69725,
+  72189, 74653, 77117, 79581, 82044, 84508, 86972, 89436, 91900, 94363, 96827, 99291, 101755, 104219, 106683, 109146,
+  111610, 114074, 116538, 119002, 121465, 123929, 126393, 128857, 131321, 133785, 136248, 138712, 141176, 143640, 146104, 148568,
+  151031, 153495, 155959, 158423, 160887, 163351, 165814, 168278, 170742, 173207, 175669, 178134, 180598, 183061, 185525, 187989 };
+static int ebits_fn(uint8_t st, int bin) { return ((st ^ bin) & 1) ? ebits_lps[st >> 1] : ebits_mps[st >> 1]; }
+#define ebits(st, bin) ebits_fn((st), (bin))
+static int last_group(int x) { if (x < 4) return x; int l = 31 - __builtin_clz((unsigned)x); return 2 * l + ((x >> (l - 1)) & 1); }
+/* byte offsets of the context models inside the image (field order of src/cabac.h:67-101) */
+enum { CTXO_QT_CBF_LUMA = 16, CTXO_QT_CBF_CHROMA = 20, CTXO_SIG_CG = 32, CTXO_SIG_LUMA = 36, CTXO_SIG_CHROMA = 63, CTXO_LAST_Y_LUMA = 78,
+       CTXO_LAST_Y_CHROMA = 93, CTXO_LAST_X_LUMA = 108, CTXO_LAST_X_CHROMA = 123, CTXO_ONE_LUMA = 138, CTXO_ONE_CHROMA = 154,
+       CTXO_ABS_LUMA = 162, CTXO_ABS_CHROMA = 166, CTXO_ROOT_CBF = 181 };
+typedef struct { const uint8_t *sig, *one, *abs, *cg, *last_x, *last_y, *cbf; uint8_t root_cbf; } rdoq_models;
+static void rdoq_models_init(rdoq_models *m, const uint8_t *c, int type)
+{
+  m->sig = c + (type ? CTXO_SIG_CHROMA : CTXO_SIG_LUMA);
+  m->one = c + (type ? CTXO_ONE_CHROMA : CTXO_ONE_LUMA);
+  m->abs = c + (type ? CTXO_ABS_CHROMA : CTXO_ABS_LUMA);
+  m->cg = c + CTXO_SIG_CG + type;
+  m->last_x = c + (type ? CTXO_LAST_X_CHROMA : CTXO_LAST_X_LUMA);
+  m->last_y = c + (type ? CTXO_LAST_Y_CHROMA : CTXO_LAST_Y_LUMA);
+  m->cbf = c + (type ? CTXO_QT_CBF_CHROMA : CTXO_QT_CBF_LUMA);
+  m->root_cbf = c[CTXO_ROOT_CBF];
+}
+typedef struct {
+  double cost_coeff[1024], cost_sig[1024];
+  int32_t inc[1024], dec[1024], sig_inc[1024], qdelta[1024];
+  double cg_sig_cost[64];
+  int32_t cg_flag[64];
+  int32_t last_x_bits[12], last_y_bits[12];
+  const uint32_t *blk;
+} rdoq_local;
+#define scaled_qp(type, qp, off) orc_get_scaled_qp((type), (qp), (off))
+static int rdoq_level_rate(const rdoq_models *m, uint32_t abs_level, int ctx_one, int ctx_abs, int rice, uint32_t c1_idx, uint32_t c2_idx)
+{
+  int rate = 32768;                                               // the sign bin
+  const uint32_t base_level = (c1_idx < 8) ? (2 + (c2_idx < 1)) : 1;
+  if (abs_level >= base_level) {
+    int symbol = (int)(abs_level - base_level);
+    if (symbol < (3 << rice)) {
+      rate += ((symbol >> rice) + 1 + rice) * 32768;
+    } else {
+      int length = rice;
+      symbol -= 3 << rice;
+      while (symbol >= (1 << length)) symbol -= 1 << (length++);
+      rate += (3 + length + 1 - rice + length) * 32768;
+    }
+    if (c1_idx < 8) {
+      rate += ebits(m->one[ctx_one], 1);
+      if (c2_idx < 1) rate += ebits(m->abs[ctx_abs], 1);
+    }
+  } else if (abs_level == 1) {
+    rate += ebits(m->one[ctx_one], 0);
+  } else if (abs_level == 2) {
+    rate += ebits(m->one[ctx_one], 1);
+    rate += ebits(m->abs[ctx_abs], 0);
+  }
+  return rate;
+}
+
+
+static int rdoq_sig_ctx(int pattern, int scan_idx, int px, int py, int log2n, int type)
+{
+  if (px + py == 0) return 0;
+  if (log2n == 2) { static const int map[16] = { 0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8 }; return map[4 * py + px]; }
+  const int offset = (log2n == 3) ? (scan_idx == 0 ? 9 : 15) : (type == 0 ? 21 : 12);
+  const int sx = px & 3, sy = py & 3;
+  int cnt;
+  if (pattern == 0) cnt = (sx + sy <= 2) ? ((sx + sy == 0) ? 2 : 1) : 0;
+  else if (pattern == 1) cnt = (sy <= 1) ? ((sy == 0) ? 2 : 1) : 0;
+  else if (pattern == 2) cnt = (sx <= 1) ? ((sx == 0) ? 2 : 1) : 0;
+  else cnt = 2;
+  return ((type == 0 && ((px >> 2) + (py >> 2)) > 0) ? 3 : 0) + offset + cnt;
+}
+
+
+static void rdoq_sign_hiding(const rdoq_local *s, double lambda, int bitdepth, int qp_scaled, int scan_idx, int log2n, int last_pos,
+                                 const int16_t *coef, int16_t *q)
+{
+  const int inv_quant = inv_quant_scales[qp_scaled % 6];
+  const long long rd_factor = (long long)(inv_quant * inv_quant * (1 << (2 * (qp_scaled / 6))) / lambda / 16 / (1 << (2 * (bitdepth - 8))) + 0.5);
+  const int last_cg = (last_pos - 1) >> 4;
+  for (int cg = last_cg; cg >= 0; --cg) {
+    const int base = cg << 4;
+    const uint32_t *pos = s->blk + base;
+    int last_nz = -1, first_nz = 16;
+    for (int k = 15; k >= 0; --k) if (q[pos[k]]) { last_nz = k; break; }
+    for (int k = 0; k <= last_nz; ++k) if (q[pos[k]]) { first_nz = k; break; }
+    if (last_nz - first_nz < 4) continue;
+    const int signbit = q[pos[first_nz]] <= 0;
+    unsigned sum = 0;
+    for (int k = first_nz; k <= last_nz; ++k) sum += (unsigned)(int)q[pos[k]];
+    if (signbit == (int)(sum & 1)) continue;
+    long long best_cost = 0x7FFFFFFFFFFFFFFFLL;
+    int best_pos = 0, best_change = 0;
+    const int start = (cg == last_cg) ? last_nz : 15;
+    for (int k = start; k >= 0; --k) {
+      const int p = pos[k];
+      const long long quant_cost = rd_factor * s->qdelta[p];
+      const int a = abs((int)q[p]);
+      long long cost;
+      int change;
+      if (a != 0) {
+        long long inc_bits = s->inc[p], dec_bits = s->dec[p];
+        if (a == 1) dec_bits -= 32768 + s->sig_inc[p];
+        if (cg == last_cg && last_nz == k && a == 1) dec_bits -= 4 * 32768;
+        inc_bits = -quant_cost + inc_bits * 1;            // PRECISION_INC = 15 - CTX_FRAC_BITS = 0
+        dec_bits = quant_cost + dec_bits * 1;
+        if (inc_bits < dec_bits) { change = 1; cost = inc_bits; }
+        else {
+          change = -1; cost = dec_bits;
+          if (k == first_nz && a == 1) cost = 0x7FFFFFFFFFFFFFFFLL;
+        }
+      } else {
+        const int bits = 32768 + s->inc[p] + s->sig_inc[p];
+        cost = -llabs(quant_cost) + (long long)bits;
+        change = 1;
+        if (k < first_nz && ((coef[p] >= 0) ? 0 : 1) != signbit) cost = 0x7FFFFFFFFFFFFFFFLL;
+      }
+      if (cost < best_cost) { best_cost = cost; best_pos = p; best_change = change; }
+    }
+    if (q[best_pos] == 32767 || q[best_pos] == -32768) best_change = -1;
+    if (coef[best_pos] >= 0) q[best_pos] = (int16_t)(q[best_pos] + best_change);
+    else q[best_pos] = (int16_t)(q[best_pos] - best_change);
+  }
+}
+
+
+void orc_rdoq(const orc_rdoq_params *pp, const uint8_t *cabac, const int16_t *coef, int16_t *q, int width, int type, int scan_idx,
+              int block_type, int tr_depth)
+{
+  const int log2n = width == 4 ? 2 : (width == 8 ? 3 : (width == 16 ? 4 : 5));
+  const int n = 1 << log2n, nn = n * n;
+  const int SH = pp->signhide_enable;
+  static __thread rdoq_local sl;
+  rdoq_local *s = &sl;
+  s->blk = orc_scan_table(scan_idx, log2n);
+  const int transform_shift = 15 - pp->bitdepth - log2n;
+  const int qp_scaled = scaled_qp(type, pp->qp, (pp->bitdepth - 8) * 6);
+  const int q_bits = 14 + qp_scaled / 6 + transform_shift;
+  const int qc = quant_scales[qp_scaled % 6];
+  const int half = 1 << (q_bits - 1);
+  const double lambda = pp->lambda;
+  const double err_scale = ldexp(32768.0, -2 * transform_shift) / qc / qc / (1 << (2 * (pp->bitdepth - 8)));
+  rdoq_models mm; rdoq_models_init(&mm, cabac, type); const rdoq_models *m = &mm;
+#define level_double(blk) ORC_MIN(abs((int)coef[blk]) * qc, 0x7FFFFFFF - half)
+
+  // find_last_scanpos (quant-generic.c:376-399)
+  int last_scanpos = -1;
+  for (int sp = nn - 1; sp >= 0; --sp) {
+    const int blk = s->blk[sp];
+    if (((level_double(blk) + half) >> q_bits) > 0) { last_scanpos = sp; break; }
+    q[blk] = 0;
+  }
+  if (last_scanpos < 0) return;
+  for (int g = 0; g < nn / 16; ++g) { s->cg_flag[g] = 0; s->cg_sig_cost[g] = 0; }
+  if (SH) s->sig_inc[s->blk[last_scanpos]] = 0;
+  {
+    const int cb = log2n - 2;
+    const int off = type ? 0 : (cb * 3 + ((cb + 1) >> 2));
+    const int sh = type ? cb : ((cb + 3) >> 2);
+    int bx = 0, by = 0, ctx;
+    const int groups = last_group(n - 1);
+    for (ctx = 0; ctx < groups; ++ctx) {
+      const int o = off + (ctx >> sh);
+      s->last_x_bits[ctx] = bx + ebits(m->last_x[o], 0); bx += ebits(m->last_x[o], 1);
+      s->last_y_bits[ctx] = by + ebits(m->last_y[o], 0); by += ebits(m->last_y[o], 1);
+    }
+    s->last_x_bits[ctx] = bx; s->last_y_bits[ctx] = by;
+  }
+
+  const int cg_last = last_scanpos >> 4;
+  const int cgs_side = n >> 2;
+  int ctx_set = (last_scanpos > 0 && type == 0) ? 2 : 0;
+  int c1 = 1, c2 = 0, rice = 0;
+  uint32_t c1_idx = 0, c2_idx = 0;
+  double base_cost = 0, block_uncoded_cost = 0;
+
+  for (int cg = cg_last; cg >= 0; --cg) {
+    const int cg_first = s->blk[cg << 4];
+    const int cgx = (cg_first & (n - 1)) >> 2, cgy = (cg_first >> log2n) >> 2;
+    const int cg_blk = cgy * cgs_side + cgx;
+    const int right = (cgx < cgs_side - 1) ? (s->cg_flag[cgy * cgs_side + cgx + 1] != 0) : 0;
+    const int lower = (cgy < cgs_side - 1) ? (s->cg_flag[(cgy + 1) * cgs_side + cgx] != 0) : 0;
+    const int pattern = (n == 4) ? -1 : right + (lower << 1);
+    double st_coded = 0, st_uncoded = 0, st_sig = 0, st_sig0 = 0;
+    int nnz_before_pos0 = 0;
+    for (int k = 15; k >= 0; --k) {
+      const int sp = (cg << 4) + k;
+      if (sp > last_scanpos) continue;
+      const int blk = s->blk[sp];
+      const int ld = level_double(blk);
+      const uint32_t max_abs = (uint32_t)((ld + half) >> q_bits);
+      const double err0 = (double)ld;
+      const double c0 = err0 * err0 * err_scale;
+      block_uncoded_cost += c0;
+      const int one_ctx = 4 * ctx_set + c1, abs_ctx = ctx_set + c2;
+      const int last = sp == last_scanpos;
+      int ctx_sig = 0;
+      if (!last) {
+        ctx_sig = rdoq_sig_ctx(pattern, scan_idx, blk & (n - 1), blk >> log2n, log2n, type);
+        if (SH) s->sig_inc[blk] = ebits(m->sig[ctx_sig], 1) - ebits(m->sig[ctx_sig], 0);
+      }
+      uint32_t level = 0;
+      double cc, cs = 0;
+      if (!last && max_abs < 3) { cs = lambda * ebits(m->sig[ctx_sig], 0); cc = c0 + cs; }
+      else cc = 1.7e+308;
+      if (max_abs != 0) {
+        const double sig_now = last ? 0.0 : lambda * ebits(m->sig[ctx_sig], 1);
+        const int lo = max_abs > 1 ? (int)max_abs - 1 : 1;
+        for (int lvl = (int)max_abs; lvl >= lo; --lvl) {
+          const double err = (double)(ld - lvl * (1 << q_bits));
+          double c = err * err * err_scale + lambda * rdoq_level_rate(m, (uint32_t)lvl, one_ctx, abs_ctx, rice, c1_idx, c2_idx);
+          c += sig_now;
+          if (c < cc) { level = (uint32_t)lvl; cc = c; cs = sig_now; }
+        }
+      }
+      s->cost_coeff[sp] = cc;
+      s->cost_sig[sp] = cs;
+      if (SH) {
+        s->qdelta[blk] = (ld - (int)level * (1 << q_bits)) >> (q_bits - 8);
+        if (level > 0) {
+          const int now = rdoq_level_rate(m, level, one_ctx, abs_ctx, rice, c1_idx, c2_idx);
+          s->inc[blk] = rdoq_level_rate(m, level + 1, one_ctx, abs_ctx, rice, c1_idx, c2_idx) - now;
+          s->dec[blk] = rdoq_level_rate(m, level - 1, one_ctx, abs_ctx, rice, c1_idx, c2_idx) - now;
+        } else {
+          s->inc[blk] = ebits(m->one[one_ctx], 0);
+        }
+      }
+      q[blk] = (int16_t)level;
+      base_cost += cc;
+      const uint32_t base_level = (c1_idx < 8) ? (2 + (c2_idx < 1)) : 1;
+      if (level >= base_level && level > (uint32_t)(3 * (1 << rice))) rice = ORC_MIN(rice + 1, 4);
+      if (level >= 1) ++c1_idx;
+      if (level > 1) { c1 = 0; c2 += (c2 < 2); ++c2_idx; }
+      else if (c1 < 3 && c1 > 0 && level) ++c1;
+      if (k == 0 && sp > 0) {
+        c2 = 0; rice = 0; c1_idx = 0; c2_idx = 0;
+        ctx_set = (sp == 16 || type != 0) ? 0 : 2;
+        if (c1 == 0) ++ctx_set;
+        c1 = 1;
+      }
+      st_sig += cs;
+      if (k == 0) st_sig0 = cs;
+      if (level) {
+        s->cg_flag[cg_blk] = 1;
+        st_coded += cc - cs;
+        st_uncoded += c0;
+        if (k != 0) ++nnz_before_pos0;
+      }
+    }
+    if (cg) {
+      const int ctx_cg = right || lower;
+      if (s->cg_flag[cg_blk] == 0) {
+        s->cg_sig_cost[cg] = lambda * ebits(m->cg[ctx_cg], 0);
+        base_cost += s->cg_sig_cost[cg] - st_sig;
+      } else if (cg < cg_last) {
+        if (nnz_before_pos0 == 0) { base_cost -= st_sig0; st_sig -= st_sig0; }
+        double cost_zero_cg = base_cost;
+        s->cg_sig_cost[cg] = lambda * ebits(m->cg[ctx_cg], 1);
+        base_cost += s->cg_sig_cost[cg];
+        cost_zero_cg += lambda * ebits(m->cg[ctx_cg], 0);
+        cost_zero_cg += st_uncoded;
+        cost_zero_cg -= st_coded;
+        cost_zero_cg -= st_sig;
+        if (cost_zero_cg < base_cost) {
+          s->cg_flag[cg_blk] = 0;
+          base_cost = cost_zero_cg;
+          s->cg_sig_cost[cg] = lambda * ebits(m->cg[ctx_cg], 0);
+          for (int k = 15; k >= 0; --k) {
+            const int sp = (cg << 4) + k, blk = s->blk[sp];
+            if (q[blk]) { q[blk] = 0; const double e = (double)level_double(blk); s->cost_coeff[sp] = e * e * err_scale; s->cost_sig[sp] = 0; }
+          }
+        }
+      }
+    } else {
+      s->cg_flag[cg_blk] = 1;
+    }
+  }
+
+  // best last position (rdo.c:884-945)
+  double best_cost;
+  if (block_type != 1 && type == 0) {
+    best_cost = block_uncoded_cost + lambda * ebits(m->root_cbf, 0);
+    base_cost += lambda * ebits(m->root_cbf, 1);
+  } else {
+    const int ctx_cbf = type ? tr_depth : !tr_depth;
+    best_cost = block_uncoded_cost + lambda * ebits(m->cbf[ctx_cbf], 0);
+    base_cost += lambda * ebits(m->cbf[ctx_cbf], 1);
+  }
+  int best_last_p1 = 0;
+  int found_last = 0;
+  for (int cg = cg_last; cg >= 0 && !found_last; --cg) {
+    const int cg_first = s->blk[cg << 4];
+    const int cg_blk = ((cg_first >> log2n) >> 2) * cgs_side + ((cg_first & (n - 1)) >> 2);
+    base_cost -= s->cg_sig_cost[cg];
+    if (!s->cg_flag[cg_blk]) continue;
+    for (int k = 15; k >= 0; --k) {
+      const int sp = (cg << 4) + k;
+      if (sp > last_scanpos) continue;
+      const int blk = s->blk[sp];
+      if (q[blk]) {
+        const int py = blk >> log2n, px = blk & (n - 1);
+        const int gx = last_group(scan_idx == 2 ? py : px), gy = last_group(scan_idx == 2 ? px : py);
+        double bits = s->last_x_bits[gx] + s->last_y_bits[gy];
+        if (gx > 3) bits += 32768 * ((gx - 2) >> 1);
+        if (gy > 3) bits += 32768 * ((gy - 2) >> 1);
+        const double total = base_cost + lambda * bits - s->cost_sig[sp];
+        if (total < best_cost) { best_last_p1 = sp + 1; best_cost = total; }
+        if (q[blk] > 1) { found_last = 1; break; }
+        base_cost -= s->cost_coeff[sp];
+        const double e = (double)level_double(blk);
+        base_cost += e * e * err_scale;
+      } else {
+        base_cost -= s->cost_sig[sp];
+      }
+    }
+  }
+  unsigned abs_sum = 0;
+  for (int sp = 0; sp < best_last_p1; ++sp) {
+    const int blk = s->blk[sp];
+    const int level = q[blk];
+    abs_sum += (unsigned)level;
+    q[blk] = (int16_t)(coef[blk] < 0 ? -level : level);
+  }
+  for (int sp = best_last_p1; sp <= last_scanpos; ++sp) q[s->blk[sp]] = 0;
+  if (SH) {
+    if (abs_sum >= 2) rdoq_sign_hiding(s, lambda, pp->bitdepth, qp_scaled, scan_idx, log2n, best_last_p1, coef, q);
+  }
+}
+#undef level_double

@@ -141,6 +141,12 @@ void orc_sao_reconstruct_color(int bitdepth, const orc_pix *rec, orc_pix *new_re
 /* ---- nal group (nal-generic.c) ---- */
 void orc_array_checksum(const orc_pix *data, int height, int width, int stride, unsigned char out[4]);
 
+/* ---- RDOQ (kvz_rdoq, src/rdo.c:661-977) ---- */
+typedef struct { double lambda; int32_t qp, bitdepth, signhide_enable, pad; } orc_rdoq_params;
+/* cabac: image of cabac_data_t.ctx (184 state bytes); coef -> q, width x width; type 0 luma / 2 chroma */
+void orc_rdoq(const orc_rdoq_params *p, const uint8_t *cabac, const int16_t *coef, int16_t *q, int width, int type, int scan_idx,
+              int block_type, int tr_depth);
+
 /* ---- deblocking, frame level (filter.c:95-792) ---- */
 typedef struct {
   int32_t width, height;          /* luma size, multiples of 8 */

@@ -364,6 +364,17 @@ class Oracle:
         self.lib.orc_array_checksum(P(data), height, width, stride, P(out))
         return out
 
+    # -- RDOQ
+    def rdoq(self, coef, width, qp, lambda_, cabac_ctx, type_=0, scan_mode=0, block_type=1, tr_depth=0, signhide=0, bitdepth=8):
+        class P_(C.Structure):
+            _fields_ = [("lambda_", C.c_double), ("qp", C.c_int32), ("bitdepth", C.c_int32), ("signhide", C.c_int32), ("pad", C.c_int32)]
+        prm = P_(lambda_, qp, bitdepth, signhide, 0)
+        co = np.ascontiguousarray(coef, np.int16)
+        cc = np.ascontiguousarray(cabac_ctx, np.uint8)
+        dest = np.full(width * width, 0x55, np.int16)
+        self.lib.orc_rdoq(C.byref(prm), P(cc), P(co), P(dest), width, type_, scan_mode, block_type, tr_depth)
+        return dest
+
     # -- deblocking (frame level)
     def deblock_frame(self, y, u, v, cus, width, height, qp, beta=0, tc=0, slice_is_b=0, per_cu_qp=0, ref_lx=None):
         """y/u/v: flat planes (copied); cus: uint8 [rows_scu, stride_scu, 20].  Returns filtered (y, u, v)."""

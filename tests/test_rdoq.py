@@ -1,7 +1,7 @@
 """RDOQ on device (ref: kvz_rdoq, src/rdo.c:661-977) against the compiled reference, bit-exact.
 
-The reference function is called through oracle/ref_shim.c with the same context models, lambda and QP.  (No plain-C
-restatement of RDOQ exists in oracle/kvz_oracle.c: the compiled reference itself is the checker for this row.)
+The reference function is called through oracle/ref_shim.c with the same context models, lambda and QP; the plain-C
+restatement oracle/kvz_oracle.c orc_rdoq is pinned against it on the CPU.
 """
 import ctypes as C
 
@@ -60,6 +60,26 @@ def test_cabac_ctx_init_matches_reference(ref):
 
 def lambda_for(qp):
     return 0.57 * 2.0 ** ((qp - 12) / 3.0)
+
+
+def test_oracle_rdoq_vs_reference(orc, ref):
+    """oracle/kvz_oracle.c orc_rdoq (plain-C restatement of rdo.c:661-977) == kvz_rdoq of the compiled reference, on the CPU."""
+    rng = np.random.default_rng(5)
+    for n, count in ((4, 120), (8, 80), (16, 30), (32, 10)):
+        for qp in (22, 32):
+            for type_ in (0, 2):
+                if n == 32 and type_ == 2:
+                    continue
+                coef = synth_coeffs(rng, n, count, energy=6.0 * 2.0 ** ((qp - 4) / 6.0))
+                for signhide in (0, 1):
+                    cabac = ref.init_contexts(qp, 2) if signhide else rng.integers(0, 126, ref.cabac_ctx_size()).astype(np.uint8)
+                    lam = lambda_for(qp) * float(rng.uniform(0.5, 2.0))
+                    for i in range(count):
+                        scan = int(rng.integers(0, 3)) if n <= 8 else 0
+                        bt, trd = int(rng.integers(1, 3)), int(rng.integers(0, 3))
+                        want = ref.rdoq(coef[i].ravel(), n, qp, lam, cabac, type_, scan, bt, trd, signhide)
+                        got = orc.rdoq(coef[i].ravel(), n, qp, lam, cabac, type_, scan, bt, trd, signhide)
+                        assert np.array_equal(want, got), (n, qp, type_, signhide, i)
 
 
 CASES = [(n, qp, type_, signhide) for n in (4, 8, 16, 32) for qp in (22, 27, 37) for type_ in (0, 2) for signhide in (0, 1)
