@@ -304,6 +304,10 @@ int    kvz_cuda_fp_get_timing(kvz_cuda_frame_pass *fp, double *ms_total /* [KVZ_
  * tests/test_framepass.py rebuilds the full region from it. */
 int    kvz_cuda_fp_run_host_compact(kvz_cuda_frame_pass *fp, const void *src_host, void *small_host, void *compact_host,
                                     uint32_t budget_chunks, void *stream);
+/* Host-side inverse (plain CPU code, no device needed): rebuild blob[coeff_begin, host_bytes) -- n_chunks * 32 bytes --
+ * from a compact buffer.  Returns 0, or KVZ_CUDA_E_ARG when the buffer holds fewer chunks than the bitmap names
+ * (fetch the tail first). */
+int    kvz_cuda_fp_expand_compact(const kvz_cuda_fp_layout *layout, const void *compact_host, size_t compact_bytes, void *coeff_region_out);
 int    kvz_cuda_fp_compact_fetch(kvz_cuda_frame_pass *fp, uint32_t first_chunk, uint32_t count, void *dst_host, void *stream);
 /* host frame in (pinned for async), result blob out (host_bytes): H2D + pass + D2H enqueued on `stream` */
 int    kvz_cuda_fp_run_host(kvz_cuda_frame_pass *fp, const void *src_host, void *result_host, void *stream);

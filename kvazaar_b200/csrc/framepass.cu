@@ -854,6 +854,33 @@ int kvz_cuda_fp_run_host_compact(kvz_cuda_frame_pass *fp, const void *src_host, 
   return 0;
 }
 
+int kvz_cuda_fp_expand_compact(const kvz_cuda_fp_layout *layout, const void *compact_host, size_t compact_bytes, void *coeff_region_out)
+{
+  KVZC_ARG(layout && compact_host && coeff_region_out && compact_bytes >= layout->compact_header_bytes);
+  const uint8_t *c = (const uint8_t *)compact_host;
+  uint32_t head[2];
+  memcpy(head, c, sizeof(head));
+  const uint64_t n_chunks = layout->n_chunks;
+  KVZC_ARG(head[1] == n_chunks);
+  KVZC_ARG((compact_bytes - layout->compact_header_bytes) / 32 >= head[0]);
+  const uint32_t *bitmap = (const uint32_t *)(c + 256);
+  const uint8_t *packed = c + layout->compact_header_bytes;
+  uint8_t *out = (uint8_t *)coeff_region_out;
+  memset(out, 0, (size_t)n_chunks * 32);
+  uint64_t src = 0;
+  for (uint64_t w = 0; w < (n_chunks + 31) / 32; ++w) {
+    uint32_t m = bitmap[w];
+    while (m) {
+      const int b = __builtin_ctz(m);
+      m &= m - 1;
+      memcpy(out + (w * 32 + b) * 32, packed + src * 32, 32);
+      ++src;
+    }
+  }
+  KVZC_ARG(src == head[0]);
+  return 0;
+}
+
 int kvz_cuda_fp_compact_fetch(kvz_cuda_frame_pass *fp, uint32_t first_chunk, uint32_t count, void *dst_host, void *stream)
 {
   KVZC_REQUIRE_DEVICE();

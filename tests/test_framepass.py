@@ -24,6 +24,32 @@ def test_layout_needs_no_gpu():
     assert lay.host_bytes > 1920 * 1080 * 3 // 2
 
 
+def test_expand_compact_host_helper():
+    """kvz_cuda_fp_expand_compact is plain host code: bitmap + packed chunks -> dense region (no GPU needed)."""
+    import ctypes as C
+    from kvazaar_b200 import api, lib
+    lay = api.fp_layout_for(128, 64)
+    n = int(lay.n_chunks)
+    rng = np.random.default_rng(9)
+    region = np.zeros((n, 32), np.uint8)
+    nz = rng.random(n) < 0.07
+    region[nz] = rng.integers(1, 256, (int(nz.sum()), 32), dtype=np.uint8)
+    hdr = int(lay.compact_header_bytes)
+    compact = np.zeros(hdr + 32 * int(nz.sum()), np.uint8)
+    compact[:8].view(np.uint32)[:] = (int(nz.sum()), n)
+    bits = np.packbits(nz, bitorder="little")
+    compact[256:256 + bits.size] = bits
+    compact[hdr:] = region[nz].ravel()
+    out = np.full(n * 32, 0xAA, np.uint8)
+    rc = lib().kvz_cuda_fp_expand_compact(C.byref(lay), C.c_void_p(compact.ctypes.data), C.c_size_t(compact.size), C.c_void_p(out.ctypes.data))
+    assert rc == 0 and np.array_equal(out, region.ravel())
+    # truncated buffer is refused
+    assert lib().kvz_cuda_fp_expand_compact(C.byref(lay), C.c_void_p(compact.ctypes.data), C.c_size_t(compact.size - 32), C.c_void_p(out.ctypes.data)) != 0
+    # the numpy expansion used by the GPU tests agrees
+    small = np.zeros(int(lay.coeff_begin), np.uint8)
+    assert np.array_equal(api.fp_expand_compact(lay, small, compact)[int(lay.coeff_begin):], region.ravel())
+
+
 def test_reference_frame_pass_is_self_consistent(ref, orc):
     """The CPU arm against independent oracle computations on a small frame."""
     import kvazaar_b200 as kb
