@@ -176,3 +176,48 @@ def test_cuda10_ipol_sao(cuda_lib, orc10):
     bands = r.integers(-7, 8, (1, 4)).astype(np.int32)
     assert int(kb.sao_band_ddistortion_batch(10, dev16(kb, orig), dev16(kb, rec), blks, [11], bands)[0]) == \
         orc10.sao_band_ddistortion(10, orig, rec, bw, bh, 11, bands[0])
+
+
+def test_oracle10_rdoq_vs_reference(orc10, ref10):
+    """orc_rdoq with bitdepth 10 == kvz_rdoq of the 10-bit reference build (transform_shift, q_bits, error scale and the
+    sign-hiding rd_factor all depend on the bit depth)."""
+    from test_rdoq import synth_coeffs, lambda_for
+    rng = np.random.default_rng(15)
+    for n, count in ((4, 60), (8, 40), (16, 16), (32, 6)):
+        for qp in (22, 34):
+            coef = synth_coeffs(rng, n, count, energy=24.0 * 2.0 ** ((qp - 4) / 6.0))
+            for signhide in (0, 1):
+                for type_ in (0, 2):
+                    if n == 32 and type_ == 2:
+                        continue
+                    cabac = ref10.init_contexts(qp, 2)
+                    lam = lambda_for(qp) * float(rng.uniform(0.5, 2.0))
+                    nz = 0
+                    for i in range(count):
+                        scan = int(rng.integers(0, 3)) if n <= 8 else 0
+                        want = ref10.rdoq(coef[i].ravel(), n, qp, lam, cabac, type_, scan, 1, 0, signhide)
+                        got = orc10.rdoq(coef[i].ravel(), n, qp, lam, cabac, type_, scan, 1, 0, signhide, bitdepth=10)
+                        assert np.array_equal(want, got), (n, qp, signhide, type_, i)
+                        nz += int(np.count_nonzero(want))
+                    assert nz > 0
+
+
+@pytest.mark.gpu
+def test_cuda10_rdoq(cuda_lib, ref10):
+    """kvz_cuda_rdoq_batch with bitdepth 10 == kvz_rdoq of the 10-bit reference build."""
+    from kvazaar_b200 import api
+    from test_rdoq import synth_coeffs, lambda_for
+    rng = np.random.default_rng(16)
+    for n, count in ((4, 120), (8, 80), (16, 40), (32, 12)):
+        for qp, signhide in ((24, 0), (33, 1)):
+            coef = synth_coeffs(rng, n, count, energy=24.0 * 2.0 ** ((qp - 4) / 6.0))
+            tus = np.zeros(count, api.RDOQ_TU)
+            tus["off_coef"] = tus["off_dest"] = np.arange(count) * n * n
+            tus["scan_idx"] = rng.integers(0, 3, count) if n <= 8 else 0
+            tus["block_type"] = 1
+            cabac = ref10.init_contexts(qp, 2)
+            lam = lambda_for(qp)
+            got = api.rdoq_batch(api.to_dev(coef.ravel()), n, tus, cabac, qp, lam, 10, signhide).cpu().numpy().reshape(count, n * n)
+            for i in range(count):
+                want = ref10.rdoq(coef[i].ravel(), n, qp, lam, cabac, 0, int(tus["scan_idx"][i]), 1, 0, signhide)
+                assert np.array_equal(want, got[i]), (n, qp, signhide, i)
