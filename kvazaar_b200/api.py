@@ -384,10 +384,10 @@ class FpLayout(C.Structure):
                 ("coeff_begin", C.c_uint64), ("n_chunks", C.c_uint64), ("compact_header_bytes", C.c_uint64)]
 
 
-def fp_layout_for(width, height, qp=27, signhide=0):
+def fp_layout_for(width, height, qp=27, signhide=0, bitdepth=8):
     """Result-blob layout; needs no GPU."""
     lay = FpLayout()
-    prm = FpParams(width, height, 8, qp, signhide, 0, 0, 0, 0.0)
+    prm = FpParams(width, height, bitdepth, qp, signhide, 0, 0, 0, 0.0)
     _ck(lib().kvz_cuda_fp_layout_for(C.byref(prm), C.byref(lay)))
     return lay
 
@@ -395,7 +395,7 @@ def fp_layout_for(width, height, qp=27, signhide=0):
 class FramePass:
     """One in-flight frame of the frame-level pass (device buffers owned by the library)."""
 
-    def __init__(self, width, height, qp=27, signhide=0, rdoq=0, lambda_=0.0, trskip=0):
+    def __init__(self, width, height, qp=27, signhide=0, rdoq=0, lambda_=0.0, trskip=0, bitdepth=8):
         _torch()
         L = lib()
         L.kvz_cuda_fp_create.restype = C.c_void_p
@@ -403,7 +403,8 @@ class FramePass:
         L.kvz_cuda_fp_result_dev.argtypes = [C.c_void_p]
         L.kvz_cuda_fp_frame_bytes.restype = C.c_size_t
         L.kvz_cuda_fp_frame_bytes.argtypes = [C.c_void_p]
-        self.params = FpParams(width, height, 8, qp, signhide, rdoq, trskip, 0, lambda_)
+        self.params = FpParams(width, height, bitdepth, qp, signhide, rdoq, trskip, 0, lambda_)
+        self.bitdepth = bitdepth
         h = L.kvz_cuda_fp_create(C.byref(self.params))
         if not h:
             raise KvzCudaError(f"kvz_cuda_fp_create failed: {L.kvz_cuda_last_error().decode()}")
@@ -451,7 +452,7 @@ class FramePass:
         return out
 
 
-def fp_sections(layout, width, height):
+def fp_sections(layout, width, height, bitdepth=8):
     """name -> (offset, dtype, count) for every section of the result blob."""
     out = {}
     for d in range(4):
@@ -477,7 +478,7 @@ def fp_sections(layout, width, height):
     out["sao_dd"] = (layout.sao_dd, np.int32, n3 * 4)
     out["sao_band_dd"] = (layout.sao_band_dd, np.int32, n3)
     out["sao_best"] = (layout.sao_best, np.int8, n3)
-    out["sao_rec"] = (layout.sao_rec, np.uint8, width * height * 3 // 2)
+    out["sao_rec"] = (layout.sao_rec, np.uint8 if bitdepth == 8 else np.uint16, width * height * 3 // 2)
     out["checksum"] = (layout.checksum, np.uint8, 12)
     return out
 

@@ -219,12 +219,14 @@ __global__ void __launch_bounds__(256) intra_recon_kernel(kvz_cuda_quant_params 
     }
 }
 
-struct SaoPlanes {
-  const uint8_t *src[3];
-  const uint8_t *rec[3];
-  uint8_t *out[3];
+template <class T>
+struct SaoPlanesT {
+  const T *src[3];
+  const T *rec[3];
+  T *out[3];
   int Wp[3], Hp[3];
 };
+using SaoPlanes = SaoPlanesT<uint8_t>;
 
 __device__ __forceinline__ void fp_eo_offsets(int eo, int &ax, int &ay)
 {
@@ -243,35 +245,41 @@ __device__ __forceinline__ int fp_eo_cat(int a, int b, int c)
 //   edge ddist      = sum_k (o_k^2 * cnt_k - 2 * o_k * sum_k)               == sum_i ((d_i - o)^2 - d_i^2), the value
 //                     kvz_sao_edge_ddistortion accumulates pixel by pixel (ref: sao_shared_generics.h:52-91)
 //   band ddist      = the same identity over the four bands                 (ref: sao_shared_generics.h:93-130)
-// so the delta-distortion "kernels" cost nothing on the device.  8-bit only (no bit-depth rounding offset).
-__global__ void __launch_bounds__(256) sao_ctu_kernel(SaoPlanes pl, int nctu, int ctus_x, int32_t *__restrict__ stats,
+// so the delta-distortion "kernels" cost nothing on the device.  Above 8 bits kvz_sao_edge_ddistortion works on the
+// rounded difference (d + 2^(bd-9)) >> (bd-8) (sao_shared_generics.h:64,83): its per-category sums are gathered next to
+// the raw ones that the statistics and the band distortion use.
+template <class T>
+__global__ void __launch_bounds__(256) sao_ctu_kernel(SaoPlanesT<T> pl, int nctu, int ctus_x, int32_t *__restrict__ stats,
                                                       int32_t *__restrict__ dd, int32_t *__restrict__ band_dd,
                                                       int8_t *__restrict__ best, int32_t *__restrict__ dec_off,
                                                       uint32_t *__restrict__ cksum_scratch)
 {
+  constexpr int BD = PixTraits<T>::kBits;
   __shared__ int s_acc[4][2][5];
+  __shared__ int s_accr[4][5];                      // sums of the rounded differences (BD > 8 only)
   __shared__ int s_band[2][4];
   const int i = blockIdx.x, color = i / nctu, ctu = i - color * nctu;
   const int Wp = pl.Wp[color], Hp = pl.Hp[color], lw = color ? 32 : 64;
   const int x0 = (ctu % ctus_x) * lw, y0 = (ctu / ctus_x) * lw;
   const int bw = min(lw, Wp - x0), bh = min(lw, Hp - y0);
-  const uint8_t *orig = pl.src[color] + (long)y0 * Wp + x0, *rec = pl.rec[color] + (long)y0 * Wp + x0;
+  const T *orig = pl.src[color] + (long)y0 * Wp + x0, *rec = pl.rec[color] + (long)y0 * Wp + x0;
   const int bp = (i * 7) % 29;
   if (i == 0 && threadIdx.x < 6) cksum_scratch[threadIdx.x] = 0;
-  for (int t = threadIdx.x; t < 48; t += blockDim.x) { if (t < 40) (&s_acc[0][0][0])[t] = 0; else (&s_band[0][0])[t - 40] = 0; }
+  for (int t = threadIdx.x; t < 68; t += blockDim.x) { if (t < 40) (&s_acc[0][0][0])[t] = 0; else if (t < 48) (&s_band[0][0])[t - 40] = 0; else (&s_accr[0][0])[t - 48] = 0; }
   __syncthreads();
-  int sum[4][5], cnt[4][5], bs[4], bc[4];
+  int sum[4][5], cnt[4][5], sumr[4][5], bs[4], bc[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     bs[e] = 0; bc[e] = 0;
 #pragma unroll
-    for (int k = 0; k < 5; ++k) { sum[e][k] = 0; cnt[e][k] = 0; }
+    for (int k = 0; k < 5; ++k) { sum[e][k] = 0; cnt[e][k] = 0; sumr[e][k] = 0; }
   }
   for (int t = threadIdx.x; t < bw * bh; t += blockDim.x) {
     const int y = t / bw, x = t - y * bw;
     const int c = rec[(long)y * Wp + x];
     const int diff = (int)orig[(long)y * Wp + x] - c;
-    const int band = (c >> 3) - bp;
+    const int diffr = BD > 8 ? (diff + (1 << (BD > 8 ? BD - 9 : 0))) >> (BD - 8) : diff;
+    const int band = (c >> (BD - 5)) - bp;
 #pragma unroll
     for (int k = 0; k < 4; ++k) { const int hit = band == k; bs[k] += hit ? diff : 0; bc[k] += hit; }
     if (x >= 1 && y >= 1 && x < bw - 1 && y < bh - 1) {        // the strategies only see the block: no outside neighbours
@@ -281,7 +289,7 @@ __global__ void __launch_bounds__(256) sao_ctu_kernel(SaoPlanes pl, int nctu, in
         fp_eo_offsets(e, ax, ay);
         const int cat = fp_eo_cat(rec[(long)(y + ay) * Wp + x + ax], rec[(long)(y - ay) * Wp + x - ax], c);
 #pragma unroll
-        for (int k = 0; k < 5; ++k) { const int hit = cat == k; sum[e][k] += hit ? diff : 0; cnt[e][k] += hit; }
+        for (int k = 0; k < 5; ++k) { const int hit = cat == k; sum[e][k] += hit ? diff : 0; cnt[e][k] += hit; if (BD > 8) sumr[e][k] += hit ? diffr : 0; }
       }
     }
   }
@@ -293,6 +301,7 @@ __global__ void __launch_bounds__(256) sao_ctu_kernel(SaoPlanes pl, int nctu, in
     for (int k = 0; k < 5; ++k) {
       const int v1 = warp_sum(sum[e][k]), v2 = warp_sum(cnt[e][k]);
       if ((threadIdx.x & 31) == 0) { atomicAdd(&s_acc[e][0][k], v1); atomicAdd(&s_acc[e][1][k], v2); }
+      if (BD > 8) { const int v3 = warp_sum(sumr[e][k]); if ((threadIdx.x & 31) == 0) atomicAdd(&s_accr[e][k], v3); }
     }
   }
   __syncthreads();
@@ -304,7 +313,7 @@ __global__ void __launch_bounds__(256) sao_ctu_kernel(SaoPlanes pl, int nctu, in
       int o[5], v = 0;
       o[0] = 0;
       for (int k = 1; k < 5; ++k) o[k] = s_acc[e][1][k] ? clip3(-7, 7, s_acc[e][0][k] / s_acc[e][1][k]) : 0;
-      for (int k = 1; k < 5; ++k) v += o[k] * o[k] * s_acc[e][1][k] - 2 * o[k] * s_acc[e][0][k];
+      for (int k = 1; k < 5; ++k) v += o[k] * o[k] * s_acc[e][1][k] - 2 * o[k] * (BD > 8 ? s_accr[e][k] : s_acc[e][0][k]);
       dd[(size_t)e * n3 + i] = v;
       if (e == 0 || v < bd) { bd = v; be = e; for (int k = 0; k < 5; ++k) off_best[k] = o[k]; }
     }
@@ -319,15 +328,16 @@ __global__ void __launch_bounds__(256) sao_ctu_kernel(SaoPlanes pl, int nctu, in
 
 // sao_reconstruct_color (edge type) of the chosen class for every CTU of the three planes; pixels on the picture
 // border (no neighbours) and CTUs without SAO are copied (ref: sao-generic.c:84-124, sao.c:302-361 call shape).
-__global__ void __launch_bounds__(256) sao_apply_kernel(SaoPlanes pl, int nctu, int ctus_x, const int8_t *__restrict__ best,
+template <class T>
+__global__ void __launch_bounds__(256) sao_apply_kernel(SaoPlanesT<T> pl, int nctu, int ctus_x, const int8_t *__restrict__ best,
                                                         const int32_t *__restrict__ dec_off)
 {
   const int i = blockIdx.x, color = i / nctu, ctu = i - color * nctu;
   const int Wp = pl.Wp[color], Hp = pl.Hp[color], lw = color ? 32 : 64;
   const int x0 = (ctu % ctus_x) * lw, y0 = (ctu / ctus_x) * lw;
   const int bw = min(lw, Wp - x0), bh = min(lw, Hp - y0);
-  const uint8_t *rec = pl.rec[color];
-  uint8_t *out = pl.out[color];
+  const T *rec = pl.rec[color];
+  T *out = pl.out[color];
   const int eo = best[i];
   int off[5];
 #pragma unroll
@@ -343,9 +353,9 @@ __global__ void __launch_bounds__(256) sao_apply_kernel(SaoPlanes pl, int nctu, 
       int ov = off[0];
 #pragma unroll
       for (int k = 1; k < 5; ++k) ov = cat == k ? off[k] : ov;
-      v = clip3(0, 255, v + ov);
+      v = clip3(0, (1 << PixTraits<T>::kBits) - 1, v + ov);
     }
-    out[o] = (uint8_t)v;
+    out[o] = (T)v;
   }
 }
 
@@ -472,39 +482,52 @@ int launch_recon_inter(const kvz_cuda_quant_params &qp, const uint8_t *src, cons
 }
 }  // namespace kvzc
 
-template <int PHASE>
-static int launch_recon_phase(const kvz_cuda_quant_params &qp, const uint8_t *src, const uint8_t *rin, int stride, int pic_w, int pic_h,
-                              int color, int log2w, int blocks_x, int nblk, const int8_t *modes, uint8_t *rec, int16_t *coeff,
+template <int PHASE, class T>
+static int launch_recon_phase(const kvz_cuda_quant_params &qp, const T *src, const T *rin, int stride, int pic_w, int pic_h,
+                              int color, int log2w, int blocks_x, int nblk, const int8_t *modes, T *rec, int16_t *coeff,
                               uint8_t *has, uint32_t *ssd, cudaStream_t st)
 {
   const int ww = 1 << (2 * log2w), g = 1024 / ww, grid = (nblk + g - 1) / g;
   switch (log2w) {
-    case 2: intra_recon_kernel<uint8_t, 2, false, PHASE><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
-    case 3: intra_recon_kernel<uint8_t, 3, false, PHASE><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
-    case 4: intra_recon_kernel<uint8_t, 4, false, PHASE><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
-    default: intra_recon_kernel<uint8_t, 5, false, PHASE><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
+    case 2: intra_recon_kernel<T, 2, false, PHASE><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
+    case 3: intra_recon_kernel<T, 3, false, PHASE><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
+    case 4: intra_recon_kernel<T, 4, false, PHASE><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
+    default: intra_recon_kernel<T, 5, false, PHASE><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
   }
   KVZC_LAUNCHED();
   return 0;
 }
 
-// 4x4 luma with transform skip (PHASE 0 fused / 1 forward / 2 inverse)
-template <int PHASE>
-static int launch_recon_trskip(const kvz_cuda_quant_params &qp, const uint8_t *src, const uint8_t *rin, int stride, int pic_w, int pic_h,
-                               int blocks_x, int nblk, const int8_t *modes, uint8_t *rec, int16_t *coeff, uint8_t *has, uint32_t *ssd, cudaStream_t st)
+// first minimum of the 35 mode costs of every block (the 16-bit rough search writes full cost tables)
+__global__ void __launch_bounds__(256) rough_argmin_kernel(const uint32_t *__restrict__ costs, int nblk, int8_t *__restrict__ best_mode,
+                                                           uint32_t *__restrict__ best_cost)
 {
-  intra_recon_kernel<uint8_t, 2, false, PHASE, true><<<(nblk + 63) / 64, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, 0, blocks_x, nblk, modes, rec, coeff, has, ssd);
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblk) return;
+  uint32_t bc = costs[(size_t)b * 35];
+  int bm = 0;
+  for (int m = 1; m < 35; ++m) { const uint32_t c = costs[(size_t)b * 35 + m]; if (c < bc) { bc = c; bm = m; } }
+  best_mode[b] = (int8_t)bm; best_cost[b] = bc;
+}
+
+// 4x4 luma with transform skip (PHASE 0 fused / 1 forward / 2 inverse)
+template <int PHASE, class T>
+static int launch_recon_trskip(const kvz_cuda_quant_params &qp, const T *src, const T *rin, int stride, int pic_w, int pic_h,
+                               int blocks_x, int nblk, const int8_t *modes, T *rec, int16_t *coeff, uint8_t *has, uint32_t *ssd, cudaStream_t st)
+{
+  intra_recon_kernel<T, 2, false, PHASE, true><<<(nblk + 63) / 64, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, 0, blocks_x, nblk, modes, rec, coeff, has, ssd);
   KVZC_LAUNCHED();
   return 0;
 }
 
 // kvz_quantize_residual_trskip's decision per 4x4 luma TU (transform.c:241-288): keep the DST result unless the
 // transform-skip result has the strictly smaller  SSD + bits * lambda; the winner's data replaces the main sections.
+template <class T>
 __global__ void __launch_bounds__(256) trskip_select_kernel(int nblk, int blocks_x, int stride, double lambda, const uint32_t *__restrict__ ssd_ts,
                                                             const double *__restrict__ bits_ts, const uint8_t *__restrict__ has_ts,
-                                                            const int16_t *__restrict__ coeff_ts, const uint8_t *__restrict__ rec_ts,
+                                                            const int16_t *__restrict__ coeff_ts, const T *__restrict__ rec_ts,
                                                             uint32_t *__restrict__ ssd, double *__restrict__ bits, uint8_t *__restrict__ has,
-                                                            int16_t *__restrict__ coeff, uint8_t *__restrict__ rec, uint8_t *__restrict__ flag)
+                                                            int16_t *__restrict__ coeff, T *__restrict__ rec, uint8_t *__restrict__ flag)
 {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= nblk) return;
@@ -518,19 +541,21 @@ __global__ void __launch_bounds__(256) trskip_select_kernel(int nblk, int blocks
   uint4 *cd = reinterpret_cast<uint4 *>(coeff + (size_t)b * 16);
   cd[0] = cs[0]; cd[1] = cs[1];
   const long o = (long)((b / blocks_x) * 4) * stride + (b % blocks_x) * 4;
-  for (int y = 0; y < 4; ++y) *reinterpret_cast<uint32_t *>(rec + o + (long)y * stride) = *reinterpret_cast<const uint32_t *>(rec_ts + o + (long)y * stride);
+  for (int y = 0; y < 4; ++y)
+    for (int x = 0; x < 4; ++x) rec[o + (long)y * stride + x] = rec_ts[o + (long)y * stride + x];
 }
 
-static int launch_recon(const kvz_cuda_quant_params &qp, const uint8_t *src, const uint8_t *rin, int stride, int pic_w, int pic_h,
-                        int color, int log2w, int blocks_x, int nblk, const int8_t *modes, uint8_t *rec, int16_t *coeff,
+template <class T>
+static int launch_recon(const kvz_cuda_quant_params &qp, const T *src, const T *rin, int stride, int pic_w, int pic_h,
+                        int color, int log2w, int blocks_x, int nblk, const int8_t *modes, T *rec, int16_t *coeff,
                         uint8_t *has, uint32_t *ssd, cudaStream_t st)
 {
   const int ww = 1 << (2 * log2w), g = 1024 / ww, grid = (nblk + g - 1) / g;
   switch (log2w) {
-    case 2: intra_recon_kernel<uint8_t, 2><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
-    case 3: intra_recon_kernel<uint8_t, 3><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
-    case 4: intra_recon_kernel<uint8_t, 4><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
-    default: intra_recon_kernel<uint8_t, 5><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
+    case 2: intra_recon_kernel<T, 2><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
+    case 3: intra_recon_kernel<T, 3><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
+    case 4: intra_recon_kernel<T, 4><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
+    default: intra_recon_kernel<T, 5><<<grid, 256, 0, st>>>(qp, src, rin, stride, pic_w, pic_h, color, blocks_x, nblk, modes, rec, coeff, has, ssd); break;
   }
   KVZC_LAUNCHED();
   return 0;
@@ -547,7 +572,7 @@ struct kvz_cuda_frame_pass {
   size_t host_bytes, total_bytes;
   uint8_t *blob = nullptr;              // device: host-visible sections first, device-only sections after
   // device-only
-  size_t off_rec_y[4], off_rec_u[3], off_rec_v[3];
+  size_t off_rec_y[4], off_rec_u[3], off_rec_v[3], off_costs35[4] = {};
   size_t off_sao_off, off_dbk_cus, off_cabac, off_src_copy, off_compact, off_tile_counts;
   size_t off_ts_rec = 0, off_ts_coeff = 0, off_ts_has = 0, off_ts_ssd = 0, off_ts_bits = 0;
   kvz_cuda_rdoq_params rdoq;
@@ -582,10 +607,11 @@ extern "C" {
 static kvz_cuda_frame_pass *fp_build(const kvz_cuda_fp_params *p, bool alloc)
 {
   if (alloc && g_device < 0 && kvz_cuda_init(-1) != 0) return nullptr;
-  if (!p || p->bitdepth != 8 || p->width % 8 || p->height % 8 || p->width < 64 || p->height < 64) {
-    set_error("frame pass: need 8-bit, width/height multiples of 8 and >= 64");
+  if (!p || (p->bitdepth != 8 && p->bitdepth != 10) || p->width % 8 || p->height % 8 || p->width < 64 || p->height < 64) {
+    set_error("frame pass: need 8- or 10-bit, width/height multiples of 8 and >= 64");
     return nullptr;
   }
+  const size_t px = p->bitdepth == 8 ? 1 : 2;            // bytes per sample (kvz_pixel)
   kvz_cuda_frame_pass *fp = new kvz_cuda_frame_pass();
   fp->prm = *p;
   const int W = fp->W = p->width, H = fp->H = p->height;
@@ -610,7 +636,7 @@ static kvz_cuda_frame_pass *fp_build(const kvz_cuda_fp_params *p, bool alloc)
   L.nctu = nctu;
   L.sao_stats = take(4 * (size_t)fp->nctu3 * 40); L.sao_dd = take(4 * (size_t)fp->nctu3 * 4);
   L.sao_band_dd = take(4 * (size_t)fp->nctu3); L.sao_best = take(fp->nctu3);
-  L.sao_rec = take((size_t)W * H * 3 / 2);
+  L.sao_rec = take((size_t)W * H * 3 / 2 * px);
   L.checksum = take(16);
   // the (large, sparse) coefficient sections come last so that the compact result is two copies: the head + the packed chunks
   L.coeff_begin = off;
@@ -624,15 +650,16 @@ static kvz_cuda_frame_pass *fp_build(const kvz_cuda_fp_params *p, bool alloc)
   L.compact_header_bytes = 256 + align_up((size_t)(L.n_chunks + 7) / 8);
   if (p->trskip) {            // scratch of the transform-skip candidate of every 4x4 luma TU
     const size_t nb3 = fp->nblk[3];
-    fp->off_ts_rec = take((size_t)W * H); fp->off_ts_coeff = take(2 * nb3 * 16); fp->off_ts_has = take(nb3);
+    fp->off_ts_rec = take((size_t)W * H * px); fp->off_ts_coeff = take(2 * nb3 * 16); fp->off_ts_has = take(nb3);
     fp->off_ts_ssd = take(4 * nb3); fp->off_ts_bits = take(8 * nb3);
   }
   fp->off_compact = take(L.compact_header_bytes + (size_t)L.n_chunks * 32);
   fp->off_tile_counts = take(4 * ((size_t)L.n_chunks / 1024 + 2));
-  for (int d = 0; d < 4; ++d) fp->off_rec_y[d] = take((size_t)W * H);
-  for (int d = 0; d < 3; ++d) { fp->off_rec_u[d] = take((size_t)W * H / 4); fp->off_rec_v[d] = take((size_t)W * H / 4); }
+  for (int d = 0; d < 4; ++d) fp->off_rec_y[d] = take((size_t)W * H * px);
+  for (int d = 0; d < 3; ++d) { fp->off_rec_u[d] = take((size_t)W * H / 4 * px); fp->off_rec_v[d] = take((size_t)W * H / 4 * px); }
+  if (px == 2) for (int d = 0; d < 4; ++d) fp->off_costs35[d] = take(4 * (size_t)fp->nblk[d] * 35);   // 16-bit rough search writes cost tables
   fp->off_sao_off = take(4 * (size_t)4 * fp->nctu3 * 5);
-  fp->off_src_copy = take((size_t)W * H * 3 / 2);
+  fp->off_src_copy = take((size_t)W * H * 3 / 2 * px);
   // deblocking input: the CU records of the uniform 8x8 intra quadtree whose reconstruction SAO works on
   // (cu_info_t image: type = CU_INTRA, depth = 3, part_size = 2Nx2N, tr_depth = 3), initialised from the host once
   fp->init_off = off;
@@ -651,7 +678,7 @@ static kvz_cuda_frame_pass *fp_build(const kvz_cuda_fp_params *p, bool alloc)
     if (kvz_cuda_cabac_ctx_init(p->qp, 2, (kvz_cuda_cabac_ctx *)(fp->host_init.data() + (fp->off_cabac - fp->init_off))) != 0) { delete fp; return nullptr; }
   }
   fp->rdoq.lambda = p->lambda > 0 ? p->lambda : 0.57 * pow(2.0, (p->qp - 12) / 3.0);
-  fp->rdoq.qp = p->qp; fp->rdoq.bitdepth = 8; fp->rdoq.signhide_enable = p->signhide; fp->rdoq.pad = 0;
+  fp->rdoq.qp = p->qp; fp->rdoq.bitdepth = p->bitdepth; fp->rdoq.signhide_enable = p->signhide; fp->rdoq.pad = 0;
   if (!alloc) return fp;
   if (cudaMalloc((void **)&fp->blob, fp->total_bytes) != cudaSuccess) { set_error("frame pass: cudaMalloc(%zu) failed", fp->total_bytes); delete fp; return nullptr; }
   cudaMemset(fp->blob, 0, fp->total_bytes);
@@ -681,19 +708,20 @@ void kvz_cuda_fp_destroy(kvz_cuda_frame_pass *fp)
 
 int kvz_cuda_fp_layout_get(const kvz_cuda_frame_pass *fp, kvz_cuda_fp_layout *out) { KVZC_ARG(fp && out); *out = fp->lay; return 0; }
 void *kvz_cuda_fp_result_dev(kvz_cuda_frame_pass *fp) { return fp ? fp->blob : nullptr; }
-size_t kvz_cuda_fp_frame_bytes(const kvz_cuda_frame_pass *fp) { return fp ? (size_t)fp->W * fp->H * 3 / 2 : 0; }
+size_t kvz_cuda_fp_frame_bytes(const kvz_cuda_frame_pass *fp) { return fp ? (size_t)fp->W * fp->H * 3 / 2 * (fp->prm.bitdepth == 8 ? 1 : 2) : 0; }
 
-int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void *rec_in_dev, void *stream)
+}  // extern "C"
+
+template <class T>
+static int fp_run_dev_t(kvz_cuda_frame_pass *fp, const void *src_dev, const void *rec_in_dev, cudaStream_t st)
 {
-  KVZC_REQUIRE_DEVICE();
-  KVZC_ARG(fp && src_dev);
-  cudaStream_t st = as_stream(stream);
+  constexpr int BD = PixTraits<T>::kBits;
   const int W = fp->W, H = fp->H;
-  const uint8_t *src = (const uint8_t *)src_dev;
-  const uint8_t *rin = rec_in_dev ? (const uint8_t *)rec_in_dev : src;
+  const T *src = (const T *)src_dev;
+  const T *rin = rec_in_dev ? (const T *)rec_in_dev : src;
   uint8_t *B = fp->blob;
   const kvz_cuda_fp_layout &L = fp->lay;
-  kvz_cuda_quant_params qp = { fp->prm.qp, 8, 1, fp->prm.signhide, 0 };
+  kvz_cuda_quant_params qp = { fp->prm.qp, BD, 1, fp->prm.signhide, 0 };
   const size_t poff[3] = { 0, (size_t)W * H, (size_t)W * H * 5 / 4 };
   if (fp->timing) fp_collect(fp);
   const bool rdoq = fp->prm.rdoq != 0;
@@ -704,13 +732,22 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
     fp_mark(fp, s0 + 0, st);
     if (nb == 0) { for (int k = 1; k < 9; ++k) fp_mark(fp, s0 + k, st); continue; }
     int8_t *modes = (int8_t *)(B + L.mode_y[d]);
-    // rough search with the mode selection fused in; the 35-entry cost tables stay on chip
-    if (int r = rough_search_u8(log2w, src, rin, W, W, H, nullptr, modes, (uint32_t *)(B + L.cost_y[d]), st)) return r;
+    if constexpr (BD == 8) {
+      // rough search with the mode selection fused in; the 35-entry cost tables stay on chip
+      if (int r = rough_search_u8(log2w, src, rin, W, W, H, nullptr, modes, (uint32_t *)(B + L.cost_y[d]), st)) return r;
+    } else {
+      // 16-bit samples: the straightforward rough-search kernel (intra.cu) + argmin
+      uint32_t *costs = (uint32_t *)(B + fp->off_costs35[d]);
+      if (int r = kvz_cuda_intra_rough_search_frame(log2w, BD, src, rin, W, W, H, costs, st)) return r;
+      rough_argmin_kernel<<<(nb + 255) / 256, 256, 0, st>>>(costs, nb, modes, (uint32_t *)(B + L.cost_y[d]));
+      KVZC_LAUNCHED();
+    }
     fp_mark(fp, s0 + 1, st);
     // luma: prediction -> transform -> quantisation -> reconstruction; with RDOQ the fused kernel is split around the
     // RDOQ launch (quant-generic.c:234-240)
     {
-      uint8_t *rec = B + fp->off_rec_y[d], *has = B + L.has_y[d];
+      T *rec = (T *)(B + fp->off_rec_y[d]);
+      uint8_t *has = B + L.has_y[d];
       int16_t *coeff = (int16_t *)(B + L.coeff_y[d]);
       uint32_t *ssd = (uint32_t *)(B + L.ssd_y[d]);
       if (!rdoq) {
@@ -730,7 +767,8 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
     if (int r = coeff_cost_launch_grid(fp->prm.signhide, cabac, (const int16_t *)(B + L.coeff_y[d]), nullptr, nb, log2w, modes, ts_flag, (double *)(B + L.bits_y[d]), nullptr, st)) return r;
     if (ts_flag) {
       // the transform-skip candidate of every 4x4 luma TU, then kvz_quantize_residual_trskip's choice (stage slot: luma bits)
-      uint8_t *rec_ts = B + fp->off_ts_rec, *has_ts = B + fp->off_ts_has;
+      T *rec_ts = (T *)(B + fp->off_ts_rec);
+      uint8_t *has_ts = B + fp->off_ts_has;
       int16_t *coeff_ts = (int16_t *)(B + fp->off_ts_coeff);
       uint32_t *ssd_ts = (uint32_t *)(B + fp->off_ts_ssd);
       double *bits_ts = (double *)(B + fp->off_ts_bits);
@@ -742,9 +780,9 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
         if (int r = launch_recon_trskip<2>(qp, src, rin, W, W, H, W / w, nb, modes, rec_ts, coeff_ts, has_ts, ssd_ts, st)) return r;
       }
       if (int r = coeff_cost_launch_grid(fp->prm.signhide, cabac, coeff_ts, nullptr, nb, log2w, modes, 1, bits_ts, nullptr, st)) return r;
-      trskip_select_kernel<<<(nb + 255) / 256, 256, 0, st>>>(nb, W / w, W, fp->rdoq.lambda, ssd_ts, bits_ts, has_ts, coeff_ts, rec_ts,
+      trskip_select_kernel<T><<<(nb + 255) / 256, 256, 0, st>>>(nb, W / w, W, fp->rdoq.lambda, ssd_ts, bits_ts, has_ts, coeff_ts, rec_ts,
                                                              (uint32_t *)(B + L.ssd_y[d]), (double *)(B + L.bits_y[d]), B + L.has_y[d],
-                                                             (int16_t *)(B + L.coeff_y[d]), B + fp->off_rec_y[d], B + L.trskip_y);
+                                                             (int16_t *)(B + L.coeff_y[d]), (T *)(B + fp->off_rec_y[d]), B + L.trskip_y);
       KVZC_LAUNCHED();
     }
     fp_mark(fp, s0 + 5, st);
@@ -759,8 +797,9 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
                                            modes, fp->prm.trskip /* counted for 4x4 chroma TUs too */, (double *)(B + L.bits_u[d]), (double *)(B + L.bits_v[d]), st, 1)) return r;
       } else
       for (int color = 1; color <= 2 && (rdoq || step == 0); ++color) {
-        const uint8_t *csrc = src + poff[color], *crin = rin + poff[color];
-        uint8_t *rec = B + (color == 1 ? fp->off_rec_u[d] : fp->off_rec_v[d]), *has = B + (color == 1 ? L.has_u[d] : L.has_v[d]);
+        const T *csrc = src + poff[color], *crin = rin + poff[color];
+        T *rec = (T *)(B + (color == 1 ? fp->off_rec_u[d] : fp->off_rec_v[d]));
+        uint8_t *has = B + (color == 1 ? L.has_u[d] : L.has_v[d]);
         int16_t *coeff = (int16_t *)(B + (color == 1 ? L.coeff_u[d] : L.coeff_v[d]));
         uint32_t *ssd = (uint32_t *)(B + (color == 1 ? L.ssd_u[d] : L.ssd_v[d]));
         int r = 0;
@@ -778,16 +817,16 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
     kvz_cuda_dbk_params dp;
     memset(&dp, 0, sizeof(dp));
     dp.width = W; dp.height = H; dp.qp = fp->prm.qp; dp.cu_stride_scu = W / 4;
-    if (int r = kvz_cuda_deblock_frame(&dp, 8, B + fp->off_rec_y[2], B + fp->off_rec_u[2], B + fp->off_rec_v[2], B + fp->off_dbk_cus, st)) return r;
+    if (int r = kvz_cuda_deblock_frame(&dp, BD, B + fp->off_rec_y[2], B + fp->off_rec_u[2], B + fp->off_rec_v[2], B + fp->off_dbk_cus, st)) return r;
   }
   fp_mark(fp, 37, st);
   // ---- SAO on the deblocked reconstruction: statistics + decisions, then reconstruction ----
   const int nctu = fp->nctu3 / 3;
-  SaoPlanes pl;
+  SaoPlanesT<T> pl;
   for (int color = 0; color < 3; ++color) {
     pl.src[color] = src + poff[color];
-    pl.rec[color] = B + (color == 0 ? fp->off_rec_y[2] : (color == 1 ? fp->off_rec_u[2] : fp->off_rec_v[2]));
-    pl.out[color] = B + L.sao_rec + poff[color];
+    pl.rec[color] = (const T *)(B + (color == 0 ? fp->off_rec_y[2] : (color == 1 ? fp->off_rec_u[2] : fp->off_rec_v[2])));
+    pl.out[color] = (T *)(B + L.sao_rec) + poff[color];
     pl.Wp[color] = color ? W / 2 : W; pl.Hp[color] = color ? H / 2 : H;
   }
   int32_t *dec_off = (int32_t *)(B + fp->off_sao_off);
@@ -800,11 +839,26 @@ int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void
   KVZC_LAUNCHED();
   fp_mark(fp, 39, st);
   // ---- picture checksum of the filtered planes ----
-  checksum3_kernel<<<dim3(148, 3), 256, 0, st>>>(pl, ck_scratch, B + L.checksum);
-  KVZC_LAUNCHED();
+  if constexpr (BD == 8) {
+    checksum3_kernel<<<dim3(148, 3), 256, 0, st>>>(pl, ck_scratch, B + L.checksum);
+    KVZC_LAUNCHED();
+  } else {
+    for (int color = 0; color < 3; ++color)
+      if (int r = kvz_cuda_array_checksum(BD, pl.out[color], pl.Hp[color], pl.Wp[color], pl.Wp[color], B + L.checksum + 4 * color, st)) return r;
+  }
   fp_mark(fp, KVZ_CUDA_FP_STAGES, st);
   if (fp->timing) fp->ev_pending = true;
   return 0;
+}
+
+extern "C" {
+
+int kvz_cuda_fp_run_dev(kvz_cuda_frame_pass *fp, const void *src_dev, const void *rec_in_dev, void *stream)
+{
+  KVZC_REQUIRE_DEVICE();
+  KVZC_ARG(fp && src_dev);
+  if (fp->prm.bitdepth == 8) return fp_run_dev_t<uint8_t>(fp, src_dev, rec_in_dev, as_stream(stream));
+  return fp_run_dev_t<uint16_t>(fp, src_dev, rec_in_dev, as_stream(stream));
 }
 
 int kvz_cuda_fp_set_timing(kvz_cuda_frame_pass *fp, int enable)

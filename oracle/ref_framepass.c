@@ -38,11 +38,11 @@ typedef struct { const kvz_api *api; kvz_config *cfg; kvz_encoder *enc; } kvzref
 
 typedef struct {
   kvzref_ctx *ctx;
-  const uint8_t *src;
+  const kvz_pixel *src;
   int W, H, qp;
   const kvz_cuda_fp_layout *L;
   uint8_t *blob;
-  uint8_t *rec[3][4];       /* per colour, per depth reconstruction planes (scratch, not part of the blob) */
+  kvz_pixel *rec[3][4];     /* per colour, per depth reconstruction planes (scratch, not part of the blob) */
   int stage;
   volatile int next;
   int total;
@@ -76,7 +76,7 @@ static void do_block(job_t *j, int d, int b, kvz_pixel *buf /* scratch: 6 * 1024
   /* --- luma rough search: 35 modes, SATD against the source block */
   memset(&refs, 0, sizeof(refs));
   orc_intra_build_reference(log2w, 0, bx * w, by * w, W, H, j->src, W, refs.ref.top, refs.ref.left);
-  for (int y = 0; y < w; ++y) memcpy(orig + y * w, j->src + (size_t)(by * w + y) * W + bx * w, w);
+  for (int y = 0; y < w; ++y) memcpy(orig + y * w, j->src + (size_t)(by * w + y) * W + bx * w, w * sizeof(kvz_pixel));
   cost_pixel_nxn_func *satd = kvz_pixels_get_satd_func(w);
   unsigned best = 0; int best_mode = 0;
   for (int mode = 0; mode < 35; ++mode) {
@@ -103,23 +103,23 @@ static void do_block(job_t *j, int d, int b, kvz_pixel *buf /* scratch: 6 * 1024
   (j->blob + L->has_y[d])[b] = (uint8_t)has;
   ((uint32_t *)(j->blob + L->ssd_y[d]))[b] = kvz_pixels_calc_ssd(orig, recb, w, w, w);
   ((double *)(j->blob + L->bits_y[d]))[b] = kvz_get_coeff_cost(state, coeff, w, 0, (int8_t)scan_for(0, w, best_mode));
-  for (int y = 0; y < w; ++y) memcpy(j->rec[0][d] + (size_t)(by * w + y) * W + bx * w, recb + y * w, w);
+  for (int y = 0; y < w; ++y) memcpy(j->rec[0][d] + (size_t)(by * w + y) * W + bx * w, recb + y * w, w * sizeof(kvz_pixel));
 
   /* --- chroma, co-located luma mode */
   if (d < 3) {
     const int wc = w / 2, Wc = W / 2;
     for (int color = 1; color <= 2; ++color) {
-      const uint8_t *plane = j->src + (color == 1 ? (size_t)W * H : (size_t)W * H * 5 / 4);
+      const kvz_pixel *plane = j->src + (color == 1 ? (size_t)W * H : (size_t)W * H * 5 / 4);
       memset(&refs, 0, sizeof(refs));
       orc_intra_build_reference(log2w - 1, color, bx * w, by * w, W, H, plane, Wc, refs.ref.top, refs.ref.left);
-      for (int y = 0; y < wc; ++y) memcpy(orig + y * wc, plane + (size_t)(by * wc + y) * Wc + bx * wc, wc);
+      for (int y = 0; y < wc; ++y) memcpy(orig + y * wc, plane + (size_t)(by * wc + y) * Wc + bx * wc, wc * sizeof(kvz_pixel));
       kvz_intra_predict(&refs, log2w - 1, best_mode, (color_t)color, pred2, true);
       coeff_t *cc = (coeff_t *)(j->blob + (color == 1 ? L->coeff_u[d] : L->coeff_v[d])) + (size_t)b * wc * wc;
       has = kvz_quantize_residual(state, &cu, wc, (color_t)color, scan_for(1, wc, best_mode), 0, wc, wc, orig, pred2, recb, cc, false);
       (j->blob + (color == 1 ? L->has_u[d] : L->has_v[d]))[b] = (uint8_t)has;
       ((double *)(j->blob + (color == 1 ? L->bits_u[d] : L->bits_v[d])))[b] = kvz_get_coeff_cost(state, cc, wc, 2, (int8_t)scan_for(1, wc, best_mode));
       ((uint32_t *)(j->blob + (color == 1 ? L->ssd_u[d] : L->ssd_v[d])))[b] = kvz_pixels_calc_ssd(orig, recb, wc, wc, wc);
-      for (int y = 0; y < wc; ++y) memcpy(j->rec[color][d] + (size_t)(by * wc + y) * Wc + bx * wc, recb + y * wc, wc);
+      for (int y = 0; y < wc; ++y) memcpy(j->rec[color][d] + (size_t)(by * wc + y) * Wc + bx * wc, recb + y * wc, wc * sizeof(kvz_pixel));
     }
   }
 }
@@ -134,14 +134,14 @@ static void do_sao(job_t *j, int i, kvz_pixel *buf /* 2 * 4096 px */)
   const int Wp = color ? W / 2 : W, Hp = color ? H / 2 : H, lw = color ? 32 : 64;
   const int x0 = (ctu % cx) * lw, y0 = (ctu / cx) * lw;
   const int bw = MIN(lw, Wp - x0), bh = MIN(lw, Hp - y0);
-  const uint8_t *splane = j->src + (color == 0 ? 0 : (color == 1 ? (size_t)W * H : (size_t)W * H * 5 / 4));
-  const uint8_t *rplane = j->rec[color][2];
-  uint8_t *sao_plane = j->blob + L->sao_rec + (color == 0 ? 0 : (color == 1 ? (size_t)W * H : (size_t)W * H * 5 / 4));
+  const kvz_pixel *splane = j->src + (color == 0 ? 0 : (color == 1 ? (size_t)W * H : (size_t)W * H * 5 / 4));
+  const kvz_pixel *rplane = j->rec[color][2];
+  kvz_pixel *sao_plane = (kvz_pixel *)(j->blob + L->sao_rec) + (color == 0 ? 0 : (color == 1 ? (size_t)W * H : (size_t)W * H * 5 / 4));
   const encoder_control_t *enc = j->ctx->enc->control;
   encoder_state_t *state = &j->ctx->enc->states[0];
   kvz_pixel *orig = buf, *rec = buf + 4096;
   /* contiguous copies, as sao_search_luma/chroma hand them to the strategies (ref: sao.c:605-669) */
-  for (int y = 0; y < bh; ++y) { memcpy(orig + y * bw, splane + (size_t)(y0 + y) * Wp + x0, bw); memcpy(rec + y * bw, rplane + (size_t)(y0 + y) * Wp + x0, bw); }
+  for (int y = 0; y < bh; ++y) { memcpy(orig + y * bw, splane + (size_t)(y0 + y) * Wp + x0, bw * sizeof(kvz_pixel)); memcpy(rec + y * bw, rplane + (size_t)(y0 + y) * Wp + x0, bw * sizeof(kvz_pixel)); }
   int32_t *stats = (int32_t *)(j->blob + L->sao_stats) + (size_t)i * 40;
   int32_t *dd = (int32_t *)(j->blob + L->sao_dd);
   int offsets[4][NUM_SAO_EDGE_CATEGORIES];
@@ -224,10 +224,9 @@ static void run_stage(job_t *j, int stage, int total, int nthreads)
 }
 
 /* ctx must have been opened with rdoq = 0, signhide as wanted, qp = the pass QP (kvzref_ctx_open in ref_shim.c) */
-int kvzref_frame_pass(kvzref_ctx *ctx, const uint8_t *src, int W, int H, int qp, const kvz_cuda_fp_layout *L,
+int kvzref_frame_pass(kvzref_ctx *ctx, const kvz_pixel *src, int W, int H, int qp, const kvz_cuda_fp_layout *L,
                       uint8_t *blob, int nthreads)
 {
-  if (KVZ_BIT_DEPTH != 8) return -1;
   job_t j; memset(&j, 0, sizeof(j));
   j.ctx = ctx; j.src = src; j.W = W; j.H = H; j.qp = qp; j.L = L; j.blob = blob;
   encoder_state_t *st = &ctx->enc->states[0];
@@ -241,8 +240,8 @@ int kvzref_frame_pass(kvzref_ctx *ctx, const uint8_t *src, int W, int H, int qp,
   st->search_cabac.update = 0;
   for (int d = 0; d < 4; ++d) {
     j.wl[d] = 32 >> d;
-    j.rec[0][d] = (uint8_t *)xaligned((size_t)W * H);
-    if (d < 3) { j.rec[1][d] = (uint8_t *)xaligned((size_t)W * H / 4); j.rec[2][d] = (uint8_t *)xaligned((size_t)W * H / 4); }
+    j.rec[0][d] = (kvz_pixel *)xaligned((size_t)W * H * sizeof(kvz_pixel));
+    if (d < 3) { j.rec[1][d] = (kvz_pixel *)xaligned((size_t)W * H / 4 * sizeof(kvz_pixel)); j.rec[2][d] = (kvz_pixel *)xaligned((size_t)W * H / 4 * sizeof(kvz_pixel)); }
   }
   run_stage(&j, 0, L->nblk[0] + L->nblk[1] + L->nblk[2] + L->nblk[3], nthreads);
   /* deblocking of the 8x8-level reconstruction (every CU: intra 8x8, 2Nx2N, one TU) through kvz_filter_deblock_lcu */
@@ -266,14 +265,15 @@ int kvzref_frame_pass(kvzref_ctx *ctx, const uint8_t *src, int W, int H, int qp,
     frame->rec = saved;
   }
   /* SAO works on the deblocked 8x8-level reconstruction; unfiltered pixels are copied first */
-  memcpy(blob + L->sao_rec, j.rec[0][2], (size_t)W * H);
-  memcpy(blob + L->sao_rec + (size_t)W * H, j.rec[1][2], (size_t)W * H / 4);
-  memcpy(blob + L->sao_rec + (size_t)W * H * 5 / 4, j.rec[2][2], (size_t)W * H / 4);
+  kvz_pixel *sao_out = (kvz_pixel *)(blob + L->sao_rec);
+  memcpy(sao_out, j.rec[0][2], (size_t)W * H * sizeof(kvz_pixel));
+  memcpy(sao_out + (size_t)W * H, j.rec[1][2], (size_t)W * H / 4 * sizeof(kvz_pixel));
+  memcpy(sao_out + (size_t)W * H * 5 / 4, j.rec[2][2], (size_t)W * H / 4 * sizeof(kvz_pixel));
   run_stage(&j, 1, 3 * L->nctu, nthreads);
   for (int color = 0; color < 3; ++color) {
     const int Wp = color ? W / 2 : W, Hp = color ? H / 2 : H;
     unsigned char ck[SEI_HASH_MAX_LENGTH] = { 0 };
-    kvz_array_checksum(blob + L->sao_rec + (color == 0 ? 0 : (color == 1 ? (size_t)W * H : (size_t)W * H * 5 / 4)), Hp, Wp, Wp, ck, 8);
+    kvz_array_checksum(sao_out + (color == 0 ? 0 : (color == 1 ? (size_t)W * H : (size_t)W * H * 5 / 4)), Hp, Wp, Wp, ck, KVZ_BIT_DEPTH);
     memcpy(blob + L->checksum + 4 * color, ck, 4);
   }
   for (int d = 0; d < 4; ++d) for (int c = 0; c < 3; ++c) free(j.rec[c][d]);

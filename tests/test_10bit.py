@@ -221,3 +221,45 @@ def test_cuda10_rdoq(cuda_lib, ref10):
             for i in range(count):
                 want = ref10.rdoq(coef[i].ravel(), n, qp, lam, cabac, 0, int(tus["scan_idx"][i]), 1, 0, signhide)
                 assert np.array_equal(want, got[i]), (n, qp, signhide, i)
+
+
+def synth_frame10(W, H, idx):
+    """10-bit I420 test frame: the 8-bit synthetic frame scaled by 4 plus two fresh low bits."""
+    from test_framepass import synth_frame
+    f8 = synth_frame(W, H, frame_idx=idx).astype(np.uint16)
+    low = np.random.default_rng(idx).integers(0, 4, f8.size).astype(np.uint16)
+    return (f8 * 4 + low).astype(np.uint16)
+
+
+def test_reference_frame_pass_10bit_runs(ref10):
+    """The CPU arm (oracle/ref_framepass.c in the KVZ_BIT_DEPTH=10 build) is deterministic and thread-count independent."""
+    from _oracle import ref_frame_pass
+    from kvazaar_b200 import api
+    W, H, qp = 136, 72, 30
+    src = synth_frame10(W, H, 2)
+    lay = api.fp_layout_for(W, H, qp, 0, 10)
+    a = ref_frame_pass(ref10, src, W, H, qp, lay, nthreads=1, rdoq=1)
+    b = ref_frame_pass(ref10, src, W, H, qp, lay, nthreads=4, rdoq=1)
+    assert np.array_equal(a, b)
+    sec = api.fp_sections(lay, W, H, 10)
+    assert api.fp_section(a, sec, "sao_rec").max() > 255 and api.fp_section(a, sec, "checksum").any()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims,qp,signhide,rdoq,trskip", [((136, 72), 30, 0, 0, 0), ((200, 136), 27, 1, 1, 0), ((320, 192), 34, 1, 1, 1)])
+def test_cuda10_frame_pass_matches_reference(cuda_lib, ref10, dims, qp, signhide, rdoq, trskip):
+    """The whole frame-level pass on 10-bit samples (config-5 bit depth): blob identical to the pass through the 10-bit
+    reference build's strategy functions."""
+    from _oracle import ref_frame_pass
+    kb = cuda_lib
+    W, H = dims
+    src = synth_frame10(W, H, W + qp)
+    fp = kb.FramePass(W, H, qp, signhide, rdoq, 0.0, trskip, 10)
+    fp.run_dev(kb.to_dev(src))
+    got = fp.result_host()
+    want = ref_frame_pass(ref10, src, W, H, qp, fp.layout, nthreads=4, signhide=signhide, rdoq=rdoq, trskip=trskip)
+    sec = kb.fp_sections(fp.layout, W, H, 10)
+    for name in sec:
+        a, b = kb.fp_section(got, sec, name), kb.fp_section(want, sec, name)
+        assert np.array_equal(a, b), (name, int(np.argmax(a != b)), a[a != b][:4], b[a != b][:4])
+    fp.close()
