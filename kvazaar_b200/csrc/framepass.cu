@@ -245,9 +245,9 @@ __device__ __forceinline__ int fp_eo_cat(int a, int b, int c)
 //   edge ddist      = sum_k (o_k^2 * cnt_k - 2 * o_k * sum_k)               == sum_i ((d_i - o)^2 - d_i^2), the value
 //                     kvz_sao_edge_ddistortion accumulates pixel by pixel (ref: sao_shared_generics.h:52-91)
 //   band ddist      = the same identity over the four bands                 (ref: sao_shared_generics.h:93-130)
-// so the delta-distortion "kernels" cost nothing on the device.  Above 8 bits kvz_sao_edge_ddistortion works on the
-// rounded difference (d + 2^(bd-9)) >> (bd-8) (sao_shared_generics.h:64,83): its per-category sums are gathered next to
-// the raw ones that the statistics and the band distortion use.
+// so the delta-distortion "kernels" cost nothing on the device.  Above 8 bits the edge statistics and the edge
+// delta-distortion both work on the rounded difference (d + 2^(bd-9)) >> (bd-8) (sao-generic.c:66,77,
+// sao_shared_generics.h:64,83); the band distortion uses the raw difference.
 template <class T>
 __global__ void __launch_bounds__(256) sao_ctu_kernel(SaoPlanesT<T> pl, int nctu, int ctus_x, int32_t *__restrict__ stats,
                                                       int32_t *__restrict__ dd, int32_t *__restrict__ band_dd,
@@ -256,7 +256,6 @@ __global__ void __launch_bounds__(256) sao_ctu_kernel(SaoPlanesT<T> pl, int nctu
 {
   constexpr int BD = PixTraits<T>::kBits;
   __shared__ int s_acc[4][2][5];
-  __shared__ int s_accr[4][5];                      // sums of the rounded differences (BD > 8 only)
   __shared__ int s_band[2][4];
   const int i = blockIdx.x, color = i / nctu, ctu = i - color * nctu;
   const int Wp = pl.Wp[color], Hp = pl.Hp[color], lw = color ? 32 : 64;
@@ -265,14 +264,14 @@ __global__ void __launch_bounds__(256) sao_ctu_kernel(SaoPlanesT<T> pl, int nctu
   const T *orig = pl.src[color] + (long)y0 * Wp + x0, *rec = pl.rec[color] + (long)y0 * Wp + x0;
   const int bp = (i * 7) % 29;
   if (i == 0 && threadIdx.x < 6) cksum_scratch[threadIdx.x] = 0;
-  for (int t = threadIdx.x; t < 68; t += blockDim.x) { if (t < 40) (&s_acc[0][0][0])[t] = 0; else if (t < 48) (&s_band[0][0])[t - 40] = 0; else (&s_accr[0][0])[t - 48] = 0; }
+  for (int t = threadIdx.x; t < 48; t += blockDim.x) { if (t < 40) (&s_acc[0][0][0])[t] = 0; else (&s_band[0][0])[t - 40] = 0; }
   __syncthreads();
-  int sum[4][5], cnt[4][5], sumr[4][5], bs[4], bc[4];
+  int sum[4][5], cnt[4][5], bs[4], bc[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     bs[e] = 0; bc[e] = 0;
 #pragma unroll
-    for (int k = 0; k < 5; ++k) { sum[e][k] = 0; cnt[e][k] = 0; sumr[e][k] = 0; }
+    for (int k = 0; k < 5; ++k) { sum[e][k] = 0; cnt[e][k] = 0; }
   }
   for (int t = threadIdx.x; t < bw * bh; t += blockDim.x) {
     const int y = t / bw, x = t - y * bw;
@@ -289,7 +288,7 @@ __global__ void __launch_bounds__(256) sao_ctu_kernel(SaoPlanesT<T> pl, int nctu
         fp_eo_offsets(e, ax, ay);
         const int cat = fp_eo_cat(rec[(long)(y + ay) * Wp + x + ax], rec[(long)(y - ay) * Wp + x - ax], c);
 #pragma unroll
-        for (int k = 0; k < 5; ++k) { const int hit = cat == k; sum[e][k] += hit ? diff : 0; cnt[e][k] += hit; if (BD > 8) sumr[e][k] += hit ? diffr : 0; }
+        for (int k = 0; k < 5; ++k) { const int hit = cat == k; sum[e][k] += hit ? diffr : 0; cnt[e][k] += hit; }
       }
     }
   }
@@ -301,7 +300,6 @@ __global__ void __launch_bounds__(256) sao_ctu_kernel(SaoPlanesT<T> pl, int nctu
     for (int k = 0; k < 5; ++k) {
       const int v1 = warp_sum(sum[e][k]), v2 = warp_sum(cnt[e][k]);
       if ((threadIdx.x & 31) == 0) { atomicAdd(&s_acc[e][0][k], v1); atomicAdd(&s_acc[e][1][k], v2); }
-      if (BD > 8) { const int v3 = warp_sum(sumr[e][k]); if ((threadIdx.x & 31) == 0) atomicAdd(&s_accr[e][k], v3); }
     }
   }
   __syncthreads();
@@ -313,7 +311,7 @@ __global__ void __launch_bounds__(256) sao_ctu_kernel(SaoPlanesT<T> pl, int nctu
       int o[5], v = 0;
       o[0] = 0;
       for (int k = 1; k < 5; ++k) o[k] = s_acc[e][1][k] ? clip3(-7, 7, s_acc[e][0][k] / s_acc[e][1][k]) : 0;
-      for (int k = 1; k < 5; ++k) v += o[k] * o[k] * s_acc[e][1][k] - 2 * o[k] * (BD > 8 ? s_accr[e][k] : s_acc[e][0][k]);
+      for (int k = 1; k < 5; ++k) v += o[k] * o[k] * s_acc[e][1][k] - 2 * o[k] * s_acc[e][0][k];
       dd[(size_t)e * n3 + i] = v;
       if (e == 0 || v < bd) { bd = v; be = e; for (int k = 0; k < 5; ++k) off_best[k] = o[k]; }
     }
