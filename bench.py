@@ -29,19 +29,27 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-W, H, QP, SIGNHIDE, RDOQ, TRSKIP = 1920, 1080, 27, 0, 0, 0
+W, H, QP, SIGNHIDE, RDOQ, TRSKIP, BITDEPTH = 1920, 1080, 27, 0, 0, 0, 8
 WORKLOAD = "1920x1080 8-bit synthetic I420, all-intra, QP27 (preset medium: SAO on, signhide off), frame-level hot-path pass"
 
 
 def set_workload(name, rdoq):
     """configs[1] (default, the one the metric is quoted on) or the configs[2] shape (2160p, QP22, sign hiding)."""
-    global W, H, QP, SIGNHIDE, RDOQ, TRSKIP, WORKLOAD
+    global W, H, QP, SIGNHIDE, RDOQ, TRSKIP, BITDEPTH, WORKLOAD
     RDOQ = int(rdoq)
     q = "RDOQ on" if RDOQ else "RDOQ off (kvz_quant)"
     WORKLOAD = f"1920x1080 8-bit synthetic I420, all-intra, QP27 (preset medium: deblock + SAO on, signhide off, {q}), frame-level hot-path pass"
     if name == "2160p":
         W, H, QP, SIGNHIDE, TRSKIP = 3840, 2160, 22, 1, 1
         WORKLOAD = f"3840x2160 8-bit synthetic I420, all-intra, QP22 (preset veryslow shape: deblock + SAO on, signhide on, transform skip on, {q}), frame-level hot-path pass"
+
+
+def set_workload_4320p10(rdoq):
+    """configs[4] shape: 7680x4320 10-bit (the intra hot path of it; tiles / inter exchange are dist.py's business)."""
+    global W, H, QP, SIGNHIDE, RDOQ, TRSKIP, BITDEPTH, WORKLOAD
+    W, H, QP, SIGNHIDE, TRSKIP, BITDEPTH, RDOQ = 7680, 4320, 22, 0, 0, 10, int(rdoq)
+    q = "RDOQ on" if RDOQ else "RDOQ off (kvz_quant)"
+    WORKLOAD = f"7680x4320 10-bit synthetic I420, all-intra, QP22 (preset slow shape: deblock + SAO on, signhide off, {q}), frame-level hot-path pass"
 
 
 def peaks():
@@ -54,7 +62,13 @@ def peaks():
 
 def synth_frames(n):
     from test_framepass import synth_frame
-    return [synth_frame(W, H, frame_idx=i) for i in range(n)]
+    if BITDEPTH == 8:
+        return [synth_frame(W, H, frame_idx=i) for i in range(n)]
+    out = []
+    for i in range(n):                       # 10-bit: the 8-bit pattern scaled by 4 plus two fresh low bits
+        f8 = synth_frame(W, H, frame_idx=i).astype(np.uint16)
+        out.append((f8 * 4 + np.random.default_rng(i).integers(0, 4, f8.size).astype(np.uint16)).astype(np.uint16))
+    return out
 
 
 class ClockSampler:
@@ -108,9 +122,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ref = Ref()
+    ref = Ref(BITDEPTH)
     cores = os.cpu_count() or 1
-    lay = kb.fp_layout_for(W, H, QP, SIGNHIDE)
+    lay = kb.fp_layout_for(W, H, QP, SIGNHIDE, BITDEPTH)
     from _oracle import aligned, al
     frames = [al(f) for f in synth_frames(4)]
     blob = aligned(int(lay.host_bytes), np.uint8)
@@ -126,7 +140,7 @@ def run_reference(args):
     sample = f"{args.steps * nper} frames {W}x{H} through the reference's selected strategy functions ({ref.selected_name('satd_8x8')})"
     line = {"impl": "reference", "metric": "hot-path frames/sec at fixed QP (per-CTU strategy kernels, all depths)", "value": fps,
             "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if BITDEPTH == 8 else "u16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames_per_step": nper},
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -138,11 +152,11 @@ def cpu_baseline(budget_s=15.0):
     from _oracle import Ref, ref_frame_pass
     import kvazaar_b200 as kb
     try:
-        ref = Ref()
+        ref = Ref(BITDEPTH)
     except Exception as e:  # pragma: no cover
         return {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
     cores = os.cpu_count() or 1
-    lay = kb.fp_layout_for(W, H, QP, SIGNHIDE)
+    lay = kb.fp_layout_for(W, H, QP, SIGNHIDE, BITDEPTH)
     from _oracle import aligned, al
     frames = [al(f) for f in synth_frames(2)]
     blob = aligned(int(lay.host_bytes), np.uint8)
@@ -155,8 +169,8 @@ def cpu_baseline(budget_s=15.0):
     out = {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "reference",
            "sample": f"{n} frames {W}x{H} in {dt:.1f}s through oracle/_ref strategy pointers ({ref.selected_name('satd_8x8')}), {cores} threads"}
     # context: the unmodified reference ENCODER (whole pipeline incl. mode decision, RDOQ, CABAC) on the same input
-    cli = os.path.join(ROOT, "oracle", "_ref", "kvazaar")
-    if os.path.exists(cli):
+    cli = os.path.join(ROOT, "oracle", "_ref", "kvazaar" if BITDEPTH == 8 else "kvazaar_10b")
+    if os.path.exists(cli) and BITDEPTH == 8:       # (the 4320p 10-bit whole-encoder run would take minutes: skipped)
         try:
             yuv = f"/tmp/kvz_bench_{H}p.yuv"
             np.concatenate(synth_frames(4)).tofile(yuv)
@@ -186,7 +200,7 @@ def run_cuda(args):
     fps_step = args.frames_per_step
     inflight = args.inflight
     streams = [torch.cuda.Stream() for _ in range(inflight)]
-    passes = [kb.FramePass(W, H, QP, SIGNHIDE, RDOQ, 0.0, TRSKIP) for _ in range(inflight)]
+    passes = [kb.FramePass(W, H, QP, SIGNHIDE, RDOQ, 0.0, TRSKIP, BITDEPTH) for _ in range(inflight)]
     frames_np = synth_frames(fps_step)
     # every rank gets its own frames (sharding = frame i of the job -> rank i mod world)
     frames_np = [np.roll(f, rank * 977) for f in frames_np]
@@ -366,7 +380,7 @@ def run_cuda(args):
     if rank == 0:
         line = {"metric": "hot-path frames/sec at fixed QP (per-CTU strategy kernels, all depths)", "value": value, "unit": "frames/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if BITDEPTH == 8 else "u16", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "frames_per_step": fps_step, "frames_in_flight": inflight, "parallelism": f"frames/{world}",
                            "l2": f"working set per step ({fps_step} distinct {passes[0].frame_bytes / 1e6:.1f} MB frames + {inflight} result/scratch blobs of "
                                  f"{passes[0].host_bytes / 1e6:.0f}+ MB each) exceeds the 126 MB L2"},
@@ -395,10 +409,13 @@ def main():
     ap.add_argument("--inflight", type=int, default=4, help="frames in flight (one stream + one result blob each)")
     ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the reference arm (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="1080p", choices=["1080p", "2160p"], help="1080p = BASELINE configs[1] (default)")
+    ap.add_argument("--workload", default="1080p", choices=["1080p", "2160p", "4320p10"], help="1080p = BASELINE configs[1] (default)")
     ap.add_argument("--rdoq", type=int, default=1, choices=[0, 1], help="1 (default): quantise with kvz_rdoq as the medium / veryslow presets do; 0: kvz_quant")
     args = ap.parse_args()
-    set_workload(args.workload, args.rdoq)
+    if args.workload == "4320p10":
+        set_workload_4320p10(args.rdoq)
+    else:
+        set_workload(args.workload, args.rdoq)
     if args.impl == "reference":
         run_reference(args)
     else:
