@@ -1,7 +1,21 @@
 // rdoq.cu -- batched kvz_rdoq: one warp per TU (see rdoq.cuh).
 #include "rdoq.cuh"
 
+#include <mutex>
+
 namespace kvzc {
+
+// one-time fill of g_scan_diag32 (the copy of this translation unit: every 32x32 RDOQ kernel lives here)
+static int rdoq_init_tables(cudaStream_t st)
+{
+  static std::once_flag once;
+  static int rc = 0;
+  std::call_once(once, [&] {
+    rdoq_init_scan32_kernel<<<1, 1024, 0, st>>>();
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) rc = KVZ_CUDA_E_RUNTIME;
+  });
+  return rc;
+}
 
 template <int LOG2N, int WARPS, bool SH>
 __global__ void __launch_bounds__(WARPS * 32) rdoq_kernel(kvz_cuda_rdoq_params p, const kvz_cuda_cabac_ctx *__restrict__ cabac,
@@ -13,19 +27,16 @@ __global__ void __launch_bounds__(WARPS * 32) rdoq_kernel(kvz_cuda_rdoq_params p
   __shared__ kvz_cuda_cabac_ctx s_ctx;
   __shared__ int32_t s_ebits[128];
   rdoq_load_ebits(s_ebits);
-  __shared__ __align__(4) int16_t s_coef[WARPS][NN], s_q[WARPS][NN];
+  __shared__ __align__(4) int16_t s_q[WARPS][NN];
   for (int i = threadIdx.x; i < (int)sizeof(kvz_cuda_cabac_ctx); i += blockDim.x) ((uint8_t *)&s_ctx)[i] = ((const uint8_t *)cabac)[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * WARPS + warp;
   const bool active = t < count;
   kvz_cuda_rdoq_tu tu = {};
-  if (active) {
-    tu = tus[t];
-    for (int e = lane; e < NN; e += 32) s_coef[warp][e] = coef[tu.off_coef + e];
-  }
+  if (active) tu = tus[t];
   __syncthreads();
   if (!active) return;
-  rdoq_tu<NN, SH>(p, &s_ctx, s_ebits, s_coef[warp], s_q[warp], LOG2N, tu.type, tu.scan_idx, tu.block_type, tu.tr_depth, scratch[warp], lane);
+  rdoq_tu<NN, SH>(p, &s_ctx, s_ebits, coef + tu.off_coef, s_q[warp], LOG2N, tu.type, tu.scan_idx, tu.block_type, tu.tr_depth, scratch[warp], lane);
   for (int e = lane; e < NN; e += 32) dest[tu.off_dest + e] = s_q[warp][e];
 }
 
@@ -40,17 +51,16 @@ __global__ void __launch_bounds__(WARPS * 32) rdoq_tu_kernel(kvz_cuda_rdoq_param
   __shared__ kvz_cuda_cabac_ctx s_ctx;
   __shared__ int32_t s_ebits[128];
   rdoq_load_ebits(s_ebits);
-  __shared__ __align__(4) int16_t s_coef[WARPS][NN], s_q[WARPS][NN];
+  __shared__ __align__(4) int16_t s_q[WARPS][NN];
   for (int i = threadIdx.x; i < (int)sizeof(kvz_cuda_cabac_ctx); i += blockDim.x) ((uint8_t *)&s_ctx)[i] = ((const uint8_t *)cabac)[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * WARPS + warp;
   kvz_cuda_tu tu = {};
   bool active = t < count;
   if (active) { tu = tus[t]; active = tu.width == (1 << LOG2N); }
-  if (active) for (int e = lane; e < NN; e += 32) s_coef[warp][e] = coeff[tu.off_coeff + e];
   __syncthreads();
   if (!active) return;
-  rdoq_tu<NN, SH>(p, &s_ctx, s_ebits, s_coef[warp], s_q[warp], LOG2N, tu.color == 0 ? 0 : 2, tu.scan_idx, tu.cu_is_intra ? 1 : 2, tu.tr_depth, scratch[warp], lane);
+  rdoq_tu<NN, SH>(p, &s_ctx, s_ebits, coeff + tu.off_coeff, s_q[warp], LOG2N, tu.color == 0 ? 0 : 2, tu.scan_idx, tu.cu_is_intra ? 1 : 2, tu.tr_depth, scratch[warp], lane);
   for (int e = lane; e < NN; e += 32) coeff[tu.off_coeff + e] = s_q[warp][e];
 }
 
@@ -66,7 +76,7 @@ __global__ void __launch_bounds__(WARPS * 32) rdoq_grid_kernel(kvz_cuda_rdoq_par
   __shared__ kvz_cuda_cabac_ctx s_ctx;
   __shared__ int32_t s_ebits[128];
   rdoq_load_ebits(s_ebits);
-  __shared__ __align__(4) int16_t s_coef[WARPS][NN], s_q[WARPS][NN];
+  __shared__ __align__(4) int16_t s_q[WARPS][NN];
   for (int i = threadIdx.x; i < (int)sizeof(kvz_cuda_cabac_ctx); i += blockDim.x) ((uint8_t *)&s_ctx)[i] = ((const uint8_t *)cabac)[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // two planes (U and V) can share one launch: TU indices [count, 2 * count) address coeff2
@@ -74,12 +84,12 @@ __global__ void __launch_bounds__(WARPS * 32) rdoq_grid_kernel(kvz_cuda_rdoq_par
   const bool active = t < (coeff2 ? 2 * count : count);
   int16_t *base = coeff;
   if (t >= count) { t -= count; base = coeff2; }
-  if (active) for (int e = lane; e < NN; e += 32) s_coef[warp][e] = base[(size_t)t * NN + e];
   __syncthreads();
   if (!active) return;
   int scan = 0;
   if ((!is_chroma && W <= 8) || (is_chroma && W == 4)) { const int m = modes[t]; scan = (m >= 6 && m <= 14) ? 2 : ((m >= 22 && m <= 30) ? 1 : 0); }
-  rdoq_tu<NN, SH>(p, &s_ctx, s_ebits, s_coef[warp], s_q[warp], LOG2N, is_chroma ? 2 : 0, scan, 1, tr_depth, scratch[warp], lane);
+  // (in place: the coefficients are read from global memory, the levels are written back after the walk)
+  rdoq_tu<NN, SH>(p, &s_ctx, s_ebits, base + (size_t)t * NN, s_q[warp], LOG2N, is_chroma ? 2 : 0, scan, 1, tr_depth, scratch[warp], lane);
   for (int e = lane; e < NN; e += 32) base[(size_t)t * NN + e] = s_q[warp][e];
 }
 
@@ -125,7 +135,8 @@ int rdoq_launch_grid(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ct
     case 2: if (SHV) rdoq_grid_thread_kernel<2, true><<<(total + 127) / 128, 128, 0, st>>>(p, ctx_dev, coeff, coeff2, count, modes, is_chroma, tr_depth); else rdoq_grid_thread_kernel<2, false><<<(total + 127) / 128, 128, 0, st>>>(p, ctx_dev, coeff, coeff2, count, modes, is_chroma, tr_depth); break;
     case 3: if (SHV) rdoq_grid_kernel<3, 8, true><<<(total + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, coeff2, count, modes, is_chroma, tr_depth); else rdoq_grid_kernel<3, 8, false><<<(total + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, coeff2, count, modes, is_chroma, tr_depth); break;
     case 4: if (SHV) rdoq_grid_kernel<4, 2, true><<<(total + 1) / 2, 64, 0, st>>>(p, ctx_dev, coeff, coeff2, count, modes, is_chroma, tr_depth); else rdoq_grid_kernel<4, 2, false><<<(total + 1) / 2, 64, 0, st>>>(p, ctx_dev, coeff, coeff2, count, modes, is_chroma, tr_depth); break;
-    default: if (SHV) rdoq_grid_kernel<5, 1, true><<<total, 32, 0, st>>>(p, ctx_dev, coeff, coeff2, count, modes, is_chroma, tr_depth); else rdoq_grid_kernel<5, 1, false><<<total, 32, 0, st>>>(p, ctx_dev, coeff, coeff2, count, modes, is_chroma, tr_depth); break;
+    default: if (int r = rdoq_init_tables(st)) return r;
+      if (SHV) rdoq_grid_kernel<5, 1, true><<<total, 32, 0, st>>>(p, ctx_dev, coeff, coeff2, count, modes, is_chroma, tr_depth); else rdoq_grid_kernel<5, 1, false><<<total, 32, 0, st>>>(p, ctx_dev, coeff, coeff2, count, modes, is_chroma, tr_depth); break;
   }
   KVZC_LAUNCHED();
   return 0;
@@ -138,7 +149,8 @@ int rdoq_launch_tus(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx *ctx
     case 4: if (SHV) rdoq_tu_kernel<2, 8, true><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, tus, count); else rdoq_tu_kernel<2, 8, false><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, tus, count); break;
     case 8: if (SHV) rdoq_tu_kernel<3, 8, true><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, tus, count); else rdoq_tu_kernel<3, 8, false><<<(count + 7) / 8, 256, 0, st>>>(p, ctx_dev, coeff, tus, count); break;
     case 16: if (SHV) rdoq_tu_kernel<4, 2, true><<<(count + 1) / 2, 64, 0, st>>>(p, ctx_dev, coeff, tus, count); else rdoq_tu_kernel<4, 2, false><<<(count + 1) / 2, 64, 0, st>>>(p, ctx_dev, coeff, tus, count); break;
-    default: if (SHV) rdoq_tu_kernel<5, 1, true><<<count, 32, 0, st>>>(p, ctx_dev, coeff, tus, count); else rdoq_tu_kernel<5, 1, false><<<count, 32, 0, st>>>(p, ctx_dev, coeff, tus, count); break;
+    default: if (int r = rdoq_init_tables(st)) return r;
+      if (SHV) rdoq_tu_kernel<5, 1, true><<<count, 32, 0, st>>>(p, ctx_dev, coeff, tus, count); else rdoq_tu_kernel<5, 1, false><<<count, 32, 0, st>>>(p, ctx_dev, coeff, tus, count); break;
   }
   KVZC_LAUNCHED();
   return 0;
@@ -163,7 +175,8 @@ extern "C" int kvz_cuda_rdoq_batch(const kvz_cuda_rdoq_params *p, const kvz_cuda
     case 4: if (SHV) rdoq_kernel<2, 8, true><<<(count + 7) / 8, 256, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); else rdoq_kernel<2, 8, false><<<(count + 7) / 8, 256, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); break;
     case 8: if (SHV) rdoq_kernel<3, 8, true><<<(count + 7) / 8, 256, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); else rdoq_kernel<3, 8, false><<<(count + 7) / 8, 256, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); break;
     case 16: if (SHV) rdoq_kernel<4, 2, true><<<(count + 1) / 2, 64, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); else rdoq_kernel<4, 2, false><<<(count + 1) / 2, 64, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); break;
-    default: if (SHV) rdoq_kernel<5, 1, true><<<count, 32, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); else rdoq_kernel<5, 1, false><<<count, 32, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); break;
+    default: if (int r = rdoq_init_tables(st)) return r;
+      if (SHV) rdoq_kernel<5, 1, true><<<count, 32, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); else rdoq_kernel<5, 1, false><<<count, 32, 0, st>>>(*p, ctx_dev, coef, dest, tus, count); break;
   }
   KVZC_LAUNCHED();
   return 0;

@@ -40,12 +40,23 @@ constexpr int RDOQ_ONE_BIT = 1 << 15;
 // position group of a last-significant coordinate (g_group_idx, rdo.c: 0,1,2,3,4,4,5,5,6,6,6,6,7,7,7,7,8..,9..)
 __device__ __forceinline__ int last_group(int x) { if (x < 4) return x; const int l = 31 - __clz(x); return 2 * l + ((x >> (l - 1)) & 1); }
 
+// scan position -> raster position of the 32x32 diagonal scan, shared by every 32x32 TU (filled once per process by
+// rdoq_init_tables); smaller blocks build their table in shared memory
+static __device__ uint16_t g_scan_diag32[1024];
+static __global__ void rdoq_init_scan32_kernel() { g_scan_diag32[threadIdx.x] = (uint16_t)scan_pos(0, 5, threadIdx.x); }
+
 // SH = sign hiding enabled: only then the per-position rate tables of kvz_sh_rates_t exist
+// SH = sign hiding enabled: only then the per-position rate tables of kvz_sh_rates_t exist.
+// cost_sig (rdo.c:683) is kept as one byte per position: the significance context (6 bits) and which of its two bin
+// costs the position carries (0: flag = 0, 1: flag = 1, 2: none -- the last coefficient or a zeroed group); the double
+// is lambda * entropy_bits again when the last-position search needs it.  That halves the table and lets all 32x32 TUs
+// of a 1080p frame be resident at once.
 template <int NN, bool SH>
 struct RdoqScratch {
-  double cost_coeff[NN], cost_sig[NN];                     // (the level-0 distortion cost_coeff0 is recomputed where needed)
+  double cost_coeff[NN];                                   // (the level-0 distortion cost_coeff0 is recomputed where needed)
+  uint8_t sig_code[NN];
   int32_t inc[SH ? NN : 1], dec[SH ? NN : 1], sig_inc[SH ? NN : 1], qdelta[SH ? NN : 1];       // kvz_sh_rates_t (rdo.h:49-58)
-  uint16_t blk[NN];                                        // scan position -> raster position
+  uint16_t blk[NN >= 1024 ? 1 : NN];                       // scan position -> raster position (32x32: g_scan_diag32)
   double cg_sig_cost[NN / 16];
   int32_t cg_flag[NN / 16];
   uint16_t cg_nz[NN / 16];                                 // per group: positions (bit k) whose level is non-zero
@@ -148,8 +159,8 @@ __device__ __forceinline__ int rdoq_sig_ctx(int pattern, int scan_idx, int px, i
 }
 
 // Sign-bit hiding on RDOQ output (rdo.c:518-653).  Serial; one thread.
-template <class Scratch>
-__device__ void rdoq_sign_hiding(const Scratch &s, double lambda, int bitdepth, int qp_scaled, int scan_idx, int log2n, int last_pos,
+template <class Scratch, class BlkT>
+__device__ void rdoq_sign_hiding(const Scratch &s, const BlkT *blk, double lambda, int bitdepth, int qp_scaled, int scan_idx, int log2n, int last_pos,
                                  const int16_t *coef, int16_t *q)
 {
   const int inv_quant = c_inv_quant_scales[qp_scaled % 6];
@@ -157,7 +168,7 @@ __device__ void rdoq_sign_hiding(const Scratch &s, double lambda, int bitdepth, 
   const int last_cg = (last_pos - 1) >> 4;
   for (int cg = last_cg; cg >= 0; --cg) {
     const int base = cg << 4;
-    const auto *pos = s.blk + base;
+    const BlkT *pos = blk + base;
     int last_nz = -1, first_nz = 16;
     for (int k = 15; k >= 0; --k) if (q[pos[k]]) { last_nz = k; break; }
     for (int k = 0; k <= last_nz; ++k) if (q[pos[k]]) { first_nz = k; break; }
@@ -223,13 +234,18 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
   const double err_scale = ldexp(32768.0, -2 * transform_shift) / qc / qc / (1 << (2 * (p.bitdepth - 8)));
   const RdoqModels m = rdoq_models(cabac, ebits_table, type);
   // distortion of quantising the coefficient at raster position blk to 0 (cost_coeff0, rdo.c:770-771)
+  // cost_sig of a position from its code byte
+  auto sig_cost_of = [&](uint8_t code) { return (code >> 6) == 2 ? 0.0 : lambda * ebits(m.sig[code & 63], code >> 6); };
   auto level0_cost = [&](int blk) { const double e = (double)min(abs((int)coef[blk]) * qc, 0x7FFFFFFF - half); return e * e * err_scale; };
 
   // ---- scan table and last significant scan position (find_last_scanpos)
+  constexpr bool GLOBAL_SCAN = NN >= 1024;
+  const uint16_t *blk_of = GLOBAL_SCAN ? g_scan_diag32 : s.blk;
   int my_last = -1;
   for (int sp = lane; sp < nn; sp += 32) {
-    const int blk = scan_pos(scan_idx, log2n, sp);
-    s.blk[sp] = (uint16_t)blk;
+    int blk;
+    if constexpr (GLOBAL_SCAN) blk = blk_of[sp];
+    else { blk = scan_pos(scan_idx, log2n, sp); s.blk[sp] = (uint16_t)blk; }
     const int ld = min(abs((int)coef[blk]) * qc, 0x7FFFFFFF - half);
     if (((ld + half) >> q_bits) > 0) my_last = sp;                       // increasing sp: the last assignment is the largest
   }
@@ -237,11 +253,11 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
   for (int o = 16; o > 0; o >>= 1) my_last = max(my_last, __shfl_xor_sync(0xffffffffu, my_last, o));
   const int last_scanpos = my_last;
   __syncwarp();
-  for (int sp = lane; sp < nn; sp += 32) if (sp > last_scanpos) q[s.blk[sp]] = 0;
+  for (int sp = lane; sp < nn; sp += 32) if (sp > last_scanpos) q[blk_of[sp]] = 0;
   if (last_scanpos < 0) { __syncwarp(); return; }
   for (int g = lane; g < nn / 16; g += 32) { s.cg_flag[g] = 0; s.cg_sig_cost[g] = 0; }
   if (lane == 0) {
-    if (SH) s.sig_inc[s.blk[last_scanpos]] = 0;
+    if (SH) s.sig_inc[blk_of[last_scanpos]] = 0;
     // last-position bin costs (calc_last_bits, rdo.c:479-508)
     const int cb = log2n - 2;
     const int off = type ? 0 : (cb * 3 + ((cb + 1) >> 2));
@@ -266,7 +282,7 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
   double base_cost = 0, block_uncoded_cost = 0;
 
   for (int cg = cg_last; cg >= 0; --cg) {
-    const int cg_first = s.blk[cg << 4];                                  // raster position of the group's first coefficient
+    const int cg_first = blk_of[cg << 4];                                  // raster position of the group's first coefficient
     const int cgx = (cg_first & (n - 1)) >> 2, cgy = (cg_first >> log2n) >> 2;
     const int cg_blk = cgy * cgs_side + cgx;
     // neighbouring coded groups: right and below (context.c:315-351); both were decided earlier in this walk
@@ -280,7 +296,7 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
       const int sp = (cg << 4) + lane;
       if (sp <= last_scanpos) {
         valid = true;
-        const int blk = s.blk[sp];
+        const int blk = blk_of[sp];
         const int ld = min(abs((int)coef[blk]) * qc, 0x7FFFFFFF - half);
         const double err = (double)ld;
         const double c0 = err * err * err_scale;
@@ -293,8 +309,9 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
           s.prep_sig0[lane] = sig0;
           s.prep_sig1[lane] = lambda * ebits(m.sig[ctx_sig], 1);
           if (SH) s.sig_inc[blk] = ebits(m.sig[ctx_sig], 1) - ebits(m.sig[ctx_sig], 0);
+          s.prep_ctx_sig[lane] = ctx_sig;
           if (!cand) {
-            s.cost_sig[sp] = sig0; s.cost_coeff[sp] = c0 + sig0;
+            s.sig_code[sp] = (uint8_t)ctx_sig; s.cost_coeff[sp] = c0 + sig0;
             q[blk] = 0;
             if (SH) s.qdelta[blk] = ld >> (q_bits - 8);
           }
@@ -330,7 +347,7 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
           base_cost += c0 + cs;
           st_sig += cs;
           if (k == 0) st_sig0 = cs;
-          if (SH) s.inc[s.blk[sp]] = ebits(m.one[4 * ctx_set + c1], 0);
+          if (SH) s.inc[blk_of[sp]] = ebits(m.one[4 * ctx_set + c1], 0);
           if (k == 0 && sp > 0) {
             c2 = 0; rice = 0; c1_idx = 0; c2_idx = 0;
             ctx_set = (sp == 16 || type != 0) ? 0 : 2;
@@ -339,7 +356,7 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
           }
           continue;
         }
-        const int blk = s.blk[sp];
+        const int blk = blk_of[sp];
         const int ld = s.prep_ld[k];
         const uint32_t max_abs = (uint32_t)((ld + half) >> q_bits);
         const int one_ctx = 4 * ctx_set + c1, abs_ctx = ctx_set + c2;
@@ -347,7 +364,8 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
         // kvz_get_coded_level (rdo.c:413-452)
         uint32_t level = 0;
         double cc, cs = 0;
-        if (!last && max_abs < 3) { cs = sig0k; cc = c0 + cs; }
+        int cs_kind = 2;
+        if (!last && max_abs < 3) { cs = sig0k; cc = c0 + cs; cs_kind = 0; }
         else cc = 1.7e+308;
         if (max_abs != 0) {
           const double sig_now = last ? 0.0 : s.prep_sig1[k];
@@ -356,11 +374,11 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
             const double err = (double)(ld - lvl * (1 << q_bits));
             double c = err * err * err_scale + lambda * rdoq_level_rate(m, (uint32_t)lvl, one_ctx, abs_ctx, rice, c1_idx, c2_idx);
             c += sig_now;
-            if (c < cc) { level = (uint32_t)lvl; cc = c; cs = sig_now; }
+            if (c < cc) { level = (uint32_t)lvl; cc = c; cs = sig_now; cs_kind = last ? 2 : 1; }
           }
         }
         s.cost_coeff[sp] = cc;
-        s.cost_sig[sp] = cs;
+        s.sig_code[sp] = (uint8_t)((last ? 0 : s.prep_ctx_sig[k]) | (cs_kind << 6));
         if (SH) {
           s.qdelta[blk] = (ld - (int)level * (1 << q_bits)) >> (q_bits - 8);
           if (level > 0) {
@@ -416,8 +434,8 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
             base_cost = cost_zero_cg;
             s.cg_sig_cost[cg] = lambda * ebits(m.cg[ctx_cg], 0);
             for (int k = 15; k >= 0; --k) {
-              const int sp = (cg << 4) + k, blk = s.blk[sp];
-              if (q[blk]) { q[blk] = 0; s.cost_coeff[sp] = level0_cost(blk); s.cost_sig[sp] = 0; }
+              const int sp = (cg << 4) + k, blk = blk_of[sp];
+              if (q[blk]) { q[blk] = 0; s.cost_coeff[sp] = level0_cost(blk); s.sig_code[sp] = 2 << 6; }
             }
           }
         }
@@ -443,7 +461,7 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
     int best_last_p1 = 0;
     bool found_last = false;
     for (int cg = cg_last; cg >= 0 && !found_last; --cg) {
-      const int cg_first = s.blk[cg << 4];
+      const int cg_first = blk_of[cg << 4];
       const int cg_blk = ((cg_first >> log2n) >> 2) * cgs_side + ((cg_first & (n - 1)) >> 2);
       base_cost -= s.cg_sig_cost[cg];
       if (!s.cg_flag[cg_blk]) continue;
@@ -453,16 +471,16 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
       double csr[BIG ? 16 : 1];
       if constexpr (BIG) {
 #pragma unroll
-        for (int k = 0; k < 16; ++k) csr[k] = s.cost_sig[(cg << 4) + k];
+        for (int k = 0; k < 16; ++k) csr[k] = sig_cost_of(s.sig_code[(cg << 4) + k]);
       }
 #pragma unroll (BIG ? 16 : 1)
       for (int k = 15; k >= 0; --k) {
         if (k > top) continue;
         const int sp = (cg << 4) + k;
         double csk;
-        if constexpr (BIG) csk = csr[k]; else csk = s.cost_sig[sp];
+        if constexpr (BIG) csk = csr[k]; else csk = sig_cost_of(s.sig_code[sp]);
         if (!((nz >> k) & 1)) { base_cost -= csk; continue; }
-        const int blk = s.blk[sp];
+        const int blk = blk_of[sp];
         const int py = blk >> log2n, px = blk & (n - 1);
         const int gx = last_group(scan_idx == 2 ? py : px), gy = last_group(scan_idx == 2 ? px : py);
         double bits = s.last_x_bits[gx] + s.last_y_bits[gy];
@@ -483,7 +501,7 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
   const int best_last_p1 = s.best_last_p1;
   int abs_sum = 0;
   for (int sp = lane; sp <= last_scanpos; sp += 32) {
-    const int blk = s.blk[sp];
+    const int blk = blk_of[sp];
     if (sp < best_last_p1) {
       const int level = q[blk];
       abs_sum += level;
@@ -495,7 +513,7 @@ __device__ void rdoq_tu(const kvz_cuda_rdoq_params &p, const kvz_cuda_cabac_ctx 
   if constexpr (SH) {
     abs_sum = warp_sum(abs_sum);
     __syncwarp();
-    if (lane == 0 && abs_sum >= 2) rdoq_sign_hiding(s, lambda, p.bitdepth, qp_scaled, scan_idx, log2n, best_last_p1, coef, q);
+    if (lane == 0 && abs_sum >= 2) rdoq_sign_hiding(s, blk_of, lambda, p.bitdepth, qp_scaled, scan_idx, log2n, best_last_p1, coef, q);
   }
   __syncwarp();
 }
@@ -709,7 +727,7 @@ __device__ void rdoq_tu_thread(const kvz_cuda_rdoq_params &p, const kvz_cuda_cab
   }
   for (int sp = best_last_p1; sp <= last_scanpos; ++sp) q[s.blk[sp]] = 0;
   if constexpr (SH) {
-    if (abs_sum >= 2) rdoq_sign_hiding(s, lambda, p.bitdepth, qp_scaled, scan_idx, log2n, best_last_p1, coef, q);
+    if (abs_sum >= 2) rdoq_sign_hiding(s, s.blk, lambda, p.bitdepth, qp_scaled, scan_idx, log2n, best_last_p1, coef, q);
   }
 }
 
