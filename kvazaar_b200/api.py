@@ -85,9 +85,10 @@ def launch_count():
 
 
 # ------------------------------------------------------------------ picture group
-def _nxn(fn, n, a, b, count):
+def _nxn(fn, n, a, b, count, out=None):
     torch = _torch()
-    out = torch.empty(count, dtype=torch.int32, device=a.device)
+    if out is None:
+        out = torch.empty(count, dtype=torch.int32, device=a.device)
     _ck(fn(n, _bits(a), _p(a), _p(b), count, _p(out), _stream()))
     return out
 
@@ -96,8 +97,8 @@ def sad_nxn_batch(n, a, b, count):
     return _nxn(lib().kvz_cuda_sad_nxn_batch, n, a, b, count)
 
 
-def satd_nxn_batch(n, a, b, count):
-    return _nxn(lib().kvz_cuda_satd_nxn_batch, n, a, b, count)
+def satd_nxn_batch(n, a, b, count, out=None):
+    return _nxn(lib().kvz_cuda_satd_nxn_batch, n, a, b, count, out)
 
 
 def cost_nxn_multi_batch(use_satd, n, preds, block_pitch, mode_pitch, num_modes, orig, count):
