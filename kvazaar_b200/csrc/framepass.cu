@@ -27,6 +27,8 @@ namespace kvzc {
 
 int rough_search_u8(int log2w, const uint8_t *src, const uint8_t *rec, int stride, int pic_w, int pic_h, uint32_t *costs,
                     int8_t *best_mode, uint32_t *best_cost, cudaStream_t st);
+int rough_search_u16(int log2w, const uint16_t *src, const uint16_t *rec, int stride, int pic_w, int pic_h, uint32_t *costs,
+                     int8_t *best_mode, uint32_t *best_cost, cudaStream_t st);
 
 // kvz_intra_recon_cu for a tile of 1024 samples (G = 1024 / W^2 TUs of one colour plane) per 256-thread CTA:
 // references -> prediction of the chosen mode -> residual -> DCT/DST -> quant (+ sign hiding) -> dequant -> inverse
@@ -733,12 +735,14 @@ static int fp_run_dev_t(kvz_cuda_frame_pass *fp, const void *src_dev, const void
     if constexpr (BD == 8) {
       // rough search with the mode selection fused in; the 35-entry cost tables stay on chip
       if (int r = rough_search_u8(log2w, src, rin, W, W, H, nullptr, modes, (uint32_t *)(B + L.cost_y[d]), st)) return r;
-    } else {
-      // 16-bit samples: the straightforward rough-search kernel (intra.cu) + argmin
+    } else if (getenv("KVZ_CUDA_ROUGH_V1")) {
+      // A/B switch: the straightforward per-pixel rough-search kernel (intra.cu) + argmin
       uint32_t *costs = (uint32_t *)(B + fp->off_costs35[d]);
       if (int r = kvz_cuda_intra_rough_search_frame(log2w, BD, src, rin, W, W, H, costs, st)) return r;
       rough_argmin_kernel<<<(nb + 255) / 256, 256, 0, st>>>(costs, nb, modes, (uint32_t *)(B + L.cost_y[d]));
       KVZC_LAUNCHED();
+    } else {
+      if (int r = rough_search_u16(log2w, src, rin, W, W, H, nullptr, modes, (uint32_t *)(B + L.cost_y[d]), st)) return r;
     }
     fp_mark(fp, s0 + 1, st);
     // luma: prediction -> transform -> quantisation -> reconstruction; with RDOQ the fused kernel is split around the

@@ -171,6 +171,8 @@ using namespace kvzc;
 namespace kvzc {
 int rough_search_u8(int log2w, const uint8_t *src, const uint8_t *rec, int stride, int pic_w, int pic_h, uint32_t *costs,
                     int8_t *best_mode, uint32_t *best_cost, cudaStream_t st);
+int rough_search_u16(int log2w, const uint16_t *src, const uint16_t *rec, int stride, int pic_w, int pic_h, uint32_t *costs,
+                     int8_t *best_mode, uint32_t *best_cost, cudaStream_t st);
 }
 
 template <class T>
@@ -230,9 +232,11 @@ int kvz_cuda_intra_rough_search_frame(int log2_width, int bitdepth, const void *
 {
   KVZC_REQUIRE_DEVICE();
   KVZC_ARG(src_plane && rec_plane && costs && log2_width >= 2 && log2_width <= 5 && pic_w % 8 == 0 && pic_h % 8 == 0);
+  // tuned kernel (rough_search.cu); KVZ_CUDA_ROUGH_V1=1 selects the straightforward one for A/B checks
+  static const bool v1 = getenv("KVZ_CUDA_ROUGH_V1") != nullptr;
+  if (bitdepth != 8 && !v1)
+    return rough_search_u16(log2_width, (const uint16_t *)src_plane, (const uint16_t *)rec_plane, stride, pic_w, pic_h, costs, nullptr, nullptr, as_stream(stream));
   if (bitdepth == 8) {
-    // tuned 8-bit kernel (rough_search.cu); KVZ_CUDA_ROUGH_V1=1 selects the straightforward one for A/B checks
-    static const bool v1 = getenv("KVZ_CUDA_ROUGH_V1") != nullptr;
     if (!v1) return rough_search_u8(log2_width, (const uint8_t *)src_plane, (const uint8_t *)rec_plane, stride, pic_w, pic_h, costs, nullptr, nullptr, as_stream(stream));
     return launch_rough<uint8_t>(log2_width, (const uint8_t *)src_plane, (const uint8_t *)rec_plane, stride, pic_w, pic_h, costs, as_stream(stream));
   }

@@ -1,4 +1,4 @@
-// rough_search.cu -- fused frame-level rough intra search for 8-bit pixels (the dominant kernel of the frame pass).
+// rough_search.cu -- fused frame-level rough intra search (the dominant kernel of the frame pass), 8- and 10-bit samples.
 //
 // Per W x W luma block: reference samples (kvz_intra_build_reference over the reconstruction plane) -> [1 2 1]
 // smoothing -> all 35 kvz_intra_predict modes -> satd_WxW against the source.  (search_intra_rough's inner loop,
@@ -14,7 +14,11 @@
 //     (the source block and its transpose are packed once and reused for all modes);
 //   * horizontal modes (2..17) are evaluated in the transposed domain against the transposed source: SATD is
 //     invariant under transposition, so the reference's final transpose pass disappears;
-//   * df == 0 needs no branch: ((32-0)*a + 0*b + 16) >> 5 == a.
+//   * df == 0 needs no branch: ((32-0)*a + 0*b + 16) >> 5 == a;
+//   * 16-bit samples (10-bit video) take the same walk: a 32-bit word already holds two samples, the (c, c+2) lane
+//     pairs come from PRMT over neighbouring words, two interpolations per IMAD pair still fit (32 * 1023 + 16 < 2^16),
+//     and the packed Hadamard stays exact: five butterfly stages of |d| <= 1023 reach 32736 < 2^15, the sixth is the
+//     2 * max(|lo|, |hi|) fold.
 // HBM traffic per block: W*W source + (4W+1) reference samples in, 35 costs out.
 #include "common.cuh"
 #include "intra.cuh"
@@ -22,13 +26,15 @@
 
 namespace kvzc {
 
+template <class T>
 __device__ __forceinline__ uint32_t interp2(uint32_t a, uint32_t b, uint32_t f0, uint32_t f1)
 {
-  return ((a * f0 + b * f1 + 0x00100010u) >> 5) & 0x00ff00ffu;     // two samples: ((32-f)*a + f*b + 16) >> 5
+  constexpr uint32_t MASK = ((1u << PixTraits<T>::kBits) - 1u) * 0x00010001u;
+  return ((a * f0 + b * f1 + 0x00100010u) >> 5) & MASK;           // two samples: ((32-f)*a + f*b + 16) >> 5
 }
 
-template <int LOG2W>
-__global__ void __launch_bounds__(128) rough_search_u8_kernel(const uint8_t *__restrict__ src, const uint8_t *__restrict__ rec,
+template <class T, int LOG2W>
+__global__ void __launch_bounds__(128) rough_search_u8_kernel(const T *__restrict__ src, const T *__restrict__ rec,
                                                               int stride, int pic_w, int pic_h, int blocks_x, int nblk,
                                                               uint32_t *__restrict__ costs, int8_t *__restrict__ best_mode,
                                                               uint32_t *__restrict__ best_cost)
@@ -41,9 +47,11 @@ __global__ void __launch_bounds__(128) rough_search_u8_kernel(const uint8_t *__r
   constexpr int ES = W == 4 ? 20 : ((EN + 3) / 4) * 4;           // 20, 28, 52, 100 bytes: odd word stride
   constexpr int R = W >= 8 ? 8 : 4;                              // rows / cols of a lane's sub-block
   constexpr int K = R / 2;                                       // packed lane registers per row
-  __shared__ __align__(16) uint8_t s_ref[GROUP][4][RS];          // top, left, smoothed top, smoothed left
-  __shared__ __align__(16) uint8_t s_plain[GROUP][4][ES];        // same, shifted so that index j = idx + W
-  __shared__ __align__(16) uint8_t s_ext[4][GROUP][ES];          // per-warp scratch: main ref with projected side part
+  constexpr bool WIDE = sizeof(T) == 2;                          // 16-bit samples
+  constexpr int PIXMAX = (1 << PixTraits<T>::kBits) - 1;
+  __shared__ __align__(16) T s_ref[GROUP][4][RS];                // top, left, smoothed top, smoothed left
+  __shared__ __align__(16) T s_plain[GROUP][4][ES];              // same, shifted so that index j = idx + W
+  __shared__ __align__(16) T s_ext[4][GROUP][ES];                // per-warp scratch: main ref with projected side part
   __shared__ int s_dc[GROUP];
   __shared__ BuildRefCtx s_ctx[GROUP];
   __shared__ uint32_t s_cost[GROUP][36];                         // per-block cost table for the fused mode selection
@@ -65,14 +73,14 @@ __global__ void __launch_bounds__(128) rough_search_u8_kernel(const uint8_t *__r
     const int gb = e / (2 * N), r = e - gb * 2 * N;
     const bool is_top = r < N;
     const int k = is_top ? r : r - N;
-    s_ref[gb][is_top ? 0 : 1][k] = (uint8_t)build_ref_entry(s_ctx[gb], rec, stride, is_top, k);
+    s_ref[gb][is_top ? 0 : 1][k] = (T)build_ref_entry(s_ctx[gb], rec, stride, is_top, k);
   }
   __syncthreads();
   for (int e = threadIdx.x; e < GROUP * 2 * N; e += 128) {
     const int gb = e / (2 * N), r = e - gb * 2 * N;
     const bool is_top = r < N;
     const int k = is_top ? r : r - N;
-    s_ref[gb][is_top ? 2 : 3][k] = (uint8_t)filter_ref_entry(s_ref[gb][0], s_ref[gb][1], is_top, k, N);
+    s_ref[gb][is_top ? 2 : 3][k] = (T)filter_ref_entry(s_ref[gb][0], s_ref[gb][1], is_top, k, N);
   }
   if (threadIdx.x < GROUP) s_dc[threadIdx.x] = dc_value(LOG2W, s_ref[threadIdx.x][0], s_ref[threadIdx.x][1]);
   __syncthreads();
@@ -85,10 +93,42 @@ __global__ void __launch_bounds__(128) rough_search_u8_kernel(const uint8_t *__r
 
   // ---- source lanes of this lane's sub-block: SA (as is) and ST (transposed), packed (c, c+2) pairs
   uint32_t SA[R][K], ST[R][K];
-  {
+  if constexpr (WIDE) {
+    // 16-bit samples: row r = R / 2 words of two samples each
+    uint32_t rows[R][R / 2];
+    const int bx = valid ? blk % blocks_x : 0, by = valid ? blk / blocks_x : 0;
+    const T *p = src + (long)(by * W + sy * R) * stride + bx * W + sx * R;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if constexpr (R == 8) {
+        const uint4 v = valid ? __ldg(reinterpret_cast<const uint4 *>(p + (long)r * stride)) : make_uint4(0, 0, 0, 0);
+        rows[r][0] = v.x; rows[r][1] = v.y; rows[r][2] = v.z; rows[r][3] = v.w;
+      } else {
+        const uint2 v = valid ? __ldg(reinterpret_cast<const uint2 *>(p + (long)r * stride)) : make_uint2(0, 0);
+        rows[r][0] = v.x; rows[r][1] = v.y;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int h = 0; h < R / 4; ++h) {                            // samples 4h .. 4h+3 of the row
+        SA[r][2 * h] = prmt(rows[r][2 * h], rows[r][2 * h + 1], 0x5410);          // (4h, 4h+2)
+        SA[r][2 * h + 1] = prmt(rows[r][2 * h], rows[r][2 * h + 1], 0x7632);      // (4h+1, 4h+3)
+      }
+    // transposed: ST[r] = column r: pairs (A[c][r], A[c+2][r]) for c = 0, 1, 4, 5
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const uint32_t sel = (r & 1) ? 0x7632u : 0x5410u;
+#pragma unroll
+      for (int q = 0; q < R / 4; ++q) {
+        ST[r][2 * q] = prmt(rows[4 * q + 0][r >> 1], rows[4 * q + 2][r >> 1], sel);
+        ST[r][2 * q + 1] = prmt(rows[4 * q + 1][r >> 1], rows[4 * q + 3][r >> 1], sel);
+      }
+    }
+  } else {
     uint32_t rows[R][K / 2 + (K < 2 ? 1 : 0)];                   // raw bytes: R rows of R bytes
     const int bx = valid ? blk % blocks_x : 0, by = valid ? blk / blocks_x : 0;
-    const uint8_t *p = src + (long)(by * W + sy * R) * stride + bx * W + sx * R;
+    const uint8_t *p = reinterpret_cast<const uint8_t *>(src) + (long)(by * W + sy * R) * stride + bx * W + sx * R;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       if constexpr (R == 8) {
@@ -124,7 +164,7 @@ __global__ void __launch_bounds__(128) rough_search_u8_kernel(const uint8_t *__r
     int d[R][K];
     if (m < 2) {
       // planar / DC: closed forms per sample (2 of 35 modes)
-      const uint8_t *top = s_ref[g][m == 0 && LOG2W > 2 ? 2 : 0], *left = s_ref[g][m == 0 && LOG2W > 2 ? 3 : 1];
+      const T *top = s_ref[g][m == 0 && LOG2W > 2 ? 2 : 0], *left = s_ref[g][m == 0 && LOG2W > 2 ? 3 : 1];
       const int dc = s_dc[g];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -151,7 +191,7 @@ __global__ void __launch_bounds__(128) rough_search_u8_kernel(const uint8_t *__r
       const int sdisp = mdisp < 0 ? -intra_sample_disp(adisp) : intra_sample_disp(adisp);
       const int filt = intra_uses_filtered(LOG2W, m, 0) ? 2 : 0;
       const int main_sel = (vertical ? 0 : 1) + filt, side_sel = (vertical ? 1 : 0) + filt;
-      const uint8_t *ext = s_plain[g][main_sel];
+      const T *ext = s_plain[g][main_sel];
       if (sdisp < 0) {
         // main reference extended to negative indices by projecting the side reference (ref: intra-generic.c:88-108)
         const int inv = intra_inv_disp(adisp);
@@ -166,32 +206,52 @@ __global__ void __launch_bounds__(128) rough_search_u8_kernel(const uint8_t *__r
       // sub-block position in the orientation being computed (transposed for horizontal modes)
       const int ex = vertical ? sx : sy, ey = vertical ? sy : sx;
       const bool edge = LOG2W < 5 && (m == 10 || m == 26) && ex == 0;         // ref: intra.c:293-300
-      const uint8_t *side_unf = s_ref[g][vertical ? 1 : 0];
+      const T *side_unf = s_ref[g][vertical ? 1 : 0];
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int pos = (ey * R + r + 1) * sdisp;
         const int di = pos >> 5;
         const uint32_t f1 = (uint32_t)(pos & 31), f0 = 32u - f1;
         const int j0 = ex * R + di + W;
-        const uint32_t *wp = reinterpret_cast<const uint32_t *>(ext + (j0 & ~3));
-        const uint32_t sh = (uint32_t)(j0 & 3) * 8;
         uint32_t P[K];
+        if constexpr (WIDE) {
+          // words of two samples; an odd start index is a 16-bit funnel shift
+          const uint32_t *wp = reinterpret_cast<const uint32_t *>(ext + (j0 & ~1));
+          const uint32_t sh = (uint32_t)(j0 & 1) * 16;
+          if constexpr (R == 8) {
+            const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = wp[3], a4 = wp[4], a5 = sh ? wp[5] : 0u;
+            const uint32_t w0 = __funnelshift_r(a0, a1, sh), w1 = __funnelshift_r(a1, a2, sh), w2 = __funnelshift_r(a2, a3, sh),
+                           w3 = __funnelshift_r(a3, a4, sh), w4 = __funnelshift_r(a4, a5, sh);
+            const uint32_t L0 = prmt(w0, w1, 0x5410), L1 = prmt(w0, w1, 0x7632), L2 = prmt(w1, w2, 0x5410);
+            const uint32_t L4 = prmt(w2, w3, 0x5410), L5 = prmt(w2, w3, 0x7632), L6 = prmt(w3, w4, 0x5410);
+            P[0] = interp2<T>(L0, L1, f0, f1); P[1] = interp2<T>(L1, L2, f0, f1);
+            P[2] = interp2<T>(L4, L5, f0, f1); P[3] = interp2<T>(L5, L6, f0, f1);
+          } else {
+            const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2], a3 = sh ? wp[3] : 0u;
+            const uint32_t w0 = __funnelshift_r(a0, a1, sh), w1 = __funnelshift_r(a1, a2, sh), w2 = __funnelshift_r(a2, a3, sh);
+            const uint32_t L0 = prmt(w0, w1, 0x5410), L1 = prmt(w0, w1, 0x7632), L2 = prmt(w1, w2, 0x5410);
+            P[0] = interp2<T>(L0, L1, f0, f1); P[1] = interp2<T>(L1, L2, f0, f1);
+          }
+        } else {
+        const uint32_t *wp = reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(ext) + (j0 & ~3));
+        const uint32_t sh = (uint32_t)(j0 & 3) * 8;
         if constexpr (R == 8) {
           const uint32_t a0 = wp[0], a1 = wp[1], a2 = wp[2];
           const uint32_t w0 = __funnelshift_r(a0, a1, sh), w1 = __funnelshift_r(a1, a2, sh), w2 = a2 >> sh;
           const uint32_t L0 = prmt(w0, 0u, 0x4240), L1 = prmt(w0, 0u, 0x4341), L4 = prmt(w1, 0u, 0x4240), L5 = prmt(w1, 0u, 0x4341);
           const uint32_t L2 = prmt(L0, L4, 0x5432), L6 = prmt(L4, w2, 0x1432);
-          P[0] = interp2(L0, L1, f0, f1); P[1] = interp2(L1, L2, f0, f1);
-          P[2] = interp2(L4, L5, f0, f1); P[3] = interp2(L5, L6, f0, f1);
+          P[0] = interp2<T>(L0, L1, f0, f1); P[1] = interp2<T>(L1, L2, f0, f1);
+          P[2] = interp2<T>(L4, L5, f0, f1); P[3] = interp2<T>(L5, L6, f0, f1);
         } else {
           const uint32_t a0 = wp[0], a1 = wp[1];
           const uint32_t w0 = __funnelshift_r(a0, a1, sh), w1 = a1 >> sh;
           const uint32_t L0 = prmt(w0, 0u, 0x4240), L1 = prmt(w0, 0u, 0x4341), L2 = prmt(L0, w1, 0x1432);
-          P[0] = interp2(L0, L1, f0, f1); P[1] = interp2(L1, L2, f0, f1);
+          P[0] = interp2<T>(L0, L1, f0, f1); P[1] = interp2<T>(L1, L2, f0, f1);
+        }
         }
         if (edge) {   // first column: + (side[y+1] - side[0]) >> 1, clipped (only modes 10 / 26, displacement 0)
-          const int v = clip3(0, 255, (int)(P[0] & 0xff) + (((int)side_unf[ey * R + r + 1] - (int)side_unf[0]) >> 1));
-          P[0] = (P[0] & 0x00ff0000u) | (uint32_t)v;
+          const int v = clip3(0, PIXMAX, (int)(P[0] & 0xffffu) + (((int)side_unf[ey * R + r + 1] - (int)side_unf[0]) >> 1));
+          P[0] = (P[0] & 0xffff0000u) | (uint32_t)v;
         }
 #pragma unroll
         for (int k = 0; k < K; ++k) d[r][k] = (int)(vertical ? SA[r][k] : ST[r][k]) - (int)P[k];
@@ -202,7 +262,7 @@ __global__ void __launch_bounds__(128) rough_search_u8_kernel(const uint8_t *__r
     else cost = (hadamard4x4_lanes(d) + 1) >> 1;
 #pragma unroll
     for (int o = SUBS / 2; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
-    if (sub == 0) s_cost[g][m] = cost;
+    if (sub == 0) s_cost[g][m] = W >= 8 ? cost >> (PixTraits<T>::kBits - 8) : cost;   // satd_NxN shifts by the extra bit depth, satd_4x4 does not
   }
   __syncthreads();
   // ---- the 35 costs of every block (optional) and the fused selection: first minimum (search order of the pass)
@@ -220,14 +280,14 @@ __global__ void __launch_bounds__(128) rough_search_u8_kernel(const uint8_t *__r
   }
 }
 
-template <int LOG2W>
-static int launch(const uint8_t *src, const uint8_t *rec, int stride, int pic_w, int pic_h, uint32_t *costs, int8_t *best_mode,
+template <class T, int LOG2W>
+static int launch(const T *src, const T *rec, int stride, int pic_w, int pic_h, uint32_t *costs, int8_t *best_mode,
                   uint32_t *best_cost, cudaStream_t st)
 {
   constexpr int W = 1 << LOG2W, SUBS = W >= 8 ? (W / 8) * (W / 8) : 1, GROUP = 32 / SUBS;
   const int bx = pic_w / W, nblk = bx * (pic_h / W);
   if (nblk == 0) return 0;
-  rough_search_u8_kernel<LOG2W><<<(nblk + GROUP - 1) / GROUP, 128, 0, st>>>(src, rec, stride, pic_w, pic_h, bx, nblk, costs, best_mode, best_cost);
+  rough_search_u8_kernel<T, LOG2W><<<(nblk + GROUP - 1) / GROUP, 128, 0, st>>>(src, rec, stride, pic_w, pic_h, bx, nblk, costs, best_mode, best_cost);
   KVZC_LAUNCHED();
   return 0;
 }
@@ -237,10 +297,22 @@ int rough_search_u8(int log2w, const uint8_t *src, const uint8_t *rec, int strid
                     int8_t *best_mode, uint32_t *best_cost, cudaStream_t st)
 {
   switch (log2w) {
-    case 2: return launch<2>(src, rec, stride, pic_w, pic_h, costs, best_mode, best_cost, st);
-    case 3: return launch<3>(src, rec, stride, pic_w, pic_h, costs, best_mode, best_cost, st);
-    case 4: return launch<4>(src, rec, stride, pic_w, pic_h, costs, best_mode, best_cost, st);
-    default: return launch<5>(src, rec, stride, pic_w, pic_h, costs, best_mode, best_cost, st);
+    case 2: return launch<uint8_t, 2>(src, rec, stride, pic_w, pic_h, costs, best_mode, best_cost, st);
+    case 3: return launch<uint8_t, 3>(src, rec, stride, pic_w, pic_h, costs, best_mode, best_cost, st);
+    case 4: return launch<uint8_t, 4>(src, rec, stride, pic_w, pic_h, costs, best_mode, best_cost, st);
+    default: return launch<uint8_t, 5>(src, rec, stride, pic_w, pic_h, costs, best_mode, best_cost, st);
+  }
+}
+
+// the same for 16-bit samples (10-bit video)
+int rough_search_u16(int log2w, const uint16_t *src, const uint16_t *rec, int stride, int pic_w, int pic_h, uint32_t *costs,
+                     int8_t *best_mode, uint32_t *best_cost, cudaStream_t st)
+{
+  switch (log2w) {
+    case 2: return launch<uint16_t, 2>(src, rec, stride, pic_w, pic_h, costs, best_mode, best_cost, st);
+    case 3: return launch<uint16_t, 3>(src, rec, stride, pic_w, pic_h, costs, best_mode, best_cost, st);
+    case 4: return launch<uint16_t, 4>(src, rec, stride, pic_w, pic_h, costs, best_mode, best_cost, st);
+    default: return launch<uint16_t, 5>(src, rec, stride, pic_w, pic_h, costs, best_mode, best_cost, st);
   }
 }
 
