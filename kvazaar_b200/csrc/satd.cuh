@@ -7,7 +7,9 @@
 //    carried per 32-bit register as  lo + hi*65536  ("arithmetic packing": plain IADD/ISUB act lane-wise,
 //    no carries leak because each lane stays inside int16).  The last butterfly stage is folded into the
 //    absolute sum with |x+y| + |x-y| = 2*max(|x|,|y|).
-//  * 10-bit pixels do not fit (1023*64 > 32767): plain int32 path.
+//  * 10-bit pixels: a full 8x8 coefficient does not fit (1023*64 > 32767), but the packed path only materialises five of
+//    the six butterfly stages (1023*32 = 32736 fits) -- the fused rough search uses it for 16-bit samples too; the
+//    batched satd_nxn kernels for 16-bit pixels still take the plain int32 path.
 #pragma once
 #include "common.cuh"
 
