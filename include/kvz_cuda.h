@@ -243,8 +243,9 @@ int kvz_cuda_array_checksum(int bitdepth, const void *data, int height, int widt
 /* ------------------------------------------------------------------ frame-level pass (framepass.cu) */
 /* Every strategy kernel of an all-intra frame, batched over all CTUs and all four quadtree depths
  * (luma block width 32,16,8,4 = depth index 0..3; chroma width/2 for depth 0..2): rough search of 35 modes ->
- * best mode -> prediction + quantize_residual reconstruction + SSD, then SAO statistics/decision/reconstruction
- * on the 8x8-level reconstruction and the picture checksum.  I420 frames, 8-bit. */
+ * best mode -> prediction + quantize_residual reconstruction (kvz_quant or kvz_rdoq; optional transform-skip choice
+ * for 4x4 luma) + SSD + CABAC bit cost of the levels, then deblocking, SAO statistics/decision/reconstruction on the
+ * 8x8-level reconstruction and the picture checksum.  Planar I420 frames, bitdepth 8 (uint8 samples) or 10 (uint16). */
 typedef struct {
   int32_t width, height, bitdepth, qp, signhide;
   int32_t rdoq;      /* cfg.rdoq_enable: quantise with kvz_rdoq (slice-initial context models) instead of kvz_quant */
