@@ -268,39 +268,50 @@ __global__ void __launch_bounds__(256) sao_ctu_kernel(SaoPlanesT<T> pl, int nctu
   if (i == 0 && threadIdx.x < 6) cksum_scratch[threadIdx.x] = 0;
   for (int t = threadIdx.x; t < 48; t += blockDim.x) { if (t < 40) (&s_acc[0][0][0])[t] = 0; else (&s_band[0][0])[t - 40] = 0; }
   __syncthreads();
-  int sum[4][5], cnt[4][5], bs[4], bc[4];
+  // Per-thread accumulators are packed (a thread sees at most 16 samples of the CTU): counts in 6-bit fields, sums of
+  // the (rounded) differences as arithmetic 16-bit lane pairs (|sum| <= 16 * 256) -- 19 registers instead of 48, which
+  // doubles the number of resident CTAs.
+  uint32_t cntp[4] = { 0, 0, 0, 0 }, bcp = 0;
+  int sump[4][3], bsp[2] = { 0, 0 };
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    bs[e] = 0; bc[e] = 0;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) { sum[e][k] = 0; cnt[e][k] = 0; }
-  }
+  for (int e = 0; e < 4; ++e) { sump[e][0] = 0; sump[e][1] = 0; sump[e][2] = 0; }
   for (int t = threadIdx.x; t < bw * bh; t += blockDim.x) {
     const int y = t / bw, x = t - y * bw;
     const int c = rec[(long)y * Wp + x];
     const int diff = (int)orig[(long)y * Wp + x] - c;
     const int diffr = BD > 8 ? (diff + (1 << (BD > 8 ? BD - 9 : 0))) >> (BD - 8) : diff;
     const int band = (c >> (BD - 5)) - bp;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { const int hit = band == k; bs[k] += hit ? diff : 0; bc[k] += hit; }
+    if (band >= 0 && band < 4) {
+      bcp += 1u << (6 * band);
+      const int v = diff * ((band & 1) ? 65536 : 1);
+      bsp[0] += band < 2 ? v : 0;
+      bsp[1] += band >= 2 ? v : 0;
+    }
     if (x >= 1 && y >= 1 && x < bw - 1 && y < bh - 1) {        // the strategies only see the block: no outside neighbours
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         int ax, ay;
         fp_eo_offsets(e, ax, ay);
         const int cat = fp_eo_cat(rec[(long)(y + ay) * Wp + x + ax], rec[(long)(y - ay) * Wp + x - ax], c);
-#pragma unroll
-        for (int k = 0; k < 5; ++k) { const int hit = cat == k; sum[e][k] += hit ? diffr : 0; cnt[e][k] += hit; }
+        cntp[e] += 1u << (6 * cat);
+        const int v = diffr * ((cat & 1) ? 65536 : 1);
+        sump[e][0] += cat < 2 ? v : 0;
+        sump[e][1] += (cat >> 1) == 1 ? v : 0;
+        sump[e][2] += cat == 4 ? diffr : 0;
       }
     }
   }
+  auto lane_lo = [](int x) { return (int)(short)x; };
+  auto lane_hi = [](int x) { return (x - (int)(short)x) >> 16; };
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    const int b1 = warp_sum(bs[e]), b2 = warp_sum(bc[e]);
+    const int bsum = (e & 1) ? lane_hi(bsp[e >> 1]) : lane_lo(bsp[e >> 1]);
+    const int b1 = warp_sum(bsum), b2 = warp_sum((int)((bcp >> (6 * e)) & 63));
     if ((threadIdx.x & 31) == 0) { atomicAdd(&s_band[0][e], b1); atomicAdd(&s_band[1][e], b2); }
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
-      const int v1 = warp_sum(sum[e][k]), v2 = warp_sum(cnt[e][k]);
+      const int sk = k == 4 ? sump[e][2] : ((k & 1) ? lane_hi(sump[e][k >> 1]) : lane_lo(sump[e][k >> 1]));
+      const int v1 = warp_sum(sk), v2 = warp_sum((int)((cntp[e] >> (6 * k)) & 63));
       if ((threadIdx.x & 31) == 0) { atomicAdd(&s_acc[e][0][k], v1); atomicAdd(&s_acc[e][1][k], v2); }
     }
   }
