@@ -8,8 +8,8 @@
 //    no carries leak because each lane stays inside int16).  The last butterfly stage is folded into the
 //    absolute sum with |x+y| + |x-y| = 2*max(|x|,|y|).
 //  * 10-bit pixels: a full 8x8 coefficient does not fit (1023*64 > 32767), but the packed path only materialises five of
-//    the six butterfly stages (1023*32 = 32736 fits) -- the fused rough search uses it for 16-bit samples too; the
-//    batched satd_nxn kernels for 16-bit pixels still take the plain int32 path.
+//    the six butterfly stages (1023*32 = 32736 fits) -- the fused rough search and the 16-bit strided sub-block SATD
+//    (satd_sub_strided<uint16_t, N>) use it; inputs must be <= 10-bit samples.
 #pragma once
 #include "common.cuh"
 
@@ -139,6 +139,34 @@ template <class T, int N> __device__ __forceinline__ uint32_t satd_sub_strided(c
     for (int x = 0; x < N; ++x) d[y][x] = (int)a[y * sa + x] - (int)b[y * sb + x];
   const uint32_t s = hadamard_abs_sum_i32<N>(d);
   return N == 4 ? (s + 1) >> 1 : (s + 2) >> 2;
+}
+
+// 16-bit samples of up to 10 significant bits: the packed path is exact too (five materialised butterfly stages of
+// |d| <= 1023 stay below 2^15, see the notes on top), with (c, c+2) lanes assembled from element loads
+__device__ __forceinline__ uint32_t pair16(const uint16_t *p, int i) { return (uint32_t)p[i] | ((uint32_t)p[i + 2] << 16); }
+template <> __device__ __forceinline__ uint32_t satd_sub_strided<uint16_t, 8>(const uint16_t *a, int sa, const uint16_t *b, int sb)
+{
+  int d[8][4];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const uint16_t *pa = a + r * sa, *pb = b + r * sb;
+    d[r][0] = (int)pair16(pa, 0) - (int)pair16(pb, 0);
+    d[r][1] = (int)pair16(pa, 1) - (int)pair16(pb, 1);
+    d[r][2] = (int)pair16(pa, 4) - (int)pair16(pb, 4);
+    d[r][3] = (int)pair16(pa, 5) - (int)pair16(pb, 5);
+  }
+  return (hadamard8x8_lanes(d) + 2) >> 2;
+}
+template <> __device__ __forceinline__ uint32_t satd_sub_strided<uint16_t, 4>(const uint16_t *a, int sa, const uint16_t *b, int sb)
+{
+  int d[4][2];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const uint16_t *pa = a + r * sa, *pb = b + r * sb;
+    d[r][0] = (int)pair16(pa, 0) - (int)pair16(pb, 0);
+    d[r][1] = (int)pair16(pa, 1) - (int)pair16(pb, 1);
+  }
+  return (hadamard4x4_lanes(d) + 1) >> 1;
 }
 
 // 8-bit strided 8x8 via packed path with unaligned-safe row loads
