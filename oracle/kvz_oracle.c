@@ -1565,3 +1565,41 @@ void orc_rdoq(const orc_rdoq_params *pp, const uint8_t *cabac, const int16_t *co
   }
 }
 #undef level_double
+
+/* ======================================================================================================
+ * Intra mode signalling cost (groundwork for SURVEY §8f rank 2, the CTU search driver): most-probable-mode
+ * derivation (kvz_intra_get_dir_luma_predictor, src/intra.c:84-127) and the bit estimates the rough search adds to
+ * the SATD (kvz_luma_mode_bits / kvz_chroma_mode_bits, src/search_intra.c:641-698) in counting mode without
+ * context adaptation.  Pinned by tests/test_rdoq.py::test_oracle_mode_bits_vs_reference.
+ * ====================================================================================================== */
+/* left / above: intra mode of the neighbouring PU, or -1 when it does not exist or is not intra; above is ignored on
+ * the first row of a CTU (y % 64 == 0) */
+void orc_intra_mpm(int left_mode, int above_mode, int y, int8_t preds[3])
+{
+  const int l = left_mode >= 0 ? left_mode : 1;                       /* DC when unavailable */
+  const int a = (above_mode >= 0 && (y % 64) != 0) ? above_mode : 1;
+  if (l == a) {
+    if (l > 1) { preds[0] = (int8_t)l; preds[1] = (int8_t)(((l + 29) % 32) + 2); preds[2] = (int8_t)(((l - 1) % 32) + 2); }
+    else { preds[0] = 0; preds[1] = 1; preds[2] = 26; }
+  } else {
+    preds[0] = (int8_t)l; preds[1] = (int8_t)a;
+    preds[2] = (l && a) ? 0 : ((l + a) < 2 ? 26 : 1);
+  }
+}
+/* cabac: image of cabac_data_t.ctx; intra_mode_model is byte 5, chroma_pred_model[0] byte 6 (src/cabac.h:67-75) */
+double orc_luma_mode_bits(const uint8_t *cabac, int luma_mode, const int8_t preds[3])
+{
+  int in_preds = 0;
+  for (int i = 0; i < 3; ++i) if (luma_mode == preds[i]) in_preds = 1;
+  double bits = 0;
+  bits += (double)ebits(cabac[5], in_preds) * (1.0 / 32768.0);      /* kvz_f_entropy_bits = kvz_entropy_bits / 2^15 */
+  bits += in_preds ? (luma_mode == preds[0] ? 1 : 2) : 5;
+  return bits;
+}
+double orc_chroma_mode_bits(const uint8_t *cabac, int chroma_mode, int luma_mode)
+{
+  double bits = 0;
+  bits += (double)ebits(cabac[6], chroma_mode != luma_mode) * (1.0 / 32768.0);
+  if (chroma_mode != luma_mode) bits += 2.0;
+  return bits;
+}

@@ -147,6 +147,11 @@ typedef struct { double lambda; int32_t qp, bitdepth, signhide_enable, pad; } or
 void orc_rdoq(const orc_rdoq_params *p, const uint8_t *cabac, const int16_t *coef, int16_t *q, int width, int type, int scan_idx,
               int block_type, int tr_depth);
 
+/* ---- intra mode signalling cost (intra.c:84-127, search_intra.c:641-698) ---- */
+void orc_intra_mpm(int left_mode, int above_mode, int y, int8_t preds[3]);
+double orc_luma_mode_bits(const uint8_t *cabac, int luma_mode, const int8_t preds[3]);
+double orc_chroma_mode_bits(const uint8_t *cabac, int chroma_mode, int luma_mode);
+
 /* ---- deblocking, frame level (filter.c:95-792) ---- */
 typedef struct {
   int32_t width, height;          /* luma size, multiples of 8 */

@@ -439,3 +439,28 @@ void kvzref_set_trskip(kvzref_ctx *c, int enable)
 {
   ((encoder_control_t *)c->enc->states[0].encoder_control)->cfg.trskip_enable = enable;
 }
+
+/* ---- intra mode signalling cost (not strategies): MPM derivation and the mode-bit estimates of the rough search ---- */
+#include "intra.h"
+#include "search_intra.h"
+void kvzref_intra_mpm(int left_mode, int above_mode, int y, int8_t *preds)
+{
+  cu_info_t left, above, cur; memset(&left, 0, sizeof(left)); memset(&above, 0, sizeof(above)); memset(&cur, 0, sizeof(cur));
+  left.type = CU_INTRA; left.intra.mode = (int8_t)left_mode;
+  above.type = CU_INTRA; above.intra.mode = (int8_t)above_mode;
+  kvz_intra_get_dir_luma_predictor(0, (uint32_t)y, preds, &cur, left_mode >= 0 ? &left : NULL, above_mode >= 0 ? &above : NULL);
+}
+double kvzref_luma_mode_bits(kvzref_ctx *c, const uint8_t *cabac_ctx, int luma_mode, const int8_t *preds)
+{
+  encoder_state_t *st = &c->enc->states[0];
+  memcpy(&st->search_cabac.ctx, cabac_ctx, sizeof(st->search_cabac.ctx));
+  st->search_cabac.only_count = 1; st->search_cabac.update = 0;
+  return kvz_luma_mode_bits(st, (int8_t)luma_mode, preds);
+}
+double kvzref_chroma_mode_bits(kvzref_ctx *c, const uint8_t *cabac_ctx, int chroma_mode, int luma_mode)
+{
+  encoder_state_t *st = &c->enc->states[0];
+  memcpy(&st->search_cabac.ctx, cabac_ctx, sizeof(st->search_cabac.ctx));
+  st->search_cabac.only_count = 1; st->search_cabac.update = 0;
+  return kvz_chroma_mode_bits(st, (int8_t)chroma_mode, (int8_t)luma_mode);
+}

@@ -129,6 +129,29 @@ def synth_levels(rng, n, count):
     return np.clip(lv, -32768, 32767).astype(np.int16)
 
 
+def test_oracle_mode_bits_vs_reference(ref, orc):
+    """MPM derivation and luma / chroma mode-bit estimates (groundwork for the CTU search driver row): oracle == reference."""
+    import ctypes as C
+    L, O = ref.lib, orc.lib
+    L.kvzref_luma_mode_bits.restype = L.kvzref_chroma_mode_bits.restype = C.c_double
+    O.orc_luma_mode_bits.restype = O.orc_chroma_mode_bits.restype = C.c_double
+    rng = np.random.default_rng(21)
+    ctx = ref.ctx(27)
+    for _ in range(400):
+        left, above, y = int(rng.integers(-1, 35)), int(rng.integers(-1, 35)), int(rng.choice([0, 8, 64, 72, 128]))
+        pw, pg = np.zeros(3, np.int8), np.zeros(3, np.int8)
+        L.kvzref_intra_mpm(left, above, y, C.c_void_p(pw.ctypes.data))
+        O.orc_intra_mpm(left, above, y, C.c_void_p(pg.ctypes.data))
+        assert np.array_equal(pw, pg), (left, above, y)
+        cabac = rng.integers(0, 126, ref.cabac_ctx_size()).astype(np.uint8)
+        mode, cmode = int(rng.integers(0, 35)), int(rng.choice([0, 1, 10, 26, 34, int(rng.integers(0, 35))]))
+        cb = np.ascontiguousarray(cabac)
+        want = L.kvzref_luma_mode_bits(ctx, C.c_void_p(cb.ctypes.data), mode, C.c_void_p(pw.ctypes.data))
+        got = O.orc_luma_mode_bits(C.c_void_p(cb.ctypes.data), mode, C.c_void_p(pg.ctypes.data))
+        assert want == got
+        assert L.kvzref_chroma_mode_bits(ctx, C.c_void_p(cb.ctypes.data), cmode, mode) == O.orc_chroma_mode_bits(C.c_void_p(cb.ctypes.data), cmode, mode)
+
+
 def test_python_coeff_cost_port_vs_reference(ref, orc):
     """oracle/coeff_cost_port.py (plain restatement of the bit count) == the compiled reference, on the CPU."""
     import importlib.util
