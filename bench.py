@@ -276,8 +276,10 @@ def run_cuda(args):
     ms_e2e = timed(step_host_compact, args.steps)
     e2e = world * fps_step * args.steps / (ms_e2e / 1000.0)
     nonzero_chunks = max(int(c.numpy()[:4].view(np.uint32)[0]) for c in compact_pin)
-    assert nonzero_chunks <= budget, f"compact budget too small: {nonzero_chunks} > {budget}"
     d2h_compact = int(lay0.coeff_begin) + int(lay0.compact_header_bytes) + 32 * budget
+    compact_ok = nonzero_chunks <= budget
+    if not compact_ok:            # denser content than the budget: the dense blob is the end-to-end result then
+        e2e, ms_e2e, d2h_compact = e2e_full, ms_e2e_full, passes[0].host_bytes
 
     # ---- live per-stage timing (CUDA events on the launching stream) -> roofline of the dominant kernel
     peak, peak_src = peaks()
@@ -387,7 +389,8 @@ def run_cuda(args):
                                  f"{passes[0].host_bytes / 1e6:.0f}+ MB each) exceeds the 126 MB L2"},
                 "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": fps_step * passes[0].frame_bytes,
                         "d2h_bytes_per_step": fps_step * d2h_compact, "ms_per_step": ms_e2e / args.steps,
-                        "result": "compact: blob head + bitmap + non-zero 32-byte coefficient chunks (lossless)",
+                        "result": "compact: blob head + bitmap + non-zero 32-byte coefficient chunks (lossless)" if compact_ok
+                                  else "dense blob (the compact chunk budget was exceeded)",
                         "nonzero_chunks_per_frame": nonzero_chunks, "chunk_budget": budget},
                 "e2e_full_blob": {"value": e2e_full, "unit": "frames/s", "d2h_bytes_per_step": fps_step * passes[0].host_bytes,
                                   "ms_per_step": ms_e2e_full / args.steps},
