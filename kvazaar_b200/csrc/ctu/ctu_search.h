@@ -1,0 +1,993 @@
+// ctu_search.h -- closed-loop intra search of one CTU, all-intra slices.
+//
+// Restates, for the execution model of ctu_common.h:
+//   search_cu / kvz_search_lcu                src/search.c:646-1068, 1209-1250   (explicit stack instead of recursion)
+//   kvz_search_cu_intra, search_intra_rough,
+//   search_intra_rdo, search_intra_trdepth,
+//   kvz_search_cu_intra_chroma                src/search_intra.c:178-900
+//   kvz_intra_recon_cu                        src/intra.c:561-698
+//   kvz_quantize_lcu_residual, _trskip        src/transform.c:225-509
+//   kvz_cu_rd_cost_luma / _chroma,
+//   cu_rd_cost_tr_split_accurate,
+//   calc_mode_bits                            src/search.c:253-582
+//   kvz_mock_encode_coding_unit               src/encode_coding_tree.c:977-1075
+// Scope: tr_depth_intra = 0, pu_depth_intra.min >= 1, rdo 0..3, no lossless, 8-bit 4:2:0.
+//
+// The mode decisions are the reference's: same candidate order, same double-precision cost expressions in the same
+// operation order (the build uses -fmad=false), same CABAC model adaptation.  What differs is how the work is laid
+// out: e.g. the rough search evaluates the SATD of all 35 modes in one data-parallel phase and then replays the
+// reference's halving search on the table.
+#pragma once
+#include "ctu_leaf.h"
+
+namespace kvzctu {
+
+#define CTU_MAX_INT 0x7FFFFFFF
+#define CTU_MAX_DOUBLE 1.7e+308
+
+struct SearchFrame {
+  int32_t x, y;
+  int32_t stage, child;
+  int32_t cbf, can_split, do_children;
+  int32_t pad;
+  double cost, split_cost;
+  CabacState pre, post;
+};
+
+struct CtuS {                       // per-CTA scalar state + scratch; shared memory on the device
+  CabacState cabac0;                // state->cabac: the real coder's models when the CTU starts (constant)
+  CabacState sc;                    // state->search_cabac
+  CabacState tmp;                   // temp_cabac of the combined-CU path (search.c:989)
+  SearchFrame fr[5];
+  double ret_cost;
+  IntraRefs refs[3];
+  int32_t satd[35], sad[35];
+  int8_t modes[40];
+  double costs[40];
+  int32_t n_modes;
+  int8_t mpm[4];
+  int8_t cmodes[8];                 // chroma candidates
+  double ccosts[8];
+  CuRec pred_cu;                    // the temporary CU of search_intra_rdo
+  int32_t ssd[4][3];                // [leaf][colour]
+  int32_t flag;
+  int32_t best_mode;
+  double best_cost;
+  // transform skip decision buffers (kvz_quantize_residual_trskip)
+  uint8_t ts_rec[2][16];
+  int16_t ts_coeff[2][16];
+  int32_t ts_has[2];
+  int32_t ts_ssd[2];
+  int32_t ts_pick;
+  TuBuf tu;
+  RdoqScratch rq;
+};
+
+struct Ctx {
+  const CtuTables *T;
+  const CtuConfig *cfg;
+  CtuWork *W;
+  CtuS *S;
+};
+
+// ------------------------------------------------------------------------------------------------ MPM, mode bits
+// kvz_intra_get_dir_luma_predictor (ref: intra.c:84-127)
+CTU_FN void intra_mpm(int y, const CuRec *left, const CuRec *above, int8_t *preds)
+{
+  int l = 1, a = 1;
+  if (left && left->type == CU_INTRA) l = left->mode;
+  if (above && above->type == CU_INTRA && (y & 63) != 0) a = above->mode;
+  if (l == a) {
+    if (l > 1) { preds[0] = (int8_t)l; preds[1] = (int8_t)(((l + 29) % 32) + 2); preds[2] = (int8_t)(((l - 1) % 32) + 2); }
+    else { preds[0] = 0; preds[1] = 1; preds[2] = 26; }
+  } else {
+    preds[0] = (int8_t)l; preds[1] = (int8_t)a;
+    if (l && a) preds[2] = 0;
+    else preds[2] = (l + a) < 2 ? 26 : 1;
+  }
+}
+// kvz_luma_mode_bits (ref: search_intra.c:641-679); leader only
+CTU_FN double luma_mode_bits(const Ctx &c, int mode, const int8_t *preds)
+{
+  double bits = 0;
+  const bool in = mode == preds[0] || mode == preds[1] || mode == preds[2];
+  cabac_bin(c.T, &c.S->sc, CTX_INTRA_MODE, in, &bits);
+  if (in) bits += (mode == preds[0]) ? 1 : 2;
+  else bits += 5;
+  return bits;
+}
+// kvz_chroma_mode_bits (ref: search_intra.c:682-701); leader only
+CTU_FN double chroma_mode_bits(const Ctx &c, int chroma_mode, int luma_mode)
+{
+  double bits = 0;
+  cabac_bin(c.T, &c.S->sc, CTX_CHROMA_PRED, chroma_mode != luma_mode, &bits);
+  if (chroma_mode != luma_mode) bits += 2.0;
+  return bits;
+}
+
+// ------------------------------------------------------------------------------------------------ work tree copies
+CTU_FN void copy_cu_info(LcuLevel *from, LcuLevel *to, int xl, int yl, int width)
+{
+  const int n = width >> 2;
+  for (int e = CTU_TID; e < n * n; e += CTU_NT) {
+    const int x = xl + 4 * (e % n), y = yl + 4 * (e / n);
+    *cu_at(to, x, y) = *cu_at(from, x, y);
+  }
+}
+CTU_FN void copy_cu_pixels(LcuLevel *from, LcuLevel *to, int xl, int yl, int width)
+{
+  for (int e = CTU_TID; e < width * width; e += CTU_NT) {
+    const int x = xl + e % width, y = yl + e / width;
+    to->rec_y[y * 64 + x] = from->rec_y[y * 64 + x];
+  }
+  const int wc = width >> 1, xc = xl >> 1, yc = yl >> 1;
+  for (int e = CTU_TID; e < wc * wc; e += CTU_NT) {
+    const int x = xc + e % wc, y = yc + e / wc;
+    to->rec_u[y * 32 + x] = from->rec_u[y * 32 + x];
+    to->rec_v[y * 32 + x] = from->rec_v[y * 32 + x];
+  }
+}
+CTU_FN void copy_cu_coeffs(LcuLevel *from, LcuLevel *to, int xl, int yl, int width)
+{
+  const int zl = zorder(64, xl, yl);
+  for (int e = CTU_TID; e < width * width; e += CTU_NT) to->coeff_y[zl + e] = from->coeff_y[zl + e];
+  const int zc = zorder(32, xl >> 1, yl >> 1), wc = width >> 1;
+  for (int e = CTU_TID; e < wc * wc; e += CTU_NT) { to->coeff_u[zc + e] = from->coeff_u[zc + e]; to->coeff_v[zc + e] = from->coeff_v[zc + e]; }
+}
+CTU_FN void work_tree_copy_up(const Ctx &c, int xl, int yl, int depth)
+{
+  const int w = 64 >> depth;
+  copy_cu_info(&c.W->lv[depth + 1], &c.W->lv[depth], xl, yl, w);
+  copy_cu_pixels(&c.W->lv[depth + 1], &c.W->lv[depth], xl, yl, w);
+  copy_cu_coeffs(&c.W->lv[depth + 1], &c.W->lv[depth], xl, yl, w);
+  CTU_SYNC();
+}
+CTU_FN void work_tree_copy_down(const Ctx &c, int xl, int yl, int depth)
+{
+  const int w = 64 >> depth;
+  for (int i = depth + 1; i <= 4; ++i) {
+    copy_cu_info(&c.W->lv[depth], &c.W->lv[i], xl, yl, w);
+    copy_cu_pixels(&c.W->lv[depth], &c.W->lv[i], xl, yl, w);
+  }
+  CTU_SYNC();
+}
+// kvz_lcu_fill_trdepth
+CTU_FN void fill_trdepth(LcuLevel *L, int xl, int yl, int depth, int tr_depth)
+{
+  const int n = (64 >> depth) >> 2;
+  for (int e = CTU_TID; e < n * n; e += CTU_NT) cu_at(L, xl + 4 * (e % n), yl + 4 * (e / n))->tr_depth = (uint8_t)tr_depth;
+  CTU_SYNC();
+}
+// lcu_fill_cu_info (intra fields only); `cu` may alias one of the targets
+CTU_FN void fill_cu_info(LcuLevel *L, int xl, int yl, int width, const CuRec *cu)
+{
+  const CuRec v = *cu;
+  CTU_SYNC();
+  const int n = width >> 2;
+  for (int e = CTU_TID; e < n * n; e += CTU_NT) {
+    CuRec *to = cu_at(L, xl + 4 * (e % n), yl + 4 * (e / n));
+    to->type = v.type; to->depth = v.depth; to->part_size = v.part_size; to->qp = v.qp;
+    to->mode = v.mode; to->mode_chroma = v.mode_chroma;
+  }
+  CTU_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------------ residual coding
+// kvz_quantize_residual for the TU of `color` at LCU-local luma position (xl, yl) of level L.  cu supplies
+// tr_depth / depth / part_size for RDOQ's cbf context.  Prediction is read from the level's reconstruction; the
+// result goes to rec_out (stride out_stride) and coeff_out (n*n).  Returns has_coeffs (uniform).
+CTU_FN int quantize_residual(const Ctx &c, LcuLevel *L, int color, int xl, int yl, int n, int scan_idx, const CuRec *cu, bool use_trskip,
+                             uint8_t *rec_out, int out_stride, int16_t *coeff_out)
+{
+  const CtuTables *T = c.T;
+  TuBuf *tu = &c.S->tu;
+  const Plane P = plane_of(c.W, L, color);
+  const int sh = color ? 1 : 0;
+  const int off = (xl >> sh) + (yl >> sh) * P.lw;
+  const uint8_t *pred = P.rec + off, *ref = P.src + off;
+  const int nn = n * n, log2n = ilog2(n);
+  const int ts_shift = 15 - 8 - log2n;
+  for (int e = CTU_TID; e < nn; e += CTU_NT) {
+    const int y = e / n, x = e - y * n;
+    tu->a[e] = (int16_t)((int)ref[y * P.lw + x] - (int)pred[y * P.lw + x]);
+  }
+  CTU_LEADER tu->has = 0;
+  CTU_SYNC();
+  const bool use_dst = (n == 4 && color == 0);
+  const int8_t *M = use_dst ? T->dst4 : T->tr[log2n - 2];
+  if (use_trskip) {
+    for (int e = CTU_TID; e < nn; e += CTU_NT) tu->b[e] = (int16_t)((uint16_t)tu->a[e] << ts_shift);
+    CTU_SYNC();
+  } else {
+    fwd_pass(tu->a, tu->t, M, n, log2n - 1);
+    fwd_pass(tu->t, tu->b, M, n, log2n + 6);
+  }
+  const int type = color == 0 ? 0 : 2;
+  if (c.cfg->rdoq_enable && (n > 4 || !c.cfg->rdoq_skip)) {
+    int tr_depth = (int)cu->tr_depth - (int)cu->depth;
+    tr_depth += (cu->part_size == SIZE_NxN ? 1 : 0);
+    if (CTU_TID < CTU_TEAM_N) rdoq_team(T, c.cfg, c.S->cabac0.ctx, tu, c.S->rq, log2n, type, scan_idx, tr_depth, CTU_TID);
+    CTU_SYNC();
+  } else {
+    quant_block(T, c.cfg, tu, n, type, scan_idx);
+  }
+  int any = 0;
+  for (int e = CTU_TID; e < nn; e += CTU_NT) { const int16_t v = tu->q[e]; coeff_out[e] = v; any |= v != 0; }
+  if (any) CTU_ATOMIC_OR(&tu->has, 1);
+  CTU_SYNC();
+  const int has = tu->has;
+  if (has) {
+    dequant_block(c.cfg, tu, n, color == 0 ? 0 : (color == 1 ? 2 : 3));
+    if (use_trskip) {
+      const int offs = 1 << (ts_shift - 1);
+      for (int e = CTU_TID; e < nn; e += CTU_NT) tu->a[e] = (int16_t)(((int)tu->b[e] + offs) >> ts_shift);
+      CTU_SYNC();
+    } else {
+      inv_pass(tu->b, tu->t, M, n, 7);
+      inv_pass(tu->t, tu->a, M, n, 12);
+    }
+    for (int e = CTU_TID; e < nn; e += CTU_NT) {
+      const int y = e / n, x = e - y * n;
+      const int16_t val = (int16_t)(tu->a[e] + (int)pred[y * P.lw + x]);
+      rec_out[y * out_stride + x] = (uint8_t)iclip(0, 255, (int)val);
+    }
+  } else if (rec_out != pred) {
+    for (int e = CTU_TID; e < nn; e += CTU_NT) {
+      const int y = e / n, x = e - y * n;
+      rec_out[y * out_stride + x] = pred[y * P.lw + x];
+    }
+  }
+  CTU_SYNC();
+  return has;
+}
+
+// quantize_tr_residual (ref: transform.c:294-415) for one colour of the leaf TU; cur_pu receives cbf / tr_skip
+CTU_FN void quantize_tr_residual(const Ctx &c, LcuLevel *L, int color, int xl, int yl, int depth, CuRec *cur_pu)
+{
+  const int sh = color ? 1 : 0;
+  const Plane P = plane_of(c.W, L, color);
+  const int px = xl >> sh, py = yl >> sh;
+  if (color != 0 && depth > 3 && ((px & 3) != 0 || (py & 3) != 0)) return;     // handled_elsewhere
+  CTU_LEADER cbf_clear(&cur_pu->cbf, depth, color);
+  CTU_SYNC();
+  const int n = color == 0 ? (64 >> depth) : (32 >> (depth == 4 ? 3 : depth));
+  const int mode = color == 0 ? cur_pu->mode : cur_pu->mode_chroma;
+  const int scan_idx = scan_order_intra(mode, depth);
+  const int off = px + py * P.lw;
+  int16_t *coeff = P.coeff + zorder(P.lw, px, py);
+  uint8_t *rec = P.rec + off;
+  int has;
+  if (n == 4 && color == 0 && c.cfg->trskip_enable) {
+    // kvz_quantize_residual_trskip (ref: transform.c:242-288)
+    CtuS *S = c.S;
+    for (int k = 0; k < 2; ++k) {
+      const int h = quantize_residual(c, L, color, xl, yl, 4, scan_idx, cur_pu, k == 1, S->ts_rec[k], 4, S->ts_coeff[k]);
+      CTU_LEADER {
+        S->ts_has[k] = h;
+        int ssd = 0;
+        for (int e = 0; e < 16; ++e) { const int d = (int)P.src[off + (e >> 2) * P.lw + (e & 3)] - (int)S->ts_rec[k][e]; ssd += d * d; }
+        S->ts_ssd[k] = ssd;
+      }
+      CTU_SYNC();
+    }
+    CTU_LEADER {
+      double cost[2];
+      for (int k = 0; k < 2; ++k) {
+        cost[k] = (double)(unsigned)S->ts_ssd[k];
+        cost[k] += coeff_cost_serial(c.T, c.cfg, &S->sc, S->ts_coeff[k], 2, 0, scan_idx, 0) * c.cfg->lambda;
+      }
+      const int pick = cost[0] <= cost[1] ? 0 : 1;
+      S->ts_pick = pick;
+      if (S->ts_has[pick]) for (int e = 0; e < 16; ++e) rec[(e >> 2) * P.lw + (e & 3)] = S->ts_rec[pick][e];
+      for (int e = 0; e < 16; ++e) coeff[e] = S->ts_coeff[pick][e];
+      cur_pu->tr_skip = (uint8_t)pick;
+    }
+    CTU_SYNC();
+    has = S->ts_has[S->ts_pick];
+  } else {
+    has = quantize_residual(c, L, color, xl, yl, n, scan_idx, cur_pu, false, rec, P.lw, coeff);
+  }
+  if (has) { CTU_LEADER cbf_set(&cur_pu->cbf, depth, color); }
+  CTU_SYNC();
+}
+
+// intra_recon_tb_leaf: prediction of one colour of the TU into the level's reconstruction
+CTU_FN void intra_recon_tb_leaf(const Ctx &c, LcuLevel *L, int x, int y, int depth, int mode, int color)
+{
+  int log2w = 6 - depth;
+  if (color != 0 && depth < 4) log2w -= 1;
+  const int sh = color ? 1 : 0;
+  const Plane P = plane_of(c.W, L, color);
+  IntraRefs *r = &c.S->refs[color];
+  build_refs(c.T, c.cfg, c.W, L, log2w, color, x, y, r);
+  predict_block(r, log2w, mode, color, P.rec + ((x & 63) >> sh) + ((y & 63) >> sh) * P.lw, P.lw);
+}
+
+// leaf part of kvz_intra_recon_cu + kvz_quantize_lcu_residual (ref: intra.c:676-696, transform.c:448-508)
+CTU_FN void intra_recon_leaf(const Ctx &c, LcuLevel *L, int x, int y, int depth, int mode_luma, int mode_chroma, CuRec *cur_cu)
+{
+  const int xl = x & 63, yl = y & 63;
+  CuRec *cur_tu = cu_at(L, xl, yl);
+  const bool has_luma = mode_luma != -1;
+  const bool has_chroma = mode_chroma != -1 && (x % 8 == 0) && (y % 8 == 0);
+  if (has_luma) intra_recon_tb_leaf(c, L, x, y, depth, mode_luma, 0);
+  if (has_chroma) { intra_recon_tb_leaf(c, L, x, y, depth, mode_chroma, 1); intra_recon_tb_leaf(c, L, x, y, depth, mode_chroma, 2); }
+  // kvz_quantize_lcu_residual(state, has_luma, has_chroma, x, y, depth, cur_cu, lcu, false)
+  CTU_LEADER {
+    if (has_luma) cbf_clear(&cur_cu->cbf, depth, 0);
+    if (has_chroma) { cbf_clear(&cur_cu->cbf, depth, 1); cbf_clear(&cur_cu->cbf, depth, 2); }
+  }
+  CTU_SYNC();
+  if (has_luma) quantize_tr_residual(c, L, 0, xl, yl, depth, cur_cu);
+  if (has_chroma) { quantize_tr_residual(c, L, 1, xl, yl, depth, cur_cu); quantize_tr_residual(c, L, 2, xl, yl, depth, cur_cu); }
+  if (cur_cu != cur_tu) {
+    CTU_LEADER {
+      if (has_luma) cbf_copy(&cur_tu->cbf, cur_cu->cbf, 0);
+      if (has_chroma) { cbf_copy(&cur_tu->cbf, cur_cu->cbf, 1); cbf_copy(&cur_tu->cbf, cur_cu->cbf, 2); }
+    }
+    CTU_SYNC();
+  }
+}
+
+// kvz_intra_recon_cu (ref: intra.c:623-698).  cur_cu == NULL: the CU record of the level at (x, y).
+CTU_FN void intra_recon_cu(const Ctx &c, LcuLevel *L, int x, int y, int depth, int mode_luma, int mode_chroma, CuRec *cur_cu)
+{
+  const int xl = x & 63, yl = y & 63;
+  if (cur_cu == NULL) cur_cu = cu_at(L, xl, yl);
+  CTU_LEADER {
+    if (mode_luma >= 0) cbf_clear(&cur_cu->cbf, depth, 0);
+    if (mode_chroma >= 0) { cbf_clear(&cur_cu->cbf, depth, 1); cbf_clear(&cur_cu->cbf, depth, 2); }
+  }
+  CTU_SYNC();
+  if (depth == 0 || cur_cu->tr_depth > depth) {
+    // with tr_depth_intra = 0 only a 64x64 CU splits, once, into its four 32x32 transform units
+    const int offset = (64 >> depth) / 2;
+    for (int k = 0; k < 4; ++k) {
+      const int cx = x + (k & 1) * offset, cy = y + (k >> 1) * offset;
+      CuRec *child = cu_at(L, cx & 63, cy & 63);
+      CTU_LEADER {
+        if (mode_luma >= 0) cbf_clear(&child->cbf, depth + 1, 0);
+        if (mode_chroma >= 0) { cbf_clear(&child->cbf, depth + 1, 1); cbf_clear(&child->cbf, depth + 1, 2); }
+      }
+      CTU_SYNC();
+      intra_recon_leaf(c, L, cx, cy, depth + 1, mode_luma, mode_chroma, child);
+    }
+    CTU_LEADER {
+      const uint16_t child_cbfs[3] = { cu_at(L, xl + offset, yl)->cbf, cu_at(L, xl, yl + offset)->cbf, cu_at(L, xl + offset, yl + offset)->cbf };
+      if (mode_luma != -1 && depth <= 3) cbf_set_conditionally(&cur_cu->cbf, child_cbfs, depth, 0);
+      if (mode_chroma != -1 && depth <= 3) { cbf_set_conditionally(&cur_cu->cbf, child_cbfs, depth, 1); cbf_set_conditionally(&cur_cu->cbf, child_cbfs, depth, 2); }
+    }
+    CTU_SYNC();
+  } else {
+    intra_recon_leaf(c, L, x, y, depth, mode_luma, mode_chroma, cur_cu);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ RD costs
+// SSDs of the leaf TUs of the CU at (xl, yl, depth) into S->ssd[leaf][colour] (leaf 0 only unless depth == 0)
+CTU_FN void leaf_ssds(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, bool luma, bool chroma)
+{
+  CtuS *S = c.S;
+  CTU_LEADER { for (int k = 0; k < 4; ++k) for (int col = 0; col < 3; ++col) S->ssd[k][col] = 0; }
+  CTU_SYNC();
+  const bool split = depth == 0;
+  const int d = split ? 1 : depth, leaves = split ? 4 : 1;
+  const int w = 64 >> d;
+  for (int k = 0; k < leaves; ++k) {
+    const int lx = xl + (k & 1) * w * (split ? 1 : 0), ly = yl + (k >> 1) * w * (split ? 1 : 0);
+    if (luma) ssd_block(&c.W->src_y[ly * 64 + lx], 64, &L->rec_y[ly * 64 + lx], 64, w, &S->ssd[k][0]);
+    if (chroma && (lx % 8 == 0) && (ly % 8 == 0)) {
+      const int wc = d <= 3 ? (64 >> (d + 1)) : (64 >> d);
+      const int ci = (ly >> 1) * 32 + (lx >> 1);
+      ssd_block(&c.W->src_u[ci], 32, &L->rec_u[ci], 32, wc, &S->ssd[k][1]);
+      ssd_block(&c.W->src_v[ci], 32, &L->rec_v[ci], 32, wc, &S->ssd[k][2]);
+    }
+  }
+}
+
+// kvz_cu_rd_cost_luma for a leaf (tr_depth == depth).  Leader only; S->ssd[leaf][0] holds the SSD.
+CTU_FN double cu_rd_cost_luma_leaf(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, const CuRec *pred_cu, int leaf)
+{
+  const CtuS *S = c.S;
+  CabacState *sc = &c.S->sc;
+  const int width = 64 >> depth;
+  CuRec *tr_cu = cu_at(L, xl, yl);
+  double coeff_bits = 0, tr_tree_bits = 0;
+  const int tr_depth = (int)tr_cu->tr_depth - depth;
+  const bool intra_split_flag = pred_cu->part_size == SIZE_NxN && depth == 3;
+  const int max_tr_depth = 0 + (intra_split_flag ? 1 : 0);
+  if (width <= 32 && width > 4 && !intra_split_flag && imin((int)tr_cu->tr_depth, depth) - (int)tr_cu->depth < max_tr_depth)
+    cabac_bin(c.T, sc, CTX_TRANS_SUBDIV + (5 - (6 - depth)), tr_depth > 0, &tr_tree_bits);
+  if (sc->update && tr_cu->tr_depth == tr_cu->depth) {
+    const int off = CTX_CBF_CHROMA + (depth - (int)tr_cu->depth);
+    cabac_bin(c.T, sc, off, cbf_is_set(tr_cu->cbf, depth, 1), &tr_tree_bits);
+    cabac_bin(c.T, sc, off, cbf_is_set(tr_cu->cbf, depth, 2), &tr_tree_bits);
+  }
+  const int is_tr_split = (int)tr_cu->tr_depth - (int)tr_cu->depth;
+  const int is_set = cbf_is_set(tr_cu->cbf, depth, 0);
+  cabac_bin(c.T, sc, CTX_CBF_LUMA + (is_tr_split ? 0 : 1), is_set, &tr_tree_bits);     // pred_cu->type == CU_INTRA
+  const int ssd = S->ssd[leaf][0];
+  if (is_set) {
+    const int scan = scan_order_intra(pred_cu->mode, depth);
+    coeff_bits += coeff_cost_serial(c.T, c.cfg, sc, &L->coeff_y[zorder(64, xl, yl)], ilog2(width), 0, scan, 0);
+  }
+  const double bits = tr_tree_bits + coeff_bits;
+  return (double)ssd * 0.8 + bits * c.cfg->lambda;
+}
+
+// kvz_cu_rd_cost_chroma for a leaf.  Leader only.
+CTU_FN double cu_rd_cost_chroma_leaf(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, const CuRec *pred_cu, int leaf)
+{
+  const CtuS *S = c.S;
+  CabacState *sc = &c.S->sc;
+  const int width = depth <= 3 ? (64 >> (depth + 1)) : (64 >> depth);
+  CuRec *tr_cu = cu_at(L, xl, yl);
+  double tr_tree_bits = 0, coeff_bits = 0;
+  if (xl % 8 != 0 || yl % 8 != 0) return 0;
+  const int u_is_set = cbf_is_set(tr_cu->cbf, depth, 1), v_is_set = cbf_is_set(tr_cu->cbf, depth, 2);
+  if (depth < 4 && (!sc->update || tr_cu->tr_depth != tr_cu->depth)) {
+    const int tr_depth = depth - (int)pred_cu->depth;
+    const int off = CTX_CBF_CHROMA + tr_depth;
+    if (tr_depth == 0 || cbf_is_set(tr_cu->cbf, depth - 1, 1)) cabac_bin(c.T, sc, off, u_is_set, &tr_tree_bits);
+    if (tr_depth == 0 || cbf_is_set(tr_cu->cbf, depth - 1, 2)) cabac_bin(c.T, sc, off, v_is_set, &tr_tree_bits);
+  }
+  const int ssd = S->ssd[leaf][1] + S->ssd[leaf][2];
+  {
+    const int scan = scan_order_intra(pred_cu->mode_chroma, depth);
+    const int index = zorder(32, xl >> 1, yl >> 1);
+    if (u_is_set) coeff_bits += coeff_cost_serial(c.T, c.cfg, sc, &L->coeff_u[index], ilog2(width), 2, scan, 0);
+    if (v_is_set) coeff_bits += coeff_cost_serial(c.T, c.cfg, sc, &L->coeff_v[index], ilog2(width), 2, scan, 0);
+  }
+  const double bits = tr_tree_bits + coeff_bits;
+  return (double)ssd * 1.5 + bits * c.cfg->lambda;
+}
+
+// cu_rd_cost_tr_split_accurate (ref: search.c:414-543), one node.  Leader only.  `leaf`: index into S->ssd.
+CTU_FN double cost_accurate_node(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, const CuRec *pred_cu, int leaf, bool *is_split)
+{
+  const CtuS *S = c.S;
+  CabacState *sc = &c.S->sc;
+  const int width = 64 >> depth;
+  CuRec *tr_cu = cu_at(L, xl, yl);
+  double coeff_bits = 0, tr_tree_bits = 0;
+  const int tr_depth = (int)tr_cu->tr_depth - depth;
+  const int cb_flag_u = cbf_is_set(tr_cu->cbf, depth, 1), cb_flag_v = cbf_is_set(tr_cu->cbf, depth, 2);
+  const bool intra_split_flag = pred_cu->part_size == SIZE_NxN && depth == 3;
+  const int max_tr_depth = 0 + (intra_split_flag ? 1 : 0);
+  if (width <= 32 && width > 4 && !intra_split_flag && imin((int)tr_cu->tr_depth, depth) - (int)tr_cu->depth < max_tr_depth)
+    cabac_bin(c.T, sc, CTX_TRANS_SUBDIV + (5 - (6 - depth)), tr_depth > 0, &tr_tree_bits);
+  {
+    const int off = CTX_CBF_CHROMA + (depth - (int)tr_cu->depth);
+    if ((int)tr_cu->depth == depth || cbf_is_set(tr_cu->cbf, depth - 1, 1)) cabac_bin(c.T, sc, off, cb_flag_u, &tr_tree_bits);
+    if ((int)tr_cu->depth == depth || cbf_is_set(tr_cu->cbf, depth - 1, 2)) cabac_bin(c.T, sc, off, cb_flag_v, &tr_tree_bits);
+  }
+  *is_split = tr_depth > 0;
+  if (tr_depth > 0) return tr_tree_bits;          // the caller sums the children and adds tr_tree_bits * lambda
+  const int cb_flag_y = cbf_is_set(tr_cu->cbf, depth, 0);
+  const int is_tr_split = depth - (int)tr_cu->depth;
+  cabac_bin(c.T, sc, CTX_CBF_LUMA + (is_tr_split ? 0 : 1), cb_flag_y, &tr_tree_bits);   // CU_INTRA
+  const unsigned luma_ssd = (unsigned)S->ssd[leaf][0];
+  if (cb_flag_y) {
+    const int scan = scan_order_intra(pred_cu->mode, depth);
+    coeff_bits += coeff_cost_serial(c.T, c.cfg, sc, &L->coeff_y[zorder(64, xl, yl)], ilog2(width), 0, scan, 0);
+  }
+  unsigned chroma_ssd = 0;
+  if (xl % 8 == 0 && yl % 8 == 0) {
+    const int chroma_width = depth <= 3 ? (64 >> (depth + 1)) : (64 >> depth);
+    chroma_ssd = (unsigned)S->ssd[leaf][1] + (unsigned)S->ssd[leaf][2];
+    const int scan = scan_order_intra(pred_cu->mode_chroma, depth);
+    const int index = zorder(32, xl >> 1, yl >> 1);
+    if (cb_flag_u) coeff_bits += coeff_cost_serial(c.T, c.cfg, sc, &L->coeff_u[index], ilog2(chroma_width), 2, scan, 0);
+    if (cb_flag_v) coeff_bits += coeff_cost_serial(c.T, c.cfg, sc, &L->coeff_v[index], ilog2(chroma_width), 2, scan, 0);
+  }
+  const double bits = tr_tree_bits + coeff_bits;
+  return luma_ssd * 0.8 + chroma_ssd * 1.5 + bits * c.cfg->lambda;
+}
+CTU_FN double cost_tr_split_accurate(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, const CuRec *pred_cu)
+{
+  bool split = false;
+  const double v = cost_accurate_node(c, L, xl, yl, depth, pred_cu, 0, &split);
+  if (!split) return v;
+  const int offset = 64 >> (depth + 1);
+  double sum = 0;
+  for (int k = 0; k < 4; ++k) {
+    bool s2 = false;
+    sum += cost_accurate_node(c, L, xl + (k & 1) * offset, yl + (k >> 1) * offset, depth + 1, pred_cu, k, &s2);
+  }
+  return sum + v * c.cfg->lambda;
+}
+
+// calc_mode_bits (ref: search.c:557-582).  Leader only.
+CTU_FN double calc_mode_bits(const Ctx &c, LcuLevel *L, const CuRec *cur_cu, int x, int y)
+{
+  const int xl = x & 63, yl = y & 63;
+  int8_t cand[3];
+  const CuRec *left = x >= 4 ? cu_at(L, xl - 4, yl) : NULL;
+  const CuRec *above = y >= 4 ? cu_at(L, xl, yl - 4) : NULL;
+  intra_mpm(y, left, above, cand);
+  double mode_bits = luma_mode_bits(c, cur_cu->mode, cand);
+  if (x % 8 == 0 && y % 8 == 0) mode_bits += chroma_mode_bits(c, cur_cu->mode_chroma, cur_cu->mode);
+  return mode_bits;
+}
+
+// kvz_mock_encode_coding_unit for an intra CU in an I slice (ref: encode_coding_tree.c:977-1075, 464-652, 672-743).
+// Leader only.
+CTU_FN double mock_encode_coding_unit(const Ctx &c, LcuLevel *L, int x, int y, int depth, const CuRec *cur_cu)
+{
+  double bits = 0;
+  CabacState *sc = &c.S->sc;
+  const int xl = x & 63, yl = y & 63;
+  const int cu_width = 64 >> depth;
+  const CuRec *left_cu = x ? cu_at(L, xl - 1, yl) : NULL;
+  const CuRec *above_cu = y ? cu_at(L, xl, yl - 1) : NULL;
+  const bool border = c.cfg->width < x + cu_width || c.cfg->height < y + cu_width;
+  if (depth != 3 && !border) {
+    int split_model = 0;
+    if (left_cu && left_cu->depth > depth) ++split_model;
+    if (above_cu && above_cu->depth > depth) ++split_model;
+    cabac_bin(c.T, sc, CTX_SPLIT + split_model, 0, &bits);
+  }
+  // kvz_encode_part_mode
+  {
+    double pb = 0;
+    if (depth == 3) cabac_bin(c.T, sc, CTX_PART_SIZE, cur_cu->part_size == SIZE_2Nx2N ? 1 : 0, &pb);
+    bits += pb;
+  }
+  // encode_intra_coding_unit in counting mode
+  const int num_pu = cur_cu->part_size == SIZE_NxN ? 4 : 1;
+  int flag[4], mpm_idx[4];
+  int mode0 = 0;
+  for (int j = 0; j < num_pu; ++j) {
+    const int pw = num_pu == 4 ? cu_width / 2 : cu_width;
+    const int pu_x = x + (num_pu == 4 ? (j & 1) * pw : 0), pu_y = y + (num_pu == 4 ? (j >> 1) * pw : 0);
+    const CuRec *cur_pu = cu_at(L, pu_x & 63, pu_y & 63);
+    // the reference takes SUB_SCU(pu_x - 1): at the CTU's left edge this is the CTU's own last column
+    const CuRec *left_pu = pu_x > 0 ? cu_at(L, (pu_x - 1) & 63, pu_y & 63) : NULL;
+    const CuRec *above_pu = ((pu_y & 63) > 0 && pu_y > 0) ? cu_at(L, pu_x & 63, (pu_y - 1) & 63) : NULL;
+    int8_t preds[3];
+    intra_mpm(pu_y, left_pu, above_pu, preds);
+    const int mode = cur_pu->mode;
+    if (j == 0) mode0 = mode;
+    mpm_idx[j] = -1;
+    for (int i = 0; i < 3; ++i) if (preds[i] == mode) { mpm_idx[j] = i; break; }
+    flag[j] = mpm_idx[j] != -1;
+  }
+  for (int j = 0; j < num_pu; ++j) cabac_bin(c.T, sc, CTX_INTRA_MODE, flag[j], &bits);
+  for (int j = 0; j < num_pu; ++j) {
+    if (flag[j]) { bits += 1; if (mpm_idx[j] != 0) bits += 1; }
+    else bits += 5;
+  }
+  {
+    const int mc = cur_cu->mode_chroma;
+    if (mc == mode0) cabac_bin(c.T, sc, CTX_CHROMA_PRED, 0, &bits);
+    else { cabac_bin(c.T, sc, CTX_CHROMA_PRED, 1, &bits); bits += 2; }
+  }
+  return bits;
+}
+
+// ------------------------------------------------------------------------------------------------ intra mode search
+// kvz_sort_modes: insertion sort, stable for equal costs
+CTU_FN void sort_modes(int8_t *modes, double *costs, int length)
+{
+  for (int i = 1; i < length; ++i) {
+    const double cur_cost = costs[i];
+    const int8_t cur_mode = modes[i];
+    int j = i;
+    while (j > 0 && cur_cost < costs[j - 1]) { costs[j] = costs[j - 1]; modes[j] = modes[j - 1]; --j; }
+    costs[j] = cur_cost; modes[j] = cur_mode;
+  }
+}
+
+// search_intra_rough (ref: search_intra.c:391-530) on the SATD / SAD table of all modes.  Leader only.
+CTU_FN int rough_search_replay(const Ctx &c, int log2w, const int8_t *mpm)
+{
+  CtuS *S = c.S;
+  const CtuConfig *cfg = c.cfg;
+  const int width = 1 << log2w;
+  const bool ts = width == 4 && cfg->trskip_enable;
+  // get_cost_dual reads state->cabac, get_cost reads state->search_cabac (search_intra.c:102, 142)
+  auto trskip_bits = [&](const CabacState *cb) {
+    double b = (double)c.T->ebits[cb->ctx[CTX_TRSKIP_LUMA] ^ 1] * (1.0 / 32768.0) - (double)c.T->ebits[cb->ctx[CTX_TRSKIP_LUMA] ^ 0] * (1.0 / 32768.0);
+    b += 2.0 * ((double)c.T->ebits[cb->ctx[CTX_TRSKIP_CHROMA] ^ 1] * (1.0 / 32768.0) - (double)c.T->ebits[cb->ctx[CTX_TRSKIP_CHROMA] ^ 0] * (1.0 / 32768.0));
+    return b;
+  };
+  auto cost_of = [&](int mode, const CabacState *cb) -> double {
+    double cost = (double)(unsigned)S->satd[mode];
+    if (ts) {
+      const double sad_cost = 1.7 * (double)(unsigned)S->sad[mode] + cfg->lambda_sqrt * trskip_bits(cb);
+      if (sad_cost < cost) cost = sad_cost;
+    }
+    return cost;
+  };
+  int8_t *modes = S->modes;
+  double *costs = S->costs;
+  int n = 0;
+  int32_t min_cost = CTU_MAX_INT, max_cost = -CTU_MAX_INT - 1;
+  int offset;
+  if (cfg->full_intra_search) offset = 1;
+  else { const int offs[4] = { 2, 4, 8, 8 }; offset = offs[log2w - 2]; }
+  for (int mode = 2; mode <= 34; mode += 2 * offset) {
+    for (int i = 0; i < 2; ++i) {
+      if (mode + i * offset <= 34) {
+        costs[n] = cost_of(mode + i * offset, &S->cabac0);
+        modes[n] = (int8_t)(mode + i * offset);
+        // the reference keeps min / max as int32 (implicit conversion of the double cost)
+        min_cost = imin(min_cost, (int32_t)costs[n]);
+        max_cost = imax(max_cost, (int32_t)costs[n]);
+        ++n;
+      }
+    }
+  }
+  int best_i = 0;
+  for (int i = 1; i < n; ++i) if (costs[i] < costs[best_i]) best_i = i;
+  int best_mode = modes[best_i];
+  double best_cost = min_cost;
+  if (min_cost != max_cost) {
+    while (offset > 1) {
+      offset >>= 1;
+      const int center = best_mode;
+      const int test[2] = { center - offset, center + offset };
+      for (int i = 0; i < 2; ++i) {
+        if (test[i] >= 2 && test[i] <= 34) {
+          costs[n] = cost_of(test[i], &S->cabac0);
+          modes[n] = (int8_t)test[i];
+          if (costs[n] < best_cost) { best_cost = costs[n]; best_mode = modes[n]; }
+          ++n;
+        }
+      }
+    }
+  }
+  const int add_modes[5] = { mpm[0], mpm[1], mpm[2], 0, 1 };
+  for (int p = 0; p < 5; ++p) {
+    bool has = false;
+    for (int i = 0; i < n; ++i) if (modes[i] == add_modes[p]) { has = true; break; }
+    if (!has) { costs[n] = cost_of(add_modes[p], &S->sc); modes[n] = (int8_t)add_modes[p]; ++n; }
+  }
+  for (int i = 0; i < n; ++i) costs[i] += cfg->lambda_sqrt * luma_mode_bits(c, modes[i], mpm);
+  return n;
+}
+
+// kvz_search_cu_intra (ref: search_intra.c:806-900): best luma mode of the CU at (x, y, depth) on level L.
+// Result in S->best_mode / S->best_cost.
+CTU_FN void search_cu_intra(const Ctx &c, LcuLevel *L, int x, int y, int depth)
+{
+  CtuS *S = c.S;
+  const CtuConfig *cfg = c.cfg;
+  const int xl = x & 63, yl = y & 63;
+  const int log2w = 6 - depth;
+  CTU_LEADER {
+    const CuRec *left = x >= 4 ? cu_at(L, xl - 1, yl) : NULL;
+    const CuRec *above = (y >= 4 && yl > 0) ? cu_at(L, xl, yl - 1) : NULL;
+    intra_mpm(y, left, above, S->mpm);
+  }
+  CTU_SYNC();
+  build_refs(c.T, cfg, c.W, L, log2w, 0, x, y, &S->refs[0]);
+  // rough search: SATD (and SAD for 4x4 transform-skip candidates) of every mode, then the reference's selection
+  rough_costs_all_modes(&S->refs[0], log2w, 0, &c.W->src_y[yl * 64 + xl], 64, 0, 34, S->satd, S->sad, log2w == 2 && cfg->trskip_enable);
+  CTU_LEADER S->n_modes = rough_search_replay(c, log2w, S->mpm);
+  CTU_SYNC();
+  fill_trdepth(L, xl, yl, depth, depth);
+  if (cfg->rdo >= 2) {
+    // search_intra_rdo (ref: search_intra.c:558-638) with tr_depth == depth
+    CTU_LEADER {
+      const int to_search = depth == 4 ? 3 : 2;
+      int check = imin(S->n_modes, to_search);
+      sort_modes(S->modes, S->costs, S->n_modes);
+      for (int p = 0; p < 3; ++p) {
+        bool found = false;
+        for (int r = 0; r < check; ++r) if (S->mpm[p] == S->modes[r]) { found = true; break; }
+        if (!found) { S->modes[check] = S->mpm[p]; ++check; }
+      }
+      S->n_modes = check;
+    }
+    CTU_SYNC();
+    const bool reconstruct_chroma = !((x & 4) || (y & 4));
+    int checked = S->n_modes;
+    for (int r = 0; r < S->n_modes; ++r) {
+      const int mode = S->modes[r];
+      CTU_LEADER {
+        const double rdo_bitcost = luma_mode_bits(c, mode, S->mpm);
+        S->costs[r] = rdo_bitcost * cfg->lambda;
+        CuRec *p = &S->pred_cu;
+        p->depth = (uint8_t)depth; p->type = CU_INTRA; p->part_size = depth == 4 ? SIZE_NxN : SIZE_2Nx2N;
+        p->mode = (int8_t)mode; p->mode_chroma = (int8_t)mode; p->cbf = 0;
+        // (tr_skip and qp of the reference's stack variable are never read)
+      }
+      CTU_SYNC();
+      fill_trdepth(L, xl, yl, depth, depth);
+      // search_intra_trdepth(depth, max_depth = depth): the no-split branch only
+      CTU_LEADER {
+        cu_at(L, xl, yl)->tr_depth = (uint8_t)depth;
+        S->pred_cu.tr_depth = (uint8_t)depth;
+        cbf_clear(&S->pred_cu.cbf, depth, 0);
+        if (reconstruct_chroma) { cbf_clear(&S->pred_cu.cbf, depth, 1); cbf_clear(&S->pred_cu.cbf, depth, 2); }
+      }
+      CTU_SYNC();
+      intra_recon_cu(c, L, x, y, depth, mode, reconstruct_chroma ? mode : -1, &S->pred_cu);
+      leaf_ssds(c, L, xl, yl, depth, true, reconstruct_chroma);
+      CTU_LEADER {
+        double nosplit = 0.0;
+        nosplit += cu_rd_cost_luma_leaf(c, L, xl, yl, depth, &S->pred_cu, 0);
+        if (reconstruct_chroma) nosplit += cu_rd_cost_chroma_leaf(c, L, xl, yl, depth, &S->pred_cu, 0);
+        S->costs[r] += nosplit;
+        S->flag = (cfg->intra_rdo_et && !cbf_is_set_any(S->pred_cu.cbf, depth)) ? 1 : 0;
+      }
+      CTU_SYNC();
+      // (kvz_lcu_fill_trdepth(depth, depth) and the pixel restore of the no-split branch are identities here)
+      if (S->flag) { checked = r + 1; break; }
+    }
+    CTU_LEADER { S->n_modes = checked; sort_modes(S->modes, S->costs, checked); }
+    CTU_SYNC();
+  }
+  CTU_LEADER {
+    int bi = 0;
+    for (int i = 1; i < S->n_modes; ++i) if (S->costs[i] < S->costs[bi]) bi = i;
+    S->best_mode = S->modes[bi];
+    S->best_cost = S->costs[bi];
+  }
+  CTU_SYNC();
+}
+
+// kvz_search_cu_intra_chroma (ref: search_intra.c:748-803) for rdo 2..3 (num_modes = 2).  Returns the mode (uniform).
+CTU_FN int search_cu_intra_chroma(const Ctx &c, LcuLevel *L, int x, int y, int depth)
+{
+  CtuS *S = c.S;
+  const int xl = x & 63, yl = y & 63;
+  const int intra_mode = cu_at(L, xl, yl)->mode;
+  const int log2wc = imax(6 - depth - 1, 2);
+  const int wc = 1 << log2wc;
+  CTU_LEADER {
+    const int8_t init[5] = { 0, 26, 10, 1, 34 };
+    for (int i = 0; i < 5; ++i) S->cmodes[i] = init[i];
+    if (intra_mode != 0 && intra_mode != 26 && intra_mode != 10 && intra_mode != 1) S->cmodes[4] = (int8_t)intra_mode;
+  }
+  CTU_SYNC();
+  build_refs(c.T, c.cfg, c.W, L, log2wc, 1, x, y, &S->refs[1]);
+  build_refs(c.T, c.cfg, c.W, L, log2wc, 2, x, y, &S->refs[2]);
+  // search_intra_chroma_rough: SATD of the five candidates on U and V (the luma mode is skipped: cost 0)
+  const int ci = (yl >> 1) * 32 + (xl >> 1);
+  rough_costs_all_modes(&S->refs[1], log2wc, 1, &c.W->src_u[ci], 32, 0, 34, S->satd, S->sad, false);
+  CTU_LEADER { for (int i = 0; i < 5; ++i) S->ccosts[i] = 0; for (int i = 0; i < 5; ++i) if (S->cmodes[i] != intra_mode) S->ccosts[i] += (double)(unsigned)S->satd[S->cmodes[i]]; }
+  CTU_SYNC();
+  rough_costs_all_modes(&S->refs[2], log2wc, 2, &c.W->src_v[ci], 32, 0, 34, S->satd, S->sad, false);
+  CTU_LEADER {
+    for (int i = 0; i < 5; ++i) if (S->cmodes[i] != intra_mode) S->ccosts[i] += (double)(unsigned)S->satd[S->cmodes[i]];
+    sort_modes(S->cmodes, S->ccosts, 5);
+  }
+  CTU_SYNC();
+  (void)wc;
+  // kvz_search_intra_chroma_rdo over the two best
+  double best_cost = CTU_MAX_INT;
+  int best_mode = 0;
+  for (int i = 0; i < 2; ++i) {
+    const int mode = S->cmodes[i];
+    intra_recon_cu(c, L, x, y, depth, -1, mode, NULL);
+    leaf_ssds(c, L, xl, yl, depth, false, true);
+    CTU_LEADER {
+      CuRec *tr_cu = cu_at(L, xl, yl);
+      double cost;
+      if (depth == 0) {
+        // kvz_cu_rd_cost_chroma recursion over the four 32x32 quadrants (ref: search.c:377-388)
+        CabacState *sc = &S->sc;
+        double tr_tree_bits = 0;
+        if (!sc->update || tr_cu->tr_depth != tr_cu->depth) {
+          cabac_bin(c.T, sc, CTX_CBF_CHROMA, cbf_is_set(tr_cu->cbf, 0, 1), &tr_tree_bits);
+          cabac_bin(c.T, sc, CTX_CBF_CHROMA, cbf_is_set(tr_cu->cbf, 0, 2), &tr_tree_bits);
+        }
+        double sum = 0;
+        for (int k = 0; k < 4; ++k) sum += cu_rd_cost_chroma_leaf(c, L, xl + (k & 1) * 32, yl + (k >> 1) * 32, 1, tr_cu, k);
+        cost = sum + tr_tree_bits * c.cfg->lambda;
+      } else {
+        cost = cu_rd_cost_chroma_leaf(c, L, xl, yl, depth, tr_cu, 0);
+      }
+      const double mode_bits = chroma_mode_bits(c, mode, intra_mode);
+      cost += mode_bits * c.cfg->lambda;
+      S->ccosts[5 + i] = cost;
+    }
+    CTU_SYNC();
+    if (S->ccosts[5 + i] < best_cost) { best_cost = S->ccosts[5 + i]; best_mode = mode; }
+  }
+  return best_mode;
+}
+
+// ------------------------------------------------------------------------------------------------ search_cu
+CTU_FN int split_model_of(LcuLevel *L, int x, int y, int depth)     // get_ctx_cu_split_model (search.c:634-641)
+{
+  const int xl = x & 63, yl = y & 63;
+  const bool condA = x >= 8 && cu_at(L, xl - 1, yl)->depth > depth;
+  const bool condL = y >= 8 && cu_at(L, xl, yl - 1)->depth > depth;
+  return (condA ? 1 : 0) + (condL ? 1 : 0);
+}
+
+// search_cu for the whole CTU at (cx, cy) (luma picture coordinates); returns with the decisions on level 0
+CTU_FN void search_ctu(const Ctx &c, int cx, int cy)
+{
+  CtuS *S = c.S;
+  const CtuConfig *cfg = c.cfg;
+  CTU_LEADER { S->fr[0].x = cx; S->fr[0].y = cy; S->fr[0].stage = 0; }
+  CTU_SYNC();
+  int d = 0;
+  for (;;) {
+    SearchFrame *F = &S->fr[d];
+    LcuLevel *L = &c.W->lv[d];
+    const int x = F->x, y = F->y;
+    const int xl = x & 63, yl = y & 63;
+    const int cu_width = 64 >> d;
+    const int stage = F->stage;
+    if (stage == 0) {
+      // ---------------- entry: this depth's own mode decision
+      if (x >= cfg->width || y >= cfg->height) {
+        CTU_LEADER { S->ret_cost = 0; }
+        CTU_SYNC();
+        if (d == 0) break;
+        --d;
+        CTU_LEADER { S->fr[d].split_cost += S->ret_cost; }
+        CTU_SYNC();
+        continue;
+      }
+      CuRec *cur_cu = cu_at(L, xl, yl);
+      CTU_LEADER {
+        F->pre = S->sc;
+        F->cost = CTU_MAX_DOUBLE;
+        cur_cu->depth = (uint8_t)(d > 3 ? 3 : d);
+        cur_cu->tr_depth = (uint8_t)(d > 0 ? d : 1);
+        cur_cu->type = CU_NOTSET;
+        cur_cu->part_size = SIZE_2Nx2N;
+        cur_cu->qp = (uint8_t)cfg->qp;
+      }
+      CTU_SYNC();
+      const bool inside = x + cu_width <= cfg->width && y + cu_width <= cfg->height;
+      if (inside) {
+        const int cwim = 64 >> cfg->pu_depth_intra_max;
+        const bool can_use_intra = (d >= cfg->pu_depth_intra_min && d <= cfg->pu_depth_intra_max) ||
+                                   (x & ~(cwim - 1)) + cwim > cfg->width || (y & ~(cwim - 1)) + cwim > cfg->height;
+        if (can_use_intra) {
+          search_cu_intra(c, L, x, y, d);
+          CTU_LEADER {
+            if (S->best_cost < F->cost) {
+              F->cost = S->best_cost;
+              cur_cu->type = CU_INTRA;
+              cur_cu->part_size = d > 3 ? SIZE_NxN : SIZE_2Nx2N;
+              cur_cu->mode = (int8_t)S->best_mode;
+            }
+          }
+          CTU_SYNC();
+        }
+        if (cur_cu->type == CU_INTRA) {
+          CTU_LEADER cur_cu->mode_chroma = cur_cu->mode;
+          CTU_SYNC();
+          fill_cu_info(L, xl, yl, cu_width, cur_cu);
+          intra_recon_cu(c, L, x, y, d, cur_cu->mode, -1, NULL);
+          if (x % 8 == 0 && y % 8 == 0) {
+            if (cfg->rdo >= 2 && cfg->intra_chroma_search) {
+              const int mc = search_cu_intra_chroma(c, L, x, y, d);
+              CTU_LEADER cur_cu->mode_chroma = (int8_t)mc;
+              CTU_SYNC();
+              fill_cu_info(L, xl, yl, cu_width, cur_cu);
+            }
+            intra_recon_cu(c, L, x, y, d, -1, cur_cu->mode_chroma, NULL);
+          }
+        }
+      }
+      if (cur_cu->type == CU_INTRA) {
+        leaf_ssds(c, L, xl, yl, d, true, true);
+        CTU_LEADER {
+          double bits = 0;
+          S->sc.update = 1;
+          if (cur_cu->part_size == SIZE_2Nx2N) bits += mock_encode_coding_unit(c, L, x, y, d, cur_cu);
+          else bits += calc_mode_bits(c, L, cur_cu, x, y);
+          double cost = bits * cfg->lambda;
+          cost += cost_tr_split_accurate(c, L, xl, yl, d, cur_cu);
+          F->cost = cost;
+          S->sc.update = 0;
+        }
+        CTU_SYNC();
+      }
+      const bool can_split = cur_cu->type == CU_NOTSET || d < cfg->pu_depth_intra_max;
+      CTU_LEADER {
+        F->can_split = can_split;
+        F->child = 0;
+        F->do_children = 0;
+        if (can_split) {
+          F->split_cost = 0.0;
+          F->cbf = cbf_is_set_any(cur_cu->cbf, d);
+          F->post = S->sc;
+          S->sc = F->pre;
+          S->sc.update = 1;
+          double split_bits = 0;
+          if (d < 3) cabac_bin(c.T, &S->sc, CTX_SPLIT + split_model_of(L, x, y, d), 1, &split_bits);
+          if (cur_cu->type == CU_INTRA && d == 3) cabac_bin(c.T, &S->sc, CTX_PART_SIZE, 0, &split_bits);
+          S->sc.update = 0;
+          F->split_cost += split_bits * cfg->lambda;
+          if (cur_cu->type == CU_NOTSET || F->cbf || cfg->cu_split_termination == 1) F->do_children = 1;
+          else F->split_cost = CTU_MAX_INT;
+        }
+        F->stage = can_split ? 1 : 3;
+      }
+      CTU_SYNC();
+      continue;
+    }
+    if (stage == 1) {
+      // ---------------- children, one at a time, while the split is still cheaper
+      if (F->do_children && F->child < 4 && F->split_cost < F->cost) {
+        const int k = F->child, half = cu_width / 2;
+        CTU_LEADER {
+          F->child = k + 1;
+          S->fr[d + 1].x = x + (k & 1) * half;
+          S->fr[d + 1].y = y + (k >> 1) * half;
+          S->fr[d + 1].stage = 0;
+        }
+        CTU_SYNC();
+        ++d;
+        continue;
+      }
+      CTU_LEADER F->stage = 2;
+      CTU_SYNC();
+      continue;
+    }
+    if (stage == 2) {
+      // ---------------- after the children: combined CU, then split / no split
+      CuRec *cur_cu = cu_at(L, xl, yl);
+      const bool inside = x + cu_width <= cfg->width && y + cu_width <= cfg->height;
+      if (cur_cu->type == CU_NOTSET && d < 4 && inside && cfg->combine_intra_cus) {
+        CuRec *cu_d1 = cu_at(&c.W->lv[d + 1], xl, yl);
+        if (cu_d1->type == CU_INTRA && cu_d1->depth == d + 1) {
+          CTU_LEADER {
+            S->tmp = S->sc;
+            S->sc = F->pre;
+            F->cost = 0;
+            double bits = 0;
+            if (d < 3) cabac_bin(c.T, &S->sc, CTX_SPLIT + split_model_of(L, x, y, d), 0, &bits);
+            S->best_cost = bits;
+            cur_cu->mode = cu_d1->mode; cur_cu->mode_chroma = cu_d1->mode_chroma;
+            cur_cu->type = CU_INTRA;
+            cur_cu->part_size = SIZE_2Nx2N;
+          }
+          CTU_SYNC();
+          fill_trdepth(L, xl, yl, d, cur_cu->tr_depth);
+          fill_cu_info(L, xl, yl, cu_width, cur_cu);
+          intra_recon_cu(c, L, x, y, d, cur_cu->mode, cur_cu->mode_chroma, NULL);
+          leaf_ssds(c, L, xl, yl, d, true, true);
+          CTU_LEADER {
+            const double mode_bits = calc_mode_bits(c, L, cur_cu, x, y) + S->best_cost;
+            double cost = F->cost;
+            cost += mode_bits * cfg->lambda;
+            cost += cost_tr_split_accurate(c, L, xl, yl, d, cur_cu);
+            F->cost = cost;
+            F->post = S->sc;
+            S->sc = S->tmp;
+          }
+          CTU_SYNC();
+        }
+      }
+      if (F->split_cost < F->cost) {
+        CTU_LEADER F->cost = F->split_cost;
+        CTU_SYNC();
+        work_tree_copy_up(c, xl, yl, d);
+      } else if (d > 0) {
+        CTU_LEADER S->sc = F->post;
+        CTU_SYNC();
+        work_tree_copy_down(c, xl, yl, d);
+      }
+      CTU_LEADER F->stage = 4;
+      CTU_SYNC();
+      continue;
+    }
+    if (stage == 3) {
+      // ---------------- no split possible at this depth
+      if (d < 4) work_tree_copy_down(c, xl, yl, d);
+      CTU_LEADER F->stage = 4;
+      CTU_SYNC();
+      continue;
+    }
+    // stage 4: return
+    CTU_LEADER S->ret_cost = F->cost;
+    CTU_SYNC();
+    if (d == 0) break;
+    --d;
+    CTU_LEADER S->fr[d].split_cost += S->ret_cost;
+    CTU_SYNC();
+  }
+}
+
+}  // namespace kvzctu
