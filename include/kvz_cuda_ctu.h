@@ -67,6 +67,7 @@ typedef struct kvz_cuda_ctu_result {
   const kvz_cuda_ctu_sao *sao;      /* per CTU: [0] luma, [1] chroma */
   const uint8_t *rec_y, *rec_u, *rec_v;   /* final picture, stride = width (/2) */
   const uint8_t *dbg_ctx;           /* per CTU: the 184 context-model bytes the CTU's search started from (may be NULL) */
+  const uint8_t *dbg_y, *dbg_u, *dbg_v;   /* the search's reconstruction before deblocking (may be NULL; verification) */
 } kvz_cuda_ctu_result;
 
 typedef struct kvz_cuda_ctu_enc kvz_cuda_ctu_enc;

@@ -108,10 +108,10 @@ static int config_in_scope(const encoder_state_t *state)
 
 static int driver_active(const encoder_state_t *state)
 {
-  if (g_state) return g_state > 0 && state->encoder_control == g_ctrl && state->frame->slicetype == KVZ_SLICE_I;
+  if (__atomic_load_n(&g_state, __ATOMIC_ACQUIRE)) return g_state > 0 && state->encoder_control == g_ctrl && state->frame->slicetype == KVZ_SLICE_I;
   pthread_mutex_lock(&g_lock);
   if (!g_state) {
-    g_state = -1;
+    int st = -1;             /* published only when the set-up is complete: other workers wait on the lock */
     const char *path = getenv("KVZ_CTU_PROVIDER");
     if (path && *path && config_in_scope(state)) {
       g_prov.lib = dlopen(path, RTLD_NOW | RTLD_LOCAL);
@@ -130,10 +130,11 @@ static int driver_active(const encoder_state_t *state)
         g_verify = mode && strcmp(mode, "verify") == 0;
         if (g_prov.supported && g_prov.open && g_prov.submit && g_prov.wait && g_prov.release && g_prov.supported(&c) == 0)
           g_enc = g_prov.open(&c, slots ? atoi(slots) : 8);
-        if (g_enc) { g_ctrl = state->encoder_control; g_state = 1; fprintf(stderr, "kvz-ctu: CTU search driver active (%s%s)\n", path, g_verify ? ", verify" : ""); }
+        if (g_enc) { g_ctrl = state->encoder_control; st = 1; fprintf(stderr, "kvz-ctu: CTU search driver active (%s%s)\n", path, g_verify ? ", verify" : ""); }
         else fprintf(stderr, "kvz-ctu: provider refused the configuration, using the reference path\n");
       }
     }
+    __atomic_store_n(&g_state, st, __ATOMIC_RELEASE);
   }
   pthread_mutex_unlock(&g_lock);
   return g_state > 0 && state->encoder_control == g_ctrl && state->frame->slicetype == KVZ_SLICE_I;
@@ -225,6 +226,21 @@ void __wrap_kvz_search_lcu(encoder_state_t *state, int x, int y, const yuv_t *ho
         else if (a->cbf != b->cbf) report("cbf", x, y, sx, sy, a->cbf, b->cbf);
         else if (a->tr_skip != b->tr_skip) report("tr_skip", x, y, sx, sy, a->tr_skip, b->tr_skip);
       }
+    if (j->res.dbg_y) {
+      const kvz_picture *rec = frame->rec;
+      int done = 0;
+      for (int yy = 0; yy < y_max && !done; ++yy)
+        for (int xx = 0; xx < x_max; ++xx)
+          if (rec->y[(size_t)(y + yy) * rec->stride + x + xx] != j->res.dbg_y[(size_t)(y + yy) * frame->width + x + xx]) {
+            report("rec_y (before deblocking)", x, y, xx, yy, rec->y[(size_t)(y + yy) * rec->stride + x + xx], j->res.dbg_y[(size_t)(y + yy) * frame->width + x + xx]); done = 1; break; }
+      done = 0;
+      for (int yy = 0; yy < y_max / 2 && !done; ++yy)
+        for (int xx = 0; xx < x_max / 2; ++xx) {
+          const size_t a = (size_t)(y / 2 + yy) * (rec->stride / 2) + x / 2 + xx, b = (size_t)(y / 2 + yy) * (frame->width / 2) + x / 2 + xx;
+          if (rec->u[a] != j->res.dbg_u[b]) { report("rec_u (before deblocking)", x, y, xx, yy, rec->u[a], j->res.dbg_u[b]); done = 1; break; }
+          if (rec->v[a] != j->res.dbg_v[b]) { report("rec_v (before deblocking)", x, y, xx, yy, rec->v[a], j->res.dbg_v[b]); done = 1; break; }
+        }
+    }
     for (int i = 0; i < 4096; ++i) if (state->coeff->y[i] != co[i]) { report("coeff_y", x, y, i, 0, state->coeff->y[i], co[i]); break; }
     for (int i = 0; i < 1024; ++i) if (state->coeff->u[i] != co[4096 + i]) { report("coeff_u", x, y, i, 0, state->coeff->u[i], co[4096 + i]); break; }
     for (int i = 0; i < 1024; ++i) if (state->coeff->v[i] != co[5120 + i]) { report("coeff_v", x, y, i, 0, state->coeff->v[i], co[5120 + i]); break; }

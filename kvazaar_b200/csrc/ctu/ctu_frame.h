@@ -15,6 +15,7 @@ struct FrameDev {
   const uint8_t *src_y, *src_u, *src_v;     // source planes, stride = width (/2)
   uint8_t *rec_y, *rec_u, *rec_v;           // reconstruction: search output, then deblocked in place
   uint8_t *out_y, *out_u, *out_v;           // final picture (after SAO)
+  uint8_t *dbg_y, *dbg_u, *dbg_v;           // optional: the search's reconstruction before deblocking (verification)
   uint8_t *hor_y, *hor_u, *hor_v;           // hor_buf_search: un-deblocked bottom row of every CTU row
   uint8_t *ver_y, *ver_u, *ver_v;           // ver_buf_search: un-deblocked right column of every CTU column
   CuRec *cu;                                // per 4x4, stride cu_stride
@@ -113,6 +114,7 @@ CTU_FN void ctu_store(const Ctx &c, const FrameDev *F, int cx, int cy)
     if (xx < x_max && yy < y_max) {
       const uint8_t v = L0->rec_y[e];
       F->rec_y[(y + yy) * Wd + x + xx] = v;
+      if (F->dbg_y) F->dbg_y[(y + yy) * Wd + x + xx] = v;
       if (yy == y_max - 1) F->hor_y[cy * Wd + x + xx] = v;
       if (xx == x_max - 1) F->ver_y[cx * H + y + yy] = v;
     }
@@ -123,6 +125,7 @@ CTU_FN void ctu_store(const Ctx &c, const FrameDev *F, int cx, int cy)
       const uint8_t u = L0->rec_u[e], v = L0->rec_v[e];
       const int o = (y / 2 + yy) * (Wd / 2) + x / 2 + xx;
       F->rec_u[o] = u; F->rec_v[o] = v;
+      if (F->dbg_u) { F->dbg_u[o] = u; F->dbg_v[o] = v; }
       if (yy == y_max / 2 - 1) { F->hor_u[cy * (Wd / 2) + x / 2 + xx] = u; F->hor_v[cy * (Wd / 2) + x / 2 + xx] = v; }
       if (xx == x_max / 2 - 1) { F->ver_u[cx * (H / 2) + y / 2 + yy] = u; F->ver_v[cx * (H / 2) + y / 2 + yy] = v; }
     }

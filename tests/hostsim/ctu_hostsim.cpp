@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <mutex>
 
 #include "../../include/kvz_cuda_ctu.h"
 #include "../../kvazaar_b200/csrc/ctu/ctu_frame.h"
@@ -20,7 +21,7 @@ static_assert(sizeof(kvz_cuda_ctu_sao) == sizeof(SaoRec), "sao layout");
 
 struct Slot {
   bool busy = false;
-  std::vector<uint8_t> src[3], rec[3], out[3], hor[3], ver[3];
+  std::vector<uint8_t> src[3], rec[3], out[3], hor[3], ver[3], dbg[3];
   std::vector<CuRec> cu;
   std::vector<int16_t> coeff;
   std::vector<SaoRec> sao;
@@ -36,6 +37,7 @@ struct kvz_cuda_ctu_enc {
   CtuS *S;
   SaoStats *st;
   std::vector<Slot> slots;
+  std::mutex mtx;                // one scratch set: pictures are searched one at a time
 };
 
 extern "C" {
@@ -65,7 +67,7 @@ kvz_cuda_ctu_enc *kvz_cuda_ctu_open(const kvz_cuda_ctu_config *cfg, int slots)
   for (Slot &s : e->slots) {
     for (int p = 0; p < 3; ++p) {
       const int pw = p ? W / 2 : W, ph = p ? H / 2 : H;
-      s.src[p].assign((size_t)pw * ph, 0); s.rec[p].assign((size_t)pw * ph, 0); s.out[p].assign((size_t)pw * ph, 0);
+      s.src[p].assign((size_t)pw * ph, 0); s.rec[p].assign((size_t)pw * ph, 0); s.out[p].assign((size_t)pw * ph, 0); s.dbg[p].assign((size_t)pw * ph, 0);
       s.hor[p].assign((size_t)pw * hl, 0); s.ver[p].assign((size_t)ph * wl, 0);
     }
     s.cu.assign((size_t)(wl * 16) * (hl * 16), CuRec());
@@ -77,6 +79,7 @@ kvz_cuda_ctu_enc *kvz_cuda_ctu_open(const kvz_cuda_ctu_config *cfg, int slots)
     F.src_y = s.src[0].data(); F.src_u = s.src[1].data(); F.src_v = s.src[2].data();
     F.rec_y = s.rec[0].data(); F.rec_u = s.rec[1].data(); F.rec_v = s.rec[2].data();
     F.out_y = s.out[0].data(); F.out_u = s.out[1].data(); F.out_v = s.out[2].data();
+    F.dbg_y = s.dbg[0].data(); F.dbg_u = s.dbg[1].data(); F.dbg_v = s.dbg[2].data();
     F.hor_y = s.hor[0].data(); F.hor_u = s.hor[1].data(); F.hor_v = s.hor[2].data();
     F.ver_y = s.ver[0].data(); F.ver_u = s.ver[1].data(); F.ver_v = s.ver[2].data();
     F.cu = s.cu.data(); F.coeff = s.coeff.data(); F.sao = s.sao.data(); F.row_ctx = s.row_ctx.data();
@@ -95,12 +98,14 @@ void kvz_cuda_ctu_close(kvz_cuda_ctu_enc *e)
 int kvz_cuda_ctu_submit(kvz_cuda_ctu_enc *e, const uint8_t *y, const uint8_t *u, const uint8_t *v, int stride_y, int stride_c,
                         const uint8_t *ctx_init, double lambda, double lambda_sqrt, int qp)
 {
+  std::lock_guard<std::mutex> lock(e->mtx);
   int id = -1;
   for (size_t i = 0; i < e->slots.size(); ++i) if (!e->slots[i].busy) { id = (int)i; break; }
   if (id < 0) return -1;
   Slot &s = e->slots[id];
   s.busy = true;
   e->cfg.lambda = lambda; e->cfg.lambda_sqrt = lambda_sqrt; e->cfg.qp = qp;
+  if (getenv("KVZ_CTU_DEBUG")) fprintf(stderr, "hostsim: qp %d lambda %.17g sqrt %.17g rdo %d pu %d-%d rdoq %d/%d sh %d ts %d sao %d dbk %d\n", qp, lambda, lambda_sqrt, e->cfg.rdo, e->cfg.pu_depth_intra_min, e->cfg.pu_depth_intra_max, e->cfg.rdoq_enable, e->cfg.rdoq_skip, e->cfg.signhide_enable, e->cfg.trskip_enable, e->cfg.sao_type, e->cfg.deblock_enable);
   const int W = e->cfg.width, H = e->cfg.height;
   for (int r = 0; r < H; ++r) memcpy(&s.src[0][(size_t)r * W], y + (size_t)r * stride_y, W);
   for (int r = 0; r < H / 2; ++r) { memcpy(&s.src[1][(size_t)r * (W / 2)], u + (size_t)r * stride_c, W / 2); memcpy(&s.src[2][(size_t)r * (W / 2)], v + (size_t)r * stride_c, W / 2); }
@@ -128,11 +133,13 @@ int kvz_cuda_ctu_wait(kvz_cuda_ctu_enc *e, int slot, kvz_cuda_ctu_result *out)
   out->sao = (const kvz_cuda_ctu_sao *)s.sao.data();
   out->rec_y = s.out[0].data(); out->rec_u = s.out[1].data(); out->rec_v = s.out[2].data();
   out->dbg_ctx = s.dbg_ctx.data();
+  out->dbg_y = s.dbg[0].data(); out->dbg_u = s.dbg[1].data(); out->dbg_v = s.dbg[2].data();
   return 0;
 }
 
 void kvz_cuda_ctu_release(kvz_cuda_ctu_enc *e, int slot)
 {
+  std::lock_guard<std::mutex> lock(e->mtx);
   if (slot >= 0 && slot < (int)e->slots.size()) e->slots[slot].busy = false;
 }
 
