@@ -145,7 +145,6 @@ struct CtuTables {
   uint8_t group_idx[32], min_in_group[10];
 };
 
-#if !defined(__CUDA_ARCH__)
 // ---- host-side table construction (product host code and the test build share it)
 namespace tables_detail {
 inline int scan_small(int scan_idx, int dim_log2, int idx)
@@ -242,7 +241,6 @@ inline void ctu_tables_init(CtuTables *t)
   static const uint8_t mig[10] = { 0, 1, 2, 3, 4, 6, 8, 12, 16, 24 };
   memcpy(t->min_in_group, mig, 10);
 }
-#endif
 
 // ---------------------------------------------------------------------------------------------- small helpers
 CTU_FN int imin(int a, int b) { return a < b ? a : b; }

@@ -27,7 +27,7 @@ struct FrameDev {
 };
 
 // ------------------------------------------------------------------------------------------------ init_lcu_t
-CTU_FN void ctu_load(const Ctx &c, const FrameDev *F, int cx, int cy)
+CTU_FN_NOINLINE void ctu_load(const Ctx &c, const FrameDev *F, int cx, int cy)
 {
   const CtuConfig *cfg = c.cfg;
   CtuWork *W = c.W;
@@ -99,7 +99,7 @@ CTU_FN void ctu_load(const Ctx &c, const FrameDev *F, int cx, int cy)
 }
 
 // ------------------------------------------------------------------------------------------------ store
-CTU_FN void ctu_store(const Ctx &c, const FrameDev *F, int cx, int cy)
+CTU_FN_NOINLINE void ctu_store(const Ctx &c, const FrameDev *F, int cx, int cy)
 {
   const CtuConfig *cfg = c.cfg;
   LcuLevel *L0 = &c.W->lv[0];
@@ -158,7 +158,7 @@ CTU_FN bool dbk_edge_wanted(const FrameDev *F, int x, int y, bool hor)
 }
 
 // luma part of 4 lines: px -> q0 of line 0; xs across the edge, ys along it (ref: filter.c:95-170, 474-520)
-CTU_FN void dbk_luma_part(uint8_t *px, int xs, int ys, int beta, int tc)
+CTU_FN_NOINLINE void dbk_luma_part(uint8_t *px, int xs, int ys, int beta, int tc)
 {
   int b[4][8];
   for (int l = 0; l < 4; ++l) for (int i = 0; i < 8; ++i) b[l][i] = px[l * ys + (i - 4) * xs];
@@ -205,7 +205,7 @@ CTU_FN void dbk_chroma_part(uint8_t *px, int xs, int ys, int tc)      // ref: fi
 }
 
 // kvz_filter_deblock_lcu on the frame planes; all CUs are intra (boundary strength 2), fixed QP
-CTU_FN void ctu_deblock(const Ctx &c, const FrameDev *F, int cx, int cy)
+CTU_FN_NOINLINE void ctu_deblock(const Ctx &c, const FrameDev *F, int cx, int cy)
 {
   const CtuConfig *cfg = c.cfg;
   const int Wd = cfg->width, H = cfg->height, Wc = Wd / 2;
@@ -278,7 +278,7 @@ CTU_FN int sao_eo_cat(int a, int b, int cc)
 }
 
 // statistics of the CTU's block of one plane (the reference works on a contiguous copy: same pixels)
-CTU_FN void sao_stats_plane(const uint8_t *org, const uint8_t *rec, int stride, int bw, int bh, int32_t edge[4][2][5], int32_t band[2][32])
+CTU_FN_NOINLINE void sao_stats_plane(const uint8_t *org, const uint8_t *rec, int stride, int bw, int bh, int32_t edge[4][2][5], int32_t band[2][32])
 {
   for (int e = CTU_TID; e < bw * bh; e += CTU_NT) {
     const int y = e / bw, x = e - y * bw;
@@ -344,7 +344,7 @@ CTU_FN int sao_band_ddist(const int32_t bd[2][32], int band_pos, const int *offs
   for (int k = 0; k < 4; ++k) { const int o = offs[k], bi = band_pos + k; if (o != 0 && bi >= 0 && bi < 32) sum += bd[1][bi] * o * o - 2 * o * bd[0][bi]; }
   return sum;
 }
-CTU_FN int sao_band_offsets(const int32_t bd[2][32], int *offsets /* [4] */, int *band_position)
+CTU_FN_NOINLINE int sao_band_offsets(const int32_t bd[2][32], int *offsets /* [4] */, int *band_position)
 {
   int dist[32], temp_offsets[32];
   for (int band = 0; band < 32; ++band) {
@@ -370,7 +370,7 @@ CTU_FN int sao_band_offsets(const int32_t bd[2][32], int *offsets /* [4] */, int
 }
 
 // sao_search_best_mode for one component group (luma: planes {0}, chroma: planes {1, 2}).  Leader only.
-CTU_FN void sao_search_best_mode(const Ctx &c, const SaoStats *st, int first_plane, int buf_cnt, SaoRec *out, const SaoRec *top, const SaoRec *left, int32_t merge_cost[3])
+CTU_FN_NOINLINE void sao_search_best_mode(const Ctx &c, const SaoStats *st, int first_plane, int buf_cnt, SaoRec *out, const SaoRec *top, const SaoRec *left, int32_t merge_cost[3])
 {
   const CtuConfig *cfg = c.cfg;
   const SaoBits sb = { c.T, c.S->cabac0.ctx };
@@ -444,7 +444,7 @@ CTU_FN void sao_search_best_mode(const Ctx &c, const SaoStats *st, int first_pla
 }
 
 // kvz_sao_search_lcu; `st` is scratch for the statistics (global or shared)
-CTU_FN void ctu_sao_search(const Ctx &c, const FrameDev *F, SaoStats *st, int cx, int cy)
+CTU_FN_NOINLINE void ctu_sao_search(const Ctx &c, const FrameDev *F, SaoStats *st, int cx, int cy)
 {
   const CtuConfig *cfg = c.cfg;
   const int Wd = cfg->width, H = cfg->height;
@@ -492,7 +492,7 @@ CTU_FN void enc_bin(const CtuTables *T, uint8_t *ctx, int off, int val)
 struct EncTrack { const Ctx *c; const FrameDev *F; CabacState *cs; const int16_t *coeff; };
 
 // encode_transform_coeff + encode_transform_unit (ref: encode_coding_tree.c:117-319), context-coded bins only
-CTU_FN void enc_transform_leaf(const EncTrack &e, int x, int y, int depth, int tr_depth, int parent_u, int parent_v)
+CTU_FN_NOINLINE void enc_transform_leaf(const EncTrack &e, int x, int y, int depth, int tr_depth, int parent_u, int parent_v)
 {
   const Ctx &c = *e.c;
   const CuRec *cur_pu = fcu(e.F, x, y);
@@ -539,7 +539,7 @@ CTU_FN void enc_transform_tree(const EncTrack &e, int x, int y, int depth)
 }
 
 // one coding unit (no further split): part mode, intra modes, transform tree
-CTU_FN void enc_coding_unit(const EncTrack &e, int x, int y, int depth)
+CTU_FN_NOINLINE void enc_coding_unit(const EncTrack &e, int x, int y, int depth)
 {
   const Ctx &c = *e.c;
   const CuRec *cur_cu = fcu(e.F, x, y);
@@ -565,7 +565,7 @@ CTU_FN void enc_coding_unit(const EncTrack &e, int x, int y, int depth)
 }
 
 // kvz_encode_coding_tree: explicit traversal of the CU quadtree in coding order
-CTU_FN void enc_coding_tree(const EncTrack &e, int x0, int y0)
+CTU_FN_NOINLINE void enc_coding_tree(const EncTrack &e, int x0, int y0)
 {
   const Ctx &c = *e.c;
   const int Wd = c.cfg->width, H = c.cfg->height;
@@ -603,7 +603,7 @@ CTU_FN void enc_coding_tree(const EncTrack &e, int x0, int y0)
 
 // The CTU's effect on the real coder's models; afterwards the row's state is published (and handed to the next row
 // after the second CTU: WPP, encoderstate.c:759-771).  Leader only inside.
-CTU_FN void ctu_track_models(const Ctx &c, const FrameDev *F, int cx, int cy)
+CTU_FN_NOINLINE void ctu_track_models(const Ctx &c, const FrameDev *F, int cx, int cy)
 {
   CTU_LEADER {
     CabacState cs = c.S->cabac0;
@@ -645,7 +645,7 @@ CTU_FN void ctu_job(const Ctx &c, const FrameDev *F, SaoStats *sao_scratch, int 
 // Final picture of one CTU area from the deblocked planes (kvz_sao_reconstruct + sao_reconstruct_color semantics,
 // sao.c:302-361, sao-generic.c:84-124): neighbours come from the deblocked picture, samples whose neighbour lies
 // outside the picture keep their value.
-CTU_FN void ctu_sao_apply(const CtuConfig *cfg, const FrameDev *F, int cx, int cy)
+CTU_FN_NOINLINE void ctu_sao_apply(const CtuConfig *cfg, const FrameDev *F, int cx, int cy)
 {
   const int Wd = cfg->width, H = cfg->height;
   const SaoRec *sl = &F->sao[2 * (cy * F->wlcu + cx)], *sc = sl + 1;

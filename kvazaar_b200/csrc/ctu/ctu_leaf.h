@@ -75,7 +75,7 @@ CTU_FN Plane plane_of(CtuWork *W, LcuLevel *L, int color)
 // ------------------------------------------------------------------------------------------------ intra references
 // kvz_intra_build_reference for the block at luma position (x, y) (picture coordinates), into `r`, followed by the
 // [1 2 1] smoothing (done eagerly: the reference's lazy flag only saves time) and the DC sum.
-CTU_FN void build_refs(const CtuTables *T, const CtuConfig *cfg, CtuWork *W, LcuLevel *L, int log2w, int color, int x, int y, IntraRefs *r)
+CTU_FN_NOINLINE void build_refs(const CtuTables *T, const CtuConfig *cfg, CtuWork *W, LcuLevel *L, int log2w, int color, int x, int y, IntraRefs *r)
 {
   const int is_c = color != 0, w = 1 << log2w;
   const Plane P = plane_of(W, L, color);
@@ -189,7 +189,7 @@ CTU_FN int intra_predict_px(const IntraRefs *r, int log2w, int mode, int color, 
   return v;
 }
 // prediction of a whole block into dst (row stride dst_stride)
-CTU_FN void predict_block(const IntraRefs *r, int log2w, int mode, int color, uint8_t *dst, int dst_stride)
+CTU_FN_NOINLINE void predict_block(const IntraRefs *r, int log2w, int mode, int color, uint8_t *dst, int dst_stride)
 {
   const int w = 1 << log2w;
   for (int e = CTU_TID; e < w * w; e += CTU_NT) {
@@ -236,7 +236,7 @@ CTU_FN int hadamard8_abs_sum(int d[64])
 
 // SATD (satd_NxN) and, for 4x4, SAD of the prediction of every mode in [mode_lo, mode_hi] against the source block.
 // satd_out / sad_out: [35] ints, zeroed here.  Items are (mode, sub-block) pairs.
-CTU_FN void rough_costs_all_modes(const IntraRefs *r, int log2w, int color, const uint8_t *src, int src_stride,
+CTU_FN_NOINLINE void rough_costs_all_modes(const IntraRefs *r, int log2w, int color, const uint8_t *src, int src_stride,
                                   int mode_lo, int mode_hi, int32_t *satd_out, int32_t *sad_out, bool want_sad)
 {
   const int w = 1 << log2w;
@@ -269,7 +269,7 @@ CTU_FN void rough_costs_all_modes(const IntraRefs *r, int log2w, int color, cons
 }
 
 // kvz_pixels_calc_ssd over a w x w block (result in *out after the call; out must be zeroed by the leader before)
-CTU_FN void ssd_block(const uint8_t *a, int sa, const uint8_t *b, int sb, int w, int32_t *out)
+CTU_FN_NOINLINE void ssd_block(const uint8_t *a, int sa, const uint8_t *b, int sb, int w, int32_t *out)
 {
   int acc = 0;
   for (int e = CTU_TID; e < w * w; e += CTU_NT) {
@@ -283,7 +283,7 @@ CTU_FN void ssd_block(const uint8_t *a, int sa, const uint8_t *b, int sb, int w,
 
 // ------------------------------------------------------------------------------------------------ transforms
 // forward: dst[k*N + j] = (int16)((sum_i M[k][i] * src[j*N + i] + add) >> shift)
-CTU_FN void fwd_pass(const int16_t *src, int16_t *dst, const int8_t *M, int n, int shift)
+CTU_FN_NOINLINE void fwd_pass(const int16_t *src, int16_t *dst, const int8_t *M, int n, int shift)
 {
   const int add = 1 << (shift - 1);
   for (int e = CTU_TID; e < n * n; e += CTU_NT) {
@@ -297,7 +297,7 @@ CTU_FN void fwd_pass(const int16_t *src, int16_t *dst, const int8_t *M, int n, i
   CTU_SYNC();
 }
 // inverse: dst[j*N + k] = clip16((sum_i M[i][k] * src[i*N + j] + add) >> shift)
-CTU_FN void inv_pass(const int16_t *src, int16_t *dst, const int8_t *M, int n, int shift)
+CTU_FN_NOINLINE void inv_pass(const int16_t *src, int16_t *dst, const int8_t *M, int n, int shift)
 {
   const int add = 1 << (shift - 1);
   for (int e = CTU_TID; e < n * n; e += CTU_NT) {
@@ -348,7 +348,7 @@ CTU_FN void quant_sign_hide_group(const CtuTables *T, const int16_t *coef, int16
 }
 
 // kvz_quant: tu->b -> tu->q (intra slice: rounding offset 171)
-CTU_FN void quant_block(const CtuTables *T, const CtuConfig *cfg, TuBuf *tu, int n, int type, int scan_idx)
+CTU_FN_NOINLINE void quant_block(const CtuTables *T, const CtuConfig *cfg, TuBuf *tu, int n, int type, int scan_idx)
 {
   const int log2n = ilog2(n);
   const int qp_scaled = scaled_qp(type, cfg->qp);
@@ -385,7 +385,7 @@ CTU_FN void quant_block(const CtuTables *T, const CtuConfig *cfg, TuBuf *tu, int
 }
 
 // kvz_dequant: tu->q -> tu->b.  type: 0 luma, 2 / 3 chroma
-CTU_FN void dequant_block(const CtuConfig *cfg, TuBuf *tu, int n, int type)
+CTU_FN_NOINLINE void dequant_block(const CtuConfig *cfg, TuBuf *tu, int n, int type)
 {
   const int transform_shift = 15 - 8 - ilog2(n);
   const int qp_scaled = scaled_qp(type, cfg->qp);
@@ -445,7 +445,7 @@ CTU_FN int sig_ctx_inc(const CtuTables *T, int pattern, int scan_idx, int px, in
 }
 
 // kvz_rdoq_sign_hiding (ref: rdo.c:518-653); serial, one thread
-CTU_FN void rdoq_sign_hiding(const RdoqScratch &s, const uint16_t *blk, double lambda, int qp_scaled, int last_pos, const int16_t *coef, int16_t *q)
+CTU_FN_NOINLINE void rdoq_sign_hiding(const RdoqScratch &s, const uint16_t *blk, double lambda, int qp_scaled, int last_pos, const int16_t *coef, int16_t *q)
 {
   const int inv_quant = inv_quant_scale(qp_scaled % 6);
   const long long rd_factor = (long long)(inv_quant * inv_quant * (1 << (2 * (qp_scaled / 6))) / lambda / 16 / (1 << (2 * (8 - 8))) + 0.5);
@@ -505,7 +505,7 @@ CTU_FN int team_sum(int v) { return v; }
 
 // kvz_rdoq for one TU, executed by one team (the first warp): coef = tu->b, levels to tu->q.  `cabac` = the models of
 // state->cabac (NOT the search copy: rdo.c:665).  type 0 luma / 2 chroma; tr_depth as in quant-generic.c:237-238.
-CTU_FN void rdoq_team(const CtuTables *T, const CtuConfig *cfg, const uint8_t *cabac, TuBuf *tu, RdoqScratch &s, int log2n, int type,
+CTU_FN_NOINLINE void rdoq_team(const CtuTables *T, const CtuConfig *cfg, const uint8_t *cabac, TuBuf *tu, RdoqScratch &s, int log2n, int type,
                       int scan_idx, int tr_depth, int lane)
 {
   const int16_t *coef = tu->b;
@@ -802,7 +802,7 @@ CTU_FN int coeff_remain_bits(int symbol, int rice)
 // kvz_get_coeff_cost's CABAC branch = kvz_encode_coeff_nxn in counting mode on a copy of the search models that is
 // kept when `update` is set (ref: rdo.c:223-264).  Leader only.  The cost estimate codes tr_skip as 0 (rdo.c:251-258);
 // the tracker of the real coder's models passes the TU's flag.
-CTU_FN double coeff_cost_serial(const CtuTables *T, const CtuConfig *cfg, CabacState *c, const int16_t *coeff, int log2n, int type, int scan_idx, int tr_skip)
+CTU_FN_NOINLINE double coeff_cost_serial(const CtuTables *T, const CtuConfig *cfg, CabacState *c, const int16_t *coeff, int log2n, int type, int scan_idx, int tr_skip)
 {
   const int n = 1 << log2n, side = n >> 2, ncg = side * side;
   uint64_t cg_flags = 0;

@@ -134,7 +134,7 @@ CTU_FN void copy_cu_coeffs(LcuLevel *from, LcuLevel *to, int xl, int yl, int wid
   const int zc = zorder(32, xl >> 1, yl >> 1), wc = width >> 1;
   for (int e = CTU_TID; e < wc * wc; e += CTU_NT) { to->coeff_u[zc + e] = from->coeff_u[zc + e]; to->coeff_v[zc + e] = from->coeff_v[zc + e]; }
 }
-CTU_FN void work_tree_copy_up(const Ctx &c, int xl, int yl, int depth)
+CTU_FN_NOINLINE void work_tree_copy_up(const Ctx &c, int xl, int yl, int depth)
 {
   const int w = 64 >> depth;
   copy_cu_info(&c.W->lv[depth + 1], &c.W->lv[depth], xl, yl, w);
@@ -142,7 +142,7 @@ CTU_FN void work_tree_copy_up(const Ctx &c, int xl, int yl, int depth)
   copy_cu_coeffs(&c.W->lv[depth + 1], &c.W->lv[depth], xl, yl, w);
   CTU_SYNC();
 }
-CTU_FN void work_tree_copy_down(const Ctx &c, int xl, int yl, int depth)
+CTU_FN_NOINLINE void work_tree_copy_down(const Ctx &c, int xl, int yl, int depth)
 {
   const int w = 64 >> depth;
   for (int i = depth + 1; i <= 4; ++i) {
@@ -152,14 +152,14 @@ CTU_FN void work_tree_copy_down(const Ctx &c, int xl, int yl, int depth)
   CTU_SYNC();
 }
 // kvz_lcu_fill_trdepth
-CTU_FN void fill_trdepth(LcuLevel *L, int xl, int yl, int depth, int tr_depth)
+CTU_FN_NOINLINE void fill_trdepth(LcuLevel *L, int xl, int yl, int depth, int tr_depth)
 {
   const int n = (64 >> depth) >> 2;
   for (int e = CTU_TID; e < n * n; e += CTU_NT) cu_at(L, xl + 4 * (e % n), yl + 4 * (e / n))->tr_depth = (uint8_t)tr_depth;
   CTU_SYNC();
 }
 // lcu_fill_cu_info (intra fields only); `cu` may alias one of the targets
-CTU_FN void fill_cu_info(LcuLevel *L, int xl, int yl, int width, const CuRec *cu)
+CTU_FN_NOINLINE void fill_cu_info(LcuLevel *L, int xl, int yl, int width, const CuRec *cu)
 {
   const CuRec v = *cu;
   CTU_SYNC();
@@ -176,7 +176,7 @@ CTU_FN void fill_cu_info(LcuLevel *L, int xl, int yl, int width, const CuRec *cu
 // kvz_quantize_residual for the TU of `color` at LCU-local luma position (xl, yl) of level L.  cu supplies
 // tr_depth / depth / part_size for RDOQ's cbf context.  Prediction is read from the level's reconstruction; the
 // result goes to rec_out (stride out_stride) and coeff_out (n*n).  Returns has_coeffs (uniform).
-CTU_FN int quantize_residual(const Ctx &c, LcuLevel *L, int color, int xl, int yl, int n, int scan_idx, const CuRec *cu, bool use_trskip,
+CTU_FN_NOINLINE int quantize_residual(const Ctx &c, LcuLevel *L, int color, int xl, int yl, int n, int scan_idx, const CuRec *cu, bool use_trskip,
                              uint8_t *rec_out, int out_stride, int16_t *coeff_out)
 {
   const CtuTables *T = c.T;
@@ -242,7 +242,7 @@ CTU_FN int quantize_residual(const Ctx &c, LcuLevel *L, int color, int xl, int y
 }
 
 // quantize_tr_residual (ref: transform.c:294-415) for one colour of the leaf TU; cur_pu receives cbf / tr_skip
-CTU_FN void quantize_tr_residual(const Ctx &c, LcuLevel *L, int color, int xl, int yl, int depth, CuRec *cur_pu)
+CTU_FN_NOINLINE void quantize_tr_residual(const Ctx &c, LcuLevel *L, int color, int xl, int yl, int depth, CuRec *cur_pu)
 {
   const int sh = color ? 1 : 0;
   const Plane P = plane_of(c.W, L, color);
@@ -292,7 +292,7 @@ CTU_FN void quantize_tr_residual(const Ctx &c, LcuLevel *L, int color, int xl, i
 }
 
 // intra_recon_tb_leaf: prediction of one colour of the TU into the level's reconstruction
-CTU_FN void intra_recon_tb_leaf(const Ctx &c, LcuLevel *L, int x, int y, int depth, int mode, int color)
+CTU_FN_NOINLINE void intra_recon_tb_leaf(const Ctx &c, LcuLevel *L, int x, int y, int depth, int mode, int color)
 {
   int log2w = 6 - depth;
   if (color != 0 && depth < 4) log2w -= 1;
@@ -304,7 +304,7 @@ CTU_FN void intra_recon_tb_leaf(const Ctx &c, LcuLevel *L, int x, int y, int dep
 }
 
 // leaf part of kvz_intra_recon_cu + kvz_quantize_lcu_residual (ref: intra.c:676-696, transform.c:448-508)
-CTU_FN void intra_recon_leaf(const Ctx &c, LcuLevel *L, int x, int y, int depth, int mode_luma, int mode_chroma, CuRec *cur_cu)
+CTU_FN_NOINLINE void intra_recon_leaf(const Ctx &c, LcuLevel *L, int x, int y, int depth, int mode_luma, int mode_chroma, CuRec *cur_cu)
 {
   const int xl = x & 63, yl = y & 63;
   CuRec *cur_tu = cu_at(L, xl, yl);
@@ -330,7 +330,7 @@ CTU_FN void intra_recon_leaf(const Ctx &c, LcuLevel *L, int x, int y, int depth,
 }
 
 // kvz_intra_recon_cu (ref: intra.c:623-698).  cur_cu == NULL: the CU record of the level at (x, y).
-CTU_FN void intra_recon_cu(const Ctx &c, LcuLevel *L, int x, int y, int depth, int mode_luma, int mode_chroma, CuRec *cur_cu)
+CTU_FN_NOINLINE void intra_recon_cu(const Ctx &c, LcuLevel *L, int x, int y, int depth, int mode_luma, int mode_chroma, CuRec *cur_cu)
 {
   const int xl = x & 63, yl = y & 63;
   if (cur_cu == NULL) cur_cu = cu_at(L, xl, yl);
@@ -365,7 +365,7 @@ CTU_FN void intra_recon_cu(const Ctx &c, LcuLevel *L, int x, int y, int depth, i
 
 // ------------------------------------------------------------------------------------------------ RD costs
 // SSDs of the leaf TUs of the CU at (xl, yl, depth) into S->ssd[leaf][colour] (leaf 0 only unless depth == 0)
-CTU_FN void leaf_ssds(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, bool luma, bool chroma)
+CTU_FN_NOINLINE void leaf_ssds(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, bool luma, bool chroma)
 {
   CtuS *S = c.S;
   CTU_LEADER { for (int k = 0; k < 4; ++k) for (int col = 0; col < 3; ++col) S->ssd[k][col] = 0; }
@@ -386,7 +386,7 @@ CTU_FN void leaf_ssds(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, bool
 }
 
 // kvz_cu_rd_cost_luma for a leaf (tr_depth == depth).  Leader only; S->ssd[leaf][0] holds the SSD.
-CTU_FN double cu_rd_cost_luma_leaf(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, const CuRec *pred_cu, int leaf)
+CTU_FN_NOINLINE double cu_rd_cost_luma_leaf(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, const CuRec *pred_cu, int leaf)
 {
   const CtuS *S = c.S;
   CabacState *sc = &c.S->sc;
@@ -416,7 +416,7 @@ CTU_FN double cu_rd_cost_luma_leaf(const Ctx &c, LcuLevel *L, int xl, int yl, in
 }
 
 // kvz_cu_rd_cost_chroma for a leaf.  Leader only.
-CTU_FN double cu_rd_cost_chroma_leaf(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, const CuRec *pred_cu, int leaf)
+CTU_FN_NOINLINE double cu_rd_cost_chroma_leaf(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, const CuRec *pred_cu, int leaf)
 {
   const CtuS *S = c.S;
   CabacState *sc = &c.S->sc;
@@ -443,7 +443,7 @@ CTU_FN double cu_rd_cost_chroma_leaf(const Ctx &c, LcuLevel *L, int xl, int yl, 
 }
 
 // cu_rd_cost_tr_split_accurate (ref: search.c:414-543), one node.  Leader only.  `leaf`: index into S->ssd.
-CTU_FN double cost_accurate_node(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, const CuRec *pred_cu, int leaf, bool *is_split)
+CTU_FN_NOINLINE double cost_accurate_node(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, const CuRec *pred_cu, int leaf, bool *is_split)
 {
   const CtuS *S = c.S;
   CabacState *sc = &c.S->sc;
@@ -483,7 +483,7 @@ CTU_FN double cost_accurate_node(const Ctx &c, LcuLevel *L, int xl, int yl, int 
   const double bits = tr_tree_bits + coeff_bits;
   return luma_ssd * 0.8 + chroma_ssd * 1.5 + bits * c.cfg->lambda;
 }
-CTU_FN double cost_tr_split_accurate(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, const CuRec *pred_cu)
+CTU_FN_NOINLINE double cost_tr_split_accurate(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, const CuRec *pred_cu)
 {
   bool split = false;
   const double v = cost_accurate_node(c, L, xl, yl, depth, pred_cu, 0, &split);
@@ -512,7 +512,7 @@ CTU_FN double calc_mode_bits(const Ctx &c, LcuLevel *L, const CuRec *cur_cu, int
 
 // kvz_mock_encode_coding_unit for an intra CU in an I slice (ref: encode_coding_tree.c:977-1075, 464-652, 672-743).
 // Leader only.
-CTU_FN double mock_encode_coding_unit(const Ctx &c, LcuLevel *L, int x, int y, int depth, const CuRec *cur_cu)
+CTU_FN_NOINLINE double mock_encode_coding_unit(const Ctx &c, LcuLevel *L, int x, int y, int depth, const CuRec *cur_cu)
 {
   double bits = 0;
   CabacState *sc = &c.S->sc;
@@ -579,7 +579,7 @@ CTU_FN void sort_modes(int8_t *modes, double *costs, int length)
 }
 
 // search_intra_rough (ref: search_intra.c:391-530) on the SATD / SAD table of all modes.  Leader only.
-CTU_FN int rough_search_replay(const Ctx &c, int log2w, const int8_t *mpm)
+CTU_FN_NOINLINE int rough_search_replay(const Ctx &c, int log2w, const int8_t *mpm)
 {
   CtuS *S = c.S;
   const CtuConfig *cfg = c.cfg;
@@ -649,7 +649,7 @@ CTU_FN int rough_search_replay(const Ctx &c, int log2w, const int8_t *mpm)
 
 // kvz_search_cu_intra (ref: search_intra.c:806-900): best luma mode of the CU at (x, y, depth) on level L.
 // Result in S->best_mode / S->best_cost.
-CTU_FN void search_cu_intra(const Ctx &c, LcuLevel *L, int x, int y, int depth)
+CTU_FN_NOINLINE void search_cu_intra(const Ctx &c, LcuLevel *L, int x, int y, int depth)
 {
   CtuS *S = c.S;
   const CtuConfig *cfg = c.cfg;
@@ -729,7 +729,7 @@ CTU_FN void search_cu_intra(const Ctx &c, LcuLevel *L, int x, int y, int depth)
 }
 
 // kvz_search_cu_intra_chroma (ref: search_intra.c:748-803) for rdo 2..3 (num_modes = 2).  Returns the mode (uniform).
-CTU_FN int search_cu_intra_chroma(const Ctx &c, LcuLevel *L, int x, int y, int depth)
+CTU_FN_NOINLINE int search_cu_intra_chroma(const Ctx &c, LcuLevel *L, int x, int y, int depth)
 {
   CtuS *S = c.S;
   const int xl = x & 63, yl = y & 63;
@@ -800,7 +800,7 @@ CTU_FN int split_model_of(LcuLevel *L, int x, int y, int depth)     // get_ctx_c
 }
 
 // search_cu for the whole CTU at (cx, cy) (luma picture coordinates); returns with the decisions on level 0
-CTU_FN void search_ctu(const Ctx &c, int cx, int cy)
+CTU_FN_NOINLINE void search_ctu(const Ctx &c, int cx, int cy)
 {
   CtuS *S = c.S;
   const CtuConfig *cfg = c.cfg;

@@ -1,0 +1,289 @@
+// ctu_driver.cu -- device-resident closed-loop intra CTU search: kernels and the C ABI of
+// include/kvz_cuda_ctu.h.  The algorithm lives in csrc/ctu/*.h (single source, see ctu_common.h).
+//
+// Execution: one CTA per CTU.  The CTUs of a picture are walked in wavefront order -- CTU (x, y) needs (x-1, y) and
+// (x+1, y-1): reconstructed border pixels, CU records, SAO parameters and the real coder's context models (WPP) --
+// one launch per anti-diagonal d = x + 2y, every picture on its own stream so that the diagonals of the pictures in
+// flight interleave on the GPU (all-intra pictures are independent).  After the last diagonal one launch applies SAO
+// (final picture) and the results are copied to pinned host memory on the same stream.
+//
+// Memory per picture slot: source / reconstruction / final planes, the per-4x4 CU records, 12 KB of coefficients per
+// CTU, and one work tree (CtuWork, 5 levels) per CTU of the longest diagonal.
+#include <condition_variable>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "../../include/kvz_cuda_ctu.h"
+#include "ctu/ctu_frame.h"
+
+using namespace kvzctu;
+
+static_assert(sizeof(kvz_cuda_ctu_config) == sizeof(CtuConfig), "config layout");
+static_assert(sizeof(kvz_cuda_ctu_cu) == sizeof(CuRec), "cu layout");
+static_assert(sizeof(kvz_cuda_ctu_sao) == sizeof(SaoRec), "sao layout");
+
+namespace {
+
+constexpr int kThreads = 128;
+
+struct KernelArgs {
+  const CtuTables *T;
+  CtuConfig cfg;
+  FrameDev F;
+  CtuWork *work;           // [max CTUs per diagonal]
+  SaoStats *sao_stats;     // [max CTUs per diagonal]
+  uint8_t *dbg_ctx;        // [nctu][184] or NULL
+};
+
+__global__ void __launch_bounds__(kThreads) ctu_diag_kernel(const __grid_constant__ KernelArgs a, int diag, int cy_lo)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  CtuS *S = reinterpret_cast<CtuS *>(smem);
+  const int cy = cy_lo + blockIdx.x;
+  const int cx = diag - 2 * cy;
+  Ctx c = { a.T, &a.cfg, a.work + blockIdx.x, S };
+  if (a.dbg_ctx) {
+    for (int i = threadIdx.x; i < CTX_COUNT; i += blockDim.x) a.dbg_ctx[(size_t)(cy * a.F.wlcu + cx) * CTX_COUNT + i] = a.F.row_ctx[cy].ctx[i];
+  }
+  ctu_job(c, &a.F, a.sao_stats + blockIdx.x, cx, cy);
+}
+
+__global__ void __launch_bounds__(kThreads) ctu_sao_apply_kernel(const __grid_constant__ KernelArgs a)
+{
+  const int cy = blockIdx.x / a.F.wlcu, cx = blockIdx.x % a.F.wlcu;
+  ctu_sao_apply(&a.cfg, &a.F, cx, cy);
+}
+
+struct Slot {
+  int state = 0;                 // 0 free, 1 submitted
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  // device
+  uint8_t *d_planes = nullptr;   // src | rec | out | dbg, each w*h*3/2
+  uint8_t *d_bufs = nullptr;     // hor / ver buffers
+  CuRec *d_cu = nullptr;
+  int16_t *d_coeff = nullptr;
+  SaoRec *d_sao = nullptr;
+  CabacState *d_row_ctx = nullptr;
+  CtuWork *d_work = nullptr;
+  SaoStats *d_stats = nullptr;
+  uint8_t *d_dbg_ctx = nullptr;
+  // pinned host
+  uint8_t *h_src = nullptr;      // staging for the upload
+  uint8_t *h_out = nullptr, *h_dbg = nullptr;
+  CuRec *h_cu = nullptr;
+  int16_t *h_coeff = nullptr;
+  SaoRec *h_sao = nullptr;
+  CabacState *h_row_ctx = nullptr;
+  uint8_t *h_dbg_ctx = nullptr;
+  KernelArgs args;
+};
+
+}  // namespace
+
+struct kvz_cuda_ctu_enc {
+  CtuConfig cfg;
+  CtuTables *d_tables = nullptr;
+  int wl = 0, hl = 0, max_diag = 0;
+  size_t plane_bytes = 0, smem = 0;
+  bool debug = false;
+  std::vector<Slot> slots;
+  std::mutex mtx;
+  std::condition_variable cv;
+  std::atomic<uint64_t> launches{0};
+};
+
+#define CTU_CHECK_PTR(expr)                                                                                         \
+  do {                                                                                                              \
+    cudaError_t e__ = (expr);                                                                                       \
+    if (e__ != cudaSuccess) {                                                                                       \
+      kvzc::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);                 \
+      kvz_cuda_ctu_close(e);                                                                                        \
+      return nullptr;                                                                                               \
+    }                                                                                                               \
+  } while (0)
+
+extern "C" {
+
+int kvz_cuda_ctu_config_supported(const kvz_cuda_ctu_config *c)
+{
+  if (!c) return -1;
+  if (c->width < 8 || c->height < 8 || (c->width & 7) || (c->height & 7) || c->width > 16384 || c->height > 16384) return -1;
+  if (c->rdo < 0 || c->rdo > 3) return -1;
+  if (c->pu_depth_intra_min < 1 || c->pu_depth_intra_max > 4 || c->pu_depth_intra_min > c->pu_depth_intra_max) return -1;
+  if (c->qp < 0 || c->qp > 51) return -1;
+  return 0;
+}
+
+void kvz_cuda_ctu_close(kvz_cuda_ctu_enc *e)
+{
+  if (!e) return;
+  for (Slot &s : e->slots) {
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    cudaFree(s.d_planes); cudaFree(s.d_bufs); cudaFree(s.d_cu); cudaFree(s.d_coeff); cudaFree(s.d_sao); cudaFree(s.d_row_ctx);
+    cudaFree(s.d_work); cudaFree(s.d_stats); cudaFree(s.d_dbg_ctx);
+    cudaFreeHost(s.h_src); cudaFreeHost(s.h_out); cudaFreeHost(s.h_dbg); cudaFreeHost(s.h_cu); cudaFreeHost(s.h_coeff); cudaFreeHost(s.h_sao);
+    cudaFreeHost(s.h_row_ctx); cudaFreeHost(s.h_dbg_ctx);
+    if (s.done) cudaEventDestroy(s.done);
+    if (s.stream) cudaStreamDestroy(s.stream);
+  }
+  cudaFree(e->d_tables);
+  delete e;
+}
+
+kvz_cuda_ctu_enc *kvz_cuda_ctu_open(const kvz_cuda_ctu_config *cfg, int slots)
+{
+  if (kvz_cuda_ctu_config_supported(cfg)) { kvzc::set_error("kvz_cuda_ctu_open: configuration outside the driver's scope"); return nullptr; }
+  if (kvzc::g_device < 0 && kvz_cuda_init(-1) != 0) return nullptr;
+  kvz_cuda_ctu_enc *e = new (std::nothrow) kvz_cuda_ctu_enc;
+  if (!e) return nullptr;
+  memcpy(&e->cfg, cfg, sizeof(CtuConfig));
+  const int W = cfg->width, H = cfg->height;
+  e->wl = (W + 63) / 64; e->hl = (H + 63) / 64;
+  e->max_diag = 0;
+  for (int d = 0; d < e->wl + 2 * (e->hl - 1); ++d) {
+    const int lo = d - (e->wl - 1) > 0 ? (d - (e->wl - 1) + 1) / 2 : 0, hi = d / 2 < e->hl - 1 ? d / 2 : e->hl - 1;
+    if (hi - lo + 1 > e->max_diag) e->max_diag = hi - lo + 1;
+  }
+  e->plane_bytes = (size_t)W * H * 3 / 2;
+  e->smem = sizeof(CtuS);
+  e->debug = getenv("KVZ_CUDA_CTU_DEBUG") != nullptr;
+  {
+    CtuTables *ht = new CtuTables;
+    ctu_tables_init(ht);
+    cudaError_t err = cudaMalloc(&e->d_tables, sizeof(CtuTables));
+    if (err == cudaSuccess) err = cudaMemcpy(e->d_tables, ht, sizeof(CtuTables), cudaMemcpyHostToDevice);
+    delete ht;
+    CTU_CHECK_PTR(err);
+  }
+  CTU_CHECK_PTR(cudaFuncSetAttribute(ctu_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  e->slots.resize(slots > 0 ? (slots > 64 ? 64 : slots) : 1);
+  const size_t nctu = (size_t)e->wl * e->hl;
+  const size_t cu_n = (size_t)(e->wl * 16) * (e->hl * 16);
+  const size_t buf_bytes = ((size_t)W * e->hl + (size_t)H * e->wl) * 3 / 2 + 64;
+  for (Slot &s : e->slots) {
+    CTU_CHECK_PTR(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CTU_CHECK_PTR(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    CTU_CHECK_PTR(cudaMalloc(&s.d_planes, e->plane_bytes * 4));
+    CTU_CHECK_PTR(cudaMalloc(&s.d_bufs, buf_bytes));
+    CTU_CHECK_PTR(cudaMalloc(&s.d_cu, cu_n * sizeof(CuRec)));
+    CTU_CHECK_PTR(cudaMalloc(&s.d_coeff, nctu * 6144 * sizeof(int16_t)));
+    CTU_CHECK_PTR(cudaMalloc(&s.d_sao, nctu * 2 * sizeof(SaoRec)));
+    CTU_CHECK_PTR(cudaMalloc(&s.d_row_ctx, e->hl * sizeof(CabacState)));
+    CTU_CHECK_PTR(cudaMalloc(&s.d_work, (size_t)e->max_diag * sizeof(CtuWork)));
+    CTU_CHECK_PTR(cudaMalloc(&s.d_stats, (size_t)e->max_diag * sizeof(SaoStats)));
+    CTU_CHECK_PTR(cudaMemset(s.d_sao, 0, nctu * 2 * sizeof(SaoRec)));
+    CTU_CHECK_PTR(cudaMemset(s.d_planes, 0, e->plane_bytes * 4));
+    CTU_CHECK_PTR(cudaMemset(s.d_bufs, 0, buf_bytes));
+    CTU_CHECK_PTR(cudaHostAlloc(&s.h_src, e->plane_bytes, cudaHostAllocDefault));
+    CTU_CHECK_PTR(cudaHostAlloc(&s.h_out, e->plane_bytes, cudaHostAllocDefault));
+    CTU_CHECK_PTR(cudaHostAlloc(&s.h_cu, cu_n * sizeof(CuRec), cudaHostAllocDefault));
+    CTU_CHECK_PTR(cudaHostAlloc(&s.h_coeff, nctu * 6144 * sizeof(int16_t), cudaHostAllocDefault));
+    CTU_CHECK_PTR(cudaHostAlloc(&s.h_sao, nctu * 2 * sizeof(SaoRec), cudaHostAllocDefault));
+    CTU_CHECK_PTR(cudaHostAlloc(&s.h_row_ctx, e->hl * sizeof(CabacState), cudaHostAllocDefault));
+    if (e->debug) {
+      CTU_CHECK_PTR(cudaMalloc(&s.d_dbg_ctx, nctu * CTX_COUNT));
+      CTU_CHECK_PTR(cudaHostAlloc(&s.h_dbg_ctx, nctu * CTX_COUNT, cudaHostAllocDefault));
+      CTU_CHECK_PTR(cudaHostAlloc(&s.h_dbg, e->plane_bytes, cudaHostAllocDefault));
+    }
+    KernelArgs &a = s.args;
+    a.T = e->d_tables;
+    a.work = s.d_work; a.sao_stats = s.d_stats; a.dbg_ctx = s.d_dbg_ctx;
+    FrameDev &F = a.F;
+    const size_t ysz = (size_t)W * H, csz = ysz / 4;
+    uint8_t *p = s.d_planes;
+    F.src_y = p; F.src_u = p + ysz; F.src_v = p + ysz + csz; p += e->plane_bytes;
+    F.rec_y = p; F.rec_u = p + ysz; F.rec_v = p + ysz + csz; p += e->plane_bytes;
+    F.out_y = p; F.out_u = p + ysz; F.out_v = p + ysz + csz; p += e->plane_bytes;
+    if (e->debug) { F.dbg_y = p; F.dbg_u = p + ysz; F.dbg_v = p + ysz + csz; } else { F.dbg_y = F.dbg_u = F.dbg_v = nullptr; }
+    uint8_t *b = s.d_bufs;
+    F.hor_y = b; b += (size_t)W * e->hl; F.hor_u = b; b += (size_t)(W / 2) * e->hl; F.hor_v = b; b += (size_t)(W / 2) * e->hl;
+    F.ver_y = b; b += (size_t)H * e->wl; F.ver_u = b; b += (size_t)(H / 2) * e->wl; F.ver_v = b;
+    F.cu = s.d_cu; F.coeff = s.d_coeff; F.sao = s.d_sao; F.row_ctx = s.d_row_ctx;
+    F.cu_stride = e->wl * 16; F.wlcu = e->wl; F.hlcu = e->hl;
+  }
+  return e;
+}
+
+int kvz_cuda_ctu_submit(kvz_cuda_ctu_enc *e, const uint8_t *y, const uint8_t *u, const uint8_t *v, int stride_y, int stride_c,
+                        const uint8_t *ctx_init, double lambda, double lambda_sqrt, int qp)
+{
+  KVZC_ARG(e && y && u && v && ctx_init && stride_y >= e->cfg.width && stride_c >= e->cfg.width / 2);
+  int id = -1;
+  {
+    std::unique_lock<std::mutex> lock(e->mtx);
+    e->cv.wait(lock, [&] { for (size_t i = 0; i < e->slots.size(); ++i) if (e->slots[i].state == 0) { id = (int)i; return true; } return false; });
+    e->slots[id].state = 1;
+  }
+  Slot &s = e->slots[id];
+  const int W = e->cfg.width, H = e->cfg.height;
+  const size_t ysz = (size_t)W * H, csz = ysz / 4;
+  for (int r = 0; r < H; ++r) memcpy(s.h_src + (size_t)r * W, y + (size_t)r * stride_y, W);
+  for (int r = 0; r < H / 2; ++r) {
+    memcpy(s.h_src + ysz + (size_t)r * (W / 2), u + (size_t)r * stride_c, W / 2);
+    memcpy(s.h_src + ysz + csz + (size_t)r * (W / 2), v + (size_t)r * stride_c, W / 2);
+  }
+  for (int r = 0; r < e->hl; ++r) { memcpy(s.h_row_ctx[r].ctx, ctx_init, CTX_COUNT); s.h_row_ctx[r].update = 0; memset(s.h_row_ctx[r].pad, 0, sizeof(s.h_row_ctx[r].pad)); }
+  s.args.cfg = e->cfg;
+  s.args.cfg.lambda = lambda; s.args.cfg.lambda_sqrt = lambda_sqrt; s.args.cfg.qp = qp;
+  cudaStream_t st = s.stream;
+  KVZC_CHECK(cudaMemcpyAsync((void *)s.args.F.src_y, s.h_src, e->plane_bytes, cudaMemcpyHostToDevice, st));
+  KVZC_CHECK(cudaMemcpyAsync(s.d_row_ctx, s.h_row_ctx, e->hl * sizeof(CabacState), cudaMemcpyHostToDevice, st));
+  KVZC_CHECK(cudaMemsetAsync(s.d_cu, 0, (size_t)(e->wl * 16) * (e->hl * 16) * sizeof(CuRec), st));
+  const int ndiag = e->wl + 2 * (e->hl - 1);
+  for (int d = 0; d < ndiag; ++d) {
+    const int lo = d - (e->wl - 1) > 0 ? (d - (e->wl - 1) + 1) / 2 : 0, hi = d / 2 < e->hl - 1 ? d / 2 : e->hl - 1;
+    if (hi < lo) continue;
+    ctu_diag_kernel<<<hi - lo + 1, kThreads, e->smem, st>>>(s.args, d, lo);
+    e->launches.fetch_add(1, std::memory_order_relaxed);
+    kvzc::g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  ctu_sao_apply_kernel<<<e->wl * e->hl, kThreads, 0, st>>>(s.args);
+  e->launches.fetch_add(1, std::memory_order_relaxed);
+  kvzc::g_launches.fetch_add(1, std::memory_order_relaxed);
+  KVZC_CHECK(cudaGetLastError());
+  const size_t nctu = (size_t)e->wl * e->hl;
+  KVZC_CHECK(cudaMemcpyAsync(s.h_cu, s.d_cu, (size_t)(e->wl * 16) * (e->hl * 16) * sizeof(CuRec), cudaMemcpyDeviceToHost, st));
+  KVZC_CHECK(cudaMemcpyAsync(s.h_coeff, s.d_coeff, nctu * 6144 * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+  KVZC_CHECK(cudaMemcpyAsync(s.h_sao, s.d_sao, nctu * 2 * sizeof(SaoRec), cudaMemcpyDeviceToHost, st));
+  KVZC_CHECK(cudaMemcpyAsync(s.h_out, s.args.F.out_y, e->plane_bytes, cudaMemcpyDeviceToHost, st));
+  if (e->debug) {
+    KVZC_CHECK(cudaMemcpyAsync(s.h_dbg_ctx, s.d_dbg_ctx, nctu * CTX_COUNT, cudaMemcpyDeviceToHost, st));
+    KVZC_CHECK(cudaMemcpyAsync(s.h_dbg, s.args.F.dbg_y, e->plane_bytes, cudaMemcpyDeviceToHost, st));
+  }
+  KVZC_CHECK(cudaEventRecord(s.done, st));
+  return id;
+}
+
+int kvz_cuda_ctu_wait(kvz_cuda_ctu_enc *e, int slot, kvz_cuda_ctu_result *out)
+{
+  KVZC_ARG(e && out && slot >= 0 && slot < (int)e->slots.size() && e->slots[slot].state == 1);
+  Slot &s = e->slots[slot];
+  KVZC_CHECK(cudaEventSynchronize(s.done));
+  const size_t ysz = (size_t)e->cfg.width * e->cfg.height, csz = ysz / 4;
+  memset(out, 0, sizeof(*out));
+  out->cu = (const kvz_cuda_ctu_cu *)s.h_cu;
+  out->cu_stride = e->wl * 16;
+  out->width_in_lcu = e->wl; out->height_in_lcu = e->hl;
+  out->coeff = s.h_coeff;
+  out->sao = (const kvz_cuda_ctu_sao *)s.h_sao;
+  out->rec_y = s.h_out; out->rec_u = s.h_out + ysz; out->rec_v = s.h_out + ysz + csz;
+  if (e->debug) { out->dbg_ctx = s.h_dbg_ctx; out->dbg_y = s.h_dbg; out->dbg_u = s.h_dbg + ysz; out->dbg_v = s.h_dbg + ysz + csz; }
+  return 0;
+}
+
+void kvz_cuda_ctu_release(kvz_cuda_ctu_enc *e, int slot)
+{
+  if (!e || slot < 0 || slot >= (int)e->slots.size()) return;
+  {
+    std::lock_guard<std::mutex> lock(e->mtx);
+    e->slots[slot].state = 0;
+  }
+  e->cv.notify_one();
+}
+
+uint64_t kvz_cuda_ctu_launches(const kvz_cuda_ctu_enc *e) { return e ? e->launches.load() : 0; }
+
+}  // extern "C"

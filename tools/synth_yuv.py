@@ -1,5 +1,8 @@
 #!/usr/bin/env python
-"""Writes the deterministic synthetic I420 clip of SURVEY.md 8(d): tools/synth_yuv.py W H FRAMES out.yuv [seed]"""
+"""Deterministic synthetic I420 clips.
+   tools/synth_yuv.py W H FRAMES out.yuv [seed] [--noisy]
+default: the clip of SURVEY.md 8(d) (ramp + drifting sinusoid + small noise);
+--noisy: strong noise, flat patches and sharp edges (exercises high coefficient levels, band SAO, transform skip)."""
 import sys
 import numpy as np
 
@@ -14,9 +17,23 @@ def synth_frame(width, height, seed=1234, frame_idx=0):
     return np.concatenate([np.clip(p, 0, 255).astype(np.uint8).ravel() for p in (luma, u, v)])
 
 
+def noisy_frame(width, height, seed=5, frame_idx=0):
+    r = np.random.default_rng(seed * 1000 + frame_idx)
+    y, x = np.mgrid[0:height, 0:width]
+    base = 128 + 70 * np.sin(x / 9.0 + frame_idx) * np.cos(y / 7.0) + r.integers(-40, 41, (height, width))
+    base[(x // 16 + y // 16) % 3 == 0] = r.integers(0, 256)
+    base[((x // 4) % 2 == 0) & ((y // 32) % 2 == 1)] += 60
+    cy, cx = np.mgrid[0:height // 2, 0:width // 2]
+    u = 128 + 50 * np.sin(cx / 5.0) + r.integers(-20, 21, cx.shape)
+    v = 128 + 50 * np.cos(cy / 3.0) + r.integers(-30, 31, cx.shape)
+    return np.concatenate([np.clip(p, 0, 255).astype(np.uint8).ravel() for p in (base, u, v)])
+
+
 if __name__ == "__main__":
-    w, h, n, out = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
-    seed = int(sys.argv[5]) if len(sys.argv) > 5 else 1234
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    noisy = "--noisy" in sys.argv
+    w, h, n, out = int(args[0]), int(args[1]), int(args[2]), args[3]
+    seed = int(args[4]) if len(args) > 4 else (5 if noisy else 1234)
     with open(out, "wb") as f:
         for i in range(n):
-            f.write(synth_frame(w, h, seed, i).tobytes())
+            f.write((noisy_frame if noisy else synth_frame)(w, h, seed, i).tobytes())
