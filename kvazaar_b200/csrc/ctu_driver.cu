@@ -162,7 +162,7 @@ kvz_cuda_ctu_enc *kvz_cuda_ctu_open(const kvz_cuda_ctu_config *cfg, int slots)
   e->slots.resize(slots > 0 ? (slots > 64 ? 64 : slots) : 1);
   const size_t nctu = (size_t)e->wl * e->hl;
   const size_t cu_n = (size_t)(e->wl * 16) * (e->hl * 16);
-  const size_t buf_bytes = ((size_t)W * e->hl + (size_t)H * e->wl) * 3 / 2 + 64;
+  const size_t buf_bytes = ((size_t)W * e->hl + (size_t)H * e->wl) * 2 + 64;      // Y + U + V rows (columns): w + w/2 + w/2
   for (Slot &s : e->slots) {
     CTU_CHECK_PTR(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CTU_CHECK_PTR(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
