@@ -13,7 +13,14 @@ LIB       := kvazaar_b200/libkvzcuda.so
 all: lib oracle ref
 lib: $(LIB)
 
-$(OBJDIR)/%.o: $(SRCDIR)/%.cu $(wildcard $(SRCDIR)/*.cuh) $(wildcard $(SRCDIR)/ctu/*.h) include/kvz_cuda.h include/kvz_cuda_ctu.h
+# make PROF=1: the CTU driver with its phase profile (diagnostic; kvz_cuda_ctu_close prints it)
+CTUFLAGS  := $(if $(PROF),-DKVZ_CTU_PROF,)
+
+$(OBJDIR)/ctu_driver.o: $(SRCDIR)/ctu_driver.cu $(wildcard $(SRCDIR)/*.cuh) $(wildcard $(SRCDIR)/ctu/*.h) include/kvz_cuda.h include/kvz_cuda_ctu.h
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) $(CTUFLAGS) -c $< -o $@
+
+$(OBJDIR)/%.o: $(SRCDIR)/%.cu $(wildcard $(SRCDIR)/*.cuh) include/kvz_cuda.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 

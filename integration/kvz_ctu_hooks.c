@@ -14,7 +14,8 @@
  * Environment:
  *   KVZ_CTU_PROVIDER = path of a library exporting the kvz_cuda_ctu_* ABI (libkvzcuda.so; tests: the host build)
  *   KVZ_CTU_MODE     = replace (default) | verify  (verify: the reference searches too, differences are reported)
- *   KVZ_CTU_SLOTS    = pictures in flight (default 8)
+ *   KVZ_CTU_SLOTS    = picture slots of the provider (default and minimum: owf + 1, the pictures the encoder keeps in
+ *                      flight -- a worker blocked on a busy slot could otherwise starve the pictures that hold the slots)
  * Without KVZ_CTU_PROVIDER, or when the configuration is outside the driver's scope, every hook falls through.
  */
 #define _GNU_SOURCE
@@ -56,7 +57,7 @@ typedef struct {
   kvz_cuda_ctu_result res;
 } job_t;
 
-#define MAX_JOBS 64
+#define MAX_JOBS 512
 static provider_t g_prov;
 static kvz_cuda_ctu_enc *g_enc;
 static const encoder_control_t *g_ctrl;
@@ -85,6 +86,8 @@ static void fill_config(const encoder_state_t *state, kvz_cuda_ctu_config *c)
   c->wpp = cfg->wpp;
   c->lambda = state->lambda; c->lambda_sqrt = state->lambda_sqrt;
 }
+
+static int cfg_owf(const encoder_state_t *state) { return state->encoder_control->cfg.owf > 0 ? state->encoder_control->cfg.owf : 0; }
 
 /* is this encoder inside the driver's scope?  (ctu_search.h header) */
 static int config_in_scope(const encoder_state_t *state)
@@ -129,7 +132,11 @@ static int driver_active(const encoder_state_t *state)
         const char *mode = getenv("KVZ_CTU_MODE");
         g_verify = mode && strcmp(mode, "verify") == 0;
         if (g_prov.supported && g_prov.open && g_prov.submit && g_prov.wait && g_prov.release && g_prov.supported(&c) == 0)
-          g_enc = g_prov.open(&c, slots ? atoi(slots) : 8);
+        {
+          int n = cfg_owf(state) + 1;
+          if (slots && atoi(slots) > n) n = atoi(slots);
+          g_enc = g_prov.open(&c, n);
+        }
         if (g_enc) { g_ctrl = state->encoder_control; st = 1; fprintf(stderr, "kvz-ctu: CTU search driver active (%s%s)\n", path, g_verify ? ", verify" : ""); }
         else fprintf(stderr, "kvz-ctu: provider refused the configuration, using the reference path\n");
       }

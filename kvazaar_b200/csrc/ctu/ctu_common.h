@@ -37,6 +37,26 @@
 #endif
 #define CTU_LEADER if (CTU_TID == 0)
 
+// Frame-level data (reconstruction planes, CU records, border buffers, SAO parameters, row context models) is written
+// by the CTA of one CTU and read by the CTAs of its neighbours, which run on other SMs inside the same launch: such
+// loads must be served by L2 (ld.global.cg), never by a possibly stale line of this SM's L1.
+#if defined(__CUDA_ARCH__)
+#define CTU_LD_FRAME(p) __ldcg(p)
+#else
+#define CTU_LD_FRAME(p) (*(p))
+#endif
+
+// Phase profile (diagnostic build, make PROF=1): cycles of the leader thread per phase, summed over all CTUs.
+enum { PR_LOAD, PR_SEARCH, PR_STORE, PR_DEBLOCK, PR_SAO, PR_TRACK, PR_REFS, PR_SATD, PR_REPLAY, PR_PREDICT, PR_QRES, PR_FWD, PR_RDOQ, PR_QUANT,
+       PR_INV, PR_SSD, PR_COST, PR_COPY, PR_COEFFCOST, PR_WAIT, PR_CHROMA, PR_RDO_LOOP, PR_N };
+#if defined(KVZ_CTU_PROF) && defined(__CUDA_ARCH__)
+#define PROF_T0(id) const long long prof_t0_##id = clock64()
+#define PROF_ADD(S, id) do { if (CTU_TID == 0) (S)->prof[id] += clock64() - prof_t0_##id; } while (0)
+#else
+#define PROF_T0(id) ((void)0)
+#define PROF_ADD(S, id) ((void)0)
+#endif
+
 namespace kvzctu {
 
 // ---------------------------------------------------------------------------------------------- configuration
@@ -59,7 +79,7 @@ struct CtuConfig {
 
 // ---------------------------------------------------------------------------------------------- CU records
 // The fields of cu_info_t (ref: src/cu.h:126-165) an intra CU uses, unpacked.
-struct CuRec {
+struct alignas(4) CuRec {
   uint8_t type, depth, part_size, tr_depth;
   uint8_t tr_skip, qp;
   int8_t mode, mode_chroma;
@@ -67,6 +87,13 @@ struct CuRec {
   uint16_t pad;
 };
 static_assert(sizeof(CuRec) == 12, "CuRec layout");
+CTU_FN CuRec ld_frame_cu(const CuRec *p)
+{
+  union { CuRec c; uint32_t w[3]; } u;
+  const uint32_t *q = (const uint32_t *)p;
+  u.w[0] = CTU_LD_FRAME(q); u.w[1] = CTU_LD_FRAME(q + 1); u.w[2] = CTU_LD_FRAME(q + 2);
+  return u.c;
+}
 enum { CU_NOTSET = 0, CU_INTRA = 1 };
 enum { SIZE_2Nx2N = 0, SIZE_NxN = 3 };
 enum { COLOR_Y = 0, COLOR_U = 1, COLOR_V = 2 };

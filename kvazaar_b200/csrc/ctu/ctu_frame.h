@@ -46,32 +46,32 @@ CTU_FN_NOINLINE void ctu_load(const Ctx &c, const FrameDev *F, int cx, int cy)
   CTU_SYNC();
   // neighbouring CU records
   for (int i = CTU_TID; i < 16; i += CTU_NT) {
-    if (y > 0 && x + 4 * i < Wd) *cu_at(L0, 4 * i, -1) = F->cu[((y - 1) >> 2) * F->cu_stride + ((x + 4 * i) >> 2)];
-    if (x > 0 && y + 4 * i < H) *cu_at(L0, -1, 4 * i) = F->cu[((y + 4 * i) >> 2) * F->cu_stride + ((x - 1) >> 2)];
+    if (y > 0 && x + 4 * i < Wd) *cu_at(L0, 4 * i, -1) = ld_frame_cu(&F->cu[((y - 1) >> 2) * F->cu_stride + ((x + 4 * i) >> 2)]);
+    if (x > 0 && y + 4 * i < H) *cu_at(L0, -1, 4 * i) = ld_frame_cu(&F->cu[((y + 4 * i) >> 2) * F->cu_stride + ((x - 1) >> 2)]);
   }
   CTU_LEADER {
-    if (x > 0 && y > 0) *cu_at(L0, -1, -1) = F->cu[((y - 1) >> 2) * F->cu_stride + ((x - 1) >> 2)];
-    if (y > 0 && x + 64 < Wd) *cu_top_right(L0) = F->cu[((y - 1) >> 2) * F->cu_stride + ((x + 64) >> 2)];
+    if (x > 0 && y > 0) *cu_at(L0, -1, -1) = ld_frame_cu(&F->cu[((y - 1) >> 2) * F->cu_stride + ((x - 1) >> 2)]);
+    if (y > 0 && x + 64 < Wd) *cu_top_right(L0) = ld_frame_cu(&F->cu[((y - 1) >> 2) * F->cu_stride + ((x + 64) >> 2)]);
   }
   // reference pixels: index 0 of the border arrays is the top-left corner sample
   if (y > 0) {
     const int x_max = imin(96, Wd - x);
     const int x_min = x > 0 ? 0 : 1;
     // luma: entries x_min .. x_max (entry e = picture column x + e - 1) from the bottom row of CTU row cy - 1
-    for (int e = x_min + CTU_TID; e <= x_max; e += CTU_NT) W->top_y[e] = F->hor_y[(cy - 1) * Wd + x + e - 1];
+    for (int e = x_min + CTU_TID; e <= x_max; e += CTU_NT) W->top_y[e] = CTU_LD_FRAME(&F->hor_y[(cy - 1) * Wd + x + e - 1]);
     for (int e = x_min + CTU_TID; e <= x_max / 2; e += CTU_NT) {
-      W->top_u[e] = F->hor_u[(cy - 1) * (Wd / 2) + x / 2 + e - 1];
-      W->top_v[e] = F->hor_v[(cy - 1) * (Wd / 2) + x / 2 + e - 1];
+      W->top_u[e] = CTU_LD_FRAME(&F->hor_u[(cy - 1) * (Wd / 2) + x / 2 + e - 1]);
+      W->top_v[e] = CTU_LD_FRAME(&F->hor_v[(cy - 1) * (Wd / 2) + x / 2 + e - 1]);
     }
   }
   if (x > 0) {
     const int y_min = y > 0 ? 0 : 1;
     // entries y_min .. 64 from the right column of CTU column cx - 1; rows below the picture are not copied by
     // the reference either way of interest (they are never read: availability is clipped to the picture)
-    for (int e = y_min + CTU_TID; e <= 64; e += CTU_NT) { const int yy = y + e - 1; if (yy < H) W->left_y[e] = F->ver_y[(cx - 1) * H + yy]; }
+    for (int e = y_min + CTU_TID; e <= 64; e += CTU_NT) { const int yy = y + e - 1; if (yy < H) W->left_y[e] = CTU_LD_FRAME(&F->ver_y[(cx - 1) * H + yy]); }
     for (int e = y_min + CTU_TID; e <= 32; e += CTU_NT) {
       const int yy = y / 2 + e - 1;
-      if (yy < H / 2) { W->left_u[e] = F->ver_u[(cx - 1) * (H / 2) + yy]; W->left_v[e] = F->ver_v[(cx - 1) * (H / 2) + yy]; }
+      if (yy < H / 2) { W->left_u[e] = CTU_LD_FRAME(&F->ver_u[(cx - 1) * (H / 2) + yy]); W->left_v[e] = CTU_LD_FRAME(&F->ver_v[(cx - 1) * (H / 2) + yy]); }
     }
   }
   // source pixels
@@ -94,7 +94,9 @@ CTU_FN_NOINLINE void ctu_load(const Ctx &c, const FrameDev *F, int cx, int cy)
     for (int i = CTU_TID; i < (int)(sizeof(LcuLevel) / 4); i += CTU_NT) p[i] = s[i];
   }
   // the models the search starts from
-  CTU_LEADER { c.S->cabac0 = F->row_ctx[cy]; c.S->cabac0.update = 0; c.S->sc = c.S->cabac0; }
+  for (int i = CTU_TID; i < (int)(sizeof(CabacState) / 4); i += CTU_NT) ((uint32_t *)&c.S->cabac0)[i] = CTU_LD_FRAME((const uint32_t *)&F->row_ctx[cy] + i);
+  CTU_SYNC();
+  CTU_LEADER { c.S->cabac0.update = 0; c.S->sc = c.S->cabac0; }
   CTU_SYNC();
 }
 
@@ -149,8 +151,8 @@ CTU_FN const CuRec *fcu(const FrameDev *F, int x, int y) { return &F->cu[(y >> 2
 // is the left (top) edge of the 8x8 unit at (x, y) a TU or PU boundary (ref: filter.c:194-246)
 CTU_FN bool dbk_edge_wanted(const FrameDev *F, int x, int y, bool hor)
 {
-  const CuRec *s = fcu(F, x, y);
-  const int tu_w = 64 >> s->tr_depth, cu_w = 64 >> s->depth;
+  const CuRec s = ld_frame_cu(fcu(F, x, y));
+  const int tu_w = 64 >> s.tr_depth, cu_w = 64 >> s.depth;
   const int pos = hor ? y : x;
   if ((pos & (tu_w - 1)) == 0) return true;
   const int cu_pos = pos & ~(cu_w - 1);
@@ -161,7 +163,7 @@ CTU_FN bool dbk_edge_wanted(const FrameDev *F, int x, int y, bool hor)
 CTU_FN_NOINLINE void dbk_luma_part(uint8_t *px, int xs, int ys, int beta, int tc)
 {
   int b[4][8];
-  for (int l = 0; l < 4; ++l) for (int i = 0; i < 8; ++i) b[l][i] = px[l * ys + (i - 4) * xs];
+  for (int l = 0; l < 4; ++l) for (int i = 0; i < 8; ++i) b[l][i] = CTU_LD_FRAME(&px[l * ys + (i - 4) * xs]);
   const int dp0 = iabs(b[0][1] - 2 * b[0][2] + b[0][3]), dq0 = iabs(b[0][4] - 2 * b[0][5] + b[0][6]);
   const int dp3 = iabs(b[3][1] - 2 * b[3][2] + b[3][3]), dq3 = iabs(b[3][4] - 2 * b[3][5] + b[3][6]);
   const int dp = dp0 + dp3, dq = dq0 + dq3;
@@ -197,7 +199,7 @@ CTU_FN void dbk_chroma_part(uint8_t *px, int xs, int ys, int tc)      // ref: fi
 {
   for (int l = 0; l < 4; ++l) {
     uint8_t *s = px + l * ys;
-    const int m2 = s[-2 * xs], m3 = s[-xs], m4 = s[0], m5 = s[xs];
+    const int m2 = CTU_LD_FRAME(&s[-2 * xs]), m3 = CTU_LD_FRAME(&s[-xs]), m4 = CTU_LD_FRAME(&s[0]), m5 = CTU_LD_FRAME(&s[xs]);
     const int delta = iclip(-tc, tc, (((m4 - m3) * 4) + m2 - m5 + 4) >> 3);
     s[-xs] = (uint8_t)iclip(0, 255, m3 + delta);
     s[0] = (uint8_t)iclip(0, 255, m4 - delta);
@@ -282,13 +284,13 @@ CTU_FN_NOINLINE void sao_stats_plane(const uint8_t *org, const uint8_t *rec, int
 {
   for (int e = CTU_TID; e < bw * bh; e += CTU_NT) {
     const int y = e / bw, x = e - y * bw;
-    const int cc = rec[y * stride + x], d = (int)org[y * stride + x] - cc;
+    const int cc = CTU_LD_FRAME(&rec[y * stride + x]), d = (int)org[y * stride + x] - cc;
     CTU_ATOMIC_ADD(&band[0][cc >> 3], d);
     CTU_ATOMIC_ADD(&band[1][cc >> 3], 1);
     if (x >= 1 && x < bw - 1 && y >= 1 && y < bh - 1) {
       const int ax[4] = { -1, 0, -1, 1 }, ay[4] = { 0, -1, -1, -1 };
       for (int k = 0; k < 4; ++k) {
-        const int a = rec[(y + ay[k]) * stride + x + ax[k]], b = rec[(y - ay[k]) * stride + x - ax[k]];
+        const int a = CTU_LD_FRAME(&rec[(y + ay[k]) * stride + x + ax[k]]), b = CTU_LD_FRAME(&rec[(y - ay[k]) * stride + x - ax[k]]);
         const int cat = sao_eo_cat(a, b, cc);
         CTU_ATOMIC_ADD(&edge[k][0][cat], d);
         CTU_ATOMIC_ADD(&edge[k][1][cat], 1);
@@ -464,7 +466,11 @@ CTU_FN_NOINLINE void ctu_sao_search(const Ctx &c, const FrameDev *F, SaoStats *s
   CTU_SYNC();
   CTU_LEADER {
     SaoRec *sl = &F->sao[2 * (cy * F->wlcu + cx)], *sc = sl + 1;
-    const SaoRec *top_l = cy ? &F->sao[2 * ((cy - 1) * F->wlcu + cx)] : NULL, *left_l = cx ? &F->sao[2 * (cy * F->wlcu + cx - 1)] : NULL;
+    // the neighbours' parameters were written by other CTAs: local copies through L2
+    SaoRec nb[4];      // top luma, top chroma, left luma, left chroma
+    if (cy) { const int32_t *q = (const int32_t *)&F->sao[2 * ((cy - 1) * F->wlcu + cx)]; for (int i = 0; i < (int)(2 * sizeof(SaoRec) / 4); ++i) ((int32_t *)&nb[0])[i] = CTU_LD_FRAME(q + i); }
+    if (cx) { const int32_t *q = (const int32_t *)&F->sao[2 * (cy * F->wlcu + cx - 1)]; for (int i = 0; i < (int)(2 * sizeof(SaoRec) / 4); ++i) ((int32_t *)&nb[2])[i] = CTU_LD_FRAME(q + i); }
+    const SaoRec *top_l = cy ? &nb[0] : NULL, *left_l = cx ? &nb[2] : NULL;
     const SaoRec *top_c = top_l ? top_l + 1 : NULL, *left_c = left_l ? left_l + 1 : NULL;
     int32_t mcl[3] = { CTU_MAX_INT, 0, 0 }, mcc[3] = { CTU_MAX_INT, 0, 0 };
     sao_search_best_mode(c, st, 0, 1, sl, top_l, left_l, mcl);
@@ -489,14 +495,17 @@ CTU_FN void enc_bin(const CtuTables *T, uint8_t *ctx, int off, int val)
   ctx[off] = ((st & 1) == val) ? T->next_mps[st] : T->next_lps[st];
 }
 
-struct EncTrack { const Ctx *c; const FrameDev *F; CabacState *cs; const int16_t *coeff; };
+// All records and coefficients come from level 0 of the work tree: after the search it holds the CTU's decisions (the
+// same values ctu_store wrote to the frame) and the border records of the left / above CTUs (ctu_load).
+struct EncTrack { const Ctx *c; LcuLevel *L0; int x0, y0; CabacState *cs; };
+CTU_FN const CuRec *tcu(const EncTrack &e, int x, int y) { return cu_at(e.L0, x - e.x0, y - e.y0); }
 
 // encode_transform_coeff + encode_transform_unit (ref: encode_coding_tree.c:117-319), context-coded bins only
 CTU_FN_NOINLINE void enc_transform_leaf(const EncTrack &e, int x, int y, int depth, int tr_depth, int parent_u, int parent_v)
 {
   const Ctx &c = *e.c;
-  const CuRec *cur_pu = fcu(e.F, x, y);
-  const CuRec *cur_cu = fcu(e.F, x & ~7, y & ~7);
+  const CuRec *cur_pu = tcu(e, x, y);
+  const CuRec *cur_cu = tcu(e, x & ~7, y & ~7);
   const int cb_y = cbf_is_set(cur_pu->cbf, depth, 0), cb_u = cbf_is_set(cur_cu->cbf, depth, 1), cb_v = cbf_is_set(cur_cu->cbf, depth, 2);
   if (depth < 4) {
     if (tr_depth == 0 || parent_u) enc_bin(c.T, e.cs->ctx, CTX_CBF_CHROMA + tr_depth, cb_u);
@@ -508,27 +517,27 @@ CTU_FN_NOINLINE void enc_transform_leaf(const EncTrack &e, int x, int y, int dep
   e.cs->update = 1;
   if (cb_y) {
     const int scan = scan_order_intra(cur_pu->mode, depth);
-    coeff_cost_serial(c.T, c.cfg, e.cs, e.coeff + zorder(64, x & 63, y & 63), ilog2(width), 0, scan, cur_pu->tr_skip);
+    coeff_cost_serial(c.T, c.cfg, e.cs, e.L0->coeff_y + zorder(64, x & 63, y & 63), ilog2(width), 0, scan, cur_pu->tr_skip);
   }
   int xx = x, yy = y;
   if (depth == 4) {
     if (x % 8 == 0 || y % 8 == 0) return;
     xx -= 4; yy -= 4;
-    cur_pu = fcu(e.F, xx, yy);
+    cur_pu = tcu(e, xx, yy);
   }
   const int cu_u = cbf_is_set(cur_pu->cbf, depth, 1), cu_v = cbf_is_set(cur_pu->cbf, depth, 2);
   if (cu_u || cu_v) {
     const int scan = scan_order_intra(cur_pu->mode_chroma, depth);
     const int zi = zorder(32, (xx >> 1) & 31, (yy >> 1) & 31);
-    if (cu_u) coeff_cost_serial(c.T, c.cfg, e.cs, e.coeff + 4096 + zi, ilog2(width_c), 2, scan, 0);
-    if (cu_v) coeff_cost_serial(c.T, c.cfg, e.cs, e.coeff + 5120 + zi, ilog2(width_c), 2, scan, 0);
+    if (cu_u) coeff_cost_serial(c.T, c.cfg, e.cs, e.L0->coeff_u + zi, ilog2(width_c), 2, scan, 0);
+    if (cu_v) coeff_cost_serial(c.T, c.cfg, e.cs, e.L0->coeff_v + zi, ilog2(width_c), 2, scan, 0);
   }
 }
 CTU_FN void enc_transform_tree(const EncTrack &e, int x, int y, int depth)
 {
   // root of the CU's transform tree: tr_depth 0
   const Ctx &c = *e.c;
-  const CuRec *cur_cu = fcu(e.F, x & ~7, y & ~7);
+  const CuRec *cur_cu = tcu(e, x & ~7, y & ~7);
   const int split = cur_cu->tr_depth > depth;
   if (!split) { enc_transform_leaf(e, x, y, depth, 0, 0, 0); return; }
   // one implicit split (64x64 CU into 32x32 TUs, or NxN into four 4x4 TUs)
@@ -542,7 +551,7 @@ CTU_FN void enc_transform_tree(const EncTrack &e, int x, int y, int depth)
 CTU_FN_NOINLINE void enc_coding_unit(const EncTrack &e, int x, int y, int depth)
 {
   const Ctx &c = *e.c;
-  const CuRec *cur_cu = fcu(e.F, x, y);
+  const CuRec *cur_cu = tcu(e, x, y);
   const int cu_width = 64 >> depth;
   if (depth == 3) enc_bin(c.T, e.cs->ctx, CTX_PART_SIZE, cur_cu->part_size == SIZE_2Nx2N ? 1 : 0);
   const int num_pu = cur_cu->part_size == SIZE_NxN ? 4 : 1;
@@ -551,9 +560,9 @@ CTU_FN_NOINLINE void enc_coding_unit(const EncTrack &e, int x, int y, int depth)
   for (int j = 0; j < num_pu; ++j) {
     const int pw = cu_width / 2;
     const int pu_x = x + (num_pu == 4 ? (j & 1) * pw : 0), pu_y = y + (num_pu == 4 ? (j >> 1) * pw : 0);
-    const CuRec *cur_pu = fcu(e.F, pu_x, pu_y);
-    const CuRec *left_pu = pu_x > 0 ? fcu(e.F, pu_x - 1, pu_y) : NULL;
-    const CuRec *above_pu = ((pu_y & 63) > 0 && pu_y > 0) ? fcu(e.F, pu_x, pu_y - 1) : NULL;
+    const CuRec *cur_pu = tcu(e, pu_x, pu_y);
+    const CuRec *left_pu = pu_x > 0 ? tcu(e, pu_x - 1, pu_y) : NULL;
+    const CuRec *above_pu = ((pu_y & 63) > 0 && pu_y > 0) ? tcu(e, pu_x, pu_y - 1) : NULL;
     int8_t preds[3];
     intra_mpm(pu_y, left_pu, above_pu, preds);
     if (j == 0) mode0 = cur_pu->mode;
@@ -575,7 +584,7 @@ CTU_FN_NOINLINE void enc_coding_tree(const EncTrack &e, int x0, int y0)
   while (sp > 0) {
     --sp;
     const int x = sx[sp], y = sy[sp], depth = sd[sp];
-    const CuRec *cur_cu = fcu(e.F, x, y);
+    const CuRec *cur_cu = tcu(e, x, y);
     const int cu_width = 64 >> depth, half = cu_width >> 1;
     const int split_flag = cur_cu->depth > depth;
     const bool border_x = Wd < x + cu_width, border_y = H < y + cu_width;
@@ -584,8 +593,8 @@ CTU_FN_NOINLINE void enc_coding_tree(const EncTrack &e, int x0, int y0)
     if (depth != 3) {
       if (!border) {
         int split_model = 0;
-        if (x > 0 && fcu(e.F, x - 1, y)->depth > depth) ++split_model;
-        if (y > 0 && fcu(e.F, x, y - 1)->depth > depth) ++split_model;
+        if (x > 0 && tcu(e, x - 1, y)->depth > depth) ++split_model;
+        if (y > 0 && tcu(e, x, y - 1)->depth > depth) ++split_model;
         enc_bin(c.T, e.cs->ctx, CTX_SPLIT + split_model, split_flag);
       }
       if (split_flag || border) {
@@ -617,7 +626,7 @@ CTU_FN_NOINLINE void ctu_track_models(const Ctx &c, const FrameDev *F, int cx, i
         enc_bin(c.T, cs.ctx, CTX_SAO_TYPE, sc->type != 0);
       }
     }
-    EncTrack e = { &c, F, &cs, F->coeff + (size_t)(cy * F->wlcu + cx) * 6144 };
+    EncTrack e = { &c, &c.W->lv[0], cx * 64, cy * 64, &cs };
     enc_coding_tree(e, cx * 64, cy * 64);
     cs.update = 0;
     F->row_ctx[cy] = cs;
@@ -629,16 +638,18 @@ CTU_FN_NOINLINE void ctu_track_models(const Ctx &c, const FrameDev *F, int cx, i
 // ------------------------------------------------------------------------------------------------ whole CTU job
 CTU_FN void ctu_job(const Ctx &c, const FrameDev *F, SaoStats *sao_scratch, int cx, int cy)
 {
-  ctu_load(c, F, cx, cy);
-  search_ctu(c, cx * 64, cy * 64);
+  { PROF_T0(PR_LOAD); ctu_load(c, F, cx, cy); PROF_ADD(c.S, PR_LOAD); }
+  { PROF_T0(PR_SEARCH); search_ctu(c, cx * 64, cy * 64); PROF_ADD(c.S, PR_SEARCH); }
+  PROF_T0(PR_STORE);
   ctu_store(c, F, cx, cy);
 #if defined(__CUDA_ARCH__)
   __threadfence();
 #endif
   CTU_SYNC();
-  if (c.cfg->deblock_enable) ctu_deblock(c, F, cx, cy);
-  if (c.cfg->sao_type) ctu_sao_search(c, F, sao_scratch, cx, cy);
-  ctu_track_models(c, F, cx, cy);
+  PROF_ADD(c.S, PR_STORE);
+  if (c.cfg->deblock_enable) { PROF_T0(PR_DEBLOCK); ctu_deblock(c, F, cx, cy); PROF_ADD(c.S, PR_DEBLOCK); }
+  if (c.cfg->sao_type) { PROF_T0(PR_SAO); ctu_sao_search(c, F, sao_scratch, cx, cy); PROF_ADD(c.S, PR_SAO); }
+  { PROF_T0(PR_TRACK); ctu_track_models(c, F, cx, cy); PROF_ADD(c.S, PR_TRACK); }
 }
 
 // ------------------------------------------------------------------------------------------------ SAO application

@@ -61,6 +61,9 @@ struct CtuS {                       // per-CTA scalar state + scratch; shared me
   int32_t ts_pick;
   TuBuf tu;
   RdoqScratch rq;
+#if defined(KVZ_CTU_PROF)
+  long long prof[PR_N];
+#endif
 };
 
 struct Ctx {
@@ -137,19 +140,23 @@ CTU_FN void copy_cu_coeffs(LcuLevel *from, LcuLevel *to, int xl, int yl, int wid
 CTU_FN_NOINLINE void work_tree_copy_up(const Ctx &c, int xl, int yl, int depth)
 {
   const int w = 64 >> depth;
+  PROF_T0(PR_COPY);
   copy_cu_info(&c.W->lv[depth + 1], &c.W->lv[depth], xl, yl, w);
   copy_cu_pixels(&c.W->lv[depth + 1], &c.W->lv[depth], xl, yl, w);
   copy_cu_coeffs(&c.W->lv[depth + 1], &c.W->lv[depth], xl, yl, w);
   CTU_SYNC();
+  PROF_ADD(c.S, PR_COPY);
 }
 CTU_FN_NOINLINE void work_tree_copy_down(const Ctx &c, int xl, int yl, int depth)
 {
   const int w = 64 >> depth;
+  PROF_T0(PR_COPY);
   for (int i = depth + 1; i <= 4; ++i) {
     copy_cu_info(&c.W->lv[depth], &c.W->lv[i], xl, yl, w);
     copy_cu_pixels(&c.W->lv[depth], &c.W->lv[i], xl, yl, w);
   }
   CTU_SYNC();
+  PROF_ADD(c.S, PR_COPY);
 }
 // kvz_lcu_fill_trdepth
 CTU_FN_NOINLINE void fill_trdepth(LcuLevel *L, int xl, int yl, int depth, int tr_depth)
@@ -181,6 +188,8 @@ CTU_FN_NOINLINE int quantize_residual(const Ctx &c, LcuLevel *L, int color, int 
 {
   const CtuTables *T = c.T;
   TuBuf *tu = &c.S->tu;
+  PROF_T0(PR_QRES);
+  PROF_T0(PR_FWD);
   const Plane P = plane_of(c.W, L, color);
   const int sh = color ? 1 : 0;
   const int off = (xl >> sh) + (yl >> sh) * P.lw;
@@ -202,15 +211,21 @@ CTU_FN_NOINLINE int quantize_residual(const Ctx &c, LcuLevel *L, int color, int 
     fwd_pass(tu->a, tu->t, M, n, log2n - 1);
     fwd_pass(tu->t, tu->b, M, n, log2n + 6);
   }
+  PROF_ADD(c.S, PR_FWD);
   const int type = color == 0 ? 0 : 2;
   if (c.cfg->rdoq_enable && (n > 4 || !c.cfg->rdoq_skip)) {
+    PROF_T0(PR_RDOQ);
     int tr_depth = (int)cu->tr_depth - (int)cu->depth;
     tr_depth += (cu->part_size == SIZE_NxN ? 1 : 0);
     if (CTU_TID < CTU_TEAM_N) rdoq_team(T, c.cfg, c.S->cabac0.ctx, tu, c.S->rq, log2n, type, scan_idx, tr_depth, CTU_TID);
     CTU_SYNC();
+    PROF_ADD(c.S, PR_RDOQ);
   } else {
+    PROF_T0(PR_QUANT);
     quant_block(T, c.cfg, tu, n, type, scan_idx);
+    PROF_ADD(c.S, PR_QUANT);
   }
+  PROF_T0(PR_INV);
   int any = 0;
   for (int e = CTU_TID; e < nn; e += CTU_NT) { const int16_t v = tu->q[e]; coeff_out[e] = v; any |= v != 0; }
   if (any) CTU_ATOMIC_OR(&tu->has, 1);
@@ -238,6 +253,8 @@ CTU_FN_NOINLINE int quantize_residual(const Ctx &c, LcuLevel *L, int color, int 
     }
   }
   CTU_SYNC();
+  PROF_ADD(c.S, PR_INV);
+  PROF_ADD(c.S, PR_QRES);
   return has;
 }
 
@@ -299,8 +316,12 @@ CTU_FN_NOINLINE void intra_recon_tb_leaf(const Ctx &c, LcuLevel *L, int x, int y
   const int sh = color ? 1 : 0;
   const Plane P = plane_of(c.W, L, color);
   IntraRefs *r = &c.S->refs[color];
+  PROF_T0(PR_REFS);
   build_refs(c.T, c.cfg, c.W, L, log2w, color, x, y, r);
+  PROF_ADD(c.S, PR_REFS);
+  PROF_T0(PR_PREDICT);
   predict_block(r, log2w, mode, color, P.rec + ((x & 63) >> sh) + ((y & 63) >> sh) * P.lw, P.lw);
+  PROF_ADD(c.S, PR_PREDICT);
 }
 
 // leaf part of kvz_intra_recon_cu + kvz_quantize_lcu_residual (ref: intra.c:676-696, transform.c:448-508)
@@ -368,6 +389,7 @@ CTU_FN_NOINLINE void intra_recon_cu(const Ctx &c, LcuLevel *L, int x, int y, int
 CTU_FN_NOINLINE void leaf_ssds(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, bool luma, bool chroma)
 {
   CtuS *S = c.S;
+  PROF_T0(PR_SSD);
   CTU_LEADER { for (int k = 0; k < 4; ++k) for (int col = 0; col < 3; ++col) S->ssd[k][col] = 0; }
   CTU_SYNC();
   const bool split = depth == 0;
@@ -383,6 +405,7 @@ CTU_FN_NOINLINE void leaf_ssds(const Ctx &c, LcuLevel *L, int xl, int yl, int de
       ssd_block(&c.W->src_v[ci], 32, &L->rec_v[ci], 32, wc, &S->ssd[k][2]);
     }
   }
+  PROF_ADD(c.S, PR_SSD);
 }
 
 // kvz_cu_rd_cost_luma for a leaf (tr_depth == depth).  Leader only; S->ssd[leaf][0] holds the SSD.
@@ -661,11 +684,18 @@ CTU_FN_NOINLINE void search_cu_intra(const Ctx &c, LcuLevel *L, int x, int y, in
     intra_mpm(y, left, above, S->mpm);
   }
   CTU_SYNC();
+  PROF_T0(PR_REFS);
   build_refs(c.T, cfg, c.W, L, log2w, 0, x, y, &S->refs[0]);
+  PROF_ADD(S, PR_REFS);
   // rough search: SATD (and SAD for 4x4 transform-skip candidates) of every mode, then the reference's selection
+  PROF_T0(PR_SATD);
   rough_costs_all_modes(&S->refs[0], log2w, 0, &c.W->src_y[yl * 64 + xl], 64, 0, 34, S->satd, S->sad, log2w == 2 && cfg->trskip_enable);
+  PROF_ADD(S, PR_SATD);
+  PROF_T0(PR_REPLAY);
   CTU_LEADER S->n_modes = rough_search_replay(c, log2w, S->mpm);
   CTU_SYNC();
+  PROF_ADD(S, PR_REPLAY);
+  PROF_T0(PR_RDO_LOOP);
   fill_trdepth(L, xl, yl, depth, depth);
   if (cfg->rdo >= 2) {
     // search_intra_rdo (ref: search_intra.c:558-638) with tr_depth == depth
@@ -705,6 +735,7 @@ CTU_FN_NOINLINE void search_cu_intra(const Ctx &c, LcuLevel *L, int x, int y, in
       CTU_SYNC();
       intra_recon_cu(c, L, x, y, depth, mode, reconstruct_chroma ? mode : -1, &S->pred_cu);
       leaf_ssds(c, L, xl, yl, depth, true, reconstruct_chroma);
+      PROF_T0(PR_COST);
       CTU_LEADER {
         double nosplit = 0.0;
         nosplit += cu_rd_cost_luma_leaf(c, L, xl, yl, depth, &S->pred_cu, 0);
@@ -713,12 +744,14 @@ CTU_FN_NOINLINE void search_cu_intra(const Ctx &c, LcuLevel *L, int x, int y, in
         S->flag = (cfg->intra_rdo_et && !cbf_is_set_any(S->pred_cu.cbf, depth)) ? 1 : 0;
       }
       CTU_SYNC();
+      PROF_ADD(S, PR_COST);
       // (kvz_lcu_fill_trdepth(depth, depth) and the pixel restore of the no-split branch are identities here)
       if (S->flag) { checked = r + 1; break; }
     }
     CTU_LEADER { S->n_modes = checked; sort_modes(S->modes, S->costs, checked); }
     CTU_SYNC();
   }
+  PROF_ADD(S, PR_RDO_LOOP);
   CTU_LEADER {
     int bi = 0;
     for (int i = 1; i < S->n_modes; ++i) if (S->costs[i] < S->costs[bi]) bi = i;
@@ -860,7 +893,9 @@ CTU_FN_NOINLINE void search_ctu(const Ctx &c, int cx, int cy)
           intra_recon_cu(c, L, x, y, d, cur_cu->mode, -1, NULL);
           if (x % 8 == 0 && y % 8 == 0) {
             if (cfg->rdo >= 2 && cfg->intra_chroma_search) {
+              PROF_T0(PR_CHROMA);
               const int mc = search_cu_intra_chroma(c, L, x, y, d);
+              PROF_ADD(S, PR_CHROMA);
               CTU_LEADER cur_cu->mode_chroma = (int8_t)mc;
               CTU_SYNC();
               fill_cu_info(L, xl, yl, cu_width, cur_cu);
@@ -871,6 +906,7 @@ CTU_FN_NOINLINE void search_ctu(const Ctx &c, int cx, int cy)
       }
       if (cur_cu->type == CU_INTRA) {
         leaf_ssds(c, L, xl, yl, d, true, true);
+        PROF_T0(PR_COST);
         CTU_LEADER {
           double bits = 0;
           S->sc.update = 1;
@@ -882,6 +918,7 @@ CTU_FN_NOINLINE void search_ctu(const Ctx &c, int cx, int cy)
           S->sc.update = 0;
         }
         CTU_SYNC();
+        PROF_ADD(S, PR_COST);
       }
       const bool can_split = cur_cu->type == CU_NOTSET || d < cfg->pu_depth_intra_max;
       CTU_LEADER {

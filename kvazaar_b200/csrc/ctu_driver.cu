@@ -1,14 +1,17 @@
 // ctu_driver.cu -- device-resident closed-loop intra CTU search: kernels and the C ABI of
 // include/kvz_cuda_ctu.h.  The algorithm lives in csrc/ctu/*.h (single source, see ctu_common.h).
 //
-// Execution: one CTA per CTU.  The CTUs of a picture are walked in wavefront order -- CTU (x, y) needs (x-1, y) and
-// (x+1, y-1): reconstructed border pixels, CU records, SAO parameters and the real coder's context models (WPP) --
-// one launch per anti-diagonal d = x + 2y, every picture on its own stream so that the diagonals of the pictures in
-// flight interleave on the GPU (all-intra pictures are independent).  After the last diagonal one launch applies SAO
-// (final picture) and the results are copied to pinned host memory on the same stream.
+// Execution: one CTA works on one CTU at a time.  A picture is ONE launch of persistent CTAs that draw CTUs from a
+// ticket counter in wavefront order (anti-diagonals d = x + 2y).  CTU (x, y) needs (x-1, y) and (x+1, y-1) --
+// reconstructed border pixels, CU records, SAO parameters and the real coder's context models (WPP) -- and waits for
+// them on the per-row progress counters (release/acquire through L2).  Tickets are handed out in dependency order and
+// only to resident CTAs, so a waiting CTA always waits for CTUs that are already being worked on: no deadlock for
+// any grid size.  Every picture has its own stream, so the pictures in flight (all-intra pictures are independent)
+// share the GPU; after the search one launch applies SAO (final picture) and the results are copied to pinned host
+// memory on the same stream.
 //
 // Memory per picture slot: source / reconstruction / final planes, the per-4x4 CU records, 12 KB of coefficients per
-// CTU, and one work tree (CtuWork, 5 levels) per CTU of the longest diagonal.
+// CTU, and one work tree (CtuWork, 5 levels) per persistent CTA.
 #include <condition_variable>
 #include <mutex>
 #include <new>
@@ -32,22 +35,63 @@ struct KernelArgs {
   const CtuTables *T;
   CtuConfig cfg;
   FrameDev F;
-  CtuWork *work;           // [max CTUs per diagonal]
-  SaoStats *sao_stats;     // [max CTUs per diagonal]
+  CtuWork *work;           // [grid]
+  SaoStats *sao_stats;     // [grid]
   uint8_t *dbg_ctx;        // [nctu][184] or NULL
+  const uint16_t *order;   // [nctu][2]: CTU coordinates by ticket (wavefront order)
+  int *sync;               // [0] ticket counter, [1 + cy] CTUs finished in row cy
+  int nctu;
+  unsigned long long *prof;  // [PR_N + 1] phase cycles (diagnostic build only), last: CTA lifetime
 };
 
-__global__ void __launch_bounds__(kThreads) ctu_diag_kernel(const __grid_constant__ KernelArgs a, int diag, int cy_lo)
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+__global__ void __launch_bounds__(kThreads) ctu_frame_kernel(const __grid_constant__ KernelArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   CtuS *S = reinterpret_cast<CtuS *>(smem);
-  const int cy = cy_lo + blockIdx.x;
-  const int cx = diag - 2 * cy;
+  __shared__ int s_ticket;
   Ctx c = { a.T, &a.cfg, a.work + blockIdx.x, S };
-  if (a.dbg_ctx) {
-    for (int i = threadIdx.x; i < CTX_COUNT; i += blockDim.x) a.dbg_ctx[(size_t)(cy * a.F.wlcu + cx) * CTX_COUNT + i] = a.F.row_ctx[cy].ctx[i];
+#if defined(KVZ_CTU_PROF)
+  const long long cta_t0 = clock64();
+  if (threadIdx.x == 0) for (int i = 0; i < PR_N; ++i) S->prof[i] = 0;
+#endif
+  for (;;) {
+    if (threadIdx.x == 0) s_ticket = atomicAdd(a.sync, 1);
+    __syncthreads();
+    const int t = s_ticket;
+    if (t >= a.nctu) break;
+    const int cx = a.order[2 * t], cy = a.order[2 * t + 1];
+    {
+      PROF_T0(PR_WAIT);
+      if (threadIdx.x == 0) {
+        // left neighbour: cx CTUs of this row are finished; above: the row has passed the top-right neighbour
+        const int need_up = cy > 0 ? min(cx + 2, a.F.wlcu) : 0;
+        while (ld_acquire(a.sync + 1 + cy) < cx) __nanosleep(200);
+        if (cy > 0) while (ld_acquire(a.sync + cy) < need_up) __nanosleep(200);
+      }
+      __syncthreads();
+      PROF_ADD(S, PR_WAIT);
+    }
+    if (a.dbg_ctx) {
+      for (int i = threadIdx.x; i < CTX_COUNT; i += blockDim.x) a.dbg_ctx[(size_t)(cy * a.F.wlcu + cx) * CTX_COUNT + i] = CTU_LD_FRAME(&a.F.row_ctx[cy].ctx[i]);
+    }
+    ctu_job(c, &a.F, a.sao_stats + blockIdx.x, cx, cy);
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); st_release(a.sync + 1 + cy, cx + 1); }
   }
-  ctu_job(c, &a.F, a.sao_stats + blockIdx.x, cx, cy);
+#if defined(KVZ_CTU_PROF)
+  if (threadIdx.x == 0 && a.prof) {
+    for (int i = 0; i < PR_N; ++i) atomicAdd(a.prof + i, (unsigned long long)S->prof[i]);
+    atomicAdd(a.prof + PR_N, (unsigned long long)(clock64() - cta_t0));
+  }
+#endif
 }
 
 __global__ void __launch_bounds__(kThreads) ctu_sao_apply_kernel(const __grid_constant__ KernelArgs a)
@@ -69,6 +113,7 @@ struct Slot {
   CabacState *d_row_ctx = nullptr;
   CtuWork *d_work = nullptr;
   SaoStats *d_stats = nullptr;
+  int *d_sync = nullptr;
   uint8_t *d_dbg_ctx = nullptr;
   // pinned host
   uint8_t *h_src = nullptr;      // staging for the upload
@@ -86,7 +131,9 @@ struct Slot {
 struct kvz_cuda_ctu_enc {
   CtuConfig cfg;
   CtuTables *d_tables = nullptr;
-  int wl = 0, hl = 0, max_diag = 0;
+  uint16_t *d_order = nullptr;
+  unsigned long long *d_prof = nullptr;
+  int wl = 0, hl = 0, max_diag = 0, grid = 0;
   size_t plane_bytes = 0, smem = 0;
   bool debug = false;
   std::vector<Slot> slots;
@@ -123,13 +170,25 @@ void kvz_cuda_ctu_close(kvz_cuda_ctu_enc *e)
   for (Slot &s : e->slots) {
     if (s.stream) cudaStreamSynchronize(s.stream);
     cudaFree(s.d_planes); cudaFree(s.d_bufs); cudaFree(s.d_cu); cudaFree(s.d_coeff); cudaFree(s.d_sao); cudaFree(s.d_row_ctx);
-    cudaFree(s.d_work); cudaFree(s.d_stats); cudaFree(s.d_dbg_ctx);
+    cudaFree(s.d_work); cudaFree(s.d_stats); cudaFree(s.d_sync); cudaFree(s.d_dbg_ctx);
     cudaFreeHost(s.h_src); cudaFreeHost(s.h_out); cudaFreeHost(s.h_dbg); cudaFreeHost(s.h_cu); cudaFreeHost(s.h_coeff); cudaFreeHost(s.h_sao);
     cudaFreeHost(s.h_row_ctx); cudaFreeHost(s.h_dbg_ctx);
     if (s.done) cudaEventDestroy(s.done);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
-  cudaFree(e->d_tables);
+#if defined(KVZ_CTU_PROF)
+  if (e->d_prof) {
+    static const char *names[PR_N + 1] = { "load", "search(total)", "store", "deblock", "sao", "track", "  refs", "  satd(rough)", "  replay", "  predict", "  quantize_residual(total)",
+      "    fwd", "    rdoq", "    quant", "    inv+rec", "  ssd", "  cost(leader)", "  copies", "  coeffcost", "wait(deps)", "  chroma search(total)", "  rdo loop(total)", "CTA lifetime" };
+    unsigned long long h[PR_N + 1];
+    if (cudaMemcpy(h, e->d_prof, sizeof(h), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      fprintf(stderr, "kvz-cuda-ctu phase profile (leader-thread cycles summed over CTAs; nested phases indented):\n");
+      for (int i = 0; i <= PR_N; ++i) fprintf(stderr, "  %-32s %14llu  %5.1f%%\n", names[i], h[i], 100.0 * (double)h[i] / (double)(h[PR_N] ? h[PR_N] : 1));
+    }
+    cudaFree(e->d_prof);
+  }
+#endif
+  cudaFree(e->d_tables); cudaFree(e->d_order);
   delete e;
 }
 
@@ -142,11 +201,17 @@ kvz_cuda_ctu_enc *kvz_cuda_ctu_open(const kvz_cuda_ctu_config *cfg, int slots)
   memcpy(&e->cfg, cfg, sizeof(CtuConfig));
   const int W = cfg->width, H = cfg->height;
   e->wl = (W + 63) / 64; e->hl = (H + 63) / 64;
+  // tickets: CTUs by anti-diagonal d = x + 2y, rows ascending inside a diagonal
+  std::vector<uint16_t> order;
   e->max_diag = 0;
   for (int d = 0; d < e->wl + 2 * (e->hl - 1); ++d) {
     const int lo = d - (e->wl - 1) > 0 ? (d - (e->wl - 1) + 1) / 2 : 0, hi = d / 2 < e->hl - 1 ? d / 2 : e->hl - 1;
     if (hi - lo + 1 > e->max_diag) e->max_diag = hi - lo + 1;
+    for (int cy = lo; cy <= hi; ++cy) { order.push_back((uint16_t)(d - 2 * cy)); order.push_back((uint16_t)cy); }
   }
+  // persistent CTAs per picture: the widest diagonal unless told otherwise (fewer: less idle waiting, more pictures resident)
+  e->grid = e->max_diag;
+  if (const char *g = getenv("KVZ_CUDA_CTU_GRID")) { const int v = atoi(g); if (v > 0) e->grid = v < e->max_diag ? v : e->max_diag; }
   e->plane_bytes = (size_t)W * H * 3 / 2;
   e->smem = sizeof(CtuS);
   e->debug = getenv("KVZ_CUDA_CTU_DEBUG") != nullptr;
@@ -158,8 +223,14 @@ kvz_cuda_ctu_enc *kvz_cuda_ctu_open(const kvz_cuda_ctu_config *cfg, int slots)
     delete ht;
     CTU_CHECK_PTR(err);
   }
-  CTU_CHECK_PTR(cudaFuncSetAttribute(ctu_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
-  e->slots.resize(slots > 0 ? (slots > 64 ? 64 : slots) : 1);
+#if defined(KVZ_CTU_PROF)
+  CTU_CHECK_PTR(cudaMalloc(&e->d_prof, (PR_N + 1) * sizeof(unsigned long long)));
+  CTU_CHECK_PTR(cudaMemset(e->d_prof, 0, (PR_N + 1) * sizeof(unsigned long long)));
+#endif
+  CTU_CHECK_PTR(cudaMalloc(&e->d_order, order.size() * sizeof(uint16_t)));
+  CTU_CHECK_PTR(cudaMemcpy(e->d_order, order.data(), order.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  CTU_CHECK_PTR(cudaFuncSetAttribute(ctu_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  e->slots.resize(slots > 0 ? (slots > 512 ? 512 : slots) : 1);
   const size_t nctu = (size_t)e->wl * e->hl;
   const size_t cu_n = (size_t)(e->wl * 16) * (e->hl * 16);
   const size_t buf_bytes = ((size_t)W * e->hl + (size_t)H * e->wl) * 2 + 64;      // Y + U + V rows (columns): w + w/2 + w/2
@@ -172,8 +243,9 @@ kvz_cuda_ctu_enc *kvz_cuda_ctu_open(const kvz_cuda_ctu_config *cfg, int slots)
     CTU_CHECK_PTR(cudaMalloc(&s.d_coeff, nctu * 6144 * sizeof(int16_t)));
     CTU_CHECK_PTR(cudaMalloc(&s.d_sao, nctu * 2 * sizeof(SaoRec)));
     CTU_CHECK_PTR(cudaMalloc(&s.d_row_ctx, e->hl * sizeof(CabacState)));
-    CTU_CHECK_PTR(cudaMalloc(&s.d_work, (size_t)e->max_diag * sizeof(CtuWork)));
-    CTU_CHECK_PTR(cudaMalloc(&s.d_stats, (size_t)e->max_diag * sizeof(SaoStats)));
+    CTU_CHECK_PTR(cudaMalloc(&s.d_work, (size_t)e->grid * sizeof(CtuWork)));
+    CTU_CHECK_PTR(cudaMalloc(&s.d_stats, (size_t)e->grid * sizeof(SaoStats)));
+    CTU_CHECK_PTR(cudaMalloc(&s.d_sync, (size_t)(e->hl + 1) * sizeof(int)));
     CTU_CHECK_PTR(cudaMemset(s.d_sao, 0, nctu * 2 * sizeof(SaoRec)));
     CTU_CHECK_PTR(cudaMemset(s.d_planes, 0, e->plane_bytes * 4));
     CTU_CHECK_PTR(cudaMemset(s.d_bufs, 0, buf_bytes));
@@ -191,6 +263,7 @@ kvz_cuda_ctu_enc *kvz_cuda_ctu_open(const kvz_cuda_ctu_config *cfg, int slots)
     KernelArgs &a = s.args;
     a.T = e->d_tables;
     a.work = s.d_work; a.sao_stats = s.d_stats; a.dbg_ctx = s.d_dbg_ctx;
+    a.order = e->d_order; a.sync = s.d_sync; a.nctu = e->wl * e->hl; a.prof = e->d_prof;
     FrameDev &F = a.F;
     const size_t ysz = (size_t)W * H, csz = ysz / 4;
     uint8_t *p = s.d_planes;
@@ -232,14 +305,10 @@ int kvz_cuda_ctu_submit(kvz_cuda_ctu_enc *e, const uint8_t *y, const uint8_t *u,
   KVZC_CHECK(cudaMemcpyAsync((void *)s.args.F.src_y, s.h_src, e->plane_bytes, cudaMemcpyHostToDevice, st));
   KVZC_CHECK(cudaMemcpyAsync(s.d_row_ctx, s.h_row_ctx, e->hl * sizeof(CabacState), cudaMemcpyHostToDevice, st));
   KVZC_CHECK(cudaMemsetAsync(s.d_cu, 0, (size_t)(e->wl * 16) * (e->hl * 16) * sizeof(CuRec), st));
-  const int ndiag = e->wl + 2 * (e->hl - 1);
-  for (int d = 0; d < ndiag; ++d) {
-    const int lo = d - (e->wl - 1) > 0 ? (d - (e->wl - 1) + 1) / 2 : 0, hi = d / 2 < e->hl - 1 ? d / 2 : e->hl - 1;
-    if (hi < lo) continue;
-    ctu_diag_kernel<<<hi - lo + 1, kThreads, e->smem, st>>>(s.args, d, lo);
-    e->launches.fetch_add(1, std::memory_order_relaxed);
-    kvzc::g_launches.fetch_add(1, std::memory_order_relaxed);
-  }
+  KVZC_CHECK(cudaMemsetAsync(s.d_sync, 0, (size_t)(e->hl + 1) * sizeof(int), st));
+  ctu_frame_kernel<<<e->grid, kThreads, e->smem, st>>>(s.args);
+  e->launches.fetch_add(1, std::memory_order_relaxed);
+  kvzc::g_launches.fetch_add(1, std::memory_order_relaxed);
   ctu_sao_apply_kernel<<<e->wl * e->hl, kThreads, 0, st>>>(s.args);
   e->launches.fetch_add(1, std::memory_order_relaxed);
   kvzc::g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -9,6 +9,7 @@
 #include <string.h>
 #include <vector>
 #include <mutex>
+#include <condition_variable>
 
 #include "../../include/kvz_cuda_ctu.h"
 #include "../../kvazaar_b200/csrc/ctu/ctu_frame.h"
@@ -38,6 +39,7 @@ struct kvz_cuda_ctu_enc {
   SaoStats *st;
   std::vector<Slot> slots;
   std::mutex mtx;                // one scratch set: pictures are searched one at a time
+  std::condition_variable cv;
 };
 
 extern "C" {
@@ -98,10 +100,10 @@ void kvz_cuda_ctu_close(kvz_cuda_ctu_enc *e)
 int kvz_cuda_ctu_submit(kvz_cuda_ctu_enc *e, const uint8_t *y, const uint8_t *u, const uint8_t *v, int stride_y, int stride_c,
                         const uint8_t *ctx_init, double lambda, double lambda_sqrt, int qp)
 {
-  std::lock_guard<std::mutex> lock(e->mtx);
+  // like the CUDA library: blocks while every slot is busy
+  std::unique_lock<std::mutex> lock(e->mtx);
   int id = -1;
-  for (size_t i = 0; i < e->slots.size(); ++i) if (!e->slots[i].busy) { id = (int)i; break; }
-  if (id < 0) return -1;
+  e->cv.wait(lock, [&] { for (size_t i = 0; i < e->slots.size(); ++i) if (!e->slots[i].busy) { id = (int)i; return true; } return false; });
   Slot &s = e->slots[id];
   s.busy = true;
   e->cfg.lambda = lambda; e->cfg.lambda_sqrt = lambda_sqrt; e->cfg.qp = qp;
@@ -139,8 +141,11 @@ int kvz_cuda_ctu_wait(kvz_cuda_ctu_enc *e, int slot, kvz_cuda_ctu_result *out)
 
 void kvz_cuda_ctu_release(kvz_cuda_ctu_enc *e, int slot)
 {
-  std::lock_guard<std::mutex> lock(e->mtx);
-  if (slot >= 0 && slot < (int)e->slots.size()) e->slots[slot].busy = false;
+  {
+    std::lock_guard<std::mutex> lock(e->mtx);
+    if (slot >= 0 && slot < (int)e->slots.size()) e->slots[slot].busy = false;
+  }
+  e->cv.notify_all();
 }
 
 uint64_t kvz_cuda_ctu_launches(const kvz_cuda_ctu_enc *) { return 0; }
