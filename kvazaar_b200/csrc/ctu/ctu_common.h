@@ -15,9 +15,11 @@
 #if defined(__CUDACC__)
 #define CTU_FN __device__ __forceinline__
 #define CTU_FN_NOINLINE __device__ __noinline__
+#define CTU_MFN __device__ __forceinline__
 #else
 #define CTU_FN static inline
 #define CTU_FN_NOINLINE static
+#define CTU_MFN inline
 #endif
 
 #if defined(__CUDA_ARCH__)

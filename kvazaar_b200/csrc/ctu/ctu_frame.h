@@ -300,7 +300,7 @@ CTU_FN_NOINLINE void sao_stats_plane(const uint8_t *org, const uint8_t *rec, int
 }
 
 // the leader-only part: sao.c:55-160 (mode bits), 208-258 (band offsets), 364-603 (best mode + merge costs)
-struct SaoBits { const CtuTables *T; const uint8_t *ctx; };
+struct SaoBits { const SmTables *T; const uint8_t *ctx; };
 CTU_FN double sao_fbits(const SaoBits &b, int off, int val) { return (double)b.T->ebits[b.ctx[off] ^ val] * (1.0 / 32768.0); }
 CTU_FN double sao_bits_prefix(const SaoBits &b, bool has_left, bool has_top, int type_bin)
 {
@@ -375,7 +375,7 @@ CTU_FN_NOINLINE int sao_band_offsets(const int32_t bd[2][32], int *offsets /* [4
 CTU_FN_NOINLINE void sao_search_best_mode(const Ctx &c, const SaoStats *st, int first_plane, int buf_cnt, SaoRec *out, const SaoRec *top, const SaoRec *left, int32_t merge_cost[3])
 {
   const CtuConfig *cfg = c.cfg;
-  const SaoBits sb = { c.T, c.S->cabac0.ctx };
+  const SaoBits sb = { &c.S->tb, c.S->cabac0.ctx };
   const double lambda = cfg->lambda;
   SaoRec edge, band;
   memset(&edge, 0, sizeof(edge)); memset(&band, 0, sizeof(band));
@@ -489,7 +489,7 @@ CTU_FN_NOINLINE void ctu_sao_search(const Ctx &c, const FrameDev *F, SaoStats *s
 }
 
 // ------------------------------------------------------------------------------------------------ real coder models
-CTU_FN void enc_bin(const CtuTables *T, uint8_t *ctx, int off, int val)
+CTU_FN void enc_bin(const SmTables *T, uint8_t *ctx, int off, int val)
 {
   const uint8_t st = ctx[off];
   ctx[off] = ((st & 1) == val) ? T->next_mps[st] : T->next_lps[st];
@@ -508,16 +508,16 @@ CTU_FN_NOINLINE void enc_transform_leaf(const EncTrack &e, int x, int y, int dep
   const CuRec *cur_cu = tcu(e, x & ~7, y & ~7);
   const int cb_y = cbf_is_set(cur_pu->cbf, depth, 0), cb_u = cbf_is_set(cur_cu->cbf, depth, 1), cb_v = cbf_is_set(cur_cu->cbf, depth, 2);
   if (depth < 4) {
-    if (tr_depth == 0 || parent_u) enc_bin(c.T, e.cs->ctx, CTX_CBF_CHROMA + tr_depth, cb_u);
-    if (tr_depth == 0 || parent_v) enc_bin(c.T, e.cs->ctx, CTX_CBF_CHROMA + tr_depth, cb_v);
+    if (tr_depth == 0 || parent_u) enc_bin(&c.S->tb, e.cs->ctx, CTX_CBF_CHROMA + tr_depth, cb_u);
+    if (tr_depth == 0 || parent_v) enc_bin(&c.S->tb, e.cs->ctx, CTX_CBF_CHROMA + tr_depth, cb_v);
   }
-  enc_bin(c.T, e.cs->ctx, CTX_CBF_LUMA + (tr_depth ? 0 : 1), cb_y);        // CU_INTRA: always signalled
+  enc_bin(&c.S->tb, e.cs->ctx, CTX_CBF_LUMA + (tr_depth ? 0 : 1), cb_y);        // CU_INTRA: always signalled
   if (!(cb_y | cb_u | cb_v)) return;
   const int width = 64 >> depth, width_c = depth == 4 ? width : width / 2;
   e.cs->update = 1;
   if (cb_y) {
     const int scan = scan_order_intra(cur_pu->mode, depth);
-    coeff_cost_serial(c.T, c.cfg, e.cs, e.L0->coeff_y + zorder(64, x & 63, y & 63), ilog2(width), 0, scan, cur_pu->tr_skip);
+    coeff_cost_serial(c.T, &c.S->tb, c.cfg, e.cs, e.L0->coeff_y + zorder(64, x & 63, y & 63), ilog2(width), 0, scan, cur_pu->tr_skip);
   }
   int xx = x, yy = y;
   if (depth == 4) {
@@ -529,8 +529,8 @@ CTU_FN_NOINLINE void enc_transform_leaf(const EncTrack &e, int x, int y, int dep
   if (cu_u || cu_v) {
     const int scan = scan_order_intra(cur_pu->mode_chroma, depth);
     const int zi = zorder(32, (xx >> 1) & 31, (yy >> 1) & 31);
-    if (cu_u) coeff_cost_serial(c.T, c.cfg, e.cs, e.L0->coeff_u + zi, ilog2(width_c), 2, scan, 0);
-    if (cu_v) coeff_cost_serial(c.T, c.cfg, e.cs, e.L0->coeff_v + zi, ilog2(width_c), 2, scan, 0);
+    if (cu_u) coeff_cost_serial(c.T, &c.S->tb, c.cfg, e.cs, e.L0->coeff_u + zi, ilog2(width_c), 2, scan, 0);
+    if (cu_v) coeff_cost_serial(c.T, &c.S->tb, c.cfg, e.cs, e.L0->coeff_v + zi, ilog2(width_c), 2, scan, 0);
   }
 }
 CTU_FN void enc_transform_tree(const EncTrack &e, int x, int y, int depth)
@@ -542,7 +542,7 @@ CTU_FN void enc_transform_tree(const EncTrack &e, int x, int y, int depth)
   if (!split) { enc_transform_leaf(e, x, y, depth, 0, 0, 0); return; }
   // one implicit split (64x64 CU into 32x32 TUs, or NxN into four 4x4 TUs)
   const int cb_u = cbf_is_set(cur_cu->cbf, depth, 1), cb_v = cbf_is_set(cur_cu->cbf, depth, 2);
-  if (depth < 4) { enc_bin(c.T, e.cs->ctx, CTX_CBF_CHROMA, cb_u); enc_bin(c.T, e.cs->ctx, CTX_CBF_CHROMA, cb_v); }
+  if (depth < 4) { enc_bin(&c.S->tb, e.cs->ctx, CTX_CBF_CHROMA, cb_u); enc_bin(&c.S->tb, e.cs->ctx, CTX_CBF_CHROMA, cb_v); }
   const int off = 64 >> (depth + 1);
   for (int k = 0; k < 4; ++k) enc_transform_leaf(e, x + (k & 1) * off, y + (k >> 1) * off, depth + 1, 1, cb_u, cb_v);
 }
@@ -553,7 +553,7 @@ CTU_FN_NOINLINE void enc_coding_unit(const EncTrack &e, int x, int y, int depth)
   const Ctx &c = *e.c;
   const CuRec *cur_cu = tcu(e, x, y);
   const int cu_width = 64 >> depth;
-  if (depth == 3) enc_bin(c.T, e.cs->ctx, CTX_PART_SIZE, cur_cu->part_size == SIZE_2Nx2N ? 1 : 0);
+  if (depth == 3) enc_bin(&c.S->tb, e.cs->ctx, CTX_PART_SIZE, cur_cu->part_size == SIZE_2Nx2N ? 1 : 0);
   const int num_pu = cur_cu->part_size == SIZE_NxN ? 4 : 1;
   int flag[4];
   int mode0 = 0;
@@ -568,8 +568,8 @@ CTU_FN_NOINLINE void enc_coding_unit(const EncTrack &e, int x, int y, int depth)
     if (j == 0) mode0 = cur_pu->mode;
     flag[j] = cur_pu->mode == preds[0] || cur_pu->mode == preds[1] || cur_pu->mode == preds[2];
   }
-  for (int j = 0; j < num_pu; ++j) enc_bin(c.T, e.cs->ctx, CTX_INTRA_MODE, flag[j]);
-  enc_bin(c.T, e.cs->ctx, CTX_CHROMA_PRED, cur_cu->mode_chroma == mode0 ? 0 : 1);
+  for (int j = 0; j < num_pu; ++j) enc_bin(&c.S->tb, e.cs->ctx, CTX_INTRA_MODE, flag[j]);
+  enc_bin(&c.S->tb, e.cs->ctx, CTX_CHROMA_PRED, cur_cu->mode_chroma == mode0 ? 0 : 1);
   enc_transform_tree(e, x, y, depth);
 }
 
@@ -595,7 +595,7 @@ CTU_FN_NOINLINE void enc_coding_tree(const EncTrack &e, int x0, int y0)
         int split_model = 0;
         if (x > 0 && tcu(e, x - 1, y)->depth > depth) ++split_model;
         if (y > 0 && tcu(e, x, y - 1)->depth > depth) ++split_model;
-        enc_bin(c.T, e.cs->ctx, CTX_SPLIT + split_model, split_flag);
+        enc_bin(&c.S->tb, e.cs->ctx, CTX_SPLIT + split_model, split_flag);
       }
       if (split_flag || border) {
         // push in reverse so that the children pop in z-order
@@ -619,11 +619,11 @@ CTU_FN_NOINLINE void ctu_track_models(const Ctx &c, const FrameDev *F, int cx, i
     cs.update = 1;
     if (c.cfg->sao_type) {
       const SaoRec *sl = &F->sao[2 * (cy * F->wlcu + cx)], *sc = sl + 1;
-      if (cx > 0) enc_bin(c.T, cs.ctx, CTX_SAO_MERGE, sl->merge_left_flag);
-      if (cy > 0 && !sl->merge_left_flag) enc_bin(c.T, cs.ctx, CTX_SAO_MERGE, sl->merge_up_flag);
+      if (cx > 0) enc_bin(&c.S->tb, cs.ctx, CTX_SAO_MERGE, sl->merge_left_flag);
+      if (cy > 0 && !sl->merge_left_flag) enc_bin(&c.S->tb, cs.ctx, CTX_SAO_MERGE, sl->merge_up_flag);
       if (!sl->merge_left_flag && !sl->merge_up_flag) {
-        enc_bin(c.T, cs.ctx, CTX_SAO_TYPE, sl->type != 0);
-        enc_bin(c.T, cs.ctx, CTX_SAO_TYPE, sc->type != 0);
+        enc_bin(&c.S->tb, cs.ctx, CTX_SAO_TYPE, sl->type != 0);
+        enc_bin(&c.S->tb, cs.ctx, CTX_SAO_TYPE, sc->type != 0);
       }
     }
     EncTrack e = { &c, &c.W->lv[0], cx * 64, cy * 64, &cs };

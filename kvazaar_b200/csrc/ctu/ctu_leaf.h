@@ -36,30 +36,88 @@ struct IntraRefs {                  // kvz_intra_references: index 0 = corner, 1
   int32_t pad;
 };
 
-struct TuBuf {
-  int16_t a[1024];                  // residual / inverse-transform output
-  int16_t b[1024];                  // transform coefficients
-  int16_t q[1024];                  // quantised levels
-  int16_t t[1024];                  // intermediate of the separable passes
-  int32_t d[1024];                  // delta_u of kvz_quant's sign hiding
-  int32_t has;                      // has_coeffs
-  int32_t ac_sum;
-  int32_t cg_nz[64];
+// ------------------------------------------------------------------------------------------------ teams
+// A team is the group of threads that evaluates one transform unit: the whole CTA for 32x32 units, one warp for the
+// smaller ones (several units -- colour planes, RDO candidates -- are then evaluated side by side, one per warp).
+struct Team { int tid, nt, warp; };
+#if defined(__CUDA_ARCH__)
+CTU_FN Team team_cta() { Team t = { (int)threadIdx.x, (int)blockDim.x, 0 }; return t; }
+CTU_FN Team team_warp() { Team t = { (int)(threadIdx.x & 31), 32, 1 }; return t; }
+CTU_FN void tsync(const Team &t) { if (t.warp) __syncwarp(); else __syncthreads(); }
+#define CTU_NWARPS ((int)(blockDim.x >> 5))
+#define CTU_WARP ((int)(threadIdx.x >> 5))
+#else
+CTU_FN Team team_cta() { Team t = { 0, 1, 0 }; return t; }
+CTU_FN Team team_warp() { Team t = { 0, 1, 1 }; return t; }
+CTU_FN void tsync(const Team &) {}
+#define CTU_NWARPS 1
+#define CTU_WARP 0
+#endif
+
+// entropy tables of the CABAC estimators, copied to shared memory once per CTA (hot in every serial section)
+struct SmTables {
+  int32_t ebits[128];
+  uint8_t next_mps[128], next_lps[128];
 };
 
-struct RdoqScratch {
-  double cost_coeff[1024];
-  uint8_t sig_code[1024];
-  int32_t inc[1024], dec[1024], sig_inc[1024], qdelta[1024];    // kvz_sh_rates_t (rdo.h:49-58)
-  double cg_sig_cost[64];
-  int32_t cg_flag[64];
-  uint16_t cg_nz[64];
-  int32_t last_x_bits[12], last_y_bits[12];
+// Scratch of one transform-unit evaluation, carved out of the team's part of the arena for nn = n*n coefficients.
+struct TuFixed {
   double prep_c0[16], prep_sig0[16], prep_sig1[16];
   int32_t prep_ld[16], prep_ctx_sig[16];
+  int32_t last_x_bits[12], last_y_bits[12];
   uint8_t prep_flags[16];
   int32_t best_last_p1;
+  int32_t has, ac_sum, ssd;
+  // transform skip decision (kvz_quantize_residual_trskip): both alternatives of a 4x4 luma unit
+  uint8_t ts_rec[2][16];
+  int16_t ts_coeff[2][16];
+  int32_t ts_has[2], ts_ssd[2];
+  int32_t ts_pick, pad;
 };
+static_assert(sizeof(TuFixed) % 8 == 0, "TuFixed alignment");
+struct TuS {
+  unsigned char *base;
+  int nn, ncg;
+  // doubles
+  CTU_MFN double *cost_coeff() const { return (double *)base; }
+  CTU_MFN double *cg_sig_cost() const { return (double *)base + nn; }
+  CTU_MFN TuFixed *fx() const { return (TuFixed *)((double *)base + nn + ncg); }
+  // 32-bit: kvz_sh_rates_t (rdo.h:49-58); d (delta_u of kvz_quant's sign hiding) shares inc: never both
+  CTU_MFN int32_t *i32() const { return (int32_t *)(base + 8 * (nn + ncg) + sizeof(TuFixed)); }
+  CTU_MFN int32_t *inc() const { return i32(); }
+  CTU_MFN int32_t *dec() const { return i32() + nn; }
+  CTU_MFN int32_t *sig_inc() const { return i32() + 2 * nn; }
+  CTU_MFN int32_t *qdelta() const { return i32() + 3 * nn; }
+  CTU_MFN int32_t *d() const { return i32(); }
+  CTU_MFN int32_t *cg_flag() const { return i32() + 4 * nn; }
+  CTU_MFN int32_t *cg_nzflag() const { return i32() + 4 * nn + ncg; }
+  // 16-bit
+  CTU_MFN int16_t *i16() const { return (int16_t *)(i32() + 4 * nn + 2 * ncg); }
+  CTU_MFN int16_t *a() const { return i16(); }             // residual / inverse-transform output
+  CTU_MFN int16_t *b() const { return i16() + nn; }        // transform coefficients
+  CTU_MFN int16_t *q() const { return i16() + 2 * nn; }    // quantised levels
+  CTU_MFN int16_t *t() const { return i16() + 3 * nn; }    // intermediate of the separable passes
+  CTU_MFN uint16_t *cg_nz() const { return (uint16_t *)(i16() + 4 * nn); }
+  // bytes
+  CTU_MFN uint8_t *u8() const { return (uint8_t *)(i16() + 4 * nn + ncg + (ncg & 1)); }
+  CTU_MFN uint8_t *sig_code() const { return u8(); }
+  CTU_MFN uint8_t *pred() const { return u8() + nn; }
+  CTU_MFN uint8_t *rec() const { return u8() + 2 * nn; }
+};
+CTU_FN int tu_scratch_bytes(int nn)
+{
+  const int ncg = nn >= 16 ? nn / 16 : 1;
+  const int b = 8 * (nn + ncg) + (int)sizeof(TuFixed) + 4 * (4 * nn + 2 * ncg) + 2 * (4 * nn + ncg + (ncg & 1)) + 3 * nn;
+  return (b + 15) & ~15;
+}
+CTU_FN TuS tu_scratch(unsigned char *arena, int nn, int slot)
+{
+  TuS t;
+  t.nn = nn; t.ncg = nn >= 16 ? nn / 16 : 1;
+  t.base = arena + (size_t)slot * tu_scratch_bytes(nn);
+  return t;
+}
+#define CTU_ARENA_BYTES 40960      // one 32x32 unit, or four units of up to 16x16 side by side
 
 // ------------------------------------------------------------------------------------------------ pixel planes
 struct Plane { uint8_t *rec; const uint8_t *src; const uint8_t *top; const uint8_t *left; int16_t *coeff; int lw; };
@@ -283,10 +341,10 @@ CTU_FN_NOINLINE void ssd_block(const uint8_t *a, int sa, const uint8_t *b, int s
 
 // ------------------------------------------------------------------------------------------------ transforms
 // forward: dst[k*N + j] = (int16)((sum_i M[k][i] * src[j*N + i] + add) >> shift)
-CTU_FN_NOINLINE void fwd_pass(const int16_t *src, int16_t *dst, const int8_t *M, int n, int shift)
+CTU_FN_NOINLINE void fwd_pass(const Team &tm, const int16_t *src, int16_t *dst, const int8_t *M, int n, int shift)
 {
   const int add = 1 << (shift - 1);
-  for (int e = CTU_TID; e < n * n; e += CTU_NT) {
+  for (int e = tm.tid; e < n * n; e += tm.nt) {
     const int k = e / n, j = e - k * n;
     const int16_t *s = src + j * n;
     const int8_t *m = M + k * n;
@@ -294,19 +352,19 @@ CTU_FN_NOINLINE void fwd_pass(const int16_t *src, int16_t *dst, const int8_t *M,
     for (int i = 0; i < n; ++i) acc += (int)m[i] * (int)s[i];
     dst[k * n + j] = (int16_t)((acc + add) >> shift);
   }
-  CTU_SYNC();
+  tsync(tm);
 }
 // inverse: dst[j*N + k] = clip16((sum_i M[i][k] * src[i*N + j] + add) >> shift)
-CTU_FN_NOINLINE void inv_pass(const int16_t *src, int16_t *dst, const int8_t *M, int n, int shift)
+CTU_FN_NOINLINE void inv_pass(const Team &tm, const int16_t *src, int16_t *dst, const int8_t *M, int n, int shift)
 {
   const int add = 1 << (shift - 1);
-  for (int e = CTU_TID; e < n * n; e += CTU_NT) {
+  for (int e = tm.tid; e < n * n; e += tm.nt) {
     const int j = e / n, k = e - j * n;
     int acc = 0;
     for (int i = 0; i < n; ++i) acc += (int)M[i * n + k] * (int)src[i * n + j];
     dst[j * n + k] = (int16_t)iclip(-32768, 32767, (acc + add) >> shift);
   }
-  CTU_SYNC();
+  tsync(tm);
 }
 
 CTU_FN int ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
@@ -347,8 +405,8 @@ CTU_FN void quant_sign_hide_group(const CtuTables *T, const int16_t *coef, int16
   else q[min_pos] = (int16_t)(q[min_pos] - final_change);
 }
 
-// kvz_quant: tu->b -> tu->q (intra slice: rounding offset 171)
-CTU_FN_NOINLINE void quant_block(const CtuTables *T, const CtuConfig *cfg, TuBuf *tu, int n, int type, int scan_idx)
+// kvz_quant: b -> q (intra slice: rounding offset 171)
+CTU_FN_NOINLINE void quant_block(const Team &tm, const CtuTables *T, const CtuConfig *cfg, const TuS &tu, int n, int type, int scan_idx)
 {
   const int log2n = ilog2(n);
   const int qp_scaled = scaled_qp(type, cfg->qp);
@@ -357,44 +415,50 @@ CTU_FN_NOINLINE void quant_block(const CtuTables *T, const CtuConfig *cfg, TuBuf
   const int q_bits = 14 + qp_scaled / 6 + transform_shift;
   const int add = 171 << (q_bits - 9);
   const int q_bits8 = q_bits - 8;
-  CTU_LEADER tu->ac_sum = 0;
-  CTU_SYNC();
+  int16_t *b = tu.b(), *q = tu.q();
+  int32_t *d = tu.d();
+  TuFixed *fx = tu.fx();
+  if (tm.tid == 0) fx->ac_sum = 0;
+  tsync(tm);
   int ac = 0;
-  for (int e = CTU_TID; e < n * n; e += CTU_NT) {
-    const int level_in = tu->b[e];
+  for (int e = tm.tid; e < n * n; e += tm.nt) {
+    const int level_in = b[e];
     const long long abs_level = iabs(level_in);
     int level = (int)((abs_level * qc + add) >> q_bits);
     ac += level;
-    tu->d[e] = (int)((abs_level * qc - ((long long)level << q_bits)) >> q_bits8);
+    d[e] = (int)((abs_level * qc - ((long long)level << q_bits)) >> q_bits8);
     level = level_in < 0 ? -level : level;
-    tu->q[e] = (int16_t)iclip(-32768, 32767, level);
+    q[e] = (int16_t)iclip(-32768, 32767, level);
   }
-  if (ac) CTU_ATOMIC_ADD(&tu->ac_sum, ac);
-  CTU_SYNC();
-  if (!cfg->signhide_enable || tu->ac_sum < 2) return;
+  if (ac) CTU_ATOMIC_ADD(&fx->ac_sum, ac);
+  tsync(tm);
+  if (!cfg->signhide_enable || fx->ac_sum < 2) return;
   const int num_cg = (n * n) >> 4;
-  for (int g = CTU_TID; g < num_cg; g += CTU_NT) {
+  int32_t *cg_nz = tu.cg_nzflag();
+  for (int g = tm.tid; g < num_cg; g += tm.nt) {
     int nz = 0;
-    for (int k = 0; k < 16; ++k) nz |= tu->q[T->scan[scan_idx][log2n - 2][g * 16 + k]] != 0;
-    tu->cg_nz[g] = nz;
+    for (int k = 0; k < 16; ++k) nz |= q[T->scan[scan_idx][log2n - 2][g * 16 + k]] != 0;
+    cg_nz[g] = nz;
   }
-  CTU_SYNC();
-  for (int g = CTU_TID; g < num_cg; g += CTU_NT)
-    if (tu->cg_nz[g]) quant_sign_hide_group(T, tu->b, tu->q, tu->d, tu->cg_nz, num_cg, g, scan_idx, log2n);
-  CTU_SYNC();
+  tsync(tm);
+  for (int g = tm.tid; g < num_cg; g += tm.nt)
+    if (cg_nz[g]) quant_sign_hide_group(T, b, q, d, cg_nz, num_cg, g, scan_idx, log2n);
+  tsync(tm);
 }
 
-// kvz_dequant: tu->q -> tu->b.  type: 0 luma, 2 / 3 chroma
-CTU_FN_NOINLINE void dequant_block(const CtuConfig *cfg, TuBuf *tu, int n, int type)
+// kvz_dequant: q -> b.  type: 0 luma, 2 / 3 chroma
+CTU_FN_NOINLINE void dequant_block(const Team &tm, const CtuConfig *cfg, const TuS &tu, int n, int type)
 {
   const int transform_shift = 15 - 8 - ilog2(n);
   const int qp_scaled = scaled_qp(type, cfg->qp);
   const int shift = 20 - 14 - transform_shift;
   const int scale = inv_quant_scale(qp_scaled % 6) << (qp_scaled / 6);
   const int add = 1 << (shift - 1);
-  for (int e = CTU_TID; e < n * n; e += CTU_NT)
-    tu->b[e] = (int16_t)iclip(-32768, 32767, ((int)tu->q[e] * scale + add) >> shift);
-  CTU_SYNC();
+  int16_t *b = tu.b();
+  const int16_t *q = tu.q();
+  for (int e = tm.tid; e < n * n; e += tm.nt)
+    b[e] = (int16_t)iclip(-32768, 32767, ((int)q[e] * scale + add) >> shift);
+  tsync(tm);
 }
 
 // ------------------------------------------------------------------------------------------------ RDOQ
@@ -445,8 +509,9 @@ CTU_FN int sig_ctx_inc(const CtuTables *T, int pattern, int scan_idx, int px, in
 }
 
 // kvz_rdoq_sign_hiding (ref: rdo.c:518-653); serial, one thread
-CTU_FN_NOINLINE void rdoq_sign_hiding(const RdoqScratch &s, const uint16_t *blk, double lambda, int qp_scaled, int last_pos, const int16_t *coef, int16_t *q)
+CTU_FN_NOINLINE void rdoq_sign_hiding(const TuS &tu, const uint16_t *blk, double lambda, int qp_scaled, int last_pos, const int16_t *coef, int16_t *q)
 {
+  const int32_t *s_inc = tu.inc(), *s_dec = tu.dec(), *s_sig_inc = tu.sig_inc(), *s_qdelta = tu.qdelta();
   const int inv_quant = inv_quant_scale(qp_scaled % 6);
   const long long rd_factor = (long long)(inv_quant * inv_quant * (1 << (2 * (qp_scaled / 6))) / lambda / 16 / (1 << (2 * (8 - 8))) + 0.5);
   const int last_cg = (last_pos - 1) >> 4;
@@ -465,13 +530,13 @@ CTU_FN_NOINLINE void rdoq_sign_hiding(const RdoqScratch &s, const uint16_t *blk,
     const int start = (cg == last_cg) ? last_nz : 15;
     for (int k = start; k >= 0; --k) {
       const int p = pos[k];
-      const long long quant_cost = rd_factor * s.qdelta[p];
+      const long long quant_cost = rd_factor * s_qdelta[p];
       const int a = iabs((int)q[p]);
       long long cost;
       int change;
       if (a != 0) {
-        long long inc_bits = s.inc[p], dec_bits = s.dec[p];
-        if (a == 1) dec_bits -= CTU_RDOQ_ONE_BIT + s.sig_inc[p];
+        long long inc_bits = s_inc[p], dec_bits = s_dec[p];
+        if (a == 1) dec_bits -= CTU_RDOQ_ONE_BIT + s_sig_inc[p];
         if (cg == last_cg && last_nz == k && a == 1) dec_bits -= 4 * CTU_RDOQ_ONE_BIT;
         inc_bits = -quant_cost + inc_bits;
         dec_bits = quant_cost + dec_bits;
@@ -481,7 +546,7 @@ CTU_FN_NOINLINE void rdoq_sign_hiding(const RdoqScratch &s, const uint16_t *blk,
           if (k == first_nz && a == 1) cost = 0x7FFFFFFFFFFFFFFFLL;
         }
       } else {
-        const int bits = CTU_RDOQ_ONE_BIT + s.inc[p] + s.sig_inc[p];
+        const int bits = CTU_RDOQ_ONE_BIT + s_inc[p] + s_sig_inc[p];
         const long long aq = quant_cost < 0 ? -quant_cost : quant_cost;
         cost = -aq + (long long)bits;
         change = 1;
@@ -505,11 +570,16 @@ CTU_FN int team_sum(int v) { return v; }
 
 // kvz_rdoq for one TU, executed by one team (the first warp): coef = tu->b, levels to tu->q.  `cabac` = the models of
 // state->cabac (NOT the search copy: rdo.c:665).  type 0 luma / 2 chroma; tr_depth as in quant-generic.c:237-238.
-CTU_FN_NOINLINE void rdoq_team(const CtuTables *T, const CtuConfig *cfg, const uint8_t *cabac, TuBuf *tu, RdoqScratch &s, int log2n, int type,
+CTU_FN_NOINLINE void rdoq_team(const CtuTables *T, const SmTables *tb, const CtuConfig *cfg, const uint8_t *cabac, const TuS &tu, int log2n, int type,
                       int scan_idx, int tr_depth, int lane)
 {
-  const int16_t *coef = tu->b;
-  int16_t *q = tu->q;
+  const int16_t *coef = tu.b();
+  int16_t *q = tu.q();
+  TuFixed &s = *tu.fx();
+  double *s_cost_coeff = tu.cost_coeff(), *s_cg_sig_cost = tu.cg_sig_cost();
+  uint8_t *s_sig_code = tu.sig_code();
+  int32_t *s_inc = tu.inc(), *s_dec = tu.dec(), *s_sig_inc = tu.sig_inc(), *s_qdelta = tu.qdelta(), *s_cg_flag = tu.cg_flag();
+  uint16_t *s_cg_nz = tu.cg_nz();
   const int n = 1 << log2n, nn = n * n;
   const int transform_shift = 15 - 8 - log2n;
   const int qp_scaled = scaled_qp(type, cfg->qp);
@@ -524,7 +594,7 @@ CTU_FN_NOINLINE void rdoq_team(const CtuTables *T, const CtuConfig *cfg, const u
   for (int i = 0; i > 2 * transform_shift; --i) err_scale *= 2.0;
   err_scale = err_scale / qc / qc / 1;
   RdoqModels m;
-  m.eb = T->ebits;
+  m.eb = tb->ebits;
   m.sig = cabac + (type ? CTX_SIG_CHROMA : CTX_SIG_LUMA);
   m.one = cabac + (type ? CTX_ONE_CHROMA : CTX_ONE_LUMA);
   m.abs = cabac + (type ? CTX_ABS_CHROMA : CTX_ABS_LUMA);
@@ -546,9 +616,9 @@ CTU_FN_NOINLINE void rdoq_team(const CtuTables *T, const CtuConfig *cfg, const u
   CTU_TEAM_SYNC();
   for (int sp = lane; sp < nn; sp += CTU_TEAM_N) if (sp > last_scanpos) q[blk_of[sp]] = 0;
   if (last_scanpos < 0) { CTU_TEAM_SYNC(); return; }
-  for (int g = lane; g < nn / 16; g += CTU_TEAM_N) { s.cg_flag[g] = 0; s.cg_sig_cost[g] = 0; }
+  for (int g = lane; g < nn / 16; g += CTU_TEAM_N) { s_cg_flag[g] = 0; s_cg_sig_cost[g] = 0; }
   if (lane == 0) {
-    if (SH) s.sig_inc[blk_of[last_scanpos]] = 0;
+    if (SH) s_sig_inc[blk_of[last_scanpos]] = 0;
     const int cb = log2n - 2;
     const int off = type ? 0 : (cb * 3 + ((cb + 1) >> 2));
     const int sh = type ? cb : ((cb + 3) >> 2);
@@ -574,8 +644,8 @@ CTU_FN_NOINLINE void rdoq_team(const CtuTables *T, const CtuConfig *cfg, const u
     const int cg_first = blk_of[cg << 4];
     const int cgx = (cg_first & (n - 1)) >> 2, cgy = (cg_first >> log2n) >> 2;
     const int cg_blk = cgy * cgs_side + cgx;
-    const int right = (cgx < cgs_side - 1) ? (s.cg_flag[cgy * cgs_side + cgx + 1] != 0) : 0;
-    const int lower = (cgy < cgs_side - 1) ? (s.cg_flag[(cgy + 1) * cgs_side + cgx] != 0) : 0;
+    const int right = (cgx < cgs_side - 1) ? (s_cg_flag[cgy * cgs_side + cgx + 1] != 0) : 0;
+    const int lower = (cgy < cgs_side - 1) ? (s_cg_flag[(cgy + 1) * cgs_side + cgx] != 0) : 0;
     const int pattern = (n == 4) ? -1 : right + (lower << 1);
     for (int k = lane; k < 16; k += CTU_TEAM_N) {
       const int sp = (cg << 4) + k;
@@ -595,12 +665,12 @@ CTU_FN_NOINLINE void rdoq_team(const CtuTables *T, const CtuConfig *cfg, const u
           const double sig0 = lambda * rq_ebits(m.sig[ctx_sig], 0);
           s.prep_sig0[k] = sig0;
           s.prep_sig1[k] = lambda * rq_ebits(m.sig[ctx_sig], 1);
-          if (SH) s.sig_inc[blk] = rq_ebits(m.sig[ctx_sig], 1) - rq_ebits(m.sig[ctx_sig], 0);
+          if (SH) s_sig_inc[blk] = rq_ebits(m.sig[ctx_sig], 1) - rq_ebits(m.sig[ctx_sig], 0);
           s.prep_ctx_sig[k] = ctx_sig;
           if (!cand) {
-            s.sig_code[sp] = (uint8_t)ctx_sig; s.cost_coeff[sp] = c0 + sig0;
+            s_sig_code[sp] = (uint8_t)ctx_sig; s_cost_coeff[sp] = c0 + sig0;
             q[blk] = 0;
-            if (SH) s.qdelta[blk] = ld >> (q_bits - 8);
+            if (SH) s_qdelta[blk] = ld >> (q_bits - 8);
           }
         }
       }
@@ -623,7 +693,7 @@ CTU_FN_NOINLINE void rdoq_team(const CtuTables *T, const CtuConfig *cfg, const u
           base_cost += c0 + cs;
           st_sig += cs;
           if (k == 0) st_sig0 = cs;
-          if (SH) s.inc[blk_of[sp]] = rq_ebits(m.one[4 * ctx_set + c1], 0);
+          if (SH) s_inc[blk_of[sp]] = rq_ebits(m.one[4 * ctx_set + c1], 0);
           if (k == 0 && sp > 0) {
             c2 = 0; rice = 0; c1_idx = 0; c2_idx = 0;
             ctx_set = (sp == 16 || type != 0) ? 0 : 2;
@@ -652,16 +722,16 @@ CTU_FN_NOINLINE void rdoq_team(const CtuTables *T, const CtuConfig *cfg, const u
             if (c < cc) { level = (uint32_t)lvl; cc = c; cs = sig_now; cs_kind = last ? 2 : 1; }
           }
         }
-        s.cost_coeff[sp] = cc;
-        s.sig_code[sp] = (uint8_t)((last ? 0 : s.prep_ctx_sig[k]) | (cs_kind << 6));
+        s_cost_coeff[sp] = cc;
+        s_sig_code[sp] = (uint8_t)((last ? 0 : s.prep_ctx_sig[k]) | (cs_kind << 6));
         if (SH) {
-          s.qdelta[blk] = (ld - (int)level * (1 << q_bits)) >> (q_bits - 8);
+          s_qdelta[blk] = (ld - (int)level * (1 << q_bits)) >> (q_bits - 8);
           if (level > 0) {
             const int now = rdoq_level_rate(m, level, one_ctx, abs_ctx, rice, c1_idx, c2_idx);
-            s.inc[blk] = rdoq_level_rate(m, level + 1, one_ctx, abs_ctx, rice, c1_idx, c2_idx) - now;
-            s.dec[blk] = rdoq_level_rate(m, level - 1, one_ctx, abs_ctx, rice, c1_idx, c2_idx) - now;
+            s_inc[blk] = rdoq_level_rate(m, level + 1, one_ctx, abs_ctx, rice, c1_idx, c2_idx) - now;
+            s_dec[blk] = rdoq_level_rate(m, level - 1, one_ctx, abs_ctx, rice, c1_idx, c2_idx) - now;
           } else {
-            s.inc[blk] = rq_ebits(m.one[one_ctx], 0);
+            s_inc[blk] = rq_ebits(m.one[one_ctx], 0);
           }
         }
         q[blk] = (int16_t)level;
@@ -682,7 +752,7 @@ CTU_FN_NOINLINE void rdoq_team(const CtuTables *T, const CtuConfig *cfg, const u
         if (k == 0) st_sig0 = cs;
         if (level) {
           nz_mask |= 1u << k;
-          s.cg_flag[cg_blk] = 1;
+          s_cg_flag[cg_blk] = 1;
           st_coded += cc - cs;
           st_uncoded += c0;
           if (k != 0) ++nnz_before_pos0;
@@ -691,33 +761,33 @@ CTU_FN_NOINLINE void rdoq_team(const CtuTables *T, const CtuConfig *cfg, const u
 
       if (cg) {
         const int ctx_cg = right || lower;
-        if (s.cg_flag[cg_blk] == 0) {
-          s.cg_sig_cost[cg] = lambda * rq_ebits(m.cg[ctx_cg], 0);
-          base_cost += s.cg_sig_cost[cg] - st_sig;
+        if (s_cg_flag[cg_blk] == 0) {
+          s_cg_sig_cost[cg] = lambda * rq_ebits(m.cg[ctx_cg], 0);
+          base_cost += s_cg_sig_cost[cg] - st_sig;
         } else if (cg < cg_last) {
           if (nnz_before_pos0 == 0) { base_cost -= st_sig0; st_sig -= st_sig0; }
           double cost_zero_cg = base_cost;
-          s.cg_sig_cost[cg] = lambda * rq_ebits(m.cg[ctx_cg], 1);
-          base_cost += s.cg_sig_cost[cg];
+          s_cg_sig_cost[cg] = lambda * rq_ebits(m.cg[ctx_cg], 1);
+          base_cost += s_cg_sig_cost[cg];
           cost_zero_cg += lambda * rq_ebits(m.cg[ctx_cg], 0);
           cost_zero_cg += st_uncoded;
           cost_zero_cg -= st_coded;
           cost_zero_cg -= st_sig;
           if (cost_zero_cg < base_cost) {
             nz_mask = 0;
-            s.cg_flag[cg_blk] = 0;
+            s_cg_flag[cg_blk] = 0;
             base_cost = cost_zero_cg;
-            s.cg_sig_cost[cg] = lambda * rq_ebits(m.cg[ctx_cg], 0);
+            s_cg_sig_cost[cg] = lambda * rq_ebits(m.cg[ctx_cg], 0);
             for (int k = 15; k >= 0; --k) {
               const int sp = (cg << 4) + k, blk = blk_of[sp];
-              if (q[blk]) { q[blk] = 0; s.cost_coeff[sp] = level0_cost(blk); s.sig_code[sp] = 2 << 6; }
+              if (q[blk]) { q[blk] = 0; s_cost_coeff[sp] = level0_cost(blk); s_sig_code[sp] = 2 << 6; }
             }
           }
         }
       } else {
-        s.cg_flag[cg_blk] = 1;
+        s_cg_flag[cg_blk] = 1;
       }
-      s.cg_nz[cg] = (uint16_t)nz_mask;
+      s_cg_nz[cg] = (uint16_t)nz_mask;
     }
     CTU_TEAM_SYNC();
   }
@@ -735,13 +805,13 @@ CTU_FN_NOINLINE void rdoq_team(const CtuTables *T, const CtuConfig *cfg, const u
     for (int cg = cg_last; cg >= 0 && !found_last; --cg) {
       const int cg_first = blk_of[cg << 4];
       const int cg_blk = ((cg_first >> log2n) >> 2) * cgs_side + ((cg_first & (n - 1)) >> 2);
-      base_cost -= s.cg_sig_cost[cg];
-      if (!s.cg_flag[cg_blk]) continue;
-      const unsigned nz = s.cg_nz[cg];
+      base_cost -= s_cg_sig_cost[cg];
+      if (!s_cg_flag[cg_blk]) continue;
+      const unsigned nz = s_cg_nz[cg];
       const int top = cg == cg_last ? (last_scanpos & 15) : 15;
       for (int k = top; k >= 0; --k) {
         const int sp = (cg << 4) + k;
-        const double csk = sig_cost_of(s.sig_code[sp]);
+        const double csk = sig_cost_of(s_sig_code[sp]);
         if (!((nz >> k) & 1)) { base_cost -= csk; continue; }
         const int blk = blk_of[sp];
         const int py = blk >> log2n, px = blk & (n - 1);
@@ -752,7 +822,7 @@ CTU_FN_NOINLINE void rdoq_team(const CtuTables *T, const CtuConfig *cfg, const u
         const double total = base_cost + lambda * bits - csk;
         if (total < best_cost) { best_last_p1 = sp + 1; best_cost = total; }
         if (q[blk] > 1) { found_last = true; break; }
-        base_cost -= s.cost_coeff[sp];
+        base_cost -= s_cost_coeff[sp];
         base_cost += level0_cost(blk);
       }
     }
@@ -775,7 +845,7 @@ CTU_FN_NOINLINE void rdoq_team(const CtuTables *T, const CtuConfig *cfg, const u
   if (SH) {
     abs_sum = team_sum(abs_sum);
     CTU_TEAM_SYNC();
-    if (lane == 0 && abs_sum >= 2) rdoq_sign_hiding(s, blk_of, lambda, qp_scaled, best_last_p1, coef, q);
+    if (lane == 0 && abs_sum >= 2) rdoq_sign_hiding(tu, blk_of, lambda, qp_scaled, best_last_p1, coef, q);
   }
   CTU_TEAM_SYNC();
 }
@@ -783,11 +853,11 @@ CTU_FN_NOINLINE void rdoq_team(const CtuTables *T, const CtuConfig *cfg, const u
 // ------------------------------------------------------------------------------------------------ CABAC bins (leader only)
 // CABAC_FBITS_UPDATE with only_count = 1 (ref: cabac.h:133-139): the bit estimate of the model's current state is
 // added first, then the model adapts when cabac->update is set.
-CTU_FN void cabac_bin(const CtuTables *T, CabacState *c, int off, int val, double *bits)
+CTU_FN void cabac_bin(const SmTables *tb, CabacState *c, int off, int val, double *bits)
 {
   const uint8_t st = c->ctx[off];
-  *bits += (double)T->ebits[st ^ val] * (1.0 / 32768.0);
-  if (c->update) c->ctx[off] = ((st & 1) == val) ? T->next_mps[st] : T->next_lps[st];
+  *bits += (double)tb->ebits[st ^ val] * (1.0 / 32768.0);
+  if (c->update) c->ctx[off] = ((st & 1) == val) ? tb->next_mps[st] : tb->next_lps[st];
 }
 
 CTU_FN int coeff_remain_bits(int symbol, int rice)
@@ -802,7 +872,7 @@ CTU_FN int coeff_remain_bits(int symbol, int rice)
 // kvz_get_coeff_cost's CABAC branch = kvz_encode_coeff_nxn in counting mode on a copy of the search models that is
 // kept when `update` is set (ref: rdo.c:223-264).  Leader only.  The cost estimate codes tr_skip as 0 (rdo.c:251-258);
 // the tracker of the real coder's models passes the TU's flag.
-CTU_FN_NOINLINE double coeff_cost_serial(const CtuTables *T, const CtuConfig *cfg, CabacState *c, const int16_t *coeff, int log2n, int type, int scan_idx, int tr_skip)
+CTU_FN_NOINLINE double coeff_cost_serial(const CtuTables *T, const SmTables *tb, const CtuConfig *cfg, CabacState *c, const int16_t *coeff, int log2n, int type, int scan_idx, int tr_skip)
 {
   const int n = 1 << log2n, side = n >> 2, ncg = side * side;
   uint64_t cg_flags = 0;
@@ -825,7 +895,7 @@ CTU_FN_NOINLINE double coeff_cost_serial(const CtuTables *T, const CtuConfig *cf
   const int pos_last = scan[scan_last];
 
   double bits = 0;
-  if (n == 4 && cfg->trskip_enable) cabac_bin(T, c, type == 0 ? CTX_TRSKIP_LUMA : CTX_TRSKIP_CHROMA, tr_skip, &bits);
+  if (n == 4 && cfg->trskip_enable) cabac_bin(tb, c, type == 0 ? CTX_TRSKIP_LUMA : CTX_TRSKIP_CHROMA, tr_skip, &bits);
   double bits_last = 0;
   {
     int lx = pos_last & (n - 1), ly = pos_last >> log2n;
@@ -836,10 +906,10 @@ CTU_FN_NOINLINE double coeff_cost_serial(const CtuTables *T, const CtuConfig *cf
     const int base_x = type ? CTX_LAST_X_CHROMA : CTX_LAST_X_LUMA;
     const int base_y = type ? CTX_LAST_Y_CHROMA : CTX_LAST_Y_LUMA;
     const int gx = T->group_idx[lx], gy = T->group_idx[ly], gmax = T->group_idx[n - 1];
-    for (int k = 0; k < gx; ++k) cabac_bin(T, c, base_x + ctx_offset + (k >> shift), 1, &bits_last);
-    if (gx < gmax) cabac_bin(T, c, base_x + ctx_offset + (gx >> shift), 0, &bits_last);
-    for (int k = 0; k < gy; ++k) cabac_bin(T, c, base_y + ctx_offset + (k >> shift), 1, &bits_last);
-    if (gy < gmax) cabac_bin(T, c, base_y + ctx_offset + (gy >> shift), 0, &bits_last);
+    for (int k = 0; k < gx; ++k) cabac_bin(tb, c, base_x + ctx_offset + (k >> shift), 1, &bits_last);
+    if (gx < gmax) cabac_bin(tb, c, base_x + ctx_offset + (gx >> shift), 0, &bits_last);
+    for (int k = 0; k < gy; ++k) cabac_bin(tb, c, base_y + ctx_offset + (k >> shift), 1, &bits_last);
+    if (gy < gmax) cabac_bin(tb, c, base_y + ctx_offset + (gy >> shift), 0, &bits_last);
     if (gx > 3) bits_last += (gx - 2) / 2;
     if (gy > 3) bits_last += (gy - 2) / 2;
   }
@@ -861,14 +931,14 @@ CTU_FN_NOINLINE double coeff_cost_serial(const CtuTables *T, const CtuConfig *cf
     const int right = (cgx < side - 1) ? (int)((cg_flags >> (cgy * side + cgx + 1)) & 1) : 0;
     const int lower = (cgy < side - 1) ? (int)((cg_flags >> ((cgy + 1) * side + cgx)) & 1) : 0;
     if (i == cg_last || i == 0) cg_flags |= 1ull << cg_blk;
-    else cabac_bin(T, c, base_cg + (right || lower), (int)((cg_flags >> cg_blk) & 1), &bits);
+    else cabac_bin(tb, c, base_cg + (right || lower), (int)((cg_flags >> cg_blk) & 1), &bits);
     if ((cg_flags >> cg_blk) & 1) {
       const int pattern = (n == 4) ? -1 : right + (lower << 1);
       for (; scan_pos_sig >= sub_pos; --scan_pos_sig) {
         const int blk = scan[scan_pos_sig];
         const int sig = coeff[blk] != 0;
         if (scan_pos_sig > sub_pos || i == 0 || num_nz)
-          cabac_bin(T, c, base_sig + sig_ctx_inc(T, pattern, scan_idx, blk & (n - 1), blk >> log2n, log2n, type), sig, &bits);
+          cabac_bin(tb, c, base_sig + sig_ctx_inc(T, pattern, scan_idx, blk & (n - 1), blk >> log2n, log2n, type), sig, &bits);
         if (sig) {
           abs_coeff[num_nz++] = iabs((int)coeff[blk]);
           if (last_nz == -1) last_nz = scan_pos_sig;
@@ -888,12 +958,12 @@ CTU_FN_NOINLINE double coeff_cost_serial(const CtuTables *T, const CtuConfig *cf
       int first_c2 = -1;
       for (int k = 0; k < num_c1; ++k) {
         const int symbol = abs_coeff[k] > 1;
-        cabac_bin(T, c, base_one + c1, symbol, &bits);
+        cabac_bin(tb, c, base_one + c1, symbol, &bits);
         if (symbol) { c1 = 0; if (first_c2 == -1) first_c2 = k; }
         else if (c1 < 3 && c1 > 0) ++c1;
       }
       if (c1 == 0 && first_c2 != -1)
-        cabac_bin(T, c, (type == 0 ? CTX_ABS_LUMA : CTX_ABS_CHROMA) + ctx_set, abs_coeff[first_c2] > 2, &bits);
+        cabac_bin(tb, c, (type == 0 ? CTX_ABS_LUMA : CTX_ABS_CHROMA) + ctx_set, abs_coeff[first_c2] > 2, &bits);
       bits += (cfg->signhide_enable && sign_hidden) ? num_nz - 1 : num_nz;
       if (c1 == 0 || num_nz > 8) {
         int first_coeff2 = 1;
@@ -912,6 +982,125 @@ CTU_FN_NOINLINE double coeff_cost_serial(const CtuTables *T, const CtuConfig *cf
   total += bits_last;
   total += bits;
   return total;
+}
+
+// ------------------------------------------------------------------------------------------------ one transform unit
+// Everything kvz_intra_recon_cu does for one colour of one transform unit (ref: intra.c:561-620 prediction,
+// transform.c:294-415 quantize_tr_residual, quant-generic.c:198-292 kvz_quantize_residual), fused and kept in the
+// team's scratch: prediction, residual, transform (or transform skip), RDOQ / quantisation, and when a level
+// survived dequantisation, inverse transform and reconstruction; plus the SSD against the source that the callers'
+// cost functions need (kvz_pixels_calc_ssd).  Results: tu.pred(), tu.q(), tu.rec(), fx->has, fx->ssd.
+struct TuJob {
+  const IntraRefs *refs;
+  const uint8_t *src;       // the unit's source pixels
+  int src_stride;
+  int color, log2n, mode, scan_idx;
+  int rdoq_tr_depth;        // context selector of RDOQ's cbf cost (quant-generic.c:237-238)
+};
+
+CTU_FN_NOINLINE void tu_core(const Team &tm, const CtuTables *T, const SmTables *tb, const CtuConfig *cfg, const uint8_t *cabac0, const TuS &tu,
+                             const TuJob &j, bool use_trskip)
+{
+  const int log2n = j.log2n, n = 1 << log2n, nn = n * n;
+  const int color = j.color;
+  const int ts_shift = 15 - 8 - log2n;
+  int16_t *a = tu.a(), *b = tu.b(), *q = tu.q(), *t = tu.t();
+  uint8_t *pred = tu.pred(), *rec = tu.rec();
+  TuFixed *fx = tu.fx();
+  for (int e = tm.tid; e < nn; e += tm.nt) {
+    const int y = e >> log2n, x = e & (n - 1);
+    const int p = intra_predict_px(j.refs, log2n, j.mode, color, x, y);
+    pred[e] = (uint8_t)p;
+    a[e] = (int16_t)((int)j.src[y * j.src_stride + x] - p);
+  }
+  if (tm.tid == 0) { fx->has = 0; fx->ssd = 0; }
+  tsync(tm);
+  const bool use_dst = (n == 4 && color == 0);
+  const int8_t *M = use_dst ? T->dst4 : T->tr[log2n - 2];
+  if (use_trskip) {
+    for (int e = tm.tid; e < nn; e += tm.nt) b[e] = (int16_t)((uint16_t)a[e] << ts_shift);
+    tsync(tm);
+  } else {
+    fwd_pass(tm, a, t, M, n, log2n - 1);
+    fwd_pass(tm, t, b, M, n, log2n + 6);
+  }
+  const int type = color == 0 ? 0 : 2;
+  if (cfg->rdoq_enable && (n > 4 || !cfg->rdoq_skip)) {
+    if (tm.tid < CTU_TEAM_N) rdoq_team(T, tb, cfg, cabac0, tu, log2n, type, j.scan_idx, j.rdoq_tr_depth, tm.tid);
+    tsync(tm);
+  } else {
+    quant_block(tm, T, cfg, tu, n, type, j.scan_idx);
+  }
+  int any = 0;
+  for (int e = tm.tid; e < nn; e += tm.nt) any |= q[e] != 0;
+  if (any) CTU_ATOMIC_OR(&fx->has, 1);
+  tsync(tm);
+  int ssd = 0;
+  if (fx->has) {
+    dequant_block(tm, cfg, tu, n, color == 0 ? 0 : (color == 1 ? 2 : 3));
+    if (use_trskip) {
+      const int offs = 1 << (ts_shift - 1);
+      for (int e = tm.tid; e < nn; e += tm.nt) a[e] = (int16_t)(((int)b[e] + offs) >> ts_shift);
+      tsync(tm);
+    } else {
+      inv_pass(tm, b, t, M, n, 7);
+      inv_pass(tm, t, a, M, n, 12);
+    }
+    for (int e = tm.tid; e < nn; e += tm.nt) {
+      const int y = e >> log2n, x = e & (n - 1);
+      const int16_t val = (int16_t)(a[e] + (int)pred[e]);
+      const int r = iclip(0, 255, (int)val);
+      rec[e] = (uint8_t)r;
+      const int d = (int)j.src[y * j.src_stride + x] - r;
+      ssd += d * d;
+    }
+  } else {
+    for (int e = tm.tid; e < nn; e += tm.nt) {
+      const int y = e >> log2n, x = e & (n - 1);
+      const int r = pred[e];
+      rec[e] = (uint8_t)r;
+      const int d = (int)j.src[y * j.src_stride + x] - r;
+      ssd += d * d;
+    }
+  }
+  if (ssd) CTU_ATOMIC_ADD(&fx->ssd, ssd);
+  tsync(tm);
+}
+
+// One colour of one transform unit including the transform-skip decision of 4x4 luma units
+// (kvz_quantize_residual_trskip, ref: transform.c:242-288).  `sc`: the search models the decision's bit costs read.
+// Returns tr_skip (uniform over the team); the chosen alternative is in tu.q() / tu.rec() / fx->has / fx->ssd.
+CTU_FN_NOINLINE int tu_eval(const Team &tm, const CtuTables *T, const SmTables *tb, const CtuConfig *cfg, const uint8_t *cabac0, CabacState *sc,
+                            const TuS &tu, const TuJob &j)
+{
+  if (!(j.log2n == 2 && j.color == 0 && cfg->trskip_enable)) {
+    tu_core(tm, T, tb, cfg, cabac0, tu, j, false);
+    return 0;
+  }
+  TuFixed *fx = tu.fx();
+  for (int k = 0; k < 2; ++k) {
+    tu_core(tm, T, tb, cfg, cabac0, tu, j, k == 1);
+    for (int e = tm.tid; e < 16; e += tm.nt) { fx->ts_rec[k][e] = tu.rec()[e]; fx->ts_coeff[k][e] = tu.q()[e]; }
+    if (tm.tid == 0) { fx->ts_has[k] = fx->has; fx->ts_ssd[k] = fx->ssd; }
+    tsync(tm);
+  }
+  if (tm.tid == 0) {
+    double cost[2];
+    for (int k = 0; k < 2; ++k) {
+      cost[k] = (double)(unsigned)fx->ts_ssd[k];
+      cost[k] += coeff_cost_serial(T, tb, cfg, sc, fx->ts_coeff[k], 2, 0, j.scan_idx, 0) * cfg->lambda;
+    }
+    fx->ts_pick = cost[0] <= cost[1] ? 0 : 1;
+  }
+  tsync(tm);
+  const int pick = fx->ts_pick;
+  // (the second alternative is still in place when it wins)
+  if (pick == 0) {
+    for (int e = tm.tid; e < 16; e += tm.nt) { tu.q()[e] = fx->ts_coeff[0][e]; tu.rec()[e] = fx->ts_rec[0][e]; }
+    if (tm.tid == 0) { fx->has = fx->ts_has[0]; fx->ssd = fx->ts_ssd[0]; }
+    tsync(tm);
+  }
+  return pick;
 }
 
 }  // namespace kvzctu

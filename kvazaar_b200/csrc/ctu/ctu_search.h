@@ -34,6 +34,8 @@ struct SearchFrame {
   CabacState pre, post;
 };
 
+struct TuRes { int32_t ssd, has, tr_skip, pad; double bits; };
+
 struct CtuS {                       // per-CTA scalar state + scratch; shared memory on the device
   CabacState cabac0;                // state->cabac: the real coder's models when the CTU starts (constant)
   CabacState sc;                    // state->search_cabac
@@ -53,17 +55,15 @@ struct CtuS {                       // per-CTA scalar state + scratch; shared me
   int32_t flag;
   int32_t best_mode;
   double best_cost;
-  // transform skip decision buffers (kvz_quantize_residual_trskip)
-  uint8_t ts_rec[2][16];
-  int16_t ts_coeff[2][16];
-  int32_t ts_has[2];
-  int32_t ts_ssd[2];
-  int32_t ts_pick;
-  TuBuf tu;
-  RdoqScratch rq;
+  SmTables tb;
+  TuRes res[8][3];                  // [RDO candidate][colour]
+  // the coefficients of the transform units reconstructed last (the CU whose cost is computed next), per colour
+  int16_t stage_y[1024], stage_c[2][256];
+  int32_t stage_key[3];             // (xl << 16) | (yl << 8) | depth of the staged unit, -1: none
 #if defined(KVZ_CTU_PROF)
   long long prof[PR_N];
 #endif
+  alignas(16) unsigned char arena[CTU_ARENA_BYTES];
 };
 
 struct Ctx {
@@ -94,7 +94,7 @@ CTU_FN double luma_mode_bits(const Ctx &c, int mode, const int8_t *preds)
 {
   double bits = 0;
   const bool in = mode == preds[0] || mode == preds[1] || mode == preds[2];
-  cabac_bin(c.T, &c.S->sc, CTX_INTRA_MODE, in, &bits);
+  cabac_bin(&c.S->tb, &c.S->sc, CTX_INTRA_MODE, in, &bits);
   if (in) bits += (mode == preds[0]) ? 1 : 2;
   else bits += 5;
   return bits;
@@ -103,7 +103,7 @@ CTU_FN double luma_mode_bits(const Ctx &c, int mode, const int8_t *preds)
 CTU_FN double chroma_mode_bits(const Ctx &c, int chroma_mode, int luma_mode)
 {
   double bits = 0;
-  cabac_bin(c.T, &c.S->sc, CTX_CHROMA_PRED, chroma_mode != luma_mode, &bits);
+  cabac_bin(&c.S->tb, &c.S->sc, CTX_CHROMA_PRED, chroma_mode != luma_mode, &bits);
   if (chroma_mode != luma_mode) bits += 2.0;
   return bits;
 }
@@ -179,185 +179,110 @@ CTU_FN_NOINLINE void fill_cu_info(LcuLevel *L, int xl, int yl, int width, const 
   CTU_SYNC();
 }
 
-// ------------------------------------------------------------------------------------------------ residual coding
-// kvz_quantize_residual for the TU of `color` at LCU-local luma position (xl, yl) of level L.  cu supplies
-// tr_depth / depth / part_size for RDOQ's cbf context.  Prediction is read from the level's reconstruction; the
-// result goes to rec_out (stride out_stride) and coeff_out (n*n).  Returns has_coeffs (uniform).
-CTU_FN_NOINLINE int quantize_residual(const Ctx &c, LcuLevel *L, int color, int xl, int yl, int n, int scan_idx, const CuRec *cu, bool use_trskip,
-                             uint8_t *rec_out, int out_stride, int16_t *coeff_out)
+// ------------------------------------------------------------------------------------------------ transform units
+CTU_FN int tu_log2(int depth, int color) { return color == 0 ? 6 - depth : (depth < 4 ? 5 - depth : 2); }
+CTU_FN int stage_key_of(int xl, int yl, int depth) { return (xl << 16) | (yl << 8) | depth; }
+// coefficients of the unit of `color` at (xl, yl, depth) on level L: the staged copy when it is this unit's
+CTU_FN const int16_t *unit_coeffs(const Ctx &c, LcuLevel *L, int color, int xl, int yl, int depth)
 {
-  const CtuTables *T = c.T;
-  TuBuf *tu = &c.S->tu;
-  PROF_T0(PR_QRES);
-  PROF_T0(PR_FWD);
-  const Plane P = plane_of(c.W, L, color);
-  const int sh = color ? 1 : 0;
-  const int off = (xl >> sh) + (yl >> sh) * P.lw;
-  const uint8_t *pred = P.rec + off, *ref = P.src + off;
-  const int nn = n * n, log2n = ilog2(n);
-  const int ts_shift = 15 - 8 - log2n;
-  for (int e = CTU_TID; e < nn; e += CTU_NT) {
-    const int y = e / n, x = e - y * n;
-    tu->a[e] = (int16_t)((int)ref[y * P.lw + x] - (int)pred[y * P.lw + x]);
-  }
-  CTU_LEADER tu->has = 0;
-  CTU_SYNC();
-  const bool use_dst = (n == 4 && color == 0);
-  const int8_t *M = use_dst ? T->dst4 : T->tr[log2n - 2];
-  if (use_trskip) {
-    for (int e = CTU_TID; e < nn; e += CTU_NT) tu->b[e] = (int16_t)((uint16_t)tu->a[e] << ts_shift);
-    CTU_SYNC();
-  } else {
-    fwd_pass(tu->a, tu->t, M, n, log2n - 1);
-    fwd_pass(tu->t, tu->b, M, n, log2n + 6);
-  }
-  PROF_ADD(c.S, PR_FWD);
-  const int type = color == 0 ? 0 : 2;
-  if (c.cfg->rdoq_enable && (n > 4 || !c.cfg->rdoq_skip)) {
-    PROF_T0(PR_RDOQ);
-    int tr_depth = (int)cu->tr_depth - (int)cu->depth;
-    tr_depth += (cu->part_size == SIZE_NxN ? 1 : 0);
-    if (CTU_TID < CTU_TEAM_N) rdoq_team(T, c.cfg, c.S->cabac0.ctx, tu, c.S->rq, log2n, type, scan_idx, tr_depth, CTU_TID);
-    CTU_SYNC();
-    PROF_ADD(c.S, PR_RDOQ);
-  } else {
-    PROF_T0(PR_QUANT);
-    quant_block(T, c.cfg, tu, n, type, scan_idx);
-    PROF_ADD(c.S, PR_QUANT);
-  }
-  PROF_T0(PR_INV);
-  int any = 0;
-  for (int e = CTU_TID; e < nn; e += CTU_NT) { const int16_t v = tu->q[e]; coeff_out[e] = v; any |= v != 0; }
-  if (any) CTU_ATOMIC_OR(&tu->has, 1);
-  CTU_SYNC();
-  const int has = tu->has;
-  if (has) {
-    dequant_block(c.cfg, tu, n, color == 0 ? 0 : (color == 1 ? 2 : 3));
-    if (use_trskip) {
-      const int offs = 1 << (ts_shift - 1);
-      for (int e = CTU_TID; e < nn; e += CTU_NT) tu->a[e] = (int16_t)(((int)tu->b[e] + offs) >> ts_shift);
-      CTU_SYNC();
-    } else {
-      inv_pass(tu->b, tu->t, M, n, 7);
-      inv_pass(tu->t, tu->a, M, n, 12);
-    }
-    for (int e = CTU_TID; e < nn; e += CTU_NT) {
-      const int y = e / n, x = e - y * n;
-      const int16_t val = (int16_t)(tu->a[e] + (int)pred[y * P.lw + x]);
-      rec_out[y * out_stride + x] = (uint8_t)iclip(0, 255, (int)val);
-    }
-  } else if (rec_out != pred) {
-    for (int e = CTU_TID; e < nn; e += CTU_NT) {
-      const int y = e / n, x = e - y * n;
-      rec_out[y * out_stride + x] = pred[y * P.lw + x];
-    }
-  }
-  CTU_SYNC();
-  PROF_ADD(c.S, PR_INV);
-  PROF_ADD(c.S, PR_QRES);
-  return has;
+  if (c.S->stage_key[color] == stage_key_of(xl, yl, depth)) return color == 0 ? c.S->stage_y : c.S->stage_c[color - 1];
+  if (color == 0) return &L->coeff_y[zorder(64, xl, yl)];
+  return (color == 1 ? L->coeff_u : L->coeff_v) + zorder(32, xl >> 1, yl >> 1);
 }
 
-// quantize_tr_residual (ref: transform.c:294-415) for one colour of the leaf TU; cur_pu receives cbf / tr_skip
-CTU_FN_NOINLINE void quantize_tr_residual(const Ctx &c, LcuLevel *L, int color, int xl, int yl, int depth, CuRec *cur_pu)
+// Runs `ntasks` independent transform-unit jobs whose largest unit has nn coefficients: one warp per job when four
+// scratch slots fit the arena, otherwise the whole CTA job after job.  f(team, slot base, task) must synchronise
+// with tsync(team) only.
+template <class F> CTU_FN void for_tu_tasks(const Ctx &c, int ntasks, int nn, F f)
 {
-  const int sh = color ? 1 : 0;
-  const Plane P = plane_of(c.W, L, color);
-  const int px = xl >> sh, py = yl >> sh;
-  if (color != 0 && depth > 3 && ((px & 3) != 0 || (py & 3) != 0)) return;     // handled_elsewhere
-  CTU_LEADER cbf_clear(&cur_pu->cbf, depth, color);
   CTU_SYNC();
-  const int n = color == 0 ? (64 >> depth) : (32 >> (depth == 4 ? 3 : depth));
-  const int mode = color == 0 ? cur_pu->mode : cur_pu->mode_chroma;
-  const int scan_idx = scan_order_intra(mode, depth);
-  const int off = px + py * P.lw;
-  int16_t *coeff = P.coeff + zorder(P.lw, px, py);
-  uint8_t *rec = P.rec + off;
-  int has;
-  if (n == 4 && color == 0 && c.cfg->trskip_enable) {
-    // kvz_quantize_residual_trskip (ref: transform.c:242-288)
-    CtuS *S = c.S;
-    for (int k = 0; k < 2; ++k) {
-      const int h = quantize_residual(c, L, color, xl, yl, 4, scan_idx, cur_pu, k == 1, S->ts_rec[k], 4, S->ts_coeff[k]);
-      CTU_LEADER {
-        S->ts_has[k] = h;
-        int ssd = 0;
-        for (int e = 0; e < 16; ++e) { const int d = (int)P.src[off + (e >> 2) * P.lw + (e & 3)] - (int)S->ts_rec[k][e]; ssd += d * d; }
-        S->ts_ssd[k] = ssd;
-      }
-      CTU_SYNC();
-    }
-    CTU_LEADER {
-      double cost[2];
-      for (int k = 0; k < 2; ++k) {
-        cost[k] = (double)(unsigned)S->ts_ssd[k];
-        cost[k] += coeff_cost_serial(c.T, c.cfg, &S->sc, S->ts_coeff[k], 2, 0, scan_idx, 0) * c.cfg->lambda;
-      }
-      const int pick = cost[0] <= cost[1] ? 0 : 1;
-      S->ts_pick = pick;
-      if (S->ts_has[pick]) for (int e = 0; e < 16; ++e) rec[(e >> 2) * P.lw + (e & 3)] = S->ts_rec[pick][e];
-      for (int e = 0; e < 16; ++e) coeff[e] = S->ts_coeff[pick][e];
-      cur_pu->tr_skip = (uint8_t)pick;
-    }
-    CTU_SYNC();
-    has = S->ts_has[S->ts_pick];
+  if (CTU_NWARPS > 1 && CTU_NWARPS * tu_scratch_bytes(nn) <= CTU_ARENA_BYTES) {
+    const Team tm = team_warp();
+    unsigned char *slot = c.S->arena + (size_t)CTU_WARP * tu_scratch_bytes(nn);
+    for (int t = CTU_WARP; t < ntasks; t += CTU_NWARPS) f(tm, slot, t);
   } else {
-    has = quantize_residual(c, L, color, xl, yl, n, scan_idx, cur_pu, false, rec, P.lw, coeff);
+    const Team tm = team_cta();
+    for (int t = 0; t < ntasks; ++t) f(tm, c.S->arena, t);
   }
-  if (has) { CTU_LEADER cbf_set(&cur_pu->cbf, depth, color); }
   CTU_SYNC();
 }
 
-// intra_recon_tb_leaf: prediction of one colour of the TU into the level's reconstruction
-CTU_FN_NOINLINE void intra_recon_tb_leaf(const Ctx &c, LcuLevel *L, int x, int y, int depth, int mode, int color)
-{
-  int log2w = 6 - depth;
-  if (color != 0 && depth < 4) log2w -= 1;
-  const int sh = color ? 1 : 0;
-  const Plane P = plane_of(c.W, L, color);
-  IntraRefs *r = &c.S->refs[color];
-  PROF_T0(PR_REFS);
-  build_refs(c.T, c.cfg, c.W, L, log2w, color, x, y, r);
-  PROF_ADD(c.S, PR_REFS);
-  PROF_T0(PR_PREDICT);
-  predict_block(r, log2w, mode, color, P.rec + ((x & 63) >> sh) + ((y & 63) >> sh) * P.lw, P.lw);
-  PROF_ADD(c.S, PR_PREDICT);
-}
+CTU_FN TuS tu_at(unsigned char *slot, int nn) { TuS t; t.base = slot; t.nn = nn; t.ncg = nn >= 16 ? nn / 16 : 1; return t; }
 
-// leaf part of kvz_intra_recon_cu + kvz_quantize_lcu_residual (ref: intra.c:676-696, transform.c:448-508)
-CTU_FN_NOINLINE void intra_recon_leaf(const Ctx &c, LcuLevel *L, int x, int y, int depth, int mode_luma, int mode_chroma, CuRec *cur_cu)
+// leaf part of kvz_intra_recon_cu + kvz_quantize_lcu_residual (ref: intra.c:676-696, transform.c:448-508): the
+// colours of the leaf are independent jobs (prediction only reads neighbours outside the unit).
+// refs_valid: bit per colour whose S->refs[] already hold this unit's references.
+CTU_FN_NOINLINE void intra_recon_leaf(const Ctx &c, LcuLevel *L, int x, int y, int depth, int mode_luma, int mode_chroma, CuRec *cur_cu, int leaf, int refs_valid)
 {
+  CtuS *S = c.S;
   const int xl = x & 63, yl = y & 63;
   CuRec *cur_tu = cu_at(L, xl, yl);
   const bool has_luma = mode_luma != -1;
   const bool has_chroma = mode_chroma != -1 && (x % 8 == 0) && (y % 8 == 0);
-  if (has_luma) intra_recon_tb_leaf(c, L, x, y, depth, mode_luma, 0);
-  if (has_chroma) { intra_recon_tb_leaf(c, L, x, y, depth, mode_chroma, 1); intra_recon_tb_leaf(c, L, x, y, depth, mode_chroma, 2); }
-  // kvz_quantize_lcu_residual(state, has_luma, has_chroma, x, y, depth, cur_cu, lcu, false)
+  const int first = has_luma ? 0 : 1, last = has_chroma ? 2 : 0;
+  if (last < first) return;
+  PROF_T0(PR_REFS);
+  for (int col = first; col <= last; ++col)
+    if (!((refs_valid >> col) & 1)) build_refs(c.T, c.cfg, c.W, L, tu_log2(depth, col), col, x, y, &S->refs[col]);
+  PROF_ADD(S, PR_REFS);
+  // cur_pu of quantize_tr_residual: the RDOQ context selector reads its depths before the cbf bits change
+  const int rdoq_tr_depth = (int)cur_cu->tr_depth - (int)cur_cu->depth + (cur_cu->part_size == SIZE_NxN ? 1 : 0);
+  PROF_T0(PR_QRES);
+  for_tu_tasks(c, last - first + 1, 1 << (2 * tu_log2(depth, first)), [&](const Team &tm, unsigned char *slot, int t) {
+    const int col = first + t;
+    const int log2n = tu_log2(depth, col), n = 1 << log2n;
+    const TuS tu = tu_at(slot, n * n);
+    const Plane P = plane_of(c.W, L, col);
+    const int sh = col ? 1 : 0;
+    const int off = (xl >> sh) + (yl >> sh) * P.lw;
+    const int mode = col == 0 ? mode_luma : mode_chroma;
+    TuJob j = { &S->refs[col], P.src + off, P.lw, col, log2n, mode, scan_order_intra(mode, depth), rdoq_tr_depth };
+    const int ts = tu_eval(tm, c.T, &S->tb, c.cfg, S->cabac0.ctx, &S->sc, tu, j);
+    // write back: reconstruction and coefficients of the level, staged copy for the cost functions
+    uint8_t *rec = P.rec + off;
+    int16_t *co = P.coeff + zorder(P.lw, xl >> sh, yl >> sh);
+    const uint8_t *r = tu.rec();
+    const int16_t *q = tu.q();
+    int16_t *stage = col == 0 ? S->stage_y : S->stage_c[col - 1];
+    for (int e = tm.tid; e < n * n; e += tm.nt) {
+      rec[(e >> log2n) * P.lw + (e & (n - 1))] = r[e];
+      co[e] = q[e];
+      stage[e] = q[e];
+    }
+    if (tm.tid == 0) {
+      const TuFixed *fx = tu.fx();
+      S->res[0][col].ssd = fx->ssd; S->res[0][col].has = fx->has; S->res[0][col].tr_skip = ts;
+      S->stage_key[col] = stage_key_of(xl, yl, depth);
+    }
+    tsync(tm);
+  });
+  PROF_ADD(S, PR_QRES);
   CTU_LEADER {
-    if (has_luma) cbf_clear(&cur_cu->cbf, depth, 0);
-    if (has_chroma) { cbf_clear(&cur_cu->cbf, depth, 1); cbf_clear(&cur_cu->cbf, depth, 2); }
+    const bool ts_branch = depth == 4 && c.cfg->trskip_enable;       // 4x4 luma units only (transform.c:366)
+    for (int col = first; col <= last; ++col) {
+      cbf_clear(&cur_cu->cbf, depth, col);
+      if (S->res[0][col].has) cbf_set(&cur_cu->cbf, depth, col);
+      if (col == 0 && ts_branch) cur_cu->tr_skip = (uint8_t)S->res[0][0].tr_skip;
+      S->ssd[leaf][col] = S->res[0][col].ssd;
+    }
+    if (cur_cu != cur_tu) for (int col = first; col <= last; ++col) cbf_copy(&cur_tu->cbf, cur_cu->cbf, col);
   }
   CTU_SYNC();
-  if (has_luma) quantize_tr_residual(c, L, 0, xl, yl, depth, cur_cu);
-  if (has_chroma) { quantize_tr_residual(c, L, 1, xl, yl, depth, cur_cu); quantize_tr_residual(c, L, 2, xl, yl, depth, cur_cu); }
-  if (cur_cu != cur_tu) {
-    CTU_LEADER {
-      if (has_luma) cbf_copy(&cur_tu->cbf, cur_cu->cbf, 0);
-      if (has_chroma) { cbf_copy(&cur_tu->cbf, cur_cu->cbf, 1); cbf_copy(&cur_tu->cbf, cur_cu->cbf, 2); }
-    }
-    CTU_SYNC();
-  }
 }
 
-// kvz_intra_recon_cu (ref: intra.c:623-698).  cur_cu == NULL: the CU record of the level at (x, y).
-CTU_FN_NOINLINE void intra_recon_cu(const Ctx &c, LcuLevel *L, int x, int y, int depth, int mode_luma, int mode_chroma, CuRec *cur_cu)
+// kvz_intra_recon_cu (ref: intra.c:623-698).  cur_cu == NULL: the CU record of the level at (x, y).  Leaves the SSDs
+// of the reconstructed colours in S->ssd[leaf][colour] (0 for the colours not touched).
+CTU_FN_NOINLINE void intra_recon_cu(const Ctx &c, LcuLevel *L, int x, int y, int depth, int mode_luma, int mode_chroma, CuRec *cur_cu, int refs_valid)
 {
   const int xl = x & 63, yl = y & 63;
   if (cur_cu == NULL) cur_cu = cu_at(L, xl, yl);
   CTU_LEADER {
     if (mode_luma >= 0) cbf_clear(&cur_cu->cbf, depth, 0);
     if (mode_chroma >= 0) { cbf_clear(&cur_cu->cbf, depth, 1); cbf_clear(&cur_cu->cbf, depth, 2); }
+    for (int k = 0; k < 4; ++k) {
+      if (mode_luma >= 0) c.S->ssd[k][0] = 0;
+      if (mode_chroma >= 0) { c.S->ssd[k][1] = 0; c.S->ssd[k][2] = 0; }
+    }
   }
   CTU_SYNC();
   if (depth == 0 || cur_cu->tr_depth > depth) {
@@ -371,7 +296,7 @@ CTU_FN_NOINLINE void intra_recon_cu(const Ctx &c, LcuLevel *L, int x, int y, int
         if (mode_chroma >= 0) { cbf_clear(&child->cbf, depth + 1, 1); cbf_clear(&child->cbf, depth + 1, 2); }
       }
       CTU_SYNC();
-      intra_recon_leaf(c, L, cx, cy, depth + 1, mode_luma, mode_chroma, child);
+      intra_recon_leaf(c, L, cx, cy, depth + 1, mode_luma, mode_chroma, child, k, 0);
     }
     CTU_LEADER {
       const uint16_t child_cbfs[3] = { cu_at(L, xl + offset, yl)->cbf, cu_at(L, xl, yl + offset)->cbf, cu_at(L, xl + offset, yl + offset)->cbf };
@@ -380,38 +305,15 @@ CTU_FN_NOINLINE void intra_recon_cu(const Ctx &c, LcuLevel *L, int x, int y, int
     }
     CTU_SYNC();
   } else {
-    intra_recon_leaf(c, L, x, y, depth, mode_luma, mode_chroma, cur_cu);
+    intra_recon_leaf(c, L, x, y, depth, mode_luma, mode_chroma, cur_cu, 0, refs_valid);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ RD costs
-// SSDs of the leaf TUs of the CU at (xl, yl, depth) into S->ssd[leaf][colour] (leaf 0 only unless depth == 0)
-CTU_FN_NOINLINE void leaf_ssds(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, bool luma, bool chroma)
+// kvz_cu_rd_cost_luma for a leaf (tr_depth == depth), the search models not adapting (update == 0: the candidates of
+// search_intra_rdo).  Leader only.  ssd / coeff_bits: the unit's SSD and kvz_get_coeff_cost (0 when cbf is clear).
+CTU_FN_NOINLINE double cu_rd_cost_luma_leaf(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, const CuRec *pred_cu, int ssd, double coeff_bits_y)
 {
-  CtuS *S = c.S;
-  PROF_T0(PR_SSD);
-  CTU_LEADER { for (int k = 0; k < 4; ++k) for (int col = 0; col < 3; ++col) S->ssd[k][col] = 0; }
-  CTU_SYNC();
-  const bool split = depth == 0;
-  const int d = split ? 1 : depth, leaves = split ? 4 : 1;
-  const int w = 64 >> d;
-  for (int k = 0; k < leaves; ++k) {
-    const int lx = xl + (k & 1) * w * (split ? 1 : 0), ly = yl + (k >> 1) * w * (split ? 1 : 0);
-    if (luma) ssd_block(&c.W->src_y[ly * 64 + lx], 64, &L->rec_y[ly * 64 + lx], 64, w, &S->ssd[k][0]);
-    if (chroma && (lx % 8 == 0) && (ly % 8 == 0)) {
-      const int wc = d <= 3 ? (64 >> (d + 1)) : (64 >> d);
-      const int ci = (ly >> 1) * 32 + (lx >> 1);
-      ssd_block(&c.W->src_u[ci], 32, &L->rec_u[ci], 32, wc, &S->ssd[k][1]);
-      ssd_block(&c.W->src_v[ci], 32, &L->rec_v[ci], 32, wc, &S->ssd[k][2]);
-    }
-  }
-  PROF_ADD(c.S, PR_SSD);
-}
-
-// kvz_cu_rd_cost_luma for a leaf (tr_depth == depth).  Leader only; S->ssd[leaf][0] holds the SSD.
-CTU_FN_NOINLINE double cu_rd_cost_luma_leaf(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, const CuRec *pred_cu, int leaf)
-{
-  const CtuS *S = c.S;
   CabacState *sc = &c.S->sc;
   const int width = 64 >> depth;
   CuRec *tr_cu = cu_at(L, xl, yl);
@@ -420,30 +322,24 @@ CTU_FN_NOINLINE double cu_rd_cost_luma_leaf(const Ctx &c, LcuLevel *L, int xl, i
   const bool intra_split_flag = pred_cu->part_size == SIZE_NxN && depth == 3;
   const int max_tr_depth = 0 + (intra_split_flag ? 1 : 0);
   if (width <= 32 && width > 4 && !intra_split_flag && imin((int)tr_cu->tr_depth, depth) - (int)tr_cu->depth < max_tr_depth)
-    cabac_bin(c.T, sc, CTX_TRANS_SUBDIV + (5 - (6 - depth)), tr_depth > 0, &tr_tree_bits);
+    cabac_bin(&c.S->tb, sc, CTX_TRANS_SUBDIV + (5 - (6 - depth)), tr_depth > 0, &tr_tree_bits);
   if (sc->update && tr_cu->tr_depth == tr_cu->depth) {
     const int off = CTX_CBF_CHROMA + (depth - (int)tr_cu->depth);
-    cabac_bin(c.T, sc, off, cbf_is_set(tr_cu->cbf, depth, 1), &tr_tree_bits);
-    cabac_bin(c.T, sc, off, cbf_is_set(tr_cu->cbf, depth, 2), &tr_tree_bits);
+    cabac_bin(&c.S->tb, sc, off, cbf_is_set(tr_cu->cbf, depth, 1), &tr_tree_bits);
+    cabac_bin(&c.S->tb, sc, off, cbf_is_set(tr_cu->cbf, depth, 2), &tr_tree_bits);
   }
   const int is_tr_split = (int)tr_cu->tr_depth - (int)tr_cu->depth;
   const int is_set = cbf_is_set(tr_cu->cbf, depth, 0);
-  cabac_bin(c.T, sc, CTX_CBF_LUMA + (is_tr_split ? 0 : 1), is_set, &tr_tree_bits);     // pred_cu->type == CU_INTRA
-  const int ssd = S->ssd[leaf][0];
-  if (is_set) {
-    const int scan = scan_order_intra(pred_cu->mode, depth);
-    coeff_bits += coeff_cost_serial(c.T, c.cfg, sc, &L->coeff_y[zorder(64, xl, yl)], ilog2(width), 0, scan, 0);
-  }
+  cabac_bin(&c.S->tb, sc, CTX_CBF_LUMA + (is_tr_split ? 0 : 1), is_set, &tr_tree_bits);     // pred_cu->type == CU_INTRA
+  if (is_set) coeff_bits += coeff_bits_y;
   const double bits = tr_tree_bits + coeff_bits;
   return (double)ssd * 0.8 + bits * c.cfg->lambda;
 }
 
-// kvz_cu_rd_cost_chroma for a leaf.  Leader only.
-CTU_FN_NOINLINE double cu_rd_cost_chroma_leaf(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, const CuRec *pred_cu, int leaf)
+// kvz_cu_rd_cost_chroma for a leaf, update == 0.  Leader only.
+CTU_FN_NOINLINE double cu_rd_cost_chroma_leaf(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, const CuRec *pred_cu, int ssd, double coeff_bits_u, double coeff_bits_v)
 {
-  const CtuS *S = c.S;
   CabacState *sc = &c.S->sc;
-  const int width = depth <= 3 ? (64 >> (depth + 1)) : (64 >> depth);
   CuRec *tr_cu = cu_at(L, xl, yl);
   double tr_tree_bits = 0, coeff_bits = 0;
   if (xl % 8 != 0 || yl % 8 != 0) return 0;
@@ -451,18 +347,26 @@ CTU_FN_NOINLINE double cu_rd_cost_chroma_leaf(const Ctx &c, LcuLevel *L, int xl,
   if (depth < 4 && (!sc->update || tr_cu->tr_depth != tr_cu->depth)) {
     const int tr_depth = depth - (int)pred_cu->depth;
     const int off = CTX_CBF_CHROMA + tr_depth;
-    if (tr_depth == 0 || cbf_is_set(tr_cu->cbf, depth - 1, 1)) cabac_bin(c.T, sc, off, u_is_set, &tr_tree_bits);
-    if (tr_depth == 0 || cbf_is_set(tr_cu->cbf, depth - 1, 2)) cabac_bin(c.T, sc, off, v_is_set, &tr_tree_bits);
+    if (tr_depth == 0 || cbf_is_set(tr_cu->cbf, depth - 1, 1)) cabac_bin(&c.S->tb, sc, off, u_is_set, &tr_tree_bits);
+    if (tr_depth == 0 || cbf_is_set(tr_cu->cbf, depth - 1, 2)) cabac_bin(&c.S->tb, sc, off, v_is_set, &tr_tree_bits);
   }
-  const int ssd = S->ssd[leaf][1] + S->ssd[leaf][2];
-  {
-    const int scan = scan_order_intra(pred_cu->mode_chroma, depth);
-    const int index = zorder(32, xl >> 1, yl >> 1);
-    if (u_is_set) coeff_bits += coeff_cost_serial(c.T, c.cfg, sc, &L->coeff_u[index], ilog2(width), 2, scan, 0);
-    if (v_is_set) coeff_bits += coeff_cost_serial(c.T, c.cfg, sc, &L->coeff_v[index], ilog2(width), 2, scan, 0);
-  }
+  if (u_is_set) coeff_bits += coeff_bits_u;
+  if (v_is_set) coeff_bits += coeff_bits_v;
   const double bits = tr_tree_bits + coeff_bits;
   return (double)ssd * 1.5 + bits * c.cfg->lambda;
+}
+
+// the same with the coefficient bits taken from the level's (or staged) coefficients; S->ssd[leaf] holds the SSDs
+CTU_FN_NOINLINE double cu_rd_cost_chroma_leaf_of_level(const Ctx &c, LcuLevel *L, int xl, int yl, int depth, const CuRec *pred_cu, int leaf)
+{
+  if (xl % 8 != 0 || yl % 8 != 0) return 0;
+  const CuRec *tr_cu = cu_at(L, xl, yl);
+  const int width = depth <= 3 ? (64 >> (depth + 1)) : (64 >> depth);
+  const int scan = scan_order_intra(pred_cu->mode_chroma, depth);
+  double bu = 0, bv = 0;
+  if (cbf_is_set(tr_cu->cbf, depth, 1)) bu = coeff_cost_serial(c.T, &c.S->tb, c.cfg, &c.S->sc, unit_coeffs(c, L, 1, xl, yl, depth), ilog2(width), 2, scan, 0);
+  if (cbf_is_set(tr_cu->cbf, depth, 2)) bv = coeff_cost_serial(c.T, &c.S->tb, c.cfg, &c.S->sc, unit_coeffs(c, L, 2, xl, yl, depth), ilog2(width), 2, scan, 0);
+  return cu_rd_cost_chroma_leaf(c, L, xl, yl, depth, pred_cu, c.S->ssd[leaf][1] + c.S->ssd[leaf][2], bu, bv);
 }
 
 // cu_rd_cost_tr_split_accurate (ref: search.c:414-543), one node.  Leader only.  `leaf`: index into S->ssd.
@@ -478,30 +382,29 @@ CTU_FN_NOINLINE double cost_accurate_node(const Ctx &c, LcuLevel *L, int xl, int
   const bool intra_split_flag = pred_cu->part_size == SIZE_NxN && depth == 3;
   const int max_tr_depth = 0 + (intra_split_flag ? 1 : 0);
   if (width <= 32 && width > 4 && !intra_split_flag && imin((int)tr_cu->tr_depth, depth) - (int)tr_cu->depth < max_tr_depth)
-    cabac_bin(c.T, sc, CTX_TRANS_SUBDIV + (5 - (6 - depth)), tr_depth > 0, &tr_tree_bits);
+    cabac_bin(&c.S->tb, sc, CTX_TRANS_SUBDIV + (5 - (6 - depth)), tr_depth > 0, &tr_tree_bits);
   {
     const int off = CTX_CBF_CHROMA + (depth - (int)tr_cu->depth);
-    if ((int)tr_cu->depth == depth || cbf_is_set(tr_cu->cbf, depth - 1, 1)) cabac_bin(c.T, sc, off, cb_flag_u, &tr_tree_bits);
-    if ((int)tr_cu->depth == depth || cbf_is_set(tr_cu->cbf, depth - 1, 2)) cabac_bin(c.T, sc, off, cb_flag_v, &tr_tree_bits);
+    if ((int)tr_cu->depth == depth || cbf_is_set(tr_cu->cbf, depth - 1, 1)) cabac_bin(&c.S->tb, sc, off, cb_flag_u, &tr_tree_bits);
+    if ((int)tr_cu->depth == depth || cbf_is_set(tr_cu->cbf, depth - 1, 2)) cabac_bin(&c.S->tb, sc, off, cb_flag_v, &tr_tree_bits);
   }
   *is_split = tr_depth > 0;
   if (tr_depth > 0) return tr_tree_bits;          // the caller sums the children and adds tr_tree_bits * lambda
   const int cb_flag_y = cbf_is_set(tr_cu->cbf, depth, 0);
   const int is_tr_split = depth - (int)tr_cu->depth;
-  cabac_bin(c.T, sc, CTX_CBF_LUMA + (is_tr_split ? 0 : 1), cb_flag_y, &tr_tree_bits);   // CU_INTRA
+  cabac_bin(&c.S->tb, sc, CTX_CBF_LUMA + (is_tr_split ? 0 : 1), cb_flag_y, &tr_tree_bits);   // CU_INTRA
   const unsigned luma_ssd = (unsigned)S->ssd[leaf][0];
   if (cb_flag_y) {
     const int scan = scan_order_intra(pred_cu->mode, depth);
-    coeff_bits += coeff_cost_serial(c.T, c.cfg, sc, &L->coeff_y[zorder(64, xl, yl)], ilog2(width), 0, scan, 0);
+    coeff_bits += coeff_cost_serial(c.T, &c.S->tb, c.cfg, sc, unit_coeffs(c, L, 0, xl, yl, depth), ilog2(width), 0, scan, 0);
   }
   unsigned chroma_ssd = 0;
   if (xl % 8 == 0 && yl % 8 == 0) {
     const int chroma_width = depth <= 3 ? (64 >> (depth + 1)) : (64 >> depth);
     chroma_ssd = (unsigned)S->ssd[leaf][1] + (unsigned)S->ssd[leaf][2];
     const int scan = scan_order_intra(pred_cu->mode_chroma, depth);
-    const int index = zorder(32, xl >> 1, yl >> 1);
-    if (cb_flag_u) coeff_bits += coeff_cost_serial(c.T, c.cfg, sc, &L->coeff_u[index], ilog2(chroma_width), 2, scan, 0);
-    if (cb_flag_v) coeff_bits += coeff_cost_serial(c.T, c.cfg, sc, &L->coeff_v[index], ilog2(chroma_width), 2, scan, 0);
+    if (cb_flag_u) coeff_bits += coeff_cost_serial(c.T, &c.S->tb, c.cfg, sc, unit_coeffs(c, L, 1, xl, yl, depth), ilog2(chroma_width), 2, scan, 0);
+    if (cb_flag_v) coeff_bits += coeff_cost_serial(c.T, &c.S->tb, c.cfg, sc, unit_coeffs(c, L, 2, xl, yl, depth), ilog2(chroma_width), 2, scan, 0);
   }
   const double bits = tr_tree_bits + coeff_bits;
   return luma_ssd * 0.8 + chroma_ssd * 1.5 + bits * c.cfg->lambda;
@@ -548,12 +451,12 @@ CTU_FN_NOINLINE double mock_encode_coding_unit(const Ctx &c, LcuLevel *L, int x,
     int split_model = 0;
     if (left_cu && left_cu->depth > depth) ++split_model;
     if (above_cu && above_cu->depth > depth) ++split_model;
-    cabac_bin(c.T, sc, CTX_SPLIT + split_model, 0, &bits);
+    cabac_bin(&c.S->tb, sc, CTX_SPLIT + split_model, 0, &bits);
   }
   // kvz_encode_part_mode
   {
     double pb = 0;
-    if (depth == 3) cabac_bin(c.T, sc, CTX_PART_SIZE, cur_cu->part_size == SIZE_2Nx2N ? 1 : 0, &pb);
+    if (depth == 3) cabac_bin(&c.S->tb, sc, CTX_PART_SIZE, cur_cu->part_size == SIZE_2Nx2N ? 1 : 0, &pb);
     bits += pb;
   }
   // encode_intra_coding_unit in counting mode
@@ -575,15 +478,15 @@ CTU_FN_NOINLINE double mock_encode_coding_unit(const Ctx &c, LcuLevel *L, int x,
     for (int i = 0; i < 3; ++i) if (preds[i] == mode) { mpm_idx[j] = i; break; }
     flag[j] = mpm_idx[j] != -1;
   }
-  for (int j = 0; j < num_pu; ++j) cabac_bin(c.T, sc, CTX_INTRA_MODE, flag[j], &bits);
+  for (int j = 0; j < num_pu; ++j) cabac_bin(&c.S->tb, sc, CTX_INTRA_MODE, flag[j], &bits);
   for (int j = 0; j < num_pu; ++j) {
     if (flag[j]) { bits += 1; if (mpm_idx[j] != 0) bits += 1; }
     else bits += 5;
   }
   {
     const int mc = cur_cu->mode_chroma;
-    if (mc == mode0) cabac_bin(c.T, sc, CTX_CHROMA_PRED, 0, &bits);
-    else { cabac_bin(c.T, sc, CTX_CHROMA_PRED, 1, &bits); bits += 2; }
+    if (mc == mode0) cabac_bin(&c.S->tb, sc, CTX_CHROMA_PRED, 0, &bits);
+    else { cabac_bin(&c.S->tb, sc, CTX_CHROMA_PRED, 1, &bits); bits += 2; }
   }
   return bits;
 }
@@ -610,8 +513,8 @@ CTU_FN_NOINLINE int rough_search_replay(const Ctx &c, int log2w, const int8_t *m
   const bool ts = width == 4 && cfg->trskip_enable;
   // get_cost_dual reads state->cabac, get_cost reads state->search_cabac (search_intra.c:102, 142)
   auto trskip_bits = [&](const CabacState *cb) {
-    double b = (double)c.T->ebits[cb->ctx[CTX_TRSKIP_LUMA] ^ 1] * (1.0 / 32768.0) - (double)c.T->ebits[cb->ctx[CTX_TRSKIP_LUMA] ^ 0] * (1.0 / 32768.0);
-    b += 2.0 * ((double)c.T->ebits[cb->ctx[CTX_TRSKIP_CHROMA] ^ 1] * (1.0 / 32768.0) - (double)c.T->ebits[cb->ctx[CTX_TRSKIP_CHROMA] ^ 0] * (1.0 / 32768.0));
+    double b = (double)c.S->tb.ebits[cb->ctx[CTX_TRSKIP_LUMA] ^ 1] * (1.0 / 32768.0) - (double)c.S->tb.ebits[cb->ctx[CTX_TRSKIP_LUMA] ^ 0] * (1.0 / 32768.0);
+    b += 2.0 * ((double)c.S->tb.ebits[cb->ctx[CTX_TRSKIP_CHROMA] ^ 1] * (1.0 / 32768.0) - (double)c.S->tb.ebits[cb->ctx[CTX_TRSKIP_CHROMA] ^ 0] * (1.0 / 32768.0));
     return b;
   };
   auto cost_of = [&](int mode, const CabacState *cb) -> double {
@@ -712,42 +615,65 @@ CTU_FN_NOINLINE void search_cu_intra(const Ctx &c, LcuLevel *L, int x, int y, in
     }
     CTU_SYNC();
     const bool reconstruct_chroma = !((x & 4) || (y & 4));
-    int checked = S->n_modes;
-    for (int r = 0; r < S->n_modes; ++r) {
-      const int mode = S->modes[r];
-      CTU_LEADER {
+    const int np = reconstruct_chroma ? 3 : 1;
+    if (reconstruct_chroma) {
+      PROF_T0(PR_REFS);
+      build_refs(c.T, cfg, c.W, L, tu_log2(depth, 1), 1, x, y, &S->refs[1]);
+      build_refs(c.T, cfg, c.W, L, tu_log2(depth, 2), 2, x, y, &S->refs[2]);
+      PROF_ADD(S, PR_REFS);
+    }
+    // The candidates (search_intra_trdepth's no-split branch, tr_depth == depth) are independent of each other and so
+    // are their colours: every (candidate, colour) pair is one transform-unit job with a private reconstruction.  The
+    // temporary CU of the reference (pred_cu: depth = tr_depth = `depth`, NxN at depth 4) only matters through RDOQ's
+    // cbf context and the cbf bits collected below.
+    const int ncand = S->n_modes;
+    const int rdoq_tr_depth = depth == 4 ? 1 : 0;
+    PROF_T0(PR_QRES);
+    for_tu_tasks(c, ncand * np, 1 << (2 * log2w), [&](const Team &tm, unsigned char *slot, int t) {
+      const int cand = t / np, col = t - cand * np;
+      const int mode = S->modes[cand];
+      const int log2n = tu_log2(depth, col), n = 1 << log2n;
+      const TuS tu = tu_at(slot, n * n);
+      const Plane P = plane_of(c.W, L, col);
+      const int sh = col ? 1 : 0;
+      const int off = (xl >> sh) + (yl >> sh) * P.lw;
+      TuJob j = { &S->refs[col], P.src + off, P.lw, col, log2n, mode, scan_order_intra(mode, depth), rdoq_tr_depth };
+      const int ts = tu_eval(tm, c.T, &S->tb, cfg, S->cabac0.ctx, &S->sc, tu, j);
+      if (tm.tid == 0) {
+        const TuFixed *fx = tu.fx();
+        TuRes *r = &S->res[cand][col];
+        r->ssd = fx->ssd; r->has = fx->has; r->tr_skip = ts;
+        // coefficient bits of kvz_cu_rd_cost_luma / _chroma: the search models are not adapted here (update == 0)
+        r->bits = fx->has ? coeff_cost_serial(c.T, &S->tb, cfg, &S->sc, tu.q(), log2n, col ? 2 : 0, j.scan_idx, 0) : 0.0;
+      }
+      tsync(tm);
+    });
+    PROF_ADD(S, PR_QRES);
+    PROF_T0(PR_COST);
+    int checked = ncand;
+    CTU_LEADER {
+      CuRec *tr_cu = cu_at(L, xl, yl);
+      tr_cu->tr_depth = (uint8_t)depth;
+      for (int r = 0; r < ncand; ++r) {
+        const int mode = S->modes[r];
         const double rdo_bitcost = luma_mode_bits(c, mode, S->mpm);
         S->costs[r] = rdo_bitcost * cfg->lambda;
         CuRec *p = &S->pred_cu;
         p->depth = (uint8_t)depth; p->type = CU_INTRA; p->part_size = depth == 4 ? SIZE_NxN : SIZE_2Nx2N;
-        p->mode = (int8_t)mode; p->mode_chroma = (int8_t)mode; p->cbf = 0;
-        // (tr_skip and qp of the reference's stack variable are never read)
-      }
-      CTU_SYNC();
-      fill_trdepth(L, xl, yl, depth, depth);
-      // search_intra_trdepth(depth, max_depth = depth): the no-split branch only
-      CTU_LEADER {
-        cu_at(L, xl, yl)->tr_depth = (uint8_t)depth;
-        S->pred_cu.tr_depth = (uint8_t)depth;
-        cbf_clear(&S->pred_cu.cbf, depth, 0);
-        if (reconstruct_chroma) { cbf_clear(&S->pred_cu.cbf, depth, 1); cbf_clear(&S->pred_cu.cbf, depth, 2); }
-      }
-      CTU_SYNC();
-      intra_recon_cu(c, L, x, y, depth, mode, reconstruct_chroma ? mode : -1, &S->pred_cu);
-      leaf_ssds(c, L, xl, yl, depth, true, reconstruct_chroma);
-      PROF_T0(PR_COST);
-      CTU_LEADER {
+        p->mode = (int8_t)mode; p->mode_chroma = (int8_t)mode; p->cbf = 0; p->tr_depth = (uint8_t)depth;
+        for (int col = 0; col < np; ++col) if (S->res[r][col].has) cbf_set(&p->cbf, depth, col);
+        // the level's record carries the candidate's cbf bits (cbf_copy in kvz_intra_recon_cu's leaf)
+        for (int col = 0; col < np; ++col) cbf_copy(&tr_cu->cbf, p->cbf, col);
         double nosplit = 0.0;
-        nosplit += cu_rd_cost_luma_leaf(c, L, xl, yl, depth, &S->pred_cu, 0);
-        if (reconstruct_chroma) nosplit += cu_rd_cost_chroma_leaf(c, L, xl, yl, depth, &S->pred_cu, 0);
+        nosplit += cu_rd_cost_luma_leaf(c, L, xl, yl, depth, p, S->res[r][0].ssd, S->res[r][0].bits);
+        if (reconstruct_chroma) nosplit += cu_rd_cost_chroma_leaf(c, L, xl, yl, depth, p, S->res[r][1].ssd + S->res[r][2].ssd, S->res[r][1].bits, S->res[r][2].bits);
         S->costs[r] += nosplit;
-        S->flag = (cfg->intra_rdo_et && !cbf_is_set_any(S->pred_cu.cbf, depth)) ? 1 : 0;
+        if (cfg->intra_rdo_et && !cbf_is_set_any(p->cbf, depth)) { S->n_modes = r + 1; break; }
       }
-      CTU_SYNC();
-      PROF_ADD(S, PR_COST);
-      // (kvz_lcu_fill_trdepth(depth, depth) and the pixel restore of the no-split branch are identities here)
-      if (S->flag) { checked = r + 1; break; }
     }
+    CTU_SYNC();
+    PROF_ADD(S, PR_COST);
+    checked = S->n_modes;
     CTU_LEADER { S->n_modes = checked; sort_modes(S->modes, S->costs, checked); }
     CTU_SYNC();
   }
@@ -794,8 +720,7 @@ CTU_FN_NOINLINE int search_cu_intra_chroma(const Ctx &c, LcuLevel *L, int x, int
   int best_mode = 0;
   for (int i = 0; i < 2; ++i) {
     const int mode = S->cmodes[i];
-    intra_recon_cu(c, L, x, y, depth, -1, mode, NULL);
-    leaf_ssds(c, L, xl, yl, depth, false, true);
+    intra_recon_cu(c, L, x, y, depth, -1, mode, NULL, depth == 0 ? 0 : 6);
     CTU_LEADER {
       CuRec *tr_cu = cu_at(L, xl, yl);
       double cost;
@@ -804,14 +729,14 @@ CTU_FN_NOINLINE int search_cu_intra_chroma(const Ctx &c, LcuLevel *L, int x, int
         CabacState *sc = &S->sc;
         double tr_tree_bits = 0;
         if (!sc->update || tr_cu->tr_depth != tr_cu->depth) {
-          cabac_bin(c.T, sc, CTX_CBF_CHROMA, cbf_is_set(tr_cu->cbf, 0, 1), &tr_tree_bits);
-          cabac_bin(c.T, sc, CTX_CBF_CHROMA, cbf_is_set(tr_cu->cbf, 0, 2), &tr_tree_bits);
+          cabac_bin(&c.S->tb, sc, CTX_CBF_CHROMA, cbf_is_set(tr_cu->cbf, 0, 1), &tr_tree_bits);
+          cabac_bin(&c.S->tb, sc, CTX_CBF_CHROMA, cbf_is_set(tr_cu->cbf, 0, 2), &tr_tree_bits);
         }
         double sum = 0;
-        for (int k = 0; k < 4; ++k) sum += cu_rd_cost_chroma_leaf(c, L, xl + (k & 1) * 32, yl + (k >> 1) * 32, 1, tr_cu, k);
+        for (int k = 0; k < 4; ++k) sum += cu_rd_cost_chroma_leaf_of_level(c, L, xl + (k & 1) * 32, yl + (k >> 1) * 32, 1, tr_cu, k);
         cost = sum + tr_tree_bits * c.cfg->lambda;
       } else {
-        cost = cu_rd_cost_chroma_leaf(c, L, xl, yl, depth, tr_cu, 0);
+        cost = cu_rd_cost_chroma_leaf_of_level(c, L, xl, yl, depth, tr_cu, 0);
       }
       const double mode_bits = chroma_mode_bits(c, mode, intra_mode);
       cost += mode_bits * c.cfg->lambda;
@@ -837,7 +762,8 @@ CTU_FN_NOINLINE void search_ctu(const Ctx &c, int cx, int cy)
 {
   CtuS *S = c.S;
   const CtuConfig *cfg = c.cfg;
-  CTU_LEADER { S->fr[0].x = cx; S->fr[0].y = cy; S->fr[0].stage = 0; }
+  for (int i = CTU_TID; i < 128; i += CTU_NT) { S->tb.ebits[i] = c.T->ebits[i]; S->tb.next_mps[i] = c.T->next_mps[i]; S->tb.next_lps[i] = c.T->next_lps[i]; }
+  CTU_LEADER { S->fr[0].x = cx; S->fr[0].y = cy; S->fr[0].stage = 0; S->stage_key[0] = S->stage_key[1] = S->stage_key[2] = -1; }
   CTU_SYNC();
   int d = 0;
   for (;;) {
@@ -890,22 +816,25 @@ CTU_FN_NOINLINE void search_ctu(const Ctx &c, int cx, int cy)
           CTU_LEADER cur_cu->mode_chroma = cur_cu->mode;
           CTU_SYNC();
           fill_cu_info(L, xl, yl, cu_width, cur_cu);
-          intra_recon_cu(c, L, x, y, d, cur_cu->mode, -1, NULL);
-          if (x % 8 == 0 && y % 8 == 0) {
-            if (cfg->rdo >= 2 && cfg->intra_chroma_search) {
-              PROF_T0(PR_CHROMA);
-              const int mc = search_cu_intra_chroma(c, L, x, y, d);
-              PROF_ADD(S, PR_CHROMA);
-              CTU_LEADER cur_cu->mode_chroma = (int8_t)mc;
-              CTU_SYNC();
-              fill_cu_info(L, xl, yl, cu_width, cur_cu);
-            }
-            intra_recon_cu(c, L, x, y, d, -1, cur_cu->mode_chroma, NULL);
+          const bool aligned = x % 8 == 0 && y % 8 == 0;
+          // the references search_cu_intra built (luma always, chroma for the RDO candidates) are still this CU's
+          const int refs_valid = 1 | ((cfg->rdo >= 2 && aligned) ? 6 : 0);
+          if (aligned && cfg->rdo >= 2 && cfg->intra_chroma_search) {
+            intra_recon_cu(c, L, x, y, d, cur_cu->mode, -1, NULL, refs_valid);
+            PROF_T0(PR_CHROMA);
+            const int mc = search_cu_intra_chroma(c, L, x, y, d);
+            PROF_ADD(S, PR_CHROMA);
+            CTU_LEADER cur_cu->mode_chroma = (int8_t)mc;
+            CTU_SYNC();
+            fill_cu_info(L, xl, yl, cu_width, cur_cu);
+            intra_recon_cu(c, L, x, y, d, -1, cur_cu->mode_chroma, NULL, 0);
+          } else {
+            // luma and chroma of the CU are independent: one pass (kvz_intra_recon_cu twice in the reference)
+            intra_recon_cu(c, L, x, y, d, cur_cu->mode, aligned ? cur_cu->mode_chroma : -1, NULL, refs_valid);
           }
         }
       }
       if (cur_cu->type == CU_INTRA) {
-        leaf_ssds(c, L, xl, yl, d, true, true);
         PROF_T0(PR_COST);
         CTU_LEADER {
           double bits = 0;
@@ -932,8 +861,8 @@ CTU_FN_NOINLINE void search_ctu(const Ctx &c, int cx, int cy)
           S->sc = F->pre;
           S->sc.update = 1;
           double split_bits = 0;
-          if (d < 3) cabac_bin(c.T, &S->sc, CTX_SPLIT + split_model_of(L, x, y, d), 1, &split_bits);
-          if (cur_cu->type == CU_INTRA && d == 3) cabac_bin(c.T, &S->sc, CTX_PART_SIZE, 0, &split_bits);
+          if (d < 3) cabac_bin(&c.S->tb, &S->sc, CTX_SPLIT + split_model_of(L, x, y, d), 1, &split_bits);
+          if (cur_cu->type == CU_INTRA && d == 3) cabac_bin(&c.S->tb, &S->sc, CTX_PART_SIZE, 0, &split_bits);
           S->sc.update = 0;
           F->split_cost += split_bits * cfg->lambda;
           if (cur_cu->type == CU_NOTSET || F->cbf || cfg->cu_split_termination == 1) F->do_children = 1;
@@ -974,7 +903,7 @@ CTU_FN_NOINLINE void search_ctu(const Ctx &c, int cx, int cy)
             S->sc = F->pre;
             F->cost = 0;
             double bits = 0;
-            if (d < 3) cabac_bin(c.T, &S->sc, CTX_SPLIT + split_model_of(L, x, y, d), 0, &bits);
+            if (d < 3) cabac_bin(&c.S->tb, &S->sc, CTX_SPLIT + split_model_of(L, x, y, d), 0, &bits);
             S->best_cost = bits;
             cur_cu->mode = cu_d1->mode; cur_cu->mode_chroma = cu_d1->mode_chroma;
             cur_cu->type = CU_INTRA;
@@ -983,8 +912,7 @@ CTU_FN_NOINLINE void search_ctu(const Ctx &c, int cx, int cy)
           CTU_SYNC();
           fill_trdepth(L, xl, yl, d, cur_cu->tr_depth);
           fill_cu_info(L, xl, yl, cu_width, cur_cu);
-          intra_recon_cu(c, L, x, y, d, cur_cu->mode, cur_cu->mode_chroma, NULL);
-          leaf_ssds(c, L, xl, yl, d, true, true);
+          intra_recon_cu(c, L, x, y, d, cur_cu->mode, cur_cu->mode_chroma, NULL, 0);
           CTU_LEADER {
             const double mode_bits = calc_mode_bits(c, L, cur_cu, x, y) + S->best_cost;
             double cost = F->cost;

@@ -52,7 +52,7 @@ __device__ __forceinline__ int ld_acquire(const int *p)
 }
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-__global__ void __launch_bounds__(kThreads) ctu_frame_kernel(const __grid_constant__ KernelArgs a)
+__global__ void __launch_bounds__(kThreads, 4) ctu_frame_kernel(const __grid_constant__ KernelArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   CtuS *S = reinterpret_cast<CtuS *>(smem);
@@ -92,6 +92,21 @@ __global__ void __launch_bounds__(kThreads) ctu_frame_kernel(const __grid_consta
     atomicAdd(a.prof + PR_N, (unsigned long long)(clock64() - cta_t0));
   }
 #endif
+}
+
+// Diagnostic alternative (KVZ_CUDA_CTU_DIAG=1): one launch per anti-diagonal, no inter-CTA waiting.
+__global__ void __launch_bounds__(kThreads, 4) ctu_diag_kernel(const __grid_constant__ KernelArgs a, int diag, int cy_lo)
+{
+  extern __shared__ __align__(16) unsigned char smem[];
+  CtuS *S = reinterpret_cast<CtuS *>(smem);
+  const int cy = cy_lo + blockIdx.x;
+  const int cx = diag - 2 * cy;
+  Ctx c = { a.T, &a.cfg, a.work + blockIdx.x, S };
+#if defined(KVZ_CTU_PROF)
+  if (threadIdx.x == 0) for (int i = 0; i < PR_N; ++i) S->prof[i] = 0;
+  __syncthreads();
+#endif
+  ctu_job(c, &a.F, a.sao_stats + blockIdx.x, cx, cy);
 }
 
 __global__ void __launch_bounds__(kThreads) ctu_sao_apply_kernel(const __grid_constant__ KernelArgs a)
@@ -135,7 +150,7 @@ struct kvz_cuda_ctu_enc {
   unsigned long long *d_prof = nullptr;
   int wl = 0, hl = 0, max_diag = 0, grid = 0;
   size_t plane_bytes = 0, smem = 0;
-  bool debug = false;
+  bool debug = false, diag_launches = false;
   std::vector<Slot> slots;
   std::mutex mtx;
   std::condition_variable cv;
@@ -209,9 +224,10 @@ kvz_cuda_ctu_enc *kvz_cuda_ctu_open(const kvz_cuda_ctu_config *cfg, int slots)
     if (hi - lo + 1 > e->max_diag) e->max_diag = hi - lo + 1;
     for (int cy = lo; cy <= hi; ++cy) { order.push_back((uint16_t)(d - 2 * cy)); order.push_back((uint16_t)cy); }
   }
+  e->diag_launches = getenv("KVZ_CUDA_CTU_DIAG") != nullptr;
   // persistent CTAs per picture: the widest diagonal unless told otherwise (fewer: less idle waiting, more pictures resident)
   e->grid = e->max_diag;
-  if (const char *g = getenv("KVZ_CUDA_CTU_GRID")) { const int v = atoi(g); if (v > 0) e->grid = v < e->max_diag ? v : e->max_diag; }
+  if (const char *g = getenv("KVZ_CUDA_CTU_GRID")) { const int v = atoi(g); if (v > 0 && !e->diag_launches) e->grid = v < e->max_diag ? v : e->max_diag; }
   e->plane_bytes = (size_t)W * H * 3 / 2;
   e->smem = sizeof(CtuS);
   e->debug = getenv("KVZ_CUDA_CTU_DEBUG") != nullptr;
@@ -230,6 +246,7 @@ kvz_cuda_ctu_enc *kvz_cuda_ctu_open(const kvz_cuda_ctu_config *cfg, int slots)
   CTU_CHECK_PTR(cudaMalloc(&e->d_order, order.size() * sizeof(uint16_t)));
   CTU_CHECK_PTR(cudaMemcpy(e->d_order, order.data(), order.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   CTU_CHECK_PTR(cudaFuncSetAttribute(ctu_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
+  CTU_CHECK_PTR(cudaFuncSetAttribute(ctu_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
   e->slots.resize(slots > 0 ? (slots > 512 ? 512 : slots) : 1);
   const size_t nctu = (size_t)e->wl * e->hl;
   const size_t cu_n = (size_t)(e->wl * 16) * (e->hl * 16);
@@ -306,9 +323,19 @@ int kvz_cuda_ctu_submit(kvz_cuda_ctu_enc *e, const uint8_t *y, const uint8_t *u,
   KVZC_CHECK(cudaMemcpyAsync(s.d_row_ctx, s.h_row_ctx, e->hl * sizeof(CabacState), cudaMemcpyHostToDevice, st));
   KVZC_CHECK(cudaMemsetAsync(s.d_cu, 0, (size_t)(e->wl * 16) * (e->hl * 16) * sizeof(CuRec), st));
   KVZC_CHECK(cudaMemsetAsync(s.d_sync, 0, (size_t)(e->hl + 1) * sizeof(int), st));
-  ctu_frame_kernel<<<e->grid, kThreads, e->smem, st>>>(s.args);
-  e->launches.fetch_add(1, std::memory_order_relaxed);
-  kvzc::g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e->diag_launches) {
+    for (int d = 0; d < e->wl + 2 * (e->hl - 1); ++d) {
+      const int lo = d - (e->wl - 1) > 0 ? (d - (e->wl - 1) + 1) / 2 : 0, hi = d / 2 < e->hl - 1 ? d / 2 : e->hl - 1;
+      if (hi < lo) continue;
+      ctu_diag_kernel<<<hi - lo + 1, kThreads, e->smem, st>>>(s.args, d, lo);
+      e->launches.fetch_add(1, std::memory_order_relaxed);
+      kvzc::g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+  } else {
+    ctu_frame_kernel<<<e->grid, kThreads, e->smem, st>>>(s.args);
+    e->launches.fetch_add(1, std::memory_order_relaxed);
+    kvzc::g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   ctu_sao_apply_kernel<<<e->wl * e->hl, kThreads, 0, st>>>(s.args);
   e->launches.fetch_add(1, std::memory_order_relaxed);
   kvzc::g_launches.fetch_add(1, std::memory_order_relaxed);
