@@ -1,21 +1,27 @@
 #!/usr/bin/env python
-"""bench.py -- frames/s of the per-CTU strategy-kernel hot path (the frame-level pass of framepass.cu).
+"""bench.py -- ENCODED frames/s at fixed QP with a bit-identical bitstream (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # the reference's own CPU (AVX2) strategy functions
+    python bench.py --gpus N --steps K --warmup W            # the CUDA CTU search driver inside the reference encoder
+    python bench.py --impl reference --steps K --warmup W    # the unmodified reference (its AVX2 strategies, all host threads)
 
-Workload (BASELINE.json configs[1]): 1920x1080 8-bit synthetic I420, all-intra, QP 27 ("medium": SAO on, no
-sign hiding).  One STEP = `frames_per_step` frames through the frame-level pass: for every quadtree depth
-(32/16/8/4) rough search of all 35 intra modes + SATD, mode selection, prediction + transform + quantisation +
-reconstruction + SSD for luma and chroma, then SAO statistics/decision/reconstruction and the picture checksum.
-`value` is frames/s with the frames already resident in HBM; `e2e` goes through the host-buffer C-ABI entry point
-(kvz_cuda_fp_run_host: pinned host frame in, 28 MB result blob out, copies inside the timed region).
-This is the hot PATH's throughput, not whole-encoder fps: mode decision / RDOQ / CABAC stay on the host and are
-outside this round's scope.  Multi-GPU: frames are sharded one set per rank, no collective (all-intra
-frames are independent), scaling = weak.
+Workload (default): BASELINE config 3 -- 3840x2160 8-bit synthetic I420, --preset veryslow -q 22 -p 1 (all-intra);
+`--workload 1080p` = config 2 (1920x1080 --preset medium -q 27 -p 1).
+
+One STEP = `frames_per_step` pictures encoded to HEVC.  Three numbers per run:
+  e2e    the headline: pictures in HOST memory go through the unchanged libkvazaar API (kvz_stream_bench.c, the loop of
+         src/encmain.c) -- host->device copy of every picture, device search, device->host copy of CU records /
+         coefficients / SAO / reconstruction, the reference's own CABAC + bitstream writer on the host threads -- and the
+         .hevc comes out.  Same program, same loop, for the reference arm (linked against the unmodified library).
+  value  the device side alone: pictures resident in HBM -> kvz_cuda_ctu_submit_device / wait_device (search, deblock,
+         SAO, final picture; results left on the device), slots pictures in flight, timed with CUDA events.
+  cpu_baseline  the unmodified reference on a bounded sample of the same clip; the CUDA arm encodes the same sample and
+         the two .hevc files must be byte-identical (`bitstream_identical`).
+Multi-GPU: all-intra pictures are independent; every rank encodes its own pictures on its own GPU with its share of
+the host threads, no data-path collective ("weak" scaling); times are max over ranks (NCCL all-reduce of the event times).
 """
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -27,48 +33,71 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
-W, H, QP, SIGNHIDE, RDOQ, TRSKIP, BITDEPTH = 1920, 1080, 27, 0, 0, 0, 8
-WORKLOAD = "1920x1080 8-bit synthetic I420, all-intra, QP27 (preset medium: SAO on, signhide off), frame-level hot-path pass"
-
-
-def set_workload(name, rdoq):
-    """configs[1] (default, the one the metric is quoted on) or the configs[2] shape (2160p, QP22, sign hiding)."""
-    global W, H, QP, SIGNHIDE, RDOQ, TRSKIP, BITDEPTH, WORKLOAD
-    RDOQ = int(rdoq)
-    q = "RDOQ on" if RDOQ else "RDOQ off (kvz_quant)"
-    WORKLOAD = f"1920x1080 8-bit synthetic I420, all-intra, QP27 (preset medium: deblock + SAO on, signhide off, {q}), frame-level hot-path pass"
-    if name == "2160p":
-        W, H, QP, SIGNHIDE, TRSKIP = 3840, 2160, 22, 1, 1
-        WORKLOAD = f"3840x2160 8-bit synthetic I420, all-intra, QP22 (preset veryslow shape: deblock + SAO on, signhide on, transform skip on, {q}), frame-level hot-path pass"
-
-
-def set_workload_4320p10(rdoq):
-    """configs[4] shape: 7680x4320 10-bit (the intra hot path of it; tiles / inter exchange are dist.py's business)."""
-    global W, H, QP, SIGNHIDE, RDOQ, TRSKIP, BITDEPTH, WORKLOAD
-    W, H, QP, SIGNHIDE, TRSKIP, BITDEPTH, RDOQ = 7680, 4320, 22, 0, 0, 10, int(rdoq)
-    q = "RDOQ on" if RDOQ else "RDOQ off (kvz_quant)"
-    WORKLOAD = f"7680x4320 10-bit synthetic I420, all-intra, QP22 (preset slow shape: deblock + SAO on, signhide off, {q}), frame-level hot-path pass"
+WORKLOADS = {
+    "2160p": dict(w=3840, h=2160, preset="veryslow", qp=22, frames_per_step=32, ref_frames_per_step=12, sample=16, owf=40, slots=40,
+                  name="BASELINE config 3: 3840x2160 8-bit synthetic I420, --preset veryslow -q 22 -p 1 (all-intra)"),
+    "1080p": dict(w=1920, h=1080, preset="medium", qp=27, frames_per_step=96, ref_frames_per_step=96, sample=64, owf=64, slots=64,
+                  name="BASELINE config 2: 1920x1080 8-bit synthetic I420, --preset medium -q 27 -p 1 (all-intra)"),
+    "64x64": dict(w=64, h=64, preset="ultrafast", qp=32, frames_per_step=64, ref_frames_per_step=64, sample=16, owf=8, slots=8,
+                  name="BASELINE config 1: 64x64 8-bit synthetic I420, --preset ultrafast -q 32 -p 1 (all-intra)"),
+}
+METRIC = "encoded frames/sec at fixed QP (bit-identical bitstream)"
+DISTINCT = 8          # distinct synthetic pictures in the clip (cycled)
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def synth_frames(n):
-    from test_framepass import synth_frame
-    if BITDEPTH == 8:
-        return [synth_frame(W, H, frame_idx=i) for i in range(n)]
-    out = []
-    for i in range(n):                       # 10-bit: the 8-bit pattern scaled by 4 plus two fresh low bits
-        f8 = synth_frame(W, H, frame_idx=i).astype(np.uint16)
-        out.append((f8 * 4 + np.random.default_rng(i).integers(0, 4, f8.size).astype(np.uint16)).astype(np.uint16))
-    return out
+def config_of(wl):
+    """identical for both arms: what is encoded, not how"""
+    return {"workload": wl["name"], "resolution": f"{wl['w']}x{wl['h']}", "preset": wl["preset"], "qp": wl["qp"], "intra_period": 1,
+            "bit_depth": 8, "clip": f"{DISTINCT} distinct synthetic pictures (tools/synth_yuv.py, seed 1234) cycled",
+            "l2": "every picture is read once; the pictures in flight (> 126 MB) exceed L2"}
+
+
+def clip_path(wl):
+    from synth_yuv import synth_frame
+    d = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    p = os.path.join(d, f"kvz_bench_{wl['w']}x{wl['h']}_{DISTINCT}.yuv")
+    size = wl["w"] * wl["h"] * 3 // 2 * DISTINCT
+    if not (os.path.exists(p) and os.path.getsize(p) == size):
+        tmp = p + f".{os.getpid()}"
+        with open(tmp, "wb") as f:
+            for i in range(DISTINCT):
+                f.write(synth_frame(wl["w"], wl["h"], 1234, i).tobytes())
+        os.replace(tmp, p)
+    return p
+
+
+def stream_bench(binary, clip, wl, out, frames_per_step, steps, warmup, extra=(), env=None, timeout=1500):
+    """one run of the streaming host (integration/kvz_stream_bench.c); returns its JSON line"""
+    e = dict(os.environ)
+    e.pop("KVZ_CTU_PROVIDER", None)
+    e.update(env or {})
+    cmd = [binary, clip, f"{wl['w']}x{wl['h']}", out, str(frames_per_step), str(steps), str(warmup),
+           f"preset={wl['preset']}", f"qp={wl['qp']}", "period=1", *extra]
+    r = subprocess.run(cmd, env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError(f"{os.path.basename(binary)} failed ({r.returncode}): {r.stderr[-1500:]}")
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+    res = json.loads(line)
+    res["stderr_tail"] = r.stderr[-400:]
+    return res
+
+
+def sha(path):
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 20), b""):
+            h.update(blk)
+    return h.hexdigest()
 
 
 class ClockSampler:
@@ -83,7 +112,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            time.sleep(0.35)          # first sample is out before the timed region starts
+            time.sleep(0.35)
         except Exception:
             self.proc = None
         return self
@@ -106,85 +135,130 @@ class ClockSampler:
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm = sorted(float(r[0]) for r in self.rows)
-        reasons = []
-        for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")):
-            if any(r[3 + i] == "Active" for r in self.rows):
-                reasons.append(name)
+        reasons = [name for i, name in enumerate(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"))
+                   if any(r[3 + i] == "Active" for r in self.rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
                 "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows)}
 
 
-def run_reference(args):
-    """The reference's own CPU implementation of the path: its strategy function pointers (AVX2 where selected),
-    driven by oracle/ref_framepass.c with all host threads.  One step = `ref_frames` frames (bounded sample)."""
-    from _oracle import Ref, ref_frame_pass
-    import kvazaar_b200 as kb
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, wl):
+    """The unmodified reference (oracle/_ref, compiled from /root/reference by oracle/Makefile): its own encoder loop,
+    its AVX2 strategies, all the host threads it wants.  Does not load any of this repository's libraries."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    ref = Ref(BITDEPTH)
+    binary = os.path.join(REF_DIR, "kvz_stream_bench_ref")
+    clip = clip_path(wl)
+    fps_step = args.frames_per_step or wl["ref_frames_per_step"]
+    r = stream_bench(binary, clip, wl, "/tmp/kvz_bench_ref_arm.hevc", fps_step, args.steps, args.warmup)
     cores = os.cpu_count() or 1
-    lay = kb.fp_layout_for(W, H, QP, SIGNHIDE, BITDEPTH)
-    from _oracle import aligned, al
-    frames = [al(f) for f in synth_frames(4)]
-    blob = aligned(int(lay.host_bytes), np.uint8)
-    nper = args.ref_frames
-    for _ in range(max(1, args.warmup)):
-        ref_frame_pass(ref, frames[0], W, H, QP, lay, nthreads=cores, signhide=SIGNHIDE, blob=blob, src_is_aligned=True, rdoq=RDOQ, trskip=TRSKIP)
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        for f in range(nper):
-            ref_frame_pass(ref, frames[(s * nper + f) % len(frames)], W, H, QP, lay, nthreads=cores, signhide=SIGNHIDE, blob=blob, src_is_aligned=True, rdoq=RDOQ, trskip=TRSKIP)
-    dt = time.perf_counter() - t0
-    fps = args.steps * nper / dt
-    sample = f"{args.steps * nper} frames {W}x{H} through the reference's selected strategy functions ({ref.selected_name('satd_8x8')})"
-    line = {"impl": "reference", "metric": "hot-path frames/sec at fixed QP (per-CTU strategy kernels, all depths)", "value": fps,
-            "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if BITDEPTH == 8 else "u16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": nper},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
-            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    sample = f"{r['frames']} pictures ({args.steps} steps of {fps_step}) after {args.warmup} warm-up steps, unmodified reference through its public API, threads=auto"
+    line = {"impl": "reference", "metric": METRIC, "value": r["fps"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": config_of(wl), "frames_per_step": fps_step,
+            "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "bitstream_sha256": sha("/tmp/kvz_bench_ref_arm.hevc"), "bitstream_bytes": r["bytes"]}
     print(json.dumps(line))
 
 
-def cpu_baseline(budget_s=15.0):
-    """Bounded sample of the same workload on the host cores, through oracle/_ref when present (kind=reference)."""
-    from _oracle import Ref, ref_frame_pass
+# ------------------------------------------------------------------------------------------------ CUDA arm
+class Config(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "width", "height", "qp", "rdo", "pu_depth_intra_min", "pu_depth_intra_max", "rdoq_enable", "rdoq_skip", "signhide_enable",
+        "trskip_enable", "sao_type", "deblock_enable", "deblock_beta", "deblock_tc", "cu_split_termination", "intra_rdo_et",
+        "combine_intra_cus", "intra_chroma_search", "full_intra_search", "wpp", "pad")] + [("lambda_", C.c_double), ("lambda_sqrt", C.c_double)]
+
+
+class DevResult(C.Structure):
+    _fields_ = [("cu", C.c_void_p), ("coeff", C.c_void_p), ("sao", C.c_void_p), ("rec", C.c_void_p), ("cu_stride", C.c_int32),
+                ("width_in_lcu", C.c_int32), ("height_in_lcu", C.c_int32), ("search_kernel_ms", C.c_float)]
+
+
+# what the reference's presets set of the fields the intra CTU search reads (src/cfg.c:486-736)
+PRESET_FIELDS = {
+    "ultrafast": dict(rdo=0, pu=(2, 3), rdoq=0, signhide=0, trskip=0, sao=0),
+    "medium": dict(rdo=0, pu=(1, 4), rdoq=1, signhide=0, trskip=0, sao=3),
+    "veryslow": dict(rdo=3, pu=(1, 4), rdoq=1, signhide=1, trskip=1, sao=3),
+}
+
+
+def driver_config(wl):
+    p = PRESET_FIELDS[wl["preset"]]
+    c = Config()
+    c.width, c.height, c.qp, c.rdo = wl["w"], wl["h"], wl["qp"], p["rdo"]
+    c.pu_depth_intra_min, c.pu_depth_intra_max = p["pu"]
+    c.rdoq_enable, c.rdoq_skip, c.signhide_enable, c.trskip_enable = p["rdoq"], 0, p["signhide"], p["trskip"]
+    c.sao_type, c.deblock_enable, c.deblock_beta, c.deblock_tc = p["sao"], 1, 0, 0
+    c.cu_split_termination, c.intra_rdo_et, c.combine_intra_cus, c.intra_chroma_search, c.full_intra_search, c.wpp = 0, 0, 1, 0, 0, 1
+    c.lambda_ = 0.57 * 2.0 ** ((wl["qp"] - 12) / 3.0)        # fixed-QP lambda (rate_control.c:678-691)
+    c.lambda_sqrt = float(np.sqrt(c.lambda_))
+    return c
+
+
+def device_leg(args, wl, local, frames_per_step, barrier):
+    """`value`: pictures resident in HBM through the driver alone; returns (seconds for K steps, launches, mean search-kernel ms)"""
+    import torch
     import kvazaar_b200 as kb
-    try:
-        ref = Ref(BITDEPTH)
-    except Exception as e:  # pragma: no cover
-        return {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
-    cores = os.cpu_count() or 1
-    lay = kb.fp_layout_for(W, H, QP, SIGNHIDE, BITDEPTH)
-    from _oracle import aligned, al
-    frames = [al(f) for f in synth_frames(2)]
-    blob = aligned(int(lay.host_bytes), np.uint8)
-    ref_frame_pass(ref, frames[0], W, H, QP, lay, nthreads=cores, signhide=SIGNHIDE, blob=blob, src_is_aligned=True, rdoq=RDOQ, trskip=TRSKIP)
-    n, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < budget_s and n < 2000:
-        ref_frame_pass(ref, frames[n % 2], W, H, QP, lay, nthreads=cores, signhide=SIGNHIDE, blob=blob, src_is_aligned=True, rdoq=RDOQ, trskip=TRSKIP)
-        n += 1
-    dt = time.perf_counter() - t0
-    out = {"value": n / dt, "unit": "frames/s", "cores": cores, "kind": "reference",
-           "sample": f"{n} frames {W}x{H} in {dt:.1f}s through oracle/_ref strategy pointers ({ref.selected_name('satd_8x8')}), {cores} threads"}
-    # context: the unmodified reference ENCODER (whole pipeline incl. mode decision, RDOQ, CABAC) on the same input
-    cli = os.path.join(ROOT, "oracle", "_ref", "kvazaar" if BITDEPTH == 8 else "kvazaar_10b")
-    if os.path.exists(cli) and BITDEPTH == 8:       # (the 4320p 10-bit whole-encoder run would take minutes: skipped)
-        try:
-            yuv = f"/tmp/kvz_bench_{H}p.yuv"
-            np.concatenate(synth_frames(4)).tofile(yuv)
-            r = subprocess.run([cli, "-i", yuv, "--input-res", f"{W}x{H}", "-o", "/tmp/kvz_bench.hevc", "--preset", "veryslow" if W > 1920 else "medium", "-q", str(QP),
-                                "-p", "1"], capture_output=True, text=True, timeout=120)
-            for ln in (r.stderr + r.stdout).splitlines():
-                if ln.strip().startswith("FPS:"):
-                    out["reference_encoder_fps"] = float(ln.split(":")[1])
-        except Exception:
-            pass
-    return out
+    lib = C.CDLL(kb.LIB_PATH)
+    lib.kvz_cuda_ctu_open.restype = C.c_void_p
+    lib.kvz_cuda_ctu_open.argtypes = [C.POINTER(Config), C.c_int]
+    lib.kvz_cuda_ctu_submit_device.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int]
+    lib.kvz_cuda_ctu_wait_device.argtypes = [C.c_void_p, C.c_int, C.POINTER(DevResult)]
+    lib.kvz_cuda_ctu_release.argtypes = [C.c_void_p, C.c_int]
+    lib.kvz_cuda_ctu_close.argtypes = [C.c_void_p]
+    lib.kvz_cuda_ctu_launches.restype = C.c_uint64
+    lib.kvz_cuda_ctu_launches.argtypes = [C.c_void_p]
+    lib.kvz_cuda_last_error.restype = C.c_char_p
+    cfg = driver_config(wl)
+    slots = args.slots or wl["slots"]
+    enc = lib.kvz_cuda_ctu_open(C.byref(cfg), slots)
+    if not enc:
+        raise RuntimeError(f"kvz_cuda_ctu_open: {lib.kvz_cuda_last_error()}")
+    ctx = np.zeros(192, np.uint8)
+    assert lib.kvz_cuda_cabac_ctx_init(wl["qp"], 2, ctx.ctypes.data_as(C.c_void_p)) == 0          # KVZ_SLICE_I
+    w, h = wl["w"], wl["h"]
+    clip = np.fromfile(clip_path(wl), dtype=np.uint8).reshape(DISTINCT, w * h * 3 // 2)
+    dev = torch.from_numpy(clip).cuda()
+    torch.cuda.synchronize()
+    res = DevResult()
+    kernel_ms = []
+
+    def run(nframes, collect):
+        pending, nxt, done = [], 0, 0
+        while done < nframes:
+            while nxt < nframes and len(pending) < slots:
+                base = dev[nxt % DISTINCT].data_ptr()
+                s = lib.kvz_cuda_ctu_submit_device(enc, base, base + w * h, base + w * h * 5 // 4, w, w // 2, ctx.ctypes.data,
+                                                   cfg.lambda_, cfg.lambda_sqrt, wl["qp"])
+                if s < 0:
+                    raise RuntimeError(f"submit: {lib.kvz_cuda_last_error()}")
+                pending.append(s)
+                nxt += 1
+            s = pending.pop(0)
+            if lib.kvz_cuda_ctu_wait_device(enc, s, C.byref(res)) != 0:
+                raise RuntimeError(f"wait: {lib.kvz_cuda_last_error()}")
+            if collect:
+                kernel_ms.append(res.search_kernel_ms)
+            lib.kvz_cuda_ctu_release(enc, s)
+            done += 1
+
+    run(args.warmup * frames_per_step, False)
+    torch.cuda.synchronize()
+    barrier()
+    l0 = lib.kvz_cuda_ctu_launches(enc)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(args.steps * frames_per_step, True)
+    e1.record()
+    torch.cuda.synchronize()
+    seconds = e0.elapsed_time(e1) / 1000.0
+    launches = int(lib.kvz_cuda_ctu_launches(enc) - l0)
+    lib.kvz_cuda_ctu_close(enc)
+    return seconds, launches, float(np.mean(kernel_ms)) if kernel_ms else None, slots
 
 
-def run_cuda(args):
+def run_cuda(args, wl):
     import torch
     import torch.distributed as dist
     import kvazaar_b200 as kb
@@ -196,234 +270,107 @@ def run_cuda(args):
     kb.init(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    L = kb.lib()
-    fps_step = args.frames_per_step
-    inflight = args.inflight
-    streams = [torch.cuda.Stream() for _ in range(inflight)]
-    passes = [kb.FramePass(W, H, QP, SIGNHIDE, RDOQ, 0.0, TRSKIP, BITDEPTH) for _ in range(inflight)]
-    frames_np = synth_frames(fps_step)
-    # every rank gets its own frames (sharding = frame i of the job -> rank i mod world)
-    frames_np = [np.roll(f, rank * 977) for f in frames_np]
-    frames_dev = [kb.to_dev(f) for f in frames_np]
-    frames_pin = [torch.from_numpy(f.copy()).pin_memory() for f in frames_np]
-    results_pin = [torch.empty(passes[0].host_bytes, dtype=torch.uint8).pin_memory() for _ in range(inflight)]
-
-    def step_dev():
-        for i in range(fps_step):
-            with torch.cuda.stream(streams[i % inflight]):
-                passes[i % inflight].run_dev(frames_dev[i])
-
-    def step_host():
-        for i in range(fps_step):
-            with torch.cuda.stream(streams[i % inflight]):
-                passes[i % inflight].run_host(frames_pin[i], results_pin[i % inflight])
-
-    # compact result: head of the blob + bitmap + non-zero coefficient chunks (lossless, kvz_cuda_fp_run_host_compact);
-    # the chunk budget is 1/8 of the region and checked after the run
-    lay0 = passes[0].layout
-    budget = int(lay0.n_chunks) // 8
-    small_pin = [torch.empty(int(lay0.coeff_begin), dtype=torch.uint8).pin_memory() for _ in range(inflight)]
-    compact_pin = [torch.empty(int(lay0.compact_header_bytes) + 32 * budget, dtype=torch.uint8).pin_memory() for _ in range(inflight)]
-
-    def step_host_compact():
-        for i in range(fps_step):
-            with torch.cuda.stream(streams[i % inflight]):
-                passes[i % inflight].run_host_compact(frames_pin[i], small_pin[i % inflight], compact_pin[i % inflight], budget)
 
     def barrier():
-        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-            torch.cuda.synchronize()
+        torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        main = torch.cuda.current_stream()
-        e0.record(main)
-        for s in streams:
-            s.wait_stream(main)
-        for _ in range(steps):
-            fn()
-        for s in streams:
-            main.wait_stream(s)
-        e1.record(main)
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t[0])
-        return ms
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    for _ in range(max(3, args.warmup)):
-        step_dev()
+    fps_step = args.frames_per_step or wl["frames_per_step"]
+    w, h = wl["w"], wl["h"]
+    clip = clip_path(wl) if rank == 0 else None
     barrier()
-    launches0 = kb.launch_count()
+    clip = clip_path(wl)
+    ctu_bin = os.path.join(REF_DIR, "kvz_stream_bench_ctu")
+    owf = args.owf or wl["owf"]
+    threads = max(4, (os.cpu_count() or 8) // world)
+    env = {"KVZ_CTU_PROVIDER": kb.LIB_PATH, "CUDA_VISIBLE_DEVICES": os.environ.get("CUDA_VISIBLE_DEVICES", ",".join(str(i) for i in range(world))).split(",")[local]}
+    extra = [f"owf={owf}"] + ([f"threads={threads}"] if world > 1 else [])
+
     with ClockSampler(local) as clk:
-        ms = timed(step_dev, args.steps)
-    launches = kb.launch_count() - launches0
-    value = world * fps_step * args.steps / (ms / 1000.0)
-
-    # ---- e2e: host buffers through the C-ABI, copies inside the timed region.  Headline e2e = the compact result
-    # (what a host that feeds CABAC needs); e2e_full_blob = every coefficient of every depth as dense int16.
-    for _ in range(3):
-        step_host()
-    ms_e2e_full = timed(step_host, args.steps)
-    e2e_full = world * fps_step * args.steps / (ms_e2e_full / 1000.0)
-    for _ in range(3):
-        step_host_compact()
-    ms_e2e = timed(step_host_compact, args.steps)
-    e2e = world * fps_step * args.steps / (ms_e2e / 1000.0)
-    nonzero_chunks = max(int(c.numpy()[:4].view(np.uint32)[0]) for c in compact_pin)
-    d2h_compact = int(lay0.coeff_begin) + int(lay0.compact_header_bytes) + 32 * budget
-    compact_ok = nonzero_chunks <= budget
-    if not compact_ok:            # denser content than the budget: the dense blob is the end-to-end result then
-        e2e, ms_e2e, d2h_compact = e2e_full, ms_e2e_full, passes[0].host_bytes
-
-    # ---- live per-stage timing (CUDA events on the launching stream) -> roofline of the dominant kernel
+        # ---- e2e: host pictures -> .hevc through the reference's API with the CTU job on the device
+        barrier()
+        r = stream_bench(ctu_bin, clip, wl, f"/tmp/kvz_bench_ctu_{rank}.hevc", fps_step, args.steps, args.warmup, extra=extra, env=env)
+        e2e_seconds = max_over_ranks(r["seconds"])
+        # ---- value: the device side alone
+        dev_seconds, launches, kernel_ms, slots = device_leg(args, wl, local, fps_step, barrier)
+        dev_seconds = max_over_ranks(dev_seconds)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    frames = args.steps * fps_step * world
+    nctu = ((w + 63) // 64) * ((h + 63) // 64)
+    h2d = fps_step * (w * h * 3 // 2 + ((h + 63) // 64) * 192)
+    d2h = fps_step * (((w + 63) // 64) * 16 * ((h + 63) // 64) * 16 * 12 + nctu * 6144 * 2 + nctu * 2 * 68 + w * h * 3 // 2)
     peak, peak_src = peaks()
-    fp = passes[0]
-    L.kvz_cuda_fp_set_timing(fp.h, 1)
-    with torch.cuda.stream(streams[0]):
-        for i in range(max(8, fps_step)):
-            fp.run_dev(frames_dev[i % fps_step])
-    torch.cuda.synchronize()
-    NST = 40
-    ms_stage = (C.c_double * NST)()
-    runs = C.c_int()
-    L.kvz_cuda_fp_get_timing(fp.h, ms_stage, C.byref(runs))
-    L.kvz_cuda_fp_set_timing(fp.h, 0)
-    stage_ms = [ms_stage[i] / max(1, runs.value) for i in range(NST)]
-    names = [f"{k}_w{32 >> d}" for d in range(4) for k in ("rough_search", "recon_luma", "rdoq_luma", "recon_luma_inv", "bits_luma",
-                                                           "recon_chroma", "rdoq_chroma", "recon_chroma_inv", "bits_chroma")] + \
-            ["deblock", "sao_stats_decide", "sao_reconstruct", "checksum"]
-    stages = {names[i]: round(stage_ms[i], 4) for i in range(NST) if stage_ms[i] > 0.0005}
-    # per-LAUNCH time of each kernel (chroma stages hold two launches: U and V; deblocking two passes)
-    per_launch = [stage_ms[i] / (2 if names[i].startswith("recon_chroma") or names[i] == "deblock" else 1) for i in range(NST)]
-    dom = int(np.argmax(per_launch))
-    ncu = {}
-    for fn in ("r01_ncu_summary.json", "r01b_ncu_summary.json"):      # later captures override earlier ones
-        try:
-            ncu.update(json.load(open(os.path.join(ROOT, "profiles", fn))))
-        except Exception:
-            pass
-
-    def alg_bytes(name):
-        """Bytes one launch must move through HBM."""
-        kind, wtxt = name.rsplit("_w", 1) if "_w" in name else (name, "0")
-        w = int(wtxt)
-        if kind == "rough_search":       # source block + 4w+1 reference samples in, 35 costs out
-            return (W // w) * (H // w) * (w * w + 4 * w + 1 + 35 * 4)
-        if kind in ("recon_luma", "recon_luma_inv"):   # source + refs in; reconstruction + int16 coefficients + has + ssd out
-            return (W // w) * (H // w) * (w * w + 4 * w + 1 + w * w + 2 * w * w + 5)
-        if kind in ("recon_chroma", "recon_chroma_inv"):   # one of the two chroma planes, blocks of w/2
-            wc = w // 2
-            return (W // w) * (H // w) * (wc * wc + 4 * wc + 1 + wc * wc + 2 * wc * wc + 5)
-        if kind == "bits_luma":          # int16 levels in, one double per block out
-            return W * H * 2 + (W // w) * (H // w) * 8
-        if kind == "bits_chroma":        # U and V in one launch
-            return 2 * ((W // 2) * (H // 2) * 2 + (W // w) * (H // w) * 8)
-        if kind == "rdoq_luma":          # int16 coefficients in, int16 levels out
-            return W * H * 4
-        if kind == "rdoq_chroma":        # U and V in one launch
-            return 2 * (W // 2) * (H // 2) * 4
-        if kind == "deblock":            # per pass (launch): the three reconstruction planes in and out + 20-byte CU records in
-            return 2 * W * H * 3 // 2 + (W // 4) * (H // 4) * 20
-        if kind == "sao_stats_decide":   # source + reconstruction of all three planes in, 40+4+1 ints per CTU-plane out
-            return 2 * W * H * 3 // 2 + 3 * ((W + 63) // 64) * ((H + 63) // 64) * 46 * 4
-        return None
-
+    alg = 2 * w * h * 3 // 2              # SURVEY.md 8(d) frame level: source read once + reconstruction written once
     roof = None
-    alg = alg_bytes(names[dom])
-    if alg:
-        ach = alg / (per_launch[dom] / 1000.0) / 1e9
-        kname = {"rough_search": "rough_search_u8_kernel", "recon_luma": "intra_recon_kernel", "recon_chroma": "intra_recon_kernel",
-                 "recon_luma_inv": "intra_recon_kernel", "recon_chroma_inv": "intra_recon_kernel", "rdoq_luma": "rdoq_grid_kernel",
-                 "rdoq_chroma": "rdoq_grid_kernel", "bits_luma": "coeff_cost_grid_kernel", "bits_chroma": "coeff_cost_grid_kernel",
-                 "sao_stats_decide": "sao_ctu_kernel", "deblock": "deblock_pass_kernel"}.get(names[dom].rsplit("_w", 1)[0], names[dom])
-        roof = {"kernel": f"{kname} [{names[dom]}]", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": ncu.get(names[dom], {}).get("dram_bytes_per_launch"), "ms_per_launch": per_launch[dom],
-                "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
-                "note": ("RDOQ is HM's serial per-TU chain (one lane of a warp walks the scan in double precision): latency bound, "
-                         f"ncu {ncu.get(names[dom], {}).get('issue_active_pct', 'n/a')}% issue-active at "
-                         f"{ncu.get(names[dom], {}).get('warps_active_pct', 'n/a')}% warps-active; "
-                         if names[dom].startswith("rdoq") else
-                         "fused per-block kernels keep predictions / transforms on chip: they are instruction-issue bound "
-                         f"(ncu: {ncu.get(names[dom], {}).get('issue_active_pct', 'n/a')}% issue-active), not HBM bound; ")
-                        + "roofline_satd_batch is the HBM-streaming kernel of the north star"}
-
-    # ---- the batched SATD kernel of the north_star (block pairs streamed from HBM), inputs > L2
-    n_pairs = 4 * 1024 * 1024            # 4M 8x8 pairs = 512 MiB of pixels > 126 MB L2
-    g = torch.Generator(device="cuda").manual_seed(7)
-    a = torch.randint(0, 256, (n_pairs * 64,), dtype=torch.uint8, device="cuda", generator=g)
-    b = torch.randint(0, 256, (n_pairs * 64,), dtype=torch.uint8, device="cuda", generator=g)
-    out = torch.empty(n_pairs, dtype=torch.int32, device="cuda")       # no allocation inside the timed launches
-    for _ in range(3):
-        kb.satd_nxn_batch(8, a, b, n_pairs, out)
-    torch.cuda.synchronize()
-    reps = 20
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-    for i in range(reps):                        # one event pair per launch: host-side gaps between launches are not kernel time
-        evs[i][0].record()
-        kb.satd_nxn_batch(8, a, b, n_pairs, out)
-        evs[i][1].record()
-    torch.cuda.synchronize()
-    per = [e0.elapsed_time(e1) for e0, e1 in evs]
-    ms_satd = float(np.mean(per))                # the reported figure is the MEAN launch duration
-    alg_satd = n_pairs * (2 * 64 + 4)        # SURVEY.md 8(d): 2*N*N*s + 4 bytes per block pair
-    ach_satd = alg_satd / (ms_satd / 1000.0) / 1e9
-    roof_satd = {"kernel": "satd_nxn_kernel<u8,8> (kvz_cuda_satd_nxn_batch)", "bound": "hbm", "achieved": ach_satd, "peak": peak,
-                 "unit": "GB/s", "frac": ach_satd / peak, "traffic": None, "ms_per_launch": ms_satd, "pairs_per_launch": n_pairs,
-                 "algorithmic_bytes_per_launch": alg_satd, "peak_source": peak_src, "checksum": int(out.to(torch.int64).sum()),
-                 "ms_per_launch_min_median_max": [round(float(np.min(per)), 5), round(float(np.median(per)), 5), round(float(np.max(per)), 5)]}
-    roof_satd["traffic"] = ncu.get("satd_nxn_kernel_8", {}).get("dram_bytes_per_launch")
-    del a, b
-
-    if rank == 0:
-        line = {"metric": "hot-path frames/sec at fixed QP (per-CTU strategy kernels, all depths)", "value": value, "unit": "frames/s",
-                "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8" if BITDEPTH == 8 else "u16", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "frames_per_step": fps_step, "frames_in_flight": inflight, "parallelism": f"frames/{world}",
-                           "l2": f"working set per step ({fps_step} distinct {passes[0].frame_bytes / 1e6:.1f} MB frames + {inflight} result/scratch blobs of "
-                                 f"{passes[0].host_bytes / 1e6:.0f}+ MB each) exceeds the 126 MB L2"},
-                "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": fps_step * passes[0].frame_bytes,
-                        "d2h_bytes_per_step": fps_step * d2h_compact, "ms_per_step": ms_e2e / args.steps,
-                        "result": "compact: blob head + bitmap + non-zero 32-byte coefficient chunks (lossless)" if compact_ok
-                                  else "dense blob (the compact chunk budget was exceeded)",
-                        "nonzero_chunks_per_frame": nonzero_chunks, "chunk_budget": budget},
-                "e2e_full_blob": {"value": e2e_full, "unit": "frames/s", "d2h_bytes_per_step": fps_step * passes[0].host_bytes,
-                                  "ms_per_step": ms_e2e_full / args.steps},
-                "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof, "roofline_satd_batch": roof_satd,
-                "stage_ms_per_frame": stages}
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line))
-    if world > 1:
+    if kernel_ms:
+        ach = alg / (kernel_ms / 1000.0) / 1e9
+        roof = {"kernel": "ctu_frame_kernel (one launch per picture: persistent CTAs, a CTU per CTA at a time)", "bound": "hbm", "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "traffic": None, "ms_per_launch": kernel_ms, "algorithmic_bytes_per_launch": alg, "peak_source": peak_src,
+                "note": "the closed-loop CTU search is a chain of dependent decisions (341 CUs per CTU, CTUs in wavefront order): latency bound by "
+                        "construction, its HBM traffic is negligible; the HBM-streaming kernel of the north star is roofline_satd_batch "
+                        "(tools/bench_framepass.py, profiles/)"}
+    line = {"metric": METRIC, "value": frames / dev_seconds, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1000.0 * e2e_seconds / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": config_of(wl), "frames_per_step": fps_step,
+            "e2e": {"value": frames / e2e_seconds, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "pictures_in_flight": owf + 1, "host_threads_per_rank": threads if world > 1 else (os.cpu_count() or 1),
+                    "path": "kvz_stream_bench_ctu: libkvazaar API -> kvz_ctu_hooks -> libkvzcuda.so (kvz_cuda_ctu_submit/wait) -> reference CABAC"},
+            "device_only": {"value": frames / dev_seconds, "unit": "frames/s", "pictures_in_flight": slots, "ms_per_step": 1000.0 * dev_seconds / args.steps},
+            "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "parallelism": f"pictures sharded over {world} GPU(s), no collective"}
+    if world == 1:
+        line.update(parity_and_baseline(args, wl, clip, ctu_bin, env, extra))
+    else:
         dist.destroy_process_group()
+    print(json.dumps(line))
+
+
+def parity_and_baseline(args, wl, clip, ctu_bin, env, extra):
+    """rank 0, N = 1: the unmodified reference on a bounded sample (cpu_baseline) and the byte comparison of the CUDA arm's
+    bitstream of the same sample"""
+    ref_bin = os.path.join(REF_DIR, "kvz_stream_bench_ref")
+    n = args.sample_frames or wl["sample"]
+    if not os.path.exists(ref_bin):
+        return {"cpu_baseline": {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}, "bitstream_identical": None}
+    a, b = "/tmp/kvz_bench_sample_ref.hevc", "/tmp/kvz_bench_sample_ctu.hevc"
+    rr = stream_bench(ref_bin, clip, wl, a, n, 1, 0)
+    rc = stream_bench(ctu_bin, clip, wl, b, n, 1, 0, extra=extra, env=env)
+    same = sha(a) == sha(b) and os.path.getsize(a) > 0
+    if not same:
+        print(f"bench.py: BITSTREAM MISMATCH on the {n}-picture sample ({rr['bytes']} vs {rc['bytes']} bytes)", file=sys.stderr)
+    cores = os.cpu_count() or 1
+    return {"cpu_baseline": {"value": rr["fps"], "unit": "frames/s", "cores": cores, "kind": "reference",
+                             "sample": f"{n} pictures of the same clip, one untimed-ramp-included run of the unmodified reference ({rr['seconds']:.1f} s), threads=auto"},
+            "bitstream_identical": bool(same), "bitstream_sha256": sha(b), "bitstream_bytes_sample": rc["bytes"]}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=8)
-    ap.add_argument("--inflight", type=int, default=4, help="frames in flight (one stream + one result blob each)")
-    ap.add_argument("--ref-frames", type=int, default=8, help="frames per step of the reference arm (bounded sample)")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="1080p", choices=["1080p", "2160p", "4320p10"], help="1080p = BASELINE configs[1] (default)")
-    ap.add_argument("--rdoq", type=int, default=1, choices=[0, 1], help="1 (default): quantise with kvz_rdoq as the medium / veryslow presets do; 0: kvz_quant")
+    ap.add_argument("--workload", default="2160p", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames-per-step", type=int, default=0)
+    ap.add_argument("--owf", type=int, default=0, help="pictures the encoder keeps in flight (CUDA arm)")
+    ap.add_argument("--slots", type=int, default=0, help="pictures in flight of the device-only leg")
+    ap.add_argument("--sample-frames", type=int, default=0)
     args = ap.parse_args()
-    if args.workload == "4320p10":
-        set_workload_4320p10(args.rdoq)
-    else:
-        set_workload(args.workload, args.rdoq)
+    wl = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, wl)
     else:
-        run_cuda(args)
+        run_cuda(args, wl)
 
 
 if __name__ == "__main__":

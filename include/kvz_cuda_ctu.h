@@ -82,6 +82,21 @@ void kvz_cuda_ctu_close(kvz_cuda_ctu_enc *enc);
 int kvz_cuda_ctu_submit(kvz_cuda_ctu_enc *enc, const uint8_t *y, const uint8_t *u, const uint8_t *v, int stride_y, int stride_c,
                         const uint8_t *ctx_init, double lambda, double lambda_sqrt, int qp);
 int kvz_cuda_ctu_wait(kvz_cuda_ctu_enc *enc, int slot, kvz_cuda_ctu_result *out);
+
+/* The same with the picture already resident in device memory and the results left there (bench.py's kernel-side
+ * figure; a caller that keeps the CABAC stage on the device would use it too).  Pointers of the result are device
+ * pointers, valid until kvz_cuda_ctu_release. */
+typedef struct kvz_cuda_ctu_device_result {
+  const kvz_cuda_ctu_cu *cu;
+  const int16_t *coeff;
+  const kvz_cuda_ctu_sao *sao;
+  const uint8_t *rec;               /* final picture: Y, U, V planes back to back, stride = width (/2) */
+  int32_t cu_stride, width_in_lcu, height_in_lcu;
+  float search_kernel_ms;           /* device time of the picture's search launch(es), CUDA events on its stream */
+} kvz_cuda_ctu_device_result;
+int kvz_cuda_ctu_submit_device(kvz_cuda_ctu_enc *enc, const uint8_t *d_y, const uint8_t *d_u, const uint8_t *d_v, int stride_y, int stride_c,
+                               const uint8_t *ctx_init, double lambda, double lambda_sqrt, int qp);
+int kvz_cuda_ctu_wait_device(kvz_cuda_ctu_enc *enc, int slot, kvz_cuda_ctu_device_result *out);
 void kvz_cuda_ctu_release(kvz_cuda_ctu_enc *enc, int slot);
 /* kernels launched by this encoder so far */
 uint64_t kvz_cuda_ctu_launches(const kvz_cuda_ctu_enc *enc);

@@ -68,6 +68,8 @@ struct TuFixed {
   uint8_t prep_flags[16];
   int32_t best_last_p1;
   int32_t has, ac_sum, ssd;
+  uint32_t cg_mask[2];              // coefficient groups (raster) with a level != 0, of the unit's final levels
+  uint32_t ts_mask[2];
   // transform skip decision (kvz_quantize_residual_trskip): both alternatives of a 4x4 luma unit
   uint8_t ts_rec[2][16];
   int16_t ts_coeff[2][16];
@@ -131,58 +133,78 @@ CTU_FN Plane plane_of(CtuWork *W, LcuLevel *L, int color)
 }
 
 // ------------------------------------------------------------------------------------------------ intra references
-// kvz_intra_build_reference for the block at luma position (x, y) (picture coordinates), into `r`, followed by the
-// [1 2 1] smoothing (done eagerly: the reference's lazy flag only saves time) and the DC sum.
-CTU_FN_NOINLINE void build_refs(const CtuTables *T, const CtuConfig *cfg, CtuWork *W, LcuLevel *L, int log2w, int color, int x, int y, IntraRefs *r)
+// kvz_intra_build_reference for the blocks of the colours in `mask` (bit per colour) at luma position (x, y) (picture
+// coordinates), into r[colour], followed by the [1 2 1] smoothing (done eagerly: the reference's lazy flag only saves
+// time; chroma never reads it) and the DC sum.  log2w[colour]: the block sizes.  One pass over all colours: the border
+// reads of the three planes overlap instead of queueing behind each other.
+CTU_FN_NOINLINE void build_refs_multi(const CtuTables *T, const CtuConfig *cfg, CtuWork *W, LcuLevel *L, const int log2w[3], int mask, int x, int y, IntraRefs *r)
 {
-  const int is_c = color != 0, w = 1 << log2w;
-  const Plane P = plane_of(W, L, color);
   const int lx = x & 63, ly = y & 63;
-  const int px = lx >> is_c, py = ly >> is_c, lw = P.lw;
   const bool has_left = x > 0, has_top = y > 0, inner = has_left && has_top;
-  // border accessors: i >= -1
-  auto top_border = [&](int i) -> int { return py ? P.rec[(px + i) + (py - 1) * lw] : P.top[1 + px + i]; };
-  auto left_border = [&](int i) -> int { return px ? P.rec[(px - 1) + (py + i) * lw] : P.left[1 + py + i]; };
-  int al = 0, at = 0;
-  if (has_left) { al = T->ref_left[ly >> 2][lx >> 2] >> is_c; al = imin(al, 2 * w); al = imin(al, (cfg->height - y) >> is_c); }
-  if (has_top) { at = T->ref_top[ly >> 2][lx >> 2] >> is_c; at = imin(at, 2 * w); at = imin(at, (cfg->width - x) >> is_c); }
-  // the _inner variant copies in groups of four, at least one group (intra.c:486-494, 512-516)
-  const int nl = inner ? imax(4, (al + 3) & ~3) : al;
-  const int ntp = inner ? imax(4, (at + 3) & ~3) : at;
-  const int n = 2 * w + 1;
-  for (int i = CTU_TID; i < 2 * n; i += CTU_NT) {
+  int n_of[3], start[4];
+  start[0] = 0;
+  for (int col = 0; col < 3; ++col) { n_of[col] = ((mask >> col) & 1) ? 2 * (1 << log2w[col]) + 1 : 0; start[col + 1] = start[col] + 2 * n_of[col]; }
+  for (int it = CTU_TID; it < start[3]; it += CTU_NT) {
+    const int color = it >= start[2] ? 2 : (it >= start[1] ? 1 : 0);
+    const int i = it - start[color], n = n_of[color], w = (n - 1) >> 1;
+    const int is_c = color != 0;
+    const Plane P = plane_of(W, L, color);
+    const int px = lx >> is_c, py = ly >> is_c, lw = P.lw;
+    int al = 0, at = 0;
+    if (has_left) { al = T->ref_left[ly >> 2][lx >> 2] >> is_c; al = imin(al, 2 * w); al = imin(al, (cfg->height - y) >> is_c); }
+    if (has_top) { at = T->ref_top[ly >> 2][lx >> 2] >> is_c; at = imin(at, 2 * w); at = imin(at, (cfg->width - x) >> is_c); }
+    // the _inner variant copies in groups of four, at least one group (intra.c:486-494, 512-516)
+    const int nl = inner ? imax(4, (al + 3) & ~3) : al;
+    const int ntp = inner ? imax(4, (at + 3) & ~3) : at;
+    // border accessors: k >= -1
+#define CTU_TOP_BORDER(k) (py ? P.rec[(px + (k)) + (py - 1) * lw] : P.top[1 + px + (k)])
+#define CTU_LEFT_BORDER(k) (px ? P.rec[(px - 1) + (py + (k)) * lw] : P.left[1 + py + (k)])
     const bool is_top = i >= n;
     const int e = is_top ? i - n : i;          // entry 0 = corner
     int v;
     if (e == 0) {
-      if (inner) v = px ? top_border(-1) : left_border(-1);
-      else v = has_left ? left_border(0) : (has_top ? top_border(0) : 128);      // "copy reference clockwise": left[1]
+      if (inner) v = px ? CTU_TOP_BORDER(-1) : CTU_LEFT_BORDER(-1);
+      else v = has_left ? CTU_LEFT_BORDER(0) : (has_top ? CTU_TOP_BORDER(0) : 128);      // "copy reference clockwise": left[1]
     } else if (!is_top) {
-      if (has_left) v = left_border(imin(e - 1, nl - 1));
-      else v = has_top ? top_border(0) : 128;
+      if (has_left) v = CTU_LEFT_BORDER(imin(e - 1, nl - 1));
+      else v = has_top ? CTU_TOP_BORDER(0) : 128;
     } else {
-      if (has_top) v = top_border(imin(e - 1, ntp - 1));
-      else v = has_left ? left_border(0) : 128;
+      if (has_top) v = CTU_TOP_BORDER(imin(e - 1, ntp - 1));
+      else v = has_left ? CTU_LEFT_BORDER(0) : 128;
     }
-    (is_top ? r->top : r->left)[e] = (uint8_t)v;
+#undef CTU_TOP_BORDER
+#undef CTU_LEFT_BORDER
+    (is_top ? r[color].top : r[color].left)[e] = (uint8_t)v;
   }
   CTU_SYNC();
-  for (int i = CTU_TID; i < 2 * n; i += CTU_NT) {
-    const bool is_top = i >= n;
-    const int e = is_top ? i - n : i;
-    const uint8_t *p = is_top ? r->top : r->left;
+  // smoothing of the luma references; one thread per colour sums the DC
+  const int n0 = n_of[0];
+  for (int i = CTU_TID; i < 2 * n0 + 3; i += CTU_NT) {
+    if (i >= 2 * n0) {
+      const int color = i - 2 * n0;
+      if ((mask >> color) & 1) {
+        const int w = 1 << log2w[color];
+        int s = 0;
+        for (int k = 1; k <= w; ++k) s += r[color].top[k] + r[color].left[k];
+        r[color].dc = (s + w) >> (log2w[color] + 1);
+      }
+      continue;
+    }
+    const bool is_top = i >= n0;
+    const int e = is_top ? i - n0 : i;
+    const uint8_t *p = is_top ? r[0].top : r[0].left;
     int v;
-    if (e == 0) v = (r->left[1] + 2 * r->left[0] + r->top[1] + 2) >> 2;
-    else if (e == n - 1) v = p[e];
+    if (e == 0) v = (r[0].left[1] + 2 * r[0].left[0] + r[0].top[1] + 2) >> 2;
+    else if (e == n0 - 1) v = p[e];
     else v = (p[e - 1] + 2 * p[e] + p[e + 1] + 2) >> 2;
-    (is_top ? r->ftop : r->fleft)[e] = (uint8_t)v;
-  }
-  CTU_LEADER {
-    int s = 0;
-    for (int i = 1; i <= w; ++i) s += r->top[i] + r->left[i];
-    r->dc = (s + w) >> (log2w + 1);
+    (is_top ? r[0].ftop : r[0].fleft)[e] = (uint8_t)v;
   }
   CTU_SYNC();
+}
+CTU_FN void build_refs(const CtuTables *T, const CtuConfig *cfg, CtuWork *W, LcuLevel *L, int log2w, int color, int x, int y, IntraRefs *r)
+{
+  int l[3] = { log2w, log2w, log2w };
+  build_refs_multi(T, cfg, W, L, l, 1 << color, x, y, r - color);
 }
 
 // ------------------------------------------------------------------------------------------------ intra prediction
@@ -261,11 +283,13 @@ CTU_FN_NOINLINE void predict_block(const IntraRefs *r, int log2w, int mode, int 
 CTU_FN int hadamard4_abs_sum(int d[16])
 {
   // rows then columns; the sum of absolute transform values does not depend on the butterfly order
+#pragma unroll
   for (int r = 0; r < 4; ++r) {
     const int a = d[4 * r] + d[4 * r + 1], b = d[4 * r] - d[4 * r + 1], c = d[4 * r + 2] + d[4 * r + 3], e = d[4 * r + 2] - d[4 * r + 3];
     d[4 * r] = a + c; d[4 * r + 1] = b + e; d[4 * r + 2] = a - c; d[4 * r + 3] = b - e;
   }
   int s = 0;
+#pragma unroll
   for (int c = 0; c < 4; ++c) {
     const int a = d[c] + d[4 + c], b = d[c] - d[4 + c], g = d[8 + c] + d[12 + c], e = d[8 + c] - d[12 + c];
     s += iabs(a + g) + iabs(b + e) + iabs(a - g) + iabs(b - e);
@@ -274,6 +298,7 @@ CTU_FN int hadamard4_abs_sum(int d[16])
 }
 CTU_FN int hadamard8_abs_sum(int d[64])
 {
+#pragma unroll
   for (int r = 0; r < 8; ++r) {
     int *p = d + 8 * r;
     const int a0 = p[0] + p[4], a1 = p[1] + p[5], a2 = p[2] + p[6], a3 = p[3] + p[7];
@@ -282,6 +307,7 @@ CTU_FN int hadamard8_abs_sum(int d[64])
     p[0] = b0 + b1; p[1] = b0 - b1; p[2] = b2 + b3; p[3] = b2 - b3; p[4] = b4 + b5; p[5] = b4 - b5; p[6] = b6 + b7; p[7] = b6 - b7;
   }
   int s = 0;
+#pragma unroll
   for (int c = 0; c < 8; ++c) {
     const int *p = d + c;
     const int a0 = p[0] + p[32], a1 = p[8] + p[40], a2 = p[16] + p[48], a3 = p[24] + p[56];
@@ -292,34 +318,99 @@ CTU_FN int hadamard8_abs_sum(int d[64])
   return s;
 }
 
-// SATD (satd_NxN) and, for 4x4, SAD of the prediction of every mode in [mode_lo, mode_hi] against the source block.
-// satd_out / sad_out: [35] ints, zeroed here.  Items are (mode, sub-block) pairs.
-CTU_FN_NOINLINE void rough_costs_all_modes(const IntraRefs *r, int log2w, int color, const uint8_t *src, int src_stride,
-                                  int mode_lo, int mode_hi, int32_t *satd_out, int32_t *sad_out, bool want_sad)
+// ---- rough search: SATD of every mode
+// Angular modes are predicted from a per-mode extended main reference: entry idx + w holds what the reference's
+// ref_main[idx + 1] holds (intra-generic.c:86-122) -- the main edge for idx >= -1, the projected side edge below --
+// so that a sample is one branch-free two-tap interpolation.  Horizontal modes are evaluated transposed (main = left,
+// block and source transposed): the SATD / SAD of a block and of its transpose are the same.
+struct RoughExt { uint8_t e[33][104]; };      // [mode - 2][idx + w], idx in [-w, 2w + 1]
+static_assert(sizeof(RoughExt) <= CTU_ARENA_BYTES, "rough-search scratch lives in the arena");
+
+CTU_FN void ang_params(int mode, bool *vertical, int *sdisp, int *inv)
+{
+  const int disp_tab[9] = { 0, 2, 5, 9, 13, 17, 21, 26, 32 };
+  const int inv_tab[9] = { 0, 4096, 1638, 910, 630, 482, 390, 315, 256 };
+  *vertical = mode >= 18;
+  const int mdisp = *vertical ? mode - 26 : 10 - mode;
+  const int adisp = iabs(mdisp);
+  *sdisp = mdisp < 0 ? -disp_tab[adisp] : disp_tab[adisp];
+  *inv = inv_tab[adisp];
+}
+
+// difference block (prediction - source) of the w8 x w8 sub-block at (bx, by) of mode m into d[], row-major, in the
+// mode's own orientation (transposed for horizontal modes)
+template <int W8>
+CTU_FN void rough_diff_block(const IntraRefs *r, const RoughExt *ext, int log2w, int color, int m, const uint8_t *src, int src_stride, int bx, int by, int *d)
+{
+  const int w = 1 << log2w;
+  if (m >= 2) {
+    bool vertical; int sdisp, inv;
+    ang_params(m, &vertical, &sdisp, &inv);
+    const uint8_t *e = ext->e[m - 2] + w;
+    // transposed domain of a horizontal mode: row index <-> picture column
+    const int ox = vertical ? bx : by, oy = vertical ? by : bx;
+    const int sx = vertical ? 1 : src_stride, sy = vertical ? src_stride : 1;
+    const bool f = intra_uses_filtered(log2w, m, color);
+    const uint8_t *side = vertical ? (f ? r->fleft : r->left) : (f ? r->ftop : r->top);
+    const bool edge = color == 0 && log2w < 5 && sdisp == 0 && ox == 0;      // modes 10 / 26: first column filtered
+#pragma unroll
+    for (int y = 0; y < W8; ++y) {
+      const int pos = (oy + y + 1) * sdisp;
+      const int di = pos >> 5, df = pos & 31;
+      const uint8_t *p = e + ox + di;
+#pragma unroll
+      for (int x = 0; x < W8; ++x) {
+        int v = ((32 - df) * (int)p[x] + df * (int)p[x + 1] + 16) >> 5;
+        if (edge && x == 0) v = iclip(0, 255, v + (((int)side[oy + y + 1] - (int)side[0]) >> 1));
+        d[y * W8 + x] = v - (int)src[(oy + y) * sy + (ox + x) * sx];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int y = 0; y < W8; ++y)
+#pragma unroll
+      for (int x = 0; x < W8; ++x)
+        d[y * W8 + x] = intra_predict_px(r, log2w, m, color, bx + x, by + y) - (int)src[(by + y) * src_stride + bx + x];
+  }
+}
+
+// SATD (satd_NxN) and, for 4x4, SAD of the prediction of every mode against the source block.
+// satd_out / sad_out: [35] ints.  `ext`: scratch (the arena: no transform-unit job is running during the rough search).
+CTU_FN_NOINLINE void rough_costs_all_modes(const IntraRefs *r, RoughExt *ext, int log2w, int color, const uint8_t *src, int src_stride,
+                                  int32_t *satd_out, int32_t *sad_out, bool want_sad)
 {
   const int w = 1 << log2w;
   for (int m = CTU_TID; m < 35; m += CTU_NT) { satd_out[m] = 0; sad_out[m] = 0; }
+  // extended main references of the 33 angular modes
+  const int len = 3 * w + 2;
+  for (int it = CTU_TID; it < 33 * len; it += CTU_NT) {
+    const int m = 2 + it / len, idx = it % len - w;
+    bool vertical; int sdisp, inv;
+    ang_params(m, &vertical, &sdisp, &inv);
+    const bool f = intra_uses_filtered(log2w, m, color);
+    const uint8_t *t = f ? r->ftop : r->top, *l = f ? r->fleft : r->left;
+    const uint8_t *rmain = vertical ? t : l, *rside = vertical ? l : t;
+    int v = 0;
+    if (idx >= -1) { if (idx + 1 <= 2 * w) v = rmain[idx + 1]; }
+    else if (sdisp < 0) v = rside[(128 + (-idx - 1) * inv) >> 8];
+    ext->e[m - 2][idx + w] = (uint8_t)v;
+  }
   CTU_SYNC();
   if (w == 4) {
-    for (int m = mode_lo + CTU_TID; m <= mode_hi; m += CTU_NT) {
+    for (int m = CTU_TID; m < 35; m += CTU_NT) {
       int d[16], sad = 0;
-      for (int e = 0; e < 16; ++e) {
-        // satd_4x4(pred, orig): the difference is pred - orig, the absolute sums do not care about the sign
-        d[e] = intra_predict_px(r, 2, m, color, e & 3, e >> 2) - (int)src[(e >> 2) * src_stride + (e & 3)];
-        sad += iabs(d[e]);
-      }
+      rough_diff_block<4>(r, ext, 2, color, m, src, src_stride, 0, 0, d);
+#pragma unroll
+      for (int e = 0; e < 16; ++e) sad += iabs(d[e]);
       satd_out[m] = (hadamard4_abs_sum(d) + 1) >> 1;
       if (want_sad) sad_out[m] = sad;
     }
   } else {
-    const int sb = w >> 3, nsb = sb * sb, items = (mode_hi - mode_lo + 1) * nsb;
+    const int sb = w >> 3, nsb = sb * sb, items = 35 * nsb;
     for (int it = CTU_TID; it < items; it += CTU_NT) {
-      const int m = mode_lo + it / nsb, k = it % nsb, bx = (k % sb) * 8, by = (k / sb) * 8;
+      const int m = it / nsb, k = it % nsb, bx = (k % sb) * 8, by = (k / sb) * 8;
       int d[64];
-      for (int e = 0; e < 64; ++e) {
-        const int xx = bx + (e & 7), yy = by + (e >> 3);
-        d[e] = intra_predict_px(r, log2w, m, color, xx, yy) - (int)src[yy * src_stride + xx];
-      }
+      rough_diff_block<8>(r, ext, log2w, color, m, src, src_stride, bx, by, d);
       CTU_ATOMIC_ADD(&satd_out[m], (hadamard8_abs_sum(d) + 2) >> 2);
     }
   }
@@ -872,11 +963,14 @@ CTU_FN int coeff_remain_bits(int symbol, int rice)
 // kvz_get_coeff_cost's CABAC branch = kvz_encode_coeff_nxn in counting mode on a copy of the search models that is
 // kept when `update` is set (ref: rdo.c:223-264).  Leader only.  The cost estimate codes tr_skip as 0 (rdo.c:251-258);
 // the tracker of the real coder's models passes the TU's flag.
-CTU_FN_NOINLINE double coeff_cost_serial(const CtuTables *T, const SmTables *tb, const CtuConfig *cfg, CabacState *c, const int16_t *coeff, int log2n, int type, int scan_idx, int tr_skip)
+#define CTU_NO_MASK 0xFFFFFFFFFFFFFFFFull       // (no unit has all 64 groups... a full 32x32 unit does: then the scan below is harmless)
+CTU_FN_NOINLINE double coeff_cost_serial(const CtuTables *T, const SmTables *tb, const CtuConfig *cfg, CabacState *c, const int16_t *coeff, int log2n, int type, int scan_idx, int tr_skip,
+                                         uint64_t known_cg_mask = CTU_NO_MASK)
 {
   const int n = 1 << log2n, side = n >> 2, ncg = side * side;
   uint64_t cg_flags = 0;
-  for (int g = 0; g < ncg; ++g) {
+  if (known_cg_mask != CTU_NO_MASK) cg_flags = known_cg_mask;
+  else for (int g = 0; g < ncg; ++g) {
     const int gy = g / side, gx = g - gy * side;
     bool any = false;
     for (int r = 0; r < 4 && !any; ++r) {
@@ -1013,7 +1107,7 @@ CTU_FN_NOINLINE void tu_core(const Team &tm, const CtuTables *T, const SmTables 
     pred[e] = (uint8_t)p;
     a[e] = (int16_t)((int)j.src[y * j.src_stride + x] - p);
   }
-  if (tm.tid == 0) { fx->has = 0; fx->ssd = 0; }
+  if (tm.tid == 0) { fx->has = 0; fx->ssd = 0; fx->cg_mask[0] = 0; fx->cg_mask[1] = 0; }
   tsync(tm);
   const bool use_dst = (n == 4 && color == 0);
   const int8_t *M = use_dst ? T->dst4 : T->tr[log2n - 2];
@@ -1031,9 +1125,19 @@ CTU_FN_NOINLINE void tu_core(const Team &tm, const CtuTables *T, const SmTables 
   } else {
     quant_block(tm, T, cfg, tu, n, type, j.scan_idx);
   }
-  int any = 0;
-  for (int e = tm.tid; e < nn; e += tm.nt) any |= q[e] != 0;
-  if (any) CTU_ATOMIC_OR(&fx->has, 1);
+  {
+    uint32_t m0 = 0, m1 = 0;
+    const int side_shift = log2n - 2;
+    for (int e = tm.tid; e < nn; e += tm.nt) {
+      if (q[e] != 0) {
+        const int g = (((e >> log2n) >> 2) << side_shift) + ((e & (n - 1)) >> 2);
+        if (g < 32) m0 |= 1u << g; else m1 |= 1u << (g - 32);
+      }
+    }
+    if (m0) CTU_ATOMIC_OR(&fx->cg_mask[0], m0);
+    if (m1) CTU_ATOMIC_OR(&fx->cg_mask[1], m1);
+    if (m0 | m1) CTU_ATOMIC_OR(&fx->has, 1);
+  }
   tsync(tm);
   int ssd = 0;
   if (fx->has) {
@@ -1081,14 +1185,14 @@ CTU_FN_NOINLINE int tu_eval(const Team &tm, const CtuTables *T, const SmTables *
   for (int k = 0; k < 2; ++k) {
     tu_core(tm, T, tb, cfg, cabac0, tu, j, k == 1);
     for (int e = tm.tid; e < 16; e += tm.nt) { fx->ts_rec[k][e] = tu.rec()[e]; fx->ts_coeff[k][e] = tu.q()[e]; }
-    if (tm.tid == 0) { fx->ts_has[k] = fx->has; fx->ts_ssd[k] = fx->ssd; }
+    if (tm.tid == 0) { fx->ts_has[k] = fx->has; fx->ts_ssd[k] = fx->ssd; fx->ts_mask[k] = fx->cg_mask[0]; }
     tsync(tm);
   }
   if (tm.tid == 0) {
     double cost[2];
     for (int k = 0; k < 2; ++k) {
       cost[k] = (double)(unsigned)fx->ts_ssd[k];
-      cost[k] += coeff_cost_serial(T, tb, cfg, sc, fx->ts_coeff[k], 2, 0, j.scan_idx, 0) * cfg->lambda;
+      cost[k] += coeff_cost_serial(T, tb, cfg, sc, fx->ts_coeff[k], 2, 0, j.scan_idx, 0, fx->ts_mask[k]) * cfg->lambda;
     }
     fx->ts_pick = cost[0] <= cost[1] ? 0 : 1;
   }
@@ -1097,7 +1201,7 @@ CTU_FN_NOINLINE int tu_eval(const Team &tm, const CtuTables *T, const SmTables *
   // (the second alternative is still in place when it wins)
   if (pick == 0) {
     for (int e = tm.tid; e < 16; e += tm.nt) { tu.q()[e] = fx->ts_coeff[0][e]; tu.rec()[e] = fx->ts_rec[0][e]; }
-    if (tm.tid == 0) { fx->has = fx->ts_has[0]; fx->ssd = fx->ts_ssd[0]; }
+    if (tm.tid == 0) { fx->has = fx->ts_has[0]; fx->ssd = fx->ts_ssd[0]; fx->cg_mask[0] = fx->ts_mask[0]; fx->cg_mask[1] = 0; }
     tsync(tm);
   }
   return pick;

@@ -44,6 +44,7 @@ struct CtuS {                       // per-CTA scalar state + scratch; shared me
   double ret_cost;
   IntraRefs refs[3];
   int32_t satd[35], sad[35];
+  double rc0[35], rc1[35], rmb[35];   // rough cost of a mode read with state->cabac / the search models, lambda_sqrt * mode bits
   int8_t modes[40];
   double costs[40];
   int32_t n_modes;
@@ -60,6 +61,7 @@ struct CtuS {                       // per-CTA scalar state + scratch; shared me
   // the coefficients of the transform units reconstructed last (the CU whose cost is computed next), per colour
   int16_t stage_y[1024], stage_c[2][256];
   int32_t stage_key[3];             // (xl << 16) | (yl << 8) | depth of the staged unit, -1: none
+  uint64_t stage_mask[3];           // its non-zero coefficient groups
 #if defined(KVZ_CTU_PROF)
   long long prof[PR_N];
 #endif
@@ -183,11 +185,19 @@ CTU_FN_NOINLINE void fill_cu_info(LcuLevel *L, int xl, int yl, int width, const 
 CTU_FN int tu_log2(int depth, int color) { return color == 0 ? 6 - depth : (depth < 4 ? 5 - depth : 2); }
 CTU_FN int stage_key_of(int xl, int yl, int depth) { return (xl << 16) | (yl << 8) | depth; }
 // coefficients of the unit of `color` at (xl, yl, depth) on level L: the staged copy when it is this unit's
-CTU_FN const int16_t *unit_coeffs(const Ctx &c, LcuLevel *L, int color, int xl, int yl, int depth)
+CTU_FN const int16_t *unit_coeffs(const Ctx &c, LcuLevel *L, int color, int xl, int yl, int depth, uint64_t *mask)
 {
-  if (c.S->stage_key[color] == stage_key_of(xl, yl, depth)) return color == 0 ? c.S->stage_y : c.S->stage_c[color - 1];
+  *mask = CTU_NO_MASK;
+  if (c.S->stage_key[color] == stage_key_of(xl, yl, depth)) { *mask = c.S->stage_mask[color]; return color == 0 ? c.S->stage_y : c.S->stage_c[color - 1]; }
   if (color == 0) return &L->coeff_y[zorder(64, xl, yl)];
   return (color == 1 ? L->coeff_u : L->coeff_v) + zorder(32, xl >> 1, yl >> 1);
+}
+
+CTU_FN double coeff_cost_of_unit(const Ctx &c, CabacState *sc, LcuLevel *L, int color, int xl, int yl, int depth, int log2n, int type, int scan)
+{
+  uint64_t mask;
+  const int16_t *co = unit_coeffs(c, L, color, xl, yl, depth, &mask);
+  return coeff_cost_serial(c.T, &c.S->tb, c.cfg, sc, co, log2n, type, scan, 0, mask);
 }
 
 // Runs `ntasks` independent transform-unit jobs whose largest unit has nn coefficients: one warp per job when four
@@ -222,8 +232,12 @@ CTU_FN_NOINLINE void intra_recon_leaf(const Ctx &c, LcuLevel *L, int x, int y, i
   const int first = has_luma ? 0 : 1, last = has_chroma ? 2 : 0;
   if (last < first) return;
   PROF_T0(PR_REFS);
-  for (int col = first; col <= last; ++col)
-    if (!((refs_valid >> col) & 1)) build_refs(c.T, c.cfg, c.W, L, tu_log2(depth, col), col, x, y, &S->refs[col]);
+  {
+    int need = 0;
+    for (int col = first; col <= last; ++col) if (!((refs_valid >> col) & 1)) need |= 1 << col;
+    const int l2[3] = { tu_log2(depth, 0), tu_log2(depth, 1), tu_log2(depth, 2) };
+    if (need) build_refs_multi(c.T, c.cfg, c.W, L, l2, need, x, y, S->refs);
+  }
   PROF_ADD(S, PR_REFS);
   // cur_pu of quantize_tr_residual: the RDOQ context selector reads its depths before the cbf bits change
   const int rdoq_tr_depth = (int)cur_cu->tr_depth - (int)cur_cu->depth + (cur_cu->part_size == SIZE_NxN ? 1 : 0);
@@ -253,6 +267,7 @@ CTU_FN_NOINLINE void intra_recon_leaf(const Ctx &c, LcuLevel *L, int x, int y, i
       const TuFixed *fx = tu.fx();
       S->res[0][col].ssd = fx->ssd; S->res[0][col].has = fx->has; S->res[0][col].tr_skip = ts;
       S->stage_key[col] = stage_key_of(xl, yl, depth);
+      S->stage_mask[col] = (uint64_t)fx->cg_mask[0] | ((uint64_t)fx->cg_mask[1] << 32);
     }
     tsync(tm);
   });
@@ -364,8 +379,8 @@ CTU_FN_NOINLINE double cu_rd_cost_chroma_leaf_of_level(const Ctx &c, LcuLevel *L
   const int width = depth <= 3 ? (64 >> (depth + 1)) : (64 >> depth);
   const int scan = scan_order_intra(pred_cu->mode_chroma, depth);
   double bu = 0, bv = 0;
-  if (cbf_is_set(tr_cu->cbf, depth, 1)) bu = coeff_cost_serial(c.T, &c.S->tb, c.cfg, &c.S->sc, unit_coeffs(c, L, 1, xl, yl, depth), ilog2(width), 2, scan, 0);
-  if (cbf_is_set(tr_cu->cbf, depth, 2)) bv = coeff_cost_serial(c.T, &c.S->tb, c.cfg, &c.S->sc, unit_coeffs(c, L, 2, xl, yl, depth), ilog2(width), 2, scan, 0);
+  if (cbf_is_set(tr_cu->cbf, depth, 1)) bu = coeff_cost_of_unit(c, &c.S->sc, L, 1, xl, yl, depth, ilog2(width), 2, scan);
+  if (cbf_is_set(tr_cu->cbf, depth, 2)) bv = coeff_cost_of_unit(c, &c.S->sc, L, 2, xl, yl, depth, ilog2(width), 2, scan);
   return cu_rd_cost_chroma_leaf(c, L, xl, yl, depth, pred_cu, c.S->ssd[leaf][1] + c.S->ssd[leaf][2], bu, bv);
 }
 
@@ -396,15 +411,15 @@ CTU_FN_NOINLINE double cost_accurate_node(const Ctx &c, LcuLevel *L, int xl, int
   const unsigned luma_ssd = (unsigned)S->ssd[leaf][0];
   if (cb_flag_y) {
     const int scan = scan_order_intra(pred_cu->mode, depth);
-    coeff_bits += coeff_cost_serial(c.T, &c.S->tb, c.cfg, sc, unit_coeffs(c, L, 0, xl, yl, depth), ilog2(width), 0, scan, 0);
+    coeff_bits += coeff_cost_of_unit(c, sc, L, 0, xl, yl, depth, ilog2(width), 0, scan);
   }
   unsigned chroma_ssd = 0;
   if (xl % 8 == 0 && yl % 8 == 0) {
     const int chroma_width = depth <= 3 ? (64 >> (depth + 1)) : (64 >> depth);
     chroma_ssd = (unsigned)S->ssd[leaf][1] + (unsigned)S->ssd[leaf][2];
     const int scan = scan_order_intra(pred_cu->mode_chroma, depth);
-    if (cb_flag_u) coeff_bits += coeff_cost_serial(c.T, &c.S->tb, c.cfg, sc, unit_coeffs(c, L, 1, xl, yl, depth), ilog2(chroma_width), 2, scan, 0);
-    if (cb_flag_v) coeff_bits += coeff_cost_serial(c.T, &c.S->tb, c.cfg, sc, unit_coeffs(c, L, 2, xl, yl, depth), ilog2(chroma_width), 2, scan, 0);
+    if (cb_flag_u) coeff_bits += coeff_cost_of_unit(c, sc, L, 1, xl, yl, depth, ilog2(chroma_width), 2, scan);
+    if (cb_flag_v) coeff_bits += coeff_cost_of_unit(c, sc, L, 2, xl, yl, depth, ilog2(chroma_width), 2, scan);
   }
   const double bits = tr_tree_bits + coeff_bits;
   return luma_ssd * 0.8 + chroma_ssd * 1.5 + bits * c.cfg->lambda;
@@ -504,27 +519,42 @@ CTU_FN void sort_modes(int8_t *modes, double *costs, int length)
   }
 }
 
-// search_intra_rough (ref: search_intra.c:391-530) on the SATD / SAD table of all modes.  Leader only.
+// The per-mode quantities of search_intra_rough (get_cost / get_cost_dual, search_intra.c:89-160, and the mode bits
+// added at :524) for all 35 modes, one mode per thread.
+CTU_FN_NOINLINE void rough_mode_costs(const Ctx &c, int log2w, const int8_t *mpm)
+{
+  CtuS *S = c.S;
+  const CtuConfig *cfg = c.cfg;
+  const bool ts = log2w == 2 && cfg->trskip_enable;
+  for (int mode = CTU_TID; mode < 35; mode += CTU_NT) {
+    // get_cost_dual reads state->cabac, get_cost reads state->search_cabac (search_intra.c:102, 142)
+    for (int k = 0; k < 2; ++k) {
+      const CabacState *cb = k == 0 ? &S->cabac0 : &S->sc;
+      double cost = (double)(unsigned)S->satd[mode];
+      if (ts) {
+        double b = (double)S->tb.ebits[cb->ctx[CTX_TRSKIP_LUMA] ^ 1] * (1.0 / 32768.0) - (double)S->tb.ebits[cb->ctx[CTX_TRSKIP_LUMA] ^ 0] * (1.0 / 32768.0);
+        b += 2.0 * ((double)S->tb.ebits[cb->ctx[CTX_TRSKIP_CHROMA] ^ 1] * (1.0 / 32768.0) - (double)S->tb.ebits[cb->ctx[CTX_TRSKIP_CHROMA] ^ 0] * (1.0 / 32768.0));
+        const double sad_cost = 1.7 * (double)(unsigned)S->sad[mode] + cfg->lambda_sqrt * b;
+        if (sad_cost < cost) cost = sad_cost;
+      }
+      (k == 0 ? S->rc0 : S->rc1)[mode] = cost;
+    }
+    // kvz_luma_mode_bits (the models do not adapt here: update == 0)
+    double bits = 0;
+    const bool in = mode == mpm[0] || mode == mpm[1] || mode == mpm[2];
+    bits += (double)S->tb.ebits[S->sc.ctx[CTX_INTRA_MODE] ^ (in ? 1 : 0)] * (1.0 / 32768.0);
+    if (in) bits += (mode == mpm[0]) ? 1 : 2;
+    else bits += 5;
+    S->rmb[mode] = cfg->lambda_sqrt * bits;
+  }
+  CTU_SYNC();
+}
+
+// search_intra_rough (ref: search_intra.c:391-530) replayed on the per-mode tables.  Leader only.
 CTU_FN_NOINLINE int rough_search_replay(const Ctx &c, int log2w, const int8_t *mpm)
 {
   CtuS *S = c.S;
   const CtuConfig *cfg = c.cfg;
-  const int width = 1 << log2w;
-  const bool ts = width == 4 && cfg->trskip_enable;
-  // get_cost_dual reads state->cabac, get_cost reads state->search_cabac (search_intra.c:102, 142)
-  auto trskip_bits = [&](const CabacState *cb) {
-    double b = (double)c.S->tb.ebits[cb->ctx[CTX_TRSKIP_LUMA] ^ 1] * (1.0 / 32768.0) - (double)c.S->tb.ebits[cb->ctx[CTX_TRSKIP_LUMA] ^ 0] * (1.0 / 32768.0);
-    b += 2.0 * ((double)c.S->tb.ebits[cb->ctx[CTX_TRSKIP_CHROMA] ^ 1] * (1.0 / 32768.0) - (double)c.S->tb.ebits[cb->ctx[CTX_TRSKIP_CHROMA] ^ 0] * (1.0 / 32768.0));
-    return b;
-  };
-  auto cost_of = [&](int mode, const CabacState *cb) -> double {
-    double cost = (double)(unsigned)S->satd[mode];
-    if (ts) {
-      const double sad_cost = 1.7 * (double)(unsigned)S->sad[mode] + cfg->lambda_sqrt * trskip_bits(cb);
-      if (sad_cost < cost) cost = sad_cost;
-    }
-    return cost;
-  };
   int8_t *modes = S->modes;
   double *costs = S->costs;
   int n = 0;
@@ -535,7 +565,7 @@ CTU_FN_NOINLINE int rough_search_replay(const Ctx &c, int log2w, const int8_t *m
   for (int mode = 2; mode <= 34; mode += 2 * offset) {
     for (int i = 0; i < 2; ++i) {
       if (mode + i * offset <= 34) {
-        costs[n] = cost_of(mode + i * offset, &S->cabac0);
+        costs[n] = S->rc0[mode + i * offset];
         modes[n] = (int8_t)(mode + i * offset);
         // the reference keeps min / max as int32 (implicit conversion of the double cost)
         min_cost = imin(min_cost, (int32_t)costs[n]);
@@ -555,7 +585,7 @@ CTU_FN_NOINLINE int rough_search_replay(const Ctx &c, int log2w, const int8_t *m
       const int test[2] = { center - offset, center + offset };
       for (int i = 0; i < 2; ++i) {
         if (test[i] >= 2 && test[i] <= 34) {
-          costs[n] = cost_of(test[i], &S->cabac0);
+          costs[n] = S->rc0[test[i]];
           modes[n] = (int8_t)test[i];
           if (costs[n] < best_cost) { best_cost = costs[n]; best_mode = modes[n]; }
           ++n;
@@ -567,9 +597,9 @@ CTU_FN_NOINLINE int rough_search_replay(const Ctx &c, int log2w, const int8_t *m
   for (int p = 0; p < 5; ++p) {
     bool has = false;
     for (int i = 0; i < n; ++i) if (modes[i] == add_modes[p]) { has = true; break; }
-    if (!has) { costs[n] = cost_of(add_modes[p], &S->sc); modes[n] = (int8_t)add_modes[p]; ++n; }
+    if (!has) { costs[n] = S->rc1[add_modes[p]]; modes[n] = (int8_t)add_modes[p]; ++n; }
   }
-  for (int i = 0; i < n; ++i) costs[i] += cfg->lambda_sqrt * luma_mode_bits(c, modes[i], mpm);
+  for (int i = 0; i < n; ++i) costs[i] += S->rmb[modes[i]];
   return n;
 }
 
@@ -588,13 +618,18 @@ CTU_FN_NOINLINE void search_cu_intra(const Ctx &c, LcuLevel *L, int x, int y, in
   }
   CTU_SYNC();
   PROF_T0(PR_REFS);
-  build_refs(c.T, cfg, c.W, L, log2w, 0, x, y, &S->refs[0]);
+  {
+    // luma for the rough search; the chroma references the CU's reconstruction (and RDO candidates) will need as well
+    const int l2[3] = { log2w, tu_log2(depth, 1), tu_log2(depth, 2) };
+    build_refs_multi(c.T, cfg, c.W, L, l2, ((x & 4) || (y & 4)) ? 1 : 7, x, y, S->refs);
+  }
   PROF_ADD(S, PR_REFS);
   // rough search: SATD (and SAD for 4x4 transform-skip candidates) of every mode, then the reference's selection
   PROF_T0(PR_SATD);
-  rough_costs_all_modes(&S->refs[0], log2w, 0, &c.W->src_y[yl * 64 + xl], 64, 0, 34, S->satd, S->sad, log2w == 2 && cfg->trskip_enable);
+  rough_costs_all_modes(&S->refs[0], (RoughExt *)S->arena, log2w, 0, &c.W->src_y[yl * 64 + xl], 64, S->satd, S->sad, log2w == 2 && cfg->trskip_enable);
   PROF_ADD(S, PR_SATD);
   PROF_T0(PR_REPLAY);
+  rough_mode_costs(c, log2w, S->mpm);
   CTU_LEADER S->n_modes = rough_search_replay(c, log2w, S->mpm);
   CTU_SYNC();
   PROF_ADD(S, PR_REPLAY);
@@ -616,12 +651,6 @@ CTU_FN_NOINLINE void search_cu_intra(const Ctx &c, LcuLevel *L, int x, int y, in
     CTU_SYNC();
     const bool reconstruct_chroma = !((x & 4) || (y & 4));
     const int np = reconstruct_chroma ? 3 : 1;
-    if (reconstruct_chroma) {
-      PROF_T0(PR_REFS);
-      build_refs(c.T, cfg, c.W, L, tu_log2(depth, 1), 1, x, y, &S->refs[1]);
-      build_refs(c.T, cfg, c.W, L, tu_log2(depth, 2), 2, x, y, &S->refs[2]);
-      PROF_ADD(S, PR_REFS);
-    }
     // The candidates (search_intra_trdepth's no-split branch, tr_depth == depth) are independent of each other and so
     // are their colours: every (candidate, colour) pair is one transform-unit job with a private reconstruction.  The
     // temporary CU of the reference (pred_cu: depth = tr_depth = `depth`, NxN at depth 4) only matters through RDOQ's
@@ -644,7 +673,8 @@ CTU_FN_NOINLINE void search_cu_intra(const Ctx &c, LcuLevel *L, int x, int y, in
         TuRes *r = &S->res[cand][col];
         r->ssd = fx->ssd; r->has = fx->has; r->tr_skip = ts;
         // coefficient bits of kvz_cu_rd_cost_luma / _chroma: the search models are not adapted here (update == 0)
-        r->bits = fx->has ? coeff_cost_serial(c.T, &S->tb, cfg, &S->sc, tu.q(), log2n, col ? 2 : 0, j.scan_idx, 0) : 0.0;
+        r->bits = fx->has ? coeff_cost_serial(c.T, &S->tb, cfg, &S->sc, tu.q(), log2n, col ? 2 : 0, j.scan_idx, 0,
+                                              (uint64_t)fx->cg_mask[0] | ((uint64_t)fx->cg_mask[1] << 32)) : 0.0;
       }
       tsync(tm);
     });
@@ -705,10 +735,10 @@ CTU_FN_NOINLINE int search_cu_intra_chroma(const Ctx &c, LcuLevel *L, int x, int
   build_refs(c.T, c.cfg, c.W, L, log2wc, 2, x, y, &S->refs[2]);
   // search_intra_chroma_rough: SATD of the five candidates on U and V (the luma mode is skipped: cost 0)
   const int ci = (yl >> 1) * 32 + (xl >> 1);
-  rough_costs_all_modes(&S->refs[1], log2wc, 1, &c.W->src_u[ci], 32, 0, 34, S->satd, S->sad, false);
+  rough_costs_all_modes(&S->refs[1], (RoughExt *)S->arena, log2wc, 1, &c.W->src_u[ci], 32, S->satd, S->sad, false);
   CTU_LEADER { for (int i = 0; i < 5; ++i) S->ccosts[i] = 0; for (int i = 0; i < 5; ++i) if (S->cmodes[i] != intra_mode) S->ccosts[i] += (double)(unsigned)S->satd[S->cmodes[i]]; }
   CTU_SYNC();
-  rough_costs_all_modes(&S->refs[2], log2wc, 2, &c.W->src_v[ci], 32, 0, 34, S->satd, S->sad, false);
+  rough_costs_all_modes(&S->refs[2], (RoughExt *)S->arena, log2wc, 2, &c.W->src_v[ci], 32, S->satd, S->sad, false);
   CTU_LEADER {
     for (int i = 0; i < 5; ++i) if (S->cmodes[i] != intra_mode) S->ccosts[i] += (double)(unsigned)S->satd[S->cmodes[i]];
     sort_modes(S->cmodes, S->ccosts, 5);
@@ -817,8 +847,8 @@ CTU_FN_NOINLINE void search_ctu(const Ctx &c, int cx, int cy)
           CTU_SYNC();
           fill_cu_info(L, xl, yl, cu_width, cur_cu);
           const bool aligned = x % 8 == 0 && y % 8 == 0;
-          // the references search_cu_intra built (luma always, chroma for the RDO candidates) are still this CU's
-          const int refs_valid = 1 | ((cfg->rdo >= 2 && aligned) ? 6 : 0);
+          // the references search_cu_intra built are still this CU's
+          const int refs_valid = aligned ? 7 : 1;
           if (aligned && cfg->rdo >= 2 && cfg->intra_chroma_search) {
             intra_recon_cu(c, L, x, y, d, cur_cu->mode, -1, NULL, refs_valid);
             PROF_T0(PR_CHROMA);

@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(kThreads, 4) ctu_frame_kernel(const __grid_con
     if (a.dbg_ctx) {
       for (int i = threadIdx.x; i < CTX_COUNT; i += blockDim.x) a.dbg_ctx[(size_t)(cy * a.F.wlcu + cx) * CTX_COUNT + i] = CTU_LD_FRAME(&a.F.row_ctx[cy].ctx[i]);
     }
-    ctu_job(c, &a.F, a.sao_stats + blockIdx.x, cx, cy);
+    // SAO statistics in shared memory (the arena is idle after the search): block-scope atomics, no L1 staleness
+    ctu_job(c, &a.F, reinterpret_cast<SaoStats *>(S->arena), cx, cy);
     __syncthreads();
     if (threadIdx.x == 0) { __threadfence(); st_release(a.sync + 1 + cy, cx + 1); }
   }
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(kThreads, 4) ctu_diag_kernel(const __grid_cons
   if (threadIdx.x == 0) for (int i = 0; i < PR_N; ++i) S->prof[i] = 0;
   __syncthreads();
 #endif
-  ctu_job(c, &a.F, a.sao_stats + blockIdx.x, cx, cy);
+  ctu_job(c, &a.F, reinterpret_cast<SaoStats *>(S->arena), cx, cy);
 }
 
 __global__ void __launch_bounds__(kThreads) ctu_sao_apply_kernel(const __grid_constant__ KernelArgs a)
@@ -119,6 +120,7 @@ struct Slot {
   int state = 0;                 // 0 free, 1 submitted
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
+  cudaEvent_t k0 = nullptr, k1 = nullptr;   // around the search kernel (timing enabled)
   // device
   uint8_t *d_planes = nullptr;   // src | rec | out | dbg, each w*h*3/2
   uint8_t *d_bufs = nullptr;     // hor / ver buffers
@@ -189,6 +191,8 @@ void kvz_cuda_ctu_close(kvz_cuda_ctu_enc *e)
     cudaFreeHost(s.h_src); cudaFreeHost(s.h_out); cudaFreeHost(s.h_dbg); cudaFreeHost(s.h_cu); cudaFreeHost(s.h_coeff); cudaFreeHost(s.h_sao);
     cudaFreeHost(s.h_row_ctx); cudaFreeHost(s.h_dbg_ctx);
     if (s.done) cudaEventDestroy(s.done);
+    if (s.k0) cudaEventDestroy(s.k0);
+    if (s.k1) cudaEventDestroy(s.k1);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
 #if defined(KVZ_CTU_PROF)
@@ -254,6 +258,8 @@ kvz_cuda_ctu_enc *kvz_cuda_ctu_open(const kvz_cuda_ctu_config *cfg, int slots)
   for (Slot &s : e->slots) {
     CTU_CHECK_PTR(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CTU_CHECK_PTR(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    CTU_CHECK_PTR(cudaEventCreate(&s.k0));
+    CTU_CHECK_PTR(cudaEventCreate(&s.k1));
     CTU_CHECK_PTR(cudaMalloc(&s.d_planes, e->plane_bytes * 4));
     CTU_CHECK_PTR(cudaMalloc(&s.d_bufs, buf_bytes));
     CTU_CHECK_PTR(cudaMalloc(&s.d_cu, cu_n * sizeof(CuRec)));
@@ -297,8 +303,9 @@ kvz_cuda_ctu_enc *kvz_cuda_ctu_open(const kvz_cuda_ctu_config *cfg, int slots)
   return e;
 }
 
-int kvz_cuda_ctu_submit(kvz_cuda_ctu_enc *e, const uint8_t *y, const uint8_t *u, const uint8_t *v, int stride_y, int stride_c,
-                        const uint8_t *ctx_init, double lambda, double lambda_sqrt, int qp)
+// common part of the two submit calls: `resident`: the planes are device memory and the results stay on the device
+static int submit_picture(kvz_cuda_ctu_enc *e, const uint8_t *y, const uint8_t *u, const uint8_t *v, int stride_y, int stride_c,
+                          const uint8_t *ctx_init, double lambda, double lambda_sqrt, int qp, bool resident)
 {
   KVZC_ARG(e && y && u && v && ctx_init && stride_y >= e->cfg.width && stride_c >= e->cfg.width / 2);
   int id = -1;
@@ -310,19 +317,27 @@ int kvz_cuda_ctu_submit(kvz_cuda_ctu_enc *e, const uint8_t *y, const uint8_t *u,
   Slot &s = e->slots[id];
   const int W = e->cfg.width, H = e->cfg.height;
   const size_t ysz = (size_t)W * H, csz = ysz / 4;
-  for (int r = 0; r < H; ++r) memcpy(s.h_src + (size_t)r * W, y + (size_t)r * stride_y, W);
-  for (int r = 0; r < H / 2; ++r) {
-    memcpy(s.h_src + ysz + (size_t)r * (W / 2), u + (size_t)r * stride_c, W / 2);
-    memcpy(s.h_src + ysz + csz + (size_t)r * (W / 2), v + (size_t)r * stride_c, W / 2);
+  cudaStream_t st = s.stream;
+  uint8_t *d_src = const_cast<uint8_t *>(s.args.F.src_y);
+  if (resident) {
+    KVZC_CHECK(cudaMemcpy2DAsync(d_src, W, y, stride_y, W, H, cudaMemcpyDeviceToDevice, st));
+    KVZC_CHECK(cudaMemcpy2DAsync(d_src + ysz, W / 2, u, stride_c, W / 2, H / 2, cudaMemcpyDeviceToDevice, st));
+    KVZC_CHECK(cudaMemcpy2DAsync(d_src + ysz + csz, W / 2, v, stride_c, W / 2, H / 2, cudaMemcpyDeviceToDevice, st));
+  } else {
+    for (int r = 0; r < H; ++r) memcpy(s.h_src + (size_t)r * W, y + (size_t)r * stride_y, W);
+    for (int r = 0; r < H / 2; ++r) {
+      memcpy(s.h_src + ysz + (size_t)r * (W / 2), u + (size_t)r * stride_c, W / 2);
+      memcpy(s.h_src + ysz + csz + (size_t)r * (W / 2), v + (size_t)r * stride_c, W / 2);
+    }
+    KVZC_CHECK(cudaMemcpyAsync(d_src, s.h_src, e->plane_bytes, cudaMemcpyHostToDevice, st));
   }
   for (int r = 0; r < e->hl; ++r) { memcpy(s.h_row_ctx[r].ctx, ctx_init, CTX_COUNT); s.h_row_ctx[r].update = 0; memset(s.h_row_ctx[r].pad, 0, sizeof(s.h_row_ctx[r].pad)); }
   s.args.cfg = e->cfg;
   s.args.cfg.lambda = lambda; s.args.cfg.lambda_sqrt = lambda_sqrt; s.args.cfg.qp = qp;
-  cudaStream_t st = s.stream;
-  KVZC_CHECK(cudaMemcpyAsync((void *)s.args.F.src_y, s.h_src, e->plane_bytes, cudaMemcpyHostToDevice, st));
   KVZC_CHECK(cudaMemcpyAsync(s.d_row_ctx, s.h_row_ctx, e->hl * sizeof(CabacState), cudaMemcpyHostToDevice, st));
   KVZC_CHECK(cudaMemsetAsync(s.d_cu, 0, (size_t)(e->wl * 16) * (e->hl * 16) * sizeof(CuRec), st));
   KVZC_CHECK(cudaMemsetAsync(s.d_sync, 0, (size_t)(e->hl + 1) * sizeof(int), st));
+  KVZC_CHECK(cudaEventRecord(s.k0, st));
   if (e->diag_launches) {
     for (int d = 0; d < e->wl + 2 * (e->hl - 1); ++d) {
       const int lo = d - (e->wl - 1) > 0 ? (d - (e->wl - 1) + 1) / 2 : 0, hi = d / 2 < e->hl - 1 ? d / 2 : e->hl - 1;
@@ -336,21 +351,53 @@ int kvz_cuda_ctu_submit(kvz_cuda_ctu_enc *e, const uint8_t *y, const uint8_t *u,
     e->launches.fetch_add(1, std::memory_order_relaxed);
     kvzc::g_launches.fetch_add(1, std::memory_order_relaxed);
   }
+  KVZC_CHECK(cudaEventRecord(s.k1, st));
   ctu_sao_apply_kernel<<<e->wl * e->hl, kThreads, 0, st>>>(s.args);
   e->launches.fetch_add(1, std::memory_order_relaxed);
   kvzc::g_launches.fetch_add(1, std::memory_order_relaxed);
   KVZC_CHECK(cudaGetLastError());
-  const size_t nctu = (size_t)e->wl * e->hl;
-  KVZC_CHECK(cudaMemcpyAsync(s.h_cu, s.d_cu, (size_t)(e->wl * 16) * (e->hl * 16) * sizeof(CuRec), cudaMemcpyDeviceToHost, st));
-  KVZC_CHECK(cudaMemcpyAsync(s.h_coeff, s.d_coeff, nctu * 6144 * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
-  KVZC_CHECK(cudaMemcpyAsync(s.h_sao, s.d_sao, nctu * 2 * sizeof(SaoRec), cudaMemcpyDeviceToHost, st));
-  KVZC_CHECK(cudaMemcpyAsync(s.h_out, s.args.F.out_y, e->plane_bytes, cudaMemcpyDeviceToHost, st));
-  if (e->debug) {
-    KVZC_CHECK(cudaMemcpyAsync(s.h_dbg_ctx, s.d_dbg_ctx, nctu * CTX_COUNT, cudaMemcpyDeviceToHost, st));
-    KVZC_CHECK(cudaMemcpyAsync(s.h_dbg, s.args.F.dbg_y, e->plane_bytes, cudaMemcpyDeviceToHost, st));
+  if (!resident) {
+    const size_t nctu = (size_t)e->wl * e->hl;
+    KVZC_CHECK(cudaMemcpyAsync(s.h_cu, s.d_cu, (size_t)(e->wl * 16) * (e->hl * 16) * sizeof(CuRec), cudaMemcpyDeviceToHost, st));
+    KVZC_CHECK(cudaMemcpyAsync(s.h_coeff, s.d_coeff, nctu * 6144 * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    KVZC_CHECK(cudaMemcpyAsync(s.h_sao, s.d_sao, nctu * 2 * sizeof(SaoRec), cudaMemcpyDeviceToHost, st));
+    KVZC_CHECK(cudaMemcpyAsync(s.h_out, s.args.F.out_y, e->plane_bytes, cudaMemcpyDeviceToHost, st));
+    if (e->debug) {
+      KVZC_CHECK(cudaMemcpyAsync(s.h_dbg_ctx, s.d_dbg_ctx, nctu * CTX_COUNT, cudaMemcpyDeviceToHost, st));
+      KVZC_CHECK(cudaMemcpyAsync(s.h_dbg, s.args.F.dbg_y, e->plane_bytes, cudaMemcpyDeviceToHost, st));
+    }
   }
   KVZC_CHECK(cudaEventRecord(s.done, st));
   return id;
+}
+
+int kvz_cuda_ctu_submit(kvz_cuda_ctu_enc *e, const uint8_t *y, const uint8_t *u, const uint8_t *v, int stride_y, int stride_c,
+                        const uint8_t *ctx_init, double lambda, double lambda_sqrt, int qp)
+{
+  return submit_picture(e, y, u, v, stride_y, stride_c, ctx_init, lambda, lambda_sqrt, qp, false);
+}
+
+int kvz_cuda_ctu_submit_device(kvz_cuda_ctu_enc *e, const uint8_t *d_y, const uint8_t *d_u, const uint8_t *d_v, int stride_y, int stride_c,
+                               const uint8_t *ctx_init, double lambda, double lambda_sqrt, int qp)
+{
+  return submit_picture(e, d_y, d_u, d_v, stride_y, stride_c, ctx_init, lambda, lambda_sqrt, qp, true);
+}
+
+int kvz_cuda_ctu_wait_device(kvz_cuda_ctu_enc *e, int slot, kvz_cuda_ctu_device_result *out)
+{
+  KVZC_ARG(e && out && slot >= 0 && slot < (int)e->slots.size() && e->slots[slot].state == 1);
+  Slot &s = e->slots[slot];
+  KVZC_CHECK(cudaEventSynchronize(s.done));
+  memset(out, 0, sizeof(*out));
+  out->cu = (const kvz_cuda_ctu_cu *)s.d_cu;
+  out->coeff = s.d_coeff;
+  out->sao = (const kvz_cuda_ctu_sao *)s.d_sao;
+  out->rec = s.args.F.out_y;
+  out->cu_stride = e->wl * 16;
+  out->width_in_lcu = e->wl; out->height_in_lcu = e->hl;
+  float ms = 0;
+  if (cudaEventElapsedTime(&ms, s.k0, s.k1) == cudaSuccess) out->search_kernel_ms = ms;
+  return 0;
 }
 
 int kvz_cuda_ctu_wait(kvz_cuda_ctu_enc *e, int slot, kvz_cuda_ctu_result *out)

@@ -139,6 +139,23 @@ int kvz_cuda_ctu_wait(kvz_cuda_ctu_enc *e, int slot, kvz_cuda_ctu_result *out)
   return 0;
 }
 
+// "device" memory of the host build is host memory
+int kvz_cuda_ctu_submit_device(kvz_cuda_ctu_enc *e, const uint8_t *y, const uint8_t *u, const uint8_t *v, int stride_y, int stride_c,
+                               const uint8_t *ctx_init, double lambda, double lambda_sqrt, int qp)
+{
+  return kvz_cuda_ctu_submit(e, y, u, v, stride_y, stride_c, ctx_init, lambda, lambda_sqrt, qp);
+}
+int kvz_cuda_ctu_wait_device(kvz_cuda_ctu_enc *e, int slot, kvz_cuda_ctu_device_result *out)
+{
+  if (slot < 0 || slot >= (int)e->slots.size() || !e->slots[slot].busy) return -1;
+  Slot &s = e->slots[slot];
+  memset(out, 0, sizeof(*out));
+  out->cu = (const kvz_cuda_ctu_cu *)s.cu.data(); out->coeff = s.coeff.data(); out->sao = (const kvz_cuda_ctu_sao *)s.sao.data();
+  out->rec = s.out[0].data();
+  out->cu_stride = s.F.cu_stride; out->width_in_lcu = s.F.wlcu; out->height_in_lcu = s.F.hlcu;
+  return 0;
+}
+
 void kvz_cuda_ctu_release(kvz_cuda_ctu_enc *e, int slot)
 {
   {

@@ -35,7 +35,7 @@ def _need(*names):
 def _hostsim():
     if not os.path.exists(HOSTSIM):
         src = os.path.join(ROOT, "tests", "hostsim", "ctu_hostsim.cpp")
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unused-function",
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unused-function", "-Wno-unknown-pragmas",
                                "-o", HOSTSIM, src])
     return HOSTSIM
 
