@@ -799,10 +799,15 @@ CTU_FN_NOINLINE void search_ctu(const Ctx &c, int cx, int cy)
   for (;;) {
     SearchFrame *F = &S->fr[d];
     LcuLevel *L = &c.W->lv[d];
+    // Every thread takes its copy of the frame's state, THEN the barrier: the leader changes that state below, and a
+    // thread that read it late would take another branch than the others (all control flow here must be uniform).
     const int x = F->x, y = F->y;
+    const int stage = F->stage;
+    const bool descend = F->do_children && F->child < 4 && F->split_cost < F->cost;
+    const int next_child = F->child;
+    CTU_SYNC();
     const int xl = x & 63, yl = y & 63;
     const int cu_width = 64 >> d;
-    const int stage = F->stage;
     if (stage == 0) {
       // ---------------- entry: this depth's own mode decision
       if (x >= cfg->width || y >= cfg->height) {
@@ -905,8 +910,8 @@ CTU_FN_NOINLINE void search_ctu(const Ctx &c, int cx, int cy)
     }
     if (stage == 1) {
       // ---------------- children, one at a time, while the split is still cheaper
-      if (F->do_children && F->child < 4 && F->split_cost < F->cost) {
-        const int k = F->child, half = cu_width / 2;
+      if (descend) {
+        const int k = next_child, half = cu_width / 2;
         CTU_LEADER {
           F->child = k + 1;
           S->fr[d + 1].x = x + (k & 1) * half;
@@ -925,9 +930,15 @@ CTU_FN_NOINLINE void search_ctu(const Ctx &c, int cx, int cy)
       // ---------------- after the children: combined CU, then split / no split
       CuRec *cur_cu = cu_at(L, xl, yl);
       const bool inside = x + cu_width <= cfg->width && y + cu_width <= cfg->height;
+      bool combine = false;
       if (cur_cu->type == CU_NOTSET && d < 4 && inside && cfg->combine_intra_cus) {
+        const CuRec *cu_d1 = cu_at(&c.W->lv[d + 1], xl, yl);
+        combine = cu_d1->type == CU_INTRA && cu_d1->depth == d + 1;
+      }
+      CTU_SYNC();       // (the decision is taken by everybody before the leader rewrites the record)
+      if (combine) {
         CuRec *cu_d1 = cu_at(&c.W->lv[d + 1], xl, yl);
-        if (cu_d1->type == CU_INTRA && cu_d1->depth == d + 1) {
+        {
           CTU_LEADER {
             S->tmp = S->sc;
             S->sc = F->pre;
@@ -955,7 +966,9 @@ CTU_FN_NOINLINE void search_ctu(const Ctx &c, int cx, int cy)
           CTU_SYNC();
         }
       }
-      if (F->split_cost < F->cost) {
+      const bool split_wins = F->split_cost < F->cost;
+      CTU_SYNC();
+      if (split_wins) {
         CTU_LEADER F->cost = F->split_cost;
         CTU_SYNC();
         work_tree_copy_up(c, xl, yl, d);
