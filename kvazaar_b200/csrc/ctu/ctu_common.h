@@ -112,12 +112,18 @@ CTU_FN void cbf_set_conditionally(uint16_t *cbf, const uint16_t child[3], int de
   if (cbf_is_set(child[0], depth + 1, plane) || cbf_is_set(child[1], depth + 1, plane) || cbf_is_set(child[2], depth + 1, plane)) cbf_set(cbf, depth, plane);
 }
 
-// One level of the work tree (ref: lcu_t, src/cu.h:299-337, and work_tree[], src/search.c:1220-1224).  The source
-// pixels and the border references are the same on every level and live in CtuWork.
-struct LcuLevel {
-  CuRec cu[17 * 17 + 1];
+// One level of the work tree (ref: lcu_t, src/cu.h:299-337, and work_tree[], src/search.c:1220-1224).  The CU records
+// are what the serial decision code reads all the time: they live in shared memory (CtuS); the pixel and coefficient
+// planes of the level stay in global memory (LcuStore) and are only touched by data-parallel phases.  The source pixels
+// and the border references are the same on every level and live in CtuWork.
+struct LcuStore {
   uint8_t rec_y[64 * 64], rec_u[32 * 32], rec_v[32 * 32];
   int16_t coeff_y[64 * 64], coeff_u[32 * 32], coeff_v[32 * 32];
+};
+struct LcuLevel {
+  CuRec cu[17 * 17 + 1];
+  uint8_t *rec_y, *rec_u, *rec_v;
+  int16_t *coeff_y, *coeff_u, *coeff_v;
 };
 CTU_FN CuRec *cu_at(LcuLevel *L, int x_px, int y_px) { return &L->cu[18 + (x_px >> 2) + (y_px >> 2) * 17]; }   // LCU_GET_CU_AT_PX
 CTU_FN CuRec *cu_top_right(LcuLevel *L) { return &L->cu[17 * 17]; }

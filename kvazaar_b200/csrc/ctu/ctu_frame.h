@@ -31,13 +31,22 @@ CTU_FN_NOINLINE void ctu_load(const Ctx &c, const FrameDev *F, int cx, int cy)
 {
   const CtuConfig *cfg = c.cfg;
   CtuWork *W = c.W;
-  LcuLevel *L0 = &W->lv[0];
+  LcuLevel *L0 = &c.S->lv[0];
   const int x = cx * 64, y = cy * 64;
   const int Wd = cfg->width, H = cfg->height;
-  // FILL(*lcu, 0)
+  // FILL(*lcu, 0) for every level of the work tree (work_tree[depth] = work_tree[0] below only differs in the border
+  // CU records), and the levels' plane pointers
   {
-    uint32_t *p = (uint32_t *)L0;
-    for (int i = CTU_TID; i < (int)(sizeof(LcuLevel) / 4); i += CTU_NT) p[i] = 0;
+    for (int d = CTU_TID; d < 5; d += CTU_NT) {
+      LcuLevel *L = &c.S->lv[d];
+      LcuStore *st = &W->store[d];
+      L->rec_y = st->rec_y; L->rec_u = st->rec_u; L->rec_v = st->rec_v;
+      L->coeff_y = st->coeff_y; L->coeff_u = st->coeff_u; L->coeff_v = st->coeff_v;
+    }
+    uint32_t *p = (uint32_t *)W->store;
+    for (int i = CTU_TID; i < (int)(5 * sizeof(LcuStore) / 4); i += CTU_NT) p[i] = 0;
+    uint32_t *q = (uint32_t *)L0->cu;
+    for (int i = CTU_TID; i < (int)(sizeof(L0->cu) / 4); i += CTU_NT) q[i] = 0;
     for (int i = CTU_TID; i < 4096; i += CTU_NT) W->src_y[i] = 0;
     for (int i = CTU_TID; i < 1024; i += CTU_NT) { W->src_u[i] = 0; W->src_v[i] = 0; }
     for (int i = CTU_TID; i < 100; i += CTU_NT) { W->top_y[i] = 0; W->left_y[i] = 0; }
@@ -89,9 +98,9 @@ CTU_FN_NOINLINE void ctu_load(const Ctx &c, const FrameDev *F, int cx, int cy)
   CTU_SYNC();
   // work_tree[depth] = work_tree[0]
   for (int d = 1; d <= 4; ++d) {
-    const uint32_t *s = (const uint32_t *)L0;
-    uint32_t *p = (uint32_t *)&W->lv[d];
-    for (int i = CTU_TID; i < (int)(sizeof(LcuLevel) / 4); i += CTU_NT) p[i] = s[i];
+    const uint32_t *s = (const uint32_t *)L0->cu;
+    uint32_t *p = (uint32_t *)c.S->lv[d].cu;
+    for (int i = CTU_TID; i < (int)(sizeof(L0->cu) / 4); i += CTU_NT) p[i] = s[i];
   }
   // the models the search starts from
   for (int i = CTU_TID; i < (int)(sizeof(CabacState) / 4); i += CTU_NT) ((uint32_t *)&c.S->cabac0)[i] = CTU_LD_FRAME((const uint32_t *)&F->row_ctx[cy] + i);
@@ -104,7 +113,7 @@ CTU_FN_NOINLINE void ctu_load(const Ctx &c, const FrameDev *F, int cx, int cy)
 CTU_FN_NOINLINE void ctu_store(const Ctx &c, const FrameDev *F, int cx, int cy)
 {
   const CtuConfig *cfg = c.cfg;
-  LcuLevel *L0 = &c.W->lv[0];
+  LcuLevel *L0 = &c.S->lv[0];
   const int x = cx * 64, y = cy * 64, Wd = cfg->width, H = cfg->height;
   const int x_max = imin(x + 64, Wd) - x, y_max = imin(y + 64, H) - y;
   for (int e = CTU_TID; e < 256; e += CTU_NT) {
@@ -517,7 +526,7 @@ CTU_FN_NOINLINE void enc_transform_leaf(const EncTrack &e, int x, int y, int dep
   e.cs->update = 1;
   if (cb_y) {
     const int scan = scan_order_intra(cur_pu->mode, depth);
-    coeff_cost_serial(c.T, &c.S->tb, c.cfg, e.cs, e.L0->coeff_y + zorder(64, x & 63, y & 63), ilog2(width), 0, scan, cur_pu->tr_skip);
+    coeff_cost_serial(&c.S->tb, &c.S->tb, c.cfg, e.cs, e.L0->coeff_y + zorder(64, x & 63, y & 63), ilog2(width), 0, scan, cur_pu->tr_skip);
   }
   int xx = x, yy = y;
   if (depth == 4) {
@@ -529,8 +538,8 @@ CTU_FN_NOINLINE void enc_transform_leaf(const EncTrack &e, int x, int y, int dep
   if (cu_u || cu_v) {
     const int scan = scan_order_intra(cur_pu->mode_chroma, depth);
     const int zi = zorder(32, (xx >> 1) & 31, (yy >> 1) & 31);
-    if (cu_u) coeff_cost_serial(c.T, &c.S->tb, c.cfg, e.cs, e.L0->coeff_u + zi, ilog2(width_c), 2, scan, 0);
-    if (cu_v) coeff_cost_serial(c.T, &c.S->tb, c.cfg, e.cs, e.L0->coeff_v + zi, ilog2(width_c), 2, scan, 0);
+    if (cu_u) coeff_cost_serial(&c.S->tb, &c.S->tb, c.cfg, e.cs, e.L0->coeff_u + zi, ilog2(width_c), 2, scan, 0);
+    if (cu_v) coeff_cost_serial(&c.S->tb, &c.S->tb, c.cfg, e.cs, e.L0->coeff_v + zi, ilog2(width_c), 2, scan, 0);
   }
 }
 CTU_FN void enc_transform_tree(const EncTrack &e, int x, int y, int depth)
@@ -626,7 +635,7 @@ CTU_FN_NOINLINE void ctu_track_models(const Ctx &c, const FrameDev *F, int cx, i
         enc_bin(&c.S->tb, cs.ctx, CTX_SAO_TYPE, sc->type != 0);
       }
     }
-    EncTrack e = { &c, &c.W->lv[0], cx * 64, cy * 64, &cs };
+    EncTrack e = { &c, &c.S->lv[0], cx * 64, cy * 64, &cs };
     enc_coding_tree(e, cx * 64, cy * 64);
     cs.update = 0;
     F->row_ctx[cy] = cs;

@@ -24,7 +24,7 @@ namespace kvzctu {
 
 // ------------------------------------------------------------------------------------------------ work memory
 struct CtuWork {                    // per resident CTU, global memory (L2 resident)
-  LcuLevel lv[5];
+  LcuStore store[5];
   uint8_t src_y[64 * 64], src_u[32 * 32], src_v[32 * 32];       // lcu->ref
   // border references from the neighbouring CTUs, index 0 = top-left corner sample (lcu->top_ref / left_ref)
   uint8_t top_y[100], top_u[52], top_v[52], left_y[100], left_u[52], left_v[52];
@@ -54,11 +54,40 @@ CTU_FN void tsync(const Team &) {}
 #define CTU_WARP 0
 #endif
 
-// entropy tables of the CABAC estimators, copied to shared memory once per CTA (hot in every serial section)
+// All tables the search reads, compact, in shared memory (copied from the host-built CtuTables once per CTU): the serial
+// sections (cost walks, RDOQ's chain) look them up constantly, and a global-memory table costs an L2 round trip per
+// dependent lookup (with 200 KB of the SM given to shared memory there is next to no L1).
 struct SmTables {
   int32_t ebits[128];
   uint8_t next_mps[128], next_lps[128];
+  uint16_t scan4[3][16], scan8[3][64], scan16[256], scan32[1024];     // 16x16 and 32x32 always scan diagonally
+  uint8_t scan_cg[3][4][64];
+  uint8_t ref_top[16][16], ref_left[16][16];
+  int8_t tr4[16], tr8[64], tr16[256], tr32[1024], dst4[16];
+  uint8_t sig_ctx4[16], group_idx[32], min_in_group[10];
+  uint8_t pad[6];
 };
+CTU_FN const uint16_t *sm_scan(const SmTables *t, int scan_idx, int l)      // l = log2n - 2
+{
+  return l == 0 ? t->scan4[scan_idx] : (l == 1 ? t->scan8[scan_idx] : (l == 2 ? t->scan16 : t->scan32));
+}
+CTU_FN const int8_t *sm_tr(const SmTables *t, int l) { return l == 0 ? t->tr4 : (l == 1 ? t->tr8 : (l == 2 ? t->tr16 : t->tr32)); }
+// every thread of the CTA
+CTU_FN void sm_tables_load(SmTables *d, const CtuTables *g)
+{
+  for (int i = CTU_TID; i < 1024; i += CTU_NT) {
+    d->scan32[i] = g->scan[0][3][i]; d->tr32[i] = g->tr[3][i];
+    if (i < 256) { d->scan16[i] = g->scan[0][2][i]; d->tr16[i] = g->tr[2][i]; ((uint8_t *)d->ref_top)[i] = ((const uint8_t *)g->ref_top)[i]; ((uint8_t *)d->ref_left)[i] = ((const uint8_t *)g->ref_left)[i]; }
+    if (i < 768) ((uint8_t *)d->scan_cg)[i] = ((const uint8_t *)g->scan_cg)[i];
+    if (i < 192) d->scan8[i / 64][i % 64] = g->scan[i / 64][1][i % 64];
+    if (i < 128) { d->ebits[i] = g->ebits[i]; d->next_mps[i] = g->next_mps[i]; d->next_lps[i] = g->next_lps[i]; }
+    if (i < 64) d->tr8[i] = g->tr[1][i];
+    if (i < 48) d->scan4[i / 16][i % 16] = g->scan[i / 16][0][i % 16];
+    if (i < 32) d->group_idx[i] = g->group_idx[i];
+    if (i < 16) { d->tr4[i] = g->tr[0][i]; d->dst4[i] = g->dst4[i]; d->sig_ctx4[i] = g->sig_ctx4[i]; }
+    if (i < 10) d->min_in_group[i] = g->min_in_group[i];
+  }
+}
 
 // Scratch of one transform-unit evaluation, carved out of the team's part of the arena for nn = n*n coefficients.
 struct TuFixed {
@@ -137,7 +166,7 @@ CTU_FN Plane plane_of(CtuWork *W, LcuLevel *L, int color)
 // coordinates), into r[colour], followed by the [1 2 1] smoothing (done eagerly: the reference's lazy flag only saves
 // time; chroma never reads it) and the DC sum.  log2w[colour]: the block sizes.  One pass over all colours: the border
 // reads of the three planes overlap instead of queueing behind each other.
-CTU_FN_NOINLINE void build_refs_multi(const CtuTables *T, const CtuConfig *cfg, CtuWork *W, LcuLevel *L, const int log2w[3], int mask, int x, int y, IntraRefs *r)
+CTU_FN_NOINLINE void build_refs_multi(const SmTables *T, const CtuConfig *cfg, CtuWork *W, LcuLevel *L, const int log2w[3], int mask, int x, int y, IntraRefs *r)
 {
   const int lx = x & 63, ly = y & 63;
   const bool has_left = x > 0, has_top = y > 0, inner = has_left && has_top;
@@ -201,7 +230,7 @@ CTU_FN_NOINLINE void build_refs_multi(const CtuTables *T, const CtuConfig *cfg, 
   }
   CTU_SYNC();
 }
-CTU_FN void build_refs(const CtuTables *T, const CtuConfig *cfg, CtuWork *W, LcuLevel *L, int log2w, int color, int x, int y, IntraRefs *r)
+CTU_FN void build_refs(const SmTables *T, const CtuConfig *cfg, CtuWork *W, LcuLevel *L, int log2w, int color, int x, int y, IntraRefs *r)
 {
   int l[3] = { log2w, log2w, log2w };
   build_refs_multi(T, cfg, W, L, l, 1 << color, x, y, r - color);
@@ -465,12 +494,12 @@ CTU_FN int quant_scale(int r) { const int t[6] = { 26214, 23302, 20560, 18396, 1
 CTU_FN int inv_quant_scale(int r) { const int t[6] = { 40, 45, 51, 57, 64, 72 }; return t[r]; }
 
 // sign-bit hiding of kvz_quant for one coefficient group (ref: quant-generic.c:84-176)
-CTU_FN void quant_sign_hide_group(const CtuTables *T, const int16_t *coef, int16_t *q, const int32_t *delta_u, const int32_t *cg_nz,
+CTU_FN void quant_sign_hide_group(const SmTables *T, const int16_t *coef, int16_t *q, const int32_t *delta_u, const int32_t *cg_nz,
                                   int num_cg, int g, int scan_idx, int log2n)
 {
   bool last_cg = true;
   for (int h = g + 1; h < num_cg; ++h) if (cg_nz[h]) { last_cg = false; break; }
-  const uint16_t *pos = &T->scan[scan_idx][log2n - 2][g * 16];
+  const uint16_t *pos = &sm_scan(T, scan_idx, log2n - 2)[g * 16];
   int first_nz = 16, last_nz = -1, abssum = 0;
   for (int k = 15; k >= 0; --k) if (q[pos[k]]) { last_nz = k; break; }
   for (int k = 0; k < 16; ++k) if (q[pos[k]]) { first_nz = k; break; }
@@ -497,7 +526,7 @@ CTU_FN void quant_sign_hide_group(const CtuTables *T, const int16_t *coef, int16
 }
 
 // kvz_quant: b -> q (intra slice: rounding offset 171)
-CTU_FN_NOINLINE void quant_block(const Team &tm, const CtuTables *T, const CtuConfig *cfg, const TuS &tu, int n, int type, int scan_idx)
+CTU_FN_NOINLINE void quant_block(const Team &tm, const SmTables *T, const CtuConfig *cfg, const TuS &tu, int n, int type, int scan_idx)
 {
   const int log2n = ilog2(n);
   const int qp_scaled = scaled_qp(type, cfg->qp);
@@ -528,7 +557,7 @@ CTU_FN_NOINLINE void quant_block(const Team &tm, const CtuTables *T, const CtuCo
   int32_t *cg_nz = tu.cg_nzflag();
   for (int g = tm.tid; g < num_cg; g += tm.nt) {
     int nz = 0;
-    for (int k = 0; k < 16; ++k) nz |= q[T->scan[scan_idx][log2n - 2][g * 16 + k]] != 0;
+    for (int k = 0; k < 16; ++k) nz |= q[sm_scan(T, scan_idx, log2n - 2)[g * 16 + k]] != 0;
     cg_nz[g] = nz;
   }
   tsync(tm);
@@ -585,7 +614,7 @@ CTU_FN int rdoq_level_rate(const RdoqModels &m, uint32_t abs_level, int ctx_one,
 }
 
 // context increment of sig_coeff_flag (ref: context.c:366-397)
-CTU_FN int sig_ctx_inc(const CtuTables *T, int pattern, int scan_idx, int px, int py, int log2n, int type)
+CTU_FN int sig_ctx_inc(const SmTables *T, int pattern, int scan_idx, int px, int py, int log2n, int type)
 {
   if (px + py == 0) return 0;
   if (log2n == 2) return T->sig_ctx4[4 * py + px];
@@ -661,7 +690,7 @@ CTU_FN int team_sum(int v) { return v; }
 
 // kvz_rdoq for one TU, executed by one team (the first warp): coef = tu->b, levels to tu->q.  `cabac` = the models of
 // state->cabac (NOT the search copy: rdo.c:665).  type 0 luma / 2 chroma; tr_depth as in quant-generic.c:237-238.
-CTU_FN_NOINLINE void rdoq_team(const CtuTables *T, const SmTables *tb, const CtuConfig *cfg, const uint8_t *cabac, const TuS &tu, int log2n, int type,
+CTU_FN_NOINLINE void rdoq_team(const SmTables *T, const SmTables *tb, const CtuConfig *cfg, const uint8_t *cabac, const TuS &tu, int log2n, int type,
                       int scan_idx, int tr_depth, int lane)
 {
   const int16_t *coef = tu.b();
@@ -696,7 +725,7 @@ CTU_FN_NOINLINE void rdoq_team(const CtuTables *T, const SmTables *tb, const Ctu
   m.root_cbf = cabac[CTX_ROOT_CBF];
   auto sig_cost_of = [&](uint8_t code) { return (code >> 6) == 2 ? 0.0 : lambda * rq_ebits(m.sig[code & 63], code >> 6); };
   auto level0_cost = [&](int blk) { const double e = (double)imin(iabs((int)coef[blk]) * qc, 0x7FFFFFFF - half); return e * e * err_scale; };
-  const uint16_t *blk_of = T->scan[scan_idx][log2n - 2];
+  const uint16_t *blk_of = sm_scan(T, scan_idx, log2n - 2);
 
   int my_last = -1;
   for (int sp = lane; sp < nn; sp += CTU_TEAM_N) {
@@ -964,7 +993,7 @@ CTU_FN int coeff_remain_bits(int symbol, int rice)
 // kept when `update` is set (ref: rdo.c:223-264).  Leader only.  The cost estimate codes tr_skip as 0 (rdo.c:251-258);
 // the tracker of the real coder's models passes the TU's flag.
 #define CTU_NO_MASK 0xFFFFFFFFFFFFFFFFull       // (no unit has all 64 groups... a full 32x32 unit does: then the scan below is harmless)
-CTU_FN_NOINLINE double coeff_cost_serial(const CtuTables *T, const SmTables *tb, const CtuConfig *cfg, CabacState *c, const int16_t *coeff, int log2n, int type, int scan_idx, int tr_skip,
+CTU_FN_NOINLINE double coeff_cost_serial(const SmTables *T, const SmTables *tb, const CtuConfig *cfg, CabacState *c, const int16_t *coeff, int log2n, int type, int scan_idx, int tr_skip,
                                          uint64_t known_cg_mask = CTU_NO_MASK)
 {
   const int n = 1 << log2n, side = n >> 2, ncg = side * side;
@@ -980,7 +1009,7 @@ CTU_FN_NOINLINE double coeff_cost_serial(const CtuTables *T, const SmTables *tb,
     if (any) cg_flags |= 1ull << g;
   }
   if (!cg_flags) return 0.0;
-  const uint16_t *scan = T->scan[scan_idx][log2n - 2];
+  const uint16_t *scan = sm_scan(T, scan_idx, log2n - 2);
   const uint8_t *scan_cg = T->scan_cg[scan_idx][log2n - 2];
   int cg_last = ncg - 1;
   while (!((cg_flags >> scan_cg[cg_last]) & 1)) --cg_last;
@@ -1092,7 +1121,7 @@ struct TuJob {
   int rdoq_tr_depth;        // context selector of RDOQ's cbf cost (quant-generic.c:237-238)
 };
 
-CTU_FN_NOINLINE void tu_core(const Team &tm, const CtuTables *T, const SmTables *tb, const CtuConfig *cfg, const uint8_t *cabac0, const TuS &tu,
+CTU_FN_NOINLINE void tu_core(const Team &tm, const SmTables *T, const SmTables *tb, const CtuConfig *cfg, const uint8_t *cabac0, const TuS &tu,
                              const TuJob &j, bool use_trskip)
 {
   const int log2n = j.log2n, n = 1 << log2n, nn = n * n;
@@ -1110,7 +1139,7 @@ CTU_FN_NOINLINE void tu_core(const Team &tm, const CtuTables *T, const SmTables 
   if (tm.tid == 0) { fx->has = 0; fx->ssd = 0; fx->cg_mask[0] = 0; fx->cg_mask[1] = 0; }
   tsync(tm);
   const bool use_dst = (n == 4 && color == 0);
-  const int8_t *M = use_dst ? T->dst4 : T->tr[log2n - 2];
+  const int8_t *M = use_dst ? T->dst4 : sm_tr(T, log2n - 2);
   if (use_trskip) {
     for (int e = tm.tid; e < nn; e += tm.nt) b[e] = (int16_t)((uint16_t)a[e] << ts_shift);
     tsync(tm);
@@ -1174,7 +1203,7 @@ CTU_FN_NOINLINE void tu_core(const Team &tm, const CtuTables *T, const SmTables 
 // One colour of one transform unit including the transform-skip decision of 4x4 luma units
 // (kvz_quantize_residual_trskip, ref: transform.c:242-288).  `sc`: the search models the decision's bit costs read.
 // Returns tr_skip (uniform over the team); the chosen alternative is in tu.q() / tu.rec() / fx->has / fx->ssd.
-CTU_FN_NOINLINE int tu_eval(const Team &tm, const CtuTables *T, const SmTables *tb, const CtuConfig *cfg, const uint8_t *cabac0, CabacState *sc,
+CTU_FN_NOINLINE int tu_eval(const Team &tm, const SmTables *T, const SmTables *tb, const CtuConfig *cfg, const uint8_t *cabac0, CabacState *sc,
                             const TuS &tu, const TuJob &j)
 {
   if (!(j.log2n == 2 && j.color == 0 && cfg->trskip_enable)) {

@@ -57,6 +57,7 @@ struct CtuS {                       // per-CTA scalar state + scratch; shared me
   int32_t best_mode;
   double best_cost;
   SmTables tb;
+  LcuLevel lv[5];                   // work tree: CU records here, planes in CtuWork::store
   TuRes res[8][3];                  // [RDO candidate][colour]
   // the coefficients of the transform units reconstructed last (the CU whose cost is computed next), per colour
   int16_t stage_y[1024], stage_c[2][256];
@@ -143,9 +144,9 @@ CTU_FN_NOINLINE void work_tree_copy_up(const Ctx &c, int xl, int yl, int depth)
 {
   const int w = 64 >> depth;
   PROF_T0(PR_COPY);
-  copy_cu_info(&c.W->lv[depth + 1], &c.W->lv[depth], xl, yl, w);
-  copy_cu_pixels(&c.W->lv[depth + 1], &c.W->lv[depth], xl, yl, w);
-  copy_cu_coeffs(&c.W->lv[depth + 1], &c.W->lv[depth], xl, yl, w);
+  copy_cu_info(&c.S->lv[depth + 1], &c.S->lv[depth], xl, yl, w);
+  copy_cu_pixels(&c.S->lv[depth + 1], &c.S->lv[depth], xl, yl, w);
+  copy_cu_coeffs(&c.S->lv[depth + 1], &c.S->lv[depth], xl, yl, w);
   CTU_SYNC();
   PROF_ADD(c.S, PR_COPY);
 }
@@ -154,8 +155,8 @@ CTU_FN_NOINLINE void work_tree_copy_down(const Ctx &c, int xl, int yl, int depth
   const int w = 64 >> depth;
   PROF_T0(PR_COPY);
   for (int i = depth + 1; i <= 4; ++i) {
-    copy_cu_info(&c.W->lv[depth], &c.W->lv[i], xl, yl, w);
-    copy_cu_pixels(&c.W->lv[depth], &c.W->lv[i], xl, yl, w);
+    copy_cu_info(&c.S->lv[depth], &c.S->lv[i], xl, yl, w);
+    copy_cu_pixels(&c.S->lv[depth], &c.S->lv[i], xl, yl, w);
   }
   CTU_SYNC();
   PROF_ADD(c.S, PR_COPY);
@@ -197,7 +198,7 @@ CTU_FN double coeff_cost_of_unit(const Ctx &c, CabacState *sc, LcuLevel *L, int 
 {
   uint64_t mask;
   const int16_t *co = unit_coeffs(c, L, color, xl, yl, depth, &mask);
-  return coeff_cost_serial(c.T, &c.S->tb, c.cfg, sc, co, log2n, type, scan, 0, mask);
+  return coeff_cost_serial(&c.S->tb, &c.S->tb, c.cfg, sc, co, log2n, type, scan, 0, mask);
 }
 
 // Runs `ntasks` independent transform-unit jobs whose largest unit has nn coefficients: one warp per job when four
@@ -236,7 +237,7 @@ CTU_FN_NOINLINE void intra_recon_leaf(const Ctx &c, LcuLevel *L, int x, int y, i
     int need = 0;
     for (int col = first; col <= last; ++col) if (!((refs_valid >> col) & 1)) need |= 1 << col;
     const int l2[3] = { tu_log2(depth, 0), tu_log2(depth, 1), tu_log2(depth, 2) };
-    if (need) build_refs_multi(c.T, c.cfg, c.W, L, l2, need, x, y, S->refs);
+    if (need) build_refs_multi(&c.S->tb, c.cfg, c.W, L, l2, need, x, y, S->refs);
   }
   PROF_ADD(S, PR_REFS);
   // cur_pu of quantize_tr_residual: the RDOQ context selector reads its depths before the cbf bits change
@@ -251,7 +252,7 @@ CTU_FN_NOINLINE void intra_recon_leaf(const Ctx &c, LcuLevel *L, int x, int y, i
     const int off = (xl >> sh) + (yl >> sh) * P.lw;
     const int mode = col == 0 ? mode_luma : mode_chroma;
     TuJob j = { &S->refs[col], P.src + off, P.lw, col, log2n, mode, scan_order_intra(mode, depth), rdoq_tr_depth };
-    const int ts = tu_eval(tm, c.T, &S->tb, c.cfg, S->cabac0.ctx, &S->sc, tu, j);
+    const int ts = tu_eval(tm, &c.S->tb, &S->tb, c.cfg, S->cabac0.ctx, &S->sc, tu, j);
     // write back: reconstruction and coefficients of the level, staged copy for the cost functions
     uint8_t *rec = P.rec + off;
     int16_t *co = P.coeff + zorder(P.lw, xl >> sh, yl >> sh);
@@ -621,7 +622,7 @@ CTU_FN_NOINLINE void search_cu_intra(const Ctx &c, LcuLevel *L, int x, int y, in
   {
     // luma for the rough search; the chroma references the CU's reconstruction (and RDO candidates) will need as well
     const int l2[3] = { log2w, tu_log2(depth, 1), tu_log2(depth, 2) };
-    build_refs_multi(c.T, cfg, c.W, L, l2, ((x & 4) || (y & 4)) ? 1 : 7, x, y, S->refs);
+    build_refs_multi(&c.S->tb, cfg, c.W, L, l2, ((x & 4) || (y & 4)) ? 1 : 7, x, y, S->refs);
   }
   PROF_ADD(S, PR_REFS);
   // rough search: SATD (and SAD for 4x4 transform-skip candidates) of every mode, then the reference's selection
@@ -667,13 +668,13 @@ CTU_FN_NOINLINE void search_cu_intra(const Ctx &c, LcuLevel *L, int x, int y, in
       const int sh = col ? 1 : 0;
       const int off = (xl >> sh) + (yl >> sh) * P.lw;
       TuJob j = { &S->refs[col], P.src + off, P.lw, col, log2n, mode, scan_order_intra(mode, depth), rdoq_tr_depth };
-      const int ts = tu_eval(tm, c.T, &S->tb, cfg, S->cabac0.ctx, &S->sc, tu, j);
+      const int ts = tu_eval(tm, &c.S->tb, &S->tb, cfg, S->cabac0.ctx, &S->sc, tu, j);
       if (tm.tid == 0) {
         const TuFixed *fx = tu.fx();
         TuRes *r = &S->res[cand][col];
         r->ssd = fx->ssd; r->has = fx->has; r->tr_skip = ts;
         // coefficient bits of kvz_cu_rd_cost_luma / _chroma: the search models are not adapted here (update == 0)
-        r->bits = fx->has ? coeff_cost_serial(c.T, &S->tb, cfg, &S->sc, tu.q(), log2n, col ? 2 : 0, j.scan_idx, 0,
+        r->bits = fx->has ? coeff_cost_serial(&c.S->tb, &S->tb, cfg, &S->sc, tu.q(), log2n, col ? 2 : 0, j.scan_idx, 0,
                                               (uint64_t)fx->cg_mask[0] | ((uint64_t)fx->cg_mask[1] << 32)) : 0.0;
       }
       tsync(tm);
@@ -731,8 +732,8 @@ CTU_FN_NOINLINE int search_cu_intra_chroma(const Ctx &c, LcuLevel *L, int x, int
     if (intra_mode != 0 && intra_mode != 26 && intra_mode != 10 && intra_mode != 1) S->cmodes[4] = (int8_t)intra_mode;
   }
   CTU_SYNC();
-  build_refs(c.T, c.cfg, c.W, L, log2wc, 1, x, y, &S->refs[1]);
-  build_refs(c.T, c.cfg, c.W, L, log2wc, 2, x, y, &S->refs[2]);
+  build_refs(&c.S->tb, c.cfg, c.W, L, log2wc, 1, x, y, &S->refs[1]);
+  build_refs(&c.S->tb, c.cfg, c.W, L, log2wc, 2, x, y, &S->refs[2]);
   // search_intra_chroma_rough: SATD of the five candidates on U and V (the luma mode is skipped: cost 0)
   const int ci = (yl >> 1) * 32 + (xl >> 1);
   rough_costs_all_modes(&S->refs[1], (RoughExt *)S->arena, log2wc, 1, &c.W->src_u[ci], 32, S->satd, S->sad, false);
@@ -792,13 +793,13 @@ CTU_FN_NOINLINE void search_ctu(const Ctx &c, int cx, int cy)
 {
   CtuS *S = c.S;
   const CtuConfig *cfg = c.cfg;
-  for (int i = CTU_TID; i < 128; i += CTU_NT) { S->tb.ebits[i] = c.T->ebits[i]; S->tb.next_mps[i] = c.T->next_mps[i]; S->tb.next_lps[i] = c.T->next_lps[i]; }
+  sm_tables_load(&S->tb, c.T);
   CTU_LEADER { S->fr[0].x = cx; S->fr[0].y = cy; S->fr[0].stage = 0; S->stage_key[0] = S->stage_key[1] = S->stage_key[2] = -1; }
   CTU_SYNC();
   int d = 0;
   for (;;) {
     SearchFrame *F = &S->fr[d];
-    LcuLevel *L = &c.W->lv[d];
+    LcuLevel *L = &c.S->lv[d];
     // Every thread takes its copy of the frame's state, THEN the barrier: the leader changes that state below, and a
     // thread that read it late would take another branch than the others (all control flow here must be uniform).
     const int x = F->x, y = F->y;
@@ -932,12 +933,12 @@ CTU_FN_NOINLINE void search_ctu(const Ctx &c, int cx, int cy)
       const bool inside = x + cu_width <= cfg->width && y + cu_width <= cfg->height;
       bool combine = false;
       if (cur_cu->type == CU_NOTSET && d < 4 && inside && cfg->combine_intra_cus) {
-        const CuRec *cu_d1 = cu_at(&c.W->lv[d + 1], xl, yl);
+        const CuRec *cu_d1 = cu_at(&c.S->lv[d + 1], xl, yl);
         combine = cu_d1->type == CU_INTRA && cu_d1->depth == d + 1;
       }
       CTU_SYNC();       // (the decision is taken by everybody before the leader rewrites the record)
       if (combine) {
-        CuRec *cu_d1 = cu_at(&c.W->lv[d + 1], xl, yl);
+        CuRec *cu_d1 = cu_at(&c.S->lv[d + 1], xl, yl);
         {
           CTU_LEADER {
             S->tmp = S->sc;

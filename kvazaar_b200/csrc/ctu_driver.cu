@@ -52,7 +52,7 @@ __device__ __forceinline__ int ld_acquire(const int *p)
 }
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-__global__ void __launch_bounds__(kThreads, 4) ctu_frame_kernel(const __grid_constant__ KernelArgs a)
+__global__ void __launch_bounds__(kThreads, 3) ctu_frame_kernel(const __grid_constant__ KernelArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   CtuS *S = reinterpret_cast<CtuS *>(smem);
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(kThreads, 4) ctu_frame_kernel(const __grid_con
 }
 
 // Diagnostic alternative (KVZ_CUDA_CTU_DIAG=1): one launch per anti-diagonal, no inter-CTA waiting.
-__global__ void __launch_bounds__(kThreads, 4) ctu_diag_kernel(const __grid_constant__ KernelArgs a, int diag, int cy_lo)
+__global__ void __launch_bounds__(kThreads, 3) ctu_diag_kernel(const __grid_constant__ KernelArgs a, int diag, int cy_lo)
 {
   extern __shared__ __align__(16) unsigned char smem[];
   CtuS *S = reinterpret_cast<CtuS *>(smem);
@@ -229,8 +229,10 @@ kvz_cuda_ctu_enc *kvz_cuda_ctu_open(const kvz_cuda_ctu_config *cfg, int slots)
     for (int cy = lo; cy <= hi; ++cy) { order.push_back((uint16_t)(d - 2 * cy)); order.push_back((uint16_t)cy); }
   }
   e->diag_launches = getenv("KVZ_CUDA_CTU_DIAG") != nullptr;
-  // persistent CTAs per picture: the widest diagonal unless told otherwise (fewer: less idle waiting, more pictures resident)
-  e->grid = e->max_diag;
+  // persistent CTAs per picture: 60 % of the widest diagonal (the average wavefront is about half of it: fewer CTAs wait
+  // idle and more pictures are resident at once); KVZ_CUDA_CTU_GRID overrides
+  e->grid = e->diag_launches ? e->max_diag : (e->max_diag * 3 + 4) / 5;
+  if (e->grid < 1) e->grid = 1;
   if (const char *g = getenv("KVZ_CUDA_CTU_GRID")) { const int v = atoi(g); if (v > 0 && !e->diag_launches) e->grid = v < e->max_diag ? v : e->max_diag; }
   e->plane_bytes = (size_t)W * H * 3 / 2;
   e->smem = sizeof(CtuS);
