@@ -56,6 +56,11 @@ int kvz_cuda_init(int device)
 {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_device >= 0) return 0;
+  // The CTU driver keeps one stream per picture in flight, and a picture's work is a dependent chain (copy, search
+  // launch, SAO launch, copies back): streams that share a hardware queue run one picture at a time.  The default of 8
+  // queues caps the pictures that really overlap at 8; ask for the maximum before the context exists (no effect, and no
+  // harm, when the host process created it already).
+  setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
   if (e != cudaSuccess || n == 0) {

@@ -44,12 +44,15 @@ struct KernelArgs {
   unsigned long long *prof;  // [PR_N + 1] phase cycles (diagnostic build only), last: CTA lifetime
 };
 
-__device__ __forceinline__ int ld_acquire(const int *p)
+// Polling load: relaxed, from L2 (an acquire load invalidates the SM's whole L1 -- CCTL.IVALL -- on every poll, which
+// also empties the L1 of the other CTAs working on that SM); the acquire fence follows once the wait is over.
+__device__ __forceinline__ int ld_relaxed(const int *p)
 {
   int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 __global__ void __launch_bounds__(kThreads, 3) ctu_frame_kernel(const __grid_constant__ KernelArgs a)
@@ -73,8 +76,9 @@ __global__ void __launch_bounds__(kThreads, 3) ctu_frame_kernel(const __grid_con
       if (threadIdx.x == 0) {
         // left neighbour: cx CTUs of this row are finished; above: the row has passed the top-right neighbour
         const int need_up = cy > 0 ? min(cx + 2, a.F.wlcu) : 0;
-        while (ld_acquire(a.sync + 1 + cy) < cx) __nanosleep(200);
-        if (cy > 0) while (ld_acquire(a.sync + cy) < need_up) __nanosleep(200);
+        while (ld_relaxed(a.sync + 1 + cy) < cx) __nanosleep(400);
+        if (cy > 0) while (ld_relaxed(a.sync + cy) < need_up) __nanosleep(400);
+        fence_acquire();
       }
       __syncthreads();
       PROF_ADD(S, PR_WAIT);
@@ -121,6 +125,7 @@ struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
   cudaEvent_t k0 = nullptr, k1 = nullptr;   // around the search kernel (timing enabled)
+  bool resident = false;
   // device
   uint8_t *d_planes = nullptr;   // src | rec | out | dbg, each w*h*3/2
   uint8_t *d_bufs = nullptr;     // hor / ver buffers
@@ -354,11 +359,24 @@ static int submit_picture(kvz_cuda_ctu_enc *e, const uint8_t *y, const uint8_t *
     kvzc::g_launches.fetch_add(1, std::memory_order_relaxed);
   }
   KVZC_CHECK(cudaEventRecord(s.k1, st));
+  KVZC_CHECK(cudaGetLastError());
+  s.resident = resident;
+  return id;
+}
+
+// Second half of a picture, enqueued by the waiting thread once the search launch has finished: SAO over the whole
+// picture and the copies to pinned memory.  Deliberately NOT enqueued at submit time: work that depends on the (long)
+// search launch would sit at the head of its hardware queue (CUDA_DEVICE_MAX_CONNECTIONS of them, 8 by default) and
+// block the pictures of other streams queued behind it -- only one picture per queue would run.
+static int finish_picture(kvz_cuda_ctu_enc *e, Slot &s)
+{
+  KVZC_CHECK(cudaEventSynchronize(s.k1));
+  cudaStream_t st = s.stream;
   ctu_sao_apply_kernel<<<e->wl * e->hl, kThreads, 0, st>>>(s.args);
   e->launches.fetch_add(1, std::memory_order_relaxed);
   kvzc::g_launches.fetch_add(1, std::memory_order_relaxed);
   KVZC_CHECK(cudaGetLastError());
-  if (!resident) {
+  if (!s.resident) {
     const size_t nctu = (size_t)e->wl * e->hl;
     KVZC_CHECK(cudaMemcpyAsync(s.h_cu, s.d_cu, (size_t)(e->wl * 16) * (e->hl * 16) * sizeof(CuRec), cudaMemcpyDeviceToHost, st));
     KVZC_CHECK(cudaMemcpyAsync(s.h_coeff, s.d_coeff, nctu * 6144 * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
@@ -370,7 +388,8 @@ static int submit_picture(kvz_cuda_ctu_enc *e, const uint8_t *y, const uint8_t *
     }
   }
   KVZC_CHECK(cudaEventRecord(s.done, st));
-  return id;
+  KVZC_CHECK(cudaEventSynchronize(s.done));
+  return 0;
 }
 
 int kvz_cuda_ctu_submit(kvz_cuda_ctu_enc *e, const uint8_t *y, const uint8_t *u, const uint8_t *v, int stride_y, int stride_c,
@@ -389,7 +408,7 @@ int kvz_cuda_ctu_wait_device(kvz_cuda_ctu_enc *e, int slot, kvz_cuda_ctu_device_
 {
   KVZC_ARG(e && out && slot >= 0 && slot < (int)e->slots.size() && e->slots[slot].state == 1);
   Slot &s = e->slots[slot];
-  KVZC_CHECK(cudaEventSynchronize(s.done));
+  if (int rc = finish_picture(e, s)) return rc;
   memset(out, 0, sizeof(*out));
   out->cu = (const kvz_cuda_ctu_cu *)s.d_cu;
   out->coeff = s.d_coeff;
@@ -406,7 +425,7 @@ int kvz_cuda_ctu_wait(kvz_cuda_ctu_enc *e, int slot, kvz_cuda_ctu_result *out)
 {
   KVZC_ARG(e && out && slot >= 0 && slot < (int)e->slots.size() && e->slots[slot].state == 1);
   Slot &s = e->slots[slot];
-  KVZC_CHECK(cudaEventSynchronize(s.done));
+  if (int rc = finish_picture(e, s)) return rc;
   const size_t ysz = (size_t)e->cfg.width * e->cfg.height, csz = ysz / 4;
   memset(out, 0, sizeof(*out));
   out->cu = (const kvz_cuda_ctu_cu *)s.h_cu;
