@@ -41,9 +41,9 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 WORKLOADS = {
-    "2160p": dict(w=3840, h=2160, preset="veryslow", qp=22, frames_per_step=32, ref_frames_per_step=12, sample=16, owf=40, slots=32,
+    "2160p": dict(w=3840, h=2160, preset="veryslow", qp=22, frames_per_step=32, ref_frames_per_step=12, sample=16, owf=44, slots=40,
                   name="BASELINE config 3: 3840x2160 8-bit synthetic I420, --preset veryslow -q 22 -p 1 (all-intra)"),
-    "1080p": dict(w=1920, h=1080, preset="medium", qp=27, frames_per_step=96, ref_frames_per_step=96, sample=64, owf=48, slots=32,
+    "1080p": dict(w=1920, h=1080, preset="medium", qp=27, frames_per_step=96, ref_frames_per_step=96, sample=64, owf=84, slots=72,
                   name="BASELINE config 2: 1920x1080 8-bit synthetic I420, --preset medium -q 27 -p 1 (all-intra)"),
     "64x64": dict(w=64, h=64, preset="ultrafast", qp=32, frames_per_step=64, ref_frames_per_step=64, sample=16, owf=8, slots=8,
                   name="BASELINE config 1: 64x64 8-bit synthetic I420, --preset ultrafast -q 32 -p 1 (all-intra)"),

@@ -93,6 +93,7 @@ int main(int argc, char **argv)
     kvz_picture *rec = NULL;
     kvz_frame_info info;
     if (!api->encoder_encode(enc, pic, &chunks, &len, &rec, NULL, &info)) { fprintf(stderr, "encode failed\n"); return 1; }
+    const int flushing = pic == NULL;
     if (pic) api->picture_free(pic);
     if (chunks) {
       for (kvz_data_chunk *c = chunks; c; c = c->next) { fwrite(c->data, 1, c->len, fo); bytes += c->len; }
@@ -105,7 +106,7 @@ int main(int argc, char **argv)
       }
     }
     if (rec) api->picture_free(rec);
-    if (fed >= total && !chunks) break;
+    if (flushing && !chunks) break;        /* no more input and no more output (src/encmain.c:735) */
   }
   const double t_end = now();
   fclose(fo);

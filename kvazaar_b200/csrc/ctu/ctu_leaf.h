@@ -460,17 +460,31 @@ CTU_FN_NOINLINE void ssd_block(const uint8_t *a, int sa, const uint8_t *b, int s
 }
 
 // ------------------------------------------------------------------------------------------------ transforms
+// two int16 x int8 products per instruction (IDP2A); the pairs must be 4-byte (samples) / 2-byte (matrix) aligned
+#if defined(__CUDA_ARCH__)
+CTU_FN int dot4_s16_s8(const int16_t *s, const int8_t *m, int acc)
+{
+  const int2 sv = *reinterpret_cast<const int2 *>(s);       // 4 samples
+  const int mv = *reinterpret_cast<const int *>(m);         // 4 matrix bytes
+  acc = __dp2a_lo(sv.x, mv, acc);
+  return __dp2a_hi(sv.y, mv, acc);
+}
+#else
+CTU_FN int dot4_s16_s8(const int16_t *s, const int8_t *m, int acc) { return acc + s[0] * m[0] + s[1] * m[1] + s[2] * m[2] + s[3] * m[3]; }
+#endif
+
 // forward: dst[k*N + j] = (int16)((sum_i M[k][i] * src[j*N + i] + add) >> shift)
 CTU_FN_NOINLINE void fwd_pass(const Team &tm, const int16_t *src, int16_t *dst, const int8_t *M, int n, int shift)
 {
   const int add = 1 << (shift - 1);
+  const int log2n = n == 4 ? 2 : (n == 8 ? 3 : (n == 16 ? 4 : 5));
   for (int e = tm.tid; e < n * n; e += tm.nt) {
-    const int k = e / n, j = e - k * n;
-    const int16_t *s = src + j * n;
-    const int8_t *m = M + k * n;
+    const int k = e >> log2n, j = e & (n - 1);
+    const int16_t *s = src + (j << log2n);
+    const int8_t *m = M + (k << log2n);
     int acc = 0;
-    for (int i = 0; i < n; ++i) acc += (int)m[i] * (int)s[i];
-    dst[k * n + j] = (int16_t)((acc + add) >> shift);
+    for (int i = 0; i < n; i += 4) acc = dot4_s16_s8(s + i, m + i, acc);
+    dst[e] = (int16_t)((acc + add) >> shift);
   }
   tsync(tm);
 }
@@ -478,11 +492,15 @@ CTU_FN_NOINLINE void fwd_pass(const Team &tm, const int16_t *src, int16_t *dst, 
 CTU_FN_NOINLINE void inv_pass(const Team &tm, const int16_t *src, int16_t *dst, const int8_t *M, int n, int shift)
 {
   const int add = 1 << (shift - 1);
+  const int log2n = n == 4 ? 2 : (n == 8 ? 3 : (n == 16 ? 4 : 5));
   for (int e = tm.tid; e < n * n; e += tm.nt) {
-    const int j = e / n, k = e - j * n;
+    const int j = e >> log2n, k = e & (n - 1);
+    const int8_t *m = M + k;
+    const int16_t *sp = src + j;
     int acc = 0;
-    for (int i = 0; i < n; ++i) acc += (int)M[i * n + k] * (int)src[i * n + j];
-    dst[j * n + k] = (int16_t)iclip(-32768, 32767, (acc + add) >> shift);
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) acc += (int)m[i << log2n] * (int)sp[i << log2n];
+    dst[e] = (int16_t)iclip(-32768, 32767, (acc + add) >> shift);
   }
   tsync(tm);
 }

@@ -12,6 +12,7 @@
 //
 // Memory per picture slot: source / reconstruction / final planes, the per-4x4 CU records, 12 KB of coefficients per
 // CTU, and one work tree (CtuWork, 5 levels) per persistent CTA.
+#include <time.h>
 #include <condition_variable>
 #include <mutex>
 #include <new>
@@ -39,8 +40,10 @@ struct KernelArgs {
   SaoStats *sao_stats;     // [grid]
   uint8_t *dbg_ctx;        // [nctu][184] or NULL
   const uint16_t *order;   // [nctu][2]: CTU coordinates by ticket (wavefront order)
-  int *sync;               // [0] ticket counter, [1 + cy] CTUs finished in row cy
+  int *sync;               // [0] ticket counter, [1 + cy] CTUs finished in row cy, [1 + hlcu] CTAs that have left
   int nctu;
+  volatile unsigned long long *host_note;   // pinned host memory: [0] completion sequence number, [1] start, [2] end (globaltimer ns)
+  unsigned long long seq;
   unsigned long long *prof;  // [PR_N + 1] phase cycles (diagnostic build only), last: CTA lifetime
 };
 
@@ -53,6 +56,12 @@ __device__ __forceinline__ int ld_relaxed(const int *p)
   return v;
 }
 __device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 __global__ void __launch_bounds__(kThreads, 3) ctu_frame_kernel(const __grid_constant__ KernelArgs a)
@@ -70,6 +79,7 @@ __global__ void __launch_bounds__(kThreads, 3) ctu_frame_kernel(const __grid_con
     __syncthreads();
     const int t = s_ticket;
     if (t >= a.nctu) break;
+    if (t == 0 && threadIdx.x == 0) a.host_note[1] = global_timer_ns();
     const int cx = a.order[2 * t], cy = a.order[2 * t + 1];
     {
       PROF_T0(PR_WAIT);
@@ -97,6 +107,16 @@ __global__ void __launch_bounds__(kThreads, 3) ctu_frame_kernel(const __grid_con
     atomicAdd(a.prof + PR_N, (unsigned long long)(clock64() - cta_t0));
   }
 #endif
+  // The last CTA to leave tells the host: no event follows the launch in the stream (it would sit at the head of the
+  // stream's hardware queue until the launch is over and hold back the pictures of the streams behind it).
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(a.sync + 1 + a.F.hlcu, 1) == (int)gridDim.x - 1) {
+      a.host_note[2] = global_timer_ns();
+      __threadfence_system();
+      a.host_note[0] = a.seq;
+    }
+  }
 }
 
 // Diagnostic alternative (KVZ_CUDA_CTU_DIAG=1): one launch per anti-diagonal, no inter-CTA waiting.
@@ -124,7 +144,9 @@ struct Slot {
   int state = 0;                 // 0 free, 1 submitted
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
-  cudaEvent_t k0 = nullptr, k1 = nullptr;   // around the search kernel (timing enabled)
+  cudaEvent_t k1 = nullptr;                 // after the search launches (diagnostic per-diagonal mode only)
+  volatile unsigned long long *h_note = nullptr;   // pinned: written by the search launch's last CTA
+  unsigned long long seq = 0;
   bool resident = false;
   // device
   uint8_t *d_planes = nullptr;   // src | rec | out | dbg, each w*h*3/2
@@ -196,8 +218,8 @@ void kvz_cuda_ctu_close(kvz_cuda_ctu_enc *e)
     cudaFreeHost(s.h_src); cudaFreeHost(s.h_out); cudaFreeHost(s.h_dbg); cudaFreeHost(s.h_cu); cudaFreeHost(s.h_coeff); cudaFreeHost(s.h_sao);
     cudaFreeHost(s.h_row_ctx); cudaFreeHost(s.h_dbg_ctx);
     if (s.done) cudaEventDestroy(s.done);
-    if (s.k0) cudaEventDestroy(s.k0);
     if (s.k1) cudaEventDestroy(s.k1);
+    cudaFreeHost((void *)s.h_note);
     if (s.stream) cudaStreamDestroy(s.stream);
   }
 #if defined(KVZ_CTU_PROF)
@@ -234,9 +256,10 @@ kvz_cuda_ctu_enc *kvz_cuda_ctu_open(const kvz_cuda_ctu_config *cfg, int slots)
     for (int cy = lo; cy <= hi; ++cy) { order.push_back((uint16_t)(d - 2 * cy)); order.push_back((uint16_t)cy); }
   }
   e->diag_launches = getenv("KVZ_CUDA_CTU_DIAG") != nullptr;
-  // persistent CTAs per picture: 60 % of the widest diagonal (the average wavefront is about half of it: fewer CTAs wait
-  // idle and more pictures are resident at once); KVZ_CUDA_CTU_GRID overrides
-  e->grid = e->diag_launches ? e->max_diag : (e->max_diag * 3 + 4) / 5;
+  // persistent CTAs per picture: 40 % of the widest diagonal (the average wavefront is about half of it; a smaller grid
+  // leaves fewer CTAs waiting idle and lets more pictures be resident at once -- measured best at 1080p, flat at 2160p,
+  // profiles/r02_grid_sweep.log); KVZ_CUDA_CTU_GRID overrides
+  e->grid = e->diag_launches ? e->max_diag : (e->max_diag * 2 + 4) / 5;
   if (e->grid < 1) e->grid = 1;
   if (const char *g = getenv("KVZ_CUDA_CTU_GRID")) { const int v = atoi(g); if (v > 0 && !e->diag_launches) e->grid = v < e->max_diag ? v : e->max_diag; }
   e->plane_bytes = (size_t)W * H * 3 / 2;
@@ -265,8 +288,9 @@ kvz_cuda_ctu_enc *kvz_cuda_ctu_open(const kvz_cuda_ctu_config *cfg, int slots)
   for (Slot &s : e->slots) {
     CTU_CHECK_PTR(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CTU_CHECK_PTR(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-    CTU_CHECK_PTR(cudaEventCreate(&s.k0));
-    CTU_CHECK_PTR(cudaEventCreate(&s.k1));
+    CTU_CHECK_PTR(cudaEventCreateWithFlags(&s.k1, cudaEventDisableTiming));
+    CTU_CHECK_PTR(cudaHostAlloc((void **)&s.h_note, 64, cudaHostAllocDefault));
+    memset((void *)s.h_note, 0, 64);
     CTU_CHECK_PTR(cudaMalloc(&s.d_planes, e->plane_bytes * 4));
     CTU_CHECK_PTR(cudaMalloc(&s.d_bufs, buf_bytes));
     CTU_CHECK_PTR(cudaMalloc(&s.d_cu, cu_n * sizeof(CuRec)));
@@ -275,7 +299,7 @@ kvz_cuda_ctu_enc *kvz_cuda_ctu_open(const kvz_cuda_ctu_config *cfg, int slots)
     CTU_CHECK_PTR(cudaMalloc(&s.d_row_ctx, e->hl * sizeof(CabacState)));
     CTU_CHECK_PTR(cudaMalloc(&s.d_work, (size_t)e->grid * sizeof(CtuWork)));
     CTU_CHECK_PTR(cudaMalloc(&s.d_stats, (size_t)e->grid * sizeof(SaoStats)));
-    CTU_CHECK_PTR(cudaMalloc(&s.d_sync, (size_t)(e->hl + 1) * sizeof(int)));
+    CTU_CHECK_PTR(cudaMalloc(&s.d_sync, (size_t)(e->hl + 2) * sizeof(int)));
     CTU_CHECK_PTR(cudaMemset(s.d_sao, 0, nctu * 2 * sizeof(SaoRec)));
     CTU_CHECK_PTR(cudaMemset(s.d_planes, 0, e->plane_bytes * 4));
     CTU_CHECK_PTR(cudaMemset(s.d_bufs, 0, buf_bytes));
@@ -343,8 +367,10 @@ static int submit_picture(kvz_cuda_ctu_enc *e, const uint8_t *y, const uint8_t *
   s.args.cfg.lambda = lambda; s.args.cfg.lambda_sqrt = lambda_sqrt; s.args.cfg.qp = qp;
   KVZC_CHECK(cudaMemcpyAsync(s.d_row_ctx, s.h_row_ctx, e->hl * sizeof(CabacState), cudaMemcpyHostToDevice, st));
   KVZC_CHECK(cudaMemsetAsync(s.d_cu, 0, (size_t)(e->wl * 16) * (e->hl * 16) * sizeof(CuRec), st));
-  KVZC_CHECK(cudaMemsetAsync(s.d_sync, 0, (size_t)(e->hl + 1) * sizeof(int), st));
-  KVZC_CHECK(cudaEventRecord(s.k0, st));
+  KVZC_CHECK(cudaMemsetAsync(s.d_sync, 0, (size_t)(e->hl + 2) * sizeof(int), st));
+  s.seq += 1;
+  s.args.host_note = s.h_note;
+  s.args.seq = s.seq;
   if (e->diag_launches) {
     for (int d = 0; d < e->wl + 2 * (e->hl - 1); ++d) {
       const int lo = d - (e->wl - 1) > 0 ? (d - (e->wl - 1) + 1) / 2 : 0, hi = d / 2 < e->hl - 1 ? d / 2 : e->hl - 1;
@@ -358,7 +384,7 @@ static int submit_picture(kvz_cuda_ctu_enc *e, const uint8_t *y, const uint8_t *
     e->launches.fetch_add(1, std::memory_order_relaxed);
     kvzc::g_launches.fetch_add(1, std::memory_order_relaxed);
   }
-  KVZC_CHECK(cudaEventRecord(s.k1, st));
+  if (e->diag_launches) KVZC_CHECK(cudaEventRecord(s.k1, st));
   KVZC_CHECK(cudaGetLastError());
   s.resident = resident;
   return id;
@@ -370,7 +396,15 @@ static int submit_picture(kvz_cuda_ctu_enc *e, const uint8_t *y, const uint8_t *
 // block the pictures of other streams queued behind it -- only one picture per queue would run.
 static int finish_picture(kvz_cuda_ctu_enc *e, Slot &s)
 {
-  KVZC_CHECK(cudaEventSynchronize(s.k1));
+  if (e->diag_launches) KVZC_CHECK(cudaEventSynchronize(s.k1));
+  else {
+    // sleep-poll the completion note (the host threads are needed by the encoder's CABAC stage)
+    unsigned spins = 0;
+    while (__atomic_load_n((const unsigned long long *)s.h_note, __ATOMIC_ACQUIRE) != s.seq) {
+      if (++spins > 20) { struct timespec ts = { 0, 200000 }; nanosleep(&ts, nullptr); }
+      if ((spins & 1023) == 0) { const cudaError_t err = cudaStreamQuery(s.stream); if (err != cudaSuccess && err != cudaErrorNotReady) KVZC_CHECK(err); }
+    }
+  }
   cudaStream_t st = s.stream;
   ctu_sao_apply_kernel<<<e->wl * e->hl, kThreads, 0, st>>>(s.args);
   e->launches.fetch_add(1, std::memory_order_relaxed);
@@ -416,8 +450,7 @@ int kvz_cuda_ctu_wait_device(kvz_cuda_ctu_enc *e, int slot, kvz_cuda_ctu_device_
   out->rec = s.args.F.out_y;
   out->cu_stride = e->wl * 16;
   out->width_in_lcu = e->wl; out->height_in_lcu = e->hl;
-  float ms = 0;
-  if (cudaEventElapsedTime(&ms, s.k0, s.k1) == cudaSuccess) out->search_kernel_ms = ms;
+  if (!e->diag_launches) out->search_kernel_ms = (float)((double)(s.h_note[2] - s.h_note[1]) * 1e-6);   // globaltimer ns of first / last CTA
   return 0;
 }
 

@@ -422,7 +422,8 @@ __global__ void __launch_bounds__(256) compact_count_kernel(const uint4 *__restr
 }
 
 // one CTA: exclusive scan of the tile counts in place, total -> header
-__global__ void __launch_bounds__(1024) compact_scan_kernel(uint32_t *__restrict__ tile_counts, int n_tiles, uint32_t n_chunks, uint32_t *__restrict__ header)
+__global__ void __launch_bounds__(1024) compact_scan_kernel(uint32_t *__restrict__ tile_counts, int n_tiles, uint32_t n_chunks, uint32_t budget_chunks,
+                                                           uint32_t *__restrict__ header)
 {
   __shared__ uint32_t s_part[1024];
   const int per = (n_tiles + 1023) / 1024;
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(1024) compact_scan_kernel(uint32_t *__restrict
   }
   uint32_t run = s_part[threadIdx.x] - local;
   for (int k = 0; k < per; ++k) { const int i = threadIdx.x * per + k; if (i < n_tiles) { const uint32_t c = tile_counts[i]; tile_counts[i] = run; run += c; } }
-  if (threadIdx.x == 1023) { header[0] = s_part[1023]; header[1] = n_chunks; }
+  if (threadIdx.x == 1023) { header[0] = s_part[1023]; header[1] = n_chunks; header[2] = s_part[1023] < budget_chunks ? s_part[1023] : budget_chunks; }
 }
 
 __global__ void __launch_bounds__(256) compact_write_kernel(const uint4 *__restrict__ region, uint32_t n_chunks, const uint32_t *__restrict__ tile_offsets,
@@ -592,6 +593,7 @@ struct kvz_cuda_frame_pass {
   // optional per-stage CUDA-event timing (bench.py's live roofline measurement)
   bool timing = false;
   cudaEvent_t ev[KVZ_CUDA_FP_STAGES + 1] = {};
+  bool rough_v1 = getenv("KVZ_CUDA_ROUGH_V1") != nullptr;   // A/B switch of the 16-bit rough search, read once
   double ms_acc[KVZ_CUDA_FP_STAGES] = {};
   int runs_timed = 0;
   bool ev_pending = false;
@@ -713,6 +715,7 @@ int kvz_cuda_fp_layout_for(const kvz_cuda_fp_params *p, kvz_cuda_fp_layout *out)
 void kvz_cuda_fp_destroy(kvz_cuda_frame_pass *fp)
 {
   if (!fp) return;
+  for (cudaEvent_t ev : fp->ev) if (ev) cudaEventDestroy(ev);
   cudaFree(fp->blob);
   delete fp;
 }
@@ -746,7 +749,7 @@ static int fp_run_dev_t(kvz_cuda_frame_pass *fp, const void *src_dev, const void
     if constexpr (BD == 8) {
       // rough search with the mode selection fused in; the 35-entry cost tables stay on chip
       if (int r = rough_search_u8(log2w, src, rin, W, W, H, nullptr, modes, (uint32_t *)(B + L.cost_y[d]), st)) return r;
-    } else if (getenv("KVZ_CUDA_ROUGH_V1")) {
+    } else if (fp->rough_v1) {
       // A/B switch: the straightforward per-pixel rough-search kernel (intra.cu) + argmin
       uint32_t *costs = (uint32_t *)(B + fp->off_costs35[d]);
       if (int r = kvz_cuda_intra_rough_search_frame(log2w, BD, src, rin, W, W, H, costs, st)) return r;
@@ -911,11 +914,11 @@ int kvz_cuda_fp_run_host_compact(kvz_cuda_frame_pass *fp, const void *src_host, 
   const uint4 *region = (const uint4 *)(B + L.coeff_begin);
   compact_count_kernel<<<n_tiles, 256, 0, st>>>(region, n_chunks, tiles);
   KVZC_LAUNCHED();
-  compact_scan_kernel<<<1, 1024, 0, st>>>(tiles, (int)n_tiles, n_chunks, (uint32_t *)cmp);
+  if (budget_chunks > n_chunks) budget_chunks = n_chunks;
+  compact_scan_kernel<<<1, 1024, 0, st>>>(tiles, (int)n_tiles, n_chunks, (uint32_t)budget_chunks, (uint32_t *)cmp);
   KVZC_LAUNCHED();
   compact_write_kernel<<<n_tiles, 256, 0, st>>>(region, n_chunks, tiles, (uint32_t *)(cmp + 256), (uint4 *)(cmp + L.compact_header_bytes));
   KVZC_LAUNCHED();
-  if (budget_chunks > n_chunks) budget_chunks = n_chunks;
   KVZC_CHECK(cudaMemcpyAsync(small_host, B, L.coeff_begin, cudaMemcpyDeviceToHost, st));
   KVZC_CHECK(cudaMemcpyAsync(compact_host, cmp, L.compact_header_bytes + (size_t)budget_chunks * 32, cudaMemcpyDeviceToHost, st));
   return 0;

@@ -62,6 +62,8 @@ def allgather_tile_reconstructions(frame, width, height, cols, rows):
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return frame
     world, rank = dist.get_world_size(), dist.get_rank()
+    if world < cols * rows:
+        raise ValueError(f"{cols}x{rows} tiles need {cols * rows} ranks (one tile per rank), have {world}: the frame would stay incomplete")
     xs, ys = tile_grid(width, height, cols, rows)
     planes = [(0, width, height, 1), (width * height, width // 2, height // 2, 2), (width * height * 5 // 4, width // 2, height // 2, 2)]
 
