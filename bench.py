@@ -294,9 +294,12 @@ def run_cuda(args, wl):
     clip = clip_path(wl)
     ctu_bin = os.path.join(REF_DIR, "kvz_stream_bench_ctu")
     owf = args.owf or wl["owf"]
-    threads = max(4, (os.cpu_count() or 8) // world)
+    # The worker that runs CTU (0,0) of a picture sleeps until the device has searched the picture, so the encoder gets
+    # one worker per picture in flight on top of this rank's share of the host cores (the reference's CABAC stage).
+    cores = max(4, (os.cpu_count() or 8) // world)
+    threads = owf + 1 + cores
     env = {"KVZ_CTU_PROVIDER": kb.LIB_PATH, "CUDA_VISIBLE_DEVICES": os.environ.get("CUDA_VISIBLE_DEVICES", ",".join(str(i) for i in range(world))).split(",")[local]}
-    extra = [f"owf={owf}"] + ([f"threads={threads}"] if world > 1 else [])
+    extra = [f"owf={owf}", f"threads={threads}"]
 
     with ClockSampler(local) as clk:
         # ---- e2e: host pictures -> .hevc through the reference's API with the CTU job on the device
@@ -328,7 +331,7 @@ def run_cuda(args, wl):
             "ms_per_step": 1000.0 * e2e_seconds / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "config": config_of(wl), "frames_per_step": fps_step,
             "e2e": {"value": frames / e2e_seconds, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "pictures_in_flight": owf + 1, "host_threads_per_rank": threads if world > 1 else (os.cpu_count() or 1),
+                    "pictures_in_flight": owf + 1, "host_threads_per_rank": threads, "host_cores_per_rank": cores,
                     "path": "kvz_stream_bench_ctu: libkvazaar API -> kvz_ctu_hooks -> libkvzcuda.so (kvz_cuda_ctu_submit/wait) -> reference CABAC"},
             "device_only": {"value": frames / dev_seconds, "unit": "frames/s", "pictures_in_flight": slots, "ms_per_step": 1000.0 * dev_seconds / args.steps},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "parallelism": f"pictures sharded over {world} GPU(s), no collective"}

@@ -150,7 +150,7 @@ enum CtxOff {
   CTX_TQ_BYPASS = 174, CTX_MVD = 175, CTX_REF_PIC = 177, CTX_MVP_IDX = 179, CTX_ROOT_CBF = 181,
   CTX_TRSKIP_LUMA = 182, CTX_TRSKIP_CHROMA = 183, CTX_COUNT = 184
 };
-struct CabacState {
+struct alignas(16) CabacState {     // 192 bytes: copied around every speculative branch, as 16-byte moves
   uint8_t ctx[CTX_COUNT];
   uint8_t update;          // cabac_data_t.update travels with every copy of the struct (ref: search.c:655, 956-958)
   uint8_t pad[7];

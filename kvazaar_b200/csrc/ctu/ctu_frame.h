@@ -37,6 +37,7 @@ CTU_FN_NOINLINE void ctu_load(const Ctx &c, const FrameDev *F, int cx, int cy)
   // FILL(*lcu, 0) for every level of the work tree (work_tree[depth] = work_tree[0] below only differs in the border
   // CU records), and the levels' plane pointers
   {
+    #pragma unroll 1
     for (int d = CTU_TID; d < 5; d += CTU_NT) {
       LcuLevel *L = &c.S->lv[d];
       LcuStore *st = &W->store[d];
@@ -44,16 +45,23 @@ CTU_FN_NOINLINE void ctu_load(const Ctx &c, const FrameDev *F, int cx, int cy)
       L->coeff_y = st->coeff_y; L->coeff_u = st->coeff_u; L->coeff_v = st->coeff_v;
     }
     uint32_t *p = (uint32_t *)W->store;
+    #pragma unroll 1
     for (int i = CTU_TID; i < (int)(5 * sizeof(LcuStore) / 4); i += CTU_NT) p[i] = 0;
     uint32_t *q = (uint32_t *)L0->cu;
+    #pragma unroll 1
     for (int i = CTU_TID; i < (int)(sizeof(L0->cu) / 4); i += CTU_NT) q[i] = 0;
+    #pragma unroll 1
     for (int i = CTU_TID; i < 4096; i += CTU_NT) W->src_y[i] = 0;
+    #pragma unroll 1
     for (int i = CTU_TID; i < 1024; i += CTU_NT) { W->src_u[i] = 0; W->src_v[i] = 0; }
+    #pragma unroll 1
     for (int i = CTU_TID; i < 100; i += CTU_NT) { W->top_y[i] = 0; W->left_y[i] = 0; }
+    #pragma unroll 1
     for (int i = CTU_TID; i < 52; i += CTU_NT) { W->top_u[i] = 0; W->top_v[i] = 0; W->left_u[i] = 0; W->left_v[i] = 0; }
   }
   CTU_SYNC();
   // neighbouring CU records
+  #pragma unroll 1
   for (int i = CTU_TID; i < 16; i += CTU_NT) {
     if (y > 0 && x + 4 * i < Wd) *cu_at(L0, 4 * i, -1) = ld_frame_cu(&F->cu[((y - 1) >> 2) * F->cu_stride + ((x + 4 * i) >> 2)]);
     if (x > 0 && y + 4 * i < H) *cu_at(L0, -1, 4 * i) = ld_frame_cu(&F->cu[((y + 4 * i) >> 2) * F->cu_stride + ((x - 1) >> 2)]);
@@ -67,7 +75,9 @@ CTU_FN_NOINLINE void ctu_load(const Ctx &c, const FrameDev *F, int cx, int cy)
     const int x_max = imin(96, Wd - x);
     const int x_min = x > 0 ? 0 : 1;
     // luma: entries x_min .. x_max (entry e = picture column x + e - 1) from the bottom row of CTU row cy - 1
+    #pragma unroll 1
     for (int e = x_min + CTU_TID; e <= x_max; e += CTU_NT) W->top_y[e] = CTU_LD_FRAME(&F->hor_y[(cy - 1) * Wd + x + e - 1]);
+    #pragma unroll 1
     for (int e = x_min + CTU_TID; e <= x_max / 2; e += CTU_NT) {
       W->top_u[e] = CTU_LD_FRAME(&F->hor_u[(cy - 1) * (Wd / 2) + x / 2 + e - 1]);
       W->top_v[e] = CTU_LD_FRAME(&F->hor_v[(cy - 1) * (Wd / 2) + x / 2 + e - 1]);
@@ -77,7 +87,9 @@ CTU_FN_NOINLINE void ctu_load(const Ctx &c, const FrameDev *F, int cx, int cy)
     const int y_min = y > 0 ? 0 : 1;
     // entries y_min .. 64 from the right column of CTU column cx - 1; rows below the picture are not copied by
     // the reference either way of interest (they are never read: availability is clipped to the picture)
+    #pragma unroll 1
     for (int e = y_min + CTU_TID; e <= 64; e += CTU_NT) { const int yy = y + e - 1; if (yy < H) W->left_y[e] = CTU_LD_FRAME(&F->ver_y[(cx - 1) * H + yy]); }
+    #pragma unroll 1
     for (int e = y_min + CTU_TID; e <= 32; e += CTU_NT) {
       const int yy = y / 2 + e - 1;
       if (yy < H / 2) { W->left_u[e] = CTU_LD_FRAME(&F->ver_u[(cx - 1) * (H / 2) + yy]); W->left_v[e] = CTU_LD_FRAME(&F->ver_v[(cx - 1) * (H / 2) + yy]); }
@@ -86,7 +98,9 @@ CTU_FN_NOINLINE void ctu_load(const Ctx &c, const FrameDev *F, int cx, int cy)
   // source pixels
   {
     const int x_max = imin(x + 64, Wd) - x, y_max = imin(y + 64, H) - y;
+    #pragma unroll 1
     for (int e = CTU_TID; e < 64 * 64; e += CTU_NT) { const int yy = e >> 6, xx = e & 63; if (xx < x_max && yy < y_max) W->src_y[e] = F->src_y[(y + yy) * Wd + x + xx]; }
+    #pragma unroll 1
     for (int e = CTU_TID; e < 32 * 32; e += CTU_NT) {
       const int yy = e >> 5, xx = e & 31;
       if (xx < x_max / 2 && yy < y_max / 2) {
@@ -100,9 +114,11 @@ CTU_FN_NOINLINE void ctu_load(const Ctx &c, const FrameDev *F, int cx, int cy)
   for (int d = 1; d <= 4; ++d) {
     const uint32_t *s = (const uint32_t *)L0->cu;
     uint32_t *p = (uint32_t *)c.S->lv[d].cu;
+    #pragma unroll 1
     for (int i = CTU_TID; i < (int)(sizeof(L0->cu) / 4); i += CTU_NT) p[i] = s[i];
   }
   // the models the search starts from
+  #pragma unroll 1
   for (int i = CTU_TID; i < (int)(sizeof(CabacState) / 4); i += CTU_NT) ((uint32_t *)&c.S->cabac0)[i] = CTU_LD_FRAME((const uint32_t *)&F->row_ctx[cy] + i);
   CTU_SYNC();
   CTU_LEADER { c.S->cabac0.update = 0; c.S->sc = c.S->cabac0; }
@@ -116,10 +132,12 @@ CTU_FN_NOINLINE void ctu_store(const Ctx &c, const FrameDev *F, int cx, int cy)
   LcuLevel *L0 = &c.S->lv[0];
   const int x = cx * 64, y = cy * 64, Wd = cfg->width, H = cfg->height;
   const int x_max = imin(x + 64, Wd) - x, y_max = imin(y + 64, H) - y;
+  #pragma unroll 1
   for (int e = CTU_TID; e < 256; e += CTU_NT) {
     const int sx = e & 15, sy = e >> 4;
     if (4 * sx < x_max && 4 * sy < y_max) F->cu[((y >> 2) + sy) * F->cu_stride + (x >> 2) + sx] = *cu_at(L0, 4 * sx, 4 * sy);
   }
+  #pragma unroll 1
   for (int e = CTU_TID; e < 64 * 64; e += CTU_NT) {
     const int yy = e >> 6, xx = e & 63;
     if (xx < x_max && yy < y_max) {
@@ -130,6 +148,7 @@ CTU_FN_NOINLINE void ctu_store(const Ctx &c, const FrameDev *F, int cx, int cy)
       if (xx == x_max - 1) F->ver_y[cx * H + y + yy] = v;
     }
   }
+  #pragma unroll 1
   for (int e = CTU_TID; e < 32 * 32; e += CTU_NT) {
     const int yy = e >> 5, xx = e & 31;
     if (xx < x_max / 2 && yy < y_max / 2) {
@@ -142,7 +161,9 @@ CTU_FN_NOINLINE void ctu_store(const Ctx &c, const FrameDev *F, int cx, int cy)
     }
   }
   int16_t *co = F->coeff + (size_t)(cy * F->wlcu + cx) * 6144;
+  #pragma unroll 1
   for (int e = CTU_TID; e < 4096; e += CTU_NT) co[e] = L0->coeff_y[e];
+  #pragma unroll 1
   for (int e = CTU_TID; e < 1024; e += CTU_NT) { co[4096 + e] = L0->coeff_u[e]; co[5120 + e] = L0->coeff_v[e]; }
   CTU_SYNC();
 }
@@ -228,6 +249,7 @@ CTU_FN_NOINLINE void ctu_deblock(const Ctx &c, const FrameDev *F, int cx, int cy
   const int tc_c = dbk_tc(iclip(0, 53, scaled_qp(2, qp) + 2 + 2 * cfg->deblock_tc));
   const int ux_n = (end_x - x0) / 8, uy_n = (end_y - y0) / 8;
   // pass 1: vertical edges of every 8x8 unit: two luma parts per unit, one chroma part where x % 16 == 0
+  #pragma unroll 1
   for (int it = CTU_TID; it < ux_n * uy_n * 3; it += CTU_NT) {
     const int part = it % 3, u = it / 3;
     const int ex = x0 + (u % ux_n) * 8, ey = y0 + (u / ux_n) * 8;
@@ -246,6 +268,7 @@ CTU_FN_NOINLINE void ctu_deblock(const Ctx &c, const FrameDev *F, int cx, int cy
   // pass 2: horizontal edges: the delayed rightmost four columns of the CTU to the left, then this CTU's units
   // (without their own rightmost four columns unless the CTU ends the picture row)
   const int left_items = x0 > 0 ? uy_n : 0;
+  #pragma unroll 1
   for (int it = CTU_TID; it < left_items + ux_n * uy_n * 3; it += CTU_NT) {
     if (it < left_items) {
       const int ey = y0 + it * 8, ex = x0 - 8;          // unit holding the delayed columns
@@ -291,6 +314,7 @@ CTU_FN int sao_eo_cat(int a, int b, int cc)
 // statistics of the CTU's block of one plane (the reference works on a contiguous copy: same pixels)
 CTU_FN_NOINLINE void sao_stats_plane(const uint8_t *org, const uint8_t *rec, int stride, int bw, int bh, int32_t edge[4][2][5], int32_t band[2][32])
 {
+  #pragma unroll 1
   for (int e = CTU_TID; e < bw * bh; e += CTU_NT) {
     const int y = e / bw, x = e - y * bw;
     const int cc = CTU_LD_FRAME(&rec[y * stride + x]), d = (int)org[y * stride + x] - cc;
@@ -463,6 +487,7 @@ CTU_FN_NOINLINE void ctu_sao_search(const Ctx &c, const FrameDev *F, SaoStats *s
   const int bw = imin(64, Wd - x0), bh = imin(64, H - y0);
   {
     int32_t *p = (int32_t *)st;
+    #pragma unroll 1
     for (int i = CTU_TID; i < (int)(sizeof(SaoStats) / 4); i += CTU_NT) p[i] = 0;
   }
   CTU_SYNC();
@@ -680,6 +705,7 @@ CTU_FN_NOINLINE void ctu_sao_apply(const CtuConfig *cfg, const FrameDev *F, int 
     const int type = cfg->sao_type ? s->type : 0;
     const int ov = plane == 2 ? 5 : 0;
     const int ax[4] = { -1, 0, -1, 1 }, ay[4] = { 0, -1, -1, -1 };
+    #pragma unroll 1
     for (int e = CTU_TID; e < bw * bh; e += CTU_NT) {
       const int y = y0 + e / bw, x = x0 + e % bw;
       const int cc = in[(size_t)y * pw + x];

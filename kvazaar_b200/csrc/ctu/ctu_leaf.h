@@ -75,6 +75,7 @@ CTU_FN const int8_t *sm_tr(const SmTables *t, int l) { return l == 0 ? t->tr4 : 
 // every thread of the CTA
 CTU_FN void sm_tables_load(SmTables *d, const CtuTables *g)
 {
+  #pragma unroll 1
   for (int i = CTU_TID; i < 1024; i += CTU_NT) {
     d->scan32[i] = g->scan[0][3][i]; d->tr32[i] = g->tr[3][i];
     if (i < 256) { d->scan16[i] = g->scan[0][2][i]; d->tr16[i] = g->tr[2][i]; ((uint8_t *)d->ref_top)[i] = ((const uint8_t *)g->ref_top)[i]; ((uint8_t *)d->ref_left)[i] = ((const uint8_t *)g->ref_left)[i]; }
@@ -173,6 +174,7 @@ CTU_FN_NOINLINE void build_refs_multi(const SmTables *T, const CtuConfig *cfg, C
   int n_of[3], start[4];
   start[0] = 0;
   for (int col = 0; col < 3; ++col) { n_of[col] = ((mask >> col) & 1) ? 2 * (1 << log2w[col]) + 1 : 0; start[col + 1] = start[col] + 2 * n_of[col]; }
+  #pragma unroll 1
   for (int it = CTU_TID; it < start[3]; it += CTU_NT) {
     const int color = it >= start[2] ? 2 : (it >= start[1] ? 1 : 0);
     const int i = it - start[color], n = n_of[color], w = (n - 1) >> 1;
@@ -208,6 +210,7 @@ CTU_FN_NOINLINE void build_refs_multi(const SmTables *T, const CtuConfig *cfg, C
   CTU_SYNC();
   // smoothing of the luma references; one thread per colour sums the DC
   const int n0 = n_of[0];
+  #pragma unroll 1
   for (int i = CTU_TID; i < 2 * n0 + 3; i += CTU_NT) {
     if (i >= 2 * n0) {
       const int color = i - 2 * n0;
@@ -301,6 +304,7 @@ CTU_FN int intra_predict_px(const IntraRefs *r, int log2w, int mode, int color, 
 CTU_FN_NOINLINE void predict_block(const IntraRefs *r, int log2w, int mode, int color, uint8_t *dst, int dst_stride)
 {
   const int w = 1 << log2w;
+  #pragma unroll 1
   for (int e = CTU_TID; e < w * w; e += CTU_NT) {
     const int y = e >> log2w, x = e & (w - 1);
     dst[y * dst_stride + x] = (uint8_t)intra_predict_px(r, log2w, mode, color, x, y);
@@ -395,11 +399,30 @@ CTU_FN void rough_diff_block(const IntraRefs *r, const RoughExt *ext, int log2w,
       }
     }
   } else {
+    // planar (filtered references for luma blocks above 4x4) and DC (unfiltered, edge-filtered for luma below 32x32)
+    const bool f = intra_uses_filtered(log2w, m, color);
+    const uint8_t *t = f ? r->ftop : r->top, *l = f ? r->fleft : r->left;
+    const int tr = t[w + 1], bl = l[w + 1], dc = r->dc;
+    const bool dc_edges = color == 0 && log2w < 5;
 #pragma unroll
-    for (int y = 0; y < W8; ++y)
+    for (int y = 0; y < W8; ++y) {
+      const int yy = by + y, ly = l[yy + 1];
 #pragma unroll
-      for (int x = 0; x < W8; ++x)
-        d[y * W8 + x] = intra_predict_px(r, log2w, m, color, bx + x, by + y) - (int)src[(by + y) * src_stride + bx + x];
+      for (int x = 0; x < W8; ++x) {
+        const int xx = bx + x;
+        int v;
+        if (m == 0) v = ((w - 1 - xx) * ly + (xx + 1) * tr + (w - 1 - yy) * (int)t[xx + 1] + (yy + 1) * bl + w) >> (log2w + 1);
+        else {
+          v = dc;
+          if (dc_edges) {
+            if (xx == 0 && yy == 0) v = (ly + 2 * dc + (int)t[1] + 2) >> 2;
+            else if (yy == 0) v = ((int)t[xx + 1] + 3 * dc + 2) >> 2;
+            else if (xx == 0) v = (ly + 3 * dc + 2) >> 2;
+          }
+        }
+        d[y * W8 + x] = v - (int)src[yy * src_stride + xx];
+      }
+    }
   }
 }
 
@@ -409,9 +432,11 @@ CTU_FN_NOINLINE void rough_costs_all_modes(const IntraRefs *r, RoughExt *ext, in
                                   int32_t *satd_out, int32_t *sad_out, bool want_sad)
 {
   const int w = 1 << log2w;
+  #pragma unroll 1
   for (int m = CTU_TID; m < 35; m += CTU_NT) { satd_out[m] = 0; sad_out[m] = 0; }
   // extended main references of the 33 angular modes
   const int len = 3 * w + 2;
+  #pragma unroll 1
   for (int it = CTU_TID; it < 33 * len; it += CTU_NT) {
     const int m = 2 + it / len, idx = it % len - w;
     bool vertical; int sdisp, inv;
@@ -426,6 +451,7 @@ CTU_FN_NOINLINE void rough_costs_all_modes(const IntraRefs *r, RoughExt *ext, in
   }
   CTU_SYNC();
   if (w == 4) {
+    #pragma unroll 1
     for (int m = CTU_TID; m < 35; m += CTU_NT) {
       int d[16], sad = 0;
       rough_diff_block<4>(r, ext, 2, color, m, src, src_stride, 0, 0, d);
@@ -436,6 +462,7 @@ CTU_FN_NOINLINE void rough_costs_all_modes(const IntraRefs *r, RoughExt *ext, in
     }
   } else {
     const int sb = w >> 3, nsb = sb * sb, items = 35 * nsb;
+    #pragma unroll 1
     for (int it = CTU_TID; it < items; it += CTU_NT) {
       const int m = it / nsb, k = it % nsb, bx = (k % sb) * 8, by = (k / sb) * 8;
       int d[64];
@@ -450,6 +477,7 @@ CTU_FN_NOINLINE void rough_costs_all_modes(const IntraRefs *r, RoughExt *ext, in
 CTU_FN_NOINLINE void ssd_block(const uint8_t *a, int sa, const uint8_t *b, int sb, int w, int32_t *out)
 {
   int acc = 0;
+  #pragma unroll 1
   for (int e = CTU_TID; e < w * w; e += CTU_NT) {
     const int y = e / w, x = e - y * w;
     const int d = (int)a[y * sa + x] - (int)b[y * sb + x];
@@ -478,6 +506,7 @@ CTU_FN_NOINLINE void fwd_pass(const Team &tm, const int16_t *src, int16_t *dst, 
 {
   const int add = 1 << (shift - 1);
   const int log2n = n == 4 ? 2 : (n == 8 ? 3 : (n == 16 ? 4 : 5));
+  #pragma unroll 1
   for (int e = tm.tid; e < n * n; e += tm.nt) {
     const int k = e >> log2n, j = e & (n - 1);
     const int16_t *s = src + (j << log2n);
@@ -493,6 +522,7 @@ CTU_FN_NOINLINE void inv_pass(const Team &tm, const int16_t *src, int16_t *dst, 
 {
   const int add = 1 << (shift - 1);
   const int log2n = n == 4 ? 2 : (n == 8 ? 3 : (n == 16 ? 4 : 5));
+  #pragma unroll 1
   for (int e = tm.tid; e < n * n; e += tm.nt) {
     const int j = e >> log2n, k = e & (n - 1);
     const int8_t *m = M + k;
@@ -559,6 +589,7 @@ CTU_FN_NOINLINE void quant_block(const Team &tm, const SmTables *T, const CtuCon
   if (tm.tid == 0) fx->ac_sum = 0;
   tsync(tm);
   int ac = 0;
+  #pragma unroll 1
   for (int e = tm.tid; e < n * n; e += tm.nt) {
     const int level_in = b[e];
     const long long abs_level = iabs(level_in);
@@ -573,12 +604,14 @@ CTU_FN_NOINLINE void quant_block(const Team &tm, const SmTables *T, const CtuCon
   if (!cfg->signhide_enable || fx->ac_sum < 2) return;
   const int num_cg = (n * n) >> 4;
   int32_t *cg_nz = tu.cg_nzflag();
+  #pragma unroll 1
   for (int g = tm.tid; g < num_cg; g += tm.nt) {
     int nz = 0;
     for (int k = 0; k < 16; ++k) nz |= q[sm_scan(T, scan_idx, log2n - 2)[g * 16 + k]] != 0;
     cg_nz[g] = nz;
   }
   tsync(tm);
+  #pragma unroll 1
   for (int g = tm.tid; g < num_cg; g += tm.nt)
     if (cg_nz[g]) quant_sign_hide_group(T, b, q, d, cg_nz, num_cg, g, scan_idx, log2n);
   tsync(tm);
@@ -594,6 +627,7 @@ CTU_FN_NOINLINE void dequant_block(const Team &tm, const CtuConfig *cfg, const T
   const int add = 1 << (shift - 1);
   int16_t *b = tu.b();
   const int16_t *q = tu.q();
+  #pragma unroll 1
   for (int e = tm.tid; e < n * n; e += tm.nt)
     b[e] = (int16_t)iclip(-32768, 32767, ((int)q[e] * scale + add) >> shift);
   tsync(tm);
@@ -746,14 +780,17 @@ CTU_FN_NOINLINE void rdoq_team(const SmTables *T, const SmTables *tb, const CtuC
   const uint16_t *blk_of = sm_scan(T, scan_idx, log2n - 2);
 
   int my_last = -1;
+  #pragma unroll 1
   for (int sp = lane; sp < nn; sp += CTU_TEAM_N) {
     const int ld = imin(iabs((int)coef[blk_of[sp]]) * qc, 0x7FFFFFFF - half);
     if (((ld + half) >> q_bits) > 0) my_last = sp;
   }
   const int last_scanpos = team_max(my_last);
   CTU_TEAM_SYNC();
+  #pragma unroll 1
   for (int sp = lane; sp < nn; sp += CTU_TEAM_N) if (sp > last_scanpos) q[blk_of[sp]] = 0;
   if (last_scanpos < 0) { CTU_TEAM_SYNC(); return; }
+  #pragma unroll 1
   for (int g = lane; g < nn / 16; g += CTU_TEAM_N) { s_cg_flag[g] = 0; s_cg_sig_cost[g] = 0; }
   if (lane == 0) {
     if (SH) s_sig_inc[blk_of[last_scanpos]] = 0;
@@ -785,6 +822,7 @@ CTU_FN_NOINLINE void rdoq_team(const SmTables *T, const SmTables *tb, const CtuC
     const int right = (cgx < cgs_side - 1) ? (s_cg_flag[cgy * cgs_side + cgx + 1] != 0) : 0;
     const int lower = (cgy < cgs_side - 1) ? (s_cg_flag[(cgy + 1) * cgs_side + cgx] != 0) : 0;
     const int pattern = (n == 4) ? -1 : right + (lower << 1);
+    #pragma unroll 1
     for (int k = lane; k < 16; k += CTU_TEAM_N) {
       const int sp = (cg << 4) + k;
       uint8_t fl = 0;
@@ -970,6 +1008,7 @@ CTU_FN_NOINLINE void rdoq_team(const SmTables *T, const SmTables *tb, const CtuC
 
   const int best_last_p1 = s.best_last_p1;
   int abs_sum = 0;
+  #pragma unroll 1
   for (int sp = lane; sp <= last_scanpos; sp += CTU_TEAM_N) {
     const int blk = blk_of[sp];
     if (sp < best_last_p1) {
@@ -1148,6 +1187,7 @@ CTU_FN_NOINLINE void tu_core(const Team &tm, const SmTables *T, const SmTables *
   int16_t *a = tu.a(), *b = tu.b(), *q = tu.q(), *t = tu.t();
   uint8_t *pred = tu.pred(), *rec = tu.rec();
   TuFixed *fx = tu.fx();
+  #pragma unroll 1
   for (int e = tm.tid; e < nn; e += tm.nt) {
     const int y = e >> log2n, x = e & (n - 1);
     const int p = intra_predict_px(j.refs, log2n, j.mode, color, x, y);
@@ -1159,6 +1199,7 @@ CTU_FN_NOINLINE void tu_core(const Team &tm, const SmTables *T, const SmTables *
   const bool use_dst = (n == 4 && color == 0);
   const int8_t *M = use_dst ? T->dst4 : sm_tr(T, log2n - 2);
   if (use_trskip) {
+    #pragma unroll 1
     for (int e = tm.tid; e < nn; e += tm.nt) b[e] = (int16_t)((uint16_t)a[e] << ts_shift);
     tsync(tm);
   } else {
@@ -1175,6 +1216,7 @@ CTU_FN_NOINLINE void tu_core(const Team &tm, const SmTables *T, const SmTables *
   {
     uint32_t m0 = 0, m1 = 0;
     const int side_shift = log2n - 2;
+    #pragma unroll 1
     for (int e = tm.tid; e < nn; e += tm.nt) {
       if (q[e] != 0) {
         const int g = (((e >> log2n) >> 2) << side_shift) + ((e & (n - 1)) >> 2);
@@ -1191,12 +1233,14 @@ CTU_FN_NOINLINE void tu_core(const Team &tm, const SmTables *T, const SmTables *
     dequant_block(tm, cfg, tu, n, color == 0 ? 0 : (color == 1 ? 2 : 3));
     if (use_trskip) {
       const int offs = 1 << (ts_shift - 1);
+      #pragma unroll 1
       for (int e = tm.tid; e < nn; e += tm.nt) a[e] = (int16_t)(((int)b[e] + offs) >> ts_shift);
       tsync(tm);
     } else {
       inv_pass(tm, b, t, M, n, 7);
       inv_pass(tm, t, a, M, n, 12);
     }
+    #pragma unroll 1
     for (int e = tm.tid; e < nn; e += tm.nt) {
       const int y = e >> log2n, x = e & (n - 1);
       const int16_t val = (int16_t)(a[e] + (int)pred[e]);
@@ -1206,6 +1250,7 @@ CTU_FN_NOINLINE void tu_core(const Team &tm, const SmTables *T, const SmTables *
       ssd += d * d;
     }
   } else {
+    #pragma unroll 1
     for (int e = tm.tid; e < nn; e += tm.nt) {
       const int y = e >> log2n, x = e & (n - 1);
       const int r = pred[e];
@@ -1231,6 +1276,7 @@ CTU_FN_NOINLINE int tu_eval(const Team &tm, const SmTables *T, const SmTables *t
   TuFixed *fx = tu.fx();
   for (int k = 0; k < 2; ++k) {
     tu_core(tm, T, tb, cfg, cabac0, tu, j, k == 1);
+    #pragma unroll 1
     for (int e = tm.tid; e < 16; e += tm.nt) { fx->ts_rec[k][e] = tu.rec()[e]; fx->ts_coeff[k][e] = tu.q()[e]; }
     if (tm.tid == 0) { fx->ts_has[k] = fx->has; fx->ts_ssd[k] = fx->ssd; fx->ts_mask[k] = fx->cg_mask[0]; }
     tsync(tm);
@@ -1247,6 +1293,7 @@ CTU_FN_NOINLINE int tu_eval(const Team &tm, const SmTables *T, const SmTables *t
   const int pick = fx->ts_pick;
   // (the second alternative is still in place when it wins)
   if (pick == 0) {
+    #pragma unroll 1
     for (int e = tm.tid; e < 16; e += tm.nt) { tu.q()[e] = fx->ts_coeff[0][e]; tu.rec()[e] = fx->ts_rec[0][e]; }
     if (tm.tid == 0) { fx->has = fx->ts_has[0]; fx->ssd = fx->ts_ssd[0]; fx->cg_mask[0] = fx->ts_mask[0]; fx->cg_mask[1] = 0; }
     tsync(tm);

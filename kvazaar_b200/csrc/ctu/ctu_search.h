@@ -115,6 +115,7 @@ CTU_FN double chroma_mode_bits(const Ctx &c, int chroma_mode, int luma_mode)
 CTU_FN void copy_cu_info(LcuLevel *from, LcuLevel *to, int xl, int yl, int width)
 {
   const int n = width >> 2;
+  #pragma unroll 1
   for (int e = CTU_TID; e < n * n; e += CTU_NT) {
     const int x = xl + 4 * (e % n), y = yl + 4 * (e / n);
     *cu_at(to, x, y) = *cu_at(from, x, y);
@@ -122,11 +123,13 @@ CTU_FN void copy_cu_info(LcuLevel *from, LcuLevel *to, int xl, int yl, int width
 }
 CTU_FN void copy_cu_pixels(LcuLevel *from, LcuLevel *to, int xl, int yl, int width)
 {
+  #pragma unroll 1
   for (int e = CTU_TID; e < width * width; e += CTU_NT) {
     const int x = xl + e % width, y = yl + e / width;
     to->rec_y[y * 64 + x] = from->rec_y[y * 64 + x];
   }
   const int wc = width >> 1, xc = xl >> 1, yc = yl >> 1;
+  #pragma unroll 1
   for (int e = CTU_TID; e < wc * wc; e += CTU_NT) {
     const int x = xc + e % wc, y = yc + e / wc;
     to->rec_u[y * 32 + x] = from->rec_u[y * 32 + x];
@@ -136,8 +139,10 @@ CTU_FN void copy_cu_pixels(LcuLevel *from, LcuLevel *to, int xl, int yl, int wid
 CTU_FN void copy_cu_coeffs(LcuLevel *from, LcuLevel *to, int xl, int yl, int width)
 {
   const int zl = zorder(64, xl, yl);
+  #pragma unroll 1
   for (int e = CTU_TID; e < width * width; e += CTU_NT) to->coeff_y[zl + e] = from->coeff_y[zl + e];
   const int zc = zorder(32, xl >> 1, yl >> 1), wc = width >> 1;
+  #pragma unroll 1
   for (int e = CTU_TID; e < wc * wc; e += CTU_NT) { to->coeff_u[zc + e] = from->coeff_u[zc + e]; to->coeff_v[zc + e] = from->coeff_v[zc + e]; }
 }
 CTU_FN_NOINLINE void work_tree_copy_up(const Ctx &c, int xl, int yl, int depth)
@@ -165,6 +170,7 @@ CTU_FN_NOINLINE void work_tree_copy_down(const Ctx &c, int xl, int yl, int depth
 CTU_FN_NOINLINE void fill_trdepth(LcuLevel *L, int xl, int yl, int depth, int tr_depth)
 {
   const int n = (64 >> depth) >> 2;
+  #pragma unroll 1
   for (int e = CTU_TID; e < n * n; e += CTU_NT) cu_at(L, xl + 4 * (e % n), yl + 4 * (e / n))->tr_depth = (uint8_t)tr_depth;
   CTU_SYNC();
 }
@@ -174,6 +180,7 @@ CTU_FN_NOINLINE void fill_cu_info(LcuLevel *L, int xl, int yl, int width, const 
   const CuRec v = *cu;
   CTU_SYNC();
   const int n = width >> 2;
+  #pragma unroll 1
   for (int e = CTU_TID; e < n * n; e += CTU_NT) {
     CuRec *to = cu_at(L, xl + 4 * (e % n), yl + 4 * (e / n));
     to->type = v.type; to->depth = v.depth; to->part_size = v.part_size; to->qp = v.qp;
@@ -259,6 +266,7 @@ CTU_FN_NOINLINE void intra_recon_leaf(const Ctx &c, LcuLevel *L, int x, int y, i
     const uint8_t *r = tu.rec();
     const int16_t *q = tu.q();
     int16_t *stage = col == 0 ? S->stage_y : S->stage_c[col - 1];
+    #pragma unroll 1
     for (int e = tm.tid; e < n * n; e += tm.nt) {
       rec[(e >> log2n) * P.lw + (e & (n - 1))] = r[e];
       co[e] = q[e];
@@ -527,6 +535,7 @@ CTU_FN_NOINLINE void rough_mode_costs(const Ctx &c, int log2w, const int8_t *mpm
   CtuS *S = c.S;
   const CtuConfig *cfg = c.cfg;
   const bool ts = log2w == 2 && cfg->trskip_enable;
+  #pragma unroll 1
   for (int mode = CTU_TID; mode < 35; mode += CTU_NT) {
     // get_cost_dual reads state->cabac, get_cost reads state->search_cabac (search_intra.c:102, 142)
     for (int k = 0; k < 2; ++k) {
@@ -559,25 +568,24 @@ CTU_FN_NOINLINE int rough_search_replay(const Ctx &c, int log2w, const int8_t *m
   int8_t *modes = S->modes;
   double *costs = S->costs;
   int n = 0;
+  uint64_t present = 0;           // modes already in the list
   int32_t min_cost = CTU_MAX_INT, max_cost = -CTU_MAX_INT - 1;
   int offset;
   if (cfg->full_intra_search) offset = 1;
   else { const int offs[4] = { 2, 4, 8, 8 }; offset = offs[log2w - 2]; }
-  for (int mode = 2; mode <= 34; mode += 2 * offset) {
-    for (int i = 0; i < 2; ++i) {
-      if (mode + i * offset <= 34) {
-        costs[n] = S->rc0[mode + i * offset];
-        modes[n] = (int8_t)(mode + i * offset);
-        // the reference keeps min / max as int32 (implicit conversion of the double cost)
-        min_cost = imin(min_cost, (int32_t)costs[n]);
-        max_cost = imax(max_cost, (int32_t)costs[n]);
-        ++n;
-      }
-    }
+  int best_mode = 2;
+  double best_of_list = CTU_MAX_DOUBLE;
+  for (int mode = 2; mode <= 34; mode += offset) {      // (mode, mode + offset) pairs of the reference's loop, in its order
+    const double cst = S->rc0[mode];
+    costs[n] = cst;
+    modes[n] = (int8_t)mode;
+    present |= 1ull << mode;
+    // the reference keeps min / max as int32 (implicit conversion of the double cost)
+    min_cost = imin(min_cost, (int32_t)cst);
+    max_cost = imax(max_cost, (int32_t)cst);
+    if (cst < best_of_list) { best_of_list = cst; best_mode = mode; }     // first minimum, as select_best_mode_index
+    ++n;
   }
-  int best_i = 0;
-  for (int i = 1; i < n; ++i) if (costs[i] < costs[best_i]) best_i = i;
-  int best_mode = modes[best_i];
   double best_cost = min_cost;
   if (min_cost != max_cost) {
     while (offset > 1) {
@@ -588,6 +596,7 @@ CTU_FN_NOINLINE int rough_search_replay(const Ctx &c, int log2w, const int8_t *m
         if (test[i] >= 2 && test[i] <= 34) {
           costs[n] = S->rc0[test[i]];
           modes[n] = (int8_t)test[i];
+          present |= 1ull << test[i];
           if (costs[n] < best_cost) { best_cost = costs[n]; best_mode = modes[n]; }
           ++n;
         }
@@ -596,9 +605,7 @@ CTU_FN_NOINLINE int rough_search_replay(const Ctx &c, int log2w, const int8_t *m
   }
   const int add_modes[5] = { mpm[0], mpm[1], mpm[2], 0, 1 };
   for (int p = 0; p < 5; ++p) {
-    bool has = false;
-    for (int i = 0; i < n; ++i) if (modes[i] == add_modes[p]) { has = true; break; }
-    if (!has) { costs[n] = S->rc1[add_modes[p]]; modes[n] = (int8_t)add_modes[p]; ++n; }
+    if (!((present >> add_modes[p]) & 1)) { costs[n] = S->rc1[add_modes[p]]; modes[n] = (int8_t)add_modes[p]; present |= 1ull << add_modes[p]; ++n; }
   }
   for (int i = 0; i < n; ++i) costs[i] += S->rmb[modes[i]];
   return n;
