@@ -9,7 +9,7 @@ Workload (default): BASELINE config 3 -- 3840x2160 8-bit synthetic I420, --prese
 
 One STEP = `frames_per_step` pictures encoded to HEVC.  Three numbers per run:
   e2e    the headline: pictures in HOST memory go through the unchanged libkvazaar API (kvz_stream_bench.c, the loop of
-         src/encmain.c) -- host->device copy of every picture, device search, device->host copy of CU records /
+         src/encmain.c; steps timed from bitstream out to bitstream out, the pipeline kept full by untimed pictures after them) -- host->device copy of every picture, device search, device->host copy of CU records /
          coefficients / SAO / reconstruction, the reference's own CABAC + bitstream writer on the host threads -- and the
          .hevc comes out.  Same program, same loop, for the reference arm (linked against the unmodified library).
   value  the device side alone: pictures resident in HBM -> kvz_cuda_ctu_submit_device / wait_device (search, deblock,
@@ -50,6 +50,7 @@ WORKLOADS = {
 }
 METRIC = "encoded frames/sec at fixed QP (bit-identical bitstream)"
 DISTINCT = 8          # distinct synthetic pictures in the clip (cycled)
+REF_COOLDOWN = 16     # untimed pictures after the timed steps (keeps the reference's pipeline full during the last step)
 
 
 def peaks():
@@ -80,12 +81,12 @@ def clip_path(wl):
     return p
 
 
-def stream_bench(binary, clip, wl, out, frames_per_step, steps, warmup, extra=(), env=None, timeout=1500):
+def stream_bench(binary, clip, wl, out, frames_per_step, steps, warmup, cooldown=0, extra=(), env=None, timeout=1500):
     """one run of the streaming host (integration/kvz_stream_bench.c); returns its JSON line"""
     e = dict(os.environ)
     e.pop("KVZ_CTU_PROVIDER", None)
     e.update(env or {})
-    cmd = [binary, clip, f"{wl['w']}x{wl['h']}", out, str(frames_per_step), str(steps), str(warmup),
+    cmd = [binary, clip, f"{wl['w']}x{wl['h']}", out, str(frames_per_step), str(steps), str(warmup), str(cooldown),
            f"preset={wl['preset']}", f"qp={wl['qp']}", "period=1", *extra]
     r = subprocess.run(cmd, env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
     if r.returncode != 0:
@@ -154,7 +155,7 @@ def run_reference(args, wl):
     binary = os.path.join(REF_DIR, "kvz_stream_bench_ref")
     clip = clip_path(wl)
     fps_step = args.frames_per_step or wl["ref_frames_per_step"]
-    r = stream_bench(binary, clip, wl, "/tmp/kvz_bench_ref_arm.hevc", fps_step, args.steps, args.warmup)
+    r = stream_bench(binary, clip, wl, "/tmp/kvz_bench_ref_arm.hevc", fps_step, args.steps, args.warmup, cooldown=REF_COOLDOWN)
     cores = os.cpu_count() or 1
     sample = f"{r['frames']} pictures ({args.steps} steps of {fps_step}) after {args.warmup} warm-up steps, unmodified reference through its public API, threads=auto"
     line = {"impl": "reference", "metric": METRIC, "value": r["fps"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -304,7 +305,7 @@ def run_cuda(args, wl):
     with ClockSampler(local) as clk:
         # ---- e2e: host pictures -> .hevc through the reference's API with the CTU job on the device
         barrier()
-        r = stream_bench(ctu_bin, clip, wl, f"/tmp/kvz_bench_ctu_{rank}.hevc", fps_step, args.steps, args.warmup, extra=extra, env=env)
+        r = stream_bench(ctu_bin, clip, wl, f"/tmp/kvz_bench_ctu_{rank}.hevc", fps_step, args.steps, args.warmup, cooldown=owf + 1, extra=extra, env=env)
         e2e_seconds = max_over_ranks(r["seconds"])
         # ---- value: the device side alone
         dev_seconds, launches, kernel_ms, slots = device_leg(args, wl, local, fps_step, barrier)
@@ -350,8 +351,8 @@ def parity_and_baseline(args, wl, clip, ctu_bin, env, extra):
     if not os.path.exists(ref_bin):
         return {"cpu_baseline": {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref missing"}, "bitstream_identical": None}
     a, b = "/tmp/kvz_bench_sample_ref.hevc", "/tmp/kvz_bench_sample_ctu.hevc"
-    rr = stream_bench(ref_bin, clip, wl, a, n, 1, 0)
-    rc = stream_bench(ctu_bin, clip, wl, b, n, 1, 0, extra=extra, env=env)
+    rr = stream_bench(ref_bin, clip, wl, a, n, 1, 0, 0)
+    rc = stream_bench(ctu_bin, clip, wl, b, n, 1, 0, 0, extra=extra, env=env)
     same = sha(a) == sha(b) and os.path.getsize(a) > 0
     if not same:
         print(f"bench.py: BITSTREAM MISMATCH on the {n}-picture sample ({rr['bytes']} vs {rc['bytes']} bytes)", file=sys.stderr)

@@ -9,12 +9,14 @@
  *                                                          libkvzcuda.so
  * so both arms of bench.py measure the same loop, the one src/encmain.c:551-745 runs minus the file reader thread.
  *
- *   kvz_stream_bench clip.yuv WxH out.hevc frames_per_step steps warmup [key=value ...]      (keys as in kvazaar --help)
+ *   kvz_stream_bench clip.yuv WxH out.hevc frames_per_step steps warmup cooldown [key=value ...]   (keys as in kvazaar --help)
  *
- * The clip's pictures are loaded before the clock starts and cycled.  (warmup + steps) * frames_per_step pictures go
- * through ONE encoder; a step ends when the bitstream of its last picture has been returned.  The timed region starts
- * when the first picture of the first timed step is handed to encoder_encode and ends when the last picture's bitstream
- * is out (the pipeline drain is inside).  One JSON line on stdout.
+ * The clip's pictures are loaded before the clock starts and cycled.  (warmup + steps) * frames_per_step + cooldown
+ * pictures go through ONE encoder; a step ends when the bitstream of its last picture has been returned, i.e. the steps
+ * are timed output to output: with warm-up steps the clock starts when the last warm-up picture's bitstream is out
+ * (without: when the first picture is handed in).  `cooldown` untimed pictures follow the timed ones so that the
+ * encoder's pipeline (owf + 1 pictures in flight) is still full while the last timed step runs; cooldown = 0 puts the
+ * pipeline drain inside the last step.  All pictures are written to out.hevc.  One JSON line on stdout.
  */
 #define _POSIX_C_SOURCE 200809L
 #include <stdio.h>
@@ -34,11 +36,11 @@ static double now(void)
 
 int main(int argc, char **argv)
 {
-  if (argc < 7) { fprintf(stderr, "usage: %s clip.yuv WxH out.hevc frames_per_step steps warmup [key=value ...]\n", argv[0]); return 2; }
+  if (argc < 8) { fprintf(stderr, "usage: %s clip.yuv WxH out.hevc frames_per_step steps warmup cooldown [key=value ...]\n", argv[0]); return 2; }
   const char *in = argv[1], *res = argv[2], *out = argv[3];
-  const int fps_step = atoi(argv[4]), steps = atoi(argv[5]), warmup = atoi(argv[6]);
+  const int fps_step = atoi(argv[4]), steps = atoi(argv[5]), warmup = atoi(argv[6]), cooldown = atoi(argv[7]);
   int w = 0, h = 0;
-  if (sscanf(res, "%dx%d", &w, &h) != 2 || fps_step < 1 || steps < 1 || warmup < 0) { fprintf(stderr, "bad arguments\n"); return 2; }
+  if (sscanf(res, "%dx%d", &w, &h) != 2 || fps_step < 1 || steps < 1 || warmup < 0 || cooldown < 0) { fprintf(stderr, "bad arguments\n"); return 2; }
 
   const kvz_api *api = kvz_api_get(8);
   kvz_config *cfg = api->config_alloc();
@@ -46,7 +48,7 @@ int main(int argc, char **argv)
   char num[32];
   snprintf(num, sizeof(num), "%d", w); api->config_parse(cfg, "width", num);
   snprintf(num, sizeof(num), "%d", h); api->config_parse(cfg, "height", num);
-  for (int i = 7; i < argc; ++i) {
+  for (int i = 8; i < argc; ++i) {
     char *eq = strchr(argv[i], '=');
     if (!eq) { fprintf(stderr, "expected key=value, got %s\n", argv[i]); return 2; }
     *eq = 0;
@@ -71,7 +73,7 @@ int main(int argc, char **argv)
   FILE *fo = fopen(out, "wb");
   if (!fo) { fprintf(stderr, "cannot open %s\n", out); return 1; }
 
-  const long total = (long)(warmup + steps) * fps_step, first_timed = (long)warmup * fps_step;
+  const long timed_end = (long)(warmup + steps) * fps_step, total = timed_end + cooldown, first_timed = (long)warmup * fps_step;
   long fed = 0, got = 0;
   unsigned long long bytes = 0;
   double t_start = 0, t_prev = 0, *step_s = calloc((size_t)steps, sizeof(double));
@@ -85,7 +87,7 @@ int main(int argc, char **argv)
         memcpy(pic->u + (size_t)r * (pic->stride / 2), f + ysz + (size_t)r * (w / 2), (size_t)w / 2);
         memcpy(pic->v + (size_t)r * (pic->stride / 2), f + ysz + csz + (size_t)r * (w / 2), (size_t)w / 2);
       }
-      if (fed == first_timed) t_start = t_prev = now();
+      if (fed == 0 && first_timed == 0) t_start = t_prev = now();
       ++fed;
     }
     kvz_data_chunk *chunks = NULL;
@@ -99,7 +101,8 @@ int main(int argc, char **argv)
       for (kvz_data_chunk *c = chunks; c; c = c->next) { fwrite(c->data, 1, c->len, fo); bytes += c->len; }
       api->chunk_free(chunks);
       ++got;
-      if (got > first_timed && (got - first_timed) % fps_step == 0) {
+      if (got == first_timed) t_start = t_prev = now();          /* the last warm-up picture is out */
+      if (got > first_timed && got <= timed_end && (got - first_timed) % fps_step == 0) {
         const double t = now();
         step_s[(got - first_timed) / fps_step - 1] = t - t_prev;
         t_prev = t;
@@ -109,12 +112,13 @@ int main(int argc, char **argv)
     if (flushing && !chunks) break;        /* no more input and no more output (src/encmain.c:735) */
   }
   const double t_end = now();
+  (void)t_end;
   fclose(fo);
   if (got != total) { fprintf(stderr, "expected %ld pictures out, got %ld\n", total, got); return 1; }
   double timed = 0;
   for (int i = 0; i < steps; ++i) timed += step_s[i];
-  printf("{\"frames\": %ld, \"seconds\": %.6f, \"fps\": %.4f, \"frames_per_step\": %d, \"steps\": %d, \"warmup\": %d, \"bytes\": %llu, \"wall_seconds\": %.6f, \"step_seconds\": [",
-         (long)steps * fps_step, timed, (double)steps * fps_step / timed, fps_step, steps, warmup, bytes, t_end - t_start);
+  printf("{\"frames\": %ld, \"seconds\": %.6f, \"fps\": %.4f, \"frames_per_step\": %d, \"steps\": %d, \"warmup\": %d, \"cooldown\": %d, \"bytes\": %llu, \"step_seconds\": [",
+         (long)steps * fps_step, timed, (double)steps * fps_step / timed, fps_step, steps, warmup, cooldown, bytes);
   for (int i = 0; i < steps; ++i) printf("%s%.6f", i ? ", " : "", step_s[i]);
   printf("]}\n");
   fflush(stdout);

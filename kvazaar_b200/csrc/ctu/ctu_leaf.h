@@ -1037,6 +1037,14 @@ CTU_FN void cabac_bin(const SmTables *tb, CabacState *c, int off, int val, doubl
   if (c->update) c->ctx[off] = ((st & 1) == val) ? tb->next_mps[st] : tb->next_lps[st];
 }
 
+// the same with an integer accumulator in units of 2^-15 bit
+CTU_FN void cabac_bin_i(const SmTables *tb, CabacState *c, int off, int val, long long *bits)
+{
+  const uint8_t st = c->ctx[off];
+  *bits += tb->ebits[st ^ val];
+  if (c->update) c->ctx[off] = ((st & 1) == val) ? tb->next_mps[st] : tb->next_lps[st];
+}
+
 CTU_FN int coeff_remain_bits(int symbol, int rice)
 {
   if (symbol < (3 << rice)) return (symbol >> rice) + 1 + rice;
@@ -1074,9 +1082,11 @@ CTU_FN_NOINLINE double coeff_cost_serial(const SmTables *T, const SmTables *tb, 
   while (!coeff[scan[scan_last]]) --scan_last;
   const int pos_last = scan[scan_last];
 
-  double bits = 0;
-  if (n == 4 && cfg->trskip_enable) cabac_bin(tb, c, type == 0 ? CTX_TRSKIP_LUMA : CTX_TRSKIP_CHROMA, tr_skip, &bits);
-  double bits_last = 0;
+  // every term is an integer multiple of 2^-15 bit: the reference's double sums are exact, so the integer sum (units of
+  // 2^-15) converted once gives the same double, without a floating-point add chain per bin
+  long long bits = 0;
+  if (n == 4 && cfg->trskip_enable) cabac_bin_i(tb, c, type == 0 ? CTX_TRSKIP_LUMA : CTX_TRSKIP_CHROMA, tr_skip, &bits);
+  long long bits_last = 0;
   {
     int lx = pos_last & (n - 1), ly = pos_last >> log2n;
     if (scan_idx == 2) { const int t = lx; lx = ly; ly = t; }
@@ -1086,12 +1096,12 @@ CTU_FN_NOINLINE double coeff_cost_serial(const SmTables *T, const SmTables *tb, 
     const int base_x = type ? CTX_LAST_X_CHROMA : CTX_LAST_X_LUMA;
     const int base_y = type ? CTX_LAST_Y_CHROMA : CTX_LAST_Y_LUMA;
     const int gx = T->group_idx[lx], gy = T->group_idx[ly], gmax = T->group_idx[n - 1];
-    for (int k = 0; k < gx; ++k) cabac_bin(tb, c, base_x + ctx_offset + (k >> shift), 1, &bits_last);
-    if (gx < gmax) cabac_bin(tb, c, base_x + ctx_offset + (gx >> shift), 0, &bits_last);
-    for (int k = 0; k < gy; ++k) cabac_bin(tb, c, base_y + ctx_offset + (k >> shift), 1, &bits_last);
-    if (gy < gmax) cabac_bin(tb, c, base_y + ctx_offset + (gy >> shift), 0, &bits_last);
-    if (gx > 3) bits_last += (gx - 2) / 2;
-    if (gy > 3) bits_last += (gy - 2) / 2;
+    for (int k = 0; k < gx; ++k) cabac_bin_i(tb, c, base_x + ctx_offset + (k >> shift), 1, &bits_last);
+    if (gx < gmax) cabac_bin_i(tb, c, base_x + ctx_offset + (gx >> shift), 0, &bits_last);
+    for (int k = 0; k < gy; ++k) cabac_bin_i(tb, c, base_y + ctx_offset + (k >> shift), 1, &bits_last);
+    if (gy < gmax) cabac_bin_i(tb, c, base_y + ctx_offset + (gy >> shift), 0, &bits_last);
+    if (gx > 3) bits_last += (long long)((gx - 2) / 2) << 15;
+    if (gy > 3) bits_last += (long long)((gy - 2) / 2) << 15;
   }
   const int base_cg = CTX_SIG_CG + type;
   const int base_sig = type == 0 ? CTX_SIG_LUMA : CTX_SIG_CHROMA;
@@ -1111,14 +1121,14 @@ CTU_FN_NOINLINE double coeff_cost_serial(const SmTables *T, const SmTables *tb, 
     const int right = (cgx < side - 1) ? (int)((cg_flags >> (cgy * side + cgx + 1)) & 1) : 0;
     const int lower = (cgy < side - 1) ? (int)((cg_flags >> ((cgy + 1) * side + cgx)) & 1) : 0;
     if (i == cg_last || i == 0) cg_flags |= 1ull << cg_blk;
-    else cabac_bin(tb, c, base_cg + (right || lower), (int)((cg_flags >> cg_blk) & 1), &bits);
+    else cabac_bin_i(tb, c, base_cg + (right || lower), (int)((cg_flags >> cg_blk) & 1), &bits);
     if ((cg_flags >> cg_blk) & 1) {
       const int pattern = (n == 4) ? -1 : right + (lower << 1);
       for (; scan_pos_sig >= sub_pos; --scan_pos_sig) {
         const int blk = scan[scan_pos_sig];
         const int sig = coeff[blk] != 0;
         if (scan_pos_sig > sub_pos || i == 0 || num_nz)
-          cabac_bin(tb, c, base_sig + sig_ctx_inc(T, pattern, scan_idx, blk & (n - 1), blk >> log2n, log2n, type), sig, &bits);
+          cabac_bin_i(tb, c, base_sig + sig_ctx_inc(T, pattern, scan_idx, blk & (n - 1), blk >> log2n, log2n, type), sig, &bits);
         if (sig) {
           abs_coeff[num_nz++] = iabs((int)coeff[blk]);
           if (last_nz == -1) last_nz = scan_pos_sig;
@@ -1138,19 +1148,19 @@ CTU_FN_NOINLINE double coeff_cost_serial(const SmTables *T, const SmTables *tb, 
       int first_c2 = -1;
       for (int k = 0; k < num_c1; ++k) {
         const int symbol = abs_coeff[k] > 1;
-        cabac_bin(tb, c, base_one + c1, symbol, &bits);
+        cabac_bin_i(tb, c, base_one + c1, symbol, &bits);
         if (symbol) { c1 = 0; if (first_c2 == -1) first_c2 = k; }
         else if (c1 < 3 && c1 > 0) ++c1;
       }
       if (c1 == 0 && first_c2 != -1)
-        cabac_bin(tb, c, (type == 0 ? CTX_ABS_LUMA : CTX_ABS_CHROMA) + ctx_set, abs_coeff[first_c2] > 2, &bits);
-      bits += (cfg->signhide_enable && sign_hidden) ? num_nz - 1 : num_nz;
+        cabac_bin_i(tb, c, (type == 0 ? CTX_ABS_LUMA : CTX_ABS_CHROMA) + ctx_set, abs_coeff[first_c2] > 2, &bits);
+      bits += (long long)((cfg->signhide_enable && sign_hidden) ? num_nz - 1 : num_nz) << 15;
       if (c1 == 0 || num_nz > 8) {
         int first_coeff2 = 1;
         for (int k = 0; k < num_nz; ++k) {
           const int base_level = (k < 8) ? (2 + first_coeff2) : 1;
           if (abs_coeff[k] >= base_level) {
-            bits += coeff_remain_bits(abs_coeff[k] - base_level, rice);
+            bits += (long long)coeff_remain_bits(abs_coeff[k] - base_level, rice) << 15;
             if (abs_coeff[k] > 3 * (1 << rice)) rice = imin(rice + 1, 4);
           }
           if (abs_coeff[k] >= 2) first_coeff2 = 0;
@@ -1158,10 +1168,7 @@ CTU_FN_NOINLINE double coeff_cost_serial(const SmTables *T, const SmTables *tb, 
       }
     }
   }
-  double total = 0;
-  total += bits_last;
-  total += bits;
-  return total;
+  return (double)(bits_last + bits) * (1.0 / 32768.0);
 }
 
 // ------------------------------------------------------------------------------------------------ one transform unit

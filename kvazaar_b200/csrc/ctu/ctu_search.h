@@ -911,31 +911,35 @@ CTU_FN_NOINLINE void search_ctu(const Ctx &c, int cx, int cy)
           if (cur_cu->type == CU_NOTSET || F->cbf || cfg->cu_split_termination == 1) F->do_children = 1;
           else F->split_cost = CTU_MAX_INT;
         }
-        F->stage = can_split ? 1 : 3;
+        F->stage = 1;
+        if (!can_split) S->ret_cost = F->cost;
       }
       CTU_SYNC();
-      continue;
-    }
-    if (stage == 1) {
-      // ---------------- children, one at a time, while the split is still cheaper
-      if (descend) {
-        const int k = next_child, half = cu_width / 2;
-        CTU_LEADER {
-          F->child = k + 1;
-          S->fr[d + 1].x = x + (k & 1) * half;
-          S->fr[d + 1].y = y + (k >> 1) * half;
-          S->fr[d + 1].stage = 0;
-        }
+      if (!can_split) {
+        // no split possible at this depth: the CU is final, return to the parent at once
+        if (d < 4) work_tree_copy_down(c, xl, yl, d);
+        if (d == 0) break;
+        --d;
+        CTU_LEADER S->fr[d].split_cost += S->ret_cost;
         CTU_SYNC();
-        ++d;
-        continue;
       }
-      CTU_LEADER F->stage = 2;
-      CTU_SYNC();
       continue;
     }
-    if (stage == 2) {
-      // ---------------- after the children: combined CU, then split / no split
+    if (stage == 1 && descend) {
+      // ---------------- children, one at a time, while the split is still cheaper
+      const int k = next_child, half = cu_width / 2;
+      CTU_LEADER {
+        F->child = k + 1;
+        S->fr[d + 1].x = x + (k & 1) * half;
+        S->fr[d + 1].y = y + (k >> 1) * half;
+        S->fr[d + 1].stage = 0;
+      }
+      CTU_SYNC();
+      ++d;
+      continue;
+    }
+    {
+      // ---------------- after the children (stage 1 without a next child): combined CU, then split / no split
       CuRec *cur_cu = cu_at(L, xl, yl);
       const bool inside = x + cu_width <= cfg->width && y + cu_width <= cfg->height;
       bool combine = false;
@@ -985,24 +989,12 @@ CTU_FN_NOINLINE void search_ctu(const Ctx &c, int cx, int cy)
         CTU_SYNC();
         work_tree_copy_down(c, xl, yl, d);
       }
-      CTU_LEADER F->stage = 4;
-      CTU_SYNC();
-      continue;
     }
-    if (stage == 3) {
-      // ---------------- no split possible at this depth
-      if (d < 4) work_tree_copy_down(c, xl, yl, d);
-      CTU_LEADER F->stage = 4;
-      CTU_SYNC();
-      continue;
-    }
-    // stage 4: return
-    CTU_LEADER S->ret_cost = F->cost;
-    CTU_SYNC();
+    // return to the parent
     if (d == 0) break;
-    --d;
-    CTU_LEADER S->fr[d].split_cost += S->ret_cost;
+    CTU_LEADER S->fr[d - 1].split_cost += F->cost;
     CTU_SYNC();
+    --d;
   }
 }
 
