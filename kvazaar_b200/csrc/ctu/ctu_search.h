@@ -59,6 +59,7 @@ struct CtuS {                       // per-CTA scalar state + scratch; shared me
   SmTables tb;
   LcuLevel lv[5];                   // work tree: CU records here, planes in CtuWork::store
   TuRes res[8][3];                  // [RDO candidate][colour]
+  TuRes res_ts[8][2];               // [RDO candidate][transform, transform skip] of a 4x4 luma unit
   // the coefficients of the transform units reconstructed last (the CU whose cost is computed next), per colour
   int16_t stage_y[1024], stage_c[2][256];
   int32_t stage_key[3];             // (xl << 16) | (yl << 8) | depth of the staged unit, -1: none
@@ -666,8 +667,15 @@ CTU_FN_NOINLINE void search_cu_intra(const Ctx &c, LcuLevel *L, int x, int y, in
     const int ncand = S->n_modes;
     const int rdoq_tr_depth = depth == 4 ? 1 : 0;
     PROF_T0(PR_QRES);
-    for_tu_tasks(c, ncand * np, 1 << (2 * log2w), [&](const Team &tm, unsigned char *slot, int t) {
-      const int cand = t / np, col = t - cand * np;
+    // 4x4 luma units with transform skip enabled: the two alternatives of kvz_quantize_residual_trskip are jobs of their
+    // own (better balance over the warps), the leader picks below; the pick's coefficient bits are the ones its luma
+    // cost needs (same call: rdo.c:251-258 codes tr_skip as 0), so they are not computed a third time
+    const bool ts_split = depth == 4 && cfg->trskip_enable;
+    const int nluma = ts_split ? 2 : 1;
+    const int per_cand = nluma + (np - 1);
+    for_tu_tasks(c, ncand * per_cand, 1 << (2 * log2w), [&](const Team &tm, unsigned char *slot, int t) {
+      const int cand = t / per_cand, k = t - cand * per_cand;
+      const int col = k < nluma ? 0 : 1 + (k - nluma);
       const int mode = S->modes[cand];
       const int log2n = tu_log2(depth, col), n = 1 << log2n;
       const TuS tu = tu_at(slot, n * n);
@@ -675,10 +683,12 @@ CTU_FN_NOINLINE void search_cu_intra(const Ctx &c, LcuLevel *L, int x, int y, in
       const int sh = col ? 1 : 0;
       const int off = (xl >> sh) + (yl >> sh) * P.lw;
       TuJob j = { &S->refs[col], P.src + off, P.lw, col, log2n, mode, scan_order_intra(mode, depth), rdoq_tr_depth };
-      const int ts = tu_eval(tm, &c.S->tb, &S->tb, cfg, S->cabac0.ctx, &S->sc, tu, j);
+      int ts = 0;
+      if (col == 0 && ts_split) tu_core(tm, &c.S->tb, &S->tb, cfg, S->cabac0.ctx, tu, j, k == 1);
+      else ts = tu_eval(tm, &c.S->tb, &S->tb, cfg, S->cabac0.ctx, &S->sc, tu, j);
       if (tm.tid == 0) {
         const TuFixed *fx = tu.fx();
-        TuRes *r = &S->res[cand][col];
+        TuRes *r = (col == 0 && ts_split) ? &S->res_ts[cand][k] : &S->res[cand][col];
         r->ssd = fx->ssd; r->has = fx->has; r->tr_skip = ts;
         // coefficient bits of kvz_cu_rd_cost_luma / _chroma: the search models are not adapted here (update == 0)
         r->bits = fx->has ? coeff_cost_serial(&c.S->tb, &S->tb, cfg, &S->sc, tu.q(), log2n, col ? 2 : 0, j.scan_idx, 0,
@@ -693,6 +703,14 @@ CTU_FN_NOINLINE void search_cu_intra(const Ctx &c, LcuLevel *L, int x, int y, in
       CuRec *tr_cu = cu_at(L, xl, yl);
       tr_cu->tr_depth = (uint8_t)depth;
       for (int r = 0; r < ncand; ++r) {
+        if (ts_split) {
+          // kvz_quantize_residual_trskip (transform.c:242-288): SSD + coefficient bits * lambda, transform skip only if cheaper
+          double tc[2];
+          for (int k = 0; k < 2; ++k) { tc[k] = (double)(unsigned)S->res_ts[r][k].ssd; tc[k] += S->res_ts[r][k].bits * cfg->lambda; }
+          const int pick = tc[0] <= tc[1] ? 0 : 1;
+          S->res[r][0] = S->res_ts[r][pick];
+          S->res[r][0].tr_skip = pick;
+        }
         const int mode = S->modes[r];
         const double rdo_bitcost = luma_mode_bits(c, mode, S->mpm);
         S->costs[r] = rdo_bitcost * cfg->lambda;
