@@ -502,10 +502,13 @@ CTU_FN int dot4_s16_s8(const int16_t *s, const int8_t *m, int acc) { return acc 
 #endif
 
 // forward: dst[k*N + j] = (int16)((sum_i M[k][i] * src[j*N + i] + add) >> shift)
-CTU_FN_NOINLINE void fwd_pass(const Team &tm, const int16_t *src, int16_t *dst, const int8_t *M, int n, int shift)
+// L2N != 0: the size is a compile-time constant (the 4x4 path: most transform units of a CTU)
+template <int L2N>
+CTU_FN_NOINLINE void fwd_pass(const Team &tm, const int16_t *src, int16_t *dst, const int8_t *M, int n_rt, int shift)
 {
   const int add = 1 << (shift - 1);
-  const int log2n = n == 4 ? 2 : (n == 8 ? 3 : (n == 16 ? 4 : 5));
+  const int n = L2N ? (1 << L2N) : n_rt;
+  const int log2n = L2N ? L2N : (n == 4 ? 2 : (n == 8 ? 3 : (n == 16 ? 4 : 5)));
   #pragma unroll 1
   for (int e = tm.tid; e < n * n; e += tm.nt) {
     const int k = e >> log2n, j = e & (n - 1);
@@ -518,10 +521,12 @@ CTU_FN_NOINLINE void fwd_pass(const Team &tm, const int16_t *src, int16_t *dst, 
   tsync(tm);
 }
 // inverse: dst[j*N + k] = clip16((sum_i M[i][k] * src[i*N + j] + add) >> shift)
-CTU_FN_NOINLINE void inv_pass(const Team &tm, const int16_t *src, int16_t *dst, const int8_t *M, int n, int shift)
+template <int L2N>
+CTU_FN_NOINLINE void inv_pass(const Team &tm, const int16_t *src, int16_t *dst, const int8_t *M, int n_rt, int shift)
 {
   const int add = 1 << (shift - 1);
-  const int log2n = n == 4 ? 2 : (n == 8 ? 3 : (n == 16 ? 4 : 5));
+  const int n = L2N ? (1 << L2N) : n_rt;
+  const int log2n = L2N ? L2N : (n == 4 ? 2 : (n == 8 ? 3 : (n == 16 ? 4 : 5)));
   #pragma unroll 1
   for (int e = tm.tid; e < n * n; e += tm.nt) {
     const int j = e >> log2n, k = e & (n - 1);
@@ -618,9 +623,11 @@ CTU_FN_NOINLINE void quant_block(const Team &tm, const SmTables *T, const CtuCon
 }
 
 // kvz_dequant: q -> b.  type: 0 luma, 2 / 3 chroma
-CTU_FN_NOINLINE void dequant_block(const Team &tm, const CtuConfig *cfg, const TuS &tu, int n, int type)
+template <int L2N>
+CTU_FN_NOINLINE void dequant_block(const Team &tm, const CtuConfig *cfg, const TuS &tu, int n_rt, int type)
 {
-  const int transform_shift = 15 - 8 - ilog2(n);
+  const int n = L2N ? (1 << L2N) : n_rt;
+  const int transform_shift = 15 - 8 - (L2N ? L2N : ilog2(n));
   const int qp_scaled = scaled_qp(type, cfg->qp);
   const int shift = 20 - 14 - transform_shift;
   const int scale = inv_quant_scale(qp_scaled % 6) << (qp_scaled / 6);
@@ -742,9 +749,11 @@ CTU_FN int team_sum(int v) { return v; }
 
 // kvz_rdoq for one TU, executed by one team (the first warp): coef = tu->b, levels to tu->q.  `cabac` = the models of
 // state->cabac (NOT the search copy: rdo.c:665).  type 0 luma / 2 chroma; tr_depth as in quant-generic.c:237-238.
-CTU_FN_NOINLINE void rdoq_team(const SmTables *T, const SmTables *tb, const CtuConfig *cfg, const uint8_t *cabac, const TuS &tu, int log2n, int type,
+template <int L2N>
+CTU_FN_NOINLINE void rdoq_team(const SmTables *T, const SmTables *tb, const CtuConfig *cfg, const uint8_t *cabac, const TuS &tu, int log2n_rt, int type,
                       int scan_idx, int tr_depth, int lane)
 {
+  const int log2n = L2N ? L2N : log2n_rt;
   const int16_t *coef = tu.b();
   int16_t *q = tu.q();
   TuFixed &s = *tu.fx();
@@ -1185,10 +1194,11 @@ struct TuJob {
   int rdoq_tr_depth;        // context selector of RDOQ's cbf cost (quant-generic.c:237-238)
 };
 
-CTU_FN_NOINLINE void tu_core(const Team &tm, const SmTables *T, const SmTables *tb, const CtuConfig *cfg, const uint8_t *cabac0, const TuS &tu,
-                             const TuJob &j, bool use_trskip)
+template <int L2N>
+CTU_FN_NOINLINE void tu_core_t(const Team &tm, const SmTables *T, const SmTables *tb, const CtuConfig *cfg, const uint8_t *cabac0, const TuS &tu,
+                               const TuJob &j, bool use_trskip)
 {
-  const int log2n = j.log2n, n = 1 << log2n, nn = n * n;
+  const int log2n = L2N ? L2N : j.log2n, n = 1 << log2n, nn = n * n;
   const int color = j.color;
   const int ts_shift = 15 - 8 - log2n;
   int16_t *a = tu.a(), *b = tu.b(), *q = tu.q(), *t = tu.t();
@@ -1210,12 +1220,12 @@ CTU_FN_NOINLINE void tu_core(const Team &tm, const SmTables *T, const SmTables *
     for (int e = tm.tid; e < nn; e += tm.nt) b[e] = (int16_t)((uint16_t)a[e] << ts_shift);
     tsync(tm);
   } else {
-    fwd_pass(tm, a, t, M, n, log2n - 1);
-    fwd_pass(tm, t, b, M, n, log2n + 6);
+    fwd_pass<L2N>(tm, a, t, M, n, log2n - 1);
+    fwd_pass<L2N>(tm, t, b, M, n, log2n + 6);
   }
   const int type = color == 0 ? 0 : 2;
   if (cfg->rdoq_enable && (n > 4 || !cfg->rdoq_skip)) {
-    if (tm.tid < CTU_TEAM_N) rdoq_team(T, tb, cfg, cabac0, tu, log2n, type, j.scan_idx, j.rdoq_tr_depth, tm.tid);
+    if (tm.tid < CTU_TEAM_N) rdoq_team<L2N>(T, tb, cfg, cabac0, tu, log2n, type, j.scan_idx, j.rdoq_tr_depth, tm.tid);
     tsync(tm);
   } else {
     quant_block(tm, T, cfg, tu, n, type, j.scan_idx);
@@ -1237,15 +1247,15 @@ CTU_FN_NOINLINE void tu_core(const Team &tm, const SmTables *T, const SmTables *
   tsync(tm);
   int ssd = 0;
   if (fx->has) {
-    dequant_block(tm, cfg, tu, n, color == 0 ? 0 : (color == 1 ? 2 : 3));
+    dequant_block<L2N>(tm, cfg, tu, n, color == 0 ? 0 : (color == 1 ? 2 : 3));
     if (use_trskip) {
       const int offs = 1 << (ts_shift - 1);
       #pragma unroll 1
       for (int e = tm.tid; e < nn; e += tm.nt) a[e] = (int16_t)(((int)b[e] + offs) >> ts_shift);
       tsync(tm);
     } else {
-      inv_pass(tm, b, t, M, n, 7);
-      inv_pass(tm, t, a, M, n, 12);
+      inv_pass<L2N>(tm, b, t, M, n, 7);
+      inv_pass<L2N>(tm, t, a, M, n, 12);
     }
     #pragma unroll 1
     for (int e = tm.tid; e < nn; e += tm.nt) {
@@ -1268,6 +1278,13 @@ CTU_FN_NOINLINE void tu_core(const Team &tm, const SmTables *T, const SmTables *
   }
   if (ssd) CTU_ATOMIC_ADD(&fx->ssd, ssd);
   tsync(tm);
+}
+
+CTU_FN void tu_core(const Team &tm, const SmTables *T, const SmTables *tb, const CtuConfig *cfg, const uint8_t *cabac0, const TuS &tu,
+                    const TuJob &j, bool use_trskip)
+{
+  if (j.log2n == 2) tu_core_t<2>(tm, T, tb, cfg, cabac0, tu, j, use_trskip);
+  else tu_core_t<0>(tm, T, tb, cfg, cabac0, tu, j, use_trskip);
 }
 
 // One colour of one transform unit including the transform-skip decision of 4x4 luma units
