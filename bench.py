@@ -41,9 +41,9 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 WORKLOADS = {
-    "2160p": dict(w=3840, h=2160, preset="veryslow", qp=22, frames_per_step=32, ref_frames_per_step=12, sample=16, owf=44, slots=40,
+    "2160p": dict(w=3840, h=2160, preset="veryslow", qp=22, frames_per_step=16, ref_frames_per_step=12, sample=16, owf=44, slots=40,
                   name="BASELINE config 3: 3840x2160 8-bit synthetic I420, --preset veryslow -q 22 -p 1 (all-intra)"),
-    "1080p": dict(w=1920, h=1080, preset="medium", qp=27, frames_per_step=96, ref_frames_per_step=96, sample=64, owf=84, slots=72,
+    "1080p": dict(w=1920, h=1080, preset="medium", qp=27, frames_per_step=64, ref_frames_per_step=64, sample=64, owf=84, slots=72,
                   name="BASELINE config 2: 1920x1080 8-bit synthetic I420, --preset medium -q 27 -p 1 (all-intra)"),
     "64x64": dict(w=64, h=64, preset="ultrafast", qp=32, frames_per_step=64, ref_frames_per_step=64, sample=16, owf=8, slots=8,
                   name="BASELINE config 1: 64x64 8-bit synthetic I420, --preset ultrafast -q 32 -p 1 (all-intra)"),
@@ -229,36 +229,42 @@ def device_leg(args, wl, local, frames_per_step, barrier):
     res = DevResult()
     kernel_ms = []
 
-    def run(nframes, collect):
-        pending, nxt, done = [], 0, 0
-        while done < nframes:
-            while nxt < nframes and len(pending) < slots:
-                base = dev[nxt % DISTINCT].data_ptr()
-                s = lib.kvz_cuda_ctu_submit_device(enc, base, base + w * h, base + w * h * 5 // 4, w, w // 2, ctx.ctypes.data,
-                                                   cfg.lambda_, cfg.lambda_sqrt, wl["qp"])
-                if s < 0:
-                    raise RuntimeError(f"submit: {lib.kvz_cuda_last_error()}")
-                pending.append(s)
-                nxt += 1
-            s = pending.pop(0)
-            if lib.kvz_cuda_ctu_wait_device(enc, s, C.byref(res)) != 0:
-                raise RuntimeError(f"wait: {lib.kvz_cuda_last_error()}")
-            if collect:
-                kernel_ms.append(res.search_kernel_ms)
-            lib.kvz_cuda_ctu_release(enc, s)
-            done += 1
-
-    run(args.warmup * frames_per_step, False)
-    torch.cuda.synchronize()
-    barrier()
-    l0 = lib.kvz_cuda_ctu_launches(enc)
+    # one continuous run, `slots` pictures in flight throughout: warm-up pictures, the timed pictures, and `slots` more so
+    # that the pipeline is still full while the last timed pictures are searched.  The timed region is completion to
+    # completion: from the moment the last warm-up picture is done to the moment the last timed picture is done.
+    n_warm, n_timed = args.warmup * frames_per_step, args.steps * frames_per_step
+    total = n_warm + n_timed + slots
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    run(args.steps * frames_per_step, True)
-    e1.record()
+    barrier()
+    l0 = l1 = lib.kvz_cuda_ctu_launches(enc)
+    if n_warm == 0:
+        e0.record()
+    pending, nxt, done = [], 0, 0
+    while done < total:
+        while nxt < total and len(pending) < slots:
+            base = dev[nxt % DISTINCT].data_ptr()
+            s = lib.kvz_cuda_ctu_submit_device(enc, base, base + w * h, base + w * h * 5 // 4, w, w // 2, ctx.ctypes.data,
+                                               cfg.lambda_, cfg.lambda_sqrt, wl["qp"])
+            if s < 0:
+                raise RuntimeError(f"submit: {lib.kvz_cuda_last_error()}")
+            pending.append(s)
+            nxt += 1
+        s = pending.pop(0)
+        if lib.kvz_cuda_ctu_wait_device(enc, s, C.byref(res)) != 0:
+            raise RuntimeError(f"wait: {lib.kvz_cuda_last_error()}")
+        lib.kvz_cuda_ctu_release(enc, s)
+        done += 1
+        if n_warm < done <= n_warm + n_timed:
+            kernel_ms.append(res.search_kernel_ms)
+        if done == n_warm:
+            e0.record()
+            l0 = lib.kvz_cuda_ctu_launches(enc)
+        if done == n_warm + n_timed:
+            e1.record()
+            l1 = lib.kvz_cuda_ctu_launches(enc)
     torch.cuda.synchronize()
     seconds = e0.elapsed_time(e1) / 1000.0
-    launches = int(lib.kvz_cuda_ctu_launches(enc) - l0)
+    launches = int(l1 - l0)
     lib.kvz_cuda_ctu_close(enc)
     return seconds, launches, float(np.mean(kernel_ms)) if kernel_ms else None, slots
 
