@@ -116,3 +116,53 @@ def test_bitstream_identical_with_cuda_strategies(tmp_path, name, w, h, frames, 
     a, b = open(ref_out, "rb").read(), open(cuda_out, "rb").read()
     assert len(a) > 100
     assert a == b, f"{name}: bitstreams differ ({len(a)} vs {len(b)} bytes)"
+
+
+def _sel_encode(tmp_path, env=None):
+    sel, ref = _need("kvazaar_sel", "kvazaar")
+    clip = str(tmp_path / "sel64.yuv")
+    _yuv(clip, 64, 64, 2)
+    outs, logs = [], []
+    for binary, e2 in ((ref, {}), (sel, env or {})):
+        e = dict(os.environ)
+        for k in list(e):
+            if k.startswith("KVAZAAR_OVERRIDE_"):
+                del e[k]
+        e.update(e2)
+        out = str(tmp_path / f"o{len(outs)}.hevc")
+        r = subprocess.run([binary, "-i", clip, "--input-res", "64x64", "-o", out, "--preset", "ultrafast", "-q", "32", "-p", "1"],
+                           env=e, stderr=subprocess.PIPE, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-1500:]
+        outs.append(open(out, "rb").read())
+        logs.append(r.stderr)
+    return outs, logs[1]
+
+
+def _chosen(log, strategy_type):
+    """the line DEBUG_STRATEGYSELECTOR marks with '>' in the block of `strategy_type` (strategyselector.c:309-320)"""
+    block = log.split(f"Choosing strategy for {strategy_type}:\n", 1)[1].split("Choosing strategy for", 1)[0]
+    return [ln for ln in block.splitlines() if ln.startswith(">")][0]
+
+
+def test_selection_library_without_device_keeps_host_strategies(tmp_path):
+    """CPU: the selector-wrapped reference registers nothing without a device and encodes like the plain reference"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("has a GPU")
+    outs, log = _sel_encode(tmp_path)
+    assert outs[0] == outs[1] and len(outs[0]) > 100
+    assert "cuda" not in _chosen(log, "satd_8x8")
+
+
+@pytest.mark.gpu
+def test_selection_through_the_reference_selector(tmp_path):
+    """The cuda entries registered inside kvz_strategyselector_init through kvz_strategyselector_register
+    (strategyselector.c:233-273): priority 50 wins the choice (:296), KVAZAAR_OVERRIDE_<type>=cuda|generic both work
+    (:286-306), and the bitstream of BASELINE config 1 stays identical in every case."""
+    outs, log = _sel_encode(tmp_path)
+    assert outs[0] == outs[1] and len(outs[0]) > 100
+    for t in ("satd_8x8", "dct_8x8", "angular_pred", "sao_edge_ddistortion", "quant", "array_checksum", "filter_hpel_blocks_hor_ver_luma"):
+        assert "> cuda (50" in _chosen(log, t), (t, _chosen(log, t))
+    outs, log = _sel_encode(tmp_path, {"KVAZAAR_OVERRIDE_satd_8x8": "generic", "KVAZAAR_OVERRIDE_dct_8x8": "cuda"})
+    assert outs[0] == outs[1]
+    assert "choosing satd_8x8:generic" in log and "choosing dct_8x8:cuda" in log

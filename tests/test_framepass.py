@@ -160,3 +160,26 @@ def test_cuda_frame_pass_full_size_1080p_medium(cuda_lib, ref):
     torch.cuda.synchronize()
     assert np.array_equal(kb.fp_expand_compact(L, small.numpy(), compact.numpy()), res_pin.numpy())
     fp.close()
+
+
+@pytest.mark.gpu
+def test_cuda_frame_pass_full_size_2160p_veryslow_shape(cuda_lib, ref):
+    """The configs[2] shape at its full size (3840x2160, QP22, RDOQ + sign hiding + transform-skip choice + deblocking +
+    SAO): one frame, every section of the result blob equals the pass through the reference's strategy functions."""
+    import os
+    import torch
+    from _oracle import ref_frame_pass
+    kb = cuda_lib
+    W, H, qp = 3840, 2160, 22
+    src = synth_frame(W, H, frame_idx=7)
+    fp = kb.FramePass(W, H, qp, 1, 1, 0.0, 1)
+    src_pin = torch.from_numpy(src.copy()).pin_memory()
+    res_pin = torch.empty(fp.host_bytes, dtype=torch.uint8).pin_memory()
+    fp.run_host(src_pin, res_pin)
+    torch.cuda.synchronize()
+    want = ref_frame_pass(ref, src, W, H, qp, fp.layout, nthreads=min(64, os.cpu_count() or 8), signhide=1, rdoq=1, trskip=1)
+    sec = kb.fp_sections(fp.layout, W, H)
+    for name in sec:
+        a, b = kb.fp_section(res_pin.numpy(), sec, name), kb.fp_section(want, sec, name)
+        assert np.array_equal(a, b), (name, int(np.argmax(a != b)))
+    fp.close()
