@@ -31,6 +31,8 @@ static_assert(sizeof(kvz_cuda_ctu_sao) == sizeof(SaoRec), "sao layout");
 namespace {
 
 constexpr int kThreads = 128;
+// three CTAs per SM: registers (168 x 128 threads) and shared memory (228 KB per SM, 1 KB reserved per CTA)
+static_assert(sizeof(CtuS) + 1024 + 64 <= 228 * 1024 / 3, "CtuS no longer fits three CTAs per SM");
 
 struct KernelArgs {
   const CtuTables *T;

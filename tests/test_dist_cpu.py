@@ -85,3 +85,68 @@ def test_allgather_tile_reconstructions_gloo_world2():
     out = mgr.dict()
     mp.spawn(_tile_worker, args=(2, port, out), nprocs=2, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+# ---- the CTU search driver's N > 1 path: pictures sharded over ranks (all-intra pictures are independent, no data-path
+# collective), each rank encodes its shard with its own provider, times are max-reduced: gloo, two ranks, host provider
+def _ctu_shard_worker(rank, world, port, clip, out_dir, out):
+    import hashlib
+    import subprocess
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        ref_dir = os.path.join(root, "oracle", "_ref")
+        w, h, frames = 128, 64, 6
+        fsz = w * h * 3 // 2
+        data = np.fromfile(clip, dtype=np.uint8).reshape(frames, fsz)
+        mine = kd.shard_frames(frames, rank, world)
+        shard = os.path.join(out_dir, f"shard{rank}.yuv")
+        data[mine].tofile(shard)
+        res = {}
+        for name, binary, env in (("ref", "kvz_stream_bench_ref", {}),
+                                  ("ctu", "kvz_stream_bench_ctu", {"KVZ_CTU_PROVIDER": os.path.join(root, "tests", "hostsim", "libkvzctu_hostsim.so")})):
+            e = dict(os.environ)
+            e.pop("KVZ_CTU_PROVIDER", None)
+            e.update(env)
+            o = os.path.join(out_dir, f"{name}{rank}.hevc")
+            r = subprocess.run([os.path.join(ref_dir, binary), shard, f"{w}x{h}", o, str(len(mine)), "1", "0", "0", "preset=medium", "qp=27", "period=1"],
+                               env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+            assert r.returncode == 0, r.stderr[-800:]
+            res[name] = hashlib.sha256(open(o, "rb").read()).hexdigest()
+        same = res["ref"] == res["ctu"]
+        # the bench's reduction: whole-job frames over the slowest rank's time
+        t = torch.tensor([1.0 + rank], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        n = torch.tensor([float(len(mine))], dtype=torch.float64)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+        out[rank] = (same, float(t.item()), float(n.item()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ctu_driver_pictures_shard_over_ranks_gloo_world2(tmp_path):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for f in ("kvz_stream_bench_ref", "kvz_stream_bench_ctu"):
+        if not os.path.exists(os.path.join(root, "oracle", "_ref", f)):
+            import pytest
+            pytest.skip("oracle/_ref stream bench hosts missing")
+    if not os.path.exists(os.path.join(root, "tests", "hostsim", "libkvzctu_hostsim.so")):
+        import subprocess
+        subprocess.check_call(["sh", os.path.join(root, "tools", "build_hostsim.sh")])
+    sys.path.insert(0, os.path.join(root, "tools"))
+    from synth_yuv import synth_frame
+    clip = str(tmp_path / "c.yuv")
+    with open(clip, "wb") as fh:
+        for i in range(6):
+            fh.write(synth_frame(128, 64, 1234, i).tobytes())
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_ctu_shard_worker, args=(2, port, clip, str(tmp_path), out), nprocs=2, join=True)
+    assert out[0][0] and out[1][0], "a rank's shard differs from the reference's bitstream of the same pictures"
+    assert out[0][1] == out[1][1] == 2.0 and out[0][2] == out[1][2] == 6.0
