@@ -37,7 +37,18 @@
 #define CTU_TEAM_N 1
 #define CTU_TEAM_SYNC() ((void)0)
 #endif
-#define CTU_LEADER if (CTU_TID == 0)
+// The leader is lane 0 of ONE of the CTA's warps, chosen per CTA (first word of the CTA's shared memory, set by the kernel):
+// the CTAs that share an SM get different leader warps, so their serial sections run on different SM sub-partitions
+// (own scheduler, own L0 instruction cache) instead of all on warp 0's.
+#if defined(__CUDACC__)
+extern __shared__ __align__(16) unsigned char ctu_smem_raw[];
+#endif
+#if defined(__CUDA_ARCH__)
+#define CTU_LEADER_TID (*reinterpret_cast<const int *>(ctu_smem_raw))
+#else
+#define CTU_LEADER_TID 0
+#endif
+#define CTU_LEADER if (CTU_TID == CTU_LEADER_TID)
 
 // Frame-level data (reconstruction planes, CU records, border buffers, SAO parameters, row context models) is written
 // by the CTA of one CTU and read by the CTAs of its neighbours, which run on other SMs inside the same launch: such
@@ -53,7 +64,7 @@ enum { PR_LOAD, PR_SEARCH, PR_STORE, PR_DEBLOCK, PR_SAO, PR_TRACK, PR_REFS, PR_S
        PR_INV, PR_SSD, PR_COST, PR_COPY, PR_COEFFCOST, PR_WAIT, PR_CHROMA, PR_RDO_LOOP, PR_N };
 #if defined(KVZ_CTU_PROF) && defined(__CUDA_ARCH__)
 #define PROF_T0(id) const long long prof_t0_##id = clock64()
-#define PROF_ADD(S, id) do { if (CTU_TID == 0) (S)->prof[id] += clock64() - prof_t0_##id; } while (0)
+#define PROF_ADD(S, id) do { if (CTU_TID == CTU_LEADER_TID) (S)->prof[id] += clock64() - prof_t0_##id; } while (0)
 #else
 #define PROF_T0(id) ((void)0)
 #define PROF_ADD(S, id) ((void)0)

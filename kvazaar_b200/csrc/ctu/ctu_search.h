@@ -37,6 +37,8 @@ struct SearchFrame {
 struct TuRes { int32_t ssd, has, tr_skip, pad; double bits; };
 
 struct CtuS {                       // per-CTA scalar state + scratch; shared memory on the device
+  int32_t leader_tid;               // MUST be first: CTU_LEADER_TID reads it through the raw shared-memory symbol
+  int32_t pad0[3];
   CabacState cabac0;                // state->cabac: the real coder's models when the CTU starts (constant)
   CabacState sc;                    // state->search_cabac
   CabacState tmp;                   // temp_cabac of the combined-CU path (search.c:989)

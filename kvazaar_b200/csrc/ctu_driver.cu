@@ -47,6 +47,7 @@ struct KernelArgs {
   volatile unsigned long long *host_note;   // pinned host memory: [0] completion sequence number, [1] start, [2] end (globaltimer ns)
   unsigned long long seq;
   unsigned long long *prof;  // [PR_N + 1] phase cycles (diagnostic build only), last: CTA lifetime
+  int *sm_counter;           // [256] CTAs started per SM so far: spreads the leader warps of co-resident CTAs
 };
 
 // Polling load: relaxed, from L2 (an acquire load invalidates the SM's whole L1 -- CCTL.IVALL -- on every poll, which
@@ -66,11 +67,14 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
 }
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
+__device__ __forceinline__ unsigned sm_id() { unsigned v; asm volatile("mov.u32 %0, %%smid;" : "=r"(v)); return v; }
+
 __global__ void __launch_bounds__(kThreads, 3) ctu_frame_kernel(const __grid_constant__ KernelArgs a)
 {
-  extern __shared__ __align__(16) unsigned char smem[];
-  CtuS *S = reinterpret_cast<CtuS *>(smem);
+  CtuS *S = reinterpret_cast<CtuS *>(ctu_smem_raw);
   __shared__ int s_ticket;
+  if (threadIdx.x == 0) S->leader_tid = a.sm_counter ? 32 * (atomicAdd(a.sm_counter + (sm_id() & 255), 1) & 3) : 0;
+  __syncthreads();
   Ctx c = { a.T, &a.cfg, a.work + blockIdx.x, S };
 #if defined(KVZ_CTU_PROF)
   const long long cta_t0 = clock64();
@@ -124,8 +128,9 @@ __global__ void __launch_bounds__(kThreads, 3) ctu_frame_kernel(const __grid_con
 // Diagnostic alternative (KVZ_CUDA_CTU_DIAG=1): one launch per anti-diagonal, no inter-CTA waiting.
 __global__ void __launch_bounds__(kThreads, 3) ctu_diag_kernel(const __grid_constant__ KernelArgs a, int diag, int cy_lo)
 {
-  extern __shared__ __align__(16) unsigned char smem[];
-  CtuS *S = reinterpret_cast<CtuS *>(smem);
+  CtuS *S = reinterpret_cast<CtuS *>(ctu_smem_raw);
+  if (threadIdx.x == 0) S->leader_tid = 0;
+  __syncthreads();
   const int cy = cy_lo + blockIdx.x;
   const int cx = diag - 2 * cy;
   Ctx c = { a.T, &a.cfg, a.work + blockIdx.x, S };
@@ -179,6 +184,7 @@ struct kvz_cuda_ctu_enc {
   CtuTables *d_tables = nullptr;
   uint16_t *d_order = nullptr;
   unsigned long long *d_prof = nullptr;
+  int *d_sm_counter = nullptr;
   int wl = 0, hl = 0, max_diag = 0, grid = 0;
   size_t plane_bytes = 0, smem = 0;
   bool debug = false, diag_launches = false;
@@ -236,7 +242,7 @@ void kvz_cuda_ctu_close(kvz_cuda_ctu_enc *e)
     cudaFree(e->d_prof);
   }
 #endif
-  cudaFree(e->d_tables); cudaFree(e->d_order);
+  cudaFree(e->d_tables); cudaFree(e->d_order); cudaFree(e->d_sm_counter);
   delete e;
 }
 
@@ -279,6 +285,8 @@ kvz_cuda_ctu_enc *kvz_cuda_ctu_open(const kvz_cuda_ctu_config *cfg, int slots)
   CTU_CHECK_PTR(cudaMalloc(&e->d_prof, (PR_N + 1) * sizeof(unsigned long long)));
   CTU_CHECK_PTR(cudaMemset(e->d_prof, 0, (PR_N + 1) * sizeof(unsigned long long)));
 #endif
+  CTU_CHECK_PTR(cudaMalloc(&e->d_sm_counter, 256 * sizeof(int)));
+  CTU_CHECK_PTR(cudaMemset(e->d_sm_counter, 0, 256 * sizeof(int)));
   CTU_CHECK_PTR(cudaMalloc(&e->d_order, order.size() * sizeof(uint16_t)));
   CTU_CHECK_PTR(cudaMemcpy(e->d_order, order.data(), order.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   CTU_CHECK_PTR(cudaFuncSetAttribute(ctu_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->smem));
@@ -319,7 +327,7 @@ kvz_cuda_ctu_enc *kvz_cuda_ctu_open(const kvz_cuda_ctu_config *cfg, int slots)
     KernelArgs &a = s.args;
     a.T = e->d_tables;
     a.work = s.d_work; a.sao_stats = s.d_stats; a.dbg_ctx = s.d_dbg_ctx;
-    a.order = e->d_order; a.sync = s.d_sync; a.nctu = e->wl * e->hl; a.prof = e->d_prof;
+    a.order = e->d_order; a.sync = s.d_sync; a.nctu = e->wl * e->hl; a.prof = e->d_prof; a.sm_counter = getenv("KVZ_CUDA_CTU_LEADER0") ? nullptr : e->d_sm_counter;   // (A/B switch: leader always warp 0)
     FrameDev &F = a.F;
     const size_t ysz = (size_t)W * H, csz = ysz / 4;
     uint8_t *p = s.d_planes;
