@@ -66,6 +66,9 @@ struct SmTables {
   int8_t tr4[16], tr8[64], tr16[256], tr32[1024], dst4[16];
   uint8_t sig_ctx4[16], group_idx[32], min_in_group[10];
   uint8_t pad[6];
+  // not a table: the absolute levels of the coefficient group being counted, one row per warp (a thread-local array
+  // indexed at run time would live in local memory, behind the 34 KB of L1 three CTAs share)
+  mutable int32_t abs_scratch[8][16];
 };
 CTU_FN const uint16_t *sm_scan(const SmTables *t, int scan_idx, int l)      // l = log2n - 2
 {
@@ -1118,7 +1121,7 @@ CTU_FN_NOINLINE double coeff_cost_serial(const SmTables *T, const SmTables *tb, 
   int scan_pos_sig = scan_last;
   for (int i = cg_last; i >= 0; --i) {
     const int sub_pos = i << 4;
-    int abs_coeff[16];
+    int32_t *abs_coeff = tb->abs_scratch[CTU_WARP & 7];
     const int cg_blk = scan_cg[i];
     const int cgy = cg_blk / side, cgx = cg_blk - cgy * side;
     int last_nz = -1, first_nz = 16, num_nz = 0, rice = 0;
