@@ -157,3 +157,34 @@ def test_cuda_bitstream_identical_config2_1080p_medium(tmp_path):
 def test_cuda_bitstream_identical_config3_2160p_veryslow(tmp_path):
     """BASELINE config 3 (the headline) at its named size: 3840x2160 --preset veryslow -q 22 -p 1, 8 frames"""
     _identity(tmp_path, _cuda_lib(), 3840, 2160, 8, "veryslow", 22, verify=False)
+
+
+# ------------------------------------------------------------------------------------------------ golden bitstreams
+# tests/golden/ctu_bitstreams.json: sha256 of what the unmodified reference writes (tools/make_golden_bitstreams.py, run in
+# the container that has /root/reference); these tests need neither /root/reference nor the plain reference binary.
+def _golden():
+    import json
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "ctu_bitstreams.json")))
+
+
+def _golden_check(tmp_path, provider, name):
+    import hashlib
+    g = _golden()[name]
+    (ctu_bin,) = _need("kvazaar_ctu")
+    clip = _clip(tmp_path, g["w"], g["h"], g["frames"], g["noisy"])
+    out = str(tmp_path / "g.hevc")
+    log = _encode(ctu_bin, clip, g["w"], g["h"], out, g["preset"], g["qp"], env={"KVZ_CTU_PROVIDER": provider})
+    assert "CTU search driver active" in log
+    data = open(out, "rb").read()
+    assert len(data) == g["bytes"] and hashlib.sha256(data).hexdigest() == g["sha256"], name
+
+
+@pytest.mark.parametrize("name", sorted(_golden()))
+def test_hostbuild_golden_bitstreams(tmp_path, name):
+    _golden_check(tmp_path, _hostsim(), name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(_golden()))
+def test_cuda_golden_bitstreams(tmp_path, name):
+    _golden_check(tmp_path, _cuda_lib(), name)
