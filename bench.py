@@ -216,7 +216,7 @@ def device_leg(args, wl, local, frames_per_step, barrier):
     lib.kvz_cuda_ctu_launches.argtypes = [C.c_void_p]
     lib.kvz_cuda_last_error.restype = C.c_char_p
     cfg = driver_config(wl)
-    slots = args.slots or wl["slots"]
+    slots = args.slots or (args.owf or wl["owf"]) + 1          # as many pictures in flight as the encoder keeps (owf + 1)
     enc = lib.kvz_cuda_ctu_open(C.byref(cfg), slots)
     if not enc:
         raise RuntimeError(f"kvz_cuda_ctu_open: {lib.kvz_cuda_last_error()}")
@@ -226,44 +226,73 @@ def device_leg(args, wl, local, frames_per_step, barrier):
     clip = np.fromfile(clip_path(wl), dtype=np.uint8).reshape(DISTINCT, w * h * 3 // 2)
     dev = torch.from_numpy(clip).cuda()
     torch.cuda.synchronize()
-    res = DevResult()
     kernel_ms = []
 
     # one continuous run, `slots` pictures in flight throughout: warm-up pictures, the timed pictures, and `slots` more so
     # that the pipeline is still full while the last timed pictures are searched.  The timed region is completion to
     # completion: from the moment the last warm-up picture is done to the moment the last timed picture is done.
+    # A few host threads drive the pipeline (each keeps its share of the pictures in flight) so that a picture that
+    # finishes early is not held up behind an older one -- the encoder waits with one worker per picture as well.
     n_warm, n_timed = args.warmup * frames_per_step, args.steps * frames_per_step
     total = n_warm + n_timed + slots
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    l0 = l1 = lib.kvz_cuda_ctu_launches(enc)
+    state = {"next": 0, "done": 0, "l0": lib.kvz_cuda_ctu_launches(enc), "l1": 0, "err": None}
     if n_warm == 0:
         e0.record()
-    pending, nxt, done = [], 0, 0
-    while done < total:
-        while nxt < total and len(pending) < slots:
-            base = dev[nxt % DISTINCT].data_ptr()
-            s = lib.kvz_cuda_ctu_submit_device(enc, base, base + w * h, base + w * h * 5 // 4, w, w // 2, ctx.ctypes.data,
-                                               cfg.lambda_, cfg.lambda_sqrt, wl["qp"])
-            if s < 0:
-                raise RuntimeError(f"submit: {lib.kvz_cuda_last_error()}")
-            pending.append(s)
-            nxt += 1
-        s = pending.pop(0)
-        if lib.kvz_cuda_ctu_wait_device(enc, s, C.byref(res)) != 0:
-            raise RuntimeError(f"wait: {lib.kvz_cuda_last_error()}")
-        lib.kvz_cuda_ctu_release(enc, s)
-        done += 1
-        if n_warm < done <= n_warm + n_timed:
-            kernel_ms.append(res.search_kernel_ms)
-        if done == n_warm:
-            e0.record()
-            l0 = lib.kvz_cuda_ctu_launches(enc)
-        if done == n_warm + n_timed:
-            e1.record()
-            l1 = lib.kvz_cuda_ctu_launches(enc)
+    lock = threading.Lock()
+    n_threads = min(8, slots)
+
+    def drive(share):
+        try:
+            torch.cuda.set_device(local)
+            res = DevResult()
+            pending = []
+            while True:
+                while len(pending) < share:
+                    with lock:
+                        i = state["next"]
+                        if i >= total:
+                            break
+                        state["next"] = i + 1
+                    base = dev[i % DISTINCT].data_ptr()
+                    s = lib.kvz_cuda_ctu_submit_device(enc, base, base + w * h, base + w * h * 5 // 4, w, w // 2, ctx.ctypes.data,
+                                                       cfg.lambda_, cfg.lambda_sqrt, wl["qp"])
+                    if s < 0:
+                        raise RuntimeError(f"submit: {lib.kvz_cuda_last_error()}")
+                    pending.append(s)
+                if not pending:
+                    return
+                s = pending.pop(0)
+                if lib.kvz_cuda_ctu_wait_device(enc, s, C.byref(res)) != 0:
+                    raise RuntimeError(f"wait: {lib.kvz_cuda_last_error()}")
+                ms = res.search_kernel_ms
+                lib.kvz_cuda_ctu_release(enc, s)
+                with lock:
+                    state["done"] += 1
+                    done = state["done"]
+                    if n_warm < done <= n_warm + n_timed:
+                        kernel_ms.append(ms)
+                    if done == n_warm:
+                        e0.record()
+                        state["l0"] = lib.kvz_cuda_ctu_launches(enc)
+                    if done == n_warm + n_timed:
+                        e1.record()
+                        state["l1"] = lib.kvz_cuda_ctu_launches(enc)
+        except Exception as ex:  # pragma: no cover
+            state["err"] = ex
+
+    shares = [slots // n_threads + (1 if t < slots % n_threads else 0) for t in range(n_threads)]
+    threads = [threading.Thread(target=drive, args=(sh,)) for sh in shares]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if state["err"]:
+        raise state["err"]
     torch.cuda.synchronize()
     seconds = e0.elapsed_time(e1) / 1000.0
+    l0, l1 = state["l0"], state["l1"]
     launches = int(l1 - l0)
     lib.kvz_cuda_ctu_close(enc)
     return seconds, launches, float(np.mean(kernel_ms)) if kernel_ms else None, slots
