@@ -1,9 +1,12 @@
 // ctu_common.h -- types, tables and the execution model of the device-resident CTU search driver.
 //
 // ONE source, two compilations:
-//   * nvcc, sm_100a: the product.  One CTA owns one CTU; every function below is called by ALL threads of the CTA
-//     with uniform control flow.  Scalar decisions live in a shared-memory state block that only the leader
-//     (thread 0) mutates between barriers; data-parallel phases are item-strided loops over the CTA.
+//   * nvcc, sm_100a: the product.  One CTA (four warps) owns one CTU at a time; every function is called by ALL threads
+//     of the CTA with uniform control flow unless it takes a Team (ctu_leaf.h): then the CTA's warps run independent
+//     transform-unit jobs side by side and synchronise inside their warp only.  Scalar decisions live in a
+//     shared-memory state block that only the leader (lane 0 of one warp) mutates between barriers -- and every thread
+//     copies the state it branches on BEFORE the barrier after which the leader may change it; data-parallel phases
+//     are item-strided loops over the CTA.
 //   * g++ (tests/hostsim, TEST INFRASTRUCTURE): the same code with a CTA of one thread and no-op barriers, so the
 //     control flow can be debugged against the compiled reference on a machine without a GPU.  The product
 //     never runs this build.

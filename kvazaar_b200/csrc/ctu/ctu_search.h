@@ -15,8 +15,11 @@
 //
 // The mode decisions are the reference's: same candidate order, same double-precision cost expressions in the same
 // operation order (the build uses -fmad=false), same CABAC model adaptation.  What differs is how the work is laid
-// out: e.g. the rough search evaluates the SATD of all 35 modes in one data-parallel phase and then replays the
-// reference's halving search on the table.
+// out: the rough search evaluates the SATD of all 35 modes in one data-parallel phase and then replays the reference's
+// halving search on the table; the RDO candidates of search_intra_rdo and the colours of a CU are independent
+// transform-unit jobs that run one per warp (for_tu_tasks) with private reconstructions, and only SSD / cbf / exact
+// coefficient bits come back to the leader, which assembles the costs in the reference's order; the cost walks that adapt
+// the context models stay serial on the leader.
 #pragma once
 #include "ctu_leaf.h"
 
