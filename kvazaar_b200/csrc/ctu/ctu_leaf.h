@@ -64,7 +64,6 @@ struct SmTables {
   uint8_t scan_cg[3][4][64];
   uint8_t ref_top[16][16], ref_left[16][16];
   int8_t tr4[16], tr8[64], tr16[256], tr32[1024], dst4[16];
-  int8_t tr4t[16], tr8t[64], tr16t[256], tr32t[1024], dst4t[16];      // transposed: rows contiguous for the inverse passes
   uint8_t sig_ctx4[16], group_idx[32], min_in_group[10];
   uint8_t pad[6];
   // not a table: the absolute levels of the coefficient group being counted, one row per warp (a thread-local array
@@ -76,22 +75,20 @@ CTU_FN const uint16_t *sm_scan(const SmTables *t, int scan_idx, int l)      // l
   return l == 0 ? t->scan4[scan_idx] : (l == 1 ? t->scan8[scan_idx] : (l == 2 ? t->scan16 : t->scan32));
 }
 CTU_FN const int8_t *sm_tr(const SmTables *t, int l) { return l == 0 ? t->tr4 : (l == 1 ? t->tr8 : (l == 2 ? t->tr16 : t->tr32)); }
-CTU_FN const int8_t *sm_trt(const SmTables *t, int l) { return l == 0 ? t->tr4t : (l == 1 ? t->tr8t : (l == 2 ? t->tr16t : t->tr32t)); }
 // every thread of the CTA
 CTU_FN void sm_tables_load(SmTables *d, const CtuTables *g)
 {
   #pragma unroll 1
   for (int i = CTU_TID; i < 1024; i += CTU_NT) {
-    d->scan32[i] = g->scan[0][3][i]; d->tr32[i] = g->tr[3][i]; d->tr32t[i] = g->tr[3][(i & 31) * 32 + (i >> 5)];
-    if (i < 256) { d->scan16[i] = g->scan[0][2][i]; d->tr16[i] = g->tr[2][i]; d->tr16t[i] = g->tr[2][(i & 15) * 16 + (i >> 4)]; ((uint8_t *)d->ref_top)[i] = ((const uint8_t *)g->ref_top)[i]; ((uint8_t *)d->ref_left)[i] = ((const uint8_t *)g->ref_left)[i]; }
+    d->scan32[i] = g->scan[0][3][i]; d->tr32[i] = g->tr[3][i];
+    if (i < 256) { d->scan16[i] = g->scan[0][2][i]; d->tr16[i] = g->tr[2][i]; ((uint8_t *)d->ref_top)[i] = ((const uint8_t *)g->ref_top)[i]; ((uint8_t *)d->ref_left)[i] = ((const uint8_t *)g->ref_left)[i]; }
     if (i < 768) ((uint8_t *)d->scan_cg)[i] = ((const uint8_t *)g->scan_cg)[i];
     if (i < 192) d->scan8[i / 64][i % 64] = g->scan[i / 64][1][i % 64];
     if (i < 128) { d->ebits[i] = g->ebits[i]; d->next_mps[i] = g->next_mps[i]; d->next_lps[i] = g->next_lps[i]; }
-    if (i < 64) { d->tr8[i] = g->tr[1][i]; d->tr8t[i] = g->tr[1][(i & 7) * 8 + (i >> 3)]; }
+    if (i < 64) d->tr8[i] = g->tr[1][i];
     if (i < 48) d->scan4[i / 16][i % 16] = g->scan[i / 16][0][i % 16];
     if (i < 32) d->group_idx[i] = g->group_idx[i];
-    if (i < 16) { d->tr4[i] = g->tr[0][i]; d->dst4[i] = g->dst4[i]; d->sig_ctx4[i] = g->sig_ctx4[i];
-                  d->tr4t[i] = g->tr[0][(i & 3) * 4 + (i >> 2)]; d->dst4t[i] = g->dst4[(i & 3) * 4 + (i >> 2)]; }
+    if (i < 16) { d->tr4[i] = g->tr[0][i]; d->dst4[i] = g->dst4[i]; d->sig_ctx4[i] = g->sig_ctx4[i]; }
     if (i < 10) d->min_in_group[i] = g->min_in_group[i];
   }
 }
@@ -526,11 +523,9 @@ CTU_FN_NOINLINE void fwd_pass(const Team &tm, const int16_t *src, int16_t *dst, 
   }
   tsync(tm);
 }
-// inverse: r[j][k] = clip16((sum_i M[i][k] * src[i][j] + add) >> shift) with both operands TRANSPOSED in memory so that
-// the sum runs over contiguous pairs (IDP2A): MT[k][i] = M[i][k], srcT[j][i] = src[i][j].  transpose_out: r is stored at
-// [k][j] (the srcT of the second pass) instead of [j][k].
+// inverse: dst[j*N + k] = clip16((sum_i M[i][k] * src[i*N + j] + add) >> shift)
 template <int L2N>
-CTU_FN_NOINLINE void inv_pass(const Team &tm, const int16_t *srcT, int16_t *dst, const int8_t *MT, int n_rt, int shift, bool transpose_out)
+CTU_FN_NOINLINE void inv_pass(const Team &tm, const int16_t *src, int16_t *dst, const int8_t *M, int n_rt, int shift)
 {
   const int add = 1 << (shift - 1);
   const int n = L2N ? (1 << L2N) : n_rt;
@@ -538,11 +533,12 @@ CTU_FN_NOINLINE void inv_pass(const Team &tm, const int16_t *srcT, int16_t *dst,
   #pragma unroll 1
   for (int e = tm.tid; e < n * n; e += tm.nt) {
     const int j = e >> log2n, k = e & (n - 1);
-    const int8_t *m = MT + (k << log2n);
-    const int16_t *sp = srcT + (j << log2n);
+    const int8_t *m = M + k;
+    const int16_t *sp = src + j;
     int acc = 0;
-    for (int i = 0; i < n; i += 4) acc = dot4_s16_s8(sp + i, m + i, acc);
-    dst[transpose_out ? (k << log2n) + j : e] = (int16_t)iclip(-32768, 32767, (acc + add) >> shift);
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) acc += (int)m[i << log2n] * (int)sp[i << log2n];
+    dst[e] = (int16_t)iclip(-32768, 32767, (acc + add) >> shift);
   }
   tsync(tm);
 }
@@ -630,13 +626,11 @@ CTU_FN_NOINLINE void quant_block(const Team &tm, const SmTables *T, const CtuCon
 }
 
 // kvz_dequant: q -> b.  type: 0 luma, 2 / 3 chroma
-// transposed: b is stored as b^T (what the inverse transform's first pass reads)
 template <int L2N>
-CTU_FN_NOINLINE void dequant_block(const Team &tm, const CtuConfig *cfg, const TuS &tu, int n_rt, int type, bool transposed)
+CTU_FN_NOINLINE void dequant_block(const Team &tm, const CtuConfig *cfg, const TuS &tu, int n_rt, int type)
 {
   const int n = L2N ? (1 << L2N) : n_rt;
-  const int lg = L2N ? L2N : ilog2(n);
-  const int transform_shift = 15 - 8 - lg;
+  const int transform_shift = 15 - 8 - (L2N ? L2N : ilog2(n));
   const int qp_scaled = scaled_qp(type, cfg->qp);
   const int shift = 20 - 14 - transform_shift;
   const int scale = inv_quant_scale(qp_scaled % 6) << (qp_scaled / 6);
@@ -645,7 +639,7 @@ CTU_FN_NOINLINE void dequant_block(const Team &tm, const CtuConfig *cfg, const T
   const int16_t *q = tu.q();
   #pragma unroll 1
   for (int e = tm.tid; e < n * n; e += tm.nt)
-    b[transposed ? ((e & (n - 1)) << lg) + (e >> lg) : e] = (int16_t)iclip(-32768, 32767, ((int)q[e] * scale + add) >> shift);
+    b[e] = (int16_t)iclip(-32768, 32767, ((int)q[e] * scale + add) >> shift);
   tsync(tm);
 }
 
@@ -1256,16 +1250,15 @@ CTU_FN_NOINLINE void tu_core_t(const Team &tm, const SmTables *T, const SmTables
   tsync(tm);
   int ssd = 0;
   if (fx->has) {
-    dequant_block<L2N>(tm, cfg, tu, n, color == 0 ? 0 : (color == 1 ? 2 : 3), !use_trskip);
+    dequant_block<L2N>(tm, cfg, tu, n, color == 0 ? 0 : (color == 1 ? 2 : 3));
     if (use_trskip) {
       const int offs = 1 << (ts_shift - 1);
       #pragma unroll 1
       for (int e = tm.tid; e < nn; e += tm.nt) a[e] = (int16_t)(((int)b[e] + offs) >> ts_shift);
       tsync(tm);
     } else {
-      const int8_t *MT = use_dst ? T->dst4t : sm_trt(T, log2n - 2);
-      inv_pass<L2N>(tm, b, t, MT, n, 7, true);
-      inv_pass<L2N>(tm, t, a, MT, n, 12, false);
+      inv_pass<L2N>(tm, b, t, M, n, 7);
+      inv_pass<L2N>(tm, t, a, M, n, 12);
     }
     #pragma unroll 1
     for (int e = tm.tid; e < nn; e += tm.nt) {
