@@ -263,3 +263,23 @@ def test_cuda10_frame_pass_matches_reference(cuda_lib, ref10, dims, qp, signhide
         a, b = kb.fp_section(got, sec, name), kb.fp_section(want, sec, name)
         assert np.array_equal(a, b), (name, int(np.argmax(a != b)), a[a != b][:4], b[a != b][:4])
     fp.close()
+
+
+@pytest.mark.gpu
+def test_cuda10_frame_pass_full_size_4320p(cuda_lib, ref10):
+    """The configs[4] shape at its full size (7680x4320 10-bit, QP22, RDOQ + deblocking + SAO): one frame, every section of
+    the result blob equals the pass through the 10-bit reference build's strategy functions."""
+    import os
+    from _oracle import ref_frame_pass
+    kb = cuda_lib
+    W, H, qp = 7680, 4320, 22
+    src = synth_frame10(W, H, 3)
+    fp = kb.FramePass(W, H, qp, 0, 1, 0.0, 0, 10)
+    fp.run_dev(kb.to_dev(src))
+    got = fp.result_host()
+    want = ref_frame_pass(ref10, src, W, H, qp, fp.layout, nthreads=min(64, os.cpu_count() or 8), signhide=0, rdoq=1, trskip=0)
+    sec = kb.fp_sections(fp.layout, W, H, 10)
+    for name in sec:
+        a, b = kb.fp_section(got, sec, name), kb.fp_section(want, sec, name)
+        assert np.array_equal(a, b), (name, int(np.argmax(a != b)))
+    fp.close()
