@@ -337,6 +337,57 @@ void *kvz_cuda_ip_result_dev(kvz_cuda_inter_pass *ip);
 int   kvz_cuda_ip_run_dev(kvz_cuda_inter_pass *ip, const void *cur_dev, const void *ref_dev, void *stream);
 int   kvz_cuda_ip_run_host(kvz_cuda_inter_pass *ip, const void *cur_host, const void *ref_host, void *result_host, void *stream);
 
+/* ------------------------------------------------------------------ integer motion estimation (me_search.cu) */
+/* SURVEY §8f rank 4.  The integer stage of search_pu_inter_ref (src/search_inter.c:1349-1383) for a batch of PUs
+ * against one reference picture, decision for decision as the reference takes them:
+ *     select_starting_point   search_inter.c:297-330   (0-vector, the predicted start MV, the merge candidates)
+ *     early_terminate         search_inter.c:436-485
+ *     hexagon_search          search_inter.c:712-792   (ime_algorithm = KVZ_IME_HEXBS)
+ *     diamond_search          search_inter.c:812-888   (ime_algorithm = KVZ_IME_DIA)
+ * every point through check_mv_cost (search_inter.c:202-247): the tile / WPP MV constraints of
+ * fracmv_within_tile (:94-181), kvz_image_calc_sad (src/image.c:407-447; references outside the picture read the
+ * edge pixels, image.c:279-398), and calc_mvd_cost (:394-433) with get_mvd_coding_cost (:333-348, cfg.mv_rdo = 0)
+ * over the two AMVP candidates (select_mv_cand :351-391).  The AMVP / merge candidates of a PU depend on the CUs
+ * coded before it; the caller passes them in (kvz_inter_get_mv_cand / kvz_inter_get_merge_cand, src/inter.c). */
+typedef struct kvz_cuda_me_params {
+  int32_t width, height;            /* luma size of the (tile's) frame: state->tile->frame->width / height */
+  int32_t bitdepth;                 /* 8 or 10 (pixels are uint8_t / uint16_t) */
+  int32_t ime_algorithm;            /* enum kvz_ime_algorithm: 0 = hexbs, 7 = dia */
+  int32_t me_max_steps;             /* cfg.me_max_steps (uint32; -1 = unlimited) */
+  int32_t me_early_termination;     /* enum kvz_me_early_termination: 0 off, 1 on, 2 sensitive */
+  int32_t mv_constraint;            /* enum kvz_mv_constraint (0 none ... 4 frame and tile with margin) */
+  int32_t wpp_owf;                  /* cfg.owf && cfg.wpp: MVs may only reach LCUs that are final in the reference */
+  int32_t delay_px;                 /* SAO_DELAY_PX (10) with SAO, else DEBLOCK_DELAY_PX (8) with deblocking, else 0 */
+  int32_t max_ref_lcu_right, max_ref_lcu_down;   /* encoder_control_t.max_inter_ref_lcu */
+  int32_t pad;
+  double  lambda_sqrt;              /* state->lambda_sqrt */
+} kvz_cuda_me_params;
+typedef struct kvz_cuda_me_merge { int16_t mv[2][2]; uint8_t dir; uint8_t pad[3]; } kvz_cuda_me_merge;   /* inter_merge_cand_t: dir, mv[list][x/y] (1/4 pel) */
+typedef struct kvz_cuda_me_pu {
+  int16_t x, y;                     /* info->origin (luma, tile-relative = frame-relative here) */
+  int16_t w, h;                     /* info->width / height */
+  int16_t mv_cand[2][2];            /* info->mv_cand (1/4 pel) */
+  int16_t start_mv[2];              /* the MV the search starts from (1/4 pel): mv_previous of search_inter.c:1284-1338, or 0 */
+  int16_t num_merge;                /* info->num_merge_cand, <= 5 */
+  int16_t pad;
+  kvz_cuda_me_merge merge[5];       /* info->merge_cand */
+} kvz_cuda_me_pu;
+typedef struct kvz_cuda_me_result {
+  double  cost;                     /* best_cost (SAD + bits * lambda_sqrt); 1.7e308 (MAX_DOUBLE) if no point was allowed */
+  int32_t bits;                     /* best_bits; INT32_MAX if no point was allowed */
+  int16_t mv[2];                    /* best_mv, 1/4 pel */
+  int32_t points;                   /* points whose SAD was computed (diagnostic) */
+  int32_t pad;
+} kvz_cuda_me_result;
+/* 0 if the parameters are inside what the device search covers */
+int kvz_cuda_me_params_supported(const kvz_cuda_me_params *p);
+/* cur / ref: luma planes in device memory (stride in pixels); pus / out: device memory, `count` records. */
+int kvz_cuda_me_search_batch(const kvz_cuda_me_params *p, const void *cur_dev, int cur_stride, const void *ref_dev, int ref_stride,
+                             const kvz_cuda_me_pu *pus_dev, int count, kvz_cuda_me_result *out_dev, void *stream);
+/* host buffers; synchronous */
+int kvz_cuda_call_me_search(const kvz_cuda_me_params *p, const void *cur, int cur_stride, const void *ref, int ref_stride,
+                            const kvz_cuda_me_pu *pus, int count, kvz_cuda_me_result *out);
+
 /* ------------------------------------------------------------------ host-buffer conveniences */
 /* ---------------------------------------------------------------------------------------------------------
  * RDOQ: kvz_rdoq (src/rdo.c:661-977) incl. kvz_rdoq_sign_hiding (rdo.c:518-653) and the

@@ -579,3 +579,29 @@ class InterPass:
                                       C.c_size_t(self.host_bytes), _stream()))
         torch.cuda.current_stream().synchronize()
         return out
+
+
+# ------------------------------------------------------------------ integer motion estimation (me_search.cu)
+# record layouts of include/kvz_cuda.h (kvz_cuda_me_merge / kvz_cuda_me_pu / kvz_cuda_me_result / kvz_cuda_me_params)
+ME_MERGE = np.dtype([("mv", "<i2", (2, 2)), ("dir", "u1"), ("pad", "u1", (3,))])
+ME_PU = np.dtype([("x", "<i2"), ("y", "<i2"), ("w", "<i2"), ("h", "<i2"), ("mv_cand", "<i2", (2, 2)), ("start_mv", "<i2", (2,)),
+                  ("num_merge", "<i2"), ("pad", "<i2"), ("merge", ME_MERGE, (5,))])
+ME_RESULT = np.dtype([("cost", "<f8"), ("bits", "<i4"), ("mv", "<i2", (2,)), ("points", "<i4"), ("pad", "<i4")])
+
+
+class MeParams(C.Structure):
+    """kvz_cuda_me_params: the configuration fields the reference's integer search reads (search_inter.c:94-247, 436-888)"""
+    _fields_ = [(n, C.c_int32) for n in ("width", "height", "bitdepth", "ime_algorithm", "me_max_steps", "me_early_termination", "mv_constraint",
+                                         "wpp_owf", "delay_px", "max_ref_lcu_right", "max_ref_lcu_down", "pad")] + [("lambda_sqrt", C.c_double)]
+
+
+def me_search_batch(params, cur, ref, pus, out=None):
+    """Integer motion search of `pus` (CUDA byte tensor holding ME_PU records) on device planes `cur` / `ref` (2-D tensors,
+    uint8 or int16-carried 10-bit); returns a CUDA byte tensor of ME_RESULT records.  One launch, current stream."""
+    torch = _torch()
+    count = pus.numel() // ME_PU.itemsize
+    if out is None:
+        out = torch.empty(count * ME_RESULT.itemsize, dtype=torch.uint8, device=cur.device)
+    _ck(lib().kvz_cuda_me_search_batch(C.byref(params), _p(cur), C.c_int(cur.stride(0)), _p(ref), C.c_int(ref.stride(0)), _p(pus), C.c_int(count),
+                                       _p(out), _stream()))
+    return out

@@ -1,0 +1,89 @@
+// me_search.cu -- integer motion estimation of a batch of PUs: kvz_cuda_me_search_batch.
+//
+// One warp per PU.  The search is a chain of dependent decisions (every point's cost decides where the next one
+// lies: search_inter.c:712-792), so the parallelism inside a PU is the SAD of one point -- its pixels spread over the
+// 32 lanes, summed with shuffles -- and the parallelism of the launch is the PUs.  All decisions are warp-uniform
+// (every lane holds the same best cost after the shuffle reduction), so there is no shared memory and no barrier.
+// Bound: latency of ~20-40 dependent points per PU; the pixels of neighbouring points overlap and stay in L1/L2, the
+// HBM traffic is one read of both pictures.
+#include "common.cuh"
+#include "me/me_search.h"
+
+namespace {
+
+constexpr int kWarpsPerCta = 4;
+
+template <typename Pix>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) me_search_kernel(kvz_cuda_me_params p, const Pix *__restrict__ cur, int cur_stride,
+                                                                      const Pix *__restrict__ ref, int ref_stride,
+                                                                      const kvz_cuda_me_pu *__restrict__ pus, int count,
+                                                                      kvz_cuda_me_result *__restrict__ out)
+{
+  const int warp = threadIdx.x >> 5;
+  const kvzme::Lanes ln = { (int)(threadIdx.x & 31), 32 };
+  const kvzme::Planes<Pix> pl = { cur, ref, cur_stride, ref_stride };
+  // whole warps leave together: the shuffles inside pu_sad always see 32 lanes
+  for (int i = blockIdx.x * kWarpsPerCta + warp; i < count; i += gridDim.x * kWarpsPerCta) {
+    const kvz_cuda_me_pu pu = pus[i];
+    kvzme::search_pu<Pix>(ln, p, pu, pl, &out[i]);
+  }
+}
+
+int check_args(const kvz_cuda_me_params *p, const void *cur, int cur_stride, const void *ref, int ref_stride, const void *pus, int count,
+               const void *out)
+{
+  KVZC_ARG(p && cur && ref && count >= 0 && (count == 0 || (pus && out)));
+  KVZC_ARG(kvzme::params_supported(*p) == 0);
+  KVZC_ARG(cur_stride >= p->width && ref_stride >= p->width);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int kvz_cuda_me_params_supported(const kvz_cuda_me_params *p) { return p ? kvzme::params_supported(*p) : -1; }
+
+extern "C" int kvz_cuda_me_search_batch(const kvz_cuda_me_params *p, const void *cur_dev, int cur_stride, const void *ref_dev, int ref_stride,
+                                        const kvz_cuda_me_pu *pus_dev, int count, kvz_cuda_me_result *out_dev, void *stream)
+{
+  KVZC_REQUIRE_DEVICE();
+  if (int e = check_args(p, cur_dev, cur_stride, ref_dev, ref_stride, pus_dev, count, out_dev)) return e;
+  if (count == 0) return 0;
+  const int ctas = (count + kWarpsPerCta - 1) / kWarpsPerCta;
+  const int cap = kvzc::g_sm_count > 0 ? kvzc::g_sm_count * 16 : 148 * 16;     // 16 CTAs of 4 warps per SM; more PUs loop
+  const int grid = ctas < cap ? ctas : cap;
+  if (p->bitdepth == 8)
+    me_search_kernel<uint8_t><<<grid, kWarpsPerCta * 32, 0, kvzc::as_stream(stream)>>>(*p, (const uint8_t *)cur_dev, cur_stride, (const uint8_t *)ref_dev,
+                                                                                    ref_stride, pus_dev, count, out_dev);
+  else
+    me_search_kernel<uint16_t><<<grid, kWarpsPerCta * 32, 0, kvzc::as_stream(stream)>>>(*p, (const uint16_t *)cur_dev, cur_stride, (const uint16_t *)ref_dev,
+                                                                                     ref_stride, pus_dev, count, out_dev);
+  KVZC_LAUNCHED();
+  return 0;
+}
+
+// host buffers, synchronous: the binding a host that keeps its pictures in host memory would call
+extern "C" int kvz_cuda_call_me_search(const kvz_cuda_me_params *p, const void *cur, int cur_stride, const void *ref, int ref_stride,
+                                       const kvz_cuda_me_pu *pus, int count, kvz_cuda_me_result *out)
+{
+  KVZC_REQUIRE_DEVICE();
+  if (int e = check_args(p, cur, cur_stride, ref, ref_stride, pus, count, out)) return e;
+  if (count == 0) return 0;
+  const size_t px = p->bitdepth == 8 ? 1 : 2;
+  const size_t cur_bytes = (size_t)cur_stride * p->height * px, ref_bytes = (size_t)ref_stride * p->height * px;
+  const size_t pu_bytes = (size_t)count * sizeof(kvz_cuda_me_pu), out_bytes = (size_t)count * sizeof(kvz_cuda_me_result);
+  uint8_t *d = nullptr;
+  const size_t o_ref = (cur_bytes + 255) & ~(size_t)255, o_pu = (o_ref + ref_bytes + 255) & ~(size_t)255, o_out = (o_pu + pu_bytes + 255) & ~(size_t)255;
+  KVZC_CHECK(cudaMalloc(&d, o_out + out_bytes));
+  cudaStream_t st = nullptr;
+  int rc = 0;
+  cudaError_t e = cudaMemcpyAsync(d, cur, cur_bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_ref, ref, ref_bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_pu, pus, pu_bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess)
+    rc = kvz_cuda_me_search_batch(p, d, cur_stride, d + o_ref, ref_stride, (const kvz_cuda_me_pu *)(d + o_pu), count, (kvz_cuda_me_result *)(d + o_out), st);
+  if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(out, d + o_out, out_bytes, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) { kvzc::set_error("kvz_cuda_call_me_search: %s", cudaGetErrorString(e)); return KVZ_CUDA_E_RUNTIME; }
+  return rc;
+}

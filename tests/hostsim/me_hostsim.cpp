@@ -1,0 +1,31 @@
+// me_hostsim.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+// Host build of the integer motion search's single-source algorithm (kvazaar_b200/csrc/me/me_search.h) with the 32
+// lane shares of every SAD walked in turn: checks the control flow of the device code against the reference without a GPU (tests/test_me_search.py).
+// Exports the same entry points as libkvzcuda.so, with host pointers.
+#include "../../kvazaar_b200/csrc/me/me_search.h"
+
+extern "C" int kvz_cuda_me_params_supported(const kvz_cuda_me_params *p) { return p ? kvzme::params_supported(*p) : -1; }
+
+template <typename Pix>
+static void run(const kvz_cuda_me_params *p, const void *cur, int cur_stride, const void *ref, int ref_stride, const kvz_cuda_me_pu *pus, int count,
+                kvz_cuda_me_result *out)
+{
+  const kvzme::Lanes ln = { 0, 32 };      // lane 0 writes the result; pu_sad walks all 32 shares
+  const kvzme::Planes<Pix> pl = { (const Pix *)cur, (const Pix *)ref, cur_stride, ref_stride };
+  for (int i = 0; i < count; ++i) kvzme::search_pu<Pix>(ln, *p, pus[i], pl, &out[i]);
+}
+
+extern "C" int kvz_cuda_call_me_search(const kvz_cuda_me_params *p, const void *cur, int cur_stride, const void *ref, int ref_stride,
+                                       const kvz_cuda_me_pu *pus, int count, kvz_cuda_me_result *out)
+{
+  if (!p || kvzme::params_supported(*p) != 0) return -2;
+  if (p->bitdepth == 8) run<uint8_t>(p, cur, cur_stride, ref, ref_stride, pus, count, out);
+  else run<uint16_t>(p, cur, cur_stride, ref, ref_stride, pus, count, out);
+  return 0;
+}
+
+extern "C" int kvz_cuda_me_search_batch(const kvz_cuda_me_params *p, const void *cur, int cur_stride, const void *ref, int ref_stride,
+                                        const kvz_cuda_me_pu *pus, int count, kvz_cuda_me_result *out, void *)
+{
+  return kvz_cuda_call_me_search(p, cur, cur_stride, ref, ref_stride, pus, count, out);
+}

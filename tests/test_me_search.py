@@ -1,0 +1,113 @@
+"""Integer motion estimation (include/kvz_cuda.h: kvz_cuda_me_search_batch).
+
+Checker: the UNMODIFIED reference's own search functions -- oracle/ref_me.c includes src/search_inter.c where it lies, so
+select_starting_point / early_terminate / hexagon_search / diamond_search / check_mv_cost / calc_mvd_cost /
+fracmv_within_tile run as compiled from the reference -- and tests/golden/me_search.npz, the same outputs committed
+(tools/make_golden_me.py), for boxes without the reference build.
+  * CPU tests: the host build of the device code (tests/hostsim/me_hostsim.cpp, one lane per PU) -- TEST INFRASTRUCTURE;
+  * GPU tests: kvazaar_b200/libkvzcuda.so, through the C ABI (device-pointer entry and host-buffer entry).
+Bar: best MV, bits and cost (IEEE double) identical for every PU.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from _me_cases import CASES, RESULT, Params, grid_case, make_case, run_host_api, run_reference, same
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOSTSIM = os.path.join(ROOT, "tests", "hostsim", "libkvzme_hostsim.so")
+
+
+def _hostsim():
+    if not os.path.exists(HOSTSIM):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unused-function", "-Wno-unknown-pragmas",
+                               "-o", HOSTSIM, os.path.join(ROOT, "tests", "hostsim", "me_hostsim.cpp")])
+    return C.CDLL(HOSTSIM)
+
+
+def _golden(name):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "me_search.npz"))
+    out = np.zeros(len(g[name + "/bits"]), RESULT)
+    out["mv"], out["bits"], out["cost"] = g[name + "/mv"], g[name + "/bits"], g[name + "/cost"]
+    return out
+
+
+def _explain(got, want, pus):
+    bad = np.nonzero((got["mv"] != want["mv"]).any(1) | (got["bits"] != want["bits"]) | (got["cost"] != want["cost"]))[0]
+    i = bad[0]
+    return f"{len(bad)} of {len(pus)} PUs differ; first: PU {i} {pus[i]} got {got[i]} want {want[i]}"
+
+
+# ------------------------------------------------------------------------------------------------ CPU
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_reference_matches_golden(name, ref, ref10):
+    """the committed golden outputs are what the compiled reference returns (pins the fixture to the reference)"""
+    p, cur, rf, pus = make_case(name)
+    want = run_reference(ref if p.bitdepth == 8 else ref10, p, cur, rf, pus)
+    assert same(want, _golden(name)), _explain(want, _golden(name), pus)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_hostbuild_matches_golden(name):
+    p, cur, rf, pus = make_case(name)
+    got = run_host_api(_hostsim(), p, cur, rf, pus)
+    assert same(got, _golden(name)), _explain(got, _golden(name), pus)
+    assert got["points"].max() > 8                     # the searches do travel
+
+
+def test_hostbuild_grid_matches_reference(ref):
+    """every 16x16 PU of a 416x240 picture with the --preset slow settings (hexbs, early termination on, WPP + SAO limits)"""
+    p, cur, rf, pus = grid_case(416, 240, 8)
+    got = run_host_api(_hostsim(), p, cur, rf, pus)
+    want = run_reference(ref, p, cur, rf, pus)
+    assert same(got, want), _explain(got, want, pus)
+
+
+def test_params_outside_scope_are_refused():
+    lib = _hostsim()
+    lib.kvz_cuda_me_params_supported.argtypes = [C.POINTER(Params)]
+    p, _, _, _ = make_case("hexbs_et_sensitive")
+    assert lib.kvz_cuda_me_params_supported(C.byref(p)) == 0
+    for field, value in (("ime_algorithm", 1), ("ime_algorithm", 2), ("bitdepth", 12), ("mv_constraint", 5), ("me_early_termination", 3)):
+        q = Params.from_buffer_copy(bytes(p))
+        setattr(q, field, value)
+        assert lib.kvz_cuda_me_params_supported(C.byref(q)) != 0, field
+
+
+# ------------------------------------------------------------------------------------------------ GPU (the product)
+def _dev_api(kb, p, cur, rf, pus):
+    """kvz_cuda_me_search_batch through the Python host layer: pictures, PU records and results in device memory"""
+    import torch
+    d_cur, d_ref, d_pus = kb.to_dev(cur), kb.to_dev(rf), kb.to_dev(pus)
+    before = kb.launch_count()
+    d_out = kb.me_search_batch(p, d_cur, d_ref, d_pus)
+    torch.cuda.synchronize()
+    assert kb.launch_count() == before + 1
+    return d_out.cpu().numpy().view(RESULT).copy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_cuda_matches_golden_and_reference(cuda_lib, name, ref, ref10):
+    kb = cuda_lib
+    p, cur, rf, pus = make_case(name)
+    got = _dev_api(kb, p, cur, rf, pus)
+    assert same(got, _golden(name)), _explain(got, _golden(name), pus)
+    want = run_reference(ref if p.bitdepth == 8 else ref10, p, cur, rf, pus)
+    assert same(got, want), _explain(got, want, pus)
+    got_host = run_host_api(C.CDLL(kb.LIB_PATH), p, cur, rf, pus)          # kvz_cuda_call_me_search: host buffers
+    assert same(got_host, want) and np.array_equal(got_host["points"], got["points"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,bd,size", [(1920, 1080, 8, 16), (1920, 1080, 10, 32), (3840, 2160, 8, 64), (832, 480, 8, 8)])
+def test_cuda_full_picture_matches_reference(cuda_lib, ref, ref10, w, h, bd, size):
+    """every size x size PU of a full picture (BASELINE config 4's frame size and settings) vs the reference's functions"""
+    p, cur, rf, pus = grid_case(w, h, bd, size)
+    got = _dev_api(cuda_lib, p, cur, rf, pus)
+    want = run_reference(ref if bd == 8 else ref10, p, cur, rf, pus)
+    assert same(got, want), _explain(got, want, pus)
+    assert (np.abs(got["mv"]).sum(1) > 0).mean() > 0.5

@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""Writes tests/golden/me_search.npz: what the UNMODIFIED reference's integer motion search (oracle/ref_me.c: the reference's
+own search_inter.c compiled in place) returns for the cases of tests/_me_cases.py.  Run in the container that has
+/root/reference (make -C oracle ref); the tests that read the file need neither the reference nor its build."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from _me_cases import CASES, make_case, run_reference  # noqa: E402
+from _oracle import Ref  # noqa: E402
+
+refs = {}
+out = {}
+for name in sorted(CASES):
+    p, cur, ref, pus = make_case(name)
+    shim = refs.setdefault(p.bitdepth, Ref(p.bitdepth))
+    r = run_reference(shim, p, cur, ref, pus)
+    out[name + "/mv"] = r["mv"].copy()
+    out[name + "/bits"] = r["bits"].copy()
+    out[name + "/cost"] = r["cost"].copy()
+    print(name, len(pus), "PUs")
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "me_search.npz"), **out)
