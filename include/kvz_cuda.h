@@ -362,7 +362,7 @@ typedef struct kvz_cuda_me_params {
   int32_t pad;
   double  lambda_sqrt;              /* state->lambda_sqrt */
 } kvz_cuda_me_params;
-typedef struct kvz_cuda_me_merge { int16_t mv[2][2]; uint8_t dir; uint8_t pad[3]; } kvz_cuda_me_merge;   /* inter_merge_cand_t: dir, mv[list][x/y] (1/4 pel) */
+typedef struct kvz_cuda_me_merge { int16_t mv[2][2]; uint8_t dir; uint8_t ref[2]; uint8_t pad; } kvz_cuda_me_merge;   /* inter_merge_cand_t (src/inter.h:47-52): mv[list][x/y] (1/4 pel), dir, ref[list] */
 typedef struct kvz_cuda_me_pu {
   int16_t x, y;                     /* info->origin (luma, tile-relative = frame-relative here) */
   int16_t w, h;                     /* info->width / height */
@@ -387,6 +387,48 @@ int kvz_cuda_me_search_batch(const kvz_cuda_me_params *p, const void *cur_dev, i
 /* host buffers; synchronous */
 int kvz_cuda_call_me_search(const kvz_cuda_me_params *p, const void *cur, int cur_stride, const void *ref, int ref_stride,
                             const kvz_cuda_me_pu *pus, int count, kvz_cuda_me_result *out);
+
+/* AMVP and merge candidates of a batch of PUs from a snapshot of the CU records (me_search.cu), as
+ *     kvz_inter_get_mv_cand_cua   src/inter.c:1365-1383 (get_spatial_merge_candidates_cua :1015-1076,
+ *                                 get_temporal_merge_candidates :836-907, get_mv_cand_from_candidates :1225-1318,
+ *                                 add_mvp_candidate :1186-1220, apply_mv_scaling_pocs :1084-1103, add_temporal_candidate :1134-1184)
+ *     kvz_inter_get_merge_cand    src/inter.c:1440-1572 (is_a0/b0_cand_coded :689-823, add_merge_candidate :1403-1425)
+ * derive them.  In the encoder the neighbours of a PU are the CUs decided before it, so a caller uses this for PUs
+ * whose neighbourhood is final (the rows above, a previous pass, the colocated picture); the result feeds
+ * kvz_cuda_me_search_batch. */
+typedef struct kvz_cuda_me_cu {       /* the fields of cu_info_t (src/cu.h:126-165) the derivation reads; one record per 4x4 luma block */
+  int16_t mv[2][2];                   /* inter.mv[list][x/y] */
+  uint8_t type;                       /* cu_type_t: 0 not set, 1 intra, 2 inter */
+  uint8_t mv_dir;                     /* 1 = L0, 2 = L1, 3 = both */
+  uint8_t mv_ref[2];                  /* index into L0 / L1 */
+} kvz_cuda_me_cu;
+typedef struct kvz_cuda_me_frame {    /* state->frame / state->frame->ref as the derivation reads them */
+  int32_t width, height;              /* encoder_control->in.width / height (= the tile frame here) */
+  int32_t poc;                        /* state->frame->poc */
+  int32_t slice_b;                    /* state->frame->slicetype == KVZ_SLICE_B */
+  int32_t tmvp_enable, max_merge;     /* cfg.tmvp_enable, cfg.max_merge */
+  int32_t used_size;                  /* state->frame->ref->used_size */
+  int32_t ref_LX_size[2];             /* state->frame->ref_LX_size */
+  int32_t pocs[16];                   /* state->frame->ref->pocs */
+  int32_t col_ref_pocs[2][16];        /* for the colocated picture c = ref_LX[0][0]: images[c]->ref_pocs[ref_LXs[c][list][mv_ref]] */
+  uint8_t ref_LX[2][16];              /* state->frame->ref_LX */
+} kvz_cuda_me_frame;
+typedef struct kvz_cuda_me_cand_pu {
+  int16_t x, y, w, h;                 /* the PU, luma samples */
+  uint8_t mv_ref[2];                  /* cur_cu->inter.mv_ref[list]: the reference index the AMVP of each list is derived for */
+  uint8_t use_a1, use_b1;             /* merge: may A1 / B1 be used (false for the second PU of Nx2N / 2NxN, search_inter.c:1628-1633) */
+} kvz_cuda_me_cand_pu;
+typedef struct kvz_cuda_me_cand_out {
+  int16_t mv_cand[2][2][2];           /* [list][candidate][x/y]; list 1 is zero when L1 is empty */
+  int32_t num_merge;
+  kvz_cuda_me_merge merge[5];         /* unused entries and fields the reference leaves unset are 0 */
+} kvz_cuda_me_cand_out;
+/* cus / col_cus: CU records of the current and of the colocated picture in device memory, `stride` records per row */
+int kvz_cuda_me_candidates_batch(const kvz_cuda_me_frame *f, const kvz_cuda_me_cu *cus_dev, int cu_stride, const kvz_cuda_me_cu *col_cus_dev,
+                                 int col_stride, const kvz_cuda_me_cand_pu *pus_dev, int count, kvz_cuda_me_cand_out *out_dev, void *stream);
+/* host buffers; synchronous.  cu_rows = rows of both CU images */
+int kvz_cuda_call_me_candidates(const kvz_cuda_me_frame *f, const kvz_cuda_me_cu *cus, int cu_stride, const kvz_cuda_me_cu *col_cus, int col_stride,
+                                int cu_rows, const kvz_cuda_me_cand_pu *pus, int count, kvz_cuda_me_cand_out *out);
 
 /* ------------------------------------------------------------------ host-buffer conveniences */
 /* ---------------------------------------------------------------------------------------------------------

@@ -583,7 +583,7 @@ class InterPass:
 
 # ------------------------------------------------------------------ integer motion estimation (me_search.cu)
 # record layouts of include/kvz_cuda.h (kvz_cuda_me_merge / kvz_cuda_me_pu / kvz_cuda_me_result / kvz_cuda_me_params)
-ME_MERGE = np.dtype([("mv", "<i2", (2, 2)), ("dir", "u1"), ("pad", "u1", (3,))])
+ME_MERGE = np.dtype([("mv", "<i2", (2, 2)), ("dir", "u1"), ("ref", "u1", (2,)), ("pad", "u1")])
 ME_PU = np.dtype([("x", "<i2"), ("y", "<i2"), ("w", "<i2"), ("h", "<i2"), ("mv_cand", "<i2", (2, 2)), ("start_mv", "<i2", (2,)),
                   ("num_merge", "<i2"), ("pad", "<i2"), ("merge", ME_MERGE, (5,))])
 ME_RESULT = np.dtype([("cost", "<f8"), ("bits", "<i4"), ("mv", "<i2", (2,)), ("points", "<i4"), ("pad", "<i4")])
@@ -604,4 +604,29 @@ def me_search_batch(params, cur, ref, pus, out=None):
         out = torch.empty(count * ME_RESULT.itemsize, dtype=torch.uint8, device=cur.device)
     _ck(lib().kvz_cuda_me_search_batch(C.byref(params), _p(cur), C.c_int(cur.stride(0)), _p(ref), C.c_int(ref.stride(0)), _p(pus), C.c_int(count),
                                        _p(out), _stream()))
+    return out
+
+
+# AMVP / merge candidate derivation: kvz_cuda_me_cu / kvz_cuda_me_cand_pu / kvz_cuda_me_cand_out / kvz_cuda_me_frame
+ME_CU = np.dtype([("mv", "<i2", (2, 2)), ("type", "u1"), ("mv_dir", "u1"), ("mv_ref", "u1", (2,))])
+ME_CAND_PU = np.dtype([("x", "<i2"), ("y", "<i2"), ("w", "<i2"), ("h", "<i2"), ("mv_ref", "u1", (2,)), ("use_a1", "u1"), ("use_b1", "u1")])
+ME_CAND_OUT = np.dtype([("mv_cand", "<i2", (2, 2, 2)), ("num_merge", "<i4"), ("merge", ME_MERGE, (5,))])
+
+
+class MeFrame(C.Structure):
+    """kvz_cuda_me_frame: reference lists and POCs as src/inter.c:836-1572 reads them from state->frame"""
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("poc", C.c_int32), ("slice_b", C.c_int32), ("tmvp_enable", C.c_int32),
+                ("max_merge", C.c_int32), ("used_size", C.c_int32), ("ref_LX_size", C.c_int32 * 2), ("pocs", C.c_int32 * 16),
+                ("col_ref_pocs", (C.c_int32 * 16) * 2), ("ref_LX", (C.c_uint8 * 16) * 2)]
+
+
+def me_candidates_batch(frame, cus, col_cus, pus, out=None):
+    """AMVP + merge candidates of `pus` (CUDA byte tensor of ME_CAND_PU records) from the CU records `cus` / `col_cus`
+    (2-D CUDA byte tensors, rows x (stride * 12) bytes); returns a CUDA byte tensor of ME_CAND_OUT records."""
+    torch = _torch()
+    count = pus.numel() // ME_CAND_PU.itemsize
+    if out is None:
+        out = torch.empty(count * ME_CAND_OUT.itemsize, dtype=torch.uint8, device=cus.device)
+    _ck(lib().kvz_cuda_me_candidates_batch(C.byref(frame), _p(cus), C.c_int(cus.stride(0) // ME_CU.itemsize), _p(col_cus),
+                                           C.c_int(col_cus.stride(0) // ME_CU.itemsize), _p(pus), C.c_int(count), _p(out), _stream()))
     return out

@@ -8,6 +8,7 @@
 // HBM traffic is one read of both pictures.
 #include "common.cuh"
 #include "me/me_search.h"
+#include "me/me_cand.h"
 
 namespace {
 
@@ -27,6 +28,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) me_search_kernel(kvz_cuda_m
     const kvz_cuda_me_pu pu = pus[i];
     kvzme::search_pu<Pix>(ln, p, pu, pl, &out[i]);
   }
+}
+
+// AMVP / merge candidates: one thread per PU, integer logic over the CU records (12-byte records, read through L1/L2)
+__global__ void __launch_bounds__(128) me_cand_kernel(kvz_cuda_me_frame f, const kvz_cuda_me_cu *__restrict__ cus, int cu_stride,
+                                                      const kvz_cuda_me_cu *__restrict__ col_cus, int col_stride,
+                                                      const kvz_cuda_me_cand_pu *__restrict__ pus, int count, kvz_cuda_me_cand_out *__restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const kvzme::CuImage cur = { cus, cu_stride }, col = { col_cus, col_stride };
+  const kvz_cuda_me_cand_pu pu = pus[i];
+  kvzme::candidates_of_pu(f, cur, col, pu, &out[i]);
 }
 
 int check_args(const kvz_cuda_me_params *p, const void *cur, int cur_stride, const void *ref, int ref_stride, const void *pus, int count,
@@ -85,5 +98,44 @@ extern "C" int kvz_cuda_call_me_search(const kvz_cuda_me_params *p, const void *
   if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(st);
   cudaFree(d);
   if (e != cudaSuccess) { kvzc::set_error("kvz_cuda_call_me_search: %s", cudaGetErrorString(e)); return KVZ_CUDA_E_RUNTIME; }
+  return rc;
+}
+
+extern "C" int kvz_cuda_me_candidates_batch(const kvz_cuda_me_frame *f, const kvz_cuda_me_cu *cus_dev, int cu_stride, const kvz_cuda_me_cu *col_cus_dev,
+                                            int col_stride, const kvz_cuda_me_cand_pu *pus_dev, int count, kvz_cuda_me_cand_out *out_dev, void *stream)
+{
+  KVZC_REQUIRE_DEVICE();
+  KVZC_ARG(f && cus_dev && col_cus_dev && count >= 0 && (count == 0 || (pus_dev && out_dev)));
+  KVZC_ARG(kvzme::frame_supported(*f) == 0);
+  KVZC_ARG(cu_stride >= (f->width + 3) / 4 && col_stride >= (f->width + 3) / 4);
+  if (count == 0) return 0;
+  me_cand_kernel<<<(count + 127) / 128, 128, 0, kvzc::as_stream(stream)>>>(*f, cus_dev, cu_stride, col_cus_dev, col_stride, pus_dev, count, out_dev);
+  KVZC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int kvz_cuda_call_me_candidates(const kvz_cuda_me_frame *f, const kvz_cuda_me_cu *cus, int cu_stride, const kvz_cuda_me_cu *col_cus,
+                                           int col_stride, int cu_rows, const kvz_cuda_me_cand_pu *pus, int count, kvz_cuda_me_cand_out *out)
+{
+  KVZC_REQUIRE_DEVICE();
+  KVZC_ARG(f && cus && col_cus && cu_rows > 0 && count >= 0 && (count == 0 || (pus && out)));
+  if (count == 0) return 0;
+  const size_t cu_bytes = (size_t)cu_stride * cu_rows * sizeof(kvz_cuda_me_cu), col_bytes = (size_t)col_stride * cu_rows * sizeof(kvz_cuda_me_cu);
+  const size_t pu_bytes = (size_t)count * sizeof(kvz_cuda_me_cand_pu), out_bytes = (size_t)count * sizeof(kvz_cuda_me_cand_out);
+  const size_t o_col = (cu_bytes + 255) & ~(size_t)255, o_pu = (o_col + col_bytes + 255) & ~(size_t)255, o_out = (o_pu + pu_bytes + 255) & ~(size_t)255;
+  uint8_t *d = nullptr;
+  KVZC_CHECK(cudaMalloc(&d, o_out + out_bytes));
+  cudaStream_t st = nullptr;
+  int rc = 0;
+  cudaError_t e = cudaMemcpyAsync(d, cus, cu_bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_col, col_cus, col_bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_pu, pus, pu_bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess)
+    rc = kvz_cuda_me_candidates_batch(f, (const kvz_cuda_me_cu *)d, cu_stride, (const kvz_cuda_me_cu *)(d + o_col), col_stride,
+                                      (const kvz_cuda_me_cand_pu *)(d + o_pu), count, (kvz_cuda_me_cand_out *)(d + o_out), st);
+  if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(out, d + o_out, out_bytes, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) { kvzc::set_error("kvz_cuda_call_me_candidates: %s", cudaGetErrorString(e)); return KVZ_CUDA_E_RUNTIME; }
   return rc;
 }

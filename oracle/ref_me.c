@@ -94,3 +94,117 @@ int kvzref_me_search(kvzref_ctx *ctx, const kvz_cuda_me_params *p, const kvz_pix
   state->lambda_sqrt = saved_lambda_sqrt;
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * AMVP and merge candidates through the reference's own kvz_inter_get_mv_cand_cua / kvz_inter_get_merge_cand
+ * (src/inter.c, linked from the unmodified library): the CU records of the test become a cu_array_t (and, for the merge
+ * candidates, the lcu_t work copy the search uses), the reference lists an image_list_t.  Parity checker for
+ * kvz_cuda_me_candidates_batch. */
+static cu_array_t *cua_from_records(const kvz_cuda_me_cu *recs, int stride, int rows, int width, int height)
+{
+  cu_array_t *cua = kvz_cu_array_alloc(width, height);
+  const int w4 = cua->width / 4, h4 = cua->height / 4;
+  for (int y = 0; y < h4 && y < rows; ++y)
+    for (int x = 0; x < w4 && x < stride; ++x) {
+      const kvz_cuda_me_cu *r = &recs[y * stride + x];
+      cu_info_t *c = &cua->data[y * w4 + x];
+      c->type = r->type;
+      if (r->type == CU_INTER) {
+        c->inter.mv_dir = r->mv_dir;
+        for (int l = 0; l < 2; ++l) { c->inter.mv[l][0] = r->mv[l][0]; c->inter.mv[l][1] = r->mv[l][1]; c->inter.mv_ref[l] = r->mv_ref[l]; }
+      }
+    }
+  return cua;
+}
+
+int kvzref_me_candidates(kvzref_ctx *ctx, const kvz_cuda_me_frame *f, const int32_t *col_pic_ref_pocs, const uint8_t *col_ref_LXs /* [2][16] */,
+                         const kvz_cuda_me_cu *cus, int cu_stride, const kvz_cuda_me_cu *col_cus, int col_stride, int cu_rows,
+                         const kvz_cuda_me_cand_pu *pus, int count, kvz_cuda_me_cand_out *out)
+{
+  encoder_state_t *state = &ctx->enc->states[0];
+  encoder_control_t *ctrl = (encoder_control_t *)state->encoder_control;
+  if (ctrl->in.width != f->width || ctrl->in.height != f->height) return -2;
+  if (state->tile->frame->width != f->width || state->tile->frame->height != f->height) return -2;
+
+  cu_array_t *cua = cua_from_records(cus, cu_stride, cu_rows, f->width, f->height);
+  cu_array_t *col = cua_from_records(col_cus, col_stride, cu_rows, f->width, f->height);
+  image_list_t *list = kvz_image_list_alloc(16);
+  kvz_picture *pics[16];
+  for (int i = 0; i < 16; ++i) {
+    pics[i] = calloc(1, sizeof(kvz_picture));
+    for (int r = 0; r < 16; ++r) pics[i]->ref_pocs[r] = col_pic_ref_pocs[r];
+    list->images[i] = pics[i];
+    list->cu_arrays[i] = col;
+    list->pocs[i] = f->pocs[i];
+    memcpy(list->ref_LXs[i], col_ref_LXs, 32);
+  }
+  list->used_size = (uint32_t)f->used_size;
+
+  /* swap the test's frame description in; everything is restored below */
+  image_list_t *saved_ref = state->frame->ref;
+  cu_array_t *saved_cua = state->tile->frame->cu_array;
+  const int32_t saved_poc = state->frame->poc;
+  const int saved_slicetype = state->frame->slicetype;
+  uint8_t saved_LX[2][16]; memcpy(saved_LX, state->frame->ref_LX, 32);
+  uint8_t saved_LX_size[2] = { state->frame->ref_LX_size[0], state->frame->ref_LX_size[1] };
+  const kvz_config saved_cfg = ctrl->cfg;
+  state->frame->ref = list;
+  state->tile->frame->cu_array = cua;
+  state->frame->poc = f->poc;
+  state->frame->slicetype = f->slice_b ? KVZ_SLICE_B : KVZ_SLICE_P;
+  memcpy(state->frame->ref_LX, f->ref_LX, 32);
+  state->frame->ref_LX_size[0] = (uint8_t)f->ref_LX_size[0];
+  state->frame->ref_LX_size[1] = (uint8_t)f->ref_LX_size[1];
+  ctrl->cfg.tmvp_enable = f->tmvp_enable;
+  ctrl->cfg.max_merge = (uint8_t)f->max_merge;
+
+  lcu_t *lcu = calloc(1, sizeof(lcu_t));
+  const int w4 = cua->width / 4;
+  for (int i = 0; i < count; ++i) {
+    const kvz_cuda_me_cand_pu *u = &pus[i];
+    memset(&out[i], 0, sizeof(out[i]));
+    cu_info_t cur; memset(&cur, 0, sizeof(cur));
+    cur.type = CU_INTER;
+    cur.inter.mv_ref[0] = u->mv_ref[0];
+    cur.inter.mv_ref[1] = u->mv_ref[1];
+    for (int l = 0; l < 2; ++l) {
+      if (f->ref_LX_size[l] <= 0) continue;
+      int16_t mvc[2][2] = { { 0, 0 }, { 0, 0 } };
+      kvz_inter_get_mv_cand_cua(state, u->x, u->y, u->w, u->h, mvc, &cur, (int8_t)l);
+      memcpy(out[i].mv_cand[l], mvc, sizeof(mvc));
+    }
+    /* the lcu_t work copy: the CUs of this LCU plus the column to the left, the row above and the top-right CU */
+    memset(lcu->cu, 0, sizeof(lcu->cu));
+    const int lx = (u->x / LCU_WIDTH) * LCU_WIDTH, ly = (u->y / LCU_WIDTH) * LCU_WIDTH;
+    for (int yl = -4; yl < LCU_WIDTH; yl += 4)
+      for (int xl = -4; xl < LCU_WIDTH; xl += 4) {
+        const int X = lx + xl, Y = ly + yl;
+        if (X < 0 || Y < 0 || X >= cua->width || Y >= cua->height) continue;
+        *LCU_GET_CU_AT_PX(lcu, xl, yl) = cua->data[(Y / 4) * w4 + X / 4];
+      }
+    if (ly > 0 && lx + LCU_WIDTH < cua->width) *LCU_GET_TOP_RIGHT_CU(lcu) = cua->data[((ly - 1) / 4) * w4 + (lx + LCU_WIDTH) / 4];
+    inter_merge_cand_t mc[MRG_MAX_NUM_CANDS];
+    memset(mc, 0, sizeof(mc));
+    out[i].num_merge = kvz_inter_get_merge_cand(state, u->x, u->y, u->w, u->h, u->use_a1 != 0, u->use_b1 != 0, mc, lcu);
+    for (int m = 0; m < MRG_MAX_NUM_CANDS; ++m) {
+      out[i].merge[m].dir = mc[m].dir;
+      for (int l = 0; l < 2; ++l) { out[i].merge[m].ref[l] = mc[m].ref[l]; out[i].merge[m].mv[l][0] = mc[m].mv[l][0]; out[i].merge[m].mv[l][1] = mc[m].mv[l][1]; }
+    }
+  }
+  free(lcu);
+
+  state->frame->ref = saved_ref;
+  state->tile->frame->cu_array = saved_cua;
+  state->frame->poc = saved_poc;
+  state->frame->slicetype = saved_slicetype;
+  memcpy(state->frame->ref_LX, saved_LX, 32);
+  state->frame->ref_LX_size[0] = saved_LX_size[0];
+  state->frame->ref_LX_size[1] = saved_LX_size[1];
+  ctrl->cfg = saved_cfg;
+  for (int i = 0; i < 16; ++i) { list->images[i] = NULL; list->cu_arrays[i] = NULL; free(pics[i]); }
+  list->used_size = 0;
+  kvz_image_list_destroy(list);
+  kvz_cu_array_free(&cua);
+  kvz_cu_array_free(&col);
+  return 0;
+}

@@ -155,3 +155,138 @@ def run_reference(ref_shim, p, cur, ref, pus):
 def same(a, b):
     """decisions and costs identical (the diagnostic point count is not part of the reference's result)"""
     return np.array_equal(a["mv"], b["mv"]) and np.array_equal(a["bits"], b["bits"]) and np.array_equal(a["cost"], b["cost"])
+
+
+# ------------------------------------------------------------------------------------------------ AMVP / merge candidates
+from kvazaar_b200.api import ME_CU as CU, ME_CAND_PU as CAND_PU, ME_CAND_OUT as CAND_OUT, MeFrame as Frame  # noqa: E402
+
+assert CU.itemsize == 12 and CAND_PU.itemsize == 12 and CAND_OUT.itemsize == 80 and C.sizeof(Frame) == 260
+
+CAND_CASES = {
+    # name -> picture size, reference structure
+    "p_one_ref":        dict(w=208, h=136, poc=5, slice_b=0, tmvp=1, max_merge=5, pocs=[4], l0=[0], l1=[], seed=1, n=500),
+    "p_four_refs":      dict(w=264, h=200, poc=9, slice_b=0, tmvp=1, max_merge=5, pocs=[8, 7, 5, 1], l0=[0, 1, 2, 3], l1=[], seed=2, n=500),
+    "b_gop":            dict(w=264, h=200, poc=4, slice_b=1, tmvp=1, max_merge=5, pocs=[0, 8, 2, 6], l0=[0, 2], l1=[1, 3], seed=3, n=500),
+    "b_lowdelay":       dict(w=208, h=136, poc=7, slice_b=1, tmvp=1, max_merge=4, pocs=[6, 5, 3], l0=[0, 1, 2], l1=[0, 1, 2], seed=4, n=500),
+    "p_no_tmvp_merge2": dict(w=136, h=72, poc=3, slice_b=0, tmvp=0, max_merge=2, pocs=[2, 1], l0=[0, 1], l1=[], seed=5, n=400),
+    "b_poc1_future":    dict(w=136, h=136, poc=1, slice_b=1, tmvp=1, max_merge=5, pocs=[0, 2], l0=[0], l1=[1], seed=6, n=400),
+    "b_far_pocs":       dict(w=320, h=192, poc=300, slice_b=1, tmvp=1, max_merge=5, pocs=[100, 299, 600, 301], l0=[1, 0], l1=[3, 2], seed=7, n=500),
+}
+
+
+def cu_image(w, h, r, list_sizes, inter_share=0.7):
+    """CU records of a picture: tiled with blocks of 8..64 samples; each block not set / intra / inter with random motion"""
+    wl, hl = (w + 63) // 64 * 64, (h + 63) // 64 * 64
+    im = np.zeros((hl // 4, wl // 4), CU)
+
+    def fill(x, y, size):
+        if size > 8 and (size == 64 or r.integers(0, 3) != 0) and r.integers(0, 4) != 0:
+            for k in range(4):
+                fill(x + (k % 2) * size // 2, y + (k // 2) * size // 2, size // 2)
+            return
+        parts = [(x, y, size, size)]
+        if r.integers(0, 4) == 0:            # two PUs side by side / on top of each other
+            parts = [(x, y, size // 2, size), (x + size // 2, y, size // 2, size)] if r.integers(0, 2) else \
+                    [(x, y, size, size // 2), (x, y + size // 2, size, size // 2)]
+        for (px, py, pw, ph) in parts:
+            rec = np.zeros((), CU)
+            t = r.random()
+            if t < inter_share:
+                rec["type"] = 2
+                dirs = [1] if list_sizes[1] == 0 else [1, 2, 3]
+                d = int(dirs[int(r.integers(0, len(dirs)))])
+                rec["mv_dir"] = d
+                for l in range(2):
+                    if d & (1 << l):
+                        rec["mv"][l] = r.integers(-80, 81, 2) if r.integers(0, 5) else 0
+                        rec["mv_ref"][l] = int(r.integers(0, list_sizes[l]))
+                    else:                   # what the unused list holds must not matter: put junk there
+                        rec["mv"][l] = r.integers(-9, 10, 2)
+                        rec["mv_ref"][l] = int(r.integers(0, 4))
+            elif t < inter_share + 0.2:
+                rec["type"] = 1
+            im[py // 4:(py + ph) // 4, px // 4:(px + pw) // 4] = rec
+
+    for y in range(0, hl, 64):
+        for x in range(0, wl, 64):
+            fill(x, y, 64)
+    # some repeated motion so that duplicate pruning happens
+    return im
+
+
+def make_cand_case(name):
+    c = CAND_CASES[name]
+    r = np.random.default_rng(3000 + c["seed"])
+    f = Frame()
+    f.width, f.height, f.poc, f.slice_b, f.tmvp_enable, f.max_merge = c["w"], c["h"], c["poc"], c["slice_b"], c["tmvp"], c["max_merge"]
+    f.used_size = len(c["pocs"])
+    for i, p in enumerate(c["pocs"]):
+        f.pocs[i] = p
+    sizes = [len(c["l0"]), len(c["l1"])]
+    f.ref_LX_size[0], f.ref_LX_size[1] = sizes
+    for l, lst in enumerate((c["l0"], c["l1"])):
+        for i, v in enumerate(lst):
+            f.ref_LX[l][i] = v
+    # the colocated picture (ref_LX[0][0]): the POCs it referred to, and its own reference lists
+    col_poc = c["pocs"][c["l0"][0]]
+    col_pic_ref_pocs = np.array([col_poc - 1 - int(r.integers(0, 6)) if i % 3 else col_poc + 1 + int(r.integers(0, 4)) for i in range(16)], np.int32)
+    col_ref_LXs = r.integers(0, 16, (2, 16)).astype(np.uint8)
+    for l in range(2):
+        for i in range(16):
+            f.col_ref_pocs[l][i] = int(col_pic_ref_pocs[col_ref_LXs[l][i]])
+    cus = cu_image(c["w"], c["h"], r, [sizes[0], sizes[1]])
+    col = cu_image(c["w"], c["h"], r, [4, 4], inter_share=0.8)
+    # a few neighbours with identical motion (duplicate pruning in the merge list)
+    flat = cus.reshape(-1)
+    inter = np.nonzero(flat["type"] == 2)[0]
+    for _ in range(len(inter) // 6):
+        a, b = r.choice(inter, 2)
+        flat[b] = flat[a]
+    n = c["n"]
+    pus = np.zeros(n, CAND_PU)
+    # PUs as the encoder forms them: a CU of 8..64 samples on its own grid, one of the part modes the inter search tries
+    # (2Nx2N, 2NxN, Nx2N, the four asymmetric splits for CUs >= 16), either PU of it
+    for i in range(n):
+        while True:
+            size = int((8, 16, 32, 64)[int(r.integers(0, 4))])
+            if size <= c["w"] and size <= c["h"]:
+                break
+        cx = int(r.integers(0, c["w"] // size)) * size
+        cy = int(r.integers(0, c["h"] // size)) * size
+        mode = int(r.integers(0, 7 if size >= 16 else 3))
+        q = size // 4
+        split = {0: None, 1: ("h", size // 2), 2: ("v", size // 2), 3: ("h", q), 4: ("h", size - q), 5: ("v", q), 6: ("v", size - q)}[mode]
+        ipu = int(r.integers(0, 2)) if split else 0
+        x, y, pw, ph = cx, cy, size, size
+        if split:
+            kind, at = split
+            if kind == "h":
+                y, ph = (cy, at) if ipu == 0 else (cy + at, size - at)
+            else:
+                x, pw = (cx, at) if ipu == 0 else (cx + at, size - at)
+        pus[i]["x"], pus[i]["y"], pus[i]["w"], pus[i]["h"] = x, y, pw, ph
+        pus[i]["mv_ref"] = [int(r.integers(0, max(1, sizes[0]))), int(r.integers(0, max(1, sizes[1])))]
+        pus[i]["use_a1"], pus[i]["use_b1"] = int(ipu == 0 or pw >= ph), int(ipu == 0 or pw <= ph)       # search_inter.c:1628-1633
+        if r.integers(0, 8) == 0:
+            pus[i]["use_a1"], pus[i]["use_b1"] = int(r.integers(0, 2)), int(r.integers(0, 2))
+    return f, col_pic_ref_pocs, col_ref_LXs, cus, col, pus
+
+
+def run_cand_host_api(lib, f, cus, col, pus):
+    out = np.zeros(len(pus), CAND_OUT)
+    lib.kvz_cuda_call_me_candidates.argtypes = [C.POINTER(Frame), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    rc = lib.kvz_cuda_call_me_candidates(C.byref(f), cus.ctypes.data, cus.shape[1], col.ctypes.data, col.shape[1], cus.shape[0], pus.ctypes.data,
+                                         len(pus), out.ctypes.data)
+    assert rc == 0, rc
+    return out
+
+
+def run_cand_reference(ref_shim, f, col_pic_ref_pocs, col_ref_LXs, cus, col, pus):
+    out = np.zeros(len(pus), CAND_OUT)
+    ctx = ref_shim.ctx(27, 0, 0, f.width, f.height)
+    fn = ref_shim.lib.kvzref_me_candidates
+    fn.argtypes = [C.c_void_p, C.POINTER(Frame), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    rc = fn(ctx, C.byref(f), col_pic_ref_pocs.ctypes.data, col_ref_LXs.ctypes.data, cus.ctypes.data, cus.shape[1], col.ctypes.data, col.shape[1],
+            cus.shape[0], pus.ctypes.data, len(pus), out.ctypes.data)
+    assert rc == 0, rc
+    return out

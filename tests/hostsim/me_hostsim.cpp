@@ -3,6 +3,7 @@
 // lane shares of every SAD walked in turn: checks the control flow of the device code against the reference without a GPU (tests/test_me_search.py).
 // Exports the same entry points as libkvzcuda.so, with host pointers.
 #include "../../kvazaar_b200/csrc/me/me_search.h"
+#include "../../kvazaar_b200/csrc/me/me_cand.h"
 
 extern "C" int kvz_cuda_me_params_supported(const kvz_cuda_me_params *p) { return p ? kvzme::params_supported(*p) : -1; }
 
@@ -28,4 +29,19 @@ extern "C" int kvz_cuda_me_search_batch(const kvz_cuda_me_params *p, const void 
                                         const kvz_cuda_me_pu *pus, int count, kvz_cuda_me_result *out, void *)
 {
   return kvz_cuda_call_me_search(p, cur, cur_stride, ref, ref_stride, pus, count, out);
+}
+
+extern "C" int kvz_cuda_call_me_candidates(const kvz_cuda_me_frame *f, const kvz_cuda_me_cu *cus, int cu_stride, const kvz_cuda_me_cu *col_cus,
+                                           int col_stride, int, const kvz_cuda_me_cand_pu *pus, int count, kvz_cuda_me_cand_out *out)
+{
+  if (!f || kvzme::frame_supported(*f) != 0) return -2;
+  const kvzme::CuImage cur = { cus, cu_stride }, col = { col_cus, col_stride };
+  for (int i = 0; i < count; ++i) kvzme::candidates_of_pu(*f, cur, col, pus[i], &out[i]);
+  return 0;
+}
+
+extern "C" int kvz_cuda_me_candidates_batch(const kvz_cuda_me_frame *f, const kvz_cuda_me_cu *cus, int cu_stride, const kvz_cuda_me_cu *col_cus,
+                                            int col_stride, const kvz_cuda_me_cand_pu *pus, int count, kvz_cuda_me_cand_out *out, void *)
+{
+  return kvz_cuda_call_me_candidates(f, cus, cu_stride, col_cus, col_stride, 0, pus, count, out);
 }

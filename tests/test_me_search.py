@@ -15,7 +15,8 @@ import subprocess
 import numpy as np
 import pytest
 
-from _me_cases import CASES, RESULT, Params, grid_case, make_case, run_host_api, run_reference, same
+from _me_cases import (CAND_CASES, CAND_OUT, CASES, PU, RESULT, Params, grid_case, make_cand_case, make_case, run_cand_host_api, run_cand_reference,
+                       run_host_api, run_reference, same)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOSTSIM = os.path.join(ROOT, "tests", "hostsim", "libkvzme_hostsim.so")
@@ -77,6 +78,64 @@ def test_params_outside_scope_are_refused():
         assert lib.kvz_cuda_me_params_supported(C.byref(q)) != 0, field
 
 
+# ---- AMVP / merge candidates
+def _golden_cand(name):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "me_search.npz"))
+    return g["cand/" + name].view(CAND_OUT)
+
+
+def _explain_cand(got, want, pus):
+    bad = [i for i in range(len(pus)) if got[i].tobytes() != want[i].tobytes()]
+    i = bad[0]
+    return f"{len(bad)} of {len(pus)} PUs differ; first: PU {i} {pus[i]}\n got  {got[i]}\n want {want[i]}"
+
+
+@pytest.mark.parametrize("name", sorted(CAND_CASES))
+def test_candidates_reference_matches_golden(name, ref):
+    f, crp, clx, cus, col, pus = make_cand_case(name)
+    want = run_cand_reference(ref, f, crp, clx, cus, col, pus)
+    assert want.tobytes() == _golden_cand(name).tobytes(), _explain_cand(want, _golden_cand(name), pus)
+
+
+@pytest.mark.parametrize("name", sorted(CAND_CASES))
+def test_candidates_hostbuild_matches_golden(name):
+    f, _, _, cus, col, pus = make_cand_case(name)
+    got = run_cand_host_api(_hostsim(), f, cus, col, pus)
+    want = _golden_cand(name)
+    assert got.tobytes() == want.tobytes(), _explain_cand(got, want, pus)
+    assert (np.abs(got["mv_cand"]).sum((1, 2, 3)) > 0).mean() > 0.5 and got["num_merge"].min() == f.max_merge
+
+
+def _search_pus_from_candidates(cand_pus, cand, r):
+    """the PU records of the search, fed with the derived candidates (list 0) -- what search_pu_inter hands to search_pu_inter_ref"""
+    pus = np.zeros(len(cand_pus), PU)
+    for k in ("x", "y", "w", "h"):
+        pus[k] = cand_pus[k]
+    pus["mv_cand"] = cand["mv_cand"][:, 0]
+    pus["num_merge"] = cand["num_merge"]
+    pus["merge"] = cand["merge"]
+    pus["start_mv"] = r.integers(-24, 25, (len(pus), 2))
+    return pus
+
+
+def _chain_case():
+    f, crp, clx, cus, col, cand_pus = make_cand_case("p_four_refs")
+    p, cur, rf, _ = grid_case(f.width, f.height, 8)
+    return f, crp, clx, cus, col, cand_pus, p, cur, rf
+
+
+def test_hostbuild_candidates_feed_the_search(ref):
+    """candidate derivation -> integer search, chained, against the reference doing the same chain"""
+    f, crp, clx, cus, col, cand_pus, p, cur, rf = _chain_case()
+    lib = _hostsim()
+    cand = run_cand_host_api(lib, f, cus, col, cand_pus)
+    want_cand = run_cand_reference(ref, f, crp, clx, cus, col, cand_pus)
+    assert cand.tobytes() == want_cand.tobytes()
+    pus = _search_pus_from_candidates(cand_pus, cand, np.random.default_rng(11))
+    got, want = run_host_api(lib, p, cur, rf, pus), run_reference(ref, p, cur, rf, pus)
+    assert same(got, want), _explain(got, want, pus)
+
+
 # ------------------------------------------------------------------------------------------------ GPU (the product)
 def _dev_api(kb, p, cur, rf, pus):
     """kvz_cuda_me_search_batch through the Python host layer: pictures, PU records and results in device memory"""
@@ -111,3 +170,39 @@ def test_cuda_full_picture_matches_reference(cuda_lib, ref, ref10, w, h, bd, siz
     want = run_reference(ref if bd == 8 else ref10, p, cur, rf, pus)
     assert same(got, want), _explain(got, want, pus)
     assert (np.abs(got["mv"]).sum(1) > 0).mean() > 0.5
+
+
+def _cand_dev_api(kb, f, cus, col, pus):
+    import torch
+    d_cus = kb.to_dev(cus.view(np.uint8).reshape(cus.shape[0], -1))
+    d_col = kb.to_dev(col.view(np.uint8).reshape(col.shape[0], -1))
+    d_out = kb.me_candidates_batch(f, d_cus, d_col, kb.to_dev(pus))
+    torch.cuda.synchronize()
+    return d_out.cpu().numpy().view(CAND_OUT).copy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CAND_CASES))
+def test_cuda_candidates_match_golden_and_reference(cuda_lib, ref, name):
+    kb = cuda_lib
+    f, crp, clx, cus, col, pus = make_cand_case(name)
+    got = _cand_dev_api(kb, f, cus, col, pus)
+    assert got.tobytes() == _golden_cand(name).tobytes(), _explain_cand(got, _golden_cand(name), pus)
+    want = run_cand_reference(ref, f, crp, clx, cus, col, pus)
+    assert got.tobytes() == want.tobytes(), _explain_cand(got, want, pus)
+    got_host = run_cand_host_api(C.CDLL(kb.LIB_PATH), f, cus, col, pus)       # kvz_cuda_call_me_candidates: host buffers
+    assert got_host.tobytes() == want.tobytes()
+
+
+@pytest.mark.gpu
+def test_cuda_candidates_feed_the_search(cuda_lib, ref):
+    """candidate derivation -> integer search on the device, the candidates staying in device memory in between"""
+    import torch
+    kb = cuda_lib
+    f, crp, clx, cus, col, cand_pus, p, cur, rf = _chain_case()
+    cand = _cand_dev_api(kb, f, cus, col, cand_pus)
+    assert cand.tobytes() == run_cand_reference(ref, f, crp, clx, cus, col, cand_pus).tobytes()
+    pus = _search_pus_from_candidates(cand_pus, cand, np.random.default_rng(11))
+    got, want = _dev_api(kb, p, cur, rf, pus), run_reference(ref, p, cur, rf, pus)
+    assert same(got, want), _explain(got, want, pus)
+    torch.cuda.synchronize()

@@ -10,7 +10,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from _me_cases import CASES, make_case, run_reference  # noqa: E402
+from _me_cases import CAND_CASES, CASES, make_cand_case, make_case, run_cand_reference, run_reference  # noqa: E402
 from _oracle import Ref  # noqa: E402
 
 refs = {}
@@ -23,4 +23,9 @@ for name in sorted(CASES):
     out[name + "/bits"] = r["bits"].copy()
     out[name + "/cost"] = r["cost"].copy()
     print(name, len(pus), "PUs")
+for name in sorted(CAND_CASES):
+    f, crp, clx, cus, col, pus = make_cand_case(name)
+    r = run_cand_reference(refs.setdefault(8, Ref(8)), f, crp, clx, cus, col, pus)
+    out["cand/" + name] = np.frombuffer(r.tobytes(), np.uint8).copy()
+    print("cand", name, len(pus), "PUs")
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "me_search.npz"), **out)
