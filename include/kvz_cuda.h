@@ -343,7 +343,9 @@ int   kvz_cuda_ip_run_host(kvz_cuda_inter_pass *ip, const void *cur_host, const 
  *     select_starting_point   search_inter.c:297-330   (0-vector, the predicted start MV, the merge candidates)
  *     early_terminate         search_inter.c:436-485
  *     hexagon_search          search_inter.c:712-792   (ime_algorithm = KVZ_IME_HEXBS)
- *     diamond_search          search_inter.c:812-888   (ime_algorithm = KVZ_IME_DIA)
+ *     diamond_search          search_inter.c:812-888   (KVZ_IME_DIA)
+ *     tz_search               search_inter.c:623-697   (KVZ_IME_TZ; kvz_tz_pattern_search :486-604)
+ *     search_mv_full          search_inter.c:891-964   (KVZ_IME_FULL, FULL8 .. FULL64)
  * every point through check_mv_cost (search_inter.c:202-247): the tile / WPP MV constraints of
  * fracmv_within_tile (:94-181), kvz_image_calc_sad (src/image.c:407-447; references outside the picture read the
  * edge pixels, image.c:279-398), and calc_mvd_cost (:394-433) with get_mvd_coding_cost (:333-348, cfg.mv_rdo = 0)
@@ -352,7 +354,7 @@ int   kvz_cuda_ip_run_host(kvz_cuda_inter_pass *ip, const void *cur_host, const 
 typedef struct kvz_cuda_me_params {
   int32_t width, height;            /* luma size of the (tile's) frame: state->tile->frame->width / height */
   int32_t bitdepth;                 /* 8 or 10 (pixels are uint8_t / uint16_t) */
-  int32_t ime_algorithm;            /* enum kvz_ime_algorithm: 0 = hexbs, 7 = dia */
+  int32_t ime_algorithm;            /* enum kvz_ime_algorithm (kvazaar.h:110-119): hexbs, tz, full, full8..64, dia */
   int32_t me_max_steps;             /* cfg.me_max_steps (uint32; -1 = unlimited) */
   int32_t me_early_termination;     /* enum kvz_me_early_termination: 0 off, 1 on, 2 sensitive */
   int32_t mv_constraint;            /* enum kvz_mv_constraint (0 none ... 4 frame and tile with margin) */

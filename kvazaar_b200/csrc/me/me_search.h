@@ -12,7 +12,8 @@
 //   calc_mvd_cost            :394-433 (num_cand = 0 in the integer stage: no merge shortcut)
 //   select_starting_point    :297-330, mv_in_merge :277-290
 //   early_terminate          :436-485
-//   hexagon_search           :712-792, diamond_search :812-888
+//   hexagon_search           :712-792, diamond_search :812-888, kvz_tz_pattern_search :486-604 (diamond pattern),
+//   tz_search                :623-697, search_mv_full :891-964
 //   search_pu_inter_ref      :1349-1383 (the order of the three stages)
 #pragma once
 #include <stdint.h>
@@ -283,6 +284,96 @@ ME_FN void diamond_search(const Lanes &ln, const kvz_cuda_me_params &p, const kv
   } while (better && steps != 0);
 }
 
+// kvz_tz_pattern_search with the diamond pattern (type 0, the only one tz_search uses): 4 points at distance 1,
+// else the 4 axis points and the 4 half-distance diagonal points
+template <typename Pix>
+ME_FN void tz_diamond(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cuda_me_pu &pu, const Planes<Pix> &pl, int dist, int cx, int cy,
+                      int &best_dist, Best &best)
+{
+  const int hd = dist / 2;
+  const int ox[8] = { 0, dist, 0, -dist, hd, hd, -hd, -hd }, oy[8] = { dist, 0, -dist, 0, hd, -hd, -hd, hd };
+  const int n_points = dist == 1 ? 4 : 8;
+  bool improved = false;
+  for (int i = 0; i < n_points; ++i)
+    if (check_mv(ln, p, pu, pl, cx + ox[i], cy + oy[i], best)) improved = true;
+  if (improved) best_dist = dist;
+}
+
+// tz_search (search_inter.c:623-697) with the reference's fixed parameters: range 96, diamond grid search from the
+// start MV and again from the 0-vector, no raster step, star refinement until a round brings nothing
+template <typename Pix>
+ME_FN void tz_search(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cuda_me_pu &pu, const Planes<Pix> &pl, Best &best)
+{
+  const int range = 96;
+  int best_dist = 0;
+  int sx = best.mvx >> 2, sy = best.mvy >> 2;
+  int idle = 0;
+  for (int dist = 1; dist <= range; dist *= 2) {
+    tz_diamond(ln, p, pu, pl, dist, sx, sy, best_dist, best);
+    if (best_dist != dist) ++idle;
+    if (idle >= 3) break;
+  }
+  if (sx != 0 || sy != 0) {
+    sx = sy = 0;
+    idle = 0;
+    for (int dist = 1; dist <= range / 2; dist *= 2) {
+      tz_diamond(ln, p, pu, pl, dist, sx, sy, best_dist, best);
+      if (best_dist != dist) ++idle;
+      if (idle >= 3) break;
+    }
+  }
+  while (best_dist > 0) {
+    best_dist = 0;
+    sx = best.mvx >> 2;
+    sy = best.mvy >> 2;
+    for (int dist = 1; dist <= range; dist *= 2) tz_diamond(ln, p, pu, pl, dist, sx, sy, best_dist, best);
+  }
+}
+
+// search_mv_full (search_inter.c:891-964): the square around the 0-vector, around the MV found so far (unless a merge
+// candidate rounds to it), and around every merge candidate, skipping what an earlier square of this last stage covered
+template <typename Pix>
+ME_FN void full_search(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cuda_me_pu &pu, const Planes<Pix> &pl, int range, Best &best)
+{
+  const int ex = best.mvx >> 2, ey = best.mvy >> 2;       // extra_mv: best_mv by value at the call
+  for (int y = -range; y <= range; ++y)
+    for (int x = -range; x <= range; ++x) check_mv(ln, p, pu, pl, x, y, best);
+  bool in_merge = false;
+  for (int i = 0; i < pu.num_merge; ++i) {
+    int mx, my;
+    if (merge_mv(pu.merge[i], mx, my) && mx == ex && my == ey) { in_merge = true; break; }
+  }
+  if (!in_merge)
+    for (int y = -range; y <= range; ++y)
+      for (int x = -range; x <= range; ++x) check_mv(ln, p, pu, pl, ex + x, ey + y, best);
+  for (int i = 0; i < pu.num_merge; ++i) {
+    const kvz_cuda_me_merge &m = pu.merge[i];
+    if (m.dir == 3) continue;
+    const int mx = m.mv[m.dir - 1][0] >> 2, my = m.mv[m.dir - 1][1] >> 2;      // truncating here, rounding in select_start: as the reference
+    if (mx == 0 && my == 0) continue;
+    for (int y = my - range; y <= my + range; ++y)
+      for (int x = mx - range; x <= mx + range; ++x) {
+        if (!mv_allowed(p, pu, x * 4, y * 4)) continue;
+        bool tested = false;
+        for (int j = -1; j < i; ++j) {
+          int xx = 0, yy = 0;
+          if (j >= 0) {
+            if (pu.merge[j].dir == 3) continue;
+            xx = pu.merge[j].mv[pu.merge[j].dir - 1][0] >> 2;
+            yy = pu.merge[j].mv[pu.merge[j].dir - 1][1] >> 2;
+          }
+          if (x >= xx - range && x <= xx + range && y >= yy - range && y <= yy + range) {
+            tested = true;
+            x = xx + range;                 // jump to the right edge of the covered square
+            break;
+          }
+        }
+        if (tested) continue;
+        check_mv(ln, p, pu, pl, x, y, best);
+      }
+  }
+}
+
 // the integer stage of search_pu_inter_ref for one PU
 template <typename Pix>
 ME_FN void search_pu(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cuda_me_pu &pu, const Planes<Pix> &pl, kvz_cuda_me_result *out)
@@ -298,8 +389,15 @@ ME_FN void search_pu(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cud
   select_start(ln, p, pu, pl, sx, sy, best);
   const bool skip = early_terminate(ln, p, pu, pl, best);
   if (!(p.me_early_termination && skip)) {
-    if (p.ime_algorithm == 7) diamond_search(ln, p, pu, pl, best);
-    else hexagon_search(ln, p, pu, pl, best);
+    switch (p.ime_algorithm) {               // enum kvz_ime_algorithm (kvazaar.h:110-119), search_inter.c:1360-1382
+      case 1: tz_search(ln, p, pu, pl, best); break;
+      case 2: case 5: full_search(ln, p, pu, pl, 32, best); break;
+      case 3: full_search(ln, p, pu, pl, 8, best); break;
+      case 4: full_search(ln, p, pu, pl, 16, best); break;
+      case 6: full_search(ln, p, pu, pl, 64, best); break;
+      case 7: diamond_search(ln, p, pu, pl, best); break;
+      default: hexagon_search(ln, p, pu, pl, best); break;
+    }
   }
   if (ln.lane == 0) {
     out->cost = best.cost;
@@ -318,7 +416,7 @@ inline int params_supported(const kvz_cuda_me_params &p)
 {
   if (p.width < 8 || p.height < 8 || p.width > 16384 || p.height > 16384) return -1;
   if (p.bitdepth != 8 && p.bitdepth != 10) return -1;
-  if (p.ime_algorithm != 0 && p.ime_algorithm != 7) return -1;      // tz and the full searches stay on the host
+  if (p.ime_algorithm < 0 || p.ime_algorithm > 7) return -1;
   if (p.me_early_termination < 0 || p.me_early_termination > 2) return -1;
   if (p.mv_constraint < 0 || p.mv_constraint > 4) return -1;
   return 0;

@@ -77,8 +77,21 @@ int kvzref_me_search(kvzref_ctx *ctx, const kvz_cuda_me_params *p, const kvz_pix
     select_starting_point(&info, best_mv, &best_cost, &best_bits, &best_mv);
     bool skip_me = early_terminate(&info, &best_cost, &best_bits, &best_mv);
     if (!(ctrl->cfg.me_early_termination && skip_me)) {
-      if (ctrl->cfg.ime_algorithm == KVZ_IME_DIA) diamond_search(&info, best_mv, ctrl->cfg.me_max_steps, &best_cost, &best_bits, &best_mv);
-      else hexagon_search(&info, best_mv, ctrl->cfg.me_max_steps, &best_cost, &best_bits, &best_mv);
+      int search_range = 32;
+      switch (ctrl->cfg.ime_algorithm) {
+        case KVZ_IME_FULL64: search_range = 64; break;
+        case KVZ_IME_FULL32: search_range = 32; break;
+        case KVZ_IME_FULL16: search_range = 16; break;
+        case KVZ_IME_FULL8: search_range = 8; break;
+        default: break;
+      }
+      switch (ctrl->cfg.ime_algorithm) {
+        case KVZ_IME_TZ: tz_search(&info, best_mv, &best_cost, &best_bits, &best_mv); break;
+        case KVZ_IME_FULL64: case KVZ_IME_FULL32: case KVZ_IME_FULL16: case KVZ_IME_FULL8: case KVZ_IME_FULL:
+          search_mv_full(&info, search_range, best_mv, &best_cost, &best_bits, &best_mv); break;
+        case KVZ_IME_DIA: diamond_search(&info, best_mv, ctrl->cfg.me_max_steps, &best_cost, &best_bits, &best_mv); break;
+        default: hexagon_search(&info, best_mv, ctrl->cfg.me_max_steps, &best_cost, &best_bits, &best_mv); break;
+      }
     }
     out[i].cost = best_cost;
     out[i].bits = (int32_t)best_bits;

@@ -25,6 +25,12 @@ CASES = {
     "hexbs_noisy":          dict(w=208, h=136, bd=8, algo=0, steps=-1, et=0, mvc=0, wpp=0, delay=0, qp=17, seed=8, n=400, noisy=True),
     "hexbs_10bit":          dict(w=208, h=136, bd=10, algo=0, steps=-1, et=1, mvc=0, wpp=1, delay=10, qp=27, seed=9, n=400),
     "dia_10bit_margin":     dict(w=136, h=72, bd=10, algo=7, steps=-1, et=2, mvc=4, wpp=0, delay=0, qp=32, seed=10, n=300),
+    "tz_et_off":            dict(w=208, h=136, bd=8, algo=1, steps=-1, et=0, mvc=0, wpp=0, delay=0, qp=27, seed=11, n=300),
+    "tz_wpp_sao_10bit":     dict(w=208, h=136, bd=10, algo=1, steps=-1, et=1, mvc=0, wpp=1, delay=10, qp=22, seed=12, n=300),
+    "tz_noisy_margin":      dict(w=136, h=72, bd=8, algo=1, steps=-1, et=0, mvc=4, wpp=0, delay=0, qp=37, seed=13, n=200, noisy=True),
+    "full8_et_off":         dict(w=136, h=72, bd=8, algo=3, steps=-1, et=0, mvc=0, wpp=1, delay=8, qp=27, seed=14, n=120),
+    "full8_frame":          dict(w=128, h=128, bd=8, algo=3, steps=-1, et=2, mvc=1, wpp=0, delay=0, qp=32, seed=15, n=120),
+    "full16_small":         dict(w=136, h=72, bd=8, algo=4, steps=-1, et=0, mvc=0, wpp=0, delay=0, qp=27, seed=16, n=40),
 }
 
 

@@ -72,7 +72,7 @@ def test_params_outside_scope_are_refused():
     lib.kvz_cuda_me_params_supported.argtypes = [C.POINTER(Params)]
     p, _, _, _ = make_case("hexbs_et_sensitive")
     assert lib.kvz_cuda_me_params_supported(C.byref(p)) == 0
-    for field, value in (("ime_algorithm", 1), ("ime_algorithm", 2), ("bitdepth", 12), ("mv_constraint", 5), ("me_early_termination", 3)):
+    for field, value in (("ime_algorithm", 8), ("ime_algorithm", -1), ("bitdepth", 12), ("mv_constraint", 5), ("me_early_termination", 3)):
         q = Params.from_buffer_copy(bytes(p))
         setattr(q, field, value)
         assert lib.kvz_cuda_me_params_supported(C.byref(q)) != 0, field
