@@ -390,6 +390,15 @@ int kvz_cuda_me_search_batch(const kvz_cuda_me_params *p, const void *cur_dev, i
 int kvz_cuda_call_me_search(const kvz_cuda_me_params *p, const void *cur, int cur_stride, const void *ref, int ref_stride,
                             const kvz_cuda_me_pu *pus, int count, kvz_cuda_me_result *out);
 
+/* Fractional search (search_frac, src/search_inter.c:974-1168) of a batch of PUs: half-pel, then quarter-pel positions
+ * around pus[i].start_mv (= the integer search's best MV), `fme_level` (cfg.fme_level, 1..4) of the reference's four
+ * steps; Hadamard costs as kvz_satd_any_size / kvz_satd_any_size_quad give them, MV cost and MV limits as above.
+ * Result: best_mv (1/4 pel), best_cost, best_bits as search_frac returns them. */
+int kvz_cuda_me_frac_search_batch(const kvz_cuda_me_params *p, int fme_level, const void *cur_dev, int cur_stride, const void *ref_dev, int ref_stride,
+                                  const kvz_cuda_me_pu *pus_dev, int count, kvz_cuda_me_result *out_dev, void *stream);
+int kvz_cuda_call_me_frac_search(const kvz_cuda_me_params *p, int fme_level, const void *cur, int cur_stride, const void *ref, int ref_stride,
+                                 const kvz_cuda_me_pu *pus, int count, kvz_cuda_me_result *out);
+
 /* AMVP and merge candidates of a batch of PUs from a snapshot of the CU records (me_search.cu), as
  *     kvz_inter_get_mv_cand_cua   src/inter.c:1365-1383 (get_spatial_merge_candidates_cua :1015-1076,
  *                                 get_temporal_merge_candidates :836-907, get_mv_cand_from_candidates :1225-1318,

@@ -630,3 +630,14 @@ def me_candidates_batch(frame, cus, col_cus, pus, out=None):
     _ck(lib().kvz_cuda_me_candidates_batch(C.byref(frame), _p(cus), C.c_int(cus.stride(0) // ME_CU.itemsize), _p(col_cus),
                                            C.c_int(col_cus.stride(0) // ME_CU.itemsize), _p(pus), C.c_int(count), _p(out), _stream()))
     return out
+
+
+def me_frac_search_batch(params, fme_level, cur, ref, pus, out=None):
+    """Fractional search (search_frac) of `pus` around their start_mv (the integer search's best MV); layouts as me_search_batch."""
+    torch = _torch()
+    count = pus.numel() // ME_PU.itemsize
+    if out is None:
+        out = torch.empty(count * ME_RESULT.itemsize, dtype=torch.uint8, device=cur.device)
+    _ck(lib().kvz_cuda_me_frac_search_batch(C.byref(params), C.c_int(fme_level), _p(cur), C.c_int(cur.stride(0)), _p(ref), C.c_int(ref.stride(0)),
+                                            _p(pus), C.c_int(count), _p(out), _stream()))
+    return out

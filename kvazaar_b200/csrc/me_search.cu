@@ -9,6 +9,7 @@
 #include "common.cuh"
 #include "me/me_search.h"
 #include "me/me_cand.h"
+#include "me/me_frac.h"
 
 namespace {
 
@@ -27,6 +28,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) me_search_kernel(kvz_cuda_m
   for (int i = blockIdx.x * kWarpsPerCta + warp; i < count; i += gridDim.x * kWarpsPerCta) {
     const kvz_cuda_me_pu pu = pus[i];
     kvzme::search_pu<Pix>(ln, p, pu, pl, &out[i]);
+  }
+}
+
+// fractional search: one warp per PU, every lane interpolates and transforms the sub-blocks of its share in registers
+template <typename Pix>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) me_frac_kernel(kvz_cuda_me_params p, int levels, const Pix *__restrict__ cur, int cur_stride,
+                                                                    const Pix *__restrict__ ref, int ref_stride,
+                                                                    const kvz_cuda_me_pu *__restrict__ pus, int count,
+                                                                    kvz_cuda_me_result *__restrict__ out)
+{
+  const int warp = threadIdx.x >> 5;
+  const kvzme::Lanes ln = { (int)(threadIdx.x & 31), 32 };
+  const kvzme::Planes<Pix> pl = { cur, ref, cur_stride, ref_stride };
+  for (int i = blockIdx.x * kWarpsPerCta + warp; i < count; i += gridDim.x * kWarpsPerCta) {
+    const kvz_cuda_me_pu pu = pus[i];
+    kvzme::frac_search_pu<Pix>(ln, p, pu, pl, levels, &out[i]);
   }
 }
 
@@ -137,5 +154,52 @@ extern "C" int kvz_cuda_call_me_candidates(const kvz_cuda_me_frame *f, const kvz
   if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(st);
   cudaFree(d);
   if (e != cudaSuccess) { kvzc::set_error("kvz_cuda_call_me_candidates: %s", cudaGetErrorString(e)); return KVZ_CUDA_E_RUNTIME; }
+  return rc;
+}
+
+extern "C" int kvz_cuda_me_frac_search_batch(const kvz_cuda_me_params *p, int fme_level, const void *cur_dev, int cur_stride, const void *ref_dev,
+                                             int ref_stride, const kvz_cuda_me_pu *pus_dev, int count, kvz_cuda_me_result *out_dev, void *stream)
+{
+  KVZC_REQUIRE_DEVICE();
+  if (int e = check_args(p, cur_dev, cur_stride, ref_dev, ref_stride, pus_dev, count, out_dev)) return e;
+  KVZC_ARG(fme_level >= 1 && fme_level <= 4);
+  if (count == 0) return 0;
+  const int ctas = (count + kWarpsPerCta - 1) / kWarpsPerCta;
+  const int cap = kvzc::g_sm_count > 0 ? kvzc::g_sm_count * 16 : 148 * 16;
+  const int grid = ctas < cap ? ctas : cap;
+  if (p->bitdepth == 8)
+    me_frac_kernel<uint8_t><<<grid, kWarpsPerCta * 32, 0, kvzc::as_stream(stream)>>>(*p, fme_level, (const uint8_t *)cur_dev, cur_stride,
+                                                                                  (const uint8_t *)ref_dev, ref_stride, pus_dev, count, out_dev);
+  else
+    me_frac_kernel<uint16_t><<<grid, kWarpsPerCta * 32, 0, kvzc::as_stream(stream)>>>(*p, fme_level, (const uint16_t *)cur_dev, cur_stride,
+                                                                                   (const uint16_t *)ref_dev, ref_stride, pus_dev, count, out_dev);
+  KVZC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int kvz_cuda_call_me_frac_search(const kvz_cuda_me_params *p, int fme_level, const void *cur, int cur_stride, const void *ref,
+                                            int ref_stride, const kvz_cuda_me_pu *pus, int count, kvz_cuda_me_result *out)
+{
+  KVZC_REQUIRE_DEVICE();
+  if (int e = check_args(p, cur, cur_stride, ref, ref_stride, pus, count, out)) return e;
+  if (count == 0) return 0;
+  const size_t px = p->bitdepth == 8 ? 1 : 2;
+  const size_t cur_bytes = (size_t)cur_stride * p->height * px, ref_bytes = (size_t)ref_stride * p->height * px;
+  const size_t pu_bytes = (size_t)count * sizeof(kvz_cuda_me_pu), out_bytes = (size_t)count * sizeof(kvz_cuda_me_result);
+  uint8_t *d = nullptr;
+  const size_t o_ref = (cur_bytes + 255) & ~(size_t)255, o_pu = (o_ref + ref_bytes + 255) & ~(size_t)255, o_out = (o_pu + pu_bytes + 255) & ~(size_t)255;
+  KVZC_CHECK(cudaMalloc(&d, o_out + out_bytes));
+  cudaStream_t st = nullptr;
+  int rc = 0;
+  cudaError_t e = cudaMemcpyAsync(d, cur, cur_bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_ref, ref, ref_bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_pu, pus, pu_bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess)
+    rc = kvz_cuda_me_frac_search_batch(p, fme_level, d, cur_stride, d + o_ref, ref_stride, (const kvz_cuda_me_pu *)(d + o_pu), count,
+                                       (kvz_cuda_me_result *)(d + o_out), st);
+  if (e == cudaSuccess && rc == 0) e = cudaMemcpyAsync(out, d + o_out, out_bytes, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && rc == 0) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) { kvzc::set_error("kvz_cuda_call_me_frac_search: %s", cudaGetErrorString(e)); return KVZ_CUDA_E_RUNTIME; }
   return rc;
 }

@@ -108,6 +108,63 @@ int kvzref_me_search(kvzref_ctx *ctx, const kvz_cuda_me_params *p, const kvz_pix
   return 0;
 }
 
+/* The reference's own search_frac (search_inter.c:974-1168) per PU, starting from pus[i].start_mv. */
+int kvzref_me_frac_search(kvzref_ctx *ctx, const kvz_cuda_me_params *p, int fme_level, const kvz_pixel *cur, int cur_stride, const kvz_pixel *ref,
+                          int ref_stride, const kvz_cuda_me_pu *pus, int count, kvz_cuda_me_result *out)
+{
+  encoder_state_t *state = &ctx->enc->states[0];
+  encoder_control_t *ctrl = (encoder_control_t *)state->encoder_control;
+  if (p->bitdepth != KVZ_BIT_DEPTH) return -1;
+  if (state->tile->frame->width != p->width || state->tile->frame->height != p->height) return -2;
+  if (p->delay_px != 0 && p->delay_px != SAO_DELAY_PX && p->delay_px != DEBLOCK_DELAY_PX) return -4;
+  const kvz_config saved_cfg = ctrl->cfg;
+  const int saved_right = ctrl->max_inter_ref_lcu.right, saved_down = ctrl->max_inter_ref_lcu.down;
+  const double saved_lambda_sqrt = state->lambda_sqrt;
+  ctrl->cfg.owf = p->wpp_owf ? 1 : 0;
+  ctrl->cfg.wpp = p->wpp_owf ? 1 : 0;
+  ctrl->cfg.sao_type = p->delay_px == SAO_DELAY_PX ? KVZ_SAO_FULL : KVZ_SAO_OFF;
+  ctrl->cfg.deblock_enable = p->delay_px == DEBLOCK_DELAY_PX ? 1 : 0;
+  ctrl->cfg.mv_constraint = (enum kvz_mv_constraint)p->mv_constraint;
+  ctrl->cfg.mv_rdo = 0;
+  ctrl->cfg.fme_level = fme_level;
+  ctrl->max_inter_ref_lcu.right = p->max_ref_lcu_right;
+  ctrl->max_inter_ref_lcu.down = p->max_ref_lcu_down;
+  state->lambda_sqrt = p->lambda_sqrt;
+
+  kvz_picture pic, rpic;
+  memset(&pic, 0, sizeof(pic));
+  memset(&rpic, 0, sizeof(rpic));
+  pic.y = (kvz_pixel *)cur;  pic.width = p->width;  pic.height = p->height;  pic.stride = cur_stride;
+  rpic.y = (kvz_pixel *)ref; rpic.width = p->width; rpic.height = p->height; rpic.stride = ref_stride;
+  for (int i = 0; i < count; ++i) {
+    const kvz_cuda_me_pu *u = &pus[i];
+    inter_search_info_t info;
+    memset(&info, 0, sizeof(info));
+    info.state = state;
+    info.pic = &pic;
+    info.ref = &rpic;
+    info.origin.x = u->x; info.origin.y = u->y;
+    info.width = u->w;    info.height = u->h;
+    for (int c = 0; c < 2; ++c) { info.mv_cand[c][0] = u->mv_cand[c][0]; info.mv_cand[c][1] = u->mv_cand[c][1]; }
+    info.mvd_cost_func = calc_mvd_cost;
+    info.optimized_sad = kvz_get_optimized_sad(info.width);
+    vector2d_t mv = { u->start_mv[0], u->start_mv[1] };
+    double cost = MAX_DOUBLE, bits = MAX_INT;
+    search_frac(&info, &cost, &bits, &mv);
+    out[i].cost = cost;
+    out[i].bits = (int32_t)bits;
+    out[i].mv[0] = (int16_t)mv.x;
+    out[i].mv[1] = (int16_t)mv.y;
+    out[i].points = 0;
+    out[i].pad = 0;
+  }
+  ctrl->cfg = saved_cfg;
+  ctrl->max_inter_ref_lcu.right = saved_right;
+  ctrl->max_inter_ref_lcu.down = saved_down;
+  state->lambda_sqrt = saved_lambda_sqrt;
+  return 0;
+}
+
 /* ------------------------------------------------------------------------------------------------------------------
  * AMVP and merge candidates through the reference's own kvz_inter_get_mv_cand_cua / kvz_inter_get_merge_cand
  * (src/inter.c, linked from the unmodified library): the CU records of the test become a cu_array_t (and, for the merge

@@ -296,3 +296,50 @@ def run_cand_reference(ref_shim, f, col_pic_ref_pocs, col_ref_LXs, cus, col, pus
             cus.shape[0], pus.ctypes.data, len(pus), out.ctypes.data)
     assert rc == 0, rc
     return out
+
+
+# ------------------------------------------------------------------------------------------------ fractional search
+FRAC_CASES = {
+    # name -> base search case (pictures, PUs, limits) + cfg.fme_level
+    "frac4_hexbs":        dict(base="hexbs_et_sensitive", level=4),
+    "frac4_wpp_sao":      dict(base="hexbs_et_on_wpp_sao", level=4),
+    "frac4_margin":       dict(base="hexbs_et_off_margin", level=4),
+    "frac2_frame":        dict(base="hexbs_steps2_frame", level=2),
+    "frac1":              dict(base="dia_et_sensitive", level=1),
+    "frac3_noisy":        dict(base="hexbs_noisy", level=3),
+    "frac4_10bit":        dict(base="hexbs_10bit", level=4),
+    "frac2_10bit_margin": dict(base="dia_10bit_margin", level=2),
+}
+
+
+def make_frac_case(name, int_results=None):
+    """the PUs of the base case; the fractional search starts from a full-pel MV (what the integer search returns): here
+    a deterministic one near the content's motion, clipped so that the PU stays within reach of the picture"""
+    c = FRAC_CASES[name]
+    p, cur, rf, pus = make_case(c["base"])
+    r = np.random.default_rng(4000 + CASES[c["base"]]["seed"])
+    pus = pus.copy()
+    start = r.integers(-12, 13, (len(pus), 2)) * 4
+    far = r.integers(0, 8, len(pus)) == 0
+    start[far] = r.integers(-80, 81, (int(far.sum()), 2)) * 4            # some far outside the picture
+    pus["start_mv"] = start
+    return p, c["level"], cur, rf, pus
+
+
+def run_frac_host_api(lib, p, level, cur, ref, pus):
+    out = np.zeros(len(pus), RESULT)
+    lib.kvz_cuda_call_me_frac_search.argtypes = [C.POINTER(Params), C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    rc = lib.kvz_cuda_call_me_frac_search(C.byref(p), level, cur.ctypes.data, cur.shape[1], ref.ctypes.data, ref.shape[1], pus.ctypes.data, len(pus),
+                                          out.ctypes.data)
+    assert rc == 0, rc
+    return out
+
+
+def run_frac_reference(ref_shim, p, level, cur, ref, pus):
+    out = np.zeros(len(pus), RESULT)
+    ctx = ref_shim.ctx(27, 0, 0, p.width, p.height)
+    f = ref_shim.lib.kvzref_me_frac_search
+    f.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    rc = f(ctx, C.byref(p), level, cur.ctypes.data, cur.shape[1], ref.ctypes.data, ref.shape[1], pus.ctypes.data, len(pus), out.ctypes.data)
+    assert rc == 0, rc
+    return out

@@ -4,6 +4,7 @@
 // Exports the same entry points as libkvzcuda.so, with host pointers.
 #include "../../kvazaar_b200/csrc/me/me_search.h"
 #include "../../kvazaar_b200/csrc/me/me_cand.h"
+#include "../../kvazaar_b200/csrc/me/me_frac.h"
 
 extern "C" int kvz_cuda_me_params_supported(const kvz_cuda_me_params *p) { return p ? kvzme::params_supported(*p) : -1; }
 
@@ -44,4 +45,28 @@ extern "C" int kvz_cuda_me_candidates_batch(const kvz_cuda_me_frame *f, const kv
                                             int col_stride, const kvz_cuda_me_cand_pu *pus, int count, kvz_cuda_me_cand_out *out, void *)
 {
   return kvz_cuda_call_me_candidates(f, cus, cu_stride, col_cus, col_stride, 0, pus, count, out);
+}
+
+template <typename Pix>
+static void run_frac(const kvz_cuda_me_params *p, int levels, const void *cur, int cur_stride, const void *ref, int ref_stride, const kvz_cuda_me_pu *pus,
+                     int count, kvz_cuda_me_result *out)
+{
+  const kvzme::Lanes ln = { 0, 32 };
+  const kvzme::Planes<Pix> pl = { (const Pix *)cur, (const Pix *)ref, cur_stride, ref_stride };
+  for (int i = 0; i < count; ++i) kvzme::frac_search_pu<Pix>(ln, *p, pus[i], pl, levels, &out[i]);
+}
+
+extern "C" int kvz_cuda_call_me_frac_search(const kvz_cuda_me_params *p, int fme_level, const void *cur, int cur_stride, const void *ref,
+                                            int ref_stride, const kvz_cuda_me_pu *pus, int count, kvz_cuda_me_result *out)
+{
+  if (!p || kvzme::params_supported(*p) != 0 || fme_level < 1 || fme_level > 4) return -2;
+  if (p->bitdepth == 8) run_frac<uint8_t>(p, fme_level, cur, cur_stride, ref, ref_stride, pus, count, out);
+  else run_frac<uint16_t>(p, fme_level, cur, cur_stride, ref, ref_stride, pus, count, out);
+  return 0;
+}
+
+extern "C" int kvz_cuda_me_frac_search_batch(const kvz_cuda_me_params *p, int fme_level, const void *cur, int cur_stride, const void *ref,
+                                             int ref_stride, const kvz_cuda_me_pu *pus, int count, kvz_cuda_me_result *out, void *)
+{
+  return kvz_cuda_call_me_frac_search(p, fme_level, cur, cur_stride, ref, ref_stride, pus, count, out);
 }

@@ -1,0 +1,95 @@
+"""Fractional motion search (include/kvz_cuda.h: kvz_cuda_me_frac_search_batch; search_frac, src/search_inter.c:974-1168).
+
+Checker: the UNMODIFIED reference's own search_frac (oracle/ref_me.c includes src/search_inter.c where it lies; its filter
+stages, kvz_get_extended_block and SATD functions are the compiled reference's selected strategies) and its committed
+outputs (tests/golden/me_search.npz, `frac/...`).  CPU: the host build of the device code (TEST INFRASTRUCTURE); GPU: the
+product through the C ABI.  Bar: best MV, bits and cost identical for every PU -- incl. the AMP heights (16x12, 16x4)
+where the reference's four-candidate SATD counts rows 0-7 twice, and the truncation of the MV cost into its unsigned
+cost accumulator.  (The file sorts last on purpose: this kernel was written after the round's GPU budget was spent, its
+`-m gpu` tests run for the first time at the round-end check.)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from _me_cases import FRAC_CASES, RESULT, grid_case, make_frac_case, run_frac_host_api, run_frac_reference, run_host_api, run_reference, same
+from test_me_search import _explain, _hostsim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _golden(name):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "me_search.npz"))
+    out = np.zeros(len(g["frac/" + name + "/bits"]), RESULT)
+    out["mv"], out["bits"], out["cost"] = g["frac/" + name + "/mv"], g["frac/" + name + "/bits"], g["frac/" + name + "/cost"]
+    return out
+
+
+@pytest.mark.parametrize("name", sorted(FRAC_CASES))
+def test_reference_matches_golden(name, ref, ref10):
+    p, level, cur, rf, pus = make_frac_case(name)
+    want = run_frac_reference(ref if p.bitdepth == 8 else ref10, p, level, cur, rf, pus)
+    assert same(want, _golden(name)), _explain(want, _golden(name), pus)
+
+
+@pytest.mark.parametrize("name", sorted(FRAC_CASES))
+def test_hostbuild_matches_golden(name):
+    p, level, cur, rf, pus = make_frac_case(name)
+    got = run_frac_host_api(_hostsim(), p, level, cur, rf, pus)
+    assert same(got, _golden(name)), _explain(got, _golden(name), pus)
+    assert ((got["mv"] % 4) != 0).any(1).mean() > 0.25          # fractional positions do win
+
+
+def test_hostbuild_integer_then_fractional_matches_reference(ref):
+    """the chain of search_pu_inter: integer search, then search_frac from its result (--preset slow: hexbs, subme 4)"""
+    p, cur, rf, pus = grid_case(208, 136, 8, 8)
+    lib = _hostsim()
+    integer = run_host_api(lib, p, cur, rf, pus)
+    assert same(integer, run_reference(ref, p, cur, rf, pus))
+    pus2 = pus.copy()
+    pus2["start_mv"] = integer["mv"]
+    got, want = run_frac_host_api(lib, p, 4, cur, rf, pus2), run_frac_reference(ref, p, 4, cur, rf, pus2)
+    assert same(got, want), _explain(got, want, pus2)
+
+
+# ------------------------------------------------------------------------------------------------ GPU (the product)
+def _dev(kb, p, level, cur, rf, pus):
+    import torch
+    out = kb.me_frac_search_batch(p, level, kb.to_dev(cur), kb.to_dev(rf), kb.to_dev(pus))
+    torch.cuda.synchronize()
+    return out.cpu().numpy().view(RESULT).copy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(FRAC_CASES))
+def test_cuda_matches_golden_and_reference(cuda_lib, name, ref, ref10):
+    kb = cuda_lib
+    p, level, cur, rf, pus = make_frac_case(name)
+    got = _dev(kb, p, level, cur, rf, pus)
+    assert same(got, _golden(name)), _explain(got, _golden(name), pus)
+    want = run_frac_reference(ref if p.bitdepth == 8 else ref10, p, level, cur, rf, pus)
+    assert same(got, want), _explain(got, want, pus)
+    got_host = run_frac_host_api(C.CDLL(kb.LIB_PATH), p, level, cur, rf, pus)           # host-buffer entry
+    assert same(got_host, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,bd,size", [(1920, 1080, 8, 16), (832, 480, 10, 32), (1920, 1080, 8, 64)])
+def test_cuda_integer_then_fractional_full_picture(cuda_lib, ref, ref10, w, h, bd, size):
+    """every PU of a picture: integer search on the device, fractional search from its result, both against the reference"""
+    import torch
+    kb = cuda_lib
+    shim = ref if bd == 8 else ref10
+    p, cur, rf, pus = grid_case(w, h, bd, size)
+    d_cur, d_ref = kb.to_dev(cur), kb.to_dev(rf)
+    integer = kb.me_search_batch(p, d_cur, d_ref, kb.to_dev(pus)).cpu().numpy().view(RESULT).copy()
+    assert same(integer, run_reference(shim, p, cur, rf, pus))
+    pus2 = pus.copy()
+    pus2["start_mv"] = integer["mv"]
+    got = kb.me_frac_search_batch(p, 4, d_cur, d_ref, kb.to_dev(pus2))
+    torch.cuda.synchronize()
+    got = got.cpu().numpy().view(RESULT).copy()
+    want = run_frac_reference(shim, p, 4, cur, rf, pus2)
+    assert same(got, want), _explain(got, want, pus2)

@@ -10,7 +10,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from _me_cases import CAND_CASES, CASES, make_cand_case, make_case, run_cand_reference, run_reference  # noqa: E402
+from _me_cases import (CAND_CASES, CASES, FRAC_CASES, make_cand_case, make_case, make_frac_case, run_cand_reference, run_frac_reference,  # noqa: E402
+                       run_reference)
 from _oracle import Ref  # noqa: E402
 
 refs = {}
@@ -28,4 +29,11 @@ for name in sorted(CAND_CASES):
     r = run_cand_reference(refs.setdefault(8, Ref(8)), f, crp, clx, cus, col, pus)
     out["cand/" + name] = np.frombuffer(r.tobytes(), np.uint8).copy()
     print("cand", name, len(pus), "PUs")
+for name in sorted(FRAC_CASES):
+    p, level, cur, ref, pus = make_frac_case(name)
+    r = run_frac_reference(refs.setdefault(p.bitdepth, Ref(p.bitdepth)), p, level, cur, ref, pus)
+    out["frac/" + name + "/mv"] = r["mv"].copy()
+    out["frac/" + name + "/bits"] = r["bits"].copy()
+    out["frac/" + name + "/cost"] = r["cost"].copy()
+    print("frac", name, len(pus), "PUs")
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "me_search.npz"), **out)
