@@ -361,7 +361,7 @@ typedef struct kvz_cuda_me_params {
   int32_t wpp_owf;                  /* cfg.owf && cfg.wpp: MVs may only reach LCUs that are final in the reference */
   int32_t delay_px;                 /* SAO_DELAY_PX (10) with SAO, else DEBLOCK_DELAY_PX (8) with deblocking, else 0 */
   int32_t max_ref_lcu_right, max_ref_lcu_down;   /* encoder_control_t.max_inter_ref_lcu */
-  int32_t pad;
+  int32_t satd_final;               /* cfg.fme_level == 0: the winner's cost is recomputed with kvz_image_calc_satd (search_inter.c:1385-1397) */
   double  lambda_sqrt;              /* state->lambda_sqrt */
 } kvz_cuda_me_params;
 typedef struct kvz_cuda_me_merge { int16_t mv[2][2]; uint8_t dir; uint8_t ref[2]; uint8_t pad; } kvz_cuda_me_merge;   /* inter_merge_cand_t (src/inter.h:47-52): mv[list][x/y] (1/4 pel), dir, ref[list] */

@@ -592,7 +592,7 @@ ME_RESULT = np.dtype([("cost", "<f8"), ("bits", "<i4"), ("mv", "<i2", (2,)), ("p
 class MeParams(C.Structure):
     """kvz_cuda_me_params: the configuration fields the reference's integer search reads (search_inter.c:94-247, 436-888)"""
     _fields_ = [(n, C.c_int32) for n in ("width", "height", "bitdepth", "ime_algorithm", "me_max_steps", "me_early_termination", "mv_constraint",
-                                         "wpp_owf", "delay_px", "max_ref_lcu_right", "max_ref_lcu_down", "pad")] + [("lambda_sqrt", C.c_double)]
+                                         "wpp_owf", "delay_px", "max_ref_lcu_right", "max_ref_lcu_down", "satd_final")] + [("lambda_sqrt", C.c_double)]
 
 
 def me_search_batch(params, cur, ref, pus, out=None):

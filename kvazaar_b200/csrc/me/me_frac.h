@@ -145,6 +145,20 @@ ME_FN uint32_t pu_satd(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_c
 #endif
 }
 
+// search_pu_inter_ref with cfg.fme_level == 0 (search_inter.c:1385-1397): no fractional search follows, so the integer
+// winner's cost becomes its Hadamard cost (kvz_image_calc_satd, src/image.c:451-510) + bits * lambda_sqrt
+template <typename Pix>
+ME_FN void search_pu_satd_final(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cuda_me_pu &pu, const Planes<Pix> &pl, kvz_cuda_me_result *out)
+{
+  Best best = search_pu_best<Pix>(ln, p, pu, pl);
+  if (best.cost < kMaxDouble) {
+    const uint32_t satd = pu_satd(ln, p, pu, pl, (best.mvx >> 2) * 4, (best.mvy >> 2) * 4, false);
+    best.cost = (double)satd;
+    best.cost += (double)best.bits * p.lambda_sqrt;
+  }
+  write_result(ln, best, out);
+}
+
 // calc_mvd_cost for a quarter-pel MV, no merge candidates
 ME_FN uint32_t qpel_mv_bits(const kvz_cuda_me_pu &pu, int qx, int qy)
 {

@@ -374,9 +374,9 @@ ME_FN void full_search(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_c
   }
 }
 
-// the integer stage of search_pu_inter_ref for one PU
+// the integer stage of search_pu_inter_ref for one PU; every lane ends with the same result
 template <typename Pix>
-ME_FN void search_pu(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cuda_me_pu &pu, const Planes<Pix> &pl, kvz_cuda_me_result *out)
+ME_FN Best search_pu_best(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cuda_me_pu &pu, const Planes<Pix> &pl)
 {
   Best best;
   best.cost = kMaxDouble;
@@ -399,6 +399,11 @@ ME_FN void search_pu(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cud
       default: hexagon_search(ln, p, pu, pl, best); break;
     }
   }
+  return best;
+}
+
+ME_FN void write_result(const Lanes &ln, const Best &best, kvz_cuda_me_result *out)
+{
   if (ln.lane == 0) {
     out->cost = best.cost;
     out->bits = best.bits;
@@ -407,6 +412,12 @@ ME_FN void search_pu(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cud
     out->points = best.points;
     out->pad = 0;
   }
+}
+
+template <typename Pix>
+ME_FN void search_pu(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cuda_me_pu &pu, const Planes<Pix> &pl, kvz_cuda_me_result *out)
+{
+  write_result(ln, search_pu_best<Pix>(ln, p, pu, pl), out);
 }
 
 #if defined(__CUDACC__)

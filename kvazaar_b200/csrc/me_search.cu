@@ -15,7 +15,7 @@ namespace {
 
 constexpr int kWarpsPerCta = 4;
 
-template <typename Pix>
+template <typename Pix, bool SATD_FINAL>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) me_search_kernel(kvz_cuda_me_params p, const Pix *__restrict__ cur, int cur_stride,
                                                                       const Pix *__restrict__ ref, int ref_stride,
                                                                       const kvz_cuda_me_pu *__restrict__ pus, int count,
@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) me_search_kernel(kvz_cuda_m
   // whole warps leave together: the shuffles inside pu_sad always see 32 lanes
   for (int i = blockIdx.x * kWarpsPerCta + warp; i < count; i += gridDim.x * kWarpsPerCta) {
     const kvz_cuda_me_pu pu = pus[i];
-    kvzme::search_pu<Pix>(ln, p, pu, pl, &out[i]);
+    if (SATD_FINAL) kvzme::search_pu_satd_final<Pix>(ln, p, pu, pl, &out[i]);      // cfg.fme_level == 0
+    else kvzme::search_pu<Pix>(ln, p, pu, pl, &out[i]);
   }
 }
 
@@ -81,12 +82,14 @@ extern "C" int kvz_cuda_me_search_batch(const kvz_cuda_me_params *p, const void 
   const int ctas = (count + kWarpsPerCta - 1) / kWarpsPerCta;
   const int cap = kvzc::g_sm_count > 0 ? kvzc::g_sm_count * 16 : 148 * 16;     // 16 CTAs of 4 warps per SM; more PUs loop
   const int grid = ctas < cap ? ctas : cap;
-  if (p->bitdepth == 8)
-    me_search_kernel<uint8_t><<<grid, kWarpsPerCta * 32, 0, kvzc::as_stream(stream)>>>(*p, (const uint8_t *)cur_dev, cur_stride, (const uint8_t *)ref_dev,
-                                                                                    ref_stride, pus_dev, count, out_dev);
-  else
-    me_search_kernel<uint16_t><<<grid, kWarpsPerCta * 32, 0, kvzc::as_stream(stream)>>>(*p, (const uint16_t *)cur_dev, cur_stride, (const uint16_t *)ref_dev,
-                                                                                     ref_stride, pus_dev, count, out_dev);
+  const cudaStream_t st = kvzc::as_stream(stream);
+  const dim3 block(kWarpsPerCta * 32);
+  const uint8_t *c8 = (const uint8_t *)cur_dev, *r8 = (const uint8_t *)ref_dev;
+  const uint16_t *c16 = (const uint16_t *)cur_dev, *r16 = (const uint16_t *)ref_dev;
+  if (p->bitdepth == 8 && !p->satd_final) me_search_kernel<uint8_t, false><<<grid, block, 0, st>>>(*p, c8, cur_stride, r8, ref_stride, pus_dev, count, out_dev);
+  else if (p->bitdepth == 8) me_search_kernel<uint8_t, true><<<grid, block, 0, st>>>(*p, c8, cur_stride, r8, ref_stride, pus_dev, count, out_dev);
+  else if (!p->satd_final) me_search_kernel<uint16_t, false><<<grid, block, 0, st>>>(*p, c16, cur_stride, r16, ref_stride, pus_dev, count, out_dev);
+  else me_search_kernel<uint16_t, true><<<grid, block, 0, st>>>(*p, c16, cur_stride, r16, ref_stride, pus_dev, count, out_dev);
   KVZC_LAUNCHED();
   return 0;
 }

@@ -93,6 +93,11 @@ int kvzref_me_search(kvzref_ctx *ctx, const kvz_cuda_me_params *p, const kvz_pix
         default: hexagon_search(&info, best_mv, ctrl->cfg.me_max_steps, &best_cost, &best_bits, &best_mv); break;
       }
     }
+    if (p->satd_final && best_cost < MAX_DOUBLE) {        /* cfg->fme_level == 0, search_inter.c:1385-1397 */
+      best_cost = kvz_image_calc_satd(&pic, info.ref, info.origin.x, info.origin.y, state->tile->offset_x + info.origin.x + (best_mv.x >> 2),
+                                      state->tile->offset_y + info.origin.y + (best_mv.y >> 2), info.width, info.height);
+      best_cost += best_bits * state->lambda_sqrt;
+    }
     out[i].cost = best_cost;
     out[i].bits = (int32_t)best_bits;
     out[i].mv[0] = (int16_t)best_mv.x;

@@ -109,6 +109,7 @@ def make_case(name):
     p.mv_constraint, p.wpp_owf, p.delay_px = c["mvc"], c["wpp"], c["delay"]
     p.max_ref_lcu_right, p.max_ref_lcu_down = 1, 1                  # encoder.c:193-194
     p.lambda_sqrt = lambda_sqrt(c["qp"])
+    p.satd_final = c.get("satd_final", 0)
     cur, ref = pictures(c["w"], c["h"], c["bd"], c["seed"], c.get("noisy", False))
     return p, cur, ref, pu_list(c["w"], c["h"], c["seed"], c["n"])
 
@@ -343,3 +344,7 @@ def run_frac_reference(ref_shim, p, level, cur, ref, pus):
     rc = f(ctx, C.byref(p), level, cur.ctypes.data, cur.shape[1], ref.ctypes.data, ref.shape[1], pus.ctypes.data, len(pus), out.ctypes.data)
     assert rc == 0, rc
     return out
+
+# cfg.fme_level == 0 (--preset ultrafast): the integer winner's cost is recomputed as Hadamard cost (search_inter.c:1385-1397)
+CASES["hexbs_satd_final"] = dict(w=208, h=136, bd=8, algo=0, steps=-1, et=2, mvc=0, wpp=1, delay=8, qp=32, seed=17, n=300, satd_final=1)
+CASES["dia_satd_final_10bit"] = dict(w=136, h=72, bd=10, algo=7, steps=-1, et=1, mvc=0, wpp=0, delay=0, qp=27, seed=18, n=200, satd_final=1)

@@ -14,7 +14,10 @@ static void run(const kvz_cuda_me_params *p, const void *cur, int cur_stride, co
 {
   const kvzme::Lanes ln = { 0, 32 };      // lane 0 writes the result; pu_sad walks all 32 shares
   const kvzme::Planes<Pix> pl = { (const Pix *)cur, (const Pix *)ref, cur_stride, ref_stride };
-  for (int i = 0; i < count; ++i) kvzme::search_pu<Pix>(ln, *p, pus[i], pl, &out[i]);
+  for (int i = 0; i < count; ++i) {
+    if (p->satd_final) kvzme::search_pu_satd_final<Pix>(ln, *p, pus[i], pl, &out[i]);
+    else kvzme::search_pu<Pix>(ln, *p, pus[i], pl, &out[i]);
+  }
 }
 
 extern "C" int kvz_cuda_call_me_search(const kvz_cuda_me_params *p, const void *cur, int cur_stride, const void *ref, int ref_stride,
