@@ -14,8 +14,8 @@ import os
 import numpy as np
 import pytest
 
-from _me_cases import FRAC_CASES, RESULT, grid_case, make_frac_case, run_frac_host_api, run_frac_reference, run_host_api, run_reference, same
-from test_me_search import _explain, _hostsim
+from _me_cases import CASES, FRAC_CASES, GPU_FIRST_RUN_DONE, RESULT, grid_case, make_frac_case, run_frac_host_api, run_frac_reference, run_host_api, run_reference, same
+from test_me_search import _explain, _hostsim, check_cuda_case
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -55,6 +55,13 @@ def test_hostbuild_integer_then_fractional_matches_reference(ref):
 
 
 # ------------------------------------------------------------------------------------------------ GPU (the product)
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(set(CASES) - set(GPU_FIRST_RUN_DONE)))
+def test_cuda_integer_search_cases_added_later(cuda_lib, name, ref, ref10):
+    """tz, full search and satd_final cases of tests/_me_cases.py (added after the integer kernel's first B200 run)"""
+    check_cuda_case(cuda_lib, name, ref, ref10)
+
+
 def _dev(kb, p, level, cur, rf, pus):
     import torch
     out = kb.me_frac_search_batch(p, level, kb.to_dev(cur), kb.to_dev(rf), kb.to_dev(pus))
@@ -93,3 +100,4 @@ def test_cuda_integer_then_fractional_full_picture(cuda_lib, ref, ref10, w, h, b
     got = got.cpu().numpy().view(RESULT).copy()
     want = run_frac_reference(shim, p, 4, cur, rf, pus2)
     assert same(got, want), _explain(got, want, pus2)
+
