@@ -373,9 +373,27 @@ def run_cuda(args, wl):
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "parallelism": f"pictures sharded over {world} GPU(s), no collective"}
     if world == 1:
         line.update(parity_and_baseline(args, wl, clip, ctu_bin, env, extra))
+        line["me_search"] = me_search_line(env)
     else:
         dist.destroy_process_group()
     print(json.dumps(line))
+
+
+def me_search_line(env):
+    """Secondary measurement, outside the timed region and in its own process (a failure there cannot touch the line above):
+    the motion-search kernels of SURVEY 8f rank 4 (tools/bench_me.py) on every 16x16 PU of a 1080p picture pair, CUDA events,
+    with the reference's own functions on one host thread as the per-core baseline and the identity check."""
+    e = dict(os.environ)
+    e["CUDA_VISIBLE_DEVICES"] = env["CUDA_VISIBLE_DEVICES"]
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_me.py")], env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                           text=True, timeout=300)
+        rows = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        if r.returncode != 0 or not rows:
+            return {"error": (r.stderr or r.stdout)[-400:]}
+        return json.loads(rows[-1])
+    except Exception as ex:  # pragma: no cover
+        return {"error": repr(ex)[:400]}
 
 
 def parity_and_baseline(args, wl, clip, ctu_bin, env, extra):

@@ -58,7 +58,7 @@ def test_hostbuild_integer_then_fractional_matches_reference(ref):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", sorted(set(CASES) - set(GPU_FIRST_RUN_DONE)))
 def test_cuda_integer_search_cases_added_later(cuda_lib, name, ref, ref10):
-    """tz, full search and satd_final cases of tests/_me_cases.py (added after the integer kernel's first B200 run)"""
+    """tz, full search and satd_final cases of tools/me_cases.py (added after the integer kernel's first B200 run)"""
     check_cuda_case(cuda_lib, name, ref, ref10)
 
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Writes tests/golden/me_search.npz: what the UNMODIFIED reference's integer motion search (oracle/ref_me.c: the reference's
-own search_inter.c compiled in place) returns for the cases of tests/_me_cases.py.  Run in the container that has
+own search_inter.c compiled in place) returns for the cases of tools/me_cases.py.  Run in the container that has
 /root/reference (make -C oracle ref); the tests that read the file need neither the reference nor its build."""
 import os
 import sys
