@@ -105,11 +105,12 @@ ME_FN uint32_t subblock_cost(const kvz_cuda_me_params &p, const kvz_cuda_me_pu &
 // One lane's share of the Hadamard cost of the whole PU at (qx, qy): the sub-blocks are numbered in the order the
 // reference visits them and dealt out round-robin.  quad = the four-candidate variant used for the fractional positions.
 template <typename Pix>
-ME_FN uint32_t pu_satd_lane(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cuda_me_pu &pu, const Planes<Pix> &pl, int qx, int qy, bool quad)
+ME_FN uint32_t pu_satd_lane(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cuda_me_pu &pu, const Planes<Pix> &pl, int qx, int qy, bool quad,
+                            int &k)             // k: running number of the work item, continues over the positions of one step
 {
   int w = pu.w, h = pu.h;
   const int wm = w % 8;
-  int x0 = 0, y0 = 0, k = 0;
+  int x0 = 0, y0 = 0;
   uint32_t s = 0;
   if (wm != 0) {                               // first column in 4x4 blocks
     for (int y = 0; y < h; y += 4)
@@ -137,11 +138,44 @@ template <typename Pix>
 ME_FN uint32_t pu_satd(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cuda_me_pu &pu, const Planes<Pix> &pl, int qx, int qy, bool quad)
 {
 #if defined(__CUDA_ARCH__)
-  return lane_sum(pu_satd_lane(ln, p, pu, pl, qx, qy, quad)) >> (p.bitdepth - 8);
+  int k = 0;
+  return lane_sum(pu_satd_lane(ln, p, pu, pl, qx, qy, quad, k)) >> (p.bitdepth - 8);
 #else
   uint32_t s = 0;
-  for (int l = 0; l < ln.n; ++l) s += pu_satd_lane(Lanes{ l, ln.n }, p, pu, pl, qx, qy, quad);
+  for (int l = 0; l < ln.n; ++l) {
+    int k = 0;
+    s += pu_satd_lane(Lanes{ l, ln.n }, p, pu, pl, qx, qy, quad, k);
+  }
   return s >> (p.bitdepth - 8);
+#endif
+}
+
+// The (up to) four candidate positions of one step at once: the sub-blocks of all of them are dealt out round-robin
+// together, so a 16x16 PU keeps 16 lanes busy instead of 4; one butterfly per position adds the shares up.
+template <typename Pix>
+ME_FN void pu_satd_step_lane(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cuda_me_pu &pu, const Planes<Pix> &pl, const int qx[4], const int qy[4],
+                             const bool use[4], uint32_t s[4])
+{
+  int k = 0;
+  for (int j = 0; j < 4; ++j) s[j] = use[j] ? pu_satd_lane(ln, p, pu, pl, qx[j], qy[j], true, k) : 0u;
+}
+
+template <typename Pix>
+ME_FN void pu_satd_step(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cuda_me_pu &pu, const Planes<Pix> &pl, const int qx[4], const int qy[4],
+                        const bool use[4], uint32_t costs[4])
+{
+#if defined(__CUDA_ARCH__)
+  uint32_t s[4];
+  pu_satd_step_lane(ln, p, pu, pl, qx, qy, use, s);
+  for (int j = 0; j < 4; ++j) costs[j] = lane_sum(s[j]) >> (p.bitdepth - 8);
+#else
+  for (int j = 0; j < 4; ++j) costs[j] = 0;
+  for (int l = 0; l < ln.n; ++l) {
+    uint32_t s[4];
+    pu_satd_step_lane(Lanes{ l, ln.n }, p, pu, pl, qx, qy, use, s);
+    for (int j = 0; j < 4; ++j) costs[j] += s[j];
+  }
+  for (int j = 0; j < 4; ++j) costs[j] >>= (p.bitdepth - 8);
 #endif
 }
 
@@ -188,14 +222,17 @@ ME_FN void frac_search_pu(const Lanes &ln, const kvz_cuda_me_params &p, const kv
     const int mv_shift = step < 2 ? 1 : 0;
     uint32_t costs[4], cbits[4];
     bool within[4];
+    int qx[4], qy[4];
     for (int j = 0; j < 4; ++j) {
-      const int qx = (mx + sqx[i + j]) * (1 << mv_shift), qy = (my + sqy[i + j]) * (1 << mv_shift);
-      within[j] = mv_allowed(p, pu, qx, qy);
-      costs[j] = 0;
+      qx[j] = (mx + sqx[i + j]) * (1 << mv_shift);
+      qy[j] = (my + sqy[i + j]) * (1 << mv_shift);
+      within[j] = mv_allowed(p, pu, qx[j], qy[j]);
+    }
+    pu_satd_step(ln, p, pu, pl, qx, qy, within, costs);      // the cost of a position that may not be used is never looked at
+    for (int j = 0; j < 4; ++j) {
       cbits[j] = 0;
-      if (within[j]) {                         // the cost of a position that may not be used is never looked at
-        costs[j] = pu_satd(ln, p, pu, pl, qx, qy, true);
-        cbits[j] = qpel_mv_bits(pu, qx, qy);
+      if (within[j]) {
+        cbits[j] = qpel_mv_bits(pu, qx[j], qy[j]);
         costs[j] = (uint32_t)((double)costs[j] + (double)cbits[j] * p.lambda_sqrt);
         ++points;
       }
