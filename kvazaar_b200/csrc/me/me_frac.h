@@ -81,10 +81,15 @@ ME_FN uint32_t subblock_cost(const kvz_cuda_me_params &p, const kvz_cuda_me_pu &
       const Pix *row = pl.ref + yy * pl.ref_stride;
       for (int c = 0; c < N; ++c) {
         int32_t s = 0;
-        for (int k = 0; k < 8; ++k) {
-          const int xx0 = bx + c + k - 3;
-          const int xx = xx0 < 0 ? 0 : (xx0 > xmax ? xmax : xx0);
-          s += luma_tap(fx, k) * (int32_t)row[xx];
+        if (fx == 0) {                         // the integer-column filter is the single tap 64 at offset 0
+          const int xx0 = bx + c;
+          s = 64 * (int32_t)row[xx0 < 0 ? 0 : (xx0 > xmax ? xmax : xx0)];
+        } else {
+          for (int k = 0; k < 8; ++k) {
+            const int xx0 = bx + c + k - 3;
+            const int xx = xx0 < 0 ? 0 : (xx0 > xmax ? xmax : xx0);
+            s += luma_tap(fx, k) * (int32_t)row[xx];
+          }
         }
         hor[r * N + c] = s >> shift1;
       }
@@ -92,7 +97,9 @@ ME_FN uint32_t subblock_cost(const kvz_cuda_me_params &p, const kvz_cuda_me_pu &
     for (int r = 0; r < N; ++r)
       for (int c = 0; c < N; ++c) {
         int32_t s = 0;
-        for (int k = 0; k < 8; ++k) s += luma_tap(fy, k) * hor[(r + k) * N + c];
+        if (fy == 0) s = 64 * hor[(r + 3) * N + c];
+        else
+          for (int k = 0; k < 8; ++k) s += luma_tap(fy, k) * hor[(r + k) * N + c];
         int32_t v = ((s + offset23) >> 6) >> shift3;
         v = v < 0 ? 0 : (v > pix_max ? pix_max : v);
         d[r * N + c] = (int32_t)pl.cur[(pu.y + sy + r) * pl.cur_stride + pu.x + sx + c] - v;
