@@ -26,7 +26,7 @@ int main(int argc, char **argv)
   int w = 0, h = 0;
   if (sscanf(res, "%dx%d", &w, &h) != 2) { fprintf(stderr, "bad resolution %s\n", res); return 2; }
 
-  const kvz_api *api = kvz_api_get(8);
+  const kvz_api *api = kvz_api_get(KVZ_BIT_DEPTH);       /* the 10-bit build (integration/Makefile: kvz_cuda_encode_10b) links libkvazaar_ref_10b.so */
   kvz_config *cfg = api->config_alloc();
   api->config_init(cfg);
   char wh[32];
@@ -55,9 +55,27 @@ int main(int argc, char **argv)
     kvz_picture *pic = NULL;
     if (!eof) {
       pic = api->picture_alloc(w, h);
+#if KVZ_BIT_DEPTH == 8
       if (fread(pic->y, 1, ysz, fi) != ysz || fread(pic->u, 1, csz, fi) != csz || fread(pic->v, 1, csz, fi) != csz) {
         api->picture_free(pic); pic = NULL; eof = 1;
       } else ++frames_in;
+#else
+      /* 8-bit input file into the wider kvz_pixel, scaled to the internal bit depth (what the CLI's reader does for
+       * --input-bitdepth 8, ref: src/yuv_io.c) */
+      {
+        static unsigned char *buf = NULL;
+        if (!buf) buf = malloc(ysz + 2 * csz);
+        if (fread(buf, 1, ysz + 2 * csz, fi) != ysz + 2 * csz) { api->picture_free(pic); pic = NULL; eof = 1; }
+        else {
+          for (int r = 0; r < h; ++r) for (int c = 0; c < w; ++c) pic->y[(size_t)r * pic->stride + c] = (kvz_pixel)(buf[(size_t)r * w + c] << (KVZ_BIT_DEPTH - 8));
+          for (int r = 0; r < h / 2; ++r) for (int c = 0; c < w / 2; ++c) {
+            pic->u[(size_t)r * (pic->stride / 2) + c] = (kvz_pixel)(buf[ysz + (size_t)r * (w / 2) + c] << (KVZ_BIT_DEPTH - 8));
+            pic->v[(size_t)r * (pic->stride / 2) + c] = (kvz_pixel)(buf[ysz + csz + (size_t)r * (w / 2) + c] << (KVZ_BIT_DEPTH - 8));
+          }
+          ++frames_in;
+        }
+      }
+#endif
     }
     kvz_data_chunk *chunks = NULL;
     uint32_t len = 0;
