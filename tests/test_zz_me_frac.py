@@ -120,7 +120,7 @@ def _tenbit_encode(tmp_path, cuda):
             f.write(synth_frame(w, h, 1234, i).tobytes())
     out = str(tmp_path / ("cuda.hevc" if cuda else "host.hevc"))
     cmd = [enc] + (["--cuda"] if cuda else []) + [clip, f"{w}x{h}", out, "preset=fast", "qp=30", "period=16", "gop=0", "threads=2", "owf=1"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-1500:]
     return open(out, "rb").read(), r.stderr, clip, (w, h)
 
