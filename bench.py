@@ -345,6 +345,16 @@ def run_cuda(args, wl):
         # ---- value: the device side alone
         dev_seconds, launches, kernel_ms, slots = device_leg(args, wl, local, fps_step, barrier)
         dev_seconds = max_over_ranks(dev_seconds)
+    # N > 1: the two exchanges of SURVEY 8e (tile all-gather of a 4320p 10-bit picture, reference-frame broadcast) timed on
+    # this process group -- they are not on the all-intra data path (pictures shard with no collective), this is their
+    # hardware measurement; outside the timed regions, every rank takes part
+    exchanges = None
+    if world > 1:
+        try:
+            from kvazaar_b200.dist import measure_exchanges
+            exchanges = measure_exchanges(torch.device("cuda", local))
+        except Exception as ex:  # pragma: no cover
+            exchanges = {"error": repr(ex)[:300]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -371,6 +381,9 @@ def run_cuda(args, wl):
                     "path": "kvz_stream_bench_ctu: libkvazaar API -> kvz_ctu_hooks -> libkvzcuda.so (kvz_cuda_ctu_submit/wait) -> reference CABAC"},
             "device_only": {"value": frames / dev_seconds, "unit": "frames/s", "pictures_in_flight": slots, "ms_per_step": 1000.0 * dev_seconds / args.steps},
             "gpu_launches": launches, "clocks": clk.summary(), "roofline": roof, "parallelism": f"pictures sharded over {world} GPU(s), no collective"}
+    if world > 1:
+        line["collective"] = "none on the data path (independent all-intra pictures); measured separately: nccl all_gather (tiles), nccl broadcast (reference picture)"
+        line["exchanges"] = exchanges
     if world == 1:
         line.update(parity_and_baseline(args, wl, clip, ctu_bin, env, extra))
         line["me_search"] = me_search_line(env)

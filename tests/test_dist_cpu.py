@@ -150,3 +150,27 @@ def test_ctu_driver_pictures_shard_over_ranks_gloo_world2(tmp_path):
     mp.spawn(_ctu_shard_worker, args=(2, port, clip, str(tmp_path), out), nprocs=2, join=True)
     assert out[0][0] and out[1][0], "a rank's shard differs from the reference's bitstream of the same pictures"
     assert out[0][1] == out[1][1] == 2.0 and out[0][2] == out[1][2] == 6.0
+
+
+# ---- the exchange measurement bench.py attaches to its N > 1 lines (kvazaar_b200/dist.py: measure_exchanges), on gloo:
+# 10-bit tiles travel as bytes (neither NCCL nor gloo has a 16-bit integer type), every rank must end up with every tile
+def _exchange_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        r = kd.measure_exchanges(torch.device("cpu"), iters=2, tile_res=(512, 256), frame_res=(256, 128))
+        out[rank] = (r["tile_allgather"]["verified"], r["reference_broadcast"]["verified"], r["tile_allgather"]["tiles"], r["ranks"])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_measure_exchanges_gloo_world2_and_4():
+    for world, tiles in ((2, "2x1"), (4, "2x2")):
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        mgr = mp.Manager()
+        out = mgr.dict()
+        mp.spawn(_exchange_worker, args=(world, port, out), nprocs=world, join=True)
+        assert dict(out) == {r: (True, True, tiles, world) for r in range(world)}
