@@ -386,20 +386,22 @@ def run_cuda(args, wl):
         line["exchanges"] = exchanges
     if world == 1:
         line.update(parity_and_baseline(args, wl, clip, ctu_bin, env, extra))
-        line["me_search"] = me_search_line(env)
+        line["me_search"] = side_measurement(env, "bench_me.py")
+        line["roofline_satd_batch"] = side_measurement(env, "time_satd.py", "--json")
     else:
         dist.destroy_process_group()
     print(json.dumps(line))
 
 
-def me_search_line(env):
-    """Secondary measurement, outside the timed region and in its own process (a failure there cannot touch the line above):
-    the motion-search kernels of SURVEY 8f rank 4 (tools/bench_me.py) on every 16x16 PU of a 1080p picture pair, CUDA events,
-    with the reference's own functions on one host thread as the per-core baseline and the identity check."""
+def side_measurement(env, tool, *tool_args):
+    """Secondary measurements, outside the timed region and each in its own process (a failure there cannot touch the line):
+    tools/bench_me.py -- the motion-search kernels of SURVEY 8f rank 4 on every 16x16 PU of a 1080p picture pair, CUDA events,
+    the reference's own functions on one host thread as per-core baseline, identity check;
+    tools/time_satd.py -- the HBM-streaming kernel of the north star (batched SATD 8x8) against the measured copy peak."""
     e = dict(os.environ)
     e["CUDA_VISIBLE_DEVICES"] = env["CUDA_VISIBLE_DEVICES"]
     try:
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_me.py")], env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), *tool_args], env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                            text=True, timeout=300)
         rows = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
         if r.returncode != 0 or not rows:
