@@ -55,10 +55,13 @@ def test_hostbuild_integer_then_fractional_matches_reference(ref):
 
 
 # ------------------------------------------------------------------------------------------------ GPU (the product)
+LATER = sorted(set(CASES) - set(GPU_FIRST_RUN_DONE))
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", sorted(set(CASES) - set(GPU_FIRST_RUN_DONE)))
+@pytest.mark.parametrize("name", [n for n in LATER if "satd_final" not in n])
 def test_cuda_integer_search_cases_added_later(cuda_lib, name, ref, ref10):
-    """tz, full search and satd_final cases of tools/me_cases.py (added after the integer kernel's first B200 run)"""
+    """tz and full search cases of tools/me_cases.py (added after the integer kernel's first B200 run; same check_mv primitive)"""
     check_cuda_case(cuda_lib, name, ref, ref10)
 
 
@@ -101,6 +104,13 @@ def test_cuda_integer_then_fractional_full_picture(cuda_lib, ref, ref10, w, h, b
     want = run_frac_reference(shim, p, 4, cur, rf, pus2)
     assert same(got, want), _explain(got, want, pus2)
 
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", [n for n in LATER if "satd_final" in n])
+def test_cuda_integer_search_with_final_hadamard_cost(cuda_lib, name, ref, ref10):
+    """cfg.fme_level == 0: the integer kernel's second instantiation (winner's cost recomputed with the Hadamard cost)"""
+    check_cuda_case(cuda_lib, name, ref, ref10)
 
 
 # ------------------------------------------------------------------------------------------------ 10-bit drop-in encode
