@@ -264,7 +264,10 @@ CTU_FN_NOINLINE void intra_recon_leaf(const Ctx &c, LcuLevel *L, int x, int y, i
     const int sh = col ? 1 : 0;
     const int off = (xl >> sh) + (yl >> sh) * P.lw;
     const int mode = col == 0 ? mode_luma : mode_chroma;
-    TuJob j = { &S->refs[col], P.src + off, P.lw, col, log2n, mode, scan_order_intra(mode, depth), rdoq_tr_depth };
+    // the scan follows the mode STORED in the CU record (quantize_tr_residual reads cur_pu->intra.mode_chroma, transform.c):
+    // the chroma mode search predicts with its candidate while the record still holds the luma mode (bits 8.. of refs_valid)
+    const int scan_mode = (col != 0 && (refs_valid >> 8)) ? (refs_valid >> 8) - 1 : mode;
+    TuJob j = { &S->refs[col], P.src + off, P.lw, col, log2n, mode, scan_order_intra(scan_mode, depth), rdoq_tr_depth };
     const int ts = tu_eval(tm, &c.S->tb, &S->tb, c.cfg, S->cabac0.ctx, &S->sc, tu, j);
     // write back: reconstruction and coefficients of the level, staged copy for the cost functions
     uint8_t *rec = P.rec + off;
@@ -326,7 +329,7 @@ CTU_FN_NOINLINE void intra_recon_cu(const Ctx &c, LcuLevel *L, int x, int y, int
         if (mode_chroma >= 0) { cbf_clear(&child->cbf, depth + 1, 1); cbf_clear(&child->cbf, depth + 1, 2); }
       }
       CTU_SYNC();
-      intra_recon_leaf(c, L, cx, cy, depth + 1, mode_luma, mode_chroma, child, k, 0);
+      intra_recon_leaf(c, L, cx, cy, depth + 1, mode_luma, mode_chroma, child, k, refs_valid & ~0xFF);
     }
     CTU_LEADER {
       const uint16_t child_cbfs[3] = { cu_at(L, xl + offset, yl)->cbf, cu_at(L, xl, yl + offset)->cbf, cu_at(L, xl + offset, yl + offset)->cbf };
@@ -781,7 +784,7 @@ CTU_FN_NOINLINE int search_cu_intra_chroma(const Ctx &c, LcuLevel *L, int x, int
   int best_mode = 0;
   for (int i = 0; i < 2; ++i) {
     const int mode = S->cmodes[i];
-    intra_recon_cu(c, L, x, y, depth, -1, mode, NULL, depth == 0 ? 0 : 6);
+    intra_recon_cu(c, L, x, y, depth, -1, mode, NULL, (depth == 0 ? 0 : 6) | ((intra_mode + 1) << 8));
     CTU_LEADER {
       CuRec *tr_cu = cu_at(L, xl, yl);
       double cost;

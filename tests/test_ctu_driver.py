@@ -107,6 +107,13 @@ def test_hostbuild_bitstream_identical(tmp_path, w, h, frames, preset, qp, noisy
     _identity(tmp_path, _hostsim(), w, h, frames, preset, qp, noisy)
 
 
+@pytest.mark.parametrize("w,h,preset,qp,noisy", [(136, 72, "veryslow", 15, True), (264, 136, "slower", 29, True), (192, 64, "veryslow", 15, False)])
+def test_hostbuild_chroma_mode_search(tmp_path, w, h, preset, qp, noisy):
+    """--intra-chroma-search (no preset sets it): the candidates are predicted with their own mode but quantised and costed
+    in the scan order of the mode the CU record still holds (the luma mode) -- found by tools/sweep_ctu_hostsim.py"""
+    _identity(tmp_path, _hostsim(), w, h, 1, preset, qp, noisy, extra=("--intra-chroma-search",))
+
+
 def test_hostbuild_out_of_scope_falls_through(tmp_path):
     """a configuration outside the driver's scope (inter pictures) must run the reference path untouched"""
     ref_bin, ctu_bin = _need("kvazaar", "kvazaar_ctu")

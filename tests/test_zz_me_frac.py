@@ -113,6 +113,14 @@ def test_cuda_integer_search_with_final_hadamard_cost(cuda_lib, name, ref, ref10
     check_cuda_case(cuda_lib, name, ref, ref10)
 
 
+# ------------------------------------------------------------------------------------------------ CTU driver, chroma mode search
+@pytest.mark.gpu
+def test_cuda_ctu_driver_chroma_mode_search(cuda_lib, tmp_path):
+    """the --intra-chroma-search fix of the CTU driver (scan order of the candidates; CPU: tests/test_ctu_driver.py) on the device"""
+    import test_ctu_driver as T
+    T._identity(tmp_path, cuda_lib.LIB_PATH, 264, 136, 1, "veryslow", 15, True, extra=("--intra-chroma-search",))
+
+
 # ------------------------------------------------------------------------------------------------ 10-bit drop-in encode
 # (kept in this last file for the same reason: first hardware run at the round-end check)
 def _tenbit_encode(tmp_path, cuda):

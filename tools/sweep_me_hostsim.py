@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Randomised sweep of the motion-search host build (the single-source device code) against the reference's own functions:
+random picture sizes, algorithms, limits, QPs, bit depths and PU lists for the integer search, the fractional search from
+its results, and the candidate derivation.  CPU only (needs oracle/_ref).   python tools/sweep_me_hostsim.py <seed> <count>"""
+import ctypes as C
+import os
+import random
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import me_cases as M  # noqa: E402
+
+seed = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+count = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+rnd = random.Random(seed)
+host = C.CDLL(os.path.join(ROOT, "tests", "hostsim", "libkvzme_hostsim.so"))
+refs = {8: M.RefShim(8), 10: M.RefShim(10)}
+bad = 0
+for it in range(count):
+    w, h = rnd.choice([64, 72, 136, 200, 264, 320]), rnd.choice([64, 72, 136, 192])
+    bd = rnd.choice([8, 8, 10])
+    algo = rnd.choice([0, 0, 0, 7, 1, 3])
+    name = f"sweep{seed}_{it}"
+    M.CASES[name] = dict(w=w, h=h, bd=bd, algo=algo, steps=rnd.choice([-1, -1, 0, 1, 3]), et=rnd.choice([0, 1, 2]), mvc=rnd.choice([0, 0, 1, 4]),
+                         wpp=rnd.choice([0, 1]), delay=rnd.choice([0, 8, 10]), qp=rnd.randint(10, 45), seed=1000 * seed + it, n=60 if algo == 3 else 150,
+                         noisy=rnd.random() < 0.3, satd_final=int(rnd.random() < 0.2))
+    p, cur, rf, pus = M.make_case(name)
+    got, want = M.run_host_api(host, p, cur, rf, pus), M.run_reference(refs[bd], p, cur, rf, pus)
+    ok = M.same(got, want)
+    # fractional search from the integer results
+    level = rnd.randint(1, 4)
+    pus2 = pus.copy()
+    pus2["start_mv"] = (want["mv"] >> 2) << 2
+    p.satd_final = 0
+    ok2 = M.same(M.run_frac_host_api(host, p, level, cur, rf, pus2), M.run_frac_reference(refs[bd], p, level, cur, rf, pus2))
+    # candidates
+    cname = f"csweep{seed}_{it}"
+    nrefs = rnd.randint(1, 4)
+    slice_b = rnd.random() < 0.5
+    poc = rnd.randint(1, 40)
+    pocs = rnd.sample([x for x in range(max(0, poc - 12), poc + 12) if x != poc], nrefs)
+    l0 = [i for i in range(nrefs)][:rnd.randint(1, nrefs)]
+    l1 = (rnd.sample(range(nrefs), rnd.randint(1, nrefs)) if slice_b else [])
+    M.CAND_CASES[cname] = dict(w=w, h=h, poc=poc, slice_b=int(slice_b), tmvp=rnd.choice([0, 1, 1]), max_merge=rnd.randint(1, 5), pocs=pocs, l0=l0, l1=l1,
+                               seed=2000 * seed + it, n=200)
+    f, crp, clx, cus, col, cpus = M.make_cand_case(cname)
+    ok3 = M.run_cand_host_api(host, f, cus, col, cpus).tobytes() == M.run_cand_reference(refs[8], f, crp, clx, cus, col, cpus).tobytes()
+    if not (ok and ok2 and ok3):
+        bad += 1
+        print("DIFF", M.CASES[name], "integer", ok, "frac level", level, ok2, "cand", M.CAND_CASES[cname], ok3, flush=True)
+print("done", count, "bad", bad, flush=True)
