@@ -27,7 +27,9 @@ for it in range(n):
     qp=rnd.randint(8,48); noisy=rnd.random()<0.4; preset=rnd.choice(presets)
     extra=[]
     for o in rnd.sample(opts_pool, rnd.randint(0,4)): extra+=o
-    clip=T._clip(tmp,w,h,1,noisy)
+    frames=rnd.choice([1,1,2,3])
+    extra+=['--threads',str(rnd.choice([0,1,2,4])),'--owf',str(rnd.choice([0,1,2,3]))]      # the hooks' picture slots and worker threads
+    clip=T._clip(tmp,w,h,frames,noisy)
     a,b=str(tmp/'a.hevc'),str(tmp/'b.hevc')
     try:
         T._encode(ref_bin,clip,w,h,a,preset,qp,extra=extra)
