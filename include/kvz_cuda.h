@@ -399,6 +399,32 @@ int kvz_cuda_me_frac_search_batch(const kvz_cuda_me_params *p, int fme_level, co
 int kvz_cuda_call_me_frac_search(const kvz_cuda_me_params *p, int fme_level, const void *cur, int cur_stride, const void *ref, int ref_stride,
                                  const kvz_cuda_me_pu *pus, int count, kvz_cuda_me_result *out);
 
+/* Merge analysis of search_pu_inter (src/search_inter.c:1667-1730, the rdo < 3 form): every merge candidate of a PU that
+ * passes the checks (bi-prediction allowed and PU larger than 8x4 / 4x8, MVs inside the limits, not a duplicate of an
+ * accepted one: merge_candidate_in_list :1575-1594) is predicted -- kvz_inter_pred_pu luma, src/inter.c:604-668: one
+ * list through kvz_sample_quarterpel_luma or a copy, two lists through the 14-bit samples and kvz_bipred_average --
+ * and costed: kvz_satd_any_size + (merge flag bits + merge_idx + merge index bin bits) * lambda_sqrt; the accepted
+ * candidates come back sorted by cost (kvz_sort_keys_by_cost, src/search.c:612-626).  The early-skip reconstruction
+ * that follows in the reference (:1735-1790) is not part of this entry. */
+typedef struct kvz_cuda_me_refs {
+  const void *plane[16];            /* luma planes of state->frame->ref->images[i] in device memory (stride = their width) */
+  int32_t stride[16];
+  uint8_t ref_LX[2][16];            /* state->frame->ref_LX: list index -> picture index */
+  int32_t bipred;                   /* cfg.bipred */
+  int32_t pad;
+  double merge_flag_bits;           /* CTX_ENTROPY_FBITS(search_cabac.ctx.cu_merge_flag_ext_model, 1) */
+  double merge_idx_bits[2];         /* CTX_ENTROPY_FBITS(search_cabac.ctx.cu_merge_idx_ext_model, 0 / 1) */
+} kvz_cuda_me_refs;
+typedef struct kvz_cuda_me_merge_cost {
+  double cost[5], bits[5];          /* per accepted candidate, in acceptance order; unused entries 1.7e308 / 0 */
+  int32_t size;                     /* accepted candidates */
+  int8_t keys[5];                   /* acceptance-order indices sorted by ascending cost; unused -1 */
+  int8_t merge_idx[5];              /* merge index of each accepted candidate */
+  int8_t pad[2];
+} kvz_cuda_me_merge_cost;
+int kvz_cuda_me_merge_cost_batch(const kvz_cuda_me_params *p, const kvz_cuda_me_refs *refs, const void *cur_dev, int cur_stride,
+                                 const kvz_cuda_me_pu *pus_dev, int count, kvz_cuda_me_merge_cost *out_dev, void *stream);
+
 /* AMVP and merge candidates of a batch of PUs from a snapshot of the CU records (me_search.cu), as
  *     kvz_inter_get_mv_cand_cua   src/inter.c:1365-1383 (get_spatial_merge_candidates_cua :1015-1076,
  *                                 get_temporal_merge_candidates :836-907, get_mv_cand_from_candidates :1225-1318,

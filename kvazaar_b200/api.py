@@ -641,3 +641,23 @@ def me_frac_search_batch(params, fme_level, cur, ref, pus, out=None):
     _ck(lib().kvz_cuda_me_frac_search_batch(C.byref(params), C.c_int(fme_level), _p(cur), C.c_int(cur.stride(0)), _p(ref), C.c_int(ref.stride(0)),
                                             _p(pus), C.c_int(count), _p(out), _stream()))
     return out
+
+
+# merge analysis: kvz_cuda_me_refs / kvz_cuda_me_merge_cost
+ME_MERGE_COST = np.dtype([("cost", "<f8", (5,)), ("bits", "<f8", (5,)), ("size", "<i4"), ("keys", "i1", (5,)), ("merge_idx", "i1", (5,)), ("pad", "i1", (2,))])
+
+
+class MeRefs(C.Structure):
+    """kvz_cuda_me_refs: the reference pictures' luma planes (device pointers), the reference lists, cfg.bipred and the merge bits"""
+    _fields_ = [("plane", C.c_void_p * 16), ("stride", C.c_int32 * 16), ("ref_LX", (C.c_uint8 * 16) * 2), ("bipred", C.c_int32), ("pad", C.c_int32),
+                ("merge_flag_bits", C.c_double), ("merge_idx_bits", C.c_double * 2)]
+
+
+def me_merge_cost_batch(params, refs, cur, pus, out=None):
+    """Merge analysis of `pus` (their merge candidates) against the pictures of `refs`; returns a CUDA byte tensor of ME_MERGE_COST records."""
+    torch = _torch()
+    count = pus.numel() // ME_PU.itemsize
+    if out is None:
+        out = torch.empty(count * ME_MERGE_COST.itemsize, dtype=torch.uint8, device=cur.device)
+    _ck(lib().kvz_cuda_me_merge_cost_batch(C.byref(params), C.byref(refs), _p(cur), C.c_int(cur.stride(0)), _p(pus), C.c_int(count), _p(out), _stream()))
+    return out

@@ -1,0 +1,190 @@
+// me_merge.h -- merge analysis of one PU: which merge candidates are usable, their luma prediction (one or two lists)
+// and Hadamard cost, sorted -- decision for decision as the reference's search_pu_inter does it for rdo < 3.
+//
+// Single source (device: one warp per PU; host test build: the 32 lane shares walked in turn).  As in me_frac.h every
+// lane predicts the 8x8 / 4x4 sub-blocks of its share straight from the reference pictures in registers: the 14-bit
+// intermediate sample of each list (the arithmetic of kvz_sample_14bit_quarterpel_luma; an integer MV gives
+// sample << (14 - bitdepth), which is what the reference's pixel copy turns into inside kvz_bipred_average), then
+//   one list :  (s + 2^(13-bitdepth)) >> (14 - bitdepth)        == kvz_sample_quarterpel_luma / the plain copy
+//   two lists:  (s0 + s1 + 2^(14-bitdepth)) >> (15 - bitdepth)  == bipred_average_{px_px,px_im,im_im}
+// clipped to the pixel range.
+//
+// What it follows in the reference (restated, nothing copied):
+//   search_pu_inter, merge analysis      src/search_inter.c:1667-1730
+//   merge_candidate_in_list              src/search_inter.c:1575-1594
+//   kvz_inter_pred_pu / inter_recon_unipred / kvz_inter_recon_bipred   src/inter.c:374-668 (luma)
+//   bipred_average_*                     src/strategies/generic/picture-generic.c:553-660
+//   kvz_satd_any_size                    src/strategies/strategies-picture.h:76-112
+//   kvz_sort_keys_by_cost                src/search.c:612-626
+#pragma once
+#include "me_frac.h"
+
+namespace kvzme {
+
+static_assert(sizeof(kvz_cuda_me_refs) == 256 && sizeof(kvz_cuda_me_merge_cost) == 96, "record layouts are part of the ABI");
+
+// 14-bit intermediate samples of the N x N block whose top-left reference position is (bx, by) + fraction (fx, fy)
+template <typename Pix, int N>
+ME_FN void hi_block(const kvz_cuda_me_params &p, const Pix *ref, int ref_stride, int bx, int by, int fx, int fy, int32_t *out)
+{
+  const int xmax = p.width - 1, ymax = p.height - 1;
+  const int shift1 = p.bitdepth - 8;
+  if (fx == 0 && fy == 0) {
+    for (int r = 0; r < N; ++r) {
+      const int yy = by + r < 0 ? 0 : (by + r > ymax ? ymax : by + r);
+      for (int c = 0; c < N; ++c) {
+        const int xx = bx + c < 0 ? 0 : (bx + c > xmax ? xmax : bx + c);
+        out[r * N + c] = (int32_t)ref[yy * ref_stride + xx] << (14 - p.bitdepth);
+      }
+    }
+    return;
+  }
+  int32_t hor[(N + 7) * N];
+  for (int r = 0; r < N + 7; ++r) {
+    const int yy0 = by + r - 3;
+    const int yy = yy0 < 0 ? 0 : (yy0 > ymax ? ymax : yy0);
+    const Pix *row = ref + yy * ref_stride;
+    for (int c = 0; c < N; ++c) {
+      int32_t s = 0;
+      if (fx == 0) {
+        const int xx0 = bx + c;
+        s = 64 * (int32_t)row[xx0 < 0 ? 0 : (xx0 > xmax ? xmax : xx0)];
+      } else {
+        for (int k = 0; k < 8; ++k) {
+          const int xx0 = bx + c + k - 3;
+          s += luma_tap(fx, k) * (int32_t)row[xx0 < 0 ? 0 : (xx0 > xmax ? xmax : xx0)];
+        }
+      }
+      hor[r * N + c] = s >> shift1;
+    }
+  }
+  for (int r = 0; r < N; ++r)
+    for (int c = 0; c < N; ++c) {
+      int32_t s = 0;
+      if (fy == 0) s = 64 * hor[(r + 3) * N + c];
+      else
+        for (int k = 0; k < 8; ++k) s += luma_tap(fy, k) * hor[(r + k) * N + c];
+      out[r * N + c] = s >> 6;
+    }
+}
+
+template <typename Pix>
+struct RefSet {
+  const Pix *plane[16];
+  int stride[16];
+};
+
+// Hadamard cost of the N x N sub-block at (sx, sy) of the PU against the prediction of a merge candidate
+template <typename Pix, int N>
+ME_FN uint32_t merge_subblock_cost(const kvz_cuda_me_params &p, const kvz_cuda_me_refs &rf, const RefSet<Pix> &rs, const kvz_cuda_me_pu &pu,
+                                   const Planes<Pix> &pl, const kvz_cuda_me_merge &cand, int sx, int sy)
+{
+  int32_t a[N * N], b[N * N];
+  const int pix_max = (1 << p.bitdepth) - 1;
+  const bool two = cand.dir == 3;
+  const int l0 = (cand.dir & 1) ? 0 : 1;                       // the (first) list in use
+  {
+    const int pic = rf.ref_LX[l0][cand.ref[l0] & 15] & 15;
+    const int qx = cand.mv[l0][0], qy = cand.mv[l0][1];
+    hi_block<Pix, N>(p, rs.plane[pic], rs.stride[pic], pu.x + sx + (qx >> 2), pu.y + sy + (qy >> 2), qx & 3, qy & 3, a);
+  }
+  if (two) {
+    const int pic = rf.ref_LX[1][cand.ref[1] & 15] & 15;
+    const int qx = cand.mv[1][0], qy = cand.mv[1][1];
+    hi_block<Pix, N>(p, rs.plane[pic], rs.stride[pic], pu.x + sx + (qx >> 2), pu.y + sy + (qy >> 2), qx & 3, qy & 3, b);
+  }
+  const int shift = two ? 15 - p.bitdepth : 14 - p.bitdepth;
+  const int32_t offset = 1 << (shift - 1);
+  for (int r = 0; r < N; ++r)
+    for (int c = 0; c < N; ++c) {
+      int32_t v = ((two ? a[r * N + c] + b[r * N + c] : a[r * N + c]) + offset) >> shift;
+      v = v < 0 ? 0 : (v > pix_max ? pix_max : v);
+      a[r * N + c] = (int32_t)pl.cur[(pu.y + sy + r) * pl.cur_stride + pu.x + sx + c] - v;
+    }
+  const uint32_t s = wht_abs_sum<N>(a);
+  return N == 4 ? (s + 1) >> 1 : (s + 2) >> 2;
+}
+
+// kvz_satd_any_size of the PU against a candidate's prediction: one lane's share, sub-blocks in the reference's order
+template <typename Pix>
+ME_FN uint32_t merge_satd_lane(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cuda_me_refs &rf, const RefSet<Pix> &rs, const kvz_cuda_me_pu &pu,
+                               const Planes<Pix> &pl, const kvz_cuda_me_merge &cand)
+{
+  int w = pu.w, h = pu.h;
+  int x0 = 0, y0 = 0, k = 0;
+  uint32_t s = 0;
+  if (w % 8 != 0) {
+    for (int y = 0; y < h; y += 4)
+      if (k++ % ln.n == ln.lane) s += merge_subblock_cost<Pix, 4>(p, rf, rs, pu, pl, cand, 0, y);
+    x0 = 4;
+    w -= 4;
+  }
+  if (h % 8 != 0) {
+    for (int x = 0; x < w; x += 4)
+      if (k++ % ln.n == ln.lane) s += merge_subblock_cost<Pix, 4>(p, rf, rs, pu, pl, cand, x0 + x, 0);
+    y0 = 4;
+    h -= 4;
+  }
+  for (int y = 0; y < h; y += 8)
+    for (int x = 0; x < w; x += 8)
+      if (k++ % ln.n == ln.lane) s += merge_subblock_cost<Pix, 8>(p, rf, rs, pu, pl, cand, x0 + x, y0 + y);
+  return s;
+}
+
+template <typename Pix>
+ME_FN uint32_t merge_satd(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cuda_me_refs &rf, const RefSet<Pix> &rs, const kvz_cuda_me_pu &pu,
+                          const Planes<Pix> &pl, const kvz_cuda_me_merge &cand)
+{
+#if defined(__CUDA_ARCH__)
+  return lane_sum(merge_satd_lane(ln, p, rf, rs, pu, pl, cand)) >> (p.bitdepth - 8);
+#else
+  uint32_t s = 0;
+  for (int l = 0; l < ln.n; ++l) s += merge_satd_lane(Lanes{ l, ln.n }, p, rf, rs, pu, pl, cand);
+  return s >> (p.bitdepth - 8);
+#endif
+}
+
+ME_FN bool same_motion(const kvz_cuda_me_merge &a, const kvz_cuda_me_merge &b)
+{
+  // all fields, also those of a list the candidate does not use: as merge_candidate_in_list compares them
+  return a.dir == b.dir && a.ref[0] == b.ref[0] && a.mv[0][0] == b.mv[0][0] && a.mv[0][1] == b.mv[0][1] && a.ref[1] == b.ref[1] &&
+         a.mv[1][0] == b.mv[1][0] && a.mv[1][1] == b.mv[1][1];
+}
+
+template <typename Pix>
+ME_FN void merge_cost_pu(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cuda_me_refs &rf, const RefSet<Pix> &rs, const kvz_cuda_me_pu &pu,
+                         const Planes<Pix> &pl, kvz_cuda_me_merge_cost *out)
+{
+  kvz_cuda_me_merge_cost m;
+  m.size = 0;
+  for (int i = 0; i < 5; ++i) { m.cost[i] = kMaxDouble; m.bits[i] = 0; m.keys[i] = -1; m.merge_idx[i] = 0; }
+  m.pad[0] = m.pad[1] = 0;
+  for (int idx = 0; idx < pu.num_merge; ++idx) {
+    const kvz_cuda_me_merge &cand = pu.merge[idx];
+    if (cand.dir == 3 && !rf.bipred) continue;
+    if (cand.dir == 3 && !(pu.w + pu.h > 12)) continue;
+    bool dup = false;
+    for (int i = 0; i < m.size && !dup; ++i) dup = same_motion(cand, pu.merge[m.merge_idx[m.keys[i]]]);
+    if (((cand.dir & 1) && !mv_allowed(p, pu, cand.mv[0][0], cand.mv[0][1])) || ((cand.dir & 2) && !mv_allowed(p, pu, cand.mv[1][0], cand.mv[1][1])) || dup)
+      continue;
+    const uint32_t satd = merge_satd(ln, p, rf, rs, pu, pl, cand);
+    const double bits = rf.merge_flag_bits + idx + rf.merge_idx_bits[idx != 0];
+    double cost = (double)satd;
+    cost += bits * p.lambda_sqrt;
+    m.merge_idx[m.size] = (int8_t)idx;
+    m.cost[m.size] = cost;
+    m.bits[m.size] = bits;
+    m.keys[m.size] = (int8_t)m.size;
+    m.size++;
+  }
+  for (int i = 1; i < m.size; ++i) {                         // kvz_sort_keys_by_cost: insertion sort, ties keep their order
+    const int8_t cur = m.keys[i];
+    const double cur_cost = m.cost[cur];
+    int j = i;
+    while (j > 0 && cur_cost < m.cost[m.keys[j - 1]]) { m.keys[j] = m.keys[j - 1]; --j; }
+    m.keys[j] = cur;
+  }
+  if (ln.lane == 0) *out = m;
+}
+
+}  // namespace kvzme

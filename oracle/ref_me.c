@@ -283,3 +283,141 @@ int kvzref_me_candidates(kvzref_ctx *ctx, const kvz_cuda_me_frame *f, const int3
   kvz_cu_array_free(&col);
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * The merge analysis of search_pu_inter (search_inter.c:1667-1730, rdo < 3) with the reference's own primitives:
+ * merge_candidate_in_list, fracmv_within_tile (static, from the included file), kvz_inter_pred_pu, kvz_satd_any_size,
+ * kvz_sort_keys_by_cost and the CTX_ENTROPY_FBITS macro on real context models.  Only the loop that sequences them is
+ * restated.  cu[i] = { x_cu, y_cu, width_cu, part_mode, i_pu } of the PU.  Parity checker for kvz_cuda_me_merge_cost_batch. */
+int kvzref_me_merge_cost(kvzref_ctx *ctx, const kvz_cuda_me_params *p, int n_pics, const kvz_pixel *const *pic_planes, const uint8_t *ref_LX /* [2][16] */,
+                         const int32_t *ref_LX_size, int bipred, int merge_flag_state, int merge_idx_state, double *bits_out /* [3] */,
+                         const kvz_pixel *cur, int cur_stride, const kvz_cuda_me_pu *pus, const int32_t *cu /* [count][5] */, int count,
+                         kvz_cuda_me_merge_cost *out)
+{
+  encoder_state_t *state = &ctx->enc->states[0];
+  encoder_control_t *ctrl = (encoder_control_t *)state->encoder_control;
+  if (p->bitdepth != KVZ_BIT_DEPTH) return -1;
+  if (state->tile->frame->width != p->width || state->tile->frame->height != p->height) return -2;
+  if (p->delay_px != 0 && p->delay_px != SAO_DELAY_PX && p->delay_px != DEBLOCK_DELAY_PX) return -4;
+
+  const kvz_config saved_cfg = ctrl->cfg;
+  const int saved_right = ctrl->max_inter_ref_lcu.right, saved_down = ctrl->max_inter_ref_lcu.down;
+  const double saved_lambda_sqrt = state->lambda_sqrt;
+  image_list_t *saved_ref = state->frame->ref;
+  uint8_t saved_LX[2][16]; memcpy(saved_LX, state->frame->ref_LX, 32);
+  uint8_t saved_LX_size[2] = { state->frame->ref_LX_size[0], state->frame->ref_LX_size[1] };
+  ctrl->cfg.owf = p->wpp_owf ? 1 : 0;
+  ctrl->cfg.wpp = p->wpp_owf ? 1 : 0;
+  ctrl->cfg.sao_type = p->delay_px == SAO_DELAY_PX ? KVZ_SAO_FULL : KVZ_SAO_OFF;
+  ctrl->cfg.deblock_enable = p->delay_px == DEBLOCK_DELAY_PX ? 1 : 0;
+  ctrl->cfg.mv_constraint = (enum kvz_mv_constraint)p->mv_constraint;
+  ctrl->cfg.bipred = bipred;
+  ctrl->max_inter_ref_lcu.right = p->max_ref_lcu_right;
+  ctrl->max_inter_ref_lcu.down = p->max_ref_lcu_down;
+  state->lambda_sqrt = p->lambda_sqrt;
+
+  image_list_t *list = kvz_image_list_alloc(16);
+  kvz_picture *pics[16];
+  for (int i = 0; i < 16; ++i) {
+    pics[i] = calloc(1, sizeof(kvz_picture));
+    pics[i]->y = (kvz_pixel *)pic_planes[i < n_pics ? i : 0];
+    pics[i]->width = p->width; pics[i]->height = p->height; pics[i]->stride = p->width;
+    list->images[i] = pics[i];
+  }
+  list->used_size = (uint32_t)n_pics;
+  state->frame->ref = list;
+  memcpy(state->frame->ref_LX, ref_LX, 32);
+  state->frame->ref_LX_size[0] = (uint8_t)ref_LX_size[0];
+  state->frame->ref_LX_size[1] = (uint8_t)ref_LX_size[1];
+
+  /* the two context models the merge bits read */
+  cabac_ctx_t saved_flag = state->search_cabac.ctx.cu_merge_flag_ext_model, saved_idx = state->search_cabac.ctx.cu_merge_idx_ext_model;
+  state->search_cabac.ctx.cu_merge_flag_ext_model.uc_state = (uint8_t)merge_flag_state;
+  state->search_cabac.ctx.cu_merge_idx_ext_model.uc_state = (uint8_t)merge_idx_state;
+  const double merge_flag_cost = CTX_ENTROPY_FBITS(&state->search_cabac.ctx.cu_merge_flag_ext_model, 1);
+  bits_out[0] = merge_flag_cost;
+  bits_out[1] = CTX_ENTROPY_FBITS(&state->search_cabac.ctx.cu_merge_idx_ext_model, 0);
+  bits_out[2] = CTX_ENTROPY_FBITS(&state->search_cabac.ctx.cu_merge_idx_ext_model, 1);
+
+  kvz_picture pic;
+  memset(&pic, 0, sizeof(pic));
+  pic.y = (kvz_pixel *)cur; pic.width = p->width; pic.height = p->height; pic.stride = cur_stride;
+  lcu_t *lcu = calloc(1, sizeof(lcu_t));
+  unit_stats_map_t *merge = calloc(1, sizeof(unit_stats_map_t));
+  for (int i = 0; i < count; ++i) {
+    const kvz_cuda_me_pu *u = &pus[i];
+    const int x_cu = cu[5 * i], y_cu = cu[5 * i + 1], width_cu = cu[5 * i + 2], part_mode = cu[5 * i + 3], i_pu = cu[5 * i + 4];
+    const int x = u->x, y = u->y, width = u->w, height = u->h;
+    const int x_local = SUB_SCU(x), y_local = SUB_SCU(y);
+    inter_search_info_t info;
+    memset(&info, 0, sizeof(info));
+    info.state = state; info.pic = &pic; info.origin.x = x; info.origin.y = y; info.width = width; info.height = height;
+    info.num_merge_cand = u->num_merge;
+    for (int m = 0; m < u->num_merge; ++m) {
+      info.merge_cand[m].dir = u->merge[m].dir;
+      for (int l = 0; l < 2; ++l) {
+        info.merge_cand[m].ref[l] = u->merge[m].ref[l];
+        info.merge_cand[m].mv[l][0] = u->merge[m].mv[l][0]; info.merge_cand[m].mv[l][1] = u->merge[m].mv[l][1];
+      }
+    }
+    /* the LCU work copy: source pixels of the PU, the CU's partitioning */
+    memset(lcu->cu, 0, sizeof(lcu->cu));
+    for (int r = 0; r < height; ++r) memcpy(&lcu->ref.y[(y_local + r) * LCU_WIDTH + x_local], &cur[(size_t)(y + r) * cur_stride + x], (size_t)width * sizeof(kvz_pixel));
+    cu_info_t *cu_rec = LCU_GET_CU_AT_PX(lcu, SUB_SCU(x_cu), SUB_SCU(y_cu));
+    cu_rec->type = CU_INTER; cu_rec->part_size = part_mode;
+    cu_info_t *cur_pu = LCU_GET_CU_AT_PX(lcu, x_local, y_local);
+    cur_pu->type = CU_INTER; cur_pu->part_size = part_mode;
+
+    merge->size = 0;
+    for (int k = 0; k < MRG_MAX_NUM_CANDS; ++k) { merge->keys[k] = -1; merge->cost[k] = MAX_DOUBLE; merge->bits[k] = 0; }
+    for (int merge_idx = 0; merge_idx < info.num_merge_cand; ++merge_idx) {
+      inter_merge_cand_t *cur_cand = &info.merge_cand[merge_idx];
+      cur_pu->inter.mv_dir = cur_cand->dir;
+      cur_pu->inter.mv_ref[0] = cur_cand->ref[0]; cur_pu->inter.mv_ref[1] = cur_cand->ref[1];
+      cur_pu->inter.mv[0][0] = cur_cand->mv[0][0]; cur_pu->inter.mv[0][1] = cur_cand->mv[0][1];
+      cur_pu->inter.mv[1][0] = cur_cand->mv[1][0]; cur_pu->inter.mv[1][1] = cur_cand->mv[1][1];
+      if (cur_pu->inter.mv_dir == 3 && !ctrl->cfg.bipred) continue;
+      if (cur_pu->inter.mv_dir == 3 && !(width + height > 12)) continue;
+      bool is_duplicate = merge_candidate_in_list(info.merge_cand, cur_cand, merge);
+      bool active_L0 = cur_pu->inter.mv_dir & 1, active_L1 = cur_pu->inter.mv_dir & 2;
+      if ((active_L0 && !fracmv_within_tile(&info, cur_pu->inter.mv[0][0], cur_pu->inter.mv[0][1])) ||
+          (active_L1 && !fracmv_within_tile(&info, cur_pu->inter.mv[1][0], cur_pu->inter.mv[1][1])) || is_duplicate) continue;
+      kvz_inter_pred_pu(state, lcu, x_cu, y_cu, width_cu, true, false, i_pu);
+      merge->unit[merge->size] = *cur_pu;
+      merge->unit[merge->size].merge_idx = merge_idx;
+      double bits = merge_flag_cost + merge_idx + CTX_ENTROPY_FBITS(&(state->search_cabac.ctx.cu_merge_idx_ext_model), merge_idx != 0);
+      merge->cost[merge->size] = kvz_satd_any_size(width, height, lcu->rec.y + y_local * LCU_WIDTH + x_local, LCU_WIDTH,
+                                                   lcu->ref.y + y_local * LCU_WIDTH + x_local, LCU_WIDTH);
+      merge->cost[merge->size] += bits * info.state->lambda_sqrt;
+      merge->bits[merge->size] = bits;
+      merge->keys[merge->size] = merge->size;
+      merge->size++;
+    }
+    kvz_sort_keys_by_cost(merge);
+    memset(&out[i], 0, sizeof(out[i]));
+    out[i].size = merge->size;
+    for (int k = 0; k < 5; ++k) {
+      out[i].cost[k] = merge->cost[k];
+      out[i].bits[k] = k < merge->size ? merge->bits[k] : 0;
+      out[i].keys[k] = merge->keys[k];
+      out[i].merge_idx[k] = k < merge->size ? (int8_t)merge->unit[k].merge_idx : 0;
+    }
+  }
+  free(merge);
+  free(lcu);
+
+  state->search_cabac.ctx.cu_merge_flag_ext_model = saved_flag;
+  state->search_cabac.ctx.cu_merge_idx_ext_model = saved_idx;
+  state->frame->ref = saved_ref;
+  memcpy(state->frame->ref_LX, saved_LX, 32);
+  state->frame->ref_LX_size[0] = saved_LX_size[0];
+  state->frame->ref_LX_size[1] = saved_LX_size[1];
+  for (int i = 0; i < 16; ++i) { list->images[i] = NULL; free(pics[i]); }
+  list->used_size = 0;
+  kvz_image_list_destroy(list);
+  ctrl->cfg = saved_cfg;
+  ctrl->max_inter_ref_lcu.right = saved_right;
+  ctrl->max_inter_ref_lcu.down = saved_down;
+  state->lambda_sqrt = saved_lambda_sqrt;
+  return 0;
+}

@@ -5,6 +5,7 @@
 #include "../../kvazaar_b200/csrc/me/me_search.h"
 #include "../../kvazaar_b200/csrc/me/me_cand.h"
 #include "../../kvazaar_b200/csrc/me/me_frac.h"
+#include "../../kvazaar_b200/csrc/me/me_merge.h"
 
 extern "C" int kvz_cuda_me_params_supported(const kvz_cuda_me_params *p) { return p ? kvzme::params_supported(*p) : -1; }
 
@@ -72,4 +73,24 @@ extern "C" int kvz_cuda_me_frac_search_batch(const kvz_cuda_me_params *p, int fm
                                              int ref_stride, const kvz_cuda_me_pu *pus, int count, kvz_cuda_me_result *out, void *)
 {
   return kvz_cuda_call_me_frac_search(p, fme_level, cur, cur_stride, ref, ref_stride, pus, count, out);
+}
+
+template <typename Pix>
+static void run_merge(const kvz_cuda_me_params *p, const kvz_cuda_me_refs *rf, const void *cur, int cur_stride, const kvz_cuda_me_pu *pus, int count,
+                      kvz_cuda_me_merge_cost *out)
+{
+  const kvzme::Lanes ln = { 0, 32 };
+  const kvzme::Planes<Pix> pl = { (const Pix *)cur, nullptr, cur_stride, 0 };
+  kvzme::RefSet<Pix> rs;
+  for (int i = 0; i < 16; ++i) { rs.plane[i] = (const Pix *)rf->plane[i]; rs.stride[i] = rf->stride[i]; }
+  for (int i = 0; i < count; ++i) kvzme::merge_cost_pu<Pix>(ln, *p, *rf, rs, pus[i], pl, &out[i]);
+}
+
+extern "C" int kvz_cuda_me_merge_cost_batch(const kvz_cuda_me_params *p, const kvz_cuda_me_refs *refs, const void *cur, int cur_stride,
+                                            const kvz_cuda_me_pu *pus, int count, kvz_cuda_me_merge_cost *out, void *)
+{
+  if (!p || !refs || kvzme::params_supported(*p) != 0) return -2;
+  if (p->bitdepth == 8) run_merge<uint8_t>(p, refs, cur, cur_stride, pus, count, out);
+  else run_merge<uint16_t>(p, refs, cur, cur_stride, pus, count, out);
+  return 0;
 }

@@ -14,7 +14,9 @@ import os
 import numpy as np
 import pytest
 
-from _me_cases import CASES, FRAC_CASES, GPU_FIRST_RUN_DONE, RESULT, grid_case, make_frac_case, run_frac_host_api, run_frac_reference, run_host_api, run_reference, same
+from _me_cases import (CASES, FRAC_CASES, GPU_FIRST_RUN_DONE, MERGE_CASES, MERGE_COST, RESULT, make_merge_case, merge_refs_struct, run_merge_host_api,
+                       run_merge_reference)
+from _me_cases import grid_case, make_frac_case, run_frac_host_api, run_frac_reference, run_host_api, run_reference, same
 from test_me_search import _explain, _hostsim, check_cuda_case
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -52,6 +54,35 @@ def test_hostbuild_integer_then_fractional_matches_reference(ref):
     pus2["start_mv"] = integer["mv"]
     got, want = run_frac_host_api(lib, p, 4, cur, rf, pus2), run_frac_reference(ref, p, 4, cur, rf, pus2)
     assert same(got, want), _explain(got, want, pus2)
+
+
+# ---- merge analysis (kvz_cuda_me_merge_cost_batch; search_pu_inter's merge loop, src/search_inter.c:1667-1730)
+def _golden_merge(name):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "me_search.npz"))
+    return g["merge/" + name].view(MERGE_COST), tuple(g["merge/" + name + "/bits"])
+
+
+def _explain_merge(got, want, pus):
+    bad = [i for i in range(len(pus)) if got[i].tobytes() != want[i].tobytes()]
+    i = bad[0]
+    return f"{len(bad)} of {len(pus)} PUs differ; first: PU {i} {pus[i]}\n got  {got[i]}\n want {want[i]}"
+
+
+@pytest.mark.parametrize("name", sorted(MERGE_CASES))
+def test_merge_reference_matches_golden(name, ref, ref10):
+    p, c, cur, planes, pus, cu = make_merge_case(name)
+    want, bits = run_merge_reference(ref if p.bitdepth == 8 else ref10, p, c, cur, planes, pus, cu)
+    gold, gbits = _golden_merge(name)
+    assert bits == gbits and want.tobytes() == gold.tobytes(), _explain_merge(want, gold, pus)
+
+
+@pytest.mark.parametrize("name", sorted(MERGE_CASES))
+def test_merge_hostbuild_matches_golden(name):
+    p, c, cur, planes, pus, _ = make_merge_case(name)
+    gold, bits = _golden_merge(name)
+    got = run_merge_host_api(_hostsim(), p, c, cur, planes, pus, bits)
+    assert got.tobytes() == gold.tobytes(), _explain_merge(got, gold, pus)
+    assert got["size"].max() >= 3 and got["size"].min() <= 1           # several accepted candidates; PUs where (almost) none may be used
 
 
 # ------------------------------------------------------------------------------------------------ GPU (the product)
@@ -111,6 +142,22 @@ def test_cuda_integer_then_fractional_full_picture(cuda_lib, ref, ref10, w, h, b
 def test_cuda_integer_search_with_final_hadamard_cost(cuda_lib, name, ref, ref10):
     """cfg.fme_level == 0: the integer kernel's second instantiation (winner's cost recomputed with the Hadamard cost)"""
     check_cuda_case(cuda_lib, name, ref, ref10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(MERGE_CASES))
+def test_cuda_merge_analysis_matches_golden_and_reference(cuda_lib, name, ref, ref10):
+    import torch
+    kb = cuda_lib
+    p, c, cur, planes, pus, cu = make_merge_case(name)
+    want, bits = run_merge_reference(ref if p.bitdepth == 8 else ref10, p, c, cur, planes, pus, cu)
+    d_planes = [kb.to_dev(pl) for pl in planes]
+    rf = merge_refs_struct(c, [t.data_ptr() for t in d_planes], p.width, bits)
+    out = kb.me_merge_cost_batch(p, rf, kb.to_dev(cur), kb.to_dev(pus))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().view(MERGE_COST).copy()
+    assert got.tobytes() == want.tobytes(), _explain_merge(got, want, pus)
+    assert got.tobytes() == _golden_merge(name)[0].tobytes()
 
 
 # ------------------------------------------------------------------------------------------------ CTU driver, chroma mode search

@@ -10,8 +10,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from _me_cases import (CAND_CASES, CASES, FRAC_CASES, make_cand_case, make_case, make_frac_case, run_cand_reference, run_frac_reference,  # noqa: E402
-                       run_reference)
+from _me_cases import (CAND_CASES, CASES, FRAC_CASES, MERGE_CASES, make_cand_case, make_case, make_frac_case, make_merge_case,  # noqa: E402
+                       run_cand_reference, run_frac_reference, run_merge_reference, run_reference)
 from _oracle import Ref  # noqa: E402
 
 refs = {}
@@ -36,4 +36,10 @@ for name in sorted(FRAC_CASES):
     out["frac/" + name + "/bits"] = r["bits"].copy()
     out["frac/" + name + "/cost"] = r["cost"].copy()
     print("frac", name, len(pus), "PUs")
+for name in sorted(MERGE_CASES):
+    p, c, cur, planes, pus, cu = make_merge_case(name)
+    r, bits = run_merge_reference(refs.setdefault(p.bitdepth, Ref(p.bitdepth)), p, c, cur, planes, pus, cu)
+    out["merge/" + name] = np.frombuffer(r.tobytes(), np.uint8).copy()
+    out["merge/" + name + "/bits"] = np.array(bits, np.float64)
+    print("merge", name, len(pus), "PUs")
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "me_search.npz"), **out)

@@ -378,3 +378,113 @@ class RefShim:
             assert c
             self._ctx[key] = C.c_void_p(c)
         return self._ctx[key]
+
+
+# ------------------------------------------------------------------------------------------------ merge analysis
+from kvazaar_b200.api import ME_MERGE_COST as MERGE_COST, MeRefs as Refs  # noqa: E402
+
+assert MERGE_COST.itemsize == 96 and C.sizeof(Refs) == 256
+
+MERGE_CASES = {
+    "merge_p_one_ref":    dict(w=208, h=136, bd=8, pics=1, l0=[0], l1=[], bipred=0, mvc=0, wpp=0, delay=0, qp=27, ctx=(30, 11), seed=1, n=300),
+    "merge_b_two_refs":   dict(w=208, h=136, bd=8, pics=2, l0=[0, 1], l1=[1, 0], bipred=1, mvc=0, wpp=1, delay=10, qp=32, ctx=(5, 70), seed=2, n=300),
+    "merge_b_four_refs":  dict(w=264, h=200, bd=8, pics=4, l0=[0, 2, 1], l1=[3, 1], bipred=1, mvc=4, wpp=0, delay=0, qp=22, ctx=(62, 62), seed=3, n=300),
+    "merge_b_nobipred":   dict(w=136, h=72, bd=8, pics=2, l0=[0], l1=[1], bipred=0, mvc=1, wpp=1, delay=8, qp=37, ctx=(100, 3), seed=4, n=250),
+    "merge_b_10bit":      dict(w=208, h=136, bd=10, pics=3, l0=[0, 1], l1=[2, 0], bipred=1, mvc=0, wpp=1, delay=10, qp=27, ctx=(17, 40), seed=5, n=250),
+}
+PART_MODES = [0, 1, 2, 4, 5, 6, 7]          # part_mode_t of the generator's split kinds: 2Nx2N 2NxN Nx2N 2NxnU 2NxnD nLx2N nRx2N
+
+
+def make_merge_case(name):
+    c = MERGE_CASES[name]
+    r = np.random.default_rng(6000 + c["seed"])
+    w, h, bd = c["w"], c["h"], c["bd"]
+    p = Params()
+    p.width, p.height, p.bitdepth = w, h, bd
+    p.mv_constraint, p.wpp_owf, p.delay_px = c["mvc"], c["wpp"], c["delay"]
+    p.max_ref_lcu_right, p.max_ref_lcu_down = 1, 1
+    p.lambda_sqrt = lambda_sqrt(c["qp"])
+    cur, ref0 = pictures(w, h, bd, 50 + c["seed"])
+    planes = [ref0] + [pictures(w, h, bd, 60 + 7 * k + c["seed"], noisy=(k == 2))[1] for k in range(1, c["pics"])]
+    sizes = [len(c["l0"]), len(c["l1"])]
+    n = c["n"]
+    pus = np.zeros(n, PU)
+    cu = np.zeros((n, 5), np.int32)
+    for i in range(n):
+        while True:
+            size = int((8, 16, 32, 64)[int(r.integers(0, 4))])
+            if size <= w and size <= h:
+                break
+        cx, cy = int(r.integers(0, w // size)) * size, int(r.integers(0, h // size)) * size
+        mode = int(r.integers(0, 7 if size >= 16 else 3))
+        q = size // 4
+        split = {0: None, 1: ("h", size // 2), 2: ("v", size // 2), 3: ("h", q), 4: ("h", size - q), 5: ("v", q), 6: ("v", size - q)}[mode]
+        ipu = int(r.integers(0, 2)) if split else 0
+        x, y, pw, ph = cx, cy, size, size
+        if split:
+            kind, at = split
+            if kind == "h":
+                y, ph = (cy, at) if ipu == 0 else (cy + at, size - at)
+            else:
+                x, pw = (cx, at) if ipu == 0 else (cx + at, size - at)
+        pus[i]["x"], pus[i]["y"], pus[i]["w"], pus[i]["h"] = x, y, pw, ph
+        cu[i] = (cx, cy, size, PART_MODES[mode], ipu)
+        nm = int(r.integers(1, 6))
+        pus[i]["num_merge"] = nm
+        for m in range(nm):
+            dirs = [1] if sizes[1] == 0 else [1, 2, 3, 3]
+            d = int(dirs[int(r.integers(0, len(dirs)))])
+            mc = pus[i]["merge"][m]
+            mc["dir"] = d
+            for l in range(2):
+                used = d & (1 << l)
+                if used or r.integers(0, 3) == 0:          # the list a candidate does not use sometimes holds leftovers
+                    rng = 600 if r.integers(0, 12) == 0 else 40
+                    mc["mv"][l] = r.integers(-rng, rng + 1, 2)
+                    if r.integers(0, 3) == 0:
+                        mc["mv"][l] = (mc["mv"][l] >> 2) << 2  # integer MVs: the copy path
+                    mc["ref"][l] = int(r.integers(0, max(1, sizes[l])))
+            if m > 0 and r.integers(0, 5) == 0:
+                pus[i]["merge"][m] = pus[i]["merge"][int(r.integers(0, m))]       # duplicates
+    return p, c, cur, planes, pus, cu
+
+
+def merge_refs_struct(c, plane_ptrs, width, bits):
+    rf = Refs()
+    for i in range(16):
+        rf.plane[i] = plane_ptrs[i if i < len(plane_ptrs) else 0]
+        rf.stride[i] = width
+    for l, lst in enumerate((c["l0"], c["l1"])):
+        for i, v in enumerate(lst):
+            rf.ref_LX[l][i] = v
+    rf.bipred = c["bipred"]
+    rf.merge_flag_bits, rf.merge_idx_bits[0], rf.merge_idx_bits[1] = bits
+    return rf
+
+
+def run_merge_reference(ref_shim, p, c, cur, planes, pus, cu):
+    out = np.zeros(len(pus), MERGE_COST)
+    bits = (C.c_double * 3)()
+    ctx = ref_shim.ctx(27, 0, 0, p.width, p.height)
+    ptrs = (C.c_void_p * 16)(*[planes[i if i < len(planes) else 0].ctypes.data for i in range(16)])
+    lx = np.zeros((2, 16), np.uint8)
+    lx[0, :len(c["l0"])] = c["l0"]
+    lx[1, :len(c["l1"])] = c["l1"]
+    sizes = (C.c_int32 * 2)(len(c["l0"]), len(c["l1"]))
+    f = ref_shim.lib.kvzref_me_merge_cost
+    f.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                  C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    cu = np.ascontiguousarray(cu, np.int32)
+    rc = f(ctx, C.byref(p), len(planes), ptrs, lx.ctypes.data, sizes, c["bipred"], c["ctx"][0], c["ctx"][1], bits, cur.ctypes.data, cur.shape[1],
+           pus.ctypes.data, cu.ctypes.data, len(pus), out.ctypes.data)
+    assert rc == 0, rc
+    return out, (bits[0], bits[1], bits[2])
+
+
+def run_merge_host_api(lib, p, c, cur, planes, pus, bits):
+    out = np.zeros(len(pus), MERGE_COST)
+    rf = merge_refs_struct(c, [pl.ctypes.data for pl in planes], p.width, bits)
+    lib.kvz_cuda_me_merge_cost_batch.argtypes = [C.POINTER(Params), C.POINTER(Refs), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    rc = lib.kvz_cuda_me_merge_cost_batch(C.byref(p), C.byref(rf), cur.ctypes.data, cur.shape[1], pus.ctypes.data, len(pus), out.ctypes.data, None)
+    assert rc == 0, rc
+    return out
