@@ -28,6 +28,11 @@ for name in FRAC_CASES:
 for name in CAND_CASES:
     f, crp, clx, cus, col, pus = make_cand_case(name)
     assert run_cand_host_api(host, f, tight(cus), tight(col), tight(pus)).tobytes() == gold["cand/" + name].tobytes(), name
+for name in MERGE_CASES:
+    p, c, cur, planes, pus, cu = make_merge_case(name)
+    bits = tuple(gold["merge/" + name + "/bits"])
+    got = run_merge_host_api(host, p, c, tight(cur), [tight(pl) for pl in planes], tight(pus), bits)
+    assert got.tobytes() == gold["merge/" + name].tobytes(), name
 print("motion search host build: issues 0, results equal to the golden outputs")
 PY
 python - <<'PY'
