@@ -42,7 +42,7 @@ def test_bench_me_bookkeeping(kb, monkeypatch):
     import time
     import kvazaar_b200
     import bench_me
-    for name in ("init", "to_dev", "me_search_batch", "me_frac_search_batch", "me_candidates_batch"):
+    for name in ("init", "to_dev", "me_search_batch", "me_frac_search_batch", "me_candidates_batch", "me_merge_cost_batch"):
         monkeypatch.setattr(kvazaar_b200, name, getattr(kb, name), raising=False)
 
     def timed(fn, iters):
@@ -51,5 +51,5 @@ def test_bench_me_bookkeeping(kb, monkeypatch):
         return (time.perf_counter() - t) * 1e3
     monkeypatch.setattr(bench_me, "timed", timed)
     line = bench_me.measure("416x240", 16, "hexbs", 8, 1, 4, True)
-    assert line["integer"]["identical"] and line["fractional"]["identical"] and line["candidates"]["identical"]
+    assert line["integer"]["identical"] and line["fractional"]["identical"] and line["candidates"]["identical"] and line["merge_analysis"]["identical"]
     assert line["pus"] == (416 // 16) * (240 // 16) and line["fractional"]["positions_per_pu"] > 8

@@ -5,8 +5,8 @@
 
 Every pu x pu block of a synthetic picture pair goes through (the settings of --preset slow: early termination on, WPP + SAO
 limits): the integer search (kvz_cuda_me_search_batch), then the fractional search from its results
-(kvz_cuda_me_frac_search_batch), and the AMVP / merge candidate derivation of as many PUs from a random CU image
-(kvz_cuda_me_candidates_batch).  CUDA events on the launching stream around `iters` launches after 3 warm-up launches.
+(kvz_cuda_me_frac_search_batch), the AMVP / merge candidate derivation of as many PUs from a random CU image
+(kvz_cuda_me_candidates_batch), and the merge analysis of those candidates (kvz_cuda_me_merge_cost_batch).  CUDA events on the launching stream around `iters` launches after 3 warm-up launches.
 The reference arm is oracle/ref_me.c (the reference's search_inter.c compiled in place, its selected AVX2 strategies) on ONE
 host thread: a per-core baseline, not the target.  One JSON line.  bench.py runs this in a subprocess after its own
 measurement and attaches the line as "me_search".
@@ -86,6 +86,32 @@ def measure(res="1920x1080", pu=16, algo="hexbs", bitdepth=8, iters=20, fme_leve
     ms3 = timed(lambda: kb.me_candidates_batch(f, d_cus, d_col, d_cpus, out3), iters)
     cand = out3.cpu().numpy().view(CAND_OUT).copy()
     line["candidates"] = {"kernel": "me_cand_kernel", "ms_per_launch": ms3, "pus_per_s": len(cpus) / ms3 * 1e3}
+
+    # ---- merge analysis of the same PUs with the derived merge candidates (P slice, four reference pictures)
+    from me_cases import MERGE_COST, PU, merge_refs_struct, pictures, run_merge_reference
+    planes = [rf] + [pictures(w, h, bitdepth, 90 + k)[1] for k in range(1, 4)]
+    mcase = {"l0": [0, 1, 2, 3], "l1": [], "bipred": 0, "ctx": (30, 11)}
+    mpus = np.zeros(len(pus), PU)
+    for k in ("x", "y", "w", "h"):
+        mpus[k] = pus[k]
+    mpus["num_merge"] = cand["num_merge"]
+    mpus["merge"] = cand["merge"]
+    d_planes = [kb.to_dev(pl) for pl in planes]
+    mbits = (2.128, 1.376, 0.702)
+    mcu = np.stack([pus["x"], pus["y"], pus["w"], np.zeros(len(pus)), np.zeros(len(pus))], 1).astype(np.int32)
+    shim_m = None
+    if with_reference:
+        shim_m = RefShim(bitdepth)
+        t = time.perf_counter(); want4, mbits = run_merge_reference(shim_m, p, mcase, cur, planes, mpus, mcu); t_m = time.perf_counter() - t
+    refs_struct = merge_refs_struct(mcase, [t_.data_ptr() for t_ in d_planes], w, mbits)
+    d_mpus = kb.to_dev(mpus)
+    out4 = kb.me_merge_cost_batch(p, refs_struct, d_cur, d_mpus)
+    ms4 = timed(lambda: kb.me_merge_cost_batch(p, refs_struct, d_cur, d_mpus, out4), iters)
+    mres = out4.cpu().numpy().view(MERGE_COST).copy()
+    line["merge_analysis"] = {"kernel": "me_merge_kernel", "ms_per_launch": ms4, "pus_per_s": len(pus) / ms4 * 1e3,
+                              "candidates_costed_per_pu": float(mres["size"].mean())}
+    if with_reference:
+        line["merge_analysis"].update({"reference_one_thread_ms": t_m * 1e3, "identical": bool(mres.tobytes() == want4.tobytes())})
 
     if with_reference:
         shim = RefShim(bitdepth)
