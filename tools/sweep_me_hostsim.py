@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Randomised sweep of the motion-search host build (the single-source device code) against the reference's own functions:
 random picture sizes, algorithms, limits, QPs, bit depths and PU lists for the integer search, the fractional search from
-its results, and the candidate derivation.  CPU only (needs oracle/_ref).   python tools/sweep_me_hostsim.py <seed> <count>"""
+its results, the candidate derivation and the merge analysis.  CPU only (needs oracle/_ref).   python tools/sweep_me_hostsim.py <seed> <count>"""
 import ctypes as C
 import os
 import random
@@ -49,7 +49,19 @@ for it in range(count):
                                seed=2000 * seed + it, n=200)
     f, crp, clx, cus, col, cpus = M.make_cand_case(cname)
     ok3 = M.run_cand_host_api(host, f, cus, col, cpus).tobytes() == M.run_cand_reference(refs[8], f, crp, clx, cus, col, cpus).tobytes()
+    # merge analysis
+    mname = f"msweep{seed}_{it}"
+    npic = rnd.randint(1, 4)
+    ml0 = [rnd.randrange(npic) for _ in range(rnd.randint(1, 3))]
+    ml1 = [rnd.randrange(npic) for _ in range(rnd.randint(0, 3))]
+    M.MERGE_CASES[mname] = dict(w=w, h=h, bd=bd, pics=npic, l0=ml0, l1=ml1, bipred=int(bool(ml1) and rnd.random() < 0.8), mvc=rnd.choice([0, 0, 1, 4]),
+                                wpp=rnd.choice([0, 1]), delay=rnd.choice([0, 8, 10]), qp=rnd.randint(10, 45), ctx=(rnd.randint(0, 125), rnd.randint(0, 125)),
+                                seed=3000 * seed + it, n=120)
+    mp, mc, mcur, mplanes, mpus, mcu = M.make_merge_case(mname)
+    mwant, mbits = M.run_merge_reference(refs[bd], mp, mc, mcur, mplanes, mpus, mcu)
+    ok4 = M.run_merge_host_api(host, mp, mc, mcur, mplanes, mpus, mbits).tobytes() == mwant.tobytes()
+    ok3 = ok3 and ok4
     if not (ok and ok2 and ok3):
         bad += 1
-        print("DIFF", M.CASES[name], "integer", ok, "frac level", level, ok2, "cand", M.CAND_CASES[cname], ok3, flush=True)
+        print("DIFF", M.CASES[name], "integer", ok, "frac level", level, ok2, "cand+merge", M.CAND_CASES[cname], ok3, "merge", M.MERGE_CASES[mname], ok4, flush=True)
 print("done", count, "bad", bad, flush=True)
