@@ -214,6 +214,12 @@ ME_FN void frac_search_pu(const Lanes &ln, const kvz_cuda_me_params &p, const kv
                           kvz_cuda_me_result *out)
 {
   const int sqx[9] = { 0, -1, 1, 0, 0, -1, 1, -1, 1 }, sqy[9] = { 0, 0, 0, -1, 1, -1, -1, 1, 1 };
+  if (!pu_valid(p, pu)) {
+    Best none;
+    none.cost = kMaxDouble; none.bits = kMaxInt; none.mvx = none.mvy = 0; none.points = 0;
+    write_result(ln, none, out);
+    return;
+  }
   int mx = pu.start_mv[0] >> 2, my = pu.start_mv[1] >> 2;
   int32_t points = 1;
   // integer position.  The reference keeps the costs in an unsigned and adds the (double) MV cost into it: truncation.

@@ -159,8 +159,11 @@ ME_FN void merge_cost_pu(const Lanes &ln, const kvz_cuda_me_params &p, const kvz
   m.size = 0;
   for (int i = 0; i < 5; ++i) { m.cost[i] = kMaxDouble; m.bits[i] = 0; m.keys[i] = -1; m.merge_idx[i] = 0; }
   m.pad[0] = m.pad[1] = 0;
-  for (int idx = 0; idx < pu.num_merge; ++idx) {
+  const int n_cand = pu_valid(p, pu) ? pu.num_merge : 0;
+  for (int idx = 0; idx < n_cand; ++idx) {
     const kvz_cuda_me_merge &cand = pu.merge[idx];
+    if (cand.dir < 1 || cand.dir > 3) continue;                                   // not a motion candidate: a bad record, not a reference case
+    if (((cand.dir & 1) && rs.plane[rf.ref_LX[0][cand.ref[0] & 15] & 15] == nullptr) || ((cand.dir & 2) && rs.plane[rf.ref_LX[1][cand.ref[1] & 15] & 15] == nullptr)) continue;
     if (cand.dir == 3 && !rf.bipred) continue;
     if (cand.dir == 3 && !(pu.w + pu.h > 12)) continue;
     bool dup = false;

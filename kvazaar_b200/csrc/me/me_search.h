@@ -63,6 +63,14 @@ struct Best {
   int32_t points;
 };
 
+// A PU record the device can work on: inside the picture, 4..64 samples in steps of 4, at most five merge candidates.
+// (The reference asserts the same about its callers; a C ABI must not fault on a bad record.)
+ME_FN bool pu_valid(const kvz_cuda_me_params &p, const kvz_cuda_me_pu &pu)
+{
+  return pu.w >= 4 && pu.h >= 4 && pu.w <= 64 && pu.h <= 64 && (pu.w & 3) == 0 && (pu.h & 3) == 0 && pu.x >= 0 && pu.y >= 0 &&
+         pu.x + pu.w <= p.width && pu.y + pu.h <= p.height && pu.num_merge >= 0 && pu.num_merge <= 5;
+}
+
 // fracmv_within_tile: may the block at MV (x, y) (1/4 pel) be referenced?
 ME_FN bool mv_allowed(const kvz_cuda_me_params &p, const kvz_cuda_me_pu &pu, int x, int y)
 {
@@ -382,6 +390,8 @@ ME_FN Best search_pu_best(const Lanes &ln, const kvz_cuda_me_params &p, const kv
   best.cost = kMaxDouble;
   best.bits = kMaxInt;
   best.points = 0;
+  best.mvx = best.mvy = 0;
+  if (!pu_valid(p, pu)) return best;       // "no point was allowed"
   int sx = pu.start_mv[0], sy = pu.start_mv[1];
   if (!mv_allowed(p, pu, sx, sy)) { sx = 0; sy = 0; }      // search_inter.c:1334-1337
   best.mvx = sx;

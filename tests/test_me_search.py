@@ -209,3 +209,25 @@ def test_cuda_candidates_feed_the_search(cuda_lib, ref):
     got, want = _dev_api(kb, p, cur, rf, pus), run_reference(ref, p, cur, rf, pus)
     assert same(got, want), _explain(got, want, pus)
     torch.cuda.synchronize()
+
+
+def test_bad_pu_records_do_not_fault():
+    """records outside the picture / with impossible sizes come back as "nothing found" instead of reading out of bounds"""
+    from _me_cases import MERGE_COST, make_merge_case, run_frac_host_api, run_merge_host_api
+    lib = _hostsim()
+    p, cur, rf, pus = make_case("hexbs_et_sensitive")
+    bad = pus[:6].copy()
+    bad[0]["x"] = p.width - 4            # sticks out on the right
+    bad[1]["y"] = -8
+    bad[2]["w"] = 0
+    bad[3]["h"] = 128
+    bad[4]["w"] = 10                     # not a multiple of 4
+    bad[5]["num_merge"] = 9
+    for got in (run_host_api(lib, p, cur, rf, bad), run_frac_host_api(lib, p, 4, cur, rf, bad)):
+        assert (got["bits"] == 0x7FFFFFFF).all() and (got["cost"] == 1.7e308).all() and (got["mv"] == 0).all()
+    mp, mc, mcur, mplanes, mpus, _ = make_merge_case("merge_b_two_refs")
+    mbad = mpus[:3].copy()
+    mbad[0]["x"], mbad[1]["h"], mbad[2]["num_merge"] = mp.width, 3, 6
+    m = run_merge_host_api(lib, mp, mc, mcur, mplanes, mbad, (1.0, 1.0, 1.0))
+    assert (m["size"] == 0).all()
+    assert m.dtype == MERGE_COST
