@@ -278,8 +278,12 @@ ME_FN int merge_candidates(const kvz_cuda_me_frame &f, Neighbours nb, const kvz_
 ME_FN void candidates_of_pu(const kvz_cuda_me_frame &f, const CuImage &cur, const CuImage &col, const kvz_cuda_me_cand_pu &pu, kvz_cuda_me_cand_out *out)
 {
   Neighbours nb = { { nullptr, nullptr }, { nullptr, nullptr, nullptr }, nullptr, nullptr };
-  spatial_neighbours(cur, f, pu.x, pu.y, pu.w, pu.h, nb);
-  temporal_neighbours(col, f, pu.x, pu.y, pu.w, pu.h, nb);
+  // a PU outside the picture (a bad record) gets no neighbours: zero AMVP candidates, zero-motion merge candidates
+  const bool valid = pu.w >= 4 && pu.h >= 4 && pu.w <= 64 && pu.h <= 64 && pu.x >= 0 && pu.y >= 0 && pu.x + pu.w <= f.width && pu.y + pu.h <= f.height;
+  if (valid) {
+    spatial_neighbours(cur, f, pu.x, pu.y, pu.w, pu.h, nb);
+    temporal_neighbours(col, f, pu.x, pu.y, pu.w, pu.h, nb);
+  }
   kvz_cuda_me_cand_out o;
   for (int l = 0; l < 2; ++l)
     for (int c = 0; c < 2; ++c) o.mv_cand[l][c][0] = o.mv_cand[l][c][1] = 0;
