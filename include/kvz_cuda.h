@@ -425,6 +425,27 @@ typedef struct kvz_cuda_me_merge_cost {
 int kvz_cuda_me_merge_cost_batch(const kvz_cuda_me_params *p, const kvz_cuda_me_refs *refs, const void *cur_dev, int cur_stride,
                                  const kvz_cuda_me_pu *pus_dev, int count, kvz_cuda_me_merge_cost *out_dev, void *stream);
 
+/* Bi-prediction from the best uni-predictions of the two lists (search_pu_inter, src/search_inter.c:1937-2031, the
+ * cfg.fast_bipred path every preset uses): kvz_inter_recon_bipred luma + kvz_satd_any_size, the MV costs of both MVs
+ * against info->mv_cand (calc_mvd_cost, mv_shift 0), reference-index and direction bits, and select_mv_cand for each
+ * list.  The caller passes the MVs / reference indices of the two uni-predictions and the AMVP candidates info->mv_cand
+ * holds at that point (those of list 1: kvz_cuda_me_candidates_batch with the PU's mv_ref). */
+typedef struct kvz_cuda_me_bipred_pu {
+  int16_t x, y, w, h;
+  int16_t mv[2][2];                 /* best_unipred[0]->inter.mv[0], best_unipred[1]->inter.mv[1] (1/4 pel) */
+  uint8_t mv_ref[2];                /* their reference indices in L0 / L1 */
+  uint8_t pad[2];
+  int16_t mv_cand[2][2];            /* info->mv_cand */
+} kvz_cuda_me_bipred_pu;
+typedef struct kvz_cuda_me_bipred_result {
+  double  cost;                     /* best_bipred_cost; 1.7e308 when bi-prediction may not be used (cfg.bipred off, w + h < 16) */
+  int32_t bits;                     /* bitcost[0] + bitcost[1] + extra_bits */
+  uint8_t mv_cand_idx[2];           /* CU_SET_MV_CAND of each list */
+  uint8_t valid, pad;
+} kvz_cuda_me_bipred_result;
+int kvz_cuda_me_bipred_batch(const kvz_cuda_me_params *p, const kvz_cuda_me_refs *refs, const void *cur_dev, int cur_stride,
+                             const kvz_cuda_me_bipred_pu *pus_dev, int count, kvz_cuda_me_bipred_result *out_dev, void *stream);
+
 /* AMVP and merge candidates of a batch of PUs from a snapshot of the CU records (me_search.cu), as
  *     kvz_inter_get_mv_cand_cua   src/inter.c:1365-1383 (get_spatial_merge_candidates_cua :1015-1076,
  *                                 get_temporal_merge_candidates :836-907, get_mv_cand_from_candidates :1225-1318,

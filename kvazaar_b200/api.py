@@ -661,3 +661,19 @@ def me_merge_cost_batch(params, refs, cur, pus, out=None):
         out = torch.empty(count * ME_MERGE_COST.itemsize, dtype=torch.uint8, device=cur.device)
     _ck(lib().kvz_cuda_me_merge_cost_batch(C.byref(params), C.byref(refs), _p(cur), C.c_int(cur.stride(0)), _p(pus), C.c_int(count), _p(out), _stream()))
     return out
+
+
+# bi-prediction from two uni-predictions: kvz_cuda_me_bipred_pu / kvz_cuda_me_bipred_result
+ME_BIPRED_PU = np.dtype([("x", "<i2"), ("y", "<i2"), ("w", "<i2"), ("h", "<i2"), ("mv", "<i2", (2, 2)), ("mv_ref", "u1", (2,)), ("pad", "u1", (2,)),
+                         ("mv_cand", "<i2", (2, 2))])
+ME_BIPRED_RESULT = np.dtype([("cost", "<f8"), ("bits", "<i4"), ("mv_cand_idx", "u1", (2,)), ("valid", "u1"), ("pad", "u1")])
+
+
+def me_bipred_batch(params, refs, cur, pus, out=None):
+    """Cost of bi-predicting `pus` (CUDA byte tensor of ME_BIPRED_PU records) from their two uni-predictions; ME_BIPRED_RESULT records."""
+    torch = _torch()
+    count = pus.numel() // ME_BIPRED_PU.itemsize
+    if out is None:
+        out = torch.empty(count * ME_BIPRED_RESULT.itemsize, dtype=torch.uint8, device=cur.device)
+    _ck(lib().kvz_cuda_me_bipred_batch(C.byref(params), C.byref(refs), _p(cur), C.c_int(cur.stride(0)), _p(pus), C.c_int(count), _p(out), _stream()))
+    return out

@@ -190,4 +190,46 @@ ME_FN void merge_cost_pu(const Lanes &ln, const kvz_cuda_me_params &p, const kvz
   if (ln.lane == 0) *out = m;
 }
 
+// ---- bi-prediction from the two best uni-predictions (search_pu_inter, search_inter.c:1937-2031)
+static_assert(sizeof(kvz_cuda_me_bipred_pu) == 28 && sizeof(kvz_cuda_me_bipred_result) == 16, "record layouts are part of the ABI");
+
+// select_mv_cand without a cost output (search_inter.c:351-391): 0 when both candidates are equal
+ME_FN int pick_mv_cand(const int16_t mv_cand[2][2], int mvx, int mvy)
+{
+  if (mv_cand[0][0] == mv_cand[1][0] && mv_cand[0][1] == mv_cand[1][1]) return 0;
+  const uint32_t c0 = mvd_bits(mvx - mv_cand[0][0], mvy - mv_cand[0][1]);
+  const uint32_t c1 = mvd_bits(mvx - mv_cand[1][0], mvy - mv_cand[1][1]);
+  return c1 < c0 ? 1 : 0;
+}
+
+template <typename Pix>
+ME_FN void bipred_pu(const Lanes &ln, const kvz_cuda_me_params &p, const kvz_cuda_me_refs &rf, const RefSet<Pix> &rs, const kvz_cuda_me_bipred_pu &bp,
+                     const Planes<Pix> &pl, kvz_cuda_me_bipred_result *out)
+{
+  kvz_cuda_me_bipred_result r;
+  r.cost = kMaxDouble; r.bits = 0; r.mv_cand_idx[0] = r.mv_cand_idx[1] = 0; r.valid = 0; r.pad = 0;
+  kvz_cuda_me_pu pu;                                   // the geometry and AMVP candidates in the shape the shared helpers take
+  pu.x = bp.x; pu.y = bp.y; pu.w = bp.w; pu.h = bp.h; pu.num_merge = 0; pu.pad = 0;
+  pu.start_mv[0] = pu.start_mv[1] = 0;
+  for (int c = 0; c < 2; ++c) { pu.mv_cand[c][0] = bp.mv_cand[c][0]; pu.mv_cand[c][1] = bp.mv_cand[c][1]; }
+  const bool planes_ok = rs.plane[rf.ref_LX[0][bp.mv_ref[0] & 15] & 15] != nullptr && rs.plane[rf.ref_LX[1][bp.mv_ref[1] & 15] & 15] != nullptr;
+  if (pu_valid(p, pu) && rf.bipred && bp.w + bp.h >= 16 && planes_ok) {
+    kvz_cuda_me_merge cand;
+    cand.dir = 3; cand.pad = 0;
+    for (int l = 0; l < 2; ++l) { cand.mv[l][0] = bp.mv[l][0]; cand.mv[l][1] = bp.mv[l][1]; cand.ref[l] = bp.mv_ref[l]; }
+    double cost = (double)merge_satd(ln, p, rf, rs, pu, pl, cand);
+    const uint32_t b0 = qpel_mv_bits(pu, bp.mv[0][0], bp.mv[0][1]), b1 = qpel_mv_bits(pu, bp.mv[1][0], bp.mv[1][1]);
+    cost += (double)b0 * p.lambda_sqrt;
+    cost += (double)b1 * p.lambda_sqrt;
+    const int extra_bits = bp.mv_ref[0] + bp.mv_ref[1] + 2;
+    cost += p.lambda_sqrt * extra_bits;
+    r.cost = cost;
+    r.bits = (int32_t)(b0 + b1) + extra_bits;
+    r.mv_cand_idx[0] = (uint8_t)pick_mv_cand(bp.mv_cand, bp.mv[0][0], bp.mv[0][1]);
+    r.mv_cand_idx[1] = (uint8_t)pick_mv_cand(bp.mv_cand, bp.mv[1][0], bp.mv[1][1]);
+    r.valid = 1;
+  }
+  if (ln.lane == 0) *out = r;
+}
+
 }  // namespace kvzme

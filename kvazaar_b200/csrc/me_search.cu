@@ -66,6 +66,23 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) me_merge_kernel(kvz_cuda_me
   }
 }
 
+// bi-prediction from two uni-predictions: one warp per PU
+template <typename Pix>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) me_bipred_kernel(kvz_cuda_me_params p, kvz_cuda_me_refs rf, const Pix *__restrict__ cur, int cur_stride,
+                                                                      const kvz_cuda_me_bipred_pu *__restrict__ pus, int count,
+                                                                      kvz_cuda_me_bipred_result *__restrict__ out)
+{
+  const int warp = threadIdx.x >> 5;
+  const kvzme::Lanes ln = { (int)(threadIdx.x & 31), 32 };
+  const kvzme::Planes<Pix> pl = { cur, nullptr, cur_stride, 0 };
+  kvzme::RefSet<Pix> rs;
+  for (int i = 0; i < 16; ++i) { rs.plane[i] = (const Pix *)rf.plane[i]; rs.stride[i] = rf.stride[i]; }
+  for (int i = blockIdx.x * kWarpsPerCta + warp; i < count; i += gridDim.x * kWarpsPerCta) {
+    const kvz_cuda_me_bipred_pu bp = pus[i];
+    kvzme::bipred_pu<Pix>(ln, p, rf, rs, bp, pl, &out[i]);
+  }
+}
+
 // AMVP / merge candidates: one thread per PU, integer logic over the CU records (12-byte records, read through L1/L2)
 __global__ void __launch_bounds__(128) me_cand_kernel(kvz_cuda_me_frame f, const kvz_cuda_me_cu *__restrict__ cus, int cu_stride,
                                                       const kvz_cuda_me_cu *__restrict__ col_cus, int col_stride,
@@ -241,6 +258,26 @@ extern "C" int kvz_cuda_me_merge_cost_batch(const kvz_cuda_me_params *p, const k
     me_merge_kernel<uint8_t><<<grid, kWarpsPerCta * 32, 0, kvzc::as_stream(stream)>>>(*p, *refs, (const uint8_t *)cur_dev, cur_stride, pus_dev, count, out_dev);
   else
     me_merge_kernel<uint16_t><<<grid, kWarpsPerCta * 32, 0, kvzc::as_stream(stream)>>>(*p, *refs, (const uint16_t *)cur_dev, cur_stride, pus_dev, count, out_dev);
+  KVZC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int kvz_cuda_me_bipred_batch(const kvz_cuda_me_params *p, const kvz_cuda_me_refs *refs, const void *cur_dev, int cur_stride,
+                                        const kvz_cuda_me_bipred_pu *pus_dev, int count, kvz_cuda_me_bipred_result *out_dev, void *stream)
+{
+  KVZC_REQUIRE_DEVICE();
+  KVZC_ARG(p && refs && cur_dev && count >= 0 && (count == 0 || (pus_dev && out_dev)));
+  KVZC_ARG(kvzme::params_supported(*p) == 0 && cur_stride >= p->width);
+  for (int l = 0; l < 2; ++l)
+    for (int i = 0; i < 16; ++i) KVZC_ARG(refs->ref_LX[l][i] < 16);
+  if (count == 0) return 0;
+  const int ctas = (count + kWarpsPerCta - 1) / kWarpsPerCta;
+  const int cap = kvzc::g_sm_count > 0 ? kvzc::g_sm_count * 16 : 148 * 16;
+  const int grid = ctas < cap ? ctas : cap;
+  if (p->bitdepth == 8)
+    me_bipred_kernel<uint8_t><<<grid, kWarpsPerCta * 32, 0, kvzc::as_stream(stream)>>>(*p, *refs, (const uint8_t *)cur_dev, cur_stride, pus_dev, count, out_dev);
+  else
+    me_bipred_kernel<uint16_t><<<grid, kWarpsPerCta * 32, 0, kvzc::as_stream(stream)>>>(*p, *refs, (const uint16_t *)cur_dev, cur_stride, pus_dev, count, out_dev);
   KVZC_LAUNCHED();
   return 0;
 }

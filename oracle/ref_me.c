@@ -421,3 +421,72 @@ int kvzref_me_merge_cost(kvzref_ctx *ctx, const kvz_cuda_me_params *p, int n_pic
   state->lambda_sqrt = saved_lambda_sqrt;
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Bi-prediction from two uni-predictions (search_pu_inter, search_inter.c:1937-2031) with the reference's own
+ * kvz_inter_recon_bipred, kvz_satd_any_size, calc_mvd_cost and select_mv_cand; only their sequence is restated (the
+ * AMVP candidates info->mv_cand holds at that point are an input).  Parity checker for kvz_cuda_me_bipred_batch. */
+int kvzref_me_bipred(kvzref_ctx *ctx, const kvz_cuda_me_params *p, int n_pics, const kvz_pixel *const *pic_planes, const uint8_t *ref_LX /* [2][16] */,
+                     int bipred, const kvz_pixel *cur, int cur_stride, const kvz_cuda_me_bipred_pu *pus, int count, kvz_cuda_me_bipred_result *out)
+{
+  encoder_state_t *state = &ctx->enc->states[0];
+  encoder_control_t *ctrl = (encoder_control_t *)state->encoder_control;
+  if (p->bitdepth != KVZ_BIT_DEPTH) return -1;
+  if (state->tile->frame->width != p->width || state->tile->frame->height != p->height) return -2;
+  const kvz_config saved_cfg = ctrl->cfg;
+  const double saved_lambda_sqrt = state->lambda_sqrt;
+  image_list_t *saved_ref = state->frame->ref;
+  uint8_t saved_LX[2][16]; memcpy(saved_LX, state->frame->ref_LX, 32);
+  ctrl->cfg.bipred = bipred;
+  ctrl->cfg.mv_rdo = 0;
+  state->lambda_sqrt = p->lambda_sqrt;
+  image_list_t *list = kvz_image_list_alloc(16);
+  kvz_picture *pics[16];
+  for (int i = 0; i < 16; ++i) {
+    pics[i] = calloc(1, sizeof(kvz_picture));
+    pics[i]->y = (kvz_pixel *)pic_planes[i < n_pics ? i : 0];
+    pics[i]->width = p->width; pics[i]->height = p->height; pics[i]->stride = p->width;
+    list->images[i] = pics[i];
+  }
+  list->used_size = (uint32_t)n_pics;
+  state->frame->ref = list;
+  memcpy(state->frame->ref_LX, ref_LX, 32);
+
+  lcu_t *lcu = calloc(1, sizeof(lcu_t));
+  for (int i = 0; i < count; ++i) {
+    const kvz_cuda_me_bipred_pu *u = &pus[i];
+    const int x = u->x, y = u->y, width = u->w, height = u->h;
+    memset(&out[i], 0, sizeof(out[i]));
+    out[i].cost = MAX_DOUBLE;
+    const bool can_use_bipred = ctrl->cfg.bipred && width + height >= 16;      /* the slice-type condition is the caller's */
+    if (!can_use_bipred) continue;
+    for (int r = 0; r < height; ++r)
+      memcpy(&lcu->ref.y[(SUB_SCU(y) + r) * LCU_WIDTH + SUB_SCU(x)], &cur[(size_t)(y + r) * cur_stride + x], (size_t)width * sizeof(kvz_pixel));
+    int16_t mv[2][2] = { { u->mv[0][0], u->mv[0][1] }, { u->mv[1][0], u->mv[1][1] } };
+    int16_t mv_cand[2][2] = { { u->mv_cand[0][0], u->mv_cand[0][1] }, { u->mv_cand[1][0], u->mv_cand[1][1] } };
+    kvz_inter_recon_bipred(state, list->images[state->frame->ref_LX[0][u->mv_ref[0]]], list->images[state->frame->ref_LX[1][u->mv_ref[1]]],
+                           x, y, width, height, mv, lcu, true, false);
+    const kvz_pixel *rec = &lcu->rec.y[SUB_SCU(y) * LCU_WIDTH + SUB_SCU(x)];
+    const kvz_pixel *src = &lcu->ref.y[SUB_SCU(y) * LCU_WIDTH + SUB_SCU(x)];
+    double best_bipred_cost = kvz_satd_any_size(width, height, rec, LCU_WIDTH, src, LCU_WIDTH);
+    double bitcost[2] = { 0, 0 };
+    best_bipred_cost += calc_mvd_cost(state, mv[0][0], mv[0][1], 0, mv_cand, NULL, 0, 0, &bitcost[0]);
+    best_bipred_cost += calc_mvd_cost(state, mv[1][0], mv[1][1], 0, mv_cand, NULL, 0, 0, &bitcost[1]);
+    const uint8_t mv_ref_coded[2] = { u->mv_ref[0], u->mv_ref[1] };
+    const int extra_bits = mv_ref_coded[0] + mv_ref_coded[1] + 2 /* mv dir cost */;
+    best_bipred_cost += state->lambda_sqrt * extra_bits;
+    out[i].cost = best_bipred_cost;
+    out[i].bits = (int32_t)(bitcost[0] + bitcost[1] + extra_bits);
+    for (int reflist = 0; reflist < 2; reflist++) out[i].mv_cand_idx[reflist] = (uint8_t)select_mv_cand(state, mv_cand, mv[reflist][0], mv[reflist][1], NULL);
+    out[i].valid = 1;
+  }
+  free(lcu);
+  state->frame->ref = saved_ref;
+  memcpy(state->frame->ref_LX, saved_LX, 32);
+  for (int i = 0; i < 16; ++i) { list->images[i] = NULL; free(pics[i]); }
+  list->used_size = 0;
+  kvz_image_list_destroy(list);
+  ctrl->cfg = saved_cfg;
+  state->lambda_sqrt = saved_lambda_sqrt;
+  return 0;
+}

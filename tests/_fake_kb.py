@@ -78,3 +78,13 @@ class FakeKB:
         assert rc == 0
         self.launches += 1
         return out
+
+    def me_bipred_batch(self, params, refs, cur, pus, out=None):
+        count = pus.numel() // api.ME_BIPRED_PU.itemsize
+        if out is None:
+            out = torch.empty(count * api.ME_BIPRED_RESULT.itemsize, dtype=torch.uint8)
+        rc = self.lib.kvz_cuda_me_bipred_batch(C.byref(params), C.byref(refs), self._p(cur), C.c_int(cur.stride(0)), self._p(pus), C.c_int(count),
+                                               self._p(out), None)
+        assert rc == 0
+        self.launches += 1
+        return out

@@ -94,3 +94,23 @@ extern "C" int kvz_cuda_me_merge_cost_batch(const kvz_cuda_me_params *p, const k
   else run_merge<uint16_t>(p, refs, cur, cur_stride, pus, count, out);
   return 0;
 }
+
+template <typename Pix>
+static void run_bipred(const kvz_cuda_me_params *p, const kvz_cuda_me_refs *rf, const void *cur, int cur_stride, const kvz_cuda_me_bipred_pu *pus, int count,
+                       kvz_cuda_me_bipred_result *out)
+{
+  const kvzme::Lanes ln = { 0, 32 };
+  const kvzme::Planes<Pix> pl = { (const Pix *)cur, nullptr, cur_stride, 0 };
+  kvzme::RefSet<Pix> rs;
+  for (int i = 0; i < 16; ++i) { rs.plane[i] = (const Pix *)rf->plane[i]; rs.stride[i] = rf->stride[i]; }
+  for (int i = 0; i < count; ++i) kvzme::bipred_pu<Pix>(ln, *p, *rf, rs, pus[i], pl, &out[i]);
+}
+
+extern "C" int kvz_cuda_me_bipred_batch(const kvz_cuda_me_params *p, const kvz_cuda_me_refs *refs, const void *cur, int cur_stride,
+                                        const kvz_cuda_me_bipred_pu *pus, int count, kvz_cuda_me_bipred_result *out, void *)
+{
+  if (!p || !refs || kvzme::params_supported(*p) != 0) return -2;
+  if (p->bitdepth == 8) run_bipred<uint8_t>(p, refs, cur, cur_stride, pus, count, out);
+  else run_bipred<uint16_t>(p, refs, cur, cur_stride, pus, count, out);
+  return 0;
+}

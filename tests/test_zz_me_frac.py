@@ -14,8 +14,8 @@ import os
 import numpy as np
 import pytest
 
-from _me_cases import (CASES, FRAC_CASES, GPU_FIRST_RUN_DONE, MERGE_CASES, MERGE_COST, RESULT, make_merge_case, merge_refs_struct, run_merge_host_api,
-                       run_merge_reference)
+from _me_cases import (BIPRED_CASES, BIPRED_RESULT, CASES, FRAC_CASES, GPU_FIRST_RUN_DONE, MERGE_CASES, MERGE_COST, RESULT, make_bipred_case, make_merge_case,
+                       merge_refs_struct, run_bipred_host_api, run_bipred_reference, run_merge_host_api, run_merge_reference)
 from _me_cases import grid_case, make_frac_case, run_frac_host_api, run_frac_reference, run_host_api, run_reference, same
 from test_me_search import _explain, _hostsim, check_cuda_case
 
@@ -83,6 +83,23 @@ def test_merge_hostbuild_matches_golden(name):
     got = run_merge_host_api(_hostsim(), p, c, cur, planes, pus, bits)
     assert got.tobytes() == gold.tobytes(), _explain_merge(got, gold, pus)
     assert got["size"].max() >= 3 and got["size"].min() <= 1           # several accepted candidates; PUs where (almost) none may be used
+
+
+# ---- bi-prediction from the two best uni-predictions (kvz_cuda_me_bipred_batch; src/search_inter.c:1937-2031)
+def _golden_bipred(name):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "me_search.npz"))
+    return g["bipred/" + name].view(BIPRED_RESULT)
+
+
+@pytest.mark.parametrize("name", sorted(BIPRED_CASES))
+def test_bipred_reference_and_hostbuild_match_golden(name, ref, ref10):
+    p, c, cur, planes, pus = make_bipred_case(name)
+    want = run_bipred_reference(ref if p.bitdepth == 8 else ref10, p, c, cur, planes, pus)
+    assert want.tobytes() == _golden_bipred(name).tobytes()
+    got = run_bipred_host_api(_hostsim(), p, c, cur, planes, pus)
+    bad = [i for i in range(len(pus)) if got[i].tobytes() != want[i].tobytes()]
+    assert not bad, (len(bad), pus[bad[0]], got[bad[0]], want[bad[0]])
+    assert bool(want["valid"].any()) == bool(c["bipred"])
 
 
 # ------------------------------------------------------------------------------------------------ GPU (the product)
@@ -158,6 +175,21 @@ def test_cuda_merge_analysis_matches_golden_and_reference(cuda_lib, name, ref, r
     got = out.cpu().numpy().view(MERGE_COST).copy()
     assert got.tobytes() == want.tobytes(), _explain_merge(got, want, pus)
     assert got.tobytes() == _golden_merge(name)[0].tobytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(BIPRED_CASES))
+def test_cuda_bipred_matches_golden_and_reference(cuda_lib, name, ref, ref10):
+    import torch
+    kb = cuda_lib
+    p, c, cur, planes, pus = make_bipred_case(name)
+    want = run_bipred_reference(ref if p.bitdepth == 8 else ref10, p, c, cur, planes, pus)
+    d_planes = [kb.to_dev(pl) for pl in planes]
+    rf = merge_refs_struct(c, [t.data_ptr() for t in d_planes], p.width, (0.0, 0.0, 0.0))
+    out = kb.me_bipred_batch(p, rf, kb.to_dev(cur), kb.to_dev(pus))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy().view(BIPRED_RESULT).copy()
+    assert got.tobytes() == want.tobytes() and got.tobytes() == _golden_bipred(name).tobytes()
 
 
 # ------------------------------------------------------------------------------------------------ CTU driver, chroma mode search

@@ -33,6 +33,10 @@ for name in MERGE_CASES:
     bits = tuple(gold["merge/" + name + "/bits"])
     got = run_merge_host_api(host, p, c, tight(cur), [tight(pl) for pl in planes], tight(pus), bits)
     assert got.tobytes() == gold["merge/" + name].tobytes(), name
+for name in BIPRED_CASES:
+    p, c, cur, planes, pus = make_bipred_case(name)
+    got = run_bipred_host_api(host, p, c, tight(cur), [tight(pl) for pl in planes], tight(pus))
+    assert got.tobytes() == gold["bipred/" + name].tobytes(), name
 print("motion search host build: issues 0, results equal to the golden outputs")
 PY
 python - <<'PY'

@@ -10,7 +10,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from _me_cases import (CAND_CASES, CASES, FRAC_CASES, MERGE_CASES, make_cand_case, make_case, make_frac_case, make_merge_case,  # noqa: E402
+from _me_cases import (BIPRED_CASES, CAND_CASES, CASES, FRAC_CASES, MERGE_CASES, make_bipred_case, run_bipred_reference, make_cand_case, make_case, make_frac_case, make_merge_case,  # noqa: E402
                        run_cand_reference, run_frac_reference, run_merge_reference, run_reference)
 from _oracle import Ref  # noqa: E402
 
@@ -42,4 +42,9 @@ for name in sorted(MERGE_CASES):
     out["merge/" + name] = np.frombuffer(r.tobytes(), np.uint8).copy()
     out["merge/" + name + "/bits"] = np.array(bits, np.float64)
     print("merge", name, len(pus), "PUs")
+for name in sorted(BIPRED_CASES):
+    p, c, cur, planes, pus = make_bipred_case(name)
+    r = run_bipred_reference(refs.setdefault(p.bitdepth, Ref(p.bitdepth)), p, c, cur, planes, pus)
+    out["bipred/" + name] = np.frombuffer(r.tobytes(), np.uint8).copy()
+    print("bipred", name, len(pus), "PUs")
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "me_search.npz"), **out)

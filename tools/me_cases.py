@@ -488,3 +488,56 @@ def run_merge_host_api(lib, p, c, cur, planes, pus, bits):
     rc = lib.kvz_cuda_me_merge_cost_batch(C.byref(p), C.byref(rf), cur.ctypes.data, cur.shape[1], pus.ctypes.data, len(pus), out.ctypes.data, None)
     assert rc == 0, rc
     return out
+
+
+# ------------------------------------------------------------------------------------------------ bi-prediction from two uni-predictions
+from kvazaar_b200.api import ME_BIPRED_PU as BIPRED_PU, ME_BIPRED_RESULT as BIPRED_RESULT  # noqa: E402
+
+assert BIPRED_PU.itemsize == 28 and BIPRED_RESULT.itemsize == 16
+
+
+def make_bipred_case(name):
+    """the pictures, reference lists and PU geometry of a B merge case; MVs / reference indices / AMVP candidates at random"""
+    p, c, cur, planes, mpus, _ = make_merge_case(name)
+    r = np.random.default_rng(7000 + c["seed"])
+    n = len(mpus)
+    pus = np.zeros(n, BIPRED_PU)
+    for k in ("x", "y", "w", "h"):
+        pus[k] = mpus[k]
+    pus["mv"] = r.integers(-48, 49, (n, 2, 2))
+    ints = r.integers(0, 3, (n, 2)) == 0
+    pus["mv"][ints] = (pus["mv"][ints] >> 2) << 2                 # integer MVs: the copy path of one or both lists
+    far = r.integers(0, 15, n) == 0
+    pus["mv"][far] = r.integers(-500, 501, (int(far.sum()), 2, 2))
+    pus["mv_ref"][:, 0] = r.integers(0, len(c["l0"]), n)
+    pus["mv_ref"][:, 1] = r.integers(0, max(1, len(c["l1"])), n)
+    pus["mv_cand"] = r.integers(-40, 41, (n, 2, 2))
+    same = r.integers(0, 4, n) == 0
+    pus["mv_cand"][same, 1] = pus["mv_cand"][same, 0]
+    return p, c, cur, planes, pus
+
+
+def run_bipred_reference(ref_shim, p, c, cur, planes, pus):
+    out = np.zeros(len(pus), BIPRED_RESULT)
+    ctx = ref_shim.ctx(27, 0, 0, p.width, p.height)
+    ptrs = (C.c_void_p * 16)(*[planes[i if i < len(planes) else 0].ctypes.data for i in range(16)])
+    lx = np.zeros((2, 16), np.uint8)
+    lx[0, :len(c["l0"])] = c["l0"]
+    lx[1, :len(c["l1"])] = c["l1"]
+    f = ref_shim.lib.kvzref_me_bipred
+    f.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    rc = f(ctx, C.byref(p), len(planes), ptrs, lx.ctypes.data, c["bipred"], cur.ctypes.data, cur.shape[1], pus.ctypes.data, len(pus), out.ctypes.data)
+    assert rc == 0, rc
+    return out
+
+
+def run_bipred_host_api(lib, p, c, cur, planes, pus):
+    out = np.zeros(len(pus), BIPRED_RESULT)
+    rf = merge_refs_struct(c, [pl.ctypes.data for pl in planes], p.width, (0.0, 0.0, 0.0))
+    lib.kvz_cuda_me_bipred_batch.argtypes = [C.POINTER(Params), C.POINTER(Refs), C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    rc = lib.kvz_cuda_me_bipred_batch(C.byref(p), C.byref(rf), cur.ctypes.data, cur.shape[1], pus.ctypes.data, len(pus), out.ctypes.data, None)
+    assert rc == 0, rc
+    return out
+
+
+BIPRED_CASES = ["merge_b_two_refs", "merge_b_four_refs", "merge_b_nobipred", "merge_b_10bit"]
