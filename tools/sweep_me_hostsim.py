@@ -61,6 +61,10 @@ for it in range(count):
     mwant, mbits = M.run_merge_reference(refs[bd], mp, mc, mcur, mplanes, mpus, mcu)
     ok4 = M.run_merge_host_api(host, mp, mc, mcur, mplanes, mpus, mbits).tobytes() == mwant.tobytes()
     ok3 = ok3 and ok4
+    if ml1:                                                   # bi-prediction of two uni-predictions on the same pictures / lists
+        M.BIPRED_CASES.append(mname)
+        bp, bc, bcur, bplanes, bpus = M.make_bipred_case(mname)
+        ok3 = ok3 and M.run_bipred_host_api(host, bp, bc, bcur, bplanes, bpus).tobytes() == M.run_bipred_reference(refs[bd], bp, bc, bcur, bplanes, bpus).tobytes()
     if not (ok and ok2 and ok3):
         bad += 1
         print("DIFF", M.CASES[name], "integer", ok, "frac level", level, ok2, "cand+merge", M.CAND_CASES[cname], ok3, "merge", M.MERGE_CASES[mname], ok4, flush=True)
