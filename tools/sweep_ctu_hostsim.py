@@ -6,7 +6,7 @@ the two .hevc files must be equal.  CPU only (needs oracle/_ref built from /root
 
     python tools/sweep_ctu_hostsim.py <seed> <count>
 
-Round 2: seeds 1-13 and 20-27, 2000 configurations.  Seeds 5 and 8 found one bug (chroma mode search, --intra-chroma-search: scan order of the
+Round 2: seeds 1-13 and 20-39, 3000 configurations (plus QP 0-6 / 49-51 and extreme content: tools/sweep_ctu_content.py).  Seeds 5 and 8 found one bug (chroma mode search, --intra-chroma-search: scan order of the
 candidates, fixed in csrc/ctu/ctu_search.h and covered by tests/test_ctu_driver.py::test_hostbuild_chroma_mode_search); 0 differences since.
 """
 import sys, os, tempfile, pathlib, random
