@@ -446,6 +446,24 @@ typedef struct kvz_cuda_me_bipred_result {
 int kvz_cuda_me_bipred_batch(const kvz_cuda_me_params *p, const kvz_cuda_me_refs *refs, const void *cur_dev, int cur_stride,
                              const kvz_cuda_me_bipred_pu *pus_dev, int count, kvz_cuda_me_bipred_result *out_dev, void *stream);
 
+/* Motion compensation of a batch of decided PUs (kvz_inter_pred_pu, src/inter.c:604-668, luma and chroma): one list through
+ * kvz_sample_quarterpel_luma / kvz_sample_octpel_chroma (or the plain copy for integer MVs), two lists through the 14-bit
+ * samples and kvz_bipred_average; reference samples outside the picture are the edge samples.  The prediction is written
+ * into an I420 picture (the PUs of a batch must not overlap). */
+typedef struct kvz_cuda_me_mc_refs {
+  const void *y[16], *u[16], *v[16];   /* planes of state->frame->ref->images[i] in device memory; luma stride = width, chroma width / 2 */
+  uint8_t ref_LX[2][16];
+} kvz_cuda_me_mc_refs;
+typedef struct kvz_cuda_me_mc_pu {
+  int16_t x, y, w, h;               /* luma samples; multiples of 4 */
+  int16_t mv[2][2];                 /* inter.mv[list] (1/4 pel) */
+  uint8_t mv_ref[2];                /* inter.mv_ref[list] */
+  uint8_t dir;                      /* inter.mv_dir: 1, 2 or 3 */
+  uint8_t pad;
+} kvz_cuda_me_mc_pu;
+int kvz_cuda_me_predict_batch(const kvz_cuda_me_params *p, const kvz_cuda_me_mc_refs *refs, const kvz_cuda_me_mc_pu *pus_dev, int count,
+                              void *pred_y_dev, void *pred_u_dev, void *pred_v_dev, void *stream);
+
 /* AMVP and merge candidates of a batch of PUs from a snapshot of the CU records (me_search.cu), as
  *     kvz_inter_get_mv_cand_cua   src/inter.c:1365-1383 (get_spatial_merge_candidates_cua :1015-1076,
  *                                 get_temporal_merge_candidates :836-907, get_mv_cand_from_candidates :1225-1318,

@@ -677,3 +677,18 @@ def me_bipred_batch(params, refs, cur, pus, out=None):
         out = torch.empty(count * ME_BIPRED_RESULT.itemsize, dtype=torch.uint8, device=cur.device)
     _ck(lib().kvz_cuda_me_bipred_batch(C.byref(params), C.byref(refs), _p(cur), C.c_int(cur.stride(0)), _p(pus), C.c_int(count), _p(out), _stream()))
     return out
+
+
+# motion compensation: kvz_cuda_me_mc_refs / kvz_cuda_me_mc_pu
+ME_MC_PU = np.dtype([("x", "<i2"), ("y", "<i2"), ("w", "<i2"), ("h", "<i2"), ("mv", "<i2", (2, 2)), ("mv_ref", "u1", (2,)), ("dir", "u1"), ("pad", "u1")])
+
+
+class MeMcRefs(C.Structure):
+    """kvz_cuda_me_mc_refs: Y / U / V planes of the reference pictures (device pointers) and the reference lists"""
+    _fields_ = [("y", C.c_void_p * 16), ("u", C.c_void_p * 16), ("v", C.c_void_p * 16), ("ref_LX", (C.c_uint8 * 16) * 2)]
+
+
+def me_predict_batch(params, refs, pus, pred_y, pred_u, pred_v):
+    """Motion compensation of `pus` (CUDA byte tensor of ME_MC_PU records, not overlapping) into the prediction planes (CUDA tensors)."""
+    count = pus.numel() // ME_MC_PU.itemsize
+    _ck(lib().kvz_cuda_me_predict_batch(C.byref(params), C.byref(refs), _p(pus), C.c_int(count), _p(pred_y), _p(pred_u), _p(pred_v), _stream()))

@@ -11,6 +11,7 @@
 #include "me/me_cand.h"
 #include "me/me_frac.h"
 #include "me/me_merge.h"
+#include "me/me_mc.h"
 
 namespace {
 
@@ -80,6 +81,21 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) me_bipred_kernel(kvz_cuda_m
   for (int i = blockIdx.x * kWarpsPerCta + warp; i < count; i += gridDim.x * kWarpsPerCta) {
     const kvz_cuda_me_bipred_pu bp = pus[i];
     kvzme::bipred_pu<Pix>(ln, p, rf, rs, bp, pl, &out[i]);
+  }
+}
+
+// motion compensation: one warp per PU, every lane writes the blocks of its share
+template <typename Pix>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) me_predict_kernel(kvz_cuda_me_params p, kvz_cuda_me_mc_refs rf, const kvz_cuda_me_mc_pu *__restrict__ pus, int count,
+                                                                       Pix *__restrict__ out_y, Pix *__restrict__ out_u, Pix *__restrict__ out_v)
+{
+  const int warp = threadIdx.x >> 5;
+  const kvzme::Lanes ln = { (int)(threadIdx.x & 31), 32 };
+  kvzme::McRefs<Pix> rs;
+  for (int i = 0; i < 16; ++i) { rs.y[i] = (const Pix *)rf.y[i]; rs.u[i] = (const Pix *)rf.u[i]; rs.v[i] = (const Pix *)rf.v[i]; }
+  for (int i = blockIdx.x * kWarpsPerCta + warp; i < count; i += gridDim.x * kWarpsPerCta) {
+    const kvz_cuda_me_mc_pu pu = pus[i];
+    kvzme::predict_pu<Pix>(ln, p, rf, rs, pu, out_y, out_u, out_v);
   }
 }
 
@@ -278,6 +294,27 @@ extern "C" int kvz_cuda_me_bipred_batch(const kvz_cuda_me_params *p, const kvz_c
     me_bipred_kernel<uint8_t><<<grid, kWarpsPerCta * 32, 0, kvzc::as_stream(stream)>>>(*p, *refs, (const uint8_t *)cur_dev, cur_stride, pus_dev, count, out_dev);
   else
     me_bipred_kernel<uint16_t><<<grid, kWarpsPerCta * 32, 0, kvzc::as_stream(stream)>>>(*p, *refs, (const uint16_t *)cur_dev, cur_stride, pus_dev, count, out_dev);
+  KVZC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int kvz_cuda_me_predict_batch(const kvz_cuda_me_params *p, const kvz_cuda_me_mc_refs *refs, const kvz_cuda_me_mc_pu *pus_dev, int count,
+                                         void *pred_y_dev, void *pred_u_dev, void *pred_v_dev, void *stream)
+{
+  KVZC_REQUIRE_DEVICE();
+  KVZC_ARG(p && refs && count >= 0 && (count == 0 || (pus_dev && pred_y_dev && pred_u_dev && pred_v_dev)));
+  KVZC_ARG(kvzme::params_supported(*p) == 0 && (p->width & 1) == 0 && (p->height & 1) == 0);
+  for (int l = 0; l < 2; ++l)
+    for (int i = 0; i < 16; ++i) KVZC_ARG(refs->ref_LX[l][i] < 16);
+  for (int i = 0; i < 16; ++i) KVZC_ARG((refs->y[i] == nullptr) == (refs->u[i] == nullptr) && (refs->y[i] == nullptr) == (refs->v[i] == nullptr));
+  if (count == 0) return 0;
+  const int ctas = (count + kWarpsPerCta - 1) / kWarpsPerCta;
+  const int cap = kvzc::g_sm_count > 0 ? kvzc::g_sm_count * 16 : 148 * 16;
+  const int grid = ctas < cap ? ctas : cap;
+  if (p->bitdepth == 8)
+    me_predict_kernel<uint8_t><<<grid, kWarpsPerCta * 32, 0, kvzc::as_stream(stream)>>>(*p, *refs, pus_dev, count, (uint8_t *)pred_y_dev, (uint8_t *)pred_u_dev, (uint8_t *)pred_v_dev);
+  else
+    me_predict_kernel<uint16_t><<<grid, kWarpsPerCta * 32, 0, kvzc::as_stream(stream)>>>(*p, *refs, pus_dev, count, (uint16_t *)pred_y_dev, (uint16_t *)pred_u_dev, (uint16_t *)pred_v_dev);
   KVZC_LAUNCHED();
   return 0;
 }

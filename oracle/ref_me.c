@@ -490,3 +490,62 @@ int kvzref_me_bipred(kvzref_ctx *ctx, const kvz_cuda_me_params *p, int n_pics, c
   state->lambda_sqrt = saved_lambda_sqrt;
   return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Motion compensation through the reference's own kvz_inter_pred_pu (luma + chroma, one or two lists): the PU's prediction
+ * is taken from the lcu_t work copy into an I420 picture.  cu[i] = { x_cu, y_cu, width_cu, part_mode, i_pu }.
+ * Parity checker for kvz_cuda_me_predict_batch. */
+int kvzref_me_predict(kvzref_ctx *ctx, const kvz_cuda_me_params *p, int n_pics, const kvz_pixel *const *ys, const kvz_pixel *const *us,
+                      const kvz_pixel *const *vs, const uint8_t *ref_LX /* [2][16] */, const kvz_cuda_me_mc_pu *pus, const int32_t *cu, int count,
+                      kvz_pixel *out_y, kvz_pixel *out_u, kvz_pixel *out_v)
+{
+  encoder_state_t *state = &ctx->enc->states[0];
+  encoder_control_t *ctrl = (encoder_control_t *)state->encoder_control;
+  if (p->bitdepth != KVZ_BIT_DEPTH) return -1;
+  if (state->tile->frame->width != p->width || state->tile->frame->height != p->height) return -2;
+  const kvz_config saved_cfg = ctrl->cfg;
+  image_list_t *saved_ref = state->frame->ref;
+  uint8_t saved_LX[2][16]; memcpy(saved_LX, state->frame->ref_LX, 32);
+  ctrl->cfg.bipred = 1;
+  image_list_t *list = kvz_image_list_alloc(16);
+  kvz_picture *pics[16];
+  for (int i = 0; i < 16; ++i) {
+    const int k = i < n_pics ? i : 0;
+    pics[i] = calloc(1, sizeof(kvz_picture));
+    pics[i]->y = (kvz_pixel *)ys[k]; pics[i]->u = (kvz_pixel *)us[k]; pics[i]->v = (kvz_pixel *)vs[k];
+    pics[i]->width = p->width; pics[i]->height = p->height; pics[i]->stride = p->width;
+    list->images[i] = pics[i];
+  }
+  list->used_size = (uint32_t)n_pics;
+  state->frame->ref = list;
+  memcpy(state->frame->ref_LX, ref_LX, 32);
+
+  lcu_t *lcu = calloc(1, sizeof(lcu_t));
+  const int W = p->width, Wc = p->width / 2;
+  for (int i = 0; i < count; ++i) {
+    const kvz_cuda_me_mc_pu *u = &pus[i];
+    const int x_cu = cu[5 * i], y_cu = cu[5 * i + 1], width_cu = cu[5 * i + 2], part_mode = cu[5 * i + 3], i_pu = cu[5 * i + 4];
+    const int xl = SUB_SCU(u->x), yl = SUB_SCU(u->y);
+    memset(lcu->cu, 0, sizeof(lcu->cu));
+    cu_info_t *cu_rec = LCU_GET_CU_AT_PX(lcu, SUB_SCU(x_cu), SUB_SCU(y_cu));
+    cu_rec->type = CU_INTER; cu_rec->part_size = part_mode;
+    cu_info_t *pu = LCU_GET_CU_AT_PX(lcu, xl, yl);
+    pu->type = CU_INTER; pu->part_size = part_mode;
+    pu->inter.mv_dir = u->dir;
+    for (int l = 0; l < 2; ++l) { pu->inter.mv_ref[l] = u->mv_ref[l]; pu->inter.mv[l][0] = u->mv[l][0]; pu->inter.mv[l][1] = u->mv[l][1]; }
+    kvz_inter_pred_pu(state, lcu, x_cu, y_cu, width_cu, true, true, i_pu);
+    for (int r = 0; r < u->h; ++r) memcpy(&out_y[(size_t)(u->y + r) * W + u->x], &lcu->rec.y[(yl + r) * LCU_WIDTH + xl], (size_t)u->w * sizeof(kvz_pixel));
+    for (int r = 0; r < u->h / 2; ++r) {
+      memcpy(&out_u[(size_t)(u->y / 2 + r) * Wc + u->x / 2], &lcu->rec.u[(yl / 2 + r) * LCU_WIDTH_C + xl / 2], (size_t)(u->w / 2) * sizeof(kvz_pixel));
+      memcpy(&out_v[(size_t)(u->y / 2 + r) * Wc + u->x / 2], &lcu->rec.v[(yl / 2 + r) * LCU_WIDTH_C + xl / 2], (size_t)(u->w / 2) * sizeof(kvz_pixel));
+    }
+  }
+  free(lcu);
+  state->frame->ref = saved_ref;
+  memcpy(state->frame->ref_LX, saved_LX, 32);
+  for (int i = 0; i < 16; ++i) { list->images[i] = NULL; free(pics[i]); }
+  list->used_size = 0;
+  kvz_image_list_destroy(list);
+  ctrl->cfg = saved_cfg;
+  return 0;
+}

@@ -88,3 +88,10 @@ class FakeKB:
         assert rc == 0
         self.launches += 1
         return out
+
+    def me_predict_batch(self, params, refs, pus, pred_y, pred_u, pred_v):
+        count = pus.numel() // api.ME_MC_PU.itemsize
+        rc = self.lib.kvz_cuda_me_predict_batch(C.byref(params), C.byref(refs), self._p(pus), C.c_int(count), self._p(pred_y), self._p(pred_u),
+                                                self._p(pred_v), None)
+        assert rc == 0
+        self.launches += 1

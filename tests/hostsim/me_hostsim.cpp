@@ -6,6 +6,7 @@
 #include "../../kvazaar_b200/csrc/me/me_cand.h"
 #include "../../kvazaar_b200/csrc/me/me_frac.h"
 #include "../../kvazaar_b200/csrc/me/me_merge.h"
+#include "../../kvazaar_b200/csrc/me/me_mc.h"
 
 extern "C" int kvz_cuda_me_params_supported(const kvz_cuda_me_params *p) { return p ? kvzme::params_supported(*p) : -1; }
 
@@ -112,5 +113,23 @@ extern "C" int kvz_cuda_me_bipred_batch(const kvz_cuda_me_params *p, const kvz_c
   if (!p || !refs || kvzme::params_supported(*p) != 0) return -2;
   if (p->bitdepth == 8) run_bipred<uint8_t>(p, refs, cur, cur_stride, pus, count, out);
   else run_bipred<uint16_t>(p, refs, cur, cur_stride, pus, count, out);
+  return 0;
+}
+
+template <typename Pix>
+static void run_predict(const kvz_cuda_me_params *p, const kvz_cuda_me_mc_refs *rf, const kvz_cuda_me_mc_pu *pus, int count, void *y, void *u, void *v)
+{
+  kvzme::McRefs<Pix> rs;
+  for (int i = 0; i < 16; ++i) { rs.y[i] = (const Pix *)rf->y[i]; rs.u[i] = (const Pix *)rf->u[i]; rs.v[i] = (const Pix *)rf->v[i]; }
+  for (int i = 0; i < count; ++i)
+    for (int l = 0; l < 32; ++l) kvzme::predict_pu<Pix>(kvzme::Lanes{ l, 32 }, *p, *rf, rs, pus[i], (Pix *)y, (Pix *)u, (Pix *)v);
+}
+
+extern "C" int kvz_cuda_me_predict_batch(const kvz_cuda_me_params *p, const kvz_cuda_me_mc_refs *refs, const kvz_cuda_me_mc_pu *pus, int count,
+                                         void *pred_y, void *pred_u, void *pred_v, void *)
+{
+  if (!p || !refs || kvzme::params_supported(*p) != 0) return -2;
+  if (p->bitdepth == 8) run_predict<uint8_t>(p, refs, pus, count, pred_y, pred_u, pred_v);
+  else run_predict<uint16_t>(p, refs, pus, count, pred_y, pred_u, pred_v);
   return 0;
 }

@@ -7,7 +7,7 @@ import torch
 import test_me_search as A
 import test_zz_me_frac as B
 from _fake_kb import FakeKB
-from _me_cases import BIPRED_CASES, CAND_CASES, CASES, FRAC_CASES, GPU_FIRST_RUN_DONE, MERGE_CASES
+from _me_cases import MC_CASES, BIPRED_CASES, CAND_CASES, CASES, FRAC_CASES, GPU_FIRST_RUN_DONE, MERGE_CASES
 
 
 @pytest.fixture()
@@ -37,6 +37,8 @@ def test_fractional_test_bodies(kb, ref, ref10):
         B.test_cuda_merge_analysis_matches_golden_and_reference(kb, name, ref, ref10)
     for name in sorted(BIPRED_CASES):
         B.test_cuda_bipred_matches_golden_and_reference(kb, name, ref, ref10)
+    for name in sorted(MC_CASES):
+        B.test_cuda_motion_compensation_matches_golden_and_reference(kb, name, ref, ref10)
 
 
 def test_bench_me_bookkeeping(kb, monkeypatch):

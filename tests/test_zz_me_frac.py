@@ -14,7 +14,7 @@ import os
 import numpy as np
 import pytest
 
-from _me_cases import (BIPRED_CASES, BIPRED_RESULT, CASES, FRAC_CASES, GPU_FIRST_RUN_DONE, MERGE_CASES, MERGE_COST, RESULT, make_bipred_case, make_merge_case,
+from _me_cases import (MC_CASES, make_mc_case, mc_refs_struct, run_mc_host_api, run_mc_reference, BIPRED_CASES, BIPRED_RESULT, CASES, FRAC_CASES, GPU_FIRST_RUN_DONE, MERGE_CASES, MERGE_COST, RESULT, make_bipred_case, make_merge_case,
                        merge_refs_struct, run_bipred_host_api, run_bipred_reference, run_merge_host_api, run_merge_reference)
 from _me_cases import grid_case, make_frac_case, run_frac_host_api, run_frac_reference, run_host_api, run_reference, same
 from test_me_search import _explain, _hostsim, check_cuda_case
@@ -100,6 +100,27 @@ def test_bipred_reference_and_hostbuild_match_golden(name, ref, ref10):
     bad = [i for i in range(len(pus)) if got[i].tobytes() != want[i].tobytes()]
     assert not bad, (len(bad), pus[bad[0]], got[bad[0]], want[bad[0]])
     assert bool(want["valid"].any()) == bool(c["bipred"])
+
+
+# ---- motion compensation (kvz_cuda_me_predict_batch; kvz_inter_pred_pu luma + chroma, src/inter.c:604-668)
+def _mc_digest(planes3):
+    import hashlib
+    return np.frombuffer(b"".join(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest() for a in planes3), np.uint8)
+
+
+def _golden_mc(name):
+    return np.load(os.path.join(ROOT, "tests", "golden", "me_search.npz"))["mc/" + name]
+
+
+@pytest.mark.parametrize("name", sorted(MC_CASES))
+def test_mc_reference_and_hostbuild_match_golden(name, ref, ref10):
+    p, c, planes, us, vs, pus, cu = make_mc_case(name)
+    want = run_mc_reference(ref if p.bitdepth == 8 else ref10, p, c, planes, us, vs, pus, cu)
+    assert np.array_equal(_mc_digest(want), _golden_mc(name))
+    got = run_mc_host_api(_hostsim(), p, c, planes, us, vs, pus)
+    for g, w_, what in zip(got, want, "YUV"):
+        assert np.array_equal(g, w_), (what, int((g != w_).sum()))
+    assert (want[0] != 0).mean() > 0.99                       # the PUs tile the whole picture
 
 
 # ------------------------------------------------------------------------------------------------ GPU (the product)
@@ -190,6 +211,24 @@ def test_cuda_bipred_matches_golden_and_reference(cuda_lib, name, ref, ref10):
     torch.cuda.synchronize()
     got = out.cpu().numpy().view(BIPRED_RESULT).copy()
     assert got.tobytes() == want.tobytes() and got.tobytes() == _golden_bipred(name).tobytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(MC_CASES))
+def test_cuda_motion_compensation_matches_golden_and_reference(cuda_lib, name, ref, ref10):
+    import torch
+    kb = cuda_lib
+    p, c, planes, us, vs, pus, cu = make_mc_case(name)
+    want = run_mc_reference(ref if p.bitdepth == 8 else ref10, p, c, planes, us, vs, pus, cu)
+    dy, du, dv = [kb.to_dev(a) for a in planes], [kb.to_dev(a) for a in us], [kb.to_dev(a) for a in vs]
+    rf = mc_refs_struct(c, [t.data_ptr() for t in dy], [t.data_ptr() for t in du], [t.data_ptr() for t in dv])
+    oy, ou, ov = [torch.zeros_like(t) for t in (dy[0], du[0], dv[0])]
+    kb.me_predict_batch(p, rf, kb.to_dev(pus), oy, ou, ov)
+    torch.cuda.synchronize()
+    got = [t.cpu().numpy().view(planes[0].dtype) for t in (oy, ou, ov)]
+    for g, w_, what in zip(got, want, "YUV"):
+        assert np.array_equal(g, w_), (what, int((g != w_).sum()))
+    assert np.array_equal(_mc_digest(got), _golden_mc(name))
 
 
 # ------------------------------------------------------------------------------------------------ CTU driver, chroma mode search

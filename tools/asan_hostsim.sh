@@ -37,6 +37,11 @@ for name in BIPRED_CASES:
     p, c, cur, planes, pus = make_bipred_case(name)
     got = run_bipred_host_api(host, p, c, tight(cur), [tight(pl) for pl in planes], tight(pus))
     assert got.tobytes() == gold["bipred/" + name].tobytes(), name
+import hashlib
+for name in MC_CASES:
+    p, c, planes, us, vs, pus, cu = make_mc_case(name)
+    got = run_mc_host_api(host, p, c, [tight(a) for a in planes], [tight(a) for a in us], [tight(a) for a in vs], tight(pus))
+    assert np.array_equal(np.frombuffer(b"".join(hashlib.sha256(a.tobytes()).digest() for a in got), np.uint8), gold["mc/" + name]), name
 print("motion search host build: issues 0, results equal to the golden outputs")
 PY
 python - <<'PY'

@@ -10,7 +10,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-from _me_cases import (BIPRED_CASES, CAND_CASES, CASES, FRAC_CASES, MERGE_CASES, make_bipred_case, run_bipred_reference, make_cand_case, make_case, make_frac_case, make_merge_case,  # noqa: E402
+from _me_cases import (MC_CASES, make_mc_case, run_mc_reference, BIPRED_CASES, CAND_CASES, CASES, FRAC_CASES, MERGE_CASES, make_bipred_case, run_bipred_reference, make_cand_case, make_case, make_frac_case, make_merge_case,  # noqa: E402
                        run_cand_reference, run_frac_reference, run_merge_reference, run_reference)
 from _oracle import Ref  # noqa: E402
 
@@ -47,4 +47,10 @@ for name in sorted(BIPRED_CASES):
     r = run_bipred_reference(refs.setdefault(p.bitdepth, Ref(p.bitdepth)), p, c, cur, planes, pus)
     out["bipred/" + name] = np.frombuffer(r.tobytes(), np.uint8).copy()
     print("bipred", name, len(pus), "PUs")
+import hashlib
+for name in sorted(MC_CASES):
+    p, c, planes, us, vs, pus, cu = make_mc_case(name)
+    oy, ou, ov = run_mc_reference(refs.setdefault(p.bitdepth, Ref(p.bitdepth)), p, c, planes, us, vs, pus, cu)
+    out["mc/" + name] = np.frombuffer(b"".join(hashlib.sha256(a.tobytes()).digest() for a in (oy, ou, ov)), np.uint8).copy()      # sha256 of Y, U, V
+    print("mc", name, len(pus), "PUs")
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "me_search.npz"), **out)

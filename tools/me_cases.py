@@ -541,3 +541,116 @@ def run_bipred_host_api(lib, p, c, cur, planes, pus):
 
 
 BIPRED_CASES = ["merge_b_two_refs", "merge_b_four_refs", "merge_b_nobipred", "merge_b_10bit"]
+
+
+# ------------------------------------------------------------------------------------------------ motion compensation
+from kvazaar_b200.api import ME_MC_PU as MC_PU, MeMcRefs as McRefs  # noqa: E402
+
+assert MC_PU.itemsize == 20 and C.sizeof(McRefs) == 416
+MC_CASES = ["merge_p_one_ref", "merge_b_two_refs", "merge_b_four_refs", "merge_b_10bit"]
+
+
+def chroma_planes(w, h, bd, seed):
+    r = np.random.default_rng(8000 + seed)
+    yy, xx = np.mgrid[0:h // 2, 0:w // 2]
+    u = np.clip(128 + 50 * np.sin(xx / 5.0 + seed) + r.integers(-20, 21, (h // 2, w // 2)), 0, 255)
+    v = np.clip(128 + 50 * np.cos(yy / 4.0 - seed) + r.integers(-20, 21, (h // 2, w // 2)), 0, 255)
+    if bd == 10:
+        return (u * 4 + r.integers(0, 4, u.shape)).astype(np.uint16), (v * 4 + r.integers(0, 4, v.shape)).astype(np.uint16)
+    return u.astype(np.uint8), v.astype(np.uint8)
+
+
+def make_mc_case(name):
+    """the pictures / reference lists of a merge case (plus chroma planes); the picture tiled with CUs of 8..64 in random part modes,
+    every PU with random motion (fractional, integer, far outside the picture) from one or two lists"""
+    p, c, _, planes, _, _ = make_merge_case(name)
+    r = np.random.default_rng(9000 + c["seed"])
+    w, h, bd = p.width, p.height, p.bitdepth
+    us, vs = zip(*[chroma_planes(w, h, bd, 10 * c["seed"] + k) for k in range(len(planes))])
+    sizes = [len(c["l0"]), len(c["l1"])]
+    pus, cu = [], []
+
+    def add(cx, cy, size):
+        if size > 8 and (cx + size > w or cy + size > h or r.integers(0, 3) != 0):
+            for k in range(4):
+                if cx + (k % 2) * size // 2 < w and cy + (k // 2) * size // 2 < h:
+                    add(cx + (k % 2) * size // 2, cy + (k // 2) * size // 2, size // 2)
+            return
+        if cx + size > w or cy + size > h:
+            return
+        mode = int(r.integers(0, 7 if size >= 16 else 3))
+        q = size // 4
+        split = {0: None, 1: ("h", size // 2), 2: ("v", size // 2), 3: ("h", q), 4: ("h", size - q), 5: ("v", q), 6: ("v", size - q)}[mode]
+        for ipu in range(2 if split else 1):
+            x, y, pw, ph = cx, cy, size, size
+            if split:
+                kind, at = split
+                if kind == "h":
+                    y, ph = (cy, at) if ipu == 0 else (cy + at, size - at)
+                else:
+                    x, pw = (cx, at) if ipu == 0 else (cx + at, size - at)
+            rec = np.zeros((), MC_PU)
+            rec["x"], rec["y"], rec["w"], rec["h"] = x, y, pw, ph
+            dirs = [1] if sizes[1] == 0 else [1, 2, 3, 3]
+            d = int(dirs[int(r.integers(0, len(dirs)))])
+            if d == 3 and pw + ph <= 12:
+                d = 1                                                  # 8x4 / 4x8 PUs are never bi-predicted
+            rec["dir"] = d
+            for l in range(2):
+                rng = 700 if r.integers(0, 15) == 0 else 48
+                rec["mv"][l] = r.integers(-rng, rng + 1, 2)
+                k = r.integers(0, 4)
+                if k == 0:
+                    rec["mv"][l] = (rec["mv"][l] >> 2) << 2            # integer luma MV (chroma may still be fractional)
+                elif k == 1:
+                    rec["mv"][l] = (rec["mv"][l] >> 3) << 3            # integer for chroma too: the copy path
+                rec["mv_ref"][l] = int(r.integers(0, max(1, sizes[l])))
+            pus.append(rec)
+            cu.append((cx, cy, size, PART_MODES[mode], ipu))
+
+    for cy in range(0, h, 64):
+        for cx in range(0, w, 64):
+            add(cx, cy, 64)
+    return p, c, planes, list(us), list(vs), np.array(pus, MC_PU), np.array(cu, np.int32)
+
+
+def mc_refs_struct(c, ys, us, vs):
+    rf = McRefs()
+    for i in range(len(ys)):
+        rf.y[i], rf.u[i], rf.v[i] = ys[i], us[i], vs[i]
+    for l, lst in enumerate((c["l0"], c["l1"])):
+        for i, v in enumerate(lst):
+            rf.ref_LX[l][i] = v
+    return rf
+
+
+def run_mc_reference(ref_shim, p, c, planes, us, vs, pus, cu):
+    dt = planes[0].dtype
+    oy, ou, ov = np.zeros((p.height, p.width), dt), np.zeros((p.height // 2, p.width // 2), dt), np.zeros((p.height // 2, p.width // 2), dt)
+    ctx = ref_shim.ctx(27, 0, 0, p.width, p.height)
+
+    def arr(lst):
+        return (C.c_void_p * 16)(*[np.ascontiguousarray(lst[i if i < len(lst) else 0]).ctypes.data for i in range(16)])
+    lx = np.zeros((2, 16), np.uint8)
+    lx[0, :len(c["l0"])] = c["l0"]
+    lx[1, :len(c["l1"])] = c["l1"]
+    f = ref_shim.lib.kvzref_me_predict
+    f.argtypes = [C.c_void_p, C.POINTER(Params), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                  C.c_void_p, C.c_void_p]
+    cu = np.ascontiguousarray(cu, np.int32)
+    rc = f(ctx, C.byref(p), len(planes), arr(planes), arr(us), arr(vs), lx.ctypes.data, pus.ctypes.data, cu.ctypes.data, len(pus), oy.ctypes.data,
+           ou.ctypes.data, ov.ctypes.data)
+    assert rc == 0, rc
+    return oy, ou, ov
+
+
+def run_mc_host_api(lib, p, c, planes, us, vs, pus):
+    dt = planes[0].dtype
+    oy, ou, ov = np.zeros((p.height, p.width), dt), np.zeros((p.height // 2, p.width // 2), dt), np.zeros((p.height // 2, p.width // 2), dt)
+    keep = [np.ascontiguousarray(a) for a in list(planes) + list(us) + list(vs)]
+    n = len(planes)
+    rf = mc_refs_struct(c, [a.ctypes.data for a in keep[:n]], [a.ctypes.data for a in keep[n:2 * n]], [a.ctypes.data for a in keep[2 * n:]])
+    lib.kvz_cuda_me_predict_batch.argtypes = [C.POINTER(Params), C.POINTER(McRefs), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = lib.kvz_cuda_me_predict_batch(C.byref(p), C.byref(rf), pus.ctypes.data, len(pus), oy.ctypes.data, ou.ctypes.data, ov.ctypes.data, None)
+    assert rc == 0, rc
+    return oy, ou, ov
