@@ -65,6 +65,12 @@ for it in range(count):
         M.BIPRED_CASES.append(mname)
         bp, bc, bcur, bplanes, bpus = M.make_bipred_case(mname)
         ok3 = ok3 and M.run_bipred_host_api(host, bp, bc, bcur, bplanes, bpus).tobytes() == M.run_bipred_reference(refs[bd], bp, bc, bcur, bplanes, bpus).tobytes()
+    # motion compensation on the same pictures / lists
+    M.MC_CASES.append(mname)
+    cp, cc, cplanes, cus_, cvs_, cpus_, ccu_ = M.make_mc_case(mname)
+    gw = M.run_mc_reference(refs[bd], cp, cc, cplanes, cus_, cvs_, cpus_, ccu_)
+    gg = M.run_mc_host_api(host, cp, cc, cplanes, cus_, cvs_, cpus_)
+    ok3 = ok3 and all(np.array_equal(a, b) for a, b in zip(gg, gw))
     if not (ok and ok2 and ok3):
         bad += 1
         print("DIFF", M.CASES[name], "integer", ok, "frac level", level, ok2, "cand+merge", M.CAND_CASES[cname], ok3, "merge", M.MERGE_CASES[mname], ok4, flush=True)
