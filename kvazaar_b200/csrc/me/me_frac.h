@@ -48,12 +48,18 @@ ME_FN uint32_t wht_abs_sum(int32_t *d)
   return s;
 }
 
-ME_FN int luma_tap(int frac, int k)
-{
-  // the standard's 8-tap luma filters for the 0, 1/4, 1/2, 3/4 positions
-  const int8_t f[4][8] = { { 0, 0, 0, 64, 0, 0, 0, 0 }, { -1, 4, -10, 58, 17, -5, 1, 0 }, { -1, 4, -11, 40, 40, -11, 4, -1 }, { 0, 1, -5, 17, 58, -10, 4, -1 } };
-  return f[frac][k];
-}
+// the standard's 8-tap luma filters for the 0, 1/4, 1/2, 3/4 positions and 4-tap chroma filters for the eight 1/8 positions
+// (constant memory on the device: the fraction is the same for every lane of a warp, so a lookup is one broadcast)
+#if defined(__CUDACC__)
+#define ME_TABLE static __device__ __constant__ const
+#else
+#define ME_TABLE static const
+#endif
+ME_TABLE int8_t kLumaTaps[4][8] = { { 0, 0, 0, 64, 0, 0, 0, 0 }, { -1, 4, -10, 58, 17, -5, 1, 0 }, { -1, 4, -11, 40, 40, -11, 4, -1 }, { 0, 1, -5, 17, 58, -10, 4, -1 } };
+ME_TABLE int8_t kChromaTaps[8][4] = { { 0, 64, 0, 0 }, { -2, 58, 10, -2 }, { -4, 54, 16, -2 }, { -6, 46, 28, -4 }, { -4, 36, 36, -4 }, { -4, 28, 46, -6 }, { -2, 16, 54, -4 }, { -2, 10, 58, -2 } };
+
+ME_FN int luma_tap(int frac, int k) { return kLumaTaps[frac][k]; }
+ME_FN int chroma_tap(int frac, int k) { return kChromaTaps[frac][k]; }
 
 // Hadamard cost of the N x N sub-block at (sx, sy) of the PU against the prediction at quarter-pel MV (qx, qy)
 template <typename Pix, int N>

@@ -16,13 +16,6 @@ namespace kvzme {
 
 static_assert(sizeof(kvz_cuda_me_mc_refs) == 416 && sizeof(kvz_cuda_me_mc_pu) == 20, "record layouts are part of the ABI");
 
-ME_FN int chroma_tap(int frac, int k)
-{
-  // the standard's 4-tap chroma filters for the eight 1/8 positions
-  const int8_t f[8][4] = { { 0, 64, 0, 0 }, { -2, 58, 10, -2 }, { -4, 54, 16, -2 }, { -6, 46, 28, -4 }, { -4, 36, 36, -4 }, { -4, 28, 46, -6 }, { -2, 16, 54, -4 }, { -2, 10, 58, -2 } };
-  return f[frac][k];
-}
-
 // 14-bit intermediate samples of an N x N chroma block at (bx, by) + fraction (fx, fy) in 1/8 units; plane of cw x ch samples
 template <typename Pix, int N>
 ME_FN void hi_block_chroma(int bitdepth, const Pix *ref, int cw, int ch, int bx, int by, int fx, int fy, int32_t *out)
